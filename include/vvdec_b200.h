@@ -1,0 +1,99 @@
+/* vvdec_b200.h — C ABI of the B200-native VVC pixel-reconstruction back end.
+ *
+ * Boundary: this library replaces the *pixel work* behind VVdeC's
+ * DecLibRecon::decompressPicture (reference: source/Lib/DecoderLib/DecLibRecon.cpp:429) and the
+ * scalar/SIMD function-pointer surface of CommonLib (TrQuant/Quant/TCoeffOps, InterpolationFilter,
+ * InterPrediction, LoopFilter, SampleAdaptiveOffset, AdaptiveLoopFilter).  VVdeC's parser keeps
+ * running on the CPU; a host-side flattener turns each parsed Picture into the SoA work lists
+ * declared here (plain pointers + sizes, no C++/torch types).
+ *
+ * Two levels of entry points:
+ *   (1) picture level  — b200_ctx_*, b200_pic_* : the DecLibRecon seam (create / decompressPicture /
+ *       waitForPrevDecompressedPic), operating on a decoded-picture buffer resident in HBM;
+ *   (2) kernel level   — b200_k1_*, b200_if_*, b200_lf_*, b200_sao_*, b200_alf_* : host-pointer
+ *       batch wrappers with the argument meaning of the reference pointer they replace, used by the
+ *       parity tests exactly like vvdec_unit_test compares `ref` against `opt`.
+ *
+ * Every function returns 0 on success, a negative B200_ERR_* otherwise; b200_last_error() gives text.
+ * All sample planes are int16 ("Pel", reference TypeDef.h:188), 4:2:0 or 4:0:0, bit depth 8..12.
+ */
+#ifndef VVDEC_B200_H
+#define VVDEC_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_API __attribute__((visibility("default")))
+
+enum {
+  B200_OK            =  0,
+  B200_ERR_CUDA      = -1,   /* a CUDA runtime call failed (maps to vvdec Exception) */
+  B200_ERR_PARAM     = -2,   /* invalid argument (maps to RecoverableException)                */
+  B200_ERR_NO_DEVICE = -3,   /* no sm_100 device: the product path refuses to run on the CPU   */
+  B200_ERR_UNSUPPORTED = -4  /* maps to UnsupportedFeatureException                            */
+};
+
+B200_API const char* b200_last_error(void);
+B200_API int         b200_device_count(void);
+B200_API const char* b200_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  residual: dequant + LFNST + inverse DCT-2/DST-7/DCT-8 + transform skip + BDPCM + joint CbCr
+ *   replaces  Quant::DeQuant* (Quant.h:143-147, Quant.cpp:122-179, :295), invResDPCM (Quant.cpp:239),
+ *             TrQuant::m_invLfnstNxN + xInvLfnst (TrQuant.cpp:79,:201), TrQuant::xIT (:410),
+ *             fastInvTrans[][] / TCoeffOps::fastInvCore / roundClip / cpyResiClip (TrQuant_EMT.cpp),
+ *             xITransformSkip (:489), invTransformCbCr (:108).
+ * One record per coded TU component (what reconstructResi, DecCu.cpp:536, iterates).
+ * ---------------------------------------------------------------------------------------------- */
+enum { B200_TR_DCT2 = 0, B200_TR_DCT8 = 1, B200_TR_DST7 = 2 };          /* == vvdec TransType */
+enum {
+  B200_TU_TS       = 1,   /* mtsIdx == MTS_SKIP                                   */
+  B200_TU_BDPCM_H  = 2,   /* bdpcmMode == 1 (accumulate along x), implies TS      */
+  B200_TU_BDPCM_V  = 4,   /* bdpcmMode == 2 (accumulate along y), implies TS      */
+  B200_TU_SCALING  = 8    /* explicit scaling list: per-position factor at slOff  */
+};
+
+typedef struct b200_tu {
+  uint16_t x, y;          /* top-left in the component's plane, samples                                  */
+  uint8_t  log2w, log2h;  /* 1..6                                                                        */
+  uint8_t  comp;          /* 0 Y, 1 Cb, 2 Cr : plane that receives the (first) residual                  */
+  uint8_t  flags;         /* B200_TU_*                                                                   */
+  uint8_t  maxX, maxY;    /* tu.maxScanPosX/Y[comp] (Unit.h:291); BDPCM: w-1,h-1                         */
+  uint8_t  trType;        /* hor | ver<<2, B200_TR_* — result of TrQuant::getTrTypes (TrQuant.cpp:330)   */
+  uint8_t  lfnst;         /* 0 off, else lfnstIdx(1|2) | set<<2 (g_lfnstLut[mode], 0..3) | transpose<<4  */
+  int8_t   ict;           /* TU::getICTMode in -3..3 (0: none): also derive the other chroma plane       */
+  int8_t   rightShift;    /* Quant::dequant's rightShift (Quant.cpp:337); <=0 means left shift           */
+  uint8_t  inBits;        /* targetInputBitDepth (Quant.cpp:347): level clip to +-2^(inBits-1)           */
+  uint8_t  scale;         /* g_InvQuantScales[sqrt2][QP_rem] (Quant.cpp:341)                             */
+  uint32_t coefOff;       /* first level of the packed (maxX+1)x(maxY+1) corner, int16 units, row-major  */
+  uint32_t slOff;         /* B200_TU_SCALING: int32 units into the scaling arena, w*h factors row-major  */
+  uint32_t rsv[2];
+} b200_tu;                /* 32 bytes */
+
+/* Picture geometry shared by all stages. Planes have no margin: kernels clamp coordinates, which is
+ * what the reference's 144-sample border extension (Picture.cpp:400-558) emulates. */
+typedef struct b200_geom {
+  int32_t width, height;       /* luma samples                       */
+  int32_t chromaFormat;        /* 0 = 4:0:0, 1 = 4:2:0               */
+  int32_t bitDepth;            /* 8..12                              */
+  int32_t ctuSize;             /* 32/64/128                          */
+  int32_t stride[3];           /* samples per row of each plane      */
+} b200_geom;
+
+/* Kernel-level K1: host planes in, host planes out (in place).
+ *   mode 0: planes hold the prediction; result = clip(pred + residual, 0, 2^bd-1)   (DecCu.cpp:455-479 reco)
+ *   mode 1: result = residual only (what invTransformNxN leaves in pResi), planes pre-filled are overwritten
+ *           only inside coded TUs. */
+B200_API int b200_k1_residual(const b200_geom* g, int16_t* const planes[3],
+                              const b200_tu* tus, size_t numTus,
+                              const int16_t* coefs, size_t numCoefs,
+                              const int32_t* scaling, size_t numScaling,
+                              int mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

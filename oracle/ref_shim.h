@@ -1,0 +1,56 @@
+/* ref_shim.h — C view of oracle/_ref/libvvdec_ref.so (the UNMODIFIED reference + our extern "C" shim).
+ * TEST INFRASTRUCTURE ONLY. `simd` = 0 selects the reference's scalar *Core functions, 1 the SIMD
+ * re-bindings (what read_x86_extension_flags() picks on the host: SSE4.1 or AVX2). */
+#ifndef REF_SHIM_H
+#define REF_SHIM_H
+#include <stdint.h>
+#include <stddef.h>
+#include "../include/vvdec_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* ref_simd_level(void);
+
+/* ---- K1, pointer level ---- */
+void ref_dequant(int simd, int width, int maxX, int maxY, int scale, const int16_t* q, size_t qStride, int32_t* coef,
+                 int rightShift, int inputMaximum, int32_t transformMaximum);
+void ref_inv_lfnst(int32_t* src, int32_t* dst, unsigned set, unsigned index, unsigned size, int zeroOutSize);
+void ref_inv_1d(int simd, int trType, int n, const int32_t* src, int32_t* dst, int shift, int line, int skipLine,
+                int skipLine2, int clip, int32_t outMin, int32_t outMax);
+void ref_cpy_resi_clip(int simd, const int32_t* src, int16_t* dst, ptrdiff_t stride, unsigned w, unsigned h,
+                       int32_t outMin, int32_t outMax, int32_t round, int32_t shift);
+
+/* ---- K1, TU level: builds a real vvdec TransformUnit/CodingUnit/SPS/PPS/Slice from syntax values, runs
+ *      (a) our flattener (vvdec_b200/vvdec_glue/flatten_tu.h) and (b) the reference's own
+ *      QpParam + TrQuant::invTransformNxN (+ invTransformICT) exactly as DecCu::reconstructResi does. ---- */
+typedef struct ref_tu_syntax {
+  int32_t w, h;            /* luma size of the CU == TU (no TU split)                 */
+  int32_t comp;            /* component under test 0/1/2                              */
+  int32_t bitDepth;
+  int32_t predMode;        /* 0 inter, 1 intra (vvdec PredMode)                       */
+  int32_t qp, chromaQpAdj; /* cu.qp, cu.chromaQpAdj                                   */
+  int32_t cbQpOffset, crQpOffset, jointQpOffset;   /* pps offsets                     */
+  int32_t depQuant;
+  int32_t mtsIdx;          /* tu.mtsIdx(comp) 0..5                                    */
+  int32_t lfnstIdx;        /* 0..2                                                    */
+  int32_t intraDirL, intraDirC;
+  int32_t mipFlag, ispMode, sbtIdx, sbtPos;
+  int32_t bdpcmL, bdpcmC;
+  int32_t jointCbCr;       /* 0..3 ; cbf bits derived                                  */
+  int32_t jointCbCrSign;
+  int32_t maxScanPosX, maxScanPosY;
+  int32_t spsMTS, spsIntraMTS, spsInterMTS, spsLFNST;   /* implicit MTS = spsMTS && !spsIntraMTS (Slice.h:1796) */
+  int32_t sepTree;         /* dual tree chroma CU                                      */
+} ref_tu_syntax;
+
+/* levels: compW*compH int16 row-major for the coded component. Outputs: resi0 = plane of the coded
+ * component's area after the reference ran (compW*compH), resi1 = other chroma plane (joint CbCr) or
+ * untouched; rec = our flattened record; coefs/numCoefs = packed corner. Returns 1 if a record was made. */
+int ref_tu_case(const ref_tu_syntax* s, const int16_t* levels, int16_t* resi0, int16_t* resi1,
+                b200_tu* rec, int16_t* coefs, int32_t* numCoefs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

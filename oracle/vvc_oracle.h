@@ -1,0 +1,50 @@
+/* vvc_oracle.h — CPU restatement ("oracle") of the VVdeC pixel-reconstruction hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may call it.
+ * The product path (vvdec_b200/csrc) never links or falls back to this code.
+ *
+ * Parity status: PINNED.  Every function here is checked bit-for-bit against the reference's own
+ * scalar *Core functions compiled from /root/reference into oracle/_ref/libvvdec_ref.so
+ * (oracle/Makefile.ref, oracle/ref_shim.cpp; tests/test_oracle_vs_ref.py), and against the golden
+ * vectors under tests/golden/ that were generated from that library (tools/make_golden.py).
+ *
+ * Plain C99, scalar, single-threaded.  Each function cites the reference file:line it restates
+ * (paths relative to /root/reference/source/Lib/CommonLib unless noted).
+ */
+#ifndef VVC_ORACLE_H
+#define VVC_ORACLE_H
+#include <stdint.h>
+#include <stddef.h>
+#include "../include/vvdec_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- K1 building blocks -------------------------------------------------------------------- */
+/* Quant.cpp:122-179 DeQuantImpl (UseScalingList = sl != NULL); q is int16 levels with stride qStride. */
+void orc_dequant(int width, int maxX, int maxY, int scale, const int32_t* sl, const int16_t* q, size_t qStride,
+                 int32_t* coef, int rightShift, int inputMaximum, int32_t transformMaximum);
+/* same, 32-bit levels (DeQuantPCM, Quant.cpp:208: BDPCM path dequantises the accumulated block in place) */
+void orc_dequant32(int width, int maxX, int maxY, int scale, const int32_t* sl, const int32_t* q, size_t qStride,
+                   int32_t* coef, int rightShift, int inputMaximum, int32_t transformMaximum);
+/* TrQuant.cpp:79-106 invLfnstNxNCore. */
+void orc_inv_lfnst(const int32_t* src, int32_t* dst, unsigned set, unsigned index, unsigned size, int zeroOutSize);
+/* TrQuant_EMT.cpp:103-121 _fastInverseMM / :126-354 fastInverse{DCT2,DCT8,DST7}_B{2..64}: one 1-D stage. */
+void orc_inv_1d(int trType, int n, const int32_t* src, int32_t* dst, int shift, int line, int skipLine, int skipLine2,
+                int clip, int32_t outMin, int32_t outMax);
+/* TrQuant_EMT.cpp:366 cpyResiClipCore. */
+void orc_cpy_resi_clip(const int32_t* src, int16_t* dst, ptrdiff_t stride, unsigned w, unsigned h,
+                       int32_t outMin, int32_t outMax, int32_t round, int32_t shift);
+/* TrQuant.cpp:290 invTransformNxN for one record (dequant → LFNST → xIT | TS), residual to resi[stride]. */
+void orc_tu_residual(const b200_tu* tu, int bitDepth, const int16_t* coefs, const int32_t* scaling,
+                     int16_t* resi, ptrdiff_t stride);
+/* DecCu.cpp:536 reconstructResi over a list + (mode 0) the pred+resi clip of Buffer.cpp:83 recoCore. */
+void orc_k1_residual(const b200_geom* g, int16_t* const planes[3], const b200_tu* tus, size_t numTus,
+                     const int16_t* coefs, const int32_t* scaling, int mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

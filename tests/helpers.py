@@ -1,0 +1,65 @@
+"""Test helpers: load the oracle (C restatement) and, when built, the reference shim."""
+import os, subprocess, ctypes as C
+import numpy as np
+from vvdec_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libvvdec_ref.so")
+
+i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+
+
+def load_oracle():
+    srcs = [os.path.join(ROOT, "oracle", f) for f in os.listdir(os.path.join(ROOT, "oracle")) if f.endswith((".c", ".h"))]
+    if not os.path.exists(ORACLE_SO) or any(os.path.getmtime(s) > os.path.getmtime(ORACLE_SO) for s in srcs):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
+    lib = C.CDLL(ORACLE_SO)
+    lib.orc_dequant.argtypes = [C.c_int] * 4 + [C.c_void_p, i16p, C.c_size_t, i32p, C.c_int, C.c_int, C.c_int32]
+    lib.orc_inv_lfnst.argtypes = [i32p, i32p, C.c_uint, C.c_uint, C.c_uint, C.c_int]
+    lib.orc_inv_1d.argtypes = [C.c_int, C.c_int, i32p, i32p] + [C.c_int] * 5 + [C.c_int32, C.c_int32]
+    lib.orc_cpy_resi_clip.argtypes = [i32p, i16p, C.c_ssize_t, C.c_uint, C.c_uint] + [C.c_int32] * 4
+    lib.orc_tu_residual.argtypes = [C.POINTER(abi.Tu), C.c_int, i16p, C.c_void_p, i16p, C.c_ssize_t]
+    lib.orc_k1_residual.argtypes = [C.POINTER(abi.Geom), C.POINTER(C.POINTER(C.c_int16)), C.c_void_p, C.c_size_t,
+                                    i16p, C.c_void_p, C.c_int]
+    return lib
+
+
+class RefTuSyntax(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ["w", "h", "comp", "bitDepth", "predMode", "qp", "chromaQpAdj", "cbQpOffset", "crQpOffset",
+                 "jointQpOffset", "depQuant", "mtsIdx", "lfnstIdx", "intraDirL", "intraDirC", "mipFlag", "ispMode",
+                 "sbtIdx", "sbtPos", "bdpcmL", "bdpcmC", "jointCbCr", "jointCbCrSign", "maxScanPosX", "maxScanPosY",
+                 "spsMTS", "spsIntraMTS", "spsInterMTS", "spsLFNST", "sepTree"]]
+
+
+def load_ref():
+    if not os.path.exists(REF_SO):
+        return None
+    lib = C.CDLL(REF_SO)
+    lib.ref_simd_level.restype = C.c_char_p
+    lib.ref_dequant.argtypes = [C.c_int] * 5 + [i16p, C.c_size_t, i32p, C.c_int, C.c_int, C.c_int32]
+    lib.ref_inv_lfnst.argtypes = [i32p, i32p, C.c_uint, C.c_uint, C.c_uint, C.c_int]
+    lib.ref_inv_1d.argtypes = [C.c_int, C.c_int, C.c_int, i32p, i32p] + [C.c_int] * 5 + [C.c_int32, C.c_int32]
+    lib.ref_cpy_resi_clip.argtypes = [C.c_int, i32p, i16p, C.c_ssize_t, C.c_uint, C.c_uint] + [C.c_int32] * 4
+    lib.ref_tu_case.argtypes = [C.POINTER(RefTuSyntax), i16p, i16p, i16p, C.POINTER(abi.Tu), i16p, C.POINTER(C.c_int32)]
+    lib.ref_tu_case.restype = C.c_int
+    return lib
+
+
+def aligned(shape, dtype, fill=0, align=64):
+    """numpy array whose data pointer is `align`-byte aligned (the reference's SIMD paths use aligned loads)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    raw = np.zeros(n * dtype.itemsize + align, np.uint8)
+    off = (-raw.ctypes.data) % align
+    a = raw[off:off + n * dtype.itemsize].view(dtype).reshape(shape)
+    a[...] = fill
+    return a
+
+
+def aligned_copy(src, align=64):
+    a = aligned(src.shape, src.dtype, align=align)
+    a[...] = src
+    return a

@@ -1,0 +1,44 @@
+"""ctypes mirror of include/vvdec_b200.h (the C-ABI structs). Keep in sync with the header."""
+import ctypes as C
+import numpy as np
+
+TR_DCT2, TR_DCT8, TR_DST7 = 0, 1, 2
+TU_TS, TU_BDPCM_H, TU_BDPCM_V, TU_SCALING = 1, 2, 4, 8
+
+
+class Tu(C.Structure):
+    _fields_ = [("x", C.c_uint16), ("y", C.c_uint16), ("log2w", C.c_uint8), ("log2h", C.c_uint8),
+                ("comp", C.c_uint8), ("flags", C.c_uint8), ("maxX", C.c_uint8), ("maxY", C.c_uint8),
+                ("trType", C.c_uint8), ("lfnst", C.c_uint8), ("ict", C.c_int8), ("rightShift", C.c_int8),
+                ("inBits", C.c_uint8), ("scale", C.c_uint8), ("coefOff", C.c_uint32), ("slOff", C.c_uint32),
+                ("rsv", C.c_uint32 * 2)]
+
+
+TU_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("log2w", "u1"), ("log2h", "u1"), ("comp", "u1"), ("flags", "u1"),
+                     ("maxX", "u1"), ("maxY", "u1"), ("trType", "u1"), ("lfnst", "u1"), ("ict", "i1"),
+                     ("rightShift", "i1"), ("inBits", "u1"), ("scale", "u1"), ("coefOff", "<u4"), ("slOff", "<u4"),
+                     ("rsv", "<u4", (2,))])
+assert TU_DTYPE.itemsize == C.sizeof(Tu) == 32
+
+
+class Geom(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("chromaFormat", C.c_int32), ("bitDepth", C.c_int32),
+                ("ctuSize", C.c_int32), ("stride", C.c_int32 * 3)]
+
+
+def make_geom(width, height, bit_depth=10, chroma_format=1, ctu=128, strides=None):
+    g = Geom(width, height, chroma_format, bit_depth, ctu)
+    cw = width >> 1 if chroma_format == 1 else 0
+    s = strides or (width, cw, cw)
+    g.stride[0], g.stride[1], g.stride[2] = s
+    return g
+
+
+def plane_ptrs(planes):
+    """planes: list of 3 contiguous int16 numpy arrays (or None). Returns (int16* [3])."""
+    arr = (C.POINTER(C.c_int16) * 3)()
+    for i, p in enumerate(planes):
+        if p is not None:
+            assert p.dtype == np.int16 and p.flags["C_CONTIGUOUS"]
+            arr[i] = p.ctypes.data_as(C.POINTER(C.c_int16))
+    return arr
