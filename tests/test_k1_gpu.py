@@ -1,0 +1,68 @@
+"""K1 parity on the GPU: CUDA kernel (through the C ABI) vs the pinned oracle, bit-exact."""
+import ctypes as C
+import numpy as np
+import pytest
+import vvdec_b200
+from vvdec_b200 import abi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(b200, oracle, W, H, bd, tus, coefs, planes, mode):
+    g = abi.make_geom(W, H, bd)
+    a = [p.copy() for p in planes]; b = [p.copy() for p in planes]
+    oracle.orc_k1_residual(C.byref(g), abi.plane_ptrs(a), tus.ctypes.data, len(tus), coefs, None, mode)
+    vvdec_b200.check(b200.b200_k1_residual(C.byref(g), abi.plane_ptrs(b), tus.ctypes.data, len(tus),
+                                            coefs.ctypes.data, len(coefs), None, 0, mode))
+    return a, b
+
+
+@pytest.mark.parametrize("seed,W,H,bd,mode", [(1, 256, 128, 10, 0), (2, 416, 240, 10, 1), (3, 256, 256, 8, 0),
+                                              (4, 384, 256, 12, 1), (5, 1920, 1080, 10, 0)])
+def test_k1_random_pictures(b200, oracle, seed, W, H, bd, mode):
+    rng = np.random.default_rng(seed)
+    cus = synth.partition(rng, W, H)
+    tus, coefs = synth.gen_tus(rng, cus, bd, p_cbf=0.9, p_mts=0.25, p_lfnst=0.2, p_ts=0.1, p_bdpcm=0.1, heavy=0.05)
+    assert len(tus) > 50
+    planes = synth.noise_planes(rng, W, H, bd)
+    a, b = _run_both(b200, oracle, W, H, bd, tus, coefs, planes, mode)
+    for c in range(3):
+        assert np.array_equal(a[c], b[c]), f"plane {c} differs at {np.argwhere(a[c] != b[c])[:5]}"
+    # feature coverage of this case
+    assert (tus["lfnst"] != 0).any() and (tus["flags"] & abi.TU_TS).any() and (tus["ict"] != 0).any()
+    assert (tus["trType"] != 0).any() and (tus["flags"] & (abi.TU_BDPCM_H | abi.TU_BDPCM_V)).any()
+
+
+def test_k1_every_size_dense_extreme(b200, oracle):
+    """All 36 TU shapes x {DCT2, DST7, DCT8} with full corners and extreme levels (overflow wrap must match)."""
+    rng = np.random.default_rng(11)
+    recs, coefs, n = [], [], 0
+    x = y = 0
+    W = 1024
+    for l2w in range(1, 7):
+        for l2h in range(1, 7):
+            for tr in (0, 2 | (2 << 2), 1 | (1 << 2), 2 | (1 << 2)):
+                w, h = 1 << l2w, 1 << l2h
+                if tr and (min(w, h) < 4 or max(w, h) > 32): continue
+                limx = 16 if (tr and w == 32) else min(w, 32); limy = 16 if (tr and h == 32) else min(h, 32)
+                if x + w > W: x = 0; y += 64
+                lv = rng.choice(np.array([-32768, 32767, -1, 1, 0, 1234], np.int16), size=limx * limy)
+                lv[-1] = 32767
+                sq = (l2w + l2h) & 1
+                recs.append((x, y, l2w, l2h, 0, 0, limx - 1, limy - 1, tr, 0, 0, int(rng.integers(-2, 6)), 16,
+                             [64, 90][sq], n, 0, (0, 0)))
+                coefs.append(lv); n += len(lv); x += w
+    tus = np.array(recs, dtype=abi.TU_DTYPE); arena = np.concatenate(coefs)
+    H = y + 64
+    planes = [np.zeros((H, W), np.int16), np.zeros((H // 2, W // 2), np.int16), np.zeros((H // 2, W // 2), np.int16)]
+    a, b = _run_both(b200, oracle, W, H, 10, tus, arena, planes, 1)
+    assert np.array_equal(a[0], b[0])
+
+
+def test_k1_empty_and_errors(b200):
+    g = abi.make_geom(64, 64, 10)
+    planes = [np.zeros((64, 64), np.int16), np.zeros((32, 32), np.int16), np.zeros((32, 32), np.int16)]
+    assert b200.b200_k1_residual(C.byref(g), abi.plane_ptrs(planes), None, 0, None, 0, None, 0, 0) == 0
+    g.bitDepth = 17
+    assert b200.b200_k1_residual(C.byref(g), abi.plane_ptrs(planes), None, 0, None, 0, None, 0, 0) == -2
+    assert b"bit depth" in b200.b200_last_error()

@@ -1,0 +1,19 @@
+"""ctypes prototypes for libvvdec_b200.so (include/vvdec_b200.h)."""
+import ctypes as C
+import numpy as np
+from . import abi
+
+i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
+PLANES = C.POINTER(C.POINTER(C.c_int16))
+
+
+def declare(lib):
+    lib.b200_last_error.restype = C.c_char_p
+    lib.b200_version.restype = C.c_char_p
+    lib.b200_device_count.restype = C.c_int
+    lib.b200_k1_residual.argtypes = [C.POINTER(abi.Geom), PLANES, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                     C.c_void_p, C.c_size_t, C.c_int]
+    lib.b200_k1_residual.restype = C.c_int
+
+
+EXPORTS = ["b200_last_error", "b200_version", "b200_device_count", "b200_k1_residual"]

@@ -1,0 +1,98 @@
+// api.cu — C-ABI entry points of libvvdec_b200.so (include/vvdec_b200.h). Host-pointer wrappers stage
+// through device scratch buffers; picture-level entry points keep everything resident (see picture.cu).
+#include "common.cuh"
+#include <stdarg.h>
+#include <mutex>
+
+namespace b200 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+  va_list ap; va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int ensure_device()
+{
+  static std::once_flag once;
+  static int status = 0;
+  std::call_once(once, [] {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { set_error("no CUDA device: vvdec_b200 has no CPU fallback"); status = B200_ERR_NO_DEVICE; return; }
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, dev);
+    if (p.major < 10) { set_error("device %s is sm_%d%d; this library is built for sm_100a only", p.name, p.major, p.minor); status = B200_ERR_NO_DEVICE; }
+  });
+  if (status) set_error("no usable sm_100 device: vvdec_b200 has no CPU fallback");
+  return status;
+}
+
+// scratch for the kernel-level host wrappers (single-threaded use, like the reference's per-thread objects)
+struct HostWrapScratch {
+  DevBuf planes[3], tus, coefs, scaling, misc[8];
+  cudaStream_t stream = nullptr;
+  int init() { if (!stream) { B200_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); } return 0; }
+};
+static HostWrapScratch g_hw;
+HostWrapScratch& host_scratch() { return g_hw; }
+
+// Upload the three host planes described by g into scratch; fills dp.
+static int upload_planes(const b200_geom* g, int16_t* const planes[3], DevPlanes& dp, cudaStream_t s)
+{
+  const int nPlanes = g->chromaFormat ? 3 : 1;
+  for (int c = 0; c < nPlanes; c++) {
+    const int ph = c ? g->height >> 1 : g->height;
+    const size_t bytes = (size_t)g->stride[c] * ph * sizeof(int16_t);
+    if (int rc = g_hw.planes[c].reserve(bytes)) return rc;
+    dp.p[c] = g_hw.planes[c].as<int16_t>(); dp.stride[c] = g->stride[c];
+    B200_CUDA(cudaMemcpyAsync(dp.p[c], planes[c], bytes, cudaMemcpyHostToDevice, s));
+  }
+  return 0;
+}
+static int download_planes(const b200_geom* g, int16_t* const planes[3], const DevPlanes& dp, cudaStream_t s)
+{
+  const int nPlanes = g->chromaFormat ? 3 : 1;
+  for (int c = 0; c < nPlanes; c++) {
+    const int ph = c ? g->height >> 1 : g->height;
+    B200_CUDA(cudaMemcpyAsync(planes[c], dp.p[c], (size_t)g->stride[c] * ph * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+  }
+  return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+B200_API const char* b200_last_error(void) { return g_err; }
+B200_API const char* b200_version(void) { return "vvdec_b200 0.1 (sm_100a)"; }
+B200_API int b200_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
+
+B200_API int b200_k1_residual(const b200_geom* g, int16_t* const planes[3], const b200_tu* tus, size_t numTus,
+                              const int16_t* coefs, size_t numCoefs, const int32_t* scaling, size_t numScaling, int mode)
+{
+  B200_CHECK(g && planes && (tus || !numTus), "b200_k1_residual: null argument");
+  B200_CHECK(g->bitDepth >= 8 && g->bitDepth <= 12, "b200_k1_residual: bit depth %d unsupported", g->bitDepth);
+  if (int rc = ensure_device()) return rc;
+  if (int rc = g_hw.init()) return rc;
+  cudaStream_t s = g_hw.stream;
+  K1Launch L; L.geom = *g; L.numTus = numTus; L.mode = mode;
+  if (int rc = upload_planes(g, planes, L.planes, s)) return rc;
+  if (int rc = g_hw.tus.reserve(numTus * sizeof(b200_tu))) return rc;
+  if (int rc = g_hw.coefs.reserve(numCoefs * sizeof(int16_t) + 16)) return rc;
+  if (int rc = g_hw.scaling.reserve(numScaling * sizeof(int32_t) + 16)) return rc;
+  B200_CUDA(cudaMemcpyAsync(g_hw.tus.p, tus, numTus * sizeof(b200_tu), cudaMemcpyHostToDevice, s));
+  if (numCoefs) B200_CUDA(cudaMemcpyAsync(g_hw.coefs.p, coefs, numCoefs * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+  if (numScaling) B200_CUDA(cudaMemcpyAsync(g_hw.scaling.p, scaling, numScaling * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  L.tus = g_hw.tus.as<b200_tu>(); L.coefs = g_hw.coefs.as<int16_t>(); L.scaling = g_hw.scaling.as<int32_t>();
+  if (int rc = launch_k1_residual(L, s)) return rc;
+  if (int rc = download_planes(g, planes, L.planes, s)) return rc;
+  B200_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+}  // extern "C"

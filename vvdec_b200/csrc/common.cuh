@@ -1,0 +1,68 @@
+// common.cuh — shared device/host helpers for the sm_100a kernels of vvdec_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "../../include/vvdec_b200.h"
+
+namespace b200 {
+
+void set_error(const char* fmt, ...);
+
+#define B200_CUDA(call)                                                                         \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      b200::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));     \
+      return B200_ERR_CUDA;                                                                     \
+    }                                                                                           \
+  } while (0)
+
+#define B200_CHECK(cond, ...)                                    \
+  do {                                                           \
+    if (!(cond)) { b200::set_error(__VA_ARGS__); return B200_ERR_PARAM; } \
+  } while (0)
+
+__device__ __forceinline__ int clip3(int lo, int hi, int v) { return min(max(v, lo), hi); }
+__device__ __forceinline__ int clip16(int v) { return min(max(v, -32768), 32767); }
+
+// Grow-only device scratch buffer.
+struct DevBuf {
+  void*  p   = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + (bytes >> 2) + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu) -> %s", want, cudaGetErrorString(e)); return B200_ERR_CUDA; }
+    cap = want;
+    return 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+  ~DevBuf() { if (p) cudaFree(p); }
+};
+
+// Device-resident picture planes (int16, no margins; kernels clamp coordinates).
+struct DevPlanes {
+  int16_t* p[3] = {nullptr, nullptr, nullptr};
+  int      stride[3] = {0, 0, 0};
+};
+
+// ---- kernel launchers (device pointers, stream-ordered) ----
+struct K1Launch {
+  b200_geom      geom;
+  DevPlanes      planes;
+  const b200_tu* tus;
+  size_t         numTus;
+  const int16_t* coefs;
+  const int32_t* scaling;
+  int            mode;    // 0: reco = clip(pred + resi); 1: store residual
+};
+int launch_k1_residual(const K1Launch& L, cudaStream_t s);
+
+int ensure_device();   // selects device 0 if none current; fails loudly when there is no sm_100 GPU
+
+}  // namespace b200

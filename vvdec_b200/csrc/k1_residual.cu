@@ -1,0 +1,229 @@
+// k1_residual.cu — K1: dequant + inverse LFNST + inverse DCT-2/DST-7/DCT-8 (+TS, BDPCM, joint CbCr)
+//                  fused with the prediction add ("reco").
+//
+// Replaces (reference, /root/reference/source/Lib/CommonLib): Quant::dequant + DeQuantImpl (Quant.cpp:122-179,
+// :295-381), invResDPCM (Quant.cpp:239), TrQuant::xInvLfnst / invLfnstNxNCore (TrQuant.cpp:79-106, :201-288),
+// TrQuant::xIT (TrQuant.cpp:410-485) with fastInvTrans[][] / fastInvCore_ / clipCore / cpyResiClipCore
+// (TrQuant_EMT.cpp:103-121, :366-405), xITransformSkip (:489), invTransformCbCr (TrQuant.cpp:108-124) and the
+// reco add of DecCu::predAndReco (DecCu.cpp:455-479 -> Buffer.cpp:83 recoCore).
+//
+// Mapping (north_star): ONE WARP PER TU record; the TU's packed level corner is staged into shared memory as
+// dequantised int16 coefficients, both 1-D stages accumulate in int32 (no tensor cores), stage-1 output lives in
+// shared memory as int16 (it is clipped to 16 bit by the standard), stage-2 output goes straight to the plane.
+// HBM traffic per TU = corner levels (2 B each) + 32 B record + w*h*2 B read (pred) + w*h*2 B write.
+#define VVC_TABLE_QUAL static __device__ const
+#include "vvc_tables.h"
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int K1_WARPS = 8;
+constexpr int K1_CBUF  = 32 * 32;   // int16 coefficients (coded corner is at most 32x32)
+constexpr int K1_TBUF  = 32 * 64;   // int16 stage-1 output: <=32 non-zero columns x <=64 rows
+
+__device__ __forceinline__ const int16_t* tr_matrix(int trType, int log2n)
+{
+  const int p4 = 1 << (2 * log2n);
+  if (trType == B200_TR_DCT2) return kTrAll + (p4 - 4) / 3;
+  return kTrAll + (trType == B200_TR_DCT8 ? 5460 : 6820) + (p4 - 16) / 3;
+}
+
+__device__ __forceinline__ int dequant_one(int level, int scale, int rightShift, int inMax)
+{
+  // Quant.cpp:146-151 / :166-171 (Intermediate_Int == int: 32-bit wrap-around arithmetic)
+  const int c = clip3(-inMax - 1, inMax, level);
+  int v;
+  if (rightShift > 0) v = (int)((unsigned)c * (unsigned)scale + (1u << (rightShift - 1))) >> rightShift;
+  else                v = (int)(((unsigned)c * (unsigned)scale) << (-rightShift));
+  return clip16(v);
+}
+
+__global__ void __launch_bounds__(K1_WARPS * 32)
+k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* __restrict__ coefs,
+                   const int32_t* __restrict__ scaling, int16_t* p0, int16_t* p1, int16_t* p2,
+                   int s0, int s1, int s2, int bitDepth, int mode)
+{
+  __shared__ int16_t s_c[K1_WARPS][K1_CBUF];
+  __shared__ int16_t s_t[K1_WARPS][K1_TBUF];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * K1_WARPS + warp;
+  if (t >= numTus) return;
+
+  const uint4* recp = reinterpret_cast<const uint4*>(tus + t);
+  const uint4 ra = __ldg(recp), rb = __ldg(recp + 1);
+  // unpack b200_tu (32 B)
+  const int tx = ra.x & 0xffff, ty = ra.x >> 16;
+  const int log2w = ra.y & 0xff, log2h = (ra.y >> 8) & 0xff, comp = (ra.y >> 16) & 0xff, flags = ra.y >> 24;
+  int maxX = ra.z & 0xff, maxY = (ra.z >> 8) & 0xff;
+  const int trType = (ra.z >> 16) & 0xff, lfnst = ra.z >> 24;
+  const int ict = (int)(int8_t)(ra.w & 0xff), rightShift = (int)(int8_t)((ra.w >> 8) & 0xff);
+  const int inBits = (ra.w >> 16) & 0xff, scale = ra.w >> 24;
+  const unsigned coefOff = rb.x, slOff = rb.y;
+
+  const int w = 1 << log2w, h = 1 << log2h;
+  int16_t* cb = s_c[warp];
+  int16_t* tb = s_t[warp];
+  const int16_t* q = coefs + coefOff;
+  const int qs = maxX + 1;
+  const int inMax = (1 << (inBits - 1)) - 1;
+  const int32_t* sl = (flags & B200_TU_SCALING) ? scaling + slOff : nullptr;
+  const bool isTS = flags & B200_TU_TS;
+
+  // coefficient tile geometry: CS = row stride of cb
+  int nzW = maxX + 1, nzH = maxY + 1;
+  if (lfnst && !isTS) { nzW = max(nzW, min(w, 8)); nzH = max(nzH, min(h, 8)); }
+  const int CS = nzW;
+
+  // ---- 1. dequant (Quant.cpp:295) ----
+  if (flags & (B200_TU_BDPCM_H | B200_TU_BDPCM_V)) {
+    // invResDPCM (Quant.cpp:239): running sum with 16-bit clip along x (H) or y (V); one lane per line.
+    const bool hor = flags & B200_TU_BDPCM_H;
+    const int lines = hor ? h : w, len = hor ? w : h;
+    for (int l = lane; l < lines; l += 32) {
+      int acc = 0;
+      for (int i = 0; i < len; i++) {
+        const int x = hor ? i : l, y = hor ? l : i;
+        const int lv = q[y * qs + x];
+        acc = i ? clip16(acc + lv) : lv;
+        const int sc = sl ? sl[y * w + x] * scale : scale;
+        cb[y * CS + x] = acc ? (int16_t)dequant_one(acc, sc, rightShift, inMax) : (int16_t)0;
+      }
+    }
+  } else {
+    for (int i = lane; i < nzW * nzH; i += 32) {
+      const int y = i / CS, x = i - y * CS;
+      int v = 0;
+      if (x <= maxX && y <= maxY) {
+        const int lv = q[y * qs + x];
+        if (lv) v = dequant_one(lv, sl ? sl[y * w + x] * scale : scale, rightShift, inMax);
+      }
+      cb[i] = (int16_t)v;
+    }
+  }
+  __syncwarp();
+
+  // ---- 2. inverse LFNST (TrQuant.cpp:201) ----
+  if (lfnst && !isTS) {
+    const int idx = (lfnst & 3) - 1, set = (lfnst >> 2) & 3, transpose = (lfnst >> 4) & 1;
+    const bool big = w >= 8 && h >= 8;
+    const int zo = ((w == 4 && h == 4) || (w == 8 && h == 8)) ? 8 : 16;
+    int myIn = 0;
+    if (lane < 16) {
+      // (x,y) of diag scan pos: {0,0},{0,1},{1,0},{0,2},{1,1},{2,0},{0,3},{1,2},{2,1},{3,0},{1,3},{2,2},{3,1},{2,3},{3,2},{3,3}
+      const unsigned long long XS = 0x3323213210210100ull;   // nibble i = x of scan pos i
+      const unsigned long long YS = 0x3231230123012010ull;   // nibble i = y of scan pos i
+      const int x = (int)((XS >> (4 * lane)) & 15), y = (int)((YS >> (4 * lane)) & 15);
+      myIn = cb[y * CS + x];
+    }
+    const int8_t* m = big ? kLfnst8x8 + (set * 2 + idx) * 48 * 16 : kLfnst4x4 + (set * 2 + idx) * 16 * 16;
+    const int nOut = big ? 48 : 16;
+    int out0 = 0, out1 = 0;
+    for (int i = 0; i < zo; i++) {
+      const int v = __shfl_sync(0xffffffffu, myIn, i);
+      if (lane < nOut)      out0 += v * m[lane * 16 + i];
+      if (lane + 32 < nOut) out1 += v * m[(lane + 32) * 16 + i];
+    }
+    out0 = clip16((out0 + 64) >> 7);
+    out1 = clip16((out1 + 64) >> 7);
+    __syncwarp();
+    // scatter (TrQuant.cpp:246-284)
+    for (int r = 0; r < 2; r++) {
+      const int j = lane + 32 * r;
+      if (j >= nOut) break;
+      const int val = r ? out1 : out0;
+      int x, y;
+      if (!big)        { const int a = j >> 2, b = j & 3; y = transpose ? b : a; x = transpose ? a : b; }
+      else if (j < 32) { const int a = j >> 3, b = j & 7; y = transpose ? b : a; x = transpose ? a : b; }
+      else             { const int k = j - 32, a = k >> 2, b = k & 3; y = transpose ? b : 4 + a; x = transpose ? 4 + a : b; }
+      cb[y * CS + x] = (int16_t)val;
+    }
+    maxX = max(maxX, min(w - 1, 7));
+    maxY = max(maxY, min(h - 1, 7));
+    __syncwarp();
+  }
+
+  // ---- output helpers ----
+  int16_t* const planes[3] = {p0, p1, p2};
+  const int strides[3] = {s0, s1, s2};
+  const int pmax = (1 << bitDepth) - 1;
+  int16_t* dst0 = planes[comp] + (size_t)ty * strides[comp] + tx;
+  const int ds0 = strides[comp];
+  const int comp1 = comp == 1 ? 2 : 1;
+  int16_t* dst1 = ict ? planes[comp1] + (size_t)ty * strides[comp1] + tx : nullptr;
+  const int ds1 = strides[comp1];
+
+  auto emit = [&](int x, int y, int r) {
+    int16_t* d = dst0 + y * ds0 + x;
+    *d = (int16_t)(mode == 0 ? clip3(0, pmax, *d + r) : r);
+    if (ict) {
+      // TrQuant.cpp:108-124 invTransformCbCr
+      const int r1 = (ict == 2) ? r : (ict == -2) ? -r : (ict > 0) ? (r >> 1) : ((-r) >> 1);
+      int16_t* e = dst1 + y * ds1 + x;
+      *e = (int16_t)(mode == 0 ? clip3(0, pmax, *e + (int)(int16_t)r1) : (int)(int16_t)r1);
+    }
+  };
+
+  // ---- 3. transform skip (TrQuant.cpp:489) ----
+  if (isTS) {
+    for (int i = lane; i < w * h; i += 32) {
+      const int y = i >> log2w, x = i & (w - 1);
+      emit(x, y, (x < nzW && y < nzH) ? (int)cb[y * CS + x] : 0);
+    }
+    return;
+  }
+
+  const int trH = trType & 3, trV = (trType >> 2) & 3;
+  const int shift1 = 7, shift2 = 20 - bitDepth;
+
+  // ---- 4. DC-only shortcut (TrQuant.cpp:429-448) ----
+  if (maxX == 0 && maxY == 0 && trH == B200_TR_DCT2 && trV == B200_TR_DCT2) {
+    int dc = ((int)cb[0] * 64 + (1 << (shift1 - 1))) >> shift1;
+    dc = (dc * 64 + (1 << (shift2 - 1))) >> shift2;
+    for (int i = lane; i < w * h; i += 32) emit(i & (w - 1), i >> log2w, dc);
+    return;
+  }
+
+  // ---- 5. zero-out aware extents (TrQuant.cpp:449-450) ----
+  const int zoW = (trH != B200_TR_DCT2 && w == 32) ? 16 : min(w, 32);
+  const int zoH = (trV != B200_TR_DCT2 && h == 32) ? 16 : min(h, 32);
+  const int nCols = min(maxX + 1, zoW);   // = w - skipWidth
+  const int nRows = min(maxY + 1, zoH);   // = h - skipHeight
+
+  // ---- 6. stage 1: vertical, round >>7, clip to 16 bit (TrQuant_EMT.cpp:103-121, clip branch) ----
+  {
+    const int16_t* mv = tr_matrix(trV, log2h);
+    for (int i = lane; i < nCols * h; i += 32) {
+      const int col = i >> log2h, j = i & (h - 1);
+      int acc = 0;
+      for (int k = 0; k < nRows; k++) acc += (int)cb[k * CS + col] * (int)__ldg(mv + (k << log2h) + j);
+      tb[i] = (int16_t)clip16((acc + (1 << (shift1 - 1))) >> shift1);
+    }
+  }
+  __syncwarp();
+
+  // ---- 7. stage 2: horizontal + final round/clip (cpyResiClipCore, TrQuant_EMT.cpp:366) + reco ----
+  {
+    const int16_t* mh = tr_matrix(trH, log2w);
+    const int rnd = 1 << (shift2 - 1);
+    for (int i = lane; i < w * h; i += 32) {
+      const int y = i >> log2w, x = i & (w - 1);
+      int acc = 0;
+      for (int k = 0; k < nCols; k++) acc += (int)tb[(k << log2h) + y] * (int)__ldg(mh + (k << log2w) + x);
+      emit(x, y, clip16((acc + rnd) >> shift2));
+    }
+  }
+}
+
+int launch_k1_residual(const K1Launch& L, cudaStream_t s)
+{
+  if (L.numTus == 0) return 0;
+  const int grid = (int)((L.numTus + K1_WARPS - 1) / K1_WARPS);
+  k1_residual_kernel<<<grid, K1_WARPS * 32, 0, s>>>(L.tus, (int)L.numTus, L.coefs, L.scaling, L.planes.p[0], L.planes.p[1],
+                                                    L.planes.p[2], L.planes.stride[0], L.planes.stride[1],
+                                                    L.planes.stride[2], L.geom.bitDepth, L.mode);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200

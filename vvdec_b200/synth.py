@@ -1,0 +1,146 @@
+"""Synthetic post-parse content: there is no VVC bitstream or encoder on the box, so the
+work lists a flattener would emit from VVdeC's parsed Picture are drawn from a seeded generator instead.
+Everything here is host-side input preparation (numpy); no pixel arithmetic of the hot path lives here."""
+import numpy as np
+from . import abi
+
+
+def partition(rng, W, H, ctu=128, min_dim=4, min_area=32, p_split=None):
+    """Random QT+BT partition of a WxH picture into CUs. Returns int array [n,4] = x,y,w,h (luma).
+    Blocks crossing the picture boundary are split until they fit (implicit boundary splits)."""
+    out = []
+    p_split = p_split or {128: 0.95, 64: 0.75, 32: 0.55, 16: 0.4, 8: 0.25, 4: 0.0}
+
+    def rec(x, y, w, h):
+        if x >= W or y >= H:
+            return
+        cross_x, cross_y = x + w > W, y + h > H
+        big = max(w, h)
+        if cross_x or cross_y:
+            if cross_x and cross_y or (w == h and w > 64):
+                mode = "q"
+            else:
+                mode = "v" if cross_x else "h"
+        else:
+            r = rng.random()
+            if r >= p_split.get(big, 0.0):
+                out.append((x, y, w, h)); return
+            opts = []
+            if w == h and w >= 8: opts += ["q", "q"]
+            if w >= 2 * min_dim and (w // 2) * h >= min_area and w <= 64: opts.append("v")
+            if h >= 2 * min_dim and w * (h // 2) >= min_area and h <= 64: opts.append("h")
+            if not opts:
+                out.append((x, y, w, h)); return
+            mode = opts[rng.integers(0, len(opts))]
+        if mode == "q":
+            hw, hh = w // 2, h // 2
+            for dy in (0, hh):
+                for dx in (0, hw):
+                    rec(x + dx, y + dy, hw, hh)
+        elif mode == "v":
+            rec(x, y, w // 2, h); rec(x + w // 2, y, w // 2, h)
+        else:
+            rec(x, y, w, h // 2); rec(x, y + h // 2, w, h // 2)
+
+    for cy in range(0, H, ctu):
+        for cx in range(0, W, ctu):
+            rec(cx, cy, ctu, ctu)
+    return np.array(out, np.int32).reshape(-1, 4)
+
+
+def _laplace_levels(rng, n, heavy=False):
+    v = rng.laplace(0, 2.0 if not heavy else 400.0, size=n)
+    return np.clip(np.rint(v), -32768, 32767).astype(np.int16)
+
+
+def gen_tus(rng, cus, bit_depth=10, p_cbf=0.5, p_mts=0.2, p_lfnst=0.1, p_ts=0.05, p_bdpcm=0.03, p_jccr=0.1,
+            p_full=0.3, chroma=True, heavy=0.02, dep_quant=True):
+    """TU records + packed level arena for a CU list (one TU per <=64x64 tile of each CU, all 3 components).
+    Mirrors what the flattener (vvdec_glue/flatten_tu.h) derives from parsed TUs; QP drawn uniformly in 22..37."""
+    recs, coefs = [], []
+    ncoef = 0
+    inv_scales = np.array([[40, 45, 51, 57, 64, 72], [57, 64, 72, 80, 90, 102]])
+    for (cx, cy, cw, ch) in cus:
+        if rng.random() >= p_cbf:
+            continue
+        qp = int(rng.integers(22, 38)) + 6 * (bit_depth - 8)
+        intra = rng.random() < 0.15
+        for ty in range(cy, cy + ch, 64):
+            for tx in range(cx, cx + cw, 64):
+                tw, th = min(64, cw), min(64, ch)
+                jccr = chroma and rng.random() < p_jccr
+                for comp in ((0, 1, 2) if chroma else (0,)):
+                    w, h = (tw, th) if comp == 0 else (tw >> 1, th >> 1)
+                    x, y = (tx, ty) if comp == 0 else (tx >> 1, ty >> 1)
+                    if min(w, h) < 2 or (comp and rng.random() < 0.3 and not jccr):
+                        continue
+                    ict = 0
+                    if comp and jccr:
+                        if comp == 2: continue
+                        ict = int(rng.choice([-3, -2, -1, 1, 2, 3]))
+                        if abs(ict) == 3: comp = 2
+                    l2w, l2h = int(np.log2(w)), int(np.log2(h))
+                    flags, tr, lfnst = 0, 0, 0
+                    r = rng.random()
+                    maxX = maxY = None
+                    if w <= 32 and h <= 32 and r < p_bdpcm and intra:
+                        flags = abi.TU_TS | (abi.TU_BDPCM_H if rng.random() < 0.5 else abi.TU_BDPCM_V)
+                        maxX, maxY = w - 1, h - 1
+                    elif w <= 32 and h <= 32 and r < p_bdpcm + p_ts:
+                        flags = abi.TU_TS
+                    elif comp == 0 and min(w, h) >= 4 and max(w, h) <= 32 and r < p_bdpcm + p_ts + p_mts:
+                        th_, tv_ = rng.choice([abi.TR_DST7, abi.TR_DCT8], size=2)
+                        tr = int(th_) | (int(tv_) << 2)
+                    elif intra and min(w, h) >= 4 and r < p_bdpcm + p_ts + p_mts + p_lfnst:
+                        lf_set = int(rng.integers(0, 4))
+                        lfnst = int(rng.integers(1, 3)) | (lf_set << 2) | ((int(rng.integers(0, 2)) if lf_set else 0) << 4)
+                    if maxX is None:
+                        limx = min(w, 32) if not (tr & 3 and w == 32) else 16
+                        limy = min(h, 32) if not ((tr >> 2) & 3 and h == 32) else 16
+                        if lfnst:
+                            # at most 16 (8 for 4x4/8x8) levels in scan order: keep inside the first 4x4 diagonal prefix
+                            maxX, maxY = int(rng.integers(0, 3)), int(rng.integers(0, 2))
+                        elif rng.random() < p_full:
+                            maxX, maxY = limx - 1, limy - 1
+                        else:
+                            maxX = min(limx - 1, int(rng.geometric(0.25)) - 1)
+                            maxY = min(limy - 1, int(rng.geometric(0.25)) - 1)
+                    is_ts = bool(flags & abi.TU_TS)
+                    sqrt2 = (not is_ts) and ((l2w + l2h) & 1)
+                    dq = dep_quant and not is_ts
+                    q = max(qp, 4) if is_ts else qp
+                    per, rem = ((q + 1) // 6, (q + 1) % 6) if dq else (q // 6, q % 6)
+                    tr_shift = 15 - bit_depth - ((l2w + l2h) >> 1) + (-1 if sqrt2 else 0)
+                    right_shift = 6 + (1 if dq else 0) - ((0 if is_ts else tr_shift) + per)
+                    in_bits = min(16, 32 + right_shift - 7)
+                    n = (maxX + 1) * (maxY + 1)
+                    lv = _laplace_levels(rng, n, rng.random() < heavy)
+                    if lfnst:
+                        # zero everything outside the first 8 scan positions (x+y<=2 covers 6 of them: safe subset)
+                        yy, xx = np.divmod(np.arange(n), maxX + 1)
+                        lv[(xx + yy) > 2] = 0
+                    if lv[-1] == 0: lv[-1] = 1
+                    recs.append((x, y, l2w, l2h, comp, flags, maxX, maxY, tr, lfnst, ict, right_shift, in_bits,
+                                 int(inv_scales[1 if sqrt2 else 0][rem]), ncoef, 0, (0, 0)))
+                    coefs.append(lv); ncoef += n
+    tus = np.array(recs, dtype=abi.TU_DTYPE) if recs else np.zeros(0, abi.TU_DTYPE)
+    arena = np.concatenate(coefs) if coefs else np.zeros(0, np.int16)
+    return tus, arena
+
+
+def noise_planes(rng, W, H, bit_depth=10, chroma=True, strides=None):
+    """Stand-in prediction / reference pictures: smooth gradient + band-limited noise, clipped to the bit depth."""
+    mx = (1 << bit_depth) - 1
+    out = []
+    for c in range(3 if chroma else 1):
+        w, h = (W, H) if c == 0 else (W >> 1, H >> 1)
+        st = strides[c] if strides else w
+        yy, xx = np.mgrid[0:h, 0:w]
+        base = (mx / 2) + (mx / 4) * np.sin(xx / (37.0 + 11 * c)) * np.cos(yy / (53.0 - 7 * c))
+        n = rng.normal(0, mx / 40, size=(h // 4 + 2, w // 4 + 2))
+        n = np.kron(n, np.ones((4, 4)))[:h, :w]
+        fine = rng.integers(-8, 9, size=(h, w))
+        p = np.zeros((h, st), np.int16)
+        p[:, :w] = np.clip(base + n + fine, 0, mx).astype(np.int16)
+        out.append(p)
+    return out
