@@ -93,6 +93,42 @@ B200_API int b200_k1_residual(const b200_geom* g, int16_t* const planes[3],
                               const int32_t* scaling, size_t numScaling,
                               int mode);
 
+/* ------------------------------------------------------------------------------------------------
+ * K3  deblocking: all vertical edges of the picture, then all horizontal edges, in place.
+ *   replaces  LoopFilter::loopFilterCTU / xDeblockCtuArea (LoopFilter.cpp:375,:418), xEdgeFilterLuma (:1463),
+ *             xEdgeFilterChroma (:1619), LoopFilter::xPelFilterLuma (LoopFilter.h:106; xPelFilterLumaCore :213),
+ *             LoopFilter::xFilteringPandQ (LoopFilter.h:122; xFilteringPandQCore :129), xPelFilterChroma (:281),
+ *             xUseStrongFiltering (:1410), xCalcDP/DQ (:1392), deriveLADFShift (:1363).
+ *   stays CPU: calcFilterStrengthsCTU (:360) — it produces the grid below from the CU/TU tree (SURVEY a14').
+ * The edge grids are the reference's LoopFilterParam arrays (TypeDef.h:694, DecLibRecon.cpp:515) re-laid as one
+ * picture-wide raster per direction: entry (x4,y4) describes the edge on the LEFT (lfV) / TOP (lfH) of the 4x4
+ * luma unit at (4*x4, 4*y4).  Chroma uses the same entries on its 8x8-sample grid (LoopFilter.cpp:462-488).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b200_lf_param {      /* == vvdec::LoopFilterParam, 6 bytes */
+  int8_t  qp[3];                    /* (QpP+QpQ+1)>>1 per component                                      */
+  uint8_t bs;                       /* Bs: bits 0-1 Y, 2-3 Cb, 4-5 Cr                                    */
+  uint8_t sideMaxFiltLength;        /* (P<<4)|Q luma max filter lengths (1,2,3,5,7); bit 7 ignored       */
+  uint8_t flags;                    /* bit 5: chroma "large" edge (both sides >= 8 chroma samples)       */
+} b200_lf_param;
+
+typedef struct b200_lf_slice {      /* Slice deblocking syntax (Slice.h getDeblockingFilter*)            */
+  int8_t  betaOffsetDiv2[3];        /* Y, Cb, Cr                                                         */
+  int8_t  tcOffsetDiv2[3];
+  uint8_t disable;                  /* slice_deblocking_filter_disabled_flag                             */
+  uint8_t rsv;
+} b200_lf_slice;
+
+typedef struct b200_lf_seq {        /* SPS luma-adaptive deblocking (LADF), Slice.h:1807-1813            */
+  int32_t ladfEnabled, ladfNumIntervals;
+  int32_t ladfQpOffset[5];
+  int32_t ladfIntervalLowerBound[5];
+} b200_lf_seq;
+
+/* Kernel-level K3 on host planes (in place). lfV/lfH: [ceil(H/4)][ceil(W/4)] rasters. ctuSlice: slice index of
+ * every CTU in raster order (NULL: all slice 0). seq may be NULL (LADF off). dirs: bit0 = vertical edges, bit1 = horizontal. */
+B200_API int b200_lf_deblock(const b200_geom* g, int16_t* const planes[3], const b200_lf_param* lfV, const b200_lf_param* lfH,
+                             const uint8_t* ctuSlice, const b200_lf_slice* slices, int numSlices, const b200_lf_seq* seq, int dirs);
+
 #ifdef __cplusplus
 }
 #endif

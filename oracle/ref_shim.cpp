@@ -33,6 +33,9 @@
 #include "CommonLib/TrQuant_EMT.h"
 #include "CommonLib/InterPrediction.h"
 #include "CommonLib/InterpolationFilter.h"
+#include "CommonLib/LoopFilter.h"
+#include "CommonLib/SampleAdaptiveOffset.h"
+#include "CommonLib/AdaptiveLoopFilter.h"
 #include "../vvdec_b200/vvdec_glue/flatten_tu.h"
 
 using namespace vvdec;
@@ -199,4 +202,131 @@ extern "C" int ref_tu_case( const ref_tu_syntax* s, const int16_t* levels, int16
     for( unsigned y = 0; y < area.height; y++ ) for( unsigned x = 0; x < area.width; x++ ) resi0[y * area.width + x] = plane.at( x, y );
   }
   return made ? 1 : 0;
+}
+
+// ================================================================================================ fake picture
+// A real vvdec Picture + CodingStructure, created through the reference's own calls (Picture::create,
+// Picture::finalInit, allocateNewSlice), so that picture-level reference functions can run on synthetic state.
+struct FakePicture
+{
+  std::shared_ptr<SPS> sps = std::make_shared<SPS>();
+  std::shared_ptr<PPS> pps = std::make_shared<PPS>();
+  std::shared_ptr<PicHeader> ph = std::make_shared<PicHeader>();
+  CUChunkCache cuCache;
+  TUChunkCache tuCache;
+  Picture pic;
+  std::vector<LoopFilterParam> lfp;
+  int W, H, ctu, W4, H4;
+
+  FakePicture( const b200_geom& g, int numSlices )
+  {
+    globalInit();
+    W = g.width; H = g.height; ctu = g.ctuSize; W4 = ( W + 3 ) >> 2; H4 = ( H + 3 ) >> 2;
+    const ChromaFormat fmt = g.chromaFormat ? CHROMA_420 : CHROMA_400;
+    sps->setChromaFormatIdc( fmt );
+    sps->setBitDepth( g.bitDepth );
+    sps->setQpBDOffset( 6 * ( g.bitDepth - 8 ) );
+    sps->setMaxPicWidthInLumaSamples( W ); sps->setMaxPicHeightInLumaSamples( H );
+    sps->setCTUSize( ctu ); sps->setMaxCUWidth( ctu ); sps->setMaxCUHeight( ctu );
+    sps->setLog2MinCodingBlockSize( 2 );
+    pps->setPicWidthInLumaSamples( W ); pps->setPicHeightInLumaSamples( H );
+    pps->pcv = std::make_unique<PreCalcValues>( *sps, *pps );
+    pic.create( fmt, Size( W, H ), ctu, ctu + 16, 0 );
+    const APS* noAps[ALF_CTB_MAX_NUM_APS] = { nullptr };
+    pic.finalInit( &cuCache, &tuCache, sps.get(), pps.get(), ph, noAps, nullptr, nullptr, false );
+    for( int i = 0; i < numSlices; i++ )
+    {
+      Slice* sl = pic.allocateNewSlice( nullptr );
+      sl->setSPS( sps.get() ); sl->setPPS( pps.get() ); sl->setPicHeader( ph.get() );
+      sl->setPic( &pic );
+      sl->getClpRngs().bd = g.bitDepth;   // Slice.cpp:407
+    }
+    CodingStructure& cs = *pic.cs;
+    const PreCalcValues& pcv = *cs.pcv;
+    lfp.assign( (size_t) pcv.num4x4CtuBlks * pcv.sizeInCtus * 2, LoopFilterParam{} );
+    for( unsigned a = 0; a < pcv.sizeInCtus; a++ )
+    {
+      CtuData& cd = cs.getCtuData( a );
+      cd.slice = pic.slices[0]; cd.pps = pps.get(); cd.sps = sps.get(); cd.ph = ph.get();
+      cd.ctuIdx = a; cd.colIdx = a % pcv.widthInCtus; cd.lineIdx = a / pcv.widthInCtus;
+      cd.lfParam[0] = lfp.data() + (size_t) a * pcv.num4x4CtuBlks;
+      cd.lfParam[1] = lfp.data() + (size_t) ( pcv.sizeInCtus + a ) * pcv.num4x4CtuBlks;
+    }
+  }
+  ~FakePicture() { pic.parseDone.unlock(); }
+
+  void setPlanes( const b200_geom& g, int16_t* const planes[3] )
+  {
+    for( int c = 0; c < ( g.chromaFormat ? 3 : 1 ); c++ )
+    {
+      PelBuf b = pic.cs->getRecoBuf( ComponentID( c ) );
+      for( unsigned y = 0; y < b.height; y++ ) memcpy( b.buf + y * b.stride, planes[c] + (size_t) y * g.stride[c], b.width * sizeof( Pel ) );
+    }
+  }
+  void getPlanes( const b200_geom& g, int16_t* const planes[3], bool fromFlt = false, PelUnitBuf* flt = nullptr )
+  {
+    for( int c = 0; c < ( g.chromaFormat ? 3 : 1 ); c++ )
+    {
+      PelBuf b = flt ? flt->bufs[c] : pic.cs->getRecoBuf( ComponentID( c ) );
+      for( unsigned y = 0; y < b.height; y++ ) memcpy( planes[c] + (size_t) y * g.stride[c], b.buf + y * b.stride, b.width * sizeof( Pel ) );
+    }
+  }
+  // raster [H4][W4] grid -> the per-CTU arrays (stride = ctu/4) the reference walks (CodingStructure.h:229)
+  void setLfGrid( int dir, const b200_lf_param* grid )
+  {
+    CodingStructure& cs = *pic.cs;
+    const int c4 = ctu >> 2;
+    for( int y4 = 0; y4 < H4; y4++ ) for( int x4 = 0; x4 < W4; x4++ )
+    {
+      const int a = cs.ctuRsAddr( x4 / c4, y4 / c4 );
+      LoopFilterParam& d = cs.getCtuData( a ).lfParam[dir][( y4 % c4 ) * c4 + ( x4 % c4 )];
+      static_assert( sizeof( LoopFilterParam ) == sizeof( b200_lf_param ), "layout" );
+      memcpy( &d, &grid[y4 * W4 + x4], sizeof( d ) );
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ K3
+extern "C" void ref_lf_pel_filter_luma( int simd, int16_t* src, ptrdiff_t step, ptrdiff_t offset, int tc, int sw, int thrCut,
+                                        int fsP, int fsQ, int bitDepth )
+{
+  static LoopFilter lfs( false ), lfv( true );
+  ClpRng clp; clp.bd = bitDepth;
+  ( simd ? lfv : lfs ).xPelFilterLuma( src, step, offset, tc, sw != 0, thrCut, fsP != 0, fsQ != 0, clp );
+}
+
+extern "C" void ref_lf_filtering_pq( int simd, int16_t* src, ptrdiff_t step, ptrdiff_t offset, int numP, int numQ, int tc )
+{
+  static LoopFilter lfs( false ), lfv( true );
+  ( simd ? lfv : lfs ).xFilteringPandQ( src, step, offset, numP, numQ, tc );
+}
+
+extern "C" int ref_lf_deblock_picture( int simd, const b200_geom* g, int16_t* const planes[3], const b200_lf_param* lfV,
+                                       const b200_lf_param* lfH, const uint8_t* ctuSlice, const b200_lf_slice* slices, int numSlices,
+                                       const b200_lf_seq* seq, int dirs )
+{
+  FakePicture fp( *g, numSlices );
+  CodingStructure& cs = *fp.pic.cs;
+  const PreCalcValues& pcv = *cs.pcv;
+  if( seq && seq->ladfEnabled )
+  {
+    fp.sps->setLadfEnabled( true ); fp.sps->setLadfNumIntervals( seq->ladfNumIntervals );
+    for( int k = 0; k < seq->ladfNumIntervals; k++ ) { fp.sps->setLadfQpOffset( seq->ladfQpOffset[k], k ); fp.sps->setLadfIntervalLowerBound( seq->ladfIntervalLowerBound[k], k ); }
+  }
+  for( int i = 0; i < numSlices; i++ )
+  {
+    Slice* sl = fp.pic.slices[i];
+    sl->setDeblockingFilterDisable( slices[i].disable );
+    sl->setDeblockingFilterBetaOffsetDiv2( slices[i].betaOffsetDiv2[0] ); sl->setDeblockingFilterTcOffsetDiv2( slices[i].tcOffsetDiv2[0] );
+    sl->setDeblockingFilterCbBetaOffsetDiv2( slices[i].betaOffsetDiv2[1] ); sl->setDeblockingFilterCbTcOffsetDiv2( slices[i].tcOffsetDiv2[1] );
+    sl->setDeblockingFilterCrBetaOffsetDiv2( slices[i].betaOffsetDiv2[2] ); sl->setDeblockingFilterCrTcOffsetDiv2( slices[i].tcOffsetDiv2[2] );
+  }
+  for( unsigned a = 0; a < pcv.sizeInCtus; a++ ) cs.getCtuData( a ).slice = fp.pic.slices[ctuSlice ? ctuSlice[a] : 0];
+  fp.setPlanes( *g, planes );
+  fp.setLfGrid( 0, lfV ); fp.setLfGrid( 1, lfH );
+  LoopFilter lf( simd != 0 );
+  if( dirs & 1 ) for( unsigned y = 0; y < pcv.heightInCtus; y++ ) for( unsigned x = 0; x < pcv.widthInCtus; x++ ) lf.loopFilterCTU( cs, MAX_NUM_CHANNEL_TYPE, x, y, EDGE_VER );
+  if( dirs & 2 ) for( unsigned y = 0; y < pcv.heightInCtus; y++ ) for( unsigned x = 0; x < pcv.widthInCtus; x++ ) lf.loopFilterCTU( cs, MAX_NUM_CHANNEL_TYPE, x, y, EDGE_HOR );
+  fp.getPlanes( *g, planes );
+  return 0;
 }

@@ -50,6 +50,17 @@ typedef struct ref_tu_syntax {
 int ref_tu_case(const ref_tu_syntax* s, const int16_t* levels, int16_t* resi0, int16_t* resi1,
                 b200_tu* rec, int16_t* coefs, int32_t* numCoefs);
 
+/* ---- K3 deblocking ---- */
+void ref_lf_pel_filter_luma(int simd, int16_t* src, ptrdiff_t step, ptrdiff_t offset, int tc, int sw, int thrCut,
+                            int filterSecondP, int filterSecondQ, int bitDepth);
+void ref_lf_filtering_pq(int simd, int16_t* src, ptrdiff_t step, ptrdiff_t offset, int numP, int numQ, int tc);
+/* Picture level: builds a real vvdec Picture/CodingStructure (SPS/PPS/PicHeader/Slice via the reference's own
+ * create/finalInit), copies planes + LoopFilterParam grids in, runs LoopFilter::loopFilterCTU(EDGE_VER) over all
+ * CTUs then (EDGE_HOR) over all CTUs — the order the CTU state machine guarantees (DecLibRecon.cpp:943-989). */
+int ref_lf_deblock_picture(int simd, const b200_geom* g, int16_t* const planes[3], const b200_lf_param* lfV,
+                           const b200_lf_param* lfH, const uint8_t* ctuSlice, const b200_lf_slice* slices, int numSlices,
+                           const b200_lf_seq* seq, int dirs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,16 @@ void orc_tu_residual(const b200_tu* tu, int bitDepth, const int16_t* coefs, cons
 void orc_k1_residual(const b200_geom* g, int16_t* const planes[3], const b200_tu* tus, size_t numTus,
                      const int16_t* coefs, const int32_t* scaling, int mode);
 
+/* ---- K3 deblocking -------------------------------------------------------------------------- */
+/* LoopFilter.cpp:213 xPelFilterLumaCore (4 lines). */
+void orc_lf_pel_filter_luma(int16_t* src, ptrdiff_t step, ptrdiff_t offset, int tc, int sw, int thrCut,
+                            int filterSecondP, int filterSecondQ, int bitDepth);
+/* LoopFilter.cpp:129 xFilteringPandQCore (4 lines). */
+void orc_lf_filtering_pq(int16_t* src, ptrdiff_t step, ptrdiff_t offset, int numP, int numQ, int tc);
+/* LoopFilter.cpp:375 loopFilterCTU over the whole picture: dirs bit0 = all vertical edges, bit1 = all horizontal. */
+void orc_lf_deblock(const b200_geom* g, int16_t* const planes[3], const b200_lf_param* lfV, const b200_lf_param* lfH,
+                    const uint8_t* ctuSlice, const b200_lf_slice* slices, const b200_lf_seq* seq, int dirs);
+
 #ifdef __cplusplus
 }
 #endif

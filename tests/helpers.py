@@ -9,6 +9,7 @@ REF_SO = os.path.join(ROOT, "oracle", "_ref", "libvvdec_ref.so")
 
 i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
 i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+i16p_off = C.c_void_p   # pointer into the middle of a buffer
 
 
 def load_oracle():
@@ -23,6 +24,10 @@ def load_oracle():
     lib.orc_tu_residual.argtypes = [C.POINTER(abi.Tu), C.c_int, i16p, C.c_void_p, i16p, C.c_ssize_t]
     lib.orc_k1_residual.argtypes = [C.POINTER(abi.Geom), C.POINTER(C.POINTER(C.c_int16)), C.c_void_p, C.c_size_t,
                                     i16p, C.c_void_p, C.c_int]
+    PL = C.POINTER(C.POINTER(C.c_int16))
+    lib.orc_lf_pel_filter_luma.argtypes = [i16p_off, C.c_ssize_t, C.c_ssize_t] + [C.c_int] * 6
+    lib.orc_lf_filtering_pq.argtypes = [i16p_off, C.c_ssize_t, C.c_ssize_t, C.c_int, C.c_int, C.c_int]
+    lib.orc_lf_deblock.argtypes = [C.POINTER(abi.Geom), PL, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     return lib
 
 
@@ -45,6 +50,10 @@ def load_ref():
     lib.ref_cpy_resi_clip.argtypes = [C.c_int, i32p, i16p, C.c_ssize_t, C.c_uint, C.c_uint] + [C.c_int32] * 4
     lib.ref_tu_case.argtypes = [C.POINTER(RefTuSyntax), i16p, i16p, i16p, C.POINTER(abi.Tu), i16p, C.POINTER(C.c_int32)]
     lib.ref_tu_case.restype = C.c_int
+    PL = C.POINTER(C.POINTER(C.c_int16))
+    lib.ref_lf_pel_filter_luma.argtypes = [C.c_int, i16p_off, C.c_ssize_t, C.c_ssize_t] + [C.c_int] * 6
+    lib.ref_lf_filtering_pq.argtypes = [C.c_int, i16p_off, C.c_ssize_t, C.c_ssize_t, C.c_int, C.c_int, C.c_int]
+    lib.ref_lf_deblock_picture.argtypes = [C.c_int, C.POINTER(abi.Geom), PL, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     return lib
 
 

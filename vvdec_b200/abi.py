@@ -42,3 +42,8 @@ def plane_ptrs(planes):
             assert p.dtype == np.int16 and p.flags["C_CONTIGUOUS"]
             arr[i] = p.ctypes.data_as(C.POINTER(C.c_int16))
     return arr
+
+
+class LfSeq(C.Structure):
+    _fields_ = [("ladfEnabled", C.c_int32), ("ladfNumIntervals", C.c_int32), ("ladfQpOffset", C.c_int32 * 5),
+                ("ladfIntervalLowerBound", C.c_int32 * 5)]

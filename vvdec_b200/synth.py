@@ -54,7 +54,7 @@ def _laplace_levels(rng, n, heavy=False):
 
 
 def gen_tus(rng, cus, bit_depth=10, p_cbf=0.5, p_mts=0.2, p_lfnst=0.1, p_ts=0.05, p_bdpcm=0.03, p_jccr=0.1,
-            p_full=0.3, chroma=True, heavy=0.02, dep_quant=True):
+            p_full=0.3, chroma=True, heavy=0.02, dep_quant=True, p_intra=0.15):
     """TU records + packed level arena for a CU list (one TU per <=64x64 tile of each CU, all 3 components).
     Mirrors what the flattener (vvdec_glue/flatten_tu.h) derives from parsed TUs; QP drawn uniformly in 22..37."""
     recs, coefs = [], []
@@ -64,7 +64,7 @@ def gen_tus(rng, cus, bit_depth=10, p_cbf=0.5, p_mts=0.2, p_lfnst=0.1, p_ts=0.05
         if rng.random() >= p_cbf:
             continue
         qp = int(rng.integers(22, 38)) + 6 * (bit_depth - 8)
-        intra = rng.random() < 0.15
+        intra = rng.random() < p_intra
         for ty in range(cy, cy + ch, 64):
             for tx in range(cx, cx + cw, 64):
                 tw, th = min(64, cw), min(64, ch)
@@ -144,3 +144,62 @@ def noise_planes(rng, W, H, bit_depth=10, chroma=True, strides=None):
         p[:, :w] = np.clip(base + n + fine, 0, mx).astype(np.int16)
         out.append(p)
     return out
+
+
+LF_DTYPE = np.dtype([("qp", "i1", (3,)), ("bs", "u1"), ("len", "u1"), ("flags", "u1")])
+LFSLICE_DTYPE = np.dtype([("beta", "i1", (3,)), ("tc", "i1", (3,)), ("disable", "u1"), ("rsv", "u1")])
+
+
+def unit_maps(cus, W, H, cu_attr=None):
+    """Paint per-4x4-unit maps from a CU list: TU id, TU width/height (TUs are the <=64 tiles of a CU), CU index."""
+    W4, H4 = (W + 3) // 4, (H + 3) // 4
+    tu_id = np.zeros((H4, W4), np.int32); tu_w = np.zeros((H4, W4), np.int16); tu_h = np.zeros((H4, W4), np.int16)
+    cu_ix = np.zeros((H4, W4), np.int32)
+    n = 0
+    for i, (cx, cy, cw, ch) in enumerate(cus):
+        cu_ix[cy // 4:(cy + ch) // 4, cx // 4:(cx + cw) // 4] = i
+        for ty in range(cy, cy + ch, 64):
+            for tx in range(cx, cx + cw, 64):
+                tw, th = min(64, cw), min(64, ch)
+                n += 1
+                sl = (slice(ty // 4, (ty + th) // 4), slice(tx // 4, (tx + tw) // 4))
+                tu_id[sl] = n; tu_w[sl] = tw; tu_h[sl] = th
+    return tu_id, tu_w, tu_h, cu_ix
+
+
+def gen_lf_grid(rng, cus, W, H, bit_depth=10, cu_intra=None, cu_qp=None, p_bs0=0.3):
+    """LoopFilterParam rasters for a CU list, consistent with the geometry the way calcFilterStrengths
+    (reference LoopFilter.cpp:495, xSetMaxFilterLengthPQFromTransformSizes :780) derives them:
+    edges only at TU boundaries; luma max lengths 1/1 next to a <=4 block, else 7 (>=32) or 3 per side;
+    chroma 'large' flag when both sides are >= 8 chroma samples; Bs 2 next to intra, else 1 or 0 at random."""
+    ncu = len(cus)
+    cu_intra = (rng.random(ncu) < 0.2) if cu_intra is None else cu_intra
+    cu_qp = rng.integers(22, 45, size=ncu) if cu_qp is None else cu_qp
+    tu_id, tu_w, tu_h, cu_ix = unit_maps(cus, W, H)
+    H4, W4 = tu_id.shape
+    out = []
+    for d in (0, 1):
+        g = np.zeros((H4, W4), LF_DTYPE)
+        if d == 0:
+            edge = np.zeros((H4, W4), bool); edge[:, 1:] = tu_id[:, 1:] != tu_id[:, :-1]
+            szQ = tu_w; szP = np.zeros_like(tu_w); szP[:, 1:] = tu_w[:, :-1]
+            cuP = np.zeros_like(cu_ix); cuP[:, 1:] = cu_ix[:, :-1]
+        else:
+            edge = np.zeros((H4, W4), bool); edge[1:, :] = tu_id[1:, :] != tu_id[:-1, :]
+            szQ = tu_h; szP = np.zeros_like(tu_h); szP[1:, :] = tu_h[:-1, :]
+            cuP = np.zeros_like(cu_ix); cuP[1:, :] = cu_ix[:-1, :]
+        intra = cu_intra[cu_ix] | cu_intra[cuP]
+        bsY = np.where(intra, 2, (rng.random((H4, W4)) >= p_bs0).astype(np.int64))
+        bsU = np.where(intra, 2, (rng.random((H4, W4)) >= p_bs0).astype(np.int64))
+        bsV = np.where(intra, 2, (rng.random((H4, W4)) >= p_bs0).astype(np.int64))
+        bs = (bsY | (bsU << 2) | (bsV << 4)) * edge
+        small = (szP <= 4) | (szQ <= 4)
+        lenP = np.where(small, 1, np.where(szP >= 32, 7, 3)); lenQ = np.where(small, 1, np.where(szQ >= 32, 7, 3))
+        qpl = (cu_qp[cu_ix] + cu_qp[cuP] + 1) >> 1
+        g["bs"] = bs
+        g["len"] = np.where(edge, 128 + (lenP << 4) + lenQ, 0)
+        g["flags"] = np.where(edge & (szP >= 16) & (szQ >= 16), 32, 0) | (edge * 3)
+        g["qp"][..., 0] = qpl
+        g["qp"][..., 1] = np.clip(qpl - 1, 0, 63); g["qp"][..., 2] = np.clip(qpl + 1, 0, 63)
+        out.append(np.ascontiguousarray(g))
+    return out[0], out[1]
