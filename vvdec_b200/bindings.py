@@ -16,4 +16,9 @@ def declare(lib):
     lib.b200_k1_residual.restype = C.c_int
 
 
-EXPORTS = ["b200_last_error", "b200_version", "b200_device_count", "b200_k1_residual"]
+    lib.b200_lf_deblock.argtypes = [C.POINTER(abi.Geom), PLANES, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.c_void_p, C.c_int]
+    lib.b200_lf_deblock.restype = C.c_int
+
+
+EXPORTS = ["b200_last_error", "b200_version", "b200_device_count", "b200_k1_residual", "b200_lf_deblock"]

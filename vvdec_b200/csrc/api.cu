@@ -2,6 +2,7 @@
 // through device scratch buffers; picture-level entry points keep everything resident (see picture.cu).
 #include "common.cuh"
 #include <stdarg.h>
+#include <string.h>
 #include <mutex>
 
 namespace b200 {
@@ -90,6 +91,35 @@ B200_API int b200_k1_residual(const b200_geom* g, int16_t* const planes[3], cons
   if (numScaling) B200_CUDA(cudaMemcpyAsync(g_hw.scaling.p, scaling, numScaling * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   L.tus = g_hw.tus.as<b200_tu>(); L.coefs = g_hw.coefs.as<int16_t>(); L.scaling = g_hw.scaling.as<int32_t>();
   if (int rc = launch_k1_residual(L, s)) return rc;
+  if (int rc = download_planes(g, planes, L.planes, s)) return rc;
+  B200_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+B200_API int b200_lf_deblock(const b200_geom* g, int16_t* const planes[3], const b200_lf_param* lfV, const b200_lf_param* lfH,
+                             const uint8_t* ctuSlice, const b200_lf_slice* slices, int numSlices, const b200_lf_seq* seq, int dirs)
+{
+  B200_CHECK(g && planes && lfV && lfH && slices, "b200_lf_deblock: null argument");
+  B200_CHECK(numSlices >= 1 && numSlices <= 64, "b200_lf_deblock: numSlices %d out of range 1..64", numSlices);
+  B200_CHECK(g->ctuSize == 32 || g->ctuSize == 64 || g->ctuSize == 128, "b200_lf_deblock: CTU size %d", g->ctuSize);
+  if (int rc = ensure_device()) return rc;
+  if (int rc = g_hw.init()) return rc;
+  cudaStream_t s = g_hw.stream;
+  LfLaunch L; L.geom = *g; L.dirs = dirs;
+  memset(&L.slices, 0, sizeof(L.slices)); memcpy(L.slices.s, slices, numSlices * sizeof(b200_lf_slice));
+  if (seq) L.seq = *seq; else memset(&L.seq, 0, sizeof(L.seq));
+  if (int rc = upload_planes(g, planes, L.planes, s)) return rc;
+  const size_t n4 = (size_t)((g->width + 3) >> 2) * ((g->height + 3) >> 2);
+  const size_t nCtu = (size_t)((g->width + g->ctuSize - 1) / g->ctuSize) * ((g->height + g->ctuSize - 1) / g->ctuSize);
+  if (int rc = g_hw.misc[0].reserve(n4 * sizeof(b200_lf_param))) return rc;
+  if (int rc = g_hw.misc[1].reserve(n4 * sizeof(b200_lf_param))) return rc;
+  if (int rc = g_hw.misc[2].reserve(nCtu)) return rc;
+  B200_CUDA(cudaMemcpyAsync(g_hw.misc[0].p, lfV, n4 * sizeof(b200_lf_param), cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaMemcpyAsync(g_hw.misc[1].p, lfH, n4 * sizeof(b200_lf_param), cudaMemcpyHostToDevice, s));
+  if (ctuSlice) B200_CUDA(cudaMemcpyAsync(g_hw.misc[2].p, ctuSlice, nCtu, cudaMemcpyHostToDevice, s));
+  L.lfV = g_hw.misc[0].as<b200_lf_param>(); L.lfH = g_hw.misc[1].as<b200_lf_param>();
+  L.ctuSlice = ctuSlice ? g_hw.misc[2].as<uint8_t>() : nullptr;
+  if (int rc = launch_lf_deblock(L, s)) return rc;
   if (int rc = download_planes(g, planes, L.planes, s)) return rc;
   B200_CUDA(cudaStreamSynchronize(s));
   return 0;

@@ -63,6 +63,15 @@ struct K1Launch {
 };
 int launch_k1_residual(const K1Launch& L, cudaStream_t s);
 
+struct LfSliceTab { b200_lf_slice s[64]; };
+struct LfLaunch {
+  b200_geom geom; DevPlanes planes;
+  const b200_lf_param *lfV, *lfH;   // device, [H4][W4] rasters
+  const uint8_t* ctuSlice;          // device or null
+  LfSliceTab slices; b200_lf_seq seq; int dirs;
+};
+int launch_lf_deblock(const LfLaunch& L, cudaStream_t s);
+
 int ensure_device();   // selects device 0 if none current; fails loudly when there is no sm_100 GPU
 
 }  // namespace b200
