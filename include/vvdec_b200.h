@@ -129,6 +129,64 @@ typedef struct b200_lf_seq {        /* SPS luma-adaptive deblocking (LADF), Slic
 B200_API int b200_lf_deblock(const b200_geom* g, int16_t* const planes[3], const b200_lf_param* lfV, const b200_lf_param* lfH,
                              const uint8_t* ctuSlice, const b200_lf_slice* slices, int numSlices, const b200_lf_seq* seq, int dirs);
 
+/* ------------------------------------------------------------------------------------------------
+ * K4  SAO: src (deblocked picture) -> dst, per CTU and component edge offset (4 directions) or band offset.
+ *   replaces  SampleAdaptiveOffset::offsetBlock (SampleAdaptiveOffset.h:120; offsetBlock_core .cpp:64-349),
+ *             SAOProcessCTU (:522), offsetCTU (:661), isProcessDisabled (:817).
+ *   stays CPU: reconstructBlkSAOParam / merge resolution (:624) and deriveLoopFilterBoundaryAvailibility (:741) —
+ *             the flattener stores their results in the per-CTU record below.
+ * ---------------------------------------------------------------------------------------------- */
+enum { B200_SAO_EO_0 = 0, B200_SAO_EO_90 = 1, B200_SAO_EO_135 = 2, B200_SAO_EO_45 = 3, B200_SAO_BO = 4, B200_SAO_OFF = 255 };
+enum { B200_AVAIL_L = 1, B200_AVAIL_R = 2, B200_AVAIL_A = 4, B200_AVAIL_B = 8,
+       B200_AVAIL_AL = 16, B200_AVAIL_AR = 32, B200_AVAIL_BL = 64, B200_AVAIL_BR = 128 };
+
+typedef struct b200_sao_ctu {
+  uint8_t type[3];        /* B200_SAO_* per component (typeIdc after merge resolution; OFF when modeIdc == SAO_MODE_OFF) */
+  uint8_t band[3];        /* BO: typeAuxInfo = first band                                                               */
+  int8_t  offset[3][5];   /* EO: offset[edgeType+2] (class order, PLAIN = 0); BO: offsets of bands band..band+3 in [0..3] */
+  uint8_t avail;          /* B200_AVAIL_* of the 8 neighbouring CTUs (slice / tile / picture limits already applied)     */
+  uint8_t rsv[2];
+} b200_sao_ctu;           /* 24 bytes */
+
+typedef struct b200_vb {  /* ph virtual boundaries (PicHeader), luma sample positions; used by SAO            */
+  int32_t numVer, numHor;
+  int32_t posX[3], posY[3];
+} b200_vb;
+
+/* Kernel-level K4: src planes -> dst planes (both host; dst must be a different buffer). vb may be NULL. */
+B200_API int b200_sao_picture(const b200_geom* g, const int16_t* const src[3], int16_t* const dst[3],
+                              const b200_sao_ctu* ctus, const b200_vb* vb);
+
+/* ------------------------------------------------------------------------------------------------
+ * K5  ALF + CC-ALF: src (SAO output) -> dst.
+ *   replaces  AdaptiveLoopFilter::processCTU / filterCTU (AdaptiveLoopFilter.cpp:466,:664, the !isCrssByVBs path),
+ *             m_deriveClassificationBlk (.h:128; .cpp:969), m_filter7x7Blk / m_filter5x5Blk (filterBlk<> :1175),
+ *             m_filterCcAlf / m_filterCcAlfBoth (:1348,:1447), prepareCTU border extension (:453, here: clamping).
+ *   stays CPU: reconstructCoeff(APSs) (:855,:888): the tables below are the *Final arrays it produces.
+ *   not yet:   slices/tiles/subpictures with loop filtering disabled across them and explicit virtual
+ *             boundaries (the isCrssByVBs path, :745-852) -> B200_ERR_UNSUPPORTED at the flattener.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b200_alf_ctu {
+  uint8_t enable[3];      /* alfCtuEnableFlag per component (bit 0)                                            */
+  uint8_t lumaSet;        /* index into lumaCoeff/lumaClip: 0..15 fixed sets, 16.. the slice's APS sets        */
+  uint8_t chromaAlt[2];   /* index into chromaCoeff/chromaClip (APS alternative, resolved per slice)           */
+  uint8_t ccIdx[2];       /* 0: CC-ALF off for Cb/Cr, else 1 + index into ccCoeff[comp]                         */
+} b200_alf_ctu;           /* 8 bytes */
+
+typedef struct b200_alf_tables {
+  const int16_t* lumaCoeff;    /* [numLumaSets][4 transposes][25 classes][13]  (lumaCoeffFinal / m_fixedFilterSetCoeffDec) */
+  const int16_t* lumaClip;     /* same shape, clipping VALUES (lumaClippFinal / m_clipDefault)                              */
+  int32_t        numLumaSets;
+  const int16_t* chromaCoeff;  /* [numChromaAlts][7]                                                                        */
+  const int16_t* chromaClip;   /* [numChromaAlts][7]                                                                        */
+  int32_t        numChromaAlts;
+  const int16_t* ccCoeff[2];   /* [numCc[c]][7]  (CcAlfFilterParam::ccAlfCoeff)                                             */
+  int32_t        numCc[2];
+} b200_alf_tables;
+
+B200_API int b200_alf_picture(const b200_geom* g, const int16_t* const src[3], int16_t* const dst[3],
+                              const b200_alf_ctu* ctus, const b200_alf_tables* tabs);
+
 #ifdef __cplusplus
 }
 #endif

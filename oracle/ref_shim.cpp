@@ -330,3 +330,190 @@ extern "C" int ref_lf_deblock_picture( int simd, const b200_geom* g, int16_t* co
   fp.getPlanes( *g, planes );
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ K4
+extern "C" void ref_sao_offset_block( int simd, int bitDepth, int typeIdx, const int* offset32, int startIdx, const int16_t* src, int16_t* dst,
+                                      ptrdiff_t srcStride, ptrdiff_t dstStride, int width, int height, unsigned avail,
+                                      int numVerVb, const int* verVb, int numHorVb, const int* horVb )
+{
+  static SampleAdaptiveOffset ss( false ), sv( true );
+  std::vector<int8_t> b1( width + 2 ), b2( width + 2 );
+  int offs[MAX_NUM_SAO_CLASSES]; memcpy( offs, offset32, sizeof( offs ) );
+  int hv[3] = { -1, -1, -1 }, vv[3] = { -1, -1, -1 };
+  for( int i = 0; i < numVerVb; i++ ) vv[i] = verVb[i];
+  for( int i = 0; i < numHorVb; i++ ) hv[i] = horVb[i];
+  ClpRng clp; clp.bd = bitDepth;
+  ( simd ? sv : ss ).offsetBlock( bitDepth, clp, typeIdx, offs, startIdx, src, dst, srcStride, dstStride, width, height,
+                                   avail & B200_AVAIL_L, avail & B200_AVAIL_R, avail & B200_AVAIL_A, avail & B200_AVAIL_B,
+                                   avail & B200_AVAIL_AL, avail & B200_AVAIL_AR, avail & B200_AVAIL_BL, avail & B200_AVAIL_BR,
+                                   &b1, &b2, numVerVb + numHorVb > 0, hv, vv, numHorVb, numVerVb );
+}
+
+// one CU per CTU so that the picture-level filters find cuPtr[0][0] / slice / tile of every CTU
+static void addCtuCUs( FakePicture& fp )
+{
+  CodingStructure& cs = *fp.pic.cs;
+  const PreCalcValues& pcv = *cs.pcv;
+  for( unsigned y = 0; y < pcv.heightInCtus; y++ ) for( unsigned x = 0; x < pcv.widthInCtus; x++ )
+  {
+    const int w = std::min<int>( pcv.maxCUWidth, pcv.lumaWidth - x * pcv.maxCUWidth ), h = std::min<int>( pcv.maxCUHeight, pcv.lumaHeight - y * pcv.maxCUHeight );
+    CodingUnit& cu = cs.addCU( UnitArea( pcv.chrFormat, Area( x * pcv.maxCUWidth, y * pcv.maxCUHeight, w, h ) ), CH_L, TREE_D, MODE_TYPE_ALL, nullptr, nullptr );
+    cu.slice = fp.pic.slices[0]; cu.pps = fp.pps.get(); cu.sps = fp.sps.get(); cu.tileIdx = 0;
+  }
+}
+
+extern "C" int ref_sao_picture( int simd, const b200_geom* g, const int16_t* const src[3], int16_t* const dst[3], const b200_sao_ctu* ctus, const b200_vb* vb )
+{
+  FakePicture fp( *g, 1 );
+  CodingStructure& cs = *fp.pic.cs;
+  const PreCalcValues& pcv = *cs.pcv;
+  fp.pps->setLoopFilterAcrossSlicesEnabledFlag( true ); fp.pps->setLoopFilterAcrossTilesEnabledFlag( true );
+  if( vb && ( vb->numVer || vb->numHor ) )
+  {
+    fp.ph->setVirtualBoundariesPresentFlag( true );
+    fp.ph->setNumVerVirtualBoundaries( vb->numVer ); fp.ph->setNumHorVirtualBoundaries( vb->numHor );
+    for( int i = 0; i < vb->numVer; i++ ) fp.ph->setVirtualBoundariesPosX( vb->posX[i], i );
+    for( int i = 0; i < vb->numHor; i++ ) fp.ph->setVirtualBoundariesPosY( vb->posY[i], i );
+  }
+  addCtuCUs( fp );
+  int16_t* s3[3] = { (int16_t*) src[0], (int16_t*) src[1], (int16_t*) src[2] };
+  fp.setPlanes( *g, s3 );
+  PelStorage tmp; tmp.create( pcv.chrFormat, Size( g->width, g->height ), g->ctuSize, 16, MEMORY_ALIGN_DEF_SIZE );
+  tmp.copyFrom( cs.getRecoBuf() );
+  for( unsigned a = 0; a < pcv.sizeInCtus; a++ )
+  {
+    SAOBlkParam& bp = cs.getCtuData( a ).saoParam;
+    bp.reset();
+    for( int c = 0; c < ( g->chromaFormat ? 3 : 1 ); c++ )
+    {
+      if( ctus[a].type[c] == B200_SAO_OFF ) continue;
+      bp[c].modeIdc = SAO_MODE_NEW; bp[c].typeIdc = ctus[a].type[c]; bp[c].typeAuxInfo = ctus[a].band[c];
+      if( ctus[a].type[c] == B200_SAO_BO ) for( int i = 0; i < 4; i++ ) bp[c].offset[( ctus[a].band[c] + i ) & 31] = ctus[a].offset[c][i];
+      else for( int i = 0; i < 5; i++ ) bp[c].offset[i] = ctus[a].offset[c][i];
+    }
+  }
+  SampleAdaptiveOffset sao( simd != 0 );
+  sao.create( g->width, g->height, pcv.chrFormat, g->ctuSize, g->ctuSize, 0, 0, tmp );
+  for( unsigned y = 0; y < pcv.heightInCtus; y++ ) for( unsigned x = 0; x < pcv.widthInCtus; x++ )
+    sao.SAOProcessCTU( cs, clipArea( UnitArea( pcv.chrFormat, Area( x * g->ctuSize, y * g->ctuSize, g->ctuSize, g->ctuSize ) ), fp.pic ) );
+  fp.getPlanes( *g, dst );
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ K5
+static PelStorage wrapPlane( const int16_t* p, ptrdiff_t stride, int w, int h, int pad )
+{
+  // padded private copy (the reference's filters read up to 3/4 samples beyond the block; callers extend borders)
+  PelStorage st; st.create( CHROMA_400, Size( w, h ), 0, pad, MEMORY_ALIGN_DEF_SIZE );
+  PelBuf b = st.bufs[0];
+  for( int y = 0; y < h; y++ ) memcpy( b.buf + y * b.stride, p + y * stride, w * sizeof( Pel ) );
+  st.extendBorderPel( pad );
+  return st;
+}
+
+extern "C" void ref_alf_classify( int simd, uint16_t* cls, const int16_t* srcLuma, ptrdiff_t stride, int planeW, int planeH,
+                                  int blkX, int blkY, int blkW, int blkH, int shift, int vbCtuHeight, int vbPos )
+{
+  static AdaptiveLoopFilter as( false ), av( true );
+  PelStorage st = wrapPlane( srcLuma, stride, planeW, planeH, 8 );
+  AlfClassifier c[64];
+  memset( c, 0, sizeof( c ) );
+  ( simd ? av : as ).m_deriveClassificationBlk( c, st.bufs[0], Area( blkX, blkY, blkW, blkH ), shift, vbCtuHeight, vbPos );
+  for( int i = 0; i < 64; i++ ) cls[i] = c[i].classIdx | ( c[i].transposeIdx << 8 );
+}
+
+extern "C" void ref_alf_filter_blk( int simd, int is7x7, const uint16_t* cls, int16_t* dst, ptrdiff_t dstStride, const int16_t* src, ptrdiff_t srcStride,
+                                    int planeW, int planeH, int blkX, int blkY, int blkW, int blkH, const int16_t* coeff, const int16_t* clip,
+                                    int bitDepth, int vbCtuHeight, int vbPos )
+{
+  static AdaptiveLoopFilter as( false ), av( true );
+  AdaptiveLoopFilter& a = simd ? av : as;
+  // the pointers take Unit buffers and a component id: put the plane into a 4:0:0 (luma) or 4:2:0 (chroma as Cb) unit
+  const bool chroma = !is7x7;
+  PelStorage s, d;
+  if( chroma ) { s.create( CHROMA_420, Size( planeW * 2, planeH * 2 ), 0, 16, MEMORY_ALIGN_DEF_SIZE ); d.create( CHROMA_420, Size( planeW * 2, planeH * 2 ), 0, 16, MEMORY_ALIGN_DEF_SIZE ); }
+  else         { s.create( CHROMA_400, Size( planeW, planeH ), 0, 8, MEMORY_ALIGN_DEF_SIZE );          d.create( CHROMA_400, Size( planeW, planeH ), 0, 8, MEMORY_ALIGN_DEF_SIZE ); }
+  const ComponentID comp = chroma ? COMPONENT_Cb : COMPONENT_Y;
+  PelBuf sb = s.bufs[comp], db = d.bufs[comp];
+  for( int y = 0; y < planeH; y++ ) { memcpy( sb.buf + y * sb.stride, src + y * srcStride, planeW * sizeof( Pel ) ); memcpy( db.buf + y * db.stride, dst + y * dstStride, planeW * sizeof( Pel ) ); }
+  s.extendBorderPel( chroma ? 8 : 8 );
+  AlfClassifier c[64];
+  if( cls ) for( int i = 0; i < 64; i++ ) c[i] = AlfClassifier( cls[i] & 0xff, cls[i] >> 8 );
+  ClpRng clp; clp.bd = bitDepth;
+  ( is7x7 ? a.m_filter7x7Blk : a.m_filter5x5Blk )( cls ? c : nullptr, d, s, Area( blkX, blkY, blkW, blkH ), comp, coeff, clip, clp, vbCtuHeight, vbPos, false );
+  for( int y = 0; y < planeH; y++ ) memcpy( dst + y * dstStride, db.buf + y * db.stride, planeW * sizeof( Pel ) );
+}
+
+extern "C" void ref_alf_ccalf_blk( int simd, int16_t* dstChroma, ptrdiff_t chromaStride, const int16_t* srcLuma, ptrdiff_t lumaStride,
+                                   int lumaW, int lumaH, int cX, int cY, int cW, int cH, const int16_t* coeff, int bitDepth, int vbCtuHeight, int vbPos )
+{
+  static AdaptiveLoopFilter as( false ), av( true );
+  PelStorage s; s.create( CHROMA_420, Size( lumaW, lumaH ), 0, 16, MEMORY_ALIGN_DEF_SIZE );
+  PelBuf lb = s.bufs[0];
+  for( int y = 0; y < lumaH; y++ ) memcpy( lb.buf + y * lb.stride, srcLuma + y * lumaStride, lumaW * sizeof( Pel ) );
+  s.extendBorderPel( 8 );
+  PelBuf dbuf( dstChroma, chromaStride, lumaW >> 1, lumaH >> 1 );
+  ClpRng clp; clp.bd = bitDepth;
+  ( simd ? av : as ).m_filterCcAlf( dbuf, s, Area( cX, cY, cW, cH ), Area( cX * 2, cY * 2, cW * 2, cH * 2 ), COMPONENT_Cb, coeff, clp, vbCtuHeight, vbPos );
+}
+
+extern "C" int ref_alf_picture( int simd, const b200_geom* g, const int16_t* const src[3], int16_t* const dst[3], const b200_alf_ctu* ctus,
+                                const b200_alf_tables* T )
+{
+  FakePicture fp( *g, 1 );
+  CodingStructure& cs = *fp.pic.cs;
+  const PreCalcValues& pcv = *cs.pcv;
+  fp.pps->setLoopFilterAcrossSlicesEnabledFlag( true ); fp.pps->setLoopFilterAcrossTilesEnabledFlag( true );
+  fp.sps->setUseALF( true ); fp.sps->setUseCCALF( true );
+  addCtuCUs( fp );
+  Slice* sl = fp.pic.slices[0];
+  { SliceMap sm; sm.addCtusToSlice( 0, pcv.widthInCtus, 0, pcv.heightInCtus, pcv.widthInCtus ); sl->setSliceMap( sm ); }
+  // APS 0..n-1 carry the luma sets 16.. ; APS 7 carries the chroma alternatives (<=8) ; APS 6/5 the CC-ALF filters (<=4 each)
+  static std::shared_ptr<APS> apsStore[ALF_CTB_MAX_NUM_APS];
+  const APS* apss[ALF_CTB_MAX_NUM_APS] = { nullptr };
+  for( int i = 0; i < ALF_CTB_MAX_NUM_APS; i++ ) { apsStore[i] = std::make_shared<APS>(); apsStore[i]->setAPSId( i ); apss[i] = apsStore[i].get(); }
+  const int nApsLuma = T->numLumaSets - NUM_FIXED_FILTER_SETS;
+  AlfApsIdVec ids;
+  for( int i = 0; i < nApsLuma; i++ )
+  {
+    AlfSliceParam& p = apsStore[i]->getAlfAPSParam();
+    memcpy( p.lumaCoeffFinal, T->lumaCoeff + (size_t) ( 16 + i ) * 1300, 1300 * sizeof( short ) );
+    memcpy( p.lumaClippFinal, T->lumaClip  + (size_t) ( 16 + i ) * 1300, 1300 * sizeof( short ) );
+    p.lumaFinalDone = true;
+    ids.push_back( i );
+  }
+  sl->setNumAlfAps( nApsLuma ); sl->setAlfApsIdsLuma( ids );
+  {
+    AlfSliceParam& p = apsStore[7]->getAlfAPSParam();
+    p.numAlternativesChroma = T->numChromaAlts;
+    memcpy( p.chromaCoeff,    T->chromaCoeff, T->numChromaAlts * 7 * sizeof( short ) );
+    memcpy( p.chrmClippFinal, T->chromaClip,  T->numChromaAlts * 7 * sizeof( short ) );
+    p.chrmFinalDone = true;
+    sl->setAlfApsIdChroma( 7 );
+  }
+  for( int c = 0; c < 2; c++ )
+  {
+    CcAlfFilterParam& p = apsStore[6 - c]->getCcAlfAPSParam();
+    for( int k = 0; k < T->numCc[c]; k++ ) memcpy( p.ccAlfCoeff[c][k], T->ccCoeff[c] + k * 7, 7 * sizeof( short ) );
+  }
+  sl->setCcAlfCbEnabledFlag( T->numCc[0] > 0 ); sl->setCcAlfCrEnabledFlag( T->numCc[1] > 0 );
+  sl->setCcAlfCbApsId( 6 ); sl->setCcAlfCrApsId( 5 );
+  sl->setAlfApss( apss );
+  for( int c = 0; c < 3; c++ ) sl->setAlfEnabledFlag( ComponentID( c ), true );
+  for( unsigned a = 0; a < pcv.sizeInCtus; a++ )
+  {
+    CtuAlfData& d = cs.getCtuData( a ).alfParam;
+    for( int c = 0; c < 3; c++ ) d.alfCtuEnableFlag[c] = ctus[a].enable[c] & 1;
+    d.alfCtbFilterIndex = ctus[a].lumaSet;
+    for( int c = 0; c < 2; c++ ) { d.alfCtuAlternative[c] = ctus[a].chromaAlt[c]; d.ccAlfFilterControl[c] = ctus[a].ccIdx[c]; }
+  }
+  int16_t* s3[3] = { (int16_t*) src[0], (int16_t*) src[1], (int16_t*) src[2] };
+  fp.setPlanes( *g, s3 );
+  PelStorage out; out.create( pcv.chrFormat, Size( g->width, g->height ), g->ctuSize, 16, MEMORY_ALIGN_DEF_SIZE );
+  AdaptiveLoopFilter alf( simd != 0 );
+  alf.create( fp.ph.get(), fp.sps.get(), fp.pps.get(), 1, out );
+  for( unsigned y = 0; y < pcv.heightInCtus; y++ ) for( unsigned x = 0; x < pcv.widthInCtus; x++ ) alf.prepareCTU( cs, x, y );
+  for( unsigned y = 0; y < pcv.heightInCtus; y++ ) for( unsigned x = 0; x < pcv.widthInCtus; x++ ) alf.processCTU( cs, x, y, 0 );
+  fp.getPlanes( *g, dst, true, &out );
+  return 0;
+}

@@ -61,6 +61,25 @@ int ref_lf_deblock_picture(int simd, const b200_geom* g, int16_t* const planes[3
                            const b200_lf_param* lfH, const uint8_t* ctuSlice, const b200_lf_slice* slices, int numSlices,
                            const b200_lf_seq* seq, int dirs);
 
+/* ---- K4 SAO ---- */
+void ref_sao_offset_block(int simd, int bitDepth, int typeIdx, const int* offset32, int startIdx /*BO first band*/, const int16_t* src, int16_t* dst,
+                          ptrdiff_t srcStride, ptrdiff_t dstStride, int width, int height, unsigned avail,
+                          int numVerVb, const int* verVb, int numHorVb, const int* horVb);
+/* real SampleAdaptiveOffset::SAOProcessCTU over a real CodingStructure (one CU per CTU, single slice/tile) */
+int ref_sao_picture(int simd, const b200_geom* g, const int16_t* const src[3], int16_t* const dst[3], const b200_sao_ctu* ctus, const b200_vb* vb);
+
+/* ---- K5 ALF ---- */
+void ref_alf_classify(int simd, uint16_t* cls /*64*/, const int16_t* srcLuma, ptrdiff_t stride, int planeW, int planeH,
+                      int blkX, int blkY, int blkW, int blkH, int shift, int vbCtuHeight, int vbPos);
+void ref_alf_filter_blk(int simd, int is7x7, const uint16_t* cls, int16_t* dst, ptrdiff_t dstStride, const int16_t* src, ptrdiff_t srcStride,
+                        int planeW, int planeH, int blkX, int blkY, int blkW, int blkH, const int16_t* coeff, const int16_t* clip,
+                        int bitDepth, int vbCtuHeight, int vbPos);
+void ref_alf_ccalf_blk(int simd, int16_t* dstChroma, ptrdiff_t chromaStride, const int16_t* srcLuma, ptrdiff_t lumaStride,
+                       int lumaW, int lumaH, int cX, int cY, int cW, int cH, const int16_t* coeff, int bitDepth, int vbCtuHeight, int vbPos);
+/* real AdaptiveLoopFilter::prepareCTU + processCTU over a real CodingStructure; APS objects are built from tabs */
+int ref_alf_picture(int simd, const b200_geom* g, const int16_t* const src[3], int16_t* const dst[3], const b200_alf_ctu* ctus,
+                    const b200_alf_tables* tabs);
+
 #ifdef __cplusplus
 }
 #endif

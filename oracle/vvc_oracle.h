@@ -54,6 +54,30 @@ void orc_lf_filtering_pq(int16_t* src, ptrdiff_t step, ptrdiff_t offset, int num
 void orc_lf_deblock(const b200_geom* g, int16_t* const planes[3], const b200_lf_param* lfV, const b200_lf_param* lfH,
                     const uint8_t* ctuSlice, const b200_lf_slice* slices, const b200_lf_seq* seq, int dirs);
 
+/* ---- K4 SAO ---------------------------------------------------------------------------------- */
+/* SampleAdaptiveOffset.cpp:64 offsetBlock_core for one CTU component (same argument meaning; vb = positions relative to the block). */
+void orc_sao_offset_block(int bitDepth, int typeIdx, const int* offset /*32*/, const int16_t* src, int16_t* dst,
+                          ptrdiff_t srcStride, ptrdiff_t dstStride, int width, int height, unsigned avail,
+                          int numVerVb, const int* verVb, int numHorVb, const int* horVb);
+/* SAOProcessCTU over the picture (SampleAdaptiveOffset.cpp:522,:661). dst must be pre-filled by the caller? No: it copies src first. */
+void orc_sao_picture(const b200_geom* g, const int16_t* const src[3], int16_t* const dst[3], const b200_sao_ctu* ctus, const b200_vb* vb);
+
+/* ---- K5 ALF ---------------------------------------------------------------------------------- */
+/* AdaptiveLoopFilter.cpp:969 deriveClassificationBlk: cls[(i/4)*8 + j/4] = classIdx | transposeIdx<<8 for the blk (<=32x32). */
+void orc_alf_classify(uint16_t* cls, const int16_t* srcLuma, ptrdiff_t stride, int blkX, int blkY, int blkW, int blkH,
+                      int shift, int vbCtuHeight, int vbPos);
+/* AdaptiveLoopFilter.cpp:1175 filterBlk<7>/<5>: cls may be NULL for chroma (5x5). src/dst are plane origins. */
+void orc_alf_filter_blk(int is7x7, const uint16_t* cls, int16_t* dst, ptrdiff_t dstStride, const int16_t* src, ptrdiff_t srcStride,
+                        int blkX, int blkY, int blkW, int blkH, const int16_t* coeff, const int16_t* clip, int bitDepth,
+                        int vbCtuHeight, int vbPos);
+/* AdaptiveLoopFilter.cpp:1348 filterBlkCcAlf (4:2:0). */
+void orc_alf_ccalf_blk(int16_t* dstChroma, ptrdiff_t chromaStride, const int16_t* srcLuma, ptrdiff_t lumaStride,
+                       int cX, int cY, int cW, int cH, const int16_t* coeff, int bitDepth, int vbCtuHeight, int vbPos);
+/* processCTU over the picture, !isCrssByVBs path (AdaptiveLoopFilter.cpp:466,:664-741); src planes are read with
+ * coordinates clamped to the picture (== prepareCTU's border extension, :453). */
+void orc_alf_picture(const b200_geom* g, const int16_t* const src[3], int16_t* const dst[3], const b200_alf_ctu* ctus,
+                     const b200_alf_tables* tabs);
+
 #ifdef __cplusplus
 }
 #endif

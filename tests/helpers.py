@@ -28,6 +28,13 @@ def load_oracle():
     lib.orc_lf_pel_filter_luma.argtypes = [i16p_off, C.c_ssize_t, C.c_ssize_t] + [C.c_int] * 6
     lib.orc_lf_filtering_pq.argtypes = [i16p_off, C.c_ssize_t, C.c_ssize_t, C.c_int, C.c_int, C.c_int]
     lib.orc_lf_deblock.argtypes = [C.POINTER(abi.Geom), PL, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    V = C.c_void_p
+    lib.orc_sao_offset_block.argtypes = [C.c_int, C.c_int, V, V, V, C.c_ssize_t, C.c_ssize_t, C.c_int, C.c_int, C.c_uint, C.c_int, V, C.c_int, V]
+    lib.orc_sao_picture.argtypes = [C.POINTER(abi.Geom), PL, PL, V, V]
+    lib.orc_alf_classify.argtypes = [V, V, C.c_ssize_t] + [C.c_int] * 7
+    lib.orc_alf_filter_blk.argtypes = [C.c_int, V, V, C.c_ssize_t, V, C.c_ssize_t] + [C.c_int] * 4 + [V, V] + [C.c_int] * 3
+    lib.orc_alf_ccalf_blk.argtypes = [V, C.c_ssize_t, V, C.c_ssize_t] + [C.c_int] * 4 + [V] + [C.c_int] * 3
+    lib.orc_alf_picture.argtypes = [C.POINTER(abi.Geom), PL, PL, V, C.POINTER(abi.AlfTables)]
     return lib
 
 
@@ -54,6 +61,13 @@ def load_ref():
     lib.ref_lf_pel_filter_luma.argtypes = [C.c_int, i16p_off, C.c_ssize_t, C.c_ssize_t] + [C.c_int] * 6
     lib.ref_lf_filtering_pq.argtypes = [C.c_int, i16p_off, C.c_ssize_t, C.c_ssize_t, C.c_int, C.c_int, C.c_int]
     lib.ref_lf_deblock_picture.argtypes = [C.c_int, C.POINTER(abi.Geom), PL, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    V = C.c_void_p
+    lib.ref_sao_offset_block.argtypes = [C.c_int, C.c_int, C.c_int, V, C.c_int, V, V, C.c_ssize_t, C.c_ssize_t, C.c_int, C.c_int, C.c_uint, C.c_int, V, C.c_int, V]
+    lib.ref_sao_picture.argtypes = [C.c_int, C.POINTER(abi.Geom), PL, PL, V, V]
+    lib.ref_alf_classify.argtypes = [C.c_int, V, V, C.c_ssize_t] + [C.c_int] * 9
+    lib.ref_alf_filter_blk.argtypes = [C.c_int, C.c_int, V, V, C.c_ssize_t, V, C.c_ssize_t] + [C.c_int] * 6 + [V, V] + [C.c_int] * 3
+    lib.ref_alf_ccalf_blk.argtypes = [C.c_int, V, C.c_ssize_t, V, C.c_ssize_t] + [C.c_int] * 6 + [V] + [C.c_int] * 3
+    lib.ref_alf_picture.argtypes = [C.c_int, C.POINTER(abi.Geom), PL, PL, V, C.POINTER(abi.AlfTables)]
     return lib
 
 

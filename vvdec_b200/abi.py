@@ -47,3 +47,27 @@ def plane_ptrs(planes):
 class LfSeq(C.Structure):
     _fields_ = [("ladfEnabled", C.c_int32), ("ladfNumIntervals", C.c_int32), ("ladfQpOffset", C.c_int32 * 5),
                 ("ladfIntervalLowerBound", C.c_int32 * 5)]
+
+
+class Vb(C.Structure):
+    _fields_ = [("numVer", C.c_int32), ("numHor", C.c_int32), ("posX", C.c_int32 * 3), ("posY", C.c_int32 * 3)]
+
+
+class AlfTables(C.Structure):
+    _fields_ = [("lumaCoeff", C.c_void_p), ("lumaClip", C.c_void_p), ("numLumaSets", C.c_int32),
+                ("chromaCoeff", C.c_void_p), ("chromaClip", C.c_void_p), ("numChromaAlts", C.c_int32),
+                ("ccCoeff", C.c_void_p * 2), ("numCc", C.c_int32 * 2)]
+
+
+def make_alf_tables(t):
+    """t: dict from synth.gen_alf (arrays must stay alive while the struct is used)."""
+    T = AlfTables()
+    T.lumaCoeff = t["lumaCoeff"].ctypes.data; T.lumaClip = t["lumaClip"].ctypes.data; T.numLumaSets = t["lumaCoeff"].shape[0]
+    T.chromaCoeff = t["chromaCoeff"].ctypes.data; T.chromaClip = t["chromaClip"].ctypes.data; T.numChromaAlts = t["chromaCoeff"].shape[0]
+    for c in range(2):
+        T.ccCoeff[c] = t["cc"][c].ctypes.data; T.numCc[c] = t["cc"][c].shape[0]
+    return T
+
+
+def const_plane_ptrs(planes):
+    return plane_ptrs(planes)

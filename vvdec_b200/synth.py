@@ -203,3 +203,76 @@ def gen_lf_grid(rng, cus, W, H, bit_depth=10, cu_intra=None, cu_qp=None, p_bs0=0
         g["qp"][..., 1] = np.clip(qpl - 1, 0, 63); g["qp"][..., 2] = np.clip(qpl + 1, 0, 63)
         out.append(np.ascontiguousarray(g))
     return out[0], out[1]
+
+
+SAO_DTYPE = np.dtype([("type", "u1", (3,)), ("band", "u1", (3,)), ("offset", "i1", (3, 5)), ("avail", "u1"), ("rsv", "u1", (2,))])
+ALFCTU_DTYPE = np.dtype([("enable", "u1", (3,)), ("lumaSet", "u1"), ("chromaAlt", "u1", (2,)), ("ccIdx", "u1", (2,))])
+assert SAO_DTYPE.itemsize == 24 and ALFCTU_DTYPE.itemsize == 8
+AV_L, AV_R, AV_A, AV_B, AV_AL, AV_AR, AV_BL, AV_BR = 1, 2, 4, 8, 16, 32, 64, 128
+
+
+def picture_avail(ctusW, ctusH):
+    """8-neighbour CTU availability when only the picture limits restrict it (single slice / tile)."""
+    av = np.zeros((ctusH, ctusW), np.uint8)
+    for y in range(ctusH):
+        for x in range(ctusW):
+            l, r, a, b = x > 0, x + 1 < ctusW, y > 0, y + 1 < ctusH
+            av[y, x] = (AV_L * l | AV_R * r | AV_A * a | AV_B * b | AV_AL * (l and a) | AV_AR * (r and a)
+                        | AV_BL * (l and b) | AV_BR * (r and b))
+    return av.reshape(-1)
+
+
+def gen_sao(rng, W, H, ctu=128, bit_depth=10, p_on=0.4, chroma=True):
+    """Per-CTU SAO records (SAO on 40 % of CTUs, EO:BO 3:1, offsets in [-7,7] scaled by 1<<max(0,bd-10))."""
+    ctusW, ctusH = (W + ctu - 1) // ctu, (H + ctu - 1) // ctu
+    n = ctusW * ctusH
+    s = np.zeros(n, SAO_DTYPE)
+    s["type"] = 255
+    scale = 1 << max(0, bit_depth - 10)
+    for i in range(n):
+        for c in range(3 if chroma else 1):
+            if rng.random() < p_on:
+                t = int(rng.integers(0, 4)) if rng.random() < 0.75 else 4
+                s["type"][i, c] = t
+                off = rng.integers(-7, 8, size=5) * scale
+                if t < 4: off[2] = 0
+                s["offset"][i, c] = off
+                s["band"][i, c] = int(rng.integers(0, 32))
+    s["avail"] = picture_avail(ctusW, ctusH)
+    return s
+
+
+ALF_TR = [[0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12], [9, 4, 10, 8, 1, 5, 11, 7, 3, 0, 2, 6, 12],
+          [0, 3, 2, 1, 8, 7, 6, 5, 4, 9, 10, 11, 12], [9, 8, 10, 4, 3, 7, 11, 5, 1, 0, 2, 6, 12]]   # AdaptiveLoopFilter.cpp:97-112
+
+
+def _fixed_sets():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "alf_fixed_sets.npy"))
+
+
+def gen_alf(rng, W, H, ctu=128, bit_depth=10, n_aps=2, n_chroma_alts=3, n_cc=(2, 3), p_luma=0.8, p_chroma=0.6, p_cc=0.3):
+    """ALF tables (16 fixed sets + n_aps random APS sets, pre-transposed like lumaCoeffFinal) and per-CTU controls."""
+    clipv = [1 << bit_depth, 1 << (bit_depth - 3), 1 << (bit_depth - 5), 1 << (bit_depth - 7)]   # m_alfClippVls
+    nsets = 16 + n_aps
+    coef = np.zeros((nsets, 4, 25, 13), np.int16); clip = np.zeros((nsets, 4, 25, 13), np.int16)
+    coef[:16] = _fixed_sets(); clip[:16] = clipv[0]
+    for s in range(16, nsets):
+        base = rng.integers(-40, 41, size=(25, 13)).astype(np.int16); base[:, 12] = 128
+        bclip = rng.choice(clipv, size=(25, 13)).astype(np.int16)
+        for t in range(4):
+            coef[s, t] = base[:, ALF_TR[t]]; clip[s, t] = bclip[:, ALF_TR[t]]
+    ccoef = rng.integers(-40, 41, size=(n_chroma_alts, 7)).astype(np.int16); ccoef[:, 6] = 128
+    cclip = rng.choice(clipv, size=(n_chroma_alts, 7)).astype(np.int16)
+    cc = [rng.integers(-63, 64, size=(n_cc[c], 7)).astype(np.int16) for c in range(2)]
+    ctusW, ctusH = (W + ctu - 1) // ctu, (H + ctu - 1) // ctu
+    n = ctusW * ctusH
+    a = np.zeros(n, ALFCTU_DTYPE)
+    a["enable"][:, 0] = rng.random(n) < p_luma
+    a["enable"][:, 1] = rng.random(n) < p_chroma; a["enable"][:, 2] = rng.random(n) < p_chroma
+    a["lumaSet"] = rng.integers(0, nsets, size=n)
+    a["chromaAlt"] = rng.integers(0, n_chroma_alts, size=(n, 2))
+    for c in range(2):
+        a["ccIdx"][:, c] = np.where(rng.random(n) < p_cc, rng.integers(1, n_cc[c] + 1, size=n), 0) if n_cc[c] else 0
+    return dict(lumaCoeff=np.ascontiguousarray(coef), lumaClip=np.ascontiguousarray(clip), chromaCoeff=ccoef, chromaClip=cclip,
+                cc=cc, ctus=a)
