@@ -21,4 +21,11 @@ def declare(lib):
     lib.b200_lf_deblock.restype = C.c_int
 
 
-EXPORTS = ["b200_last_error", "b200_version", "b200_device_count", "b200_k1_residual", "b200_lf_deblock"]
+    lib.b200_sao_picture.argtypes = [C.POINTER(abi.Geom), PLANES, PLANES, C.c_void_p, C.c_void_p]
+    lib.b200_sao_picture.restype = C.c_int
+    lib.b200_alf_picture.argtypes = [C.POINTER(abi.Geom), PLANES, PLANES, C.c_void_p, C.POINTER(abi.AlfTables)]
+    lib.b200_alf_picture.restype = C.c_int
+
+
+EXPORTS = ["b200_last_error", "b200_version", "b200_device_count", "b200_k1_residual", "b200_lf_deblock",
+           "b200_sao_picture", "b200_alf_picture"]

@@ -125,4 +125,70 @@ B200_API int b200_lf_deblock(const b200_geom* g, int16_t* const planes[3], const
   return 0;
 }
 
+static int upload_src_alloc_dst(const b200_geom* g, const int16_t* const src[3], DevPlanes& ds, DevPlanes& dd, cudaStream_t s)
+{
+  const int nPlanes = g->chromaFormat ? 3 : 1;
+  for (int c = 0; c < nPlanes; c++) {
+    const int ph = c ? g->height >> 1 : g->height;
+    const size_t bytes = (size_t)g->stride[c] * ph * sizeof(int16_t);
+    if (int rc = g_hw.planes[c].reserve(bytes)) return rc;
+    if (int rc = g_hw.misc[3 + c].reserve(bytes)) return rc;
+    ds.p[c] = g_hw.planes[c].as<int16_t>(); dd.p[c] = g_hw.misc[3 + c].as<int16_t>(); ds.stride[c] = dd.stride[c] = g->stride[c];
+    B200_CUDA(cudaMemcpyAsync(ds.p[c], src[c], bytes, cudaMemcpyHostToDevice, s));
+  }
+  return 0;
+}
+
+B200_API int b200_sao_picture(const b200_geom* g, const int16_t* const src[3], int16_t* const dst[3], const b200_sao_ctu* ctus, const b200_vb* vb)
+{
+  B200_CHECK(g && src && dst && ctus, "b200_sao_picture: null argument");
+  B200_CHECK((g->width & 7) == 0 && (g->stride[0] & 3) == 0 && (!g->chromaFormat || (g->stride[1] & 3) == 0), "b200_sao_picture: width must be a multiple of 8, strides of 4");
+  if (int rc = ensure_device()) return rc;
+  if (int rc = g_hw.init()) return rc;
+  cudaStream_t s = g_hw.stream;
+  SaoLaunch L; L.geom = *g;
+  if (vb) L.vb = *vb; else memset(&L.vb, 0, sizeof(L.vb));
+  if (int rc = upload_src_alloc_dst(g, src, L.src, L.dst, s)) return rc;
+  const size_t nCtu = (size_t)((g->width + g->ctuSize - 1) / g->ctuSize) * ((g->height + g->ctuSize - 1) / g->ctuSize);
+  if (int rc = g_hw.misc[0].reserve(nCtu * sizeof(b200_sao_ctu))) return rc;
+  B200_CUDA(cudaMemcpyAsync(g_hw.misc[0].p, ctus, nCtu * sizeof(b200_sao_ctu), cudaMemcpyHostToDevice, s));
+  L.ctus = g_hw.misc[0].as<b200_sao_ctu>();
+  if (int rc = launch_sao(L, s)) return rc;
+  if (int rc = download_planes(g, dst, L.dst, s)) return rc;
+  B200_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+B200_API int b200_alf_picture(const b200_geom* g, const int16_t* const src[3], int16_t* const dst[3], const b200_alf_ctu* ctus, const b200_alf_tables* T)
+{
+  B200_CHECK(g && src && dst && ctus && T, "b200_alf_picture: null argument");
+  B200_CHECK((g->width & 7) == 0 && (g->stride[0] & 3) == 0 && (!g->chromaFormat || (g->stride[1] & 3) == 0), "b200_alf_picture: width must be a multiple of 8, strides of 4");
+  B200_CHECK(T->numLumaSets >= 16 && T->numLumaSets <= 24, "b200_alf_picture: numLumaSets %d", T->numLumaSets);
+  if (int rc = ensure_device()) return rc;
+  if (int rc = g_hw.init()) return rc;
+  cudaStream_t s = g_hw.stream;
+  AlfLaunch L; L.geom = *g;
+  if (int rc = upload_src_alloc_dst(g, src, L.src, L.dst, s)) return rc;
+  const size_t nCtu = (size_t)((g->width + g->ctuSize - 1) / g->ctuSize) * ((g->height + g->ctuSize - 1) / g->ctuSize);
+  const size_t nL = (size_t)T->numLumaSets * 1300, nC = (size_t)T->numChromaAlts * 7, n0 = (size_t)T->numCc[0] * 7, n1 = (size_t)T->numCc[1] * 7;
+  const size_t tabElems = 2 * nL + 2 * nC + n0 + n1 + 8;
+  if (int rc = g_hw.misc[0].reserve(nCtu * sizeof(b200_alf_ctu))) return rc;
+  if (int rc = g_hw.misc[1].reserve(tabElems * sizeof(int16_t))) return rc;
+  B200_CUDA(cudaMemcpyAsync(g_hw.misc[0].p, ctus, nCtu * sizeof(b200_alf_ctu), cudaMemcpyHostToDevice, s));
+  int16_t* d = g_hw.misc[1].as<int16_t>();
+  auto up = [&](const int16_t* h, size_t n, const int16_t*& out) -> int {
+    out = d; if (n) B200_CUDA(cudaMemcpyAsync(d, h, n * sizeof(int16_t), cudaMemcpyHostToDevice, s)); d += n; return 0; };
+  if (int rc = up(T->lumaCoeff, nL, L.lumaCoeff)) return rc;
+  if (int rc = up(T->lumaClip, nL, L.lumaClip)) return rc;
+  if (int rc = up(T->chromaCoeff, nC, L.chromaCoeff)) return rc;
+  if (int rc = up(T->chromaClip, nC, L.chromaClip)) return rc;
+  if (int rc = up(T->ccCoeff[0], n0, L.cc[0])) return rc;
+  if (int rc = up(T->ccCoeff[1], n1, L.cc[1])) return rc;
+  L.ctus = g_hw.misc[0].as<b200_alf_ctu>();
+  if (int rc = launch_alf(L, s)) return rc;
+  if (int rc = download_planes(g, dst, L.dst, s)) return rc;
+  B200_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
 }  // extern "C"

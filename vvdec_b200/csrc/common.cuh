@@ -72,6 +72,15 @@ struct LfLaunch {
 };
 int launch_lf_deblock(const LfLaunch& L, cudaStream_t s);
 
+struct SaoLaunch { b200_geom geom; DevPlanes src, dst; const b200_sao_ctu* ctus; b200_vb vb; };
+int launch_sao(const SaoLaunch& L, cudaStream_t s);
+
+struct AlfLaunch {
+  b200_geom geom; DevPlanes src, dst; const b200_alf_ctu* ctus;
+  const int16_t *lumaCoeff, *lumaClip, *chromaCoeff, *chromaClip, *cc[2];
+};
+int launch_alf(const AlfLaunch& L, cudaStream_t s);
+
 int ensure_device();   // selects device 0 if none current; fails loudly when there is no sm_100 GPU
 
 }  // namespace b200

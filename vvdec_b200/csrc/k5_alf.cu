@@ -1,0 +1,243 @@
+// k5_alf.cu — K5: adaptive loop filter. Luma: one CTA per 32x32 block (the reference's classification block): the block
+// plus a 4-sample halo is staged in shared memory (coordinates clamped to the picture = prepareCTU's border extension),
+// 4 threads per 4x4 block compute the Laplacian sums (warp-shuffle reduce), then every thread filters 4 samples with
+// the 7x7 diamond.  Chroma: one thread per 4 samples does the 5x5 diamond and adds CC-ALF from the pre-ALF luma.
+//
+// Replaces (reference, source/Lib/CommonLib/AdaptiveLoopFilter.cpp): processCTU :466, filterCTU :664 (!isCrssByVBs
+// path), filterAreaLuma :498, deriveClassificationBlk :969, filterBlk<ALF_FILTER_7|5> :1175, filterAreaChroma :546,
+// filterBlkCcAlf :1348, filterBlkCcAlfBoth :1447, prepareCTU :453.
+// HBM traffic: S*2 B read + S*2 B written (+ halo re-reads served by L2) + 8 B/CTU + filter tables once.
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int TB = 32;            // tile (block) size
+constexpr int HALO = 4;
+constexpr int TS = TB + 2 * HALO; // 40
+
+struct AlfParams {
+  const int16_t* src[3]; int16_t* dst[3]; int stride[3];
+  int W, H, bitDepth, ctuSize, ctuLog2, ctusW;
+  const b200_alf_ctu* ctus;
+  const int16_t *lumaCoeff, *lumaClip, *chromaCoeff, *chromaClip, *cc0, *cc1;
+};
+
+__device__ __forceinline__ int clipd(int c, int ref, int a, int b) { return clip3(-c, c, a - ref) + clip3(-c, c, b - ref); }
+
+__global__ void __launch_bounds__(256) alf_luma_kernel(const AlfParams P)
+{
+  __shared__ int16_t t[TS][TS + 2];
+  __shared__ uint16_t s_cls[64];
+  const int bx0 = blockIdx.x * TB, by0 = blockIdx.y * TB;
+  const int tid = threadIdx.x;
+  const b200_alf_ctu cp = P.ctus[(by0 >> P.ctuLog2) * P.ctusW + (bx0 >> P.ctuLog2)];
+  const int stride = P.stride[0];
+  const int bw = min(TB, P.W - bx0), bh = min(TB, P.H - by0);
+
+  if (!(cp.enable[0] & 1)) {   // unfiltered CTUs are copied (AdaptiveLoopFilter.cpp:717)
+    for (int i = tid; i < bh * (bw >> 2); i += 256) {
+      const int y = i / (bw >> 2), x = (i - y * (bw >> 2)) * 4;
+      *reinterpret_cast<uint2*>(P.dst[0] + (size_t)(by0 + y) * stride + bx0 + x) = *reinterpret_cast<const uint2*>(P.src[0] + (size_t)(by0 + y) * stride + bx0 + x);
+    }
+    return;
+  }
+
+  // ---- stage tile + halo, clamped ----
+  for (int i = tid; i < TS * TS; i += 256) {
+    const int ty = i / TS, tx = i - ty * TS;
+    const int gx = min(max(bx0 + tx - HALO, 0), P.W - 1), gy = min(max(by0 + ty - HALO, 0), P.H - 1);
+    t[ty][tx] = P.src[0][(size_t)gy * stride + gx];
+  }
+  __syncthreads();
+
+  const int vbH = P.ctuSize, vbPos = P.ctuSize - 4;
+
+  // ---- classification (AdaptiveLoopFilter.cpp:969): thread = (4x4 block b, row pair r) ----
+  {
+    const int b = tid >> 2, r = tid & 3;
+    const int bxi = b & 7, byi = b >> 3;
+    const int y0 = by0 + byi * 4, x0l = bxi * 4;              // block origin: global y, tile-local x
+    const bool aboveVb = (y0 & (vbH - 1)) == vbPos - 4, belowVb = (y0 & (vbH - 1)) == vbPos;
+    int sV = 0, sH = 0, sD0 = 0, sD1 = 0;
+    const bool skip = (aboveVb && r == 3) || (belowVb && r == 0);
+    if (!skip) {
+      const int gy = y0 - 2 + 2 * r;                          // first row of the pair (global)
+      const int ly = byi * 4 - 2 + 2 * r + HALO;              // tile row
+      int up = -1, dn2 = 2;
+      if (gy > 0 && (gy & (vbH - 1)) == vbPos - 2) dn2 = 1;
+      else if (gy > 0 && (gy & (vbH - 1)) == vbPos) up = 0;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int lx = x0l - 2 + 2 * c + HALO;
+        const int a = t[ly][lx] << 1, bb = t[ly + 1][lx + 1] << 1;
+        sV  += abs(a - t[ly + up][lx] - t[ly + 1][lx])          + abs(bb - t[ly][lx + 1] - t[ly + dn2][lx + 1]);
+        sH  += abs(a - t[ly][lx + 1] - t[ly][lx - 1])           + abs(bb - t[ly + 1][lx + 2] - t[ly + 1][lx]);
+        sD0 += abs(a - t[ly + up][lx - 1] - t[ly + 1][lx + 1])  + abs(bb - t[ly][lx] - t[ly + dn2][lx + 2]);
+        sD1 += abs(a - t[ly + 1][lx - 1] - t[ly + up][lx + 1])  + abs(bb - t[ly + dn2][lx] - t[ly][lx + 2]);
+      }
+    }
+#pragma unroll
+    for (int m = 1; m < 4; m <<= 1) {
+      sV += __shfl_xor_sync(0xffffffffu, sV, m); sH += __shfl_xor_sync(0xffffffffu, sH, m);
+      sD0 += __shfl_xor_sync(0xffffffffu, sD0, m); sD1 += __shfl_xor_sync(0xffffffffu, sD1, m);
+    }
+    if (r == 0) {
+      const int shift = P.bitDepth + 4;
+      const int act = clip3(0, 15, ((sV + sH) * ((aboveVb || belowVb) ? 96 : 64)) >> shift);
+      const unsigned long long TH = 0x4333333333222210ull;    // th[16] = {0,1,2,2,2,2,2,3,3,3,3,3,3,3,3,4}
+      int classIdx = (int)((TH >> (4 * act)) & 15);
+      int hv1, hv0, d1, d0, dirHV, dirD;
+      if (sV > sH) { hv1 = sV; hv0 = sH; dirHV = 1; } else { hv1 = sH; hv0 = sV; dirHV = 3; }
+      if (sD0 > sD1) { d1 = sD0; d0 = sD1; dirD = 0; } else { d1 = sD1; d0 = sD0; dirD = 2; }
+      int hvd1, hvd0, mainDir, secDir;
+      if ((unsigned)d1 * (unsigned)hv0 > (unsigned)hv1 * (unsigned)d0) { hvd1 = d1; hvd0 = d0; mainDir = dirD; secDir = dirHV; }
+      else { hvd1 = hv1; hvd0 = hv0; mainDir = dirHV; secDir = dirD; }
+      int strength = 0;
+      if (hvd1 > 2 * hvd0) strength = 1;
+      if (hvd1 * 2 > 9 * hvd0) strength = 2;
+      if (strength) classIdx += (((mainDir & 1) << 1) + strength) * 5;
+      const unsigned TT = 0x31322010u;                         // transposeTable[8] = {0,1,0,2,2,3,1,3}
+      const int tr = (TT >> (4 * (mainDir * 2 + (secDir >> 1)))) & 15;
+      s_cls[b] = (uint16_t)(classIdx | (tr << 8));
+    }
+  }
+  __syncthreads();
+
+  // ---- 7x7 diamond (AdaptiveLoopFilter.cpp:1175): thread = row (tid>>3), 4 samples at x = (tid&7)*4 ----
+  {
+    const int ry = tid >> 3, rx = (tid & 7) * 4;
+    if (ry >= bh || rx >= bw) return;
+    const uint16_t k = s_cls[(ry >> 2) * 8 + (rx >> 2)];
+    const int off = (k & 0xff) * 13 + (k >> 8) * 13 * 25 + cp.lumaSet * 4 * 25 * 13;
+    const int16_t* f = P.lumaCoeff + off; const int16_t* c = P.lumaClip + off;
+    int fc[12], cc[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) { fc[i] = __ldg(f + i); cc[i] = __ldg(c + i); }
+    const int gy = by0 + ry, yVb = gy & (vbH - 1);
+    int lim = 3;
+    if (yVb < vbPos && yVb >= vbPos - 4) lim = vbPos - 1 - yVb;
+    else if (yVb >= vbPos && yVb <= vbPos + 3) lim = yVb - vbPos;
+    const bool nearVb = yVb == vbPos - 1 || yVb == vbPos;
+    const int r1 = min(1, lim), r2 = min(2, lim), r3 = min(3, lim);
+    const int ly = ry + HALO;
+    const int pmax = (1 << P.bitDepth) - 1;
+    int out[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int lx = rx + i + HALO;
+      const int cur = t[ly][lx];
+      int sum = 0;
+      sum += fc[0]  * clipd(cc[0],  cur, t[ly + r3][lx],     t[ly - r3][lx]);
+      sum += fc[1]  * clipd(cc[1],  cur, t[ly + r2][lx + 1], t[ly - r2][lx - 1]);
+      sum += fc[2]  * clipd(cc[2],  cur, t[ly + r2][lx],     t[ly - r2][lx]);
+      sum += fc[3]  * clipd(cc[3],  cur, t[ly + r2][lx - 1], t[ly - r2][lx + 1]);
+      sum += fc[4]  * clipd(cc[4],  cur, t[ly + r1][lx + 2], t[ly - r1][lx - 2]);
+      sum += fc[5]  * clipd(cc[5],  cur, t[ly + r1][lx + 1], t[ly - r1][lx - 1]);
+      sum += fc[6]  * clipd(cc[6],  cur, t[ly + r1][lx],     t[ly - r1][lx]);
+      sum += fc[7]  * clipd(cc[7],  cur, t[ly + r1][lx - 1], t[ly - r1][lx + 1]);
+      sum += fc[8]  * clipd(cc[8],  cur, t[ly + r1][lx - 2], t[ly - r1][lx + 2]);
+      sum += fc[9]  * clipd(cc[9],  cur, t[ly][lx + 3], t[ly][lx - 3]);
+      sum += fc[10] * clipd(cc[10], cur, t[ly][lx + 2], t[ly][lx - 2]);
+      sum += fc[11] * clipd(cc[11], cur, t[ly][lx + 1], t[ly][lx - 1]);
+      sum = nearVb ? (sum + 512) >> 10 : (sum + 64) >> 7;
+      out[i] = clip3(0, pmax, sum + cur);
+    }
+    uint2 o;
+    o.x = (unsigned)(out[0] & 0xffff) | ((unsigned)out[1] << 16);
+    o.y = (unsigned)(out[2] & 0xffff) | ((unsigned)out[3] << 16);
+    *reinterpret_cast<uint2*>(P.dst[0] + (size_t)gy * stride + bx0 + rx) = o;
+  }
+}
+
+// chroma 5x5 diamond + CC-ALF, 4:2:0. One thread per 4 chroma samples of one component.
+__global__ void __launch_bounds__(256) alf_chroma_kernel(const AlfParams P)
+{
+  const int c = 1 + blockIdx.z;
+  const int pw = P.W >> 1, ph = P.H >> 1;
+  const int x = (blockIdx.x * 32 + threadIdx.x) * 4, y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= pw || y >= ph) return;
+  const int cs = P.ctuSize >> 1;
+  const b200_alf_ctu cp = P.ctus[(y / cs) * P.ctusW + (x / cs)];
+  const int stride = P.stride[c];
+  const int16_t* s = P.src[c];
+  const int pmax = (1 << P.bitDepth) - 1;
+  int out[4];
+  auto at = [&](int xx, int yy) { return (int)s[(size_t)min(max(yy, 0), ph - 1) * stride + min(max(xx, 0), pw - 1)]; };
+  if (cp.enable[c] & 1) {
+    const int16_t* f = P.chromaCoeff + cp.chromaAlt[c - 1] * 7; const int16_t* cl = P.chromaClip + cp.chromaAlt[c - 1] * 7;
+    int fc[6], cc[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) { fc[i] = __ldg(f + i); cc[i] = __ldg(cl + i); }
+    const int vbH = cs, vbPos = cs - 2, yVb = y & (vbH - 1);
+    int lim = 2;
+    if (yVb < vbPos && yVb >= vbPos - 2) lim = vbPos - 1 - yVb;
+    else if (yVb >= vbPos && yVb <= vbPos + 1) lim = yVb - vbPos;
+    const bool nearVb = yVb == vbPos - 1 || yVb == vbPos;
+    const int r1 = min(1, lim), r2 = min(2, lim);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int xx = x + i, cur = at(xx, y);
+      int sum = 0;
+      sum += fc[0] * clipd(cc[0], cur, at(xx, y + r2),     at(xx, y - r2));
+      sum += fc[1] * clipd(cc[1], cur, at(xx + 1, y + r1), at(xx - 1, y - r1));
+      sum += fc[2] * clipd(cc[2], cur, at(xx, y + r1),     at(xx, y - r1));
+      sum += fc[3] * clipd(cc[3], cur, at(xx - 1, y + r1), at(xx + 1, y - r1));
+      sum += fc[4] * clipd(cc[4], cur, at(xx + 2, y), at(xx - 2, y));
+      sum += fc[5] * clipd(cc[5], cur, at(xx + 1, y), at(xx - 1, y));
+      sum = nearVb ? (sum + 512) >> 10 : (sum + 64) >> 7;
+      out[i] = clip3(0, pmax, sum + cur);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = s[(size_t)y * stride + x + i];
+  }
+  const int ccIdx = cp.ccIdx[c - 1];
+  if (ccIdx) {   // filterBlkCcAlf (AdaptiveLoopFilter.cpp:1348): 7-tap luma-difference filter on the PRE-ALF luma
+    const int16_t* f = (c == 1 ? P.cc0 : P.cc1) + (ccIdx - 1) * 7;
+    int fc[7];
+#pragma unroll
+    for (int i = 0; i < 7; i++) fc[i] = __ldg(f + i);
+    const int16_t* L = P.src[0]; const int ls = P.stride[0];
+    const int ly = y << 1, pos = ly & (P.ctuSize - 1), vbPos = P.ctuSize - 4;
+    int o1 = 1, o2 = -1, o3 = 2;
+    if (pos == vbPos - 2 || pos == vbPos + 1) o3 = 1;
+    else if (pos == vbPos - 1 || pos == vbPos) o1 = o2 = o3 = 0;
+    auto lat = [&](int xx, int yy) { return (int)L[(size_t)min(max(yy, 0), P.H - 1) * ls + min(max(xx, 0), P.W - 1)]; };
+    const int half = (1 << P.bitDepth) >> 1;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int lx = (x + i) << 1, cur = lat(lx, ly);
+      int sum = fc[0] * (lat(lx, ly + o2) - cur) + fc[1] * (lat(lx - 1, ly) - cur) + fc[2] * (lat(lx + 1, ly) - cur)
+              + fc[3] * (lat(lx - 1, ly + o1) - cur) + fc[4] * (lat(lx, ly + o1) - cur) + fc[5] * (lat(lx + 1, ly + o1) - cur)
+              + fc[6] * (lat(lx, ly + o3) - cur);
+      sum = (sum + 64) >> 7;
+      sum = clip3(0, pmax, sum + half) - half;
+      out[i] = clip3(0, pmax, sum + out[i]);
+    }
+  }
+  uint2 o;
+  o.x = (unsigned)(out[0] & 0xffff) | ((unsigned)out[1] << 16);
+  o.y = (unsigned)(out[2] & 0xffff) | ((unsigned)out[3] << 16);
+  *reinterpret_cast<uint2*>(P.dst[c] + (size_t)y * stride + x) = o;
+}
+
+int launch_alf(const AlfLaunch& L, cudaStream_t s)
+{
+  AlfParams P;
+  for (int c = 0; c < 3; c++) { P.src[c] = L.src.p[c]; P.dst[c] = L.dst.p[c]; P.stride[c] = L.src.stride[c]; }
+  P.W = L.geom.width; P.H = L.geom.height; P.bitDepth = L.geom.bitDepth; P.ctuSize = L.geom.ctuSize;
+  P.ctuLog2 = P.ctuSize == 128 ? 7 : P.ctuSize == 64 ? 6 : 5; P.ctusW = (P.W + P.ctuSize - 1) / P.ctuSize;
+  P.ctus = L.ctus; P.lumaCoeff = L.lumaCoeff; P.lumaClip = L.lumaClip; P.chromaCoeff = L.chromaCoeff; P.chromaClip = L.chromaClip;
+  P.cc0 = L.cc[0]; P.cc1 = L.cc[1];
+  dim3 grdL((P.W + TB - 1) / TB, (P.H + TB - 1) / TB);
+  alf_luma_kernel<<<grdL, 256, 0, s>>>(P);
+  B200_CUDA(cudaGetLastError());
+  if (L.geom.chromaFormat == 1) {
+    dim3 blk(32, 8), grd(((P.W >> 1) / 4 + 31) / 32, ((P.H >> 1) + 7) / 8, 2);
+    alf_chroma_kernel<<<grd, blk, 0, s>>>(P);
+    B200_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace b200
