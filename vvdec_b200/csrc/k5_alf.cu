@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) alf_luma_kernel(const AlfParams P)
     if (r == 0) {
       const int shift = P.bitDepth + 4;
       const int act = clip3(0, 15, ((sV + sH) * ((aboveVb || belowVb) ? 96 : 64)) >> shift);
-      const unsigned long long TH = 0x4333333333222210ull;    // th[16] = {0,1,2,2,2,2,2,3,3,3,3,3,3,3,3,4}
+      const unsigned long long TH = 0x4333333332222210ull;    // th[16] = {0,1,2,2,2,2,2,3,3,3,3,3,3,3,3,4}
       int classIdx = (int)((TH >> (4 * act)) & 15);
       int hv1, hv0, d1, d0, dirHV, dirD;
       if (sV > sH) { hv1 = sV; hv0 = sH; dirHV = 1; } else { hv1 = sH; hv0 = sV; dirHV = 3; }
