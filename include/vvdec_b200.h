@@ -187,6 +187,47 @@ typedef struct b200_alf_tables {
 B200_API int b200_alf_picture(const b200_geom* g, const int16_t* const src[3], int16_t* const dst[3],
                               const b200_alf_ctu* ctus, const b200_alf_tables* tabs);
 
+/* ------------------------------------------------------------------------------------------------
+ * K2  inter prediction (motion compensation) into the current picture's planes.
+ *   replaces  InterPrediction::motionCompensation (InterPrediction.cpp:1372) and below: xPredInterBi :686, xPredInterUni :623,
+ *             xPredInterBlk :750, xSubPuBio :551 + applyBiOptFlow :1290 (BioGradFilter / BiOptFlow / PaddBIO pointers,
+ *             InterPrediction.h:77-80,146), xProcessDMVR :1847 (xinitMC, xBIPMVRefine, xDMVRSubPixelErrorSurface, xPrefetchPad,
+ *             xFinalPaddedMCForDMVR; RdCost SAD :107-221), xPredAffineBlk :934 (+ applyPROF / profGradFilter), xWeightedAverage
+ *             :1346 (addAvg Buffer.cpp:441, addWeightedAvg :372), clipMvInPic (Mv.cpp:64), and the InterpolationFilter pointer
+ *             table (InterpolationFilter.h:113-120; .cpp:424-962).
+ *   stays CPU: merge/AMVP/affine/TMVP motion derivation (MIDER) and the mode decisions of motionCompensation :1411-1440
+ *             (bioApplied, checkDMVRCondition UnitTools.cpp:1277, xCheckIdenticalMotion :404) — the flattener stores them as flags.
+ *   not yet:   explicit weighted prediction, GEO blending, CIIP, IBC, RPR-scaled references, wrap-around, sub-pictures.
+ * One record per CU (ATMVP: per merged sub-PU run, InterPrediction.cpp:438). Reference pictures live in DPB slots.
+ * ---------------------------------------------------------------------------------------------- */
+enum {
+  B200_PU_BDOF    = 1,    /* bioApplied (motionCompensation :1411-1428)                                          */
+  B200_PU_DMVR    = 2,    /* dmvrApplied; refined MV deltas are written to dmvrMv[dmvrOff + subblock]             */
+  B200_PU_ALTHPEL = 4,    /* cu.imv() == IMV_HPEL: alternative half-sample luma filter                            */
+  B200_PU_AFFINE  = 8,    /* cu.affineFlag(): mv = CPMV0, cpmv = CPMV1/2; sub-block MVs as PU::setAllAffineMv     */
+  B200_PU_AFFINE6 = 16,   /* 6-parameter model (else 4-parameter)                                                 */
+  B200_PU_PROF0   = 32,   /* PROF enabled for list 0 / 1 (sps PROF && !ph dis_prof; the kernel applies the CPMV-equality and */
+  B200_PU_PROF1   = 64    /* spread-over-limit exclusions of xPredAffineBlk :1036-1040 itself)                     */
+};
+
+typedef struct b200_pu {
+  uint16_t x, y;            /* luma position                                                                       */
+  uint8_t  w, h;            /* luma size, 4..128                                                                   */
+  uint8_t  flags;           /* B200_PU_*                                                                           */
+  int8_t   bcwW1;           /* weight of list 1 out of 8 (g_BcwWeights[g_BcwInternBcw[BcwIdx]]); 4 = plain average */
+  int8_t   refSlot[2];      /* DPB slot of the reference picture per list; -1: list unused                         */
+  uint8_t  interDir;        /* cu.interDir() (1 L0, 2 L1, 3 bi) — used by the affine spread check                  */
+  uint8_t  rsv;
+  uint32_t dmvrOff;         /* cu.mvdL0SubPuOff                                                                    */
+  int32_t  mv[2][2];        /* [list][hor,ver] in 1/16 sample, as in cu.mv[list][0] (NOT clipped: kernels apply clipMvInPic) */
+  int32_t  cpmv[2][2][2];   /* [list][1|2][hor,ver]: cu.mv[list][1], cu.mv[list][2] (affine only)                  */
+} b200_pu;                  /* 64 bytes */
+
+/* Kernel-level K2 on host planes: refs[slot*3 + comp] are the reference pictures (same geometry as g), dst the current
+ * picture (only PU areas are written).  dmvrMv: int32 [n][2] (hor,ver deltas, Mv layout of m_dmvrMvCache), may be NULL. */
+B200_API int b200_mc_predict(const b200_geom* g, int16_t* const dst[3], const int16_t* const* refs, int numSlots,
+                             const b200_pu* pus, size_t numPus, int32_t* dmvrMv, size_t numDmvr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,7 @@
 #include "CommonLib/LoopFilter.h"
 #include "CommonLib/SampleAdaptiveOffset.h"
 #include "CommonLib/AdaptiveLoopFilter.h"
+#include "CommonLib/RdCost.h"
 #include "../vvdec_b200/vvdec_glue/flatten_tu.h"
 
 using namespace vvdec;
@@ -516,4 +517,91 @@ extern "C" int ref_alf_picture( int simd, const b200_geom* g, const int16_t* con
   for( unsigned y = 0; y < pcv.heightInCtus; y++ ) for( unsigned x = 0; x < pcv.widthInCtus; x++ ) alf.processCTU( cs, x, y, 0 );
   fp.getPlanes( *g, dst, true, &out );
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ K2
+extern "C" int ref_mc_predict( int simd, const b200_geom* g, int16_t* const dst[3], const int16_t* const* refs, const b200_pu* pus, size_t numPus,
+                               int32_t* dmvrMv, size_t numDmvr )
+{
+  FakePicture cur( *g, 1 );
+  std::unique_ptr<FakePicture> ref[4];
+  for( int s = 0; s < 4; s++ )
+  {
+    ref[s].reset( new FakePicture( *g, 1 ) );
+    int16_t* p3[3] = { (int16_t*) refs[s * 3], (int16_t*) refs[s * 3 + 1], (int16_t*) refs[s * 3 + 2] };
+    ref[s]->setPlanes( *g, p3 );
+    ref[s]->pic.extendPicBorder();
+  }
+  CodingStructure& cs = *cur.pic.cs;
+  const PreCalcValues& pcv = *cs.pcv;
+  SPS& sps = *cur.sps;
+  sps.setUseBIO( true ); sps.setUseDMVR( true ); sps.setUseBcw( true ); sps.setUseAffine( true ); sps.setUseAffineType( true ); sps.setUsePROF( true );
+  Slice* sl = cur.pic.slices[0];
+  sl->setSliceType( B_SLICE ); sl->setPOC( 8 );
+  const int pocs[4] = { 4, 0, 12, 16 };
+  for( int l = 0; l < 2; l++ ) for( int i = 0; i < 2; i++ )
+  {
+    sl->m_apcRefPicList[l][i] = &ref[l * 2 + i]->pic;
+    sl->m_aiRefPOCList [l][i] = pocs[l * 2 + i];
+    sl->m_bIsUsedAsLongTerm[l][i] = false;
+    ref[l * 2 + i]->pic.poc = pocs[l * 2 + i];
+  }
+  sl->setNumRefIdx( REF_PIC_LIST_0, 2 ); sl->setNumRefIdx( REF_PIC_LIST_1, 2 );
+  sl->resetWpScaling();
+
+  std::vector<MotionInfo> motion( (size_t) pcv.num4x4CtuBlks * pcv.sizeInCtus );
+  std::vector<Mv> dmvrCache( (size_t) pcv.num8x8CtuBlks * pcv.sizeInCtus + 16 );
+  for( unsigned a = 0; a < pcv.sizeInCtus; a++ ) cs.getCtuData( a ).motion = motion.data() + (size_t) a * pcv.num4x4CtuBlks;
+  cs.m_dmvrMvCache = dmvrCache.data();
+
+  static RdCost rdScalar( false ), rdSimd( true );
+  std::unique_ptr<InterPrediction> ip( new InterPrediction() );
+  ip->init( simd ? &rdSimd : &rdScalar, pcv.chrFormat, g->ctuSize, simd != 0 );
+
+  PelStorage predStore; predStore.create( pcv.chrFormat, Size( 128, 128 ), 0, 0, MEMORY_ALIGN_DEF_SIZE );
+  int rc = 0;
+  for( size_t n = 0; n < numPus; n++ )
+  {
+    const b200_pu& pu = pus[n];
+    const UnitArea ua( pcv.chrFormat, Area( pu.x, pu.y, pu.w, pu.h ) );
+    CodingUnit& cu = cs.addCU( ua, CH_L, TREE_D, MODE_TYPE_ALL, nullptr, nullptr );
+    cu.slice = sl; cu.pps = cur.pps.get(); cu.sps = cur.sps.get();
+    cu.setPredMode( MODE_INTER );
+    for( int l = 0; l < 2; l++ )
+    {
+      cu.refIdx[l] = pu.refSlot[l] < 0 ? -1 : ( pu.refSlot[l] & 1 );
+      cu.mv[l][0] = Mv( pu.mv[l][0], pu.mv[l][1] );
+      cu.mv[l][1] = Mv( pu.cpmv[l][0][0], pu.cpmv[l][0][1] );
+      cu.mv[l][2] = Mv( pu.cpmv[l][1][0], pu.cpmv[l][1][1] );
+    }
+    cu.setInterDir( pu.interDir );
+    cu.setImv( ( pu.flags & B200_PU_ALTHPEL ) ? IMV_HPEL : IMV_OFF );
+    int bcwIdx = BCW_DEFAULT;
+    for( int i = 0; i < BCW_NUM; i++ ) if( getBcwWeight( g_BcwInternBcw[i], REF_PIC_LIST_1 ) == pu.bcwW1 ) bcwIdx = i;
+    cu.setBcwIdx( bcwIdx );
+    const bool wantDmvr = pu.flags & B200_PU_DMVR, wantBio = pu.flags & B200_PU_BDOF, affine = pu.flags & B200_PU_AFFINE;
+    cu.setMergeFlag( wantDmvr );          // DMVR needs a regular merge CU; without it bio alone is decided by POC distances / size
+    cu.setMergeType( MRG_TYPE_DEFAULT_N );
+    cu.setSmvdMode( ( !wantBio && !affine && pu.refSlot[0] >= 0 && pu.refSlot[1] >= 0 && pu.bcwW1 == 4 ) ? 1 : 0 );   // smvd switches BDOF off without touching the pixels
+    cu.setAffineFlag( affine );
+    cu.setAffineType( ( pu.flags & B200_PU_AFFINE6 ) ? AFFINEMODEL_6PARAM : AFFINEMODEL_4PARAM );
+    cur.ph->setDisProfFlag( affine && !( pu.flags & ( B200_PU_PROF0 | B200_PU_PROF1 ) ) );
+    if( affine ) { for( int l = 0; l < 2; l++ ) if( cu.refIdx[l] >= 0 ) PU::setAllAffineMv( cu, cu.mv[l][0], cu.mv[l][1], cu.mv[l][2], RefPicList( l ) ); }
+    PU::spanMotionInfo( cu );
+
+    PelUnitBuf predBuf = predStore.getBuf( UnitArea( pcv.chrFormat, Area( 0, 0, pu.w, pu.h ) ) );
+    ip->motionCompensation( cu, predBuf, true, true );
+    if( (bool) cu.dmvrCondition() != wantDmvr ) rc = -1;
+    for( int c = 0; c < ( g->chromaFormat ? 3 : 1 ); c++ )
+    {
+      const PelBuf& b = predBuf.bufs[c];
+      for( unsigned y = 0; y < b.height; y++ ) memcpy( dst[c] + (size_t) ( ( pu.y >> ( c ? 1 : 0 ) ) + y ) * g->stride[c] + ( pu.x >> ( c ? 1 : 0 ) ), b.buf + y * b.stride, b.width * sizeof( Pel ) );
+    }
+    if( wantDmvr && dmvrMv )
+    {
+      const int nSub = std::max( 1, pu.w >> 4 ) * std::max( 1, pu.h >> 4 );
+      for( int k = 0; k < nSub && pu.dmvrOff + k < numDmvr; k++ ) { const Mv& m = cs.m_dmvrMvCache[cu.mvdL0SubPuOff + k]; dmvrMv[( pu.dmvrOff + k ) * 2] = m.hor; dmvrMv[( pu.dmvrOff + k ) * 2 + 1] = m.ver; }
+    }
+  }
+  return rc;
 }

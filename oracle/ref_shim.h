@@ -80,6 +80,14 @@ void ref_alf_ccalf_blk(int simd, int16_t* dstChroma, ptrdiff_t chromaStride, con
 int ref_alf_picture(int simd, const b200_geom* g, const int16_t* const src[3], int16_t* const dst[3], const b200_alf_ctu* ctus,
                     const b200_alf_tables* tabs);
 
+/* ---- K2 inter prediction: the real InterPrediction::motionCompensation on real CodingUnits ----
+ * refs[slot*3+comp]: 4 reference pictures; list 0 = {slot 0 (POC 4), slot 1 (POC 0)}, list 1 = {slot 2 (POC 12), slot 3 (POC 16)},
+ * current POC 8, so (slot 0, slot 2) and (slot 1, slot 3) are the equal-distance pairs BDOF / DMVR require.
+ * Each PU becomes a CU (merge flags etc. chosen so that the reference itself derives the same bio/dmvr decision as pu->flags;
+ * returns -1 if it did not). pred = the CU's prediction (written to dst planes), dmvrMv = m_dmvrMvCache. */
+int ref_mc_predict(int simd, const b200_geom* g, int16_t* const dst[3], const int16_t* const* refs, const b200_pu* pus, size_t numPus,
+                   int32_t* dmvrMv, size_t numDmvr);
+
 #ifdef __cplusplus
 }
 #endif

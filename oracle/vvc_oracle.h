@@ -78,6 +78,11 @@ void orc_alf_ccalf_blk(int16_t* dstChroma, ptrdiff_t chromaStride, const int16_t
 void orc_alf_picture(const b200_geom* g, const int16_t* const src[3], int16_t* const dst[3], const b200_alf_ctu* ctus,
                      const b200_alf_tables* tabs);
 
+/* ---- K2 inter prediction --------------------------------------------------------------------- */
+/* InterPrediction.cpp:1372 motionCompensation for a list of PUs (regular uni/bi, BCW, BDOF, DMVR, affine + PROF).
+ * refs[slot*3+comp]; reference samples outside the picture are read with clamped coordinates (== border extension). */
+void orc_mc_predict(const b200_geom* g, int16_t* const dst[3], const int16_t* const* refs, const b200_pu* pus, size_t numPus, int32_t* dmvrMv);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,7 @@ def load_oracle():
     lib.orc_alf_filter_blk.argtypes = [C.c_int, V, V, C.c_ssize_t, V, C.c_ssize_t] + [C.c_int] * 4 + [V, V] + [C.c_int] * 3
     lib.orc_alf_ccalf_blk.argtypes = [V, C.c_ssize_t, V, C.c_ssize_t] + [C.c_int] * 4 + [V] + [C.c_int] * 3
     lib.orc_alf_picture.argtypes = [C.POINTER(abi.Geom), PL, PL, V, C.POINTER(abi.AlfTables)]
+    lib.orc_mc_predict.argtypes = [C.POINTER(abi.Geom), PL, C.POINTER(C.c_void_p), V, C.c_size_t, V]
     return lib
 
 
@@ -68,6 +69,8 @@ def load_ref():
     lib.ref_alf_filter_blk.argtypes = [C.c_int, C.c_int, V, V, C.c_ssize_t, V, C.c_ssize_t] + [C.c_int] * 6 + [V, V] + [C.c_int] * 3
     lib.ref_alf_ccalf_blk.argtypes = [C.c_int, V, C.c_ssize_t, V, C.c_ssize_t] + [C.c_int] * 6 + [V] + [C.c_int] * 3
     lib.ref_alf_picture.argtypes = [C.c_int, C.POINTER(abi.Geom), PL, PL, V, C.POINTER(abi.AlfTables)]
+    lib.ref_mc_predict.argtypes = [C.c_int, C.POINTER(abi.Geom), PL, C.POINTER(C.c_void_p), V, C.c_size_t, V, C.c_size_t]
+    lib.ref_mc_predict.restype = C.c_int
     return lib
 
 
@@ -86,3 +89,12 @@ def aligned_copy(src, align=64):
     a = aligned(src.shape, src.dtype, align=align)
     a[...] = src
     return a
+
+
+def ref_ptrs(ref_pics):
+    """ref_pics: list of [Y, Cb, Cr] int16 arrays per DPB slot -> (const int16_t* [slots*3])."""
+    arr = (C.c_void_p * (3 * len(ref_pics)))()
+    for s, pl in enumerate(ref_pics):
+        for c in range(3):
+            arr[s * 3 + c] = pl[c].ctypes.data
+    return arr

@@ -276,3 +276,64 @@ def gen_alf(rng, W, H, ctu=128, bit_depth=10, n_aps=2, n_chroma_alts=3, n_cc=(2,
         a["ccIdx"][:, c] = np.where(rng.random(n) < p_cc, rng.integers(1, n_cc[c] + 1, size=n), 0) if n_cc[c] else 0
     return dict(lumaCoeff=np.ascontiguousarray(coef), lumaClip=np.ascontiguousarray(clip), chromaCoeff=ccoef, chromaClip=cclip,
                 cc=cc, ctus=a)
+
+
+PU_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("w", "u1"), ("h", "u1"), ("flags", "u1"), ("bcwW1", "i1"), ("refSlot", "i1", (2,)),
+                     ("interDir", "u1"), ("rsv", "u1"), ("dmvrOff", "<u4"), ("mv", "<i4", (2, 2)), ("cpmv", "<i4", (2, 2, 2))])
+assert PU_DTYPE.itemsize == 64
+PU_BDOF, PU_DMVR, PU_ALTHPEL, PU_AFFINE, PU_AFFINE6, PU_PROF0, PU_PROF1 = 1, 2, 4, 8, 16, 32, 64
+
+
+def gen_pus(rng, cus, W, H, p_inter=1.0, p_bi=0.6, p_dmvr=0.35, p_bdof=0.35, p_affine=0.12, p_bcw=0.15, mv_sigma=6.0, p_int_mv=0.15):
+    """Inter PU records for a CU list (MVs ~ N(0, 6 px) in 1/16 units; refs from 4 DPB slots:
+    list 0 = {0, 1}, list 1 = {2, 3}; (0,2) and (1,3) are the equal-POC-distance pairs that allow BDOF / DMVR)."""
+    recs = []
+    dmvr_off = 0
+    for (x, y, w, h) in cus:
+        if w > 128 or h > 128 or rng.random() >= p_inter:
+            continue
+        r = np.zeros((), PU_DTYPE)
+        r["x"], r["y"], r["w"], r["h"] = x, y, w, h
+        r["bcwW1"] = 4
+        mv = np.rint(rng.normal(0, mv_sigma * 16, size=(2, 2))).astype(np.int64)
+        if rng.random() < p_int_mv: mv = (mv >> 4) << 4
+        if rng.random() < 0.1: mv[:, rng.integers(0, 2)] &= ~15                      # one integer component
+        if rng.random() < 0.03: mv += rng.integers(-3000, 3000, size=(2, 2))          # far outside the picture -> clipMv
+        r["mv"] = mv
+        can_bi = (w + h) > 12
+        bi = can_bi and rng.random() < p_bi
+        big = w >= 8 and h >= 8 and w * h >= 128
+        flags = 0
+        if bi:
+            u = rng.random()
+            if big and u < p_dmvr:
+                pair = int(rng.integers(0, 2)); r["refSlot"] = (pair, 2 + pair)
+                flags |= PU_DMVR | (PU_BDOF if rng.random() < 0.8 else 0)
+            elif big and u < p_dmvr + p_bdof:
+                pair = int(rng.integers(0, 2)); r["refSlot"] = (pair, 2 + pair)
+                flags |= PU_BDOF
+            else:
+                r["refSlot"] = (int(rng.integers(0, 2)), 2 + int(rng.integers(0, 2)))
+                if w * h >= 256 and rng.random() < p_bcw: r["bcwW1"] = int(rng.choice([-2, 3, 5, 10]))
+            r["interDir"] = 3
+        else:
+            l = int(rng.integers(0, 2))
+            r["refSlot"] = (int(rng.integers(0, 2)), -1) if l == 0 else (-1, 2 + int(rng.integers(0, 2)))
+            r["interDir"] = 1 + l
+        if not (flags & (PU_DMVR | PU_BDOF)) and w >= 8 and h >= 8 and rng.random() < p_affine:
+            flags |= PU_AFFINE | (PU_AFFINE6 if rng.random() < 0.5 else 0)
+            if rng.random() < 0.8: flags |= PU_PROF0 | PU_PROF1
+            big_d = rng.random() < 0.15
+            for l in range(2):
+                d = rng.integers(-400, 401, size=(2, 2)) if big_d else rng.integers(-24, 25, size=(2, 2))
+                if rng.random() < 0.1: d[:] = 0
+                r["cpmv"][l] = mv[l] + d
+        elif not (flags & PU_DMVR) and rng.random() < 0.1:
+            flags |= PU_ALTHPEL
+        if big:
+            r["dmvrOff"] = dmvr_off
+            dmvr_off += max(1, w >> 4) * max(1, h >> 4)
+        r["flags"] = flags
+        recs.append(r)
+    pus = np.array(recs, PU_DTYPE) if recs else np.zeros(0, PU_DTYPE)
+    return pus, dmvr_off
