@@ -27,5 +27,9 @@ def declare(lib):
     lib.b200_alf_picture.restype = C.c_int
 
 
-EXPORTS = ["b200_last_error", "b200_version", "b200_device_count", "b200_k1_residual", "b200_lf_deblock",
+    lib.b200_mc_predict.argtypes = [C.POINTER(abi.Geom), PLANES, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    lib.b200_mc_predict.restype = C.c_int
+
+
+EXPORTS = ["b200_mc_predict", "b200_last_error", "b200_version", "b200_device_count", "b200_k1_residual", "b200_lf_deblock",
            "b200_sao_picture", "b200_alf_picture"]

@@ -63,6 +63,17 @@ static int download_planes(const b200_geom* g, int16_t* const planes[3], const D
   return 0;
 }
 
+void build_mc_tiles(const b200_pu* pus, size_t numPus, std::vector<uint32_t>& tilesT, std::vector<uint32_t>& tilesA)
+{
+  tilesT.clear(); tilesA.clear();
+  for (size_t i = 0; i < numPus; i++) {
+    const b200_pu& p = pus[i];
+    std::vector<uint32_t>& dstv = (p.flags & B200_PU_AFFINE) ? tilesA : tilesT;
+    for (int ty = 0; ty * 16 < p.h; ty++)
+      for (int tx = 0; tx * 16 < p.w; tx++) dstv.push_back((uint32_t)(i << 6) | (ty << 3) | tx);
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -187,6 +198,56 @@ B200_API int b200_alf_picture(const b200_geom* g, const int16_t* const src[3], i
   L.ctus = g_hw.misc[0].as<b200_alf_ctu>();
   if (int rc = launch_alf(L, s)) return rc;
   if (int rc = download_planes(g, dst, L.dst, s)) return rc;
+  B200_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+B200_API int b200_mc_predict(const b200_geom* g, int16_t* const dst[3], const int16_t* const* refs, int numSlots,
+                             const b200_pu* pus, size_t numPus, int32_t* dmvrMv, size_t numDmvr)
+{
+  B200_CHECK(g && dst && refs && (pus || !numPus), "b200_mc_predict: null argument");
+  B200_CHECK(numSlots >= 1 && numSlots <= 64, "b200_mc_predict: numSlots %d", numSlots);
+  B200_CHECK(numPus < (1u << 26), "b200_mc_predict: too many PUs");
+  for (size_t i = 0; i < numPus; i++) {
+    B200_CHECK(pus[i].refSlot[0] < numSlots && pus[i].refSlot[1] < numSlots && (pus[i].refSlot[0] >= 0 || pus[i].refSlot[1] >= 0), "b200_mc_predict: PU %zu has invalid reference slots", i);
+    B200_CHECK(!((pus[i].flags & B200_PU_DMVR) && g->bitDepth > 10), "b200_mc_predict: DMVR needs bit depth <= 10 (as the reference)");
+  }
+  if (int rc = ensure_device()) return rc;
+  if (int rc = g_hw.init()) return rc;
+  cudaStream_t s = g_hw.stream;
+  McLaunch L; L.geom = *g;
+  if (int rc = upload_planes(g, dst, L.dst, s)) return rc;
+  const int nPlanes = g->chromaFormat ? 3 : 1;
+  size_t planeBytes[3] = {0, 0, 0}, total = 0;
+  for (int c = 0; c < nPlanes; c++) { planeBytes[c] = (((size_t)g->stride[c] * (c ? g->height >> 1 : g->height) * 2) + 255) & ~(size_t)255; total += planeBytes[c]; }
+  if (int rc = g_hw.misc[3].reserve(total * numSlots)) return rc;
+  std::vector<const int16_t*> ptrs(numSlots * 3, nullptr);
+  char* base = g_hw.misc[3].as<char>();
+  for (int sl = 0; sl < numSlots; sl++) {
+    size_t off = 0;
+    for (int c = 0; c < nPlanes; c++) {
+      char* d = base + (size_t)sl * total + off;
+      B200_CUDA(cudaMemcpyAsync(d, refs[sl * 3 + c], (size_t)g->stride[c] * (c ? g->height >> 1 : g->height) * 2, cudaMemcpyHostToDevice, s));
+      ptrs[sl * 3 + c] = reinterpret_cast<const int16_t*>(d); off += planeBytes[c];
+    }
+  }
+  std::vector<uint32_t> tT, tA;
+  build_mc_tiles(pus, numPus, tT, tA);
+  if (int rc = g_hw.misc[4].reserve(ptrs.size() * sizeof(void*))) return rc;
+  if (int rc = g_hw.misc[5].reserve(numPus * sizeof(b200_pu) + 64)) return rc;
+  if (int rc = g_hw.misc[6].reserve((tT.size() + tA.size()) * 4 + 64)) return rc;
+  if (int rc = g_hw.misc[7].reserve(numDmvr * 8 + 64)) return rc;
+  B200_CUDA(cudaMemcpyAsync(g_hw.misc[4].p, ptrs.data(), ptrs.size() * sizeof(void*), cudaMemcpyHostToDevice, s));
+  if (numPus) B200_CUDA(cudaMemcpyAsync(g_hw.misc[5].p, pus, numPus * sizeof(b200_pu), cudaMemcpyHostToDevice, s));
+  if (tT.size()) B200_CUDA(cudaMemcpyAsync(g_hw.misc[6].p, tT.data(), tT.size() * 4, cudaMemcpyHostToDevice, s));
+  if (tA.size()) B200_CUDA(cudaMemcpyAsync(g_hw.misc[6].as<uint32_t>() + tT.size(), tA.data(), tA.size() * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaMemsetAsync(g_hw.misc[7].p, 0, numDmvr * 8 + 64, s));
+  L.refs = g_hw.misc[4].as<const int16_t*>(); for (int c = 0; c < 3; c++) L.refStride[c] = g->stride[c];
+  L.pus = g_hw.misc[5].as<b200_pu>(); L.tilesT = g_hw.misc[6].as<uint32_t>(); L.tilesA = L.tilesT + tT.size();
+  L.numTilesT = (int)tT.size(); L.numTilesA = (int)tA.size(); L.dmvrMv = dmvrMv ? g_hw.misc[7].as<int32_t>() : nullptr;
+  if (int rc = launch_mc(L, s)) return rc;
+  if (int rc = download_planes(g, dst, L.dst, s)) return rc;
+  if (dmvrMv && numDmvr) B200_CUDA(cudaMemcpyAsync(dmvrMv, g_hw.misc[7].p, numDmvr * 8, cudaMemcpyDeviceToHost, s));
   B200_CUDA(cudaStreamSynchronize(s));
   return 0;
 }

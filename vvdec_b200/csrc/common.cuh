@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 #include "../../include/vvdec_b200.h"
 
 namespace b200 {
@@ -80,6 +81,19 @@ struct AlfLaunch {
   const int16_t *lumaCoeff, *lumaClip, *chromaCoeff, *chromaClip, *cc[2];
 };
 int launch_alf(const AlfLaunch& L, cudaStream_t s);
+
+struct McLaunch {
+  b200_geom geom; DevPlanes dst;
+  const int16_t* const* refs;       // device array [numSlots*3] of device plane pointers
+  int refStride[3];
+  const b200_pu* pus;               // device
+  const uint32_t *tilesT, *tilesA;  // device tile lists: translational (regular/BDOF/DMVR) and affine; (puIdx<<6)|(ty<<3)|tx
+  int numTilesT, numTilesA;
+  int32_t* dmvrMv;                  // device or null
+};
+int launch_mc(const McLaunch& L, cudaStream_t s);
+// host: expand PUs into <=16x16 tiles
+void build_mc_tiles(const b200_pu* pus, size_t numPus, std::vector<uint32_t>& tilesT, std::vector<uint32_t>& tilesA);
 
 int ensure_device();   // selects device 0 if none current; fails loudly when there is no sm_100 GPU
 
