@@ -228,6 +228,58 @@ typedef struct b200_pu {
 B200_API int b200_mc_predict(const b200_geom* g, int16_t* const dst[3], const int16_t* const* refs, int numSlots,
                              const b200_pu* pus, size_t numPus, int32_t* dmvrMv, size_t numDmvr);
 
+/* ------------------------------------------------------------------------------------------------
+ * Picture level: the DecLibRecon seam (reference DecoderLib/DecLibRecon.h:184-191, .cpp:429 decompressPicture,
+ * :684 waitForPrevDecompressedPic).  A context owns the decoded-picture buffer (DPB) in device memory, a ring of
+ * work-list arenas and one CUDA stream; pictures are processed in submission order (a picture may reference any
+ * slot written by an earlier submission — the stream order replaces the reference's reconDone barriers).
+ *   per picture:  H2D work lists -> K2 (prediction into the work plane) -> K1 (residual + reco, in place) ->
+ *                 K3 deblock V,H (in place) -> K4 SAO (-> second work plane) -> K5 ALF/CC-ALF (-> DPB slot)
+ * Intra-predicted / IBC / CIIP samples are not produced on the GPU yet: the caller supplies them in
+ * `given` (whole planes, uploaded before K2), inter PUs and residuals overwrite/add on top.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b200_ctx b200_ctx;
+
+typedef struct b200_picture {
+  int32_t dstSlot;                       /* DPB slot that receives the final picture                                  */
+  int32_t flags;                         /* B200_PIC_*                                                                */
+  const int16_t* given[3];               /* optional planes (geometry strides) with pre-reconstructed samples, or NULL */
+  const b200_pu* pus; size_t numPus;     /* K2 */
+  size_t numDmvr;                        /*     size of the DMVR MV-delta output (entries)                            */
+  const b200_tu* tus; size_t numTus;     /* K1 */
+  const int16_t* coefs; size_t numCoefs;
+  const int32_t* scaling; size_t numScaling;
+  const b200_lf_param *lfV, *lfH;        /* K3 (B200_PIC_DEBLOCK) */
+  const uint8_t* ctuSlice; const b200_lf_slice* lfSlices; int32_t numLfSlices; const b200_lf_seq* lfSeq;
+  const b200_sao_ctu* sao;               /* K4 (B200_PIC_SAO) */
+  const b200_vb* vb;
+  const b200_alf_ctu* alf;               /* K5 (B200_PIC_ALF) */
+  const b200_alf_tables* alfTabs;
+} b200_picture;
+enum { B200_PIC_DEBLOCK = 1, B200_PIC_SAO = 2, B200_PIC_ALF = 4 };
+
+/* create(): reference DecLibRecon::create (DecLibRecon.cpp:392). numSlots = DPB size, numArenas = pictures whose work
+ * lists may be resident at once (>= 2 for upload/compute overlap). device < 0: current device. */
+B200_API int  b200_ctx_create(b200_ctx** ctx, const b200_geom* g, int numSlots, int numArenas, int device);
+B200_API void b200_ctx_destroy(b200_ctx* ctx);
+/* Host planes -> DPB slot (e.g. an IRAP picture reconstructed elsewhere, or test content). Synchronous. */
+B200_API int  b200_ctx_load_slot(b200_ctx* ctx, int slot, const int16_t* const planes[3]);
+/* decompressPicture(): non-blocking. Copies the work lists to the next arena (async H2D) and enqueues all kernels.
+ * Returns the arena handle (>= 0) or a negative error. */
+B200_API int  b200_decompress_picture(b200_ctx* ctx, const b200_picture* pic);
+/* Split form for device-resident benchmarking: upload once, run many times. */
+B200_API int  b200_pic_upload(b200_ctx* ctx, const b200_picture* pic);            /* -> arena handle */
+B200_API int  b200_pic_run(b200_ctx* ctx, int arena);
+/* waitForPrevDecompressedPic(): blocks until every picture submitted so far is final; copies the DMVR MV deltas of
+ * `arena` (needed by the CPU's TaskFinishMotionInfo, DecCu.cpp:161) to dmvrMv (may be NULL). */
+B200_API int  b200_wait_picture(b200_ctx* ctx, int arena, int32_t* dmvrMv, size_t numDmvr);
+/* Output: DPB slot -> host planes (vvdec_frame planes; xAddPicture vvdecimpl.cpp:957). Synchronous D2H. */
+B200_API int  b200_get_frame(b200_ctx* ctx, int slot, int16_t* const planes[3]);
+/* Timing helpers for bench.py: CUDA events on the context stream. */
+B200_API int  b200_ctx_mark(b200_ctx* ctx, int which /*0 start, 1 stop*/);
+B200_API int  b200_ctx_elapsed_ms(b200_ctx* ctx, float* ms);
+B200_API long long b200_ctx_kernel_launches(b200_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,3 +98,26 @@ def ref_ptrs(ref_pics):
         for c in range(3):
             arr[s * 3 + c] = pl[c].ctypes.data
     return arr
+
+
+def oracle_decompress(oracle, g, dpb, pic):
+    """CPU chain of the whole back end on one synthetic picture: K2 -> K1 -> K3 -> K4 -> K5 with the pinned oracle.
+    dpb: list of [Y,Cb,Cr] per slot (refs are read from it); returns the new picture planes and the DMVR deltas."""
+    W, H = g.width, g.height
+    cur = [np.zeros((H, W), np.int16), np.zeros((H // 2, W // 2), np.int16), np.zeros((H // 2, W // 2), np.int16)]
+    dm = np.zeros((pic["ndmvr"] + 1, 2), np.int32)
+    st = pic["struct"]
+    oracle.orc_mc_predict(C.byref(g), abi.plane_ptrs(cur), ref_ptrs(dpb), pic["pus"].ctypes.data, len(pic["pus"]), dm.ctypes.data)
+    oracle.orc_k1_residual(C.byref(g), abi.plane_ptrs(cur), pic["tus"].ctypes.data, len(pic["tus"]), pic["coefs"], None, 0)
+    if st.flags & abi.PIC_DEBLOCK:
+        oracle.orc_lf_deblock(C.byref(g), abi.plane_ptrs(cur), pic["lfV"].ctypes.data, pic["lfH"].ctypes.data, None,
+                              pic["lfSlices"].ctypes.data, None, 3)
+    if st.flags & abi.PIC_SAO:
+        nxt = [np.zeros_like(p) for p in cur]
+        oracle.orc_sao_picture(C.byref(g), abi.plane_ptrs(cur), abi.plane_ptrs(nxt), pic["sao"].ctypes.data, None)
+        cur = nxt
+    if st.flags & abi.PIC_ALF:
+        nxt = [np.zeros_like(p) for p in cur]
+        oracle.orc_alf_picture(C.byref(g), abi.plane_ptrs(cur), abi.plane_ptrs(nxt), pic["alf"]["ctus"].ctypes.data, C.byref(pic["alfTabs"]))
+        cur = nxt
+    return cur, dm

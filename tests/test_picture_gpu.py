@@ -1,0 +1,49 @@
+"""Picture-level parity on the GPU: b200_decompress_picture (DecLibRecon seam, device-resident DPB, all five kernel families
+chained) vs the pinned oracle chain, over a short GOP where later pictures reference earlier reconstructed ones."""
+import ctypes as C
+import numpy as np
+import pytest
+import vvdec_b200
+from vvdec_b200 import abi, synth
+from tests.helpers import oracle_decompress
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("seed,W,H,flagsets", [(1, 416, 240, [(1, 1, 1), (1, 0, 1), (0, 0, 0), (1, 1, 0)]), (2, 1920, 1080, [(1, 1, 1), (1, 1, 1)])])
+def test_gop_decompress(b200, oracle, seed, W, H, flagsets):
+    rng = np.random.default_rng(seed)
+    bd = 10
+    g = abi.make_geom(W, H, bd)
+    ctx = C.c_void_p()
+    vvdec_b200.check(b200.b200_ctx_create(C.byref(ctx), C.byref(g), 6, 3, -1))
+    try:
+        dpb = [synth.noise_planes(rng, W, H, bd) for _ in range(4)] + [None, None]
+        for s in range(4):
+            vvdec_b200.check(b200.b200_ctx_load_slot(ctx, s, abi.plane_ptrs(dpb[s])))
+        dpb[4] = [p.copy() for p in dpb[0]]; dpb[5] = [p.copy() for p in dpb[0]]
+        order = [4, 5, 0, 2, 1, 3]          # destination slots: later pictures overwrite the initial references
+        for i, (db, sa, al) in enumerate(flagsets):
+            dst = order[i % len(order)]
+            pic = synth.gen_picture(rng, W, H, bd, dst_slot=dst, deblock=db, sao=sa, alf=al)
+            want, dm_want = oracle_decompress(oracle, g, dpb[:4], pic)
+            h = b200.b200_decompress_picture(ctx, C.byref(pic["struct"]))
+            assert h >= 0, b200.b200_last_error()
+            dm = np.zeros((pic["ndmvr"] + 1, 2), np.int32)
+            vvdec_b200.check(b200.b200_wait_picture(ctx, h, dm.ctypes.data, len(dm)))
+            got = [np.zeros_like(p) for p in want]
+            vvdec_b200.check(b200.b200_get_frame(ctx, dst, abi.plane_ptrs(got)))
+            for c in range(3):
+                assert np.array_equal(want[c], got[c]), f"picture {i} plane {c}: {len(np.argwhere(want[c] != got[c]))} diffs"
+            assert np.array_equal(dm, dm_want)
+            dpb[dst] = want
+        assert b200.b200_ctx_kernel_launches(ctx) >= 5
+    finally:
+        b200.b200_ctx_destroy(ctx)
+
+
+def test_ctx_errors(b200):
+    g = abi.make_geom(100, 64, 10)
+    ctx = C.c_void_p()
+    assert b200.b200_ctx_create(C.byref(ctx), C.byref(g), 4, 2, -1) == -2
+    assert b"multiple of 8" in b200.b200_last_error()

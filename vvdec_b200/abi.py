@@ -71,3 +71,16 @@ def make_alf_tables(t):
 
 def const_plane_ptrs(planes):
     return plane_ptrs(planes)
+
+
+PIC_DEBLOCK, PIC_SAO, PIC_ALF = 1, 2, 4
+
+
+class Picture(C.Structure):
+    _fields_ = [("dstSlot", C.c_int32), ("flags", C.c_int32), ("given", C.c_void_p * 3),
+                ("pus", C.c_void_p), ("numPus", C.c_size_t), ("numDmvr", C.c_size_t),
+                ("tus", C.c_void_p), ("numTus", C.c_size_t), ("coefs", C.c_void_p), ("numCoefs", C.c_size_t),
+                ("scaling", C.c_void_p), ("numScaling", C.c_size_t),
+                ("lfV", C.c_void_p), ("lfH", C.c_void_p), ("ctuSlice", C.c_void_p), ("lfSlices", C.c_void_p),
+                ("numLfSlices", C.c_int32), ("lfSeq", C.c_void_p),
+                ("sao", C.c_void_p), ("vb", C.c_void_p), ("alf", C.c_void_p), ("alfTabs", C.c_void_p)]

@@ -31,5 +31,21 @@ def declare(lib):
     lib.b200_mc_predict.restype = C.c_int
 
 
-EXPORTS = ["b200_mc_predict", "b200_last_error", "b200_version", "b200_device_count", "b200_k1_residual", "b200_lf_deblock",
+    CTX = C.c_void_p
+    lib.b200_ctx_create.argtypes = [C.POINTER(CTX), C.POINTER(abi.Geom), C.c_int, C.c_int, C.c_int]
+    lib.b200_ctx_destroy.argtypes = [CTX]; lib.b200_ctx_destroy.restype = None
+    lib.b200_ctx_load_slot.argtypes = [CTX, C.c_int, PLANES]
+    lib.b200_decompress_picture.argtypes = [CTX, C.POINTER(abi.Picture)]
+    lib.b200_pic_upload.argtypes = [CTX, C.POINTER(abi.Picture)]
+    lib.b200_pic_run.argtypes = [CTX, C.c_int]
+    lib.b200_wait_picture.argtypes = [CTX, C.c_int, C.c_void_p, C.c_size_t]
+    lib.b200_get_frame.argtypes = [CTX, C.c_int, PLANES]
+    lib.b200_ctx_mark.argtypes = [CTX, C.c_int]
+    lib.b200_ctx_elapsed_ms.argtypes = [CTX, C.POINTER(C.c_float)]
+    lib.b200_ctx_kernel_launches.argtypes = [CTX]; lib.b200_ctx_kernel_launches.restype = C.c_longlong
+
+
+EXPORTS = ["b200_ctx_create", "b200_ctx_destroy", "b200_ctx_load_slot", "b200_decompress_picture", "b200_pic_upload", "b200_pic_run",
+           "b200_wait_picture", "b200_get_frame", "b200_ctx_mark", "b200_ctx_elapsed_ms", "b200_ctx_kernel_launches",
+           "b200_mc_predict", "b200_last_error", "b200_version", "b200_device_count", "b200_k1_residual", "b200_lf_deblock",
            "b200_sao_picture", "b200_alf_picture"]

@@ -206,7 +206,7 @@ B200_API int b200_mc_predict(const b200_geom* g, int16_t* const dst[3], const in
                              const b200_pu* pus, size_t numPus, int32_t* dmvrMv, size_t numDmvr)
 {
   B200_CHECK(g && dst && refs && (pus || !numPus), "b200_mc_predict: null argument");
-  B200_CHECK(numSlots >= 1 && numSlots <= 64, "b200_mc_predict: numSlots %d", numSlots);
+  B200_CHECK(numSlots >= 1 && numSlots <= B200_MAX_SLOTS, "b200_mc_predict: numSlots %d", numSlots);
   B200_CHECK(numPus < (1u << 26), "b200_mc_predict: too many PUs");
   for (size_t i = 0; i < numPus; i++) {
     B200_CHECK(pus[i].refSlot[0] < numSlots && pus[i].refSlot[1] < numSlots && (pus[i].refSlot[0] >= 0 || pus[i].refSlot[1] >= 0), "b200_mc_predict: PU %zu has invalid reference slots", i);
@@ -233,16 +233,15 @@ B200_API int b200_mc_predict(const b200_geom* g, int16_t* const dst[3], const in
   }
   std::vector<uint32_t> tT, tA;
   build_mc_tiles(pus, numPus, tT, tA);
-  if (int rc = g_hw.misc[4].reserve(ptrs.size() * sizeof(void*))) return rc;
   if (int rc = g_hw.misc[5].reserve(numPus * sizeof(b200_pu) + 64)) return rc;
   if (int rc = g_hw.misc[6].reserve((tT.size() + tA.size()) * 4 + 64)) return rc;
   if (int rc = g_hw.misc[7].reserve(numDmvr * 8 + 64)) return rc;
-  B200_CUDA(cudaMemcpyAsync(g_hw.misc[4].p, ptrs.data(), ptrs.size() * sizeof(void*), cudaMemcpyHostToDevice, s));
   if (numPus) B200_CUDA(cudaMemcpyAsync(g_hw.misc[5].p, pus, numPus * sizeof(b200_pu), cudaMemcpyHostToDevice, s));
   if (tT.size()) B200_CUDA(cudaMemcpyAsync(g_hw.misc[6].p, tT.data(), tT.size() * 4, cudaMemcpyHostToDevice, s));
   if (tA.size()) B200_CUDA(cudaMemcpyAsync(g_hw.misc[6].as<uint32_t>() + tT.size(), tA.data(), tA.size() * 4, cudaMemcpyHostToDevice, s));
   B200_CUDA(cudaMemsetAsync(g_hw.misc[7].p, 0, numDmvr * 8 + 64, s));
-  L.refs = g_hw.misc[4].as<const int16_t*>(); for (int c = 0; c < 3; c++) L.refStride[c] = g->stride[c];
+  memset(L.refs, 0, sizeof(L.refs)); for (size_t i = 0; i < ptrs.size(); i++) L.refs[i] = ptrs[i];
+  for (int c = 0; c < 3; c++) L.refStride[c] = g->stride[c];
   L.pus = g_hw.misc[5].as<b200_pu>(); L.tilesT = g_hw.misc[6].as<uint32_t>(); L.tilesA = L.tilesT + tT.size();
   L.numTilesT = (int)tT.size(); L.numTilesA = (int)tA.size(); L.dmvrMv = dmvrMv ? g_hw.misc[7].as<int32_t>() : nullptr;
   if (int rc = launch_mc(L, s)) return rc;

@@ -82,9 +82,10 @@ struct AlfLaunch {
 };
 int launch_alf(const AlfLaunch& L, cudaStream_t s);
 
+constexpr int B200_MAX_SLOTS = 32;
 struct McLaunch {
   b200_geom geom; DevPlanes dst;
-  const int16_t* const* refs;       // device array [numSlots*3] of device plane pointers
+  const int16_t* refs[B200_MAX_SLOTS * 3];   // device plane pointers per DPB slot
   int refStride[3];
   const b200_pu* pus;               // device
   const uint32_t *tilesT, *tilesA;  // device tile lists: translational (regular/BDOF/DMVR) and affine; (puIdx<<6)|(ty<<3)|tx

@@ -23,7 +23,7 @@ constexpr int IFO = 8192;   // IF_INTERNAL_OFFS
 
 struct McParams {
   int16_t* dst[3]; int dstStride[3];
-  const int16_t* const* refs;     // device array [numSlots*3]
+  const int16_t* refs[B200_MAX_SLOTS * 3];   // device plane pointers, by value (no table in memory -> no sync when the DPB mapping changes)
   int refStride[3];
   int W, H, bitDepth, ctuSize, chroma;
   const b200_pu* pus; const uint32_t* tiles; int numTiles;
@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(256) mc_tile_kernel(const McParams P)
   const bool bi = pu.refSlot[0] >= 0 && pu.refSlot[1] >= 0;
   const bool altHpel = pu.flags & B200_PU_ALTHPEL;
   const bool dmvr = pu.flags & B200_PU_DMVR;
+  const bool is4x4 = pu.w == 4 && pu.h == 4;   // InterpolationFilter::filterHor/Ver pick the 6-tap table for 4x4 blocks (:1062,:1155)
   bool bio = pu.flags & B200_PU_BDOF;
   const int nList = bi ? 2 : 1, l0 = pu.refSlot[0] >= 0 ? 0 : 1;
 
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(256) mc_tile_kernel(const McParams P)
     int s;
     if (xF == 0) s = 64 * sW[l][y * WS + x + 3];
     else {
-      const int8_t* f = luma_taps(xF, false, altHpel);
+      const int8_t* f = luma_taps(xF, is4x4, altHpel);
       s = 0;
 #pragma unroll
       for (int t = 0; t < 8; t++) s += f[t] * sW[l][y * WS + x + t];
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(256) mc_tile_kernel(const McParams P)
         int s;
         if (yF == 0) s = 64 * sHf[l][(y + 3) * 16 + x];
         else {
-          const int8_t* f = luma_taps(yF, false, altHpel);
+          const int8_t* f = luma_taps(yF, is4x4, altHpel);
           s = 0;
 #pragma unroll
           for (int t = 0; t < 8; t++) s += f[t] * sHf[l][(y + t) * 16 + x];
@@ -588,7 +589,8 @@ int launch_mc(const McLaunch& L, cudaStream_t s)
 {
   McParams P;
   for (int c = 0; c < 3; c++) { P.dst[c] = L.dst.p[c]; P.dstStride[c] = L.dst.stride[c]; P.refStride[c] = L.refStride[c]; }
-  P.refs = L.refs; P.W = L.geom.width; P.H = L.geom.height; P.bitDepth = L.geom.bitDepth; P.ctuSize = L.geom.ctuSize; P.chroma = L.geom.chromaFormat == 1;
+  for (int i = 0; i < B200_MAX_SLOTS * 3; i++) P.refs[i] = L.refs[i];
+  P.W = L.geom.width; P.H = L.geom.height; P.bitDepth = L.geom.bitDepth; P.ctuSize = L.geom.ctuSize; P.chroma = L.geom.chromaFormat == 1;
   P.pus = L.pus; P.dmvrMv = L.dmvrMv;
   if (L.numTilesT) { P.tiles = L.tilesT; P.numTiles = L.numTilesT; mc_tile_kernel<<<L.numTilesT, 256, 0, s>>>(P); B200_CUDA(cudaGetLastError()); }
   if (L.numTilesA) { P.tiles = L.tilesA; P.numTiles = L.numTilesA; mc_affine_kernel<<<L.numTilesA, 256, 0, s>>>(P); B200_CUDA(cudaGetLastError()); }

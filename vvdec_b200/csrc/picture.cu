@@ -1,0 +1,268 @@
+// picture.cu — picture-level context: device-resident DPB, work-list arenas, and the per-picture kernel chain
+// (the B200 replacement of DecLibRecon::decompressPicture's CTU task graph, reference DecoderLib/DecLibRecon.cpp:429-682).
+#include "common.cuh"
+#include <string.h>
+#include <vector>
+
+namespace b200 {
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct Arena {
+  DevBuf buf;                       // one allocation, sub-allocated per picture
+  // device views
+  const b200_pu* pus = nullptr; const uint32_t *tilesT = nullptr, *tilesA = nullptr; int nT = 0, nA = 0; size_t numPus = 0;
+  const b200_tu* tus = nullptr; size_t numTus = 0; const int16_t* coefs = nullptr; const int32_t* scaling = nullptr;
+  const b200_lf_param *lfV = nullptr, *lfH = nullptr; const uint8_t* ctuSlice = nullptr; LfSliceTab lfSlices; b200_lf_seq lfSeq;
+  const b200_sao_ctu* sao = nullptr; b200_vb vb;
+  const b200_alf_ctu* alf = nullptr; const int16_t *lumaCoeff = nullptr, *lumaClip = nullptr, *chromaCoeff = nullptr, *chromaClip = nullptr, *cc[2] = {nullptr, nullptr};
+  int32_t* dmvrMv = nullptr; size_t numDmvr = 0;
+  int16_t* given[3] = {nullptr, nullptr, nullptr};
+  int dstSlot = 0, flags = 0;
+  bool valid = false;
+};
+
+}  // namespace b200
+
+using namespace b200;
+
+struct b200_ctx {
+  b200_geom g;
+  int numSlots = 0, numArenas = 0, device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  size_t planeBytes[3] = {0, 0, 0}, picBytes = 0;
+  std::vector<int16_t*> bufs;          // numSlots + 2 picture buffers
+  std::vector<int> slotBuf;            // slot -> buffer index
+  int work[2] = {0, 0};                // indices of the two work buffers
+  std::vector<Arena> arenas;
+  int nextArena = 0;
+  long long launches = 0;
+  std::vector<uint32_t> hT, hA;
+
+  DevPlanes planes(int buf) const {
+    DevPlanes d; char* b = reinterpret_cast<char*>(bufs[buf]);
+    d.p[0] = reinterpret_cast<int16_t*>(b); d.p[1] = reinterpret_cast<int16_t*>(b + planeBytes[0]); d.p[2] = reinterpret_cast<int16_t*>(b + planeBytes[0] + planeBytes[1]);
+    for (int c = 0; c < 3; c++) d.stride[c] = g.stride[c];
+    return d;
+  }
+};
+
+extern "C" {
+
+B200_API int b200_ctx_create(b200_ctx** out, const b200_geom* g, int numSlots, int numArenas, int device)
+{
+  B200_CHECK(out && g, "b200_ctx_create: null argument");
+  B200_CHECK(numSlots >= 1 && numSlots <= B200_MAX_SLOTS && numArenas >= 1 && numArenas <= 256, "b200_ctx_create: numSlots %d / numArenas %d out of range", numSlots, numArenas);
+  B200_CHECK((g->width & 7) == 0 && (g->height & 7) == 0, "b200_ctx_create: picture size must be a multiple of 8");
+  B200_CHECK(g->chromaFormat == 0 || g->chromaFormat == 1, "b200_ctx_create: only 4:0:0 and 4:2:0");
+  B200_CHECK(g->ctuSize == 32 || g->ctuSize == 64 || g->ctuSize == 128, "b200_ctx_create: CTU size %d", g->ctuSize);
+  if (int rc = ensure_device()) return rc;
+  if (device >= 0) B200_CUDA(cudaSetDevice(device));
+  b200_ctx* c = new b200_ctx;
+  c->g = *g; c->numSlots = numSlots; c->numArenas = numArenas;
+  B200_CUDA(cudaGetDevice(&c->device));
+  B200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  B200_CUDA(cudaEventCreate(&c->ev[0])); B200_CUDA(cudaEventCreate(&c->ev[1]));
+  for (int k = 0; k < 3; k++) c->planeBytes[k] = (k == 0 || g->chromaFormat) ? align256((size_t)g->stride[k] * (k ? g->height >> 1 : g->height) * 2) : 0;
+  c->picBytes = c->planeBytes[0] + c->planeBytes[1] + c->planeBytes[2];
+  c->bufs.resize(numSlots + 2); c->slotBuf.resize(numSlots);
+  for (int i = 0; i < numSlots + 2; i++) { B200_CUDA(cudaMalloc(&c->bufs[i], c->picBytes)); B200_CUDA(cudaMemset(c->bufs[i], 0, c->picBytes)); }
+  for (int s = 0; s < numSlots; s++) c->slotBuf[s] = s;
+  c->work[0] = numSlots; c->work[1] = numSlots + 1;
+  c->arenas.resize(numArenas);
+  *out = c;
+  return 0;
+}
+
+B200_API void b200_ctx_destroy(b200_ctx* c)
+{
+  if (!c) return;
+  cudaStreamSynchronize(c->stream);
+  for (auto p : c->bufs) cudaFree(p);
+  cudaEventDestroy(c->ev[0]); cudaEventDestroy(c->ev[1]);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+B200_API int b200_ctx_load_slot(b200_ctx* c, int slot, const int16_t* const planes[3])
+{
+  B200_CHECK(c && planes && slot >= 0 && slot < c->numSlots, "b200_ctx_load_slot: bad argument");
+  DevPlanes d = c->planes(c->slotBuf[slot]);
+  for (int k = 0; k < (c->g.chromaFormat ? 3 : 1); k++)
+    B200_CUDA(cudaMemcpyAsync(d.p[k], planes[k], (size_t)c->g.stride[k] * (k ? c->g.height >> 1 : c->g.height) * 2, cudaMemcpyHostToDevice, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
+{
+  B200_CHECK(c && p, "b200_pic_upload: null argument");
+  B200_CHECK(p->dstSlot >= 0 && p->dstSlot < c->numSlots, "b200_pic_upload: dstSlot %d", p->dstSlot);
+  B200_CHECK(!(p->flags & B200_PIC_DEBLOCK) || (p->lfV && p->lfH && p->lfSlices && p->numLfSlices >= 1 && p->numLfSlices <= 64), "b200_pic_upload: deblocking data missing");
+  B200_CHECK(!(p->flags & B200_PIC_SAO) || p->sao, "b200_pic_upload: SAO data missing");
+  B200_CHECK(!(p->flags & B200_PIC_ALF) || (p->alf && p->alfTabs && p->alfTabs->numLumaSets >= 16), "b200_pic_upload: ALF data missing");
+  for (size_t i = 0; i < p->numPus; i++)
+    B200_CHECK(p->pus[i].refSlot[0] < c->numSlots && p->pus[i].refSlot[1] < c->numSlots && (p->pus[i].refSlot[0] >= 0 || p->pus[i].refSlot[1] >= 0), "b200_pic_upload: PU %zu has invalid reference slots", i);
+  B200_CUDA(cudaSetDevice(c->device));
+  const int ai = c->nextArena; c->nextArena = (c->nextArena + 1) % c->numArenas;
+  Arena& A = c->arenas[ai];
+  const b200_geom& g = c->g;
+  const size_t n4 = (size_t)((g.width + 3) >> 2) * ((g.height + 3) >> 2);
+  const size_t nCtu = (size_t)((g.width + g.ctuSize - 1) / g.ctuSize) * ((g.height + g.ctuSize - 1) / g.ctuSize);
+  build_mc_tiles(p->pus, p->numPus, c->hT, c->hA);
+  const b200_alf_tables* T = p->alfTabs;
+  const size_t nL = (p->flags & B200_PIC_ALF) ? (size_t)T->numLumaSets * 1300 : 0, nC = (p->flags & B200_PIC_ALF) ? (size_t)T->numChromaAlts * 7 : 0;
+  const size_t n0 = (p->flags & B200_PIC_ALF) ? (size_t)T->numCc[0] * 7 : 0, n1 = (p->flags & B200_PIC_ALF) ? (size_t)T->numCc[1] * 7 : 0;
+  // ---- layout ----
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes + 16); return o; };
+  const size_t oPus = take(p->numPus * sizeof(b200_pu)), oT = take((c->hT.size() + c->hA.size()) * 4);
+  const size_t oTus = take(p->numTus * sizeof(b200_tu)), oCoef = take(p->numCoefs * 2), oScal = take(p->numScaling * 4);
+  const size_t oLfV = take((p->flags & B200_PIC_DEBLOCK) ? n4 * 6 : 0), oLfH = take((p->flags & B200_PIC_DEBLOCK) ? n4 * 6 : 0), oCs = take(nCtu);
+  const size_t oSao = take((p->flags & B200_PIC_SAO) ? nCtu * sizeof(b200_sao_ctu) : 0);
+  const size_t oAlf = take((p->flags & B200_PIC_ALF) ? nCtu * sizeof(b200_alf_ctu) : 0), oTab = take((2 * nL + 2 * nC + n0 + n1) * 2);
+  const size_t oDm = take(p->numDmvr * 8);
+  const bool hasGiven = p->given[0] != nullptr;
+  const size_t oGiven = take(hasGiven ? c->picBytes : 0);
+  if (off > A.buf.cap) { B200_CUDA(cudaStreamSynchronize(c->stream)); }      // the arena may still be in use by queued kernels
+  if (int rc = A.buf.reserve(off)) return rc;
+  char* base = A.buf.as<char>();
+  cudaStream_t s = c->stream;
+  auto h2d = [&](size_t o, const void* src, size_t bytes) -> int { if (bytes) B200_CUDA(cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, s)); return 0; };
+  if (int rc = h2d(oPus, p->pus, p->numPus * sizeof(b200_pu))) return rc;
+  if (int rc = h2d(oT, c->hT.data(), c->hT.size() * 4)) return rc;
+  if (int rc = h2d(oT + c->hT.size() * 4, c->hA.data(), c->hA.size() * 4)) return rc;
+  if (int rc = h2d(oTus, p->tus, p->numTus * sizeof(b200_tu))) return rc;
+  if (int rc = h2d(oCoef, p->coefs, p->numCoefs * 2)) return rc;
+  if (int rc = h2d(oScal, p->scaling, p->numScaling * 4)) return rc;
+  if (p->flags & B200_PIC_DEBLOCK) {
+    if (int rc = h2d(oLfV, p->lfV, n4 * 6)) return rc;
+    if (int rc = h2d(oLfH, p->lfH, n4 * 6)) return rc;
+    if (p->ctuSlice) if (int rc = h2d(oCs, p->ctuSlice, nCtu)) return rc;
+    memset(&A.lfSlices, 0, sizeof(A.lfSlices)); memcpy(A.lfSlices.s, p->lfSlices, p->numLfSlices * sizeof(b200_lf_slice));
+    if (p->lfSeq) A.lfSeq = *p->lfSeq; else memset(&A.lfSeq, 0, sizeof(A.lfSeq));
+  }
+  if (p->flags & B200_PIC_SAO) { if (int rc = h2d(oSao, p->sao, nCtu * sizeof(b200_sao_ctu))) return rc; if (p->vb) A.vb = *p->vb; else memset(&A.vb, 0, sizeof(A.vb)); }
+  if (p->flags & B200_PIC_ALF) {
+    if (int rc = h2d(oAlf, p->alf, nCtu * sizeof(b200_alf_ctu))) return rc;
+    size_t o = oTab;
+    auto up = [&](const int16_t* src, size_t n, const int16_t*& view) -> int { view = reinterpret_cast<const int16_t*>(base + o); int rc = h2d(o, src, n * 2); o += n * 2; return rc; };
+    if (int rc = up(T->lumaCoeff, nL, A.lumaCoeff)) return rc;
+    if (int rc = up(T->lumaClip, nL, A.lumaClip)) return rc;
+    if (int rc = up(T->chromaCoeff, nC, A.chromaCoeff)) return rc;
+    if (int rc = up(T->chromaClip, nC, A.chromaClip)) return rc;
+    if (int rc = up(T->ccCoeff[0], n0, A.cc[0])) return rc;
+    if (int rc = up(T->ccCoeff[1], n1, A.cc[1])) return rc;
+  }
+  if (hasGiven) {
+    size_t o = oGiven;
+    for (int k = 0; k < (g.chromaFormat ? 3 : 1); k++) {
+      A.given[k] = reinterpret_cast<int16_t*>(base + o);
+      if (int rc = h2d(o, p->given[k], (size_t)g.stride[k] * (k ? g.height >> 1 : g.height) * 2)) return rc;
+      o += c->planeBytes[k];
+    }
+  } else A.given[0] = A.given[1] = A.given[2] = nullptr;
+  A.pus = reinterpret_cast<const b200_pu*>(base + oPus); A.numPus = p->numPus;
+  A.tilesT = reinterpret_cast<const uint32_t*>(base + oT); A.tilesA = A.tilesT + c->hT.size(); A.nT = (int)c->hT.size(); A.nA = (int)c->hA.size();
+  A.tus = reinterpret_cast<const b200_tu*>(base + oTus); A.numTus = p->numTus;
+  A.coefs = reinterpret_cast<const int16_t*>(base + oCoef); A.scaling = reinterpret_cast<const int32_t*>(base + oScal);
+  A.lfV = reinterpret_cast<const b200_lf_param*>(base + oLfV); A.lfH = reinterpret_cast<const b200_lf_param*>(base + oLfH);
+  A.ctuSlice = p->ctuSlice ? reinterpret_cast<const uint8_t*>(base + oCs) : nullptr;
+  A.sao = reinterpret_cast<const b200_sao_ctu*>(base + oSao); A.alf = reinterpret_cast<const b200_alf_ctu*>(base + oAlf);
+  A.dmvrMv = p->numDmvr ? reinterpret_cast<int32_t*>(base + oDm) : nullptr; A.numDmvr = p->numDmvr;
+  A.dstSlot = p->dstSlot; A.flags = p->flags; A.valid = true;
+  return ai;
+}
+
+B200_API int b200_pic_run(b200_ctx* c, int ai)
+{
+  B200_CHECK(c && ai >= 0 && ai < c->numArenas && c->arenas[ai].valid, "b200_pic_run: bad arena %d", ai);
+  B200_CUDA(cudaSetDevice(c->device));
+  Arena& A = c->arenas[ai];
+  cudaStream_t s = c->stream;
+  const b200_geom& g = c->g;
+  int cur = c->work[0], other = c->work[1];
+  DevPlanes P = c->planes(cur);
+  // 0. pre-reconstructed (intra stand-in) samples
+  if (A.given[0]) {
+    for (int k = 0; k < (g.chromaFormat ? 3 : 1); k++)
+      B200_CUDA(cudaMemcpyAsync(P.p[k], A.given[k], (size_t)g.stride[k] * (k ? g.height >> 1 : g.height) * 2, cudaMemcpyDeviceToDevice, s));
+  }
+  // 1. K2 inter prediction
+  if (A.numPus) {
+    McLaunch L; L.geom = g; L.dst = P; memset(L.refs, 0, sizeof(L.refs));
+    for (int sl = 0; sl < c->numSlots; sl++) { DevPlanes d = c->planes(c->slotBuf[sl]); for (int k = 0; k < 3; k++) L.refs[sl * 3 + k] = d.p[k]; }
+    for (int k = 0; k < 3; k++) L.refStride[k] = g.stride[k];
+    L.pus = A.pus; L.tilesT = A.tilesT; L.tilesA = A.tilesA; L.numTilesT = A.nT; L.numTilesA = A.nA; L.dmvrMv = A.dmvrMv;
+    if (int rc = launch_mc(L, s)) return rc;
+    c->launches += (A.nT ? 1 : 0) + (A.nA ? 1 : 0);
+  }
+  // 2. K1 residual + reco
+  if (A.numTus) {
+    K1Launch L; L.geom = g; L.planes = P; L.tus = A.tus; L.numTus = A.numTus; L.coefs = A.coefs; L.scaling = A.scaling; L.mode = 0;
+    if (int rc = launch_k1_residual(L, s)) return rc;
+    c->launches += 1;
+  }
+  // 3. K3 deblocking
+  if (A.flags & B200_PIC_DEBLOCK) {
+    LfLaunch L; L.geom = g; L.planes = P; L.lfV = A.lfV; L.lfH = A.lfH; L.ctuSlice = A.ctuSlice; L.slices = A.lfSlices; L.seq = A.lfSeq; L.dirs = 3;
+    if (int rc = launch_lf_deblock(L, s)) return rc;
+    c->launches += 2;
+  }
+  // 4. K4 SAO (out of place)
+  if (A.flags & B200_PIC_SAO) {
+    SaoLaunch L; L.geom = g; L.src = P; L.dst = c->planes(other); L.ctus = A.sao; L.vb = A.vb;
+    if (int rc = launch_sao(L, s)) return rc;
+    c->launches += 1;
+    std::swap(cur, other); P = c->planes(cur);
+  }
+  // 5. K5 ALF (out of place, straight into a buffer that becomes the DPB slot)
+  if (A.flags & B200_PIC_ALF) {
+    AlfLaunch L; L.geom = g; L.src = P; L.dst = c->planes(other); L.ctus = A.alf;
+    L.lumaCoeff = A.lumaCoeff; L.lumaClip = A.lumaClip; L.chromaCoeff = A.chromaCoeff; L.chromaClip = A.chromaClip; L.cc[0] = A.cc[0]; L.cc[1] = A.cc[1];
+    if (int rc = launch_alf(L, s)) return rc;
+    c->launches += g.chromaFormat ? 2 : 1;
+    std::swap(cur, other);
+  }
+  // 6. the buffer holding the result becomes the slot's buffer; the slot's old buffer becomes a work buffer (swapBufs, DecLibRecon.cpp:423)
+  const int old = c->slotBuf[A.dstSlot];
+  c->slotBuf[A.dstSlot] = cur;
+  c->work[0] = old; c->work[1] = other;
+  return 0;
+}
+
+B200_API int b200_decompress_picture(b200_ctx* c, const b200_picture* p)
+{
+  const int ai = b200_pic_upload(c, p);
+  if (ai < 0) return ai;
+  if (int rc = b200_pic_run(c, ai)) return rc;
+  return ai;
+}
+
+B200_API int b200_wait_picture(b200_ctx* c, int ai, int32_t* dmvrMv, size_t numDmvr)
+{
+  B200_CHECK(c, "b200_wait_picture: null context");
+  if (dmvrMv && ai >= 0 && ai < c->numArenas && c->arenas[ai].dmvrMv) {
+    const size_t n = numDmvr < c->arenas[ai].numDmvr ? numDmvr : c->arenas[ai].numDmvr;
+    B200_CUDA(cudaMemcpyAsync(dmvrMv, c->arenas[ai].dmvrMv, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  }
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+B200_API int b200_get_frame(b200_ctx* c, int slot, int16_t* const planes[3])
+{
+  B200_CHECK(c && planes && slot >= 0 && slot < c->numSlots, "b200_get_frame: bad argument");
+  DevPlanes d = c->planes(c->slotBuf[slot]);
+  for (int k = 0; k < (c->g.chromaFormat ? 3 : 1); k++)
+    B200_CUDA(cudaMemcpyAsync(planes[k], d.p[k], (size_t)c->g.stride[k] * (k ? c->g.height >> 1 : c->g.height) * 2, cudaMemcpyDeviceToHost, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+B200_API int b200_ctx_mark(b200_ctx* c, int which) { B200_CHECK(c && (which == 0 || which == 1), "b200_ctx_mark"); B200_CUDA(cudaEventRecord(c->ev[which], c->stream)); return 0; }
+B200_API int b200_ctx_elapsed_ms(b200_ctx* c, float* ms) { B200_CHECK(c && ms, "b200_ctx_elapsed_ms"); B200_CUDA(cudaEventSynchronize(c->ev[1])); B200_CUDA(cudaEventElapsedTime(ms, c->ev[0], c->ev[1])); return 0; }
+B200_API long long b200_ctx_kernel_launches(b200_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

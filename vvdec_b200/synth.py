@@ -337,3 +337,34 @@ def gen_pus(rng, cus, W, H, p_inter=1.0, p_bi=0.6, p_dmvr=0.35, p_bdof=0.35, p_a
         recs.append(r)
     pus = np.array(recs, PU_DTYPE) if recs else np.zeros(0, PU_DTYPE)
     return pus, dmvr_off
+
+
+def gen_picture(rng, W, H, bit_depth=10, ctu=128, dst_slot=0, cu_kw=None, pu_kw=None, tu_kw=None, sao_p=0.4, alf_kw=None,
+                deblock=True, sao=True, alf=True):
+    """One synthetic post-parse picture: partition -> inter PUs (all CUs inter: intra-coded samples would
+    be 'given' pixels) -> TUs/levels -> deblocking grids -> SAO / ALF CTU parameters.
+    Returns a dict of numpy arrays (kept alive by the caller) plus `struct`, the abi.Picture that points into them."""
+    from . import abi as A
+    import ctypes as C
+    cus = partition(rng, W, H, ctu=ctu, **(cu_kw or {}))
+    pus, ndmvr = gen_pus(rng, cus, W, H, **(pu_kw or {}))
+    tus, coefs = gen_tus(rng, cus, bit_depth, **({"p_cbf": 0.35, "p_intra": 0.0, "p_lfnst": 0.0, "p_bdpcm": 0.0} | (tu_kw or {})))
+    d = dict(cus=cus, pus=pus, ndmvr=ndmvr, tus=tus, coefs=coefs)
+    p = A.Picture(); p.dstSlot = dst_slot; p.flags = 0
+    p.pus = pus.ctypes.data; p.numPus = len(pus); p.numDmvr = ndmvr + 1
+    p.tus = tus.ctypes.data; p.numTus = len(tus); p.coefs = coefs.ctypes.data; p.numCoefs = len(coefs)
+    if deblock:
+        qp = rng.integers(22, 45, size=len(cus))
+        d["lfV"], d["lfH"] = gen_lf_grid(rng, cus, W, H, bit_depth, cu_intra=np.zeros(len(cus), bool), cu_qp=qp)
+        d["lfSlices"] = np.zeros(1, LFSLICE_DTYPE)
+        p.flags |= A.PIC_DEBLOCK; p.lfV = d["lfV"].ctypes.data; p.lfH = d["lfH"].ctypes.data
+        p.lfSlices = d["lfSlices"].ctypes.data; p.numLfSlices = 1
+    if sao:
+        d["sao"] = gen_sao(rng, W, H, ctu, bit_depth, p_on=sao_p)
+        p.flags |= A.PIC_SAO; p.sao = d["sao"].ctypes.data
+    if alf:
+        d["alf"] = gen_alf(rng, W, H, ctu, bit_depth, **(alf_kw or {}))
+        d["alfTabs"] = A.make_alf_tables(d["alf"])
+        p.flags |= A.PIC_ALF; p.alf = d["alf"]["ctus"].ctypes.data; p.alfTabs = C.addressof(d["alfTabs"])
+    d["struct"] = p
+    return d
