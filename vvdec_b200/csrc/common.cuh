@@ -53,6 +53,9 @@ struct DevPlanes {
 };
 
 // ---- kernel launchers (device pointers, stream-ordered) ----
+// optional per-family event recorder (picture.cu); launchers call prof->begin(f)/end(f) around their kernels
+struct KProf { virtual void begin(int family, cudaStream_t s) = 0; virtual void end(int family, cudaStream_t s) = 0; virtual ~KProf() {} };
+
 struct K1Launch {
   b200_geom      geom;
   DevPlanes      planes;
@@ -62,7 +65,7 @@ struct K1Launch {
   const int32_t* scaling;
   int            mode;    // 0: reco = clip(pred + resi); 1: store residual
 };
-int launch_k1_residual(const K1Launch& L, cudaStream_t s);
+int launch_k1_residual(const K1Launch& L, cudaStream_t s, KProf* prof = nullptr);
 
 struct LfSliceTab { b200_lf_slice s[64]; };
 struct LfLaunch {
@@ -71,16 +74,16 @@ struct LfLaunch {
   const uint8_t* ctuSlice;          // device or null
   LfSliceTab slices; b200_lf_seq seq; int dirs;
 };
-int launch_lf_deblock(const LfLaunch& L, cudaStream_t s);
+int launch_lf_deblock(const LfLaunch& L, cudaStream_t s, KProf* prof = nullptr);
 
 struct SaoLaunch { b200_geom geom; DevPlanes src, dst; const b200_sao_ctu* ctus; b200_vb vb; };
-int launch_sao(const SaoLaunch& L, cudaStream_t s);
+int launch_sao(const SaoLaunch& L, cudaStream_t s, KProf* prof = nullptr);
 
 struct AlfLaunch {
   b200_geom geom; DevPlanes src, dst; const b200_alf_ctu* ctus;
   const int16_t *lumaCoeff, *lumaClip, *chromaCoeff, *chromaClip, *cc[2];
 };
-int launch_alf(const AlfLaunch& L, cudaStream_t s);
+int launch_alf(const AlfLaunch& L, cudaStream_t s, KProf* prof = nullptr);
 
 constexpr int B200_MAX_SLOTS = 32;
 struct McLaunch {
@@ -92,7 +95,7 @@ struct McLaunch {
   int numTilesT, numTilesA;
   int32_t* dmvrMv;                  // device or null
 };
-int launch_mc(const McLaunch& L, cudaStream_t s);
+int launch_mc(const McLaunch& L, cudaStream_t s, KProf* prof = nullptr);
 // host: expand PUs into <=16x16 tiles
 void build_mc_tiles(const b200_pu* pus, size_t numPus, std::vector<uint32_t>& tilesT, std::vector<uint32_t>& tilesA);
 

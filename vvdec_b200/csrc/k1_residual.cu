@@ -215,14 +215,16 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* _
   }
 }
 
-int launch_k1_residual(const K1Launch& L, cudaStream_t s)
+int launch_k1_residual(const K1Launch& L, cudaStream_t s, KProf* prof)
 {
   if (L.numTus == 0) return 0;
+  if (prof) prof->begin(B200_KF_K1, s);
   const int grid = (int)((L.numTus + K1_WARPS - 1) / K1_WARPS);
   k1_residual_kernel<<<grid, K1_WARPS * 32, 0, s>>>(L.tus, (int)L.numTus, L.coefs, L.scaling, L.planes.p[0], L.planes.p[1],
                                                     L.planes.p[2], L.planes.stride[0], L.planes.stride[1],
                                                     L.planes.stride[2], L.geom.bitDepth, L.mode);
   B200_CUDA(cudaGetLastError());
+  if (prof) prof->end(B200_KF_K1, s);
   return 0;
 }
 

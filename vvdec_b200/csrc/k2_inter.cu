@@ -585,15 +585,15 @@ __global__ void __launch_bounds__(256) mc_affine_kernel(const McParams P)
   }
 }
 
-int launch_mc(const McLaunch& L, cudaStream_t s)
+int launch_mc(const McLaunch& L, cudaStream_t s, KProf* prof)
 {
   McParams P;
   for (int c = 0; c < 3; c++) { P.dst[c] = L.dst.p[c]; P.dstStride[c] = L.dst.stride[c]; P.refStride[c] = L.refStride[c]; }
   for (int i = 0; i < B200_MAX_SLOTS * 3; i++) P.refs[i] = L.refs[i];
   P.W = L.geom.width; P.H = L.geom.height; P.bitDepth = L.geom.bitDepth; P.ctuSize = L.geom.ctuSize; P.chroma = L.geom.chromaFormat == 1;
   P.pus = L.pus; P.dmvrMv = L.dmvrMv;
-  if (L.numTilesT) { P.tiles = L.tilesT; P.numTiles = L.numTilesT; mc_tile_kernel<<<L.numTilesT, 256, 0, s>>>(P); B200_CUDA(cudaGetLastError()); }
-  if (L.numTilesA) { P.tiles = L.tilesA; P.numTiles = L.numTilesA; mc_affine_kernel<<<L.numTilesA, 256, 0, s>>>(P); B200_CUDA(cudaGetLastError()); }
+  if (L.numTilesT) { if (prof) prof->begin(B200_KF_MC_TILE, s); P.tiles = L.tilesT; P.numTiles = L.numTilesT; mc_tile_kernel<<<L.numTilesT, 256, 0, s>>>(P); B200_CUDA(cudaGetLastError()); if (prof) prof->end(B200_KF_MC_TILE, s); }
+  if (L.numTilesA) { if (prof) prof->begin(B200_KF_MC_AFFINE, s); P.tiles = L.tilesA; P.numTiles = L.numTilesA; mc_affine_kernel<<<L.numTilesA, 256, 0, s>>>(P); B200_CUDA(cudaGetLastError()); if (prof) prof->end(B200_KF_MC_AFFINE, s); }
   return 0;
 }
 

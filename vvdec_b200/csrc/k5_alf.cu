@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(256) alf_chroma_kernel(const AlfParams P)
   *reinterpret_cast<uint2*>(P.dst[c] + (size_t)y * stride + x) = o;
 }
 
-int launch_alf(const AlfLaunch& L, cudaStream_t s)
+int launch_alf(const AlfLaunch& L, cudaStream_t s, KProf* prof)
 {
   AlfParams P;
   for (int c = 0; c < 3; c++) { P.src[c] = L.src.p[c]; P.dst[c] = L.dst.p[c]; P.stride[c] = L.src.stride[c]; }
@@ -230,12 +230,16 @@ int launch_alf(const AlfLaunch& L, cudaStream_t s)
   P.ctus = L.ctus; P.lumaCoeff = L.lumaCoeff; P.lumaClip = L.lumaClip; P.chromaCoeff = L.chromaCoeff; P.chromaClip = L.chromaClip;
   P.cc0 = L.cc[0]; P.cc1 = L.cc[1];
   dim3 grdL((P.W + TB - 1) / TB, (P.H + TB - 1) / TB);
+  if (prof) prof->begin(B200_KF_ALF_LUMA, s);
   alf_luma_kernel<<<grdL, 256, 0, s>>>(P);
   B200_CUDA(cudaGetLastError());
+  if (prof) prof->end(B200_KF_ALF_LUMA, s);
   if (L.geom.chromaFormat == 1) {
     dim3 blk(32, 8), grd(((P.W >> 1) / 4 + 31) / 32, ((P.H >> 1) + 7) / 8, 2);
+    if (prof) prof->begin(B200_KF_ALF_CHROMA, s);
     alf_chroma_kernel<<<grd, blk, 0, s>>>(P);
     B200_CUDA(cudaGetLastError());
+    if (prof) prof->end(B200_KF_ALF_CHROMA, s);
   }
   return 0;
 }

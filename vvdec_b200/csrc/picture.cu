@@ -26,8 +26,17 @@ struct Arena {
 
 using namespace b200;
 
+struct CtxProf : b200::KProf {
+  struct Rec { int family; cudaEvent_t a, b; };
+  std::vector<Rec> recs; std::vector<cudaEvent_t> pool; Rec cur{};
+  cudaEvent_t get() { cudaEvent_t e; if (!pool.empty()) { e = pool.back(); pool.pop_back(); } else cudaEventCreate(&e); return e; }
+  void begin(int f, cudaStream_t s) override { cur.family = f; cur.a = get(); cur.b = get(); cudaEventRecord(cur.a, s); }
+  void end(int, cudaStream_t s) override { cudaEventRecord(cur.b, s); recs.push_back(cur); }
+};
+
 struct b200_ctx {
   b200_geom g;
+  CtxProf prof; bool profiling = false;
   int numSlots = 0, numArenas = 0, device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -171,6 +180,7 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   A.ctuSlice = p->ctuSlice ? reinterpret_cast<const uint8_t*>(base + oCs) : nullptr;
   A.sao = reinterpret_cast<const b200_sao_ctu*>(base + oSao); A.alf = reinterpret_cast<const b200_alf_ctu*>(base + oAlf);
   A.dmvrMv = p->numDmvr ? reinterpret_cast<int32_t*>(base + oDm) : nullptr; A.numDmvr = p->numDmvr;
+  if (p->numDmvr) B200_CUDA(cudaMemsetAsync(base + oDm, 0, p->numDmvr * 8, s));   // entries of non-DMVR CUs stay zero, like m_dmvrMvCache users expect
   A.dstSlot = p->dstSlot; A.flags = p->flags; A.valid = true;
   return ai;
 }
@@ -195,25 +205,25 @@ B200_API int b200_pic_run(b200_ctx* c, int ai)
     for (int sl = 0; sl < c->numSlots; sl++) { DevPlanes d = c->planes(c->slotBuf[sl]); for (int k = 0; k < 3; k++) L.refs[sl * 3 + k] = d.p[k]; }
     for (int k = 0; k < 3; k++) L.refStride[k] = g.stride[k];
     L.pus = A.pus; L.tilesT = A.tilesT; L.tilesA = A.tilesA; L.numTilesT = A.nT; L.numTilesA = A.nA; L.dmvrMv = A.dmvrMv;
-    if (int rc = launch_mc(L, s)) return rc;
+    if (int rc = launch_mc(L, s, c->profiling ? &c->prof : nullptr)) return rc;
     c->launches += (A.nT ? 1 : 0) + (A.nA ? 1 : 0);
   }
   // 2. K1 residual + reco
   if (A.numTus) {
     K1Launch L; L.geom = g; L.planes = P; L.tus = A.tus; L.numTus = A.numTus; L.coefs = A.coefs; L.scaling = A.scaling; L.mode = 0;
-    if (int rc = launch_k1_residual(L, s)) return rc;
+    if (int rc = launch_k1_residual(L, s, c->profiling ? &c->prof : nullptr)) return rc;
     c->launches += 1;
   }
   // 3. K3 deblocking
   if (A.flags & B200_PIC_DEBLOCK) {
     LfLaunch L; L.geom = g; L.planes = P; L.lfV = A.lfV; L.lfH = A.lfH; L.ctuSlice = A.ctuSlice; L.slices = A.lfSlices; L.seq = A.lfSeq; L.dirs = 3;
-    if (int rc = launch_lf_deblock(L, s)) return rc;
+    if (int rc = launch_lf_deblock(L, s, c->profiling ? &c->prof : nullptr)) return rc;
     c->launches += 2;
   }
   // 4. K4 SAO (out of place)
   if (A.flags & B200_PIC_SAO) {
     SaoLaunch L; L.geom = g; L.src = P; L.dst = c->planes(other); L.ctus = A.sao; L.vb = A.vb;
-    if (int rc = launch_sao(L, s)) return rc;
+    if (int rc = launch_sao(L, s, c->profiling ? &c->prof : nullptr)) return rc;
     c->launches += 1;
     std::swap(cur, other); P = c->planes(cur);
   }
@@ -221,7 +231,7 @@ B200_API int b200_pic_run(b200_ctx* c, int ai)
   if (A.flags & B200_PIC_ALF) {
     AlfLaunch L; L.geom = g; L.src = P; L.dst = c->planes(other); L.ctus = A.alf;
     L.lumaCoeff = A.lumaCoeff; L.lumaClip = A.lumaClip; L.chromaCoeff = A.chromaCoeff; L.chromaClip = A.chromaClip; L.cc[0] = A.cc[0]; L.cc[1] = A.cc[1];
-    if (int rc = launch_alf(L, s)) return rc;
+    if (int rc = launch_alf(L, s, c->profiling ? &c->prof : nullptr)) return rc;
     c->launches += g.chromaFormat ? 2 : 1;
     std::swap(cur, other);
   }
@@ -264,5 +274,20 @@ B200_API int b200_get_frame(b200_ctx* c, int slot, int16_t* const planes[3])
 B200_API int b200_ctx_mark(b200_ctx* c, int which) { B200_CHECK(c && (which == 0 || which == 1), "b200_ctx_mark"); B200_CUDA(cudaEventRecord(c->ev[which], c->stream)); return 0; }
 B200_API int b200_ctx_elapsed_ms(b200_ctx* c, float* ms) { B200_CHECK(c && ms, "b200_ctx_elapsed_ms"); B200_CUDA(cudaEventSynchronize(c->ev[1])); B200_CUDA(cudaEventElapsedTime(ms, c->ev[0], c->ev[1])); return 0; }
 B200_API long long b200_ctx_kernel_launches(b200_ctx* c) { return c ? c->launches : 0; }
+
+B200_API int b200_ctx_set_profiling(b200_ctx* c, int on) { B200_CHECK(c, "b200_ctx_set_profiling"); c->profiling = on != 0; return 0; }
+
+B200_API int b200_ctx_get_kernel_ms(b200_ctx* c, float ms[8], int counts[8])
+{
+  B200_CHECK(c && ms && counts, "b200_ctx_get_kernel_ms");
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 8; i++) { ms[i] = 0; counts[i] = 0; }
+  for (auto& r : c->prof.recs) { float t = 0; cudaEventElapsedTime(&t, r.a, r.b); ms[r.family] += t; counts[r.family]++; c->prof.pool.push_back(r.a); c->prof.pool.push_back(r.b); }
+  c->prof.recs.clear();
+  return 0;
+}
+
+B200_API int b200_host_register(void* ptr, size_t bytes) { B200_CHECK(ptr && bytes, "b200_host_register"); if (int rc = ensure_device()) return rc; B200_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault)); return 0; }
+B200_API int b200_host_unregister(void* ptr) { B200_CHECK(ptr, "b200_host_unregister"); B200_CUDA(cudaHostUnregister(ptr)); return 0; }
 
 }  // extern "C"

@@ -9,7 +9,7 @@ def partition(rng, W, H, ctu=128, min_dim=4, min_area=32, p_split=None):
     """Random QT+BT partition of a WxH picture into CUs. Returns int array [n,4] = x,y,w,h (luma).
     Blocks crossing the picture boundary are split until they fit (implicit boundary splits)."""
     out = []
-    p_split = p_split or {128: 0.95, 64: 0.75, 32: 0.55, 16: 0.4, 8: 0.25, 4: 0.0}
+    p_split = p_split or {128: 0.94, 64: 0.68, 32: 0.6, 16: 0.6, 8: 0.5, 4: 0.0}
 
     def rec(x, y, w, h):
         if x >= W or y >= H:
@@ -26,7 +26,7 @@ def partition(rng, W, H, ctu=128, min_dim=4, min_area=32, p_split=None):
             if r >= p_split.get(big, 0.0):
                 out.append((x, y, w, h)); return
             opts = []
-            if w == h and w >= 8: opts += ["q", "q"]
+            if w == h and w >= 16: opts += ["q", "q"]
             if w >= 2 * min_dim and (w // 2) * h >= min_area and w <= 64: opts.append("v")
             if h >= 2 * min_dim and w * (h // 2) >= min_area and h <= 64: opts.append("h")
             if not opts:
