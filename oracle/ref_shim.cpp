@@ -37,6 +37,9 @@
 #include "CommonLib/SampleAdaptiveOffset.h"
 #include "CommonLib/AdaptiveLoopFilter.h"
 #include "CommonLib/RdCost.h"
+#include <chrono>
+#include <thread>
+#include <atomic>
 #include "../vvdec_b200/vvdec_glue/flatten_tu.h"
 
 using namespace vvdec;
@@ -604,4 +607,269 @@ extern "C" int ref_mc_predict( int simd, const b200_geom* g, int16_t* const dst[
     }
   }
   return rc;
+}
+
+// ================================================================================================ whole back end, multi-threaded
+template<class F> static void parallelFor( int n, int threads, F f )
+{
+  std::atomic<int> next{ 0 };
+  std::vector<std::thread> pool;
+  for( int t = 0; t < threads; t++ ) pool.emplace_back( [&, t] { for( int i = next++; i < n; i = next++ ) f( i, t ); } );
+  for( auto& th : pool ) th.join();
+}
+
+static void fillCuFromPu( CodingUnit& cu, const b200_pu& pu, FakePicture& cur, Slice* sl )
+{
+  memset( (void*) &cu, 0, sizeof( cu ) );
+  const UnitArea ua( cur.pic.cs->pcv->chrFormat, Area( pu.x, pu.y, pu.w, pu.h ) );
+  cu.UnitArea::operator=( ua );
+  cu.cs = cur.pic.cs.get(); cu.slice = sl; cu.pps = cur.pps.get(); cu.sps = cur.sps.get();
+  cu.ctuData = &cu.cs->getCtuData( cu.cs->ctuRsAddr( Position( pu.x, pu.y ), CH_L ) );
+  cu.setChType( CH_L ); cu.setTreeType( TREE_D ); cu.setModeType( MODE_TYPE_ALL );
+  cu.setPredMode( MODE_INTER );
+  cu.mvdL0SubPuOff = pu.dmvrOff;
+  for( int l = 0; l < 2; l++ )
+  {
+    cu.refIdx[l] = pu.refSlot[l] < 0 ? -1 : ( pu.refSlot[l] & 1 );
+    cu.mv[l][0] = Mv( pu.mv[l][0], pu.mv[l][1] ); cu.mv[l][1] = Mv( pu.cpmv[l][0][0], pu.cpmv[l][0][1] ); cu.mv[l][2] = Mv( pu.cpmv[l][1][0], pu.cpmv[l][1][1] );
+  }
+  cu.setInterDir( pu.interDir );
+  cu.setImv( ( pu.flags & B200_PU_ALTHPEL ) ? IMV_HPEL : IMV_OFF );
+  int bcwIdx = BCW_DEFAULT;
+  for( int i = 0; i < BCW_NUM; i++ ) if( getBcwWeight( g_BcwInternBcw[i], REF_PIC_LIST_1 ) == pu.bcwW1 ) bcwIdx = i;
+  cu.setBcwIdx( bcwIdx );
+  const bool wantDmvr = pu.flags & B200_PU_DMVR, wantBio = pu.flags & B200_PU_BDOF, affine = pu.flags & B200_PU_AFFINE;
+  cu.setMergeFlag( wantDmvr ); cu.setMergeType( MRG_TYPE_DEFAULT_N );
+  cu.setSmvdMode( ( !wantBio && !affine && pu.refSlot[0] >= 0 && pu.refSlot[1] >= 0 && pu.bcwW1 == 4 ) ? 1 : 0 );
+  cu.setAffineFlag( affine );
+  cu.setAffineType( ( pu.flags & B200_PU_AFFINE6 ) ? AFFINEMODEL_6PARAM : AFFINEMODEL_4PARAM );
+  if( affine ) { for( int l = 0; l < 2; l++ ) if( cu.refIdx[l] >= 0 ) PU::setAllAffineMv( cu, cu.mv[l][0], cu.mv[l][1], cu.mv[l][2], RefPicList( l ) ); }
+  PU::spanMotionInfo( cu );
+}
+
+// K1 for one record with the reference's kernels (glue restated from TrQuant.cpp:201-485 / Quant.cpp:295-381)
+static void refTuResidual( const b200_tu& tu, int bitDepth, const int16_t* coefs, TrQuant& tq, Quant& qnt, TCoeffOps& ops, TCoeff* dq, TCoeff* tmp, TCoeff* blk, Pel* resi, ptrdiff_t stride )
+{
+  const int w = 1 << tu.log2w, h = 1 << tu.log2h;
+  int maxX = tu.maxX, maxY = tu.maxY;
+  const int inputMaximum = ( 1 << ( tu.inBits - 1 ) ) - 1;
+  const int16_t* q = coefs + tu.coefOff;
+  memset( dq, 0, sizeof( TCoeff ) * w * h );
+  if( tu.flags & ( B200_TU_BDPCM_H | B200_TU_BDPCM_V ) )
+  {
+    for( int y = 0; y < h; y++ ) for( int x = 0; x < w; x++ )
+    {
+      int v = q[y * ( maxX + 1 ) + x];
+      if( ( tu.flags & B200_TU_BDPCM_H ) && x > 0 ) v = Clip3( -32768, 32767, dq[y * w + x - 1] + v );
+      if( ( tu.flags & B200_TU_BDPCM_V ) && y > 0 ) v = Clip3( -32768, 32767, dq[( y - 1 ) * w + x] + v );
+      dq[y * w + x] = v;
+    }
+    qnt.DeQuantPCM( w, w - 1, h - 1, tu.scale, dq, w, dq, tu.rightShift, inputMaximum, 32767 );
+  }
+  else
+  {
+    // the reference reads the levels in place from the reco plane (zero outside the coded corner, CABACReader.cpp:2457); its SIMD
+    // DeQuant loads groups of 4/8 levels per row, so the packed corner is first laid out with the TU's stride like the plane has it
+    alignas( 32 ) TCoeffSig lv[64 * 64];
+    const int lw = std::max( w, 8 );
+    memset( lv, 0, sizeof( TCoeffSig ) * lw * ( maxY + 1 ) );
+    for( int y = 0; y <= maxY; y++ ) memcpy( lv + y * lw, q + y * ( maxX + 1 ), ( maxX + 1 ) * sizeof( TCoeffSig ) );
+    qnt.DeQuant( w, maxX, maxY, tu.scale, lv, lw, dq, tu.rightShift, inputMaximum, 32767 );
+  }
+  if( tu.lfnst && !( tu.flags & B200_TU_TS ) )
+  {
+    static const uint8_t sx[16] = { 0,0,1,0,1,2,0,1,2,3,1,2,3,2,3,3 }, sy[16] = { 0,1,0,2,1,0,3,2,1,0,3,2,1,3,2,3 };
+    const bool big = w >= 8 && h >= 8; const int sb = big ? 8 : 4, tr = ( tu.lfnst >> 4 ) & 1;
+    int in[16], out[48];
+    for( int i = 0; i < 16; i++ ) in[i] = dq[sy[i] * w + sx[i]];
+    tq.m_invLfnstNxN( in, out, ( tu.lfnst >> 2 ) & 3, ( tu.lfnst & 3 ) - 1, sb, ( ( w == 4 && h == 4 ) || ( w == 8 && h == 8 ) ) ? 8 : 16 );
+    const int* o = out;
+    if( tr ) { if( sb == 4 ) { for( int y = 0; y < 4; y++ ) for( int x = 0; x < 4; x++ ) dq[y * w + x] = o[x * 4 + y]; }
+               else for( int y = 0; y < 8; y++ ) { for( int x = 0; x < 4; x++ ) dq[y * w + x] = o[x * 8 + y]; if( y < 4 ) for( int x = 4; x < 8; x++ ) dq[y * w + x] = o[32 + ( x - 4 ) * 4 + y]; } }
+    else for( int y = 0; y < sb; y++ ) { const int n = y < 4 ? sb : 4; for( int x = 0; x < n; x++ ) dq[y * w + x] = *o++; }
+    maxX = std::max( maxX, std::min( w - 1, 7 ) ); maxY = std::max( maxY, std::min( h - 1, 7 ) );
+  }
+  if( tu.flags & B200_TU_TS ) { for( int y = 0; y < h; y++ ) for( int x = 0; x < w; x++ ) resi[y * stride + x] = Pel( dq[y * w + x] ); return; }
+  const int trH = tu.trType & 3, trV = ( tu.trType >> 2 ) & 3, shift1 = 7, shift2 = 20 - bitDepth;
+  if( maxX == 0 && maxY == 0 && trH == DCT2 && trV == DCT2 )
+  {
+    int dc = ( dq[0] * 64 + 64 ) >> shift1; dc = ( dc * 64 + ( 1 << ( shift2 - 1 ) ) ) >> shift2;
+    for( int y = 0; y < h; y++ ) for( int x = 0; x < w; x++ ) resi[y * stride + x] = Pel( dc );
+    return;
+  }
+  const int skipW = std::max( ( trH != DCT2 && w == 32 ) ? 16 : w > 32 ? w - 32 : 0, w - maxX - 1 );
+  const int skipH = std::max( ( trV != DCT2 && h == 32 ) ? 16 : h > 32 ? h - 32 : 0, h - maxY - 1 );
+  fastInvTrans[trV][tu.log2h - 1]( dq,  tmp, shift1, w, skipW, skipH, true,  -32768, 32767 );
+  fastInvTrans[trH][tu.log2w - 1]( tmp, blk, shift2, h, 0,     skipW, false, -32768, 32767 );
+  ops.cpyResiClip[tu.log2w]( blk, resi, stride, w, h, -32768, 32767, 1 << ( shift2 - 1 ), shift2 );
+}
+
+extern "C" double ref_decompress_picture_out( const b200_geom* g, const int16_t* const* refs, const b200_picture* pic, int threads, int simd, int16_t* const out[3] )
+{
+  using clk = std::chrono::steady_clock;
+  threads = std::max( 1, threads );
+  FakePicture cur( *g, 1 );
+  std::unique_ptr<FakePicture> ref[4];
+  for( int s = 0; s < 4; s++ )
+  {
+    ref[s].reset( new FakePicture( *g, 1 ) );
+    int16_t* p3[3] = { (int16_t*) refs[s * 3], (int16_t*) refs[s * 3 + 1], (int16_t*) refs[s * 3 + 2] };
+    ref[s]->setPlanes( *g, p3 );
+    if( s ) ref[s]->pic.extendPicBorder();
+  }
+  CodingStructure& cs = *cur.pic.cs;
+  const PreCalcValues& pcv = *cs.pcv;
+  SPS& sps = *cur.sps;
+  sps.setUseBIO( true ); sps.setUseDMVR( true ); sps.setUseBcw( true ); sps.setUseAffine( true ); sps.setUseAffineType( true ); sps.setUsePROF( true );
+  sps.setUseALF( true ); sps.setUseCCALF( true );
+  cur.pps->setLoopFilterAcrossSlicesEnabledFlag( true ); cur.pps->setLoopFilterAcrossTilesEnabledFlag( true );
+  Slice* sl = cur.pic.slices[0];
+  sl->setSliceType( B_SLICE ); sl->setPOC( 8 );
+  const int pocs[4] = { 4, 0, 12, 16 };
+  for( int l = 0; l < 2; l++ ) for( int i = 0; i < 2; i++ )
+  { sl->m_apcRefPicList[l][i] = &ref[l * 2 + i]->pic; sl->m_aiRefPOCList[l][i] = pocs[l * 2 + i]; sl->m_bIsUsedAsLongTerm[l][i] = false; ref[l * 2 + i]->pic.poc = pocs[l * 2 + i]; }
+  sl->setNumRefIdx( REF_PIC_LIST_0, 2 ); sl->setNumRefIdx( REF_PIC_LIST_1, 2 );
+  sl->resetWpScaling();
+  { SliceMap sm; sm.addCtusToSlice( 0, pcv.widthInCtus, 0, pcv.heightInCtus, pcv.widthInCtus ); sl->setSliceMap( sm ); }
+  std::vector<MotionInfo> motion( (size_t) pcv.num4x4CtuBlks * pcv.sizeInCtus );
+  std::vector<Mv> dmvrCache( std::max<size_t>( pic->numDmvr + 64, (size_t) pcv.num8x8CtuBlks * pcv.sizeInCtus ) );
+  for( unsigned a = 0; a < pcv.sizeInCtus; a++ ) cs.getCtuData( a ).motion = motion.data() + (size_t) a * pcv.num4x4CtuBlks;
+  cs.m_dmvrMvCache = dmvrCache.data();
+  addCtuCUs( cur );
+  g_tCoeffOps = simd ? g_simdOps : g_scalarOps;
+
+  // deblocking / SAO / ALF parameters
+  const bool doLf = pic->flags & B200_PIC_DEBLOCK, doSao = pic->flags & B200_PIC_SAO, doAlf = pic->flags & B200_PIC_ALF;
+  if( doLf )
+  {
+    sl->setDeblockingFilterDisable( pic->lfSlices[0].disable );
+    sl->setDeblockingFilterBetaOffsetDiv2( pic->lfSlices[0].betaOffsetDiv2[0] ); sl->setDeblockingFilterTcOffsetDiv2( pic->lfSlices[0].tcOffsetDiv2[0] );
+    sl->setDeblockingFilterCbBetaOffsetDiv2( pic->lfSlices[0].betaOffsetDiv2[1] ); sl->setDeblockingFilterCbTcOffsetDiv2( pic->lfSlices[0].tcOffsetDiv2[1] );
+    sl->setDeblockingFilterCrBetaOffsetDiv2( pic->lfSlices[0].betaOffsetDiv2[2] ); sl->setDeblockingFilterCrTcOffsetDiv2( pic->lfSlices[0].tcOffsetDiv2[2] );
+    cur.setLfGrid( 0, pic->lfV ); cur.setLfGrid( 1, pic->lfH );
+  }
+  PelStorage fltBuf; fltBuf.create( pcv.chrFormat, Size( g->width, g->height ), g->ctuSize, 16, MEMORY_ALIGN_DEF_SIZE );
+  if( doSao ) for( unsigned a = 0; a < pcv.sizeInCtus; a++ )
+  {
+    SAOBlkParam& bp = cs.getCtuData( a ).saoParam; bp.reset();
+    for( int c = 0; c < 3; c++ )
+    {
+      const b200_sao_ctu& sc = pic->sao[a];
+      if( sc.type[c] == B200_SAO_OFF ) continue;
+      bp[c].modeIdc = SAO_MODE_NEW; bp[c].typeIdc = sc.type[c]; bp[c].typeAuxInfo = sc.band[c];
+      if( sc.type[c] == B200_SAO_BO ) for( int i = 0; i < 4; i++ ) bp[c].offset[( sc.band[c] + i ) & 31] = sc.offset[c][i];
+      else for( int i = 0; i < 5; i++ ) bp[c].offset[i] = sc.offset[c][i];
+    }
+  }
+  static std::shared_ptr<APS> apsStore[ALF_CTB_MAX_NUM_APS];
+  if( doAlf )
+  {
+    const b200_alf_tables* T = pic->alfTabs;
+    const APS* apss[ALF_CTB_MAX_NUM_APS] = { nullptr };
+    for( int i = 0; i < ALF_CTB_MAX_NUM_APS; i++ ) { apsStore[i] = std::make_shared<APS>(); apsStore[i]->setAPSId( i ); apss[i] = apsStore[i].get(); }
+    AlfApsIdVec ids;
+    for( int i = 0; i < T->numLumaSets - 16; i++ )
+    {
+      AlfSliceParam& p = apsStore[i]->getAlfAPSParam();
+      memcpy( p.lumaCoeffFinal, T->lumaCoeff + (size_t) ( 16 + i ) * 1300, 2600 ); memcpy( p.lumaClippFinal, T->lumaClip + (size_t) ( 16 + i ) * 1300, 2600 );
+      p.lumaFinalDone = true; ids.push_back( i );
+    }
+    sl->setNumAlfAps( T->numLumaSets - 16 ); sl->setAlfApsIdsLuma( ids );
+    AlfSliceParam& pc = apsStore[7]->getAlfAPSParam();
+    pc.numAlternativesChroma = T->numChromaAlts;
+    memcpy( pc.chromaCoeff, T->chromaCoeff, T->numChromaAlts * 14 ); memcpy( pc.chrmClippFinal, T->chromaClip, T->numChromaAlts * 14 ); pc.chrmFinalDone = true;
+    sl->setAlfApsIdChroma( 7 );
+    for( int c = 0; c < 2; c++ ) for( int k = 0; k < T->numCc[c]; k++ ) memcpy( apsStore[6 - c]->getCcAlfAPSParam().ccAlfCoeff[c][k], T->ccCoeff[c] + k * 7, 14 );
+    sl->setCcAlfCbEnabledFlag( T->numCc[0] > 0 ); sl->setCcAlfCrEnabledFlag( T->numCc[1] > 0 ); sl->setCcAlfCbApsId( 6 ); sl->setCcAlfCrApsId( 5 );
+    sl->setAlfApss( apss );
+    for( int c = 0; c < 3; c++ ) sl->setAlfEnabledFlag( ComponentID( c ), true );
+    for( unsigned a = 0; a < pcv.sizeInCtus; a++ )
+    {
+      CtuAlfData& d = cs.getCtuData( a ).alfParam;
+      for( int c = 0; c < 3; c++ ) d.alfCtuEnableFlag[c] = pic->alf[a].enable[c] & 1;
+      d.alfCtbFilterIndex = pic->alf[a].lumaSet;
+      for( int c = 0; c < 2; c++ ) { d.alfCtuAlternative[c] = pic->alf[a].chromaAlt[c]; d.ccAlfFilterControl[c] = pic->alf[a].ccIdx[c]; }
+    }
+  }
+  // per-thread resources (as DecLibRecon's m_pcThreadResource)
+  static RdCost rdScalar( false ), rdSimd( true );
+  std::vector<std::unique_ptr<InterPrediction>> ips; std::vector<std::unique_ptr<TrQuant>> tqs; std::vector<std::unique_ptr<Quant>> qns;
+  for( int t = 0; t < threads; t++ )
+  {
+    ips.emplace_back( new InterPrediction() ); ips.back()->init( simd ? &rdSimd : &rdScalar, pcv.chrFormat, g->ctuSize, simd != 0 );
+    tqs.emplace_back( new TrQuant( ips.back().get() ) ); qns.emplace_back( new Quant( nullptr, simd != 0 ) );
+  }
+  TCoeffOps ops = simd ? g_simdOps : g_scalarOps;
+  LoopFilter lf( simd != 0 );
+  SampleAdaptiveOffset sao( simd != 0 );
+  AdaptiveLoopFilter alf( simd != 0 );
+  if( doAlf ) alf.create( cur.ph.get(), cur.sps.get(), cur.pps.get(), threads, fltBuf );
+  PelUnitBuf reco = cs.getRecoBuf();
+  const int wC = pcv.widthInCtus, hC = pcv.heightInCtus;
+
+  // ------------------------------------------------------------------ timed region
+  const auto t0 = clk::now();
+  ref[0]->pic.extendPicBorder();                                   // one reference-picture border extension per picture
+  // K2: per PU (dynamic scheduling over chunks of 16 PUs)
+  {
+    const int nChunks = ( (int) pic->numPus + 15 ) / 16;
+    parallelFor( nChunks, threads, [&]( int ch, int t ) {
+      CodingUnit cu;
+      for( size_t n = (size_t) ch * 16; n < std::min<size_t>( pic->numPus, (size_t) ch * 16 + 16 ); n++ )
+      {
+        const b200_pu& pu = pic->pus[n];
+        fillCuFromPu( cu, pu, cur, sl );
+        PelUnitBuf predBuf = reco.subBuf( UnitArea( pcv.chrFormat, Area( pu.x, pu.y, pu.w, pu.h ) ) );   // rootCbf==0 style: MC writes straight into the picture (DecCu.cpp:405)
+        ips[t]->motionCompensation( cu, predBuf, true, true );
+      }
+    } );
+  }
+  // K1: per TU chunk
+  {
+    const int nChunks = ( (int) pic->numTus + 31 ) / 32;
+    parallelFor( nChunks, threads, [&]( int ch, int t ) {
+      TCoeff* dq  = tqs[t]->m_dqnt; TCoeff* tmp = tqs[t]->m_tmp; TCoeff* blk = tqs[t]->m_blk;
+      alignas( 32 ) Pel r0[64 * 64]; alignas( 32 ) Pel r1[64 * 64];
+      const int pmax = ( 1 << g->bitDepth ) - 1;
+      for( size_t n = (size_t) ch * 32; n < std::min<size_t>( pic->numTus, (size_t) ch * 32 + 32 ); n++ )
+      {
+        const b200_tu& tu = pic->tus[n];
+        const int w = 1 << tu.log2w, h = 1 << tu.log2h;
+        refTuResidual( tu, g->bitDepth, pic->coefs, *tqs[t], *qns[t], ops, dq, tmp, blk, r0, w );
+        int nOut = 1, comp1 = 0;
+        if( tu.ict ) { comp1 = tu.comp == 1 ? 2 : 1; nOut = 2; const int m = tu.ict; for( int i = 0; i < w * h; i++ ) { const int c = r0[i]; r1[i] = Pel( m == 2 ? c : m == -2 ? -c : m > 0 ? ( c >> 1 ) : ( ( -c ) >> 1 ) ); } }
+        for( int o = 0; o < nOut; o++ )
+        {
+          PelBuf pb = reco.bufs[o ? comp1 : tu.comp]; const Pel* r = o ? r1 : r0;
+          Pel* d = pb.buf + tu.y * pb.stride + tu.x;
+          for( int y = 0; y < h; y++, d += pb.stride, r += w ) for( int x = 0; x < w; x++ ) d[x] = Pel( Clip3( 0, pmax, d[x] + r[x] ) );   // recoCore, Buffer.cpp:83
+        }
+      }
+    } );
+  }
+  if( doLf )
+  {
+    parallelFor( wC * hC, threads, [&]( int a, int ) { lf.loopFilterCTU( cs, MAX_NUM_CHANNEL_TYPE, a % wC, a / wC, EDGE_VER ); } );
+    parallelFor( wC * hC, threads, [&]( int a, int ) { lf.loopFilterCTU( cs, MAX_NUM_CHANNEL_TYPE, a % wC, a / wC, EDGE_HOR ); } );
+  }
+  if( doSao )
+  {
+    fltBuf.copyFrom( cs.getRecoBuf() );                              // SAOPrepareCTULine copies the deblocked rows (SampleAdaptiveOffset.cpp:400)
+    sao.create( g->width, g->height, pcv.chrFormat, g->ctuSize, g->ctuSize, 0, 0, fltBuf );
+    parallelFor( wC * hC, threads, [&]( int a, int ) {
+      sao.SAOProcessCTU( cs, clipArea( UnitArea( pcv.chrFormat, Area( ( a % wC ) * g->ctuSize, ( a / wC ) * g->ctuSize, g->ctuSize, g->ctuSize ) ), cur.pic ) ); } );
+  }
+  if( doAlf )
+  {
+    parallelFor( wC * hC, threads, [&]( int a, int ) { alf.prepareCTU( cs, a % wC, a / wC ); } );
+    parallelFor( wC * hC, threads, [&]( int a, int t ) { alf.processCTU( cs, a % wC, a / wC, t ); } );
+  }
+  const double secs = std::chrono::duration<double>( clk::now() - t0 ).count();
+  if( out ) { if( doAlf ) cur.getPlanes( *g, out, true, &fltBuf ); else cur.getPlanes( *g, out ); }
+  return secs;
+}
+
+extern "C" double ref_decompress_picture_mt( const b200_geom* g, const int16_t* const* refs, const b200_picture* pic, int threads, int simd )
+{
+  return ref_decompress_picture_out( g, refs, pic, threads, simd, nullptr );
 }

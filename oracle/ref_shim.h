@@ -88,6 +88,16 @@ int ref_alf_picture(int simd, const b200_geom* g, const int16_t* const src[3], i
 int ref_mc_predict(int simd, const b200_geom* g, int16_t* const dst[3], const int16_t* const* refs, const b200_pu* pus, size_t numPus,
                    int32_t* dmvrMv, size_t numDmvr);
 
+/* ---- whole back end on the host cores: the CPU baseline / reference arm of bench.py ----
+ * Runs one picture (same b200_picture work lists the GPU gets, references = 4 DPB slots) through the REFERENCE's kernels with
+ * `threads` std::threads: K2 = real InterPrediction::motionCompensation per PU; K1 = the reference's DeQuant / invLfnst /
+ * fastInvTrans / cpyResiClip pointers driven per TU (the TU walk is restated, the arithmetic is the reference's); K3 = real
+ * LoopFilter::loopFilterCTU; K4 = real SAOProcessCTU; K5 = real ALF prepareCTU + processCTU. Reference-picture border extension
+ * of one picture is included (every picture is extended once when it becomes a reference, DecLibRecon.cpp:236).
+ * Returns the seconds spent in the timed part (setup of the fake vvdec objects excluded); out (may be NULL) receives the picture. */
+double ref_decompress_picture_mt(const b200_geom* g, const int16_t* const* refs, const b200_picture* pic, int threads, int simd);
+double ref_decompress_picture_out(const b200_geom* g, const int16_t* const* refs, const b200_picture* pic, int threads, int simd, int16_t* const out[3]);
+
 #ifdef __cplusplus
 }
 #endif

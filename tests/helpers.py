@@ -71,6 +71,10 @@ def load_ref():
     lib.ref_alf_picture.argtypes = [C.c_int, C.POINTER(abi.Geom), PL, PL, V, C.POINTER(abi.AlfTables)]
     lib.ref_mc_predict.argtypes = [C.c_int, C.POINTER(abi.Geom), PL, C.POINTER(C.c_void_p), V, C.c_size_t, V, C.c_size_t]
     lib.ref_mc_predict.restype = C.c_int
+    lib.ref_decompress_picture_out.argtypes = [C.POINTER(abi.Geom), C.POINTER(C.c_void_p), C.POINTER(abi.Picture), C.c_int, C.c_int, PL]
+    lib.ref_decompress_picture_out.restype = C.c_double
+    lib.ref_decompress_picture_mt.argtypes = [C.POINTER(abi.Geom), C.POINTER(C.c_void_p), C.POINTER(abi.Picture), C.c_int, C.c_int]
+    lib.ref_decompress_picture_mt.restype = C.c_double
     return lib
 
 

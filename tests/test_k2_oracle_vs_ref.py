@@ -59,7 +59,7 @@ def test_dmvr(oracle, ref, simd):
 
 @pytest.mark.parametrize("simd", [0, 1])
 def test_affine_prof(oracle, ref, simd):
-    pus, nd, refs = _case(4, 416, 240, 10, p_dmvr=0, p_bdof=0, p_affine=0.9)
+    pus, nd, refs = _case(4, 416, 240, 10, p_dmvr=0, p_bdof=0, p_affine=0.9, p_prof=0.8)
     _compare(oracle, ref, simd, 416, 240, 10, pus, nd, refs)
     f = pus["flags"]
     assert (f & synth.PU_AFFINE).sum() > 20 and (f & synth.PU_AFFINE6).any() and (f & synth.PU_PROF0).any()

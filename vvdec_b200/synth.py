@@ -98,13 +98,19 @@ def gen_tus(rng, cus, bit_depth=10, p_cbf=0.5, p_mts=0.2, p_lfnst=0.1, p_ts=0.05
                         limx = min(w, 32) if not (tr & 3 and w == 32) else 16
                         limy = min(h, 32) if not ((tr >> 2) & 3 and h == 32) else 16
                         if lfnst:
-                            # at most 16 (8 for 4x4/8x8) levels in scan order: keep inside the first 4x4 diagonal prefix
-                            maxX, maxY = int(rng.integers(0, 3)), int(rng.integers(0, 2))
+                            # at most 16 (8 for 4x4/8x8) levels in scan order, all inside the first 4x4 coefficient group
+                            maxX, maxY = 3, 3
                         elif rng.random() < p_full:
                             maxX, maxY = limx - 1, limy - 1
                         else:
                             maxX = min(limx - 1, int(rng.geometric(0.25)) - 1)
                             maxY = min(limy - 1, int(rng.geometric(0.25)) - 1)
+                        if not (flags & abi.TU_TS) and not (maxX == 0 and maxY == 0):
+                            # the parser reports the coded corner in whole coefficient groups (CABACReader.cpp:2447-2452): 4x4, or
+                            # 2x8 / 8x2 for 2-wide / 2-high blocks; only a lone DC coefficient gives (0,0)
+                            cgw, cgh = (2, 8) if w == 2 else (8, 2) if h == 2 else (4, 4)
+                            maxX = min(limx, (maxX // cgw + 1) * cgw) - 1
+                            maxY = min(limy, (maxY // cgh + 1) * cgh) - 1
                     is_ts = bool(flags & abi.TU_TS)
                     sqrt2 = (not is_ts) and ((l2w + l2h) & 1)
                     dq = dep_quant and not is_ts
@@ -284,7 +290,7 @@ assert PU_DTYPE.itemsize == 64
 PU_BDOF, PU_DMVR, PU_ALTHPEL, PU_AFFINE, PU_AFFINE6, PU_PROF0, PU_PROF1 = 1, 2, 4, 8, 16, 32, 64
 
 
-def gen_pus(rng, cus, W, H, p_inter=1.0, p_bi=0.6, p_dmvr=0.35, p_bdof=0.35, p_affine=0.12, p_bcw=0.15, mv_sigma=6.0, p_int_mv=0.15):
+def gen_pus(rng, cus, W, H, p_inter=1.0, p_bi=0.6, p_dmvr=0.35, p_bdof=0.35, p_affine=0.12, p_bcw=0.15, mv_sigma=6.0, p_int_mv=0.15, p_prof=1.0):
     """Inter PU records for a CU list (MVs ~ N(0, 6 px) in 1/16 units; refs from 4 DPB slots:
     list 0 = {0, 1}, list 1 = {2, 3}; (0,2) and (1,3) are the equal-POC-distance pairs that allow BDOF / DMVR)."""
     recs = []
@@ -322,7 +328,7 @@ def gen_pus(rng, cus, W, H, p_inter=1.0, p_bi=0.6, p_dmvr=0.35, p_bdof=0.35, p_a
             r["interDir"] = 1 + l
         if not (flags & (PU_DMVR | PU_BDOF)) and w >= 8 and h >= 8 and rng.random() < p_affine:
             flags |= PU_AFFINE | (PU_AFFINE6 if rng.random() < 0.5 else 0)
-            if rng.random() < 0.8: flags |= PU_PROF0 | PU_PROF1
+            if rng.random() < p_prof: flags |= PU_PROF0 | PU_PROF1   # PROF is a sequence/picture-level switch (sps_prof / ph_prof_disabled)
             big_d = rng.random() < 0.15
             for l in range(2):
                 d = rng.integers(-400, 401, size=(2, 2)) if big_d else rng.integers(-24, 25, size=(2, 2))
