@@ -59,13 +59,17 @@ struct KProf { virtual void begin(int family, cudaStream_t s) = 0; virtual void 
 struct K1Launch {
   b200_geom      geom;
   DevPlanes      planes;
-  const b200_tu* tus;
+  const b200_tu* tus;        // device, bucketed by size class (see k1_class_of): clsCount[0] records of class 0 first, ...
   size_t         numTus;
+  size_t         clsCount[4];
   const int16_t* coefs;
   const int32_t* scaling;
   int            mode;    // 0: reco = clip(pred + resi); 1: store residual
 };
 int launch_k1_residual(const K1Launch& L, cudaStream_t s, KProf* prof = nullptr);
+int k1_class_of(const b200_tu& t);
+// host: stable bucket sort of TU records by size class into `out`, counts into clsCount
+void bucket_tus(const b200_tu* tus, size_t n, std::vector<b200_tu>& out, size_t clsCount[4]);
 
 struct LfSliceTab { b200_lf_slice s[64]; };
 struct LfLaunch {
@@ -91,13 +95,18 @@ struct McLaunch {
   const int16_t* refs[B200_MAX_SLOTS * 3];   // device plane pointers per DPB slot
   int refStride[3];
   const b200_pu* pus;               // device
-  const uint32_t *tilesT, *tilesA;  // device tile lists: translational (regular/BDOF/DMVR) and affine; (puIdx<<6)|(ty<<3)|tx
-  int numTilesT, numTilesA;
+  // device tile lists, tile = (puIdx<<6)|(ty<<3)|tx.  Translational tiles are bucketed by [mode: 0 uni,1 bi,2 BDOF,3 DMVR][log2(samples)-5: 32,64,128,256]
+  struct Cls { const uint32_t* tiles; int n; } cls[4][4];
+  const uint32_t* tilesA; int numTilesA;
   int32_t* dmvrMv;                  // device or null
 };
 int launch_mc(const McLaunch& L, cudaStream_t s, KProf* prof = nullptr);
 // host: expand PUs into <=16x16 tiles
-void build_mc_tiles(const b200_pu* pus, size_t numPus, std::vector<uint32_t>& tilesT, std::vector<uint32_t>& tilesA);
+struct McTileLists { std::vector<uint32_t> cls[4][4], aff; size_t total() const { size_t n = aff.size(); for (auto& m : cls) for (auto& v : m) n += v.size(); return n; } };
+void build_mc_tiles(const b200_pu* pus, size_t numPus, McTileLists& out);
+// copies the bucketed lists back to back into a device buffer (async) and fills L.cls / L.tilesA
+int upload_mc_tiles(const McTileLists& T, uint32_t* dev, McLaunch& L, cudaStream_t s);
+int mc_launch_count(const McLaunch& L);
 
 int ensure_device();   // selects device 0 if none current; fails loudly when there is no sm_100 GPU
 

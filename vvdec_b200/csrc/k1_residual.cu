@@ -18,8 +18,10 @@
 namespace b200 {
 
 constexpr int K1_WARPS = 8;
-constexpr int K1_CBUF  = 32 * 32;   // int16 coefficients (coded corner is at most 32x32)
-constexpr int K1_TBUF  = 32 * 64;   // int16 stage-1 output: <=32 non-zero columns x <=64 rows
+// TU size classes (host buckets the records, order inside a picture is irrelevant: TUs never overlap):
+//   class 0: w,h <= 8   class 1: <= 16   class 2: <= 32   class 3: a 64 dimension
+// per warp: CB int16 dequantised coefficients (coded corner, at most min(w,32)*min(h,32)), TB int16 stage-1 output (<= min(w,32)*h)
+template <int CLS> struct K1Cfg { static constexpr int CB = CLS == 0 ? 64 : CLS == 1 ? 256 : 1024, TB = CLS == 0 ? 64 : CLS == 1 ? 256 : CLS == 2 ? 1024 : 2048; };
 
 __device__ __forceinline__ const int16_t* tr_matrix(int trType, int log2n)
 {
@@ -38,13 +40,14 @@ __device__ __forceinline__ int dequant_one(int level, int scale, int rightShift,
   return clip16(v);
 }
 
+template <int CLS>
 __global__ void __launch_bounds__(K1_WARPS * 32)
 k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* __restrict__ coefs,
                    const int32_t* __restrict__ scaling, int16_t* p0, int16_t* p1, int16_t* p2,
                    int s0, int s1, int s2, int bitDepth, int mode)
 {
-  __shared__ int16_t s_c[K1_WARPS][K1_CBUF];
-  __shared__ int16_t s_t[K1_WARPS][K1_TBUF];
+  __shared__ int16_t s_c[K1_WARPS][K1Cfg<CLS>::CB];
+  __shared__ int16_t s_t[K1_WARPS][K1Cfg<CLS>::TB];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * K1_WARPS + warp;
@@ -144,14 +147,11 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* _
   }
 
   // ---- output helpers ----
-  int16_t* const planes[3] = {p0, p1, p2};
-  const int strides[3] = {s0, s1, s2};
   const int pmax = (1 << bitDepth) - 1;
-  int16_t* dst0 = planes[comp] + (size_t)ty * strides[comp] + tx;
-  const int ds0 = strides[comp];
-  const int comp1 = comp == 1 ? 2 : 1;
-  int16_t* dst1 = ict ? planes[comp1] + (size_t)ty * strides[comp1] + tx : nullptr;
-  const int ds1 = strides[comp1];
+  const int ds0 = comp == 0 ? s0 : comp == 1 ? s1 : s2;
+  int16_t* dst0 = (comp == 0 ? p0 : comp == 1 ? p1 : p2) + (size_t)ty * ds0 + tx;
+  const int ds1 = comp == 1 ? s2 : s1;                       // the other chroma plane (joint CbCr)
+  int16_t* dst1 = ict ? (comp == 1 ? p2 : p1) + (size_t)ty * ds1 + tx : nullptr;
 
   auto emit = [&](int x, int y, int r) {
     int16_t* d = dst0 + y * ds0 + x;
@@ -215,15 +215,24 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* _
   }
 }
 
+int k1_class_of(const b200_tu& t) { const int m = t.log2w > t.log2h ? t.log2w : t.log2h; return m <= 3 ? 0 : m == 4 ? 1 : m == 5 ? 2 : 3; }
+
 int launch_k1_residual(const K1Launch& L, cudaStream_t s, KProf* prof)
 {
   if (L.numTus == 0) return 0;
   if (prof) prof->begin(B200_KF_K1, s);
-  const int grid = (int)((L.numTus + K1_WARPS - 1) / K1_WARPS);
-  k1_residual_kernel<<<grid, K1_WARPS * 32, 0, s>>>(L.tus, (int)L.numTus, L.coefs, L.scaling, L.planes.p[0], L.planes.p[1],
-                                                    L.planes.p[2], L.planes.stride[0], L.planes.stride[1],
-                                                    L.planes.stride[2], L.geom.bitDepth, L.mode);
-  B200_CUDA(cudaGetLastError());
+  size_t off = 0;
+  for (int c = 0; c < 4; c++) {
+    const size_t n = L.clsCount[c];
+    if (!n) continue;
+    const int grid = (int)((n + K1_WARPS - 1) / K1_WARPS);
+#define K1_GO(C) k1_residual_kernel<C><<<grid, K1_WARPS * 32, 0, s>>>(L.tus + off, (int)n, L.coefs, L.scaling, L.planes.p[0], L.planes.p[1], L.planes.p[2], \
+                                                                   L.planes.stride[0], L.planes.stride[1], L.planes.stride[2], L.geom.bitDepth, L.mode)
+    switch (c) { case 0: K1_GO(0); break; case 1: K1_GO(1); break; case 2: K1_GO(2); break; default: K1_GO(3); break; }
+#undef K1_GO
+    B200_CUDA(cudaGetLastError());
+    off += n;
+  }
   if (prof) prof->end(B200_KF_K1, s);
   return 0;
 }

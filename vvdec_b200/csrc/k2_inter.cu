@@ -73,265 +73,353 @@ __device__ int div_for_maxq7(long long N, long long D)
 }
 
 // ------------------------------------------------------------------------------------------------ translational tiles (+BDOF, DMVR)
-constexpr int WS = 24;   // luma window row stride (23 used)
+// MODE: 0 uni, 1 bi (average / BCW), 2 bi + BDOF, 3 DMVR (+BDOF per sub-block).  blockDim.x = tw*th (32..256): one thread per luma
+// sample; tw, th are powers of two (4, 8, 16), so all index arithmetic is shifts.  Dynamic shared memory, laid out per launch class.
+struct TileSmem {
+  int16_t *w[2], *h[2];           // luma window (stride tw+7) and H-filtered rows (stride tw) per list
+  int16_t *cw[2][2], *chf[2][2];  // chroma [list][comp]: window (stride cw+3), H-filtered rows (stride cw)
+  int16_t *p[2], *g[2][2];        // BDOF: 14-bit predictions with ring (stride tw+2), gradX/gradY
+};
 
-__global__ void __launch_bounds__(256) mc_tile_kernel(const McParams P)
+__host__ __device__ inline int mc_smem_elems(int mode, int n)   // n = tw*th; worst case over the shapes of that size
 {
-  __shared__ int16_t sW[2][23 * WS];        // luma windows / (DMVR) bilinear buffers 20x20
-  __shared__ int16_t sHf[2][23 * 16];       // after horizontal filter
-  __shared__ int16_t sP[2][18 * 18];        // 14-bit predictions with 1-sample ring
-  __shared__ int16_t sG[2][2][18 * 18];     // gradX / gradY
-  __shared__ int     sVxy[16][2];
+  // window: 16x16 -> 23x23; 128 -> 23x15; 64 -> 23x11 (>15x15); 32 -> 15x11.  hf: (th+7)*tw worst = n + 7*16|8.
+  const int win = n == 256 ? 529 : n == 128 ? 345 : n == 64 ? 253 : 165;
+  const int hf  = n + 7 * (n >= 64 ? 16 : 8);
+  const int cwin = n == 256 ? 121 : n == 128 ? 77 : n == 64 ? 55 : 35;     // (cw+3)(ch+3)
+  const int chf = (n >> 2) + 3 * (n >= 64 ? 8 : 4);
+  const int lists = mode == 0 ? 1 : 2;
+  int e = lists * (win + hf + 2 * (cwin + chf));
+  if (mode >= 2) e += 2 * 324 + 4 * 324;                                   // P + gradients (18x18)
+  if (mode == 3) e = max(e, 2 * 400) + 0;                                   // bilinear 20x20 x2 shares the window area
+  return (e + 64) & ~1;
+}
+
+template <int MODE>
+__global__ void mc_kernel(const McParams P)
+{
+  extern __shared__ int16_t smem[];
   __shared__ unsigned sSad[25];
-  __shared__ int     sDec[4];               // dmvX, dmvY, bio, -
-  __shared__ int16_t sCW[4][11 * 12], sCH[4][11 * 8], sCP[4][64];
+  __shared__ int sDec[3];
+  __shared__ int sVxy[16][2];
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
   const uint32_t tile = P.tiles[blockIdx.x];
-  const b200_pu pu = P.pus[tile >> 6];
+  const b200_pu& pu = P.pus[tile >> 6];
+  const int puW = pu.w, puH = pu.h, puX = pu.x, puY = pu.y, flags = pu.flags;
   const int tx0 = (tile & 7) * 16, ty0 = ((tile >> 3) & 7) * 16;
-  const int tw = min(16, pu.w - tx0), th = min(16, pu.h - ty0);
-  const int bx = pu.x + tx0, by = pu.y + ty0;              // tile position (luma)
+  const int tw = min(16, puW - tx0), th = min(16, puH - ty0);
+  const int l2w = 31 - __clz(tw);
+  const int bx = puX + tx0, by = puY + ty0;
   const int bd = P.bitDepth, pmax = (1 << bd) - 1, hr = max(2, 14 - bd), sh1 = 6 - hr;
-  const bool bi = pu.refSlot[0] >= 0 && pu.refSlot[1] >= 0;
-  const bool altHpel = pu.flags & B200_PU_ALTHPEL;
-  const bool dmvr = pu.flags & B200_PU_DMVR;
-  const bool is4x4 = pu.w == 4 && pu.h == 4;   // InterpolationFilter::filterHor/Ver pick the 6-tap table for 4x4 blocks (:1062,:1155)
-  bool bio = pu.flags & B200_PU_BDOF;
-  const int nList = bi ? 2 : 1, l0 = pu.refSlot[0] >= 0 ? 0 : 1;
+  constexpr bool BI = MODE != 0;
+  const bool altHpel = flags & B200_PU_ALTHPEL;
+  const bool is4x4 = puW == 4 && puH == 4;
+  const int l0 = BI ? 0 : (pu.refSlot[0] >= 0 ? 0 : 1);     // first (or only) list
+  constexpr int NL = BI ? 2 : 1;
+  const int cw = tw >> 1, ch = th >> 1, l2cw = l2w - 1;
+  const int chroma = P.chroma;
 
-  RefPl R[2][3];
+  // ---- shared memory carve-up (strides depend on the tile shape) ----
+  TileSmem S;
+  {
+    int16_t* q = smem;
+    const int win = (tw + 7) * (th + 7), hf = (th + 7) * tw, cwin = (cw + 3) * (ch + 3), chf = (ch + 3) * cw;
 #pragma unroll
-  for (int l = 0; l < 2; l++)
+    for (int l = 0; l < NL; l++) { S.w[l] = q; q += win; S.h[l] = q; q += hf; }
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-      const int slot = pu.refSlot[l] < 0 ? 0 : pu.refSlot[l];
-      R[l][c].p = P.refs[slot * 3 + c]; R[l][c].w = c ? P.W >> 1 : P.W; R[l][c].h = c ? P.H >> 1 : P.H; R[l][c].stride = P.refStride[c];
-    }
-
-  int mv[2][2];                                             // MV used for the final MC (clipped)
-  Win win[2][2];                                            // [list][luma|chroma] access windows
-  int org[2][2][2];                                         // [list][luma|chroma][x|y]: integer reference position of output sample (0,0)
+    for (int l = 0; l < NL; l++)
 #pragma unroll
-  for (int l = 0; l < 2; l++) {
-    mv[l][0] = pu.mv[l][0]; mv[l][1] = pu.mv[l][1];
-    clip_mv(mv[l][0], mv[l][1], pu.x, pu.y, P);            // relative to the CU (xPredInterUni :651; xinitMC :1811)
-#pragma unroll
-    for (int k = 0; k < 2; k++) { win[l][k].x0 = win[l][k].y0 = -(1 << 20); win[l][k].x1 = win[l][k].y1 = 1 << 20; }
+      for (int c = 0; c < 2; c++) { S.cw[l][c] = q; q += cwin; S.chf[l][c] = q; q += chf; }
+    if (MODE >= 2) { S.p[0] = q; q += 324; S.p[1] = q; q += 324; S.g[0][0] = q; q += 324; S.g[0][1] = q; q += 324; S.g[1][0] = q; q += 324; S.g[1][1] = q; q += 324; }
   }
 
-  // ================================================================ DMVR search (xProcessDMVR :1847)
-  if (dmvr) {
-    // bilinear 10-bit predictions (tw+4)x(th+4) around the clipped merge MV - 2 (xinitMC :1804)
-    for (int i = tid; i < 2 * (tw + 4) * (th + 4); i += 256) {
-      const int l = i / ((tw + 4) * (th + 4)), j = i - l * (tw + 4) * (th + 4);
-      const int y = j / (tw + 4), x = j - y * (tw + 4);
-      // the search buffer of the whole CU starts at CU + mv - 2; this tile's part starts tx0,ty0 further
-      const int mx = mv[l][0] - 32, my = mv[l][1] - 32;
-      const int xF = mx & 15, yF = my & 15, X = pu.x + tx0 + (mx >> 4) + x, Y = pu.y + ty0 + (my >> 4) + y;
-      const int8_t* fh = kIfBilin4 + xF * 2; const int8_t* fv = kIfBilin4 + yF * 2;
+  // ---- per-list reference planes and motion ----
+  const int16_t* rp[NL][3]; int mvx[NL], mvy[NL];
+#pragma unroll
+  for (int li = 0; li < NL; li++) {
+    const int l = BI ? li : l0;
+    const int slot = pu.refSlot[l];
+#pragma unroll
+    for (int c = 0; c < 3; c++) rp[li][c] = P.refs[slot * 3 + c];
+    mvx[li] = pu.mv[l][0]; mvy[li] = pu.mv[l][1];
+  }
+  const int W = P.W, H = P.H, CWp = W >> 1, CHp = H >> 1, rs0 = P.refStride[0], rs1 = P.refStride[1];
+  int ox[NL], oy[NL], ocx[NL], ocy[NL];                       // integer reference position of output (0,0), luma / chroma
+  int wx0[NL][2], wy0[NL][2], wx1[NL][2], wy1[NL][2];         // DMVR padded-window limits [list][luma|chroma]
+  int fmx[NL], fmy[NL];                                       // final (clipped) MVs
+  bool bio = MODE == 2;
+
+  if (MODE == 3) {
+    // ================================================================ DMVR search (xProcessDMVR :1847)
+    int16_t* B0 = smem; int16_t* B1 = smem + 400;            // bilinear buffers 20x20 (stride 20)
+    const int BW = tw + 4, BH = th + 4;
+#pragma unroll
+    for (int li = 0; li < 2; li++) {
+      int cx = mvx[li], cy = mvy[li];
+      clip_mv(cx, cy, puX, puY, P);                          // xinitMC :1811: relative to the CU
+      const int mx = cx - 32, my = cy - 32;
+      const int xF = mx & 15, yF = my & 15, X0 = puX + tx0 + (mx >> 4), Y0 = puY + ty0 + (my >> 4);
+      const int f0 = kIfBilin4[xF * 2], f1 = kIfBilin4[xF * 2 + 1], g0 = kIfBilin4[yF * 2], g1 = kIfBilin4[yF * 2 + 1];
       const int s1 = 4 - (10 - bd), o1 = 1 << (s1 - 1);
-      const RefPl& r = R[l][0];
-      int v;
-      if (xF == 0 && yF == 0) v = ldc(r, X, Y) << (10 - bd);
-      else if (yF == 0) v = (fh[0] * ldc(r, X, Y) + fh[1] * ldc(r, X + 1, Y) + o1) >> s1;
-      else if (xF == 0) v = (fv[0] * ldc(r, X, Y) + fv[1] * ldc(r, X, Y + 1) + o1) >> s1;
-      else {
-        const int a = (int16_t)((fh[0] * ldc(r, X, Y) + fh[1] * ldc(r, X + 1, Y) + o1) >> s1);
-        const int b = (int16_t)((fh[0] * ldc(r, X, Y + 1) + fh[1] * ldc(r, X + 1, Y + 1) + o1) >> s1);
-        v = (fv[0] * a + fv[1] * b + 8) >> 4;
+      const int16_t* r = rp[li][0];
+      int16_t* B = li ? B1 : B0;
+      for (int y = tid >> 5; y < BH; y += nthr >> 5) {
+        const int x = tid & 31;
+        if (x < BW) {
+          const int Y = min(max(Y0 + y, 0), H - 1), Y1 = min(max(Y0 + y + 1, 0), H - 1), X = min(max(X0 + x, 0), W - 1), X1 = min(max(X0 + x + 1, 0), W - 1);
+          const int a00 = r[(size_t)Y * rs0 + X];
+          int v;
+          if (xF == 0 && yF == 0) v = a00 << (10 - bd);
+          else if (yF == 0) v = (f0 * a00 + f1 * r[(size_t)Y * rs0 + X1] + o1) >> s1;
+          else if (xF == 0) v = (g0 * a00 + g1 * r[(size_t)Y1 * rs0 + X] + o1) >> s1;
+          else {
+            const int a = (int16_t)((f0 * a00 + f1 * r[(size_t)Y * rs0 + X1] + o1) >> s1);
+            const int b = (int16_t)((f0 * r[(size_t)Y1 * rs0 + X] + f1 * r[(size_t)Y1 * rs0 + X1] + o1) >> s1);
+            v = (g0 * a + g1 * b + 8) >> 4;
+          }
+          B[y * 20 + x] = (int16_t)v;
+        }
       }
-      sW[l][y * WS + x] = (int16_t)v;
     }
     if (tid < 25) sSad[tid] = 0;
     __syncthreads();
-    if (tid < 200) {                                       // SAD over every second row (RdCost.cpp:113-135), 25 positions x 8 rows
-      const int p = tid >> 3, y = (tid & 7) * 2;
-      if (y < th) {
-        const int u = p % 5 - 2, v = p / 5 - 2;
-        const int16_t* a = &sW[0][(2 + v + y) * WS + 2 + u]; const int16_t* b = &sW[1][(2 - v + y) * WS + 2 - u];
-        unsigned s = 0;
-        for (int x = 0; x < tw; x++) s += abs(a[x] - b[x]);
-        atomicAdd(&sSad[p], s);
-      }
+    // SAD over every second row (RdCost.cpp:113-135): item = (position p, row pair r); each item sums tw columns
+    for (int it = tid; it < 25 * (th >> 1); it += nthr) {
+      const int p = it / (th >> 1), y = (it - p * (th >> 1)) * 2;
+      const int u = p % 5 - 2, v = p / 5 - 2;
+      const int16_t* a = B0 + (2 + v + y) * 20 + 2 + u; const int16_t* b = B1 + (2 - v + y) * 20 + 2 - u;
+      unsigned s = 0;
+      for (int x = 0; x < tw; x++) s += abs(a[x] - b[x]);
+      atomicAdd(&sSad[p], s);
     }
     __syncthreads();
     if (tid == 0) {
-      unsigned sads[25];
-      for (int i = 0; i < 25; i++) sads[i] = sSad[i];
-      unsigned minCost = sads[12]; minCost -= minCost >> 2;  // (:1924-1925)
+      unsigned minCost = sSad[12]; minCost -= minCost >> 2;  // (:1924-1925)
       int dx = 0, dy = 0;
       if (minCost >= (unsigned)(tw * th)) {
-        sads[12] = minCost;
-        int bu = 0, bv = 0;
-        for (int i = 0; i < 25; i++) if (sads[i] < minCost) { minCost = sads[i]; bu = i % 5 - 2; bv = i / 5 - 2; }   // xBIPMVRefine, raster order, strict <
+        const unsigned c12 = minCost;
+        int bi_ = 12;
+        for (int i = 0; i < 25; i++) { const unsigned v = i == 12 ? c12 : sSad[i]; if (v < minCost) { minCost = v; bi_ = i; } }   // xBIPMVRefine: raster order, strict <
+        const int bu = bi_ % 5 - 2, bv = bi_ / 5 - 2;
         dx = bu * 16; dy = bv * 16;
-        if (abs(dx) != 32 && abs(dy) != 32) {              // xDMVRSubPixelErrorSurface / xSubPelErrorSrfc
-          const unsigned* c = &sads[(bv + 2) * 5 + bu + 2];
-          const unsigned long long s0 = c[0], sl = c[-1], st = c[-5], sr = c[1], sb = c[5];
-          {
-            const long long num = (long long)(sl - sr) * 16, den = (long long)(sl + sr - (s0 << 1));
-            if (den != 0) dx += (sl != s0 && sr != s0) ? div_for_maxq7(num, den) : (sl == s0 ? -8 : 8);
-          }
-          {
-            const long long num = (long long)(st - sb) * 16, den = (long long)(st + sb - (s0 << 1));
-            if (den != 0) dy += (st != s0 && sb != s0) ? div_for_maxq7(num, den) : (st == s0 ? -8 : 8);
-          }
+        if (abs(dx) != 32 && abs(dy) != 32) {                // xDMVRSubPixelErrorSurface / xSubPelErrorSrfc
+          auto at = [&](int i) -> unsigned long long { return i == 12 ? c12 : sSad[i]; };
+          const unsigned long long s0 = at(bi_), sl = at(bi_ - 1), st = at(bi_ - 5), sr = at(bi_ + 1), sb = at(bi_ + 5);
+          { const long long num = (long long)(sl - sr) * 16, den = (long long)(sl + sr - (s0 << 1));
+            if (den != 0) dx += (sl != s0 && sr != s0) ? div_for_maxq7(num, den) : (sl == s0 ? -8 : 8); }
+          { const long long num = (long long)(st - sb) * 16, den = (long long)(st + sb - (s0 << 1));
+            if (den != 0) dy += (st != s0 && sb != s0) ? div_for_maxq7(num, den) : (st == s0 ? -8 : 8); }
         }
       }
-      sDec[0] = dx; sDec[1] = dy;
-      sDec[2] = (minCost < (unsigned)(2 * tw * th)) ? 0 : 1;  // bioAppliedSubblk (:1984)
+      sDec[0] = dx; sDec[1] = dy; sDec[2] = (minCost < (unsigned)(2 * tw * th)) ? 0 : 1;   // bioAppliedSubblk (:1984)
       if (P.dmvrMv) {
-        const int num = (ty0 >> 4) * max(1, pu.w >> 4) + (tx0 >> 4);
+        const int num = (ty0 >> 4) * max(1, puW >> 4) + (tx0 >> 4);
         P.dmvrMv[(pu.dmvrOff + num) * 2] = dx; P.dmvrMv[(pu.dmvrOff + num) * 2 + 1] = dy;
       }
     }
     __syncthreads();
-    bio = bio && sDec[2];
+    bio = (flags & B200_PU_BDOF) && sDec[2];
     const int dmx = sDec[0], dmy = sDec[1];
 #pragma unroll
-    for (int l = 0; l < 2; l++) {
-      const int mrgx = pu.mv[l][0], mrgy = pu.mv[l][1];
-      const int rx = clip3(-(1 << 17), (1 << 17) - 1, l ? mrgx - dmx : mrgx + dmx), ry = clip3(-(1 << 17), (1 << 17) - 1, l ? mrgy - dmy : mrgy + dmy);
+    for (int li = 0; li < 2; li++) {
+      const int mrgx = mvx[li], mrgy = mvy[li];
+      const int rx = clip3(-(1 << 17), (1 << 17) - 1, li ? mrgx - dmx : mrgx + dmx), ry = clip3(-(1 << 17), (1 << 17) - 1, li ? mrgy - dmy : mrgy + dmy);
       int cx = rx, cy = ry;
-      clip_mv(cx, cy, bx, by, P);                          // cMvClipped, relative to the sub-block (:1749)
-      mv[l][0] = cx; mv[l][1] = cy;
+      clip_mv(cx, cy, bx, by, P);                            // cMvClipped, relative to the sub-block (:1749)
+      fmx[li] = cx; fmy[li] = cy;
 #pragma unroll
-      for (int k = 0; k < 2; k++) {                        // k = 0 luma, 1 chroma (xFinalPaddedMCForDMVR :1757-1778, xPrefetchPad :1525)
-        const int sh = 4 + k, taps = k ? 4 : 8, cs = k;
+      for (int k = 0; k < 2; k++) {                          // k = 0 luma, 1 chroma (xFinalPaddedMCForDMVR :1757-1778, xPrefetchPad :1525)
+        const int sh = 4 + k, taps = k ? 4 : 8;
         const int dIx = (rx >> sh) - (mrgx >> sh), dIy = (ry >> sh) - (mrgy >> sh);
+        int X, Y;
         if (dIx || dIy) {
           int pmx = mrgx - ((taps / 2 - 1) << sh), pmy = mrgy - ((taps / 2 - 1) << sh);
           clip_mv(pmx, pmy, bx, by, P);
-          Win w; w.x0 = (bx >> cs) + (pmx >> sh); w.y0 = (by >> cs) + (pmy >> sh);
-          w.x1 = w.x0 + (tw >> cs) + taps - 2; w.y1 = w.y0 + (th >> cs) + taps - 2;
-          win[l][k] = w;
-          org[l][k][0] = w.x0 + (taps / 2 - 1) + dIx; org[l][k][1] = w.y0 + (taps / 2 - 1) + dIy;
+          wx0[li][k] = (bx >> k) + (pmx >> sh); wy0[li][k] = (by >> k) + (pmy >> sh);
+          wx1[li][k] = wx0[li][k] + (tw >> k) + taps - 2; wy1[li][k] = wy0[li][k] + (th >> k) + taps - 2;
+          X = wx0[li][k] + (taps / 2 - 1) + dIx; Y = wy0[li][k] + (taps / 2 - 1) + dIy;
         } else {
-          org[l][k][0] = (bx >> cs) + (cx >> sh); org[l][k][1] = (by >> cs) + (cy >> sh);
+          wx0[li][k] = wy0[li][k] = -(1 << 20); wx1[li][k] = wy1[li][k] = 1 << 20;
+          X = (bx >> k) + (cx >> sh); Y = (by >> k) + (cy >> sh);
         }
+        if (k == 0) { ox[li] = X; oy[li] = Y; } else { ocx[li] = X; ocy[li] = Y; }
       }
     }
   } else {
 #pragma unroll
-    for (int l = 0; l < 2; l++) {
-      org[l][0][0] = bx + (mv[l][0] >> 4); org[l][0][1] = by + (mv[l][1] >> 4);
-      org[l][1][0] = (bx >> 1) + (mv[l][0] >> 5); org[l][1][1] = (by >> 1) + (mv[l][1] >> 5);
+    for (int li = 0; li < NL; li++) {
+      int cx = mvx[li], cy = mvy[li];
+      clip_mv(cx, cy, puX, puY, P);                          // relative to the CU (xPredInterUni :651)
+      fmx[li] = cx; fmy[li] = cy;
+      ox[li] = bx + (cx >> 4); oy[li] = by + (cy >> 4); ocx[li] = (bx >> 1) + (cx >> 5); ocy[li] = (by >> 1) + (cy >> 5);
     }
   }
-  if (!bi) bio = false;
 
-  // ================================================================ luma: stage windows, H filter, V filter
-  __syncthreads();
-  for (int i = tid; i < nList * (tw + 7) * (th + 7); i += 256) {
-    const int li = i / ((tw + 7) * (th + 7)), j = i - li * (tw + 7) * (th + 7);
-    const int l = bi ? li : l0;
-    const int y = j / (tw + 7), x = j - y * (tw + 7);
-    sW[l][y * WS + x] = (int16_t)ldw(R[l][0], win[l][0], org[l][0][0] + x - 3, org[l][0][1] + y - 3);
-  }
-  __syncthreads();
-  for (int i = tid; i < nList * (th + 7) * tw; i += 256) {
-    const int li = i / ((th + 7) * tw), j = i - li * (th + 7) * tw;
-    const int l = bi ? li : l0;
-    const int y = j / tw, x = j - y * tw;
-    const int xF = mv[l][0] & 15;
-    int s;
-    if (xF == 0) s = 64 * sW[l][y * WS + x + 3];
-    else {
-      const int8_t* f = luma_taps(xF, is4x4, altHpel);
-      s = 0;
-#pragma unroll
-      for (int t = 0; t < 8; t++) s += f[t] * sW[l][y * WS + x + t];
-    }
-    sHf[l][y * 16 + x] = (int16_t)((s - (IFO << sh1)) >> sh1);
-  }
-  __syncthreads();
+  // ================================================================ stage A: windows (luma 8-tap footprint, chroma 4-tap footprint)
   {
-    const int y = tid >> 4, x = tid & 15;
-    if (x < tw && y < th) {
-      int pred[2] = { 0, 0 };
-      for (int li = 0; li < nList; li++) {
-        const int l = bi ? li : l0;
-        const int yF = mv[l][1] & 15;
-        int s;
-        if (yF == 0) s = 64 * sHf[l][(y + 3) * 16 + x];
-        else {
-          const int8_t* f = luma_taps(yF, is4x4, altHpel);
-          s = 0;
+    const int warp = tid >> 5, lane = tid & 31, nw = max(1, nthr >> 5);
 #pragma unroll
-          for (int t = 0; t < 8; t++) s += f[t] * sHf[l][(y + t) * 16 + x];
+    for (int li = 0; li < NL; li++) {
+      const int16_t* r = rp[li][0];
+      const int X = ox[li] - 3 + lane;
+      int xc;
+      if (MODE == 3) xc = min(max(min(max(X, wx0[li][0]), wx1[li][0]), 0), W - 1); else xc = min(max(X, 0), W - 1);
+      if (lane < tw + 7)
+        for (int y = warp; y < th + 7; y += nw) {
+          int Y = oy[li] - 3 + y;
+          if (MODE == 3) Y = min(max(Y, wy0[li][0]), wy1[li][0]);
+          Y = min(max(Y, 0), H - 1);
+          S.w[li][y * (tw + 7) + lane] = r[(size_t)Y * rs0 + xc];
         }
-        pred[li] = s;
+      if (chroma) {
+        // both chroma components: lanes 0..15 Cb, 16..31 Cr (cw+3 <= 11)
+        const int c = lane >> 4, xl = lane & 15;
+        const int16_t* rc = c ? rp[li][2] : rp[li][1];
+        const int Xc = ocx[li] - 1 + xl;
+        int xcc;
+        if (MODE == 3) xcc = min(max(min(max(Xc, wx0[li][1]), wx1[li][1]), 0), CWp - 1); else xcc = min(max(Xc, 0), CWp - 1);
+        if (xl < cw + 3)
+          for (int y = warp; y < ch + 3; y += nw) {
+            int Y = ocy[li] - 1 + y;
+            if (MODE == 3) Y = min(max(Y, wy0[li][1]), wy1[li][1]);
+            Y = min(max(Y, 0), CHp - 1);
+            (c ? S.cw[li][1] : S.cw[li][0])[y * (cw + 3) + xl] = rc[(size_t)Y * rs1 + xcc];
+          }
       }
-      int16_t* d = P.dst[0] + (size_t)(by + y) * P.dstStride[0] + bx + x;
-      if (!bi) *d = (int16_t)clip3(0, pmax, (pred[0] + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr));
-      else if (!bio) *d = (int16_t)avg_bi((int16_t)(pred[0] >> 6), (int16_t)(pred[1] >> 6), pu.bcwW1, hr, pmax);
-      else { sP[0][(y + 1) * 18 + x + 1] = (int16_t)(pred[0] >> 6); sP[1][(y + 1) * 18 + x + 1] = (int16_t)(pred[1] >> 6); }
+    }
+  }
+  __syncthreads();
+
+  // ================================================================ stage B: horizontal filters
+#pragma unroll
+  for (int li = 0; li < NL; li++) {
+    const int xF = fmx[li] & 15;
+    int f[8];
+    { const int8_t* t = luma_taps(xF, is4x4, altHpel);
+#pragma unroll
+      for (int k = 0; k < 8; k++) f[k] = xF ? (int)t[k] : (k == 3 ? 64 : 0); }
+    for (int i = tid; i < (th + 7) << l2w; i += nthr) {
+      const int y = i >> l2w, x = i & (tw - 1);
+      const int16_t* s = S.w[li] + y * (tw + 7) + x;
+      int a = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) a += f[k] * s[k];
+      S.h[li][i] = (int16_t)((a - (IFO << sh1)) >> sh1);
+    }
+    if (chroma) {
+      const int8_t* t = kIfChroma + (fmx[li] & 31) * 4;
+      const int c0 = t[0], c1 = t[1], c2 = t[2], c3 = t[3];
+      for (int i = tid; i < 2 * ((ch + 3) << l2cw); i += nthr) {
+        const int c = i >= ((ch + 3) << l2cw), j = c ? i - ((ch + 3) << l2cw) : i;
+        const int y = j >> l2cw, x = j & (cw - 1);
+        const int16_t* s = (c ? S.cw[li][1] : S.cw[li][0]) + y * (cw + 3) + x;
+        (c ? S.chf[li][1] : S.chf[li][0])[j] = (int16_t)((c0 * s[0] + c1 * s[1] + c2 * s[2] + c3 * s[3] - (IFO << sh1)) >> sh1);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ================================================================ stage C: vertical filters + combine
+  {
+    const int y = tid >> l2w, x = tid & (tw - 1);
+    int pr[NL];
+#pragma unroll
+    for (int li = 0; li < NL; li++) {
+      const int yF = fmy[li] & 15;
+      const int8_t* t = luma_taps(yF, is4x4, altHpel);
+      const int16_t* s = S.h[li] + (y << l2w) + x;
+      int a = 0;
+      if (yF == 0) a = 64 * s[3 << l2w];
+      else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) a += (int)t[k] * s[k << l2w];
+      }
+      pr[li] = a;
+    }
+    int16_t* d = P.dst[0] + (size_t)(by + y) * P.dstStride[0] + bx + x;
+    if (!BI) *d = (int16_t)clip3(0, pmax, (pr[0] + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr));
+    else if (!bio) *d = (int16_t)avg_bi((int16_t)(pr[0] >> 6), (int16_t)(pr[NL - 1] >> 6), MODE == 1 ? pu.bcwW1 : 4, hr, pmax);
+    else { S.p[0][(y + 1) * 18 + x + 1] = (int16_t)(pr[0] >> 6); S.p[1][(y + 1) * 18 + x + 1] = (int16_t)(pr[NL - 1] >> 6); }
+  }
+  if (chroma) {
+    for (int i = tid; i < 2 * (ch << l2cw); i += nthr) {
+      const int c = i >= (ch << l2cw), j = c ? i - (ch << l2cw) : i;
+      const int y = j >> l2cw, x = j & (cw - 1);
+      int pr[NL];
+#pragma unroll
+      for (int li = 0; li < NL; li++) {
+        const int8_t* t = kIfChroma + (fmy[li] & 31) * 4;
+        const int16_t* s = (c ? S.chf[li][1] : S.chf[li][0]) + (y << l2cw) + x;
+        pr[li] = t[0] * s[0] + t[1] * s[1 << l2cw] + t[2] * s[2 << l2cw] + t[3] * s[3 << l2cw];
+      }
+      int16_t* d = (c ? P.dst[2] : P.dst[1]) + (size_t)((by >> 1) + y) * (c ? P.dstStride[2] : P.dstStride[1]) + (bx >> 1) + x;
+      if (!BI) *d = (int16_t)clip3(0, pmax, (pr[0] + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr));
+      else *d = (int16_t)avg_bi((int16_t)(pr[0] >> 6), (int16_t)(pr[NL - 1] >> 6), MODE == 1 ? pu.bcwW1 : 4, hr, pmax);
     }
   }
 
   // ================================================================ BDOF (applyBiOptFlow :1290)
-  if (bio) {
+  if (MODE >= 2) {
+    if (!bio) return;                                        // CTA-uniform
     // ring of integer reference samples around the block (xPredInterBlk :847-885); the windows already hold them
-    for (int i = tid; i < 2 * 2 * (tw + th + 2); i += 256) {
-      const int l = i / (2 * (tw + th + 2)), j = i - l * 2 * (tw + th + 2);
+    for (int i = tid; i < 4 * (tw + th + 2); i += nthr) {
+      const int li = i >= 2 * (tw + th + 2), j = li ? i - 2 * (tw + th + 2) : i;
       int x, y;
       if (j < tw + 2) { x = j; y = 0; } else if (j < 2 * (tw + 2)) { x = j - (tw + 2); y = th + 1; }
       else if (j < 2 * (tw + 2) + th) { x = 0; y = j - 2 * (tw + 2) + 1; } else { x = tw + 1; y = j - 2 * (tw + 2) - th + 1; }
-      const int xo = (mv[l][0] & 15) < 8 ? 1 : 0, yo = (mv[l][1] & 15) < 8 ? 1 : 0;
-      // P(x,y) <- window sample at output position (x-1-xo+..): window origin = output(-3,-3)
-      const int v = sW[l][(y - yo + 3) * WS + (x - xo + 3)];
-      sP[l][y * 18 + x] = (int16_t)((int16_t)(v << hr) - IFO);
+      const int mxl = li ? fmx[NL - 1] : fmx[0], myl = li ? fmy[NL - 1] : fmy[0];
+      const int xo = (mxl & 15) < 8 ? 1 : 0, yo = (myl & 15) < 8 ? 1 : 0;
+      const int16_t* wl = li ? S.w[NL - 1] : S.w[0];
+      const int v = wl[(y - yo + 3) * (tw + 7) + (x - xo + 3)];
+      (li ? S.p[1] : S.p[0])[y * 18 + x] = (int16_t)((int16_t)(v << hr) - IFO);
     }
     __syncthreads();
-    // gradients on the interior (gradFilterCore<true> :212), then replicate gradients AND predictions into the ring (:236-266)
     {
-      const int y = tid >> 4, x = tid & 15;
-      if (x < tw && y < th) {
+      const int y = tid >> l2w, x = tid & (tw - 1);
 #pragma unroll
-        for (int l = 0; l < 2; l++) {
-          const int16_t* p = &sP[l][(y + 1) * 18 + x + 1];
-          sG[l][0][(y + 1) * 18 + x + 1] = (int16_t)((p[1] >> 6) - (p[-1] >> 6));
-          sG[l][1][(y + 1) * 18 + x + 1] = (int16_t)((p[18] >> 6) - (p[-18] >> 6));
-        }
+      for (int l = 0; l < 2; l++) {                          // gradFilterCore<true> :212
+        const int16_t* p = &S.p[l][(y + 1) * 18 + x + 1];
+        S.g[l][0][(y + 1) * 18 + x + 1] = (int16_t)((p[1] >> 6) - (p[-1] >> 6));
+        S.g[l][1][(y + 1) * 18 + x + 1] = (int16_t)((p[18] >> 6) - (p[-18] >> 6));
       }
     }
     __syncthreads();
-    for (int i = tid; i < 6 * 2 * th; i += 256) {          // left / right columns of 6 arrays
+    for (int i = tid; i < 12 * th; i += nthr) {              // replicate left / right columns of the 6 arrays (:236-266)
       const int a = i / (2 * th), j = i - a * 2 * th, y = (j >> 1) + 1, right = j & 1;
-      int16_t* A = a < 2 ? sP[a] : sG[(a - 2) >> 1][(a - 2) & 1];
+      int16_t* A = S.p[0] + a * 324;   // p0,p1,g00,g01,g10,g11 are contiguous
       if (right) A[y * 18 + tw + 1] = A[y * 18 + tw]; else A[y * 18] = A[y * 18 + 1];
     }
     __syncthreads();
-    for (int i = tid; i < 6 * 2 * (tw + 2); i += 256) {    // top / bottom rows (incl. corners)
+    for (int i = tid; i < 12 * (tw + 2); i += nthr) {        // top / bottom rows incl. corners
       const int a = i / (2 * (tw + 2)), j = i - a * 2 * (tw + 2), x = j >> 1, bottom = j & 1;
-      int16_t* A = a < 2 ? sP[a] : sG[(a - 2) >> 1][(a - 2) & 1];
+      int16_t* A = S.p[0] + a * 324;
       if (bottom) A[(th + 1) * 18 + x] = A[th * 18 + x]; else A[x] = A[18 + x];
     }
     __syncthreads();
-    // per 4x4 block: sums over the 6x6 window (calcBIOSums :134); 16 threads per block
     {
-      const int blk = tid >> 4, k = tid & 15;
-      const int bxx = (blk & 3) * 4, byy = (blk >> 2) * 4;
+      // per 4x4 block: sums over the 6x6 window (calcBIOSums :134); 16 threads per block = the block's own 16 sample threads
+      const int y = tid >> l2w, x = tid & (tw - 1);
+      const int bxx = x & ~3, byy = y & ~3, k = (y & 3) * 4 + (x & 3);
       int sAX = 0, sAY = 0, sDX = 0, sDY = 0, sS = 0;
-      if (bxx < tw && byy < th) {
-        for (int j = k; j < 36; j += 16) {
-          const int yy = j / 6, xx = j - yy * 6, i = (byy + yy) * 18 + bxx + xx;
-          const int gX = (sG[0][0][i] + sG[1][0][i]) >> 1, gY = (sG[0][1][i] + sG[1][1][i]) >> 1;
-          const int dI = (sP[1][i] >> 4) - (sP[0][i] >> 4);
-          sAX += abs(gX); sAY += abs(gY);
-          sDX += gX < 0 ? -dI : (gX == 0 ? 0 : dI);
-          sDY += gY < 0 ? -dI : (gY == 0 ? 0 : dI);
-          sS  += gY < 0 ? -gX : (gY == 0 ? 0 : gX);
-        }
+      for (int j = k; j < 36; j += 16) {
+        const int yy = j / 6, xx = j - yy * 6, i = (byy + yy) * 18 + bxx + xx;
+        const int gX = (S.g[0][0][i] + S.g[1][0][i]) >> 1, gY = (S.g[0][1][i] + S.g[1][1][i]) >> 1;
+        const int dI = (S.p[1][i] >> 4) - (S.p[0][i] >> 4);
+        sAX += abs(gX); sAY += abs(gY);
+        sDX += gX < 0 ? -dI : (gX == 0 ? 0 : dI);
+        sDY += gY < 0 ? -dI : (gY == 0 ? 0 : dI);
+        sS  += gY < 0 ? -gX : (gY == 0 ? 0 : gX);
       }
-#pragma unroll
-      for (int m = 1; m < 16; m <<= 1) {
-        sAX += __shfl_xor_sync(0xffffffffu, sAX, m); sAY += __shfl_xor_sync(0xffffffffu, sAY, m);
-        sDX += __shfl_xor_sync(0xffffffffu, sDX, m); sDY += __shfl_xor_sync(0xffffffffu, sDY, m);
-        sS  += __shfl_xor_sync(0xffffffffu, sS, m);
-      }
+      // the 16 threads of a 4x4 block are not contiguous lanes (rows of the tile interleave): reduce through shared atomics
+      const int blk = (byy >> 2) * 4 + (bxx >> 2);
+      __shared__ int sSum[16][5];
+      if (k == 0) { sSum[blk][0] = 0; sSum[blk][1] = 0; sSum[blk][2] = 0; sSum[blk][3] = 0; sSum[blk][4] = 0; }
+      __syncthreads();
+      atomicAdd(&sSum[blk][0], sAX); atomicAdd(&sSum[blk][1], sAY); atomicAdd(&sSum[blk][2], sDX); atomicAdd(&sSum[blk][3], sDY); atomicAdd(&sSum[blk][4], sS);
+      __syncthreads();
       if (k == 0) {
+        sAX = sSum[blk][0]; sAY = sSum[blk][1]; sDX = sSum[blk][2]; sDY = sSum[blk][3]; sS = sSum[blk][4];
         int vx = sAX == 0 ? 0 : shift_msb(sDX * 4, sAX);
         vx = clip3(-15, 15, vx);
         const int mainG = sS >> 12, secG = sS & 4095;
@@ -341,58 +429,11 @@ __global__ void __launch_bounds__(256) mc_tile_kernel(const McParams P)
         vy = clip3(-15, 15, vy);
         sVxy[blk][0] = vx; sVxy[blk][1] = vy;
       }
-    }
-    __syncthreads();
-    {
-      const int y = tid >> 4, x = tid & 15;
-      if (x < tw && y < th) {                                // addBIOAvg4 (:109)
-        const int blk = (y >> 2) * 4 + (x >> 2), i = (y + 1) * 18 + x + 1;
-        const int b = sVxy[blk][0] * (sG[0][0][i] - sG[1][0][i]) + sVxy[blk][1] * (sG[0][1][i] - sG[1][1][i]);
-        const int shiftNum = 15 - bd, offset = (1 << (shiftNum - 1)) + 2 * IFO;
-        P.dst[0][(size_t)(by + y) * P.dstStride[0] + bx + x] = (int16_t)clip3(0, pmax, (int)(int16_t)((sP[0][i] + sP[1][i] + b + offset) >> shiftNum));
-      }
-    }
-  }
-
-  // ================================================================ chroma 4:2:0: 4-tap, both components
-  if (!P.chroma) return;
-  const int cw = tw >> 1, ch = th >> 1;
-  const int nJobs = nList * 2;                               // (list, comp)
-  for (int i = tid; i < nJobs * (cw + 3) * (ch + 3); i += 256) {
-    const int job = i / ((cw + 3) * (ch + 3)), j = i - job * (cw + 3) * (ch + 3);
-    const int l = bi ? (job >> 1) : l0, c = 1 + (job & 1);
-    const int y = j / (cw + 3), x = j - y * (cw + 3);
-    sCW[job][y * 12 + x] = (int16_t)ldw(R[l][c], win[l][1], org[l][1][0] + x - 1, org[l][1][1] + y - 1);
-  }
-  __syncthreads();
-  for (int i = tid; i < nJobs * (ch + 3) * cw; i += 256) {
-    const int job = i / ((ch + 3) * cw), j = i - job * (ch + 3) * cw;
-    const int l = bi ? (job >> 1) : l0;
-    const int y = j / cw, x = j - y * cw;
-    const int8_t* f = kIfChroma + (mv[l][0] & 31) * 4;
-    int s = 0;
-#pragma unroll
-    for (int t = 0; t < 4; t++) s += f[t] * sCW[job][y * 12 + x + t];
-    sCH[job][y * 8 + x] = (int16_t)((s - (IFO << sh1)) >> sh1);
-  }
-  __syncthreads();
-  for (int i = tid; i < nJobs * ch * cw; i += 256) {
-    const int job = i / (ch * cw), j = i - job * ch * cw;
-    const int l = bi ? (job >> 1) : l0, c = 1 + (job & 1);
-    const int y = j / cw, x = j - y * cw;
-    const int8_t* f = kIfChroma + (mv[l][1] & 31) * 4;
-    int s = 0;
-#pragma unroll
-    for (int t = 0; t < 4; t++) s += f[t] * sCH[job][(y + t) * 8 + x];
-    if (!bi) P.dst[c][(size_t)((by >> 1) + y) * P.dstStride[c] + (bx >> 1) + x] = (int16_t)clip3(0, pmax, (s + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr));
-    else sCP[job][y * 8 + x] = (int16_t)(s >> 6);
-  }
-  if (bi) {
-    __syncthreads();
-    for (int i = tid; i < 2 * ch * cw; i += 256) {
-      const int c = i / (ch * cw), j = i - c * ch * cw, y = j / cw, x = j - y * cw;
-      P.dst[1 + c][(size_t)((by >> 1) + y) * P.dstStride[1 + c] + (bx >> 1) + x] =
-          (int16_t)avg_bi(sCP[c][y * 8 + x], sCP[2 + c][y * 8 + x], dmvr ? 4 : pu.bcwW1, hr, pmax);
+      __syncthreads();
+      const int i = (y + 1) * 18 + x + 1;                    // addBIOAvg4 (:109)
+      const int b = sVxy[blk][0] * (S.g[0][0][i] - S.g[1][0][i]) + sVxy[blk][1] * (S.g[0][1][i] - S.g[1][1][i]);
+      const int shiftNum = 15 - bd, offset = (1 << (shiftNum - 1)) + 2 * IFO;
+      P.dst[0][(size_t)(by + y) * P.dstStride[0] + bx + x] = (int16_t)clip3(0, pmax, (int)(int16_t)((S.p[0][i] + S.p[1][i] + b + offset) >> shiftNum));
     }
   }
 }
@@ -592,9 +633,35 @@ int launch_mc(const McLaunch& L, cudaStream_t s, KProf* prof)
   for (int i = 0; i < B200_MAX_SLOTS * 3; i++) P.refs[i] = L.refs[i];
   P.W = L.geom.width; P.H = L.geom.height; P.bitDepth = L.geom.bitDepth; P.ctuSize = L.geom.ctuSize; P.chroma = L.geom.chromaFormat == 1;
   P.pus = L.pus; P.dmvrMv = L.dmvrMv;
-  if (L.numTilesT) { if (prof) prof->begin(B200_KF_MC_TILE, s); P.tiles = L.tilesT; P.numTiles = L.numTilesT; mc_tile_kernel<<<L.numTilesT, 256, 0, s>>>(P); B200_CUDA(cudaGetLastError()); if (prof) prof->end(B200_KF_MC_TILE, s); }
+  bool any = false;
+  for (int m = 0; m < 4; m++) for (int k = 0; k < 4; k++) any |= L.cls[m][k].n > 0;
+  if (any) {
+    if (prof) prof->begin(B200_KF_MC_TILE, s);
+    for (int m = 0; m < 4; m++) for (int k = 0; k < 4; k++) {
+      const McLaunch::Cls& c = L.cls[m][k];
+      if (!c.n) continue;
+      const int nthr = 32 << k;
+      const size_t smem = (size_t)mc_smem_elems(m, nthr) * 2;
+      P.tiles = c.tiles; P.numTiles = c.n;
+      switch (m) {
+        case 0: mc_kernel<0><<<c.n, nthr, smem, s>>>(P); break;
+        case 1: mc_kernel<1><<<c.n, nthr, smem, s>>>(P); break;
+        case 2: mc_kernel<2><<<c.n, nthr, smem, s>>>(P); break;
+        default: mc_kernel<3><<<c.n, nthr, smem, s>>>(P); break;
+      }
+      B200_CUDA(cudaGetLastError());
+    }
+    if (prof) prof->end(B200_KF_MC_TILE, s);
+  }
   if (L.numTilesA) { if (prof) prof->begin(B200_KF_MC_AFFINE, s); P.tiles = L.tilesA; P.numTiles = L.numTilesA; mc_affine_kernel<<<L.numTilesA, 256, 0, s>>>(P); B200_CUDA(cudaGetLastError()); if (prof) prof->end(B200_KF_MC_AFFINE, s); }
   return 0;
+}
+
+int mc_launch_count(const McLaunch& L)
+{
+  int n = L.numTilesA ? 1 : 0;
+  for (int m = 0; m < 4; m++) for (int k = 0; k < 4; k++) n += L.cls[m][k].n > 0;
+  return n;
 }
 
 }  // namespace b200

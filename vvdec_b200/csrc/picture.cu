@@ -11,8 +11,8 @@ static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 struct Arena {
   DevBuf buf;                       // one allocation, sub-allocated per picture
   // device views
-  const b200_pu* pus = nullptr; const uint32_t *tilesT = nullptr, *tilesA = nullptr; int nT = 0, nA = 0; size_t numPus = 0;
-  const b200_tu* tus = nullptr; size_t numTus = 0; const int16_t* coefs = nullptr; const int32_t* scaling = nullptr;
+  const b200_pu* pus = nullptr; McLaunch mcTiles; size_t numPus = 0;   // mcTiles: only cls / tilesA / numTilesA are used
+  const b200_tu* tus = nullptr; size_t numTus = 0; size_t tuCls[4] = {0, 0, 0, 0}; const int16_t* coefs = nullptr; const int32_t* scaling = nullptr;
   const b200_lf_param *lfV = nullptr, *lfH = nullptr; const uint8_t* ctuSlice = nullptr; LfSliceTab lfSlices; b200_lf_seq lfSeq;
   const b200_sao_ctu* sao = nullptr; b200_vb vb;
   const b200_alf_ctu* alf = nullptr; const int16_t *lumaCoeff = nullptr, *lumaClip = nullptr, *chromaCoeff = nullptr, *chromaClip = nullptr, *cc[2] = {nullptr, nullptr};
@@ -47,7 +47,8 @@ struct b200_ctx {
   std::vector<Arena> arenas;
   int nextArena = 0;
   long long launches = 0;
-  std::vector<uint32_t> hT, hA;
+  McTileLists hTiles;
+  std::vector<b200_tu> hTus;
 
   DevPlanes planes(int buf) const {
     DevPlanes d; char* b = reinterpret_cast<char*>(bufs[buf]);
@@ -119,14 +120,14 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   const b200_geom& g = c->g;
   const size_t n4 = (size_t)((g.width + 3) >> 2) * ((g.height + 3) >> 2);
   const size_t nCtu = (size_t)((g.width + g.ctuSize - 1) / g.ctuSize) * ((g.height + g.ctuSize - 1) / g.ctuSize);
-  build_mc_tiles(p->pus, p->numPus, c->hT, c->hA);
+  build_mc_tiles(p->pus, p->numPus, c->hTiles);
   const b200_alf_tables* T = p->alfTabs;
   const size_t nL = (p->flags & B200_PIC_ALF) ? (size_t)T->numLumaSets * 1300 : 0, nC = (p->flags & B200_PIC_ALF) ? (size_t)T->numChromaAlts * 7 : 0;
   const size_t n0 = (p->flags & B200_PIC_ALF) ? (size_t)T->numCc[0] * 7 : 0, n1 = (p->flags & B200_PIC_ALF) ? (size_t)T->numCc[1] * 7 : 0;
   // ---- layout ----
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes + 16); return o; };
-  const size_t oPus = take(p->numPus * sizeof(b200_pu)), oT = take((c->hT.size() + c->hA.size()) * 4);
+  const size_t oPus = take(p->numPus * sizeof(b200_pu)), oT = take(c->hTiles.total() * 4);
   const size_t oTus = take(p->numTus * sizeof(b200_tu)), oCoef = take(p->numCoefs * 2), oScal = take(p->numScaling * 4);
   const size_t oLfV = take((p->flags & B200_PIC_DEBLOCK) ? n4 * 6 : 0), oLfH = take((p->flags & B200_PIC_DEBLOCK) ? n4 * 6 : 0), oCs = take(nCtu);
   const size_t oSao = take((p->flags & B200_PIC_SAO) ? nCtu * sizeof(b200_sao_ctu) : 0);
@@ -140,9 +141,9 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   cudaStream_t s = c->stream;
   auto h2d = [&](size_t o, const void* src, size_t bytes) -> int { if (bytes) B200_CUDA(cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, s)); return 0; };
   if (int rc = h2d(oPus, p->pus, p->numPus * sizeof(b200_pu))) return rc;
-  if (int rc = h2d(oT, c->hT.data(), c->hT.size() * 4)) return rc;
-  if (int rc = h2d(oT + c->hT.size() * 4, c->hA.data(), c->hA.size() * 4)) return rc;
-  if (int rc = h2d(oTus, p->tus, p->numTus * sizeof(b200_tu))) return rc;
+  if (int rc = upload_mc_tiles(c->hTiles, reinterpret_cast<uint32_t*>(base + oT), A.mcTiles, s)) return rc;
+  bucket_tus(p->tus, p->numTus, c->hTus, A.tuCls);
+  if (int rc = h2d(oTus, c->hTus.data(), p->numTus * sizeof(b200_tu))) return rc;
   if (int rc = h2d(oCoef, p->coefs, p->numCoefs * 2)) return rc;
   if (int rc = h2d(oScal, p->scaling, p->numScaling * 4)) return rc;
   if (p->flags & B200_PIC_DEBLOCK) {
@@ -173,7 +174,6 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
     }
   } else A.given[0] = A.given[1] = A.given[2] = nullptr;
   A.pus = reinterpret_cast<const b200_pu*>(base + oPus); A.numPus = p->numPus;
-  A.tilesT = reinterpret_cast<const uint32_t*>(base + oT); A.tilesA = A.tilesT + c->hT.size(); A.nT = (int)c->hT.size(); A.nA = (int)c->hA.size();
   A.tus = reinterpret_cast<const b200_tu*>(base + oTus); A.numTus = p->numTus;
   A.coefs = reinterpret_cast<const int16_t*>(base + oCoef); A.scaling = reinterpret_cast<const int32_t*>(base + oScal);
   A.lfV = reinterpret_cast<const b200_lf_param*>(base + oLfV); A.lfH = reinterpret_cast<const b200_lf_param*>(base + oLfH);
@@ -204,15 +204,15 @@ B200_API int b200_pic_run(b200_ctx* c, int ai)
     McLaunch L; L.geom = g; L.dst = P; memset(L.refs, 0, sizeof(L.refs));
     for (int sl = 0; sl < c->numSlots; sl++) { DevPlanes d = c->planes(c->slotBuf[sl]); for (int k = 0; k < 3; k++) L.refs[sl * 3 + k] = d.p[k]; }
     for (int k = 0; k < 3; k++) L.refStride[k] = g.stride[k];
-    L.pus = A.pus; L.tilesT = A.tilesT; L.tilesA = A.tilesA; L.numTilesT = A.nT; L.numTilesA = A.nA; L.dmvrMv = A.dmvrMv;
+    L.pus = A.pus; memcpy(L.cls, A.mcTiles.cls, sizeof(L.cls)); L.tilesA = A.mcTiles.tilesA; L.numTilesA = A.mcTiles.numTilesA; L.dmvrMv = A.dmvrMv;
     if (int rc = launch_mc(L, s, c->profiling ? &c->prof : nullptr)) return rc;
-    c->launches += (A.nT ? 1 : 0) + (A.nA ? 1 : 0);
+    c->launches += mc_launch_count(L);
   }
   // 2. K1 residual + reco
   if (A.numTus) {
-    K1Launch L; L.geom = g; L.planes = P; L.tus = A.tus; L.numTus = A.numTus; L.coefs = A.coefs; L.scaling = A.scaling; L.mode = 0;
+    K1Launch L; L.geom = g; L.planes = P; L.tus = A.tus; L.numTus = A.numTus; memcpy(L.clsCount, A.tuCls, sizeof(L.clsCount)); L.coefs = A.coefs; L.scaling = A.scaling; L.mode = 0;
     if (int rc = launch_k1_residual(L, s, c->profiling ? &c->prof : nullptr)) return rc;
-    c->launches += 1;
+    for (int k = 0; k < 4; k++) c->launches += A.tuCls[k] ? 1 : 0;
   }
   // 3. K3 deblocking
   if (A.flags & B200_PIC_DEBLOCK) {
