@@ -275,6 +275,11 @@ B200_API int  b200_pic_run(b200_ctx* ctx, int arena);
 B200_API int  b200_wait_picture(b200_ctx* ctx, int arena, int32_t* dmvrMv, size_t numDmvr);
 /* Output: DPB slot -> host planes (vvdec_frame planes; xAddPicture vvdecimpl.cpp:957). Synchronous D2H. */
 B200_API int  b200_get_frame(b200_ctx* ctx, int slot, int16_t* const planes[3]);
+/* Asynchronous output: the D2H copy runs on a second stream after the picture is final and overlaps the next pictures' kernels;
+ * the context makes later pictures wait before they overwrite a buffer that is still being read.  Returns a ticket (>= 0);
+ * b200_frame_wait(ticket) blocks until those planes are complete in host memory (pinned memory recommended). */
+B200_API int  b200_get_frame_async(b200_ctx* ctx, int slot, int16_t* const planes[3]);
+B200_API int  b200_frame_wait(b200_ctx* ctx, int ticket);
 /* Timing helpers for bench.py: CUDA events on the context stream. */
 B200_API int  b200_ctx_mark(b200_ctx* ctx, int which /*0 start, 1 stop*/);
 B200_API int  b200_ctx_elapsed_ms(b200_ctx* ctx, float* ms);

@@ -137,7 +137,8 @@ B200_API int b200_k1_residual(const b200_geom* g, int16_t* const planes[3], cons
   if (numCoefs) B200_CUDA(cudaMemcpyAsync(g_hw.coefs.p, coefs, numCoefs * sizeof(int16_t), cudaMemcpyHostToDevice, s));
   if (numScaling) B200_CUDA(cudaMemcpyAsync(g_hw.scaling.p, scaling, numScaling * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   L.tus = g_hw.tus.as<b200_tu>(); L.coefs = g_hw.coefs.as<int16_t>(); L.scaling = g_hw.scaling.as<int32_t>();
-  if (int rc = launch_k1_residual(L, s)) return rc;
+  StreamSet ss(s);
+  if (int rc = launch_k1_residual(L, ss)) return rc;
   if (int rc = download_planes(g, planes, L.planes, s)) return rc;
   B200_CUDA(cudaStreamSynchronize(s));
   return 0;
@@ -278,7 +279,8 @@ B200_API int b200_mc_predict(const b200_geom* g, int16_t* const dst[3], const in
   memset(L.refs, 0, sizeof(L.refs)); for (size_t i = 0; i < ptrs.size(); i++) L.refs[i] = ptrs[i];
   for (int c = 0; c < 3; c++) L.refStride[c] = g->stride[c];
   L.pus = g_hw.misc[5].as<b200_pu>(); L.dmvrMv = dmvrMv ? g_hw.misc[7].as<int32_t>() : nullptr;
-  if (int rc = launch_mc(L, s)) return rc;
+  StreamSet ss(s);
+  if (int rc = launch_mc(L, ss)) return rc;
   if (int rc = download_planes(g, dst, L.dst, s)) return rc;
   if (dmvrMv && numDmvr) B200_CUDA(cudaMemcpyAsync(dmvrMv, g_hw.misc[7].p, numDmvr * 8, cudaMemcpyDeviceToHost, s));
   B200_CUDA(cudaStreamSynchronize(s));

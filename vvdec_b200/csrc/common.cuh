@@ -56,6 +56,23 @@ struct DevPlanes {
 // optional per-family event recorder (picture.cu); launchers call prof->begin(f)/end(f) around their kernels
 struct KProf { virtual void begin(int family, cudaStream_t s) = 0; virtual void end(int family, cudaStream_t s) = 0; virtual ~KProf() {} };
 
+// Fork/join helper: independent kernels of one stage are spread over auxiliary streams so that their tails overlap.
+struct StreamSet {
+  cudaStream_t main = nullptr; cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr}; int nAux = 0;
+  cudaEvent_t forkEv = nullptr, joinEv[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool used[4] = {false, false, false, false};
+  StreamSet() {}
+  explicit StreamSet(cudaStream_t s) : main(s) {}
+  cudaStream_t pick(int i) {            // stream for the i-th independent kernel of the current stage
+    if (nAux == 0) return main;
+    const int k = i % (nAux + 1);
+    if (k == nAux) return main;
+    if (!used[k]) { cudaEventRecord(forkEv, main); cudaStreamWaitEvent(aux[k], forkEv, 0); used[k] = true; }
+    return aux[k];
+  }
+  void join() { for (int k = 0; k < nAux; k++) if (used[k]) { cudaEventRecord(joinEv[k], aux[k]); cudaStreamWaitEvent(main, joinEv[k], 0); used[k] = false; } }
+};
+
 struct K1Launch {
   b200_geom      geom;
   DevPlanes      planes;
@@ -66,7 +83,7 @@ struct K1Launch {
   const int32_t* scaling;
   int            mode;    // 0: reco = clip(pred + resi); 1: store residual
 };
-int launch_k1_residual(const K1Launch& L, cudaStream_t s, KProf* prof = nullptr);
+int launch_k1_residual(const K1Launch& L, StreamSet& ss, KProf* prof = nullptr);
 int k1_class_of(const b200_tu& t);
 // host: stable bucket sort of TU records by size class into `out`, counts into clsCount
 void bucket_tus(const b200_tu* tus, size_t n, std::vector<b200_tu>& out, size_t clsCount[4]);
@@ -100,7 +117,7 @@ struct McLaunch {
   const uint32_t* tilesA; int numTilesA;
   int32_t* dmvrMv;                  // device or null
 };
-int launch_mc(const McLaunch& L, cudaStream_t s, KProf* prof = nullptr);
+int launch_mc(const McLaunch& L, StreamSet& ss, KProf* prof = nullptr);
 // host: expand PUs into <=16x16 tiles
 struct McTileLists { std::vector<uint32_t> cls[4][4], aff; size_t total() const { size_t n = aff.size(); for (auto& m : cls) for (auto& v : m) n += v.size(); return n; } };
 void build_mc_tiles(const b200_pu* pus, size_t numPus, McTileLists& out);

@@ -217,23 +217,25 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* _
 
 int k1_class_of(const b200_tu& t) { const int m = t.log2w > t.log2h ? t.log2w : t.log2h; return m <= 3 ? 0 : m == 4 ? 1 : m == 5 ? 2 : 3; }
 
-int launch_k1_residual(const K1Launch& L, cudaStream_t s, KProf* prof)
+int launch_k1_residual(const K1Launch& L, StreamSet& ss, KProf* prof)
 {
   if (L.numTus == 0) return 0;
-  if (prof) prof->begin(B200_KF_K1, s);
-  size_t off = 0;
-  for (int c = 0; c < 4; c++) {
-    const size_t n = L.clsCount[c];
+  if (prof) prof->begin(B200_KF_K1, ss.main);
+  size_t offs[4]; { size_t o = 0; for (int c = 0; c < 4; c++) { offs[c] = o; o += L.clsCount[c]; } }
+  int launched = 0;
+  for (int c = 3; c >= 0; c--) {          // largest TUs first: their long CTAs overlap the small classes on the other streams
+    const size_t n = L.clsCount[c], off = offs[c];
     if (!n) continue;
+    cudaStream_t s = ss.pick(launched++);
     const int grid = (int)((n + K1_WARPS - 1) / K1_WARPS);
 #define K1_GO(C) k1_residual_kernel<C><<<grid, K1_WARPS * 32, 0, s>>>(L.tus + off, (int)n, L.coefs, L.scaling, L.planes.p[0], L.planes.p[1], L.planes.p[2], \
                                                                    L.planes.stride[0], L.planes.stride[1], L.planes.stride[2], L.geom.bitDepth, L.mode)
     switch (c) { case 0: K1_GO(0); break; case 1: K1_GO(1); break; case 2: K1_GO(2); break; default: K1_GO(3); break; }
 #undef K1_GO
     B200_CUDA(cudaGetLastError());
-    off += n;
   }
-  if (prof) prof->end(B200_KF_K1, s);
+  ss.join();
+  if (prof) prof->end(B200_KF_K1, ss.main);
   return 0;
 }
 

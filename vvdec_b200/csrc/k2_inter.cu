@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(256) mc_affine_kernel(const McParams P)
   }
 }
 
-int launch_mc(const McLaunch& L, cudaStream_t s, KProf* prof)
+int launch_mc(const McLaunch& L, StreamSet& ss, KProf* prof)
 {
   McParams P;
   for (int c = 0; c < 3; c++) { P.dst[c] = L.dst.p[c]; P.dstStride[c] = L.dst.stride[c]; P.refStride[c] = L.refStride[c]; }
@@ -635,11 +635,13 @@ int launch_mc(const McLaunch& L, cudaStream_t s, KProf* prof)
   P.pus = L.pus; P.dmvrMv = L.dmvrMv;
   bool any = false;
   for (int m = 0; m < 4; m++) for (int k = 0; k < 4; k++) any |= L.cls[m][k].n > 0;
+  int launched = 0;
+  if (prof) prof->begin(B200_KF_MC_TILE, ss.main);
   if (any) {
-    if (prof) prof->begin(B200_KF_MC_TILE, s);
-    for (int m = 0; m < 4; m++) for (int k = 0; k < 4; k++) {
+    for (int m = 3; m >= 0; m--) for (int k = 3; k >= 0; k--) {      // heaviest classes first (DMVR 16x16 ... uni 8x4)
       const McLaunch::Cls& c = L.cls[m][k];
       if (!c.n) continue;
+      cudaStream_t s = ss.pick(launched++);
       const int nthr = 32 << k;
       const size_t smem = (size_t)mc_smem_elems(m, nthr) * 2;
       P.tiles = c.tiles; P.numTiles = c.n;
@@ -651,9 +653,10 @@ int launch_mc(const McLaunch& L, cudaStream_t s, KProf* prof)
       }
       B200_CUDA(cudaGetLastError());
     }
-    if (prof) prof->end(B200_KF_MC_TILE, s);
   }
-  if (L.numTilesA) { if (prof) prof->begin(B200_KF_MC_AFFINE, s); P.tiles = L.tilesA; P.numTiles = L.numTilesA; mc_affine_kernel<<<L.numTilesA, 256, 0, s>>>(P); B200_CUDA(cudaGetLastError()); if (prof) prof->end(B200_KF_MC_AFFINE, s); }
+  if (L.numTilesA) { cudaStream_t s = ss.pick(launched++); P.tiles = L.tilesA; P.numTiles = L.numTilesA; mc_affine_kernel<<<L.numTilesA, 256, 0, s>>>(P); B200_CUDA(cudaGetLastError()); }
+  ss.join();
+  if (prof) prof->end(B200_KF_MC_TILE, ss.main);      // with forked streams the affine tiles are inside the same interval
   return 0;
 }
 

@@ -38,8 +38,11 @@ struct b200_ctx {
   b200_geom g;
   CtxProf prof; bool profiling = false;
   int numSlots = 0, numArenas = 0, device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copyStream = nullptr;
+  StreamSet ss;
   cudaEvent_t ev[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> readDone; std::vector<char> readPending;   // per picture buffer: an async D2H is (maybe) still reading it
+  cudaEvent_t ticketEv[16]; cudaEvent_t finalEv = nullptr; int nextTicket = 0;
   size_t planeBytes[3] = {0, 0, 0}, picBytes = 0;
   std::vector<int16_t*> bufs;          // numSlots + 2 picture buffers
   std::vector<int> slotBuf;            // slot -> buffer index
@@ -73,10 +76,18 @@ B200_API int b200_ctx_create(b200_ctx** out, const b200_geom* g, int numSlots, i
   c->g = *g; c->numSlots = numSlots; c->numArenas = numArenas;
   B200_CUDA(cudaGetDevice(&c->device));
   B200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  B200_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+  c->ss.main = c->stream; c->ss.nAux = 3;
+  B200_CUDA(cudaEventCreateWithFlags(&c->ss.forkEv, cudaEventDisableTiming));
+  for (int k = 0; k < c->ss.nAux; k++) { B200_CUDA(cudaStreamCreateWithFlags(&c->ss.aux[k], cudaStreamNonBlocking)); B200_CUDA(cudaEventCreateWithFlags(&c->ss.joinEv[k], cudaEventDisableTiming)); }
   B200_CUDA(cudaEventCreate(&c->ev[0])); B200_CUDA(cudaEventCreate(&c->ev[1]));
+  B200_CUDA(cudaEventCreateWithFlags(&c->finalEv, cudaEventDisableTiming));
+  for (auto& e : c->ticketEv) B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (int k = 0; k < 3; k++) c->planeBytes[k] = (k == 0 || g->chromaFormat) ? align256((size_t)g->stride[k] * (k ? g->height >> 1 : g->height) * 2) : 0;
   c->picBytes = c->planeBytes[0] + c->planeBytes[1] + c->planeBytes[2];
   c->bufs.resize(numSlots + 2); c->slotBuf.resize(numSlots);
+  c->readDone.resize(numSlots + 2); c->readPending.assign(numSlots + 2, 0);
+  for (auto& e : c->readDone) B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (int i = 0; i < numSlots + 2; i++) { B200_CUDA(cudaMalloc(&c->bufs[i], c->picBytes)); B200_CUDA(cudaMemset(c->bufs[i], 0, c->picBytes)); }
   for (int s = 0; s < numSlots; s++) c->slotBuf[s] = s;
   c->work[0] = numSlots; c->work[1] = numSlots + 1;
@@ -88,8 +99,13 @@ B200_API int b200_ctx_create(b200_ctx** out, const b200_geom* g, int numSlots, i
 B200_API void b200_ctx_destroy(b200_ctx* c)
 {
   if (!c) return;
-  cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copyStream);
   for (auto p : c->bufs) cudaFree(p);
+  for (auto e : c->readDone) cudaEventDestroy(e);
+  for (auto e : c->ticketEv) cudaEventDestroy(e);
+  cudaEventDestroy(c->finalEv); cudaStreamDestroy(c->copyStream);
+  for (int k = 0; k < c->ss.nAux; k++) { cudaStreamSynchronize(c->ss.aux[k]); cudaStreamDestroy(c->ss.aux[k]); cudaEventDestroy(c->ss.joinEv[k]); }
+  cudaEventDestroy(c->ss.forkEv);
   cudaEventDestroy(c->ev[0]); cudaEventDestroy(c->ev[1]);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -193,6 +209,7 @@ B200_API int b200_pic_run(b200_ctx* c, int ai)
   cudaStream_t s = c->stream;
   const b200_geom& g = c->g;
   int cur = c->work[0], other = c->work[1];
+  for (int b : {cur, other}) if (c->readPending[b]) { B200_CUDA(cudaStreamWaitEvent(s, c->readDone[b], 0)); c->readPending[b] = 0; }   // async output copies still reading these buffers
   DevPlanes P = c->planes(cur);
   // 0. pre-reconstructed (intra stand-in) samples
   if (A.given[0]) {
@@ -205,13 +222,13 @@ B200_API int b200_pic_run(b200_ctx* c, int ai)
     for (int sl = 0; sl < c->numSlots; sl++) { DevPlanes d = c->planes(c->slotBuf[sl]); for (int k = 0; k < 3; k++) L.refs[sl * 3 + k] = d.p[k]; }
     for (int k = 0; k < 3; k++) L.refStride[k] = g.stride[k];
     L.pus = A.pus; memcpy(L.cls, A.mcTiles.cls, sizeof(L.cls)); L.tilesA = A.mcTiles.tilesA; L.numTilesA = A.mcTiles.numTilesA; L.dmvrMv = A.dmvrMv;
-    if (int rc = launch_mc(L, s, c->profiling ? &c->prof : nullptr)) return rc;
+    if (int rc = launch_mc(L, c->ss, c->profiling ? &c->prof : nullptr)) return rc;
     c->launches += mc_launch_count(L);
   }
   // 2. K1 residual + reco
   if (A.numTus) {
     K1Launch L; L.geom = g; L.planes = P; L.tus = A.tus; L.numTus = A.numTus; memcpy(L.clsCount, A.tuCls, sizeof(L.clsCount)); L.coefs = A.coefs; L.scaling = A.scaling; L.mode = 0;
-    if (int rc = launch_k1_residual(L, s, c->profiling ? &c->prof : nullptr)) return rc;
+    if (int rc = launch_k1_residual(L, c->ss, c->profiling ? &c->prof : nullptr)) return rc;
     for (int k = 0; k < 4; k++) c->launches += A.tuCls[k] ? 1 : 0;
   }
   // 3. K3 deblocking
@@ -268,6 +285,28 @@ B200_API int b200_get_frame(b200_ctx* c, int slot, int16_t* const planes[3])
   for (int k = 0; k < (c->g.chromaFormat ? 3 : 1); k++)
     B200_CUDA(cudaMemcpyAsync(planes[k], d.p[k], (size_t)c->g.stride[k] * (k ? c->g.height >> 1 : c->g.height) * 2, cudaMemcpyDeviceToHost, c->stream));
   B200_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+B200_API int b200_get_frame_async(b200_ctx* c, int slot, int16_t* const planes[3])
+{
+  B200_CHECK(c && planes && slot >= 0 && slot < c->numSlots, "b200_get_frame_async: bad argument");
+  const int buf = c->slotBuf[slot];
+  DevPlanes d = c->planes(buf);
+  B200_CUDA(cudaEventRecord(c->finalEv, c->stream));                 // everything submitted so far (incl. this slot's picture) is final after this
+  B200_CUDA(cudaStreamWaitEvent(c->copyStream, c->finalEv, 0));
+  for (int k = 0; k < (c->g.chromaFormat ? 3 : 1); k++)
+    B200_CUDA(cudaMemcpyAsync(planes[k], d.p[k], (size_t)c->g.stride[k] * (k ? c->g.height >> 1 : c->g.height) * 2, cudaMemcpyDeviceToHost, c->copyStream));
+  B200_CUDA(cudaEventRecord(c->readDone[buf], c->copyStream)); c->readPending[buf] = 1;
+  const int t = c->nextTicket; c->nextTicket = (c->nextTicket + 1) & 15;
+  B200_CUDA(cudaEventRecord(c->ticketEv[t], c->copyStream));
+  return t;
+}
+
+B200_API int b200_frame_wait(b200_ctx* c, int ticket)
+{
+  B200_CHECK(c && ticket >= 0 && ticket < 16, "b200_frame_wait: bad ticket");
+  B200_CUDA(cudaEventSynchronize(c->ticketEv[ticket]));
   return 0;
 }
 
