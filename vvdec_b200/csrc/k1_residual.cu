@@ -21,7 +21,13 @@ constexpr int K1_WARPS = 8;
 // TU size classes (host buckets the records, order inside a picture is irrelevant: TUs never overlap):
 //   class 0: w,h <= 8   class 1: <= 16   class 2: <= 32   class 3: a 64 dimension
 // per warp: CB int16 dequantised coefficients (coded corner, at most min(w,32)*min(h,32)), TB int16 stage-1 output (<= min(w,32)*h)
-template <int CLS> struct K1Cfg { static constexpr int CB = CLS == 0 ? 64 : CLS == 1 ? 256 : 1024, TB = CLS == 0 ? 64 : CLS == 1 ? 256 : CLS == 2 ? 1024 : 2048; };
+// threads per TU: one warp for the small classes, a whole CTA for the big ones (a 64x64 TU is ~200k MACs: one warp would take >100 us)
+template <int CLS> struct K1Cfg {
+  static constexpr int CB = CLS == 0 ? 64 : CLS == 1 ? 256 : 1024, TB = CLS == 0 ? 64 : CLS == 1 ? 256 : CLS == 2 ? 1024 : 2048;
+  static constexpr int G = CLS <= 1 ? 32 : CLS == 2 ? 128 : 256;       // group size (threads per TU)
+  static constexpr int THREADS = CLS <= 1 ? K1_WARPS * 32 : G;         // big classes: exactly one group per CTA (they use __syncthreads)
+  static constexpr int GROUPS = THREADS / G;                           // TUs per CTA
+};
 
 __device__ __forceinline__ const int16_t* tr_matrix(int trType, int log2n)
 {
@@ -41,17 +47,20 @@ __device__ __forceinline__ int dequant_one(int level, int scale, int rightShift,
 }
 
 template <int CLS>
-__global__ void __launch_bounds__(K1_WARPS * 32)
+__global__ void __launch_bounds__(K1Cfg<CLS>::THREADS)
 k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* __restrict__ coefs,
                    const int32_t* __restrict__ scaling, int16_t* p0, int16_t* p1, int16_t* p2,
                    int s0, int s1, int s2, int bitDepth, int mode)
 {
-  __shared__ int16_t s_c[K1_WARPS][K1Cfg<CLS>::CB];
-  __shared__ int16_t s_t[K1_WARPS][K1Cfg<CLS>::TB];
+  constexpr int G = K1Cfg<CLS>::G, GROUPS = K1Cfg<CLS>::GROUPS;
+  __shared__ int16_t s_c[GROUPS][K1Cfg<CLS>::CB];
+  __shared__ int16_t s_t[GROUPS][K1Cfg<CLS>::TB];
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t = blockIdx.x * K1_WARPS + warp;
-  if (t >= numTus) return;
+  // `lane` = index inside the TU's thread group, `warp` = group index in the CTA (names kept from the one-warp-per-TU version)
+  const int warp = threadIdx.x / G, lane = threadIdx.x % G;
+  const int t = blockIdx.x * GROUPS + warp;
+  if (t >= numTus) return;                                   // G == blockDim for the big classes, so the whole CTA leaves together
+  auto gsync = [&]() { if (G == 32) __syncwarp(); else __syncthreads(); };
 
   const uint4* recp = reinterpret_cast<const uint4*>(tus + t);
   const uint4 ra = __ldg(recp), rb = __ldg(recp + 1);
@@ -83,7 +92,7 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* _
     // invResDPCM (Quant.cpp:239): running sum with 16-bit clip along x (H) or y (V); one lane per line.
     const bool hor = flags & B200_TU_BDPCM_H;
     const int lines = hor ? h : w, len = hor ? w : h;
-    for (int l = lane; l < lines; l += 32) {
+    for (int l = lane; l < lines; l += G) {
       int acc = 0;
       for (int i = 0; i < len; i++) {
         const int x = hor ? i : l, y = hor ? l : i;
@@ -94,7 +103,7 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* _
       }
     }
   } else {
-    for (int i = lane; i < nzW * nzH; i += 32) {
+    for (int i = lane; i < nzW * nzH; i += G) {
       const int y = i / CS, x = i - y * CS;
       int v = 0;
       if (x <= maxX && y <= maxY) {
@@ -104,10 +113,11 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* _
       cb[i] = (int16_t)v;
     }
   }
-  __syncwarp();
+  gsync();
 
   // ---- 2. inverse LFNST (TrQuant.cpp:201) ----
   if (lfnst && !isTS) {
+   if (lane < 32) {     // LFNST works on 16 coefficients: the first warp of the group does it
     const int idx = (lfnst & 3) - 1, set = (lfnst >> 2) & 3, transpose = (lfnst >> 4) & 1;
     const bool big = w >= 8 && h >= 8;
     const int zo = ((w == 4 && h == 4) || (w == 8 && h == 8)) ? 8 : 16;
@@ -141,9 +151,10 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* _
       else             { const int k = j - 32, a = k >> 2, b = k & 3; y = transpose ? b : 4 + a; x = transpose ? 4 + a : b; }
       cb[y * CS + x] = (int16_t)val;
     }
+   }
     maxX = max(maxX, min(w - 1, 7));
     maxY = max(maxY, min(h - 1, 7));
-    __syncwarp();
+    gsync();
   }
 
   // ---- output helpers ----
@@ -166,7 +177,7 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* _
 
   // ---- 3. transform skip (TrQuant.cpp:489) ----
   if (isTS) {
-    for (int i = lane; i < w * h; i += 32) {
+    for (int i = lane; i < w * h; i += G) {
       const int y = i >> log2w, x = i & (w - 1);
       emit(x, y, (x < nzW && y < nzH) ? (int)cb[y * CS + x] : 0);
     }
@@ -180,7 +191,7 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* _
   if (maxX == 0 && maxY == 0 && trH == B200_TR_DCT2 && trV == B200_TR_DCT2) {
     int dc = ((int)cb[0] * 64 + (1 << (shift1 - 1))) >> shift1;
     dc = (dc * 64 + (1 << (shift2 - 1))) >> shift2;
-    for (int i = lane; i < w * h; i += 32) emit(i & (w - 1), i >> log2w, dc);
+    for (int i = lane; i < w * h; i += G) emit(i & (w - 1), i >> log2w, dc);
     return;
   }
 
@@ -193,20 +204,20 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* _
   // ---- 6. stage 1: vertical, round >>7, clip to 16 bit (TrQuant_EMT.cpp:103-121, clip branch) ----
   {
     const int16_t* mv = tr_matrix(trV, log2h);
-    for (int i = lane; i < nCols * h; i += 32) {
+    for (int i = lane; i < nCols * h; i += G) {
       const int col = i >> log2h, j = i & (h - 1);
       int acc = 0;
       for (int k = 0; k < nRows; k++) acc += (int)cb[k * CS + col] * (int)__ldg(mv + (k << log2h) + j);
       tb[i] = (int16_t)clip16((acc + (1 << (shift1 - 1))) >> shift1);
     }
   }
-  __syncwarp();
+  gsync();
 
   // ---- 7. stage 2: horizontal + final round/clip (cpyResiClipCore, TrQuant_EMT.cpp:366) + reco ----
   {
     const int16_t* mh = tr_matrix(trH, log2w);
     const int rnd = 1 << (shift2 - 1);
-    for (int i = lane; i < w * h; i += 32) {
+    for (int i = lane; i < w * h; i += G) {
       const int y = i >> log2w, x = i & (w - 1);
       int acc = 0;
       for (int k = 0; k < nCols; k++) acc += (int)tb[(k << log2h) + y] * (int)__ldg(mh + (k << log2w) + x);
@@ -227,8 +238,9 @@ int launch_k1_residual(const K1Launch& L, StreamSet& ss, KProf* prof)
     const size_t n = L.clsCount[c], off = offs[c];
     if (!n) continue;
     cudaStream_t s = ss.pick(launched++);
-    const int grid = (int)((n + K1_WARPS - 1) / K1_WARPS);
-#define K1_GO(C) k1_residual_kernel<C><<<grid, K1_WARPS * 32, 0, s>>>(L.tus + off, (int)n, L.coefs, L.scaling, L.planes.p[0], L.planes.p[1], L.planes.p[2], \
+    const int groups = c <= 1 ? K1_WARPS : 1;
+    const int grid = (int)((n + groups - 1) / groups);
+#define K1_GO(C) k1_residual_kernel<C><<<grid, K1Cfg<C>::THREADS, 0, s>>>(L.tus + off, (int)n, L.coefs, L.scaling, L.planes.p[0], L.planes.p[1], L.planes.p[2], \
                                                                    L.planes.stride[0], L.planes.stride[1], L.planes.stride[2], L.geom.bitDepth, L.mode)
     switch (c) { case 0: K1_GO(0); break; case 1: K1_GO(1); break; case 2: K1_GO(2); break; default: K1_GO(3); break; }
 #undef K1_GO

@@ -183,7 +183,9 @@ __global__ void __launch_bounds__(256) lf_kernel(const LfParams P, const LfSlice
       int shift = P.seq.ladfQpOffset[0];
       const int lvl = DIR == 0 ? (src[0] + src[3 * stride] + src[-1] + src[3 * stride - 1]) >> 2
                                : (src[0] + src[3] + src[-stride] + src[-stride + 3]) >> 2;
-      for (int k = 1; k < P.seq.ladfNumIntervals; k++) { if (lvl > P.seq.ladfIntervalLowerBound[k]) shift = P.seq.ladfQpOffset[k]; else break; }
+      bool go = true;
+#pragma unroll
+      for (int k = 1; k < 5; k++) { if (go && k < P.seq.ladfNumIntervals && lvl > P.seq.ladfIntervalLowerBound[k]) shift = P.seq.ladfQpOffset[k]; else go = false; }
       qp += shift;
     }
     const int maxP = (lens >> 4) & 7, maxQ = lens & 7;
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(256) lf_kernel(const LfParams P, const LfSlice
     const int cx = x >> 1, cy = y >> 1;
     const bool horCtb = DIR == 1 && (cy & ((P.ctuSize >> 1) - 1)) == 0;
     const bool large = (flags >> 5) & 1;
-#pragma unroll 1
+#pragma unroll
     for (int c = 1; c <= 2; c++) {
       const int bsc = (bsAll >> (2 * c)) & 3;
       if (!(bsc == 2 || (large && bsc == 1))) continue;
@@ -235,14 +237,14 @@ __global__ void __launch_bounds__(256) lf_kernel(const LfParams P, const LfSlice
       int16_t* src = P.plane[c] + (size_t)cy * stride + cx;
       const int off = DIR == 0 ? 1 : stride, step = DIR == 0 ? stride : 1;
       const int qp = c == 1 ? qpU : qpV;
-      const int tc = tc_of(clip3(0, 65, qp + 2 * (bsc - 1) + sl.tcOffsetDiv2[c] * 2), bd);
+      const int tc = tc_of(clip3(0, 65, qp + 2 * (bsc - 1) + (c == 1 ? sl.tcOffsetDiv2[1] : sl.tcOffsetDiv2[2]) * 2), bd);
       Line L0, L1;
       const int nP = horCtb ? 2 : 4;
       load_line(L0, src, off, nP, 4);
       load_line(L1, src + step, off, nP, 4);
       bool sw = false;
       if (large) {
-        const int beta = c_betaTable[clip3(0, 63, qp + sl.betaOffsetDiv2[c] * 2)] * (1 << (bd - 8));
+        const int beta = c_betaTable[clip3(0, 63, qp + (c == 1 ? sl.betaOffsetDiv2[1] : sl.betaOffsetDiv2[2]) * 2)] * (1 << (bd - 8));
         // xCalcDP<true> (LoopFilter.cpp:1395): |p1 - 2*p1 + p0| at the horizontal CTB boundary
         const int dp0 = horCtb ? abs(L0.p[1] - 2 * L0.p[1] + L0.p[0]) : dP(L0, 0), dq0 = dQ(L0, 0);
         const int dp3 = horCtb ? abs(L1.p[1] - 2 * L1.p[1] + L1.p[0]) : dP(L1, 0), dq3 = dQ(L1, 0);
