@@ -26,8 +26,8 @@ import numpy as np
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
-    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
@@ -292,7 +292,7 @@ def run_reference(args):
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
-        if a.steps == 64 and a.warmup == 8: a.steps, a.warmup = 4, 1
+        if a.steps == 400 and a.warmup == 16: a.steps, a.warmup = 4, 1
         run_reference(a)
     else:
         run_b200(a)

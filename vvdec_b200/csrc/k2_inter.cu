@@ -95,7 +95,8 @@ __host__ __device__ inline int mc_smem_elems(int mode, int n)   // n = tw*th; wo
   return (e + 64) & ~1;
 }
 
-template <int MODE>
+// OPT: luma outputs per thread (1: blockDim = tw*th; 4: blockDim = tw*th/4, each thread filters 4 adjacent samples so that 11 loads feed 32 MACs)
+template <int MODE, int OPT>
 __global__ void mc_kernel(const McParams P)
 {
   extern __shared__ int16_t smem[];
@@ -299,13 +300,32 @@ __global__ void mc_kernel(const McParams P)
     { const int8_t* t = luma_taps(xF, is4x4, altHpel);
 #pragma unroll
       for (int k = 0; k < 8; k++) f[k] = xF ? (int)t[k] : (k == 3 ? 64 : 0); }
-    for (int i = tid; i < (th + 7) << l2w; i += nthr) {
-      const int y = i >> l2w, x = i & (tw - 1);
-      const int16_t* s = S.w[li] + y * (tw + 7) + x;
-      int a = 0;
+    if (OPT == 1) {
+      for (int i = tid; i < (th + 7) << l2w; i += nthr) {
+        const int y = i >> l2w, x = i & (tw - 1);
+        const int16_t* s = S.w[li] + y * (tw + 7) + x;
+        int a = 0;
 #pragma unroll
-      for (int k = 0; k < 8; k++) a += f[k] * s[k];
-      S.h[li][i] = (int16_t)((a - (IFO << sh1)) >> sh1);
+        for (int k = 0; k < 8; k++) a += f[k] * s[k];
+        S.h[li][i] = (int16_t)((a - (IFO << sh1)) >> sh1);
+      }
+    } else {
+      const int l2g = l2w - 2;                               // groups of 4 outputs per row
+      for (int i = tid; i < (th + 7) << l2g; i += nthr) {
+        const int y = i >> l2g, x = (i & ((tw >> 2) - 1)) << 2;
+        const int16_t* s = S.w[li] + y * (tw + 7) + x;
+        int v[11];
+#pragma unroll
+        for (int k = 0; k < 11; k++) v[k] = s[k];
+        int16_t* o = S.h[li] + (y << l2w) + x;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          int a = 0;
+#pragma unroll
+          for (int k = 0; k < 8; k++) a += f[k] * v[j + k];
+          o[j] = (int16_t)((a - (IFO << sh1)) >> sh1);
+        }
+      }
     }
     if (chroma) {
       const int8_t* t = kIfChroma + (fmx[li] & 31) * 4;
@@ -321,26 +341,35 @@ __global__ void mc_kernel(const McParams P)
   __syncthreads();
 
   // ================================================================ stage C: vertical filters + combine
-  {
-    const int y = tid >> l2w, x = tid & (tw - 1);
-    int pr[NL];
+  if (tid < (tw * th) / OPT) {
+    const int x = tid & (tw - 1), y = (tid >> l2w) * OPT;
+    int pr[NL][OPT];
 #pragma unroll
     for (int li = 0; li < NL; li++) {
       const int yF = fmy[li] & 15;
       const int8_t* t = luma_taps(yF, is4x4, altHpel);
-      const int16_t* s = S.h[li] + (y << l2w) + x;
-      int a = 0;
-      if (yF == 0) a = 64 * s[3 << l2w];
-      else {
+      int f[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) a += (int)t[k] * s[k << l2w];
+      for (int k = 0; k < 8; k++) f[k] = yF ? (int)t[k] : (k == 3 ? 64 : 0);
+      const int16_t* s = S.h[li] + (y << l2w) + x;
+      int v[7 + OPT];
+#pragma unroll
+      for (int k = 0; k < 7 + OPT; k++) v[k] = s[k << l2w];
+#pragma unroll
+      for (int j = 0; j < OPT; j++) {
+        int a = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) a += f[k] * v[j + k];
+        pr[li][j] = a;
       }
-      pr[li] = a;
     }
-    int16_t* d = P.dst[0] + (size_t)(by + y) * P.dstStride[0] + bx + x;
-    if (!BI) *d = (int16_t)clip3(0, pmax, (pr[0] + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr));
-    else if (!bio) *d = (int16_t)avg_bi((int16_t)(pr[0] >> 6), (int16_t)(pr[NL - 1] >> 6), MODE == 1 ? pu.bcwW1 : 4, hr, pmax);
-    else { S.p[0][(y + 1) * 18 + x + 1] = (int16_t)(pr[0] >> 6); S.p[1][(y + 1) * 18 + x + 1] = (int16_t)(pr[NL - 1] >> 6); }
+#pragma unroll
+    for (int j = 0; j < OPT; j++) {
+      int16_t* d = P.dst[0] + (size_t)(by + y + j) * P.dstStride[0] + bx + x;
+      if (!BI) *d = (int16_t)clip3(0, pmax, (pr[0][j] + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr));
+      else if (!bio) *d = (int16_t)avg_bi((int16_t)(pr[0][j] >> 6), (int16_t)(pr[NL - 1][j] >> 6), MODE == 1 ? pu.bcwW1 : 4, hr, pmax);
+      else { S.p[0][(y + j + 1) * 18 + x + 1] = (int16_t)(pr[0][j] >> 6); S.p[1][(y + j + 1) * 18 + x + 1] = (int16_t)(pr[NL - 1][j] >> 6); }
+    }
   }
   if (chroma) {
     for (int i = tid; i < 2 * (ch << l2cw); i += nthr) {
@@ -375,8 +404,8 @@ __global__ void mc_kernel(const McParams P)
       (li ? S.p[1] : S.p[0])[y * 18 + x] = (int16_t)((int16_t)(v << hr) - IFO);
     }
     __syncthreads();
-    {
-      const int y = tid >> l2w, x = tid & (tw - 1);
+    for (int sI = tid; sI < tw * th; sI += nthr) {
+      const int y = sI >> l2w, x = sI & (tw - 1);
 #pragma unroll
       for (int l = 0; l < 2; l++) {                          // gradFilterCore<true> :212
         const int16_t* p = &S.p[l][(y + 1) * 18 + x + 1];
@@ -398,28 +427,25 @@ __global__ void mc_kernel(const McParams P)
     }
     __syncthreads();
     {
-      // per 4x4 block: sums over the 6x6 window (calcBIOSums :134); 16 threads per block = the block's own 16 sample threads
-      const int y = tid >> l2w, x = tid & (tw - 1);
-      const int bxx = x & ~3, byy = y & ~3, k = (y & 3) * 4 + (x & 3);
-      int sAX = 0, sAY = 0, sDX = 0, sDY = 0, sS = 0;
-      for (int j = k; j < 36; j += 16) {
+      // per 4x4 block: sums over the 6x6 window (calcBIOSums :134): work items = (block, 36 window samples), reduced through shared atomics
+      __shared__ int sSum[16][5];
+      const int nBlk = (tw >> 2) * (th >> 2), l2bw = l2w - 2;
+      for (int i = tid; i < 16 * 5; i += nthr) (&sSum[0][0])[i] = 0;
+      __syncthreads();
+      for (int it = tid; it < nBlk * 36; it += nthr) {
+        const int blk = it / 36, j = it - blk * 36;
+        const int bxx = (blk & ((tw >> 2) - 1)) << 2, byy = (blk >> l2bw) << 2;
         const int yy = j / 6, xx = j - yy * 6, i = (byy + yy) * 18 + bxx + xx;
         const int gX = (S.g[0][0][i] + S.g[1][0][i]) >> 1, gY = (S.g[0][1][i] + S.g[1][1][i]) >> 1;
         const int dI = (S.p[1][i] >> 4) - (S.p[0][i] >> 4);
-        sAX += abs(gX); sAY += abs(gY);
-        sDX += gX < 0 ? -dI : (gX == 0 ? 0 : dI);
-        sDY += gY < 0 ? -dI : (gY == 0 ? 0 : dI);
-        sS  += gY < 0 ? -gX : (gY == 0 ? 0 : gX);
+        atomicAdd(&sSum[blk][0], abs(gX)); atomicAdd(&sSum[blk][1], abs(gY));
+        atomicAdd(&sSum[blk][2], gX < 0 ? -dI : (gX == 0 ? 0 : dI));
+        atomicAdd(&sSum[blk][3], gY < 0 ? -dI : (gY == 0 ? 0 : dI));
+        atomicAdd(&sSum[blk][4], gY < 0 ? -gX : (gY == 0 ? 0 : gX));
       }
-      // the 16 threads of a 4x4 block are not contiguous lanes (rows of the tile interleave): reduce through shared atomics
-      const int blk = (byy >> 2) * 4 + (bxx >> 2);
-      __shared__ int sSum[16][5];
-      if (k == 0) { sSum[blk][0] = 0; sSum[blk][1] = 0; sSum[blk][2] = 0; sSum[blk][3] = 0; sSum[blk][4] = 0; }
       __syncthreads();
-      atomicAdd(&sSum[blk][0], sAX); atomicAdd(&sSum[blk][1], sAY); atomicAdd(&sSum[blk][2], sDX); atomicAdd(&sSum[blk][3], sDY); atomicAdd(&sSum[blk][4], sS);
-      __syncthreads();
-      if (k == 0) {
-        sAX = sSum[blk][0]; sAY = sSum[blk][1]; sDX = sSum[blk][2]; sDY = sSum[blk][3]; sS = sSum[blk][4];
+      for (int blk = tid; blk < nBlk; blk += nthr) {
+        const int sAX = sSum[blk][0], sAY = sSum[blk][1], sDX = sSum[blk][2], sDY = sSum[blk][3], sS = sSum[blk][4];
         int vx = sAX == 0 ? 0 : shift_msb(sDX * 4, sAX);
         vx = clip3(-15, 15, vx);
         const int mainG = sS >> 12, secG = sS & 4095;
@@ -430,10 +456,13 @@ __global__ void mc_kernel(const McParams P)
         sVxy[blk][0] = vx; sVxy[blk][1] = vy;
       }
       __syncthreads();
-      const int i = (y + 1) * 18 + x + 1;                    // addBIOAvg4 (:109)
-      const int b = sVxy[blk][0] * (S.g[0][0][i] - S.g[1][0][i]) + sVxy[blk][1] * (S.g[0][1][i] - S.g[1][1][i]);
-      const int shiftNum = 15 - bd, offset = (1 << (shiftNum - 1)) + 2 * IFO;
-      P.dst[0][(size_t)(by + y) * P.dstStride[0] + bx + x] = (int16_t)clip3(0, pmax, (int)(int16_t)((S.p[0][i] + S.p[1][i] + b + offset) >> shiftNum));
+      for (int sI = tid; sI < tw * th; sI += nthr) {         // addBIOAvg4 (:109)
+        const int y = sI >> l2w, x = sI & (tw - 1);
+        const int blk = ((y >> 2) << l2bw) + (x >> 2), i = (y + 1) * 18 + x + 1;
+        const int b = sVxy[blk][0] * (S.g[0][0][i] - S.g[1][0][i]) + sVxy[blk][1] * (S.g[0][1][i] - S.g[1][1][i]);
+        const int shiftNum = 15 - bd, offset = (1 << (shiftNum - 1)) + 2 * IFO;
+        P.dst[0][(size_t)(by + y) * P.dstStride[0] + bx + x] = (int16_t)clip3(0, pmax, (int)(int16_t)((S.p[0][i] + S.p[1][i] + b + offset) >> shiftNum));
+      }
     }
   }
 }
@@ -642,14 +671,24 @@ int launch_mc(const McLaunch& L, StreamSet& ss, KProf* prof)
       const McLaunch::Cls& c = L.cls[m][k];
       if (!c.n) continue;
       cudaStream_t s = ss.pick(launched++);
-      const int nthr = 32 << k;
-      const size_t smem = (size_t)mc_smem_elems(m, nthr) * 2;
+      const int nsamp = 32 << k;
+      const size_t smem = (size_t)mc_smem_elems(m, nsamp) * 2;
       P.tiles = c.tiles; P.numTiles = c.n;
-      switch (m) {
-        case 0: mc_kernel<0><<<c.n, nthr, smem, s>>>(P); break;
-        case 1: mc_kernel<1><<<c.n, nthr, smem, s>>>(P); break;
-        case 2: mc_kernel<2><<<c.n, nthr, smem, s>>>(P); break;
-        default: mc_kernel<3><<<c.n, nthr, smem, s>>>(P); break;
+      if (k >= 2) {            // 128 / 256 samples: 4 luma outputs per thread -> 32 / 64 threads
+        const int nthr = nsamp >> 2;
+        switch (m) {
+          case 0: mc_kernel<0, 4><<<c.n, nthr, smem, s>>>(P); break;
+          case 1: mc_kernel<1, 4><<<c.n, nthr, smem, s>>>(P); break;
+          case 2: mc_kernel<2, 4><<<c.n, nthr, smem, s>>>(P); break;
+          default: mc_kernel<3, 4><<<c.n, nthr, smem, s>>>(P); break;
+        }
+      } else {
+        switch (m) {
+          case 0: mc_kernel<0, 1><<<c.n, nsamp, smem, s>>>(P); break;
+          case 1: mc_kernel<1, 1><<<c.n, nsamp, smem, s>>>(P); break;
+          case 2: mc_kernel<2, 1><<<c.n, nsamp, smem, s>>>(P); break;
+          default: mc_kernel<3, 1><<<c.n, nsamp, smem, s>>>(P); break;
+        }
       }
       B200_CUDA(cudaGetLastError());
     }

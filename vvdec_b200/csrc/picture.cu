@@ -20,6 +20,7 @@ struct Arena {
   int16_t* given[3] = {nullptr, nullptr, nullptr};
   int dstSlot = 0, flags = 0;
   bool valid = false;
+  cudaEvent_t uploaded = nullptr, done = nullptr; bool donePending = false;   // H2D finished / kernels reading this arena finished
 };
 
 }  // namespace b200
@@ -38,7 +39,7 @@ struct b200_ctx {
   b200_geom g;
   CtxProf prof; bool profiling = false;
   int numSlots = 0, numArenas = 0, device = 0;
-  cudaStream_t stream = nullptr, copyStream = nullptr;
+  cudaStream_t stream = nullptr, copyStream = nullptr, upStream = nullptr;   // kernels / frame output D2H / work-list H2D
   StreamSet ss;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   std::vector<cudaEvent_t> readDone; std::vector<char> readPending;   // per picture buffer: an async D2H is (maybe) still reading it
@@ -77,6 +78,7 @@ B200_API int b200_ctx_create(b200_ctx** out, const b200_geom* g, int numSlots, i
   B200_CUDA(cudaGetDevice(&c->device));
   B200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   B200_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+  B200_CUDA(cudaStreamCreateWithFlags(&c->upStream, cudaStreamNonBlocking));
   c->ss.main = c->stream; c->ss.nAux = 3;
   B200_CUDA(cudaEventCreateWithFlags(&c->ss.forkEv, cudaEventDisableTiming));
   for (int k = 0; k < c->ss.nAux; k++) { B200_CUDA(cudaStreamCreateWithFlags(&c->ss.aux[k], cudaStreamNonBlocking)); B200_CUDA(cudaEventCreateWithFlags(&c->ss.joinEv[k], cudaEventDisableTiming)); }
@@ -92,6 +94,7 @@ B200_API int b200_ctx_create(b200_ctx** out, const b200_geom* g, int numSlots, i
   for (int s = 0; s < numSlots; s++) c->slotBuf[s] = s;
   c->work[0] = numSlots; c->work[1] = numSlots + 1;
   c->arenas.resize(numArenas);
+  for (auto& A : c->arenas) { B200_CUDA(cudaEventCreateWithFlags(&A.uploaded, cudaEventDisableTiming)); B200_CUDA(cudaEventCreateWithFlags(&A.done, cudaEventDisableTiming)); }
   *out = c;
   return 0;
 }
@@ -99,7 +102,9 @@ B200_API int b200_ctx_create(b200_ctx** out, const b200_geom* g, int numSlots, i
 B200_API void b200_ctx_destroy(b200_ctx* c)
 {
   if (!c) return;
-  cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copyStream);
+  cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copyStream); cudaStreamSynchronize(c->upStream);
+  for (auto& A : c->arenas) { cudaEventDestroy(A.uploaded); cudaEventDestroy(A.done); }
+  cudaStreamDestroy(c->upStream);
   for (auto p : c->bufs) cudaFree(p);
   for (auto e : c->readDone) cudaEventDestroy(e);
   for (auto e : c->ticketEv) cudaEventDestroy(e);
@@ -151,10 +156,11 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   const size_t oDm = take(p->numDmvr * 8);
   const bool hasGiven = p->given[0] != nullptr;
   const size_t oGiven = take(hasGiven ? c->picBytes : 0);
-  if (off > A.buf.cap) { B200_CUDA(cudaStreamSynchronize(c->stream)); }      // the arena may still be in use by queued kernels
+  if (off > A.buf.cap) { B200_CUDA(cudaStreamSynchronize(c->stream)); B200_CUDA(cudaStreamSynchronize(c->upStream)); A.donePending = false; }   // realloc: nothing may still use the old buffer
   if (int rc = A.buf.reserve(off)) return rc;
   char* base = A.buf.as<char>();
-  cudaStream_t s = c->stream;
+  cudaStream_t s = c->upStream;                                       // H2D on its own stream: overlaps the kernels of earlier pictures
+  if (A.donePending) { B200_CUDA(cudaStreamWaitEvent(s, A.done, 0)); A.donePending = false; }   // kernels of the arena's previous picture
   auto h2d = [&](size_t o, const void* src, size_t bytes) -> int { if (bytes) B200_CUDA(cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, s)); return 0; };
   if (int rc = h2d(oPus, p->pus, p->numPus * sizeof(b200_pu))) return rc;
   if (int rc = upload_mc_tiles(c->hTiles, reinterpret_cast<uint32_t*>(base + oT), A.mcTiles, s)) return rc;
@@ -198,6 +204,7 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   A.dmvrMv = p->numDmvr ? reinterpret_cast<int32_t*>(base + oDm) : nullptr; A.numDmvr = p->numDmvr;
   if (p->numDmvr) B200_CUDA(cudaMemsetAsync(base + oDm, 0, p->numDmvr * 8, s));   // entries of non-DMVR CUs stay zero, like m_dmvrMvCache users expect
   A.dstSlot = p->dstSlot; A.flags = p->flags; A.valid = true;
+  B200_CUDA(cudaEventRecord(A.uploaded, s));
   return ai;
 }
 
@@ -207,6 +214,7 @@ B200_API int b200_pic_run(b200_ctx* c, int ai)
   B200_CUDA(cudaSetDevice(c->device));
   Arena& A = c->arenas[ai];
   cudaStream_t s = c->stream;
+  B200_CUDA(cudaStreamWaitEvent(s, A.uploaded, 0));
   const b200_geom& g = c->g;
   int cur = c->work[0], other = c->work[1];
   for (int b : {cur, other}) if (c->readPending[b]) { B200_CUDA(cudaStreamWaitEvent(s, c->readDone[b], 0)); c->readPending[b] = 0; }   // async output copies still reading these buffers
@@ -252,6 +260,7 @@ B200_API int b200_pic_run(b200_ctx* c, int ai)
     c->launches += g.chromaFormat ? 2 : 1;
     std::swap(cur, other);
   }
+  B200_CUDA(cudaEventRecord(A.done, s)); A.donePending = true;
   // 6. the buffer holding the result becomes the slot's buffer; the slot's old buffer becomes a work buffer (swapBufs, DecLibRecon.cpp:423)
   const int old = c->slotBuf[A.dstSlot];
   c->slotBuf[A.dstSlot] = cur;
@@ -274,6 +283,7 @@ B200_API int b200_wait_picture(b200_ctx* c, int ai, int32_t* dmvrMv, size_t numD
     const size_t n = numDmvr < c->arenas[ai].numDmvr ? numDmvr : c->arenas[ai].numDmvr;
     B200_CUDA(cudaMemcpyAsync(dmvrMv, c->arenas[ai].dmvrMv, n * 8, cudaMemcpyDeviceToHost, c->stream));
   }
+  B200_CUDA(cudaStreamSynchronize(c->upStream));
   B200_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
