@@ -427,33 +427,47 @@ __global__ void mc_kernel(const McParams P)
     }
     __syncthreads();
     {
-      // per 4x4 block: sums over the 6x6 window (calcBIOSums :134): work items = (block, 36 window samples), reduced through shared atomics
-      __shared__ int sSum[16][5];
+      // per 4x4 block: sums over the 6x6 window (calcBIOSums :134)
       const int nBlk = (tw >> 2) * (th >> 2), l2bw = l2w - 2;
-      for (int i = tid; i < 16 * 5; i += nthr) (&sSum[0][0])[i] = 0;
-      __syncthreads();
-      for (int it = tid; it < nBlk * 36; it += nthr) {
-        const int blk = it / 36, j = it - blk * 36;
-        const int bxx = (blk & ((tw >> 2) - 1)) << 2, byy = (blk >> l2bw) << 2;
-        const int yy = j / 6, xx = j - yy * 6, i = (byy + yy) * 18 + bxx + xx;
-        const int gX = (S.g[0][0][i] + S.g[1][0][i]) >> 1, gY = (S.g[0][1][i] + S.g[1][1][i]) >> 1;
-        const int dI = (S.p[1][i] >> 4) - (S.p[0][i] >> 4);
-        atomicAdd(&sSum[blk][0], abs(gX)); atomicAdd(&sSum[blk][1], abs(gY));
-        atomicAdd(&sSum[blk][2], gX < 0 ? -dI : (gX == 0 ? 0 : dI));
-        atomicAdd(&sSum[blk][3], gY < 0 ? -dI : (gY == 0 ? 0 : dI));
-        atomicAdd(&sSum[blk][4], gY < 0 ? -gX : (gY == 0 ? 0 : gX));
-      }
-      __syncthreads();
-      for (int blk = tid; blk < nBlk; blk += nthr) {
-        const int sAX = sSum[blk][0], sAY = sSum[blk][1], sDX = sSum[blk][2], sDY = sSum[blk][3], sS = sSum[blk][4];
-        int vx = sAX == 0 ? 0 : shift_msb(sDX * 4, sAX);
-        vx = clip3(-15, 15, vx);
-        const int mainG = sS >> 12, secG = sS & 4095;
-        int tmp = vx * mainG;
-        tmp = ((tmp * (1 << 12)) + vx * secG) >> 1;
-        int vy = sAY == 0 ? 0 : shift_msb(sDY * 4 - tmp, sAY);
-        vy = clip3(-15, 15, vy);
-        sVxy[blk][0] = vx; sVxy[blk][1] = vy;
+      // 4 lanes per block: lane part p sums window rows p and p+4 (rows 4,5 only for p<2); quad shuffle reduce; lane 0 derives (vx,vy)
+      for (int it = tid; it < ((nBlk * 4 + 31) & ~31); it += nthr) {
+        const int blk = it >> 2, part = it & 3;
+        int sAX = 0, sAY = 0, sDX = 0, sDY = 0, sS = 0;
+        if (blk < nBlk) {
+          const int bxx = (blk & ((tw >> 2) - 1)) << 2, byy = (blk >> l2bw) << 2;
+#pragma unroll
+          for (int rr = 0; rr < 2; rr++) {
+            const int yy = part + 4 * rr;
+            if (yy < 6) {
+#pragma unroll
+              for (int xx = 0; xx < 6; xx++) {
+                const int i = (byy + yy) * 18 + bxx + xx;
+                const int gX = (S.g[0][0][i] + S.g[1][0][i]) >> 1, gY = (S.g[0][1][i] + S.g[1][1][i]) >> 1;
+                const int dI = (S.p[1][i] >> 4) - (S.p[0][i] >> 4);
+                sAX += abs(gX); sAY += abs(gY);
+                sDX += gX < 0 ? -dI : (gX == 0 ? 0 : dI);
+                sDY += gY < 0 ? -dI : (gY == 0 ? 0 : dI);
+                sS  += gY < 0 ? -gX : (gY == 0 ? 0 : gX);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int m = 1; m < 4; m <<= 1) {
+          sAX += __shfl_xor_sync(0xffffffffu, sAX, m); sAY += __shfl_xor_sync(0xffffffffu, sAY, m);
+          sDX += __shfl_xor_sync(0xffffffffu, sDX, m); sDY += __shfl_xor_sync(0xffffffffu, sDY, m);
+          sS  += __shfl_xor_sync(0xffffffffu, sS, m);
+        }
+        if (part == 0 && blk < nBlk) {
+          int vx = sAX == 0 ? 0 : shift_msb(sDX * 4, sAX);
+          vx = clip3(-15, 15, vx);
+          const int mainG = sS >> 12, secG = sS & 4095;
+          int tmp = vx * mainG;
+          tmp = ((tmp * (1 << 12)) + vx * secG) >> 1;
+          int vy = sAY == 0 ? 0 : shift_msb(sDY * 4 - tmp, sAY);
+          vy = clip3(-15, 15, vy);
+          sVxy[blk][0] = vx; sVxy[blk][1] = vy;
+        }
       }
       __syncthreads();
       for (int sI = tid; sI < tw * th; sI += nthr) {         // addBIOAvg4 (:109)
