@@ -610,13 +610,34 @@ extern "C" int ref_mc_predict( int simd, const b200_geom* g, int16_t* const dst[
 }
 
 // ================================================================================================ whole back end, multi-threaded
-template<class F> static void parallelFor( int n, int threads, F f )
+// Persistent worker pool (the reference keeps its worker threads alive across pictures too: Utilities/ThreadPool.h); items are handed out
+// dynamically through an atomic counter.
+struct WorkerPool
 {
-  std::atomic<int> next{ 0 };
-  std::vector<std::thread> pool;
-  for( int t = 0; t < threads; t++ ) pool.emplace_back( [&, t] { for( int i = next++; i < n; i = next++ ) f( i, t ); } );
-  for( auto& th : pool ) th.join();
-}
+  std::vector<std::thread> workers;
+  std::mutex m; std::condition_variable cvGo, cvDone;
+  std::function<void( int, int )> job; int n = 0; std::atomic<int> next{ 0 }; int gen = 0, running = 0; bool stop = false;
+  explicit WorkerPool( int threads )
+  {
+    for( int t = 0; t < threads; t++ ) workers.emplace_back( [this, t] {
+      int seen = 0;
+      for( ;; )
+      {
+        { std::unique_lock<std::mutex> lk( m ); cvGo.wait( lk, [&] { return stop || gen != seen; } ); if( stop ) return; seen = gen; }
+        for( int i = next++; i < n; i = next++ ) job( i, t );
+        { std::lock_guard<std::mutex> lk( m ); if( --running == 0 ) cvDone.notify_one(); }
+      }
+    } );
+  }
+  ~WorkerPool() { { std::lock_guard<std::mutex> lk( m ); stop = true; } cvGo.notify_all(); for( auto& w : workers ) w.join(); }
+  template<class F> void run( int count, F f )
+  {
+    { std::lock_guard<std::mutex> lk( m ); job = f; n = count; next = 0; running = (int) workers.size(); gen++; }
+    cvGo.notify_all();
+    std::unique_lock<std::mutex> lk( m ); cvDone.wait( lk, [&] { return running == 0; } );
+  }
+};
+template<class F> static void parallelFor( int n, WorkerPool& pool, F f ) { pool.run( n, f ); }
 
 static void fillCuFromPu( CodingUnit& cu, const b200_pu& pu, FakePicture& cur, Slice* sl )
 {
@@ -808,12 +829,24 @@ extern "C" double ref_decompress_picture_out( const b200_geom* g, const int16_t*
   const int wC = pcv.widthInCtus, hC = pcv.heightInCtus;
 
   // ------------------------------------------------------------------ timed region
+  WorkerPool pool( threads );
+  if( doSao ) sao.create( g->width, g->height, pcv.chrFormat, g->ctuSize, g->ctuSize, 0, 0, fltBuf );
   const auto t0 = clk::now();
-  ref[0]->pic.extendPicBorder();                                   // one reference-picture border extension per picture
+  // one reference-picture border extension per picture, as the six tasks DecLibRecon.cpp:291-374 issues
+  parallelFor( 6, pool, [&]( int k, int ) {
+    Picture& rpic = ref[0]->pic;
+    switch( k ) {
+      case 0: rpic.extendPicBorder( true, false, false, false ); break;
+      case 1: rpic.extendPicBorder( false, true, false, false ); break;
+      case 2: rpic.extendPicBorder( false, false, true, false, CH_L ); break;
+      case 3: rpic.extendPicBorder( false, false, false, true, CH_L ); break;
+      case 4: rpic.extendPicBorder( false, false, true, false, CH_C ); break;
+      default: rpic.extendPicBorder( false, false, false, true, CH_C ); break;
+    } } );
   // K2: per PU (dynamic scheduling over chunks of 16 PUs)
   {
     const int nChunks = ( (int) pic->numPus + 15 ) / 16;
-    parallelFor( nChunks, threads, [&]( int ch, int t ) {
+    parallelFor( nChunks, pool, [&]( int ch, int t ) {
       CodingUnit cu;
       for( size_t n = (size_t) ch * 16; n < std::min<size_t>( pic->numPus, (size_t) ch * 16 + 16 ); n++ )
       {
@@ -827,7 +860,7 @@ extern "C" double ref_decompress_picture_out( const b200_geom* g, const int16_t*
   // K1: per TU chunk
   {
     const int nChunks = ( (int) pic->numTus + 31 ) / 32;
-    parallelFor( nChunks, threads, [&]( int ch, int t ) {
+    parallelFor( nChunks, pool, [&]( int ch, int t ) {
       TCoeff* dq  = tqs[t]->m_dqnt; TCoeff* tmp = tqs[t]->m_tmp; TCoeff* blk = tqs[t]->m_blk;
       alignas( 32 ) Pel r0[64 * 64]; alignas( 32 ) Pel r1[64 * 64];
       const int pmax = ( 1 << g->bitDepth ) - 1;
@@ -849,20 +882,22 @@ extern "C" double ref_decompress_picture_out( const b200_geom* g, const int16_t*
   }
   if( doLf )
   {
-    parallelFor( wC * hC, threads, [&]( int a, int ) { lf.loopFilterCTU( cs, MAX_NUM_CHANNEL_TYPE, a % wC, a / wC, EDGE_VER ); } );
-    parallelFor( wC * hC, threads, [&]( int a, int ) { lf.loopFilterCTU( cs, MAX_NUM_CHANNEL_TYPE, a % wC, a / wC, EDGE_HOR ); } );
+    parallelFor( wC * hC, pool, [&]( int a, int ) { lf.loopFilterCTU( cs, MAX_NUM_CHANNEL_TYPE, a % wC, a / wC, EDGE_VER ); } );
+    parallelFor( wC * hC, pool, [&]( int a, int ) { lf.loopFilterCTU( cs, MAX_NUM_CHANNEL_TYPE, a % wC, a / wC, EDGE_HOR ); } );
   }
   if( doSao )
   {
-    fltBuf.copyFrom( cs.getRecoBuf() );                              // SAOPrepareCTULine copies the deblocked rows (SampleAdaptiveOffset.cpp:400)
-    sao.create( g->width, g->height, pcv.chrFormat, g->ctuSize, g->ctuSize, 0, 0, fltBuf );
-    parallelFor( wC * hC, threads, [&]( int a, int ) {
+    // SAOPrepareCTULine copies the deblocked rows (SampleAdaptiveOffset.cpp:400), one CTU line per task
+    parallelFor( hC, pool, [&]( int r, int ) {
+      const UnitArea line = clipArea( UnitArea( pcv.chrFormat, Area( 0, r * g->ctuSize, g->width, g->ctuSize ) ), cur.pic );
+      fltBuf.subBuf( line ).copyFrom( cs.getRecoBuf().subBuf( line ) ); } );
+    parallelFor( wC * hC, pool, [&]( int a, int ) {
       sao.SAOProcessCTU( cs, clipArea( UnitArea( pcv.chrFormat, Area( ( a % wC ) * g->ctuSize, ( a / wC ) * g->ctuSize, g->ctuSize, g->ctuSize ) ), cur.pic ) ); } );
   }
   if( doAlf )
   {
-    parallelFor( wC * hC, threads, [&]( int a, int ) { alf.prepareCTU( cs, a % wC, a / wC ); } );
-    parallelFor( wC * hC, threads, [&]( int a, int t ) { alf.processCTU( cs, a % wC, a / wC, t ); } );
+    parallelFor( wC * hC, pool, [&]( int a, int ) { alf.prepareCTU( cs, a % wC, a / wC ); } );
+    parallelFor( wC * hC, pool, [&]( int a, int t ) { alf.processCTU( cs, a % wC, a / wC, t ); } );
   }
   const double secs = std::chrono::duration<double>( clk::now() - t0 ).count();
   if( out ) { if( doAlf ) cur.getPlanes( *g, out, true, &fltBuf ); else cur.getPlanes( *g, out ); }

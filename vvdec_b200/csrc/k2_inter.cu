@@ -91,7 +91,7 @@ __host__ __device__ inline int mc_smem_elems(int mode, int n)   // n = tw*th; wo
   const int lists = mode == 0 ? 1 : 2;
   int e = lists * (win + hf + 2 * (cwin + chf));
   if (mode >= 2) e += 2 * 324 + 4 * 324;                                   // P + gradients (18x18)
-  if (mode == 3) e = max(e, 2 * 400) + 0;                                   // bilinear 20x20 x2 shares the window area
+  if (mode == 3) e = max(e, 2 * 400 + 2 * 441);                             // bilinear 20x20 x2 + raw 21x21 x2 share the window area
   return (e + 64) & ~1;
 }
 
@@ -154,32 +154,52 @@ __global__ void mc_kernel(const McParams P)
   if (MODE == 3) {
     // ================================================================ DMVR search (xProcessDMVR :1847)
     int16_t* B0 = smem; int16_t* B1 = smem + 400;            // bilinear buffers 20x20 (stride 20)
+    int16_t* R0 = smem + 800;                                // raw integer windows (BW+1)x(BH+1), stride 21, per list
     const int BW = tw + 4, BH = th + 4;
+    int bxF[2], byF[2];
+    {
+      const int warp = tid >> 5, lane = tid & 31, nw = max(1, nthr >> 5);
+      constexpr int NB = 8;
+      int X0[2], Y0[2];
 #pragma unroll
-    for (int li = 0; li < 2; li++) {
-      int cx = mvx[li], cy = mvy[li];
-      clip_mv(cx, cy, puX, puY, P);                          // xinitMC :1811: relative to the CU
-      const int mx = cx - 32, my = cy - 32;
-      const int xF = mx & 15, yF = my & 15, X0 = puX + tx0 + (mx >> 4), Y0 = puY + ty0 + (my >> 4);
-      const int f0 = kIfBilin4[xF * 2], f1 = kIfBilin4[xF * 2 + 1], g0 = kIfBilin4[yF * 2], g1 = kIfBilin4[yF * 2 + 1];
+      for (int li = 0; li < 2; li++) {
+        int cx = mvx[li], cy = mvy[li];
+        clip_mv(cx, cy, puX, puY, P);                        // xinitMC :1811: relative to the CU
+        const int mx = cx - 32, my = cy - 32;
+        bxF[li] = mx & 15; byF[li] = my & 15; X0[li] = min(max(puX + tx0 + (mx >> 4) + lane, 0), W - 1); Y0[li] = puY + ty0 + (my >> 4);
+      }
+      if (lane < BW + 1)
+        for (int y0 = warp; y0 < BH + 1; y0 += nw * NB) {
+          int16_t v[2][NB];
+#pragma unroll
+          for (int li = 0; li < 2; li++)
+#pragma unroll
+            for (int k = 0; k < NB; k++) {
+              const int y = y0 + k * nw;
+              if (y < BH + 1) v[li][k] = __ldg(rp[li][0] + (size_t)min(max(Y0[li] + y, 0), H - 1) * rs0 + X0[li]);
+            }
+#pragma unroll
+          for (int li = 0; li < 2; li++)
+#pragma unroll
+            for (int k = 0; k < NB; k++) {
+              const int y = y0 + k * nw;
+              if (y < BH + 1) R0[li * 441 + y * 21 + lane] = v[li][k];
+            }
+        }
+    }
+    __syncthreads();
+    {
       const int s1 = 4 - (10 - bd), o1 = 1 << (s1 - 1);
-      const int16_t* r = rp[li][0];
-      int16_t* B = li ? B1 : B0;
-      for (int y = tid >> 5; y < BH; y += nthr >> 5) {
-        const int x = tid & 31;
+      for (int i = tid; i < 2 * BH * 32; i += nthr) {        // item = (list, row, column lane)
+        const int x = i & 31, yy = i >> 5, li = yy >= BH, y = li ? yy - BH : yy;
         if (x < BW) {
-          const int Y = min(max(Y0 + y, 0), H - 1), Y1 = min(max(Y0 + y + 1, 0), H - 1), X = min(max(X0 + x, 0), W - 1), X1 = min(max(X0 + x + 1, 0), W - 1);
-          const int a00 = r[(size_t)Y * rs0 + X];
-          int v;
-          if (xF == 0 && yF == 0) v = a00 << (10 - bd);
-          else if (yF == 0) v = (f0 * a00 + f1 * r[(size_t)Y * rs0 + X1] + o1) >> s1;
-          else if (xF == 0) v = (g0 * a00 + g1 * r[(size_t)Y1 * rs0 + X] + o1) >> s1;
-          else {
-            const int a = (int16_t)((f0 * a00 + f1 * r[(size_t)Y * rs0 + X1] + o1) >> s1);
-            const int b = (int16_t)((f0 * r[(size_t)Y1 * rs0 + X] + f1 * r[(size_t)Y1 * rs0 + X1] + o1) >> s1);
-            v = (g0 * a + g1 * b + 8) >> 4;
-          }
-          B[y * 20 + x] = (int16_t)v;
+          const int xF = li ? bxF[1] : bxF[0], yF = li ? byF[1] : byF[0];
+          const int f0 = kIfBilin4[xF * 2], f1 = kIfBilin4[xF * 2 + 1], g0 = kIfBilin4[yF * 2], g1 = kIfBilin4[yF * 2 + 1];
+          const int16_t* r = R0 + li * 441 + y * 21 + x;
+          // two-step form; equals the reference's one-step special cases for xF == 0 or yF == 0 at bit depths <= 10
+          const int a = (int16_t)((f0 * r[0] + f1 * r[1] + o1) >> s1);
+          const int b = (int16_t)((f0 * r[21] + f1 * r[22] + o1) >> s1);
+          (li ? B1 : B0)[y * 20 + x] = (int16_t)((g0 * a + g1 * b + 8) >> 4);
         }
       }
     }
@@ -258,36 +278,66 @@ __global__ void mc_kernel(const McParams P)
   }
 
   // ================================================================ stage A: windows (luma 8-tap footprint, chroma 4-tap footprint)
+  // lane = column, warp = row; rows go in batches of NB with every load of a batch (both lists) issued before the first shared store,
+  // so a tile pays one DRAM round trip per batch instead of one per row.
   {
     const int warp = tid >> 5, lane = tid & 31, nw = max(1, nthr >> 5);
+    constexpr int NB = 8;
+    int xc[NL], ylo[NL], yhi[NL];
 #pragma unroll
     for (int li = 0; li < NL; li++) {
-      const int16_t* r = rp[li][0];
-      const int X = ox[li] - 3 + lane;
-      int xc;
-      if (MODE == 3) xc = min(max(min(max(X, wx0[li][0]), wx1[li][0]), 0), W - 1); else xc = min(max(X, 0), W - 1);
-      if (lane < tw + 7)
-        for (int y = warp; y < th + 7; y += nw) {
-          int Y = oy[li] - 3 + y;
-          if (MODE == 3) Y = min(max(Y, wy0[li][0]), wy1[li][0]);
-          Y = min(max(Y, 0), H - 1);
-          S.w[li][y * (tw + 7) + lane] = r[(size_t)Y * rs0 + xc];
-        }
-      if (chroma) {
-        // both chroma components: lanes 0..15 Cb, 16..31 Cr (cw+3 <= 11)
-        const int c = lane >> 4, xl = lane & 15;
-        const int16_t* rc = c ? rp[li][2] : rp[li][1];
-        const int Xc = ocx[li] - 1 + xl;
-        int xcc;
-        if (MODE == 3) xcc = min(max(min(max(Xc, wx0[li][1]), wx1[li][1]), 0), CWp - 1); else xcc = min(max(Xc, 0), CWp - 1);
-        if (xl < cw + 3)
-          for (int y = warp; y < ch + 3; y += nw) {
-            int Y = ocy[li] - 1 + y;
-            if (MODE == 3) Y = min(max(Y, wy0[li][1]), wy1[li][1]);
-            Y = min(max(Y, 0), CHp - 1);
-            (c ? S.cw[li][1] : S.cw[li][0])[y * (cw + 3) + xl] = rc[(size_t)Y * rs1 + xcc];
+      const int xlo = MODE == 3 ? clip3(0, W - 1, wx0[li][0]) : 0, xhi = MODE == 3 ? clip3(0, W - 1, wx1[li][0]) : W - 1;
+      ylo[li] = MODE == 3 ? clip3(0, H - 1, wy0[li][0]) : 0; yhi[li] = MODE == 3 ? clip3(0, H - 1, wy1[li][0]) : H - 1;
+      xc[li] = min(max(ox[li] - 3 + lane, xlo), xhi);
+    }
+    if (lane < tw + 7)
+      for (int y0 = warp; y0 < th + 7; y0 += nw * NB) {
+        int16_t v[NL][NB];
+#pragma unroll
+        for (int li = 0; li < NL; li++)
+#pragma unroll
+          for (int k = 0; k < NB; k++) {
+            const int y = y0 + k * nw;
+            if (y < th + 7) v[li][k] = __ldg(rp[li][0] + (size_t)min(max(oy[li] - 3 + y, ylo[li]), yhi[li]) * rs0 + xc[li]);
+          }
+#pragma unroll
+        for (int li = 0; li < NL; li++)
+#pragma unroll
+          for (int k = 0; k < NB; k++) {
+            const int y = y0 + k * nw;
+            if (y < th + 7) S.w[li][y * (tw + 7) + lane] = v[li][k];
           }
       }
+    if (chroma) {
+      // both chroma components: lanes 0..15 Cb, 16..31 Cr (cw+3 <= 11)
+      const int c = lane >> 4, xl = lane & 15;
+      int xcc[NL], cylo[NL], cyhi[NL];
+#pragma unroll
+      for (int li = 0; li < NL; li++) {
+        const int xlo = MODE == 3 ? clip3(0, CWp - 1, wx0[li][1]) : 0, xhi = MODE == 3 ? clip3(0, CWp - 1, wx1[li][1]) : CWp - 1;
+        cylo[li] = MODE == 3 ? clip3(0, CHp - 1, wy0[li][1]) : 0; cyhi[li] = MODE == 3 ? clip3(0, CHp - 1, wy1[li][1]) : CHp - 1;
+        xcc[li] = min(max(ocx[li] - 1 + xl, xlo), xhi);
+      }
+      if (xl < cw + 3)
+        for (int y0 = warp; y0 < ch + 3; y0 += nw * NB) {
+          int16_t v[NL][NB];
+#pragma unroll
+          for (int li = 0; li < NL; li++) {
+            const int16_t* rc = c ? rp[li][2] : rp[li][1];
+#pragma unroll
+            for (int k = 0; k < NB; k++) {
+              const int y = y0 + k * nw;
+              if (y < ch + 3) v[li][k] = __ldg(rc + (size_t)min(max(ocy[li] - 1 + y, cylo[li]), cyhi[li]) * rs1 + xcc[li]);
+            }
+          }
+#pragma unroll
+          for (int li = 0; li < NL; li++)
+#pragma unroll
+            for (int k = 0; k < NB; k++) {
+              const int y = y0 + k * nw;
+              if (y < ch + 3) (c ? S.cw[li][1] : S.cw[li][0])[y * (cw + 3) + xl] = v[li][k];
+            }
+        }
     }
   }
   __syncthreads();
