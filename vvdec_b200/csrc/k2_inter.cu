@@ -13,7 +13,7 @@
 // InterpolationFilter.cpp filter<> :556, filterCopy :424, filterWxH_N4/N8 :805,:881; Buffer.cpp addAvg :441, addWeightedAvg :372;
 // RdCost.cpp xGetSAD8/16(+X5) :107-221; Mv.cpp clipMvInPic :64; UnitTools.cpp PU::setAllAffineMv :2689.
 // HBM traffic per bi-predicted 16x16 tile: 2*(23*23 + 2*11*11)*2 B read + (256 + 128)*2 B written + 64 B record share.
-#define VVC_TABLE_QUAL static __device__ const
+#define VVC_TABLE_QUAL static __device__ const __align__(16)
 #include "vvc_tables.h"
 #include "common.cuh"
 
@@ -26,6 +26,7 @@ struct McParams {
   const int16_t* refs[B200_MAX_SLOTS * 3];   // device plane pointers, by value (no table in memory -> no sync when the DPB mapping changes)
   int refStride[3];
   int W, H, bitDepth, ctuSize, chroma;
+  int fastOk;                                // plane strides are even -> rows are word-addressable
   const b200_pu* pus; const uint32_t* tiles; int numTiles;
   int32_t* dmvrMv;
 };
@@ -47,6 +48,13 @@ __device__ __forceinline__ const int8_t* luma_taps(int frac, bool is4x4, bool al
   if (is4x4) return kIfLuma4x4 + frac * 8;
   if (frac == 8 && altHpel) return kIfAltHpel;
   return kIfLuma + frac * 8;
+}
+
+__device__ __forceinline__ void load_taps8(const int8_t* t, int f[8])   // rows of the tables are 8-byte aligned
+{
+  const int2 w = __ldg(reinterpret_cast<const int2*>(t));
+#pragma unroll
+  for (int k = 0; k < 4; k++) { f[k] = (w.x << (24 - 8 * k)) >> 24; f[4 + k] = (w.y << (24 - 8 * k)) >> 24; }
 }
 
 __device__ __forceinline__ int avg_bi(int p0, int p1, int w1, int hr, int pmax)
@@ -76,30 +84,30 @@ __device__ int div_for_maxq7(long long N, long long D)
 // MODE: 0 uni, 1 bi (average / BCW), 2 bi + BDOF, 3 DMVR (+BDOF per sub-block).  blockDim.x = tw*th (32..256): one thread per luma
 // sample; tw, th are powers of two (4, 8, 16), so all index arithmetic is shifts.  Dynamic shared memory, laid out per launch class.
 struct TileSmem {
-  int16_t *w[2], *h[2];           // luma window (stride tw+7) and H-filtered rows (stride tw) per list
-  int16_t *cw[2][2], *chf[2][2];  // chroma [list][comp]: window (stride cw+3), H-filtered rows (stride cw)
-  int16_t *p[2], *g[2][2];        // BDOF: 14-bit predictions with ring (stride tw+2), gradX/gradY
+  int16_t *w[2], *h[2];           // luma window (stride tw+8) and H-filtered rows (stride tw) per list
+  int16_t *cw[2][2], *chf[2][2];  // chroma [list][comp]: window (stride cw+4), H-filtered rows (stride cw)
+  int16_t *p[2];                  // BDOF: 14-bit predictions with ring (stride 18)
 };
 
 __host__ __device__ inline int mc_smem_elems(int mode, int n)   // n = tw*th; worst case over the shapes of that size
 {
-  // window: 16x16 -> 23x23; 128 -> 23x15; 64 -> 23x11 (>15x15); 32 -> 15x11.  hf: (th+7)*tw worst = n + 7*16|8.
-  const int win = n == 256 ? 529 : n == 128 ? 345 : n == 64 ? 253 : 165;
+  // window (tw+8)x(th+7): 16x16 -> 24x23; 128 -> 24x15 | 16x23; 64 -> 12x23; 32 -> 12x15.  hf: (th+7)*tw worst = n + 7*16|8.
+  const int win = n == 256 ? 552 : n == 128 ? 368 : n == 64 ? 276 : 180;
   const int hf  = n + 7 * (n >= 64 ? 16 : 8);
-  const int cwin = n == 256 ? 121 : n == 128 ? 77 : n == 64 ? 55 : 35;     // (cw+3)(ch+3)
+  const int cwin = n == 256 ? 132 : n == 128 ? 88 : n == 64 ? 66 : 42;     // (cw+4)(ch+3)
   const int chf = (n >> 2) + 3 * (n >= 64 ? 8 : 4);
   const int lists = mode == 0 ? 1 : 2;
   int e = lists * (win + hf + 2 * (cwin + chf));
-  if (mode >= 2) e += 2 * 324 + 4 * 324;                                   // P + gradients (18x18)
+  if (mode >= 2) e = max(e, 8 * n) + 2 * 324;                              // BDOF: per-sample records (16 B) reuse the window area; P0/P1 18x18 behind
   if (mode == 3) e = max(e, 2 * 400 + 2 * 441);                             // bilinear 20x20 x2 + raw 21x21 x2 share the window area
-  return (e + 64) & ~1;
+  return (e + 64) & ~7;
 }
 
 // OPT: luma outputs per thread (1: blockDim = tw*th; 4: blockDim = tw*th/4, each thread filters 4 adjacent samples so that 11 loads feed 32 MACs)
 template <int MODE, int OPT>
 __global__ void mc_kernel(const McParams P)
 {
-  extern __shared__ int16_t smem[];
+  extern __shared__ __align__(16) int16_t smem[];
   __shared__ unsigned sSad[25];
   __shared__ int sDec[3];
   __shared__ int sVxy[16][2];
@@ -120,19 +128,20 @@ __global__ void mc_kernel(const McParams P)
   constexpr int NL = BI ? 2 : 1;
   const int cw = tw >> 1, ch = th >> 1, l2cw = l2w - 1;
   const int chroma = P.chroma;
+  const int WS = tw + 8, CS = cw + 4;                        // window strides: even, so a row is a run of 32-bit words
 
   // ---- shared memory carve-up (strides depend on the tile shape) ----
   TileSmem S;
   {
     int16_t* q = smem;
-    const int win = (tw + 7) * (th + 7), hf = (th + 7) * tw, cwin = (cw + 3) * (ch + 3), chf = (ch + 3) * cw;
+    const int win = WS * (th + 7), hf = (th + 7) * tw, cwin = CS * (ch + 3), chf = (ch + 3) * cw;
 #pragma unroll
     for (int l = 0; l < NL; l++) { S.w[l] = q; q += win; S.h[l] = q; q += hf; }
 #pragma unroll
     for (int l = 0; l < NL; l++)
 #pragma unroll
       for (int c = 0; c < 2; c++) { S.cw[l][c] = q; q += cwin; S.chf[l][c] = q; q += chf; }
-    if (MODE >= 2) { S.p[0] = q; q += 324; S.p[1] = q; q += 324; S.g[0][0] = q; q += 324; S.g[0][1] = q; q += 324; S.g[1][0] = q; q += 324; S.g[1][1] = q; q += 324; }
+    if (MODE >= 2) { if (q < smem + 8 * tw * th) q = smem + 8 * tw * th; S.p[0] = q; S.p[1] = q + 324; }
   }
 
   // ---- per-list reference planes and motion ----
@@ -278,66 +287,84 @@ __global__ void mc_kernel(const McParams P)
   }
 
   // ================================================================ stage A: windows (luma 8-tap footprint, chroma 4-tap footprint)
-  // lane = column, warp = row; rows go in batches of NB with every load of a batch (both lists) issued before the first shared store,
-  // so a tile pays one DRAM round trip per batch instead of one per row.
+  // Interior tiles (the footprint lies inside the picture and no DMVR window clamp applies) copy whole 32-bit words, 16 lanes per luma
+  // row / 8 lanes per chroma row; the footprint's first sample then sits at index wofs (0/1) of each shared row.  Boundary tiles take
+  // the per-sample path with clamped coordinates (= the reference's border extension / padded DMVR window).  Loads of a batch are all
+  // issued before the first shared store.
+  int wofs[NL], cofs[NL];
   {
     const int warp = tid >> 5, lane = tid & 31, nw = max(1, nthr >> 5);
-    constexpr int NB = 8;
-    int xc[NL], ylo[NL], yhi[NL];
+    constexpr int NB = 6;
 #pragma unroll
     for (int li = 0; li < NL; li++) {
-      const int xlo = MODE == 3 ? clip3(0, W - 1, wx0[li][0]) : 0, xhi = MODE == 3 ? clip3(0, W - 1, wx1[li][0]) : W - 1;
-      ylo[li] = MODE == 3 ? clip3(0, H - 1, wy0[li][0]) : 0; yhi[li] = MODE == 3 ? clip3(0, H - 1, wy1[li][0]) : H - 1;
-      xc[li] = min(max(ox[li] - 3 + lane, xlo), xhi);
-    }
-    if (lane < tw + 7)
-      for (int y0 = warp; y0 < th + 7; y0 += nw * NB) {
-        int16_t v[NL][NB];
+      bool fast = P.fastOk && ox[li] >= 4 && ox[li] + tw + 4 < W && oy[li] >= 3 && oy[li] + th + 3 < H;
+      if (MODE == 3) fast = fast && wx1[li][0] == (1 << 20);
+      wofs[li] = fast ? ((ox[li] - 3) & 1) : 0;
+      if (fast) {
+        const int half = lane >> 4, wl = lane & 15;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(rp[li][0] + (size_t)(oy[li] - 3) * rs0 + ((ox[li] - 3) & ~1)) + wl;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(S.w[li]) + wl;
+        if (wl < (WS >> 1))
+          for (int y0 = warp * 2 + half; y0 < th + 7; y0 += nw * 2 * NB) {
+            uint32_t v[NB];
 #pragma unroll
-        for (int li = 0; li < NL; li++)
+            for (int k = 0; k < NB; k++) { const int y = y0 + k * nw * 2; if (y < th + 7) v[k] = __ldg(src + (size_t)y * (rs0 >> 1)); }
 #pragma unroll
-          for (int k = 0; k < NB; k++) {
-            const int y = y0 + k * nw;
-            if (y < th + 7) v[li][k] = __ldg(rp[li][0] + (size_t)min(max(oy[li] - 3 + y, ylo[li]), yhi[li]) * rs0 + xc[li]);
+            for (int k = 0; k < NB; k++) { const int y = y0 + k * nw * 2; if (y < th + 7) dst[y * (WS >> 1)] = v[k]; }
           }
+      } else {
+        const int xlo = MODE == 3 ? clip3(0, W - 1, wx0[li][0]) : 0, xhi = MODE == 3 ? clip3(0, W - 1, wx1[li][0]) : W - 1;
+        const int ylo = MODE == 3 ? clip3(0, H - 1, wy0[li][0]) : 0, yhi = MODE == 3 ? clip3(0, H - 1, wy1[li][0]) : H - 1;
+        const int xc = min(max(ox[li] - 3 + lane, xlo), xhi);
+        if (lane < tw + 7)
+          for (int y0 = warp; y0 < th + 7; y0 += nw * NB) {
+            int16_t v[NB];
 #pragma unroll
-        for (int li = 0; li < NL; li++)
+            for (int k = 0; k < NB; k++) { const int y = y0 + k * nw; if (y < th + 7) v[k] = __ldg(rp[li][0] + (size_t)min(max(oy[li] - 3 + y, ylo), yhi) * rs0 + xc); }
 #pragma unroll
-          for (int k = 0; k < NB; k++) {
-            const int y = y0 + k * nw;
-            if (y < th + 7) S.w[li][y * (tw + 7) + lane] = v[li][k];
+            for (int k = 0; k < NB; k++) { const int y = y0 + k * nw; if (y < th + 7) S.w[li][y * WS + lane] = v[k]; }
           }
       }
-    if (chroma) {
-      // both chroma components: lanes 0..15 Cb, 16..31 Cr (cw+3 <= 11)
-      const int c = lane >> 4, xl = lane & 15;
-      int xcc[NL], cylo[NL], cyhi[NL];
+      cofs[li] = 0;
+      if (chroma) {
+        bool cfast = P.fastOk && ocx[li] >= 2 && ocx[li] + cw + 2 < CWp && ocy[li] >= 1 && ocy[li] + ch + 1 < CHp;
+        if (MODE == 3) cfast = cfast && wx1[li][1] == (1 << 20);
+        cofs[li] = cfast ? ((ocx[li] - 1) & 1) : 0;
+        if (cfast) {
+          // row items r in [0, 2*(ch+3)): Cb rows then Cr rows; 8 lanes per row item, 4 row items per warp pass
+          const int sub = lane >> 3, wl = lane & 7;
+          const size_t cbase = (size_t)(ocy[li] - 1) * rs1 + ((ocx[li] - 1) & ~1);
+          if (wl < (CS >> 1))
+            for (int r0 = warp * 4 + sub; r0 < 2 * (ch + 3); r0 += nw * 4 * NB) {
+              uint32_t v[NB];
 #pragma unroll
-      for (int li = 0; li < NL; li++) {
-        const int xlo = MODE == 3 ? clip3(0, CWp - 1, wx0[li][1]) : 0, xhi = MODE == 3 ? clip3(0, CWp - 1, wx1[li][1]) : CWp - 1;
-        cylo[li] = MODE == 3 ? clip3(0, CHp - 1, wy0[li][1]) : 0; cyhi[li] = MODE == 3 ? clip3(0, CHp - 1, wy1[li][1]) : CHp - 1;
-        xcc[li] = min(max(ocx[li] - 1 + xl, xlo), xhi);
-      }
-      if (xl < cw + 3)
-        for (int y0 = warp; y0 < ch + 3; y0 += nw * NB) {
-          int16_t v[NL][NB];
+              for (int k = 0; k < NB; k++) {
+                const int r = r0 + k * nw * 4;
+                if (r < 2 * (ch + 3)) { const int c = r >= ch + 3, y = c ? r - (ch + 3) : r; v[k] = __ldg(reinterpret_cast<const uint32_t*>((c ? rp[li][2] : rp[li][1]) + cbase + (size_t)y * rs1) + wl); }
+              }
 #pragma unroll
-          for (int li = 0; li < NL; li++) {
-            const int16_t* rc = c ? rp[li][2] : rp[li][1];
-#pragma unroll
-            for (int k = 0; k < NB; k++) {
-              const int y = y0 + k * nw;
-              if (y < ch + 3) v[li][k] = __ldg(rc + (size_t)min(max(ocy[li] - 1 + y, cylo[li]), cyhi[li]) * rs1 + xcc[li]);
+              for (int k = 0; k < NB; k++) {
+                const int r = r0 + k * nw * 4;
+                if (r < 2 * (ch + 3)) { const int c = r >= ch + 3, y = c ? r - (ch + 3) : r; (reinterpret_cast<uint32_t*>(c ? S.cw[li][1] : S.cw[li][0]))[y * (CS >> 1) + wl] = v[k]; }
+              }
             }
-          }
+        } else {
+          // both chroma components: lanes 0..15 Cb, 16..31 Cr (cw+3 <= 11)
+          const int c = lane >> 4, xl = lane & 15;
+          const int xlo = MODE == 3 ? clip3(0, CWp - 1, wx0[li][1]) : 0, xhi = MODE == 3 ? clip3(0, CWp - 1, wx1[li][1]) : CWp - 1;
+          const int ylo = MODE == 3 ? clip3(0, CHp - 1, wy0[li][1]) : 0, yhi = MODE == 3 ? clip3(0, CHp - 1, wy1[li][1]) : CHp - 1;
+          const int xcc = min(max(ocx[li] - 1 + xl, xlo), xhi);
+          const int16_t* rc = c ? rp[li][2] : rp[li][1];
+          if (xl < cw + 3)
+            for (int y0 = warp; y0 < ch + 3; y0 += nw * NB) {
+              int16_t v[NB];
 #pragma unroll
-          for (int li = 0; li < NL; li++)
+              for (int k = 0; k < NB; k++) { const int y = y0 + k * nw; if (y < ch + 3) v[k] = __ldg(rc + (size_t)min(max(ocy[li] - 1 + y, ylo), yhi) * rs1 + xcc); }
 #pragma unroll
-            for (int k = 0; k < NB; k++) {
-              const int y = y0 + k * nw;
-              if (y < ch + 3) (c ? S.cw[li][1] : S.cw[li][0])[y * (cw + 3) + xl] = v[li][k];
+              for (int k = 0; k < NB; k++) { const int y = y0 + k * nw; if (y < ch + 3) (c ? S.cw[li][1] : S.cw[li][0])[y * CS + xl] = v[k]; }
             }
         }
+      }
     }
   }
   __syncthreads();
@@ -345,15 +372,13 @@ __global__ void mc_kernel(const McParams P)
   // ================================================================ stage B: horizontal filters
 #pragma unroll
   for (int li = 0; li < NL; li++) {
-    const int xF = fmx[li] & 15;
     int f[8];
-    { const int8_t* t = luma_taps(xF, is4x4, altHpel);
-#pragma unroll
-      for (int k = 0; k < 8; k++) f[k] = xF ? (int)t[k] : (k == 3 ? 64 : 0); }
+    load_taps8(luma_taps(fmx[li] & 15, is4x4, altHpel), f);  // row 0 of the tables is {0,0,0,64,0,0,0,0}: full-pel is the same formula
+    const int16_t* sw = S.w[li] + wofs[li];
     if (OPT == 1) {
       for (int i = tid; i < (th + 7) << l2w; i += nthr) {
         const int y = i >> l2w, x = i & (tw - 1);
-        const int16_t* s = S.w[li] + y * (tw + 7) + x;
+        const int16_t* s = sw + y * WS + x;
         int a = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) a += f[k] * s[k];
@@ -363,7 +388,7 @@ __global__ void mc_kernel(const McParams P)
       const int l2g = l2w - 2;                               // groups of 4 outputs per row
       for (int i = tid; i < (th + 7) << l2g; i += nthr) {
         const int y = i >> l2g, x = (i & ((tw >> 2) - 1)) << 2;
-        const int16_t* s = S.w[li] + y * (tw + 7) + x;
+        const int16_t* s = sw + y * WS + x;
         int v[11];
 #pragma unroll
         for (int k = 0; k < 11; k++) v[k] = s[k];
@@ -383,7 +408,7 @@ __global__ void mc_kernel(const McParams P)
       for (int i = tid; i < 2 * ((ch + 3) << l2cw); i += nthr) {
         const int c = i >= ((ch + 3) << l2cw), j = c ? i - ((ch + 3) << l2cw) : i;
         const int y = j >> l2cw, x = j & (cw - 1);
-        const int16_t* s = (c ? S.cw[li][1] : S.cw[li][0]) + y * (cw + 3) + x;
+        const int16_t* s = (c ? S.cw[li][1] : S.cw[li][0]) + cofs[li] + y * CS + x;
         (c ? S.chf[li][1] : S.chf[li][0])[j] = (int16_t)((c0 * s[0] + c1 * s[1] + c2 * s[2] + c3 * s[3] - (IFO << sh1)) >> sh1);
       }
     }
@@ -391,17 +416,15 @@ __global__ void mc_kernel(const McParams P)
   __syncthreads();
 
   // ================================================================ stage C: vertical filters + combine
-  if (tid < (tw * th) / OPT) {
-    const int x = tid & (tw - 1), y = (tid >> l2w) * OPT;
+  // thread -> samples (x, y0 .. y0+OPT-1); with BDOF the same thread keeps its samples' terms in registers until the final combine
+  const int sx = tid & (tw - 1), sy = (tid >> l2w) * OPT;
+  {
     int pr[NL][OPT];
 #pragma unroll
     for (int li = 0; li < NL; li++) {
-      const int yF = fmy[li] & 15;
-      const int8_t* t = luma_taps(yF, is4x4, altHpel);
       int f[8];
-#pragma unroll
-      for (int k = 0; k < 8; k++) f[k] = yF ? (int)t[k] : (k == 3 ? 64 : 0);
-      const int16_t* s = S.h[li] + (y << l2w) + x;
+      load_taps8(luma_taps(fmy[li] & 15, is4x4, altHpel), f);
+      const int16_t* s = S.h[li] + (sy << l2w) + sx;
       int v[7 + OPT];
 #pragma unroll
       for (int k = 0; k < 7 + OPT; k++) v[k] = s[k << l2w];
@@ -415,10 +438,10 @@ __global__ void mc_kernel(const McParams P)
     }
 #pragma unroll
     for (int j = 0; j < OPT; j++) {
-      int16_t* d = P.dst[0] + (size_t)(by + y + j) * P.dstStride[0] + bx + x;
+      int16_t* d = P.dst[0] + (size_t)(by + sy + j) * P.dstStride[0] + bx + sx;
       if (!BI) *d = (int16_t)clip3(0, pmax, (pr[0][j] + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr));
       else if (!bio) *d = (int16_t)avg_bi((int16_t)(pr[0][j] >> 6), (int16_t)(pr[NL - 1][j] >> 6), MODE == 1 ? pu.bcwW1 : 4, hr, pmax);
-      else { S.p[0][(y + j + 1) * 18 + x + 1] = (int16_t)(pr[0][j] >> 6); S.p[1][(y + j + 1) * 18 + x + 1] = (int16_t)(pr[NL - 1][j] >> 6); }
+      else { S.p[0][(sy + j + 1) * 18 + sx + 1] = (int16_t)(pr[0][j] >> 6); S.p[1][(sy + j + 1) * 18 + sx + 1] = (int16_t)(pr[NL - 1][j] >> 6); }
     }
   }
   if (chroma) {
@@ -449,84 +472,82 @@ __global__ void mc_kernel(const McParams P)
       else if (j < 2 * (tw + 2) + th) { x = 0; y = j - 2 * (tw + 2) + 1; } else { x = tw + 1; y = j - 2 * (tw + 2) - th + 1; }
       const int mxl = li ? fmx[NL - 1] : fmx[0], myl = li ? fmy[NL - 1] : fmy[0];
       const int xo = (mxl & 15) < 8 ? 1 : 0, yo = (myl & 15) < 8 ? 1 : 0;
-      const int16_t* wl = li ? S.w[NL - 1] : S.w[0];
-      const int v = wl[(y - yo + 3) * (tw + 7) + (x - xo + 3)];
+      const int16_t* wl = li ? S.w[NL - 1] + wofs[NL - 1] : S.w[0] + wofs[0];
+      const int v = wl[(y - yo + 3) * WS + (x - xo + 3)];
       (li ? S.p[1] : S.p[0])[y * 18 + x] = (int16_t)((int16_t)(v << hr) - IFO);
     }
     __syncthreads();
-    for (int sI = tid; sI < tw * th; sI += nthr) {
-      const int y = sI >> l2w, x = sI & (tw - 1);
+    // per sample: gradients of both lists (gradFilterCore<true> :212) folded into the five summands of calcBIOSums (:134), one 16-byte
+    // record per sample; the padded border of the reference (PaddBIOCore :269, replication of the outermost samples) becomes a clamp of
+    // the record index when the 6x6 windows are summed.  The terms of the final combine stay in this thread's registers.
+    uint4* Q = reinterpret_cast<uint4*>(smem);
+    int dgx[OPT], dgy[OPT], psum[OPT];
+    {
+      int q0[OPT + 2], q1[OPT + 2];                          // column sx, rows sy-1 .. sy+OPT (>> 6)
 #pragma unroll
-      for (int l = 0; l < 2; l++) {                          // gradFilterCore<true> :212
-        const int16_t* p = &S.p[l][(y + 1) * 18 + x + 1];
-        S.g[l][0][(y + 1) * 18 + x + 1] = (int16_t)((p[1] >> 6) - (p[-1] >> 6));
-        S.g[l][1][(y + 1) * 18 + x + 1] = (int16_t)((p[18] >> 6) - (p[-18] >> 6));
+      for (int r = 0; r < OPT + 2; r++) { q0[r] = S.p[0][(sy + r) * 18 + sx + 1] >> 6; q1[r] = S.p[1][(sy + r) * 18 + sx + 1] >> 6; }
+#pragma unroll
+      for (int j = 0; j < OPT; j++) {
+        const int i = (sy + j + 1) * 18 + sx + 1;
+        const int p0 = S.p[0][i], p1 = S.p[1][i];
+        const int g0x = (S.p[0][i + 1] >> 6) - (S.p[0][i - 1] >> 6), g1x = (S.p[1][i + 1] >> 6) - (S.p[1][i - 1] >> 6);
+        const int g0y = q0[j + 2] - q0[j], g1y = q1[j + 2] - q1[j];
+        const int tX = (g0x + g1x) >> 1, tY = (g0y + g1y) >> 1, dI = (p1 >> 4) - (p0 >> 4);
+        uint4 rec;
+        rec.x = (unsigned)abs(tX) | ((unsigned)abs(tY) << 16);
+        rec.y = (unsigned)(tX < 0 ? -dI : (tX == 0 ? 0 : dI));
+        rec.z = (unsigned)(tY < 0 ? -dI : (tY == 0 ? 0 : dI));
+        rec.w = (unsigned)(tY < 0 ? -tX : (tY == 0 ? 0 : tX));
+        Q[((sy + j) << l2w) + sx] = rec;
+        dgx[j] = g0x - g1x; dgy[j] = g0y - g1y; psum[j] = p0 + p1;
       }
     }
     __syncthreads();
-    for (int i = tid; i < 12 * th; i += nthr) {              // replicate left / right columns of the 6 arrays (:236-266)
-      const int a = i / (2 * th), j = i - a * 2 * th, y = (j >> 1) + 1, right = j & 1;
-      int16_t* A = S.p[0] + a * 324;   // p0,p1,g00,g01,g10,g11 are contiguous
-      if (right) A[y * 18 + tw + 1] = A[y * 18 + tw]; else A[y * 18] = A[y * 18 + 1];
-    }
-    __syncthreads();
-    for (int i = tid; i < 12 * (tw + 2); i += nthr) {        // top / bottom rows incl. corners
-      const int a = i / (2 * (tw + 2)), j = i - a * 2 * (tw + 2), x = j >> 1, bottom = j & 1;
-      int16_t* A = S.p[0] + a * 324;
-      if (bottom) A[(th + 1) * 18 + x] = A[th * 18 + x]; else A[x] = A[18 + x];
-    }
-    __syncthreads();
-    {
-      // per 4x4 block: sums over the 6x6 window (calcBIOSums :134)
-      const int nBlk = (tw >> 2) * (th >> 2), l2bw = l2w - 2;
-      // 4 lanes per block: lane part p sums window rows p and p+4 (rows 4,5 only for p<2); quad shuffle reduce; lane 0 derives (vx,vy)
-      for (int it = tid; it < ((nBlk * 4 + 31) & ~31); it += nthr) {
-        const int blk = it >> 2, part = it & 3;
-        int sAX = 0, sAY = 0, sDX = 0, sDY = 0, sS = 0;
-        if (blk < nBlk) {
-          const int bxx = (blk & ((tw >> 2) - 1)) << 2, byy = (blk >> l2bw) << 2;
+    const int nBlk = (tw >> 2) * (th >> 2), l2bw = l2w - 2;
+    // 4 lanes per 4x4 block: lane part p sums window rows p and p+4 (rows 4,5 only for p<2); quad shuffle reduce; lane 0 derives (vx,vy)
+    for (int it = tid; it < ((nBlk * 4 + 31) & ~31); it += nthr) {
+      const int blk = it >> 2, part = it & 3;
+      unsigned sA = 0; int sDX = 0, sDY = 0, sS = 0;
+      if (blk < nBlk) {
+        const int bxx = (blk & ((tw >> 2) - 1)) << 2, byy = (blk >> l2bw) << 2;
 #pragma unroll
-          for (int rr = 0; rr < 2; rr++) {
-            const int yy = part + 4 * rr;
-            if (yy < 6) {
+        for (int rr = 0; rr < 2; rr++) {
+          const int yy = part + 4 * rr;
+          if (yy < 6) {
+            const uint4* row = Q + (min(max(byy + yy - 1, 0), th - 1) << l2w);
 #pragma unroll
-              for (int xx = 0; xx < 6; xx++) {
-                const int i = (byy + yy) * 18 + bxx + xx;
-                const int gX = (S.g[0][0][i] + S.g[1][0][i]) >> 1, gY = (S.g[0][1][i] + S.g[1][1][i]) >> 1;
-                const int dI = (S.p[1][i] >> 4) - (S.p[0][i] >> 4);
-                sAX += abs(gX); sAY += abs(gY);
-                sDX += gX < 0 ? -dI : (gX == 0 ? 0 : dI);
-                sDY += gY < 0 ? -dI : (gY == 0 ? 0 : dI);
-                sS  += gY < 0 ? -gX : (gY == 0 ? 0 : gX);
-              }
+            for (int xx = 0; xx < 6; xx++) {
+              const uint4 r = row[min(max(bxx + xx - 1, 0), tw - 1)];
+              sA += r.x; sDX += (int)r.y; sDY += (int)r.z; sS += (int)r.w;
             }
           }
         }
+      }
 #pragma unroll
-        for (int m = 1; m < 4; m <<= 1) {
-          sAX += __shfl_xor_sync(0xffffffffu, sAX, m); sAY += __shfl_xor_sync(0xffffffffu, sAY, m);
-          sDX += __shfl_xor_sync(0xffffffffu, sDX, m); sDY += __shfl_xor_sync(0xffffffffu, sDY, m);
-          sS  += __shfl_xor_sync(0xffffffffu, sS, m);
-        }
-        if (part == 0 && blk < nBlk) {
-          int vx = sAX == 0 ? 0 : shift_msb(sDX * 4, sAX);
-          vx = clip3(-15, 15, vx);
-          const int mainG = sS >> 12, secG = sS & 4095;
-          int tmp = vx * mainG;
-          tmp = ((tmp * (1 << 12)) + vx * secG) >> 1;
-          int vy = sAY == 0 ? 0 : shift_msb(sDY * 4 - tmp, sAY);
-          vy = clip3(-15, 15, vy);
-          sVxy[blk][0] = vx; sVxy[blk][1] = vy;
-        }
+      for (int m = 1; m < 4; m <<= 1) {
+        sA += __shfl_xor_sync(0xffffffffu, sA, m);
+        sDX += __shfl_xor_sync(0xffffffffu, sDX, m); sDY += __shfl_xor_sync(0xffffffffu, sDY, m);
+        sS  += __shfl_xor_sync(0xffffffffu, sS, m);
       }
-      __syncthreads();
-      for (int sI = tid; sI < tw * th; sI += nthr) {         // addBIOAvg4 (:109)
-        const int y = sI >> l2w, x = sI & (tw - 1);
-        const int blk = ((y >> 2) << l2bw) + (x >> 2), i = (y + 1) * 18 + x + 1;
-        const int b = sVxy[blk][0] * (S.g[0][0][i] - S.g[1][0][i]) + sVxy[blk][1] * (S.g[0][1][i] - S.g[1][1][i]);
-        const int shiftNum = 15 - bd, offset = (1 << (shiftNum - 1)) + 2 * IFO;
-        P.dst[0][(size_t)(by + y) * P.dstStride[0] + bx + x] = (int16_t)clip3(0, pmax, (int)(int16_t)((S.p[0][i] + S.p[1][i] + b + offset) >> shiftNum));
+      if (part == 0 && blk < nBlk) {
+        const int sAX = sA & 0xffff, sAY = sA >> 16;         // 36 * 256 < 2^16: the packed halves cannot carry
+        int vx = sAX == 0 ? 0 : shift_msb(sDX * 4, sAX);
+        vx = clip3(-15, 15, vx);
+        const int mainG = sS >> 12, secG = sS & 4095;
+        int tmp = vx * mainG;
+        tmp = ((tmp * (1 << 12)) + vx * secG) >> 1;
+        int vy = sAY == 0 ? 0 : shift_msb(sDY * 4 - tmp, sAY);
+        vy = clip3(-15, 15, vy);
+        sVxy[blk][0] = vx; sVxy[blk][1] = vy;
       }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < OPT; j++) {                          // addBIOAvg4 (:109)
+      const int y = sy + j, blk = ((y >> 2) << l2bw) + (sx >> 2);
+      const int b = sVxy[blk][0] * dgx[j] + sVxy[blk][1] * dgy[j];
+      const int shiftNum = 15 - bd, offset = (1 << (shiftNum - 1)) + 2 * IFO;
+      P.dst[0][(size_t)(by + y) * P.dstStride[0] + bx + sx] = (int16_t)clip3(0, pmax, (int)(int16_t)((psum[j] + b + offset) >> shiftNum));
     }
   }
 }
@@ -724,6 +745,7 @@ int launch_mc(const McLaunch& L, StreamSet& ss, KProf* prof)
   McParams P;
   for (int c = 0; c < 3; c++) { P.dst[c] = L.dst.p[c]; P.dstStride[c] = L.dst.stride[c]; P.refStride[c] = L.refStride[c]; }
   for (int i = 0; i < B200_MAX_SLOTS * 3; i++) P.refs[i] = L.refs[i];
+  P.fastOk = !(L.refStride[0] & 1) && !(L.refStride[1] & 1) && !(L.refStride[2] & 1);
   P.W = L.geom.width; P.H = L.geom.height; P.bitDepth = L.geom.bitDepth; P.ctuSize = L.geom.ctuSize; P.chroma = L.geom.chromaFormat == 1;
   P.pus = L.pus; P.dmvrMv = L.dmvrMv;
   bool any = false;
