@@ -89,17 +89,23 @@ struct TileSmem {
   int16_t *p[2];                  // BDOF: 14-bit predictions with ring (stride 18)
 };
 
+constexpr int HS = 16, CHS = 8;   // constant row strides of the H-filtered arrays (luma / chroma): column walks use immediate offsets
+constexpr int DMVR_TAIL = 1640;   // DMVR scratch behind the windows: bilinear 20x20 x2 + their 1-sample-shifted copies (1600), later the
+                                  // shifted final windows (2 x 552 luma, 4 x 132 chroma)
+
 __host__ __device__ inline int mc_smem_elems(int mode, int n)   // n = tw*th; worst case over the shapes of that size
 {
-  // window (tw+8)x(th+7): 16x16 -> 24x23; 128 -> 24x15 | 16x23; 64 -> 12x23; 32 -> 12x15.  hf: (th+7)*tw worst = n + 7*16|8.
+  // window (tw+8)x(th+7): 16x16 -> 24x23; 128 -> 24x15 | 16x23; 64 -> 12x23; 32 -> 12x15.  hf: (th+7)*HS.
   const int win = n == 256 ? 552 : n == 128 ? 368 : n == 64 ? 276 : 180;
-  const int hf  = n + 7 * (n >= 64 ? 16 : 8);
+  const int hf  = (n == 256 ? 23 : n == 128 ? 23 : n == 64 ? 23 : 15) * HS;
   const int cwin = n == 256 ? 132 : n == 128 ? 88 : n == 64 ? 66 : 42;     // (cw+4)(ch+3)
-  const int chf = (n >> 2) + 3 * (n >= 64 ? 8 : 4);
+  const int chf = (n == 256 ? 11 : n == 128 ? 11 : n == 64 ? 11 : 7) * CHS;
   const int lists = mode == 0 ? 1 : 2;
   int e = lists * (win + hf + 2 * (cwin + chf));
-  if (mode >= 2) e = max(e, 8 * n) + 2 * 324;                              // BDOF: per-sample records (16 B) reuse the window area; P0/P1 18x18 behind
-  if (mode == 3) e = max(e, 2 * 400 + 2 * 441);                             // bilinear 20x20 x2 + raw 21x21 x2 share the window area
+  if (mode == 3) e = max(e, 2 * 441);                                       // boundary DMVR tiles stage raw 21x21 windows here first
+  if (mode >= 2) e = max(e, 8 * n);                                         // BDOF per-sample records (16 B) reuse the window area
+  if (mode == 3) e += DMVR_TAIL;
+  if (mode >= 2) e += 2 * 324;                                              // P0/P1 18x18
   return (e + 64) & ~7;
 }
 
@@ -132,16 +138,18 @@ __global__ void mc_kernel(const McParams P)
 
   // ---- shared memory carve-up (strides depend on the tile shape) ----
   TileSmem S;
+  int16_t* tail = smem;                                      // DMVR scratch (MODE 3)
   {
     int16_t* q = smem;
-    const int win = WS * (th + 7), hf = (th + 7) * tw, cwin = CS * (ch + 3), chf = (ch + 3) * cw;
+    const int win = WS * (th + 7), hf = (th + 7) * HS, cwin = CS * (ch + 3), chf = (ch + 3) * CHS;
 #pragma unroll
     for (int l = 0; l < NL; l++) { S.w[l] = q; q += win; S.h[l] = q; q += hf; }
 #pragma unroll
     for (int l = 0; l < NL; l++)
 #pragma unroll
       for (int c = 0; c < 2; c++) { S.cw[l][c] = q; q += cwin; S.chf[l][c] = q; q += chf; }
-    if (MODE >= 2) { if (q < smem + 8 * tw * th) q = smem + 8 * tw * th; S.p[0] = q; S.p[1] = q + 324; }
+    if (MODE == 3 && q < smem + 2 * 441) q = smem + 2 * 441;
+    if (MODE >= 2) { if (q < smem + 8 * tw * th) q = smem + 8 * tw * th; if (MODE == 3) { tail = q; q += DMVR_TAIL; } S.p[0] = q; S.p[1] = q + 324; }
   }
 
   // ---- per-list reference planes and motion ----
@@ -160,14 +168,56 @@ __global__ void mc_kernel(const McParams P)
   int fmx[NL], fmy[NL];                                       // final (clipped) MVs
   bool bio = MODE == 2;
 
+  int wofs[NL], cofs[NL];                                     // index of the footprint's first sample in each shared window row
+  bool dmvrFast = false;
   if (MODE == 3) {
     // ================================================================ DMVR search (xProcessDMVR :1847)
-    int16_t* B0 = smem; int16_t* B1 = smem + 400;            // bilinear buffers 20x20 (stride 20)
-    int16_t* R0 = smem + 800;                                // raw integer windows (BW+1)x(BH+1), stride 21, per list
+    // Interior tiles: the 8-tap / 4-tap footprints of the INITIAL motion are copied once (word-wide); the bilinear search window
+    // (xinitMC :1804, 2 integer samples around the block) is a sub-window of the luma footprint, and the padded window of the final MC
+    // (xPrefetchPad :1525 / xFinalPaddedMCForDMVR :1731) is that same footprint shifted by the integer part of the refinement and
+    // clamped to it.  Boundary tiles (footprint touching the picture edge, where MV clipping may act) go sample by sample.
+    int16_t* B0 = tail; int16_t* B1 = tail + 400;            // bilinear buffers 20x20 (stride 20) ...
+    int16_t* B0s = tail + 800; int16_t* B1s = tail + 1200;   // ... and copies shifted by one sample, so that every SAD row is word-aligned
     const int BW = tw + 4, BH = th + 4;
+    const int warp = tid >> 5, lane = tid & 31, nw = max(1, nthr >> 5);
+    int ix[2], iy[2], icx[2], icy[2];
+    dmvrFast = P.fastOk;
+#pragma unroll
+    for (int li = 0; li < 2; li++) {
+      ix[li] = bx + (mvx[li] >> 4); iy[li] = by + (mvy[li] >> 4); icx[li] = (bx >> 1) + (mvx[li] >> 5); icy[li] = (by >> 1) + (mvy[li] >> 5);
+      dmvrFast = dmvrFast && ix[li] >= 6 && ix[li] + tw + 8 < W && iy[li] >= 6 && iy[li] + th + 8 < H;
+      dmvrFast = dmvrFast && (!chroma || (icx[li] >= 4 && icx[li] + cw + 5 < CWp && icy[li] >= 3 && icy[li] + ch + 4 < CHp));
+    }
+    const int16_t* braw[2]; int bstr;                        // raw integer samples of the search window: (BW+1)x(BH+1) per list
     int bxF[2], byF[2];
-    {
-      const int warp = tid >> 5, lane = tid & 31, nw = max(1, nthr >> 5);
+    if (dmvrFast) {
+#pragma unroll
+      for (int li = 0; li < 2; li++) {
+        bxF[li] = mvx[li] & 15; byF[li] = mvy[li] & 15;
+        wofs[li] = (ix[li] - 3) & 1;
+        {
+          const int half = lane >> 4, wl = lane & 15, rw = rs0 >> 1;
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(rp[li][0] + (size_t)(iy[li] - 3) * rs0 + ((ix[li] - 3) & ~1)) + (size_t)(warp * 2 + half) * rw + wl;
+          uint32_t* dst = reinterpret_cast<uint32_t*>(S.w[li]) + (warp * 2 + half) * (WS >> 1) + wl;
+          if (wl < (WS >> 1))
+#pragma unroll 4
+            for (int y = warp * 2 + half; y < th + 7; y += nw * 2) { *dst = __ldg(src); src += (size_t)(nw * 2) * rw; dst += nw * 2 * (WS >> 1); }
+        }
+        cofs[li] = (icx[li] - 1) & 1;
+        if (chroma) {
+          const int sub = lane >> 3, wl = lane & 7, rwc = rs1 >> 1, npc = (ch + 6) >> 2;   // 4 rows per pass, npc passes per component
+          const size_t cbase = (size_t)(icy[li] - 1) * rs1 + ((icx[li] - 1) & ~1);
+          for (int q = warp; q < 2 * npc; q += nw) {
+            const int c = q >= npc, y = ((c ? q - npc : q) << 2) + sub;
+            if (y < ch + 3 && wl < (CS >> 1))
+              reinterpret_cast<uint32_t*>(c ? S.cw[li][1] : S.cw[li][0])[y * (CS >> 1) + wl] = __ldg(reinterpret_cast<const uint32_t*>((c ? rp[li][2] : rp[li][1]) + cbase) + (size_t)y * rwc + wl);
+          }
+        }
+        braw[li] = S.w[li] + WS + wofs[li] + 1;
+      }
+      bstr = WS;
+    } else {
+      int16_t* R0 = smem;                                    // raw windows, stride 21
       constexpr int NB = 8;
       int X0[2], Y0[2];
 #pragma unroll
@@ -176,7 +226,9 @@ __global__ void mc_kernel(const McParams P)
         clip_mv(cx, cy, puX, puY, P);                        // xinitMC :1811: relative to the CU
         const int mx = cx - 32, my = cy - 32;
         bxF[li] = mx & 15; byF[li] = my & 15; X0[li] = min(max(puX + tx0 + (mx >> 4) + lane, 0), W - 1); Y0[li] = puY + ty0 + (my >> 4);
+        braw[li] = R0 + li * 441;
       }
+      bstr = 21;
       if (lane < BW + 1)
         for (int y0 = warp; y0 < BH + 1; y0 += nw * NB) {
           int16_t v[2][NB];
@@ -196,32 +248,43 @@ __global__ void mc_kernel(const McParams P)
             }
         }
     }
+    if (tid < 25) sSad[tid] = 0;
     __syncthreads();
     {
+      // bilinear interpolation to 10 bit (filterN2_2D, InterpolationFilter.cpp:1133): one thread per (list, column) walks down the rows
+      // and keeps the previous row's horizontal result.  Two-step form; equals the reference's one-step special cases for
+      // xF == 0 or yF == 0 at bit depths <= 10.  Coefficients are (16 - frac, frac).
       const int s1 = 4 - (10 - bd), o1 = 1 << (s1 - 1);
-      for (int i = tid; i < 2 * BH * 32; i += nthr) {        // item = (list, row, column lane)
-        const int x = i & 31, yy = i >> 5, li = yy >= BH, y = li ? yy - BH : yy;
-        if (x < BW) {
-          const int xF = li ? bxF[1] : bxF[0], yF = li ? byF[1] : byF[0];
-          const int f0 = kIfBilin4[xF * 2], f1 = kIfBilin4[xF * 2 + 1], g0 = kIfBilin4[yF * 2], g1 = kIfBilin4[yF * 2 + 1];
-          const int16_t* r = R0 + li * 441 + y * 21 + x;
-          // two-step form; equals the reference's one-step special cases for xF == 0 or yF == 0 at bit depths <= 10
-          const int a = (int16_t)((f0 * r[0] + f1 * r[1] + o1) >> s1);
-          const int b = (int16_t)((f0 * r[21] + f1 * r[22] + o1) >> s1);
-          (li ? B1 : B0)[y * 20 + x] = (int16_t)((g0 * a + g1 * b + 8) >> 4);
+      for (int i = tid; i < 2 * BW; i += nthr) {
+        const int li = i >= BW, x = li ? i - BW : i;
+        const int f1 = li ? bxF[1] : bxF[0], f0 = 16 - f1, g1 = li ? byF[1] : byF[0], g0 = 16 - g1;
+        const int16_t* r = (li ? braw[1] : braw[0]) + x;
+        int16_t* o = (li ? B1 : B0) + x; int16_t* os = (li ? B1s : B0s) + x - 1;
+        int prev = (int16_t)((f0 * r[0] + f1 * r[1] + o1) >> s1);
+        for (int y = 0; y < BH; y++) {
+          r += bstr;
+          const int cur = (int16_t)((f0 * r[0] + f1 * r[1] + o1) >> s1);
+          const int16_t v = (int16_t)((g0 * prev + g1 * cur + 8) >> 4);
+          o[y * 20] = v; if (x) os[y * 20] = v;
+          prev = cur;
         }
       }
     }
-    if (tid < 25) sSad[tid] = 0;
     __syncthreads();
-    // SAD over every second row (RdCost.cpp:113-135): item = (position p, row pair r); each item sums tw columns
-    for (int it = tid; it < 25 * (th >> 1); it += nthr) {
-      const int p = it / (th >> 1), y = (it - p * (th >> 1)) * 2;
-      const int u = p % 5 - 2, v = p / 5 - 2;
-      const int16_t* a = B0 + (2 + v + y) * 20 + 2 + u; const int16_t* b = B1 + (2 - v + y) * 20 + 2 - u;
-      unsigned s = 0;
-      for (int x = 0; x < tw; x++) s += abs(a[x] - b[x]);
-      atomicAdd(&sSad[p], s);
+    {
+      // SAD over every second row (RdCost.cpp:113-135): item = (position p, row pair); samples are 10-bit non-negative, so two of them
+      // go through one packed max/min/subtract, and the two running halves cannot carry (8 words * 1023 < 2^16)
+      const int l2hh = 30 - __clz(th);                       // log2(th / 2)
+      for (int it = tid; it < (25 << l2hh); it += nthr) {
+        const int p = it >> l2hh, y = (it & ((th >> 1) - 1)) * 2;
+        const int u = p % 5 - 2, v = p / 5 - 2, odd = u & 1;
+        const uint32_t* a = reinterpret_cast<const uint32_t*>((odd ? B0s : B0) + (2 + v + y) * 20 + 2 + u - odd);
+        const uint32_t* b = reinterpret_cast<const uint32_t*>((odd ? B1s : B1) + (2 - v + y) * 20 + 2 - u - odd);
+        uint32_t acc = 0;
+#pragma unroll 4
+        for (int x = 0; x < (tw >> 1); x++) acc += __vmaxs2(a[x], b[x]) - __vmins2(a[x], b[x]);
+        atomicAdd(&sSad[p], (acc & 0xffff) + (acc >> 16));
+      }
     }
     __syncthreads();
     if (tid == 0) {
@@ -256,24 +319,45 @@ __global__ void mc_kernel(const McParams P)
       const int mrgx = mvx[li], mrgy = mvy[li];
       const int rx = clip3(-(1 << 17), (1 << 17) - 1, li ? mrgx - dmx : mrgx + dmx), ry = clip3(-(1 << 17), (1 << 17) - 1, li ? mrgy - dmy : mrgy + dmy);
       int cx = rx, cy = ry;
-      clip_mv(cx, cy, bx, by, P);                            // cMvClipped, relative to the sub-block (:1749)
+      clip_mv(cx, cy, bx, by, P);                            // cMvClipped, relative to the sub-block (:1749); no-op for interior tiles
       fmx[li] = cx; fmy[li] = cy;
-#pragma unroll
-      for (int k = 0; k < 2; k++) {                          // k = 0 luma, 1 chroma (xFinalPaddedMCForDMVR :1757-1778, xPrefetchPad :1525)
-        const int sh = 4 + k, taps = k ? 4 : 8;
-        const int dIx = (rx >> sh) - (mrgx >> sh), dIy = (ry >> sh) - (mrgy >> sh);
-        int X, Y;
-        if (dIx || dIy) {
-          int pmx = mrgx - ((taps / 2 - 1) << sh), pmy = mrgy - ((taps / 2 - 1) << sh);
-          clip_mv(pmx, pmy, bx, by, P);
-          wx0[li][k] = (bx >> k) + (pmx >> sh); wy0[li][k] = (by >> k) + (pmy >> sh);
-          wx1[li][k] = wx0[li][k] + (tw >> k) + taps - 2; wy1[li][k] = wy0[li][k] + (th >> k) + taps - 2;
-          X = wx0[li][k] + (taps / 2 - 1) + dIx; Y = wy0[li][k] + (taps / 2 - 1) + dIy;
-        } else {
-          wx0[li][k] = wy0[li][k] = -(1 << 20); wx1[li][k] = wy1[li][k] = 1 << 20;
-          X = (bx >> k) + (cx >> sh); Y = (by >> k) + (cy >> sh);
+      if (dmvrFast) {
+        // shifted + clamped copies of the footprints into the (now free) bilinear scratch
+        const int dIx = (rx >> 4) - (mrgx >> 4), dIy = (ry >> 4) - (mrgy >> 4);
+        if (dIx | dIy) {
+          const int16_t* T = S.w[li] + wofs[li]; int16_t* D = tail + li * 552;
+          const int xs = min(max(lane + dIx, 0), tw + 6);
+          if (lane < tw + 7)
+            for (int y = warp; y < th + 7; y += nw) D[y * WS + lane] = T[min(max(y + dIy, 0), th + 6) * WS + xs];
+          S.w[li] = D; wofs[li] = 0;
         }
-        if (k == 0) { ox[li] = X; oy[li] = Y; } else { ocx[li] = X; ocy[li] = Y; }
+        const int dCx = (rx >> 5) - (mrgx >> 5), dCy = (ry >> 5) - (mrgy >> 5);
+        if (chroma && (dCx | dCy)) {
+          const int c = lane >> 4, xl = lane & 15;
+          const int16_t* T = (c ? S.cw[li][1] : S.cw[li][0]) + cofs[li]; int16_t* D = tail + 1104 + (li * 2 + c) * 132;
+          const int xs = min(max(xl + dCx, 0), cw + 2);
+          if (xl < cw + 3)
+            for (int y = warp; y < ch + 3; y += nw) D[y * CS + xl] = T[min(max(y + dCy, 0), ch + 2) * CS + xs];
+          S.cw[li][0] = tail + 1104 + (li * 2) * 132; S.cw[li][1] = tail + 1104 + (li * 2 + 1) * 132; cofs[li] = 0;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {                        // k = 0 luma, 1 chroma (xFinalPaddedMCForDMVR :1757-1778, xPrefetchPad :1525)
+          const int sh = 4 + k, taps = k ? 4 : 8;
+          const int dIx = (rx >> sh) - (mrgx >> sh), dIy = (ry >> sh) - (mrgy >> sh);
+          int X, Y;
+          if (dIx || dIy) {
+            int pmx = mrgx - ((taps / 2 - 1) << sh), pmy = mrgy - ((taps / 2 - 1) << sh);
+            clip_mv(pmx, pmy, bx, by, P);
+            wx0[li][k] = (bx >> k) + (pmx >> sh); wy0[li][k] = (by >> k) + (pmy >> sh);
+            wx1[li][k] = wx0[li][k] + (tw >> k) + taps - 2; wy1[li][k] = wy0[li][k] + (th >> k) + taps - 2;
+            X = wx0[li][k] + (taps / 2 - 1) + dIx; Y = wy0[li][k] + (taps / 2 - 1) + dIy;
+          } else {
+            wx0[li][k] = wy0[li][k] = -(1 << 20); wx1[li][k] = wy1[li][k] = 1 << 20;
+            X = (bx >> k) + (cx >> sh); Y = (by >> k) + (cy >> sh);
+          }
+          if (k == 0) { ox[li] = X; oy[li] = Y; } else { ocx[li] = X; ocy[li] = Y; }
+        }
       }
     }
   } else {
@@ -289,41 +373,28 @@ __global__ void mc_kernel(const McParams P)
   // ================================================================ stage A: windows (luma 8-tap footprint, chroma 4-tap footprint)
   // Interior tiles (the footprint lies inside the picture and no DMVR window clamp applies) copy whole 32-bit words, 16 lanes per luma
   // row / 8 lanes per chroma row; the footprint's first sample then sits at index wofs (0/1) of each shared row.  Boundary tiles take
-  // the per-sample path with clamped coordinates (= the reference's border extension / padded DMVR window).  Loads of a batch are all
-  // issued before the first shared store.
-  int wofs[NL], cofs[NL];
-  {
+  // the per-sample path with clamped coordinates (= the reference's border extension / padded DMVR window).
+  if (!(MODE == 3 && dmvrFast)) {
     const int warp = tid >> 5, lane = tid & 31, nw = max(1, nthr >> 5);
-    constexpr int NB = 6;
 #pragma unroll
     for (int li = 0; li < NL; li++) {
       bool fast = P.fastOk && ox[li] >= 4 && ox[li] + tw + 4 < W && oy[li] >= 3 && oy[li] + th + 3 < H;
       if (MODE == 3) fast = fast && wx1[li][0] == (1 << 20);
       wofs[li] = fast ? ((ox[li] - 3) & 1) : 0;
       if (fast) {
-        const int half = lane >> 4, wl = lane & 15;
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(rp[li][0] + (size_t)(oy[li] - 3) * rs0 + ((ox[li] - 3) & ~1)) + wl;
-        uint32_t* dst = reinterpret_cast<uint32_t*>(S.w[li]) + wl;
+        const int half = lane >> 4, wl = lane & 15, rw = rs0 >> 1;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(rp[li][0] + (size_t)(oy[li] - 3) * rs0 + ((ox[li] - 3) & ~1)) + (size_t)(warp * 2 + half) * rw + wl;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(S.w[li]) + (warp * 2 + half) * (WS >> 1) + wl;
         if (wl < (WS >> 1))
-          for (int y0 = warp * 2 + half; y0 < th + 7; y0 += nw * 2 * NB) {
-            uint32_t v[NB];
-#pragma unroll
-            for (int k = 0; k < NB; k++) { const int y = y0 + k * nw * 2; if (y < th + 7) v[k] = __ldg(src + (size_t)y * (rs0 >> 1)); }
-#pragma unroll
-            for (int k = 0; k < NB; k++) { const int y = y0 + k * nw * 2; if (y < th + 7) dst[y * (WS >> 1)] = v[k]; }
-          }
+#pragma unroll 4
+          for (int y = warp * 2 + half; y < th + 7; y += nw * 2) { *dst = __ldg(src); src += (size_t)(nw * 2) * rw; dst += nw * 2 * (WS >> 1); }
       } else {
         const int xlo = MODE == 3 ? clip3(0, W - 1, wx0[li][0]) : 0, xhi = MODE == 3 ? clip3(0, W - 1, wx1[li][0]) : W - 1;
         const int ylo = MODE == 3 ? clip3(0, H - 1, wy0[li][0]) : 0, yhi = MODE == 3 ? clip3(0, H - 1, wy1[li][0]) : H - 1;
         const int xc = min(max(ox[li] - 3 + lane, xlo), xhi);
         if (lane < tw + 7)
-          for (int y0 = warp; y0 < th + 7; y0 += nw * NB) {
-            int16_t v[NB];
-#pragma unroll
-            for (int k = 0; k < NB; k++) { const int y = y0 + k * nw; if (y < th + 7) v[k] = __ldg(rp[li][0] + (size_t)min(max(oy[li] - 3 + y, ylo), yhi) * rs0 + xc); }
-#pragma unroll
-            for (int k = 0; k < NB; k++) { const int y = y0 + k * nw; if (y < th + 7) S.w[li][y * WS + lane] = v[k]; }
-          }
+#pragma unroll 4
+          for (int y = warp; y < th + 7; y += nw) S.w[li][y * WS + lane] = __ldg(rp[li][0] + (size_t)min(max(oy[li] - 3 + y, ylo), yhi) * rs0 + xc);
       }
       cofs[li] = 0;
       if (chroma) {
@@ -331,23 +402,13 @@ __global__ void mc_kernel(const McParams P)
         if (MODE == 3) cfast = cfast && wx1[li][1] == (1 << 20);
         cofs[li] = cfast ? ((ocx[li] - 1) & 1) : 0;
         if (cfast) {
-          // row items r in [0, 2*(ch+3)): Cb rows then Cr rows; 8 lanes per row item, 4 row items per warp pass
-          const int sub = lane >> 3, wl = lane & 7;
+          const int sub = lane >> 3, wl = lane & 7, rwc = rs1 >> 1, npc = (ch + 6) >> 2;   // 4 rows per pass, npc passes per component
           const size_t cbase = (size_t)(ocy[li] - 1) * rs1 + ((ocx[li] - 1) & ~1);
-          if (wl < (CS >> 1))
-            for (int r0 = warp * 4 + sub; r0 < 2 * (ch + 3); r0 += nw * 4 * NB) {
-              uint32_t v[NB];
-#pragma unroll
-              for (int k = 0; k < NB; k++) {
-                const int r = r0 + k * nw * 4;
-                if (r < 2 * (ch + 3)) { const int c = r >= ch + 3, y = c ? r - (ch + 3) : r; v[k] = __ldg(reinterpret_cast<const uint32_t*>((c ? rp[li][2] : rp[li][1]) + cbase + (size_t)y * rs1) + wl); }
-              }
-#pragma unroll
-              for (int k = 0; k < NB; k++) {
-                const int r = r0 + k * nw * 4;
-                if (r < 2 * (ch + 3)) { const int c = r >= ch + 3, y = c ? r - (ch + 3) : r; (reinterpret_cast<uint32_t*>(c ? S.cw[li][1] : S.cw[li][0]))[y * (CS >> 1) + wl] = v[k]; }
-              }
-            }
+          for (int q = warp; q < 2 * npc; q += nw) {
+            const int c = q >= npc, y = ((c ? q - npc : q) << 2) + sub;
+            if (y < ch + 3 && wl < (CS >> 1))
+              reinterpret_cast<uint32_t*>(c ? S.cw[li][1] : S.cw[li][0])[y * (CS >> 1) + wl] = __ldg(reinterpret_cast<const uint32_t*>((c ? rp[li][2] : rp[li][1]) + cbase) + (size_t)y * rwc + wl);
+          }
         } else {
           // both chroma components: lanes 0..15 Cb, 16..31 Cr (cw+3 <= 11)
           const int c = lane >> 4, xl = lane & 15;
@@ -355,14 +416,10 @@ __global__ void mc_kernel(const McParams P)
           const int ylo = MODE == 3 ? clip3(0, CHp - 1, wy0[li][1]) : 0, yhi = MODE == 3 ? clip3(0, CHp - 1, wy1[li][1]) : CHp - 1;
           const int xcc = min(max(ocx[li] - 1 + xl, xlo), xhi);
           const int16_t* rc = c ? rp[li][2] : rp[li][1];
+          int16_t* dc = c ? S.cw[li][1] : S.cw[li][0];
           if (xl < cw + 3)
-            for (int y0 = warp; y0 < ch + 3; y0 += nw * NB) {
-              int16_t v[NB];
-#pragma unroll
-              for (int k = 0; k < NB; k++) { const int y = y0 + k * nw; if (y < ch + 3) v[k] = __ldg(rc + (size_t)min(max(ocy[li] - 1 + y, ylo), yhi) * rs1 + xcc); }
-#pragma unroll
-              for (int k = 0; k < NB; k++) { const int y = y0 + k * nw; if (y < ch + 3) (c ? S.cw[li][1] : S.cw[li][0])[y * CS + xl] = v[k]; }
-            }
+#pragma unroll 4
+            for (int y = warp; y < ch + 3; y += nw) dc[y * CS + xl] = __ldg(rc + (size_t)min(max(ocy[li] - 1 + y, ylo), yhi) * rs1 + xcc);
         }
       }
     }
@@ -382,7 +439,7 @@ __global__ void mc_kernel(const McParams P)
         int a = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) a += f[k] * s[k];
-        S.h[li][i] = (int16_t)((a - (IFO << sh1)) >> sh1);
+        S.h[li][y * HS + x] = (int16_t)((a - (IFO << sh1)) >> sh1);
       }
     } else {
       const int l2g = l2w - 2;                               // groups of 4 outputs per row
@@ -392,7 +449,7 @@ __global__ void mc_kernel(const McParams P)
         int v[11];
 #pragma unroll
         for (int k = 0; k < 11; k++) v[k] = s[k];
-        int16_t* o = S.h[li] + (y << l2w) + x;
+        int16_t* o = S.h[li] + y * HS + x;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           int a = 0;
@@ -409,7 +466,7 @@ __global__ void mc_kernel(const McParams P)
         const int c = i >= ((ch + 3) << l2cw), j = c ? i - ((ch + 3) << l2cw) : i;
         const int y = j >> l2cw, x = j & (cw - 1);
         const int16_t* s = (c ? S.cw[li][1] : S.cw[li][0]) + cofs[li] + y * CS + x;
-        (c ? S.chf[li][1] : S.chf[li][0])[j] = (int16_t)((c0 * s[0] + c1 * s[1] + c2 * s[2] + c3 * s[3] - (IFO << sh1)) >> sh1);
+        (c ? S.chf[li][1] : S.chf[li][0])[y * CHS + x] = (int16_t)((c0 * s[0] + c1 * s[1] + c2 * s[2] + c3 * s[3] - (IFO << sh1)) >> sh1);
       }
     }
   }
@@ -424,10 +481,10 @@ __global__ void mc_kernel(const McParams P)
     for (int li = 0; li < NL; li++) {
       int f[8];
       load_taps8(luma_taps(fmy[li] & 15, is4x4, altHpel), f);
-      const int16_t* s = S.h[li] + (sy << l2w) + sx;
+      const int16_t* s = S.h[li] + sy * HS + sx;
       int v[7 + OPT];
 #pragma unroll
-      for (int k = 0; k < 7 + OPT; k++) v[k] = s[k << l2w];
+      for (int k = 0; k < 7 + OPT; k++) v[k] = s[k * HS];
 #pragma unroll
       for (int j = 0; j < OPT; j++) {
         int a = 0;
@@ -452,8 +509,8 @@ __global__ void mc_kernel(const McParams P)
 #pragma unroll
       for (int li = 0; li < NL; li++) {
         const int8_t* t = kIfChroma + (fmy[li] & 31) * 4;
-        const int16_t* s = (c ? S.chf[li][1] : S.chf[li][0]) + (y << l2cw) + x;
-        pr[li] = t[0] * s[0] + t[1] * s[1 << l2cw] + t[2] * s[2 << l2cw] + t[3] * s[3 << l2cw];
+        const int16_t* s = (c ? S.chf[li][1] : S.chf[li][0]) + y * CHS + x;
+        pr[li] = t[0] * s[0] + t[1] * s[CHS] + t[2] * s[2 * CHS] + t[3] * s[3 * CHS];
       }
       int16_t* d = (c ? P.dst[2] : P.dst[1]) + (size_t)((by >> 1) + y) * (c ? P.dstStride[2] : P.dstStride[1]) + (bx >> 1) + x;
       if (!BI) *d = (int16_t)clip3(0, pmax, (pr[0] + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr));
