@@ -233,7 +233,8 @@ B200_API int b200_alf_picture(const b200_geom* g, const int16_t* const src[3], i
   if (int rc = up(T->ccCoeff[0], n0, L.cc[0])) return rc;
   if (int rc = up(T->ccCoeff[1], n1, L.cc[1])) return rc;
   L.ctus = g_hw.misc[0].as<b200_alf_ctu>();
-  if (int rc = launch_alf(L, s)) return rc;
+  StreamSet ss(s);
+  if (int rc = launch_alf(L, ss)) return rc;
   if (int rc = download_planes(g, dst, L.dst, s)) return rc;
   B200_CUDA(cudaStreamSynchronize(s));
   return 0;

@@ -104,7 +104,7 @@ struct AlfLaunch {
   b200_geom geom; DevPlanes src, dst; const b200_alf_ctu* ctus;
   const int16_t *lumaCoeff, *lumaClip, *chromaCoeff, *chromaClip, *cc[2];
 };
-int launch_alf(const AlfLaunch& L, cudaStream_t s, KProf* prof = nullptr);
+int launch_alf(const AlfLaunch& L, StreamSet& ss, KProf* prof = nullptr);   // luma on ss.main, chroma (independent) on an auxiliary stream
 
 constexpr int B200_MAX_SLOTS = 32;
 struct McLaunch {

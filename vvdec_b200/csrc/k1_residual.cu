@@ -7,11 +7,14 @@
 // (TrQuant_EMT.cpp:103-121, :366-405), xITransformSkip (:489), invTransformCbCr (TrQuant.cpp:108-124) and the
 // reco add of DecCu::predAndReco (DecCu.cpp:455-479 -> Buffer.cpp:83 recoCore).
 //
-// Mapping (north_star): ONE WARP PER TU record; the TU's packed level corner is staged into shared memory as
-// dequantised int16 coefficients, both 1-D stages accumulate in int32 (no tensor cores), stage-1 output lives in
-// shared memory as int16 (it is clipped to 16 bit by the standard), stage-2 output goes straight to the plane.
+// Mapping (north_star): one thread group per TU record (a warp for TUs up to 16x16, 128 / 256 threads for 32 / 64); the TU's packed
+// level corner is staged into shared memory as dequantised int16 coefficients, both 1-D stages accumulate in int32 (no tensor cores),
+// stage-1 output lives in shared memory as int16 (it is clipped to 16 bit by the standard), stage-2 output goes straight to the plane.
+// Both stages are 16-bit x 8-bit dot products taken two basis rows at a time (IDP.2A): the operand blocks are stored with rows k, k+1
+// interleaved (one 32-bit word per pair), the cores come from kTrPair (bytes (m[k][j], m[k+1][j])), and every thread produces four
+// neighbouring outputs from one operand word and one 8-byte core load per row pair.
 // HBM traffic per TU = corner levels (2 B each) + 32 B record + w*h*2 B read (pred) + w*h*2 B write.
-#define VVC_TABLE_QUAL static __device__ const
+#define VVC_TABLE_QUAL static __device__ const __align__(16)
 #include "vvc_tables.h"
 #include "common.cuh"
 
@@ -29,11 +32,12 @@ template <int CLS> struct K1Cfg {
   static constexpr int GROUPS = THREADS / G;                           // TUs per CTA
 };
 
-__device__ __forceinline__ const int16_t* tr_matrix(int trType, int log2n)
+__device__ __forceinline__ const int16_t* tr_pair(int trType, int log2n)   // row-paired core (see gen_tables.cpp)
 {
   const int p4 = 1 << (2 * log2n);
-  if (trType == B200_TR_DCT2) return kTrAll + (p4 - 4) / 3;
-  return kTrAll + (trType == B200_TR_DCT8 ? 5460 : 6820) + (p4 - 16) / 3;
+  if (log2n == 1) return kTrPair;                            // 2-point DCT-2 (chroma of 4-wide luma); its single pair row sits in front
+  if (trType == B200_TR_DCT2) return kTrPair + 2 + (p4 - 4) / 6;
+  return kTrPair + 2 + (trType == B200_TR_DCT8 ? 2730 : 3410) + (p4 - 16) / 6;
 }
 
 __device__ __forceinline__ int dequant_one(int level, int scale, int rightShift, int inMax)
@@ -53,8 +57,8 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* _
                    int s0, int s1, int s2, int bitDepth, int mode)
 {
   constexpr int G = K1Cfg<CLS>::G, GROUPS = K1Cfg<CLS>::GROUPS;
-  __shared__ int16_t s_c[GROUPS][K1Cfg<CLS>::CB];
-  __shared__ int16_t s_t[GROUPS][K1Cfg<CLS>::TB];
+  __shared__ __align__(16) int16_t s_c[GROUPS][K1Cfg<CLS>::CB];
+  __shared__ __align__(16) int16_t s_t[GROUPS][K1Cfg<CLS>::TB];
 
   // `lane` = index inside the TU's thread group, `warp` = group index in the CTA (names kept from the one-warp-per-TU version)
   const int warp = threadIdx.x / G, lane = threadIdx.x % G;
@@ -86,6 +90,8 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* _
   int nzW = maxX + 1, nzH = maxY + 1;
   if (lfnst && !isTS) { nzW = max(nzW, min(w, 8)); nzH = max(nzH, min(h, 8)); }
   const int CS = nzW;
+  const int nzHe = (nzH + 1) & ~1;                           // rows are stored in pairs; an odd last row gets a zero partner
+  auto cbi = [&](int y, int x) { return (((y >> 1) * CS + x) << 1) + (y & 1); };
 
   // ---- 1. dequant (Quant.cpp:295) ----
   if (flags & (B200_TU_BDPCM_H | B200_TU_BDPCM_V)) {
@@ -99,18 +105,18 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* _
         const int lv = q[y * qs + x];
         acc = i ? clip16(acc + lv) : lv;
         const int sc = sl ? sl[y * w + x] * scale : scale;
-        cb[y * CS + x] = acc ? (int16_t)dequant_one(acc, sc, rightShift, inMax) : (int16_t)0;
+        cb[cbi(y, x)] = acc ? (int16_t)dequant_one(acc, sc, rightShift, inMax) : (int16_t)0;
       }
     }
   } else {
-    for (int i = lane; i < nzW * nzH; i += G) {
+    for (int i = lane; i < nzW * nzHe; i += G) {
       const int y = i / CS, x = i - y * CS;
       int v = 0;
       if (x <= maxX && y <= maxY) {
         const int lv = q[y * qs + x];
         if (lv) v = dequant_one(lv, sl ? sl[y * w + x] * scale : scale, rightShift, inMax);
       }
-      cb[i] = (int16_t)v;
+      cb[cbi(y, x)] = (int16_t)v;
     }
   }
   gsync();
@@ -127,7 +133,7 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* _
       const unsigned long long XS = 0x3323213210210100ull;   // nibble i = x of scan pos i
       const unsigned long long YS = 0x3231230123012010ull;   // nibble i = y of scan pos i
       const int x = (int)((XS >> (4 * lane)) & 15), y = (int)((YS >> (4 * lane)) & 15);
-      myIn = cb[y * CS + x];
+      myIn = cb[cbi(y, x)];
     }
     const int8_t* m = big ? kLfnst8x8 + (set * 2 + idx) * 48 * 16 : kLfnst4x4 + (set * 2 + idx) * 16 * 16;
     const int nOut = big ? 48 : 16;
@@ -149,7 +155,7 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* _
       if (!big)        { const int a = j >> 2, b = j & 3; y = transpose ? b : a; x = transpose ? a : b; }
       else if (j < 32) { const int a = j >> 3, b = j & 7; y = transpose ? b : a; x = transpose ? a : b; }
       else             { const int k = j - 32, a = k >> 2, b = k & 3; y = transpose ? b : 4 + a; x = transpose ? 4 + a : b; }
-      cb[y * CS + x] = (int16_t)val;
+      cb[cbi(y, x)] = (int16_t)val;
     }
    }
     maxX = max(maxX, min(w - 1, 7));
@@ -179,7 +185,7 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* _
   if (isTS) {
     for (int i = lane; i < w * h; i += G) {
       const int y = i >> log2w, x = i & (w - 1);
-      emit(x, y, (x < nzW && y < nzH) ? (int)cb[y * CS + x] : 0);
+      emit(x, y, (x < nzW && y < nzH) ? (int)cb[cbi(y, x)] : 0);
     }
     return;
   }
@@ -202,26 +208,46 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* _
   const int nRows = min(maxY + 1, zoH);   // = h - skipHeight
 
   // ---- 6. stage 1: vertical, round >>7, clip to 16 bit (TrQuant_EMT.cpp:103-121, clip branch) ----
+  // item = (column, group of 4 output rows); output columns are stored in pairs for stage 2; an odd last column gets a zero partner
   {
-    const int16_t* mv = tr_matrix(trV, log2h);
-    for (int i = lane; i < nCols * h; i += G) {
-      const int col = i >> log2h, j = i & (h - 1);
-      int acc = 0;
-      for (int k = 0; k < nRows; k++) acc += (int)cb[k * CS + col] * (int)__ldg(mv + (k << log2h) + j);
-      tb[i] = (int16_t)clip16((acc + (1 << (shift1 - 1))) >> shift1);
+    const int16_t* mv = tr_pair(trV, log2h);
+    const int nColsE = (nCols + 1) & ~1, nKp = (nRows + 1) >> 1, l2g = max(log2h - 2, 0);   // h == 2: one group, two live outputs
+    for (int i = lane; i < (nColsE << l2g); i += G) {
+      const int col = i >> l2g, j = (i & ((1 << l2g) - 1)) << 2;
+      int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      if (col < nCols) {
+        const uint32_t* c2 = reinterpret_cast<const uint32_t*>(cb) + col;
+        const uint2* m2 = reinterpret_cast<const uint2*>(mv + j);
+        for (int kp = 0; kp < nKp; kp++) {
+          const int a = (int)c2[kp * CS];
+          const uint2 m = __ldg(m2 + ((kp << log2h) >> 2));
+          a0 = __dp2a_lo(a, (int)m.x, a0); a1 = __dp2a_hi(a, (int)m.x, a1); a2 = __dp2a_lo(a, (int)m.y, a2); a3 = __dp2a_hi(a, (int)m.y, a3);
+        }
+      }
+      int16_t* o = tb + ((((col >> 1) << log2h) + j) << 1) + (col & 1);
+      o[0] = (int16_t)clip16((a0 + (1 << (shift1 - 1))) >> shift1); o[2] = (int16_t)clip16((a1 + (1 << (shift1 - 1))) >> shift1);
+      if (h >= 4) { o[4] = (int16_t)clip16((a2 + (1 << (shift1 - 1))) >> shift1); o[6] = (int16_t)clip16((a3 + (1 << (shift1 - 1))) >> shift1); }
     }
   }
   gsync();
 
   // ---- 7. stage 2: horizontal + final round/clip (cpyResiClipCore, TrQuant_EMT.cpp:366) + reco ----
   {
-    const int16_t* mh = tr_matrix(trH, log2w);
+    const int16_t* mh = tr_pair(trH, log2w);
     const int rnd = 1 << (shift2 - 1);
-    for (int i = lane; i < w * h; i += G) {
-      const int y = i >> log2w, x = i & (w - 1);
-      int acc = 0;
-      for (int k = 0; k < nCols; k++) acc += (int)tb[(k << log2h) + y] * (int)__ldg(mh + (k << log2w) + x);
-      emit(x, y, clip16((acc + rnd) >> shift2));
+    const int nKp = (nCols + 1) >> 1, l2g = max(log2w - 2, 0);
+    const uint32_t* t2 = reinterpret_cast<const uint32_t*>(tb);
+    for (int i = lane; i < (h << l2g); i += G) {
+      const int y = i >> l2g, x = (i & ((1 << l2g) - 1)) << 2;
+      const uint2* m2 = reinterpret_cast<const uint2*>(mh + x);
+      int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      for (int kp = 0; kp < nKp; kp++) {
+        const int a = (int)t2[(kp << log2h) + y];
+        const uint2 m = __ldg(m2 + ((kp << log2w) >> 2));
+        a0 = __dp2a_lo(a, (int)m.x, a0); a1 = __dp2a_hi(a, (int)m.x, a1); a2 = __dp2a_lo(a, (int)m.y, a2); a3 = __dp2a_hi(a, (int)m.y, a3);
+      }
+      emit(x, y, clip16((a0 + rnd) >> shift2)); emit(x + 1, y, clip16((a1 + rnd) >> shift2));
+      if (w >= 4) { emit(x + 2, y, clip16((a2 + rnd) >> shift2)); emit(x + 3, y, clip16((a3 + rnd) >> shift2)); }
     }
   }
 }

@@ -1,7 +1,8 @@
 // k5_alf.cu — K5: adaptive loop filter. Luma: one CTA per 32x32 block (the reference's classification block): the block
 // plus a 4-sample halo is staged in shared memory (coordinates clamped to the picture = prepareCTU's border extension),
 // 4 threads per 4x4 block compute the Laplacian sums (warp-shuffle reduce), then every thread filters 4 samples with
-// the 7x7 diamond.  Chroma: one thread per 4 samples does the 5x5 diamond and adds CC-ALF from the pre-ALF luma.
+// the 7x7 diamond, two output samples per 32-bit lane: packed 16-bit subtract / clamp (VIADD.16x2, VIMNMX.S16x2) and a
+// 16x8-bit dot product per tap (IDP.2A); coefficients outside int8 (only +128 is legal) fall back to scalar arithmetic.  Chroma: one thread per 4 samples does the 5x5 diamond and adds CC-ALF from the pre-ALF luma.
 //
 // Replaces (reference, source/Lib/CommonLib/AdaptiveLoopFilter.cpp): processCTU :466, filterCTU :664 (!isCrssByVBs
 // path), filterAreaLuma :498, deriveClassificationBlk :969, filterBlk<ALF_FILTER_7|5> :1175, filterAreaChroma :546,
@@ -14,10 +15,12 @@ namespace b200 {
 constexpr int TB = 32;            // tile (block) size
 constexpr int HALO = 4;
 constexpr int TS = TB + 2 * HALO; // 40
+constexpr int TSW = 44;           // shared row stride in samples (88 B: every row is 8-byte aligned)
 
 struct AlfParams {
   const int16_t* src[3]; int16_t* dst[3]; int stride[3];
   int W, H, bitDepth, ctuSize, ctuLog2, ctusW;
+  int vecOk;                      // luma stride is a multiple of 4 samples: rows can be copied 8 bytes at a time
   const b200_alf_ctu* ctus;
   const int16_t *lumaCoeff, *lumaClip, *chromaCoeff, *chromaClip, *cc0, *cc1;
 };
@@ -26,7 +29,7 @@ __device__ __forceinline__ int clipd(int c, int ref, int a, int b) { return clip
 
 __global__ void __launch_bounds__(256) alf_luma_kernel(const AlfParams P)
 {
-  __shared__ int16_t t[TS][TS + 2];
+  __shared__ __align__(16) int16_t t[TS][TSW];
   __shared__ uint16_t s_cls[64];
   const int bx0 = blockIdx.x * TB, by0 = blockIdx.y * TB;
   const int tid = threadIdx.x;
@@ -43,10 +46,18 @@ __global__ void __launch_bounds__(256) alf_luma_kernel(const AlfParams P)
   }
 
   // ---- stage tile + halo, clamped ----
-  for (int i = tid; i < TS * TS; i += 256) {
-    const int ty = i / TS, tx = i - ty * TS;
-    const int gx = min(max(bx0 + tx - HALO, 0), P.W - 1), gy = min(max(by0 + ty - HALO, 0), P.H - 1);
-    t[ty][tx] = P.src[0][(size_t)gy * stride + gx];
+  if (P.vecOk && bx0 >= HALO && bx0 + TB + HALO <= P.W && by0 >= HALO && by0 + TB + HALO <= P.H) {
+    const int16_t* s0 = P.src[0] + (size_t)(by0 - HALO) * stride + bx0 - HALO;      // interior tile: 40 rows x 10 8-byte words
+    for (int i = tid; i < TS * (TS / 4); i += 256) {
+      const int ty = i / (TS / 4), c = i - ty * (TS / 4);
+      *reinterpret_cast<uint2*>(&t[ty][c * 4]) = __ldg(reinterpret_cast<const uint2*>(s0 + (size_t)ty * stride) + c);
+    }
+  } else {
+    for (int i = tid; i < TS * TS; i += 256) {
+      const int ty = i / TS, tx = i - ty * TS;
+      const int gx = min(max(bx0 + tx - HALO, 0), P.W - 1), gy = min(max(by0 + ty - HALO, 0), P.H - 1);
+      t[ty][tx] = P.src[0][(size_t)gy * stride + gx];
+    }
   }
   __syncthreads();
 
@@ -121,8 +132,73 @@ __global__ void __launch_bounds__(256) alf_luma_kernel(const AlfParams P)
     const int r1 = min(1, lim), r2 = min(2, lim), r3 = min(3, lim);
     const int ly = ry + HALO;
     const int pmax = (1 << P.bitDepth) - 1;
-    // the 4 outputs share most taps: fetch the diamond's union once (46 samples instead of 4 x 25)
     const int lx0 = rx + HALO;
+    int out[4];
+    bool wide = P.bitDepth > 12;                              // packed halves hold sums of two clipped differences: 2 * 2^bd must fit 16 bit
+#pragma unroll
+    for (int i = 0; i < 12; i++) wide |= fc[i] != (int)(int8_t)fc[i];
+    if (!wide) {
+      // rows as aligned sample pairs (lx0 is a multiple of 4); odd offsets are built with one byte-permute from two neighbours
+      const uint32_t* R0 = reinterpret_cast<const uint32_t*>(&t[ly][0]) + (lx0 >> 1);
+      const uint32_t* P1 = reinterpret_cast<const uint32_t*>(&t[ly + r1][0]) + (lx0 >> 1); const uint32_t* M1 = reinterpret_cast<const uint32_t*>(&t[ly - r1][0]) + (lx0 >> 1);
+      const uint32_t* P2 = reinterpret_cast<const uint32_t*>(&t[ly + r2][0]) + (lx0 >> 1); const uint32_t* M2 = reinterpret_cast<const uint32_t*>(&t[ly - r2][0]) + (lx0 >> 1);
+      const uint32_t* P3 = reinterpret_cast<const uint32_t*>(&t[ly + r3][0]) + (lx0 >> 1); const uint32_t* M3 = reinterpret_cast<const uint32_t*>(&t[ly - r3][0]) + (lx0 >> 1);
+      uint32_t r0w[6], p1w[4], m1w[4], p2w[4], m2w[4], p3w[2], m3w[2];
+#pragma unroll
+      for (int k = 0; k < 6; k++) r0w[k] = R0[k - 2];                                  // samples lx0-4 .. lx0+7
+#pragma unroll
+      for (int k = 0; k < 4; k++) { p1w[k] = P1[k - 1]; m1w[k] = M1[k - 1]; p2w[k] = P2[k - 1]; m2w[k] = M2[k - 1]; }   // lx0-2 .. lx0+5
+#pragma unroll
+      for (int k = 0; k < 2; k++) { p3w[k] = P3[k]; m3w[k] = M3[k]; }
+      uint32_t r0s[5], p1s[3], m1s[3], p2s[3], m2s[3];                                 // pairs starting at odd offsets
+#pragma unroll
+      for (int k = 0; k < 5; k++) r0s[k] = __byte_perm(r0w[k], r0w[k + 1], 0x5432);   // offsets -3,-1,1,3,5
+#pragma unroll
+      for (int k = 0; k < 3; k++) {                                                    // offsets -1,1,3
+        p1s[k] = __byte_perm(p1w[k], p1w[k + 1], 0x5432); m1s[k] = __byte_perm(m1w[k], m1w[k + 1], 0x5432);
+        p2s[k] = __byte_perm(p2w[k], p2w[k + 1], 0x5432); m2s[k] = __byte_perm(m2w[k], m2w[k + 1], 0x5432);
+      }
+      int accLo[2] = {0, 0}, accHi[2] = {0, 0};
+      uint32_t ncur[2] = {__vneg2(r0w[2]), __vneg2(r0w[3])};
+      // pair of samples at offset j (relative to lx0) of each row, j compile-time
+#define R0P(j) (((j) & 1) ? r0s[((j) + 3) >> 1] : r0w[((j) + 4) >> 1])
+#define P1P(j) (((j) & 1) ? p1s[((j) + 1) >> 1] : p1w[((j) + 2) >> 1])
+#define M1P(j) (((j) & 1) ? m1s[((j) + 1) >> 1] : m1w[((j) + 2) >> 1])
+#define P2P(j) (((j) & 1) ? p2s[((j) + 1) >> 1] : p2w[((j) + 2) >> 1])
+#define M2P(j) (((j) & 1) ? m2s[((j) + 1) >> 1] : m2w[((j) + 2) >> 1])
+#define ALF_TAP(n, A0, B0, A1, B1) { \
+        const uint32_t cp = (uint32_t)cc[n] * 0x10001u, cn = __vneg2(cp); const int kl = fc[n] & 0xff, kh = kl << 8; \
+        uint32_t d0 = __vmins2(__vmaxs2(__vadd2(A0, ncur[0]), cn), cp), e0 = __vmins2(__vmaxs2(__vadd2(B0, ncur[0]), cn), cp); \
+        uint32_t d1 = __vmins2(__vmaxs2(__vadd2(A1, ncur[1]), cn), cp), e1 = __vmins2(__vmaxs2(__vadd2(B1, ncur[1]), cn), cp); \
+        d0 = __vadd2(d0, e0); d1 = __vadd2(d1, e1); \
+        accLo[0] = __dp2a_lo((int)d0, kl, accLo[0]); accHi[0] = __dp2a_lo((int)d0, kh, accHi[0]); \
+        accLo[1] = __dp2a_lo((int)d1, kl, accLo[1]); accHi[1] = __dp2a_lo((int)d1, kh, accHi[1]); }
+      ALF_TAP(0,  p3w[0],  m3w[0],  p3w[1],  m3w[1])
+      ALF_TAP(1,  P2P(1),  M2P(-1), P2P(3),  M2P(1))
+      ALF_TAP(2,  P2P(0),  M2P(0),  P2P(2),  M2P(2))
+      ALF_TAP(3,  P2P(-1), M2P(1),  P2P(1),  M2P(3))
+      ALF_TAP(4,  P1P(2),  M1P(-2), P1P(4),  M1P(0))
+      ALF_TAP(5,  P1P(1),  M1P(-1), P1P(3),  M1P(1))
+      ALF_TAP(6,  P1P(0),  M1P(0),  P1P(2),  M1P(2))
+      ALF_TAP(7,  P1P(-1), M1P(1),  P1P(1),  M1P(3))
+      ALF_TAP(8,  P1P(-2), M1P(2),  P1P(0),  M1P(4))
+      ALF_TAP(9,  R0P(3),  R0P(-3), R0P(5),  R0P(-1))
+      ALF_TAP(10, R0P(2),  R0P(-2), R0P(4),  R0P(0))
+      ALF_TAP(11, R0P(1),  R0P(-1), R0P(3),  R0P(1))
+#undef ALF_TAP
+#undef R0P
+#undef P1P
+#undef M1P
+#undef P2P
+#undef M2P
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const int c0 = (int)(int16_t)(r0w[2 + q] & 0xffff), c1 = (int)r0w[2 + q] >> 16;
+        const int s0 = nearVb ? (accLo[q] + 512) >> 10 : (accLo[q] + 64) >> 7, s1 = nearVb ? (accHi[q] + 512) >> 10 : (accHi[q] + 64) >> 7;
+        out[2 * q] = clip3(0, pmax, s0 + c0); out[2 * q + 1] = clip3(0, pmax, s1 + c1);
+      }
+    } else {
+    // the 4 outputs share most taps: fetch the diamond's union once (46 samples instead of 4 x 25)
     int r0[10], p1[8], m1[8], p2[6], m2[6], p3[4], m3[4];
 #pragma unroll
     for (int k = 0; k < 10; k++) r0[k] = t[ly][lx0 - 3 + k];
@@ -132,7 +208,6 @@ __global__ void __launch_bounds__(256) alf_luma_kernel(const AlfParams P)
     for (int k = 0; k < 6; k++) { p2[k] = t[ly + r2][lx0 - 1 + k]; m2[k] = t[ly - r2][lx0 - 1 + k]; }
 #pragma unroll
     for (int k = 0; k < 4; k++) { p3[k] = t[ly + r3][lx0 + k]; m3[k] = t[ly - r3][lx0 + k]; }
-    int out[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const int cur = r0[i + 3];
@@ -151,6 +226,7 @@ __global__ void __launch_bounds__(256) alf_luma_kernel(const AlfParams P)
       sum += fc[11] * clipd(cc[11], cur, r0[i + 4], r0[i + 2]);
       sum = nearVb ? (sum + 512) >> 10 : (sum + 64) >> 7;
       out[i] = clip3(0, pmax, sum + cur);
+    }
     }
     uint2 o;
     o.x = (unsigned)(out[0] & 0xffff) | ((unsigned)out[1] << 16);
@@ -231,26 +307,30 @@ __global__ void __launch_bounds__(256) alf_chroma_kernel(const AlfParams P)
   *reinterpret_cast<uint2*>(P.dst[c] + (size_t)y * stride + x) = o;
 }
 
-int launch_alf(const AlfLaunch& L, cudaStream_t s, KProf* prof)
+int launch_alf(const AlfLaunch& L, StreamSet& ss, KProf* prof)
 {
+  cudaStream_t s = ss.main;
   AlfParams P;
   for (int c = 0; c < 3; c++) { P.src[c] = L.src.p[c]; P.dst[c] = L.dst.p[c]; P.stride[c] = L.src.stride[c]; }
   P.W = L.geom.width; P.H = L.geom.height; P.bitDepth = L.geom.bitDepth; P.ctuSize = L.geom.ctuSize;
   P.ctuLog2 = P.ctuSize == 128 ? 7 : P.ctuSize == 64 ? 6 : 5; P.ctusW = (P.W + P.ctuSize - 1) / P.ctuSize;
   P.ctus = L.ctus; P.lumaCoeff = L.lumaCoeff; P.lumaClip = L.lumaClip; P.chromaCoeff = L.chromaCoeff; P.chromaClip = L.chromaClip;
   P.cc0 = L.cc[0]; P.cc1 = L.cc[1];
+  P.vecOk = (P.stride[0] & 3) == 0 && (reinterpret_cast<uintptr_t>(P.src[0]) & 7) == 0;
   dim3 grdL((P.W + TB - 1) / TB, (P.H + TB - 1) / TB);
+  if (L.geom.chromaFormat == 1) {                           // chroma + CC-ALF only read the SAO output: runs beside the luma kernel
+    cudaStream_t sc = ss.pick(0);
+    dim3 blk(32, 8), grd(((P.W >> 1) / 4 + 31) / 32, ((P.H >> 1) + 7) / 8, 2);
+    if (prof) prof->begin(B200_KF_ALF_CHROMA, sc);
+    alf_chroma_kernel<<<grd, blk, 0, sc>>>(P);
+    B200_CUDA(cudaGetLastError());
+    if (prof) prof->end(B200_KF_ALF_CHROMA, sc);
+  }
   if (prof) prof->begin(B200_KF_ALF_LUMA, s);
   alf_luma_kernel<<<grdL, 256, 0, s>>>(P);
   B200_CUDA(cudaGetLastError());
   if (prof) prof->end(B200_KF_ALF_LUMA, s);
-  if (L.geom.chromaFormat == 1) {
-    dim3 blk(32, 8), grd(((P.W >> 1) / 4 + 31) / 32, ((P.H >> 1) + 7) / 8, 2);
-    if (prof) prof->begin(B200_KF_ALF_CHROMA, s);
-    alf_chroma_kernel<<<grd, blk, 0, s>>>(P);
-    B200_CUDA(cudaGetLastError());
-    if (prof) prof->end(B200_KF_ALF_CHROMA, s);
-  }
+  ss.join();
   return 0;
 }
 

@@ -256,7 +256,7 @@ B200_API int b200_pic_run(b200_ctx* c, int ai)
   if (A.flags & B200_PIC_ALF) {
     AlfLaunch L; L.geom = g; L.src = P; L.dst = c->planes(other); L.ctus = A.alf;
     L.lumaCoeff = A.lumaCoeff; L.lumaClip = A.lumaClip; L.chromaCoeff = A.chromaCoeff; L.chromaClip = A.chromaClip; L.cc[0] = A.cc[0]; L.cc[1] = A.cc[1];
-    if (int rc = launch_alf(L, s, c->profiling ? &c->prof : nullptr)) return rc;
+    if (int rc = launch_alf(L, c->ss, c->profiling ? &c->prof : nullptr)) return rc;
     c->launches += g.chromaFormat ? 2 : 1;
     std::swap(cur, other);
   }
