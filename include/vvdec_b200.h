@@ -264,10 +264,17 @@ B200_API int  b200_ctx_create(b200_ctx** ctx, const b200_geom* g, int numSlots, 
 B200_API void b200_ctx_destroy(b200_ctx* ctx);
 /* Host planes -> DPB slot (e.g. an IRAP picture reconstructed elsewhere, or test content). Synchronous. */
 B200_API int  b200_ctx_load_slot(b200_ctx* ctx, int slot, const int16_t* const planes[3]);
-/* decompressPicture(): non-blocking. Copies the work lists to the next arena (async H2D) and enqueues all kernels.
- * Returns the arena handle (>= 0) or a negative error. */
+/* decompressPicture() = b200_pic_upload + b200_pic_run.  Returns the arena handle (>= 0) or a negative error.
+ *
+ * b200_pic_upload: non-blocking, no per-record host work.  The caller's arrays are copied as they are to the next arena (async H2D on
+ *   the context's upload stream: pass pinned memory, see b200_host_register); two small kernels validate the PU / TU records and sort
+ *   their indices into the work lists of the compute kernels on the device.
+ * b200_pic_run: enqueues the picture's kernel chain.  It sizes the grids from the list lengths the upload produced, so it waits (host)
+ *   until that upload has finished; a caller that uploads picture n+1 before it runs picture n (a parser running ahead of
+ *   reconstruction) never waits.  An invalid record (reference slot outside the DPB, impossible block size, BDOF/DMVR on a block that
+ *   cannot have it, DMVR at more than 10 bit) makes it return B200_ERR_PARAM without running anything.
+ * A handle may be run several times (device-resident benchmarking). */
 B200_API int  b200_decompress_picture(b200_ctx* ctx, const b200_picture* pic);
-/* Split form for device-resident benchmarking: upload once, run many times. */
 B200_API int  b200_pic_upload(b200_ctx* ctx, const b200_picture* pic);            /* -> arena handle */
 B200_API int  b200_pic_run(b200_ctx* ctx, int arena);
 /* waitForPrevDecompressedPic(): blocks until every picture submitted so far is final; copies the DMVR MV deltas of

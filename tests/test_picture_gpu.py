@@ -47,3 +47,30 @@ def test_ctx_errors(b200):
     ctx = C.c_void_p()
     assert b200.b200_ctx_create(C.byref(ctx), C.byref(g), 4, 2, -1) == -2
     assert b"multiple of 8" in b200.b200_last_error()
+
+
+def test_invalid_records_are_reported(b200):
+    """Records are validated on the device while they are bucketed: a PU pointing at a DPB slot the context does not have (or a TU with
+    an impossible size) makes b200_pic_run / b200_decompress_picture refuse the picture with B200_ERR_PARAM."""
+    rng = np.random.default_rng(5)
+    W, H, bd = 416, 240, 10
+    g = abi.make_geom(W, H, bd)
+    ctx = C.c_void_p()
+    vvdec_b200.check(b200.b200_ctx_create(C.byref(ctx), C.byref(g), 6, 2, -1))
+    try:
+        ref = synth.noise_planes(rng, W, H, bd)
+        for s in range(6): vvdec_b200.check(b200.b200_ctx_load_slot(ctx, s, abi.plane_ptrs(ref)))
+        pic = synth.gen_picture(rng, W, H, bd, dst_slot=4, deblock=0, sao=0, alf=0)
+        h = b200.b200_decompress_picture(ctx, C.byref(pic["struct"])); assert h >= 0
+        assert b200.b200_wait_picture(ctx, h, None, 0) == 0
+        orig = pic["pus"]["refSlot"][3].copy()
+        pic["pus"]["refSlot"][3] = (17, -1)
+        assert b200.b200_decompress_picture(ctx, C.byref(pic["struct"])) == -2 and b"PU list" in b200.b200_last_error()
+        pic["pus"]["refSlot"][3] = orig
+        pic["tus"]["log2w"][0] = 7
+        assert b200.b200_decompress_picture(ctx, C.byref(pic["struct"])) == -2 and b"TU list" in b200.b200_last_error()
+        pic["tus"]["log2w"][0] = 2
+        h = b200.b200_decompress_picture(ctx, C.byref(pic["struct"])); assert h >= 0      # the context is still usable
+        assert b200.b200_wait_picture(ctx, h, None, 0) == 0
+    finally:
+        b200.b200_ctx_destroy(ctx)

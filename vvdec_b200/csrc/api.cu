@@ -63,48 +63,24 @@ static int download_planes(const b200_geom* g, int16_t* const planes[3], const D
   return 0;
 }
 
-void bucket_tus(const b200_tu* tus, size_t n, std::vector<b200_tu>& out, size_t clsCount[4])
+int num_sms()
 {
-  size_t cnt[4] = {0, 0, 0, 0}, pos[4];
-  for (size_t i = 0; i < n; i++) cnt[k1_class_of(tus[i])]++;
-  pos[0] = 0; for (int c = 1; c < 4; c++) pos[c] = pos[c - 1] + cnt[c - 1];
-  out.resize(n);
-  for (size_t i = 0; i < n; i++) out[pos[k1_class_of(tus[i])]++] = tus[i];
-  for (int c = 0; c < 4; c++) clsCount[c] = cnt[c];
+  static int cache[64] = {0};
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!cache[dev]) { int n = 0; if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148; cache[dev] = n; }
+  return cache[dev];
 }
 
-void build_mc_tiles(const b200_pu* pus, size_t numPus, McTileLists& out)
+// waits for a bucketing pass, copies its list lengths to the host and turns its error bits into B200_ERR_PARAM
+int fetch_list_meta(const int* metaDev, int* cnt, int nLists, const char* what, cudaStream_t s)
 {
-  for (auto& m : out.cls) for (auto& v : m) v.clear();
-  out.aff.clear();
-  for (size_t i = 0; i < numPus; i++) {
-    const b200_pu& p = pus[i];
-    const bool bi = p.refSlot[0] >= 0 && p.refSlot[1] >= 0;
-    const int mode = (p.flags & B200_PU_DMVR) ? 3 : (bi && (p.flags & B200_PU_BDOF)) ? 2 : bi ? 1 : 0;
-    for (int ty = 0; ty * 16 < p.h; ty++)
-      for (int tx = 0; tx * 16 < p.w; tx++) {
-        const uint32_t t = (uint32_t)(i << 6) | (ty << 3) | tx;
-        if (p.flags & B200_PU_AFFINE) { out.aff.push_back(t); continue; }
-        const int tw = p.w - tx * 16 < 16 ? p.w - tx * 16 : 16, th = p.h - ty * 16 < 16 ? p.h - ty * 16 : 16;
-        int n = tw * th, k = 0;
-        if (n < 32) n = 32;                 // 4x4 (not legal for inter, kept for exactness) rides in the 32-thread class
-        while ((32 << k) < n) k++;
-        out.cls[mode][k].push_back(t);
-      }
-  }
-}
-
-int upload_mc_tiles(const McTileLists& T, uint32_t* dev, McLaunch& L, cudaStream_t s)
-{
-  size_t off = 0;
-  for (int m = 0; m < 4; m++) for (int k = 0; k < 4; k++) {
-    const auto& v = T.cls[m][k];
-    L.cls[m][k].tiles = dev + off; L.cls[m][k].n = (int)v.size();
-    if (!v.empty()) B200_CUDA(cudaMemcpyAsync(dev + off, v.data(), v.size() * 4, cudaMemcpyHostToDevice, s));
-    off += v.size();
-  }
-  L.tilesA = dev + off; L.numTilesA = (int)T.aff.size();
-  if (!T.aff.empty()) B200_CUDA(cudaMemcpyAsync(dev + off, T.aff.data(), T.aff.size() * 4, cudaMemcpyHostToDevice, s));
+  int h[LM_INTS];
+  B200_CUDA(cudaMemcpyAsync(h, metaDev, sizeof(h), cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaStreamSynchronize(s));
+  for (int i = 0; i < nLists; i++) cnt[i] = h[LM_CNT + i];
+  B200_CHECK(!(h[LM_ERR] & 1), "%s: invalid record (reference slots, block size or flag combination)", what);
+  B200_CHECK(!(h[LM_ERR] & 2), "%s: more tiles than the picture can hold (overlapping PUs?)", what);
   return 0;
 }
 
@@ -131,12 +107,15 @@ B200_API int b200_k1_residual(const b200_geom* g, int16_t* const planes[3], cons
   if (int rc = g_hw.tus.reserve(numTus * sizeof(b200_tu))) return rc;
   if (int rc = g_hw.coefs.reserve(numCoefs * sizeof(int16_t) + 16)) return rc;
   if (int rc = g_hw.scaling.reserve(numScaling * sizeof(int32_t) + 16)) return rc;
-  static std::vector<b200_tu> sorted;
-  bucket_tus(tus, numTus, sorted, L.clsCount);
-  if (numTus) B200_CUDA(cudaMemcpyAsync(g_hw.tus.p, sorted.data(), numTus * sizeof(b200_tu), cudaMemcpyHostToDevice, s));
+  if (int rc = g_hw.misc[4].reserve(numTus * 4 + LM_INTS * sizeof(int) + 256)) return rc;
+  if (numTus) B200_CUDA(cudaMemcpyAsync(g_hw.tus.p, tus, numTus * sizeof(b200_tu), cudaMemcpyHostToDevice, s));
   if (numCoefs) B200_CUDA(cudaMemcpyAsync(g_hw.coefs.p, coefs, numCoefs * sizeof(int16_t), cudaMemcpyHostToDevice, s));
   if (numScaling) B200_CUDA(cudaMemcpyAsync(g_hw.scaling.p, scaling, numScaling * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   L.tus = g_hw.tus.as<b200_tu>(); L.coefs = g_hw.coefs.as<int16_t>(); L.scaling = g_hw.scaling.as<int32_t>();
+  int* meta = g_hw.misc[4].as<int>(); uint32_t* idx = reinterpret_cast<uint32_t*>(meta + LM_INTS);
+  if (int rc = launch_tu_bucket(L.tus, numTus, idx, meta, s)) return rc;
+  L.idx = idx; L.meta = meta;
+  if (int rc = fetch_list_meta(meta, L.cnt, K1_LISTS, "b200_k1_residual", s)) return rc;
   StreamSet ss(s);
   if (int rc = launch_k1_residual(L, ss)) return rc;
   if (int rc = download_planes(g, planes, L.planes, s)) return rc;
@@ -269,13 +248,15 @@ B200_API int b200_mc_predict(const b200_geom* g, int16_t* const dst[3], const in
       ptrs[sl * 3 + c] = reinterpret_cast<const int16_t*>(d); off += planeBytes[c];
     }
   }
-  static McTileLists TL;
-  build_mc_tiles(pus, numPus, TL);
+  const size_t capTiles = mc_tile_capacity(*g, numPus);
   if (int rc = g_hw.misc[5].reserve(numPus * sizeof(b200_pu) + 64)) return rc;
-  if (int rc = g_hw.misc[6].reserve(TL.total() * 4 + 64)) return rc;
+  if (int rc = g_hw.misc[6].reserve(capTiles * 4 + LM_INTS * sizeof(int) + 256)) return rc;
   if (int rc = g_hw.misc[7].reserve(numDmvr * 8 + 64)) return rc;
   if (numPus) B200_CUDA(cudaMemcpyAsync(g_hw.misc[5].p, pus, numPus * sizeof(b200_pu), cudaMemcpyHostToDevice, s));
-  if (int rc = upload_mc_tiles(TL, g_hw.misc[6].as<uint32_t>(), L, s)) return rc;
+  int* meta = g_hw.misc[6].as<int>(); uint32_t* tiles = reinterpret_cast<uint32_t*>(meta + LM_INTS);
+  if (int rc = launch_mc_bucket(g_hw.misc[5].as<b200_pu>(), numPus, tiles, capTiles, meta, numSlots, g->bitDepth, s)) return rc;
+  L.tiles = tiles; L.meta = meta;
+  if (int rc = fetch_list_meta(meta, L.cnt, MC_LISTS, "b200_mc_predict", s)) return rc;
   B200_CUDA(cudaMemsetAsync(g_hw.misc[7].p, 0, numDmvr * 8 + 64, s));
   memset(L.refs, 0, sizeof(L.refs)); for (size_t i = 0; i < ptrs.size(); i++) L.refs[i] = ptrs[i];
   for (int c = 0; c < 3; c++) L.refStride[c] = g->stride[c];

@@ -73,20 +73,29 @@ struct StreamSet {
   void join() { for (int k = 0; k < nAux; k++) if (used[k]) { cudaEventRecord(joinEv[k], aux[k]); cudaStreamWaitEvent(main, joinEv[k], 0); used[k] = false; } }
 };
 
+// ---- device work lists (bucket.cu): index lists + a small block of ints ("meta") per array ----
+constexpr int MC_LISTS = 17;     // mode*4 + size class (mode 0 uni, 1 bi, 2 bi+BDOF, 3 DMVR; 32/64/128/256 samples), 16 = affine tiles
+constexpr int K1_LISTS = 4;      // TU max dimension <= 8, 16, 32, 64
+constexpr int LM_CNT = 0, LM_OFF = 32, LM_CUR = 64, LM_DONE = 96, LM_ERR = 97, LM_INTS = 128;   // meta layout: counts, offsets, cursors, ticket, error bits
+int launch_mc_bucket(const b200_pu* pus, size_t numPus, uint32_t* tiles, size_t capTiles, int* meta, int numSlots, int bitDepth, cudaStream_t s);
+int launch_tu_bucket(const b200_tu* tus, size_t numTus, uint32_t* idx, int* meta, cudaStream_t s);
+size_t mc_tile_capacity(const b200_geom& g, size_t numPus);
+int num_sms();                   // SM count of the current device (persistent-style grids are sized from it)
+int fetch_list_meta(const int* metaDev, int* cnt, int nLists, const char* what, cudaStream_t s);   // synchronises s: list lengths to the host, error bits -> B200_ERR_PARAM
+
 struct K1Launch {
   b200_geom      geom;
   DevPlanes      planes;
-  const b200_tu* tus;        // device, bucketed by size class (see k1_class_of): clsCount[0] records of class 0 first, ...
+  const b200_tu* tus;        // device, caller order
   size_t         numTus;
-  size_t         clsCount[4];
+  const uint32_t* idx;       // device: TU indices bucketed by size class (launch_tu_bucket)
+  const int*     meta;       // device: counts / offsets of the 4 lists
+  int            cnt[K1_LISTS];   // the same counts on the host (read back after bucketing): exact grids, empty lists are not launched
   const int16_t* coefs;
   const int32_t* scaling;
   int            mode;    // 0: reco = clip(pred + resi); 1: store residual
 };
 int launch_k1_residual(const K1Launch& L, StreamSet& ss, KProf* prof = nullptr);
-int k1_class_of(const b200_tu& t);
-// host: stable bucket sort of TU records by size class into `out`, counts into clsCount
-void bucket_tus(const b200_tu* tus, size_t n, std::vector<b200_tu>& out, size_t clsCount[4]);
 
 struct LfSliceTab { b200_lf_slice s[64]; };
 struct LfLaunch {
@@ -112,18 +121,14 @@ struct McLaunch {
   const int16_t* refs[B200_MAX_SLOTS * 3];   // device plane pointers per DPB slot
   int refStride[3];
   const b200_pu* pus;               // device
-  // device tile lists, tile = (puIdx<<6)|(ty<<3)|tx.  Translational tiles are bucketed by [mode: 0 uni,1 bi,2 BDOF,3 DMVR][log2(samples)-5: 32,64,128,256]
-  struct Cls { const uint32_t* tiles; int n; } cls[4][4];
-  const uint32_t* tilesA; int numTilesA;
+  const uint32_t* tiles;            // device: tile = (puIdx<<6)|(ty<<3)|tx, bucketed into MC_LISTS lists (launch_mc_bucket)
+  const int* meta;                  // device: counts / offsets of the lists
+  int cnt[MC_LISTS];                // the same counts on the host (read back after bucketing): exact grids, empty lists are not launched
   int32_t* dmvrMv;                  // device or null
 };
 int launch_mc(const McLaunch& L, StreamSet& ss, KProf* prof = nullptr);
-// host: expand PUs into <=16x16 tiles
-struct McTileLists { std::vector<uint32_t> cls[4][4], aff; size_t total() const { size_t n = aff.size(); for (auto& m : cls) for (auto& v : m) n += v.size(); return n; } };
-void build_mc_tiles(const b200_pu* pus, size_t numPus, McTileLists& out);
-// copies the bucketed lists back to back into a device buffer (async) and fills L.cls / L.tilesA
-int upload_mc_tiles(const McTileLists& T, uint32_t* dev, McLaunch& L, cudaStream_t s);
 int mc_launch_count(const McLaunch& L);
+int k1_launch_count(const K1Launch& L);
 
 int ensure_device();   // selects device 0 if none current; fails loudly when there is no sm_100 GPU
 

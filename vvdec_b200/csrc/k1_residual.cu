@@ -17,6 +17,7 @@
 #define VVC_TABLE_QUAL static __device__ const __align__(16)
 #include "vvc_tables.h"
 #include "common.cuh"
+#include <algorithm>
 
 namespace b200 {
 
@@ -50,20 +51,13 @@ __device__ __forceinline__ int dequant_one(int level, int scale, int rightShift,
   return clip16(v);
 }
 
+// one TU, executed by a group of G threads (`lane` = index in the group); all exits are uniform over the group
 template <int CLS>
-__global__ void __launch_bounds__(K1Cfg<CLS>::THREADS)
-k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* __restrict__ coefs,
-                   const int32_t* __restrict__ scaling, int16_t* p0, int16_t* p1, int16_t* p2,
-                   int s0, int s1, int s2, int bitDepth, int mode)
+__device__ __forceinline__ void k1_tu(const b200_tu* __restrict__ tus, int t, const int16_t* __restrict__ coefs, const int32_t* __restrict__ scaling,
+                                      int16_t* p0, int16_t* p1, int16_t* p2, int s0, int s1, int s2, int bitDepth, int mode,
+                                      int16_t* cb, int16_t* tb, int lane)
 {
-  constexpr int G = K1Cfg<CLS>::G, GROUPS = K1Cfg<CLS>::GROUPS;
-  __shared__ __align__(16) int16_t s_c[GROUPS][K1Cfg<CLS>::CB];
-  __shared__ __align__(16) int16_t s_t[GROUPS][K1Cfg<CLS>::TB];
-
-  // `lane` = index inside the TU's thread group, `warp` = group index in the CTA (names kept from the one-warp-per-TU version)
-  const int warp = threadIdx.x / G, lane = threadIdx.x % G;
-  const int t = blockIdx.x * GROUPS + warp;
-  if (t >= numTus) return;                                   // G == blockDim for the big classes, so the whole CTA leaves together
+  constexpr int G = K1Cfg<CLS>::G;
   auto gsync = [&]() { if (G == 32) __syncwarp(); else __syncthreads(); };
 
   const uint4* recp = reinterpret_cast<const uint4*>(tus + t);
@@ -78,8 +72,6 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* _
   const unsigned coefOff = rb.x, slOff = rb.y;
 
   const int w = 1 << log2w, h = 1 << log2h;
-  int16_t* cb = s_c[warp];
-  int16_t* tb = s_t[warp];
   const int16_t* q = coefs + coefOff;
   const int qs = maxX + 1;
   const int inMax = (1 << (inBits - 1)) - 1;
@@ -252,21 +244,33 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, int numTus, const int16_t* _
   }
 }
 
-int k1_class_of(const b200_tu& t) { const int m = t.log2w > t.log2h ? t.log2w : t.log2h; return m <= 3 ? 0 : m == 4 ? 1 : m == 5 ? 2 : 3; }
+// One thread group per entry of its class's index list (the host sizes the grid from the list length it reads back after bucketing).
+template <int CLS>
+__global__ void __launch_bounds__(K1Cfg<CLS>::THREADS)
+k1_residual_kernel(const b200_tu* __restrict__ tus, const uint32_t* __restrict__ idx, const int* __restrict__ meta, const int16_t* __restrict__ coefs,
+                   const int32_t* __restrict__ scaling, int16_t* p0, int16_t* p1, int16_t* p2,
+                   int s0, int s1, int s2, int bitDepth, int mode)
+{
+  constexpr int G = K1Cfg<CLS>::G, GROUPS = K1Cfg<CLS>::GROUPS;
+  __shared__ __align__(16) int16_t s_c[GROUPS][K1Cfg<CLS>::CB];
+  __shared__ __align__(16) int16_t s_t[GROUPS][K1Cfg<CLS>::TB];
+  const int grp = threadIdx.x / G, lane = threadIdx.x % G;
+  const int i = blockIdx.x * GROUPS + grp;
+  if (i >= meta[LM_CNT + CLS]) return;                       // G == blockDim for the big classes: the whole CTA leaves together
+  k1_tu<CLS>(tus, (int)idx[meta[LM_OFF + CLS] + i], coefs, scaling, p0, p1, p2, s0, s1, s2, bitDepth, mode, s_c[grp], s_t[grp], lane);
+}
 
 int launch_k1_residual(const K1Launch& L, StreamSet& ss, KProf* prof)
 {
   if (L.numTus == 0) return 0;
   if (prof) prof->begin(B200_KF_K1, ss.main);
-  size_t offs[4]; { size_t o = 0; for (int c = 0; c < 4; c++) { offs[c] = o; o += L.clsCount[c]; } }
   int launched = 0;
   for (int c = 3; c >= 0; c--) {          // largest TUs first: their long CTAs overlap the small classes on the other streams
-    const size_t n = L.clsCount[c], off = offs[c];
-    if (!n) continue;
+    if (!L.cnt[c]) continue;
     cudaStream_t s = ss.pick(launched++);
     const int groups = c <= 1 ? K1_WARPS : 1;
-    const int grid = (int)((n + groups - 1) / groups);
-#define K1_GO(C) k1_residual_kernel<C><<<grid, K1Cfg<C>::THREADS, 0, s>>>(L.tus + off, (int)n, L.coefs, L.scaling, L.planes.p[0], L.planes.p[1], L.planes.p[2], \
+    const int grid = (L.cnt[c] + groups - 1) / groups;
+#define K1_GO(C) k1_residual_kernel<C><<<grid, K1Cfg<C>::THREADS, 0, s>>>(L.tus, L.idx, L.meta, L.coefs, L.scaling, L.planes.p[0], L.planes.p[1], L.planes.p[2], \
                                                                    L.planes.stride[0], L.planes.stride[1], L.planes.stride[2], L.geom.bitDepth, L.mode)
     switch (c) { case 0: K1_GO(0); break; case 1: K1_GO(1); break; case 2: K1_GO(2); break; default: K1_GO(3); break; }
 #undef K1_GO
@@ -276,5 +280,7 @@ int launch_k1_residual(const K1Launch& L, StreamSet& ss, KProf* prof)
   if (prof) prof->end(B200_KF_K1, ss.main);
   return 0;
 }
+
+int k1_launch_count(const K1Launch& L) { int n = 0; for (int c = 0; c < K1_LISTS; c++) n += L.cnt[c] > 0; return n; }
 
 }  // namespace b200

@@ -16,6 +16,7 @@
 #define VVC_TABLE_QUAL static __device__ const __align__(16)
 #include "vvc_tables.h"
 #include "common.cuh"
+#include <algorithm>
 
 namespace b200 {
 
@@ -27,7 +28,7 @@ struct McParams {
   int refStride[3];
   int W, H, bitDepth, ctuSize, chroma;
   int fastOk;                                // plane strides are even -> rows are word-addressable
-  const b200_pu* pus; const uint32_t* tiles; int numTiles;
+  const b200_pu* pus; const uint32_t* tiles; const int* meta;   // device lists (bucket.cu)
   int32_t* dmvrMv;
 };
 
@@ -111,15 +112,9 @@ __host__ __device__ inline int mc_smem_elems(int mode, int n)   // n = tw*th; wo
 
 // OPT: luma outputs per thread (1: blockDim = tw*th; 4: blockDim = tw*th/4, each thread filters 4 adjacent samples so that 11 loads feed 32 MACs)
 template <int MODE, int OPT>
-__global__ void mc_kernel(const McParams P)
+__device__ __forceinline__ void mc_tile(const McParams& P, const uint32_t tile, int16_t* smem, unsigned* sSad, int* sDec, int (*sVxy)[2])
 {
-  extern __shared__ __align__(16) int16_t smem[];
-  __shared__ unsigned sSad[25];
-  __shared__ int sDec[3];
-  __shared__ int sVxy[16][2];
-
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const uint32_t tile = P.tiles[blockIdx.x];
   const b200_pu& pu = P.pus[tile >> 6];
   const int puW = pu.w, puH = pu.h, puX = pu.x, puY = pu.y, flags = pu.flags;
   const int tx0 = (tile & 7) * 16, ty0 = ((tile >> 3) & 7) * 16;
@@ -609,6 +604,19 @@ __global__ void mc_kernel(const McParams P)
   }
 }
 
+// One CTA per entry of one tile list (bucket.cu); the host sizes the grid from the list length it reads back after bucketing, and the
+// hardware scheduler balances the lists of all streams.
+template <int MODE, int OPT>
+__global__ void __launch_bounds__(64, 12) mc_kernel(const McParams P, const int list)
+{
+  extern __shared__ __align__(16) int16_t smem[];
+  __shared__ unsigned sSad[25];
+  __shared__ int sDec[3];
+  __shared__ int sVxy[16][2];
+  if ((int)blockIdx.x >= P.meta[LM_CNT + list]) return;
+  mc_tile<MODE, OPT>(P, P.tiles[P.meta[LM_OFF + list] + blockIdx.x], smem, sSad, sDec, sVxy);
+}
+
 // ------------------------------------------------------------------------------------------------ affine tiles (xPredAffineBlk :934)
 __device__ __forceinline__ void round_affine(int& x, int& y, int s) { const int o = 1 << (s - 1); x = (x + o - (x >= 0)) >> s; y = (y + o - (y >= 0)) >> s; }
 
@@ -655,7 +663,7 @@ __device__ __forceinline__ void aff_sub_mv(const AffModel& M, const b200_pu& pu,
   mx = clip3(-(1 << 17), (1 << 17) - 1, mx); my = clip3(-(1 << 17), (1 << 17) - 1, my);
 }
 
-__global__ void __launch_bounds__(256) mc_affine_kernel(const McParams P)
+__device__ __forceinline__ void mc_affine_tile(const McParams& P, const uint32_t tile)
 {
   __shared__ int16_t sHf[2][16][9 * 4];     // per sub-block: 9 rows x 4 cols after horizontal filter
   __shared__ int16_t sE[2][16][36];         // PROF 6x6 buffers
@@ -663,7 +671,6 @@ __global__ void __launch_bounds__(256) mc_affine_kernel(const McParams P)
   __shared__ int16_t sCH[2][2][4][7 * 4];   // chroma: [list][comp][sub-block] 7 rows x 4 cols
 
   const int tid = threadIdx.x;
-  const uint32_t tile = P.tiles[blockIdx.x];
   const b200_pu pu = P.pus[tile >> 6];
   const int tx0 = (tile & 7) * 16, ty0 = ((tile >> 3) & 7) * 16;
   const int tw = min(16, pu.w - tx0), th = min(16, pu.h - ty0);
@@ -797,6 +804,12 @@ __global__ void __launch_bounds__(256) mc_affine_kernel(const McParams P)
   }
 }
 
+__global__ void __launch_bounds__(256) mc_affine_kernel(const McParams P)
+{
+  if ((int)blockIdx.x >= P.meta[LM_CNT + 16]) return;
+  mc_affine_tile(P, P.tiles[P.meta[LM_OFF + 16] + blockIdx.x]);
+}
+
 int launch_mc(const McLaunch& L, StreamSet& ss, KProf* prof)
 {
   McParams P;
@@ -804,49 +817,36 @@ int launch_mc(const McLaunch& L, StreamSet& ss, KProf* prof)
   for (int i = 0; i < B200_MAX_SLOTS * 3; i++) P.refs[i] = L.refs[i];
   P.fastOk = !(L.refStride[0] & 1) && !(L.refStride[1] & 1) && !(L.refStride[2] & 1);
   P.W = L.geom.width; P.H = L.geom.height; P.bitDepth = L.geom.bitDepth; P.ctuSize = L.geom.ctuSize; P.chroma = L.geom.chromaFormat == 1;
-  P.pus = L.pus; P.dmvrMv = L.dmvrMv;
-  bool any = false;
-  for (int m = 0; m < 4; m++) for (int k = 0; k < 4; k++) any |= L.cls[m][k].n > 0;
+  P.pus = L.pus; P.dmvrMv = L.dmvrMv; P.tiles = L.tiles; P.meta = L.meta;
   int launched = 0;
   if (prof) prof->begin(B200_KF_MC_TILE, ss.main);
-  if (any) {
-    for (int m = 3; m >= 0; m--) for (int k = 3; k >= 0; k--) {      // heaviest classes first (DMVR 16x16 ... uni 8x4)
-      const McLaunch::Cls& c = L.cls[m][k];
-      if (!c.n) continue;
-      cudaStream_t s = ss.pick(launched++);
-      const int nsamp = 32 << k;
-      const size_t smem = (size_t)mc_smem_elems(m, nsamp) * 2;
-      P.tiles = c.tiles; P.numTiles = c.n;
-      if (k >= 2) {            // 128 / 256 samples: 4 luma outputs per thread -> 32 / 64 threads
-        const int nthr = nsamp >> 2;
-        switch (m) {
-          case 0: mc_kernel<0, 4><<<c.n, nthr, smem, s>>>(P); break;
-          case 1: mc_kernel<1, 4><<<c.n, nthr, smem, s>>>(P); break;
-          case 2: mc_kernel<2, 4><<<c.n, nthr, smem, s>>>(P); break;
-          default: mc_kernel<3, 4><<<c.n, nthr, smem, s>>>(P); break;
-        }
-      } else {
-        switch (m) {
-          case 0: mc_kernel<0, 1><<<c.n, nsamp, smem, s>>>(P); break;
-          case 1: mc_kernel<1, 1><<<c.n, nsamp, smem, s>>>(P); break;
-          case 2: mc_kernel<2, 1><<<c.n, nsamp, smem, s>>>(P); break;
-          default: mc_kernel<3, 1><<<c.n, nsamp, smem, s>>>(P); break;
-        }
+  for (int m = 3; m >= 0; m--) for (int k = 3; k >= 0; k--) {      // heaviest lists first (DMVR 16x16 ... uni 8x4)
+    const int nsamp = 32 << k, list = m * 4 + k, grid = L.cnt[list];
+    if (!grid || (m >= 2 && k < 2)) continue;                       // BDOF / DMVR tiles have at least 128 samples (bucket.cu rejects others)
+    cudaStream_t s = ss.pick(launched++);
+    const size_t smem = (size_t)mc_smem_elems(m, nsamp) * 2;
+    if (k >= 2) {            // 128 / 256 samples: 4 luma outputs per thread -> 32 / 64 threads
+      const int nthr = nsamp >> 2;
+      switch (m) {
+        case 0: mc_kernel<0, 4><<<grid, nthr, smem, s>>>(P, list); break;
+        case 1: mc_kernel<1, 4><<<grid, nthr, smem, s>>>(P, list); break;
+        case 2: mc_kernel<2, 4><<<grid, nthr, smem, s>>>(P, list); break;
+        default: mc_kernel<3, 4><<<grid, nthr, smem, s>>>(P, list); break;
       }
-      B200_CUDA(cudaGetLastError());
+    } else {
+      switch (m) {
+        case 0: mc_kernel<0, 1><<<grid, nsamp, smem, s>>>(P, list); break;
+        default: mc_kernel<1, 1><<<grid, nsamp, smem, s>>>(P, list); break;
+      }
     }
+    B200_CUDA(cudaGetLastError());
   }
-  if (L.numTilesA) { cudaStream_t s = ss.pick(launched++); P.tiles = L.tilesA; P.numTiles = L.numTilesA; mc_affine_kernel<<<L.numTilesA, 256, 0, s>>>(P); B200_CUDA(cudaGetLastError()); }
+  if (L.cnt[16]) { cudaStream_t s = ss.pick(launched++); mc_affine_kernel<<<L.cnt[16], 256, 0, s>>>(P); B200_CUDA(cudaGetLastError()); }
   ss.join();
   if (prof) prof->end(B200_KF_MC_TILE, ss.main);      // with forked streams the affine tiles are inside the same interval
   return 0;
 }
 
-int mc_launch_count(const McLaunch& L)
-{
-  int n = L.numTilesA ? 1 : 0;
-  for (int m = 0; m < 4; m++) for (int k = 0; k < 4; k++) n += L.cls[m][k].n > 0;
-  return n;
-}
+int mc_launch_count(const McLaunch& L) { int n = L.cnt[16] > 0; for (int m = 0; m < 4; m++) for (int k = 0; k < 4; k++) n += L.cnt[m * 4 + k] > 0 && !(m >= 2 && k < 2); return n; }
 
 }  // namespace b200

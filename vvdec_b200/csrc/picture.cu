@@ -11,8 +11,9 @@ static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 struct Arena {
   DevBuf buf;                       // one allocation, sub-allocated per picture
   // device views
-  const b200_pu* pus = nullptr; McLaunch mcTiles; size_t numPus = 0;   // mcTiles: only cls / tilesA / numTilesA are used
-  const b200_tu* tus = nullptr; size_t numTus = 0; size_t tuCls[4] = {0, 0, 0, 0}; const int16_t* coefs = nullptr; const int32_t* scaling = nullptr;
+  const b200_pu* pus = nullptr; size_t numPus = 0; const uint32_t* tiles = nullptr; int* mcMeta = nullptr;   // device lists built by bucket.cu
+  int* hMeta = nullptr;             // pinned host copy of both meta blocks (list lengths + error bits), valid once `uploaded` has fired
+  const b200_tu* tus = nullptr; size_t numTus = 0; const uint32_t* tuIdx = nullptr; int* tuMeta = nullptr; const int16_t* coefs = nullptr; const int32_t* scaling = nullptr;
   const b200_lf_param *lfV = nullptr, *lfH = nullptr; const uint8_t* ctuSlice = nullptr; LfSliceTab lfSlices; b200_lf_seq lfSeq;
   const b200_sao_ctu* sao = nullptr; b200_vb vb;
   const b200_alf_ctu* alf = nullptr; const int16_t *lumaCoeff = nullptr, *lumaClip = nullptr, *chromaCoeff = nullptr, *chromaClip = nullptr, *cc[2] = {nullptr, nullptr};
@@ -51,8 +52,6 @@ struct b200_ctx {
   std::vector<Arena> arenas;
   int nextArena = 0;
   long long launches = 0;
-  McTileLists hTiles;
-  std::vector<b200_tu> hTus;
 
   DevPlanes planes(int buf) const {
     DevPlanes d; char* b = reinterpret_cast<char*>(bufs[buf]);
@@ -94,7 +93,7 @@ B200_API int b200_ctx_create(b200_ctx** out, const b200_geom* g, int numSlots, i
   for (int s = 0; s < numSlots; s++) c->slotBuf[s] = s;
   c->work[0] = numSlots; c->work[1] = numSlots + 1;
   c->arenas.resize(numArenas);
-  for (auto& A : c->arenas) { B200_CUDA(cudaEventCreateWithFlags(&A.uploaded, cudaEventDisableTiming)); B200_CUDA(cudaEventCreateWithFlags(&A.done, cudaEventDisableTiming)); }
+  for (auto& A : c->arenas) { B200_CUDA(cudaEventCreateWithFlags(&A.uploaded, cudaEventDisableTiming)); B200_CUDA(cudaEventCreateWithFlags(&A.done, cudaEventDisableTiming)); B200_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&A.hMeta), 2 * LM_INTS * sizeof(int), cudaHostAllocDefault)); }
   *out = c;
   return 0;
 }
@@ -103,7 +102,7 @@ B200_API void b200_ctx_destroy(b200_ctx* c)
 {
   if (!c) return;
   cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copyStream); cudaStreamSynchronize(c->upStream);
-  for (auto& A : c->arenas) { cudaEventDestroy(A.uploaded); cudaEventDestroy(A.done); }
+  for (auto& A : c->arenas) { cudaEventDestroy(A.uploaded); cudaEventDestroy(A.done); if (A.hMeta) cudaFreeHost(A.hMeta); }
   cudaStreamDestroy(c->upStream);
   for (auto p : c->bufs) cudaFree(p);
   for (auto e : c->readDone) cudaEventDestroy(e);
@@ -133,22 +132,23 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   B200_CHECK(!(p->flags & B200_PIC_DEBLOCK) || (p->lfV && p->lfH && p->lfSlices && p->numLfSlices >= 1 && p->numLfSlices <= 64), "b200_pic_upload: deblocking data missing");
   B200_CHECK(!(p->flags & B200_PIC_SAO) || p->sao, "b200_pic_upload: SAO data missing");
   B200_CHECK(!(p->flags & B200_PIC_ALF) || (p->alf && p->alfTabs && p->alfTabs->numLumaSets >= 16), "b200_pic_upload: ALF data missing");
-  for (size_t i = 0; i < p->numPus; i++)
-    B200_CHECK(p->pus[i].refSlot[0] < c->numSlots && p->pus[i].refSlot[1] < c->numSlots && (p->pus[i].refSlot[0] >= 0 || p->pus[i].refSlot[1] >= 0), "b200_pic_upload: PU %zu has invalid reference slots", i);
+  B200_CHECK(p->numPus < (1u << 26) && p->numTus < (1u << 31), "b200_pic_upload: too many records");
   B200_CUDA(cudaSetDevice(c->device));
   const int ai = c->nextArena; c->nextArena = (c->nextArena + 1) % c->numArenas;
   Arena& A = c->arenas[ai];
   const b200_geom& g = c->g;
   const size_t n4 = (size_t)((g.width + 3) >> 2) * ((g.height + 3) >> 2);
   const size_t nCtu = (size_t)((g.width + g.ctuSize - 1) / g.ctuSize) * ((g.height + g.ctuSize - 1) / g.ctuSize);
-  build_mc_tiles(p->pus, p->numPus, c->hTiles);
+  // No per-record work on the host: the caller's arrays are copied as they are; the records are validated and sorted into the
+  // kernels' work lists on the device (bucket.cu), errors surface in b200_pic_run.
+  const size_t capTiles = mc_tile_capacity(g, 0);
   const b200_alf_tables* T = p->alfTabs;
   const size_t nL = (p->flags & B200_PIC_ALF) ? (size_t)T->numLumaSets * 1300 : 0, nC = (p->flags & B200_PIC_ALF) ? (size_t)T->numChromaAlts * 7 : 0;
   const size_t n0 = (p->flags & B200_PIC_ALF) ? (size_t)T->numCc[0] * 7 : 0, n1 = (p->flags & B200_PIC_ALF) ? (size_t)T->numCc[1] * 7 : 0;
   // ---- layout ----
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes + 16); return o; };
-  const size_t oPus = take(p->numPus * sizeof(b200_pu)), oT = take(c->hTiles.total() * 4);
+  const size_t oPus = take(p->numPus * sizeof(b200_pu)), oT = take(capTiles * 4), oMeta = take(2 * LM_INTS * sizeof(int)), oIdx = take(p->numTus * 4);
   const size_t oTus = take(p->numTus * sizeof(b200_tu)), oCoef = take(p->numCoefs * 2), oScal = take(p->numScaling * 4);
   const size_t oLfV = take((p->flags & B200_PIC_DEBLOCK) ? n4 * 6 : 0), oLfH = take((p->flags & B200_PIC_DEBLOCK) ? n4 * 6 : 0), oCs = take(nCtu);
   const size_t oSao = take((p->flags & B200_PIC_SAO) ? nCtu * sizeof(b200_sao_ctu) : 0);
@@ -163,9 +163,7 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   if (A.donePending) { B200_CUDA(cudaStreamWaitEvent(s, A.done, 0)); A.donePending = false; }   // kernels of the arena's previous picture
   auto h2d = [&](size_t o, const void* src, size_t bytes) -> int { if (bytes) B200_CUDA(cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, s)); return 0; };
   if (int rc = h2d(oPus, p->pus, p->numPus * sizeof(b200_pu))) return rc;
-  if (int rc = upload_mc_tiles(c->hTiles, reinterpret_cast<uint32_t*>(base + oT), A.mcTiles, s)) return rc;
-  bucket_tus(p->tus, p->numTus, c->hTus, A.tuCls);
-  if (int rc = h2d(oTus, c->hTus.data(), p->numTus * sizeof(b200_tu))) return rc;
+  if (int rc = h2d(oTus, p->tus, p->numTus * sizeof(b200_tu))) return rc;
   if (int rc = h2d(oCoef, p->coefs, p->numCoefs * 2)) return rc;
   if (int rc = h2d(oScal, p->scaling, p->numScaling * 4)) return rc;
   if (p->flags & B200_PIC_DEBLOCK) {
@@ -204,6 +202,13 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   A.dmvrMv = p->numDmvr ? reinterpret_cast<int32_t*>(base + oDm) : nullptr; A.numDmvr = p->numDmvr;
   if (p->numDmvr) B200_CUDA(cudaMemsetAsync(base + oDm, 0, p->numDmvr * 8, s));   // entries of non-DMVR CUs stay zero, like m_dmvrMvCache users expect
   A.dstSlot = p->dstSlot; A.flags = p->flags; A.valid = true;
+  // work lists: validated and bucketed on the device, behind the copies
+  A.mcMeta = reinterpret_cast<int*>(base + oMeta); A.tuMeta = A.mcMeta + LM_INTS;
+  if (int rc = launch_mc_bucket(reinterpret_cast<const b200_pu*>(base + oPus), p->numPus, reinterpret_cast<uint32_t*>(base + oT), capTiles, A.mcMeta, c->numSlots, g.bitDepth, s)) return rc;
+  if (int rc = launch_tu_bucket(reinterpret_cast<const b200_tu*>(base + oTus), p->numTus, reinterpret_cast<uint32_t*>(base + oIdx), A.tuMeta, s)) return rc;
+  A.tiles = reinterpret_cast<const uint32_t*>(base + oT); A.tuIdx = reinterpret_cast<const uint32_t*>(base + oIdx);
+  c->launches += 4;
+  B200_CUDA(cudaMemcpyAsync(A.hMeta, A.mcMeta, 2 * LM_INTS * sizeof(int), cudaMemcpyDeviceToHost, s));   // list lengths for b200_pic_run's grids
   B200_CUDA(cudaEventRecord(A.uploaded, s));
   return ai;
 }
@@ -214,6 +219,12 @@ B200_API int b200_pic_run(b200_ctx* c, int ai)
   B200_CUDA(cudaSetDevice(c->device));
   Arena& A = c->arenas[ai];
   cudaStream_t s = c->stream;
+  // the grids are sized from the list lengths the bucketing kernels produced: the host waits for this picture's upload (a caller that
+  // uploads picture n+1 before it runs picture n never waits here)
+  B200_CUDA(cudaEventSynchronize(A.uploaded));
+  B200_CHECK(!(A.hMeta[LM_ERR] & 1), "b200_pic_run: the picture's PU list holds an invalid record (reference slots, block size or flag combination)");
+  B200_CHECK(!(A.hMeta[LM_ERR] & 2), "b200_pic_run: more MC tiles than the picture can hold (overlapping PUs?)");
+  B200_CHECK(!A.hMeta[LM_INTS + LM_ERR], "b200_pic_run: the picture's TU list holds an invalid record");
   B200_CUDA(cudaStreamWaitEvent(s, A.uploaded, 0));
   const b200_geom& g = c->g;
   int cur = c->work[0], other = c->work[1];
@@ -229,15 +240,17 @@ B200_API int b200_pic_run(b200_ctx* c, int ai)
     McLaunch L; L.geom = g; L.dst = P; memset(L.refs, 0, sizeof(L.refs));
     for (int sl = 0; sl < c->numSlots; sl++) { DevPlanes d = c->planes(c->slotBuf[sl]); for (int k = 0; k < 3; k++) L.refs[sl * 3 + k] = d.p[k]; }
     for (int k = 0; k < 3; k++) L.refStride[k] = g.stride[k];
-    L.pus = A.pus; memcpy(L.cls, A.mcTiles.cls, sizeof(L.cls)); L.tilesA = A.mcTiles.tilesA; L.numTilesA = A.mcTiles.numTilesA; L.dmvrMv = A.dmvrMv;
+    L.pus = A.pus; L.tiles = A.tiles; L.meta = A.mcMeta; L.dmvrMv = A.dmvrMv;
+    for (int l = 0; l < MC_LISTS; l++) L.cnt[l] = A.hMeta[LM_CNT + l];
     if (int rc = launch_mc(L, c->ss, c->profiling ? &c->prof : nullptr)) return rc;
     c->launches += mc_launch_count(L);
   }
   // 2. K1 residual + reco
   if (A.numTus) {
-    K1Launch L; L.geom = g; L.planes = P; L.tus = A.tus; L.numTus = A.numTus; memcpy(L.clsCount, A.tuCls, sizeof(L.clsCount)); L.coefs = A.coefs; L.scaling = A.scaling; L.mode = 0;
+    K1Launch L; L.geom = g; L.planes = P; L.tus = A.tus; L.numTus = A.numTus; L.idx = A.tuIdx; L.meta = A.tuMeta; L.coefs = A.coefs; L.scaling = A.scaling; L.mode = 0;
+    for (int l = 0; l < K1_LISTS; l++) L.cnt[l] = A.hMeta[LM_INTS + LM_CNT + l];
     if (int rc = launch_k1_residual(L, c->ss, c->profiling ? &c->prof : nullptr)) return rc;
-    for (int k = 0; k < 4; k++) c->launches += A.tuCls[k] ? 1 : 0;
+    c->launches += k1_launch_count(L);
   }
   // 3. K3 deblocking
   if (A.flags & B200_PIC_DEBLOCK) {
