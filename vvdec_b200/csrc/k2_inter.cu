@@ -607,7 +607,7 @@ __device__ __forceinline__ void mc_tile(const McParams& P, const uint32_t tile, 
 // One CTA per entry of one tile list (bucket.cu); the host sizes the grid from the list length it reads back after bucketing, and the
 // hardware scheduler balances the lists of all streams.
 template <int MODE, int OPT>
-__global__ void __launch_bounds__(64, 12) mc_kernel(const McParams P, const int list)
+__global__ void __launch_bounds__(64, MODE >= 2 ? 12 : 16) mc_kernel(const McParams P, const int list)
 {
   extern __shared__ __align__(16) int16_t smem[];
   __shared__ unsigned sSad[25];

@@ -12,7 +12,7 @@ namespace b200 {
 
 struct SaoParams {
   const int16_t* src[3]; int16_t* dst[3]; int stride[3];
-  int W, H, bitDepth, ctuSize, ctusW, chroma;
+  int W, H, bitDepth, ctuSize, ctuLog2, ctusW, chroma;
   const b200_sao_ctu* ctus;
   b200_vb vb;
 };
@@ -28,43 +28,34 @@ __global__ void __launch_bounds__(256) sao_kernel(const SaoParams P)
   if (x >= pw || y >= ph) return;
   const int stride = c == 0 ? P.stride[0] : c == 1 ? P.stride[1] : P.stride[2];
   const int16_t* s = c == 0 ? P.src[0] : c == 1 ? P.src[1] : P.src[2];
-  const int cs = P.ctuSize >> sh;                       // CTU size in this plane
-  const int cxi = x / cs, cyi = y / cs;
-  // the 24-byte CTU record as six 32-bit words (one L1 line for the whole warp)
-  const uint32_t* cpw = reinterpret_cast<const uint32_t*>(P.ctus + cyi * P.ctusW + cxi);
-  const uint32_t w0 = __ldg(cpw), w1 = __ldg(cpw + 1);
-  const int type = c == 0 ? (w0 & 0xff) : c == 1 ? ((w0 >> 8) & 0xff) : ((w0 >> 16) & 0xff);
+  const int l2cs = P.ctuLog2 - sh, cs = 1 << l2cs;            // CTU size in this plane
+  const int cxi = x >> l2cs, cyi = y >> l2cs;
+  const uint8_t* rec = reinterpret_cast<const uint8_t*>(P.ctus + cyi * P.ctusW + cxi);   // 24-byte record, one L1 line for the whole warp
+  const int type = __ldg(rec + c);
   uint2* dptr = reinterpret_cast<uint2*>((c == 0 ? P.dst[0] : c == 1 ? P.dst[1] : P.dst[2]) + (size_t)y * stride + x);
   const uint2 ctr = *reinterpret_cast<const uint2*>(s + (size_t)y * stride + x);
   if (type == B200_SAO_OFF) { *dptr = ctr; return; }
-  // offsets: bytes 6..20 of the record = offset[3][5]
-  const uint32_t w2 = __ldg(cpw + 2), w3 = __ldg(cpw + 3), w4 = __ldg(cpw + 4), w5 = __ldg(cpw + 5);
-  auto rec_byte = [&](int b) -> int { const uint32_t w = b < 8 ? w1 : b < 12 ? w2 : b < 16 ? w3 : b < 20 ? w4 : w5; return (int)(int8_t)((w >> ((b & 3) * 8)) & 0xff); };
-  int off[5];
-#pragma unroll
-  for (int k = 0; k < 5; k++) off[k] = rec_byte(6 + c * 5 + k);
-  const int band = c == 0 ? (w0 >> 24) : c == 1 ? (w1 & 0xff) : ((w1 >> 8) & 0xff);
-  const unsigned avail = (w5 >> 8) & 0xff;                  // byte 21
+  // the component's five offsets as bytes 0..4 of a word pair: one byte-permute selects offset[k]
+  const uint8_t* ob = rec + 6 + c * 5;
+  const uint32_t offLo = __ldg(ob) | (__ldg(ob + 1) << 8) | (__ldg(ob + 2) << 16) | (__ldg(ob + 3) << 24), offHi = __ldg(ob + 4);
+  auto offset_of = [&](int k) -> int { return (int)(int8_t)__byte_perm(offLo, offHi, k); };
   int v[4] = { (int)(int16_t)(ctr.x & 0xffff), (int)(int16_t)(ctr.x >> 16), (int)(int16_t)(ctr.y & 0xffff), (int)(int16_t)(ctr.y >> 16) };
   int r[4] = { v[0], v[1], v[2], v[3] };
   const int pmax = (1 << P.bitDepth) - 1;
   if (type == B200_SAO_BO) {
-    const int shiftBits = P.bitDepth - 5;
+    const int shiftBits = P.bitDepth - 5, band = __ldg(rec + 3 + c);
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const int k = ((v[i] >> shiftBits) - band) & 31;
-      if (k < 4) r[i] = clip3(0, pmax, v[i] + (k == 0 ? off[0] : k == 1 ? off[1] : k == 2 ? off[2] : off[3]));
+      if (k < 4) r[i] = clip3(0, pmax, v[i] + offset_of(k));
     }
   } else {
     // neighbour offsets of the class: EO_0 (-1,0)/(+1,0); EO_90 (0,-1)/(0,+1); EO_135 (-1,-1)/(+1,+1); EO_45 (+1,-1)/(-1,+1)
     const int dx = type == B200_SAO_EO_90 ? 0 : (type == B200_SAO_EO_45 ? -1 : 1);
     const int dy = type == B200_SAO_EO_0 ? 0 : 1;
-    const int x0c = cxi * cs, y0c = cyi * cs;
+    const int x0c = cxi << l2cs, y0c = cyi << l2cs;
     const int w = min(cs, pw - x0c), h = min(cs, ph - y0c);
-    const int nV = type == B200_SAO_EO_90 ? 0 : P.vb.numVer, nH = type == B200_SAO_EO_0 ? 0 : P.vb.numHor;
-    const int ly = y - y0c;
-    // rows of the two neighbours; interior threads (not on the CTU border) skip the availability logic
-    const bool interior = ly > 0 && ly < h - 1 && (x - x0c) > 0 && (x - x0c) + 4 < w && nV == 0 && nH == 0;
+    const int lx = x - x0c, ly = y - y0c;
     // neighbour samples of the 4 outputs, fetched as two 8-byte vectors + at most two scalars (rows / columns clamped: clamped
     // values are only ever used by samples that the availability test rejects)
     int na[4], nb[4];
@@ -84,30 +75,38 @@ __global__ void __launch_bounds__(256) sao_kernel(const SaoParams P)
         else              { na[0] = A[1]; na[1] = A[2]; na[2] = A[3]; na[3] = rowA[xr]; nb[0] = rowB[xl]; nb[1] = B[0]; nb[2] = B[1]; nb[3] = B[2]; }
       }
     }
+    // which of the 4 samples may be filtered (bit i): both neighbours must lie in the CTU or in an available neighbouring CTU.
+    // Neighbour A = (-dx,-dy) is above (dy = 1) or in the row; only sample 0 / 3 of a thread on the CTU's left / right column can
+    // leave the CTU sideways.
+    unsigned okMask = 0xf;
+    if (ly == 0 || ly == h - 1 || lx == 0 || lx + 4 >= w) {
+      const unsigned avail = __ldg(rec + 21);
+      const bool up = dy && ly == 0, dn = dy && ly == h - 1;
+      const unsigned midA = up ? B200_AVAIL_A : 0, leftA = up ? B200_AVAIL_AL : B200_AVAIL_L, rightA = up ? B200_AVAIL_AR : B200_AVAIL_R;
+      const unsigned midB = dn ? B200_AVAIL_B : 0, leftB = dn ? B200_AVAIL_BL : B200_AVAIL_L, rightB = dn ? B200_AVAIL_BR : B200_AVAIL_R;
+      unsigned a0 = midA, a3 = midA, b0 = midB, b3 = midB;   // requirements of neighbour A / B for sample 0 and sample 3 (1 and 2 stay inside)
+      if (dx == 1)  { if (lx == 0) a0 = leftA;  if (lx + 4 == w) b3 = rightB; }   // A looks left, B looks right
+      if (dx == -1) { if (lx + 4 == w) a3 = rightA; if (lx == 0) b0 = leftB; }    // A looks right, B looks left
+      const unsigned need0 = a0 | b0, need3 = a3 | b3, needM = midA | midB;
+      if ((need0 & avail) != need0) okMask &= ~1u;
+      if ((needM & avail) != needM) okMask &= ~6u;
+      if ((need3 & avail) != need3) okMask &= ~8u;
+    }
+    if (P.vb.numVer | P.vb.numHor) {                        // picture-uniform: virtual boundaries (samples next to one are not filtered)
+      const int nV = type == B200_SAO_EO_90 ? 0 : P.vb.numVer, nH = type == B200_SAO_EO_0 ? 0 : P.vb.numHor;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int gx = x + i;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { const int p = P.vb.posX[k] >> sh; if (k < nV && (gx == p || gx == p - 1)) okMask &= ~(1u << i); }
+#pragma unroll
+        for (int k = 0; k < 3; k++) { const int p = P.vb.posY[k] >> sh; if (k < nH && (y == p || y == p - 1)) okMask &= ~(1u << i); }
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const int gx = x + i;
-      bool ok = true;
-      if (!interior) {
-        const int lx = gx - x0c;
-#pragma unroll
-        for (int n = 0; n < 2; n++) {
-          const int nx = lx + (n ? dx : -dx), ny = ly + (n ? dy : -dy);
-          const bool l = nx < 0, rr = nx >= w, a = ny < 0, b = ny >= h;
-          unsigned bit = 0;
-          if (a)      bit = l ? B200_AVAIL_AL : rr ? B200_AVAIL_AR : B200_AVAIL_A;
-          else if (b) bit = l ? B200_AVAIL_BL : rr ? B200_AVAIL_BR : B200_AVAIL_B;
-          else        bit = l ? B200_AVAIL_L : rr ? B200_AVAIL_R : 0;
-          if (bit && !(avail & bit)) ok = false;
-        }
-#pragma unroll
-        for (int k = 0; k < 3; k++) { const int p = P.vb.posX[k] >> sh; if (k < nV && (gx == p || gx == p - 1)) ok = false; }
-#pragma unroll
-        for (int k = 0; k < 3; k++) { const int p = P.vb.posY[k] >> sh; if (k < nH && (y == p || y == p - 1)) ok = false; }
-      }
-      if (!ok) continue;
       const int e = sgn(v[i] - na[i]) + sgn(v[i] - nb[i]);
-      r[i] = clip3(0, pmax, v[i] + (e == -2 ? off[0] : e == -1 ? off[1] : e == 0 ? off[2] : e == 1 ? off[3] : off[4]));
+      if (okMask & (1u << i)) r[i] = clip3(0, pmax, v[i] + offset_of(e + 2));
     }
   }
   uint2 o;
@@ -121,6 +120,7 @@ int launch_sao(const SaoLaunch& L, cudaStream_t s, KProf* prof)
   SaoParams P;
   for (int c = 0; c < 3; c++) { P.src[c] = L.src.p[c]; P.dst[c] = L.dst.p[c]; P.stride[c] = L.src.stride[c]; }
   P.W = L.geom.width; P.H = L.geom.height; P.bitDepth = L.geom.bitDepth; P.ctuSize = L.geom.ctuSize;
+  P.ctuLog2 = P.ctuSize == 128 ? 7 : P.ctuSize == 64 ? 6 : 5;
   P.ctusW = (P.W + P.ctuSize - 1) / P.ctuSize; P.chroma = L.geom.chromaFormat == 1;
   P.ctus = L.ctus; P.vb = L.vb;
   dim3 blk(32, 8), grd((P.W / 4 + 31) / 32, (P.H + 7) / 8, P.chroma ? 3 : 1);

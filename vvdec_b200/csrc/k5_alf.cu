@@ -21,6 +21,7 @@ struct AlfParams {
   const int16_t* src[3]; int16_t* dst[3]; int stride[3];
   int W, H, bitDepth, ctuSize, ctuLog2, ctusW;
   int vecOk;                      // luma stride is a multiple of 4 samples: rows can be copied 8 bytes at a time
+  int vecOkC;                     // the same for all three planes (chroma kernel: chroma rows and the co-located luma rows)
   const b200_alf_ctu* ctus;
   const int16_t *lumaCoeff, *lumaClip, *chromaCoeff, *chromaClip, *cc0, *cc1;
 };
@@ -235,20 +236,26 @@ __global__ void __launch_bounds__(256) alf_luma_kernel(const AlfParams P)
   }
 }
 
-// chroma 5x5 diamond + CC-ALF, 4:2:0. One thread per 4 chroma samples of one component.
+// chroma 5x5 diamond + CC-ALF, 4:2:0. One thread per 4 chroma samples of one component.  Threads away from the left / right picture
+// edge fetch their rows as 8- / 16-byte vectors (row indices are clamped, which is the reference's border extension); edge threads
+// read sample by sample with clamped coordinates.
+__device__ __forceinline__ void unpack4(const uint2 u, int* d) { d[0] = (int)(int16_t)(u.x & 0xffff); d[1] = (int)u.x >> 16; d[2] = (int)(int16_t)(u.y & 0xffff); d[3] = (int)u.y >> 16; }
+
 __global__ void __launch_bounds__(256) alf_chroma_kernel(const AlfParams P)
 {
   const int c = 1 + blockIdx.z;
   const int pw = P.W >> 1, ph = P.H >> 1;
   const int x = (blockIdx.x * 32 + threadIdx.x) * 4, y = blockIdx.y * 8 + threadIdx.y;
   if (x >= pw || y >= ph) return;
-  const int cs = P.ctuSize >> 1;
-  const b200_alf_ctu cp = P.ctus[(y / cs) * P.ctusW + (x / cs)];
+  const int l2cs = P.ctuLog2 - 1, cs = 1 << l2cs;
+  const b200_alf_ctu cp = P.ctus[(y >> l2cs) * P.ctusW + (x >> l2cs)];
   const int stride = P.stride[c];
   const int16_t* s = P.src[c];
   const int pmax = (1 << P.bitDepth) - 1;
+  const bool inner = P.vecOkC && x >= 4 && x + 8 <= pw;
   int out[4];
-  auto at = [&](int xx, int yy) { return (int)s[(size_t)min(max(yy, 0), ph - 1) * stride + min(max(xx, 0), pw - 1)]; };
+  auto rowp = [&](int yy) { return s + (size_t)min(max(yy, 0), ph - 1) * stride; };
+  auto at = [&](int xx, int yy) { return (int)rowp(yy)[min(max(xx, 0), pw - 1)]; };
   if (cp.enable[c] & 1) {
     const int16_t* f = P.chromaCoeff + cp.chromaAlt[c - 1] * 7; const int16_t* cl = P.chromaClip + cp.chromaAlt[c - 1] * 7;
     int fc[6], cc[6];
@@ -260,22 +267,41 @@ __global__ void __launch_bounds__(256) alf_chroma_kernel(const AlfParams P)
     else if (yVb >= vbPos && yVb <= vbPos + 1) lim = yVb - vbPos;
     const bool nearVb = yVb == vbPos - 1 || yVb == vbPos;
     const int r1 = min(1, lim), r2 = min(2, lim);
+    // rows as windows: r0[k] = sample x-2+k (8), p1/m1[k] = sample x-1+k of rows y+-r1 (6), p2/m2[k] = sample x+k of rows y+-r2 (4)
+    int r0[8], p1[6], m1[6], p2[4], m2[4];
+    if (inner) {
+      int t[4];
+      const int16_t* q = rowp(y) + x;
+      unpack4(__ldg(reinterpret_cast<const uint2*>(q - 4)), t); r0[0] = t[2]; r0[1] = t[3];
+      unpack4(__ldg(reinterpret_cast<const uint2*>(q)), r0 + 2);
+      unpack4(__ldg(reinterpret_cast<const uint2*>(q + 4)), t); r0[6] = t[0]; r0[7] = t[1];
+      q = rowp(y + r1) + x; p1[0] = q[-1]; unpack4(__ldg(reinterpret_cast<const uint2*>(q)), p1 + 1); p1[5] = q[4];
+      q = rowp(y - r1) + x; m1[0] = q[-1]; unpack4(__ldg(reinterpret_cast<const uint2*>(q)), m1 + 1); m1[5] = q[4];
+      unpack4(__ldg(reinterpret_cast<const uint2*>(rowp(y + r2) + x)), p2);
+      unpack4(__ldg(reinterpret_cast<const uint2*>(rowp(y - r2) + x)), m2);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; k++) r0[k] = at(x - 2 + k, y);
+#pragma unroll
+      for (int k = 0; k < 6; k++) { p1[k] = at(x - 1 + k, y + r1); m1[k] = at(x - 1 + k, y - r1); }
+#pragma unroll
+      for (int k = 0; k < 4; k++) { p2[k] = at(x + k, y + r2); m2[k] = at(x + k, y - r2); }
+    }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const int xx = x + i, cur = at(xx, y);
+      const int cur = r0[i + 2];
       int sum = 0;
-      sum += fc[0] * clipd(cc[0], cur, at(xx, y + r2),     at(xx, y - r2));
-      sum += fc[1] * clipd(cc[1], cur, at(xx + 1, y + r1), at(xx - 1, y - r1));
-      sum += fc[2] * clipd(cc[2], cur, at(xx, y + r1),     at(xx, y - r1));
-      sum += fc[3] * clipd(cc[3], cur, at(xx - 1, y + r1), at(xx + 1, y - r1));
-      sum += fc[4] * clipd(cc[4], cur, at(xx + 2, y), at(xx - 2, y));
-      sum += fc[5] * clipd(cc[5], cur, at(xx + 1, y), at(xx - 1, y));
+      sum += fc[0] * clipd(cc[0], cur, p2[i],     m2[i]);
+      sum += fc[1] * clipd(cc[1], cur, p1[i + 2], m1[i]);
+      sum += fc[2] * clipd(cc[2], cur, p1[i + 1], m1[i + 1]);
+      sum += fc[3] * clipd(cc[3], cur, p1[i],     m1[i + 2]);
+      sum += fc[4] * clipd(cc[4], cur, r0[i + 4], r0[i]);
+      sum += fc[5] * clipd(cc[5], cur, r0[i + 3], r0[i + 1]);
       sum = nearVb ? (sum + 512) >> 10 : (sum + 64) >> 7;
       out[i] = clip3(0, pmax, sum + cur);
     }
   } else {
-#pragma unroll
-    for (int i = 0; i < 4; i++) out[i] = s[(size_t)y * stride + x + i];
+    unpack4(*reinterpret_cast<const uint2*>(s + (size_t)y * stride + x), out);
   }
   const int ccIdx = cp.ccIdx[c - 1];
   if (ccIdx) {   // filterBlkCcAlf (AdaptiveLoopFilter.cpp:1348): 7-tap luma-difference filter on the PRE-ALF luma
@@ -288,14 +314,33 @@ __global__ void __launch_bounds__(256) alf_chroma_kernel(const AlfParams P)
     int o1 = 1, o2 = -1, o3 = 2;
     if (pos == vbPos - 2 || pos == vbPos + 1) o3 = 1;
     else if (pos == vbPos - 1 || pos == vbPos) o1 = o2 = o3 = 0;
-    auto lat = [&](int xx, int yy) { return (int)L[(size_t)min(max(yy, 0), P.H - 1) * ls + min(max(xx, 0), P.W - 1)]; };
+    auto lrow = [&](int yy) { return L + (size_t)min(max(yy, 0), P.H - 1) * ls; };
+    auto lat = [&](int xx, int yy) { return (int)lrow(yy)[min(max(xx, 0), P.W - 1)]; };
     const int half = (1 << P.bitDepth) >> 1;
+    // luma windows: a[k], b[k] = luma sample 2x-1+k of rows ly, ly+o1 (9); up[i], dn[i] = luma sample 2(x+i) of rows ly+o2, ly+o3
+    int a[9], bb[9], up[4], dn[4];
+    if (inner) {
+      int t[4];
+      const int16_t* q = lrow(ly) + 2 * x;
+      a[0] = q[-1]; unpack4(__ldg(reinterpret_cast<const uint2*>(q)), a + 1); unpack4(__ldg(reinterpret_cast<const uint2*>(q + 4)), a + 5);
+      q = lrow(ly + o1) + 2 * x;
+      bb[0] = q[-1]; unpack4(__ldg(reinterpret_cast<const uint2*>(q)), bb + 1); unpack4(__ldg(reinterpret_cast<const uint2*>(q + 4)), bb + 5);
+      q = lrow(ly + o2) + 2 * x;
+      unpack4(__ldg(reinterpret_cast<const uint2*>(q)), t); up[0] = t[0]; up[1] = t[2]; unpack4(__ldg(reinterpret_cast<const uint2*>(q + 4)), t); up[2] = t[0]; up[3] = t[2];
+      q = lrow(ly + o3) + 2 * x;
+      unpack4(__ldg(reinterpret_cast<const uint2*>(q)), t); dn[0] = t[0]; dn[1] = t[2]; unpack4(__ldg(reinterpret_cast<const uint2*>(q + 4)), t); dn[2] = t[0]; dn[3] = t[2];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; k++) { a[k] = lat(2 * x - 1 + k, ly); bb[k] = lat(2 * x - 1 + k, ly + o1); }
+#pragma unroll
+      for (int i = 0; i < 4; i++) { up[i] = lat(2 * (x + i), ly + o2); dn[i] = lat(2 * (x + i), ly + o3); }
+    }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const int lx = (x + i) << 1, cur = lat(lx, ly);
-      int sum = fc[0] * (lat(lx, ly + o2) - cur) + fc[1] * (lat(lx - 1, ly) - cur) + fc[2] * (lat(lx + 1, ly) - cur)
-              + fc[3] * (lat(lx - 1, ly + o1) - cur) + fc[4] * (lat(lx, ly + o1) - cur) + fc[5] * (lat(lx + 1, ly + o1) - cur)
-              + fc[6] * (lat(lx, ly + o3) - cur);
+      const int cur = a[2 * i + 1];
+      int sum = fc[0] * (up[i] - cur) + fc[1] * (a[2 * i] - cur) + fc[2] * (a[2 * i + 2] - cur)
+              + fc[3] * (bb[2 * i] - cur) + fc[4] * (bb[2 * i + 1] - cur) + fc[5] * (bb[2 * i + 2] - cur)
+              + fc[6] * (dn[i] - cur);
       sum = (sum + 64) >> 7;
       sum = clip3(0, pmax, sum + half) - half;
       out[i] = clip3(0, pmax, sum + out[i]);
@@ -317,6 +362,7 @@ int launch_alf(const AlfLaunch& L, StreamSet& ss, KProf* prof)
   P.ctus = L.ctus; P.lumaCoeff = L.lumaCoeff; P.lumaClip = L.lumaClip; P.chromaCoeff = L.chromaCoeff; P.chromaClip = L.chromaClip;
   P.cc0 = L.cc[0]; P.cc1 = L.cc[1];
   P.vecOk = (P.stride[0] & 3) == 0 && (reinterpret_cast<uintptr_t>(P.src[0]) & 7) == 0;
+  P.vecOkC = P.vecOk && (P.stride[1] & 3) == 0 && (P.stride[2] & 3) == 0 && (reinterpret_cast<uintptr_t>(P.src[1]) & 7) == 0 && (reinterpret_cast<uintptr_t>(P.src[2]) & 7) == 0;
   dim3 grdL((P.W + TB - 1) / TB, (P.H + TB - 1) / TB);
   if (L.geom.chromaFormat == 1) {                           // chroma + CC-ALF only read the SAO output: runs beside the luma kernel
     cudaStream_t sc = ss.pick(0);
