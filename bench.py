@@ -247,8 +247,18 @@ def run_b200(args):
     dom = max(per, key=lambda k: per[k]["ms_per_picture"])
     ach = per[dom]["bytes_per_picture"] / (per[dom]["ms_per_picture"] * 1e-3) / 1e9
     total_k = sum(v["ms_per_picture"] for v in per.values())
+    # DRAM bytes the family's launches of one picture moved, from the committed ncu pass of this same command (tools/ncu_traffic.py);
+    # only valid for the configuration it was captured on
+    traffic, traffic_src = None, None
+    try:
+        if (args.width, args.height) == (3840, 2160):
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_v15.json")))
+            traffic = int(tj["per_family"][dom]["dram_read_bytes"] + tj["per_family"][dom]["dram_write_bytes"]); traffic_src = "profiles/r01_traffic_v15.json"
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4),
-            "traffic": None, "peak_source": peaks["src"] + " (of measured)" if peaks["src"] == "measured" else "fallback",
+            "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": int(per[dom]["bytes_per_picture"]),
+            "note": "family of kernels launched together on forked streams (one launch list per tile class); issue-bound, not HBM-bound (DESIGN.md 5)", "peak_source": peaks["src"] + " (of measured)" if peaks["src"] == "measured" else "fallback",
             "share_of_step": round(per[dom]["ms_per_picture"] / total_k, 3),
             "per_kernel": {k: {"ms": round(v["ms_per_picture"], 4), "GBps": round(v["bytes_per_picture"] / (v["ms_per_picture"] * 1e-3) / 1e9, 1) if v["ms_per_picture"] > 0 else None} for k, v in per.items()}}
     fps = world * args.steps / (ms_dev * 1e-3)
