@@ -235,10 +235,33 @@ B200_API int b200_mc_predict(const b200_geom* g, int16_t* const dst[3], const in
  * slot written by an earlier submission — the stream order replaces the reference's reconDone barriers).
  *   per picture:  H2D work lists -> K2 (prediction into the work plane) -> K1 (residual + reco, in place) ->
  *                 K3 deblock V,H (in place) -> K4 SAO (-> second work plane) -> K5 ALF/CC-ALF (-> DPB slot)
+ *   with LMCS:    K2 stores forward-mapped luma -> K1 luma TUs -> per-VPDU chroma scale -> K1 chroma TUs (scaled residual) ->
+ *                 inverse luma map -> K3 ...
  * Intra-predicted / IBC / CIIP samples are not produced on the GPU yet: the caller supplies them in
  * `given` (whole planes, uploaded before K2), inter PUs and residuals overwrite/add on top.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct b200_ctx b200_ctx;
+
+/* LMCS (luma mapping with chroma scaling), reference CommonLib/Reshape.cpp.  The tables are the members Reshape::constructReshaper
+ * (:317-373) derives from the LMCS APS — the glue copies them out of the per-thread Reshape object after initSlice:
+ *   forward map of the inter-predicted luma (rspBufFwd :410 -> rspFwdCore, Buffer.cpp:321), fused into K2's luma stores;
+ *   chroma residual scaling (calculateChromaAdjVpduNei :192, scaleSignal Buffer.cpp:412) in K1's chroma pass;
+ *   inverse map of the reconstructed luma before deblocking (rspCtuBcw :377 -> applyLut with m_invLUT).
+ * One record per VPDU (64x64 luma for 128-CTUs, else one per CTU; raster order, ceil(W/size) per row): position of the CU that
+ * covers the VPDU's top-left sample (cs.getCU at :217) and whether that CU has a left / above neighbour CU the reference may read
+ * (getCURestricted :218-219: inside the picture, same slice and tile). */
+typedef struct b200_lmcs_vpdu { uint16_t x, y; uint8_t availLeft, availAbove; } b200_lmcs_vpdu;   /* 6 bytes */
+typedef struct b200_lmcs {
+  int32_t chromaAdj;              /* ph_chroma_residual_scale_flag (SliceReshapeInfo::enableChromaAdj)                 */
+  int32_t minBinIdx, maxBinIdx;   /* reshaperModelMinBinIdx / MaxBinIdx                                                 */
+  int32_t orgCW;                  /* m_initCW = (1 << bitDepth) / 16                                                    */
+  int16_t reshapePivot[17];       /* m_reshapePivot (LmcsPivot)                                                         */
+  int16_t inputPivot[17];         /* m_inputPivot                                                                       */
+  int16_t fwdScaleCoef[16];       /* m_fwdScaleCoef                                                                     */
+  int32_t chromaAdjHelpLUT[16];   /* m_chromaAdjHelpLUT                                                                 */
+  const int16_t* invLUT;          /* m_invLUT, 1 << bitDepth entries                                                    */
+  const b200_lmcs_vpdu* vpdus;    /* needed when chromaAdj != 0                                                         */
+} b200_lmcs;
 
 typedef struct b200_picture {
   int32_t dstSlot;                       /* DPB slot that receives the final picture                                  */
@@ -255,8 +278,10 @@ typedef struct b200_picture {
   const b200_vb* vb;
   const b200_alf_ctu* alf;               /* K5 (B200_PIC_ALF) */
   const b200_alf_tables* alfTabs;
+  const b200_lmcs* lmcs;                 /* B200_PIC_LMCS: every slice of the picture has LMCS on and all CUs are inter
+                                            (samples in `given` must already be in the mapped domain)                  */
 } b200_picture;
-enum { B200_PIC_DEBLOCK = 1, B200_PIC_SAO = 2, B200_PIC_ALF = 4 };
+enum { B200_PIC_DEBLOCK = 1, B200_PIC_SAO = 2, B200_PIC_ALF = 4, B200_PIC_LMCS = 8 };
 
 /* create(): reference DecLibRecon::create (DecLibRecon.cpp:392). numSlots = DPB size, numArenas = pictures whose work
  * lists may be resident at once (>= 2 for upload/compute overlap). device < 0: current device. */

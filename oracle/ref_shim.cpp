@@ -35,6 +35,7 @@
 #include "CommonLib/InterpolationFilter.h"
 #include "CommonLib/LoopFilter.h"
 #include "CommonLib/SampleAdaptiveOffset.h"
+#include "CommonLib/Reshape.h"
 #include "CommonLib/AdaptiveLoopFilter.h"
 #include "CommonLib/RdCost.h"
 #include <chrono>
@@ -609,6 +610,95 @@ extern "C" int ref_mc_predict( int simd, const b200_geom* g, int16_t* const dst[
   return rc;
 }
 
+// ================================================================================================ LMCS (Reshape)
+static std::unique_ptr<Reshape> g_rsp;
+static PelBufferOps g_pelOpsScalar, g_pelOpsSimd; static bool g_pelOpsInit = false;
+static void initPelOps()
+{
+  if( g_pelOpsInit ) return;
+  g_pelOpsScalar = PelBufferOps();
+  g_pelOpsSimd = PelBufferOps();
+#if ENABLE_SIMD_OPT_BUFFER && defined( TARGET_SIMD_X86 )
+  g_pelOpsSimd.initPelBufOpsX86();
+#endif
+  g_pelOpsInit = true;
+}
+
+static void fillReshapeFromTables( Reshape& r, int bitDepth, const b200_lmcs* L )
+{
+  r.createDec( bitDepth );
+  r.m_sliceReshapeInfo.sliceReshaperEnableFlag = true; r.m_sliceReshapeInfo.sliceReshaperModelPresentFlag = true;
+  r.m_sliceReshapeInfo.enableChromaAdj = L->chromaAdj;
+  r.m_sliceReshapeInfo.reshaperModelMinBinIdx = L->minBinIdx; r.m_sliceReshapeInfo.reshaperModelMaxBinIdx = L->maxBinIdx;
+  r.m_initCW = (uint16_t) L->orgCW;
+  for( int i = 0; i < 17; i++ ) { r.m_reshapePivot[i] = L->reshapePivot[i]; r.m_inputPivot[i] = L->inputPivot[i]; }
+  for( int i = 0; i < 16; i++ )
+  {
+    r.m_fwdScaleCoef[i] = L->fwdScaleCoef[i]; r.m_chromaAdjHelpLUT[i] = L->chromaAdjHelpLUT[i];
+    const int binCW = L->reshapePivot[i + 1] - L->reshapePivot[i];                       // constructReshaper :341-353
+    r.m_binCW[i] = (uint16_t) binCW; r.m_invScaleCoef[i] = binCW ? Pel( L->orgCW * ( 1 << FP_PREC ) / binCW ) : Pel( 0 );
+  }
+  memcpy( r.m_invLUT, L->invLUT, sizeof( Pel ) << bitDepth );
+}
+
+extern "C" int ref_lmcs_build( int bitDepth, int minBin, int maxBin, const int* deltaCW, int chrResScalingOffset, int chromaAdj, b200_lmcs* out, int16_t* invLut )
+{
+  globalInit();
+  g_rsp.reset( new Reshape() );
+  Reshape& r = *g_rsp;
+  r.createDec( bitDepth );
+  SliceReshapeInfo& si = r.m_sliceReshapeInfo;
+  si.sliceReshaperEnableFlag = true; si.sliceReshaperModelPresentFlag = true; si.enableChromaAdj = chromaAdj;
+  si.reshaperModelMinBinIdx = minBin; si.reshaperModelMaxBinIdx = maxBin; si.chrResScalingOffset = chrResScalingOffset;
+  for( int i = 0; i < PIC_CODE_CW_BINS; i++ ) si.reshaperModelBinCWDelta[i] = deltaCW[i];
+  try { r.constructReshaper(); } catch( ... ) { return -1; }
+  memset( out, 0, sizeof( *out ) );
+  out->chromaAdj = chromaAdj; out->minBinIdx = minBin; out->maxBinIdx = maxBin; out->orgCW = r.m_initCW;
+  for( int i = 0; i < 17; i++ ) { out->reshapePivot[i] = r.m_reshapePivot[i]; out->inputPivot[i] = r.m_inputPivot[i]; }
+  for( int i = 0; i < 16; i++ ) { out->fwdScaleCoef[i] = r.m_fwdScaleCoef[i]; out->chromaAdjHelpLUT[i] = r.m_chromaAdjHelpLUT[i]; }
+  memcpy( invLut, r.m_invLUT, sizeof( Pel ) << bitDepth );
+  out->invLUT = invLut;
+  return 0;
+}
+
+extern "C" void ref_lmcs_fwd_block( int simd, int16_t* ptr, ptrdiff_t stride, int w, int h )
+{
+  initPelOps();
+  const PelBufferOps saved = g_pelBufOP; g_pelBufOP = simd ? g_pelOpsSimd : g_pelOpsScalar;
+  PelBuf b( ptr, stride, w, h );
+  g_rsp->rspBufFwd( b );
+  g_pelBufOP = saved;
+}
+
+extern "C" void ref_lmcs_inv_block( int simd, int16_t* ptr, ptrdiff_t stride, int w, int h )
+{
+  initPelOps();
+  const Reshape& r = *g_rsp;
+  const PelBufferOps& ops = simd ? g_pelOpsSimd : g_pelOpsScalar;
+  // the two branches of Reshape::rspCtuBcw (:399-406)
+  if( ops.rspBcw ) ops.rspBcw( ptr, stride, w, h, r.m_lumaBD, r.m_sliceReshapeInfo.reshaperModelMinBinIdx, r.m_sliceReshapeInfo.reshaperModelMaxBinIdx, r.m_reshapePivot.data(), r.m_invScaleCoef.data(), r.m_inputPivot.data() );
+  else             ops.applyLut( ptr, stride, w, h, r.m_invLUT );
+}
+
+extern "C" void ref_lmcs_scale_block( int16_t* ptr, ptrdiff_t stride, int w, int h, int scale, int bitDepth )
+{
+  PelBuf b( ptr, stride, w, h );
+  ClpRng rng; rng.bd = bitDepth;
+  b.scaleSignal( scale, rng );
+}
+
+extern "C" int ref_lmcs_vpdu_scale( const b200_geom* g, int16_t* const planes[3], int x, int y )
+{
+  FakePicture fp( *g, 1 );
+  addCtuCUs( fp );
+  fp.setPlanes( *g, planes );
+  CodingStructure& cs = *fp.pic.cs;
+  TransformUnit tu; memset( (void*) &tu, 0, sizeof( tu ) );
+  tu.cu = cs.getCU( Position( x, y ), CH_L );
+  g_rsp->setVPDULoc( -1, -1 );
+  return g_rsp->calculateChromaAdjVpduNei( tu, Position( x, y ) );
+}
+
 // ================================================================================================ whole back end, multi-threaded
 // Persistent worker pool (the reference keeps its worker threads alive across pictures too: Utilities/ThreadPool.h); items are handed out
 // dynamically through an atomic counter.
@@ -820,6 +910,13 @@ extern "C" double ref_decompress_picture_out( const b200_geom* g, const int16_t*
     ips.emplace_back( new InterPrediction() ); ips.back()->init( simd ? &rdSimd : &rdScalar, pcv.chrFormat, g->ctuSize, simd != 0 );
     tqs.emplace_back( new TrQuant( ips.back().get() ) ); qns.emplace_back( new Quant( nullptr, simd != 0 ) );
   }
+  const bool doLmcs = ( pic->flags & B200_PIC_LMCS ) && pic->lmcs;
+  std::vector<std::unique_ptr<Reshape>> rsps;
+  if( doLmcs )
+  {
+    initPelOps();
+    for( int t = 0; t < threads; t++ ) { rsps.emplace_back( new Reshape() ); fillReshapeFromTables( *rsps.back(), g->bitDepth, pic->lmcs ); }
+  }
   TCoeffOps ops = simd ? g_simdOps : g_scalarOps;
   LoopFilter lf( simd != 0 );
   SampleAdaptiveOffset sao( simd != 0 );
@@ -854,12 +951,16 @@ extern "C" double ref_decompress_picture_out( const b200_geom* g, const int16_t*
         fillCuFromPu( cu, pu, cur, sl );
         PelUnitBuf predBuf = reco.subBuf( UnitArea( pcv.chrFormat, Area( pu.x, pu.y, pu.w, pu.h ) ) );   // rootCbf==0 style: MC writes straight into the picture (DecCu.cpp:405)
         ips[t]->motionCompensation( cu, predBuf, true, true );
+        if( doLmcs ) rsps[t]->rspBufFwd( predBuf.Y() );             // DecCu.cpp:458-476
       }
     } );
   }
-  // K1: per TU chunk
+  // K1: per TU chunk.  With LMCS chroma scaling (DecCu.cpp:483 finishLMCSAndReco) the luma TUs go first: the chroma scale of a VPDU is
+  // derived from the reconstructed (mapped-domain) luma next to it — for an all-inter picture that is order-independent once luma is done.
   {
+    const bool twoPhase = doLmcs && pic->lmcs->chromaAdj;
     const int nChunks = ( (int) pic->numTus + 31 ) / 32;
+    for( int phase = 0; phase < ( twoPhase ? 2 : 1 ); phase++ )
     parallelFor( nChunks, pool, [&]( int ch, int t ) {
       TCoeff* dq  = tqs[t]->m_dqnt; TCoeff* tmp = tqs[t]->m_tmp; TCoeff* blk = tqs[t]->m_blk;
       alignas( 32 ) Pel r0[64 * 64]; alignas( 32 ) Pel r1[64 * 64];
@@ -867,10 +968,23 @@ extern "C" double ref_decompress_picture_out( const b200_geom* g, const int16_t*
       for( size_t n = (size_t) ch * 32; n < std::min<size_t>( pic->numTus, (size_t) ch * 32 + 32 ); n++ )
       {
         const b200_tu& tu = pic->tus[n];
+        if( twoPhase && ( tu.comp != 0 ) != ( phase == 1 ) ) continue;
         const int w = 1 << tu.log2w, h = 1 << tu.log2h;
         refTuResidual( tu, g->bitDepth, pic->coefs, *tqs[t], *qns[t], ops, dq, tmp, blk, r0, w );
         int nOut = 1, comp1 = 0;
         if( tu.ict ) { comp1 = tu.comp == 1 ? 2 : 1; nOut = 2; const int m = tu.ict; for( int i = 0; i < w * h; i++ ) { const int c = r0[i]; r1[i] = Pel( m == 2 ? c : m == -2 ? -c : m > 0 ? ( c >> 1 ) : ( ( -c ) >> 1 ) ); } }
+        if( twoPhase && tu.comp != 0 && w * h > 4 )
+        {
+          // the real Reshape::calculateChromaAdjVpduNei on the (one CU per CTU) structure + the real AreaBuf::scaleSignal
+          TransformUnit rtu; memset( (void*) &rtu, 0, sizeof( rtu ) );
+          const Position lumaPos( tu.x * 2, tu.y * 2 );
+          rtu.cu = cs.getCU( lumaPos, CH_L );
+          rsps[t]->setVPDULoc( -1, -1 );
+          const int sc = rsps[t]->calculateChromaAdjVpduNei( rtu, lumaPos );
+          ClpRng rng; rng.bd = g->bitDepth;
+          PelBuf b0( r0, w, w, h ); b0.scaleSignal( sc, rng );
+          if( nOut == 2 ) { PelBuf b1( r1, w, w, h ); b1.scaleSignal( sc, rng ); }
+        }
         for( int o = 0; o < nOut; o++ )
         {
           PelBuf pb = reco.bufs[o ? comp1 : tu.comp]; const Pel* r = o ? r1 : r0;
@@ -880,6 +994,15 @@ extern "C" double ref_decompress_picture_out( const b200_geom* g, const int16_t*
       }
     } );
   }
+  if( doLmcs )   // RSP stage (DecLibRecon.cpp:935): inverse map per CTU
+    parallelFor( wC * hC, pool, [&]( int a, int t ) {
+      const int x = ( a % wC ) * g->ctuSize, y = ( a / wC ) * g->ctuSize, w = std::min( g->ctuSize, g->width - x ), h = std::min( g->ctuSize, g->height - y );
+      PelBuf b = reco.bufs[0].subBuf( Position( x, y ), Size( w, h ) );
+      const Reshape& r = *rsps[t];
+      const PelBufferOps& pops = simd ? g_pelOpsSimd : g_pelOpsScalar;
+      if( pops.rspBcw ) pops.rspBcw( b.buf, b.stride, w, h, r.m_lumaBD, r.m_sliceReshapeInfo.reshaperModelMinBinIdx, r.m_sliceReshapeInfo.reshaperModelMaxBinIdx, r.m_reshapePivot.data(), r.m_invScaleCoef.data(), r.m_inputPivot.data() );
+      else              pops.applyLut( b.buf, b.stride, w, h, r.m_invLUT );
+    } );
   if( doLf )
   {
     parallelFor( wC * hC, pool, [&]( int a, int ) { lf.loopFilterCTU( cs, MAX_NUM_CHANNEL_TYPE, a % wC, a / wC, EDGE_VER ); } );

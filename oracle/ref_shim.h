@@ -96,6 +96,13 @@ int ref_mc_predict(int simd, const b200_geom* g, int16_t* const dst[3], const in
  * of one picture is included (every picture is extended once when it becomes a reference, DecLibRecon.cpp:236).
  * Returns the seconds spent in the timed part (setup of the fake vvdec objects excluded); out (may be NULL) receives the picture. */
 double ref_decompress_picture_mt(const b200_geom* g, const int16_t* const* refs, const b200_picture* pic, int threads, int simd);
+/* LMCS through the real Reshape class (CommonLib/Reshape.cpp) and the PelBufferOps pointers it dispatches to.
+ * ref_lmcs_build: createDec + the SliceReshapeInfo fields + constructReshaper(); fills `out` (tables) and invLut[1 << bitDepth]; returns 0 if the model is legal. */
+int  ref_lmcs_build(int bitDepth, int minBin, int maxBin, const int* deltaCW, int chrResScalingOffset, int chromaAdj, b200_lmcs* out, int16_t* invLut);
+void ref_lmcs_fwd_block(int simd, int16_t* ptr, ptrdiff_t stride, int w, int h);                 /* Reshape::rspBufFwd */
+void ref_lmcs_inv_block(int simd, int16_t* ptr, ptrdiff_t stride, int w, int h);                 /* what rspCtuBcw applies to a CTU */
+void ref_lmcs_scale_block(int16_t* ptr, ptrdiff_t stride, int w, int h, int scale, int bitDepth); /* AreaBuf<Pel>::scaleSignal */
+int  ref_lmcs_vpdu_scale(const b200_geom* g, int16_t* const planes[3], int x, int y);            /* calculateChromaAdjVpduNei on a picture with one CU per CTU */
 double ref_decompress_picture_out(const b200_geom* g, const int16_t* const* refs, const b200_picture* pic, int threads, int simd, int16_t* const out[3]);
 
 #ifdef __cplusplus

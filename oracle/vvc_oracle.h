@@ -44,6 +44,21 @@ void orc_tu_residual(const b200_tu* tu, int bitDepth, const int16_t* coefs, cons
 void orc_k1_residual(const b200_geom* g, int16_t* const planes[3], const b200_tu* tus, size_t numTus,
                      const int16_t* coefs, const int32_t* scaling, int mode);
 
+/* ---- LMCS (Reshape.cpp) ------------------------------------------------------------------------- */
+/* Buffer.cpp:321 rspFwdCore on a w x h block (the luma prediction of one inter CU, DecCu.cpp:460-474). */
+void orc_lmcs_fwd_block(int16_t* ptr, ptrdiff_t stride, int w, int h, int bitDepth, const b200_lmcs* L);
+/* rspBufFwd over the luma area of every PU of a list. */
+void orc_lmcs_fwd_pus(const b200_geom* g, int16_t* luma, const b200_pu* pus, size_t numPus, const b200_lmcs* L);
+/* Reshape.cpp:192 calculateChromaAdjVpduNei for VPDU record v (averages the mapped-domain luma left of / above the CU at (v.x,v.y)). */
+int orc_lmcs_vpdu_scale(const b200_geom* g, const int16_t* luma, const b200_lmcs* L, const b200_lmcs_vpdu* v);
+/* Buffer.cpp:412 scaleSignal on one residual sample. */
+int orc_lmcs_scale_resi(int r, int scale, int bitDepth);
+/* DecCu.cpp:483 finishLMCSAndReco order for an all-inter picture: luma TUs (reco), chroma scale per VPDU, chroma TUs (scaled residual, reco). */
+void orc_k1_residual_lmcs(const b200_geom* g, int16_t* const planes[3], const b200_tu* tus, size_t numTus,
+                          const int16_t* coefs, const int32_t* scaling, const b200_lmcs* L);
+/* Reshape.cpp:377 rspCtuBcw over the whole luma plane (Buffer.cpp:200 applyLutCore). */
+void orc_lmcs_inv_plane(const b200_geom* g, int16_t* luma, const b200_lmcs* L);
+
 /* ---- K3 deblocking -------------------------------------------------------------------------- */
 /* LoopFilter.cpp:213 xPelFilterLumaCore (4 lines). */
 void orc_lf_pel_filter_luma(int16_t* src, ptrdiff_t step, ptrdiff_t offset, int tc, int sw, int thrCut,

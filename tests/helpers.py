@@ -36,6 +36,13 @@ def load_oracle():
     lib.orc_alf_ccalf_blk.argtypes = [V, C.c_ssize_t, V, C.c_ssize_t] + [C.c_int] * 4 + [V] + [C.c_int] * 3
     lib.orc_alf_picture.argtypes = [C.POINTER(abi.Geom), PL, PL, V, C.POINTER(abi.AlfTables)]
     lib.orc_mc_predict.argtypes = [C.POINTER(abi.Geom), PL, C.POINTER(C.c_void_p), V, C.c_size_t, V]
+    LP = C.POINTER(abi.Lmcs)
+    lib.orc_lmcs_fwd_block.argtypes = [V, C.c_ssize_t, C.c_int, C.c_int, C.c_int, LP]
+    lib.orc_lmcs_fwd_pus.argtypes = [C.POINTER(abi.Geom), i16p, V, C.c_size_t, LP]
+    lib.orc_lmcs_vpdu_scale.argtypes = [C.POINTER(abi.Geom), i16p, LP, C.POINTER(abi.LmcsVpdu)]
+    lib.orc_lmcs_scale_resi.argtypes = [C.c_int] * 3
+    lib.orc_k1_residual_lmcs.argtypes = [C.POINTER(abi.Geom), PL, V, C.c_size_t, i16p, V, LP]
+    lib.orc_lmcs_inv_plane.argtypes = [C.POINTER(abi.Geom), i16p, LP]
     return lib
 
 
@@ -71,6 +78,11 @@ def load_ref():
     lib.ref_alf_picture.argtypes = [C.c_int, C.POINTER(abi.Geom), PL, PL, V, C.POINTER(abi.AlfTables)]
     lib.ref_mc_predict.argtypes = [C.c_int, C.POINTER(abi.Geom), PL, C.POINTER(C.c_void_p), V, C.c_size_t, V, C.c_size_t]
     lib.ref_mc_predict.restype = C.c_int
+    lib.ref_lmcs_build.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(abi.Lmcs), i16p]
+    lib.ref_lmcs_fwd_block.argtypes = [C.c_int, V, C.c_ssize_t, C.c_int, C.c_int]
+    lib.ref_lmcs_inv_block.argtypes = [C.c_int, V, C.c_ssize_t, C.c_int, C.c_int]
+    lib.ref_lmcs_scale_block.argtypes = [V, C.c_ssize_t, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.ref_lmcs_vpdu_scale.argtypes = [C.POINTER(abi.Geom), PL, C.c_int, C.c_int]
     lib.ref_decompress_picture_out.argtypes = [C.POINTER(abi.Geom), C.POINTER(C.c_void_p), C.POINTER(abi.Picture), C.c_int, C.c_int, PL]
     lib.ref_decompress_picture_out.restype = C.c_double
     lib.ref_decompress_picture_mt.argtypes = [C.POINTER(abi.Geom), C.POINTER(C.c_void_p), C.POINTER(abi.Picture), C.c_int, C.c_int]
@@ -112,7 +124,14 @@ def oracle_decompress(oracle, g, dpb, pic):
     dm = np.zeros((pic["ndmvr"] + 1, 2), np.int32)
     st = pic["struct"]
     oracle.orc_mc_predict(C.byref(g), abi.plane_ptrs(cur), ref_ptrs(dpb), pic["pus"].ctypes.data, len(pic["pus"]), dm.ctypes.data)
-    oracle.orc_k1_residual(C.byref(g), abi.plane_ptrs(cur), pic["tus"].ctypes.data, len(pic["tus"]), pic["coefs"], None, 0)
+    if st.flags & abi.PIC_LMCS:
+        # DecCu.cpp:458-476 forward map of every inter CU's luma prediction; :483 finishLMCSAndReco; DecLibRecon.cpp:935 inverse map
+        L = C.byref(pic["lmcs"]["struct"])
+        oracle.orc_lmcs_fwd_pus(C.byref(g), cur[0], pic["pus"].ctypes.data, len(pic["pus"]), L)
+        oracle.orc_k1_residual_lmcs(C.byref(g), abi.plane_ptrs(cur), pic["tus"].ctypes.data, len(pic["tus"]), pic["coefs"], None, L)
+        oracle.orc_lmcs_inv_plane(C.byref(g), cur[0], L)
+    else:
+        oracle.orc_k1_residual(C.byref(g), abi.plane_ptrs(cur), pic["tus"].ctypes.data, len(pic["tus"]), pic["coefs"], None, 0)
     if st.flags & abi.PIC_DEBLOCK:
         oracle.orc_lf_deblock(C.byref(g), abi.plane_ptrs(cur), pic["lfV"].ctypes.data, pic["lfH"].ctypes.data, None,
                               pic["lfSlices"].ctypes.data, None, 3)

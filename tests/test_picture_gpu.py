@@ -74,3 +74,31 @@ def test_invalid_records_are_reported(b200):
         assert b200.b200_wait_picture(ctx, h, None, 0) == 0
     finally:
         b200.b200_ctx_destroy(ctx)
+
+
+@pytest.mark.parametrize("W,H,ctu,chroma_adj", [(416, 240, 128, True), (416, 240, 64, True), (832, 480, 128, False), (1920, 1080, 128, True)])
+def test_lmcs_picture(b200, oracle, W, H, ctu, chroma_adj):
+    """LMCS on: forward-mapped luma prediction fused into K2, luma TUs -> per-VPDU chroma scale -> scaled chroma
+    TUs, inverse map before deblocking — against the oracle chain (which tests/test_lmcs_oracle_vs_ref.py pins to the real Reshape)."""
+    rng = np.random.default_rng(W + ctu)
+    bd = 10
+    g = abi.make_geom(W, H, bd, ctu=ctu)
+    ctx = C.c_void_p()
+    vvdec_b200.check(b200.b200_ctx_create(C.byref(ctx), C.byref(g), 6, 2, -1))
+    try:
+        dpb = [synth.noise_planes(rng, W, H, bd) for _ in range(4)]
+        for s in range(4): vvdec_b200.check(b200.b200_ctx_load_slot(ctx, s, abi.plane_ptrs(dpb[s])))
+        for k in range(2):
+            pic = synth.gen_picture(rng, W, H, bd, ctu=ctu, dst_slot=4 + k, lmcs=True, lmcs_chroma=chroma_adj)
+            want, dm_want = oracle_decompress(oracle, g, dpb, pic)
+            h = b200.b200_decompress_picture(ctx, C.byref(pic["struct"]))
+            assert h >= 0, b200.b200_last_error()
+            dm = np.zeros((pic["ndmvr"] + 1, 2), np.int32)
+            vvdec_b200.check(b200.b200_wait_picture(ctx, h, dm.ctypes.data, len(dm)))
+            got = [np.zeros_like(p) for p in want]
+            vvdec_b200.check(b200.b200_get_frame(ctx, 4 + k, abi.plane_ptrs(got)))
+            for c in range(3):
+                assert np.array_equal(want[c], got[c]), f"picture {k} plane {c}: {len(np.argwhere(want[c] != got[c]))} diffs"
+            assert np.array_equal(dm, dm_want)
+    finally:
+        b200.b200_ctx_destroy(ctx)

@@ -73,7 +73,7 @@ def const_plane_ptrs(planes):
     return plane_ptrs(planes)
 
 
-PIC_DEBLOCK, PIC_SAO, PIC_ALF = 1, 2, 4
+PIC_DEBLOCK, PIC_SAO, PIC_ALF, PIC_LMCS = 1, 2, 4, 8
 
 
 class Picture(C.Structure):
@@ -83,4 +83,15 @@ class Picture(C.Structure):
                 ("scaling", C.c_void_p), ("numScaling", C.c_size_t),
                 ("lfV", C.c_void_p), ("lfH", C.c_void_p), ("ctuSlice", C.c_void_p), ("lfSlices", C.c_void_p),
                 ("numLfSlices", C.c_int32), ("lfSeq", C.c_void_p),
-                ("sao", C.c_void_p), ("vb", C.c_void_p), ("alf", C.c_void_p), ("alfTabs", C.c_void_p)]
+                ("sao", C.c_void_p), ("vb", C.c_void_p), ("alf", C.c_void_p), ("alfTabs", C.c_void_p), ("lmcs", C.c_void_p)]
+
+
+class LmcsVpdu(C.Structure):
+    _fields_ = [("x", C.c_uint16), ("y", C.c_uint16), ("availLeft", C.c_uint8), ("availAbove", C.c_uint8)]
+
+
+class Lmcs(C.Structure):
+    """b200_lmcs: the tables Reshape::constructReshaper derives (see include/vvdec_b200.h)."""
+    _fields_ = [("chromaAdj", C.c_int32), ("minBinIdx", C.c_int32), ("maxBinIdx", C.c_int32), ("orgCW", C.c_int32),
+                ("reshapePivot", C.c_int16 * 17), ("inputPivot", C.c_int16 * 17), ("fwdScaleCoef", C.c_int16 * 16),
+                ("chromaAdjHelpLUT", C.c_int32 * 16), ("invLUT", C.c_void_p), ("vpdus", C.c_void_p)]

@@ -28,6 +28,20 @@ void set_error(const char* fmt, ...);
 __device__ __forceinline__ int clip3(int lo, int hi, int v) { return min(max(v, lo), hi); }
 __device__ __forceinline__ int clip16(int v) { return min(max(v, -32768), 32767); }
 
+// LMCS forward map of one predicted luma sample (rspFwdCore, reference CommonLib/Buffer.cpp:321); L points at the uploaded b200_lmcs
+__device__ __forceinline__ int lmcs_fwd(const b200_lmcs* __restrict__ L, int log2OrgCW, int v, int pmax)
+{
+  const int idx = v >> log2OrgCW;
+  return clip3(0, pmax, (int)__ldg(&L->reshapePivot[idx]) + (((int)__ldg(&L->fwdScaleCoef[idx]) * (v - (int)__ldg(&L->inputPivot[idx])) + (1 << 10)) >> 11));
+}
+// LMCS chroma residual scaling of one sample (AreaBuf<Pel>::scaleSignal, Buffer.cpp:412)
+__device__ __forceinline__ int lmcs_scale(int r, int scale, int maxAbs)
+{
+  r = clip3(-maxAbs - 1, maxAbs, r);
+  const int a = abs(r), v = (a * scale + (1 << 10)) >> 11;
+  return clip16(r >= 0 ? v : -v);
+}
+
 // Grow-only device scratch buffer.
 struct DevBuf {
   void*  p   = nullptr;
@@ -94,6 +108,8 @@ struct K1Launch {
   const int16_t* coefs;
   const int32_t* scaling;
   int            mode;    // 0: reco = clip(pred + resi); 1: store residual
+  int            compSel = 0;             // 0 all TUs, 1 luma TUs only, 2 chroma TUs only (LMCS chroma scaling needs luma first)
+  const int*     vpduScale = nullptr;     // device: LMCS chroma residual scale per VPDU, or null
 };
 int launch_k1_residual(const K1Launch& L, StreamSet& ss, KProf* prof = nullptr);
 
@@ -125,10 +141,15 @@ struct McLaunch {
   const int* meta;                  // device: counts / offsets of the lists
   int cnt[MC_LISTS];                // the same counts on the host (read back after bucketing): exact grids, empty lists are not launched
   int32_t* dmvrMv;                  // device or null
+  const b200_lmcs* lmcs = nullptr;  // device copy of the LMCS tables: luma predictions are stored forward-mapped; null = LMCS off
 };
 int launch_mc(const McLaunch& L, StreamSet& ss, KProf* prof = nullptr);
 int mc_launch_count(const McLaunch& L);
 int k1_launch_count(const K1Launch& L);
+
+struct LmcsLaunch { b200_geom geom; DevPlanes planes; const b200_lmcs* lmcs; const b200_lmcs_vpdu* vpdus; const int16_t* invLut; int* scale; };
+int launch_lmcs_vpdu(const LmcsLaunch& L, cudaStream_t s);   // per-VPDU chroma residual scale from the reconstructed (mapped) luma
+int launch_lmcs_inv(const LmcsLaunch& L, cudaStream_t s);    // inverse map of the luma plane, in place
 
 int ensure_device();   // selects device 0 if none current; fails loudly when there is no sm_100 GPU
 

@@ -55,7 +55,7 @@ __device__ __forceinline__ int dequant_one(int level, int scale, int rightShift,
 template <int CLS>
 __device__ __forceinline__ void k1_tu(const b200_tu* __restrict__ tus, int t, const int16_t* __restrict__ coefs, const int32_t* __restrict__ scaling,
                                       int16_t* p0, int16_t* p1, int16_t* p2, int s0, int s1, int s2, int bitDepth, int mode,
-                                      int16_t* cb, int16_t* tb, int lane)
+                                      int compSel, const int* __restrict__ vpduScale, int vpduGeo, int16_t* cb, int16_t* tb, int lane)
 {
   constexpr int G = K1Cfg<CLS>::G;
   auto gsync = [&]() { if (G == 32) __syncwarp(); else __syncthreads(); };
@@ -70,6 +70,7 @@ __device__ __forceinline__ void k1_tu(const b200_tu* __restrict__ tus, int t, co
   const int ict = (int)(int8_t)(ra.w & 0xff), rightShift = (int)(int8_t)((ra.w >> 8) & 0xff);
   const int inBits = (ra.w >> 16) & 0xff, scale = ra.w >> 24;
   const unsigned coefOff = rb.x, slOff = rb.y;
+  if ((compSel == 1 && comp != 0) || (compSel == 2 && comp == 0)) return;   // LMCS: luma pass / chroma pass
 
   const int w = 1 << log2w, h = 1 << log2h;
   const int16_t* q = coefs + coefOff;
@@ -162,14 +163,20 @@ __device__ __forceinline__ void k1_tu(const b200_tu* __restrict__ tus, int t, co
   const int ds1 = comp == 1 ? s2 : s1;                       // the other chroma plane (joint CbCr)
   int16_t* dst1 = ict ? (comp == 1 ? p2 : p1) + (size_t)ty * ds1 + tx : nullptr;
 
+  // LMCS chroma residual scaling (DecCu.cpp:483 finishLMCSAndReco): scale of the VPDU that holds the TU's luma block; blocks of
+  // at most 4 samples are not scaled (:506).  vpduGeo = log2(VPDU size) | VPDUs per row << 8.
+  int lmScale = 0;
+  if (vpduScale && comp != 0 && w * h > 4) lmScale = __ldg(vpduScale + ((ty * 2) >> (vpduGeo & 0xff)) * (vpduGeo >> 8) + ((tx * 2) >> (vpduGeo & 0xff)));
   auto emit = [&](int x, int y, int r) {
     int16_t* d = dst0 + y * ds0 + x;
-    *d = (int16_t)(mode == 0 ? clip3(0, pmax, *d + r) : r);
+    const int rs = lmScale ? lmcs_scale(r, lmScale, pmax) : r;
+    *d = (int16_t)(mode == 0 ? clip3(0, pmax, *d + rs) : rs);
     if (ict) {
       // TrQuant.cpp:108-124 invTransformCbCr
-      const int r1 = (ict == 2) ? r : (ict == -2) ? -r : (ict > 0) ? (r >> 1) : ((-r) >> 1);
+      int r1 = (int)(int16_t)((ict == 2) ? r : (ict == -2) ? -r : (ict > 0) ? (r >> 1) : ((-r) >> 1));
+      if (lmScale) r1 = lmcs_scale(r1, lmScale, pmax);
       int16_t* e = dst1 + y * ds1 + x;
-      *e = (int16_t)(mode == 0 ? clip3(0, pmax, *e + (int)(int16_t)r1) : (int)(int16_t)r1);
+      *e = (int16_t)(mode == 0 ? clip3(0, pmax, *e + r1) : r1);
     }
   };
 
@@ -249,7 +256,7 @@ template <int CLS>
 __global__ void __launch_bounds__(K1Cfg<CLS>::THREADS)
 k1_residual_kernel(const b200_tu* __restrict__ tus, const uint32_t* __restrict__ idx, const int* __restrict__ meta, const int16_t* __restrict__ coefs,
                    const int32_t* __restrict__ scaling, int16_t* p0, int16_t* p1, int16_t* p2,
-                   int s0, int s1, int s2, int bitDepth, int mode)
+                   int s0, int s1, int s2, int bitDepth, int mode, int compSel, const int* __restrict__ vpduScale, int vpduGeo)
 {
   constexpr int G = K1Cfg<CLS>::G, GROUPS = K1Cfg<CLS>::GROUPS;
   __shared__ __align__(16) int16_t s_c[GROUPS][K1Cfg<CLS>::CB];
@@ -257,13 +264,16 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, const uint32_t* __restrict__
   const int grp = threadIdx.x / G, lane = threadIdx.x % G;
   const int i = blockIdx.x * GROUPS + grp;
   if (i >= meta[LM_CNT + CLS]) return;                       // G == blockDim for the big classes: the whole CTA leaves together
-  k1_tu<CLS>(tus, (int)idx[meta[LM_OFF + CLS] + i], coefs, scaling, p0, p1, p2, s0, s1, s2, bitDepth, mode, s_c[grp], s_t[grp], lane);
+  k1_tu<CLS>(tus, (int)idx[meta[LM_OFF + CLS] + i], coefs, scaling, p0, p1, p2, s0, s1, s2, bitDepth, mode, compSel, vpduScale, vpduGeo, s_c[grp], s_t[grp], lane);
 }
 
 int launch_k1_residual(const K1Launch& L, StreamSet& ss, KProf* prof)
 {
   if (L.numTus == 0) return 0;
   if (prof) prof->begin(B200_KF_K1, ss.main);
+  const int vs = L.geom.ctuSize == 128 ? 64 : L.geom.ctuSize;
+  int vpduGeo = 0; while ((1 << (vpduGeo + 1)) <= vs) vpduGeo++;
+  vpduGeo |= ((L.geom.width + vs - 1) / vs) << 8;
   int launched = 0;
   for (int c = 3; c >= 0; c--) {          // largest TUs first: their long CTAs overlap the small classes on the other streams
     if (!L.cnt[c]) continue;
@@ -271,7 +281,7 @@ int launch_k1_residual(const K1Launch& L, StreamSet& ss, KProf* prof)
     const int groups = c <= 1 ? K1_WARPS : 1;
     const int grid = (L.cnt[c] + groups - 1) / groups;
 #define K1_GO(C) k1_residual_kernel<C><<<grid, K1Cfg<C>::THREADS, 0, s>>>(L.tus, L.idx, L.meta, L.coefs, L.scaling, L.planes.p[0], L.planes.p[1], L.planes.p[2], \
-                                                                   L.planes.stride[0], L.planes.stride[1], L.planes.stride[2], L.geom.bitDepth, L.mode)
+                                                                   L.planes.stride[0], L.planes.stride[1], L.planes.stride[2], L.geom.bitDepth, L.mode, L.compSel, L.vpduScale, vpduGeo)
     switch (c) { case 0: K1_GO(0); break; case 1: K1_GO(1); break; case 2: K1_GO(2); break; default: K1_GO(3); break; }
 #undef K1_GO
     B200_CUDA(cudaGetLastError());

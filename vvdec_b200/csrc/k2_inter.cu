@@ -30,7 +30,11 @@ struct McParams {
   int fastOk;                                // plane strides are even -> rows are word-addressable
   const b200_pu* pus; const uint32_t* tiles; const int* meta;   // device lists (bucket.cu)
   int32_t* dmvrMv;
+  const b200_lmcs* lmcs; int lmcsLog2;       // LMCS: luma predictions are stored forward-mapped (DecCu.cpp:458-476); null = off
 };
+
+// final luma prediction sample -> what is stored (identity without LMCS)
+#define LUMA_OUT(v) (P.lmcs ? lmcs_fwd(P.lmcs, P.lmcsLog2, (v), pmax) : (v))
 
 struct RefPl { const int16_t* p; int w, h, stride; };
 __device__ __forceinline__ int ldc(const RefPl& r, int x, int y) { return r.p[(size_t)min(max(y, 0), r.h - 1) * r.stride + min(max(x, 0), r.w - 1)]; }
@@ -491,8 +495,8 @@ __device__ __forceinline__ void mc_tile(const McParams& P, const uint32_t tile, 
 #pragma unroll
     for (int j = 0; j < OPT; j++) {
       int16_t* d = P.dst[0] + (size_t)(by + sy + j) * P.dstStride[0] + bx + sx;
-      if (!BI) *d = (int16_t)clip3(0, pmax, (pr[0][j] + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr));
-      else if (!bio) *d = (int16_t)avg_bi((int16_t)(pr[0][j] >> 6), (int16_t)(pr[NL - 1][j] >> 6), MODE == 1 ? pu.bcwW1 : 4, hr, pmax);
+      if (!BI) *d = (int16_t)LUMA_OUT(clip3(0, pmax, (pr[0][j] + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr)));
+      else if (!bio) *d = (int16_t)LUMA_OUT(avg_bi((int16_t)(pr[0][j] >> 6), (int16_t)(pr[NL - 1][j] >> 6), MODE == 1 ? pu.bcwW1 : 4, hr, pmax));
       else { S.p[0][(sy + j + 1) * 18 + sx + 1] = (int16_t)(pr[0][j] >> 6); S.p[1][(sy + j + 1) * 18 + sx + 1] = (int16_t)(pr[NL - 1][j] >> 6); }
     }
   }
@@ -599,7 +603,7 @@ __device__ __forceinline__ void mc_tile(const McParams& P, const uint32_t tile, 
       const int y = sy + j, blk = ((y >> 2) << l2bw) + (sx >> 2);
       const int b = sVxy[blk][0] * dgx[j] + sVxy[blk][1] * dgy[j];
       const int shiftNum = 15 - bd, offset = (1 << (shiftNum - 1)) + 2 * IFO;
-      P.dst[0][(size_t)(by + y) * P.dstStride[0] + bx + sx] = (int16_t)clip3(0, pmax, (int)(int16_t)((psum[j] + b + offset) >> shiftNum));
+      P.dst[0][(size_t)(by + y) * P.dstStride[0] + bx + sx] = (int16_t)LUMA_OUT(clip3(0, pmax, (int)(int16_t)((psum[j] + b + offset) >> shiftNum)));
     }
   }
 }
@@ -731,7 +735,7 @@ __device__ __forceinline__ void mc_affine_tile(const McParams& P, const uint32_t
       }
       if (M[l].prof) sE[l][sb][(y + 1) * 6 + x + 1] = (int16_t)(s >> 6);
       else if (bi)   sP[l][0][(sby + y) * 16 + sbx + x] = (int16_t)(s >> 6);
-      else P.dst[0][(size_t)(by + sby + y) * P.dstStride[0] + bx + sbx + x] = (int16_t)clip3(0, pmax, (s + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr));
+      else P.dst[0][(size_t)(by + sby + y) * P.dstStride[0] + bx + sbx + x] = (int16_t)LUMA_OUT(clip3(0, pmax, (s + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr)));
     }
     __syncwarp();
     if (sbValid && M[l].prof) {                              // gradFilterCore<false> :212 + applyPROFCore :61
@@ -748,7 +752,7 @@ __device__ __forceinline__ void mc_affine_tile(const McParams& P, const uint32_t
       const int dI = clip3(-lim, lim - 1, dh * gX + dv * gY);
       int v = (int16_t)(E[c] + dI);
       if (bi) sP[l][0][(sby + y) * 16 + sbx + x] = (int16_t)v;
-      else P.dst[0][(size_t)(by + sby + y) * P.dstStride[0] + bx + sbx + x] = (int16_t)clip3(0, pmax, (int)(int16_t)((v + (1 << (hr - 1)) + IFO) >> hr));
+      else P.dst[0][(size_t)(by + sby + y) * P.dstStride[0] + bx + sbx + x] = (int16_t)LUMA_OUT(clip3(0, pmax, (int)(int16_t)((v + (1 << (hr - 1)) + IFO) >> hr)));
     }
   }
 
@@ -795,7 +799,7 @@ __device__ __forceinline__ void mc_affine_tile(const McParams& P, const uint32_t
   __syncthreads();
   {
     const int y = tid >> 4, x = tid & 15;
-    if (x < tw && y < th) P.dst[0][(size_t)(by + y) * P.dstStride[0] + bx + x] = (int16_t)avg_bi(sP[0][0][y * 16 + x], sP[1][0][y * 16 + x], pu.bcwW1, hr, pmax);
+    if (x < tw && y < th) P.dst[0][(size_t)(by + y) * P.dstStride[0] + bx + x] = (int16_t)LUMA_OUT(avg_bi(sP[0][0][y * 16 + x], sP[1][0][y * 16 + x], pu.bcwW1, hr, pmax));
     if (P.chroma && tid < 128) {
       const int c = tid >> 6, j = tid & 63, yy = j >> 3, xx = j & 7;
       if (xx < (tw >> 1) && yy < (th >> 1))
@@ -818,6 +822,7 @@ int launch_mc(const McLaunch& L, StreamSet& ss, KProf* prof)
   P.fastOk = !(L.refStride[0] & 1) && !(L.refStride[1] & 1) && !(L.refStride[2] & 1);
   P.W = L.geom.width; P.H = L.geom.height; P.bitDepth = L.geom.bitDepth; P.ctuSize = L.geom.ctuSize; P.chroma = L.geom.chromaFormat == 1;
   P.pus = L.pus; P.dmvrMv = L.dmvrMv; P.tiles = L.tiles; P.meta = L.meta;
+  P.lmcs = L.lmcs; P.lmcsLog2 = 0; { int o = (1 << L.geom.bitDepth) / 16; while ((1 << (P.lmcsLog2 + 1)) <= o) P.lmcsLog2++; }
   int launched = 0;
   if (prof) prof->begin(B200_KF_MC_TILE, ss.main);
   for (int m = 3; m >= 0; m--) for (int k = 3; k >= 0; k--) {      // heaviest lists first (DMVR 16x16 ... uni 8x4)

@@ -157,7 +157,7 @@ __device__ __forceinline__ void filter_chroma(const Line& L, int16_t* s, int off
 }
 
 template <int DIR>   // 0: vertical edges (filter across x), 1: horizontal edges (filter across y)
-__global__ void __launch_bounds__(256) lf_kernel(const LfParams P, const LfSliceTab T)
+__global__ void __launch_bounds__(256, 3) lf_kernel(const LfParams P, const LfSliceTab T)
 {
   const int x4 = blockIdx.x * 32 + threadIdx.x, y4 = blockIdx.y * 8 + threadIdx.y;
   if (x4 >= P.W4 || y4 >= P.H4) return;

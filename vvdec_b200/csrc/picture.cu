@@ -18,6 +18,7 @@ struct Arena {
   const b200_sao_ctu* sao = nullptr; b200_vb vb;
   const b200_alf_ctu* alf = nullptr; const int16_t *lumaCoeff = nullptr, *lumaClip = nullptr, *chromaCoeff = nullptr, *chromaClip = nullptr, *cc[2] = {nullptr, nullptr};
   int32_t* dmvrMv = nullptr; size_t numDmvr = 0;
+  const b200_lmcs* lmcs = nullptr; const int16_t* lmcsInv = nullptr; const b200_lmcs_vpdu* lmcsVpdus = nullptr; int* lmcsScale = nullptr; bool lmcsChromaAdj = false;
   int16_t* given[3] = {nullptr, nullptr, nullptr};
   int dstSlot = 0, flags = 0;
   bool valid = false;
@@ -133,6 +134,7 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   B200_CHECK(!(p->flags & B200_PIC_SAO) || p->sao, "b200_pic_upload: SAO data missing");
   B200_CHECK(!(p->flags & B200_PIC_ALF) || (p->alf && p->alfTabs && p->alfTabs->numLumaSets >= 16), "b200_pic_upload: ALF data missing");
   B200_CHECK(p->numPus < (1u << 26) && p->numTus < (1u << 31), "b200_pic_upload: too many records");
+  B200_CHECK(!(p->flags & B200_PIC_LMCS) || (p->lmcs && p->lmcs->invLUT && (!p->lmcs->chromaAdj || p->lmcs->vpdus) && p->lmcs->orgCW == (1 << c->g.bitDepth) / 16), "b200_pic_upload: LMCS data missing or inconsistent");
   B200_CUDA(cudaSetDevice(c->device));
   const int ai = c->nextArena; c->nextArena = (c->nextArena + 1) % c->numArenas;
   Arena& A = c->arenas[ai];
@@ -154,6 +156,9 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   const size_t oSao = take((p->flags & B200_PIC_SAO) ? nCtu * sizeof(b200_sao_ctu) : 0);
   const size_t oAlf = take((p->flags & B200_PIC_ALF) ? nCtu * sizeof(b200_alf_ctu) : 0), oTab = take((2 * nL + 2 * nC + n0 + n1) * 2);
   const size_t oDm = take(p->numDmvr * 8);
+  const bool lm = p->flags & B200_PIC_LMCS;
+  const int vs = g.ctuSize == 128 ? 64 : g.ctuSize; const size_t nVpdu = (size_t)((g.width + vs - 1) / vs) * ((g.height + vs - 1) / vs);
+  const size_t oLm = take(lm ? sizeof(b200_lmcs) : 0), oLmLut = take(lm ? sizeof(int16_t) << g.bitDepth : 0), oLmVp = take(lm ? nVpdu * sizeof(b200_lmcs_vpdu) : 0), oLmSc = take(lm ? nVpdu * sizeof(int) : 0);
   const bool hasGiven = p->given[0] != nullptr;
   const size_t oGiven = take(hasGiven ? c->picBytes : 0);
   if (off > A.buf.cap) { B200_CUDA(cudaStreamSynchronize(c->stream)); B200_CUDA(cudaStreamSynchronize(c->upStream)); A.donePending = false; }   // realloc: nothing may still use the old buffer
@@ -185,6 +190,13 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
     if (int rc = up(T->ccCoeff[0], n0, A.cc[0])) return rc;
     if (int rc = up(T->ccCoeff[1], n1, A.cc[1])) return rc;
   }
+  if (lm) {
+    if (int rc = h2d(oLm, p->lmcs, sizeof(b200_lmcs))) return rc;
+    if (int rc = h2d(oLmLut, p->lmcs->invLUT, sizeof(int16_t) << g.bitDepth)) return rc;
+    if (p->lmcs->chromaAdj) if (int rc = h2d(oLmVp, p->lmcs->vpdus, nVpdu * sizeof(b200_lmcs_vpdu))) return rc;
+    A.lmcs = reinterpret_cast<const b200_lmcs*>(base + oLm); A.lmcsInv = reinterpret_cast<const int16_t*>(base + oLmLut);
+    A.lmcsVpdus = reinterpret_cast<const b200_lmcs_vpdu*>(base + oLmVp); A.lmcsScale = reinterpret_cast<int*>(base + oLmSc); A.lmcsChromaAdj = p->lmcs->chromaAdj != 0;
+  } else { A.lmcs = nullptr; A.lmcsChromaAdj = false; }
   if (hasGiven) {
     size_t o = oGiven;
     for (int k = 0; k < (g.chromaFormat ? 3 : 1); k++) {
@@ -240,18 +252,29 @@ B200_API int b200_pic_run(b200_ctx* c, int ai)
     McLaunch L; L.geom = g; L.dst = P; memset(L.refs, 0, sizeof(L.refs));
     for (int sl = 0; sl < c->numSlots; sl++) { DevPlanes d = c->planes(c->slotBuf[sl]); for (int k = 0; k < 3; k++) L.refs[sl * 3 + k] = d.p[k]; }
     for (int k = 0; k < 3; k++) L.refStride[k] = g.stride[k];
-    L.pus = A.pus; L.tiles = A.tiles; L.meta = A.mcMeta; L.dmvrMv = A.dmvrMv;
+    L.pus = A.pus; L.tiles = A.tiles; L.meta = A.mcMeta; L.dmvrMv = A.dmvrMv; L.lmcs = A.lmcs;
     for (int l = 0; l < MC_LISTS; l++) L.cnt[l] = A.hMeta[LM_CNT + l];
     if (int rc = launch_mc(L, c->ss, c->profiling ? &c->prof : nullptr)) return rc;
     c->launches += mc_launch_count(L);
   }
-  // 2. K1 residual + reco
+  // 2. K1 residual + reco.  With LMCS chroma scaling: luma TUs, the per-VPDU scale from the reconstructed luma, then the chroma TUs.
+  LmcsLaunch LM; LM.geom = g; LM.planes = P; LM.lmcs = A.lmcs; LM.vpdus = A.lmcsVpdus; LM.invLut = A.lmcsInv; LM.scale = A.lmcsScale;
   if (A.numTus) {
     K1Launch L; L.geom = g; L.planes = P; L.tus = A.tus; L.numTus = A.numTus; L.idx = A.tuIdx; L.meta = A.tuMeta; L.coefs = A.coefs; L.scaling = A.scaling; L.mode = 0;
     for (int l = 0; l < K1_LISTS; l++) L.cnt[l] = A.hMeta[LM_INTS + LM_CNT + l];
-    if (int rc = launch_k1_residual(L, c->ss, c->profiling ? &c->prof : nullptr)) return rc;
-    c->launches += k1_launch_count(L);
+    if (A.lmcs && A.lmcsChromaAdj) {
+      L.compSel = 1;
+      if (int rc = launch_k1_residual(L, c->ss, c->profiling ? &c->prof : nullptr)) return rc;
+      if (int rc = launch_lmcs_vpdu(LM, s)) return rc;
+      L.compSel = 2; L.vpduScale = A.lmcsScale;
+      if (int rc = launch_k1_residual(L, c->ss, c->profiling ? &c->prof : nullptr)) return rc;
+      c->launches += 2 * k1_launch_count(L) + 1;
+    } else {
+      if (int rc = launch_k1_residual(L, c->ss, c->profiling ? &c->prof : nullptr)) return rc;
+      c->launches += k1_launch_count(L);
+    }
   }
+  if (A.lmcs) { if (int rc = launch_lmcs_inv(LM, s)) return rc; c->launches += 1; }   // RSP stage (DecLibRecon.cpp:935)
   // 3. K3 deblocking
   if (A.flags & B200_PIC_DEBLOCK) {
     LfLaunch L; L.geom = g; L.planes = P; L.lfV = A.lfV; L.lfH = A.lfH; L.ctuSlice = A.ctuSlice; L.slices = A.lfSlices; L.seq = A.lfSeq; L.dirs = 3;

@@ -345,8 +345,64 @@ def gen_pus(rng, cus, W, H, p_inter=1.0, p_bi=0.6, p_dmvr=0.35, p_bdof=0.35, p_a
     return pus, dmvr_off
 
 
+LMCS_VPDU_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("availLeft", "u1"), ("availAbove", "u1")])
+
+
+def lmcs_tables(bit_depth, min_bin, max_bin, delta_cw, chr_offset):
+    """Reshape::constructReshaper (reference CommonLib/Reshape.cpp:317-373) restated for the generator: code-word deltas of the LMCS
+    APS -> pivots, forward scale, chroma-scale LUT, inverse LUT.  tests/test_lmcs_oracle_vs_ref.py checks it against the real class."""
+    FP = 11
+    n = 1 << bit_depth; org = n // 16; l2 = org.bit_length() - 1
+    bin_cw = [0] * 16
+    for i in range(min_bin, max_bin + 1): bin_cw[i] = delta_cw[i] + org
+    piv = [0] * 17; inp = [0] * 17; fwd = [0] * 16; inv = [0] * 16; cadj = [1 << FP] * 16
+    for i in range(16):
+        piv[i + 1] = piv[i] + bin_cw[i]; inp[i + 1] = inp[i] + org
+        fwd[i] = (bin_cw[i] * (1 << FP) + (1 << (l2 - 1))) >> l2
+        if bin_cw[i]:
+            inv[i] = org * (1 << FP) // bin_cw[i]; cadj[i] = org * (1 << FP) // (bin_cw[i] + chr_offset)
+    lut = np.zeros(n, np.int16)
+    for v in range(n):
+        idx = min_bin
+        while idx <= max_bin and not v < piv[idx + 1]: idx += 1
+        idx = min(idx, 15)
+        lut[v] = min(max(inp[idx] + ((inv[idx] * (v - piv[idx]) + (1 << (FP - 1))) >> FP), 0), n - 1)
+    return dict(orgCW=org, reshapePivot=piv, inputPivot=inp, fwdScaleCoef=fwd, chromaAdjHelpLUT=cadj, invLUT=lut)
+
+
+def gen_lmcs(rng, bit_depth, cus, W, H, ctu, chroma_adj=True):
+    """A legal random LMCS model (code words are multiples of 1 << (bd-5), so the pivot constraint of Reshape.cpp:355-363 holds) and the
+    per-VPDU records: position of the CU covering each VPDU's top-left sample, neighbours available inside the picture (one slice, one tile)."""
+    from . import abi as A
+    import ctypes as C
+    org = (1 << bit_depth) // 16; step = 1 << (bit_depth - 5)
+    min_bin = int(rng.integers(0, 3)); max_bin = int(rng.integers(12, 16))
+    while True:
+        cw = rng.integers(1, 5, size=16) * step            # 0.5x .. 2x of the identity code word
+        if int(cw[min_bin:max_bin + 1].sum()) <= (1 << bit_depth) - 1: break
+    delta = [int(cw[i]) - org if min_bin <= i <= max_bin else 0 for i in range(16)]
+    # lmcsCW[i] + lmcsDeltaCrs must stay in [OrgCW >> 3, (OrgCW << 3) - 1] (Reshape.cpp:332-333)
+    chr_off = int(rng.integers(max(-7, (org >> 3) - int(cw[min_bin:max_bin + 1].min())), 8)) if chroma_adj else 0
+    t = lmcs_tables(bit_depth, min_bin, max_bin, delta, chr_off)
+    vs = 64 if ctu == 128 else ctu
+    vW, vH = (W + vs - 1) // vs, (H + vs - 1) // vs
+    # CU lookup on the 4x4 grid
+    owner = np.zeros(((H + 3) // 4, (W + 3) // 4), np.int32)
+    for i, (x, y, w, h) in enumerate(cus): owner[y // 4:(y + h) // 4, x // 4:(x + w) // 4] = i
+    vp = np.zeros(vW * vH, LMCS_VPDU_DTYPE)
+    for j in range(vH):
+        for i in range(vW):
+            x, y, w, h = cus[owner[j * vs // 4, i * vs // 4]]
+            vp[j * vW + i] = (x, y, x > 0, y > 0)
+    L = A.Lmcs(); L.chromaAdj = int(chroma_adj); L.minBinIdx = min_bin; L.maxBinIdx = max_bin; L.orgCW = t["orgCW"]
+    for i in range(17): L.reshapePivot[i] = t["reshapePivot"][i]; L.inputPivot[i] = t["inputPivot"][i]
+    for i in range(16): L.fwdScaleCoef[i] = t["fwdScaleCoef"][i]; L.chromaAdjHelpLUT[i] = t["chromaAdjHelpLUT"][i]
+    L.invLUT = t["invLUT"].ctypes.data; L.vpdus = vp.ctypes.data
+    return dict(struct=L, invLUT=t["invLUT"], vpdus=vp, minBin=min_bin, maxBin=max_bin, delta=delta, chrOff=chr_off, tables=t)
+
+
 def gen_picture(rng, W, H, bit_depth=10, ctu=128, dst_slot=0, cu_kw=None, pu_kw=None, tu_kw=None, sao_p=0.4, alf_kw=None,
-                deblock=True, sao=True, alf=True):
+                deblock=True, sao=True, alf=True, lmcs=False, lmcs_chroma=True):
     """One synthetic post-parse picture: partition -> inter PUs (all CUs inter: intra-coded samples would
     be 'given' pixels) -> TUs/levels -> deblocking grids -> SAO / ALF CTU parameters.
     Returns a dict of numpy arrays (kept alive by the caller) plus `struct`, the abi.Picture that points into them."""
@@ -372,5 +428,8 @@ def gen_picture(rng, W, H, bit_depth=10, ctu=128, dst_slot=0, cu_kw=None, pu_kw=
         d["alf"] = gen_alf(rng, W, H, ctu, bit_depth, **(alf_kw or {}))
         d["alfTabs"] = A.make_alf_tables(d["alf"])
         p.flags |= A.PIC_ALF; p.alf = d["alf"]["ctus"].ctypes.data; p.alfTabs = C.addressof(d["alfTabs"])
+    if lmcs:
+        d["lmcs"] = gen_lmcs(rng, bit_depth, cus, W, H, ctu, chroma_adj=lmcs_chroma)
+        p.flags |= A.PIC_LMCS; p.lmcs = C.addressof(d["lmcs"]["struct"])
     d["struct"] = p
     return d
