@@ -312,6 +312,15 @@ B200_API int  b200_get_frame(b200_ctx* ctx, int slot, int16_t* const planes[3]);
  * b200_frame_wait(ticket) blocks until those planes are complete in host memory (pinned memory recommended). */
 B200_API int  b200_get_frame_async(b200_ctx* ctx, int slot, int16_t* const planes[3]);
 B200_API int  b200_frame_wait(b200_ctx* ctx, int ticket);
+/* Output formats of the application layer, converted on the device before the D2H copy:
+ *   B200_OUT_16    int16 planes, stride = geometry stride (what vvdecFrame carries for bit depths > 8)
+ *   B200_OUT_PYUV  4 samples in 5 bytes, rows back to back, W*5/4 bytes per row — the `.pyuv` / --pyuv writer of vvdecapp
+ *                  (App/vvdecapp/vvdecHelper.h:106-150); 10-bit only, width divisible by 8 (vvdecapp.cpp:1179)
+ *   B200_OUT_8     one byte per sample, sample >> (bitDepth - 8), rows back to back (vvdecHelper.h:75-104)
+ * planes[c] must hold b200_frame_bytes(g, fmt, c) bytes.  Returns a ticket for b200_frame_wait, like b200_get_frame_async. */
+enum { B200_OUT_16 = 0, B200_OUT_PYUV = 1, B200_OUT_8 = 2 };
+B200_API size_t b200_frame_bytes(const b200_geom* g, int fmt, int comp);
+B200_API int  b200_get_frame_fmt_async(b200_ctx* ctx, int slot, int fmt, void* const planes[3]);
 /* Timing helpers for bench.py: CUDA events on the context stream. */
 B200_API int  b200_ctx_mark(b200_ctx* ctx, int which /*0 start, 1 stop*/);
 B200_API int  b200_ctx_elapsed_ms(b200_ctx* ctx, float* ms);

@@ -36,6 +36,16 @@
 #include "CommonLib/LoopFilter.h"
 #include "CommonLib/SampleAdaptiveOffset.h"
 #include "CommonLib/Reshape.h"
+#include <assert.h>
+#include <fstream>
+#include <chrono>
+#include <ctime>
+#include <iomanip>
+#include "vvdec/vvdec.h"
+#include "MD5.h"
+namespace b200_ref_app {      // the application's static helpers (plane writers); every header they include is already in
+#include "vvdecHelper.h"
+}
 #include "CommonLib/AdaptiveLoopFilter.h"
 #include "CommonLib/RdCost.h"
 #include <chrono>
@@ -608,6 +618,20 @@ extern "C" int ref_mc_predict( int simd, const b200_geom* g, int16_t* const dst[
     }
   }
   return rc;
+}
+
+// ================================================================================================ output writer of vvdecapp
+extern "C" size_t ref_write_component( const int16_t* src, ptrdiff_t stride, int w, int h, int fmt, uint8_t* dst, size_t cap )
+{
+  vvdecPlane pl; memset( &pl, 0, sizeof( pl ) );
+  // vvdecPlane::stride is in bytes (vvdec.h:459) and the pyuv loop halves it (:128); the 8-bit loop adds it to an unsigned short* (:93), i.e.
+  // walks it as samples — feed each branch the unit its pointer arithmetic uses
+  pl.ptr = (unsigned char*) src; pl.width = w; pl.height = h; pl.stride = (uint32_t) ( fmt == 2 ? stride : stride * 2 ); pl.bytesPerSample = 2;
+  std::ostringstream os;
+  b200_ref_app::_writeComponentToFile( &os, &pl, nullptr, fmt == 2 ? 1 : 2, fmt == 1 );
+  const std::string out = os.str();
+  memcpy( dst, out.data(), std::min( cap, out.size() ) );
+  return out.size();
 }
 
 // ================================================================================================ LMCS (Reshape)

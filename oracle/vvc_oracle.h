@@ -59,6 +59,12 @@ void orc_k1_residual_lmcs(const b200_geom* g, int16_t* const planes[3], const b2
 /* Reshape.cpp:377 rspCtuBcw over the whole luma plane (Buffer.cpp:200 applyLutCore). */
 void orc_lmcs_inv_plane(const b200_geom* g, int16_t* luma, const b200_lmcs* L);
 
+/* ---- output formats (App/vvdecapp/vvdecHelper.h:63 _writeComponentToFile) ---------------------------------------- */
+/* :115-128 packed yuv: 4 samples -> 5 bytes per group, rows back to back (w * 5 / 4 bytes). */
+void orc_pack_pyuv(const int16_t* src, ptrdiff_t stride, int w, int h, uint8_t* dst);
+/* :86-93 8-bit narrowing (the writer's >> 2 for 10 bit; >> (bitDepth - 8) in general). */
+void orc_narrow8(const int16_t* src, ptrdiff_t stride, int w, int h, int bitDepth, uint8_t* dst);
+
 /* ---- K3 deblocking -------------------------------------------------------------------------- */
 /* LoopFilter.cpp:213 xPelFilterLumaCore (4 lines). */
 void orc_lf_pel_filter_luma(int16_t* src, ptrdiff_t step, ptrdiff_t offset, int tc, int sw, int thrCut,

@@ -43,6 +43,9 @@ def load_oracle():
     lib.orc_lmcs_scale_resi.argtypes = [C.c_int] * 3
     lib.orc_k1_residual_lmcs.argtypes = [C.POINTER(abi.Geom), PL, V, C.c_size_t, i16p, V, LP]
     lib.orc_lmcs_inv_plane.argtypes = [C.POINTER(abi.Geom), i16p, LP]
+    u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+    lib.orc_pack_pyuv.argtypes = [i16p, C.c_ssize_t, C.c_int, C.c_int, u8p]
+    lib.orc_narrow8.argtypes = [i16p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, u8p]
     return lib
 
 
@@ -78,6 +81,8 @@ def load_ref():
     lib.ref_alf_picture.argtypes = [C.c_int, C.POINTER(abi.Geom), PL, PL, V, C.POINTER(abi.AlfTables)]
     lib.ref_mc_predict.argtypes = [C.c_int, C.POINTER(abi.Geom), PL, C.POINTER(C.c_void_p), V, C.c_size_t, V, C.c_size_t]
     lib.ref_mc_predict.restype = C.c_int
+    lib.ref_write_component.argtypes = [i16p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS"), C.c_size_t]
+    lib.ref_write_component.restype = C.c_size_t
     lib.ref_lmcs_build.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(abi.Lmcs), i16p]
     lib.ref_lmcs_fwd_block.argtypes = [C.c_int, V, C.c_ssize_t, C.c_int, C.c_int]
     lib.ref_lmcs_inv_block.argtypes = [C.c_int, V, C.c_ssize_t, C.c_int, C.c_int]

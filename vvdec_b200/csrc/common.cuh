@@ -151,6 +151,8 @@ struct LmcsLaunch { b200_geom geom; DevPlanes planes; const b200_lmcs* lmcs; con
 int launch_lmcs_vpdu(const LmcsLaunch& L, cudaStream_t s);   // per-VPDU chroma residual scale from the reconstructed (mapped) luma
 int launch_lmcs_inv(const LmcsLaunch& L, cudaStream_t s);    // inverse map of the luma plane, in place
 
+int launch_pack(const DevPlanes& src, const b200_geom& g, int fmt, uint8_t* const dst[3], cudaStream_t s);   // output.cu: pyuv / 8-bit conversion
+
 int ensure_device();   // selects device 0 if none current; fails loudly when there is no sm_100 GPU
 
 }  // namespace b200

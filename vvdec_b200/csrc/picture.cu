@@ -46,6 +46,7 @@ struct b200_ctx {
   cudaEvent_t ev[2] = {nullptr, nullptr};
   std::vector<cudaEvent_t> readDone; std::vector<char> readPending;   // per picture buffer: an async D2H is (maybe) still reading it
   cudaEvent_t ticketEv[16]; cudaEvent_t finalEv = nullptr; int nextTicket = 0;
+  DevBuf outStage[2]; int nextStage = 0;   // converted output frames (pyuv / 8 bit) waiting for their D2H copy
   size_t planeBytes[3] = {0, 0, 0}, picBytes = 0;
   std::vector<int16_t*> bufs;          // numSlots + 2 picture buffers
   std::vector<int> slotBuf;            // slot -> buffer index
@@ -344,6 +345,42 @@ B200_API int b200_get_frame_async(b200_ctx* c, int slot, int16_t* const planes[3
   for (int k = 0; k < (c->g.chromaFormat ? 3 : 1); k++)
     B200_CUDA(cudaMemcpyAsync(planes[k], d.p[k], (size_t)c->g.stride[k] * (k ? c->g.height >> 1 : c->g.height) * 2, cudaMemcpyDeviceToHost, c->copyStream));
   B200_CUDA(cudaEventRecord(c->readDone[buf], c->copyStream)); c->readPending[buf] = 1;
+  const int t = c->nextTicket; c->nextTicket = (c->nextTicket + 1) & 15;
+  B200_CUDA(cudaEventRecord(c->ticketEv[t], c->copyStream));
+  return t;
+}
+
+B200_API size_t b200_frame_bytes(const b200_geom* g, int fmt, int comp)
+{
+  if (!g || comp < 0 || comp > 2 || (comp && !g->chromaFormat)) return 0;
+  const size_t W = comp ? g->width >> 1 : g->width, H = comp ? g->height >> 1 : g->height;
+  if (fmt == B200_OUT_PYUV) return W / 4 * 5 * H;
+  if (fmt == B200_OUT_8) return W * H;
+  return (size_t)g->stride[comp] * H * 2;
+}
+
+B200_API int b200_get_frame_fmt_async(b200_ctx* c, int slot, int fmt, void* const planes[3])
+{
+  B200_CHECK(c && planes && slot >= 0 && slot < c->numSlots, "b200_get_frame_fmt_async: bad argument");
+  if (fmt == B200_OUT_16) { int16_t* const p16[3] = {(int16_t*)planes[0], (int16_t*)planes[1], (int16_t*)planes[2]}; return b200_get_frame_async(c, slot, p16); }
+  B200_CHECK(fmt == B200_OUT_PYUV || fmt == B200_OUT_8, "b200_get_frame_fmt_async: unknown format %d", fmt);
+  if (fmt == B200_OUT_PYUV && (c->g.bitDepth != 10 || (c->g.width & 7))) { set_error("b200_get_frame_fmt_async: pyuv needs 10 bit and a width divisible by 8 (as vvdecapp)"); return B200_ERR_UNSUPPORTED; }
+  B200_CUDA(cudaSetDevice(c->device));
+  const int nPl = c->g.chromaFormat ? 3 : 1;
+  size_t bytes[3] = {0, 0, 0}, off[3] = {0, 0, 0}, total = 0;
+  for (int k = 0; k < nPl; k++) { bytes[k] = b200_frame_bytes(&c->g, fmt, k); off[k] = total; total += (bytes[k] + 255) & ~(size_t)255; }
+  const int st = c->nextStage; c->nextStage ^= 1;
+  if (total > c->outStage[st].cap) B200_CUDA(cudaStreamSynchronize(c->copyStream));          // growing: no copy may still read the old block
+  if (int rc = c->outStage[st].reserve(total)) return rc;
+  const int buf = c->slotBuf[slot];
+  DevPlanes d = c->planes(buf);
+  B200_CUDA(cudaEventRecord(c->finalEv, c->stream));
+  B200_CUDA(cudaStreamWaitEvent(c->copyStream, c->finalEv, 0));
+  uint8_t* dst[3]; for (int k = 0; k < 3; k++) dst[k] = c->outStage[st].as<uint8_t>() + off[k];
+  if (int rc = launch_pack(d, c->g, fmt, dst, c->copyStream)) return rc;                      // on the copy stream: the kernel stream runs on
+  c->launches += nPl;
+  B200_CUDA(cudaEventRecord(c->readDone[buf], c->copyStream)); c->readPending[buf] = 1;       // the picture buffer is free once it is packed
+  for (int k = 0; k < nPl; k++) B200_CUDA(cudaMemcpyAsync(planes[k], dst[k], bytes[k], cudaMemcpyDeviceToHost, c->copyStream));
   const int t = c->nextTicket; c->nextTicket = (c->nextTicket + 1) & 15;
   B200_CUDA(cudaEventRecord(c->ticketEv[t], c->copyStream));
   return t;
