@@ -33,6 +33,14 @@ struct McParams {
   const b200_lmcs* lmcs; int lmcsLog2;       // LMCS: luma predictions are stored forward-mapped (DecCu.cpp:458-476); null = off
 };
 
+// asynchronous 4-byte global -> shared copies (LDGSTS): a tile issues its whole footprint without waiting on any load, then waits once
+__device__ __forceinline__ void cp_async4(void* smemDst, const void* gmemSrc)
+{
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(d), "l"(gmemSrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 // final luma prediction sample -> what is stored (identity without LMCS)
 #define LUMA_OUT(v) (P.lmcs ? lmcs_fwd(P.lmcs, P.lmcsLog2, (v), pmax) : (v))
 
@@ -200,7 +208,7 @@ __device__ __forceinline__ void mc_tile(const McParams& P, const uint32_t tile, 
           uint32_t* dst = reinterpret_cast<uint32_t*>(S.w[li]) + (warp * 2 + half) * (WS >> 1) + wl;
           if (wl < (WS >> 1))
 #pragma unroll 4
-            for (int y = warp * 2 + half; y < th + 7; y += nw * 2) { *dst = __ldg(src); src += (size_t)(nw * 2) * rw; dst += nw * 2 * (WS >> 1); }
+            for (int y = warp * 2 + half; y < th + 7; y += nw * 2) { cp_async4(dst, src); src += (size_t)(nw * 2) * rw; dst += nw * 2 * (WS >> 1); }
         }
         cofs[li] = (icx[li] - 1) & 1;
         if (chroma) {
@@ -209,7 +217,7 @@ __device__ __forceinline__ void mc_tile(const McParams& P, const uint32_t tile, 
           for (int q = warp; q < 2 * npc; q += nw) {
             const int c = q >= npc, y = ((c ? q - npc : q) << 2) + sub;
             if (y < ch + 3 && wl < (CS >> 1))
-              reinterpret_cast<uint32_t*>(c ? S.cw[li][1] : S.cw[li][0])[y * (CS >> 1) + wl] = __ldg(reinterpret_cast<const uint32_t*>((c ? rp[li][2] : rp[li][1]) + cbase) + (size_t)y * rwc + wl);
+              cp_async4(reinterpret_cast<uint32_t*>(c ? S.cw[li][1] : S.cw[li][0]) + y * (CS >> 1) + wl, reinterpret_cast<const uint32_t*>((c ? rp[li][2] : rp[li][1]) + cbase) + (size_t)y * rwc + wl);
           }
         }
         braw[li] = S.w[li] + WS + wofs[li] + 1;
@@ -248,6 +256,7 @@ __device__ __forceinline__ void mc_tile(const McParams& P, const uint32_t tile, 
         }
     }
     if (tid < 25) sSad[tid] = 0;
+    cp_async_wait_all();
     __syncthreads();
     {
       // bilinear interpolation to 10 bit (filterN2_2D, InterpolationFilter.cpp:1133): one thread per (list, column) walks down the rows
@@ -386,7 +395,7 @@ __device__ __forceinline__ void mc_tile(const McParams& P, const uint32_t tile, 
         uint32_t* dst = reinterpret_cast<uint32_t*>(S.w[li]) + (warp * 2 + half) * (WS >> 1) + wl;
         if (wl < (WS >> 1))
 #pragma unroll 4
-          for (int y = warp * 2 + half; y < th + 7; y += nw * 2) { *dst = __ldg(src); src += (size_t)(nw * 2) * rw; dst += nw * 2 * (WS >> 1); }
+          for (int y = warp * 2 + half; y < th + 7; y += nw * 2) { cp_async4(dst, src); src += (size_t)(nw * 2) * rw; dst += nw * 2 * (WS >> 1); }
       } else {
         const int xlo = MODE == 3 ? clip3(0, W - 1, wx0[li][0]) : 0, xhi = MODE == 3 ? clip3(0, W - 1, wx1[li][0]) : W - 1;
         const int ylo = MODE == 3 ? clip3(0, H - 1, wy0[li][0]) : 0, yhi = MODE == 3 ? clip3(0, H - 1, wy1[li][0]) : H - 1;
@@ -406,7 +415,7 @@ __device__ __forceinline__ void mc_tile(const McParams& P, const uint32_t tile, 
           for (int q = warp; q < 2 * npc; q += nw) {
             const int c = q >= npc, y = ((c ? q - npc : q) << 2) + sub;
             if (y < ch + 3 && wl < (CS >> 1))
-              reinterpret_cast<uint32_t*>(c ? S.cw[li][1] : S.cw[li][0])[y * (CS >> 1) + wl] = __ldg(reinterpret_cast<const uint32_t*>((c ? rp[li][2] : rp[li][1]) + cbase) + (size_t)y * rwc + wl);
+              cp_async4(reinterpret_cast<uint32_t*>(c ? S.cw[li][1] : S.cw[li][0]) + y * (CS >> 1) + wl, reinterpret_cast<const uint32_t*>((c ? rp[li][2] : rp[li][1]) + cbase) + (size_t)y * rwc + wl);
           }
         } else {
           // both chroma components: lanes 0..15 Cb, 16..31 Cr (cw+3 <= 11)
@@ -423,6 +432,7 @@ __device__ __forceinline__ void mc_tile(const McParams& P, const uint32_t tile, 
       }
     }
   }
+  cp_async_wait_all();
   __syncthreads();
 
   // ================================================================ stage B: horizontal filters

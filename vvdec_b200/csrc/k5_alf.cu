@@ -26,6 +26,12 @@ struct AlfParams {
   const int16_t *lumaCoeff, *lumaClip, *chromaCoeff, *chromaClip, *cc0, *cc1;
 };
 
+__device__ __forceinline__ void cp_async8(void* smemDst, const void* gmemSrc)   // asynchronous 8-byte global -> shared copy (LDGSTS)
+{
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(d), "l"(gmemSrc));
+}
+
 __device__ __forceinline__ int clipd(int c, int ref, int a, int b) { return clip3(-c, c, a - ref) + clip3(-c, c, b - ref); }
 
 __global__ void __launch_bounds__(256) alf_luma_kernel(const AlfParams P)
@@ -51,8 +57,9 @@ __global__ void __launch_bounds__(256) alf_luma_kernel(const AlfParams P)
     const int16_t* s0 = P.src[0] + (size_t)(by0 - HALO) * stride + bx0 - HALO;      // interior tile: 40 rows x 10 8-byte words
     for (int i = tid; i < TS * (TS / 4); i += 256) {
       const int ty = i / (TS / 4), c = i - ty * (TS / 4);
-      *reinterpret_cast<uint2*>(&t[ty][c * 4]) = __ldg(reinterpret_cast<const uint2*>(s0 + (size_t)ty * stride) + c);
+      cp_async8(&t[ty][c * 4], reinterpret_cast<const uint2*>(s0 + (size_t)ty * stride) + c);
     }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
   } else {
     for (int i = tid; i < TS * TS; i += 256) {
       const int ty = i / TS, tx = i - ty * TS;
