@@ -217,16 +217,31 @@ typedef struct b200_pu {
   int8_t   bcwW1;           /* weight of list 1 out of 8 (g_BcwWeights[g_BcwInternBcw[BcwIdx]]); 4 = plain average */
   int8_t   refSlot[2];      /* DPB slot of the reference picture per list; -1: list unused                         */
   uint8_t  interDir;        /* cu.interDir() (1 L0, 2 L1, 3 bi) — used by the affine spread check                  */
-  uint8_t  rsv;
+  uint8_t  wpIdx;           /* explicit weighted prediction: 1-based index into the picture's b200_wp table, 0 = none */
   uint32_t dmvrOff;         /* cu.mvdL0SubPuOff                                                                    */
   int32_t  mv[2][2];        /* [list][hor,ver] in 1/16 sample, as in cu.mv[list][0] (NOT clipped: kernels apply clipMvInPic) */
   int32_t  cpmv[2][2][2];   /* [list][1|2][hor,ver]: cu.mv[list][1], cu.mv[list][2] (affine only)                  */
 } b200_pu;                  /* 64 bytes */
 
+/* Explicit weighted prediction (reference CommonLib/WeightPrediction.cpp): one entry per (refIdx0, refIdx1) combination in use = what
+ * WeightPrediction::getWpScaling (:67-147) returns for it.  Applies to translational and affine PUs without BDOF / DMVR / BCW
+ * (InterPrediction.cpp:733-741: B slices with pps_weighted_bipred and BcwIdx == default, P slices with pps_weighted_pred).
+ *   bi  (addWeightBi  :164): clip((w0*(P0+8192) + w1*(P1+8192) + (1 << s >> 1) + offset * (1 << (s-1))) >> s),  s = shift + max(2, 14-bd)
+ *   uni (addWeightUni :238): clip(((w0*(P+8192) + (s ? 1 << (s-1) : 0)) >> s) + offset) */
+typedef struct b200_wp {
+  int16_t w0[3], w1[3];     /* per component; uni-prediction: w0 is the weight of the list in use                         */
+  int16_t offset[3];        /* bi: o0 + o1, uni: o — iOffset << (bitDepth - 8)                                          */
+  uint8_t shift[3];         /* bi: log2WeightDenom + 1, uni: log2WeightDenom                                            */
+  uint8_t rsv[3];
+} b200_wp;                  /* 24 bytes */
+
 /* Kernel-level K2 on host planes: refs[slot*3 + comp] are the reference pictures (same geometry as g), dst the current
  * picture (only PU areas are written).  dmvrMv: int32 [n][2] (hor,ver deltas, Mv layout of m_dmvrMvCache), may be NULL. */
 B200_API int b200_mc_predict(const b200_geom* g, int16_t* const dst[3], const int16_t* const* refs, int numSlots,
                              const b200_pu* pus, size_t numPus, int32_t* dmvrMv, size_t numDmvr);
+/* the same with an explicit-weighted-prediction table (wp may be NULL when no PU has wpIdx != 0) */
+B200_API int b200_mc_predict_wp(const b200_geom* g, int16_t* const dst[3], const int16_t* const* refs, int numSlots,
+                                const b200_pu* pus, size_t numPus, int32_t* dmvrMv, size_t numDmvr, const b200_wp* wp, int numWp);
 
 /* ------------------------------------------------------------------------------------------------
  * Picture level: the DecLibRecon seam (reference DecoderLib/DecLibRecon.h:184-191, .cpp:429 decompressPicture,
@@ -278,6 +293,7 @@ typedef struct b200_picture {
   const b200_vb* vb;
   const b200_alf_ctu* alf;               /* K5 (B200_PIC_ALF) */
   const b200_alf_tables* alfTabs;
+  const b200_wp* wp; int32_t numWp;      /* explicit weighted prediction entries referenced by b200_pu::wpIdx, or NULL / 0 */
   const b200_lmcs* lmcs;                 /* B200_PIC_LMCS: every slice of the picture has LMCS on and all CUs are inter
                                             (samples in `given` must already be in the mapped domain)                  */
 } b200_picture;

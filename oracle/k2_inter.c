@@ -82,6 +82,19 @@ static void average(const int16_t* a, const int16_t* b, int w, int h, int sstrid
   }
 }
 
+/* explicit weighted prediction: addWeightBi (WeightPrediction.cpp:164-236, via wghtAvg = addWeightedAvgCore) / addWeightUni (:238-331);
+ * a, b: 14-bit intermediates (b == NULL: uni-prediction) */
+static void weighted(const int16_t* a, const int16_t* b, int w, int h, int sstride, int bd, const b200_wp* e, int comp, int16_t* d, int ds)
+{
+  const int pmax = (1 << bd) - 1, shiftNum = 14 - bd < 2 ? 2 : 14 - bd, shift = e->shift[comp] + shiftNum;
+  for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+    int v;
+    if (b) v = (e->w0[comp] * (a[y * sstride + x] + IF_OFFS) + e->w1[comp] * (b[y * sstride + x] + IF_OFFS) + ((1 << shift) >> 1) + e->offset[comp] * (1 << (shift - 1))) >> shift;
+    else   v = ((e->w0[comp] * (a[y * sstride + x] + IF_OFFS) + (shift > 0 ? 1 << (shift - 1) : 0)) >> shift) + e->offset[comp];
+    d[y * ds + x] = (int16_t)clip3(0, pmax, v);
+  }
+}
+
 /* ---- BDOF: xPredInterBlk bio tail (:847-885) + applyBiOptFlow (:1290) + gradFilterCore<true> (:212) + BiOptFlowCore (:162) ---- */
 static inline int shift_msb(int numer, int denom) { int m = 0; while (m < 32 && denom >= (1 << m)) m++; return numer >> (m - 1); }   /* rightShiftMSB :92 */
 
@@ -394,6 +407,11 @@ static void affine_list(const b200_geom* g, const b200_pu* pu, int l, const Plan
 /* ---- PU driver (motionCompensation :1372) ---- */
 void orc_mc_predict(const b200_geom* g, int16_t* const dst[3], const int16_t* const* refs, const b200_pu* pus, size_t numPus, int32_t* dmvrMv)
 {
+  orc_mc_predict_wp(g, dst, refs, pus, numPus, dmvrMv, NULL);
+}
+
+void orc_mc_predict_wp(const b200_geom* g, int16_t* const dst[3], const int16_t* const* refs, const b200_pu* pus, size_t numPus, int32_t* dmvrMv, const b200_wp* wp)
+{
   const int nComp = g->chromaFormat ? 3 : 1, bd = g->bitDepth;
   int16_t* tmp[2][3];
   for (int l = 0; l < 2; l++) for (int c = 0; c < 3; c++) tmp[l][c] = (int16_t*)malloc(130 * 130 * 2);
@@ -407,17 +425,33 @@ void orc_mc_predict(const b200_geom* g, int16_t* const dst[3], const int16_t* co
     int16_t* d[3]; for (int c = 0; c < nComp; c++) d[c] = dst[c] + (size_t)(pu->y >> (c ? 1 : 0)) * g->stride[c] + (pu->x >> (c ? 1 : 0));
     if (pu->flags & B200_PU_DMVR) { dmvr_pu(g, pu, R[0], R[1], dst, dmvrMv); continue; }
     if (pu->flags & B200_PU_AFFINE) {
-      if (!bi) { const int l = pu->refSlot[0] >= 0 ? 0 : 1; affine_list(g, pu, l, R[l], 0, d, g->stride); continue; }
+      const b200_wp* we = (wp && pu->wpIdx) ? &wp[pu->wpIdx - 1] : NULL;
       const int os[3] = { pu->w, pu->w >> 1, pu->w >> 1 };
+      if (!bi) {
+        const int l = pu->refSlot[0] >= 0 ? 0 : 1;
+        if (!we) { affine_list(g, pu, l, R[l], 0, d, g->stride); continue; }
+        affine_list(g, pu, l, R[l], 1, tmp[0], os);                      /* xPredInterUni(bi = true) + xWeightedPredictionBi/Uni (InterPrediction.cpp:707-741) */
+        for (int c = 0; c < nComp; c++) weighted(tmp[0][c], NULL, pu->w >> (c ? 1 : 0), pu->h >> (c ? 1 : 0), os[c], bd, we, c, d[c], g->stride[c]);
+        continue;
+      }
       affine_list(g, pu, 0, R[0], 1, tmp[0], os); affine_list(g, pu, 1, R[1], 1, tmp[1], os);
-      for (int c = 0; c < nComp; c++) average(tmp[0][c], tmp[1][c], pu->w >> (c ? 1 : 0), pu->h >> (c ? 1 : 0), os[c], bd, pu->bcwW1, d[c], g->stride[c]);
+      for (int c = 0; c < nComp; c++) {
+        if (we) weighted(tmp[0][c], tmp[1][c], pu->w >> (c ? 1 : 0), pu->h >> (c ? 1 : 0), os[c], bd, we, c, d[c], g->stride[c]);
+        else    average(tmp[0][c], tmp[1][c], pu->w >> (c ? 1 : 0), pu->h >> (c ? 1 : 0), os[c], bd, pu->bcwW1, d[c], g->stride[c]);
+      }
       continue;
     }
     int mv[2][2];
     for (int l = 0; l < 2; l++) { mv[l][0] = pu->mv[l][0]; mv[l][1] = pu->mv[l][1]; clip_mv(mv[l], pu->x, pu->y, g); }
+    const b200_wp* we = (wp && pu->wpIdx) ? &wp[pu->wpIdx - 1] : NULL;
     if (!bi) {
       const int l = pu->refSlot[0] >= 0 ? 0 : 1;
-      for (int c = 0; c < nComp; c++) pred_block(g, &R[l][c], c, pu->x, pu->y, pu->w, pu->h, mv[l], altHpel, 1, d[c], g->stride[c]);
+      for (int c = 0; c < nComp; c++) {
+        if (!we) { pred_block(g, &R[l][c], c, pu->x, pu->y, pu->w, pu->h, mv[l], altHpel, 1, d[c], g->stride[c]); continue; }
+        const int sw = pu->w >> (c ? 1 : 0), sh = pu->h >> (c ? 1 : 0);
+        pred_block(g, &R[l][c], c, pu->x, pu->y, pu->w, pu->h, mv[l], altHpel, 0, tmp[0][c], sw);
+        weighted(tmp[0][c], NULL, sw, sh, sw, bd, we, c, d[c], g->stride[c]);
+      }
       continue;
     }
     if (pu->flags & B200_PU_BDOF) {                                       /* xSubPuBio :551: <=16x16 sub-blocks, MV clipped relative to the CU */
@@ -439,7 +473,8 @@ void orc_mc_predict(const b200_geom* g, int16_t* const dst[3], const int16_t* co
       const int sw = pu->w >> (c ? 1 : 0), sh = pu->h >> (c ? 1 : 0);
       pred_block(g, &R[0][c], c, pu->x, pu->y, pu->w, pu->h, mv[0], altHpel, 0, tmp[0][c], sw);
       pred_block(g, &R[1][c], c, pu->x, pu->y, pu->w, pu->h, mv[1], altHpel, 0, tmp[1][c], sw);
-      average(tmp[0][c], tmp[1][c], sw, sh, sw, bd, pu->bcwW1, d[c], g->stride[c]);
+      if (we) weighted(tmp[0][c], tmp[1][c], sw, sh, sw, bd, we, c, d[c], g->stride[c]);
+      else    average(tmp[0][c], tmp[1][c], sw, sh, sw, bd, pu->bcwW1, d[c], g->stride[c]);
     }
   }
   for (int l = 0; l < 2; l++) for (int c = 0; c < 3; c++) free(tmp[l][c]);

@@ -534,6 +534,21 @@ extern "C" int ref_alf_picture( int simd, const b200_geom* g, const int16_t* con
 }
 
 // ------------------------------------------------------------------------------------------------ K2
+static const int32_t* g_refWpRaw = nullptr;
+extern "C" void ref_set_wp( const int32_t* raw ) { g_refWpRaw = raw; }
+static void applyWp( FakePicture& cur, Slice* sl )
+{
+  cur.pps->setWPBiPred( g_refWpRaw != nullptr );
+  if( !g_refWpRaw ) return;
+  for( int l = 0; l < 2; l++ ) for( int i = 0; i < 2; i++ ) for( int c = 0; c < 3; c++ )
+  {
+    const int32_t* r = g_refWpRaw + ( ( l * 2 + i ) * 3 + c ) * 3;
+    WPScalingParam& w = sl->m_weightPredTable[l][i][c];
+    w.uiLog2WeightDenom = r[0]; w.iWeight = r[1]; w.iOffset = r[2];
+    w.bPresentFlag = r[1] != ( 1 << r[0] ) || r[2] != 0;
+  }
+}
+
 extern "C" int ref_mc_predict( int simd, const b200_geom* g, int16_t* const dst[3], const int16_t* const* refs, const b200_pu* pus, size_t numPus,
                                int32_t* dmvrMv, size_t numDmvr )
 {
@@ -562,6 +577,7 @@ extern "C" int ref_mc_predict( int simd, const b200_geom* g, int16_t* const dst[
   }
   sl->setNumRefIdx( REF_PIC_LIST_0, 2 ); sl->setNumRefIdx( REF_PIC_LIST_1, 2 );
   sl->resetWpScaling();
+  applyWp( cur, sl );
 
   std::vector<MotionInfo> motion( (size_t) pcv.num4x4CtuBlks * pcv.sizeInCtus );
   std::vector<Mv> dmvrCache( (size_t) pcv.num8x8CtuBlks * pcv.sizeInCtus + 16 );
@@ -865,6 +881,7 @@ extern "C" double ref_decompress_picture_out( const b200_geom* g, const int16_t*
   { sl->m_apcRefPicList[l][i] = &ref[l * 2 + i]->pic; sl->m_aiRefPOCList[l][i] = pocs[l * 2 + i]; sl->m_bIsUsedAsLongTerm[l][i] = false; ref[l * 2 + i]->pic.poc = pocs[l * 2 + i]; }
   sl->setNumRefIdx( REF_PIC_LIST_0, 2 ); sl->setNumRefIdx( REF_PIC_LIST_1, 2 );
   sl->resetWpScaling();
+  applyWp( cur, sl );
   { SliceMap sm; sm.addCtusToSlice( 0, pcv.widthInCtus, 0, pcv.heightInCtus, pcv.widthInCtus ); sl->setSliceMap( sm ); }
   std::vector<MotionInfo> motion( (size_t) pcv.num4x4CtuBlks * pcv.sizeInCtus );
   std::vector<Mv> dmvrCache( std::max<size_t>( pic->numDmvr + 64, (size_t) pcv.num8x8CtuBlks * pcv.sizeInCtus ) );

@@ -96,6 +96,9 @@ int ref_mc_predict(int simd, const b200_geom* g, int16_t* const dst[3], const in
  * of one picture is included (every picture is extended once when it becomes a reference, DecLibRecon.cpp:236).
  * Returns the seconds spent in the timed part (setup of the fake vvdec objects excluded); out (may be NULL) receives the picture. */
 double ref_decompress_picture_mt(const b200_geom* g, const int16_t* const* refs, const b200_picture* pic, int threads, int simd);
+/* Explicit weighted prediction for the following ref_mc_predict / ref_decompress_picture_* calls: raw[list][refIdx][comp][3] =
+ * (log2WeightDenom, iWeight, iOffset) as parsed into Slice::m_weightPredTable (pps_weighted_bipred on); NULL switches it off. */
+void ref_set_wp(const int32_t* raw);
 /* The application's plane writer (App/vvdecapp/vvdecHelper.h:63 _writeComponentToFile) into a memory stream: fmt 1 = pyuv, 2 = 8 bit. Returns bytes written. */
 size_t ref_write_component(const int16_t* src, ptrdiff_t stride, int w, int h, int fmt, uint8_t* dst, size_t cap);
 /* LMCS through the real Reshape class (CommonLib/Reshape.cpp) and the PelBufferOps pointers it dispatches to.

@@ -103,6 +103,8 @@ void orc_alf_picture(const b200_geom* g, const int16_t* const src[3], int16_t* c
 /* InterPrediction.cpp:1372 motionCompensation for a list of PUs (regular uni/bi, BCW, BDOF, DMVR, affine + PROF).
  * refs[slot*3+comp]; reference samples outside the picture are read with clamped coordinates (== border extension). */
 void orc_mc_predict(const b200_geom* g, int16_t* const dst[3], const int16_t* const* refs, const b200_pu* pus, size_t numPus, int32_t* dmvrMv);
+/* the same with explicit weighted prediction (WeightPrediction.cpp:164 addWeightBi, :238 addWeightUni) for PUs with wpIdx != 0 */
+void orc_mc_predict_wp(const b200_geom* g, int16_t* const dst[3], const int16_t* const* refs, const b200_pu* pus, size_t numPus, int32_t* dmvrMv, const b200_wp* wp);
 
 #ifdef __cplusplus
 }

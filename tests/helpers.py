@@ -36,6 +36,7 @@ def load_oracle():
     lib.orc_alf_ccalf_blk.argtypes = [V, C.c_ssize_t, V, C.c_ssize_t] + [C.c_int] * 4 + [V] + [C.c_int] * 3
     lib.orc_alf_picture.argtypes = [C.POINTER(abi.Geom), PL, PL, V, C.POINTER(abi.AlfTables)]
     lib.orc_mc_predict.argtypes = [C.POINTER(abi.Geom), PL, C.POINTER(C.c_void_p), V, C.c_size_t, V]
+    lib.orc_mc_predict_wp.argtypes = [C.POINTER(abi.Geom), PL, C.POINTER(C.c_void_p), V, C.c_size_t, V, V]
     LP = C.POINTER(abi.Lmcs)
     lib.orc_lmcs_fwd_block.argtypes = [V, C.c_ssize_t, C.c_int, C.c_int, C.c_int, LP]
     lib.orc_lmcs_fwd_pus.argtypes = [C.POINTER(abi.Geom), i16p, V, C.c_size_t, LP]
@@ -81,6 +82,7 @@ def load_ref():
     lib.ref_alf_picture.argtypes = [C.c_int, C.POINTER(abi.Geom), PL, PL, V, C.POINTER(abi.AlfTables)]
     lib.ref_mc_predict.argtypes = [C.c_int, C.POINTER(abi.Geom), PL, C.POINTER(C.c_void_p), V, C.c_size_t, V, C.c_size_t]
     lib.ref_mc_predict.restype = C.c_int
+    lib.ref_set_wp.argtypes = [C.c_void_p]
     lib.ref_write_component.argtypes = [i16p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS"), C.c_size_t]
     lib.ref_write_component.restype = C.c_size_t
     lib.ref_lmcs_build.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(abi.Lmcs), i16p]
@@ -128,7 +130,8 @@ def oracle_decompress(oracle, g, dpb, pic):
     cur = [np.zeros((H, W), np.int16), np.zeros((H // 2, W // 2), np.int16), np.zeros((H // 2, W // 2), np.int16)]
     dm = np.zeros((pic["ndmvr"] + 1, 2), np.int32)
     st = pic["struct"]
-    oracle.orc_mc_predict(C.byref(g), abi.plane_ptrs(cur), ref_ptrs(dpb), pic["pus"].ctypes.data, len(pic["pus"]), dm.ctypes.data)
+    oracle.orc_mc_predict_wp(C.byref(g), abi.plane_ptrs(cur), ref_ptrs(dpb), pic["pus"].ctypes.data, len(pic["pus"]), dm.ctypes.data,
+                             pic["wp"].ctypes.data if "wp" in pic else None)
     if st.flags & abi.PIC_LMCS:
         # DecCu.cpp:458-476 forward map of every inter CU's luma prediction; :483 finishLMCSAndReco; DecLibRecon.cpp:935 inverse map
         L = C.byref(pic["lmcs"]["struct"])

@@ -71,3 +71,31 @@ def test_mixed_pictures(oracle, ref, seed, W, H, bd, simd):
     # compiled out, InterpolationFilter.cpp:447-463), so the 12-bit case runs without DMVR.
     pus, nd, refs = _case(seed, W, H, bd, **({"p_dmvr": 0.0} if bd > 10 else {}))
     _compare(oracle, ref, simd, W, H, bd, pus, nd, refs)
+
+
+@pytest.mark.parametrize("simd", [0, 1])
+@pytest.mark.parametrize("bd", [8, 10])
+def test_explicit_weighted_prediction(oracle, ref, simd, bd):
+    """pps_weighted_bipred: the real xWeightedPredictionBi -> addWeightBi / addWeightUni (WeightPrediction.cpp) against the oracle's
+    `weighted`, for uni, bi, BCW (which bypasses WP) and affine (+PROF) CUs; the b200_wp entries come from the generator's restatement
+    of getWpScaling."""
+    W, H = 256, 128
+    for seed in (1, 2, 3):
+        pus, ndmvr, refs = _case(seed * 7 + bd, W, H, bd, p_dmvr=0.0, p_bdof=0.0, p_affine=0.2, p_bcw=0.3)
+        rng = np.random.default_rng(seed)
+        raw, ent = synth.gen_wp(rng, bd, pus)
+        assert (pus["wpIdx"] != 0).any() and (pus["wpIdx"] == 0).any()
+        g = abi.make_geom(W, H, bd)
+        a = [np.full((H, W), -1, np.int16), np.full((H // 2, W // 2), -1, np.int16), np.full((H // 2, W // 2), -1, np.int16)]
+        b = [p.copy() for p in a]
+        da = np.zeros((ndmvr + 1, 2), np.int32); db = np.zeros((ndmvr + 1, 2), np.int32)
+        rp = ref_ptrs(refs)
+        oracle.orc_mc_predict_wp(C.byref(g), abi.plane_ptrs(a), rp, pus.ctypes.data, len(pus), da.ctypes.data, ent.ctypes.data)
+        ref.ref_set_wp(raw.ctypes.data)
+        try:
+            rc = ref.ref_mc_predict(simd, C.byref(g), abi.plane_ptrs(b), rp, pus.ctypes.data, len(pus), db.ctypes.data, ndmvr)
+        finally:
+            ref.ref_set_wp(None)
+        assert rc == 0
+        for c in range(3):
+            assert np.array_equal(a[c], b[c]), f"plane {c}: {len(np.argwhere(a[c] != b[c]))} diffs"

@@ -102,3 +102,26 @@ def test_lmcs_picture(b200, oracle, W, H, ctu, chroma_adj):
             assert np.array_equal(dm, dm_want)
     finally:
         b200.b200_ctx_destroy(ctx)
+
+
+def test_weighted_prediction_picture(b200, oracle):
+    """Explicit weighted prediction at picture level (together with LMCS: the weighted luma is what gets forward-mapped)."""
+    W, H, bd = 832, 480, 10
+    rng = np.random.default_rng(31)
+    g = abi.make_geom(W, H, bd)
+    ctx = C.c_void_p()
+    vvdec_b200.check(b200.b200_ctx_create(C.byref(ctx), C.byref(g), 6, 2, -1))
+    try:
+        dpb = [synth.noise_planes(rng, W, H, bd) for _ in range(4)]
+        for s in range(4): vvdec_b200.check(b200.b200_ctx_load_slot(ctx, s, abi.plane_ptrs(dpb[s])))
+        for k, lm in enumerate((False, True)):
+            pic = synth.gen_picture(rng, W, H, bd, dst_slot=4 + k, wp=True, lmcs=lm, pu_kw=dict(p_dmvr=0.0, p_bdof=0.0, p_bcw=0.3))
+            want, _ = oracle_decompress(oracle, g, dpb, pic)
+            h = b200.b200_decompress_picture(ctx, C.byref(pic["struct"])); assert h >= 0, b200.b200_last_error()
+            vvdec_b200.check(b200.b200_wait_picture(ctx, h, None, 0))
+            got = [np.zeros_like(p) for p in want]
+            vvdec_b200.check(b200.b200_get_frame(ctx, 4 + k, abi.plane_ptrs(got)))
+            for c in range(3):
+                assert np.array_equal(want[c], got[c]), f"picture {k} plane {c}: {len(np.argwhere(want[c] != got[c]))} diffs"
+    finally:
+        b200.b200_ctx_destroy(ctx)

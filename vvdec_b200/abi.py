@@ -83,7 +83,7 @@ class Picture(C.Structure):
                 ("scaling", C.c_void_p), ("numScaling", C.c_size_t),
                 ("lfV", C.c_void_p), ("lfH", C.c_void_p), ("ctuSlice", C.c_void_p), ("lfSlices", C.c_void_p),
                 ("numLfSlices", C.c_int32), ("lfSeq", C.c_void_p),
-                ("sao", C.c_void_p), ("vb", C.c_void_p), ("alf", C.c_void_p), ("alfTabs", C.c_void_p), ("lmcs", C.c_void_p)]
+                ("sao", C.c_void_p), ("vb", C.c_void_p), ("alf", C.c_void_p), ("alfTabs", C.c_void_p), ("wp", C.c_void_p), ("numWp", C.c_int32), ("lmcs", C.c_void_p)]
 
 
 class LmcsVpdu(C.Structure):

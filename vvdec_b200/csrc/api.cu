@@ -222,6 +222,12 @@ B200_API int b200_alf_picture(const b200_geom* g, const int16_t* const src[3], i
 B200_API int b200_mc_predict(const b200_geom* g, int16_t* const dst[3], const int16_t* const* refs, int numSlots,
                              const b200_pu* pus, size_t numPus, int32_t* dmvrMv, size_t numDmvr)
 {
+  return b200_mc_predict_wp(g, dst, refs, numSlots, pus, numPus, dmvrMv, numDmvr, nullptr, 0);
+}
+
+B200_API int b200_mc_predict_wp(const b200_geom* g, int16_t* const dst[3], const int16_t* const* refs, int numSlots,
+                                const b200_pu* pus, size_t numPus, int32_t* dmvrMv, size_t numDmvr, const b200_wp* wp, int numWp)
+{
   B200_CHECK(g && dst && refs && (pus || !numPus), "b200_mc_predict: null argument");
   B200_CHECK(numSlots >= 1 && numSlots <= B200_MAX_SLOTS, "b200_mc_predict: numSlots %d", numSlots);
   B200_CHECK(numPus < (1u << 26), "b200_mc_predict: too many PUs");
@@ -254,8 +260,14 @@ B200_API int b200_mc_predict(const b200_geom* g, int16_t* const dst[3], const in
   if (int rc = g_hw.misc[7].reserve(numDmvr * 8 + 64)) return rc;
   if (numPus) B200_CUDA(cudaMemcpyAsync(g_hw.misc[5].p, pus, numPus * sizeof(b200_pu), cudaMemcpyHostToDevice, s));
   int* meta = g_hw.misc[6].as<int>(); uint32_t* tiles = reinterpret_cast<uint32_t*>(meta + LM_INTS);
-  if (int rc = launch_mc_bucket(g_hw.misc[5].as<b200_pu>(), numPus, tiles, capTiles, meta, numSlots, g->bitDepth, s)) return rc;
+  if (int rc = launch_mc_bucket(g_hw.misc[5].as<b200_pu>(), numPus, tiles, capTiles, meta, numSlots, g->bitDepth, wp ? numWp : 0, s)) return rc;
   L.tiles = tiles; L.meta = meta;
+  if (wp && numWp > 0) {
+    B200_CHECK(numWp <= 255, "b200_mc_predict_wp: at most 255 weighted-prediction entries");
+    if (int rc = g_hw.misc[2].reserve(numWp * sizeof(b200_wp))) return rc;
+    B200_CUDA(cudaMemcpyAsync(g_hw.misc[2].p, wp, numWp * sizeof(b200_wp), cudaMemcpyHostToDevice, s));
+    L.wp = g_hw.misc[2].as<b200_wp>();
+  }
   if (int rc = fetch_list_meta(meta, L.cnt, MC_LISTS, "b200_mc_predict", s)) return rc;
   B200_CUDA(cudaMemsetAsync(g_hw.misc[7].p, 0, numDmvr * 8 + 64, s));
   memset(L.refs, 0, sizeof(L.refs)); for (size_t i = 0; i < ptrs.size(); i++) L.refs[i] = ptrs[i];

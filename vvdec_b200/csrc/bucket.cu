@@ -18,11 +18,11 @@ __device__ __forceinline__ int mc_list_of(int w, int h, int flags, bool bi, int 
 }
 
 struct PuHead { int w, h, flags; bool bi, ok; };
-__device__ __forceinline__ PuHead pu_head(const b200_pu* pus, int i, int slotsBd)   // slotsBd = numSlots | bitDepth << 8
+__device__ __forceinline__ PuHead pu_head(const b200_pu* pus, int i, int slotsBd)   // slotsBd = numSlots | bitDepth << 8 | numWp << 16
 {
   const b200_pu& p = pus[i];
   PuHead r; r.w = p.w; r.h = p.h; r.flags = p.flags;
-  const int s0 = p.refSlot[0], s1 = p.refSlot[1], numSlots = slotsBd & 0xff, bitDepth = slotsBd >> 8;
+  const int s0 = p.refSlot[0], s1 = p.refSlot[1], numSlots = slotsBd & 0xff, bitDepth = (slotsBd >> 8) & 0xff, numWp = slotsBd >> 16;
   r.bi = s0 >= 0 && s1 >= 0;
   r.ok = s0 < numSlots && s1 < numSlots && (s0 >= 0 || s1 >= 0) && r.w >= 4 && r.h >= 4 && r.w <= 128 && r.h <= 128 && !(r.w & 3) && !(r.h & 3);
   // BDOF / DMVR blocks are at least 8x8 with 128 samples (conditions at InterPrediction.cpp:1372-1420); DMVR also needs both lists and
@@ -30,7 +30,10 @@ __device__ __forceinline__ PuHead pu_head(const b200_pu* pus, int i, int slotsBd
   const bool big = r.w >= 8 && r.h >= 8 && r.w * r.h >= 128, aff = r.flags & B200_PU_AFFINE;
   if ((r.flags & B200_PU_DMVR) && (!r.bi || !big || aff)) r.ok = false;
   if ((r.flags & B200_PU_BDOF) && r.bi && !aff && !big) r.ok = false;
-  if ((r.flags & B200_PU_DMVR) && bitDepth > 10) r.ok = false;   // DMVR is defined for bit depths <= 10 only (as in the reference)
+  if ((r.flags & B200_PU_DMVR) && bitDepth > 10) r.ok = false;
+  // explicit weights: the entry must exist; the reference never combines them with BDOF / DMVR / BCW (InterPrediction.cpp:733, :1406-1420)
+  const int wpIdx = p.wpIdx;
+  if (wpIdx && (wpIdx > numWp || (r.flags & B200_PU_DMVR) || ((r.flags & B200_PU_BDOF) && r.bi && !aff) || p.bcwW1 != 4)) r.ok = false;   // DMVR is defined for bit depths <= 10 only (as in the reference)
   return r;
 }
 
@@ -120,9 +123,9 @@ __global__ void __launch_bounds__(256) tu_scatter_kernel(const b200_tu* __restri
   if (ok) idx[base[c] + my] = (uint32_t)i;
 }
 
-int launch_mc_bucket(const b200_pu* pus, size_t numPus, uint32_t* tiles, size_t capTiles, int* meta, int numSlots, int bitDepth, cudaStream_t s)
+int launch_mc_bucket(const b200_pu* pus, size_t numPus, uint32_t* tiles, size_t capTiles, int* meta, int numSlots, int bitDepth, int numWp, cudaStream_t s)
 {
-  numSlots |= bitDepth << 8;
+  numSlots |= (bitDepth << 8) | (numWp << 16);
   B200_CUDA(cudaMemsetAsync(meta, 0, LM_INTS * sizeof(int), s));
   if (!numPus) return 0;
   const int grid = (int)((numPus + 255) / 256);

@@ -30,6 +30,7 @@ struct McParams {
   int fastOk;                                // plane strides are even -> rows are word-addressable
   const b200_pu* pus; const uint32_t* tiles; const int* meta;   // device lists (bucket.cu)
   int32_t* dmvrMv;
+  const b200_wp* wp;                         // explicit weighted prediction entries (b200_pu::wpIdx), or null
   const b200_lmcs* lmcs; int lmcsLog2;       // LMCS: luma predictions are stored forward-mapped (DecCu.cpp:458-476); null = off
 };
 
@@ -76,6 +77,18 @@ __device__ __forceinline__ int avg_bi(int p0, int p1, int w1, int hr, int pmax)
   if (w1 == 4) v = (p0 + p1 + (1 << hr) + 2 * IFO) >> (hr + 1);
   else         v = (p0 * (8 - w1) + p1 * w1 + (1 << (hr + 2)) + (IFO << 3)) >> (hr + 3);
   return clip3(0, pmax, v);
+}
+
+// explicit weighted prediction (WeightPrediction.cpp:164 addWeightBi / :238 addWeightUni) on 14-bit intermediates
+__device__ __forceinline__ int wp_uni(const b200_wp* e, int comp, int p, int hr, int pmax)
+{
+  const int s = e->shift[comp] + hr;
+  return clip3(0, pmax, ((e->w0[comp] * (p + IFO) + (s > 0 ? 1 << (s - 1) : 0)) >> s) + e->offset[comp]);
+}
+__device__ __forceinline__ int wp_bi(const b200_wp* e, int comp, int p0, int p1, int hr, int pmax)
+{
+  const int s = e->shift[comp] + hr;
+  return clip3(0, pmax, (e->w0[comp] * (p0 + IFO) + e->w1[comp] * (p1 + IFO) + ((1 << s) >> 1) + e->offset[comp] * (1 << (s - 1))) >> s);
 }
 
 __device__ __forceinline__ int shift_msb(int numer, int denom) { return numer >> (31 - __clz(denom)); }   // rightShiftMSB (:92), denom > 0
@@ -141,6 +154,7 @@ __device__ __forceinline__ void mc_tile(const McParams& P, const uint32_t tile, 
   constexpr int NL = BI ? 2 : 1;
   const int cw = tw >> 1, ch = th >> 1, l2cw = l2w - 1;
   const int chroma = P.chroma;
+  const b200_wp* we = (MODE <= 1 && P.wp && pu.wpIdx) ? P.wp + pu.wpIdx - 1 : nullptr;   // explicit weights (never with BDOF / DMVR)
   const int WS = tw + 8, CS = cw + 4;                        // window strides: even, so a row is a run of 32-bit words
 
   // ---- shared memory carve-up (strides depend on the tile shape) ----
@@ -505,7 +519,8 @@ __device__ __forceinline__ void mc_tile(const McParams& P, const uint32_t tile, 
 #pragma unroll
     for (int j = 0; j < OPT; j++) {
       int16_t* d = P.dst[0] + (size_t)(by + sy + j) * P.dstStride[0] + bx + sx;
-      if (!BI) *d = (int16_t)LUMA_OUT(clip3(0, pmax, (pr[0][j] + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr)));
+      if (MODE <= 1 && we) *d = (int16_t)LUMA_OUT(BI ? wp_bi(we, 0, (int16_t)(pr[0][j] >> 6), (int16_t)(pr[NL - 1][j] >> 6), hr, pmax) : wp_uni(we, 0, (int16_t)(pr[0][j] >> 6), hr, pmax));
+      else if (!BI) *d = (int16_t)LUMA_OUT(clip3(0, pmax, (pr[0][j] + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr)));
       else if (!bio) *d = (int16_t)LUMA_OUT(avg_bi((int16_t)(pr[0][j] >> 6), (int16_t)(pr[NL - 1][j] >> 6), MODE == 1 ? pu.bcwW1 : 4, hr, pmax));
       else { S.p[0][(sy + j + 1) * 18 + sx + 1] = (int16_t)(pr[0][j] >> 6); S.p[1][(sy + j + 1) * 18 + sx + 1] = (int16_t)(pr[NL - 1][j] >> 6); }
     }
@@ -522,7 +537,8 @@ __device__ __forceinline__ void mc_tile(const McParams& P, const uint32_t tile, 
         pr[li] = t[0] * s[0] + t[1] * s[CHS] + t[2] * s[2 * CHS] + t[3] * s[3 * CHS];
       }
       int16_t* d = (c ? P.dst[2] : P.dst[1]) + (size_t)((by >> 1) + y) * (c ? P.dstStride[2] : P.dstStride[1]) + (bx >> 1) + x;
-      if (!BI) *d = (int16_t)clip3(0, pmax, (pr[0] + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr));
+      if (MODE <= 1 && we) *d = (int16_t)(BI ? wp_bi(we, 1 + c, (int16_t)(pr[0] >> 6), (int16_t)(pr[NL - 1] >> 6), hr, pmax) : wp_uni(we, 1 + c, (int16_t)(pr[0] >> 6), hr, pmax));
+      else if (!BI) *d = (int16_t)clip3(0, pmax, (pr[0] + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr));
       else *d = (int16_t)avg_bi((int16_t)(pr[0] >> 6), (int16_t)(pr[NL - 1] >> 6), MODE == 1 ? pu.bcwW1 : 4, hr, pmax);
     }
   }
@@ -691,6 +707,7 @@ __device__ __forceinline__ void mc_affine_tile(const McParams& P, const uint32_t
   const int bx = pu.x + tx0, by = pu.y + ty0;
   const int bd = P.bitDepth, pmax = (1 << bd) - 1, hr = max(2, 14 - bd), sh1 = 6 - hr;
   const bool bi = pu.refSlot[0] >= 0 && pu.refSlot[1] >= 0;
+  const b200_wp* we = (P.wp && pu.wpIdx) ? P.wp + pu.wpIdx - 1 : nullptr;
   const int nList = bi ? 2 : 1, l0 = pu.refSlot[0] >= 0 ? 0 : 1;
   const int hMin = (-P.ctuSize - 8 - pu.x + 1) * 16, hMax = (P.W + 8 - pu.x - 1) * 16;
   const int vMin = (-P.ctuSize - 8 - pu.y + 1) * 16, vMax = (P.H + 8 - pu.y - 1) * 16;
@@ -745,7 +762,7 @@ __device__ __forceinline__ void mc_affine_tile(const McParams& P, const uint32_t
       }
       if (M[l].prof) sE[l][sb][(y + 1) * 6 + x + 1] = (int16_t)(s >> 6);
       else if (bi)   sP[l][0][(sby + y) * 16 + sbx + x] = (int16_t)(s >> 6);
-      else P.dst[0][(size_t)(by + sby + y) * P.dstStride[0] + bx + sbx + x] = (int16_t)LUMA_OUT(clip3(0, pmax, (s + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr)));
+      else P.dst[0][(size_t)(by + sby + y) * P.dstStride[0] + bx + sbx + x] = (int16_t)LUMA_OUT(we ? wp_uni(we, 0, (int16_t)(s >> 6), hr, pmax) : clip3(0, pmax, (s + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr)));
     }
     __syncwarp();
     if (sbValid && M[l].prof) {                              // gradFilterCore<false> :212 + applyPROFCore :61
@@ -762,7 +779,7 @@ __device__ __forceinline__ void mc_affine_tile(const McParams& P, const uint32_t
       const int dI = clip3(-lim, lim - 1, dh * gX + dv * gY);
       int v = (int16_t)(E[c] + dI);
       if (bi) sP[l][0][(sby + y) * 16 + sbx + x] = (int16_t)v;
-      else P.dst[0][(size_t)(by + sby + y) * P.dstStride[0] + bx + sbx + x] = (int16_t)LUMA_OUT(clip3(0, pmax, (int)(int16_t)((v + (1 << (hr - 1)) + IFO) >> hr)));
+      else P.dst[0][(size_t)(by + sby + y) * P.dstStride[0] + bx + sbx + x] = (int16_t)LUMA_OUT(we ? wp_uni(we, 0, v, hr, pmax) : clip3(0, pmax, (int)(int16_t)((v + (1 << (hr - 1)) + IFO) >> hr)));
     }
   }
 
@@ -802,18 +819,18 @@ __device__ __forceinline__ void mc_affine_tile(const McParams& P, const uint32_t
 #pragma unroll
       for (int t = 0; t < 4; t++) s += fv[t] * sCH[li][c - 1][cs][(y + t) * 4 + x];
       if (bi) sP[l][c][(csy + y) * 8 + csx + x] = (int16_t)(s >> 6);
-      else P.dst[c][(size_t)((by >> 1) + csy + y) * P.dstStride[c] + (bx >> 1) + csx + x] = (int16_t)clip3(0, pmax, (s + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr));
+      else P.dst[c][(size_t)((by >> 1) + csy + y) * P.dstStride[c] + (bx >> 1) + csx + x] = (int16_t)(we ? wp_uni(we, c, (int16_t)(s >> 6), hr, pmax) : clip3(0, pmax, (s + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr)));
     }
   }
   if (!bi) return;
   __syncthreads();
   {
     const int y = tid >> 4, x = tid & 15;
-    if (x < tw && y < th) P.dst[0][(size_t)(by + y) * P.dstStride[0] + bx + x] = (int16_t)LUMA_OUT(avg_bi(sP[0][0][y * 16 + x], sP[1][0][y * 16 + x], pu.bcwW1, hr, pmax));
+    if (x < tw && y < th) P.dst[0][(size_t)(by + y) * P.dstStride[0] + bx + x] = (int16_t)LUMA_OUT(we ? wp_bi(we, 0, sP[0][0][y * 16 + x], sP[1][0][y * 16 + x], hr, pmax) : avg_bi(sP[0][0][y * 16 + x], sP[1][0][y * 16 + x], pu.bcwW1, hr, pmax));
     if (P.chroma && tid < 128) {
       const int c = tid >> 6, j = tid & 63, yy = j >> 3, xx = j & 7;
       if (xx < (tw >> 1) && yy < (th >> 1))
-        P.dst[1 + c][(size_t)((by >> 1) + yy) * P.dstStride[1 + c] + (bx >> 1) + xx] = (int16_t)avg_bi(sP[0][1 + c][yy * 8 + xx], sP[1][1 + c][yy * 8 + xx], pu.bcwW1, hr, pmax);
+        P.dst[1 + c][(size_t)((by >> 1) + yy) * P.dstStride[1 + c] + (bx >> 1) + xx] = (int16_t)(we ? wp_bi(we, 1 + c, sP[0][1 + c][yy * 8 + xx], sP[1][1 + c][yy * 8 + xx], hr, pmax) : avg_bi(sP[0][1 + c][yy * 8 + xx], sP[1][1 + c][yy * 8 + xx], pu.bcwW1, hr, pmax));
     }
   }
 }
@@ -832,6 +849,7 @@ int launch_mc(const McLaunch& L, StreamSet& ss, KProf* prof)
   P.fastOk = !(L.refStride[0] & 1) && !(L.refStride[1] & 1) && !(L.refStride[2] & 1);
   P.W = L.geom.width; P.H = L.geom.height; P.bitDepth = L.geom.bitDepth; P.ctuSize = L.geom.ctuSize; P.chroma = L.geom.chromaFormat == 1;
   P.pus = L.pus; P.dmvrMv = L.dmvrMv; P.tiles = L.tiles; P.meta = L.meta;
+  P.wp = L.wp;
   P.lmcs = L.lmcs; P.lmcsLog2 = 0; { int o = (1 << L.geom.bitDepth) / 16; while ((1 << (P.lmcsLog2 + 1)) <= o) P.lmcsLog2++; }
   int launched = 0;
   if (prof) prof->begin(B200_KF_MC_TILE, ss.main);

@@ -18,6 +18,7 @@ struct Arena {
   const b200_sao_ctu* sao = nullptr; b200_vb vb;
   const b200_alf_ctu* alf = nullptr; const int16_t *lumaCoeff = nullptr, *lumaClip = nullptr, *chromaCoeff = nullptr, *chromaClip = nullptr, *cc[2] = {nullptr, nullptr};
   int32_t* dmvrMv = nullptr; size_t numDmvr = 0;
+  const b200_wp* wp = nullptr;
   const b200_lmcs* lmcs = nullptr; const int16_t* lmcsInv = nullptr; const b200_lmcs_vpdu* lmcsVpdus = nullptr; int* lmcsScale = nullptr; bool lmcsChromaAdj = false;
   int16_t* given[3] = {nullptr, nullptr, nullptr};
   int dstSlot = 0, flags = 0;
@@ -135,6 +136,7 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   B200_CHECK(!(p->flags & B200_PIC_SAO) || p->sao, "b200_pic_upload: SAO data missing");
   B200_CHECK(!(p->flags & B200_PIC_ALF) || (p->alf && p->alfTabs && p->alfTabs->numLumaSets >= 16), "b200_pic_upload: ALF data missing");
   B200_CHECK(p->numPus < (1u << 26) && p->numTus < (1u << 31), "b200_pic_upload: too many records");
+  B200_CHECK(p->numWp >= 0 && p->numWp <= 255 && (p->wp || !p->numWp), "b200_pic_upload: weighted-prediction table (at most 255 entries)");
   B200_CHECK(!(p->flags & B200_PIC_LMCS) || (p->lmcs && p->lmcs->invLUT && (!p->lmcs->chromaAdj || p->lmcs->vpdus) && p->lmcs->orgCW == (1 << c->g.bitDepth) / 16), "b200_pic_upload: LMCS data missing or inconsistent");
   B200_CUDA(cudaSetDevice(c->device));
   const int ai = c->nextArena; c->nextArena = (c->nextArena + 1) % c->numArenas;
@@ -157,6 +159,7 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   const size_t oSao = take((p->flags & B200_PIC_SAO) ? nCtu * sizeof(b200_sao_ctu) : 0);
   const size_t oAlf = take((p->flags & B200_PIC_ALF) ? nCtu * sizeof(b200_alf_ctu) : 0), oTab = take((2 * nL + 2 * nC + n0 + n1) * 2);
   const size_t oDm = take(p->numDmvr * 8);
+  const size_t oWp = take((size_t)p->numWp * sizeof(b200_wp));
   const bool lm = p->flags & B200_PIC_LMCS;
   const int vs = g.ctuSize == 128 ? 64 : g.ctuSize; const size_t nVpdu = (size_t)((g.width + vs - 1) / vs) * ((g.height + vs - 1) / vs);
   const size_t oLm = take(lm ? sizeof(b200_lmcs) : 0), oLmLut = take(lm ? sizeof(int16_t) << g.bitDepth : 0), oLmVp = take(lm ? nVpdu * sizeof(b200_lmcs_vpdu) : 0), oLmSc = take(lm ? nVpdu * sizeof(int) : 0);
@@ -191,6 +194,8 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
     if (int rc = up(T->ccCoeff[0], n0, A.cc[0])) return rc;
     if (int rc = up(T->ccCoeff[1], n1, A.cc[1])) return rc;
   }
+  if (int rc = h2d(oWp, p->wp, (size_t)p->numWp * sizeof(b200_wp))) return rc;
+  A.wp = p->numWp ? reinterpret_cast<const b200_wp*>(base + oWp) : nullptr;
   if (lm) {
     if (int rc = h2d(oLm, p->lmcs, sizeof(b200_lmcs))) return rc;
     if (int rc = h2d(oLmLut, p->lmcs->invLUT, sizeof(int16_t) << g.bitDepth)) return rc;
@@ -217,7 +222,7 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   A.dstSlot = p->dstSlot; A.flags = p->flags; A.valid = true;
   // work lists: validated and bucketed on the device, behind the copies
   A.mcMeta = reinterpret_cast<int*>(base + oMeta); A.tuMeta = A.mcMeta + LM_INTS;
-  if (int rc = launch_mc_bucket(reinterpret_cast<const b200_pu*>(base + oPus), p->numPus, reinterpret_cast<uint32_t*>(base + oT), capTiles, A.mcMeta, c->numSlots, g.bitDepth, s)) return rc;
+  if (int rc = launch_mc_bucket(reinterpret_cast<const b200_pu*>(base + oPus), p->numPus, reinterpret_cast<uint32_t*>(base + oT), capTiles, A.mcMeta, c->numSlots, g.bitDepth, p->numWp, s)) return rc;
   if (int rc = launch_tu_bucket(reinterpret_cast<const b200_tu*>(base + oTus), p->numTus, reinterpret_cast<uint32_t*>(base + oIdx), A.tuMeta, s)) return rc;
   A.tiles = reinterpret_cast<const uint32_t*>(base + oT); A.tuIdx = reinterpret_cast<const uint32_t*>(base + oIdx);
   c->launches += 4;
@@ -253,7 +258,7 @@ B200_API int b200_pic_run(b200_ctx* c, int ai)
     McLaunch L; L.geom = g; L.dst = P; memset(L.refs, 0, sizeof(L.refs));
     for (int sl = 0; sl < c->numSlots; sl++) { DevPlanes d = c->planes(c->slotBuf[sl]); for (int k = 0; k < 3; k++) L.refs[sl * 3 + k] = d.p[k]; }
     for (int k = 0; k < 3; k++) L.refStride[k] = g.stride[k];
-    L.pus = A.pus; L.tiles = A.tiles; L.meta = A.mcMeta; L.dmvrMv = A.dmvrMv; L.lmcs = A.lmcs;
+    L.pus = A.pus; L.tiles = A.tiles; L.meta = A.mcMeta; L.dmvrMv = A.dmvrMv; L.lmcs = A.lmcs; L.wp = A.wp;
     for (int l = 0; l < MC_LISTS; l++) L.cnt[l] = A.hMeta[LM_CNT + l];
     if (int rc = launch_mc(L, c->ss, c->profiling ? &c->prof : nullptr)) return rc;
     c->launches += mc_launch_count(L);

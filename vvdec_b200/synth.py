@@ -285,7 +285,7 @@ def gen_alf(rng, W, H, ctu=128, bit_depth=10, n_aps=2, n_chroma_alts=3, n_cc=(2,
 
 
 PU_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("w", "u1"), ("h", "u1"), ("flags", "u1"), ("bcwW1", "i1"), ("refSlot", "i1", (2,)),
-                     ("interDir", "u1"), ("rsv", "u1"), ("dmvrOff", "<u4"), ("mv", "<i4", (2, 2)), ("cpmv", "<i4", (2, 2, 2))])
+                     ("interDir", "u1"), ("wpIdx", "u1"), ("dmvrOff", "<u4"), ("mv", "<i4", (2, 2)), ("cpmv", "<i4", (2, 2, 2))])
 assert PU_DTYPE.itemsize == 64
 PU_BDOF, PU_DMVR, PU_ALTHPEL, PU_AFFINE, PU_AFFINE6, PU_PROF0, PU_PROF1 = 1, 2, 4, 8, 16, 32, 64
 
@@ -345,6 +345,45 @@ def gen_pus(rng, cus, W, H, p_inter=1.0, p_bi=0.6, p_dmvr=0.35, p_bdof=0.35, p_a
     return pus, dmvr_off
 
 
+WP_DTYPE = np.dtype([("w0", "<i2", (3,)), ("w1", "<i2", (3,)), ("offset", "<i2", (3,)), ("shift", "u1", (3,)), ("rsv", "u1", (3,))])
+assert WP_DTYPE.itemsize == 24
+
+
+def gen_wp(rng, bit_depth, pus):
+    """Explicit weighted prediction for a B picture with pps_weighted_bipred: random (log2WeightDenom, iWeight, iOffset) per
+    (list, refIdx, component) as a slice header carries them, the b200_wp entries WeightPrediction::getWpScaling (reference
+    WeightPrediction.cpp:67-147) derives for every (refIdx0, refIdx1) combination, and pus['wpIdx'] set for the PUs they apply to
+    (BcwIdx == default, InterPrediction.cpp:733).  Returns (raw int32 [2][2][3][3], entries)."""
+    raw = np.zeros((2, 2, 3, 3), np.int32)
+    den = [int(rng.integers(0, 8)), int(rng.integers(0, 8))]          # luma_log2_weight_denom, chroma
+    for l in range(2):
+        for i in range(2):
+            for c in range(3):
+                d = den[0] if c == 0 else den[1]
+                plain = rng.random() < 0.25
+                raw[l, i, c] = (d, (1 << d) if plain else (1 << d) + int(rng.integers(-128, 128)), 0 if plain else int(rng.integers(-128, 128)))
+    sc = 1 << (bit_depth - 8)
+    ent = np.zeros(8, WP_DTYPE); idx = {}
+    k = 0
+    for r0 in (-1, 0, 1):
+        for r1 in (-1, 0, 1):
+            if r0 < 0 and r1 < 0: continue
+            e = ent[k]
+            for c in range(3):
+                if r0 >= 0 and r1 >= 0:
+                    e["w0"][c] = raw[0, r0, c, 1]; e["w1"][c] = raw[1, r1, c, 1]
+                    e["offset"][c] = (raw[0, r0, c, 2] + raw[1, r1, c, 2]) * sc; e["shift"][c] = raw[0, r0, c, 0] + 1
+                else:
+                    l, r = (0, r0) if r0 >= 0 else (1, r1)
+                    e["w0"][c] = raw[l, r, c, 1]; e["offset"][c] = raw[l, r, c, 2] * sc; e["shift"][c] = raw[l, r, c, 0]
+            idx[(r0, r1)] = k + 1; k += 1
+    for p in pus:
+        r0 = -1 if p["refSlot"][0] < 0 else int(p["refSlot"][0]) & 1
+        r1 = -1 if p["refSlot"][1] < 0 else int(p["refSlot"][1]) & 1
+        p["wpIdx"] = idx[(r0, r1)] if p["bcwW1"] == 4 else 0
+    return raw, ent
+
+
 LMCS_VPDU_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("availLeft", "u1"), ("availAbove", "u1")])
 
 
@@ -402,7 +441,7 @@ def gen_lmcs(rng, bit_depth, cus, W, H, ctu, chroma_adj=True):
 
 
 def gen_picture(rng, W, H, bit_depth=10, ctu=128, dst_slot=0, cu_kw=None, pu_kw=None, tu_kw=None, sao_p=0.4, alf_kw=None,
-                deblock=True, sao=True, alf=True, lmcs=False, lmcs_chroma=True):
+                deblock=True, sao=True, alf=True, lmcs=False, lmcs_chroma=True, wp=False):
     """One synthetic post-parse picture: partition -> inter PUs (all CUs inter: intra-coded samples would
     be 'given' pixels) -> TUs/levels -> deblocking grids -> SAO / ALF CTU parameters.
     Returns a dict of numpy arrays (kept alive by the caller) plus `struct`, the abi.Picture that points into them."""
@@ -428,6 +467,9 @@ def gen_picture(rng, W, H, bit_depth=10, ctu=128, dst_slot=0, cu_kw=None, pu_kw=
         d["alf"] = gen_alf(rng, W, H, ctu, bit_depth, **(alf_kw or {}))
         d["alfTabs"] = A.make_alf_tables(d["alf"])
         p.flags |= A.PIC_ALF; p.alf = d["alf"]["ctus"].ctypes.data; p.alfTabs = C.addressof(d["alfTabs"])
+    if wp:   # explicit weighted prediction: such pictures carry no BDOF / DMVR PUs (pass pu_kw=dict(p_dmvr=0, p_bdof=0))
+        d["wpRaw"], d["wp"] = gen_wp(rng, bit_depth, pus)
+        p.wp = d["wp"].ctypes.data; p.numWp = len(d["wp"])
     if lmcs:
         d["lmcs"] = gen_lmcs(rng, bit_depth, cus, W, H, ctu, chroma_adj=lmcs_chroma)
         p.flags |= A.PIC_LMCS; p.lmcs = C.addressof(d["lmcs"]["struct"])
