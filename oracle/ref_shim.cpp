@@ -4,6 +4,7 @@
 // CPU baseline for bench.py.  Same construction trick as tests/vvdec_unit_test/vvdec_unit_test.cpp.
 #include "ref_shim.h"
 #include <mutex>
+#include <random>
 #include <memory>
 #include <cstring>
 #include <string>
@@ -36,6 +37,7 @@
 #include "CommonLib/LoopFilter.h"
 #include "CommonLib/SampleAdaptiveOffset.h"
 #include "CommonLib/Reshape.h"
+#include "../vvdec_b200/vvdec_glue/flatten_pu.h"
 #include <assert.h>
 #include <fstream>
 #include <chrono>
@@ -768,6 +770,88 @@ struct WorkerPool
   }
 };
 template<class F> static void parallelFor( int n, WorkerPool& pool, F f ) { pool.run( n, f ); }
+
+extern "C" int ref_flatten_pu_case( int simd, const b200_geom* g, const int16_t* const* refs, int altRefs, const ref_cu_syntax* cus, int numCus,
+                                    int16_t* const dst[3], b200_pu* recs, int capRecs, int32_t* dmvrMv, int numDmvr )
+{
+  FakePicture cur( *g, 1 );
+  std::unique_ptr<FakePicture> ref[4];
+  for( int s = 0; s < 4; s++ )
+  {
+    ref[s].reset( new FakePicture( *g, 1 ) );
+    int16_t* p3[3] = { (int16_t*) refs[s * 3], (int16_t*) refs[s * 3 + 1], (int16_t*) refs[s * 3 + 2] };
+    ref[s]->setPlanes( *g, p3 );
+    ref[s]->pic.extendPicBorder();
+  }
+  CodingStructure& cs = *cur.pic.cs;
+  const PreCalcValues& pcv = *cs.pcv;
+  SPS& sps = *cur.sps;
+  sps.setUseBIO( true ); sps.setUseDMVR( true ); sps.setUseBcw( true ); sps.setUseAffine( true ); sps.setUseAffineType( true ); sps.setUsePROF( true );
+  Slice* sl = cur.pic.slices[0];
+  sl->setSliceType( B_SLICE ); sl->setPOC( 8 );
+  const int slotOf[2][2] = { { 0, 1 }, { 2, altRefs ? 0 : 3 } }, pocOf[4] = { 4, 0, 12, 16 };
+  b200glue::SlotMap sm; memset( &sm, -1, sizeof( sm ) );
+  for( int s = 0; s < 4; s++ ) ref[s]->pic.poc = pocOf[s];
+  for( int l = 0; l < 2; l++ ) for( int i = 0; i < 2; i++ )
+  {
+    sl->m_apcRefPicList[l][i] = &ref[slotOf[l][i]]->pic; sl->m_aiRefPOCList[l][i] = pocOf[slotOf[l][i]]; sl->m_bIsUsedAsLongTerm[l][i] = false;
+    sm.slot[l][i] = (int8_t) slotOf[l][i];
+  }
+  sl->setNumRefIdx( REF_PIC_LIST_0, 2 ); sl->setNumRefIdx( REF_PIC_LIST_1, 2 );
+  sl->resetWpScaling();
+  applyWp( cur, sl );
+  std::vector<MotionInfo> motion( (size_t) pcv.num4x4CtuBlks * pcv.sizeInCtus );
+  std::vector<Mv> dmvrCache( (size_t) std::max<size_t>( numDmvr + 64, (size_t) pcv.num8x8CtuBlks * pcv.sizeInCtus + 16 ) );
+  for( unsigned a = 0; a < pcv.sizeInCtus; a++ ) cs.getCtuData( a ).motion = motion.data() + (size_t) a * pcv.num4x4CtuBlks;
+  cs.m_dmvrMvCache = dmvrCache.data();
+  static RdCost rdScalar( false ), rdSimd( true );
+  std::unique_ptr<InterPrediction> ip( new InterPrediction() );
+  ip->init( simd ? &rdSimd : &rdScalar, pcv.chrFormat, g->ctuSize, simd != 0 );
+  PelUnitBuf reco = cs.getRecoBuf();
+  // (refIdx0, refIdx1) -> 1-based b200_wp index, the order synth.gen_wp uses
+  auto wpIdxOf = []( int r0, int r1 ) { int k = 0; for( int a = -1; a <= 1; a++ ) for( int b = -1; b <= 1; b++ ) { if( a < 0 && b < 0 ) continue; k++; if( a == r0 && b == r1 ) return k; } return 0; };
+  int n = 0; uint32_t dmvrOff = 0;
+  for( int i = 0; i < numCus; i++ )
+  {
+    const ref_cu_syntax& c = cus[i];
+    const UnitArea ua( pcv.chrFormat, Area( c.x, c.y, c.w, c.h ) );
+    CodingUnit& cu = cs.addCU( ua, CH_L, TREE_D, MODE_TYPE_ALL, nullptr, nullptr );
+    cu.slice = sl; cu.pps = cur.pps.get(); cu.sps = cur.sps.get();
+    cu.setPredMode( MODE_INTER );
+    for( int l = 0; l < 2; l++ ) { cu.refIdx[l] = c.refIdx[l]; for( int k = 0; k < 3; k++ ) cu.mv[l][k] = Mv( c.mv[l][k][0], c.mv[l][k][1] ); }
+    cu.setInterDir( ( c.refIdx[0] >= 0 ? 1 : 0 ) + ( c.refIdx[1] >= 0 ? 2 : 0 ) );
+    cu.setImv( c.imvHpel ? IMV_HPEL : IMV_OFF );
+    cu.setBcwIdx( c.bcwIdx ); cu.setMergeFlag( c.mergeFlag ); cu.setMmvdFlag( c.mmvdFlag ); cu.setSmvdMode( c.smvd );
+    cu.setMergeType( c.sbTmvp ? MRG_TYPE_SUBPU_ATMVP : MRG_TYPE_DEFAULT_N );
+    cu.setAffineFlag( c.affine ); cu.setAffineType( c.affine6 ? AFFINEMODEL_6PARAM : AFFINEMODEL_4PARAM );
+    cu.mvdL0SubPuOff = dmvrOff;
+    if( c.w >= 8 && c.h >= 8 && c.w * c.h >= 128 ) dmvrOff += std::max( 1, c.w >> 4 ) * std::max( 1, c.h >> 4 );
+    if( c.affine ) { for( int l = 0; l < 2; l++ ) if( cu.refIdx[l] >= 0 ) PU::setAllAffineMv( cu, cu.mv[l][0], cu.mv[l][1], cu.mv[l][2], RefPicList( l ) ); }
+    else PU::spanMotionInfo( cu );
+    if( c.sbTmvp )
+    {
+      // seeded 8x8 motion field with few distinct candidates, so that runs of equal motion occur
+      std::mt19937 rng( c.sbSeed );
+      MotionInfo cand[3];
+      for( auto& m : cand ) { const int dir = 1 + rng() % 3; for( int l = 0; l < 2; l++ ) { m.miRefIdx[l] = ( dir >> l ) & 1 ? int8_t( rng() % 2 ) : int8_t( MI_NOT_VALID ); m.mv[l] = Mv( int( rng() % 257 ) - 128, int( rng() % 257 ) - 128 ); } }
+      for( int y = c.y; y < c.y + c.h; y += 8 ) for( int x = c.x; x < c.x + c.w; x += 8 )
+      {
+        const MotionInfo& m = cand[rng() % 3];
+        for( int yy = 0; yy < 8 && y + yy < c.y + c.h; yy += 4 ) for( int xx = 0; xx < 8 && x + xx < c.x + c.w; xx += 4 )
+          cs.getCtuData( cs.ctuRsAddr( Position( x + xx, y + yy ), CH_L ) ).motion[cs.inCtuPos( Position( x + xx, y + yy ), CH_L )] = m;
+      }
+    }
+    PelUnitBuf predBuf = reco.subBuf( ua );
+    ip->motionCompensation( cu, predBuf, true, true );
+    b200glue::FlattenPuResult rc = b200glue::FLATTEN_PU_OK;
+    if( c.sbTmvp ) rc = b200glue::flattenSbTmvp( cu, sm, wpIdxOf, [&]( const b200_pu& r ) { if( n < capRecs ) recs[n] = r; n++; } );
+    else { b200_pu r; rc = b200glue::flattenPU( cu, sm, wpIdxOf, r ); if( rc == b200glue::FLATTEN_PU_OK ) { if( n < capRecs ) recs[n] = r; n++; } }
+    if( rc != b200glue::FLATTEN_PU_OK ) return -1 - i;
+  }
+  cur.getPlanes( *g, dst );
+  if( dmvrMv ) for( int i = 0; i < numDmvr; i++ ) { dmvrMv[2 * i] = dmvrCache[i].hor; dmvrMv[2 * i + 1] = dmvrCache[i].ver; }
+  return n;
+}
 
 static void fillCuFromPu( CodingUnit& cu, const b200_pu& pu, FakePicture& cur, Slice* sl )
 {

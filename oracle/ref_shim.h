@@ -96,6 +96,19 @@ int ref_mc_predict(int simd, const b200_geom* g, int16_t* const dst[3], const in
  * of one picture is included (every picture is extended once when it becomes a reference, DecLibRecon.cpp:236).
  * Returns the seconds spent in the timed part (setup of the fake vvdec objects excluded); out (may be NULL) receives the picture. */
 double ref_decompress_picture_mt(const b200_geom* g, const int16_t* const* refs, const b200_picture* pic, int threads, int simd);
+/* Flattener pin (vvdec_b200/vvdec_glue/flatten_pu.h): builds real inter CodingUnits from the syntax below, runs the real
+ * InterPrediction::motionCompensation on each (prediction written to dst) and b200glue::flattenPU / flattenSbTmvp on the same CU.
+ * Reference lists: L0 = {slot 0 (POC 4), slot 1 (POC 0)}, L1 = {slot 2 (POC 12), slot 3 (POC 16) or, with altRefs, slot 0 again};
+ * current POC 8.  Returns the number of records written to `recs` (<= capRecs), or -1 - i if CU i was refused by the flattener. */
+typedef struct ref_cu_syntax {
+  int32_t x, y, w, h;
+  int32_t refIdx[2];
+  int32_t mv[2][3][2];            /* [list][cpmv 0..2][hor,ver], 1/16 sample */
+  int32_t affine, affine6, mergeFlag, mmvdFlag, smvd, bcwIdx, imvHpel;
+  int32_t sbTmvp, sbSeed;         /* MRG_TYPE_SUBPU_ATMVP with a seeded 8x8 motion field */
+} ref_cu_syntax;
+int ref_flatten_pu_case(int simd, const b200_geom* g, const int16_t* const* refs, int altRefs, const ref_cu_syntax* cus, int numCus,
+                        int16_t* const dst[3], b200_pu* recs, int capRecs, int32_t* dmvrMv, int numDmvr);
 /* Explicit weighted prediction for the following ref_mc_predict / ref_decompress_picture_* calls: raw[list][refIdx][comp][3] =
  * (log2WeightDenom, iWeight, iOffset) as parsed into Slice::m_weightPredTable (pps_weighted_bipred on); NULL switches it off. */
 void ref_set_wp(const int32_t* raw);

@@ -83,6 +83,7 @@ def load_ref():
     lib.ref_mc_predict.argtypes = [C.c_int, C.POINTER(abi.Geom), PL, C.POINTER(C.c_void_p), V, C.c_size_t, V, C.c_size_t]
     lib.ref_mc_predict.restype = C.c_int
     lib.ref_set_wp.argtypes = [C.c_void_p]
+    lib.ref_flatten_pu_case.argtypes = [C.c_int, C.POINTER(abi.Geom), C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, PL, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.ref_write_component.argtypes = [i16p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS"), C.c_size_t]
     lib.ref_write_component.restype = C.c_size_t
     lib.ref_lmcs_build.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(abi.Lmcs), i16p]
