@@ -207,7 +207,11 @@ enum {
   B200_PU_AFFINE  = 8,    /* cu.affineFlag(): mv = CPMV0, cpmv = CPMV1/2; sub-block MVs as PU::setAllAffineMv     */
   B200_PU_AFFINE6 = 16,   /* 6-parameter model (else 4-parameter)                                                 */
   B200_PU_PROF0   = 32,   /* PROF enabled for list 0 / 1 (sps PROF && !ph dis_prof; the kernel applies the CPMV-equality and */
-  B200_PU_PROF1   = 64    /* spread-over-limit exclusions of xPredAffineBlk :1036-1040 itself)                     */
+  B200_PU_PROF1   = 64,   /* spread-over-limit exclusions of xPredAffineBlk :1036-1040 itself)                     */
+  B200_PU_GEO     = 128   /* cu.geoFlag(): geometric partitioning (motionCompensationGeo :1461, xWeightedGeoBlk
+                             InterpolationFilter.cpp:1217).  refSlot[0]/mv[0] = partition 0 (interDirrefIdxGeo0, cu.mv[0][1]),
+                             refSlot[1]/mv[1] = partition 1 (interDirrefIdxGeo1, cu.mv[1][1]) — both set, whatever lists they
+                             come from; bcwW1 carries cu.geoSplitDir (0..63); w, h in 8..64                            */
 };
 
 typedef struct b200_pu {

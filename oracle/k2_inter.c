@@ -95,6 +95,24 @@ static void weighted(const int16_t* a, const int16_t* b, int w, int h, int sstri
   }
 }
 
+/* GEO blending (InterpolationFilter.cpp:1217 xWeightedGeoBlk): a = partition 0 (tmpGeoBuf0), b = partition 1, 14-bit intermediates */
+static void geo_blend(const int16_t* a, const int16_t* b, int w, int h, int sstride, int bd, int comp, int cuW, int cuH, int splitDir, int16_t* d, int ds)
+{
+  const int pmax = (1 << bd) - 1, shift = (14 - bd < 2 ? 2 : 14 - bd) + 3, offset = (1 << (shift - 1)) + (IF_OFFS << 3);
+  const int sc = comp ? 1 : 0, angle = kGeoParams[splitDir * 2];
+  int l2w = 0, l2h = 0; while ((1 << l2w) < cuW) l2w++; while ((1 << l2h) < cuH) l2h++;
+  const int16_t* wo = &kGeoWeightOffset[((splitDir * 4 + (l2h - 3)) * 4 + (l2w - 3)) * 2];
+  const uint8_t* M = &kGeoWeights[(size_t)kGeoAngle2Mask[angle] * VVC_GEO_MASK_SIZE * VVC_GEO_MASK_SIZE];
+  const int mir = kGeoAngle2Mirror[angle];
+  for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+    const int row = mir == 2 ? VVC_GEO_MASK_SIZE - 1 - wo[1] - (y << sc) : wo[1] + (y << sc);
+    const int col = mir == 1 ? VVC_GEO_MASK_SIZE - 1 - wo[0] - (x << sc) : wo[0] + (x << sc);
+    const int wt = M[row * VVC_GEO_MASK_SIZE + col];
+    const int v = (wt * a[y * sstride + x] + (8 - wt) * b[y * sstride + x] + offset) >> shift;
+    d[y * ds + x] = (int16_t)clip3(0, pmax, v);
+  }
+}
+
 /* ---- BDOF: xPredInterBlk bio tail (:847-885) + applyBiOptFlow (:1290) + gradFilterCore<true> (:212) + BiOptFlowCore (:162) ---- */
 static inline int shift_msb(int numer, int denom) { int m = 0; while (m < 32 && denom >= (1 << m)) m++; return numer >> (m - 1); }   /* rightShiftMSB :92 */
 
@@ -424,6 +442,17 @@ void orc_mc_predict_wp(const b200_geom* g, int16_t* const dst[3], const int16_t*
     const int bi = pu->refSlot[0] >= 0 && pu->refSlot[1] >= 0, altHpel = (pu->flags & B200_PU_ALTHPEL) != 0;
     int16_t* d[3]; for (int c = 0; c < nComp; c++) d[c] = dst[c] + (size_t)(pu->y >> (c ? 1 : 0)) * g->stride[c] + (pu->x >> (c ? 1 : 0));
     if (pu->flags & B200_PU_DMVR) { dmvr_pu(g, pu, R[0], R[1], dst, dmvrMv); continue; }
+    if (pu->flags & B200_PU_GEO) {                                       /* motionCompensationGeo :1461: two uni-predictions of the whole CU, blended */
+      int mvg[2][2];
+      for (int l = 0; l < 2; l++) { mvg[l][0] = pu->mv[l][0]; mvg[l][1] = pu->mv[l][1]; clip_mv(mvg[l], pu->x, pu->y, g); }
+      for (int c = 0; c < nComp; c++) {
+        const int sw = pu->w >> (c ? 1 : 0), sh = pu->h >> (c ? 1 : 0);
+        pred_block(g, &R[0][c], c, pu->x, pu->y, pu->w, pu->h, mvg[0], altHpel, 0, tmp[0][c], sw);
+        pred_block(g, &R[1][c], c, pu->x, pu->y, pu->w, pu->h, mvg[1], altHpel, 0, tmp[1][c], sw);
+        geo_blend(tmp[0][c], tmp[1][c], sw, sh, sw, bd, c, pu->w, pu->h, pu->bcwW1, d[c], g->stride[c]);
+      }
+      continue;
+    }
     if (pu->flags & B200_PU_AFFINE) {
       const b200_wp* we = (wp && pu->wpIdx) ? &wp[pu->wpIdx - 1] : NULL;
       const int os[3] = { pu->w, pu->w >> 1, pu->w >> 1 };

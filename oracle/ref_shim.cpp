@@ -536,6 +536,19 @@ extern "C" int ref_alf_picture( int simd, const b200_geom* g, const int16_t* con
 }
 
 // ------------------------------------------------------------------------------------------------ K2
+// GEO CU from a record: partition p uses DPB slot refSlot[p] = list (slot >> 1), refIdx (slot & 1) in the shims' reference-list layout
+static void setupGeo( CodingUnit& cu, const b200_pu& pu )
+{
+  cu.setGeoFlag( true ); cu.geoSplitDir = (uint8_t) pu.bcwW1; cu.setMergeFlag( true ); cu.setBcwIdx( BCW_DEFAULT ); cu.setSmvdMode( 0 ); cu.setAffineFlag( false );
+  cu.setInterDirrefIdxGeo0( uint8_t( ( ( ( pu.refSlot[0] >> 1 ) + 1 ) << 4 ) | ( pu.refSlot[0] & 1 ) ) );
+  cu.setInterDirrefIdxGeo1( uint8_t( ( ( ( pu.refSlot[1] >> 1 ) + 1 ) << 4 ) | ( pu.refSlot[1] & 1 ) ) );
+  cu.mv[0][1] = Mv( pu.mv[0][0], pu.mv[0][1] ); cu.mv[1][1] = Mv( pu.mv[1][0], pu.mv[1][1] );
+}
+static void runMc( InterPrediction& ip, CodingUnit& cu, PelUnitBuf& buf )
+{
+  if( cu.geoFlag() ) ip.motionCompensationGeo( cu, buf ); else ip.motionCompensation( cu, buf, true, true );
+}
+
 static const int32_t* g_refWpRaw = nullptr;
 extern "C" void ref_set_wp( const int32_t* raw ) { g_refWpRaw = raw; }
 static void applyWp( FakePicture& cur, Slice* sl )
@@ -619,10 +632,10 @@ extern "C" int ref_mc_predict( int simd, const b200_geom* g, int16_t* const dst[
     cu.setAffineType( ( pu.flags & B200_PU_AFFINE6 ) ? AFFINEMODEL_6PARAM : AFFINEMODEL_4PARAM );
     cur.ph->setDisProfFlag( affine && !( pu.flags & ( B200_PU_PROF0 | B200_PU_PROF1 ) ) );
     if( affine ) { for( int l = 0; l < 2; l++ ) if( cu.refIdx[l] >= 0 ) PU::setAllAffineMv( cu, cu.mv[l][0], cu.mv[l][1], cu.mv[l][2], RefPicList( l ) ); }
-    PU::spanMotionInfo( cu );
+    if( pu.flags & B200_PU_GEO ) setupGeo( cu, pu ); else PU::spanMotionInfo( cu );
 
     PelUnitBuf predBuf = predStore.getBuf( UnitArea( pcv.chrFormat, Area( 0, 0, pu.w, pu.h ) ) );
-    ip->motionCompensation( cu, predBuf, true, true );
+    runMc( *ip, cu, predBuf );
     if( (bool) cu.dmvrCondition() != wantDmvr ) rc = -1;
     for( int c = 0; c < ( g->chromaFormat ? 3 : 1 ); c++ )
     {
@@ -826,7 +839,8 @@ extern "C" int ref_flatten_pu_case( int simd, const b200_geom* g, const int16_t*
     cu.setAffineFlag( c.affine ); cu.setAffineType( c.affine6 ? AFFINEMODEL_6PARAM : AFFINEMODEL_4PARAM );
     cu.mvdL0SubPuOff = dmvrOff;
     if( c.w >= 8 && c.h >= 8 && c.w * c.h >= 128 ) dmvrOff += std::max( 1, c.w >> 4 ) * std::max( 1, c.h >> 4 );
-    if( c.affine ) { for( int l = 0; l < 2; l++ ) if( cu.refIdx[l] >= 0 ) PU::setAllAffineMv( cu, cu.mv[l][0], cu.mv[l][1], cu.mv[l][2], RefPicList( l ) ); }
+    if( c.geo ) { cu.setGeoFlag( true ); cu.geoSplitDir = (uint8_t) c.geoSplitDir; cu.setInterDirrefIdxGeo0( (uint8_t) c.geoDir0 ); cu.setInterDirrefIdxGeo1( (uint8_t) c.geoDir1 ); cu.setMergeFlag( true ); }
+    else if( c.affine ) { for( int l = 0; l < 2; l++ ) if( cu.refIdx[l] >= 0 ) PU::setAllAffineMv( cu, cu.mv[l][0], cu.mv[l][1], cu.mv[l][2], RefPicList( l ) ); }
     else PU::spanMotionInfo( cu );
     if( c.sbTmvp )
     {
@@ -842,7 +856,7 @@ extern "C" int ref_flatten_pu_case( int simd, const b200_geom* g, const int16_t*
       }
     }
     PelUnitBuf predBuf = reco.subBuf( ua );
-    ip->motionCompensation( cu, predBuf, true, true );
+    runMc( *ip, cu, predBuf );
     b200glue::FlattenPuResult rc = b200glue::FLATTEN_PU_OK;
     if( c.sbTmvp ) rc = b200glue::flattenSbTmvp( cu, sm, wpIdxOf, [&]( const b200_pu& r ) { if( n < capRecs ) recs[n] = r; n++; } );
     else { b200_pu r; rc = b200glue::flattenPU( cu, sm, wpIdxOf, r ); if( rc == b200glue::FLATTEN_PU_OK ) { if( n < capRecs ) recs[n] = r; n++; } }
@@ -879,7 +893,7 @@ static void fillCuFromPu( CodingUnit& cu, const b200_pu& pu, FakePicture& cur, S
   cu.setAffineFlag( affine );
   cu.setAffineType( ( pu.flags & B200_PU_AFFINE6 ) ? AFFINEMODEL_6PARAM : AFFINEMODEL_4PARAM );
   if( affine ) { for( int l = 0; l < 2; l++ ) if( cu.refIdx[l] >= 0 ) PU::setAllAffineMv( cu, cu.mv[l][0], cu.mv[l][1], cu.mv[l][2], RefPicList( l ) ); }
-  PU::spanMotionInfo( cu );
+  if( pu.flags & B200_PU_GEO ) setupGeo( cu, pu ); else PU::spanMotionInfo( cu );
 }
 
 // K1 for one record with the reference's kernels (glue restated from TrQuant.cpp:201-485 / Quant.cpp:295-381)
@@ -1075,7 +1089,7 @@ extern "C" double ref_decompress_picture_out( const b200_geom* g, const int16_t*
         const b200_pu& pu = pic->pus[n];
         fillCuFromPu( cu, pu, cur, sl );
         PelUnitBuf predBuf = reco.subBuf( UnitArea( pcv.chrFormat, Area( pu.x, pu.y, pu.w, pu.h ) ) );   // rootCbf==0 style: MC writes straight into the picture (DecCu.cpp:405)
-        ips[t]->motionCompensation( cu, predBuf, true, true );
+        runMc( *ips[t], cu, predBuf );
         if( doLmcs ) rsps[t]->rspBufFwd( predBuf.Y() );             // DecCu.cpp:458-476
       }
     } );

@@ -106,6 +106,7 @@ typedef struct ref_cu_syntax {
   int32_t mv[2][3][2];            /* [list][cpmv 0..2][hor,ver], 1/16 sample */
   int32_t affine, affine6, mergeFlag, mmvdFlag, smvd, bcwIdx, imvHpel;
   int32_t sbTmvp, sbSeed;         /* MRG_TYPE_SUBPU_ATMVP with a seeded 8x8 motion field */
+  int32_t geo, geoSplitDir, geoDir0, geoDir1;   /* geoFlag; interDirrefIdxGeo0/1 = (list + 1) << 4 | refIdx; partition MVs in mv[0][1], mv[1][1] */
 } ref_cu_syntax;
 int ref_flatten_pu_case(int simd, const b200_geom* g, const int16_t* const* refs, int altRefs, const ref_cu_syntax* cus, int numCus,
                         int16_t* const dst[3], b200_pu* recs, int capRecs, int32_t* dmvrMv, int numDmvr);

@@ -14,7 +14,8 @@ pytestmark = pytest.mark.ref
 class CuSyntax(C.Structure):
     _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("w", C.c_int32), ("h", C.c_int32), ("refIdx", C.c_int32 * 2), ("mv", C.c_int32 * 2 * 3 * 2),
                 ("affine", C.c_int32), ("affine6", C.c_int32), ("mergeFlag", C.c_int32), ("mmvdFlag", C.c_int32), ("smvd", C.c_int32),
-                ("bcwIdx", C.c_int32), ("imvHpel", C.c_int32), ("sbTmvp", C.c_int32), ("sbSeed", C.c_int32)]
+                ("bcwIdx", C.c_int32), ("imvHpel", C.c_int32), ("sbTmvp", C.c_int32), ("sbSeed", C.c_int32),
+                ("geo", C.c_int32), ("geoSplitDir", C.c_int32), ("geoDir0", C.c_int32), ("geoDir1", C.c_int32)]
 
 
 def gen_cus(rng, W, H, wp):
@@ -35,7 +36,10 @@ def gen_cus(rng, W, H, wp):
                 d = rng.integers(-24, 25, size=2) if k else np.zeros(2, int)
                 c.mv[l][k][0], c.mv[l][k][1] = int(base[l][0] + d[0]), int(base[l][1] + d[1])
         u = rng.random()
-        if w >= 8 and h >= 8 and u < 0.15:
+        if 8 <= w <= 64 and 8 <= h <= 64 and w < 8 * h and h < 8 * w and rng.random() < 0.12:
+            c.geo = 1; c.geoSplitDir = int(rng.integers(0, 64)); c.mergeFlag = 1
+            c.geoDir0 = ((int(rng.integers(0, 2)) + 1) << 4) | int(rng.integers(0, 2)); c.geoDir1 = ((int(rng.integers(0, 2)) + 1) << 4) | int(rng.integers(0, 2))
+        elif w >= 8 and h >= 8 and u < 0.15:
             c.affine = 1; c.affine6 = int(rng.random() < 0.5)
             if rng.random() < 0.2:
                 for k in range(3): c.mv[1][k][0], c.mv[1][k][1] = c.mv[0][k][0], c.mv[0][k][1]
@@ -47,7 +51,7 @@ def gen_cus(rng, W, H, wp):
             c.imvHpel = int(not c.mergeFlag and rng.random() < 0.15)
             if c.imvHpel:                                               # half-sample AMVR: MVs are multiples of 8
                 for l in range(2): c.mv[l][0][0] &= ~7; c.mv[l][0][1] &= ~7
-        if bi and not c.sbTmvp and w * h >= 256 and rng.random() < 0.2: c.bcwIdx = int(rng.integers(1, 5))   # internal-domain index, BCW_DEFAULT = 0
+        if bi and not c.sbTmvp and not c.geo and w * h >= 256 and rng.random() < 0.2: c.bcwIdx = int(rng.integers(1, 5))   # internal-domain index, BCW_DEFAULT = 0
         else: c.bcwIdx = 0
         out.append(c)
     return (CuSyntax * len(out))(*out)
@@ -87,5 +91,5 @@ def test_flatten_pu(oracle, ref, simd, alt_refs, wp):
                 raise AssertionError(f"seed {seed} plane {c}: {len(d)} diffs, first at {(y, x)}; record {hit[:1]}")
         assert np.array_equal(dm, dm_want)
         kinds = recs["flags"]
-        assert (kinds & 8).any() and (wp or ((kinds & 1).any() and (kinds & 2).any()))   # affine, and (without explicit weights) BDOF and DMVR occurred
+        assert (kinds & 128).any() and (kinds & 8).any() and (wp or ((kinds & 1).any() and (kinds & 2).any()))   # affine, and (without explicit weights) BDOF and DMVR occurred
         if wp: assert (recs["wpIdx"] != 0).any()

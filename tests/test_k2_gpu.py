@@ -28,7 +28,8 @@ def _compare(b200, oracle, W, H, bd, pus, ndmvr, refs):
 
 @pytest.mark.parametrize("name,kw", [("regular", dict(p_dmvr=0, p_bdof=0, p_affine=0)), ("bdof", dict(p_dmvr=0, p_bdof=0.9, p_affine=0, p_bi=0.9)),
                                       ("dmvr", dict(p_dmvr=0.9, p_bdof=0.05, p_affine=0, p_bi=0.9, mv_sigma=2.0)),
-                                      ("affine", dict(p_dmvr=0, p_bdof=0, p_affine=0.9, p_prof=0.8))])
+                                      ("affine", dict(p_dmvr=0, p_bdof=0, p_affine=0.9, p_prof=0.8)),
+                                      ("geo", dict(p_geo=0.7, p_dmvr=0.1, p_bdof=0.1))])
 def test_mc_modes(b200, oracle, name, kw):
     pus, nd, refs = _case(11, 416, 240, 10, **kw)
     _compare(b200, oracle, 416, 240, 10, pus, nd, refs)

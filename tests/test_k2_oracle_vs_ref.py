@@ -99,3 +99,19 @@ def test_explicit_weighted_prediction(oracle, ref, simd, bd):
         assert rc == 0
         for c in range(3):
             assert np.array_equal(a[c], b[c]), f"plane {c}: {len(np.argwhere(a[c] != b[c]))} diffs"
+
+
+@pytest.mark.parametrize("simd", [0, 1])
+@pytest.mark.parametrize("bd", [8, 10])
+def test_geo(oracle, ref, simd, bd):
+    """Geometric partitioning: the real motionCompensationGeo (two uni-predictions + xWeightedGeoBlk) against the oracle's geo_blend with
+    the dumped weight tables; all 64 split directions occur over the seeds, partitions from the same or different lists."""
+    W, H = 384, 256
+    seen = set()
+    for seed in (1, 2, 3, 4):
+        pus, ndmvr, refs = _case(seed * 3 + bd, W, H, bd, p_geo=0.6, p_dmvr=0.1, p_bdof=0.1)
+        geo = pus[(pus["flags"] & 128) != 0]
+        assert len(geo) > 30
+        seen |= set(int(v) for v in geo["bcwW1"])
+        _compare(oracle, ref, simd, W, H, bd, pus, ndmvr, refs)
+    assert len(seen) >= 60

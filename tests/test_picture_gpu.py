@@ -105,7 +105,7 @@ def test_lmcs_picture(b200, oracle, W, H, ctu, chroma_adj):
 
 
 def test_weighted_prediction_picture(b200, oracle):
-    """Explicit weighted prediction at picture level (together with LMCS: the weighted luma is what gets forward-mapped)."""
+    """Explicit weighted prediction and GEO at picture level (together with LMCS: the combined luma is what gets forward-mapped)."""
     W, H, bd = 832, 480, 10
     rng = np.random.default_rng(31)
     g = abi.make_geom(W, H, bd)
@@ -115,7 +115,7 @@ def test_weighted_prediction_picture(b200, oracle):
         dpb = [synth.noise_planes(rng, W, H, bd) for _ in range(4)]
         for s in range(4): vvdec_b200.check(b200.b200_ctx_load_slot(ctx, s, abi.plane_ptrs(dpb[s])))
         for k, lm in enumerate((False, True)):
-            pic = synth.gen_picture(rng, W, H, bd, dst_slot=4 + k, wp=True, lmcs=lm, pu_kw=dict(p_dmvr=0.0, p_bdof=0.0, p_bcw=0.3))
+            pic = synth.gen_picture(rng, W, H, bd, dst_slot=4 + k, wp=True, lmcs=lm, pu_kw=dict(p_dmvr=0.0, p_bdof=0.0, p_bcw=0.3, p_geo=0.15))
             want, _ = oracle_decompress(oracle, g, dpb, pic)
             h = b200.b200_decompress_picture(ctx, C.byref(pic["struct"])); assert h >= 0, b200.b200_last_error()
             vvdec_b200.check(b200.b200_wait_picture(ctx, h, None, 0))

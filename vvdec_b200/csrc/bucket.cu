@@ -12,7 +12,7 @@ namespace b200 {
 __device__ __forceinline__ int mc_list_of(int w, int h, int flags, bool bi, int tx, int ty)
 {
   if (flags & B200_PU_AFFINE) return 16;
-  const int mode = (flags & B200_PU_DMVR) ? 3 : (bi && (flags & B200_PU_BDOF)) ? 2 : bi ? 1 : 0;
+  const int mode = (flags & B200_PU_GEO) ? 1 : (flags & B200_PU_DMVR) ? 3 : (bi && (flags & B200_PU_BDOF)) ? 2 : bi ? 1 : 0;
   const int tw = min(16, w - tx * 16), th = min(16, h - ty * 16), n = tw * th;
   return mode * 4 + (n <= 32 ? 0 : n <= 64 ? 1 : n <= 128 ? 2 : 3);
 }
@@ -31,9 +31,13 @@ __device__ __forceinline__ PuHead pu_head(const b200_pu* pus, int i, int slotsBd
   if ((r.flags & B200_PU_DMVR) && (!r.bi || !big || aff)) r.ok = false;
   if ((r.flags & B200_PU_BDOF) && r.bi && !aff && !big) r.ok = false;
   if ((r.flags & B200_PU_DMVR) && bitDepth > 10) r.ok = false;
+  // GEO (InterPrediction.cpp:1461): two partitions = both 'lists' set, 8..64 luma samples per side, never with another tool; bcwW1 = split direction
+  if (r.flags & B200_PU_GEO) {
+    if (!r.bi || r.w < 8 || r.h < 8 || r.w > 64 || r.h > 64 || (r.w & (r.w - 1)) || (r.h & (r.h - 1)) || (r.flags & (B200_PU_DMVR | B200_PU_BDOF | B200_PU_AFFINE)) || p.wpIdx || (uint8_t)p.bcwW1 > 63) r.ok = false;
+  }
   // explicit weights: the entry must exist; the reference never combines them with BDOF / DMVR / BCW (InterPrediction.cpp:733, :1406-1420)
   const int wpIdx = p.wpIdx;
-  if (wpIdx && (wpIdx > numWp || (r.flags & B200_PU_DMVR) || ((r.flags & B200_PU_BDOF) && r.bi && !aff) || p.bcwW1 != 4)) r.ok = false;   // DMVR is defined for bit depths <= 10 only (as in the reference)
+  if (wpIdx && (wpIdx > numWp || (r.flags & B200_PU_DMVR) || ((r.flags & B200_PU_BDOF) && r.bi && !aff) || p.bcwW1 != 4) && !(r.flags & B200_PU_GEO)) r.ok = false;   // DMVR is defined for bit depths <= 10 only (as in the reference)
   return r;
 }
 

@@ -91,6 +91,21 @@ __device__ __forceinline__ int wp_bi(const b200_wp* e, int comp, int p0, int p1,
   return clip3(0, pmax, (e->w0[comp] * (p0 + IFO) + e->w1[comp] * (p1 + IFO) + ((1 << s) >> 1) + e->offset[comp] * (1 << (s - 1))) >> s);
 }
 
+// GEO blending weight of sample (x, y) of component scale sc in a CU of 2^l2w x 2^l2h luma samples (xWeightedGeoBlk, InterpolationFilter.cpp:1217)
+__device__ __forceinline__ int geo_weight(int splitDir, int l2w, int l2h, int x, int y, int sc)
+{
+  const int angle = kGeoParams[splitDir * 2], mir = kGeoAngle2Mirror[angle];
+  const int16_t* wo = &kGeoWeightOffset[((splitDir * 4 + (l2h - 3)) * 4 + (l2w - 3)) * 2];
+  const int row = mir == 2 ? VVC_GEO_MASK_SIZE - 1 - wo[1] - (y << sc) : wo[1] + (y << sc);
+  const int col = mir == 1 ? VVC_GEO_MASK_SIZE - 1 - wo[0] - (x << sc) : wo[0] + (x << sc);
+  return kGeoWeights[(kGeoAngle2Mask[angle] * VVC_GEO_MASK_SIZE + row) * VVC_GEO_MASK_SIZE + col];
+}
+__device__ __forceinline__ int geo_blend(int wt, int p0, int p1, int hr, int pmax)
+{
+  const int s = hr + 3;
+  return clip3(0, pmax, (wt * p0 + (8 - wt) * p1 + (1 << (s - 1)) + (IFO << 3)) >> s);
+}
+
 __device__ __forceinline__ int shift_msb(int numer, int denom) { return numer >> (31 - __clz(denom)); }   // rightShiftMSB (:92), denom > 0
 
 __device__ int div_for_maxq7(long long N, long long D)
@@ -155,6 +170,8 @@ __device__ __forceinline__ void mc_tile(const McParams& P, const uint32_t tile, 
   const int cw = tw >> 1, ch = th >> 1, l2cw = l2w - 1;
   const int chroma = P.chroma;
   const b200_wp* we = (MODE <= 1 && P.wp && pu.wpIdx) ? P.wp + pu.wpIdx - 1 : nullptr;   // explicit weights (never with BDOF / DMVR)
+  const bool geo = MODE == 1 && (flags & B200_PU_GEO);      // geometric partitioning: the two 'lists' are the two partitions' uni-predictions
+  const int gl2w = 31 - __clz(puW), gl2h = 31 - __clz(puH);
   const int WS = tw + 8, CS = cw + 4;                        // window strides: even, so a row is a run of 32-bit words
 
   // ---- shared memory carve-up (strides depend on the tile shape) ----
@@ -519,7 +536,8 @@ __device__ __forceinline__ void mc_tile(const McParams& P, const uint32_t tile, 
 #pragma unroll
     for (int j = 0; j < OPT; j++) {
       int16_t* d = P.dst[0] + (size_t)(by + sy + j) * P.dstStride[0] + bx + sx;
-      if (MODE <= 1 && we) *d = (int16_t)LUMA_OUT(BI ? wp_bi(we, 0, (int16_t)(pr[0][j] >> 6), (int16_t)(pr[NL - 1][j] >> 6), hr, pmax) : wp_uni(we, 0, (int16_t)(pr[0][j] >> 6), hr, pmax));
+      if (MODE == 1 && geo) *d = (int16_t)LUMA_OUT(geo_blend(geo_weight(pu.bcwW1, gl2w, gl2h, tx0 + sx, ty0 + sy + j, 0), (int16_t)(pr[0][j] >> 6), (int16_t)(pr[NL - 1][j] >> 6), hr, pmax));
+      else if (MODE <= 1 && we) *d = (int16_t)LUMA_OUT(BI ? wp_bi(we, 0, (int16_t)(pr[0][j] >> 6), (int16_t)(pr[NL - 1][j] >> 6), hr, pmax) : wp_uni(we, 0, (int16_t)(pr[0][j] >> 6), hr, pmax));
       else if (!BI) *d = (int16_t)LUMA_OUT(clip3(0, pmax, (pr[0][j] + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr)));
       else if (!bio) *d = (int16_t)LUMA_OUT(avg_bi((int16_t)(pr[0][j] >> 6), (int16_t)(pr[NL - 1][j] >> 6), MODE == 1 ? pu.bcwW1 : 4, hr, pmax));
       else { S.p[0][(sy + j + 1) * 18 + sx + 1] = (int16_t)(pr[0][j] >> 6); S.p[1][(sy + j + 1) * 18 + sx + 1] = (int16_t)(pr[NL - 1][j] >> 6); }
@@ -537,7 +555,8 @@ __device__ __forceinline__ void mc_tile(const McParams& P, const uint32_t tile, 
         pr[li] = t[0] * s[0] + t[1] * s[CHS] + t[2] * s[2 * CHS] + t[3] * s[3 * CHS];
       }
       int16_t* d = (c ? P.dst[2] : P.dst[1]) + (size_t)((by >> 1) + y) * (c ? P.dstStride[2] : P.dstStride[1]) + (bx >> 1) + x;
-      if (MODE <= 1 && we) *d = (int16_t)(BI ? wp_bi(we, 1 + c, (int16_t)(pr[0] >> 6), (int16_t)(pr[NL - 1] >> 6), hr, pmax) : wp_uni(we, 1 + c, (int16_t)(pr[0] >> 6), hr, pmax));
+      if (MODE == 1 && geo) *d = (int16_t)geo_blend(geo_weight(pu.bcwW1, gl2w, gl2h, (tx0 >> 1) + x, (ty0 >> 1) + y, 1), (int16_t)(pr[0] >> 6), (int16_t)(pr[NL - 1] >> 6), hr, pmax);
+      else if (MODE <= 1 && we) *d = (int16_t)(BI ? wp_bi(we, 1 + c, (int16_t)(pr[0] >> 6), (int16_t)(pr[NL - 1] >> 6), hr, pmax) : wp_uni(we, 1 + c, (int16_t)(pr[0] >> 6), hr, pmax));
       else if (!BI) *d = (int16_t)clip3(0, pmax, (pr[0] + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr));
       else *d = (int16_t)avg_bi((int16_t)(pr[0] >> 6), (int16_t)(pr[NL - 1] >> 6), MODE == 1 ? pu.bcwW1 : 4, hr, pmax);
     }

@@ -287,10 +287,10 @@ def gen_alf(rng, W, H, ctu=128, bit_depth=10, n_aps=2, n_chroma_alts=3, n_cc=(2,
 PU_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("w", "u1"), ("h", "u1"), ("flags", "u1"), ("bcwW1", "i1"), ("refSlot", "i1", (2,)),
                      ("interDir", "u1"), ("wpIdx", "u1"), ("dmvrOff", "<u4"), ("mv", "<i4", (2, 2)), ("cpmv", "<i4", (2, 2, 2))])
 assert PU_DTYPE.itemsize == 64
-PU_BDOF, PU_DMVR, PU_ALTHPEL, PU_AFFINE, PU_AFFINE6, PU_PROF0, PU_PROF1 = 1, 2, 4, 8, 16, 32, 64
+PU_BDOF, PU_DMVR, PU_ALTHPEL, PU_AFFINE, PU_AFFINE6, PU_PROF0, PU_PROF1, PU_GEO = 1, 2, 4, 8, 16, 32, 64, 128
 
 
-def gen_pus(rng, cus, W, H, p_inter=1.0, p_bi=0.6, p_dmvr=0.35, p_bdof=0.35, p_affine=0.12, p_bcw=0.15, mv_sigma=6.0, p_int_mv=0.15, p_prof=1.0):
+def gen_pus(rng, cus, W, H, p_inter=1.0, p_bi=0.6, p_dmvr=0.35, p_bdof=0.35, p_affine=0.12, p_bcw=0.15, mv_sigma=6.0, p_int_mv=0.15, p_prof=1.0, p_geo=0.0):
     """Inter PU records for a CU list (MVs ~ N(0, 6 px) in 1/16 units; refs from 4 DPB slots:
     list 0 = {0, 1}, list 1 = {2, 3}; (0,2) and (1,3) are the equal-POC-distance pairs that allow BDOF / DMVR)."""
     recs = []
@@ -306,6 +306,13 @@ def gen_pus(rng, cus, W, H, p_inter=1.0, p_bi=0.6, p_dmvr=0.35, p_bdof=0.35, p_a
         if rng.random() < 0.1: mv[:, rng.integers(0, 2)] &= ~15                      # one integer component
         if rng.random() < 0.03: mv += rng.integers(-3000, 3000, size=(2, 2))          # far outside the picture -> clipMv
         r["mv"] = mv
+        if p_geo and 8 <= w <= 64 and 8 <= h <= 64 and w < 8 * h and h < 8 * w and rng.random() < p_geo:
+            # geometric partitioning: two uni-predicted partitions (any slots, also from the same list), split direction in bcwW1
+            r["refSlot"] = (int(rng.integers(0, 4)), int(rng.integers(0, 4))); r["interDir"] = 3
+            r["bcwW1"] = int(rng.integers(0, 64)); r["flags"] = PU_GEO
+            if w >= 8 and h >= 8 and w * h >= 128:
+                r["dmvrOff"] = dmvr_off; dmvr_off += max(1, w >> 4) * max(1, h >> 4)
+            recs.append(r); continue
         can_bi = (w + h) > 12
         bi = can_bi and rng.random() < p_bi
         big = w >= 8 and h >= 8 and w * h >= 128
@@ -380,7 +387,7 @@ def gen_wp(rng, bit_depth, pus):
     for p in pus:
         r0 = -1 if p["refSlot"][0] < 0 else int(p["refSlot"][0]) & 1
         r1 = -1 if p["refSlot"][1] < 0 else int(p["refSlot"][1]) & 1
-        p["wpIdx"] = idx[(r0, r1)] if p["bcwW1"] == 4 else 0
+        p["wpIdx"] = idx[(r0, r1)] if p["bcwW1"] == 4 and not (p["flags"] & PU_GEO) else 0    # GEO never combines with explicit weights (xPredInterBi :731)
     return raw, ent
 
 

@@ -41,9 +41,26 @@ inline FlattenPuResult flattenPU( const CodingUnit& cu, const SlotMap& sm, WpIdx
 {
   if( !CU::isInter( cu ) || CU::isIBC( cu ) ) return FLATTEN_PU_NOT_INTER;
   // tools the device path does not have: the caller sends such CUs (or the picture) down the CPU path
-  if( cu.geoFlag() || cu.ciipFlag() || cu.mergeType() == MRG_TYPE_SUBPU_ATMVP || cu.sps->getUseWrapAround() ) return FLATTEN_PU_UNSUPPORTED;   // SbTMVP: flattenSbTmvp
+  if( cu.ciipFlag() || cu.mergeType() == MRG_TYPE_SUBPU_ATMVP || cu.sps->getUseWrapAround() ) return FLATTEN_PU_UNSUPPORTED;   // SbTMVP: flattenSbTmvp
   const Slice& slice = *cu.slice;
   const PPS&   pps   = *cu.pps;
+  if( cu.geoFlag() )
+  {
+    // motionCompensationGeo (:1461-1497): partition p = uni-prediction from list (geoDir_p >> 4) - 1, refIdx geoDir_p & 15, MV cu.mv[p][1]
+    memset( &r, 0, sizeof( r ) );
+    r.x = cu.lx(); r.y = cu.ly(); r.w = cu.lwidth(); r.h = cu.lheight(); r.interDir = 3; r.dmvrOff = cu.mvdL0SubPuOff;
+    const uint8_t dir[2] = { cu.interDirrefIdxGeo0(), cu.interDirrefIdxGeo1() };
+    for( int p = 0; p < 2; p++ )
+    {
+      const int list = ( dir[p] >> 4 ) - 1, idx = dir[p] & 15;
+      if( list < 0 || list > 1 || slice.getRefPic( RefPicList( list ), idx )->isRefScaled( cu.pps ) ) return FLATTEN_PU_UNSUPPORTED;
+      r.refSlot[p] = sm.slot[list][idx];
+      r.mv[p][0] = cu.mv[p][1].hor; r.mv[p][1] = cu.mv[p][1].ver;
+    }
+    r.flags = B200_PU_GEO | ( cu.imv() == IMV_HPEL ? B200_PU_ALTHPEL : 0 );
+    r.bcwW1 = (int8_t) cu.geoSplitDir;
+    return FLATTEN_PU_OK;
+  }
   for( int l = 0; l < 2; l++ )
     if( cu.refIdx[l] >= 0 && slice.getRefPic( RefPicList( l ), cu.refIdx[l] )->isRefScaled( cu.pps ) ) return FLATTEN_PU_UNSUPPORTED;   // RPR
   if( slice.getRefPic( REF_PIC_LIST_0, 0 )->subPictures.size() > 1 ) return FLATTEN_PU_UNSUPPORTED;                                   // clipMvInSubpic
