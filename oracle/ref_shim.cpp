@@ -986,6 +986,7 @@ extern "C" double ref_decompress_picture_out( const b200_geom* g, const int16_t*
   for( unsigned a = 0; a < pcv.sizeInCtus; a++ ) cs.getCtuData( a ).motion = motion.data() + (size_t) a * pcv.num4x4CtuBlks;
   cs.m_dmvrMvCache = dmvrCache.data();
   addCtuCUs( cur );
+  if( pic->given[0] ) { int16_t* gp[3] = { (int16_t*) pic->given[0], (int16_t*) pic->given[1], (int16_t*) pic->given[2] }; cur.setPlanes( *g, gp ); }   // pre-reconstructed (intra) samples
   g_tCoeffOps = simd ? g_simdOps : g_scalarOps;
 
   // deblocking / SAO / ALF parameters

@@ -131,6 +131,8 @@ def oracle_decompress(oracle, g, dpb, pic):
     cur = [np.zeros((H, W), np.int16), np.zeros((H // 2, W // 2), np.int16), np.zeros((H // 2, W // 2), np.int16)]
     dm = np.zeros((pic["ndmvr"] + 1, 2), np.int32)
     st = pic["struct"]
+    if "given" in pic:                                          # pre-reconstructed (intra) samples: b200_picture::given
+        cur = [p.copy() for p in pic["given"]]
     oracle.orc_mc_predict_wp(C.byref(g), abi.plane_ptrs(cur), ref_ptrs(dpb), pic["pus"].ctypes.data, len(pic["pus"]), dm.ctypes.data,
                              pic["wp"].ctypes.data if "wp" in pic else None)
     if st.flags & abi.PIC_LMCS:

@@ -448,22 +448,25 @@ def gen_lmcs(rng, bit_depth, cus, W, H, ctu, chroma_adj=True):
 
 
 def gen_picture(rng, W, H, bit_depth=10, ctu=128, dst_slot=0, cu_kw=None, pu_kw=None, tu_kw=None, sao_p=0.4, alf_kw=None,
-                deblock=True, sao=True, alf=True, lmcs=False, lmcs_chroma=True, wp=False):
+                deblock=True, sao=True, alf=True, lmcs=False, lmcs_chroma=True, wp=False, inter=True, given=None, cu_intra=None):
     """One synthetic post-parse picture: partition -> inter PUs (all CUs inter: intra-coded samples would
     be 'given' pixels) -> TUs/levels -> deblocking grids -> SAO / ALF CTU parameters.
     Returns a dict of numpy arrays (kept alive by the caller) plus `struct`, the abi.Picture that points into them."""
     from . import abi as A
     import ctypes as C
     cus = partition(rng, W, H, ctu=ctu, **(cu_kw or {}))
-    pus, ndmvr = gen_pus(rng, cus, W, H, **(pu_kw or {}))
+    pus, ndmvr = gen_pus(rng, cus, W, H, **(pu_kw or {})) if inter else (np.zeros(0, PU_DTYPE), 0)
     tus, coefs = gen_tus(rng, cus, bit_depth, **({"p_cbf": 0.35, "p_intra": 0.0, "p_lfnst": 0.0, "p_bdpcm": 0.0} | (tu_kw or {})))
     d = dict(cus=cus, pus=pus, ndmvr=ndmvr, tus=tus, coefs=coefs)
     p = A.Picture(); p.dstSlot = dst_slot; p.flags = 0
+    if given is not None:                                       # pre-reconstructed samples (an intra picture's predictions stand in here)
+        d["given"] = given
+        for c in range(3): p.given[c] = given[c].ctypes.data
     p.pus = pus.ctypes.data; p.numPus = len(pus); p.numDmvr = ndmvr + 1
     p.tus = tus.ctypes.data; p.numTus = len(tus); p.coefs = coefs.ctypes.data; p.numCoefs = len(coefs)
     if deblock:
         qp = rng.integers(22, 45, size=len(cus))
-        d["lfV"], d["lfH"] = gen_lf_grid(rng, cus, W, H, bit_depth, cu_intra=np.zeros(len(cus), bool), cu_qp=qp)
+        d["lfV"], d["lfH"] = gen_lf_grid(rng, cus, W, H, bit_depth, cu_intra=np.zeros(len(cus), bool) if cu_intra is None else np.ones(len(cus), bool) if cu_intra is True else cu_intra, cu_qp=qp)
         d["lfSlices"] = np.zeros(1, LFSLICE_DTYPE)
         p.flags |= A.PIC_DEBLOCK; p.lfV = d["lfV"].ctypes.data; p.lfH = d["lfH"].ctypes.data
         p.lfSlices = d["lfSlices"].ctypes.data; p.numLfSlices = 1
