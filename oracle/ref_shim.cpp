@@ -38,6 +38,8 @@
 #include "CommonLib/SampleAdaptiveOffset.h"
 #include "CommonLib/Reshape.h"
 #include "../vvdec_b200/vvdec_glue/flatten_pu.h"
+#include "../vvdec_b200/vvdec_glue/flatten_filters.h"
+#include "../vvdec_b200/vvdec_glue/DecLibReconB200.h"   // compile check of the drop-in class against the reference headers
 #include <assert.h>
 #include <fstream>
 #include <chrono>
@@ -474,17 +476,11 @@ extern "C" void ref_alf_ccalf_blk( int simd, int16_t* dstChroma, ptrdiff_t chrom
   ( simd ? av : as ).m_filterCcAlf( dbuf, s, Area( cX, cY, cW, cH ), Area( cX * 2, cY * 2, cW * 2, cH * 2 ), COMPONENT_Cb, coeff, clp, vbCtuHeight, vbPos );
 }
 
-extern "C" int ref_alf_picture( int simd, const b200_geom* g, const int16_t* const src[3], int16_t* const dst[3], const b200_alf_ctu* ctus,
-                                const b200_alf_tables* T )
+// APS / slice / CTU state of the ALF stage from the flattened tables (the inverse of b200glue::buildAlfTables / flattenALF)
+static void setupAlfSlice( FakePicture& fp, Slice* sl, const b200_alf_ctu* ctus, const b200_alf_tables* T )
 {
-  FakePicture fp( *g, 1 );
   CodingStructure& cs = *fp.pic.cs;
   const PreCalcValues& pcv = *cs.pcv;
-  fp.pps->setLoopFilterAcrossSlicesEnabledFlag( true ); fp.pps->setLoopFilterAcrossTilesEnabledFlag( true );
-  fp.sps->setUseALF( true ); fp.sps->setUseCCALF( true );
-  addCtuCUs( fp );
-  Slice* sl = fp.pic.slices[0];
-  { SliceMap sm; sm.addCtusToSlice( 0, pcv.widthInCtus, 0, pcv.heightInCtus, pcv.widthInCtus ); sl->setSliceMap( sm ); }
   // APS 0..n-1 carry the luma sets 16.. ; APS 7 carries the chroma alternatives (<=8) ; APS 6/5 the CC-ALF filters (<=4 each)
   static std::shared_ptr<APS> apsStore[ALF_CTB_MAX_NUM_APS];
   const APS* apss[ALF_CTB_MAX_NUM_APS] = { nullptr };
@@ -512,6 +508,7 @@ extern "C" int ref_alf_picture( int simd, const b200_geom* g, const int16_t* con
   {
     CcAlfFilterParam& p = apsStore[6 - c]->getCcAlfAPSParam();
     for( int k = 0; k < T->numCc[c]; k++ ) memcpy( p.ccAlfCoeff[c][k], T->ccCoeff[c] + k * 7, 7 * sizeof( short ) );
+    p.ccAlfFilterCount[c] = (uint8_t) T->numCc[c];
   }
   sl->setCcAlfCbEnabledFlag( T->numCc[0] > 0 ); sl->setCcAlfCrEnabledFlag( T->numCc[1] > 0 );
   sl->setCcAlfCbApsId( 6 ); sl->setCcAlfCrApsId( 5 );
@@ -524,6 +521,20 @@ extern "C" int ref_alf_picture( int simd, const b200_geom* g, const int16_t* con
     d.alfCtbFilterIndex = ctus[a].lumaSet;
     for( int c = 0; c < 2; c++ ) { d.alfCtuAlternative[c] = ctus[a].chromaAlt[c]; d.ccAlfFilterControl[c] = ctus[a].ccIdx[c]; }
   }
+}
+
+extern "C" int ref_alf_picture( int simd, const b200_geom* g, const int16_t* const src[3], int16_t* const dst[3], const b200_alf_ctu* ctus,
+                                const b200_alf_tables* T )
+{
+  FakePicture fp( *g, 1 );
+  CodingStructure& cs = *fp.pic.cs;
+  const PreCalcValues& pcv = *cs.pcv;
+  fp.pps->setLoopFilterAcrossSlicesEnabledFlag( true ); fp.pps->setLoopFilterAcrossTilesEnabledFlag( true );
+  fp.sps->setUseALF( true ); fp.sps->setUseCCALF( true );
+  addCtuCUs( fp );
+  Slice* sl = fp.pic.slices[0];
+  { SliceMap sm; sm.addCtusToSlice( 0, pcv.widthInCtus, 0, pcv.heightInCtus, pcv.widthInCtus ); sl->setSliceMap( sm ); }
+  setupAlfSlice( fp, sl, ctus, T );
   int16_t* s3[3] = { (int16_t*) src[0], (int16_t*) src[1], (int16_t*) src[2] };
   fp.setPlanes( *g, s3 );
   PelStorage out; out.create( pcv.chrFormat, Size( g->width, g->height ), g->ctuSize, 16, MEMORY_ALIGN_DEF_SIZE );
@@ -649,6 +660,53 @@ extern "C" int ref_mc_predict( int simd, const b200_geom* g, int16_t* const dst[
     }
   }
   return rc;
+}
+
+// ================================================================================================ filter flatteners (vvdec_glue/flatten_filters.h)
+// Fills the reference structures from flattened input (as the filter shims above do), then runs the flatteners on them: what comes
+// back must be the input.  SAO availability comes from the real deriveLoopFilterBoundaryAvailibility.
+extern "C" int ref_flatten_filters( const b200_geom* g, const b200_lf_param* lfV, const b200_lf_param* lfH, const b200_sao_ctu* sao, const b200_alf_ctu* alf,
+                                    const b200_alf_tables* T, b200_lf_param* lfVOut, b200_lf_param* lfHOut, b200_sao_ctu* saoOut, b200_alf_ctu* alfOut,
+                                    int16_t* lumaCoeffOut, int16_t* lumaClipOut, int16_t* chromaCoeffOut, int16_t* chromaClipOut, int16_t* cc0Out, int16_t* cc1Out, int32_t counts[4] )
+{
+  FakePicture fp( *g, 1 );
+  CodingStructure& cs = *fp.pic.cs;
+  const PreCalcValues& pcv = *cs.pcv;
+  fp.pps->setLoopFilterAcrossSlicesEnabledFlag( true ); fp.pps->setLoopFilterAcrossTilesEnabledFlag( true );
+  fp.sps->setUseALF( true ); fp.sps->setUseCCALF( true );
+  addCtuCUs( fp );
+  Slice* sl = fp.pic.slices[0];
+  { SliceMap sm; sm.addCtusToSlice( 0, pcv.widthInCtus, 0, pcv.heightInCtus, pcv.widthInCtus ); sl->setSliceMap( sm ); }
+  fp.setLfGrid( 0, lfV ); fp.setLfGrid( 1, lfH );
+  for( unsigned a = 0; a < pcv.sizeInCtus; a++ ) { b200glue::flattenLfCtu( cs, a, 0, lfVOut ); b200glue::flattenLfCtu( cs, a, 1, lfHOut ); }
+  PelStorage flt; flt.create( pcv.chrFormat, Size( g->width, g->height ), g->ctuSize, 16, MEMORY_ALIGN_DEF_SIZE );
+  SampleAdaptiveOffset saoF( false );
+  saoF.create( g->width, g->height, pcv.chrFormat, g->ctuSize, g->ctuSize, 0, 0, flt );
+  for( unsigned a = 0; a < pcv.sizeInCtus; a++ )
+  {
+    SAOBlkParam& bp = cs.getCtuData( a ).saoParam; bp.reset();
+    for( int c = 0; c < 3; c++ )
+    {
+      if( sao[a].type[c] == B200_SAO_OFF ) continue;
+      bp[c].modeIdc = SAO_MODE_NEW; bp[c].typeIdc = sao[a].type[c]; bp[c].typeAuxInfo = sao[a].band[c];
+      if( sao[a].type[c] == B200_SAO_BO ) for( int i = 0; i < 4; i++ ) bp[c].offset[( sao[a].band[c] + i ) & 31] = sao[a].offset[c][i];
+      else for( int i = 0; i < 5; i++ ) bp[c].offset[i] = sao[a].offset[c][i];
+    }
+    bool av[8];
+    saoF.deriveLoopFilterBoundaryAvailibility( cs, Position( ( a % pcv.widthInCtus ) * g->ctuSize, ( a / pcv.widthInCtus ) * g->ctuSize ), av[0], av[1], av[2], av[3], av[4], av[5], av[6], av[7] );
+    b200glue::flattenSAO( bp, av, g->chromaFormat ? 3 : 1, saoOut[a] );
+  }
+  setupAlfSlice( fp, sl, alf, T );
+  for( unsigned a = 0; a < pcv.sizeInCtus; a++ ) b200glue::flattenALF( cs.getCtuData( a ).alfParam, alfOut[a] );
+  AdaptiveLoopFilter alfF( false );
+  alfF.create( fp.ph.get(), fp.sps.get(), fp.pps.get(), 1, flt );      // fills m_clipDefault for the bit depth
+  b200glue::AlfTableStore store;
+  const b200_alf_tables R = b200glue::buildAlfTables( *sl, &alfF.m_fixedFilterSetCoeffDec[0][0], alfF.m_clipDefault, store );
+  memcpy( lumaCoeffOut, R.lumaCoeff, store.lumaCoeff.size() * 2 ); memcpy( lumaClipOut, R.lumaClip, store.lumaClip.size() * 2 );
+  memcpy( chromaCoeffOut, R.chromaCoeff, store.chromaCoeff.size() * 2 ); memcpy( chromaClipOut, R.chromaClip, store.chromaClip.size() * 2 );
+  memcpy( cc0Out, R.ccCoeff[0], store.cc[0].size() * 2 ); memcpy( cc1Out, R.ccCoeff[1], store.cc[1].size() * 2 );
+  counts[0] = R.numLumaSets; counts[1] = R.numChromaAlts; counts[2] = R.numCc[0]; counts[3] = R.numCc[1];
+  return 0;
 }
 
 // ================================================================================================ output writer of vvdecapp

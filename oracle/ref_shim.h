@@ -96,6 +96,10 @@ int ref_mc_predict(int simd, const b200_geom* g, int16_t* const dst[3], const in
  * of one picture is included (every picture is extended once when it becomes a reference, DecLibRecon.cpp:236).
  * Returns the seconds spent in the timed part (setup of the fake vvdec objects excluded); out (may be NULL) receives the picture. */
 double ref_decompress_picture_mt(const b200_geom* g, const int16_t* const* refs, const b200_picture* pic, int threads, int simd);
+/* Filter flatteners (vvdec_b200/vvdec_glue/flatten_filters.h): reference structures filled from the flattened input, flattened again. */
+int ref_flatten_filters(const b200_geom* g, const b200_lf_param* lfV, const b200_lf_param* lfH, const b200_sao_ctu* sao, const b200_alf_ctu* alf,
+                        const b200_alf_tables* T, b200_lf_param* lfVOut, b200_lf_param* lfHOut, b200_sao_ctu* saoOut, b200_alf_ctu* alfOut,
+                        int16_t* lumaCoeffOut, int16_t* lumaClipOut, int16_t* chromaCoeffOut, int16_t* chromaClipOut, int16_t* cc0Out, int16_t* cc1Out, int32_t counts[4]);
 /* Flattener pin (vvdec_b200/vvdec_glue/flatten_pu.h): builds real inter CodingUnits from the syntax below, runs the real
  * InterPrediction::motionCompensation on each (prediction written to dst) and b200glue::flattenPU / flattenSbTmvp on the same CU.
  * Reference lists: L0 = {slot 0 (POC 4), slot 1 (POC 0)}, L1 = {slot 2 (POC 12), slot 3 (POC 16) or, with altRefs, slot 0 again};
