@@ -125,12 +125,30 @@ def h2d_bytes(pic):
     return n
 
 
+def bind_to_gpu_numa_node(local):
+    """Run this process (and first-touch its pinned buffers) on the NUMA node the GPU hangs off: H2D/D2H then do not cross the socket link."""
+    try:
+        import subprocess
+        bdf = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)], capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if bdf.startswith("00000000:"): bdf = bdf[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0: return {"node": None}
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-"); cpus += list(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except Exception as e:
+        return {"node": None, "error": str(e)[:80]}
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 def run_b200(args):
     import torch, torch.distributed as dist
     import vvdec_b200
     from vvdec_b200 import abi
     rank, world, local = dist_env()
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
@@ -296,7 +314,7 @@ def run_b200(args):
                        "l2": "inputs larger than L2 (6x25 MB DPB + %d work-list arenas cycled)" % args.gop, "parallelism": f"gop-per-gpu x{world}"},
             "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(np.mean([h2d_bytes(p) for p in pics])),
                     "d2h_bytes_per_step": int(sum(o.nbytes for o in out)), "diag": e2e_diag, "api": "b200_pic_upload (one picture ahead) + b200_pic_run + b200_get_frame_async (D2H overlapped with the next picture), pinned host buffers; every step uploads one picture's work lists and downloads one frame"},
-            "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof}
+            "gpu_launches": int(launches), "numa": numa, "clocks": sampler.summary(), "roofline": roof}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, pics, refs)
     print(json.dumps(line), flush=True)

@@ -93,6 +93,14 @@ extern "C" void ref_dequant( int simd, int width, int maxX, int maxY, int scale,
   ( simd ? qv : qs ).DeQuant( width, maxX, maxY, scale, q, qStride, coef, rightShift, inputMaximum, transformMaximum );
 }
 
+extern "C" void ref_dequant_scaling( int simd, int width, int maxX, int maxY, int scaleQP, const int32_t* dequantCoef, const int16_t* q, size_t qStride, int32_t* coef,
+                                     int rightShift, int inputMaximum, int32_t transformMaximum )
+{
+  globalInit();
+  static Quant qs( nullptr, false ), qv( nullptr, true );
+  ( simd ? qv : qs ).DeQuantScaling( width, maxX, maxY, scaleQP, dequantCoef, q, qStride, coef, rightShift, inputMaximum, transformMaximum );
+}
+
 static InterPrediction* sharedIP() { static InterPrediction* ip = new InterPrediction(); return ip; }
 static TrQuant*         sharedTQ() { static TrQuant* tq = new TrQuant( sharedIP() ); return tq; }
 

@@ -96,6 +96,9 @@ int ref_mc_predict(int simd, const b200_geom* g, int16_t* const dst[3], const in
  * of one picture is included (every picture is extended once when it becomes a reference, DecLibRecon.cpp:236).
  * Returns the seconds spent in the timed part (setup of the fake vvdec objects excluded); out (may be NULL) receives the picture. */
 double ref_decompress_picture_mt(const b200_geom* g, const int16_t* const* refs, const b200_picture* pic, int threads, int simd);
+/* Quant::DeQuantScaling / DeQuantScalingCore (Quant.cpp:182): dequantisation with a per-position scaling-list table (piDequantCoef). */
+void ref_dequant_scaling(int simd, int width, int maxX, int maxY, int scaleQP, const int32_t* dequantCoef, const int16_t* q, size_t qStride, int32_t* coef,
+                         int rightShift, int inputMaximum, int32_t transformMaximum);
 /* Filter flatteners (vvdec_b200/vvdec_glue/flatten_filters.h): reference structures filled from the flattened input, flattened again. */
 int ref_flatten_filters(const b200_geom* g, const b200_lf_param* lfV, const b200_lf_param* lfH, const b200_sao_ctu* sao, const b200_alf_ctu* alf,
                         const b200_alf_tables* T, b200_lf_param* lfVOut, b200_lf_param* lfHOut, b200_sao_ctu* saoOut, b200_alf_ctu* alfOut,

@@ -64,6 +64,7 @@ def load_ref():
     lib = C.CDLL(REF_SO)
     lib.ref_simd_level.restype = C.c_char_p
     lib.ref_dequant.argtypes = [C.c_int] * 5 + [i16p, C.c_size_t, i32p, C.c_int, C.c_int, C.c_int32]
+    lib.ref_dequant_scaling.argtypes = [C.c_int] * 5 + [i32p, i16p, C.c_size_t, i32p, C.c_int, C.c_int, C.c_int32]
     lib.ref_inv_lfnst.argtypes = [i32p, i32p, C.c_uint, C.c_uint, C.c_uint, C.c_int]
     lib.ref_inv_1d.argtypes = [C.c_int, C.c_int, C.c_int, i32p, i32p] + [C.c_int] * 5 + [C.c_int32, C.c_int32]
     lib.ref_cpy_resi_clip.argtypes = [C.c_int, i32p, i16p, C.c_ssize_t, C.c_uint, C.c_uint] + [C.c_int32] * 4

@@ -67,3 +67,28 @@ def test_k1_empty_and_errors(b200):
     g.bitDepth = 17
     assert b200.b200_k1_residual(C.byref(g), abi.plane_ptrs(planes), None, 0, None, 0, None, 0, 0) == -2
     assert b"bit depth" in b200.b200_last_error()
+
+
+@pytest.mark.parametrize("seed,W,H,bd", [(31, 416, 240, 10), (32, 256, 256, 8)])
+def test_k1_explicit_scaling_lists(b200, oracle, seed, W, H, bd):
+    """Explicit scaling lists (Quant.cpp:386-576 tables / :182 DeQuantScalingCore): per-position dequantisation table of the
+    TU's shape, +4 right shift; TS and LFNST TUs stay flat (sps_scaling_matrix_for_lfnst_disabled)."""
+    rng = np.random.default_rng(seed)
+    cus = synth.partition(rng, W, H)
+    sl = synth.gen_scaling_lists(rng)
+    tus, coefs = synth.gen_tus(rng, cus, bd, p_cbf=0.9, p_mts=0.25, p_lfnst=0.1, p_ts=0.1, p_bdpcm=0.05, p_intra=0.5, scaling=sl)
+    assert (tus["flags"] & abi.TU_SCALING).any() and not (tus["flags"] & abi.TU_SCALING).all()
+    planes = synth.noise_planes(rng, W, H, bd)
+    g = abi.make_geom(W, H, bd)
+    a = [p.copy() for p in planes]; b = [p.copy() for p in planes]
+    arena = sl["arena"]
+    oracle.orc_k1_residual(C.byref(g), abi.plane_ptrs(a), tus.ctypes.data, len(tus), coefs, arena.ctypes.data, 0)
+    vvdec_b200.check(b200.b200_k1_residual(C.byref(g), abi.plane_ptrs(b), tus.ctypes.data, len(tus), coefs.ctypes.data, len(coefs),
+                                            arena.ctypes.data, len(arena), 0))
+    for c in range(3):
+        assert np.array_equal(a[c], b[c]), f"plane {c} differs at {np.argwhere(a[c] != b[c])[:5]}"
+    # and the lists matter: the flat result is different
+    tus2 = tus.copy(); tus2["flags"] &= ~np.uint8(abi.TU_SCALING)
+    c2 = [p.copy() for p in planes]
+    oracle.orc_k1_residual(C.byref(g), abi.plane_ptrs(c2), tus2.ctypes.data, len(tus2), coefs, None, 0)
+    assert not np.array_equal(a[0], c2[0])

@@ -34,6 +34,26 @@ def test_dequant(oracle, ref, simd):
         assert np.array_equal(a, b), (case, w, h, maxX, maxY, scale, rs)
 
 
+@pytest.mark.parametrize("simd", [0, 1])
+def test_dequant_scaling_lists(oracle, ref, simd):
+    """Explicit scaling lists: Quant::DeQuantScaling with a per-position table (what getDequantCoeff returns: list value, 16 = neutral)
+    and the +4 right shift of LOG2_SCALING_LIST_NEUTRAL_VALUE (Quant.cpp:345)."""
+    rng = np.random.default_rng(11)
+    for case in range(300):
+        w = 1 << rng.integers(2, 7); h = 1 << rng.integers(2, 7)
+        maxX = int(rng.integers(0, min(w, 32))); maxY = int(rng.integers(0, min(h, 32)))
+        scale = int(rng.choice([40, 45, 51, 57, 64, 72, 80, 90, 102]))
+        rs = int(rng.integers(0, 16))
+        in_bits = min(16, 32 + rs - 7)
+        in_max = (1 << (in_bits - 1)) - 1
+        sl = rng.integers(1, 256, size=w * h).astype(np.int32) if case % 4 else np.full(w * h, 16, np.int32)
+        q = (rng.laplace(0, 40, size=(h, w))).clip(-32768, 32767).astype(np.int16)
+        a = np.zeros(w * h, np.int32); b = np.zeros(w * h, np.int32)
+        oracle.orc_dequant(w, maxX, maxY, scale, sl.ctypes.data, q, w, a, rs, in_max, 32767)
+        ref.ref_dequant_scaling(simd, w, maxX, maxY, scale, sl, q, w, b, rs, in_max, 32767)
+        assert np.array_equal(a, b), (case, w, h, maxX, maxY, scale, rs)
+
+
 def test_inv_lfnst(oracle, ref):
     rng = np.random.default_rng(2)
     for case in range(400):

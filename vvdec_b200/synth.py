@@ -54,9 +54,11 @@ def _laplace_levels(rng, n, heavy=False):
 
 
 def gen_tus(rng, cus, bit_depth=10, p_cbf=0.5, p_mts=0.2, p_lfnst=0.1, p_ts=0.05, p_bdpcm=0.03, p_jccr=0.1,
-            p_full=0.3, chroma=True, heavy=0.02, dep_quant=True, p_intra=0.15):
+            p_full=0.3, chroma=True, heavy=0.02, dep_quant=True, p_intra=0.15, scaling=None):
     """TU records + packed level arena for a CU list (one TU per <=64x64 tile of each CU, all 3 components).
-    Mirrors what the flattener (vvdec_glue/flatten_tu.h) derives from parsed TUs; QP drawn uniformly in 22..37."""
+    Mirrors what the flattener (vvdec_glue/flatten_tu.h) derives from parsed TUs; QP drawn uniformly in 22..37.
+    scaling: None, or the dict of gen_scaling_lists(): non-TS, non-LFNST TUs then use explicit scaling lists (Quant.cpp:309-312):
+    B200_TU_SCALING, slOff -> the table of their (log2w, log2h), right shift + 4."""
     recs, coefs = [], []
     ncoef = 0
     inv_scales = np.array([[40, 45, 51, 57, 64, 72], [57, 64, 72, 80, 90, 102]])
@@ -118,6 +120,9 @@ def gen_tus(rng, cus, bit_depth=10, p_cbf=0.5, p_mts=0.2, p_lfnst=0.1, p_ts=0.05
                     per, rem = ((q + 1) // 6, (q + 1) % 6) if dq else (q // 6, q % 6)
                     tr_shift = 15 - bit_depth - ((l2w + l2h) >> 1) + (-1 if sqrt2 else 0)
                     right_shift = 6 + (1 if dq else 0) - ((0 if is_ts else tr_shift) + per)
+                    sl_off = 0
+                    if scaling is not None and not is_ts and not lfnst:
+                        flags |= abi.TU_SCALING; right_shift += 4; sl_off = scaling["off"][(l2w, l2h)]
                     in_bits = min(16, 32 + right_shift - 7)
                     n = (maxX + 1) * (maxY + 1)
                     lv = _laplace_levels(rng, n, rng.random() < heavy)
@@ -127,11 +132,24 @@ def gen_tus(rng, cus, bit_depth=10, p_cbf=0.5, p_mts=0.2, p_lfnst=0.1, p_ts=0.05
                         lv[(xx + yy) > 2] = 0
                     if lv[-1] == 0: lv[-1] = 1
                     recs.append((x, y, l2w, l2h, comp, flags, maxX, maxY, tr, lfnst, ict, right_shift, in_bits,
-                                 int(inv_scales[1 if sqrt2 else 0][rem]), ncoef, 0, (0, 0)))
+                                 int(inv_scales[1 if sqrt2 else 0][rem]), ncoef, sl_off, (0, 0)))
                     coefs.append(lv); ncoef += n
     tus = np.array(recs, dtype=abi.TU_DTYPE) if recs else np.zeros(0, abi.TU_DTYPE)
     arena = np.concatenate(coefs) if coefs else np.zeros(0, np.int16)
     return tus, arena
+
+
+def gen_scaling_lists(rng):
+    """One dequantisation table per block shape, laid out as Quant::getDequantCoeff returns them (w*h int32, value 16 = neutral), back to
+    back in one arena; 'off' maps (log2w, log2h) to the table's offset.  Low frequencies get smaller values, as typical lists do."""
+    off, parts, o = {}, [], 0
+    for l2w in range(1, 7):
+        for l2h in range(1, 7):
+            w, h = 1 << l2w, 1 << l2h
+            yy, xx = np.mgrid[0:h, 0:w]
+            t = 8 + ((xx * 8) // w + (yy * 8) // h) * int(rng.integers(1, 12)) + rng.integers(0, 4, size=(h, w))
+            off[(l2w, l2h)] = o; parts.append(np.clip(t, 1, 255).astype(np.int32).reshape(-1)); o += w * h
+    return dict(off=off, arena=np.concatenate(parts))
 
 
 def noise_planes(rng, W, H, bit_depth=10, chroma=True, strides=None):
