@@ -333,6 +333,9 @@ def cpu_baseline(args, pics, refs, threads=None):
     cores = threads or os.cpu_count()
     if ref is not None and hasattr(ref, "ref_decompress_picture_mt"):
         ref.ref_decompress_picture_mt.restype = C.c_double
+        try: os.sched_setaffinity(0, range(os.cpu_count()))          # the GPU arm binds itself to the GPU's NUMA node; the CPU baseline gets every core
+        except Exception: pass
+        ref.ref_decompress_picture_mt(C.byref(g), helpers.ref_ptrs(refs), C.byref(pics[0]["struct"]), cores, 1)   # untimed warm-up (page faults, thread start-up)
         t = 0.0
         for i in range(n):
             t += ref.ref_decompress_picture_mt(C.byref(g), helpers.ref_ptrs(refs), C.byref(pics[i]["struct"]), cores, 1)

@@ -96,3 +96,20 @@ def test_k5_golden(oracle):
     out = [np.zeros_like(p) for p in src]
     oracle.orc_alf_picture(C.byref(g), abi.plane_ptrs(src), abi.plane_ptrs(out), t["ctus"].ctypes.data, C.byref(T))
     for c in range(3): assert np.array_equal(out[c], z[f"out{c}"])
+
+
+def chain_inputs():
+    z = _load("chain_geo_wp_lmcs_picture.npz"); g, W, H = geom_of(z)
+    refs = [[np.ascontiguousarray(z[f"ref{s}_{c}"]) for c in range(3)] for s in range(4)]
+    from vvdec_b200 import synth
+    pic = synth.load_picture(z, g.bitDepth)
+    return z, g, refs, pic
+
+
+def test_chain_golden(oracle):
+    """Whole chain with GEO + explicit weighted prediction + LMCS (chroma scaling) against the reference arm's stored output."""
+    from tests.helpers import oracle_decompress
+    z, g, refs, pic = chain_inputs()
+    assert (pic["pus"]["flags"] & 128).any() and (pic["pus"]["wpIdx"] != 0).any()
+    out, _ = oracle_decompress(oracle, g, refs, pic)
+    for c in range(3): assert np.array_equal(out[c], z[f"out{c}"]), f"plane {c}"

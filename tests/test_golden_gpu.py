@@ -38,3 +38,20 @@ def test_k5_golden_gpu(b200):
     out = [np.zeros_like(p) for p in src]
     vvdec_b200.check(b200.b200_alf_picture(C.byref(g), abi.plane_ptrs(src), abi.plane_ptrs(out), t["ctus"].ctypes.data, C.byref(T)))
     for c in range(3): assert np.array_equal(out[c], z[f"out{c}"])
+
+
+def test_chain_golden_gpu(b200):
+    """The stored output of the reference arm for a picture with GEO + explicit weighted prediction + LMCS, through b200_decompress_picture."""
+    z, g, refs, pic = G.chain_inputs()
+    ctx = C.c_void_p()
+    vvdec_b200.check(b200.b200_ctx_create(C.byref(ctx), C.byref(g), 5, 1, -1))
+    try:
+        for s in range(4): vvdec_b200.check(b200.b200_ctx_load_slot(ctx, s, abi.plane_ptrs(refs[s])))
+        pic["struct"].dstSlot = 4
+        h = b200.b200_decompress_picture(ctx, C.byref(pic["struct"])); assert h >= 0, b200.b200_last_error()
+        vvdec_b200.check(b200.b200_wait_picture(ctx, h, None, 0))
+        got = [np.zeros_like(np.ascontiguousarray(z[f"out{c}"])) for c in range(3)]
+        vvdec_b200.check(b200.b200_get_frame(ctx, 4, abi.plane_ptrs(got)))
+        for c in range(3): assert np.array_equal(got[c], z[f"out{c}"]), f"plane {c}"
+    finally:
+        b200.b200_ctx_destroy(ctx)

@@ -94,6 +94,27 @@ def pictures():
                         **{f"in{c}": src[c] for c in range(3)}, **{f"out{c}": o5[c] for c in range(3)})
 
 
+def chain():
+    """Whole back end on one small picture with the tools added after the first fixtures: GEO, explicit weighted prediction, LMCS with
+    chroma scaling, on top of K2 -> K1 -> K3 -> K4 -> K5; output of the reference arm (the reference's own kernels, SIMD off)."""
+    W, H, bd, ctu = 256, 128, 10, 128
+    g = abi.make_geom(W, H, bd, ctu=ctu)
+    rng = np.random.default_rng(303)
+    refs = [synth.noise_planes(rng, W, H, bd) for _ in range(4)]
+    pic = synth.gen_picture(rng, W, H, bd, ctu=ctu, dst_slot=0, wp=True, lmcs=True, pu_kw=dict(p_dmvr=0.0, p_bdof=0.0, p_bcw=0.3, p_geo=0.2), tu_kw=dict(p_cbf=0.7))
+    vp = pic["lmcs"]["vpdus"]                                   # the reference arm's CU structure is one CU per CTU (tests/test_lmcs_oracle_vs_ref.py)
+    for j in range((H + 63) // 64):
+        for i in range((W + 63) // 64):
+            cx, cy = i * 64 // ctu * ctu, j * 64 // ctu * ctu
+            vp[j * ((W + 63) // 64) + i] = (cx, cy, cx > 0, cy > 0)
+    out = [np.zeros((H, W), np.int16), np.zeros((H // 2, W // 2), np.int16), np.zeros((H // 2, W // 2), np.int16)]
+    ref.ref_set_wp(pic["wpRaw"].ctypes.data)
+    try: ref.ref_decompress_picture_out(C.byref(g), ref_ptrs(refs), C.byref(pic["struct"]), 2, 0, abi.plane_ptrs(out))
+    finally: ref.ref_set_wp(None)
+    np.savez_compressed(os.path.join(OUT, "chain_geo_wp_lmcs_picture.npz"), geom=[W, H, bd, ctu], **synth.save_picture(pic),
+                        **{f"ref{s}_{c}": refs[s][c] for s in range(4) for c in range(3)}, **{f"out{c}": out[c] for c in range(3)})
+
+
 if __name__ == "__main__":
-    k1(); pictures()
+    k1(); pictures(); chain()
     print({f: os.path.getsize(os.path.join(OUT, f)) for f in sorted(os.listdir(OUT))})

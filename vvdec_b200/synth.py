@@ -503,3 +503,54 @@ def gen_picture(rng, W, H, bit_depth=10, ctu=128, dst_slot=0, cu_kw=None, pu_kw=
         p.flags |= A.PIC_LMCS; p.lmcs = C.addressof(d["lmcs"]["struct"])
     d["struct"] = p
     return d
+
+
+# ---- a whole picture as a flat dict of arrays (golden fixtures): save_picture(d) -> {name: ndarray}, load_picture(z) -> the dict of gen_picture
+def save_picture(d):
+    out = dict(pus=d["pus"], ndmvr=np.int64(d["ndmvr"]), tus=d["tus"], coefs=d["coefs"], dstSlot=np.int64(d["struct"].dstSlot))
+    for k in ("lfV", "lfH", "lfSlices", "sao", "wp", "wpRaw"):
+        if k in d: out[k] = d[k]
+    if "alf" in d:
+        a = d["alf"]
+        out.update(alf_ctus=a["ctus"], alf_lumaCoeff=a["lumaCoeff"][16:], alf_lumaClip=a["lumaClip"][16:], alf_chromaCoeff=a["chromaCoeff"],
+                   alf_chromaClip=a["chromaClip"], alf_cc0=a["cc"][0], alf_cc1=a["cc"][1])
+    if "lmcs" in d:
+        L = d["lmcs"]["struct"]
+        out.update(lmcs_scalars=np.array([L.chromaAdj, L.minBinIdx, L.maxBinIdx, L.orgCW], np.int32), lmcs_reshapePivot=np.array(list(L.reshapePivot), np.int16),
+                   lmcs_inputPivot=np.array(list(L.inputPivot), np.int16), lmcs_fwdScaleCoef=np.array(list(L.fwdScaleCoef), np.int16),
+                   lmcs_chromaAdjHelpLUT=np.array(list(L.chromaAdjHelpLUT), np.int32), lmcs_invLUT=d["lmcs"]["invLUT"], lmcs_vpdus=d["lmcs"]["vpdus"])
+    return out
+
+
+def load_picture(z, bit_depth):
+    """z: mapping from save_picture (e.g. an opened .npz)."""
+    fixed_sets = (_fixed_sets(), np.full((16, 4, 25, 13), 1 << bit_depth, np.int16))
+    from . import abi as A
+    import ctypes as C
+    d = dict(pus=np.ascontiguousarray(z["pus"]), ndmvr=int(z["ndmvr"]), tus=np.ascontiguousarray(z["tus"]), coefs=np.ascontiguousarray(z["coefs"]))
+    p = A.Picture(); p.dstSlot = int(z["dstSlot"]); p.flags = 0
+    p.pus = d["pus"].ctypes.data; p.numPus = len(d["pus"]); p.numDmvr = d["ndmvr"] + 1
+    p.tus = d["tus"].ctypes.data; p.numTus = len(d["tus"]); p.coefs = d["coefs"].ctypes.data; p.numCoefs = len(d["coefs"])
+    if "lfV" in z:
+        for k in ("lfV", "lfH", "lfSlices"): d[k] = np.ascontiguousarray(z[k])
+        p.flags |= A.PIC_DEBLOCK; p.lfV = d["lfV"].ctypes.data; p.lfH = d["lfH"].ctypes.data; p.lfSlices = d["lfSlices"].ctypes.data; p.numLfSlices = len(d["lfSlices"])
+    if "sao" in z:
+        d["sao"] = np.ascontiguousarray(z["sao"]); p.flags |= A.PIC_SAO; p.sao = d["sao"].ctypes.data
+    if "alf_ctus" in z:
+        d["alf"] = dict(ctus=np.ascontiguousarray(z["alf_ctus"]), lumaCoeff=np.ascontiguousarray(np.concatenate([fixed_sets[0], z["alf_lumaCoeff"]])),
+                        lumaClip=np.ascontiguousarray(np.concatenate([fixed_sets[1], z["alf_lumaClip"]])), chromaCoeff=np.ascontiguousarray(z["alf_chromaCoeff"]),
+                        chromaClip=np.ascontiguousarray(z["alf_chromaClip"]), cc=[np.ascontiguousarray(z["alf_cc0"]), np.ascontiguousarray(z["alf_cc1"])])
+        d["alfTabs"] = A.make_alf_tables(d["alf"])
+        p.flags |= A.PIC_ALF; p.alf = d["alf"]["ctus"].ctypes.data; p.alfTabs = C.addressof(d["alfTabs"])
+    if "wp" in z:
+        d["wp"] = np.ascontiguousarray(z["wp"]); d["wpRaw"] = np.ascontiguousarray(z["wpRaw"]); p.wp = d["wp"].ctypes.data; p.numWp = len(d["wp"])
+    if "lmcs_scalars" in z:
+        L = A.Lmcs(); sc = z["lmcs_scalars"]; L.chromaAdj, L.minBinIdx, L.maxBinIdx, L.orgCW = [int(v) for v in sc]
+        for i in range(17): L.reshapePivot[i] = int(z["lmcs_reshapePivot"][i]); L.inputPivot[i] = int(z["lmcs_inputPivot"][i])
+        for i in range(16): L.fwdScaleCoef[i] = int(z["lmcs_fwdScaleCoef"][i]); L.chromaAdjHelpLUT[i] = int(z["lmcs_chromaAdjHelpLUT"][i])
+        lut = np.ascontiguousarray(z["lmcs_invLUT"]); vp = np.ascontiguousarray(z["lmcs_vpdus"])
+        L.invLUT = lut.ctypes.data; L.vpdus = vp.ctypes.data
+        d["lmcs"] = dict(struct=L, invLUT=lut, vpdus=vp)
+        p.flags |= A.PIC_LMCS; p.lmcs = C.addressof(L)
+    d["struct"] = p
+    return d
