@@ -288,6 +288,7 @@ def gen_alf(rng, W, H, ctu=128, bit_depth=10, n_aps=2, n_chroma_alts=3, n_cc=(2,
             coef[s, t] = base[:, ALF_TR[t]]; clip[s, t] = bclip[:, ALF_TR[t]]
     ccoef = rng.integers(-40, 41, size=(n_chroma_alts, 7)).astype(np.int16); ccoef[:, 6] = 128
     cclip = rng.choice(clipv, size=(n_chroma_alts, 7)).astype(np.int16)
+    cclip[0, :] = clipv[0]                                      # first alternative without clipping (clip index 0), as encoders mostly signal
     cc = [rng.integers(-63, 64, size=(n_cc[c], 7)).astype(np.int16) for c in range(2)]
     ctusW, ctusH = (W + ctu - 1) // ctu, (H + ctu - 1) // ctu
     n = ctusW * ctusH
