@@ -70,6 +70,19 @@ def test_invalid_records_are_reported(b200):
         pic["tus"]["log2w"][0] = 7
         assert b200.b200_decompress_picture(ctx, C.byref(pic["struct"])) == -2 and b"TU list" in b200.b200_last_error()
         pic["tus"]["log2w"][0] = 2
+        # records that would touch memory outside the picture or outside the uploaded arrays are refused too
+        for arr, field, idx, bad, what in (("pus", "x", 5, W - 4 + 8, b"PU list"), ("pus", "y", 5, H, b"PU list"), ("pus", "x", 5, 2, b"PU list"),
+                                           ("tus", "coefOff", 1, 1 << 30, b"TU list"), ("tus", "x", 1, W, b"TU list"), ("tus", "maxX", 1, 200, b"TU list")):
+            keep = pic[arr][field][idx].copy()
+            pic[arr][field][idx] = bad
+            assert b200.b200_decompress_picture(ctx, C.byref(pic["struct"])) == -2 and what in b200.b200_last_error(), (arr, field)
+            pic[arr][field][idx] = keep
+        dm = np.flatnonzero(pic["pus"]["flags"] & synth.PU_DMVR)
+        if dm.size:
+            keep = pic["pus"]["dmvrOff"][dm[0]].copy()
+            pic["pus"]["dmvrOff"][dm[0]] = 1 << 30
+            assert b200.b200_decompress_picture(ctx, C.byref(pic["struct"])) == -2 and b"PU list" in b200.b200_last_error()
+            pic["pus"]["dmvrOff"][dm[0]] = keep
         h = b200.b200_decompress_picture(ctx, C.byref(pic["struct"])); assert h >= 0      # the context is still usable
         assert b200.b200_wait_picture(ctx, h, None, 0) == 0
     finally:

@@ -113,7 +113,7 @@ B200_API int b200_k1_residual(const b200_geom* g, int16_t* const planes[3], cons
   if (numScaling) B200_CUDA(cudaMemcpyAsync(g_hw.scaling.p, scaling, numScaling * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   L.tus = g_hw.tus.as<b200_tu>(); L.coefs = g_hw.coefs.as<int16_t>(); L.scaling = g_hw.scaling.as<int32_t>();
   int* meta = g_hw.misc[4].as<int>(); uint32_t* idx = reinterpret_cast<uint32_t*>(meta + LM_INTS);
-  if (int rc = launch_tu_bucket(L.tus, numTus, idx, meta, s)) return rc;
+  if (int rc = launch_tu_bucket(L.tus, numTus, idx, meta, *g, numCoefs, numScaling, s)) return rc;
   L.idx = idx; L.meta = meta;
   if (int rc = fetch_list_meta(meta, L.cnt, K1_LISTS, "b200_k1_residual", s)) return rc;
   StreamSet ss(s);
@@ -260,7 +260,7 @@ B200_API int b200_mc_predict_wp(const b200_geom* g, int16_t* const dst[3], const
   if (int rc = g_hw.misc[7].reserve(numDmvr * 8 + 64)) return rc;
   if (numPus) B200_CUDA(cudaMemcpyAsync(g_hw.misc[5].p, pus, numPus * sizeof(b200_pu), cudaMemcpyHostToDevice, s));
   int* meta = g_hw.misc[6].as<int>(); uint32_t* tiles = reinterpret_cast<uint32_t*>(meta + LM_INTS);
-  if (int rc = launch_mc_bucket(g_hw.misc[5].as<b200_pu>(), numPus, tiles, capTiles, meta, numSlots, g->bitDepth, wp ? numWp : 0, s)) return rc;
+  if (int rc = launch_mc_bucket(g_hw.misc[5].as<b200_pu>(), numPus, tiles, capTiles, meta, *g, numSlots, wp ? numWp : 0, numDmvr, s)) return rc;
   L.tiles = tiles; L.meta = meta;
   if (wp && numWp > 0) {
     B200_CHECK(numWp <= 255, "b200_mc_predict_wp: at most 255 weighted-prediction entries");

@@ -18,13 +18,18 @@ __device__ __forceinline__ int mc_list_of(int w, int h, int flags, bool bi, int 
 }
 
 struct PuHead { int w, h, flags; bool bi, ok; };
-__device__ __forceinline__ PuHead pu_head(const b200_pu* pus, int i, int slotsBd)   // slotsBd = numSlots | bitDepth << 8 | numWp << 16
+struct PuLimits { int slotsBd, W, H; unsigned numDmvr; };   // slotsBd = numSlots | bitDepth << 8 | numWp << 16
+__device__ __forceinline__ PuHead pu_head(const b200_pu* pus, int i, const PuLimits lim)
 {
+  const int slotsBd = lim.slotsBd;
   const b200_pu& p = pus[i];
   PuHead r; r.w = p.w; r.h = p.h; r.flags = p.flags;
   const int s0 = p.refSlot[0], s1 = p.refSlot[1], numSlots = slotsBd & 0xff, bitDepth = (slotsBd >> 8) & 0xff, numWp = slotsBd >> 16;
   r.bi = s0 >= 0 && s1 >= 0;
   r.ok = s0 < numSlots && s1 < numSlots && (s0 >= 0 || s1 >= 0) && r.w >= 4 && r.h >= 4 && r.w <= 128 && r.h <= 128 && !(r.w & 3) && !(r.h & 3);
+  // the block must lie inside the picture on the 4x4 grid (kernels write every sample of it), DMVR deltas inside the output array
+  if ((p.x & 3) || (p.y & 3) || p.x + r.w > lim.W || p.y + r.h > lim.H) r.ok = false;
+  if ((r.flags & B200_PU_DMVR) && (unsigned long long)p.dmvrOff + (unsigned)(max(1, r.w >> 4) * max(1, r.h >> 4)) > lim.numDmvr) r.ok = false;
   // BDOF / DMVR blocks are at least 8x8 with 128 samples (conditions at InterPrediction.cpp:1372-1420); DMVR also needs both lists and
   // is never affine.  A BDOF flag on a uni-predicted or affine PU is ignored, as the launch-side classification always did.
   const bool big = r.w >= 8 && r.h >= 8 && r.w * r.h >= 128, aff = r.flags & B200_PU_AFFINE;
@@ -41,7 +46,7 @@ __device__ __forceinline__ PuHead pu_head(const b200_pu* pus, int i, int slotsBd
   return r;
 }
 
-__global__ void __launch_bounds__(256) mc_count_kernel(const b200_pu* __restrict__ pus, int numPus, int* meta, int numSlots, int cap)
+__global__ void __launch_bounds__(256) mc_count_kernel(const b200_pu* __restrict__ pus, int numPus, int* meta, const PuLimits numSlots, int cap)
 {
   __shared__ int h[MC_LISTS]; __shared__ int sLast;
   if (threadIdx.x < MC_LISTS) h[threadIdx.x] = 0;
@@ -66,7 +71,7 @@ __global__ void __launch_bounds__(256) mc_count_kernel(const b200_pu* __restrict
   }
 }
 
-__global__ void __launch_bounds__(256) mc_scatter_kernel(const b200_pu* __restrict__ pus, int numPus, int* meta, uint32_t* __restrict__ tiles, int numSlots)
+__global__ void __launch_bounds__(256) mc_scatter_kernel(const b200_pu* __restrict__ pus, int numPus, int* meta, uint32_t* __restrict__ tiles, const PuLimits numSlots)
 {
   __shared__ int h[MC_LISTS], base[MC_LISTS];
   if (threadIdx.x < MC_LISTS) h[threadIdx.x] = 0;
@@ -85,20 +90,31 @@ __global__ void __launch_bounds__(256) mc_scatter_kernel(const b200_pu* __restri
   }
 }
 
-__device__ __forceinline__ int tu_class(const b200_tu* tus, int i, bool& ok)
+struct TuLimits { int W, H, chroma; unsigned numCoefs, numScaling; };
+__device__ __forceinline__ int tu_class(const b200_tu* tus, int i, bool& ok, const TuLimits lim)
 {
-  const int l2w = tus[i].log2w, l2h = tus[i].log2h, m = max(l2w, l2h);
-  ok = l2w >= 1 && l2h >= 1 && m <= 6 && tus[i].comp < 3;
+  const b200_tu& t = tus[i];
+  const int l2w = t.log2w, l2h = t.log2h, m = max(l2w, l2h);
+  ok = l2w >= 1 && l2h >= 1 && m <= 6 && t.comp < 3;
+  if (ok) {
+    // inside its plane (the joint-CbCr partner plane has the same geometry), level corner and scaling table inside their arrays
+    const int w = 1 << l2w, h = 1 << l2h, pw = t.comp ? lim.W >> 1 : lim.W, ph = t.comp ? lim.H >> 1 : lim.H;
+    const bool ts = t.flags & B200_TU_TS;
+    if ((t.comp && !lim.chroma) || t.x + w > pw || t.y + h > ph || t.maxX >= w || t.maxY >= h || (!ts && (t.maxX >= 32 || t.maxY >= 32))) ok = false;
+    if ((unsigned long long)t.coefOff + (unsigned)((t.maxX + 1) * (t.maxY + 1)) > lim.numCoefs) ok = false;
+    if ((t.flags & B200_TU_SCALING) && (unsigned long long)t.slOff + (unsigned)(w * h) > lim.numScaling) ok = false;
+    if (t.inBits < 1 || t.inBits > 32 || t.rightShift < -31 || t.rightShift > 31) ok = false;
+  }
   return m <= 3 ? 0 : m == 4 ? 1 : m == 5 ? 2 : 3;
 }
 
-__global__ void __launch_bounds__(256) tu_count_kernel(const b200_tu* __restrict__ tus, int numTus, int* meta)
+__global__ void __launch_bounds__(256) tu_count_kernel(const b200_tu* __restrict__ tus, int numTus, int* meta, const TuLimits lim)
 {
   __shared__ int h[K1_LISTS]; __shared__ int sLast;
   if (threadIdx.x < K1_LISTS) h[threadIdx.x] = 0;
   __syncthreads();
   const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i < numTus) { bool ok; const int c = tu_class(tus, i, ok); if (ok) atomicAdd(&h[c], 1); else atomicOr(&meta[LM_ERR], 1); }
+  if (i < numTus) { bool ok; const int c = tu_class(tus, i, ok, lim); if (ok) atomicAdd(&h[c], 1); else atomicOr(&meta[LM_ERR], 1); }
   __syncthreads();
   if (threadIdx.x < K1_LISTS && h[threadIdx.x]) atomicAdd(&meta[LM_CNT + threadIdx.x], h[threadIdx.x]);
   __threadfence();
@@ -112,14 +128,14 @@ __global__ void __launch_bounds__(256) tu_count_kernel(const b200_tu* __restrict
   }
 }
 
-__global__ void __launch_bounds__(256) tu_scatter_kernel(const b200_tu* __restrict__ tus, int numTus, int* meta, uint32_t* __restrict__ idx)
+__global__ void __launch_bounds__(256) tu_scatter_kernel(const b200_tu* __restrict__ tus, int numTus, int* meta, uint32_t* __restrict__ idx, const TuLimits lim)
 {
   __shared__ int h[K1_LISTS], base[K1_LISTS];
   if (threadIdx.x < K1_LISTS) h[threadIdx.x] = 0;
   __syncthreads();
   const int i = blockIdx.x * 256 + threadIdx.x;
   bool ok = false; int c = 0, my = 0;
-  if (i < numTus) c = tu_class(tus, i, ok);
+  if (i < numTus) c = tu_class(tus, i, ok, lim);
   if (ok) my = atomicAdd(&h[c], 1);
   __syncthreads();
   if (threadIdx.x < K1_LISTS) { const int n = h[threadIdx.x]; base[threadIdx.x] = meta[LM_OFF + threadIdx.x] + (n ? atomicAdd(&meta[LM_CUR + threadIdx.x], n) : 0); }
@@ -127,9 +143,10 @@ __global__ void __launch_bounds__(256) tu_scatter_kernel(const b200_tu* __restri
   if (ok) idx[base[c] + my] = (uint32_t)i;
 }
 
-int launch_mc_bucket(const b200_pu* pus, size_t numPus, uint32_t* tiles, size_t capTiles, int* meta, int numSlots, int bitDepth, int numWp, cudaStream_t s)
+int launch_mc_bucket(const b200_pu* pus, size_t numPus, uint32_t* tiles, size_t capTiles, int* meta, const b200_geom& g, int numSlotsIn, int numWp, size_t numDmvr, cudaStream_t s)
 {
-  numSlots |= (bitDepth << 8) | (numWp << 16);
+  PuLimits numSlots; numSlots.slotsBd = numSlotsIn | (g.bitDepth << 8) | (numWp << 16); numSlots.W = g.width; numSlots.H = g.height;
+  numSlots.numDmvr = (unsigned)(numDmvr > 0xffffffffu ? 0xffffffffu : numDmvr);
   B200_CUDA(cudaMemsetAsync(meta, 0, LM_INTS * sizeof(int), s));
   if (!numPus) return 0;
   const int grid = (int)((numPus + 255) / 256);
@@ -139,13 +156,15 @@ int launch_mc_bucket(const b200_pu* pus, size_t numPus, uint32_t* tiles, size_t 
   return 0;
 }
 
-int launch_tu_bucket(const b200_tu* tus, size_t numTus, uint32_t* idx, int* meta, cudaStream_t s)
+int launch_tu_bucket(const b200_tu* tus, size_t numTus, uint32_t* idx, int* meta, const b200_geom& g, size_t numCoefs, size_t numScaling, cudaStream_t s)
 {
+  TuLimits lim; lim.W = g.width; lim.H = g.height; lim.chroma = g.chromaFormat != 0;
+  lim.numCoefs = (unsigned)(numCoefs > 0xffffffffu ? 0xffffffffu : numCoefs); lim.numScaling = (unsigned)(numScaling > 0xffffffffu ? 0xffffffffu : numScaling);
   B200_CUDA(cudaMemsetAsync(meta, 0, LM_INTS * sizeof(int), s));
   if (!numTus) return 0;
   const int grid = (int)((numTus + 255) / 256);
-  tu_count_kernel<<<grid, 256, 0, s>>>(tus, (int)numTus, meta);
-  tu_scatter_kernel<<<grid, 256, 0, s>>>(tus, (int)numTus, meta, idx);
+  tu_count_kernel<<<grid, 256, 0, s>>>(tus, (int)numTus, meta, lim);
+  tu_scatter_kernel<<<grid, 256, 0, s>>>(tus, (int)numTus, meta, idx, lim);
   B200_CUDA(cudaGetLastError());
   return 0;
 }

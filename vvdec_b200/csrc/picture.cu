@@ -222,8 +222,8 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   A.dstSlot = p->dstSlot; A.flags = p->flags; A.valid = true;
   // work lists: validated and bucketed on the device, behind the copies
   A.mcMeta = reinterpret_cast<int*>(base + oMeta); A.tuMeta = A.mcMeta + LM_INTS;
-  if (int rc = launch_mc_bucket(reinterpret_cast<const b200_pu*>(base + oPus), p->numPus, reinterpret_cast<uint32_t*>(base + oT), capTiles, A.mcMeta, c->numSlots, g.bitDepth, p->numWp, s)) return rc;
-  if (int rc = launch_tu_bucket(reinterpret_cast<const b200_tu*>(base + oTus), p->numTus, reinterpret_cast<uint32_t*>(base + oIdx), A.tuMeta, s)) return rc;
+  if (int rc = launch_mc_bucket(reinterpret_cast<const b200_pu*>(base + oPus), p->numPus, reinterpret_cast<uint32_t*>(base + oT), capTiles, A.mcMeta, g, c->numSlots, p->numWp, p->numDmvr, s)) return rc;
+  if (int rc = launch_tu_bucket(reinterpret_cast<const b200_tu*>(base + oTus), p->numTus, reinterpret_cast<uint32_t*>(base + oIdx), A.tuMeta, g, p->numCoefs, p->numScaling, s)) return rc;
   A.tiles = reinterpret_cast<const uint32_t*>(base + oT); A.tuIdx = reinterpret_cast<const uint32_t*>(base + oIdx);
   c->launches += 4;
   B200_CUDA(cudaMemcpyAsync(A.hMeta, A.mcMeta, 2 * LM_INTS * sizeof(int), cudaMemcpyDeviceToHost, s));   // list lengths for b200_pic_run's grids
