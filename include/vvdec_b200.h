@@ -341,6 +341,13 @@ B200_API int  b200_frame_wait(b200_ctx* ctx, int ticket);
 enum { B200_OUT_16 = 0, B200_OUT_PYUV = 1, B200_OUT_8 = 2 };
 B200_API size_t b200_frame_bytes(const b200_geom* g, int fmt, int comp);
 B200_API int  b200_get_frame_fmt_async(b200_ctx* ctx, int slot, int fmt, void* const planes[3]);
+/* Decoded-picture hash computed on the device: what calcCRC / calcChecksum (CommonLib/PicYuvMD5.cpp:138,:179) produce for
+ * the decoded picture hash SEI check (calcAndPrintHashStatus :261), so a verify-only run reads back 6 / 12 bytes instead of the frame.
+ * method uses the vvdecHashType values (vvdec/sei.h): 1 CRC (2 bytes per component), 2 checksum (4 bytes per component); the digest bytes
+ * are in PictureHash::hash order (Y, Cb, Cr).  MD5 (0) is one serial chain per plane and returns B200_ERR_UNSUPPORTED.
+ * digest must hold 12 bytes (pinned memory recommended).  Returns a ticket for b200_frame_wait. */
+enum { B200_HASH_MD5 = 0, B200_HASH_CRC = 1, B200_HASH_CHECKSUM = 2 };
+B200_API int  b200_frame_hash_async(b200_ctx* ctx, int slot, int method, uint8_t* digest);
 /* Timing helpers for bench.py: CUDA events on the context stream. */
 B200_API int  b200_ctx_mark(b200_ctx* ctx, int which /*0 start, 1 stop*/);
 B200_API int  b200_ctx_elapsed_ms(b200_ctx* ctx, float* ms);

@@ -37,6 +37,7 @@
 #include "CommonLib/LoopFilter.h"
 #include "CommonLib/SampleAdaptiveOffset.h"
 #include "CommonLib/Reshape.h"
+#include "CommonLib/SEI_internal.h"
 #include "../vvdec_b200/vvdec_glue/flatten_pu.h"
 #include "../vvdec_b200/vvdec_glue/flatten_filters.h"
 #include "../vvdec_b200/vvdec_glue/DecLibReconB200.h"   // compile check of the drop-in class against the reference headers
@@ -729,6 +730,25 @@ extern "C" size_t ref_write_component( const int16_t* src, ptrdiff_t stride, int
   const std::string out = os.str();
   memcpy( dst, out.data(), std::min( cap, out.size() ) );
   return out.size();
+}
+
+// defined (non-static, but not declared in any header) in CommonLib/PicYuvMD5.cpp:138,:179,:198
+namespace vvdec {
+uint32_t calcCRC( const CPelUnitBuf& pic, PictureHash& digest, const BitDepths& bitDepths );
+uint32_t calcChecksum( const CPelUnitBuf& pic, PictureHash& digest, const BitDepths& bitDepths );
+uint32_t calcMD5( const CPelUnitBuf& pic, PictureHash& digest, const BitDepths& bitDepths );
+}
+extern "C" int ref_picture_hash( int method, int bitDepth, int16_t* const planes[3], const ptrdiff_t strides[3], int w, int h, uint8_t* digest, int cap )
+{
+  PelUnitBuf ub;
+  ub.chromaFormat = CHROMA_420;
+  for( int c = 0; c < 3; c++ ) ub.bufs.push_back( PelBuf( planes[c], strides[c], c ? w >> 1 : w, c ? h >> 1 : h ) );
+  BitDepths bd; bd.recon = bitDepth;
+  PictureHash dg;
+  if( method == 1 ) calcCRC( ub, dg, bd ); else if( method == 2 ) calcChecksum( ub, dg, bd ); else calcMD5( ub, dg, bd );
+  const int n = (int) dg.hash.size();
+  for( int i = 0; i < n && i < cap; i++ ) digest[i] = dg.hash[i];
+  return n;
 }
 
 // ================================================================================================ LMCS (Reshape)

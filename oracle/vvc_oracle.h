@@ -64,6 +64,8 @@ void orc_lmcs_inv_plane(const b200_geom* g, int16_t* luma, const b200_lmcs* L);
 void orc_pack_pyuv(const int16_t* src, ptrdiff_t stride, int w, int h, uint8_t* dst);
 /* :86-93 8-bit narrowing (the writer's >> 2 for 10 bit; >> (bitDepth - 8) in general). */
 void orc_narrow8(const int16_t* src, ptrdiff_t stride, int w, int h, int bitDepth, uint8_t* dst);
+/* decoded-picture hash of one plane: method 1 CRC (2 bytes), 2 checksum (4 bytes); returns the digest length */
+int orc_plane_hash(int method, int bitDepth, const int16_t* src, ptrdiff_t stride, int w, int h, uint8_t* digest);
 
 /* ---- K3 deblocking -------------------------------------------------------------------------- */
 /* LoopFilter.cpp:213 xPelFilterLumaCore (4 lines). */

@@ -34,3 +34,31 @@ def test_frame_formats(b200, oracle, W, H):
                 assert np.array_equal(outs[c], want), (fmt, c)
     finally:
         b200.b200_ctx_destroy(ctx)
+
+
+@pytest.mark.parametrize("W,H,bd", [(416, 240, 10), (24, 16, 10), (1920, 1080, 10), (416, 240, 8), (3840, 2160, 10), (72, 40, 12)])
+def test_frame_hash(b200, oracle, W, H, bd):
+    """b200_frame_hash_async (CRC by chunk reduction + GF(2) polynomial recombination, checksum by atomic sums) against the oracle's
+    serial restatement of calcCRC / calcChecksum, which tests/test_output_oracle_vs_ref.py pins to the reference."""
+    rng = np.random.default_rng(W + bd)
+    g = abi.make_geom(W, H, bd)
+    ctx = C.c_void_p()
+    vvdec_b200.check(b200.b200_ctx_create(C.byref(ctx), C.byref(g), 2, 1, -1))
+    try:
+        pl = synth.noise_planes(rng, W, H, bd)
+        pl[0][0, :4] = [0, (1 << bd) - 1, 255 % (1 << bd), 256 % (1 << bd)]
+        vvdec_b200.check(b200.b200_ctx_load_slot(ctx, 1, abi.plane_ptrs(pl)))
+        tickets = []
+        for method, n in ((1, 2), (2, 4)):
+            dig = np.full(12, 0xEE, np.uint8)
+            t = b200.b200_frame_hash_async(ctx, 1, method, dig.ctypes.data); assert t >= 0, b200.b200_last_error()
+            tickets.append((t, method, n, dig))
+        for t, method, n, dig in tickets:
+            vvdec_b200.check(b200.b200_frame_wait(ctx, t))
+            for c in range(3):
+                want = np.zeros(4, np.uint8)
+                assert oracle.orc_plane_hash(method, bd, pl[c], pl[c].shape[1], W >> (c > 0), H >> (c > 0), want) == n
+                assert np.array_equal(dig[c * n:(c + 1) * n], want[:n]), (method, c)
+        assert b200.b200_frame_hash_async(ctx, 1, 0, dig.ctypes.data) == -4 and b"MD5" in b200.b200_last_error()
+    finally:
+        b200.b200_ctx_destroy(ctx)

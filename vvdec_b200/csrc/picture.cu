@@ -55,6 +55,7 @@ struct b200_ctx {
   std::vector<Arena> arenas;
   int nextArena = 0;
   long long launches = 0;
+  DevBuf hashBuf;                    // b200_frame_hash_async: accumulators + digest per ticket
 
   DevPlanes planes(int buf) const {
     DevPlanes d; char* b = reinterpret_cast<char*>(bufs[buf]);
@@ -387,6 +388,27 @@ B200_API int b200_get_frame_fmt_async(b200_ctx* c, int slot, int fmt, void* cons
   B200_CUDA(cudaEventRecord(c->readDone[buf], c->copyStream)); c->readPending[buf] = 1;       // the picture buffer is free once it is packed
   for (int k = 0; k < nPl; k++) B200_CUDA(cudaMemcpyAsync(planes[k], dst[k], bytes[k], cudaMemcpyDeviceToHost, c->copyStream));
   const int t = c->nextTicket; c->nextTicket = (c->nextTicket + 1) & 15;
+  B200_CUDA(cudaEventRecord(c->ticketEv[t], c->copyStream));
+  return t;
+}
+
+B200_API int b200_frame_hash_async(b200_ctx* c, int slot, int method, uint8_t* digest)
+{
+  B200_CHECK(c && digest && slot >= 0 && slot < c->numSlots, "b200_frame_hash_async: bad argument");
+  if (method == B200_HASH_MD5) { set_error("b200_frame_hash_async: MD5 is a serial chain over each plane and is not computed on the device; use CRC or checksum"); return B200_ERR_UNSUPPORTED; }
+  B200_CHECK(method == B200_HASH_CRC || method == B200_HASH_CHECKSUM, "b200_frame_hash_async: unknown method %d", method);
+  B200_CUDA(cudaSetDevice(c->device));
+  if (int rc = c->hashBuf.reserve(16 * 32)) return rc;                                        // per ticket: 3 accumulators + 12 digest bytes
+  const int t = c->nextTicket; c->nextTicket = (c->nextTicket + 1) & 15;
+  uint32_t* acc = c->hashBuf.as<uint32_t>() + t * 8; uint8_t* dig = reinterpret_cast<uint8_t*>(acc + 4);
+  const int buf = c->slotBuf[slot];
+  B200_CUDA(cudaEventRecord(c->finalEv, c->stream));
+  B200_CUDA(cudaStreamWaitEvent(c->copyStream, c->finalEv, 0));
+  B200_CUDA(cudaMemsetAsync(acc, 0, 32, c->copyStream));
+  if (int rc = launch_hash(c->planes(buf), c->g, method, acc, dig, c->copyStream)) return rc;
+  c->launches += (c->g.chromaFormat ? 3 : 1) + 1;
+  B200_CUDA(cudaEventRecord(c->readDone[buf], c->copyStream)); c->readPending[buf] = 1;
+  B200_CUDA(cudaMemcpyAsync(digest, dig, 12, cudaMemcpyDeviceToHost, c->copyStream));
   B200_CUDA(cudaEventRecord(c->ticketEv[t], c->copyStream));
   return t;
 }
