@@ -77,6 +77,16 @@ def test_invalid_records_are_reported(b200):
             pic[arr][field][idx] = bad
             assert b200.b200_decompress_picture(ctx, C.byref(pic["struct"])) == -2 and what in b200.b200_last_error(), (arr, field)
             pic[arr][field][idx] = keep
+        fpic = synth.gen_picture(rng, W, H, bd, dst_slot=4)               # with filters: CTU records are range-checked too
+        for arr, field, bad in (("alf", "lumaSet", 250), ("sao", "type", 7), ("alf", "ccIdx", 200)):
+            recs = fpic["alf"]["ctus"] if arr == "alf" else fpic["sao"]
+            keep = recs[0].copy()
+            recs[field][0] = bad
+            if arr == "alf": recs["enable"][0] = 1
+            assert b200.b200_decompress_picture(ctx, C.byref(fpic["struct"])) == -2 and b"CTU record" in b200.b200_last_error(), (arr, field)
+            recs[0] = keep
+        h = b200.b200_decompress_picture(ctx, C.byref(fpic["struct"])); assert h >= 0
+        assert b200.b200_wait_picture(ctx, h, None, 0) == 0
         dm = np.flatnonzero(pic["pus"]["flags"] & synth.PU_DMVR)
         if dm.size:
             keep = pic["pus"]["dmvrOff"][dm[0]].copy()

@@ -175,4 +175,30 @@ size_t mc_tile_capacity(const b200_geom& g, size_t numPus)
   return (size_t)((g.width + 3) >> 2) * ((g.height + 3) >> 2) + numPus * 64;
 }
 
+// Per-CTU side information (SAO / ALF / slice index): every index the filter kernels use to address a table is range-checked here
+// (error bit 4 of the PU meta block), so that a malformed record cannot make them read outside the uploaded arrays.
+__global__ void __launch_bounds__(256) ctu_validate_kernel(const b200_sao_ctu* __restrict__ sao, const b200_alf_ctu* __restrict__ alf, const uint8_t* __restrict__ ctuSlice,
+                                                           int nCtu, const CtuLimits lim, int* meta)
+{
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= nCtu) return;
+  bool ok = true;
+  if (sao) for (int c = 0; c < 3; c++) { const int t = sao[i].type[c]; if (t != B200_SAO_OFF && (t > B200_SAO_BO || (t == B200_SAO_BO && sao[i].band[c] > 31))) ok = false; }
+  if (alf) {
+    const b200_alf_ctu a = alf[i];
+    if ((a.enable[0] & 1) && a.lumaSet >= lim.numLumaSets) ok = false;
+    for (int c = 0; c < 2; c++) { if ((a.enable[1 + c] & 1) && a.chromaAlt[c] >= lim.numChromaAlts) ok = false; if (a.ccIdx[c] > lim.numCc[c]) ok = false; }
+  }
+  if (ctuSlice && ctuSlice[i] >= lim.numLfSlices) ok = false;
+  if (!ok) atomicOr(&meta[LM_ERR], 4);
+}
+
+int launch_ctu_validate(const b200_sao_ctu* sao, const b200_alf_ctu* alf, const uint8_t* ctuSlice, int nCtu, const CtuLimits& lim, int* meta, cudaStream_t s)
+{
+  if (!nCtu || (!sao && !alf && !ctuSlice)) return 0;
+  ctu_validate_kernel<<<(nCtu + 255) / 256, 256, 0, s>>>(sao, alf, ctuSlice, nCtu, lim, meta);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace b200

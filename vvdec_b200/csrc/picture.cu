@@ -227,6 +227,14 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   if (int rc = launch_tu_bucket(reinterpret_cast<const b200_tu*>(base + oTus), p->numTus, reinterpret_cast<uint32_t*>(base + oIdx), A.tuMeta, g, p->numCoefs, p->numScaling, s)) return rc;
   A.tiles = reinterpret_cast<const uint32_t*>(base + oT); A.tuIdx = reinterpret_cast<const uint32_t*>(base + oIdx);
   c->launches += 4;
+  {
+    CtuLimits lim; const bool alfOn = p->flags & B200_PIC_ALF;
+    lim.numLumaSets = alfOn ? T->numLumaSets : 0; lim.numChromaAlts = alfOn ? T->numChromaAlts : 0; lim.numCc[0] = alfOn ? T->numCc[0] : 0; lim.numCc[1] = alfOn ? T->numCc[1] : 0;
+    lim.numLfSlices = p->numLfSlices;
+    const bool any = (p->flags & (B200_PIC_SAO | B200_PIC_ALF)) || ((p->flags & B200_PIC_DEBLOCK) && p->ctuSlice);
+    if (int rc = launch_ctu_validate((p->flags & B200_PIC_SAO) ? A.sao : nullptr, alfOn ? A.alf : nullptr, (p->flags & B200_PIC_DEBLOCK) ? A.ctuSlice : nullptr, (int)nCtu, lim, A.mcMeta, s)) return rc;
+    if (any) c->launches += 1;
+  }
   B200_CUDA(cudaMemcpyAsync(A.hMeta, A.mcMeta, 2 * LM_INTS * sizeof(int), cudaMemcpyDeviceToHost, s));   // list lengths for b200_pic_run's grids
   B200_CUDA(cudaEventRecord(A.uploaded, s));
   return ai;
@@ -243,6 +251,7 @@ B200_API int b200_pic_run(b200_ctx* c, int ai)
   B200_CUDA(cudaEventSynchronize(A.uploaded));
   B200_CHECK(!(A.hMeta[LM_ERR] & 1), "b200_pic_run: the picture's PU list holds an invalid record (reference slots, block size or flag combination)");
   B200_CHECK(!(A.hMeta[LM_ERR] & 2), "b200_pic_run: more MC tiles than the picture can hold (overlapping PUs?)");
+  B200_CHECK(!(A.hMeta[LM_ERR] & 4), "b200_pic_run: a CTU record (SAO type / band, ALF filter index, slice index) is out of range");
   B200_CHECK(!A.hMeta[LM_INTS + LM_ERR], "b200_pic_run: the picture's TU list holds an invalid record");
   B200_CUDA(cudaStreamWaitEvent(s, A.uploaded, 0));
   const b200_geom& g = c->g;
