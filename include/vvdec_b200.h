@@ -341,6 +341,23 @@ B200_API int  b200_frame_wait(b200_ctx* ctx, int ticket);
 enum { B200_OUT_16 = 0, B200_OUT_PYUV = 1, B200_OUT_8 = 2 };
 B200_API size_t b200_frame_bytes(const b200_geom* g, int fmt, int comp);
 B200_API int  b200_get_frame_fmt_async(b200_ctx* ctx, int slot, int fmt, void* const planes[3]);
+/* Film grain synthesis on the output frame: the per-sample part of the reference's VFGS model,
+ *   replaces  FilmGrainImpl::add_grain_block / make_grain_pattern / scale_and_output (FilmGrain/FilmGrainImpl.cpp:129,:198,:247 and their
+ *             SSE4.1/AVX2 versions FilmGrainImpl_X86_SIMD.h), driven per line by FilmGrain::add_grain_line (FilmGrain.cpp:836) from
+ *             VVDecImpl::xAddGrain (vvdec/vvdecimpl.cpp:898; 16-line tasks on the decoder's thread pool).
+ * The tables are what FilmGrain::updateFGC -> init_sei (FilmGrain.cpp:560,:730 — host code, once per SEI) leaves in FilmGrainImpl, the
+ * line seeds what FilmGrain::prepareBlockSeeds (:794) produces for this frame.  The DPB picture is not modified (it may still be
+ * referenced): grain is added on the way out.  8 and 10 bit, 4:2:0 / 4:0:0 (FilmGrainImpl::set_depth :357). */
+typedef struct b200_film_grain {
+  const int8_t*   pattern;       /* [2][8][64][64]  FilmGrainImpl::pattern[luma|chroma][0..7]; chroma uses the top-left 32x32 of each      */
+  const uint8_t*  sLUT;          /* [3][256]        FilmGrainImpl::sLUT  (scale by 8-bit intensity)                                         */
+  const uint8_t*  pLUT;          /* [3][256]        FilmGrainImpl::pLUT  (pattern index << 4 by intensity; index < 8)                       */
+  const uint32_t* lineSeeds;     /* [(height+15)/16] FilmGrain::m_line_seeds                                                                */
+  uint8_t         scaleShift;    /* FilmGrainImpl::scale_shift after set_depth / set_scale_shift; scaleShift + bitDepth - 8 in 8..13       */
+  uint8_t         compPresent[3];/* fgs.comp_model_present_flag                                                                            */
+} b200_film_grain;
+/* Like b200_get_frame_fmt_async, with grain added before the format conversion.  The arrays are copied before the call returns. */
+B200_API int  b200_get_frame_grain_async(b200_ctx* ctx, int slot, int fmt, void* const planes[3], const b200_film_grain* fg);
 /* Decoded-picture hash computed on the device: what calcCRC / calcChecksum (CommonLib/PicYuvMD5.cpp:138,:179) produce for
  * the decoded picture hash SEI check (calcAndPrintHashStatus :261), so a verify-only run reads back 6 / 12 bytes instead of the frame.
  * method uses the vvdecHashType values (vvdec/sei.h): 1 CRC (2 bytes per component), 2 checksum (4 bytes per component); the digest bytes

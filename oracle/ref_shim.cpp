@@ -57,6 +57,13 @@ namespace b200_ref_app {      // the application's static helpers (plane writers
 #include <thread>
 #include <atomic>
 #include "../vvdec_b200/vvdec_glue/flatten_tu.h"
+#include <memory>
+#include "vvdec/sei.h"
+#include "FilmGrain/FilmGrainImpl.h"
+#define class struct            // FilmGrain's state is private by default class access: open it for the glue flattener (test code only)
+#include "FilmGrain/FilmGrain.h"
+#undef class
+#include "../vvdec_b200/vvdec_glue/flatten_output.h"
 
 using namespace vvdec;
 
@@ -749,6 +756,77 @@ extern "C" int ref_picture_hash( int method, int bitDepth, int16_t* const planes
   const int n = (int) dg.hash.size();
   for( int i = 0; i < n && i < cap; i++ ) digest[i] = dg.hash[i];
   return n;
+}
+
+// ================================================================================================ film grain
+// The real FilmGrain (firmware + SIMD line kernels) over `frames` consecutive frames, as VVDecImpl::xAddGrain drives it (vvdecimpl.cpp:898);
+// the tables and line seeds of the LAST frame come back through the glue flattener, so that oracle / device can redo that frame.
+// scalarImpl selects FilmGrainImpl (the C model) instead of the SIMD class the decoder runs on x86: they differ where a scale LUT entry is
+// >= 128 at 10 bit (FilmGrainImpl_X86_SIMD.h:450,:478 sign-extend the uint8 scale; the C model :282 keeps it unsigned).
+// sei: modelId, log2ScaleFactor, then per component: present, numModelValues, numIntervals, then per interval: lower, upper, 6 model values.
+static std::unique_ptr<FilmGrain> g_fg;
+static b200glue::FilmGrainTables  g_fgTabs;
+extern "C" int ref_film_grain( const int* sei, int scalarImpl, int bitDepth, int w, int h, int frames, int16_t* const planes[3], const ptrdiff_t strides[3],
+                               int8_t* pattern, uint8_t* sLUT, uint8_t* pLUT, uint32_t* lineSeeds, int* scaleShift, uint8_t* compPresent )
+{
+  try
+  {
+    auto fgc = std::make_unique<vvdecSEIFilmGrainCharacteristics>();
+    memset( fgc.get(), 0, sizeof( *fgc ) );
+    fgc->filmGrainModelId = (uint8_t) *sei++; fgc->log2ScaleFactor = (uint8_t) *sei++;
+    for( int c = 0; c < 3; c++ )
+    {
+      vvdecCompModel& cm = fgc->compModel[c];
+      cm.presentFlag = *sei++ != 0; cm.numModelValues = (uint8_t) *sei++; cm.numIntensityIntervals = (uint16_t) *sei++;
+      for( int i = 0; i < cm.numIntensityIntervals; i++ )
+      {
+        cm.intensityValues[i].intensityIntervalLowerBound = (uint8_t) *sei++; cm.intensityValues[i].intensityIntervalUpperBound = (uint8_t) *sei++;
+        for( int v = 0; v < 6; v++ ) cm.intensityValues[i].compModelValue[v] = *sei++;
+      }
+    }
+    g_fg = std::make_unique<FilmGrain>();                    // constructs the SIMD implementation on x86 (FilmGrain.cpp:722)
+    if( scalarImpl ) g_fg->m_impl = std::make_unique<FilmGrainImpl>();   // the C model (FilmGrainImpl.cpp)
+    g_fg->updateFGC( fgc.get() );
+    const int bytes = bitDepth > 8 ? 2 : 1;
+    std::vector<uint8_t> buf[3];
+    for( int f = 0; f < frames; f++ )
+    {
+      g_fg->setDepth( bitDepth );
+      g_fg->setColorFormat( planes[1] ? VVDEC_CF_YUV420_PLANAR : VVDEC_CF_YUV400_PLANAR );
+      g_fg->prepareBlockSeeds( w, h );
+      if( f + 1 < frames ) continue;                     // earlier frames only advance the seed state
+      g_fgTabs.flatten( *g_fg );
+      // frame copy with the sample size of the output frame (8-bit frames are byte planes, xCreateFrame vvdecimpl.cpp:1238) and a row pitch with
+      // slack: the line kernels always finish the last 16-sample block, also when it sticks out of the picture
+      uint8_t* base[3] = { nullptr, nullptr, nullptr }; ptrdiff_t sb[3] = { 0, 0, 0 };
+      const int nPl = planes[1] ? 3 : 1;
+      for( int c = 0; c < nPl; c++ )
+      {
+        const int cw = c ? w >> 1 : w, ch = c ? h >> 1 : h;
+        sb[c] = (ptrdiff_t) ( cw + 64 ) * bytes; buf[c].assign( (size_t) sb[c] * ( ch + 1 ), 0 ); base[c] = buf[c].data();
+        for( int y = 0; y < ch; y++ ) for( int x = 0; x < cw; x++ )
+        {
+          if( bytes == 2 ) ( (uint16_t*) ( base[c] + y * sb[c] ) )[x] = (uint16_t) planes[c][y * strides[c] + x];
+          else             base[c][y * sb[c] + x] = (uint8_t) planes[c][y * strides[c] + x];
+        }
+      }
+      for( int y = 0; y < h; y++ )
+        g_fg->add_grain_line( base[0] + sb[0] * y, base[1] ? base[1] + sb[1] * ( y / 2 ) : nullptr, base[2] ? base[2] + sb[2] * ( y / 2 ) : nullptr, y, w );
+      for( int c = 0; c < nPl; c++ )
+      {
+        const int cw = c ? w >> 1 : w, ch = c ? h >> 1 : h;
+        for( int y = 0; y < ch; y++ ) for( int x = 0; x < cw; x++ )
+          planes[c][y * strides[c] + x] = bytes == 2 ? (int16_t) ( (uint16_t*) ( base[c] + y * sb[c] ) )[x] : (int16_t) base[c][y * sb[c] + x];
+      }
+    }
+    memcpy( pattern, g_fgTabs.pattern.data(), g_fgTabs.pattern.size() );
+    memcpy( sLUT, g_fgTabs.sLUT, 768 ); memcpy( pLUT, g_fgTabs.pLUT, 768 );
+    memcpy( lineSeeds, g_fgTabs.lineSeeds.data(), g_fgTabs.lineSeeds.size() * 4 );
+    *scaleShift = g_fgTabs.fg.scaleShift;
+    for( int c = 0; c < 3; c++ ) compPresent[c] = g_fgTabs.fg.compPresent[c];
+    return 0;
+  }
+  catch( std::exception& e ) { fprintf( stderr, "ref_film_grain: %s\n", e.what() ); return -1; }
 }
 
 // ================================================================================================ LMCS (Reshape)

@@ -122,6 +122,9 @@ int ref_flatten_pu_case(int simd, const b200_geom* g, const int16_t* const* refs
 void ref_set_wp(const int32_t* raw);
 /* The application's plane writer (App/vvdecapp/vvdecHelper.h:63 _writeComponentToFile) into a memory stream: fmt 1 = pyuv, 2 = 8 bit. Returns bytes written. */
 size_t ref_write_component(const int16_t* src, ptrdiff_t stride, int w, int h, int fmt, uint8_t* dst, size_t cap);
+/* the real FilmGrain (updateFGC + SIMD line kernels) on the last of `frames` frames; tables / line seeds of that frame are returned (see ref_shim.cpp) */
+int ref_film_grain(const int* sei, int scalarImpl, int bitDepth, int w, int h, int frames, int16_t* const planes[3], const ptrdiff_t strides[3],
+                   int8_t* pattern, uint8_t* sLUT, uint8_t* pLUT, uint32_t* lineSeeds, int* scaleShift, uint8_t* compPresent);
 /* calcCRC (method 1) / calcChecksum (method 2) / calcMD5 (method 0) of a 4:2:0 picture (CommonLib/PicYuvMD5.cpp); returns the digest length in bytes */
 int ref_picture_hash(int method, int bitDepth, int16_t* const planes[3], const ptrdiff_t strides[3], int w, int h, uint8_t* digest, int cap);
 /* LMCS through the real Reshape class (CommonLib/Reshape.cpp) and the PelBufferOps pointers it dispatches to.

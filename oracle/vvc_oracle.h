@@ -65,6 +65,10 @@ void orc_pack_pyuv(const int16_t* src, ptrdiff_t stride, int w, int h, uint8_t* 
 /* :86-93 8-bit narrowing (the writer's >> 2 for 10 bit; >> (bitDepth - 8) in general). */
 void orc_narrow8(const int16_t* src, ptrdiff_t stride, int w, int h, int bitDepth, uint8_t* dst);
 /* decoded-picture hash of one plane: method 1 CRC (2 bytes), 2 checksum (4 bytes); returns the digest length */
+/* film grain synthesis, per-sample part (FilmGrainImpl::add_grain_block); tables as FilmGrainImpl holds them after FilmGrain::updateFGC:
+ * pattern [2][8][64][64], sLUT / pLUT [3][256], lineSeeds [(h+15)/16] (FilmGrain::prepareBlockSeeds); 4:2:0, planes in place */
+void orc_film_grain(int16_t* const planes[3], const ptrdiff_t strides[3], int w, int h, int bitDepth, const int8_t* pattern, const uint8_t* sLUT,
+                    const uint8_t* pLUT, const uint32_t* lineSeeds, int scaleShift, const uint8_t compPresent[3]);
 int orc_plane_hash(int method, int bitDepth, const int16_t* src, ptrdiff_t stride, int w, int h, uint8_t* digest);
 
 /* ---- K3 deblocking -------------------------------------------------------------------------- */

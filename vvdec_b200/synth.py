@@ -555,3 +555,31 @@ def load_picture(z, bit_depth):
         p.flags |= A.PIC_LMCS; p.lmcs = C.addressof(L)
     d["struct"] = p
     return d
+
+
+# ---------------------------------------------------------------------------------------------------------------- film grain
+def gen_fgc_sei(rng, model_id=0, present=(1, 1, 1), max_intervals=4, max_scale=200):
+    """Film grain characteristics SEI parameters in the flat int layout oracle/ref_shim.cpp:ref_film_grain reads: modelId, log2ScaleFactor, then
+    per component present, numModelValues, numIntervals and per interval lower, upper, 6 model values (vvdecSEIFilmGrainCharacteristics, sei.h:208).
+    Frequency-filtering model (0): values = scale, h cutoff, v cutoff (2..14); auto-regressive model (1): scale, AR coefficients."""
+    out = [model_id, int(rng.integers(2, 6))]
+    for c in range(3):
+        if not present[c]: out += [0, 0, 0]; continue
+        n = int(rng.integers(1, max_intervals + 1))
+        bounds = np.sort(rng.choice(np.arange(1, 255), size=2 * n, replace=False))
+        nv = 3 if model_id == 0 else 6
+        out += [1, nv, n]
+        for i in range(n):
+            if model_id == 0: vals = [int(rng.integers(20, max_scale)), int(rng.integers(2, 15)), int(rng.integers(2, 15)), 0, 0, 0]
+            else: vals = [int(rng.integers(20, max_scale)), int(rng.integers(-60, 60)), int(rng.integers(-30, 30)), int(rng.integers(-30, 30)), 1 << out[1], int(rng.integers(-20, 20))]
+            out += [int(bounds[2 * i]), int(bounds[2 * i + 1])] + vals
+    return np.array(out, np.int32)
+
+
+def gen_film_grain_tables(rng, H):
+    """Random tables in the shape FilmGrainImpl holds them (no SEI / firmware involved): for device-vs-oracle tests on the GPU box."""
+    pattern = rng.integers(-127, 128, size=(2, 8, 64, 64)).astype(np.int8)
+    sLUT = rng.integers(0, 256, size=(3, 256)).astype(np.uint8)
+    pLUT = (rng.integers(0, 8, size=(3, 256)) << 4).astype(np.uint8)
+    seeds = rng.integers(0, 1 << 32, size=(H + 15) // 16, dtype=np.uint64).astype(np.uint32)
+    return pattern, sLUT, pLUT, seeds
