@@ -113,3 +113,15 @@ def test_chain_golden(oracle):
     assert (pic["pus"]["flags"] & 128).any() and (pic["pus"]["wpIdx"] != 0).any()
     out, _ = oracle_decompress(oracle, g, refs, pic)
     for c in range(3): assert np.array_equal(out[c], z[f"out{c}"]), f"plane {c}"
+
+
+def test_film_grain_golden(oracle):
+    """tests/golden/film_grain_fgc.npz: tables from the reference's FGC firmware, output of its SIMD line kernels (third frame of a sequence)."""
+    z = _load("film_grain_fgc.npz")
+    W, H, bd = [int(v) for v in z["geom"]]
+    got = _planes(z, "src")
+    strides = (C.c_ssize_t * 3)(*[p.shape[1] for p in got])
+    tabs = [np.ascontiguousarray(z[k]) for k in ("pattern", "sLUT", "pLUT", "seeds", "present")]
+    oracle.orc_film_grain(abi.plane_ptrs(got), strides, W, H, bd, tabs[0].ctypes.data, tabs[1].ctypes.data, tabs[2].ctypes.data, tabs[3].ctypes.data, int(z["shift"]), tabs[4].ctypes.data)
+    for c in range(3):
+        assert np.array_equal(got[c], z[f"out{c}"]), c

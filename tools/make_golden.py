@@ -115,6 +115,25 @@ def chain():
                         **{f"ref{s}_{c}": refs[s][c] for s in range(4) for c in range(3)}, **{f"out{c}": out[c] for c in range(3)})
 
 
+def film_grain():
+    """Film grain: an FGC SEI (frequency-filtering model, three components) through the reference's firmware (FilmGrain::updateFGC) and its SIMD
+    line kernels on the third frame of a sequence (seed state carried over); tables as the glue flattener exports them."""
+    W, H, bd = 208, 96, 10
+    rng = np.random.default_rng(404)
+    sei = synth.gen_fgc_sei(rng, 0, (1, 1, 1), max_scale=128)
+    src = synth.noise_planes(rng, W, H, bd)
+    out = [p.copy() for p in src]
+    pattern = np.zeros((2, 8, 64, 64), np.int8); sLUT = np.zeros((3, 256), np.uint8); pLUT = np.zeros((3, 256), np.uint8)
+    seeds = np.zeros((H + 15) // 16, np.uint32); shift = C.c_int(0); present = np.zeros(3, np.uint8)
+    strides = (C.c_ssize_t * 3)(*[p.shape[1] for p in out])
+    assert ref.ref_film_grain(sei.ctypes.data, 0, bd, W, H, 3, abi.plane_ptrs(out), strides, pattern.ctypes.data, sLUT.ctypes.data, pLUT.ctypes.data,
+                              seeds.ctypes.data, C.byref(shift), present.ctypes.data) == 0
+    np.savez_compressed(os.path.join(OUT, "film_grain_fgc.npz"), geom=[W, H, bd], sei=sei, pattern=pattern, sLUT=sLUT, pLUT=pLUT, seeds=seeds, shift=shift.value,
+                        present=present, **{f"src{c}": src[c] for c in range(3)}, **{f"out{c}": out[c] for c in range(3)})
+
+
 if __name__ == "__main__":
-    k1(); pictures(); chain()
+    import sys
+    if len(sys.argv) > 1: [globals()[n]() for n in sys.argv[1:]]
+    else: k1(); pictures(); chain(); film_grain()
     print({f: os.path.getsize(os.path.join(OUT, f)) for f in sorted(os.listdir(OUT))})

@@ -90,6 +90,12 @@ class LmcsVpdu(C.Structure):
     _fields_ = [("x", C.c_uint16), ("y", C.c_uint16), ("availLeft", C.c_uint8), ("availAbove", C.c_uint8)]
 
 
+class FilmGrain(C.Structure):
+    """b200_film_grain: FilmGrainImpl's tables + the frame's line seeds (see include/vvdec_b200.h)."""
+    _fields_ = [("pattern", C.c_void_p), ("sLUT", C.c_void_p), ("pLUT", C.c_void_p), ("lineSeeds", C.c_void_p),
+                ("scaleShift", C.c_uint8), ("compPresent", C.c_uint8 * 3)]
+
+
 class Lmcs(C.Structure):
     """b200_lmcs: the tables Reshape::constructReshaper derives (see include/vvdec_b200.h)."""
     _fields_ = [("chromaAdj", C.c_int32), ("minBinIdx", C.c_int32), ("maxBinIdx", C.c_int32), ("orgCW", C.c_int32),

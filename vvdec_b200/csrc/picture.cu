@@ -55,6 +55,7 @@ struct b200_ctx {
   std::vector<Arena> arenas;
   int nextArena = 0;
   long long launches = 0;
+  DevBuf grainStage[2], grainTab;    // b200_get_frame_grain_async: grained copy of the frame, device copies of the tables + block seeds
   DevBuf hashBuf;                    // b200_frame_hash_async: accumulators + digest per ticket
 
   DevPlanes planes(int buf) const {
@@ -396,6 +397,57 @@ B200_API int b200_get_frame_fmt_async(b200_ctx* c, int slot, int fmt, void* cons
   c->launches += nPl;
   B200_CUDA(cudaEventRecord(c->readDone[buf], c->copyStream)); c->readPending[buf] = 1;       // the picture buffer is free once it is packed
   for (int k = 0; k < nPl; k++) B200_CUDA(cudaMemcpyAsync(planes[k], dst[k], bytes[k], cudaMemcpyDeviceToHost, c->copyStream));
+  const int t = c->nextTicket; c->nextTicket = (c->nextTicket + 1) & 15;
+  B200_CUDA(cudaEventRecord(c->ticketEv[t], c->copyStream));
+  return t;
+}
+
+B200_API int b200_get_frame_grain_async(b200_ctx* c, int slot, int fmt, void* const planes[3], const b200_film_grain* fg)
+{
+  B200_CHECK(c && planes && fg && slot >= 0 && slot < c->numSlots, "b200_get_frame_grain_async: bad argument");
+  B200_CHECK(fg->pattern && fg->sLUT && fg->pLUT && fg->lineSeeds, "b200_get_frame_grain_async: table missing");
+  B200_CHECK(fmt == B200_OUT_16 || fmt == B200_OUT_PYUV || fmt == B200_OUT_8, "b200_get_frame_grain_async: unknown format %d", fmt);
+  const b200_geom& g = c->g;
+  if (g.bitDepth != 8 && g.bitDepth != 10) { set_error("b200_get_frame_grain_async: film grain needs 8 or 10 bit (FilmGrainImpl::set_depth)"); return B200_ERR_UNSUPPORTED; }
+  if (fmt == B200_OUT_PYUV && (g.bitDepth != 10 || (g.width & 7))) { set_error("b200_get_frame_grain_async: pyuv needs 10 bit and a width divisible by 8 (as vvdecapp)"); return B200_ERR_UNSUPPORTED; }
+  const int bs = g.bitDepth - 8;
+  B200_CHECK(fg->scaleShift + bs >= 8 && fg->scaleShift + bs <= 13, "b200_get_frame_grain_async: scaleShift %d out of range (FilmGrainImpl.cpp:142)", fg->scaleShift);
+  B200_CHECK(g.width > 128, "b200_get_frame_grain_async: width must exceed 128 (FilmGrainImpl.cpp:140)");
+  for (int k = 0; k < 768; k++) B200_CHECK((fg->pLUT[k] >> 4) < 8, "b200_get_frame_grain_async: pLUT[%d] selects pattern %d (only 8 exist)", k, fg->pLUT[k] >> 4);
+  B200_CUDA(cudaSetDevice(c->device));
+  const int nPl = g.chromaFormat ? 3 : 1, nbx = (g.width + 15) / 16, nby = (g.height + 15) / 16;
+  const int st = c->nextStage; c->nextStage ^= 1;
+  // device copies of the tables: [pattern 64 KB][sLUT][pLUT][line seeds][block seeds]; every use is ordered on the copy stream
+  const size_t oS = 2 * 8 * 4096, oP = oS + 768, oL = oP + 768, oB = oL + (size_t)nby * 4, tabBytes = oB + (size_t)nbx * nby * 4;
+  if (tabBytes > c->grainTab.cap || c->picBytes > c->grainStage[st].cap) B200_CUDA(cudaStreamSynchronize(c->copyStream));   // growing: nothing may still use the old block
+  if (int rc = c->grainTab.reserve(tabBytes)) return rc;
+  if (int rc = c->grainStage[st].reserve(c->picBytes)) return rc;
+  uint8_t* tb = c->grainTab.as<uint8_t>();
+  B200_CUDA(cudaMemcpyAsync(tb, fg->pattern, oS, cudaMemcpyHostToDevice, c->copyStream));
+  B200_CUDA(cudaMemcpyAsync(tb + oS, fg->sLUT, 768, cudaMemcpyHostToDevice, c->copyStream));
+  B200_CUDA(cudaMemcpyAsync(tb + oP, fg->pLUT, 768, cudaMemcpyHostToDevice, c->copyStream));
+  B200_CUDA(cudaMemcpyAsync(tb + oL, fg->lineSeeds, (size_t)nby * 4, cudaMemcpyHostToDevice, c->copyStream));
+  const int buf = c->slotBuf[slot];
+  DevPlanes src = c->planes(buf), gr = src;
+  { uint8_t* b = c->grainStage[st].as<uint8_t>(); gr.p[0] = reinterpret_cast<int16_t*>(b); gr.p[1] = reinterpret_cast<int16_t*>(b + c->planeBytes[0]); gr.p[2] = reinterpret_cast<int16_t*>(b + c->planeBytes[0] + c->planeBytes[1]); }
+  B200_CUDA(cudaEventRecord(c->finalEv, c->stream));
+  B200_CUDA(cudaStreamWaitEvent(c->copyStream, c->finalEv, 0));
+  if (int rc = launch_film_grain(src, gr, g, reinterpret_cast<const int8_t*>(tb), tb + oS, tb + oP, reinterpret_cast<const uint32_t*>(tb + oL),
+                                 reinterpret_cast<uint32_t*>(tb + oB), fg->scaleShift, fg->compPresent, c->copyStream)) return rc;
+  c->launches += 1 + nPl;
+  B200_CUDA(cudaEventRecord(c->readDone[buf], c->copyStream)); c->readPending[buf] = 1;       // the picture buffer is free once the grained copy exists
+  if (fmt == B200_OUT_16) {
+    for (int k = 0; k < nPl; k++) B200_CUDA(cudaMemcpyAsync(planes[k], gr.p[k], (size_t)g.stride[k] * (k ? g.height >> 1 : g.height) * 2, cudaMemcpyDeviceToHost, c->copyStream));
+  } else {
+    size_t bytes[3] = {0, 0, 0}, off[3] = {0, 0, 0}, total = 0;
+    for (int k = 0; k < nPl; k++) { bytes[k] = b200_frame_bytes(&g, fmt, k); off[k] = total; total += (bytes[k] + 255) & ~(size_t)255; }
+    if (total > c->outStage[st].cap) B200_CUDA(cudaStreamSynchronize(c->copyStream));
+    if (int rc = c->outStage[st].reserve(total)) return rc;
+    uint8_t* dst[3]; for (int k = 0; k < 3; k++) dst[k] = c->outStage[st].as<uint8_t>() + off[k];
+    if (int rc = launch_pack(gr, g, fmt, dst, c->copyStream)) return rc;
+    c->launches += nPl;
+    for (int k = 0; k < nPl; k++) B200_CUDA(cudaMemcpyAsync(planes[k], dst[k], bytes[k], cudaMemcpyDeviceToHost, c->copyStream));
+  }
   const int t = c->nextTicket; c->nextTicket = (c->nextTicket + 1) & 15;
   B200_CUDA(cudaEventRecord(c->ticketEv[t], c->copyStream));
   return t;
