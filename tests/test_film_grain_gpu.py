@@ -70,7 +70,8 @@ def test_film_grain_golden(b200):
     W, H, bd = [int(v) for v in z["geom"]]
     g = abi.make_geom(W, H, bd)
     src = [np.ascontiguousarray(z[f"src{c}"]) for c in range(3)]
-    fg = make_fg(np.ascontiguousarray(z["pattern"]), np.ascontiguousarray(z["sLUT"]), np.ascontiguousarray(z["pLUT"]), np.ascontiguousarray(z["seeds"]), int(z["shift"]), z["present"])
+    tabs = [np.ascontiguousarray(z[k]) for k in ("pattern", "sLUT", "pLUT", "seeds")]          # must outlive the call: the struct only holds pointers
+    fg = make_fg(tabs[0], tabs[1], tabs[2], tabs[3], int(z["shift"]), z["present"])
     outs = run_device(b200, g, src, fg)
     for c in range(3):
         cw, ch = (W, H) if c == 0 else (W // 2, H // 2)
