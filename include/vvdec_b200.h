@@ -341,6 +341,32 @@ B200_API int  b200_frame_wait(b200_ctx* ctx, int ticket);
 enum { B200_OUT_16 = 0, B200_OUT_PYUV = 1, B200_OUT_8 = 2 };
 B200_API size_t b200_frame_bytes(const b200_geom* g, int fmt, int comp);
 B200_API int  b200_get_frame_fmt_async(b200_ctx* ctx, int slot, int fmt, void* const planes[3]);
+/* ------------------------------------------------------------------------------------------------
+ * K6  intra prediction of one transform block (first slice: regular modes).
+ *   replaces  IntraPrediction::initIntraPatternChType (IntraPrediction.cpp:947) = xFillReferenceSamples :1072 (the sample copies /
+ *             substitution, not the availability analysis) + xFilterReferenceSamples :1251, and IntraPrediction::predIntraAng :474 =
+ *             xPredIntraPlanarCore :154, xPredIntraDc :541, xPredIntraAng :592 (wide angles, reference extension, cubic / Gauss /
+ *             linear interpolation, angular PDPC), IntraPredSampleFilterCore :212 (PDPC of planar / DC), xPredIntraBDPCM :850,
+ *             as DecCu::predAndReco calls them for a regular intra TU (DecCu.cpp:329-371).
+ * The availability analysis (cs.getCURestricted walks, IntraPrediction.cpp:1098-1130) stays host code in the flattener and arrives as
+ * three counts.  Not covered (the flattener must refuse them): MIP, CCLM, ISP, palette, ACT.
+ * Blocks of one list are processed in list order; a block may read what earlier blocks of the list wrote. */
+enum { B200_INTRA_PLANAR = 0, B200_INTRA_DC = 1 /* 2..66 angular */, B200_INTRA_BDPCM_HOR = 67, B200_INTRA_BDPCM_VER = 68 };
+enum { B200_INTRA_FILTER_REF = 1, B200_INTRA_AVAIL_TL = 2 };
+typedef struct b200_intra_tu {
+  uint16_t x, y;          /* top-left in the component's plane, samples                                              */
+  uint8_t  log2w, log2h;  /* 2..6 (chroma: height may be 2 = log2h 1)                                                */
+  uint8_t  comp;          /* 0 Y, 1 Cb, 2 Cr                                                                         */
+  uint8_t  mode;          /* PU::getFinalIntraMode (before the wide-angle mapping), or B200_INTRA_BDPCM_*            */
+  uint8_t  multiRefIdx;   /* cu.multiRefIdx() for luma (0, 1, 2), 0 for chroma                                       */
+  uint8_t  flags;         /* B200_INTRA_FILTER_REF: useFilteredIntraRefSamples (:1301); B200_INTRA_AVAIL_TL: m_neighborSize[0] */
+  uint8_t  numAbove;      /* m_neighborSize[1]: available units above + above-right (unit = 4 luma / 2 chroma samples) */
+  uint8_t  numLeft;       /* m_neighborSize[2]: available units left + below-left                                    */
+  uint32_t rsv;
+} b200_intra_tu;          /* 16 bytes */
+/* Kernel-level K6: host planes in (reconstructed neighbourhood), prediction written into the blocks, host planes out. */
+B200_API int b200_intra_predict(const b200_geom* g, int16_t* const planes[3], const b200_intra_tu* tus, size_t numTus);
+
 /* Film grain synthesis on the output frame: the per-sample part of the reference's VFGS model,
  *   replaces  FilmGrainImpl::add_grain_block / make_grain_pattern / scale_and_output (FilmGrain/FilmGrainImpl.cpp:129,:198,:247 and their
  *             SSE4.1/AVX2 versions FilmGrainImpl_X86_SIMD.h), driven per line by FilmGrain::add_grain_line (FilmGrain.cpp:836) from

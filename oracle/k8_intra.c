@@ -1,0 +1,239 @@
+/* k8_intra.c — CPU restatement of regular intra prediction (planar, DC, angular incl. wide angles, MRL, PDPC, BDPCM prediction).
+ * TEST INFRASTRUCTURE ONLY (see vvc_oracle.h).  Follows /root/reference/source/Lib/CommonLib/IntraPrediction.cpp:
+ *   reference samples  xFillReferenceSamples :1072-1249 (given the three availability counts), xFilterReferenceSamples :1251-1287
+ *   prediction         predIntraAng :474-517, xPredIntraPlanarCore :154-210, xGetPredValDc :412-441, xPredIntraAng :592-848,
+ *                      IntraPredAngleCore :301-331, IntraPredAngleChroma :333-356, IntraPredSampleFilterCore :212-238, xPredIntraBDPCM :850-885
+ * Pinned by tests/test_intra_oracle_vs_ref.py against the real IntraPrediction (scalar and SIMD). */
+#include "vvc_oracle.h"
+#include "../vvdec_b200/csrc/vvc_tables.h"
+#include <string.h>
+#include <stdlib.h>
+
+static int ilog2(int v) { int r = 0; while (v > 1) { v >>= 1; r++; } return r; }
+static int iclip(int lo, int hi, int v) { return v < lo ? lo : v > hi ? hi : v; }
+static int imin(int a, int b) { return a < b ? a : b; }
+static int imax(int a, int b) { return a > b ? a : b; }
+
+static const int kAng[32] = {0, 1, 2, 3, 4, 6, 8, 10, 12, 14, 16, 18, 20, 23, 26, 29, 32, 35, 39, 45, 51, 57, 64, 73, 86, 102, 128, 171, 256, 341, 512, 1024};
+static const int kInvAng[32] = {0, 16384, 8192, 5461, 4096, 2731, 2048, 1638, 1365, 1170, 1024, 910, 819, 712, 630, 565,
+                                512, 468, 420, 364, 321, 287, 256, 224, 191, 161, 128, 96, 64, 48, 32, 16};
+static const int kIntraFilterThr[2][8] = {{24, 24, 24, 14, 2, 0, 0, 0}, {40, 40, 40, 28, 4, 0, 0, 0}};   /* m_aucIntraFilter :72 */
+
+static int wide_angle(int w, int h, int mode)     /* getWideAngle :443 */
+{
+  if (mode > 1 && mode <= 66) {
+    static const int shift[6] = {0, 6, 10, 12, 14, 15};
+    const int d = abs(ilog2(w) - ilog2(h));
+    if (w > h && mode < 2 + shift[d]) mode += 65;
+    else if (h > w && mode > 66 - shift[d]) mode -= 65;
+  }
+  return mode;
+}
+
+/* ref: (2h + mrl + 1) rows x stride (= 2w + 1 + mrl); row 0 = top-left + above row, column 0 = left column (reference layout) */
+static void fill_ref(const int16_t* plane, ptrdiff_t ps, int x0, int y0, int w, int h, int mrl, int unitW, int unitH, int availTL, int numAbove, int numLeft,
+                     int bitDepth, int16_t* ref, int stride)
+{
+  const int predSize = 2 * w, predHSize = 2 * h;
+  const int totalUnits = (predSize + unitW - 1) / unitW + (predHSize + unitH - 1) / unitH + 1;
+  const int16_t* src = plane + (ptrdiff_t)y0 * ps + x0;
+  const int dc = 1 << (bitDepth - 1), n = availTL + numAbove + numLeft;
+  if (n == 0) {
+    for (int j = 0; j <= predSize + mrl; j++) ref[j] = (int16_t)dc;
+    for (int i = 1; i <= predHSize + mrl; i++) ref[i * stride] = (int16_t)dc;
+  } else if (n == totalUnits) {
+    const int16_t* p = src - (1 + mrl) * ps - (1 + mrl);
+    for (int j = 0; j <= predSize + mrl; j++) ref[j] = p[j];
+    p = src - mrl * ps - (1 + mrl);
+    for (int i = 1; i <= predHSize + mrl; i++) { ref[i * stride] = *p; p += ps; }
+  } else if (numLeft > 0) {
+    const int16_t* p = src - (1 + mrl);
+    int16_t* d = ref + (1 + mrl) * stride;
+    int t = imin(numLeft * unitH, predHSize);
+    for (int i = 0; i < t; i++) d[i * stride] = p[i * ps];
+    for (int i = t; i < predHSize; i++) d[i * stride] = d[(t - 1) * stride];
+    if (availTL) {
+      p = src - (1 + mrl) * ps - (1 + mrl);
+      for (int j = 0; j <= mrl; j++) ref[j] = p[j];
+      for (int i = 1; i <= mrl; i++) ref[i * stride] = p[i * ps];
+    } else {
+      const int16_t v = src[-(1 + mrl)];
+      ref[0] = v;
+      for (int i = 1; i <= mrl; i++) { ref[i] = v; ref[i * stride] = v; }
+    }
+    d = ref + 1 + mrl;
+    if (numAbove) {
+      p = src - ps * (1 + mrl);
+      t = imin(numAbove * unitW, predSize);
+      for (int j = 0; j < t; j++) d[j] = p[j];
+      for (int j = t; j < predSize; j++) d[j] = d[t - 1];
+    } else for (int j = 0; j < predSize; j++) d[j] = d[-1];
+  } else {
+    const int16_t* p = src - ps * (1 + mrl);
+    int16_t* d = ref + 1 + mrl;
+    const int t = imin(numAbove * unitW, predSize);
+    for (int j = 0; j < t; j++) d[j] = p[j];
+    for (int j = t; j < predSize; j++) d[j] = d[t - 1];
+    const int16_t v = p[0];
+    ref[0] = v;
+    for (int i = 1; i <= mrl; i++) { ref[i] = v; ref[i * stride] = v; }
+    d = ref + (1 + mrl) * stride;
+    for (int i = 0; i < predHSize; i++) d[i * stride] = v;
+  }
+}
+
+static void filter_ref(const int16_t* u, int16_t* f, int w, int h)      /* :1251, multiRefIdx == 0 */
+{
+  const int predSize = 2 * w, predHSize = 2 * h, s = predSize + 1;
+  f[predHSize * s] = u[predHSize * s];
+  for (int i = predHSize - 1; i >= 1; i--) f[i * s] = (int16_t)((u[(i + 1) * s] + 2 * u[i * s] + u[(i - 1) * s] + 2) >> 2);
+  f[0] = (int16_t)((u[s] + 2 * u[0] + u[1] + 2) >> 2);
+  for (int j = 1; j < predSize; j++) f[j] = (int16_t)((u[j + 1] + 2 * u[j] + u[j - 1] + 2) >> 2);
+  f[predSize] = u[predSize];
+}
+
+#define AT(x, y) src[(y) * stride + (x)]
+
+static void pred_planar(const int16_t* src, int stride, int w, int h, int16_t* dst, ptrdiff_t ds)
+{
+  const int l2w = ilog2(w), l2h = ilog2(h);
+  int left[65], top[65], bottom[64], right[64];
+  for (int k = 0; k <= w; k++) top[k] = AT(k + 1, 0);
+  for (int k = 0; k <= h; k++) left[k] = AT(0, k + 1);
+  const int bl = left[h], tr = top[w];
+  for (int k = 0; k < w; k++) { bottom[k] = bl - top[k]; top[k] <<= l2h; }
+  for (int k = 0; k < h; k++) { right[k] = tr - left[k]; left[k] <<= l2w; }
+  for (int y = 0; y < h; y++) {
+    int hor = left[y];
+    for (int x = 0; x < w; x++) {
+      hor += right[y]; top[x] += bottom[x];
+      dst[y * ds + x] = (int16_t)(((hor << l2h) + (top[x] << l2w) + (1 << (l2w + l2h))) >> (1 + l2w + l2h));
+    }
+  }
+}
+
+static void pred_angular(const int16_t* src, int stride, int w0, int h0, int chroma, int dirMode, int mrl, int filtered, int doPDPC, int pmax, int16_t* dst, ptrdiff_t ds)
+{
+  int w = w0, h = h0;
+  const int predMode = wide_angle(w, h, dirMode), ver = predMode >= 34;
+  const int angMode = ver ? predMode - 50 : -(predMode - 18), absMode = abs(angMode);
+  const int invAngle = kInvAng[absMode], absAng = kAng[absMode], angle = angMode < 0 ? -absAng : absAng;
+  const int topLen = 2 * w0, leftLen = 2 * h0;
+  int16_t refAbove[2 * 128 + 3 + 33 * 3], refLeft[2 * 128 + 3 + 33 * 3], *refMain, *refSide;
+  (void)filtered;
+  if (angle < 0) {
+    for (int x = 0; x <= w + 1 + mrl; x++) refAbove[x + h] = AT(x, 0);
+    for (int y = 0; y <= h + 1 + mrl; y++) refLeft[y + w] = AT(0, y);
+    refMain = ver ? refAbove + h : refLeft + w; refSide = ver ? refLeft + w : refAbove + h;
+    const int sizeSide = ver ? h : w;
+    for (int k = -sizeSide; k <= -1; k++) refMain[k] = refSide[imin((-k * invAngle + 256) >> 9, sizeSide)];
+  } else {
+    for (int x = 0; x <= topLen + mrl; x++) refAbove[x] = AT(x, 0);
+    for (int y = 0; y <= leftLen + mrl; y++) refLeft[y] = AT(0, y);
+    refMain = ver ? refAbove : refLeft; refSide = ver ? refLeft : refAbove;
+    const int l2r = ilog2(w) - ilog2(h), s = imax(0, ver ? l2r : -l2r), maxIndex = (mrl << s) + 2, refLength = ver ? topLen : leftLen;
+    const int16_t val = refMain[refLength + mrl];
+    for (int z = 1; z <= maxIndex; z++) refMain[refLength + mrl + z] = val;
+  }
+  int16_t tmp[64 * 64];
+  const ptrdiff_t ts = ver ? ds : 64;
+  int16_t* out = ver ? dst : tmp;
+  if (!ver) { const int t = w; w = h; h = t; }
+  refMain += mrl; refSide += mrl;
+  if (angle == 0) {
+    if (doPDPC) {
+      const int scale = (ilog2(w) - 2 + ilog2(h) - 2 + 2) >> 2;
+      const int lev[4] = {imin(3, w), imin(6, w), imin(12, w), imin(24, w)};
+      const int topLeft = AT(0, 0);
+      for (int y = 0; y < h; y++) {
+        const int left = refSide[y + 1];
+        for (int x = 0; x < lev[scale]; x++) { const int wL = 32 >> imin(31, (x << 1) >> scale); out[y * ts + x] = (int16_t)iclip(0, pmax, (wL * (left - topLeft) + refMain[x + 1] * 64 + 32) >> 6); }
+        for (int x = lev[scale]; x < w; x++) out[y * ts + x] = refMain[x + 1];
+      }
+    } else for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) out[y * ts + x] = refMain[x + 1];
+  } else {
+    if (absAng & 0x1f) {
+      int deltaPos = angle * (1 + mrl);
+      if (!chroma) {
+        const int diff = imin(abs(predMode - 18), abs(predMode - 50)), log2Size = (ilog2(w) + ilog2(h)) >> 1;
+        const int interpolationFlag = diff > kIntraFilterThr[0][log2Size];       /* filterFlag, and the angle is fractional here */
+        const int cubic = !interpolationFlag || mrl > 0;
+        for (int y = 0; y < h; y++, deltaPos += angle) {
+          const int dI = deltaPos >> 5, dF = deltaPos & 31;
+          int f[4];
+          if (cubic) for (int k = 0; k < 4; k++) f[k] = kIfChroma[dF * 4 + k];    /* InterpolationFilter::getChromaFilterTable(0) */
+          else { f[0] = 16 - (dF >> 1); f[1] = 32 - (dF >> 1); f[2] = 16 + (dF >> 1); f[3] = dF >> 1; }   /* g_intraGaussFilter :94 */
+          for (int x = 0; x < w; x++) {
+            const int16_t* p = refMain + dI + x;
+            int v = (int16_t)((f[0] * p[0] + f[1] * p[1] + f[2] * p[2] + f[3] * p[3] + 32) >> 6);
+            if (cubic) v = iclip(0, pmax, v);
+            out[y * ts + x] = (int16_t)v;
+          }
+        }
+      } else {
+        for (int y = 0; y < h; y++, deltaPos += angle) {
+          const int dI = deltaPos >> 5, dF = deltaPos & 31;
+          for (int x = 0; x < w; x++) out[y * ts + x] = (int16_t)(((32 - dF) * refMain[dI + 1 + x] + dF * refMain[dI + 2 + x] + 16) >> 5);
+        }
+      }
+    } else {
+      int deltaPos = angle * (1 + mrl);
+      for (int y = 0; y < h; y++, deltaPos += angle) for (int x = 0; x < w; x++) out[y * ts + x] = refMain[(deltaPos >> 5) + 1 + x];
+    }
+    if (angle > 0 && doPDPC) {
+      const int sideSize = h;                                     /* predMode >= DIA ? block height : block width = h after the swap */
+      const int angularScale = imin(2, ilog2(sideSize) - (ilog2(3 * invAngle - 2) - 8));
+      if (angularScale >= 0)
+        for (int y = 0; y < h; y++) {
+          int invAngleSum = 256;
+          for (int x = 0; x < imin(3 << angularScale, w); x++) {
+            invAngleSum += invAngle;
+            const int wL = 32 >> (2 * x >> angularScale), left = refSide[y + (invAngleSum >> 9) + 1], p = out[y * ts + x];
+            out[y * ts + x] = (int16_t)(p + ((wL * (left - p) + 32) >> 6));
+          }
+        }
+    }
+  }
+  if (!ver) for (int y = 0; y < h0; y++) for (int x = 0; x < w0; x++) dst[y * ds + x] = tmp[x * 64 + y];
+}
+
+void orc_intra_tu(const b200_geom* g, int16_t* const planes[3], const b200_intra_tu* t)
+{
+  const int c = t->comp, w = 1 << t->log2w, h = 1 << t->log2h, mrl = c ? 0 : t->multiRefIdx, pmax = (1 << g->bitDepth) - 1;
+  const int unit = c ? 2 : 4, stride = 2 * w + 1 + mrl, rows = 2 * h + 1 + mrl;
+  int16_t* ref = (int16_t*)calloc((size_t)stride * rows * 2 + 64, sizeof(int16_t));
+  int16_t* flt = ref + (size_t)stride * rows + 32;
+  fill_ref(planes[c], g->stride[c], t->x, t->y, w, h, mrl, unit, unit, (t->flags & B200_INTRA_AVAIL_TL) ? 1 : 0, t->numAbove, t->numLeft, g->bitDepth, ref, stride);
+  const int16_t* src = ref;
+  if ((t->flags & B200_INTRA_FILTER_REF) && !c && !mrl) { filter_ref(ref, flt, w, h); src = flt; }
+  int16_t* dst = planes[c] + (ptrdiff_t)t->y * g->stride[c] + t->x;
+  const ptrdiff_t ds = g->stride[c];
+  const int doPDPC = w >= 4 && h >= 4 && mrl == 0;
+  if (t->mode == B200_INTRA_PLANAR) pred_planar(src, stride, w, h, dst, ds);
+  else if (t->mode == B200_INTRA_DC) {
+    int sum = 0;
+    const int denom = w == h ? w << 1 : imax(w, h);
+    if (w >= h) for (int i = 0; i < w; i++) sum += AT(mrl + 1 + i, 0);
+    if (w <= h) for (int i = 0; i < h; i++) sum += AT(0, mrl + 1 + i);
+    const int16_t dc = (int16_t)((sum + (denom >> 1)) >> ilog2(denom));
+    for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) dst[y * ds + x] = dc;
+  } else if (t->mode == B200_INTRA_BDPCM_HOR) { for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) dst[y * ds + x] = AT(0, y + 1); }
+  else if (t->mode == B200_INTRA_BDPCM_VER) { for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) dst[y * ds + x] = AT(x + 1, 0); }
+  else pred_angular(src, stride, w, h, c != 0, t->mode, mrl, 0, doPDPC, pmax, dst, ds);
+  if (doPDPC && t->mode <= B200_INTRA_DC) {                    /* IntraPredSampleFilterCore :212 */
+    const int scale = (t->log2w - 2 + t->log2h - 2 + 2) >> 2;
+    for (int y = 0; y < h; y++) {
+      const int wT = 32 >> imin(31, (y << 1) >> scale), left = AT(0, y + 1);
+      for (int x = 0; x < w; x++) {
+        const int wL = 32 >> imin(31, (x << 1) >> scale), top = AT(x + 1, 0), v = dst[y * ds + x];
+        dst[y * ds + x] = (int16_t)(v + ((wL * (left - v) + wT * (top - v) + 32) >> 6));
+      }
+    }
+  }
+  free(ref);
+}
+
+void orc_intra_predict(const b200_geom* g, int16_t* const planes[3], const b200_intra_tu* tus, size_t numTus)
+{
+  for (size_t i = 0; i < numTus; i++) orc_intra_tu(g, planes, &tus[i]);
+}

@@ -57,6 +57,8 @@ namespace b200_ref_app {      // the application's static helpers (plane writers
 #include <thread>
 #include <atomic>
 #include "../vvdec_b200/vvdec_glue/flatten_tu.h"
+#include "CommonLib/IntraPrediction.h"
+#include "../vvdec_b200/vvdec_glue/flatten_intra.h"
 #include <memory>
 #include "vvdec/sei.h"
 #include "FilmGrain/FilmGrainImpl.h"
@@ -756,6 +758,76 @@ extern "C" int ref_picture_hash( int method, int bitDepth, int16_t* const planes
   const int n = (int) dg.hash.size();
   for( int i = 0; i < n && i < cap; i++ ) digest[i] = dg.hash[i];
   return n;
+}
+
+// ================================================================================================ intra prediction
+// A picture whose CUs (single tree, one TU each, decoding order) are all intra; the planes hold the reconstruction of the neighbourhood.
+// The LAST CU of the list is predicted with the real IntraPrediction, exactly as DecCu::predAndReco drives it (DecCu.cpp:329-371), into the
+// planes; its records come back through the glue flattener, and the flattener's availability is checked against m_neighborSize.
+extern "C" int ref_intra_case( int simd, const b200_geom* g, int16_t* const planes[3], const ref_intra_cu* cus, int numCus, b200_intra_tu* recs, int capRecs )
+{
+  try
+  {
+    FakePicture cur( *g, 1 );
+    cur.setPlanes( *g, planes );
+    CodingStructure& cs = *cur.pic.cs;
+    const PreCalcValues& pcv = *cs.pcv;
+    Slice* sl = cur.pic.slices[0];
+    sl->setSliceType( I_SLICE );
+    CodingUnit* last = nullptr;
+    for( int i = 0; i < numCus; i++ )
+    {
+      const ref_intra_cu& c = cus[i];
+      UnitArea ua( pcv.chrFormat, Area( c.x, c.y, c.w, c.h ) );
+      if( c.rsv[0] ) { ua.blocks[1].width = ua.blocks[1].height = 0; ua.blocks[2].width = ua.blocks[2].height = 0; }   // luma CU of a local dual tree (4xN, 8x4)
+      const Position pos( c.x, c.y );
+      const CodingUnit* left  = cs.getCURestricted( pos.offset( -1, 0 ), pos, 0, 0, CH_L );       // as CABACReader::coding_tree does for every CU
+      const CodingUnit* above = cs.getCURestricted( pos.offset( 0, -1 ), pos, 0, 0, CH_L );
+      CodingUnit& cu = cs.addCU( ua, CH_L, c.rsv[0] ? TREE_L : TREE_D, c.rsv[0] ? MODE_TYPE_INTRA : MODE_TYPE_ALL, left, above );
+      cu.slice = sl; cu.pps = cur.pps.get(); cu.sps = cur.sps.get();
+      cu.setPredMode( MODE_INTRA );
+      cu.intraDir[0] = c.dirL; cu.intraDir[1] = c.dirC;
+      cu.setMultiRefIdx( c.multiRefIdx ); cu.setBdpcmMode( c.bdpcm ); cu.setBdpcmModeChroma( c.bdpcmC );
+      cs.addTU( ua, CH_L, cu );
+      last = &cu;
+    }
+    if( !last ) return -1;
+    IntraPrediction ip;
+    ip.init( pcv.chrFormat, g->bitDepth );                              // x86: installs the SIMD kernels (IntraPrediction.cpp:399)
+    if( !simd )
+    {
+      IntraPrediction scalar;                                           // the constructor installs the C kernels (:362-376)
+      ip.IntraPredAngleCore4 = scalar.IntraPredAngleCore4; ip.IntraPredAngleCore8 = scalar.IntraPredAngleCore8;
+      ip.IntraPredAngleChroma4 = scalar.IntraPredAngleChroma4; ip.IntraPredAngleChroma8 = scalar.IntraPredAngleChroma8;
+      ip.IntraPredSampleFilter8 = scalar.IntraPredSampleFilter8; ip.IntraPredSampleFilter16 = scalar.IntraPredSampleFilter16;
+      ip.xPredIntraPlanar = scalar.xPredIntraPlanar; ip.GetLumaRecPixel420 = scalar.GetLumaRecPixel420;
+    }
+    CodingUnit& cu = *last;
+    TransformUnit& tu = cu.firstTU;
+    int n = 0;
+    for( const CompArea& area : tu.blocks )
+    {
+      if( !area.valid() ) continue;
+      const ComponentID compID = area.compID();
+      b200_intra_tu r;
+      if( b200glue::flattenIntraTU( tu, compID, r ) != b200glue::FLATTEN_INTRA_OK ) return -2;
+      PelBuf piPred = cs.getRecoBuf( area );
+      const bool filt = isLuma( compID ) && cu.ispMode() == NOT_INTRA_SUBPARTITIONS && IntraPrediction::useFilteredIntraRefSamples( compID, cu, tu );
+      ip.initIntraPatternChType( tu, area, filt );
+      if( ( ( r.flags & B200_INTRA_AVAIL_TL ) ? 1 : 0 ) != ip.m_neighborSize[0] || r.numAbove != ip.m_neighborSize[1] || r.numLeft != ip.m_neighborSize[2] )
+      {
+        fprintf( stderr, "ref_intra_case: availability mismatch comp %d: glue (%d %d %d) reference (%d %d %d)\n", (int) compID, ( r.flags >> 1 ) & 1, r.numAbove, r.numLeft,
+                 ip.m_neighborSize[0], ip.m_neighborSize[1], ip.m_neighborSize[2] );
+        return -3;
+      }
+      ip.predIntraAng( compID, piPred, cu, filt );
+      if( n < capRecs ) recs[n] = r;
+      n++;
+    }
+    cur.getPlanes( *g, planes );
+    return n;
+  }
+  catch( std::exception& e ) { fprintf( stderr, "ref_intra_case: %s\n", e.what() ); return -9; }
 }
 
 // ================================================================================================ film grain

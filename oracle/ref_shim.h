@@ -122,6 +122,10 @@ int ref_flatten_pu_case(int simd, const b200_geom* g, const int16_t* const* refs
 void ref_set_wp(const int32_t* raw);
 /* The application's plane writer (App/vvdecapp/vvdecHelper.h:63 _writeComponentToFile) into a memory stream: fmt 1 = pyuv, 2 = 8 bit. Returns bytes written. */
 size_t ref_write_component(const int16_t* src, ptrdiff_t stride, int w, int h, int fmt, uint8_t* dst, size_t cap);
+/* one intra CU of a test layout (luma samples; single tree; one TU) */
+typedef struct ref_intra_cu { uint16_t x, y, w, h; uint8_t dirL, dirC, multiRefIdx, bdpcm, bdpcmC, rsv[3]; } ref_intra_cu;
+/* the real IntraPrediction on the last CU of the list (see ref_shim.cpp); returns the number of records (3), < 0 on error */
+int ref_intra_case(int simd, const b200_geom* g, int16_t* const planes[3], const ref_intra_cu* cus, int numCus, b200_intra_tu* recs, int capRecs);
 /* the real FilmGrain (updateFGC + SIMD line kernels) on the last of `frames` frames; tables / line seeds of that frame are returned (see ref_shim.cpp) */
 int ref_film_grain(const int* sei, int scalarImpl, int bitDepth, int w, int h, int frames, int16_t* const planes[3], const ptrdiff_t strides[3],
                    int8_t* pattern, uint8_t* sLUT, uint8_t* pLUT, uint32_t* lineSeeds, int* scaleShift, uint8_t* compPresent);

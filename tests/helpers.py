@@ -47,6 +47,7 @@ def load_oracle():
     u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
     lib.orc_pack_pyuv.argtypes = [i16p, C.c_ssize_t, C.c_int, C.c_int, u8p]
     lib.orc_narrow8.argtypes = [i16p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, u8p]
+    lib.orc_intra_predict.argtypes = [C.POINTER(abi.Geom), PL, C.c_void_p, C.c_size_t]
     lib.orc_film_grain.argtypes = [PL, C.POINTER(C.c_ssize_t), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.orc_plane_hash.argtypes = [C.c_int, C.c_int, i16p, C.c_ssize_t, C.c_int, C.c_int, u8p]
     return lib
@@ -89,6 +90,7 @@ def load_ref():
     lib.ref_flatten_pu_case.argtypes = [C.c_int, C.POINTER(abi.Geom), C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, PL, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.ref_write_component.argtypes = [i16p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS"), C.c_size_t]
     lib.ref_write_component.restype = C.c_size_t
+    lib.ref_intra_case.argtypes = [C.c_int, C.POINTER(abi.Geom), PL, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.ref_film_grain.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, PL, C.POINTER(C.c_ssize_t)] + [C.c_void_p] * 4 + [C.POINTER(C.c_int), C.c_void_p]
     lib.ref_picture_hash.argtypes = [C.c_int, C.c_int, PL, C.POINTER(C.c_ssize_t), C.c_int, C.c_int, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS"), C.c_int]
     lib.ref_lmcs_build.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(abi.Lmcs), i16p]

@@ -1,0 +1,73 @@
+"""K6 intra prediction (regular modes): the oracle against the real IntraPrediction (reference sample derivation, [1 2 1] filter,
+planar / DC / angular incl. wide angles / MRL / PDPC / BDPCM prediction; C and SIMD kernels), on random CU layouts where the predicted CU has
+whatever neighbourhood the decoding order gives it.  The records come from the glue flattener (flatten_intra.h), whose availability counts the
+shim checks against IntraPrediction::m_neighborSize."""
+import ctypes as C
+import numpy as np
+import pytest
+from vvdec_b200 import abi, synth
+
+pytestmark = pytest.mark.ref
+
+CHROMA_MODES = [0, 1, 18, 50, 2, 34, 66, 70, 70, 70, 23, 45, 61]       # 70 = DM (PU::getFinalIntraMode -> the luma mode)
+
+
+def run_case(oracle, ref, rng, W, H, bd, ctu, simd, layout, k, dirL, dirC, mrl, bdpcm, bdpcmC=0):
+    g = abi.make_geom(W, H, bd, ctu=ctu)
+    planes = synth.noise_planes(rng, W, H, bd)
+    cus = np.zeros(k + 1, synth.REF_INTRA_CU_DTYPE)
+    for i in range(k + 1):
+        cus[i]["x"], cus[i]["y"], cus[i]["w"], cus[i]["h"] = layout[i]
+        cus[i]["dirL"], cus[i]["dirC"] = 0, 0
+    cus[k]["dirL"], cus[k]["dirC"], cus[k]["multiRefIdx"], cus[k]["bdpcm"], cus[k]["bdpcmC"] = dirL, dirC, mrl, bdpcm, bdpcmC
+    x, y, w, h = layout[k]
+    luma_only = w < 8 or (w // 2) * (h // 2) < 16                       # such luma blocks are CUs of a local dual tree: no chroma of their own
+    cus[k]["rsv"][0] = luma_only
+    want = [p.copy() for p in planes]
+    recs = np.zeros(3, abi.INTRA_TU_DTYPE)
+    n = ref.ref_intra_case(simd, C.byref(g), abi.plane_ptrs(want), cus.ctypes.data, k + 1, recs.ctypes.data, 3)
+    assert n == (1 if luma_only else 3), n
+    recs = recs[:n]
+    got = [p.copy() for p in planes]
+    oracle.orc_intra_predict(C.byref(g), abi.plane_ptrs(got), recs.ctypes.data, n)
+    for c in range(3):
+        assert np.array_equal(got[c], want[c]), (c, layout[k], dirL, dirC, mrl, bdpcm, recs[c])
+    assert not np.array_equal(want[0][y:y + h, x:x + w], planes[0][y:y + h, x:x + w])
+    return recs
+
+
+@pytest.mark.parametrize("simd", [0, 1])
+@pytest.mark.parametrize("W,H,bd,ctu,seed", [(256, 128, 10, 128, 1), (192, 128, 10, 64, 2), (256, 128, 8, 128, 3), (136, 72, 10, 64, 4), (256, 256, 12, 128, 5)])
+def test_intra_random_layouts(oracle, ref, W, H, bd, ctu, seed, simd):
+    if simd and bd > 10: pytest.skip("the x86 chroma kernels multiply in 16 bit: exact up to 10 bit (Main10), the C kernels are the 12-bit reference")
+    rng = np.random.default_rng(seed)
+    seen = set()
+    for it in range(60):
+        layout = synth.gen_intra_layout(rng, W, H, ctu, min_size=8 if it % 3 else 4, p_split=0.6 + 0.3 * rng.random())
+        k = 0 if it == 0 else int(rng.integers(len(layout)))           # it 0: the first CU of the picture has no neighbours at all
+        if it == 1: k = next(i for i, c in enumerate(layout) if c[1] == 0 and c[0] > 0)      # top picture edge: left only
+        if it == 2: k = next(i for i, c in enumerate(layout) if c[0] == 0 and c[1] > 0)      # left picture edge: above only
+        x, y, w, h = layout[k]
+        kind = it % 6
+        dirL, mrl, bdpcm = int(rng.integers(0, 67)), 0, 0
+        if kind == 4: mrl, dirL = int(rng.integers(1, 3)), int(rng.integers(1, 67))
+        if kind == 5 and w <= 32 and h <= 32: bdpcm = int(rng.integers(1, 3))
+        if kind == 0: dirL = int(rng.integers(0, 2))
+        dirC = CHROMA_MODES[int(rng.integers(len(CHROMA_MODES)))]
+        recs = run_case(oracle, ref, rng, W, H, bd, ctu, simd, layout, k, dirL, dirC, mrl, bdpcm)
+        seen.add((int(recs[0]["numAbove"]) > 0, int(recs[0]["numLeft"]) > 0, bool(recs[0]["flags"] & 2)))
+    assert len(seen) >= 4                                              # corner / edge / interior neighbourhoods all occurred
+
+
+@pytest.mark.parametrize("w,h", [(4, 4), (4, 16), (16, 4), (8, 32), (32, 8), (64, 64), (64, 16), (16, 64), (8, 8), (4, 32), (32, 4), (64, 8), (8, 64)])
+def test_intra_all_modes_per_shape(oracle, ref, w, h):
+    """Every mode (incl. the wide-angle remapped ones) and both MRL lines for each block shape, interior position, C kernels and SIMD kernels."""
+    rng = np.random.default_rng(w * 131 + h)
+    W, H, ctu = 256, 128, 128
+    # hand-made layout: the block at (64, 64) with everything before it in decoding order present
+    layout = [(0, 0, 64, 64), (64, 0, 64, 64), (0, 64, 64, 64), (64, 64, w, h)]
+    for mode in range(67):
+        for mrl in (0, 1, 2):
+            if mrl and (mode == 0 or (mode + mrl) % 4): continue          # planar has no MRL; sample the rest
+            if (w == 4 or h == 4) and False: continue
+            run_case(oracle, ref, rng, W, H, 10, ctu, (mode + mrl) & 1, layout, 3, mode, CHROMA_MODES[mode % len(CHROMA_MODES)], mrl, 0)

@@ -583,3 +583,35 @@ def gen_film_grain_tables(rng, H):
     pLUT = (rng.integers(0, 8, size=(3, 256)) << 4).astype(np.uint8)
     seeds = rng.integers(0, 1 << 32, size=(H + 15) // 16, dtype=np.uint64).astype(np.uint32)
     return pattern, sLUT, pLUT, seeds
+
+
+# ---------------------------------------------------------------------------------------------------------------- intra layouts
+REF_INTRA_CU_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("w", "<u2"), ("h", "<u2"), ("dirL", "u1"), ("dirC", "u1"), ("multiRefIdx", "u1"), ("bdpcm", "u1"),
+                               ("bdpcmC", "u1"), ("rsv", "u1", 3)])
+
+
+def gen_intra_layout(rng, W, H, ctu=128, min_size=8, max_size=64, p_split=0.75):
+    """CU rectangles (luma samples) of a picture in decoding order: CTUs in raster order, inside a CTU a random quad / binary tree in z-order
+    (every CU at most max_size wide and high: one TU per CU)."""
+    out = []
+
+    def rec(x, y, w, h):
+        if x >= W or y >= H: return
+        must = w > max_size or h > max_size or x + w > W or y + h > H
+        can_q = w == h and w // 2 >= min_size
+        can_v, can_h = w // 2 >= min_size, h // 2 >= min_size
+        if must or ((can_q or can_v or can_h) and rng.random() < p_split):
+            opts = ([0] if can_q else []) + ([] if must and (w > max_size and h > max_size) else ([1] if can_v else []) + ([2] if can_h else []))
+            if not opts: opts = [0]
+            k = opts[int(rng.integers(len(opts)))]
+            if k == 0:
+                for dy in (0, h // 2):
+                    for dx in (0, w // 2): rec(x + dx, y + dy, w // 2, h // 2)
+            elif k == 1: rec(x, y, w // 2, h); rec(x + w // 2, y, w // 2, h)
+            else: rec(x, y, w, h // 2); rec(x, y + h // 2, w, h // 2)
+        else:
+            out.append((x, y, w, h))
+
+    for cy in range(0, H, ctu):
+        for cx in range(0, W, ctu): rec(cx, cy, ctu, ctu)
+    return out

@@ -1,0 +1,85 @@
+// flatten_intra.h — host-side flattener for K6: one intra TransformUnit component -> b200_intra_tu.  Glue that lives INSIDE a VVdeC build.
+// The record carries the decisions DecCu::predAndReco / IntraPrediction take from the CU tree: final mode, multi reference line, whether
+// the [1 2 1] reference filter applies, and the neighbour availability xFillReferenceSamples derives (IntraPrediction.cpp:1098-1130) — the
+// cs.getCURestricted walks are pointer chasing over the CU map and stay on the host.  No pixel arithmetic.
+// Pinned by tests/test_intra_oracle_vs_ref.py (availability against IntraPrediction::m_neighborSize, the rest through the prediction).
+#pragma once
+#include <string.h>
+#include <algorithm>
+#include "vvdec_b200.h"
+#include "CommonLib/CommonDef.h"
+#include "CommonLib/Unit.h"
+#include "CommonLib/UnitTools.h"
+#include "CommonLib/CodingStructure.h"
+#include "CommonLib/IntraPrediction.h"
+
+namespace b200glue
+{
+using namespace vvdec;
+
+enum FlattenIntraResult { FLATTEN_INTRA_OK = 0, FLATTEN_INTRA_UNSUPPORTED = 1 };
+
+// the TU of `cu` that covers `pos` (IntraPrediction.cpp:1329, file-static there)
+inline const TransformUnit* intraTuAt( const CodingUnit& cu, const Position& pos, const ChannelType chType )
+{
+  const TransformUnit* ptu = &cu.firstTU;
+  if( !ptu->next ) return ptu;
+  while( !( ptu->blocks[chType].x + ptu->blocks[chType].width > pos.x && ptu->blocks[chType].y + ptu->blocks[chType].height > pos.y ) ) ptu = ptu->next;
+  return ptu;
+}
+
+// units available along the above(-right) row / left(-below) column starting at posLT: isAboveAvailable / isLeftAvailable (:1343, :1373)
+inline int intraUnitsAvailable( const TransformUnit& tu, const ChannelType chType, const Position& posLT, const int numUnits, const int unitSize, const bool above )
+{
+  const CodingUnit&      cu = *tu.cu;
+  const CodingStructure& cs = *cu.cs;
+  const int maxD = numUnits * unitSize;
+  Position refPos = above ? posLT.offset( 0, -1 ) : posLT.offset( -1, 0 );
+  const TransformUnit* nb = nullptr;
+  int d = 0;
+  while( d < maxD )
+  {
+    const CodingUnit* cuN = cs.getCURestricted( refPos, cu, chType, nb ? nullptr : ( above ? cu.above : cu.left ) );
+    if( !cuN ) break;
+    nb = intraTuAt( *cuN, refPos, chType );
+    if( cuN->ctuData == cu.ctuData && nb->idx >= tu.idx ) break;
+    const int diff = above ? (int) nb->blocks[chType].width - refPos.x + nb->blocks[chType].x : (int) nb->blocks[chType].height - refPos.y + nb->blocks[chType].y;
+    d += diff;
+    if( above ) refPos.x += diff; else refPos.y += diff;
+  }
+  return std::min( d / unitSize, numUnits );
+}
+
+inline FlattenIntraResult flattenIntraTU( const TransformUnit& tu, const ComponentID compID, b200_intra_tu& r )
+{
+  const CodingUnit&      cu     = *tu.cu;
+  const CodingStructure& cs     = *cu.cs;
+  const PreCalcValues&   pcv    = *cs.pcv;
+  const ChannelType      chType = toChannelType( compID );
+  const CompArea&        area   = tu.blocks[compID];
+  memset( &r, 0, sizeof( r ) );
+  if( cu.colorTransform() || CU::isMIP( cu, chType ) || ( isLuma( compID ) && cu.ispMode() ) ) return FLATTEN_INTRA_UNSUPPORTED;
+  const uint32_t finalMode = PU::getFinalIntraMode( cu, chType );
+  if( !isLuma( compID ) && PU::isLMCMode( finalMode ) ) return FLATTEN_INTRA_UNSUPPORTED;
+  const int bdpcm = isLuma( compID ) ? cu.bdpcmMode() : cu.bdpcmModeChroma();
+  r.x = (uint16_t) area.x; r.y = (uint16_t) area.y; r.log2w = (uint8_t) getLog2( area.width ); r.log2h = (uint8_t) getLog2( area.height ); r.comp = (uint8_t) compID;
+  r.mode = bdpcm ? ( bdpcm == 1 ? B200_INTRA_BDPCM_HOR : B200_INTRA_BDPCM_VER ) : (uint8_t) finalMode;
+  r.multiRefIdx = isLuma( compID ) ? (uint8_t) cu.multiRefIdx() : 0;
+  if( isLuma( compID ) && IntraPrediction::useFilteredIntraRefSamples( compID, cu, tu ) ) r.flags |= B200_INTRA_FILTER_REF;    // DecCu.cpp:339
+
+  // neighbourhood (xFillReferenceSamples :1086-1130)
+  const int csx = getChannelTypeScaleX( chType, pcv.chrFormat ), csy = getChannelTypeScaleY( chType, pcv.chrFormat );
+  const int unitW = pcv.minCUWidth >> csx, unitH = pcv.minCUHeight >> csy;
+  const int totalAbove = ( 2 * (int) area.width + unitW - 1 ) / unitW, totalLeft = ( 2 * (int) area.height + unitH - 1 ) / unitH;
+  const int numAbove = area.width / unitW, numLeft = area.height / unitH;
+  const Position posLT = area.pos();
+  const bool sameCTU = ( posLT.x & ( pcv.maxCUWidthMask >> csx ) ) && ( posLT.y & ( pcv.maxCUHeightMask >> csy ) );
+  if( sameCTU || cs.getCURestricted( posLT.offset( -1, -1 ), cu, chType, cu.left ? cu.left : cu.above ) ) r.flags |= B200_INTRA_AVAIL_TL;
+  if( cu.above || area.y > cu.blocks[chType].y )
+    r.numAbove = (uint8_t) ( numAbove + intraUnitsAvailable( tu, chType, Position( posLT.x + (PosType) area.width, posLT.y ), totalAbove - numAbove, unitW, true ) );
+  if( cu.left || area.x > cu.blocks[chType].x )
+    r.numLeft = (uint8_t) ( numLeft + intraUnitsAvailable( tu, chType, Position( posLT.x, posLT.y + (PosType) area.height ), totalLeft - numLeft, unitH, false ) );
+  return FLATTEN_INTRA_OK;
+}
+
+}   // namespace b200glue
