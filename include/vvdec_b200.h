@@ -352,7 +352,7 @@ B200_API int  b200_get_frame_fmt_async(b200_ctx* ctx, int slot, int fmt, void* c
  * three counts.  Not covered (the flattener must refuse them): MIP, CCLM, ISP, palette, ACT.
  * Blocks of one list are processed in list order; a block may read what earlier blocks of the list wrote. */
 enum { B200_INTRA_PLANAR = 0, B200_INTRA_DC = 1 /* 2..66 angular */, B200_INTRA_BDPCM_HOR = 67, B200_INTRA_BDPCM_VER = 68 };
-enum { B200_INTRA_FILTER_REF = 1, B200_INTRA_AVAIL_TL = 2 };
+enum { B200_INTRA_FILTER_REF = 1, B200_INTRA_AVAIL_TL = 2, B200_INTRA_ADD_RESI = 4 /* reconstruct: clip(pred + residual), see b200_intra_reconstruct */ };
 typedef struct b200_intra_tu {
   uint16_t x, y;          /* top-left in the component's plane, samples                                              */
   uint8_t  log2w, log2h;  /* 2..6 (chroma: height may be 2 = log2h 1)                                                */
@@ -366,6 +366,10 @@ typedef struct b200_intra_tu {
 } b200_intra_tu;          /* 16 bytes */
 /* Kernel-level K6: host planes in (reconstructed neighbourhood), prediction written into the blocks, host planes out. */
 B200_API int b200_intra_predict(const b200_geom* g, int16_t* const planes[3], const b200_intra_tu* tus, size_t numTus);
+/* The same with the reconstruction step of DecCu::predAndReco (DecCu.cpp:390-398): blocks flagged B200_INTRA_ADD_RESI store
+ * clip(pred + resi[comp][same position]) — what the next block of the list then reads as its reference.  resi planes have the picture's
+ * geometry (e.g. the output of b200_k1_residual in mode 1). */
+B200_API int b200_intra_reconstruct(const b200_geom* g, int16_t* const planes[3], const int16_t* const resi[3], const b200_intra_tu* tus, size_t numTus);
 
 /* Film grain synthesis on the output frame: the per-sample part of the reference's VFGS model,
  *   replaces  FilmGrainImpl::add_grain_block / make_grain_pattern / scale_and_output (FilmGrain/FilmGrainImpl.cpp:129,:198,:247 and their

@@ -237,3 +237,19 @@ void orc_intra_predict(const b200_geom* g, int16_t* const planes[3], const b200_
 {
   for (size_t i = 0; i < numTus; i++) orc_intra_tu(g, planes, &tus[i]);
 }
+
+/* prediction + reconstruction (DecCu.cpp:390-398): blocks flagged B200_INTRA_ADD_RESI become clip(pred + resi) before the next block reads them */
+void orc_intra_reconstruct(const b200_geom* g, int16_t* const planes[3], const int16_t* const resi[3], const b200_intra_tu* tus, size_t numTus)
+{
+  const int pmax = (1 << g->bitDepth) - 1;
+  for (size_t i = 0; i < numTus; i++) {
+    const b200_intra_tu* t = &tus[i];
+    orc_intra_tu(g, planes, t);
+    if (resi && resi[t->comp] && (t->flags & B200_INTRA_ADD_RESI))
+      for (int y = 0; y < (1 << t->log2h); y++)
+        for (int x = 0; x < (1 << t->log2w); x++) {
+          const ptrdiff_t o = (ptrdiff_t)(t->y + y) * g->stride[t->comp] + t->x + x;
+          planes[t->comp][o] = (int16_t)iclip(0, pmax, planes[t->comp][o] + resi[t->comp][o]);
+        }
+  }
+}

@@ -764,7 +764,44 @@ extern "C" int ref_picture_hash( int method, int bitDepth, int16_t* const planes
 // A picture whose CUs (single tree, one TU each, decoding order) are all intra; the planes hold the reconstruction of the neighbourhood.
 // The LAST CU of the list is predicted with the real IntraPrediction, exactly as DecCu::predAndReco drives it (DecCu.cpp:329-371), into the
 // planes; its records come back through the glue flattener, and the flattener's availability is checked against m_neighborSize.
-extern "C" int ref_intra_case( int simd, const b200_geom* g, int16_t* const planes[3], const ref_intra_cu* cus, int numCus, b200_intra_tu* recs, int capRecs )
+static int intraPredictCu( IntraPrediction& ip, CodingStructure& cs, CodingUnit& cu, const b200_geom* g, const int16_t* const resi[3], bool addResi, b200_intra_tu* recs, int capRecs, int& n )
+{
+  TransformUnit& tu = cu.firstTU;
+  for( const CompArea& area : tu.blocks )
+  {
+    if( !area.valid() ) continue;
+    const ComponentID compID = area.compID();
+    b200_intra_tu r;
+    if( b200glue::flattenIntraTU( tu, compID, r ) != b200glue::FLATTEN_INTRA_OK ) return -2;
+    PelBuf piPred = cs.getRecoBuf( area );
+    const bool filt = isLuma( compID ) && cu.ispMode() == NOT_INTRA_SUBPARTITIONS && IntraPrediction::useFilteredIntraRefSamples( compID, cu, tu );
+    ip.initIntraPatternChType( tu, area, filt );
+    if( ( ( r.flags & B200_INTRA_AVAIL_TL ) ? 1 : 0 ) != ip.m_neighborSize[0] || r.numAbove != ip.m_neighborSize[1] || r.numLeft != ip.m_neighborSize[2] )
+    {
+      fprintf( stderr, "ref_intra: availability mismatch comp %d: glue (%d %d %d) reference (%d %d %d)\n", (int) compID, ( r.flags >> 1 ) & 1, r.numAbove, r.numLeft,
+               ip.m_neighborSize[0], ip.m_neighborSize[1], ip.m_neighborSize[2] );
+      return -3;
+    }
+    ip.predIntraAng( compID, piPred, cu, filt );
+    if( addResi && resi && resi[compID] )
+    {                                                          // piReco.reconstruct( piPred, piResi, clpRng ) (DecCu.cpp:392)
+      r.flags |= B200_INTRA_ADD_RESI;
+      const int pmax = ( 1 << g->bitDepth ) - 1;
+      for( unsigned y = 0; y < area.height; y++ ) for( unsigned x = 0; x < area.width; x++ )
+      {
+        Pel& p = piPred.buf[y * piPred.stride + x];
+        p = (Pel) std::min( pmax, std::max( 0, p + resi[compID][( area.y + y ) * g->stride[compID] + area.x + x] ) );
+      }
+    }
+    if( n < capRecs ) recs[n] = r;
+    n++;
+  }
+  return 0;
+}
+
+// all != 0: every CU of the list is predicted (and, with rsv[1] set and resi given, reconstructed) in order — a whole intra picture
+extern "C" int ref_intra_case( int simd, const b200_geom* g, int16_t* const planes[3], const int16_t* const resi[3], const ref_intra_cu* cus, int numCus, int all,
+                               b200_intra_tu* recs, int capRecs )
 {
   try
   {
@@ -774,7 +811,17 @@ extern "C" int ref_intra_case( int simd, const b200_geom* g, int16_t* const plan
     const PreCalcValues& pcv = *cs.pcv;
     Slice* sl = cur.pic.slices[0];
     sl->setSliceType( I_SLICE );
-    CodingUnit* last = nullptr;
+    IntraPrediction ip;
+    ip.init( pcv.chrFormat, g->bitDepth );                              // x86: installs the SIMD kernels (IntraPrediction.cpp:399)
+    if( !simd )
+    {
+      IntraPrediction scalar;                                           // the constructor installs the C kernels (:362-376)
+      ip.IntraPredAngleCore4 = scalar.IntraPredAngleCore4; ip.IntraPredAngleCore8 = scalar.IntraPredAngleCore8;
+      ip.IntraPredAngleChroma4 = scalar.IntraPredAngleChroma4; ip.IntraPredAngleChroma8 = scalar.IntraPredAngleChroma8;
+      ip.IntraPredSampleFilter8 = scalar.IntraPredSampleFilter8; ip.IntraPredSampleFilter16 = scalar.IntraPredSampleFilter16;
+      ip.xPredIntraPlanar = scalar.xPredIntraPlanar; ip.GetLumaRecPixel420 = scalar.GetLumaRecPixel420;
+    }
+    int n = 0;
     for( int i = 0; i < numCus; i++ )
     {
       const ref_intra_cu& c = cus[i];
@@ -789,40 +836,8 @@ extern "C" int ref_intra_case( int simd, const b200_geom* g, int16_t* const plan
       cu.intraDir[0] = c.dirL; cu.intraDir[1] = c.dirC;
       cu.setMultiRefIdx( c.multiRefIdx ); cu.setBdpcmMode( c.bdpcm ); cu.setBdpcmModeChroma( c.bdpcmC );
       cs.addTU( ua, CH_L, cu );
-      last = &cu;
-    }
-    if( !last ) return -1;
-    IntraPrediction ip;
-    ip.init( pcv.chrFormat, g->bitDepth );                              // x86: installs the SIMD kernels (IntraPrediction.cpp:399)
-    if( !simd )
-    {
-      IntraPrediction scalar;                                           // the constructor installs the C kernels (:362-376)
-      ip.IntraPredAngleCore4 = scalar.IntraPredAngleCore4; ip.IntraPredAngleCore8 = scalar.IntraPredAngleCore8;
-      ip.IntraPredAngleChroma4 = scalar.IntraPredAngleChroma4; ip.IntraPredAngleChroma8 = scalar.IntraPredAngleChroma8;
-      ip.IntraPredSampleFilter8 = scalar.IntraPredSampleFilter8; ip.IntraPredSampleFilter16 = scalar.IntraPredSampleFilter16;
-      ip.xPredIntraPlanar = scalar.xPredIntraPlanar; ip.GetLumaRecPixel420 = scalar.GetLumaRecPixel420;
-    }
-    CodingUnit& cu = *last;
-    TransformUnit& tu = cu.firstTU;
-    int n = 0;
-    for( const CompArea& area : tu.blocks )
-    {
-      if( !area.valid() ) continue;
-      const ComponentID compID = area.compID();
-      b200_intra_tu r;
-      if( b200glue::flattenIntraTU( tu, compID, r ) != b200glue::FLATTEN_INTRA_OK ) return -2;
-      PelBuf piPred = cs.getRecoBuf( area );
-      const bool filt = isLuma( compID ) && cu.ispMode() == NOT_INTRA_SUBPARTITIONS && IntraPrediction::useFilteredIntraRefSamples( compID, cu, tu );
-      ip.initIntraPatternChType( tu, area, filt );
-      if( ( ( r.flags & B200_INTRA_AVAIL_TL ) ? 1 : 0 ) != ip.m_neighborSize[0] || r.numAbove != ip.m_neighborSize[1] || r.numLeft != ip.m_neighborSize[2] )
-      {
-        fprintf( stderr, "ref_intra_case: availability mismatch comp %d: glue (%d %d %d) reference (%d %d %d)\n", (int) compID, ( r.flags >> 1 ) & 1, r.numAbove, r.numLeft,
-                 ip.m_neighborSize[0], ip.m_neighborSize[1], ip.m_neighborSize[2] );
-        return -3;
-      }
-      ip.predIntraAng( compID, piPred, cu, filt );
-      if( n < capRecs ) recs[n] = r;
-      n++;
+      if( all || i == numCus - 1 )
+        if( int rc = intraPredictCu( ip, cs, cu, g, resi, c.rsv[1] != 0, recs, capRecs, n ) ) return rc;
     }
     cur.getPlanes( *g, planes );
     return n;

@@ -1,7 +1,7 @@
 """Test helpers: load the oracle (C restatement) and, when built, the reference shim."""
 import os, subprocess, ctypes as C
 import numpy as np
-from vvdec_b200 import abi
+from vvdec_b200 import abi, synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
@@ -48,6 +48,7 @@ def load_oracle():
     lib.orc_pack_pyuv.argtypes = [i16p, C.c_ssize_t, C.c_int, C.c_int, u8p]
     lib.orc_narrow8.argtypes = [i16p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, u8p]
     lib.orc_intra_predict.argtypes = [C.POINTER(abi.Geom), PL, C.c_void_p, C.c_size_t]
+    lib.orc_intra_reconstruct.argtypes = [C.POINTER(abi.Geom), PL, PL, C.c_void_p, C.c_size_t]
     lib.orc_film_grain.argtypes = [PL, C.POINTER(C.c_ssize_t), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.orc_plane_hash.argtypes = [C.c_int, C.c_int, i16p, C.c_ssize_t, C.c_int, C.c_int, u8p]
     return lib
@@ -90,7 +91,7 @@ def load_ref():
     lib.ref_flatten_pu_case.argtypes = [C.c_int, C.POINTER(abi.Geom), C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, PL, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.ref_write_component.argtypes = [i16p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS"), C.c_size_t]
     lib.ref_write_component.restype = C.c_size_t
-    lib.ref_intra_case.argtypes = [C.c_int, C.POINTER(abi.Geom), PL, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.ref_intra_case.argtypes = [C.c_int, C.POINTER(abi.Geom), PL, PL, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
     lib.ref_film_grain.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, PL, C.POINTER(C.c_ssize_t)] + [C.c_void_p] * 4 + [C.POINTER(C.c_int), C.c_void_p]
     lib.ref_picture_hash.argtypes = [C.c_int, C.c_int, PL, C.POINTER(C.c_ssize_t), C.c_int, C.c_int, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS"), C.c_int]
     lib.ref_lmcs_build.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(abi.Lmcs), i16p]
@@ -162,3 +163,27 @@ def oracle_decompress(oracle, g, dpb, pic):
         oracle.orc_alf_picture(C.byref(g), abi.plane_ptrs(cur), abi.plane_ptrs(nxt), pic["alf"]["ctus"].ctypes.data, C.byref(pic["alfTabs"]))
         cur = nxt
     return cur, dm
+
+
+def intra_picture_case(ref, rng, W, H, bd, ctu, simd, p_resi=0.5, **layout_kw):
+    """A whole all-intra picture through the real IntraPrediction: every CU predicted from the reconstruction of the earlier ones, with the
+    pred + residual step on some CUs.  Returns geometry, start planes, residual planes, records (from the reference's flattener) and the result."""
+    g = abi.make_geom(W, H, bd, ctu=ctu)
+    layout = synth.gen_intra_layout(rng, W, H, ctu, **layout_kw)
+    planes = synth.noise_planes(rng, W, H, bd)
+    resi = [rng.integers(-40, 41, size=p.shape).astype(np.int16) for p in planes]
+    cus = np.zeros(len(layout), synth.REF_INTRA_CU_DTYPE)
+    chroma = [0, 1, 18, 50, 2, 34, 66, 70, 70, 70, 23, 45, 61]
+    for i, (x, y, w, h) in enumerate(layout):
+        cus[i]["x"], cus[i]["y"], cus[i]["w"], cus[i]["h"] = x, y, w, h
+        cus[i]["dirL"], cus[i]["dirC"] = int(rng.integers(0, 67)), chroma[int(rng.integers(len(chroma)))]
+        r = rng.random()
+        if r < 0.15 and y % ctu: cus[i]["multiRefIdx"], cus[i]["dirL"] = int(rng.integers(1, 3)), int(rng.integers(1, 67))
+        elif r < 0.25 and w <= 32 and h <= 32: cus[i]["bdpcm"] = int(rng.integers(1, 3))
+        cus[i]["rsv"][0] = w < 8 or (w // 2) * (h // 2) < 16
+        cus[i]["rsv"][1] = rng.random() < p_resi
+    out = [p.copy() for p in planes]
+    recs = np.zeros(3 * len(layout), abi.INTRA_TU_DTYPE)
+    n = ref.ref_intra_case(simd, C.byref(g), abi.plane_ptrs(out), abi.plane_ptrs(resi), cus.ctypes.data, len(layout), 1, recs.ctypes.data, len(recs))
+    assert n > 0, n
+    return g, planes, resi, recs[:n], out

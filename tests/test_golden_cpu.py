@@ -125,3 +125,15 @@ def test_film_grain_golden(oracle):
     oracle.orc_film_grain(abi.plane_ptrs(got), strides, W, H, bd, tabs[0].ctypes.data, tabs[1].ctypes.data, tabs[2].ctypes.data, tabs[3].ctypes.data, int(z["shift"]), tabs[4].ctypes.data)
     for c in range(3):
         assert np.array_equal(got[c], z[f"out{c}"]), c
+
+
+def test_k6_intra_golden(oracle):
+    """tests/golden/k6_intra_picture.npz: an all-intra picture chained through the reference's IntraPrediction (SIMD), with residual adds."""
+    z = _load("k6_intra_picture.npz")
+    W, H, bd, ctu = [int(v) for v in z["geom"]]
+    g = abi.make_geom(W, H, bd, ctu=ctu)
+    got, resi = _planes(z, "src"), _planes(z, "resi")
+    recs = np.ascontiguousarray(z["recs"])
+    oracle.orc_intra_reconstruct(C.byref(g), abi.plane_ptrs(got), abi.plane_ptrs(resi), recs.ctypes.data, len(recs))
+    for c in range(3):
+        assert np.array_equal(got[c], z[f"out{c}"]), c

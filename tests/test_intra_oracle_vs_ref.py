@@ -25,7 +25,7 @@ def run_case(oracle, ref, rng, W, H, bd, ctu, simd, layout, k, dirL, dirC, mrl, 
     cus[k]["rsv"][0] = luma_only
     want = [p.copy() for p in planes]
     recs = np.zeros(3, abi.INTRA_TU_DTYPE)
-    n = ref.ref_intra_case(simd, C.byref(g), abi.plane_ptrs(want), cus.ctypes.data, k + 1, recs.ctypes.data, 3)
+    n = ref.ref_intra_case(simd, C.byref(g), abi.plane_ptrs(want), None, cus.ctypes.data, k + 1, 0, recs.ctypes.data, 3)
     assert n == (1 if luma_only else 3), n
     recs = recs[:n]
     got = [p.copy() for p in planes]
@@ -33,6 +33,11 @@ def run_case(oracle, ref, rng, W, H, bd, ctu, simd, layout, k, dirL, dirC, mrl, 
     for c in range(3):
         assert np.array_equal(got[c], want[c]), (c, layout[k], dirL, dirC, mrl, bdpcm, recs[c])
     assert not np.array_equal(want[0][y:y + h, x:x + w], planes[0][y:y + h, x:x + w])
+    # the synthetic generator used by the GPU tests derives the same records (availability from the decoding order, filter decision, DM)
+    mine = synth.gen_intra_records(rng, layout, W, H, modes={k: (dirL, dirC, mrl, bdpcm)}, upto=k)
+    mine = mine[-n:]
+    for f in ("x", "y", "log2w", "log2h", "comp", "mode", "multiRefIdx", "flags", "numAbove", "numLeft"):
+        assert np.array_equal(mine[f], recs[f]), (f, mine[f], recs[f], layout[k])
     return recs
 
 
@@ -71,3 +76,17 @@ def test_intra_all_modes_per_shape(oracle, ref, w, h):
             if mrl and (mode == 0 or (mode + mrl) % 4): continue          # planar has no MRL; sample the rest
             if (w == 4 or h == 4) and False: continue
             run_case(oracle, ref, rng, W, H, 10, ctu, (mode + mrl) & 1, layout, 3, mode, CHROMA_MODES[mode % len(CHROMA_MODES)], mrl, 0)
+
+
+from tests.helpers import intra_picture_case
+
+
+@pytest.mark.parametrize("W,H,bd,ctu,simd,seed", [(256, 128, 10, 128, 1, 11), (192, 128, 10, 64, 0, 12), (416, 240, 8, 128, 1, 13), (256, 256, 12, 128, 0, 14)])
+def test_intra_picture_chain(oracle, ref, W, H, bd, ctu, simd, seed):
+    rng = np.random.default_rng(seed)
+    g, planes, resi, recs, want = intra_picture_case(ref, rng, W, H, bd, ctu, simd, min_size=8)
+    got = [p.copy() for p in planes]
+    oracle.orc_intra_reconstruct(C.byref(g), abi.plane_ptrs(got), abi.plane_ptrs(resi), recs.ctypes.data, len(recs))
+    for c in range(3):
+        assert np.array_equal(got[c], want[c]), c
+    assert (recs["flags"] & 4).any() and not (recs["flags"] & 4).all()

@@ -132,8 +132,17 @@ def film_grain():
                         present=present, **{f"src{c}": src[c] for c in range(3)}, **{f"out{c}": out[c] for c in range(3)})
 
 
+def intra():
+    """An all-intra picture through the reference's IntraPrediction (SIMD kernels): every CU predicted from the reconstruction of the earlier ones
+    (regular modes, MRL, BDPCM prediction), pred + residual on about half of the CUs; records from the glue flattener."""
+    rng = np.random.default_rng(505)
+    g, planes, resi, recs, out = helpers.intra_picture_case(ref, rng, 192, 128, 10, 64, 1, min_size=8)
+    np.savez_compressed(os.path.join(OUT, "k6_intra_picture.npz"), geom=[192, 128, 10, 64], recs=recs, **{f"src{c}": planes[c] for c in range(3)},
+                        **{f"resi{c}": resi[c] for c in range(3)}, **{f"out{c}": out[c] for c in range(3)})
+
+
 if __name__ == "__main__":
     import sys
     if len(sys.argv) > 1: [globals()[n]() for n in sys.argv[1:]]
-    else: k1(); pictures(); chain(); film_grain()
+    else: k1(); pictures(); chain(); film_grain(); intra()
     print({f: os.path.getsize(os.path.join(OUT, f)) for f in sorted(os.listdir(OUT))})

@@ -186,6 +186,58 @@ B200_API int b200_sao_picture(const b200_geom* g, const int16_t* const src[3], i
   return 0;
 }
 
+B200_API int b200_intra_reconstruct(const b200_geom* g, int16_t* const planes[3], const int16_t* const resi[3], const b200_intra_tu* tus, size_t numTus)
+{
+  B200_CHECK(g && planes && (tus || !numTus), "b200_intra_reconstruct: null argument");
+  B200_CHECK(g->bitDepth >= 8 && g->bitDepth <= 12, "b200_intra_reconstruct: bit depth %d unsupported", g->bitDepth);
+  const int nPl = g->chromaFormat ? 3 : 1;
+  for (size_t i = 0; i < numTus; i++) {                      // kernel-level wrapper: records are checked here (the picture path checks on the device)
+    const b200_intra_tu& t = tus[i];
+    const int w = 1 << t.log2w, h = 1 << t.log2h, pw = t.comp ? g->width >> 1 : g->width, ph = t.comp ? g->height >> 1 : g->height, unit = t.comp ? 2 : 4;
+    B200_CHECK(t.comp < nPl && t.log2w >= 2 && t.log2w <= 6 && t.log2h >= 1 && t.log2h <= 6 && t.x + w <= pw && t.y + h <= ph && !(t.x % unit) && !(t.y % unit),
+               "b200_intra_reconstruct: record %zu: bad geometry", i);
+    B200_CHECK(t.mode <= B200_INTRA_BDPCM_VER && t.multiRefIdx <= 2 && (!t.multiRefIdx || !t.comp), "b200_intra_reconstruct: record %zu: bad mode / reference line", i);
+    B200_CHECK(t.numAbove <= 2 * w / unit && t.numLeft <= 2 * h / unit && (!t.numAbove || t.y > t.multiRefIdx) && (!t.numLeft || t.x > t.multiRefIdx)
+               && (!(t.flags & B200_INTRA_AVAIL_TL) || (t.x > t.multiRefIdx && t.y > t.multiRefIdx)) && t.x + (int)t.numAbove * unit <= pw && t.y + (int)t.numLeft * unit <= ph,
+               "b200_intra_reconstruct: record %zu: availability outside the picture", i);
+  }
+  if (int rc = ensure_device()) return rc;
+  if (int rc = g_hw.init()) return rc;
+  cudaStream_t s = g_hw.stream;
+  IntraLaunch L; L.geom = *g; L.numTus = numTus;
+  if (int rc = upload_planes(g, planes, L.planes, s)) return rc;
+  for (int c = 0; c < 3; c++) {
+    L.resi[c] = nullptr; L.owner[c] = nullptr; L.ownerStride[c] = 0; L.ownerBytes[c] = 0;
+    if (c >= nPl) continue;
+    const int pw = c ? g->width >> 1 : g->width, ph = c ? g->height >> 1 : g->height, unit = c ? 2 : 4;
+    L.ownerStride[c] = (pw + unit - 1) / unit; L.ownerBytes[c] = (size_t)L.ownerStride[c] * ((ph + unit - 1) / unit) * sizeof(int);
+    if (int rc = g_hw.misc[c].reserve(L.ownerBytes[c])) return rc;
+    L.owner[c] = g_hw.misc[c].as<int>();
+    if (resi && resi[c]) {
+      const size_t bytes = (size_t)g->stride[c] * ph * sizeof(int16_t);
+      if (int rc = g_hw.misc[3 + c].reserve(bytes)) return rc;
+      B200_CUDA(cudaMemcpyAsync(g_hw.misc[3 + c].p, resi[c], bytes, cudaMemcpyHostToDevice, s));
+      L.resi[c] = g_hw.misc[3 + c].as<int16_t>();
+    }
+  }
+  if (int rc = g_hw.tus.reserve(numTus * sizeof(b200_intra_tu) + 16)) return rc;
+  if (int rc = g_hw.misc[6].reserve((numTus + 2) * sizeof(int))) return rc;
+  if (numTus) B200_CUDA(cudaMemcpyAsync(g_hw.tus.p, tus, numTus * sizeof(b200_intra_tu), cudaMemcpyHostToDevice, s));
+  L.tus = g_hw.tus.as<b200_intra_tu>(); L.sync = g_hw.misc[6].as<int>();
+  if (int rc = launch_intra(L, s)) return rc;
+  int err = 0;
+  if (numTus) B200_CUDA(cudaMemcpyAsync(&err, L.sync + numTus + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (int rc = download_planes(g, planes, L.planes, s)) return rc;
+  B200_CUDA(cudaStreamSynchronize(s));
+  B200_CHECK(!err, "b200_intra_reconstruct: a block waited for a neighbour that never finished (list not in decoding order?)");
+  return 0;
+}
+
+B200_API int b200_intra_predict(const b200_geom* g, int16_t* const planes[3], const b200_intra_tu* tus, size_t numTus)
+{
+  return b200_intra_reconstruct(g, planes, nullptr, tus, numTus);
+}
+
 B200_API int b200_alf_picture(const b200_geom* g, const int16_t* const src[3], int16_t* const dst[3], const b200_alf_ctu* ctus, const b200_alf_tables* T)
 {
   B200_CHECK(g && src && dst && ctus && T, "b200_alf_picture: null argument");

@@ -1,0 +1,256 @@
+// k6_intra.cu — K6: regular intra prediction (planar, DC, angular incl. wide angles, multi reference line, PDPC, BDPCM prediction) of a
+// list of transform blocks in decoding order, with the residual add that makes a block's reconstruction the next block's reference.
+// Replaces (reference, source/Lib/CommonLib/IntraPrediction.cpp): xFillReferenceSamples :1072 (sample copies / substitution),
+// xFilterReferenceSamples :1251, predIntraAng :474, xPredIntraPlanarCore :154, xGetPredValDc :412, xPredIntraAng :592,
+// IntraPredAngleCore :301, IntraPredAngleChroma :333, IntraPredSampleFilterCore :212, xPredIntraBDPCM :850 and the pred + resi clip of
+// DecCu::predAndReco (DecCu.cpp:390-398).
+//
+// Scheduling.  Intra blocks depend on their neighbours' reconstruction, so the list is a dataflow graph.  CTAs take blocks in list order from
+// a ticket counter; a block waits (bounded spin on per-block `done` words) for the earlier blocks of the list that own the units its
+// available reference samples lie in (`owner` maps filled by a pre-pass, one word per 4x4 luma / 2x2 chroma unit).  Tickets are handed out
+// in decoding order and only to running CTAs, so the oldest unfinished block never waits on a block that has not started: no deadlock,
+// whatever the residency.  Reference samples are read with ld.global.cg (L2): another SM wrote them.
+// Inside a block every sample is independent once the two reference arrays are in shared memory: one thread computes several samples.
+#include "common.cuh"
+#define VVC_TABLE_QUAL static __device__ const __align__(16)
+#include "vvc_tables.h"
+
+namespace b200 {
+
+constexpr int IT_THREADS = 128;
+constexpr int IT_REF = 2 * 64 + 8;           // top / left array: 2*size + 1 + multiRefIdx entries
+constexpr int IT_ORG = 72;                   // origin of the main / side arrays (room for the negative extension, <= 64)
+constexpr int IT_ARR = IT_ORG + 2 * 64 + 80; // main / side arrays incl. replication tail ((mrl << s) + 2 <= 34)
+
+__constant__ int cAng[32] = {0, 1, 2, 3, 4, 6, 8, 10, 12, 14, 16, 18, 20, 23, 26, 29, 32, 35, 39, 45, 51, 57, 64, 73, 86, 102, 128, 171, 256, 341, 512, 1024};
+__constant__ int cInvAng[32] = {0, 16384, 8192, 5461, 4096, 2731, 2048, 1638, 1365, 1170, 1024, 910, 819, 712, 630, 565,
+                                512, 468, 420, 364, 321, 287, 256, 224, 191, 161, 128, 96, 64, 48, 32, 16};
+__constant__ int cIntraFilterThr[8] = {24, 24, 24, 14, 2, 0, 0, 0};
+
+struct IntraParams {
+  int16_t* planes[3]; const int16_t* resi[3]; int stride[3]; int W, H, bitDepth;
+  const b200_intra_tu* tus; int numTus;
+  int* owner[3]; int ownerStride[3];        // per unit: index of the list entry that writes it, -1: not written by this list
+  int* done; int* ticket; int* err;
+};
+
+__device__ __forceinline__ int wide_angle(int w, int h, int mode)
+{
+  if (mode > 1 && mode <= 66) {
+    const int shift[6] = {0, 6, 10, 12, 14, 15};
+    const int d = abs((31 - __clz(w)) - (31 - __clz(h)));
+    if (w > h && mode < 2 + shift[d]) mode += 65;
+    else if (h > w && mode > 66 - shift[d]) mode -= 65;
+  }
+  return mode;
+}
+
+__global__ void __launch_bounds__(256) intra_owner_kernel(const IntraParams P)
+{
+  const int i = blockIdx.x;
+  const b200_intra_tu t = P.tus[i];
+  const int c = t.comp, unit = c ? 2 : 4, uw = max(1, (1 << t.log2w) / unit), uh = max(1, (1 << t.log2h) / unit);
+  for (int k = threadIdx.x; k < uw * uh; k += blockDim.x) P.owner[c][(t.y / unit + k / uw) * P.ownerStride[c] + t.x / unit + k % uw] = i;
+}
+
+__device__ __forceinline__ int pix(const int16_t* __restrict__ plane, int stride, int x, int y) { return __ldcg(plane + (size_t)y * stride + x); }
+
+__global__ void __launch_bounds__(IT_THREADS) intra_kernel(const IntraParams P)
+{
+  __shared__ int16_t sT[2][IT_REF], sL[2][IT_REF];          // [0] unfiltered, [1] filtered
+  __shared__ int16_t sM[IT_ARR], sS[IT_ARR];
+  __shared__ int sTicket, sSum;
+  const int tid = threadIdx.x;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) { sTicket = atomicAdd(P.ticket, 1); sSum = 0; }
+    __syncthreads();
+    const int me = sTicket;
+    if (me >= P.numTus) return;
+    const b200_intra_tu t = P.tus[me];
+    const int c = t.comp, w = 1 << t.log2w, h = 1 << t.log2h, mrl = c ? 0 : t.multiRefIdx, unit = c ? 2 : 4;
+    const int x0 = t.x, y0 = t.y, ps = P.stride[c], pmax = (1 << P.bitDepth) - 1;
+    const int16_t* plane = P.planes[c];
+    const int availTL = (t.flags & B200_INTRA_AVAIL_TL) ? 1 : 0, numAbove = t.numAbove, numLeft = t.numLeft;
+
+    // ---- wait for the earlier blocks this one reads from
+    {
+      int ux = -1, uy = -1;
+      if (tid == 0) { if (availTL) { ux = x0 - 1; uy = y0 - 1; } }
+      else if (tid <= numAbove) { ux = x0 + (tid - 1) * unit; uy = y0 - 1; }
+      else if (tid - 64 >= 0 && tid - 64 < numLeft) { ux = x0 - 1; uy = y0 + (tid - 64) * unit; }
+      if (ux >= 0 && uy >= 0) {
+        const int o = P.owner[c][(uy / unit) * P.ownerStride[c] + ux / unit];
+        if (o >= 0 && o < me) {
+          const volatile int* d = P.done + o;
+          int spins = 0;
+          const volatile int* e = P.err;
+          while (*d == 0) { __nanosleep(64); if (*e || ++spins > (1 << 22)) { atomicOr(P.err, 1); break; } }   // bounded: a broken list must not hang the GPU
+        }
+      }
+      __threadfence();
+    }
+    __syncthreads();
+
+    // ---- reference samples (xFillReferenceSamples): T[j] = row above incl. the corner, L[i] = left column, T[0] = L[0] = corner
+    const int predSize = 2 * w, predHSize = 2 * h;
+    const int totalUnits = (predSize + unit - 1) / unit + (predHSize + unit - 1) / unit + 1, n = availTL + numAbove + numLeft;
+    const int aboveLen = min(numAbove * unit, predSize), leftLen = min(numLeft * unit, predHSize);
+    int16_t *T = sT[0], *L = sL[0];
+    for (int j = tid; j <= predSize + mrl; j += IT_THREADS) {
+      int v;
+      if (n == 0) v = 1 << (P.bitDepth - 1);
+      else if (n == totalUnits) v = pix(plane, ps, x0 - 1 - mrl + j, y0 - 1 - mrl);
+      else if (j <= mrl) {                                     // corner part of the row
+        if (numLeft > 0) v = availTL ? pix(plane, ps, x0 - 1 - mrl + j, y0 - 1 - mrl) : pix(plane, ps, x0 - 1 - mrl, y0);
+        else v = pix(plane, ps, x0, y0 - 1 - mrl);
+      } else {
+        const int k = j - 1 - mrl;
+        if (numAbove) v = pix(plane, ps, x0 + min(k, aboveLen - 1), y0 - 1 - mrl);
+        else v = availTL ? pix(plane, ps, x0 - 1, y0 - 1 - mrl) : pix(plane, ps, x0 - 1 - mrl, y0);    // = T[mrl]; numLeft > 0 here
+      }
+      T[j] = (int16_t)v;
+    }
+    for (int i = tid; i <= predHSize + mrl; i += IT_THREADS) {
+      if (i == 0) continue;                                    // L[0] is T[0], set below
+      int v;
+      if (n == 0) v = 1 << (P.bitDepth - 1);
+      else if (n == totalUnits) v = pix(plane, ps, x0 - 1 - mrl, y0 - 1 - mrl + i);
+      else if (numLeft > 0) {
+        if (i <= mrl) v = availTL ? pix(plane, ps, x0 - 1 - mrl, y0 - 1 - mrl + i) : pix(plane, ps, x0 - 1 - mrl, y0);
+        else v = pix(plane, ps, x0 - 1 - mrl, y0 + min(i - 1 - mrl, leftLen - 1));
+      } else v = pix(plane, ps, x0, y0 - 1 - mrl);
+      L[i] = (int16_t)v;
+    }
+    __syncthreads();
+    if (tid == 0) L[0] = T[0];
+    __syncthreads();
+    if ((t.flags & B200_INTRA_FILTER_REF) && !c && !mrl) {     // xFilterReferenceSamples
+      int16_t *FT = sT[1], *FL = sL[1];
+      for (int j = tid; j <= predSize; j += IT_THREADS)
+        FT[j] = j == 0 ? (int16_t)((L[1] + 2 * T[0] + T[1] + 2) >> 2) : j == predSize ? T[j] : (int16_t)((T[j + 1] + 2 * T[j] + T[j - 1] + 2) >> 2);
+      for (int i = tid + 1; i <= predHSize; i += IT_THREADS)
+        FL[i] = i == predHSize ? L[i] : (int16_t)((L[i + 1] + 2 * L[i] + L[i - 1] + 2) >> 2);
+      __syncthreads();
+      if (tid == 0) FL[0] = FT[0];
+      T = FT; L = FL;
+      __syncthreads();
+    }
+
+    const int mode = t.mode;
+    const bool doPDPC = w >= 4 && h >= 4 && mrl == 0;
+    int16_t* dst = P.planes[c] + (size_t)y0 * ps + x0;
+    const int16_t* rs = (P.resi[c] && (t.flags & B200_INTRA_ADD_RESI)) ? P.resi[c] + (size_t)y0 * ps + x0 : nullptr;
+#define IT_STORE(x, y, v) do { int v_ = (v); if (rs) v_ = clip3(0, pmax, v_ + rs[(size_t)(y) * ps + (x)]); dst[(size_t)(y) * ps + (x)] = (int16_t)v_; } while (0)
+
+    if (mode == B200_INTRA_PLANAR || mode == B200_INTRA_DC) {
+      int dc = 0;
+      if (mode == B200_INTRA_DC) {                             // xGetPredValDc
+        int part = 0;
+        for (int i = tid; i < w + h; i += IT_THREADS) {
+          if (i < w) { if (w >= h) part += T[mrl + 1 + i]; }
+          else if (w <= h) part += L[mrl + 1 + i - w];
+        }
+        for (int o = 16; o; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+        if ((tid & 31) == 0) atomicAdd(&sSum, part);
+        __syncthreads();
+        const int denom = w == h ? w << 1 : max(w, h);
+        dc = (sSum + (denom >> 1)) >> (31 - __clz(denom));
+      }
+      const int l2w = t.log2w, l2h = t.log2h, scale = (l2w - 2 + l2h - 2 + 2) >> 2;
+      const int bl = L[h + 1], tr = T[w + 1];
+      for (int k = tid; k < w * h; k += IT_THREADS) {
+        const int y = k >> l2w, x = k & (w - 1);
+        int v;
+        if (mode == B200_INTRA_PLANAR) {                       // xPredIntraPlanarCore in closed form
+          const int hor = (L[y + 1] << l2w) + (x + 1) * (tr - L[y + 1]), vert = (T[x + 1] << l2h) + (y + 1) * (bl - T[x + 1]);
+          v = ((hor << l2h) + (vert << l2w) + (1 << (l2w + l2h))) >> (1 + l2w + l2h);
+        } else v = dc;
+        v = (int16_t)v;
+        if (doPDPC) {                                          // IntraPredSampleFilterCore
+          const int wT = 32 >> min(31, (y << 1) >> scale), wL = 32 >> min(31, (x << 1) >> scale);
+          v = (int16_t)(v + ((wL * (L[y + 1] - v) + wT * (T[x + 1] - v) + 32) >> 6));
+        }
+        IT_STORE(x, y, v);
+      }
+    } else if (mode >= B200_INTRA_BDPCM_HOR) {
+      for (int k = tid; k < w * h; k += IT_THREADS) { const int y = k >> t.log2w, x = k & (w - 1); IT_STORE(x, y, mode == B200_INTRA_BDPCM_HOR ? L[y + 1] : T[x + 1]); }
+    } else {
+      // ---- angular (xPredIntraAng): main / side reference arrays, then every sample on its own
+      const int predMode = wide_angle(w, h, mode);
+      const bool ver = predMode >= 34;
+      const int angMode = ver ? predMode - 50 : -(predMode - 18), absMode = abs(angMode);
+      const int invAngle = cInvAng[absMode], absAng = cAng[absMode], angle = angMode < 0 ? -absAng : absAng;
+      const int16_t *mainSrc = ver ? T : L, *sideSrc = ver ? L : T;
+      const int mw = ver ? w : h, mh = ver ? h : w;            // block size along the main / the side reference
+      int16_t *M = sM + IT_ORG, *S = sS + IT_ORG;
+      if (angle < 0) {
+        for (int k = tid - mh; k <= mw + 1 + mrl; k += IT_THREADS) M[k] = k >= 0 ? mainSrc[k] : sideSrc[min((-k * invAngle + 256) >> 9, mh)];
+        for (int k = tid; k <= mh + 1 + mrl; k += IT_THREADS) S[k] = sideSrc[k];
+      } else {
+        const int l2r = (31 - __clz(mw)) - (31 - __clz(mh)), s = max(0, l2r), maxIndex = (mrl << s) + 2, refLength = 2 * mw;
+        for (int k = tid; k <= refLength + mrl + maxIndex; k += IT_THREADS) M[k] = mainSrc[min(k, refLength + mrl)];
+        for (int k = tid; k <= 2 * mh + mrl; k += IT_THREADS) S[k] = sideSrc[k];
+      }
+      __syncthreads();
+      const int16_t *Mp = M + mrl, *Sp = S + mrl;
+      const int l2mw = 31 - __clz(mw), l2mh = 31 - __clz(mh);
+      const int topLeft = T[0];
+      const int scale0 = (l2mw - 2 + l2mh - 2 + 2) >> 2;
+      const int lev = min(3 << scale0, mw);                    // lev[scale] = min(3, 6, 12, 24; width)
+      const bool frac = (absAng & 31) != 0;
+      const int diff = min(abs(predMode - 18), abs(predMode - 50));
+      const bool cubic = !(diff > cIntraFilterThr[(l2mw + l2mh) >> 1]) || mrl > 0;
+      int angularScale = -1;
+      if (angle > 0 && doPDPC) angularScale = min(2, l2mh - ((31 - __clz(3 * invAngle - 2)) - 8));
+      for (int k = tid; k < mw * mh; k += IT_THREADS) {
+        const int yy = k >> l2mw, xx = k & (mw - 1);
+        int v;
+        if (angle == 0) {
+          if (doPDPC && xx < lev) { const int wL = 32 >> min(31, (xx << 1) >> scale0); v = clip3(0, pmax, (wL * (Sp[yy + 1] - topLeft) + Mp[xx + 1] * 64 + 32) >> 6); }
+          else v = Mp[xx + 1];
+        } else {
+          const int deltaPos = angle * (1 + mrl + yy), dI = deltaPos >> 5, dF = deltaPos & 31;
+          if (!frac) v = Mp[dI + 1 + xx];
+          else if (c) v = (int16_t)(((32 - dF) * Mp[dI + 1 + xx] + dF * Mp[dI + 2 + xx] + 16) >> 5);
+          else {
+            const int16_t* p = Mp + dI + xx;
+            int f0, f1, f2, f3;
+            if (cubic) { f0 = kIfChroma[dF * 4]; f1 = kIfChroma[dF * 4 + 1]; f2 = kIfChroma[dF * 4 + 2]; f3 = kIfChroma[dF * 4 + 3]; }
+            else { f0 = 16 - (dF >> 1); f1 = 32 - (dF >> 1); f2 = 16 + (dF >> 1); f3 = dF >> 1; }
+            v = (int16_t)((f0 * p[0] + f1 * p[1] + f2 * p[2] + f3 * p[3] + 32) >> 6);
+            if (cubic) v = clip3(0, pmax, v);
+          }
+          if (angularScale >= 0 && xx < min(3 << angularScale, mw)) {
+            const int invAngleSum = 256 + (xx + 1) * invAngle, wL = 32 >> (2 * xx >> angularScale), left = Sp[yy + (invAngleSum >> 9) + 1];
+            v = (int16_t)(v + ((wL * (left - v) + 32) >> 6));
+          }
+        }
+        if (ver) IT_STORE(xx, yy, v); else IT_STORE(yy, xx, v);
+      }
+    }
+#undef IT_STORE
+    // ---- publish
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicExch(P.done + me, 1);
+  }
+}
+
+int launch_intra(const IntraLaunch& L, cudaStream_t s)
+{
+  if (!L.numTus) return 0;
+  IntraParams P;
+  for (int c = 0; c < 3; c++) { P.planes[c] = L.planes.p[c]; P.resi[c] = L.resi[c]; P.stride[c] = L.planes.stride[c]; P.owner[c] = L.owner[c]; P.ownerStride[c] = L.ownerStride[c]; }
+  P.W = L.geom.width; P.H = L.geom.height; P.bitDepth = L.geom.bitDepth; P.tus = L.tus; P.numTus = (int)L.numTus;
+  P.done = L.sync; P.ticket = L.sync + L.numTus; P.err = L.sync + L.numTus + 1;
+  B200_CUDA(cudaMemsetAsync(L.sync, 0, (L.numTus + 2) * sizeof(int), s));
+  for (int c = 0; c < (L.geom.chromaFormat ? 3 : 1); c++) B200_CUDA(cudaMemsetAsync(L.owner[c], 0xff, L.ownerBytes[c], s));
+  intra_owner_kernel<<<(unsigned)L.numTus, 64, 0, s>>>(P);
+  const int ctas = (int)std::min<size_t>(L.numTus, (size_t)num_sms() * 8);
+  intra_kernel<<<ctas, IT_THREADS, 0, s>>>(P);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200

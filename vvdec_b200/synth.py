@@ -615,3 +615,66 @@ def gen_intra_layout(rng, W, H, ctu=128, min_size=8, max_size=64, p_split=0.75):
     for cy in range(0, H, ctu):
         for cx in range(0, W, ctu): rec(cx, cy, ctu, ctu)
     return out
+
+
+_INTRA_ANG = [0, 1, 2, 3, 4, 6, 8, 10, 12, 14, 16, 18, 20, 23, 26, 29, 32, 35, 39, 45, 51, 57, 64, 73, 86, 102, 128, 171, 256, 341, 512, 1024]
+_INTRA_THR = [24, 24, 24, 14, 2, 0, 0, 0]
+
+
+def intra_wide_angle(w, h, mode):
+    """IntraPrediction::getWideAngle (IntraPrediction.cpp:443)."""
+    if 1 < mode <= 66:
+        shift = [0, 6, 10, 12, 14, 15][abs(int(np.log2(w)) - int(np.log2(h)))]
+        if w > h and mode < 2 + shift: return mode + 65
+        if h > w and mode > 66 - shift: return mode - 65
+    return mode
+
+
+def intra_filter_ref(w, h, mode, mrl, bdpcm):
+    """IntraPrediction::useFilteredIntraRefSamples (:1301) for a luma block."""
+    if mrl or bdpcm or mode == 1: return False
+    if mode == 0: return w * h > 32
+    pm = intra_wide_angle(w, h, mode)
+    diff = min(abs(pm - 18), abs(pm - 50))
+    ang = _INTRA_ANG[abs(pm - 50 if pm >= 34 else -(pm - 18))]
+    return diff > _INTRA_THR[(int(np.log2(w)) + int(np.log2(h))) >> 1] and (ang & 31) == 0
+
+
+def gen_intra_records(rng, layout, W, H, modes=None, p_mrl=0.15, p_bdpcm=0.08, p_resi=0.0, upto=None):
+    """b200_intra_tu records (Y, Cb, Cr per CU, decoding order) for a single-tree all-intra layout of gen_intra_layout: random modes, MRL on some luma
+    blocks, BDPCM prediction on some, availability as xFillReferenceSamples derives it from the decoding order (pinned against the reference's own
+    analysis through the glue flattener by tests/test_intra_oracle_vs_ref.py).  Luma blocks whose chroma would be narrower than 4 or smaller than 16
+    samples are luma-only (local dual tree; their chroma is not generated)."""
+    A = abi
+    owner = np.full(((H + 3) // 4, (W + 3) // 4), 1 << 30, np.int64)
+    for i, (x, y, w, h) in enumerate(layout): owner[y // 4:(y + h) // 4, x // 4:(x + w) // 4] = i
+    recs = []
+    chroma_modes = [0, 1, 18, 50, 2, 34, 66, -1, -1, -1, 23, 45, 61]
+    for i, (x, y, w, h) in enumerate(layout if upto is None else layout[:upto + 1]):
+        if modes is not None and i in modes: dirL, dirC, mrl, bdpcm = modes[i]
+        else:
+            dirL, mrl, bdpcm = int(rng.integers(0, 67)), 0, 0
+            if rng.random() < p_mrl and y % 128: mrl, dirL = int(rng.integers(1, 3)), int(rng.integers(1, 67))
+            elif rng.random() < p_bdpcm and w <= 32 and h <= 32: bdpcm = int(rng.integers(1, 3))
+            dirC = chroma_modes[int(rng.integers(len(chroma_modes)))]
+        if dirC < 0 or dirC == 70: dirC = dirL                          # DM
+        def avail(ux, uy): return 0 <= ux < owner.shape[1] and 0 <= uy < owner.shape[0] and owner[uy, ux] < i
+        tl = avail(x // 4 - 1, y // 4 - 1)
+        na = 0
+        while na < 2 * w // 4 and avail(x // 4 + na, y // 4 - 1): na += 1
+        nl = 0
+        while nl < 2 * h // 4 and avail(x // 4 - 1, y // 4 + nl): nl += 1
+        luma_only = w < 8 or (w // 2) * (h // 2) < 16
+        for c in range(1 if luma_only else 3):
+            r = np.zeros((), A.INTRA_TU_DTYPE)
+            sh = 1 if c else 0
+            r["x"], r["y"], r["log2w"], r["log2h"], r["comp"] = x >> sh, y >> sh, int(np.log2(w >> sh)), int(np.log2(h >> sh)), c
+            if c == 0: r["mode"] = (A.INTRA_BDPCM_HOR if bdpcm == 1 else A.INTRA_BDPCM_VER) if bdpcm else dirL
+            else: r["mode"] = dirC
+            r["multiRefIdx"] = mrl if c == 0 else 0
+            fl = A.INTRA_AVAIL_TL if tl else 0
+            if c == 0 and intra_filter_ref(w, h, dirL, mrl, bdpcm): fl |= A.INTRA_FILTER_REF
+            if rng.random() < p_resi: fl |= 4
+            r["flags"], r["numAbove"], r["numLeft"] = fl, na, nl
+            recs.append(r)
+    return np.array(recs, A.INTRA_TU_DTYPE)

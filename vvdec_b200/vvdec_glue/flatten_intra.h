@@ -67,18 +67,23 @@ inline FlattenIntraResult flattenIntraTU( const TransformUnit& tu, const Compone
   r.multiRefIdx = isLuma( compID ) ? (uint8_t) cu.multiRefIdx() : 0;
   if( isLuma( compID ) && IntraPrediction::useFilteredIntraRefSamples( compID, cu, tu ) ) r.flags |= B200_INTRA_FILTER_REF;    // DecCu.cpp:339
 
-  // neighbourhood (xFillReferenceSamples :1086-1130)
-  const int csx = getChannelTypeScaleX( chType, pcv.chrFormat ), csy = getChannelTypeScaleY( chType, pcv.chrFormat );
+  // neighbourhood (xFillReferenceSamples :1086-1130).  The reference analyses it once per TU, for the first component of the CU's channel
+  // type, and reuses the three counts for the other components (m_lastCUidx, :1101): in a single tree the chroma blocks take the luma block's.
+  const ComponentID anaComp = getFirstComponentOfChannel( cu.chType() );
+  const ChannelType anaCh   = toChannelType( anaComp );
+  const CompArea&   ana     = tu.blocks[anaComp].valid() ? tu.blocks[anaComp] : area;
+  const ChannelType ch      = tu.blocks[anaComp].valid() ? anaCh : chType;
+  const int csx = getChannelTypeScaleX( ch, pcv.chrFormat ), csy = getChannelTypeScaleY( ch, pcv.chrFormat );
   const int unitW = pcv.minCUWidth >> csx, unitH = pcv.minCUHeight >> csy;
-  const int totalAbove = ( 2 * (int) area.width + unitW - 1 ) / unitW, totalLeft = ( 2 * (int) area.height + unitH - 1 ) / unitH;
-  const int numAbove = area.width / unitW, numLeft = area.height / unitH;
-  const Position posLT = area.pos();
+  const int totalAbove = ( 2 * (int) ana.width + unitW - 1 ) / unitW, totalLeft = ( 2 * (int) ana.height + unitH - 1 ) / unitH;
+  const int numAbove = ana.width / unitW, numLeft = ana.height / unitH;
+  const Position posLT = ana.pos();
   const bool sameCTU = ( posLT.x & ( pcv.maxCUWidthMask >> csx ) ) && ( posLT.y & ( pcv.maxCUHeightMask >> csy ) );
-  if( sameCTU || cs.getCURestricted( posLT.offset( -1, -1 ), cu, chType, cu.left ? cu.left : cu.above ) ) r.flags |= B200_INTRA_AVAIL_TL;
-  if( cu.above || area.y > cu.blocks[chType].y )
-    r.numAbove = (uint8_t) ( numAbove + intraUnitsAvailable( tu, chType, Position( posLT.x + (PosType) area.width, posLT.y ), totalAbove - numAbove, unitW, true ) );
-  if( cu.left || area.x > cu.blocks[chType].x )
-    r.numLeft = (uint8_t) ( numLeft + intraUnitsAvailable( tu, chType, Position( posLT.x, posLT.y + (PosType) area.height ), totalLeft - numLeft, unitH, false ) );
+  if( sameCTU || cs.getCURestricted( posLT.offset( -1, -1 ), cu, ch, cu.left ? cu.left : cu.above ) ) r.flags |= B200_INTRA_AVAIL_TL;
+  if( cu.above || ana.y > cu.blocks[ch].y )
+    r.numAbove = (uint8_t) ( numAbove + intraUnitsAvailable( tu, ch, Position( posLT.x + (PosType) ana.width, posLT.y ), totalAbove - numAbove, unitW, true ) );
+  if( cu.left || ana.x > cu.blocks[ch].x )
+    r.numLeft = (uint8_t) ( numLeft + intraUnitsAvailable( tu, ch, Position( posLT.x, posLT.y + (PosType) ana.height ), totalLeft - numLeft, unitH, false ) );
   return FLATTEN_INTRA_OK;
 }
 
