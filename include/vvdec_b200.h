@@ -53,7 +53,9 @@ enum {
   B200_TU_TS       = 1,   /* mtsIdx == MTS_SKIP                                   */
   B200_TU_BDPCM_H  = 2,   /* bdpcmMode == 1 (accumulate along x), implies TS      */
   B200_TU_BDPCM_V  = 4,   /* bdpcmMode == 2 (accumulate along y), implies TS      */
-  B200_TU_SCALING  = 8    /* explicit scaling list: per-position factor at slOff  */
+  B200_TU_SCALING  = 8,   /* explicit scaling list: per-position factor at slOff  */
+  B200_TU_RESI     = 16   /* picture path: TU of an intra CU — the residual goes to the picture's residual planes and K6
+                             (b200_picture::intraTus, B200_INTRA_ADD_RESI) reconstructs the block in decoding order */
 };
 
 typedef struct b200_tu {
@@ -248,6 +250,36 @@ B200_API int b200_mc_predict_wp(const b200_geom* g, int16_t* const dst[3], const
                                 const b200_pu* pus, size_t numPus, int32_t* dmvrMv, size_t numDmvr, const b200_wp* wp, int numWp);
 
 /* ------------------------------------------------------------------------------------------------
+ * K6  intra prediction of one transform block (SURVEY 8f-1, first slice: regular modes).
+ *   replaces  IntraPrediction::initIntraPatternChType (IntraPrediction.cpp:947) = xFillReferenceSamples :1072 (the sample copies /
+ *             substitution, not the availability analysis) + xFilterReferenceSamples :1251, and IntraPrediction::predIntraAng :474 =
+ *             xPredIntraPlanarCore :154, xPredIntraDc :541, xPredIntraAng :592 (wide angles, reference extension, cubic / Gauss /
+ *             linear interpolation, angular PDPC), IntraPredSampleFilterCore :212 (PDPC of planar / DC), xPredIntraBDPCM :850,
+ *             as DecCu::predAndReco calls them for a regular intra TU (DecCu.cpp:329-371).
+ * The availability analysis (cs.getCURestricted walks, IntraPrediction.cpp:1098-1130) stays host code in the flattener and arrives as
+ * three counts.  Not covered (the flattener must refuse them): MIP, CCLM, ISP, palette, ACT.
+ * Blocks of one list are processed in list order; a block may read what earlier blocks of the list wrote. */
+enum { B200_INTRA_PLANAR = 0, B200_INTRA_DC = 1 /* 2..66 angular */, B200_INTRA_BDPCM_HOR = 67, B200_INTRA_BDPCM_VER = 68 };
+enum { B200_INTRA_FILTER_REF = 1, B200_INTRA_AVAIL_TL = 2, B200_INTRA_ADD_RESI = 4 /* reconstruct: clip(pred + residual), see b200_intra_reconstruct */ };
+typedef struct b200_intra_tu {
+  uint16_t x, y;          /* top-left in the component's plane, samples                                              */
+  uint8_t  log2w, log2h;  /* 2..6 (chroma: height may be 2 = log2h 1)                                                */
+  uint8_t  comp;          /* 0 Y, 1 Cb, 2 Cr                                                                         */
+  uint8_t  mode;          /* PU::getFinalIntraMode (before the wide-angle mapping), or B200_INTRA_BDPCM_*            */
+  uint8_t  multiRefIdx;   /* cu.multiRefIdx() for luma (0, 1, 2), 0 for chroma                                       */
+  uint8_t  flags;         /* B200_INTRA_FILTER_REF: useFilteredIntraRefSamples (:1301); B200_INTRA_AVAIL_TL: m_neighborSize[0] */
+  uint8_t  numAbove;      /* m_neighborSize[1]: available units above + above-right (unit = 4 luma / 2 chroma samples) */
+  uint8_t  numLeft;       /* m_neighborSize[2]: available units left + below-left                                    */
+  uint32_t rsv;
+} b200_intra_tu;          /* 16 bytes */
+/* Kernel-level K6: host planes in (reconstructed neighbourhood), prediction written into the blocks, host planes out. */
+B200_API int b200_intra_predict(const b200_geom* g, int16_t* const planes[3], const b200_intra_tu* tus, size_t numTus);
+/* The same with the reconstruction step of DecCu::predAndReco (DecCu.cpp:390-398): blocks flagged B200_INTRA_ADD_RESI store
+ * clip(pred + resi[comp][same position]) — what the next block of the list then reads as its reference.  resi planes have the picture's
+ * geometry (e.g. the output of b200_k1_residual in mode 1). */
+B200_API int b200_intra_reconstruct(const b200_geom* g, int16_t* const planes[3], const int16_t* const resi[3], const b200_intra_tu* tus, size_t numTus);
+
+/* ------------------------------------------------------------------------------------------------
  * Picture level: the DecLibRecon seam (reference DecoderLib/DecLibRecon.h:184-191, .cpp:429 decompressPicture,
  * :684 waitForPrevDecompressedPic).  A context owns the decoded-picture buffer (DPB) in device memory, a ring of
  * work-list arenas and one CUDA stream; pictures are processed in submission order (a picture may reference any
@@ -300,6 +332,8 @@ typedef struct b200_picture {
   const b200_wp* wp; int32_t numWp;      /* explicit weighted prediction entries referenced by b200_pu::wpIdx, or NULL / 0 */
   const b200_lmcs* lmcs;                 /* B200_PIC_LMCS: every slice of the picture has LMCS on and all CUs are inter
                                             (samples in `given` must already be in the mapped domain)                  */
+  const b200_intra_tu* intraTus;         /* K6: intra blocks of the picture in decoding order (regular modes), or NULL.  Runs after K2 and K1:  */
+  size_t numIntraTus;                    /* blocks read the reconstruction of inter and earlier intra neighbours.  Not together with LMCS.       */
 } b200_picture;
 enum { B200_PIC_DEBLOCK = 1, B200_PIC_SAO = 2, B200_PIC_ALF = 4, B200_PIC_LMCS = 8 };
 
@@ -341,36 +375,6 @@ B200_API int  b200_frame_wait(b200_ctx* ctx, int ticket);
 enum { B200_OUT_16 = 0, B200_OUT_PYUV = 1, B200_OUT_8 = 2 };
 B200_API size_t b200_frame_bytes(const b200_geom* g, int fmt, int comp);
 B200_API int  b200_get_frame_fmt_async(b200_ctx* ctx, int slot, int fmt, void* const planes[3]);
-/* ------------------------------------------------------------------------------------------------
- * K6  intra prediction of one transform block (SURVEY 8f-1, first slice: regular modes).
- *   replaces  IntraPrediction::initIntraPatternChType (IntraPrediction.cpp:947) = xFillReferenceSamples :1072 (the sample copies /
- *             substitution, not the availability analysis) + xFilterReferenceSamples :1251, and IntraPrediction::predIntraAng :474 =
- *             xPredIntraPlanarCore :154, xPredIntraDc :541, xPredIntraAng :592 (wide angles, reference extension, cubic / Gauss /
- *             linear interpolation, angular PDPC), IntraPredSampleFilterCore :212 (PDPC of planar / DC), xPredIntraBDPCM :850,
- *             as DecCu::predAndReco calls them for a regular intra TU (DecCu.cpp:329-371).
- * The availability analysis (cs.getCURestricted walks, IntraPrediction.cpp:1098-1130) stays host code in the flattener and arrives as
- * three counts.  Not covered (the flattener must refuse them): MIP, CCLM, ISP, palette, ACT.
- * Blocks of one list are processed in list order; a block may read what earlier blocks of the list wrote. */
-enum { B200_INTRA_PLANAR = 0, B200_INTRA_DC = 1 /* 2..66 angular */, B200_INTRA_BDPCM_HOR = 67, B200_INTRA_BDPCM_VER = 68 };
-enum { B200_INTRA_FILTER_REF = 1, B200_INTRA_AVAIL_TL = 2, B200_INTRA_ADD_RESI = 4 /* reconstruct: clip(pred + residual), see b200_intra_reconstruct */ };
-typedef struct b200_intra_tu {
-  uint16_t x, y;          /* top-left in the component's plane, samples                                              */
-  uint8_t  log2w, log2h;  /* 2..6 (chroma: height may be 2 = log2h 1)                                                */
-  uint8_t  comp;          /* 0 Y, 1 Cb, 2 Cr                                                                         */
-  uint8_t  mode;          /* PU::getFinalIntraMode (before the wide-angle mapping), or B200_INTRA_BDPCM_*            */
-  uint8_t  multiRefIdx;   /* cu.multiRefIdx() for luma (0, 1, 2), 0 for chroma                                       */
-  uint8_t  flags;         /* B200_INTRA_FILTER_REF: useFilteredIntraRefSamples (:1301); B200_INTRA_AVAIL_TL: m_neighborSize[0] */
-  uint8_t  numAbove;      /* m_neighborSize[1]: available units above + above-right (unit = 4 luma / 2 chroma samples) */
-  uint8_t  numLeft;       /* m_neighborSize[2]: available units left + below-left                                    */
-  uint32_t rsv;
-} b200_intra_tu;          /* 16 bytes */
-/* Kernel-level K6: host planes in (reconstructed neighbourhood), prediction written into the blocks, host planes out. */
-B200_API int b200_intra_predict(const b200_geom* g, int16_t* const planes[3], const b200_intra_tu* tus, size_t numTus);
-/* The same with the reconstruction step of DecCu::predAndReco (DecCu.cpp:390-398): blocks flagged B200_INTRA_ADD_RESI store
- * clip(pred + resi[comp][same position]) — what the next block of the list then reads as its reference.  resi planes have the picture's
- * geometry (e.g. the output of b200_k1_residual in mode 1). */
-B200_API int b200_intra_reconstruct(const b200_geom* g, int16_t* const planes[3], const int16_t* const resi[3], const b200_intra_tu* tus, size_t numTus);
-
 /* Film grain synthesis on the output frame: the per-sample part of the reference's VFGS model,
  *   replaces  FilmGrainImpl::add_grain_block / make_grain_pattern / scale_and_output (FilmGrain/FilmGrainImpl.cpp:129,:198,:247 and their
  *             SSE4.1/AVX2 versions FilmGrainImpl_X86_SIMD.h), driven per line by FilmGrain::add_grain_line (FilmGrain.cpp:836) from

@@ -97,7 +97,7 @@ static void filter_ref(const int16_t* u, int16_t* f, int w, int h)      /* :1251
 static void pred_planar(const int16_t* src, int stride, int w, int h, int16_t* dst, ptrdiff_t ds)
 {
   const int l2w = ilog2(w), l2h = ilog2(h);
-  int left[65], top[65], bottom[64], right[64];
+  int left[65] = {0}, top[65] = {0}, bottom[64], right[64];
   for (int k = 0; k <= w; k++) top[k] = AT(k + 1, 0);
   for (int k = 0; k <= h; k++) left[k] = AT(0, k + 1);
   const int bl = left[h], tr = top[w];

@@ -149,6 +149,14 @@ def oracle_decompress(oracle, g, dpb, pic):
         oracle.orc_lmcs_fwd_pus(C.byref(g), cur[0], pic["pus"].ctypes.data, len(pic["pus"]), L)
         oracle.orc_k1_residual_lmcs(C.byref(g), abi.plane_ptrs(cur), pic["tus"].ctypes.data, len(pic["tus"]), pic["coefs"], None, L)
         oracle.orc_lmcs_inv_plane(C.byref(g), cur[0], L)
+    elif "intraTus" in pic:
+        # intra CUs on the device: their TUs (TU_RESI) leave the residual in separate planes, K6 predicts + reconstructs them in decoding order
+        tus = pic["tus"]; rs = (tus["flags"] & abi.TU_RESI) != 0
+        t0, t1 = np.ascontiguousarray(tus[~rs]), np.ascontiguousarray(tus[rs])
+        resi = [np.zeros_like(p) for p in cur]
+        oracle.orc_k1_residual(C.byref(g), abi.plane_ptrs(cur), t0.ctypes.data, len(t0), pic["coefs"], None, 0)
+        oracle.orc_k1_residual(C.byref(g), abi.plane_ptrs(resi), t1.ctypes.data, len(t1), pic["coefs"], None, 1)
+        oracle.orc_intra_reconstruct(C.byref(g), abi.plane_ptrs(cur), abi.plane_ptrs(resi), pic["intraTus"].ctypes.data, len(pic["intraTus"]))
     else:
         oracle.orc_k1_residual(C.byref(g), abi.plane_ptrs(cur), pic["tus"].ctypes.data, len(pic["tus"]), pic["coefs"], None, 0)
     if st.flags & abi.PIC_DEBLOCK:

@@ -148,3 +148,36 @@ def test_weighted_prediction_picture(b200, oracle):
                 assert np.array_equal(want[c], got[c]), f"picture {k} plane {c}: {len(np.argwhere(want[c] != got[c]))} diffs"
     finally:
         b200.b200_ctx_destroy(ctx)
+
+
+@pytest.mark.parametrize("W,H,ctu,intra_frac,seed", [(416, 240, 128, 0.25, 1), (416, 240, 64, 1.0, 2), (832, 480, 128, 0.15, 3), (1920, 1080, 128, 0.3, 4)])
+def test_picture_with_intra_cus(b200, oracle, W, H, ctu, intra_frac, seed):
+    """Intra CUs reconstructed on the device inside the picture chain (regular modes): K2 for the inter CUs, K1 (inter TUs reconstruct, TUs
+    of intra CUs leave their residual in the residual planes), K6 over the intra blocks in decoding order — each reads the reconstruction of inter and
+    earlier intra neighbours — then deblocking / SAO / ALF.  intra_frac 1.0 is an I picture."""
+    rng = np.random.default_rng(seed)
+    bd = 10
+    g = abi.make_geom(W, H, bd, ctu=ctu)
+    ctx = C.c_void_p()
+    vvdec_b200.check(b200.b200_ctx_create(C.byref(ctx), C.byref(g), 6, 2, -1))
+    try:
+        dpb = [synth.noise_planes(rng, W, H, bd) for _ in range(4)]
+        for s in range(4): vvdec_b200.check(b200.b200_ctx_load_slot(ctx, s, abi.plane_ptrs(dpb[s])))
+        for i in range(2):
+            pic = synth.gen_picture(rng, W, H, bd, ctu=ctu, dst_slot=4 + i, intra_frac=intra_frac)
+            assert len(pic["intraTus"]) > 0 and (pic["tus"]["flags"] & abi.TU_RESI).any() and (pic["intraTus"]["flags"] & abi.INTRA_ADD_RESI).any()
+            want, dm_want = oracle_decompress(oracle, g, dpb, pic)
+            h = b200.b200_decompress_picture(ctx, C.byref(pic["struct"])); assert h >= 0, b200.b200_last_error()
+            dm = np.zeros((pic["ndmvr"] + 1, 2), np.int32)
+            vvdec_b200.check(b200.b200_wait_picture(ctx, h, dm.ctypes.data, len(dm)))
+            got = [np.zeros_like(p) for p in want]
+            vvdec_b200.check(b200.b200_get_frame(ctx, 4 + i, abi.plane_ptrs(got)))
+            for c in range(3):
+                assert np.array_equal(want[c], got[c]), f"picture {i} plane {c}: {len(np.argwhere(want[c] != got[c]))} diffs"
+            assert np.array_equal(dm, dm_want)
+        # a record whose availability reaches outside the picture is refused
+        bad = pic["intraTus"]; keep = bad[0].copy(); bad[0]["numAbove"] = 3; bad[0]["y"] = 0
+        assert b200.b200_decompress_picture(ctx, C.byref(pic["struct"])) == -2 and b"intra block record" in b200.b200_last_error()
+        bad[0] = keep
+    finally:
+        b200.b200_ctx_destroy(ctx)

@@ -3,7 +3,7 @@ import ctypes as C
 import numpy as np
 
 TR_DCT2, TR_DCT8, TR_DST7 = 0, 1, 2
-TU_TS, TU_BDPCM_H, TU_BDPCM_V, TU_SCALING = 1, 2, 4, 8
+TU_TS, TU_BDPCM_H, TU_BDPCM_V, TU_SCALING, TU_RESI = 1, 2, 4, 8, 16
 
 
 class Tu(C.Structure):
@@ -83,7 +83,8 @@ class Picture(C.Structure):
                 ("scaling", C.c_void_p), ("numScaling", C.c_size_t),
                 ("lfV", C.c_void_p), ("lfH", C.c_void_p), ("ctuSlice", C.c_void_p), ("lfSlices", C.c_void_p),
                 ("numLfSlices", C.c_int32), ("lfSeq", C.c_void_p),
-                ("sao", C.c_void_p), ("vb", C.c_void_p), ("alf", C.c_void_p), ("alfTabs", C.c_void_p), ("wp", C.c_void_p), ("numWp", C.c_int32), ("lmcs", C.c_void_p)]
+                ("sao", C.c_void_p), ("vb", C.c_void_p), ("alf", C.c_void_p), ("alfTabs", C.c_void_p), ("wp", C.c_void_p), ("numWp", C.c_int32), ("lmcs", C.c_void_p),
+                ("intraTus", C.c_void_p), ("numIntraTus", C.c_size_t)]
 
 
 class LmcsVpdu(C.Structure):
@@ -98,7 +99,7 @@ class IntraTu(C.Structure):
 
 INTRA_TU_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("log2w", "u1"), ("log2h", "u1"), ("comp", "u1"), ("mode", "u1"), ("multiRefIdx", "u1"), ("flags", "u1"),
                            ("numAbove", "u1"), ("numLeft", "u1"), ("rsv", "<u4")])
-INTRA_FILTER_REF, INTRA_AVAIL_TL = 1, 2
+INTRA_FILTER_REF, INTRA_AVAIL_TL, INTRA_ADD_RESI = 1, 2, 4
 INTRA_BDPCM_HOR, INTRA_BDPCM_VER = 67, 68
 
 

@@ -113,6 +113,7 @@ struct K1Launch {
   int            mode;    // 0: reco = clip(pred + resi); 1: store residual
   int            compSel = 0;             // 0 all TUs, 1 luma TUs only, 2 chroma TUs only (LMCS chroma scaling needs luma first)
   const int*     vpduScale = nullptr;     // device: LMCS chroma residual scale per VPDU, or null
+  int16_t*       resi[3] = {nullptr, nullptr, nullptr};   // residual planes (same strides) for TUs flagged B200_TU_RESI, or null: the flag is ignored
 };
 int launch_k1_residual(const K1Launch& L, StreamSet& ss, KProf* prof = nullptr);
 
@@ -160,6 +161,7 @@ int launch_pack(const DevPlanes& src, const b200_geom& g, int fmt, uint8_t* cons
 // K6 (k6_intra.cu): blocks in decoding order; sync = numTus + 2 ints (done flags, ticket, error bit); owner[c] = one int per 4x4 luma / 2x2 chroma unit
 struct IntraLaunch { b200_geom geom; DevPlanes planes; const int16_t* resi[3]; const b200_intra_tu* tus; size_t numTus; int* owner[3]; int ownerStride[3]; size_t ownerBytes[3]; int* sync; };
 int launch_intra(const IntraLaunch& L, cudaStream_t s);
+int launch_intra_validate(const b200_intra_tu* tus, size_t numTus, const b200_geom& g, int* meta, cudaStream_t s);   // error bit 8 of the PU meta block (after launch_mc_bucket)
 int launch_film_grain(const DevPlanes& src, const DevPlanes& dst, const b200_geom& g, const int8_t* pattern, const uint8_t* sLUT, const uint8_t* pLUT,
                       const uint32_t* lineSeeds, uint32_t* seeds, int scaleShift, const uint8_t present[3], cudaStream_t s);   // film_grain.cu
 int launch_hash(const DevPlanes& src, const b200_geom& g, int method, uint32_t* acc, uint8_t* digest, cudaStream_t s);   // hash.cu: CRC / checksum of the planes

@@ -54,7 +54,7 @@ __device__ __forceinline__ int dequant_one(int level, int scale, int rightShift,
 // one TU, executed by a group of G threads (`lane` = index in the group); all exits are uniform over the group
 template <int CLS>
 __device__ __forceinline__ void k1_tu(const b200_tu* __restrict__ tus, int t, const int16_t* __restrict__ coefs, const int32_t* __restrict__ scaling,
-                                      int16_t* p0, int16_t* p1, int16_t* p2, int s0, int s1, int s2, int bitDepth, int mode,
+                                      int16_t* p0, int16_t* p1, int16_t* p2, int16_t* r0, int16_t* r1, int16_t* r2, int s0, int s1, int s2, int bitDepth, int mode,
                                       int compSel, const int* __restrict__ vpduScale, int vpduGeo, int16_t* cb, int16_t* tb, int lane)
 {
   constexpr int G = K1Cfg<CLS>::G;
@@ -71,6 +71,7 @@ __device__ __forceinline__ void k1_tu(const b200_tu* __restrict__ tus, int t, co
   const int inBits = (ra.w >> 16) & 0xff, scale = ra.w >> 24;
   const unsigned coefOff = rb.x, slOff = rb.y;
   if ((compSel == 1 && comp != 0) || (compSel == 2 && comp == 0)) return;   // LMCS: luma pass / chroma pass
+  if ((flags & B200_TU_RESI) && r0) { p0 = r0; p1 = r1; p2 = r2; mode = 1; }  // TU of an intra CU: residual to the residual planes, K6 reconstructs
 
   const int w = 1 << log2w, h = 1 << log2h;
   const int16_t* q = coefs + coefOff;
@@ -255,7 +256,7 @@ __device__ __forceinline__ void k1_tu(const b200_tu* __restrict__ tus, int t, co
 template <int CLS>
 __global__ void __launch_bounds__(K1Cfg<CLS>::THREADS)
 k1_residual_kernel(const b200_tu* __restrict__ tus, const uint32_t* __restrict__ idx, const int* __restrict__ meta, const int16_t* __restrict__ coefs,
-                   const int32_t* __restrict__ scaling, int16_t* p0, int16_t* p1, int16_t* p2,
+                   const int32_t* __restrict__ scaling, int16_t* p0, int16_t* p1, int16_t* p2, int16_t* r0, int16_t* r1, int16_t* r2,
                    int s0, int s1, int s2, int bitDepth, int mode, int compSel, const int* __restrict__ vpduScale, int vpduGeo)
 {
   constexpr int G = K1Cfg<CLS>::G, GROUPS = K1Cfg<CLS>::GROUPS;
@@ -264,7 +265,7 @@ k1_residual_kernel(const b200_tu* __restrict__ tus, const uint32_t* __restrict__
   const int grp = threadIdx.x / G, lane = threadIdx.x % G;
   const int i = blockIdx.x * GROUPS + grp;
   if (i >= meta[LM_CNT + CLS]) return;                       // G == blockDim for the big classes: the whole CTA leaves together
-  k1_tu<CLS>(tus, (int)idx[meta[LM_OFF + CLS] + i], coefs, scaling, p0, p1, p2, s0, s1, s2, bitDepth, mode, compSel, vpduScale, vpduGeo, s_c[grp], s_t[grp], lane);
+  k1_tu<CLS>(tus, (int)idx[meta[LM_OFF + CLS] + i], coefs, scaling, p0, p1, p2, r0, r1, r2, s0, s1, s2, bitDepth, mode, compSel, vpduScale, vpduGeo, s_c[grp], s_t[grp], lane);
 }
 
 int launch_k1_residual(const K1Launch& L, StreamSet& ss, KProf* prof)
@@ -280,7 +281,7 @@ int launch_k1_residual(const K1Launch& L, StreamSet& ss, KProf* prof)
     cudaStream_t s = ss.pick(launched++);
     const int groups = c <= 1 ? K1_WARPS : 1;
     const int grid = (L.cnt[c] + groups - 1) / groups;
-#define K1_GO(C) k1_residual_kernel<C><<<grid, K1Cfg<C>::THREADS, 0, s>>>(L.tus, L.idx, L.meta, L.coefs, L.scaling, L.planes.p[0], L.planes.p[1], L.planes.p[2], \
+#define K1_GO(C) k1_residual_kernel<C><<<grid, K1Cfg<C>::THREADS, 0, s>>>(L.tus, L.idx, L.meta, L.coefs, L.scaling, L.planes.p[0], L.planes.p[1], L.planes.p[2], L.resi[0], L.resi[1], L.resi[2], \
                                                                    L.planes.stride[0], L.planes.stride[1], L.planes.stride[2], L.geom.bitDepth, L.mode, L.compSel, L.vpduScale, vpduGeo)
     switch (c) { case 0: K1_GO(0); break; case 1: K1_GO(1); break; case 2: K1_GO(2); break; default: K1_GO(3); break; }
 #undef K1_GO

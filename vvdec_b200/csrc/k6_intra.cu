@@ -237,6 +237,28 @@ __global__ void __launch_bounds__(IT_THREADS) intra_kernel(const IntraParams P)
   }
 }
 
+// record checks of the picture path (the kernel-level wrapper checks on the host): everything K6 uses as an address
+__global__ void __launch_bounds__(256) intra_validate_kernel(const b200_intra_tu* __restrict__ tus, int n, int W, int H, int chroma, int* meta)
+{
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const b200_intra_tu t = tus[i];
+  const int w = 1 << t.log2w, h = 1 << t.log2h, pw = t.comp ? W >> 1 : W, ph = t.comp ? H >> 1 : H, unit = t.comp ? 2 : 4, m = t.multiRefIdx;
+  bool ok = t.comp < (chroma ? 3 : 1) && t.log2w >= 2 && t.log2w <= 6 && t.log2h >= 1 && t.log2h <= 6 && t.x + w <= pw && t.y + h <= ph && !(t.x % unit) && !(t.y % unit);
+  ok = ok && t.mode <= B200_INTRA_BDPCM_VER && m <= 2 && (!m || !t.comp);
+  ok = ok && t.numAbove <= 2 * w / unit && t.numLeft <= 2 * h / unit && (!t.numAbove || t.y > m) && (!t.numLeft || t.x > m)
+          && (!(t.flags & B200_INTRA_AVAIL_TL) || (t.x > m && t.y > m)) && t.x + (int)t.numAbove * unit <= pw && t.y + (int)t.numLeft * unit <= ph;
+  if (!ok) atomicOr(&meta[LM_ERR], 8);
+}
+
+int launch_intra_validate(const b200_intra_tu* tus, size_t numTus, const b200_geom& g, int* meta, cudaStream_t s)
+{
+  if (!numTus) return 0;
+  intra_validate_kernel<<<(unsigned)((numTus + 255) / 256), 256, 0, s>>>(tus, (int)numTus, g.width, g.height, g.chromaFormat != 0, meta);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launch_intra(const IntraLaunch& L, cudaStream_t s)
 {
   if (!L.numTus) return 0;

@@ -21,6 +21,7 @@ struct Arena {
   const b200_wp* wp = nullptr;
   const b200_lmcs* lmcs = nullptr; const int16_t* lmcsInv = nullptr; const b200_lmcs_vpdu* lmcsVpdus = nullptr; int* lmcsScale = nullptr; bool lmcsChromaAdj = false;
   int16_t* given[3] = {nullptr, nullptr, nullptr};
+  const b200_intra_tu* intraTus = nullptr; size_t numIntraTus = 0; int* intraOwner[3] = {nullptr, nullptr, nullptr}; int intraOwnerStride[3] = {0, 0, 0}; size_t intraOwnerBytes[3] = {0, 0, 0}; int* intraSync = nullptr;   // K6
   int dstSlot = 0, flags = 0;
   bool valid = false;
   cudaEvent_t uploaded = nullptr, done = nullptr; bool donePending = false;   // H2D finished / kernels reading this arena finished
@@ -56,6 +57,7 @@ struct b200_ctx {
   int nextArena = 0;
   long long launches = 0;
   DevBuf grainStage[2], grainTab;    // b200_get_frame_grain_async: grained copy of the frame, device copies of the tables + block seeds
+  DevBuf resiBuf;                    // residual planes of intra CUs (K1 -> K6), allocated with the first picture that carries intra blocks
   DevBuf hashBuf;                    // b200_frame_hash_async: accumulators + digest per ticket
 
   DevPlanes planes(int buf) const {
@@ -98,7 +100,7 @@ B200_API int b200_ctx_create(b200_ctx** out, const b200_geom* g, int numSlots, i
   for (int s = 0; s < numSlots; s++) c->slotBuf[s] = s;
   c->work[0] = numSlots; c->work[1] = numSlots + 1;
   c->arenas.resize(numArenas);
-  for (auto& A : c->arenas) { B200_CUDA(cudaEventCreateWithFlags(&A.uploaded, cudaEventDisableTiming)); B200_CUDA(cudaEventCreateWithFlags(&A.done, cudaEventDisableTiming)); B200_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&A.hMeta), 2 * LM_INTS * sizeof(int), cudaHostAllocDefault)); }
+  for (auto& A : c->arenas) { B200_CUDA(cudaEventCreateWithFlags(&A.uploaded, cudaEventDisableTiming)); B200_CUDA(cudaEventCreateWithFlags(&A.done, cudaEventDisableTiming)); B200_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&A.hMeta), (2 * LM_INTS + 4) * sizeof(int), cudaHostAllocDefault)); }
   *out = c;
   return 0;
 }
@@ -140,6 +142,8 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   B200_CHECK(p->numPus < (1u << 26) && p->numTus < (1u << 31), "b200_pic_upload: too many records");
   B200_CHECK(p->numWp >= 0 && p->numWp <= 255 && (p->wp || !p->numWp), "b200_pic_upload: weighted-prediction table (at most 255 entries)");
   B200_CHECK(!(p->flags & B200_PIC_LMCS) || (p->lmcs && p->lmcs->invLUT && (!p->lmcs->chromaAdj || p->lmcs->vpdus) && p->lmcs->orgCW == (1 << c->g.bitDepth) / 16), "b200_pic_upload: LMCS data missing or inconsistent");
+  B200_CHECK(!p->numIntraTus || (p->intraTus && p->numIntraTus < (1u << 30)), "b200_pic_upload: intra list missing");
+  if (p->numIntraTus && (p->flags & B200_PIC_LMCS)) { set_error("b200_pic_upload: intra blocks together with LMCS are not supported on the device"); return B200_ERR_UNSUPPORTED; }
   B200_CUDA(cudaSetDevice(c->device));
   const int ai = c->nextArena; c->nextArena = (c->nextArena + 1) % c->numArenas;
   Arena& A = c->arenas[ai];
@@ -167,6 +171,13 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   const size_t oLm = take(lm ? sizeof(b200_lmcs) : 0), oLmLut = take(lm ? sizeof(int16_t) << g.bitDepth : 0), oLmVp = take(lm ? nVpdu * sizeof(b200_lmcs_vpdu) : 0), oLmSc = take(lm ? nVpdu * sizeof(int) : 0);
   const bool hasGiven = p->given[0] != nullptr;
   const size_t oGiven = take(hasGiven ? c->picBytes : 0);
+  size_t oOwn[3] = {0, 0, 0}, ownBytes[3] = {0, 0, 0}; int ownStride[3] = {0, 0, 0};
+  const size_t oIntra = take(p->numIntraTus * sizeof(b200_intra_tu)), oSync = take(p->numIntraTus ? (p->numIntraTus + 2) * sizeof(int) : 0);
+  for (int k = 0; k < (g.chromaFormat ? 3 : 1) && p->numIntraTus; k++) {
+    const int pw = k ? g.width >> 1 : g.width, ph = k ? g.height >> 1 : g.height, unit = k ? 2 : 4;
+    ownStride[k] = (pw + unit - 1) / unit; ownBytes[k] = (size_t)ownStride[k] * ((ph + unit - 1) / unit) * sizeof(int); oOwn[k] = take(ownBytes[k]);
+  }
+  if (p->numIntraTus) if (int rc = c->resiBuf.reserve(c->picBytes)) return rc;
   if (off > A.buf.cap) { B200_CUDA(cudaStreamSynchronize(c->stream)); B200_CUDA(cudaStreamSynchronize(c->upStream)); A.donePending = false; }   // realloc: nothing may still use the old buffer
   if (int rc = A.buf.reserve(off)) return rc;
   char* base = A.buf.as<char>();
@@ -221,6 +232,9 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   A.sao = reinterpret_cast<const b200_sao_ctu*>(base + oSao); A.alf = reinterpret_cast<const b200_alf_ctu*>(base + oAlf);
   A.dmvrMv = p->numDmvr ? reinterpret_cast<int32_t*>(base + oDm) : nullptr; A.numDmvr = p->numDmvr;
   if (p->numDmvr) B200_CUDA(cudaMemsetAsync(base + oDm, 0, p->numDmvr * 8, s));   // entries of non-DMVR CUs stay zero, like m_dmvrMvCache users expect
+  if (int rc = h2d(oIntra, p->intraTus, p->numIntraTus * sizeof(b200_intra_tu))) return rc;
+  A.intraTus = reinterpret_cast<const b200_intra_tu*>(base + oIntra); A.numIntraTus = p->numIntraTus; A.intraSync = reinterpret_cast<int*>(base + oSync);
+  for (int k = 0; k < 3; k++) { A.intraOwner[k] = ownBytes[k] ? reinterpret_cast<int*>(base + oOwn[k]) : nullptr; A.intraOwnerStride[k] = ownStride[k]; A.intraOwnerBytes[k] = ownBytes[k]; }
   A.dstSlot = p->dstSlot; A.flags = p->flags; A.valid = true;
   // work lists: validated and bucketed on the device, behind the copies
   A.mcMeta = reinterpret_cast<int*>(base + oMeta); A.tuMeta = A.mcMeta + LM_INTS;
@@ -236,6 +250,7 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
     if (int rc = launch_ctu_validate((p->flags & B200_PIC_SAO) ? A.sao : nullptr, alfOn ? A.alf : nullptr, (p->flags & B200_PIC_DEBLOCK) ? A.ctuSlice : nullptr, (int)nCtu, lim, A.mcMeta, s)) return rc;
     if (any) c->launches += 1;
   }
+  if (A.numIntraTus) { if (int rc = launch_intra_validate(A.intraTus, A.numIntraTus, g, A.mcMeta, s)) return rc; c->launches += 1; }
   B200_CUDA(cudaMemcpyAsync(A.hMeta, A.mcMeta, 2 * LM_INTS * sizeof(int), cudaMemcpyDeviceToHost, s));   // list lengths for b200_pic_run's grids
   B200_CUDA(cudaEventRecord(A.uploaded, s));
   return ai;
@@ -252,6 +267,7 @@ B200_API int b200_pic_run(b200_ctx* c, int ai)
   B200_CUDA(cudaEventSynchronize(A.uploaded));
   B200_CHECK(!(A.hMeta[LM_ERR] & 1), "b200_pic_run: the picture's PU list holds an invalid record (reference slots, block size or flag combination)");
   B200_CHECK(!(A.hMeta[LM_ERR] & 2), "b200_pic_run: more MC tiles than the picture can hold (overlapping PUs?)");
+  B200_CHECK(!(A.hMeta[LM_ERR] & 8), "b200_pic_run: an intra block record is invalid (geometry, mode, or availability reaching outside the picture)");
   B200_CHECK(!(A.hMeta[LM_ERR] & 4), "b200_pic_run: a CTU record (SAO type / band, ALF filter index, slice index) is out of range");
   B200_CHECK(!A.hMeta[LM_INTS + LM_ERR], "b200_pic_run: the picture's TU list holds an invalid record");
   B200_CUDA(cudaStreamWaitEvent(s, A.uploaded, 0));
@@ -278,6 +294,7 @@ B200_API int b200_pic_run(b200_ctx* c, int ai)
   LmcsLaunch LM; LM.geom = g; LM.planes = P; LM.lmcs = A.lmcs; LM.vpdus = A.lmcsVpdus; LM.invLut = A.lmcsInv; LM.scale = A.lmcsScale;
   if (A.numTus) {
     K1Launch L; L.geom = g; L.planes = P; L.tus = A.tus; L.numTus = A.numTus; L.idx = A.tuIdx; L.meta = A.tuMeta; L.coefs = A.coefs; L.scaling = A.scaling; L.mode = 0;
+    if (A.numIntraTus) { uint8_t* rb = c->resiBuf.as<uint8_t>(); L.resi[0] = reinterpret_cast<int16_t*>(rb); L.resi[1] = reinterpret_cast<int16_t*>(rb + c->planeBytes[0]); L.resi[2] = reinterpret_cast<int16_t*>(rb + c->planeBytes[0] + c->planeBytes[1]); }
     for (int l = 0; l < K1_LISTS; l++) L.cnt[l] = A.hMeta[LM_INTS + LM_CNT + l];
     if (A.lmcs && A.lmcsChromaAdj) {
       L.compSel = 1;
@@ -290,6 +307,17 @@ B200_API int b200_pic_run(b200_ctx* c, int ai)
       if (int rc = launch_k1_residual(L, c->ss, c->profiling ? &c->prof : nullptr)) return rc;
       c->launches += k1_launch_count(L);
     }
+  }
+  // 2b. K6 intra blocks in decoding order: prediction from the reconstruction so far (inter CUs, earlier intra blocks) + their residual
+  A.hMeta[2 * LM_INTS] = 0;
+  if (A.numIntraTus) {
+    IntraLaunch L; L.geom = g; L.planes = P; L.tus = A.intraTus; L.numTus = A.numIntraTus; L.sync = A.intraSync;
+    uint8_t* rb = c->resiBuf.as<uint8_t>();
+    L.resi[0] = reinterpret_cast<int16_t*>(rb); L.resi[1] = reinterpret_cast<int16_t*>(rb + c->planeBytes[0]); L.resi[2] = reinterpret_cast<int16_t*>(rb + c->planeBytes[0] + c->planeBytes[1]);
+    for (int k = 0; k < 3; k++) { L.owner[k] = A.intraOwner[k]; L.ownerStride[k] = A.intraOwnerStride[k]; L.ownerBytes[k] = A.intraOwnerBytes[k]; }
+    if (int rc = launch_intra(L, s)) return rc;
+    c->launches += 2;
+    B200_CUDA(cudaMemcpyAsync(A.hMeta + 2 * LM_INTS, A.intraSync + A.numIntraTus + 1, sizeof(int), cudaMemcpyDeviceToHost, s));   // timeout bit, read by b200_wait_picture
   }
   if (A.lmcs) { if (int rc = launch_lmcs_inv(LM, s)) return rc; c->launches += 1; }   // RSP stage (DecLibRecon.cpp:935)
   // 3. K3 deblocking
@@ -338,6 +366,8 @@ B200_API int b200_wait_picture(b200_ctx* c, int ai, int32_t* dmvrMv, size_t numD
   }
   B200_CUDA(cudaStreamSynchronize(c->upStream));
   B200_CUDA(cudaStreamSynchronize(c->stream));
+  if (ai >= 0 && ai < c->numArenas && c->arenas[ai].numIntraTus)
+    B200_CHECK(!c->arenas[ai].hMeta[2 * LM_INTS], "b200_wait_picture: an intra block waited for a neighbour that never finished (intra list not in decoding order?)");
   return 0;
 }
 

@@ -467,17 +467,41 @@ def gen_lmcs(rng, bit_depth, cus, W, H, ctu, chroma_adj=True):
 
 
 def gen_picture(rng, W, H, bit_depth=10, ctu=128, dst_slot=0, cu_kw=None, pu_kw=None, tu_kw=None, sao_p=0.4, alf_kw=None,
-                deblock=True, sao=True, alf=True, lmcs=False, lmcs_chroma=True, wp=False, inter=True, given=None, cu_intra=None):
+                deblock=True, sao=True, alf=True, lmcs=False, lmcs_chroma=True, wp=False, inter=True, given=None, cu_intra=None, intra_frac=0.0):
     """One synthetic post-parse picture: partition -> inter PUs (all CUs inter: intra-coded samples would
     be 'given' pixels) -> TUs/levels -> deblocking grids -> SAO / ALF CTU parameters.
     Returns a dict of numpy arrays (kept alive by the caller) plus `struct`, the abi.Picture that points into them."""
     from . import abi as A
     import ctypes as C
-    cus = partition(rng, W, H, ctu=ctu, **(cu_kw or {}))
-    pus, ndmvr = gen_pus(rng, cus, W, H, **(pu_kw or {})) if inter else (np.zeros(0, PU_DTYPE), 0)
-    tus, coefs = gen_tus(rng, cus, bit_depth, **({"p_cbf": 0.35, "p_intra": 0.0, "p_lfnst": 0.0, "p_bdpcm": 0.0} | (tu_kw or {})))
+    if intra_frac > 0:
+        # intra CUs on the device (K6): CUs in decoding order, at most 64x64 (one TU per component); a fraction of them intra, the others inter.
+        # Intra CUs: TUs flagged TU_RESI (residual -> residual planes) + b200_intra_tu records with ADD_RESI where a TU carries a residual.
+        cus = gen_intra_layout(rng, W, H, ctu, **({"min_size": 8} | (cu_kw or {})))
+        is_intra = rng.random(len(cus)) < intra_frac
+        inter_cus = [cu for cu, f in zip(cus, is_intra) if not f]; intra_cus = [cu for cu, f in zip(cus, is_intra) if f]
+        pus, ndmvr = gen_pus(rng, inter_cus, W, H, **(pu_kw or {})) if inter_cus else (np.zeros(0, PU_DTYPE), 0)
+        tkw = {"p_cbf": 0.35, "p_intra": 0.0, "p_lfnst": 0.0, "p_bdpcm": 0.0} | (tu_kw or {})
+        tus0, coefs0 = gen_tus(rng, inter_cus, bit_depth, **tkw)
+        tus1, coefs1 = gen_tus(rng, intra_cus, bit_depth, **(tkw | {"p_intra": 1.0, "p_cbf": 0.6, "p_lfnst": 0.15, "p_bdpcm": 0.05}))
+        tus1["coefOff"] += len(coefs0); tus1["flags"] |= A.TU_RESI
+        tus, coefs = np.concatenate([tus0, tus1]), np.concatenate([coefs0, coefs1])
+        irecs = gen_intra_records(rng, cus, W, H, only=is_intra)
+        coded = set()
+        for t in tus1:
+            coded.add((int(t["comp"]), int(t["x"]), int(t["y"]))); 
+            if t["ict"]: coded.add((3 - int(t["comp"]), int(t["x"]), int(t["y"])))
+        for r in irecs:
+            if (int(r["comp"]), int(r["x"]), int(r["y"])) in coded: r["flags"] |= A.INTRA_ADD_RESI
+        if cu_intra is None: cu_intra = is_intra
+    else:
+        cus = partition(rng, W, H, ctu=ctu, **(cu_kw or {}))
+        pus, ndmvr = gen_pus(rng, cus, W, H, **(pu_kw or {})) if inter else (np.zeros(0, PU_DTYPE), 0)
+        tus, coefs = gen_tus(rng, cus, bit_depth, **({"p_cbf": 0.35, "p_intra": 0.0, "p_lfnst": 0.0, "p_bdpcm": 0.0} | (tu_kw or {})))
+        irecs = None
     d = dict(cus=cus, pus=pus, ndmvr=ndmvr, tus=tus, coefs=coefs)
     p = A.Picture(); p.dstSlot = dst_slot; p.flags = 0
+    if irecs is not None:
+        d["intraTus"] = irecs; p.intraTus = irecs.ctypes.data; p.numIntraTus = len(irecs)
     if given is not None:                                       # pre-reconstructed samples (an intra picture's predictions stand in here)
         d["given"] = given
         for c in range(3): p.given[c] = given[c].ctypes.data
@@ -640,7 +664,7 @@ def intra_filter_ref(w, h, mode, mrl, bdpcm):
     return diff > _INTRA_THR[(int(np.log2(w)) + int(np.log2(h))) >> 1] and (ang & 31) == 0
 
 
-def gen_intra_records(rng, layout, W, H, modes=None, p_mrl=0.15, p_bdpcm=0.08, p_resi=0.0, upto=None):
+def gen_intra_records(rng, layout, W, H, modes=None, p_mrl=0.15, p_bdpcm=0.08, p_resi=0.0, upto=None, only=None):
     """b200_intra_tu records (Y, Cb, Cr per CU, decoding order) for a single-tree all-intra layout of gen_intra_layout: random modes, MRL on some luma
     blocks, BDPCM prediction on some, availability as xFillReferenceSamples derives it from the decoding order (pinned against the reference's own
     analysis through the glue flattener by tests/test_intra_oracle_vs_ref.py).  Luma blocks whose chroma would be narrower than 4 or smaller than 16
@@ -658,6 +682,7 @@ def gen_intra_records(rng, layout, W, H, modes=None, p_mrl=0.15, p_bdpcm=0.08, p
             elif rng.random() < p_bdpcm and w <= 32 and h <= 32: bdpcm = int(rng.integers(1, 3))
             dirC = chroma_modes[int(rng.integers(len(chroma_modes)))]
         if dirC < 0 or dirC == 70: dirC = dirL                          # DM
+        if only is not None and not only[i]: continue                   # an inter CU of a mixed picture: a neighbour, not a block of the list
         def avail(ux, uy): return 0 <= ux < owner.shape[1] and 0 <= uy < owner.shape[0] and owner[uy, ux] < i
         tl = avail(x // 4 - 1, y // 4 - 1)
         na = 0
