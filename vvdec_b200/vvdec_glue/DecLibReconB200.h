@@ -7,7 +7,7 @@
 //
 // The CPU keeps: parsing (DecLibParser / DecSlice), motion derivation (DecCu::TaskDeriveCtuMotionInfo, DecCu.cpp:62), boundary strengths
 // (LoopFilter::calcFilterStrengthsCTU, LoopFilter.cpp:360), TaskFinishMotionInfo (DecCu.cpp:161).  Pictures that use a tool the device path
-// does not have (intra / IBC / CIIP CUs, RPR, wrap-around, sub-picture clipping, virtual-boundary ALF) throw UnsupportedFeatureException; a
+// does not have (MIP / CCLM / ISP intra blocks, IBC / CIIP CUs, RPR, wrap-around, sub-picture clipping, virtual-boundary ALF) throw UnsupportedFeatureException; a
 // deployment keeps a stock DecLibRecon next to this class and routes those pictures to it.
 #pragma once
 #include <vector>
@@ -16,6 +16,7 @@
 #include "flatten_tu.h"
 #include "flatten_pu.h"
 #include "flatten_filters.h"
+#include "flatten_intra.h"
 #include "CommonLib/Picture.h"
 #include "CommonLib/LoopFilter.h"
 #include "CommonLib/Reshape.h"
@@ -44,7 +45,7 @@ class DecLibReconB200
   std::map<const Picture*, int> m_slotOf;          // DPB slot of every picture the device holds
   std::vector<const Picture*>   m_slotOwner;
   // per-picture work lists (pinned)
-  PinnedVec<b200_pu> m_pus; PinnedVec<b200_tu> m_tus; PinnedVec<int16_t> m_coefs;
+  PinnedVec<b200_pu> m_pus; PinnedVec<b200_tu> m_tus; PinnedVec<int16_t> m_coefs; PinnedVec<b200_intra_tu> m_intra;
   PinnedVec<b200_lf_param> m_lf[2]; PinnedVec<b200_sao_ctu> m_sao; PinnedVec<b200_alf_ctu> m_alf; PinnedVec<b200_lmcs_vpdu> m_vpdus;
   PinnedVec<int32_t> m_dmvr;
   std::vector<b200_wp> m_wp; std::map<std::pair<int, int>, int> m_wpIdx;
@@ -94,8 +95,7 @@ public:
       CtuData& cd = cs.getCtuData( a );
       cd.motion = &m_motionInfo[(size_t) pcv.num4x4CtuBlks * a];
       const UnitArea ctuArea = getCtuArea( cs, a % pcv.widthInCtus, a / pcv.widthInCtus, true );
-      if( cd.slice->isIntra() ) THROW_UNSUPPORTED( "DecLibReconB200: intra slices go to the CPU back end (SURVEY 8f-1)" );
-      m_cCuDecoder.TaskDeriveCtuMotionInfo( cs, a, ctuArea, hist[a / pcv.widthInCtus] );
+      if( !cd.slice->isIntra() ) m_cCuDecoder.TaskDeriveCtuMotionInfo( cs, a, ctuArea, hist[a / pcv.widthInCtus] );            // ctuTask MIDER (DecLibRecon.cpp:762-781)
     }
     for( unsigned a = 0; a < pcv.sizeInCtus; a++ )
     {
@@ -120,11 +120,29 @@ public:
     };
 
     // ---- flatten CUs / TUs (TaskTrafoCtu + TaskInterCtu walks, DecCu.cpp:106-134) ----
-    m_pus.clear(); m_tus.clear(); m_coefs.clear();
+    m_pus.clear(); m_tus.clear(); m_coefs.clear(); m_intra.clear();
     for( unsigned a = 0; a < pcv.sizeInCtus; a++ )
       for( auto& cu : cs.traverseCUs( a ) )
       {
-        if( !CU::isInter( cu ) || cu.ciipFlag() ) THROW_UNSUPPORTED( "DecLibReconB200: intra / IBC / CIIP CU (SURVEY 8f-1)" );
+        if( CU::isIntra( cu ) )
+        {
+          // K6: regular intra modes on the device.  One b200_intra_tu per TU component in decoding order (the order DecCu::predAndReco walks them,
+          // DecCu.cpp:284-288); the residual of a coded component goes through K1 into the residual planes (B200_TU_RESI) and is added by K6.
+          if( sps.getUseReshaper() && cs.picHeader->getLmcsEnabledFlag() ) THROW_UNSUPPORTED( "DecLibReconB200: intra CUs with LMCS" );
+          for( auto& tu : TUTraverser( &cu.firstTU, cu.lastTU->next ) )
+            for( const CompArea& area : tu.blocks )
+            {
+              if( !area.valid() ) continue;
+              b200_intra_tu ir;
+              if( flattenIntraTU( tu, area.compID(), ir ) != FLATTEN_INTRA_OK ) THROW_UNSUPPORTED( "DecLibReconB200: MIP / CCLM / ISP / ACT intra block (SURVEY 8f-1)" );
+              b200_tu r;
+              if( flattenTU( tu, area.compID(), *m_trQuant, m_coefs.v, r ) ) { r.flags |= B200_TU_RESI; m_tus.v.push_back( r ); }
+              if( TU::getCbf( tu, area.compID() ) || ( isChroma( area.compID() ) && tu.jointCbCr ) ) ir.flags |= B200_INTRA_ADD_RESI;      // DecCu.cpp:390
+              m_intra.v.push_back( ir );
+            }
+          continue;
+        }
+        if( !CU::isInter( cu ) || cu.ciipFlag() ) THROW_UNSUPPORTED( "DecLibReconB200: IBC / CIIP CU (SURVEY 8f-1)" );
         FlattenPuResult rc;
         if( cu.mergeType() == MRG_TYPE_SUBPU_ATMVP ) rc = flattenSbTmvp( cu, sm, wpIdxOf, [&]( const b200_pu& r ) { m_pus.v.push_back( r ); } );
         else { b200_pu r; rc = flattenPU( cu, sm, wpIdxOf, r ); if( rc == FLATTEN_PU_OK ) m_pus.v.push_back( r ); }
@@ -179,7 +197,7 @@ public:
 
     // ---- submit ----
     for( PinnedVec<b200_lf_param>& l : m_lf ) l.pin();
-    m_pus.pin(); m_tus.pin(); m_coefs.pin(); m_sao.pin(); m_alf.pin();
+    m_pus.pin(); m_tus.pin(); m_coefs.pin(); m_sao.pin(); m_alf.pin(); m_intra.pin();
     b200_picture p{};
     p.dstSlot = slotFor( pic );
     p.flags = ( slice0.getDeblockingFilterDisable() ? 0 : B200_PIC_DEBLOCK ) | ( doSao ? B200_PIC_SAO : 0 ) | ( doAlf ? B200_PIC_ALF : 0 ) | ( doLmcs ? B200_PIC_LMCS : 0 );
@@ -188,6 +206,7 @@ public:
     p.lfV = m_lf[0].v.data(); p.lfH = m_lf[1].v.data(); p.lfSlices = &m_lfSlice; p.numLfSlices = 1; p.lfSeq = &m_lfSeq;
     p.sao = m_sao.v.data(); p.vb = &m_vb; p.alf = m_alf.v.data(); p.alfTabs = &m_alfTabs;
     p.wp = m_wp.data(); p.numWp = (int32_t) m_wp.size(); p.lmcs = doLmcs ? &m_lmcs : nullptr;
+    p.intraTus = m_intra.v.data(); p.numIntraTus = m_intra.v.size();
     m_arena = b200_decompress_picture( m_ctx, &p );
     check( m_arena );
   }
@@ -200,7 +219,8 @@ public:
     m_dmvr.v.assign( m_dmvrMvCache.size() * 2, 0 ); m_dmvr.pin();
     check( b200_wait_picture( m_ctx, m_arena, m_dmvr.v.data(), m_dmvrMvCache.size() ) );
     for( size_t i = 0; i < m_dmvrMvCache.size(); i++ ) m_dmvrMvCache[i] = Mv( m_dmvr.v[2 * i], m_dmvr.v[2 * i + 1] );
-    for( unsigned a = 0; a < pcv.sizeInCtus; a++ ) m_cCuDecoder.TaskFinishMotionInfo( cs, a, a % pcv.widthInCtus, a / pcv.widthInCtus );   // colMotion for later TMVP (DecCu.cpp:161)
+    for( unsigned a = 0; a < pcv.sizeInCtus; a++ )                                                                                         // colMotion for later TMVP (DecCu.cpp:161),
+      if( !cs.getCtuData( a ).slice->isIntra() && pic->stillReferenced ) m_cCuDecoder.TaskFinishMotionInfo( cs, a, a % pcv.widthInCtus, a / pcv.widthInCtus );   // under ctuTask's conditions (DecLibRecon.cpp:860-867)
     if( pic->neededForOutput )
     {
       int16_t* planes[3] = { cs.getRecoBuf( COMPONENT_Y ).buf, nullptr, nullptr };
