@@ -222,14 +222,15 @@ B200_API int b200_intra_reconstruct(const b200_geom* g, int16_t* const planes[3]
   }
   if (int rc = g_hw.tus.reserve(numTus * sizeof(b200_intra_tu) + 16)) return rc;
   if (int rc = g_hw.misc[6].reserve((numTus + 2) * sizeof(int))) return rc;
+  if (int rc = g_hw.misc[7].reserve(intra_order_ints(*g, numTus) * sizeof(int))) return rc;
   if (numTus) B200_CUDA(cudaMemcpyAsync(g_hw.tus.p, tus, numTus * sizeof(b200_intra_tu), cudaMemcpyHostToDevice, s));
-  L.tus = g_hw.tus.as<b200_intra_tu>(); L.sync = g_hw.misc[6].as<int>();
+  L.tus = g_hw.tus.as<b200_intra_tu>(); L.sync = g_hw.misc[6].as<int>(); L.order = g_hw.misc[7].as<int>();
   if (int rc = launch_intra(L, s)) return rc;
   int err = 0;
   if (numTus) B200_CUDA(cudaMemcpyAsync(&err, L.sync + numTus + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
   if (int rc = download_planes(g, planes, L.planes, s)) return rc;
   B200_CUDA(cudaStreamSynchronize(s));
-  B200_CHECK(!err, "b200_intra_reconstruct: a block waited for a neighbour that never finished (list not in decoding order?)");
+  B200_CHECK(!err, "b200_intra_reconstruct: a block waited for a neighbour that never finished, or the blocks of a CTU are not contiguous (list not in decoding order?)");
   return 0;
 }
 

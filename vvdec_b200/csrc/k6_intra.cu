@@ -5,13 +5,15 @@
 // IntraPredAngleCore :301, IntraPredAngleChroma :333, IntraPredSampleFilterCore :212, xPredIntraBDPCM :850 and the pred + resi clip of
 // DecCu::predAndReco (DecCu.cpp:390-398).
 //
-// Scheduling.  Intra blocks depend on their neighbours' reconstruction, so the list is a dataflow graph.  CTAs take blocks in list order from
+// Scheduling.  Intra blocks depend on their neighbours' reconstruction, so the list is a dataflow graph.  CTAs take blocks in order from
 // a ticket counter; a block waits (bounded spin on per-block `done` words) for the earlier blocks of the list that own the units its
 // available reference samples lie in (`owner` maps filled by a pre-pass, one word per 4x4 luma / 2x2 chroma unit).  Tickets are handed out
 // in decoding order and only to running CTAs, so the oldest unfinished block never waits on a block that has not started: no deadlock,
 // whatever the residency.  Reference samples are read with ld.global.cg (L2): another SM wrote them.
 // Inside a block every sample is independent once the two reference arrays are in shared memory: one thread computes several samples.
 #include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
 #define VVC_TABLE_QUAL static __device__ const __align__(16)
 #include "vvc_tables.h"
 
@@ -32,6 +34,8 @@ struct IntraParams {
   const b200_intra_tu* tus; int numTus;
   int* owner[3]; int ownerStride[3];        // per unit: index of the list entry that writes it, -1: not written by this list
   int* done; int* ticket; int* err;
+  const int* perm;                          // processing order (wavefront over CTUs), or null: list order
+  int* ctuCnt; int* ctuFirst; int* ctuBase; int ctuLog2, ctusW, ctusH;
 };
 
 __device__ __forceinline__ int wide_angle(int w, int h, int mode)
@@ -53,9 +57,40 @@ __global__ void __launch_bounds__(256) intra_owner_kernel(const IntraParams P)
   for (int k = threadIdx.x; k < uw * uh; k += blockDim.x) P.owner[c][(t.y / unit + k / uw) * P.ownerStride[c] + t.x / unit + k % uw] = i;
 }
 
+// Processing order.  The list is in decoding order (CTU raster); handing tickets out in that order keeps only the next few CTUs of a CTU row
+// in flight.  Any topological order of the dependency graph keeps the no-deadlock argument, and so does the wavefront order
+// key(CTU) = x + 2 y (left, above, above-left and above-right CTUs all have smaller keys): CTUs of one anti-diagonal run side by side.
+// perm = blocks sorted by key, decoding order kept inside a CTU (its blocks are contiguous in the list).
+__device__ __forceinline__ int intra_ctu_of(const IntraParams& P, const b200_intra_tu& t)
+{
+  const int sh = t.comp ? 1 : 0;
+  return (((int)t.y << sh) >> P.ctuLog2) * P.ctusW + (((int)t.x << sh) >> P.ctuLog2);
+}
+__global__ void __launch_bounds__(256) intra_ctu_count_kernel(const IntraParams P)
+{
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= P.numTus) return;
+  const int c = intra_ctu_of(P, P.tus[i]);
+  atomicAdd(&P.ctuCnt[c], 1); atomicMin(&P.ctuFirst[c], i);
+}
+__global__ void intra_ctu_base_kernel(const IntraParams P)
+{
+  int run = 0;
+  for (int d = 0; d < P.ctusW + 2 * P.ctusH; d++)
+    for (int y = 0; y < P.ctusH; y++) { const int x = d - 2 * y; if (x >= 0 && x < P.ctusW) { P.ctuBase[y * P.ctusW + x] = run; run += P.ctuCnt[y * P.ctusW + x]; } }
+}
+__global__ void __launch_bounds__(256) intra_perm_kernel(const IntraParams P, int* perm)
+{
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= P.numTus) return;
+  const int c = intra_ctu_of(P, P.tus[i]), r = i - P.ctuFirst[c];
+  if (r >= P.ctuCnt[c]) { atomicOr(P.err, 2); return; }       // the CTU's blocks are not contiguous in the list
+  perm[P.ctuBase[c] + r] = i;
+}
+
 __device__ __forceinline__ int pix(const int16_t* __restrict__ plane, int stride, int x, int y) { return __ldcg(plane + (size_t)y * stride + x); }
 
-__global__ void __launch_bounds__(IT_THREADS) intra_kernel(const IntraParams P)
+__global__ void __launch_bounds__(IT_THREADS, 12) intra_kernel(const IntraParams P)
 {
   __shared__ int16_t sT[2][IT_REF], sL[2][IT_REF];          // [0] unfiltered, [1] filtered
   __shared__ int16_t sM[IT_ARR], sS[IT_ARR];
@@ -65,8 +100,8 @@ __global__ void __launch_bounds__(IT_THREADS) intra_kernel(const IntraParams P)
     __syncthreads();
     if (tid == 0) { sTicket = atomicAdd(P.ticket, 1); sSum = 0; }
     __syncthreads();
-    const int me = sTicket;
-    if (me >= P.numTus) return;
+    if (sTicket >= P.numTus) return;
+    const int me = P.perm ? P.perm[sTicket] : sTicket;
     const b200_intra_tu t = P.tus[me];
     const int c = t.comp, w = 1 << t.log2w, h = 1 << t.log2h, mrl = c ? 0 : t.multiRefIdx, unit = c ? 2 : 4;
     const int x0 = t.x, y0 = t.y, ps = P.stride[c], pmax = (1 << P.bitDepth) - 1;
@@ -75,10 +110,11 @@ __global__ void __launch_bounds__(IT_THREADS) intra_kernel(const IntraParams P)
 
     // ---- wait for the earlier blocks this one reads from
     {
+      for (int dep = tid; dep < 96; dep += IT_THREADS) {               // dependency slots: 0 corner, 1..32 above units, 64..95 left units
       int ux = -1, uy = -1;
-      if (tid == 0) { if (availTL) { ux = x0 - 1; uy = y0 - 1; } }
-      else if (tid <= numAbove) { ux = x0 + (tid - 1) * unit; uy = y0 - 1; }
-      else if (tid - 64 >= 0 && tid - 64 < numLeft) { ux = x0 - 1; uy = y0 + (tid - 64) * unit; }
+      if (dep == 0) { if (availTL) { ux = x0 - 1; uy = y0 - 1; } }
+      else if (dep <= numAbove) { ux = x0 + (dep - 1) * unit; uy = y0 - 1; }
+      else if (dep - 64 >= 0 && dep - 64 < numLeft) { ux = x0 - 1; uy = y0 + (dep - 64) * unit; }
       if (ux >= 0 && uy >= 0) {
         const int o = P.owner[c][(uy / unit) * P.ownerStride[c] + ux / unit];
         if (o >= 0 && o < me) {
@@ -87,6 +123,7 @@ __global__ void __launch_bounds__(IT_THREADS) intra_kernel(const IntraParams P)
           const volatile int* e = P.err;
           while (*d == 0) { __nanosleep(64); if (*e || ++spins > (1 << 22)) { atomicOr(P.err, 1); break; } }   // bounded: a broken list must not hang the GPU
         }
+      }
       }
       __threadfence();
     }
@@ -268,8 +305,24 @@ int launch_intra(const IntraLaunch& L, cudaStream_t s)
   P.done = L.sync; P.ticket = L.sync + L.numTus; P.err = L.sync + L.numTus + 1;
   B200_CUDA(cudaMemsetAsync(L.sync, 0, (L.numTus + 2) * sizeof(int), s));
   for (int c = 0; c < (L.geom.chromaFormat ? 3 : 1); c++) B200_CUDA(cudaMemsetAsync(L.owner[c], 0xff, L.ownerBytes[c], s));
+  P.perm = nullptr; P.ctuCnt = P.ctuFirst = P.ctuBase = nullptr;
+  P.ctuLog2 = L.geom.ctuSize == 128 ? 7 : L.geom.ctuSize == 64 ? 6 : 5; P.ctusW = (L.geom.width + L.geom.ctuSize - 1) / L.geom.ctuSize; P.ctusH = (L.geom.height + L.geom.ctuSize - 1) / L.geom.ctuSize;
+  static const bool listOrder = getenv("B200_INTRA_ORDER") && !strcmp(getenv("B200_INTRA_ORDER"), "decode");   // measurement switch: tickets in list order
+  // the wavefront order pays off when CTUs are dense with intra blocks (I pictures: 14 ms vs 65 ms at 4K); for the few intra CUs of a B picture the
+  // chains are short and the three extra launches cost more than they give (0.79 vs 0.70 ms), so those keep the list order
+  if (L.order && !listOrder && L.numTus >= 100 * std::max<size_t>(1, (size_t)L.geom.width * L.geom.height >> 14)) {   // >= 100 blocks per 128x128 luma area
+    const size_t nCtu = (size_t)P.ctusW * P.ctusH;
+    int* perm = L.order; P.ctuCnt = perm + L.numTus; P.ctuFirst = P.ctuCnt + nCtu; P.ctuBase = P.ctuFirst + nCtu;
+    B200_CUDA(cudaMemsetAsync(P.ctuCnt, 0, nCtu * sizeof(int), s));
+    B200_CUDA(cudaMemsetAsync(P.ctuFirst, 0x7f, nCtu * sizeof(int), s));
+    const unsigned grid = (unsigned)((L.numTus + 255) / 256);
+    intra_ctu_count_kernel<<<grid, 256, 0, s>>>(P);
+    intra_ctu_base_kernel<<<1, 1, 0, s>>>(P);
+    intra_perm_kernel<<<grid, 256, 0, s>>>(P, perm);
+    P.perm = perm;
+  }
   intra_owner_kernel<<<(unsigned)L.numTus, 64, 0, s>>>(P);
-  const int ctas = (int)std::min<size_t>(L.numTus, (size_t)num_sms() * 8);
+  const int ctas = (int)std::min<size_t>(L.numTus, (size_t)num_sms() * 12);
   intra_kernel<<<ctas, IT_THREADS, 0, s>>>(P);
   B200_CUDA(cudaGetLastError());
   return 0;

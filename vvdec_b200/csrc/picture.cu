@@ -21,7 +21,7 @@ struct Arena {
   const b200_wp* wp = nullptr;
   const b200_lmcs* lmcs = nullptr; const int16_t* lmcsInv = nullptr; const b200_lmcs_vpdu* lmcsVpdus = nullptr; int* lmcsScale = nullptr; bool lmcsChromaAdj = false;
   int16_t* given[3] = {nullptr, nullptr, nullptr};
-  const b200_intra_tu* intraTus = nullptr; size_t numIntraTus = 0; int* intraOwner[3] = {nullptr, nullptr, nullptr}; int intraOwnerStride[3] = {0, 0, 0}; size_t intraOwnerBytes[3] = {0, 0, 0}; int* intraSync = nullptr;   // K6
+  const b200_intra_tu* intraTus = nullptr; size_t numIntraTus = 0; int* intraOwner[3] = {nullptr, nullptr, nullptr}; int intraOwnerStride[3] = {0, 0, 0}; size_t intraOwnerBytes[3] = {0, 0, 0}; int* intraSync = nullptr; int* intraOrder = nullptr;   // K6
   int dstSlot = 0, flags = 0;
   bool valid = false;
   cudaEvent_t uploaded = nullptr, done = nullptr; bool donePending = false;   // H2D finished / kernels reading this arena finished
@@ -172,7 +172,7 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   const bool hasGiven = p->given[0] != nullptr;
   const size_t oGiven = take(hasGiven ? c->picBytes : 0);
   size_t oOwn[3] = {0, 0, 0}, ownBytes[3] = {0, 0, 0}; int ownStride[3] = {0, 0, 0};
-  const size_t oIntra = take(p->numIntraTus * sizeof(b200_intra_tu)), oSync = take(p->numIntraTus ? (p->numIntraTus + 2) * sizeof(int) : 0);
+  const size_t oIntra = take(p->numIntraTus * sizeof(b200_intra_tu)), oSync = take(p->numIntraTus ? (p->numIntraTus + 2) * sizeof(int) : 0), oOrder = take(p->numIntraTus ? intra_order_ints(g, p->numIntraTus) * sizeof(int) : 0);
   for (int k = 0; k < (g.chromaFormat ? 3 : 1) && p->numIntraTus; k++) {
     const int pw = k ? g.width >> 1 : g.width, ph = k ? g.height >> 1 : g.height, unit = k ? 2 : 4;
     ownStride[k] = (pw + unit - 1) / unit; ownBytes[k] = (size_t)ownStride[k] * ((ph + unit - 1) / unit) * sizeof(int); oOwn[k] = take(ownBytes[k]);
@@ -233,7 +233,7 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   A.dmvrMv = p->numDmvr ? reinterpret_cast<int32_t*>(base + oDm) : nullptr; A.numDmvr = p->numDmvr;
   if (p->numDmvr) B200_CUDA(cudaMemsetAsync(base + oDm, 0, p->numDmvr * 8, s));   // entries of non-DMVR CUs stay zero, like m_dmvrMvCache users expect
   if (int rc = h2d(oIntra, p->intraTus, p->numIntraTus * sizeof(b200_intra_tu))) return rc;
-  A.intraTus = reinterpret_cast<const b200_intra_tu*>(base + oIntra); A.numIntraTus = p->numIntraTus; A.intraSync = reinterpret_cast<int*>(base + oSync);
+  A.intraTus = reinterpret_cast<const b200_intra_tu*>(base + oIntra); A.numIntraTus = p->numIntraTus; A.intraSync = reinterpret_cast<int*>(base + oSync); A.intraOrder = reinterpret_cast<int*>(base + oOrder);
   for (int k = 0; k < 3; k++) { A.intraOwner[k] = ownBytes[k] ? reinterpret_cast<int*>(base + oOwn[k]) : nullptr; A.intraOwnerStride[k] = ownStride[k]; A.intraOwnerBytes[k] = ownBytes[k]; }
   A.dstSlot = p->dstSlot; A.flags = p->flags; A.valid = true;
   // work lists: validated and bucketed on the device, behind the copies
@@ -311,12 +311,12 @@ B200_API int b200_pic_run(b200_ctx* c, int ai)
   // 2b. K6 intra blocks in decoding order: prediction from the reconstruction so far (inter CUs, earlier intra blocks) + their residual
   A.hMeta[2 * LM_INTS] = 0;
   if (A.numIntraTus) {
-    IntraLaunch L; L.geom = g; L.planes = P; L.tus = A.intraTus; L.numTus = A.numIntraTus; L.sync = A.intraSync;
+    IntraLaunch L; L.geom = g; L.planes = P; L.tus = A.intraTus; L.numTus = A.numIntraTus; L.sync = A.intraSync; L.order = A.intraOrder;
     uint8_t* rb = c->resiBuf.as<uint8_t>();
     L.resi[0] = reinterpret_cast<int16_t*>(rb); L.resi[1] = reinterpret_cast<int16_t*>(rb + c->planeBytes[0]); L.resi[2] = reinterpret_cast<int16_t*>(rb + c->planeBytes[0] + c->planeBytes[1]);
     for (int k = 0; k < 3; k++) { L.owner[k] = A.intraOwner[k]; L.ownerStride[k] = A.intraOwnerStride[k]; L.ownerBytes[k] = A.intraOwnerBytes[k]; }
     if (int rc = launch_intra(L, s)) return rc;
-    c->launches += 2;
+    c->launches += 5;
     B200_CUDA(cudaMemcpyAsync(A.hMeta + 2 * LM_INTS, A.intraSync + A.numIntraTus + 1, sizeof(int), cudaMemcpyDeviceToHost, s));   // timeout bit, read by b200_wait_picture
   }
   if (A.lmcs) { if (int rc = launch_lmcs_inv(LM, s)) return rc; c->launches += 1; }   // RSP stage (DecLibRecon.cpp:935)
