@@ -257,9 +257,10 @@ B200_API int b200_mc_predict_wp(const b200_geom* g, int16_t* const dst[3], const
  *             linear interpolation, angular PDPC), IntraPredSampleFilterCore :212 (PDPC of planar / DC), xPredIntraBDPCM :850,
  *             as DecCu::predAndReco calls them for a regular intra TU (DecCu.cpp:329-371).
  * The availability analysis (cs.getCURestricted walks, IntraPrediction.cpp:1098-1130) stays host code in the flattener and arrives as
- * three counts.  Not covered (the flattener must refuse them): MIP, CCLM, ISP, palette, ACT.
+ * three counts.  Not covered (the flattener must refuse them): CCLM, ISP, palette, ACT.
  * Blocks of one list are processed in list order; a block may read what earlier blocks of the list wrote. */
-enum { B200_INTRA_PLANAR = 0, B200_INTRA_DC = 1 /* 2..66 angular */, B200_INTRA_BDPCM_HOR = 67, B200_INTRA_BDPCM_VER = 68 };
+enum { B200_INTRA_PLANAR = 0, B200_INTRA_DC = 1 /* 2..66 angular */, B200_INTRA_BDPCM_HOR = 67, B200_INTRA_BDPCM_VER = 68,
+       B200_INTRA_MIP = 69 /* matrix intra prediction: b200_intra_tu::mip = mode index | transposed << 7 */ };
 enum { B200_INTRA_FILTER_REF = 1, B200_INTRA_AVAIL_TL = 2, B200_INTRA_ADD_RESI = 4 /* reconstruct: clip(pred + residual), see b200_intra_reconstruct */ };
 typedef struct b200_intra_tu {
   uint16_t x, y;          /* top-left in the component's plane, samples                                              */
@@ -270,7 +271,8 @@ typedef struct b200_intra_tu {
   uint8_t  flags;         /* B200_INTRA_FILTER_REF: useFilteredIntraRefSamples (:1301); B200_INTRA_AVAIL_TL: m_neighborSize[0] */
   uint8_t  numAbove;      /* m_neighborSize[1]: available units above + above-right (unit = 4 luma / 2 chroma samples) */
   uint8_t  numLeft;       /* m_neighborSize[2]: available units left + below-left                                    */
-  uint32_t rsv;
+  uint8_t  mip;           /* B200_INTRA_MIP: cu.intraDir[luma] (MIP mode index) | cu.mipTransposedFlag() << 7                    */
+  uint8_t  rsv[3];
 } b200_intra_tu;          /* 16 bytes */
 /* Kernel-level K6: host planes in (reconstructed neighbourhood), prediction written into the blocks, host planes out. */
 B200_API int b200_intra_predict(const b200_geom* g, int16_t* const planes[3], const b200_intra_tu* tus, size_t numTus);

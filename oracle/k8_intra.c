@@ -197,6 +197,58 @@ static void pred_angular(const int16_t* src, int stride, int w0, int h0, int chr
   if (!ver) for (int y = 0; y < h0; y++) for (int x = 0; x < w0; x++) dst[y * ds + x] = tmp[x * 64 + y];
 }
 
+/* Matrix intra prediction.  Follows MatrixIntraPrediction.cpp: deriveBoundaryData :67-121 (Haar down-sampling of the two boundaries, rebase on the
+ * first entry), computeReducedPred :281-330 (matrix stage, transposed variant), predictionUpsampling :233-262 / predictionUpsampling1D :190-230
+ * (linear interpolation, horizontally on the rows of the reduced prediction, then vertically), initPredBlockParams :139-160; size classes
+ * getMipSizeId (UnitTools.cpp:3748); weights MipData.h (shift 6, offset 32). */
+static void pred_mip(const int16_t* src, int stride, int w, int h, int modeIdx, int transpose, int bitDepth, int16_t* dst, ptrdiff_t ds)
+{
+  const int sizeId = (w == 4 && h == 4) ? 0 : (w == 4 || h == 4 || (w == 8 && h == 8)) ? 1 : 2;
+  const int bdry = sizeId == 0 ? 2 : 4, red = sizeId < 2 ? 4 : 8, upH = w / red, upV = h / red, inSize = 2 * bdry;
+  int top[64], left[64], in[8], inT[8];
+  for (int x = 0; x < w; x++) top[x] = AT(x + 1, 0);
+  for (int y = 0; y < h; y++) left[y] = AT(0, y + 1);
+  for (int k = 0; k < 2; k++) {                                  /* boundaryDownsampling1D */
+    const int* full = k ? left : top; const int len = k ? h : w;
+    for (int d = 0; d < bdry; d++) {
+      if (bdry < len) { const int f = len / bdry; int sum = 0; for (int j = 0; j < f; j++) sum += full[d * f + j]; in[k * bdry + d] = (sum + (f >> 1)) >> ilog2(f); }
+      else in[k * bdry + d] = full[d];
+    }
+  }
+  for (int d = 0; d < bdry; d++) { inT[d] = in[bdry + d]; inT[bdry + d] = in[d]; }
+  int* input = transpose ? inT : in;
+  const int inputOffset = input[0];
+  input[0] = sizeId < 2 ? (1 << (bitDepth - 1)) - inputOffset : 0;
+  for (int i = 1; i < inSize; i++) input[i] -= inputOffset;
+  const uint8_t* weight = sizeId == 0 ? &kMip4x4[modeIdx * 64] : sizeId == 1 ? &kMip8x8[modeIdx * 128] : &kMip16x16[modeIdx * 448];
+  const int redSize = sizeId == 2;
+  int sum = 0; for (int i = 0; i < inSize; i++) sum += input[i];
+  const int offset = 32 - 32 * sum, pmax = (1 << bitDepth) - 1;
+  int R[64];
+  for (int pos = 0; pos < red * red; pos++) {
+    int acc = offset;
+    for (int i = redSize; i < inSize; i++) acc += input[i] * weight[i - redSize];
+    weight += inSize - redSize;
+    const int v = iclip(0, pmax, (acc >> 6) + inputOffset);
+    if (transpose) R[(pos % red) * red + pos / red] = v; else R[pos] = v;
+  }
+  const int l2H = ilog2(upH), l2V = ilog2(upV);
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      const int k = y / upV, i = y % upV;
+      int hv[2];                                                  /* horizontally up-sampled value on reduced rows k - 1 and k at column x */
+      for (int q = 0; q < 2; q++) {
+        const int kk = k - 1 + q;
+        if (kk < 0) { hv[q] = top[x]; continue; }
+        if (upH == 1) { hv[q] = R[kk * red + x]; continue; }
+        const int j = x / upH, ii = x % upH;
+        const int before = j == 0 ? left[(kk + 1) * upV - 1] : R[kk * red + j - 1], behind = R[kk * red + j];
+        hv[q] = (int16_t)((int16_t)(before * upH + (upH >> 1)) + (ii + 1) * (int16_t)(behind - before)) >> l2H;
+      }
+      dst[y * ds + x] = upV == 1 ? (int16_t)hv[1] : (int16_t)(((int16_t)(hv[0] * upV + (upV >> 1)) + (i + 1) * (int16_t)(hv[1] - hv[0])) >> l2V);
+    }
+}
+
 void orc_intra_tu(const b200_geom* g, int16_t* const planes[3], const b200_intra_tu* t)
 {
   const int c = t->comp, w = 1 << t->log2w, h = 1 << t->log2h, mrl = c ? 0 : t->multiRefIdx, pmax = (1 << g->bitDepth) - 1;
@@ -219,6 +271,7 @@ void orc_intra_tu(const b200_geom* g, int16_t* const planes[3], const b200_intra
     for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) dst[y * ds + x] = dc;
   } else if (t->mode == B200_INTRA_BDPCM_HOR) { for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) dst[y * ds + x] = AT(0, y + 1); }
   else if (t->mode == B200_INTRA_BDPCM_VER) { for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) dst[y * ds + x] = AT(x + 1, 0); }
+  else if (t->mode == B200_INTRA_MIP) pred_mip(src, stride, w, h, t->mip & 0x7f, t->mip >> 7, g->bitDepth, dst, ds);
   else pred_angular(src, stride, w, h, c != 0, t->mode, mrl, 0, doPDPC, pmax, dst, ds);
   if (doPDPC && t->mode <= B200_INTRA_DC) {                    /* IntraPredSampleFilterCore :212 */
     const int scale = (t->log2w - 2 + t->log2h - 2 + 2) >> 2;

@@ -782,7 +782,13 @@ static int intraPredictCu( IntraPrediction& ip, CodingStructure& cs, CodingUnit&
                ip.m_neighborSize[0], ip.m_neighborSize[1], ip.m_neighborSize[2] );
       return -3;
     }
-    ip.predIntraAng( compID, piPred, cu, filt );
+    if( CU::isMIP( cu, toChannelType( compID ) ) )
+    {                                                          // DecCu.cpp:321-326
+      ip.initIntraPatternChType( tu, area );
+      ip.initIntraMip( cu, area );
+      ip.predIntraMip( compID, piPred, cu );
+    }
+    else ip.predIntraAng( compID, piPred, cu, filt );
     if( addResi && resi && resi[compID] )
     {                                                          // piReco.reconstruct( piPred, piResi, clpRng ) (DecCu.cpp:392)
       r.flags |= B200_INTRA_ADD_RESI;
@@ -835,6 +841,7 @@ extern "C" int ref_intra_case( int simd, const b200_geom* g, int16_t* const plan
       cu.setPredMode( MODE_INTRA );
       cu.intraDir[0] = c.dirL; cu.intraDir[1] = c.dirC;
       cu.setMultiRefIdx( c.multiRefIdx ); cu.setBdpcmMode( c.bdpcm ); cu.setBdpcmModeChroma( c.bdpcmC );
+      if( c.rsv[2] & 1 ) { cu.setMipFlag( true ); cu.setMipTransposedFlag( ( c.rsv[2] & 2 ) != 0 ); }      // dirL is the MIP mode index then
       cs.addTU( ua, CH_L, cu );
       if( all || i == numCus - 1 )
         if( int rc = intraPredictCu( ip, cs, cu, g, resi, c.rsv[1] != 0, recs, capRecs, n ) ) return rc;

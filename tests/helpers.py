@@ -188,6 +188,9 @@ def intra_picture_case(ref, rng, W, H, bd, ctu, simd, p_resi=0.5, **layout_kw):
         r = rng.random()
         if r < 0.15 and y % ctu: cus[i]["multiRefIdx"], cus[i]["dirL"] = int(rng.integers(1, 3)), int(rng.integers(1, 67))
         elif r < 0.25 and w <= 32 and h <= 32: cus[i]["bdpcm"] = int(rng.integers(1, 3))
+        elif r < 0.45:                                               # matrix intra prediction
+            n_modes = 16 if (w, h) == (4, 4) else 8 if (w == 4 or h == 4 or (w, h) == (8, 8)) else 6
+            cus[i]["dirL"] = int(rng.integers(0, n_modes)); cus[i]["rsv"][2] = 1 | (int(rng.integers(0, 2)) << 1)
         cus[i]["rsv"][0] = w < 8 or (w // 2) * (h // 2) < 16
         cus[i]["rsv"][1] = rng.random() < p_resi
     out = [p.copy() for p in planes]

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.ref
 CHROMA_MODES = [0, 1, 18, 50, 2, 34, 66, 70, 70, 70, 23, 45, 61]       # 70 = DM (PU::getFinalIntraMode -> the luma mode)
 
 
-def run_case(oracle, ref, rng, W, H, bd, ctu, simd, layout, k, dirL, dirC, mrl, bdpcm, bdpcmC=0):
+def run_case(oracle, ref, rng, W, H, bd, ctu, simd, layout, k, dirL, dirC, mrl, bdpcm, bdpcmC=0, mip=0):
     g = abi.make_geom(W, H, bd, ctu=ctu)
     planes = synth.noise_planes(rng, W, H, bd)
     cus = np.zeros(k + 1, synth.REF_INTRA_CU_DTYPE)
@@ -23,6 +23,7 @@ def run_case(oracle, ref, rng, W, H, bd, ctu, simd, layout, k, dirL, dirC, mrl, 
     x, y, w, h = layout[k]
     luma_only = w < 8 or (w // 2) * (h // 2) < 16                       # such luma blocks are CUs of a local dual tree: no chroma of their own
     cus[k]["rsv"][0] = luma_only
+    cus[k]["rsv"][2] = mip                                           # bit 0 MIP (dirL = MIP mode index), bit 1 transposed
     want = [p.copy() for p in planes]
     recs = np.zeros(3, abi.INTRA_TU_DTYPE)
     n = ref.ref_intra_case(simd, C.byref(g), abi.plane_ptrs(want), None, cus.ctypes.data, k + 1, 0, recs.ctypes.data, 3)
@@ -34,9 +35,9 @@ def run_case(oracle, ref, rng, W, H, bd, ctu, simd, layout, k, dirL, dirC, mrl, 
         assert np.array_equal(got[c], want[c]), (c, layout[k], dirL, dirC, mrl, bdpcm, recs[c])
     assert not np.array_equal(want[0][y:y + h, x:x + w], planes[0][y:y + h, x:x + w])
     # the synthetic generator used by the GPU tests derives the same records (availability from the decoding order, filter decision, DM)
-    mine = synth.gen_intra_records(rng, layout, W, H, modes={k: (dirL, dirC, mrl, bdpcm)}, upto=k)
+    mine = synth.gen_intra_records(rng, layout, W, H, modes={k: (dirL, dirC, mrl, bdpcm, mip)}, upto=k)
     mine = mine[-n:]
-    for f in ("x", "y", "log2w", "log2h", "comp", "mode", "multiRefIdx", "flags", "numAbove", "numLeft"):
+    for f in ("x", "y", "log2w", "log2h", "comp", "mode", "multiRefIdx", "flags", "numAbove", "numLeft", "mip"):
         assert np.array_equal(mine[f], recs[f]), (f, mine[f], recs[f], layout[k])
     return recs
 
@@ -90,3 +91,15 @@ def test_intra_picture_chain(oracle, ref, W, H, bd, ctu, simd, seed):
     for c in range(3):
         assert np.array_equal(got[c], want[c]), c
     assert (recs["flags"] & 4).any() and not (recs["flags"] & 4).all()
+
+
+@pytest.mark.parametrize("w,h", [(4, 4), (4, 8), (8, 4), (8, 8), (4, 16), (16, 4), (16, 16), (8, 16), (32, 8), (32, 32), (64, 64), (64, 16), (16, 64), (8, 32), (64, 32)])
+def test_intra_mip_all_modes(oracle, ref, w, h):
+    """Matrix intra prediction: every mode of the block's size class, plain and transposed, interior and picture-corner positions."""
+    rng = np.random.default_rng(w * 7 + h)
+    W, H, ctu = 256, 128, 128
+    n_modes = 16 if (w, h) == (4, 4) else 8 if (w == 4 or h == 4 or (w, h) == (8, 8)) else 6
+    for layout, k in (([(0, 0, 64, 64), (64, 0, 64, 64), (0, 64, 64, 64), (64, 64, w, h)], 3), ([(0, 0, w, h)], 0), ([(0, 0, 64, 64), (64, 0, w, h)], 1)):
+        for mode in range(n_modes):
+            for tr in (0, 1):
+                run_case(oracle, ref, rng, W, H, 10 if mode % 2 else 8, ctu, mode & 1, layout, k, mode, 70, 0, 0, mip=1 | (tr << 1))

@@ -27,7 +27,7 @@ def test_intra_picture_vs_oracle(b200, oracle, W, H, bd, ctu, min_size, p_resi, 
     for c in range(3):
         bad = np.argwhere(got[c] != want[c])
         assert len(bad) == 0, (c, len(bad), bad[:4].tolist())
-    assert len(np.unique(recs["mode"])) > 40 and (recs["multiRefIdx"] > 0).any() and (recs["mode"] >= 67).any()
+    assert len(np.unique(recs["mode"])) > 40 and (recs["multiRefIdx"] > 0).any() and (recs["mode"] == 67).any() and (recs["mode"] == abi.INTRA_MIP).any()
 
 
 def test_intra_predict_only_and_golden(b200, oracle):

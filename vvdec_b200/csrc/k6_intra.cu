@@ -210,6 +210,51 @@ __global__ void __launch_bounds__(IT_THREADS, 12) intra_kernel(const IntraParams
         }
         IT_STORE(x, y, v);
       }
+    } else if (mode == B200_INTRA_MIP) {
+      // ---- matrix intra prediction (PredictorMIP): reduced boundary -> matrix stage -> linear up-sampling; sM holds the reduced prediction
+      const int sizeId = (w == 4 && h == 4) ? 0 : (w == 4 || h == 4 || (w == 8 && h == 8)) ? 1 : 2;
+      const int bdry = sizeId == 0 ? 2 : 4, red = sizeId < 2 ? 4 : 8, upH = w / red, upV = h / red, inSize = 2 * bdry;
+      const int modeIdx = t.mip & 0x7f; const bool transpose = t.mip >> 7;
+      int16_t* in = sS;                                          // the (rebased) input vector, [inSize]; in[8] = the offset taken out
+      if (tid < inSize) {                                        // boundaryDownsampling1D of the top / left boundary, in the order the matrix wants
+        const bool fromLeft = (tid >= bdry) != transpose; const int d = tid % bdry, len = fromLeft ? h : w;
+        const int16_t* full = (fromLeft ? L : T) + 1;
+        int v;
+        if (bdry < len) { const int f = len / bdry; int sum = 0; for (int j = 0; j < f; j++) sum += full[d * f + j]; v = (sum + (f >> 1)) >> (31 - __clz(f)); }
+        else v = full[d];
+        in[tid] = (int16_t)v;
+      }
+      __syncthreads();
+      const int inputOffset = in[0];
+      __syncthreads();
+      if (tid < inSize) in[tid] = (int16_t)(tid == 0 ? (sizeId < 2 ? (1 << (P.bitDepth - 1)) - inputOffset : 0) : in[tid] - inputOffset);
+      __syncthreads();
+      if (tid < red * red) {                                     // computeReducedPred: one output per thread
+        const int redSize = sizeId == 2, stride = inSize - redSize;
+        const uint8_t* wgt = (sizeId == 0 ? kMip4x4 + modeIdx * 64 : sizeId == 1 ? kMip8x8 + modeIdx * 128 : kMip16x16 + modeIdx * 448) + tid * stride;
+        int sum = 0, acc = 0;
+        for (int i = 0; i < inSize; i++) sum += in[i];
+        for (int i = redSize; i < inSize; i++) acc += in[i] * wgt[i - redSize];
+        const int v = clip3(0, pmax, ((acc + 32 - 32 * sum) >> 6) + inputOffset);
+        sM[transpose ? (tid % red) * red + tid / red : tid] = (int16_t)v;
+      }
+      __syncthreads();
+      const int l2H = 31 - __clz(upH), l2V = 31 - __clz(upV);
+      for (int k = tid; k < w * h; k += IT_THREADS) {
+        const int y = k >> t.log2w, x = k & (w - 1), kr = y / upV, i = y % upV;
+        int hv[2];                                               // horizontally up-sampled rows kr - 1 (or the top boundary) and kr at column x
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          const int kk = kr - 1 + q;
+          if (kk < 0) hv[q] = T[x + 1];
+          else if (upH == 1) hv[q] = sM[kk * red + x];
+          else {
+            const int j = x / upH, ii = x % upH, before = j == 0 ? L[(kk + 1) * upV] : sM[kk * red + j - 1], behind = sM[kk * red + j];
+            hv[q] = (before * upH + (upH >> 1) + (ii + 1) * (behind - before)) >> l2H;
+          }
+        }
+        IT_STORE(x, y, upV == 1 ? hv[1] : (hv[0] * upV + (upV >> 1) + (i + 1) * (hv[1] - hv[0])) >> l2V);
+      }
     } else if (mode >= B200_INTRA_BDPCM_HOR) {
       for (int k = tid; k < w * h; k += IT_THREADS) { const int y = k >> t.log2w, x = k & (w - 1); IT_STORE(x, y, mode == B200_INTRA_BDPCM_HOR ? L[y + 1] : T[x + 1]); }
     } else {
@@ -282,7 +327,8 @@ __global__ void __launch_bounds__(256) intra_validate_kernel(const b200_intra_tu
   const b200_intra_tu t = tus[i];
   const int w = 1 << t.log2w, h = 1 << t.log2h, pw = t.comp ? W >> 1 : W, ph = t.comp ? H >> 1 : H, unit = t.comp ? 2 : 4, m = t.multiRefIdx;
   bool ok = t.comp < (chroma ? 3 : 1) && t.log2w >= 2 && t.log2w <= 6 && t.log2h >= 1 && t.log2h <= 6 && t.x + w <= pw && t.y + h <= ph && !(t.x % unit) && !(t.y % unit);
-  ok = ok && t.mode <= B200_INTRA_BDPCM_VER && m <= 2 && (!m || !t.comp);
+  ok = ok && t.mode <= B200_INTRA_MIP && m <= 2 && (!m || !t.comp);
+  if (t.mode == B200_INTRA_MIP) ok = ok && !t.comp && !m && (t.mip & 0x7f) < ((w == 4 && h == 4) ? 16 : (w == 4 || h == 4 || (w == 8 && h == 8)) ? 8 : 6);
   ok = ok && t.numAbove <= 2 * w / unit && t.numLeft <= 2 * h / unit && (!t.numAbove || t.y > m) && (!t.numLeft || t.x > m)
           && (!(t.flags & B200_INTRA_AVAIL_TL) || (t.x > m && t.y > m)) && t.x + (int)t.numAbove * unit <= pw && t.y + (int)t.numLeft * unit <= ph;
   if (!ok) atomicOr(&meta[LM_ERR], 8);

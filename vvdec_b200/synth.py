@@ -664,7 +664,7 @@ def intra_filter_ref(w, h, mode, mrl, bdpcm):
     return diff > _INTRA_THR[(int(np.log2(w)) + int(np.log2(h))) >> 1] and (ang & 31) == 0
 
 
-def gen_intra_records(rng, layout, W, H, modes=None, p_mrl=0.15, p_bdpcm=0.08, p_resi=0.0, upto=None, only=None):
+def gen_intra_records(rng, layout, W, H, modes=None, p_mrl=0.15, p_bdpcm=0.08, p_resi=0.0, upto=None, only=None, p_mip=0.15):
     """b200_intra_tu records (Y, Cb, Cr per CU, decoding order) for a single-tree all-intra layout of gen_intra_layout: random modes, MRL on some luma
     blocks, BDPCM prediction on some, availability as xFillReferenceSamples derives it from the decoding order (pinned against the reference's own
     analysis through the glue flattener by tests/test_intra_oracle_vs_ref.py).  Luma blocks whose chroma would be narrower than 4 or smaller than 16
@@ -675,13 +675,18 @@ def gen_intra_records(rng, layout, W, H, modes=None, p_mrl=0.15, p_bdpcm=0.08, p
     recs = []
     chroma_modes = [0, 1, 18, 50, 2, 34, 66, -1, -1, -1, 23, 45, 61]
     for i, (x, y, w, h) in enumerate(layout if upto is None else layout[:upto + 1]):
-        if modes is not None and i in modes: dirL, dirC, mrl, bdpcm = modes[i]
+        mip = 0
+        if modes is not None and i in modes:
+            m = modes[i]; dirL, dirC, mrl, bdpcm = m[:4]; mip = m[4] if len(m) > 4 else 0
         else:
             dirL, mrl, bdpcm = int(rng.integers(0, 67)), 0, 0
             if rng.random() < p_mrl and y % 128: mrl, dirL = int(rng.integers(1, 3)), int(rng.integers(1, 67))
             elif rng.random() < p_bdpcm and w <= 32 and h <= 32: bdpcm = int(rng.integers(1, 3))
+            elif rng.random() < p_mip:                                   # matrix intra prediction: dirL is the MIP mode index of the size class
+                n_modes = 16 if (w, h) == (4, 4) else 8 if (w == 4 or h == 4 or (w, h) == (8, 8)) else 6
+                dirL, mip = int(rng.integers(0, n_modes)), 1 | (int(rng.integers(0, 2)) << 1)
             dirC = chroma_modes[int(rng.integers(len(chroma_modes)))]
-        if dirC < 0 or dirC == 70: dirC = dirL                          # DM
+        if dirC < 0 or dirC == 70: dirC = 0 if mip else dirL            # DM (a MIP luma CU counts as planar: PU::getCoLocatedIntraLumaMode)
         if only is not None and not only[i]: continue                   # an inter CU of a mixed picture: a neighbour, not a block of the list
         def avail(ux, uy): return 0 <= ux < owner.shape[1] and 0 <= uy < owner.shape[0] and owner[uy, ux] < i
         tl = avail(x // 4 - 1, y // 4 - 1)
@@ -694,11 +699,12 @@ def gen_intra_records(rng, layout, W, H, modes=None, p_mrl=0.15, p_bdpcm=0.08, p
             r = np.zeros((), A.INTRA_TU_DTYPE)
             sh = 1 if c else 0
             r["x"], r["y"], r["log2w"], r["log2h"], r["comp"] = x >> sh, y >> sh, int(np.log2(w >> sh)), int(np.log2(h >> sh)), c
-            if c == 0: r["mode"] = (A.INTRA_BDPCM_HOR if bdpcm == 1 else A.INTRA_BDPCM_VER) if bdpcm else dirL
+            if c == 0 and mip: r["mode"], r["mip"] = A.INTRA_MIP, dirL | ((mip >> 1) << 7)
+            elif c == 0: r["mode"] = (A.INTRA_BDPCM_HOR if bdpcm == 1 else A.INTRA_BDPCM_VER) if bdpcm else dirL
             else: r["mode"] = dirC
             r["multiRefIdx"] = mrl if c == 0 else 0
             fl = A.INTRA_AVAIL_TL if tl else 0
-            if c == 0 and intra_filter_ref(w, h, dirL, mrl, bdpcm): fl |= A.INTRA_FILTER_REF
+            if c == 0 and not mip and intra_filter_ref(w, h, dirL, mrl, bdpcm): fl |= A.INTRA_FILTER_REF
             if rng.random() < p_resi: fl |= 4
             r["flags"], r["numAbove"], r["numLeft"] = fl, na, nl
             recs.append(r)

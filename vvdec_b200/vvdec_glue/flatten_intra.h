@@ -58,14 +58,17 @@ inline FlattenIntraResult flattenIntraTU( const TransformUnit& tu, const Compone
   const ChannelType      chType = toChannelType( compID );
   const CompArea&        area   = tu.blocks[compID];
   memset( &r, 0, sizeof( r ) );
-  if( cu.colorTransform() || CU::isMIP( cu, chType ) || ( isLuma( compID ) && cu.ispMode() ) ) return FLATTEN_INTRA_UNSUPPORTED;
+  if( cu.colorTransform() || ( isLuma( compID ) && cu.ispMode() ) ) return FLATTEN_INTRA_UNSUPPORTED;
+  const bool mip = CU::isMIP( cu, chType );
+  if( mip && !isLuma( compID ) ) return FLATTEN_INTRA_UNSUPPORTED;                                       // MIP chroma exists in 4:4:4 only
   const uint32_t finalMode = PU::getFinalIntraMode( cu, chType );
   if( !isLuma( compID ) && PU::isLMCMode( finalMode ) ) return FLATTEN_INTRA_UNSUPPORTED;
   const int bdpcm = isLuma( compID ) ? cu.bdpcmMode() : cu.bdpcmModeChroma();
   r.x = (uint16_t) area.x; r.y = (uint16_t) area.y; r.log2w = (uint8_t) getLog2( area.width ); r.log2h = (uint8_t) getLog2( area.height ); r.comp = (uint8_t) compID;
   r.mode = bdpcm ? ( bdpcm == 1 ? B200_INTRA_BDPCM_HOR : B200_INTRA_BDPCM_VER ) : (uint8_t) finalMode;
+  if( mip ) { r.mode = B200_INTRA_MIP; r.mip = (uint8_t) ( cu.intraDir[CHANNEL_TYPE_LUMA] | ( cu.mipTransposedFlag() ? 0x80 : 0 ) ); }        // predIntraMip :1926
   r.multiRefIdx = isLuma( compID ) ? (uint8_t) cu.multiRefIdx() : 0;
-  if( isLuma( compID ) && IntraPrediction::useFilteredIntraRefSamples( compID, cu, tu ) ) r.flags |= B200_INTRA_FILTER_REF;    // DecCu.cpp:339
+  if( !mip && isLuma( compID ) && IntraPrediction::useFilteredIntraRefSamples( compID, cu, tu ) ) r.flags |= B200_INTRA_FILTER_REF;    // DecCu.cpp:339 (MIP: unfiltered, :323)
 
   // neighbourhood (xFillReferenceSamples :1086-1130).  The reference analyses it once per TU, for the first component of the CU's channel
   // type, and reuses the three counts for the other components (m_lastCUidx, :1101): in a single tree the chroma blocks take the luma block's.
