@@ -250,10 +250,10 @@ __global__ void __launch_bounds__(IT_THREADS, 12) intra_kernel(const IntraParams
           else if (upH == 1) hv[q] = sM[kk * red + x];
           else {
             const int j = x / upH, ii = x % upH, before = j == 0 ? L[(kk + 1) * upV] : sM[kk * red + j - 1], behind = sM[kk * red + j];
-            hv[q] = (before * upH + (upH >> 1) + (ii + 1) * (behind - before)) >> l2H;
+            hv[q] = (int16_t)(before * upH + (upH >> 1) + (ii + 1) * (behind - before)) >> l2H;   // the reference accumulates in Pel (int16): wraps at 12 bit x 16
           }
         }
-        IT_STORE(x, y, upV == 1 ? hv[1] : (hv[0] * upV + (upV >> 1) + (i + 1) * (hv[1] - hv[0])) >> l2V);
+        IT_STORE(x, y, upV == 1 ? hv[1] : (int16_t)(hv[0] * upV + (upV >> 1) + (i + 1) * (hv[1] - hv[0])) >> l2V);
       }
     } else if (mode >= B200_INTRA_BDPCM_HOR) {
       for (int k = tid; k < w * h; k += IT_THREADS) { const int y = k >> t.log2w, x = k & (w - 1); IT_STORE(x, y, mode == B200_INTRA_BDPCM_HOR ? L[y + 1] : T[x + 1]); }
