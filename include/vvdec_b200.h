@@ -260,8 +260,11 @@ B200_API int b200_mc_predict_wp(const b200_geom* g, int16_t* const dst[3], const
  * three counts.  Not covered (the flattener must refuse them): CCLM, ISP, palette, ACT.
  * Blocks of one list are processed in list order; a block may read what earlier blocks of the list wrote. */
 enum { B200_INTRA_PLANAR = 0, B200_INTRA_DC = 1 /* 2..66 angular */, B200_INTRA_BDPCM_HOR = 67, B200_INTRA_BDPCM_VER = 68,
-       B200_INTRA_MIP = 69 /* matrix intra prediction: b200_intra_tu::mip = mode index | transposed << 7 */ };
-enum { B200_INTRA_FILTER_REF = 1, B200_INTRA_AVAIL_TL = 2, B200_INTRA_ADD_RESI = 4 /* reconstruct: clip(pred + residual), see b200_intra_reconstruct */ };
+       B200_INTRA_MIP = 69 /* matrix intra prediction: b200_intra_tu::mip = mode index | transposed << 7 */,
+       B200_INTRA_LM = 70, B200_INTRA_MDLM_L = 71, B200_INTRA_MDLM_T = 72 /* cross-component linear model (LM_CHROMA_IDX, MDLM_L_IDX, MDLM_T_IDX), chroma only */ };
+enum { B200_INTRA_FILTER_REF = 1, B200_INTRA_AVAIL_TL = 2, B200_INTRA_ADD_RESI = 4 /* reconstruct: clip(pred + residual), see b200_intra_reconstruct */,
+       B200_INTRA_LM_ABOVE = 8, B200_INTRA_LM_LEFT = 16 /* CCLM: the CU has an above / left neighbour (xGetLumaRecPixels :1461,:1464) */,
+       B200_INTRA_LM_COLLOCATED = 32 /* CCLM: sps_chroma_vertical_collocated_flag (SPS::getCclmCollocatedChromaFlag) */ };
 typedef struct b200_intra_tu {
   uint16_t x, y;          /* top-left in the component's plane, samples                                              */
   uint8_t  log2w, log2h;  /* 2..6 (chroma: height may be 2 = log2h 1)                                                */
@@ -272,7 +275,8 @@ typedef struct b200_intra_tu {
   uint8_t  numAbove;      /* m_neighborSize[1]: available units above + above-right (unit = 4 luma / 2 chroma samples) */
   uint8_t  numLeft;       /* m_neighborSize[2]: available units left + below-left                                    */
   uint8_t  mip;           /* B200_INTRA_MIP: cu.intraDir[luma] (MIP mode index) | cu.mipTransposedFlag() << 7                    */
-  uint8_t  rsv[3];
+  uint8_t  lmAbove, lmLeft;/* CCLM: template units (2 chroma samples) xGetLMParameters finds available above(+right) / left(+below) (:1762-1795) */
+  uint8_t  rsv;
 } b200_intra_tu;          /* 16 bytes */
 /* Kernel-level K6: host planes in (reconstructed neighbourhood), prediction written into the blocks, host planes out. */
 B200_API int b200_intra_predict(const b200_geom* g, int16_t* const planes[3], const b200_intra_tu* tus, size_t numTus);

@@ -249,6 +249,87 @@ static void pred_mip(const int16_t* src, int stride, int w, int h, int modeIdx, 
     }
 }
 
+/* Cross-component linear model (CCLM), 4:2:0.  Follows IntraPrediction.cpp: xGetLumaRecPixels :1403-1683 (down-sampled reconstructed luma of the
+ * block, one row above and one column left; 3-tap at the first row of a CTU, 5-tap for collocated chroma, else 6-tap, with edge replication where
+ * the CU has no left / above neighbour), xGetLMParameters :1694-1904 (up to four template positions, min / max pairs, a = diffC * DivSig >> y,
+ * b, shift), predIntraChromaLM :519-539 (clip(((a * luma) >> shift) + b), Buffer.cpp:99 linTfCore).
+ * T / L: the block's unfiltered chroma reference arrays (curChroma0 = getPredictorPtr).  luma: reconstructed luma plane. */
+static void pred_cclm(const b200_geom* g, const int16_t* luma, ptrdiff_t ls, const int16_t* src, int stride, const b200_intra_tu* t, int16_t* dst, ptrdiff_t ds)
+{
+  const int w = 1 << t->log2w, h = 1 << t->log2h, mode = t->mode, unit = 2, pmax = (1 << g->bitDepth) - 1;
+  const int aboveCu = (t->flags & B200_INTRA_LM_ABOVE) != 0, leftCu = (t->flags & B200_INTRA_LM_LEFT) != 0, colloc = (t->flags & B200_INTRA_LM_COLLOCATED) != 0;
+  const int lx = t->x * 2, ly = t->y * 2;
+  const int firstRowOfCtu = (ly & (g->ctuSize - 1)) == 0;
+  const int16_t* rec = luma + (ptrdiff_t)ly * ls + lx;
+  enum { TS = 2 * 64 + 1 };
+  static _Thread_local int16_t tmp[(64 + 1) * TS + TS];
+  int16_t* d0 = tmp + TS + 1;                                       /* (0,0) of the block; row -1 / column -1 hold the template */
+  /* above template row */
+  if (aboveCu) {
+    /* the reference fills 2W samples for MDLM_T whatever exists there; only the lmAbove available units are ever read (:1770), so only those are made */
+    const int n = mode == B200_INTRA_MDLM_T ? unit * t->lmAbove : w;
+    for (int i = 0; i < n; i++) {
+      const int edge = i == 0 && !leftCu;
+      if (firstRowOfCtu) { const int16_t* p = rec - ls; d0[-TS + i] = (int16_t)((p[2 * i] * 2 + p[2 * i - (edge ? 0 : 1)] + p[2 * i + 1] + 2) >> 2); }
+      else if (colloc) { const int16_t* p = rec - 2 * ls; d0[-TS + i] = (int16_t)((p[2 * i - ls] + p[2 * i] * 4 + p[2 * i - (edge ? 0 : 1)] + p[2 * i + 1] + p[2 * i + ls] + 4) >> 3); }
+      else { const int16_t* p = rec - 2 * ls; const int m = edge ? 0 : 1;
+             d0[-TS + i] = (int16_t)((p[2 * i] * 2 + p[2 * i - m] + p[2 * i + 1] + p[2 * i + ls] * 2 + p[2 * i - m + ls] + p[2 * i + 1 + ls] + 4) >> 3); }
+    }
+  }
+  /* left template column */
+  if (leftCu) {
+    const int n = mode == B200_INTRA_MDLM_L ? unit * t->lmLeft : h;
+    const int16_t* p = rec - 3;
+    for (int j = 0; j < n; j++, p += 2 * ls) {
+      if (colloc) d0[j * TS - 1] = (int16_t)((p[1 - ((j == 0 && !aboveCu) ? 0 : ls)] + p[1] * 4 + p[0] + p[2] + p[1 + ls] + 4) >> 3);
+      else d0[j * TS - 1] = (int16_t)((p[1] * 2 + p[0] + p[2] + p[1 + ls] * 2 + p[ls] + p[2 + ls] + 4) >> 3);
+    }
+  }
+  /* the block */
+  for (int j = 0; j < h; j++) {
+    const int16_t* p = rec + (ptrdiff_t)2 * j * ls;
+    for (int i = 0; i < w; i++) {
+      const int m = (i == 0 && !leftCu) ? 0 : 1;
+      if (colloc) { const int up = (j == 0 && !aboveCu) ? 0 : ls; d0[j * TS + i] = (int16_t)((p[2 * i - up] + p[2 * i] * 4 + p[2 * i - m] + p[2 * i + 1] + p[2 * i + ls] + 4) >> 3); }
+      else d0[j * TS + i] = (int16_t)((p[2 * i] * 2 + p[2 * i + 1] + p[2 * i - m] + p[2 * i + ls] * 2 + p[2 * i + 1 + ls] + p[2 * i - m + ls] + 4) >> 3);
+    }
+  }
+  /* parameters */
+  const int tuWU = w / unit, tuHU = h / unit;
+  int aboveAvail = 0, leftAvail = 0, topNum = 0, leftNum = 0;
+  if (mode == B200_INTRA_MDLM_T) { aboveAvail = t->lmAbove >= tuWU; topNum = unit * t->lmAbove; }
+  else if (mode == B200_INTRA_MDLM_L) { leftAvail = t->lmLeft >= tuHU; leftNum = unit * t->lmLeft; }
+  else { aboveAvail = aboveCu; leftAvail = leftCu; topNum = w; leftNum = h; }
+  const int aboveIs4 = leftAvail ? 0 : 1, leftIs4 = aboveAvail ? 0 : 1;
+  const int start0 = topNum >> (2 + aboveIs4), step0 = imax(1, topNum >> (1 + aboveIs4)), start1 = leftNum >> (2 + leftIs4), step1 = imax(1, leftNum >> (1 + leftIs4));
+  int sl[4] = {0, 0, 0, 0}, sc[4] = {0, 0, 0, 0}, cntT = 0, cntL = 0;
+  if (aboveAvail) { cntT = imin(topNum, (1 + aboveIs4) << 1); for (int k = 0, pos = start0; k < cntT; k++, pos += step0) { sl[k] = d0[-TS + pos]; sc[k] = AT(1 + pos, 0); } }
+  if (leftAvail) { cntL = imin(leftNum, (1 + leftIs4) << 1); for (int k = 0, pos = start1; k < cntL; k++, pos += step1) { sl[k + cntT] = d0[pos * TS - 1]; sc[k + cntT] = AT(0, 1 + pos); } }
+  if (cntT + cntL == 2) { sl[3] = sl[0]; sc[3] = sc[0]; sl[2] = sl[1]; sc[2] = sc[1]; sl[0] = sl[1]; sc[0] = sc[1]; sl[1] = sl[3]; sc[1] = sc[3]; }
+  int mn[2] = {0, 2}, mx[2] = {1, 3}, *pmn = mn, *pmx = mx, tt;
+  if (sl[pmn[0]] > sl[pmn[1]]) { tt = pmn[0]; pmn[0] = pmn[1]; pmn[1] = tt; }
+  if (sl[pmx[0]] > sl[pmx[1]]) { tt = pmx[0]; pmx[0] = pmx[1]; pmx[1] = tt; }
+  if (sl[pmn[0]] > sl[pmx[1]]) { int* q = pmn; pmn = pmx; pmx = q; }
+  if (sl[pmn[1]] > sl[pmx[0]]) { tt = pmn[1]; pmn[1] = pmx[0]; pmx[0] = tt; }
+  const int minL = (sl[pmn[0]] + sl[pmn[1]] + 1) >> 1, minC = (sc[pmn[0]] + sc[pmn[1]] + 1) >> 1, maxL = (sl[pmx[0]] + sl[pmx[1]] + 1) >> 1, maxC = (sc[pmx[0]] + sc[pmx[1]] + 1) >> 1;
+  int a, b, shift;
+  if (leftAvail || aboveAvail) {
+    const int diff = maxL - minL;
+    if (diff > 0) {
+      static const uint8_t divSig[16] = {0, 7, 6, 5, 5, 4, 4, 3, 3, 2, 2, 1, 1, 1, 1, 0};
+      const int diffC = maxC - minC;
+      int x = ilog2(diff);
+      const int normDiff = (diff << 4 >> x) & 15, v = divSig[normDiff] | 8;
+      x += normDiff != 0;
+      const int y = diffC == 0 ? 0 : ilog2(abs(diffC)) + 1, add = 1 << y >> 1;
+      a = (diffC * v + add) >> y; shift = 3 + x - y;
+      if (shift < 1) { shift = 1; a = a == 0 ? 0 : a < 0 ? -15 : 15; }
+      b = minC - ((a * minL) >> shift);
+    } else { a = 0; b = minC; shift = 0; }
+  } else { a = 0; b = 1 << (g->bitDepth - 1); shift = 0; }
+  for (int j = 0; j < h; j++) for (int i = 0; i < w; i++) dst[j * ds + i] = (int16_t)iclip(0, pmax, ((a * d0[j * TS + i]) >> shift) + b);
+}
+
 void orc_intra_tu(const b200_geom* g, int16_t* const planes[3], const b200_intra_tu* t)
 {
   const int c = t->comp, w = 1 << t->log2w, h = 1 << t->log2h, mrl = c ? 0 : t->multiRefIdx, pmax = (1 << g->bitDepth) - 1;
@@ -271,6 +352,7 @@ void orc_intra_tu(const b200_geom* g, int16_t* const planes[3], const b200_intra
     for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) dst[y * ds + x] = dc;
   } else if (t->mode == B200_INTRA_BDPCM_HOR) { for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) dst[y * ds + x] = AT(0, y + 1); }
   else if (t->mode == B200_INTRA_BDPCM_VER) { for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) dst[y * ds + x] = AT(x + 1, 0); }
+  else if (t->mode >= B200_INTRA_LM) pred_cclm(g, planes[0], g->stride[0], src, stride, t, dst, ds);
   else if (t->mode == B200_INTRA_MIP) pred_mip(src, stride, w, h, t->mip & 0x7f, t->mip >> 7, g->bitDepth, dst, ds);
   else pred_angular(src, stride, w, h, c != 0, t->mode, mrl, 0, doPDPC, pmax, dst, ds);
   if (doPDPC && t->mode <= B200_INTRA_DC) {                    /* IntraPredSampleFilterCore :212 */

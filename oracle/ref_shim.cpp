@@ -788,6 +788,12 @@ static int intraPredictCu( IntraPrediction& ip, CodingStructure& cs, CodingUnit&
       ip.initIntraMip( cu, area );
       ip.predIntraMip( compID, piPred, cu );
     }
+    else if( compID != COMPONENT_Y && PU::isLMCMode( PU::getFinalIntraMode( cu, toChannelType( compID ) ) ) )
+    {                                                          // DecCu.cpp:327-332
+      ip.initIntraPatternChType( tu, area );
+      ip.xGetLumaRecPixels( cu, area );
+      ip.predIntraChromaLM( compID, piPred, cu, area, PU::getFinalIntraMode( cu, toChannelType( compID ) ) );
+    }
     else ip.predIntraAng( compID, piPred, cu, filt );
     if( addResi && resi && resi[compID] )
     {                                                          // piReco.reconstruct( piPred, piResi, clpRng ) (DecCu.cpp:392)
@@ -807,7 +813,7 @@ static int intraPredictCu( IntraPrediction& ip, CodingStructure& cs, CodingUnit&
 
 // all != 0: every CU of the list is predicted (and, with rsv[1] set and resi given, reconstructed) in order — a whole intra picture
 extern "C" int ref_intra_case( int simd, const b200_geom* g, int16_t* const planes[3], const int16_t* const resi[3], const ref_intra_cu* cus, int numCus, int all,
-                               b200_intra_tu* recs, int capRecs )
+                               b200_intra_tu* recs, int capRecs, int cclmCollocated )
 {
   try
   {
@@ -817,6 +823,7 @@ extern "C" int ref_intra_case( int simd, const b200_geom* g, int16_t* const plan
     const PreCalcValues& pcv = *cs.pcv;
     Slice* sl = cur.pic.slices[0];
     sl->setSliceType( I_SLICE );
+    cur.sps->setVerCollocatedChromaFlag( cclmCollocated != 0 );        // = getCclmCollocatedChromaFlag (Slice.h:1793)
     IntraPrediction ip;
     ip.init( pcv.chrFormat, g->bitDepth );                              // x86: installs the SIMD kernels (IntraPrediction.cpp:399)
     if( !simd )

@@ -91,7 +91,7 @@ def load_ref():
     lib.ref_flatten_pu_case.argtypes = [C.c_int, C.POINTER(abi.Geom), C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, PL, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.ref_write_component.argtypes = [i16p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS"), C.c_size_t]
     lib.ref_write_component.restype = C.c_size_t
-    lib.ref_intra_case.argtypes = [C.c_int, C.POINTER(abi.Geom), PL, PL, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    lib.ref_intra_case.argtypes = [C.c_int, C.POINTER(abi.Geom), PL, PL, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
     lib.ref_film_grain.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, PL, C.POINTER(C.c_ssize_t)] + [C.c_void_p] * 4 + [C.POINTER(C.c_int), C.c_void_p]
     lib.ref_picture_hash.argtypes = [C.c_int, C.c_int, PL, C.POINTER(C.c_ssize_t), C.c_int, C.c_int, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS"), C.c_int]
     lib.ref_lmcs_build.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(abi.Lmcs), i16p]
@@ -173,7 +173,7 @@ def oracle_decompress(oracle, g, dpb, pic):
     return cur, dm
 
 
-def intra_picture_case(ref, rng, W, H, bd, ctu, simd, p_resi=0.5, **layout_kw):
+def intra_picture_case(ref, rng, W, H, bd, ctu, simd, p_resi=0.5, colloc=0, **layout_kw):
     """A whole all-intra picture through the real IntraPrediction: every CU predicted from the reconstruction of the earlier ones, with the
     pred + residual step on some CUs.  Returns geometry, start planes, residual planes, records (from the reference's flattener) and the result."""
     g = abi.make_geom(W, H, bd, ctu=ctu)
@@ -181,7 +181,7 @@ def intra_picture_case(ref, rng, W, H, bd, ctu, simd, p_resi=0.5, **layout_kw):
     planes = synth.noise_planes(rng, W, H, bd)
     resi = [rng.integers(-40, 41, size=p.shape).astype(np.int16) for p in planes]
     cus = np.zeros(len(layout), synth.REF_INTRA_CU_DTYPE)
-    chroma = [0, 1, 18, 50, 2, 34, 66, 70, 70, 70, 23, 45, 61]
+    chroma = [0, 1, 18, 50, 2, 34, 66, 70, 70, 70, 23, 45, 61, 67, 67, 68, 69]      # 67..69: LM, MDLM_L, MDLM_T
     for i, (x, y, w, h) in enumerate(layout):
         cus[i]["x"], cus[i]["y"], cus[i]["w"], cus[i]["h"] = x, y, w, h
         cus[i]["dirL"], cus[i]["dirC"] = int(rng.integers(0, 67)), chroma[int(rng.integers(len(chroma)))]
@@ -195,6 +195,6 @@ def intra_picture_case(ref, rng, W, H, bd, ctu, simd, p_resi=0.5, **layout_kw):
         cus[i]["rsv"][1] = rng.random() < p_resi
     out = [p.copy() for p in planes]
     recs = np.zeros(3 * len(layout), abi.INTRA_TU_DTYPE)
-    n = ref.ref_intra_case(simd, C.byref(g), abi.plane_ptrs(out), abi.plane_ptrs(resi), cus.ctypes.data, len(layout), 1, recs.ctypes.data, len(recs))
+    n = ref.ref_intra_case(simd, C.byref(g), abi.plane_ptrs(out), abi.plane_ptrs(resi), cus.ctypes.data, len(layout), 1, recs.ctypes.data, len(recs), colloc)
     assert n > 0, n
     return g, planes, resi, recs[:n], out

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.ref
 CHROMA_MODES = [0, 1, 18, 50, 2, 34, 66, 70, 70, 70, 23, 45, 61]       # 70 = DM (PU::getFinalIntraMode -> the luma mode)
 
 
-def run_case(oracle, ref, rng, W, H, bd, ctu, simd, layout, k, dirL, dirC, mrl, bdpcm, bdpcmC=0, mip=0):
+def run_case(oracle, ref, rng, W, H, bd, ctu, simd, layout, k, dirL, dirC, mrl, bdpcm, bdpcmC=0, mip=0, colloc=0):
     g = abi.make_geom(W, H, bd, ctu=ctu)
     planes = synth.noise_planes(rng, W, H, bd)
     cus = np.zeros(k + 1, synth.REF_INTRA_CU_DTYPE)
@@ -26,7 +26,7 @@ def run_case(oracle, ref, rng, W, H, bd, ctu, simd, layout, k, dirL, dirC, mrl, 
     cus[k]["rsv"][2] = mip                                           # bit 0 MIP (dirL = MIP mode index), bit 1 transposed
     want = [p.copy() for p in planes]
     recs = np.zeros(3, abi.INTRA_TU_DTYPE)
-    n = ref.ref_intra_case(simd, C.byref(g), abi.plane_ptrs(want), None, cus.ctypes.data, k + 1, 0, recs.ctypes.data, 3)
+    n = ref.ref_intra_case(simd, C.byref(g), abi.plane_ptrs(want), None, cus.ctypes.data, k + 1, 0, recs.ctypes.data, 3, colloc)
     assert n == (1 if luma_only else 3), n
     recs = recs[:n]
     got = [p.copy() for p in planes]
@@ -35,9 +35,9 @@ def run_case(oracle, ref, rng, W, H, bd, ctu, simd, layout, k, dirL, dirC, mrl, 
         assert np.array_equal(got[c], want[c]), (c, layout[k], dirL, dirC, mrl, bdpcm, recs[c])
     assert not np.array_equal(want[0][y:y + h, x:x + w], planes[0][y:y + h, x:x + w])
     # the synthetic generator used by the GPU tests derives the same records (availability from the decoding order, filter decision, DM)
-    mine = synth.gen_intra_records(rng, layout, W, H, modes={k: (dirL, dirC, mrl, bdpcm, mip)}, upto=k)
+    mine = synth.gen_intra_records(rng, layout, W, H, modes={k: (dirL, dirC, mrl, bdpcm, mip)}, upto=k, colloc=colloc)
     mine = mine[-n:]
-    for f in ("x", "y", "log2w", "log2h", "comp", "mode", "multiRefIdx", "flags", "numAbove", "numLeft", "mip"):
+    for f in ("x", "y", "log2w", "log2h", "comp", "mode", "multiRefIdx", "flags", "numAbove", "numLeft", "mip", "lmAbove", "lmLeft"):
         assert np.array_equal(mine[f], recs[f]), (f, mine[f], recs[f], layout[k])
     return recs
 
@@ -85,7 +85,8 @@ from tests.helpers import intra_picture_case
 @pytest.mark.parametrize("W,H,bd,ctu,simd,seed", [(256, 128, 10, 128, 1, 11), (192, 128, 10, 64, 0, 12), (416, 240, 8, 128, 1, 13), (256, 256, 12, 128, 0, 14)])
 def test_intra_picture_chain(oracle, ref, W, H, bd, ctu, simd, seed):
     rng = np.random.default_rng(seed)
-    g, planes, resi, recs, want = intra_picture_case(ref, rng, W, H, bd, ctu, simd, min_size=8)
+    g, planes, resi, recs, want = intra_picture_case(ref, rng, W, H, bd, ctu, simd, colloc=seed & 1, min_size=8)
+    assert (recs["mode"] >= abi.INTRA_LM).any() and (recs["mode"] == abi.INTRA_MIP).any()
     got = [p.copy() for p in planes]
     oracle.orc_intra_reconstruct(C.byref(g), abi.plane_ptrs(got), abi.plane_ptrs(resi), recs.ctypes.data, len(recs))
     for c in range(3):
@@ -103,3 +104,20 @@ def test_intra_mip_all_modes(oracle, ref, w, h):
         for mode in range(n_modes):
             for tr in (0, 1):
                 run_case(oracle, ref, rng, W, H, 10 if mode % 2 else 8, ctu, mode & 1, layout, k, mode, 70, 0, 0, mip=1 | (tr << 1))
+
+
+@pytest.mark.parametrize("colloc", [0, 1])
+@pytest.mark.parametrize("w,h", [(8, 8), (16, 16), (32, 32), (64, 64), (16, 8), (8, 16), (64, 16), (16, 64), (32, 8), (8, 32), (16, 4), (64, 32)])
+def test_intra_cclm(oracle, ref, w, h, colloc):
+    """Cross-component linear model (LM, MDLM_L, MDLM_T): luma down-sampling (3 / 5 / 6 tap: first CTU row, collocated chroma, default), template
+    selection and parameter derivation, for interior blocks, CTU-row starts and picture edges (no left / no above neighbour)."""
+    rng = np.random.default_rng(w * 5 + h + colloc)
+    W, H, ctu = 256, 256, 128
+    layouts = [([(0, 0, 64, 64), (64, 0, 64, 64), (0, 64, 64, 64), (64, 64, w, h)], 3),          # interior
+               ([(0, 0, 128, 64), (0, 64, 64, 64), (64, 64, 64, 64), (0, 128, w, h)], 3) if False else ([(0, 0, 64, 64), (64, 0, 64, 64), (0, 64, 64, 64), (64, 64, 64, 64), (0, 128, w, h)], 4),   # first row of a CTU, left picture edge
+               ([(0, 0, w, h)], 0),                                                               # picture corner: no template at all
+               ([(0, 0, 64, 64), (64, 0, w, h)], 1)]                                              # top picture edge: left only
+    for layout, k in layouts:
+        for mode in (67, 68, 69):
+            for rep in range(3):
+                run_case(oracle, ref, rng, W, H, 10 if rep else 8, ctu, rep & 1, layout, k, int(rng.integers(0, 67)), mode, 0, 0, colloc=colloc)

@@ -664,7 +664,7 @@ def intra_filter_ref(w, h, mode, mrl, bdpcm):
     return diff > _INTRA_THR[(int(np.log2(w)) + int(np.log2(h))) >> 1] and (ang & 31) == 0
 
 
-def gen_intra_records(rng, layout, W, H, modes=None, p_mrl=0.15, p_bdpcm=0.08, p_resi=0.0, upto=None, only=None, p_mip=0.15):
+def gen_intra_records(rng, layout, W, H, modes=None, p_mrl=0.15, p_bdpcm=0.08, p_resi=0.0, upto=None, only=None, p_mip=0.15, colloc=0, p_lm=0.0):
     """b200_intra_tu records (Y, Cb, Cr per CU, decoding order) for a single-tree all-intra layout of gen_intra_layout: random modes, MRL on some luma
     blocks, BDPCM prediction on some, availability as xFillReferenceSamples derives it from the decoding order (pinned against the reference's own
     analysis through the glue flattener by tests/test_intra_oracle_vs_ref.py).  Luma blocks whose chroma would be narrower than 4 or smaller than 16
@@ -686,7 +686,9 @@ def gen_intra_records(rng, layout, W, H, modes=None, p_mrl=0.15, p_bdpcm=0.08, p
                 n_modes = 16 if (w, h) == (4, 4) else 8 if (w == 4 or h == 4 or (w, h) == (8, 8)) else 6
                 dirL, mip = int(rng.integers(0, n_modes)), 1 | (int(rng.integers(0, 2)) << 1)
             dirC = chroma_modes[int(rng.integers(len(chroma_modes)))]
+            if rng.random() < p_lm: dirC = int(rng.integers(67, 70))
         if dirC < 0 or dirC == 70: dirC = 0 if mip else dirL            # DM (a MIP luma CU counts as planar: PU::getCoLocatedIntraLumaMode)
+        lm = dirC in (67, 68, 69)                                       # LM_CHROMA_IDX, MDLM_L_IDX, MDLM_T_IDX
         if only is not None and not only[i]: continue                   # an inter CU of a mixed picture: a neighbour, not a block of the list
         def avail(ux, uy): return 0 <= ux < owner.shape[1] and 0 <= uy < owner.shape[0] and owner[uy, ux] < i
         tl = avail(x // 4 - 1, y // 4 - 1)
@@ -701,11 +703,19 @@ def gen_intra_records(rng, layout, W, H, modes=None, p_mrl=0.15, p_bdpcm=0.08, p
             r["x"], r["y"], r["log2w"], r["log2h"], r["comp"] = x >> sh, y >> sh, int(np.log2(w >> sh)), int(np.log2(h >> sh)), c
             if c == 0 and mip: r["mode"], r["mip"] = A.INTRA_MIP, dirL | ((mip >> 1) << 7)
             elif c == 0: r["mode"] = (A.INTRA_BDPCM_HOR if bdpcm == 1 else A.INTRA_BDPCM_VER) if bdpcm else dirL
-            else: r["mode"] = dirC
+            else: r["mode"] = dirC + 3 if lm else dirC                # B200_INTRA_LM = 70 ...
             r["multiRefIdx"] = mrl if c == 0 else 0
             fl = A.INTRA_AVAIL_TL if tl else 0
             if c == 0 and not mip and intra_filter_ref(w, h, dirL, mrl, bdpcm): fl |= A.INTRA_FILTER_REF
             if rng.random() < p_resi: fl |= 4
+            if c and lm:
+                cw, chh = w >> 1, h >> 1
+                if na: fl |= A.INTRA_LM_ABOVE
+                if nl: fl |= A.INTRA_LM_LEFT
+                if colloc: fl |= A.INTRA_LM_COLLOCATED
+                r["lmAbove"] = cw // 2 if na else 0; r["lmLeft"] = chh // 2 if nl else 0
+                if dirC == 69 and na: r["lmAbove"] = min(na, cw // 2 + min(cw // 2, chh // 2))
+                if dirC == 68 and nl: r["lmLeft"] = min(nl, chh // 2 + min(chh // 2, cw // 2))
             r["flags"], r["numAbove"], r["numLeft"] = fl, na, nl
             recs.append(r)
     return np.array(recs, A.INTRA_TU_DTYPE)

@@ -62,10 +62,12 @@ inline FlattenIntraResult flattenIntraTU( const TransformUnit& tu, const Compone
   const bool mip = CU::isMIP( cu, chType );
   if( mip && !isLuma( compID ) ) return FLATTEN_INTRA_UNSUPPORTED;                                       // MIP chroma exists in 4:4:4 only
   const uint32_t finalMode = PU::getFinalIntraMode( cu, chType );
-  if( !isLuma( compID ) && PU::isLMCMode( finalMode ) ) return FLATTEN_INTRA_UNSUPPORTED;
+  const bool lm = !isLuma( compID ) && PU::isLMCMode( finalMode );
+  if( lm && cu.chromaFormat != CHROMA_420 ) return FLATTEN_INTRA_UNSUPPORTED;
   const int bdpcm = isLuma( compID ) ? cu.bdpcmMode() : cu.bdpcmModeChroma();
   r.x = (uint16_t) area.x; r.y = (uint16_t) area.y; r.log2w = (uint8_t) getLog2( area.width ); r.log2h = (uint8_t) getLog2( area.height ); r.comp = (uint8_t) compID;
   r.mode = bdpcm ? ( bdpcm == 1 ? B200_INTRA_BDPCM_HOR : B200_INTRA_BDPCM_VER ) : (uint8_t) finalMode;
+  if( lm ) r.mode = (uint8_t) ( B200_INTRA_LM + ( finalMode - LM_CHROMA_IDX ) );
   if( mip ) { r.mode = B200_INTRA_MIP; r.mip = (uint8_t) ( cu.intraDir[CHANNEL_TYPE_LUMA] | ( cu.mipTransposedFlag() ? 0x80 : 0 ) ); }        // predIntraMip :1926
   r.multiRefIdx = isLuma( compID ) ? (uint8_t) cu.multiRefIdx() : 0;
   if( !mip && isLuma( compID ) && IntraPrediction::useFilteredIntraRefSamples( compID, cu, tu ) ) r.flags |= B200_INTRA_FILTER_REF;    // DecCu.cpp:339 (MIP: unfiltered, :323)
@@ -87,6 +89,22 @@ inline FlattenIntraResult flattenIntraTU( const TransformUnit& tu, const Compone
     r.numAbove = (uint8_t) ( numAbove + intraUnitsAvailable( tu, ch, Position( posLT.x + (PosType) ana.width, posLT.y ), totalAbove - numAbove, unitW, true ) );
   if( cu.left || ana.x > cu.blocks[ch].x )
     r.numLeft = (uint8_t) ( numLeft + intraUnitsAvailable( tu, ch, Position( posLT.x, posLT.y + (PosType) ana.height ), totalLeft - numLeft, unitH, false ) );
+  if( lm )
+  {
+    // CCLM: what xGetLumaRecPixels (:1461-1465) and xGetLMParameters (:1762-1795) derive from the CU map, in the chroma channel
+    const int unit = ( 1 << MIN_CU_LOG2 ) >> getComponentScaleX( compID, cu.chromaFormat );
+    const bool above = cu.above || area.y > cu.blocks[CH_C].y, left = cu.left || area.x > cu.blocks[CH_C].x;
+    if( above ) r.flags |= B200_INTRA_LM_ABOVE;
+    if( left )  r.flags |= B200_INTRA_LM_LEFT;
+    if( cu.sps->getCclmCollocatedChromaFlag() ) r.flags |= B200_INTRA_LM_COLLOCATED;
+    const int aboveUnits = area.width / unit, leftUnits = area.height / unit;
+    const int totalAbove = ( 2 * (int) area.width + unit - 1 ) / unit, totalLeft = ( 2 * (int) area.height + unit - 1 ) / unit;
+    r.lmAbove = above ? (uint8_t) aboveUnits : 0; r.lmLeft = left ? (uint8_t) leftUnits : 0;
+    if( finalMode == MDLM_T_IDX && above )
+      r.lmAbove = (uint8_t) ( aboveUnits + intraUnitsAvailable( tu, CHANNEL_TYPE_CHROMA, Position( area.x + (PosType) area.width, area.y ), std::min( totalAbove - aboveUnits, (int) area.height / unit ), unit, true ) );
+    if( finalMode == MDLM_L_IDX && left )
+      r.lmLeft = (uint8_t) ( leftUnits + intraUnitsAvailable( tu, CHANNEL_TYPE_CHROMA, Position( area.x, area.y + (PosType) area.height ), std::min( totalLeft - leftUnits, (int) area.width / unit ), unit, false ) );
+  }
   return FLATTEN_INTRA_OK;
 }
 
