@@ -18,7 +18,7 @@ def test_intra_picture_vs_oracle(b200, oracle, W, H, bd, ctu, min_size, p_resi, 
     rng = np.random.default_rng(seed)
     g = abi.make_geom(W, H, bd, ctu=ctu)
     layout = synth.gen_intra_layout(rng, W, H, ctu, min_size=min_size)
-    recs = synth.gen_intra_records(rng, layout, W, H, p_resi=p_resi)
+    recs = synth.gen_intra_records(rng, layout, W, H, p_resi=p_resi, p_lm=0.25, colloc=seed & 1)
     planes = synth.noise_planes(rng, W, H, bd)
     resi = [rng.integers(-40, 41, size=p.shape).astype(np.int16) for p in planes]
     want = [p.copy() for p in planes]; got = [p.copy() for p in planes]
@@ -28,6 +28,7 @@ def test_intra_picture_vs_oracle(b200, oracle, W, H, bd, ctu, min_size, p_resi, 
         bad = np.argwhere(got[c] != want[c])
         assert len(bad) == 0, (c, len(bad), bad[:4].tolist())
     assert len(np.unique(recs["mode"])) > 40 and (recs["multiRefIdx"] > 0).any() and (recs["mode"] == 67).any() and (recs["mode"] == abi.INTRA_MIP).any()
+    assert all((recs["mode"] == m).any() for m in (abi.INTRA_LM, abi.INTRA_MDLM_L, abi.INTRA_MDLM_T))
 
 
 def test_intra_predict_only_and_golden(b200, oracle):

@@ -95,6 +95,8 @@ __global__ void __launch_bounds__(IT_THREADS, 12) intra_kernel(const IntraParams
   __shared__ int16_t sT[2][IT_REF], sL[2][IT_REF];          // [0] unfiltered, [1] filtered
   __shared__ int16_t sM[IT_ARR], sS[IT_ARR];
   __shared__ int sTicket, sSum;
+  __shared__ int16_t sLm[32 * 32], sLmTop[64], sLmLeft[64];   // CCLM: down-sampled luma of the block, of the row above, of the column left
+  __shared__ int sLmPar[3];
   const int tid = threadIdx.x;
   for (;;) {
     __syncthreads();
@@ -124,6 +126,22 @@ __global__ void __launch_bounds__(IT_THREADS, 12) intra_kernel(const IntraParams
           while (*d == 0) { __nanosleep(64); if (*e || ++spins > (1 << 22)) { atomicOr(P.err, 1); break; } }   // bounded: a broken list must not hang the GPU
         }
       }
+      }
+      if (t.mode >= B200_INTRA_LM) {
+        // CCLM reads reconstructed luma: the co-located block, up to 3 rows above and 3 columns left of it, as far as the templates go
+        const bool aCu = t.flags & B200_INTRA_LM_ABOVE, lCu = t.flags & B200_INTRA_LM_LEFT;
+        const int nA = max(w, aCu ? (t.mode == B200_INTRA_MDLM_T ? 2 * t.lmAbove : w) : 0), nL = max(h, lCu ? (t.mode == B200_INTRA_MDLM_L ? 2 * t.lmLeft : h) : 0);
+        const int ux0 = max(0, (2 * x0 - (lCu ? 4 : 0)) >> 2), ux1 = min(P.W - 1, 2 * x0 + 2 * nA - 1) >> 2;
+        const int uy0 = max(0, (2 * y0 - (aCu ? 4 : 0)) >> 2), uy1 = min(P.H - 1, 2 * y0 + 2 * nL - 1) >> 2;
+        const int uw = ux1 - ux0 + 1, nU = uw * (uy1 - uy0 + 1);
+        for (int u = tid; u < nU; u += IT_THREADS) {
+          const int o = P.owner[0][(uy0 + u / uw) * P.ownerStride[0] + ux0 + u % uw];
+          if (o >= 0 && o < me) {
+            const volatile int* d = P.done + o; const volatile int* e = P.err;
+            int spins = 0;
+            while (*d == 0) { __nanosleep(64); if (*e || ++spins > (1 << 22)) { atomicOr(P.err, 1); break; } }
+          }
+        }
       }
       __threadfence();
     }
@@ -210,6 +228,77 @@ __global__ void __launch_bounds__(IT_THREADS, 12) intra_kernel(const IntraParams
         }
         IT_STORE(x, y, v);
       }
+    } else if (mode >= B200_INTRA_LM) {
+      // ---- cross-component linear model (xGetLumaRecPixels, xGetLMParameters, predIntraChromaLM), 4:2:0
+      const bool aCu = t.flags & B200_INTRA_LM_ABOVE, lCu = t.flags & B200_INTRA_LM_LEFT, colloc = t.flags & B200_INTRA_LM_COLLOCATED;
+      const int ls = P.stride[0];
+      const int16_t* rec = P.planes[0] + (size_t)(2 * y0) * ls + 2 * x0;
+      const bool firstRowOfCtu = ((2 * y0) & ((1 << P.ctuLog2) - 1)) == 0;
+      const int nTop = aCu ? (mode == B200_INTRA_MDLM_T ? 2 * t.lmAbove : w) : 0, nLeft = lCu ? (mode == B200_INTRA_MDLM_L ? 2 * t.lmLeft : h) : 0;
+#define LUMA(p_, o_) ((int)__ldcg((p_) + (o_)))
+      for (int k = tid; k < nTop + nLeft + w * h; k += IT_THREADS) {
+        if (k < nTop) {                                          // row above the block
+          const int i = k, m = (i == 0 && !lCu) ? 0 : 1;
+          int v;
+          if (firstRowOfCtu) { const int16_t* p = rec - ls; v = (LUMA(p, 2 * i) * 2 + LUMA(p, 2 * i - m) + LUMA(p, 2 * i + 1) + 2) >> 2; }
+          else if (colloc) { const int16_t* p = rec - 2 * ls; v = (LUMA(p, 2 * i - ls) + LUMA(p, 2 * i) * 4 + LUMA(p, 2 * i - m) + LUMA(p, 2 * i + 1) + LUMA(p, 2 * i + ls) + 4) >> 3; }
+          else { const int16_t* p = rec - 2 * ls; v = (LUMA(p, 2 * i) * 2 + LUMA(p, 2 * i - m) + LUMA(p, 2 * i + 1) + LUMA(p, 2 * i + ls) * 2 + LUMA(p, 2 * i - m + ls) + LUMA(p, 2 * i + 1 + ls) + 4) >> 3; }
+          sLmTop[i] = (int16_t)v;
+        } else if (k < nTop + nLeft) {                           // column left of the block
+          const int j = k - nTop; const int16_t* p = rec - 3 + (size_t)(2 * j) * ls;
+          int v;
+          if (colloc) v = (LUMA(p, 1 - ((j == 0 && !aCu) ? 0 : ls)) + LUMA(p, 1) * 4 + LUMA(p, 0) + LUMA(p, 2) + LUMA(p, 1 + ls) + 4) >> 3;
+          else v = (LUMA(p, 1) * 2 + LUMA(p, 0) + LUMA(p, 2) + LUMA(p, 1 + ls) * 2 + LUMA(p, ls) + LUMA(p, 2 + ls) + 4) >> 3;
+          sLmLeft[j] = (int16_t)v;
+        } else {                                                 // the block
+          const int q = k - nTop - nLeft, j = q >> t.log2w, i = q & (w - 1), m = (i == 0 && !lCu) ? 0 : 1;
+          const int16_t* p = rec + (size_t)(2 * j) * ls;
+          int v;
+          if (colloc) { const int up = (j == 0 && !aCu) ? 0 : ls; v = (LUMA(p, 2 * i - up) + LUMA(p, 2 * i) * 4 + LUMA(p, 2 * i - m) + LUMA(p, 2 * i + 1) + LUMA(p, 2 * i + ls) + 4) >> 3; }
+          else v = (LUMA(p, 2 * i) * 2 + LUMA(p, 2 * i + 1) + LUMA(p, 2 * i - m) + LUMA(p, 2 * i + ls) * 2 + LUMA(p, 2 * i + 1 + ls) + LUMA(p, 2 * i - m + ls) + 4) >> 3;
+          sLm[q] = (int16_t)v;
+        }
+      }
+#undef LUMA
+      __syncthreads();
+      if (tid == 0) {                                            // xGetLMParameters: four template positions -> a, b, shift
+        const int tuWU = w >> 1, tuHU = h >> 1;
+        bool aboveAvail = false, leftAvail = false; int topNum = 0, leftNum = 0;
+        if (mode == B200_INTRA_MDLM_T) { aboveAvail = t.lmAbove >= tuWU; topNum = 2 * t.lmAbove; }
+        else if (mode == B200_INTRA_MDLM_L) { leftAvail = t.lmLeft >= tuHU; leftNum = 2 * t.lmLeft; }
+        else { aboveAvail = aCu; leftAvail = lCu; topNum = w; leftNum = h; }
+        const int aboveIs4 = leftAvail ? 0 : 1, leftIs4 = aboveAvail ? 0 : 1;
+        const int start0 = topNum >> (2 + aboveIs4), step0 = max(1, topNum >> (1 + aboveIs4)), start1 = leftNum >> (2 + leftIs4), step1 = max(1, leftNum >> (1 + leftIs4));
+        int sl[4] = {0, 0, 0, 0}, sc[4] = {0, 0, 0, 0}, cntT = 0, cntL = 0;
+        if (aboveAvail) { cntT = min(topNum, (1 + aboveIs4) << 1); for (int k = 0, pos = start0; k < cntT; k++, pos += step0) { sl[k] = sLmTop[pos]; sc[k] = T[1 + pos]; } }
+        if (leftAvail) { cntL = min(leftNum, (1 + leftIs4) << 1); for (int k = 0, pos = start1; k < cntL; k++, pos += step1) { sl[k + cntT] = sLmLeft[pos]; sc[k + cntT] = L[1 + pos]; } }
+        if (cntT + cntL == 2) { sl[3] = sl[0]; sc[3] = sc[0]; sl[2] = sl[1]; sc[2] = sc[1]; sl[0] = sl[1]; sc[0] = sc[1]; sl[1] = sl[3]; sc[1] = sc[3]; }
+        int mn0 = 0, mn1 = 2, mx0 = 1, mx1 = 3, tt;
+        if (sl[mn0] > sl[mn1]) { tt = mn0; mn0 = mn1; mn1 = tt; }
+        if (sl[mx0] > sl[mx1]) { tt = mx0; mx0 = mx1; mx1 = tt; }
+        if (sl[mn0] > sl[mx1]) { tt = mn0; mn0 = mx0; mx0 = tt; tt = mn1; mn1 = mx1; mx1 = tt; }     // the two groups change roles
+        if (sl[mn1] > sl[mx0]) { tt = mn1; mn1 = mx0; mx0 = tt; }
+        const int minL = (sl[mn0] + sl[mn1] + 1) >> 1, minC = (sc[mn0] + sc[mn1] + 1) >> 1, maxL = (sl[mx0] + sl[mx1] + 1) >> 1, maxC = (sc[mx0] + sc[mx1] + 1) >> 1;
+        int a = 0, b = 1 << (P.bitDepth - 1), shift = 0;
+        if (leftAvail || aboveAvail) {
+          const int diff = maxL - minL;
+          if (diff > 0) {
+            const int diffC = maxC - minC;
+            int x = 31 - __clz(diff);
+            const int normDiff = (diff << 4 >> x) & 15;
+            const int v = (int)((0x0765544332211110ull >> (4 * (15 - normDiff))) & 15) | 8;   // DivSigTable {0,7,6,5,5,4,4,3,3,2,2,1,1,1,1,0}
+            x += normDiff != 0;
+            const int y = diffC == 0 ? 0 : (31 - __clz(abs(diffC))) + 1, add = 1 << y >> 1;
+            a = (diffC * v + add) >> y; shift = 3 + x - y;
+            if (shift < 1) { shift = 1; a = a == 0 ? 0 : a < 0 ? -15 : 15; }
+            b = minC - ((a * minL) >> shift);
+          } else { a = 0; b = minC; shift = 0; }
+        }
+        sLmPar[0] = a; sLmPar[1] = b; sLmPar[2] = shift;
+      }
+      __syncthreads();
+      const int a = sLmPar[0], b = sLmPar[1], shift = sLmPar[2];
+      for (int k = tid; k < w * h; k += IT_THREADS) { const int y = k >> t.log2w, x = k & (w - 1); IT_STORE(x, y, clip3(0, pmax, ((a * sLm[k]) >> shift) + b)); }
     } else if (mode == B200_INTRA_MIP) {
       // ---- matrix intra prediction (PredictorMIP): reduced boundary -> matrix stage -> linear up-sampling; sM holds the reduced prediction
       const int sizeId = (w == 4 && h == 4) ? 0 : (w == 4 || h == 4 || (w == 8 && h == 8)) ? 1 : 2;
@@ -327,7 +416,9 @@ __global__ void __launch_bounds__(256) intra_validate_kernel(const b200_intra_tu
   const b200_intra_tu t = tus[i];
   const int w = 1 << t.log2w, h = 1 << t.log2h, pw = t.comp ? W >> 1 : W, ph = t.comp ? H >> 1 : H, unit = t.comp ? 2 : 4, m = t.multiRefIdx;
   bool ok = t.comp < (chroma ? 3 : 1) && t.log2w >= 2 && t.log2w <= 6 && t.log2h >= 1 && t.log2h <= 6 && t.x + w <= pw && t.y + h <= ph && !(t.x % unit) && !(t.y % unit);
-  ok = ok && t.mode <= B200_INTRA_MIP && m <= 2 && (!m || !t.comp);
+  ok = ok && t.mode <= B200_INTRA_MDLM_T && m <= 2 && (!m || !t.comp);
+  if (t.mode >= B200_INTRA_LM) ok = ok && t.comp && t.log2w <= 5 && t.log2h <= 5 && t.lmAbove <= w && t.lmLeft <= h && (!(t.flags & B200_INTRA_LM_ABOVE) || t.y >= 2) && (!(t.flags & B200_INTRA_LM_LEFT) || t.x >= 2)
+                                  && t.x + max(w, 2 * t.lmAbove) <= pw && t.y + max(h, 2 * t.lmLeft) <= ph;
   if (t.mode == B200_INTRA_MIP) ok = ok && !t.comp && !m && (t.mip & 0x7f) < ((w == 4 && h == 4) ? 16 : (w == 4 || h == 4 || (w == 8 && h == 8)) ? 8 : 6);
   ok = ok && t.numAbove <= 2 * w / unit && t.numLeft <= 2 * h / unit && (!t.numAbove || t.y > m) && (!t.numLeft || t.x > m)
           && (!(t.flags & B200_INTRA_AVAIL_TL) || (t.x > m && t.y > m)) && t.x + (int)t.numAbove * unit <= pw && t.y + (int)t.numLeft * unit <= ph;

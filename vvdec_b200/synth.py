@@ -485,7 +485,7 @@ def gen_picture(rng, W, H, bit_depth=10, ctu=128, dst_slot=0, cu_kw=None, pu_kw=
         tus1, coefs1 = gen_tus(rng, intra_cus, bit_depth, **(tkw | {"p_intra": 1.0, "p_cbf": 0.6, "p_lfnst": 0.15, "p_bdpcm": 0.05}))
         tus1["coefOff"] += len(coefs0); tus1["flags"] |= A.TU_RESI
         tus, coefs = np.concatenate([tus0, tus1]), np.concatenate([coefs0, coefs1])
-        irecs = gen_intra_records(rng, cus, W, H, only=is_intra)
+        irecs = gen_intra_records(rng, cus, W, H, only=is_intra, p_lm=0.2, colloc=int(rng.integers(0, 2)))
         coded = set()
         for t in tus1:
             coded.add((int(t["comp"]), int(t["x"]), int(t["y"]))); 
