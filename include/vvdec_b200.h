@@ -257,7 +257,8 @@ B200_API int b200_mc_predict_wp(const b200_geom* g, int16_t* const dst[3], const
  *             linear interpolation, angular PDPC), IntraPredSampleFilterCore :212 (PDPC of planar / DC), xPredIntraBDPCM :850,
  *             as DecCu::predAndReco calls them for a regular intra TU (DecCu.cpp:329-371).
  * The availability analysis (cs.getCURestricted walks, IntraPrediction.cpp:1098-1130) stays host code in the flattener and arrives as
- * three counts.  Not covered (the flattener must refuse them): CCLM, ISP, palette, ACT.
+ *             xGetLumaRecPixels :1403 / xGetLMParameters :1694 / predIntraChromaLM :519 (CCLM, 4:2:0),
+ * three counts.  Not covered (the flattener must refuse them): ISP, palette, ACT; CIIP and IBC CUs (inter side).
  * Blocks of one list are processed in list order; a block may read what earlier blocks of the list wrote. */
 enum { B200_INTRA_PLANAR = 0, B200_INTRA_DC = 1 /* 2..66 angular */, B200_INTRA_BDPCM_HOR = 67, B200_INTRA_BDPCM_VER = 68,
        B200_INTRA_MIP = 69 /* matrix intra prediction: b200_intra_tu::mip = mode index | transposed << 7 */,

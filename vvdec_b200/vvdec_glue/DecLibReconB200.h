@@ -7,7 +7,7 @@
 //
 // The CPU keeps: parsing (DecLibParser / DecSlice), motion derivation (DecCu::TaskDeriveCtuMotionInfo, DecCu.cpp:62), boundary strengths
 // (LoopFilter::calcFilterStrengthsCTU, LoopFilter.cpp:360), TaskFinishMotionInfo (DecCu.cpp:161).  Pictures that use a tool the device path
-// does not have (MIP / CCLM / ISP intra blocks, IBC / CIIP CUs, RPR, wrap-around, sub-picture clipping, virtual-boundary ALF) throw UnsupportedFeatureException; a
+// does not have (ISP intra blocks, IBC / CIIP CUs, RPR, wrap-around, sub-picture clipping, virtual-boundary ALF) throw UnsupportedFeatureException; a
 // deployment keeps a stock DecLibRecon next to this class and routes those pictures to it.
 #pragma once
 #include <vector>
@@ -134,7 +134,7 @@ public:
             {
               if( !area.valid() ) continue;
               b200_intra_tu ir;
-              if( flattenIntraTU( tu, area.compID(), ir ) != FLATTEN_INTRA_OK ) THROW_UNSUPPORTED( "DecLibReconB200: MIP / CCLM / ISP / ACT intra block (SURVEY 8f-1)" );
+              if( flattenIntraTU( tu, area.compID(), ir ) != FLATTEN_INTRA_OK ) THROW_UNSUPPORTED( "DecLibReconB200: ISP / ACT intra block (SURVEY 8f-1)" );
               b200_tu r;
               if( flattenTU( tu, area.compID(), *m_trQuant, m_coefs.v, r ) ) { r.flags |= B200_TU_RESI; m_tus.v.push_back( r ); }
               if( TU::getCbf( tu, area.compID() ) || ( isChroma( area.compID() ) && tu.jointCbCr ) ) ir.flags |= B200_INTRA_ADD_RESI;      // DecCu.cpp:390
