@@ -250,15 +250,17 @@ B200_API int b200_mc_predict_wp(const b200_geom* g, int16_t* const dst[3], const
                                 const b200_pu* pus, size_t numPus, int32_t* dmvrMv, size_t numDmvr, const b200_wp* wp, int numWp);
 
 /* ------------------------------------------------------------------------------------------------
- * K6  intra prediction of one transform block (first slice: regular modes).
+ * K6  intra prediction of one transform block: regular modes, matrix intra prediction, cross-component linear model.
  *   replaces  IntraPrediction::initIntraPatternChType (IntraPrediction.cpp:947) = xFillReferenceSamples :1072 (the sample copies /
  *             substitution, not the availability analysis) + xFilterReferenceSamples :1251, and IntraPrediction::predIntraAng :474 =
  *             xPredIntraPlanarCore :154, xPredIntraDc :541, xPredIntraAng :592 (wide angles, reference extension, cubic / Gauss /
- *             linear interpolation, angular PDPC), IntraPredSampleFilterCore :212 (PDPC of planar / DC), xPredIntraBDPCM :850,
- *             as DecCu::predAndReco calls them for a regular intra TU (DecCu.cpp:329-371).
- * The availability analysis (cs.getCURestricted walks, IntraPrediction.cpp:1098-1130) stays host code in the flattener and arrives as
+ *             linear interpolation, angular PDPC), IntraPredSampleFilterCore :212 (PDPC of planar / DC), xPredIntraBDPCM :850;
+ *             initIntraMip / predIntraMip :1906,:1919 with PredictorMIP (MatrixIntraPrediction.cpp:67-330: boundary down-sampling,
+ *             matrix stage, up-sampling; weights MipData.h);
  *             xGetLumaRecPixels :1403 / xGetLMParameters :1694 / predIntraChromaLM :519 (CCLM, 4:2:0),
- * three counts.  Not covered (the flattener must refuse them): ISP, palette, ACT; CIIP and IBC CUs (inter side).
+ *             as DecCu::predAndReco calls them for an intra TU (DecCu.cpp:316-371).
+ * The availability analysis (cs.getCURestricted walks, IntraPrediction.cpp:1098-1130, :1762-1795) stays host code in the flattener and
+ * arrives as counts.  Not covered (the flattener must refuse them): ISP, palette, ACT; CIIP and IBC CUs (inter side); intra with LMCS.
  * Blocks of one list are processed in list order; a block may read what earlier blocks of the list wrote. */
 enum { B200_INTRA_PLANAR = 0, B200_INTRA_DC = 1 /* 2..66 angular */, B200_INTRA_BDPCM_HOR = 67, B200_INTRA_BDPCM_VER = 68,
        B200_INTRA_MIP = 69 /* matrix intra prediction: b200_intra_tu::mip = mode index | transposed << 7 */,
