@@ -260,7 +260,8 @@ B200_API int b200_mc_predict_wp(const b200_geom* g, int16_t* const dst[3], const
  *             xGetLumaRecPixels :1403 / xGetLMParameters :1694 / predIntraChromaLM :519 (CCLM, 4:2:0),
  *             as DecCu::predAndReco calls them for an intra TU (DecCu.cpp:316-371).
  * The availability analysis (cs.getCURestricted walks, IntraPrediction.cpp:1098-1130, :1762-1795) stays host code in the flattener and
- * arrives as counts.  Not covered (the flattener must refuse them): ISP, palette, ACT; CIIP and IBC CUs (inter side); intra with LMCS.
+ * arrives as counts.  CIIP CUs (predBlendIntraCiip :887) are blocks of this list too: planar prediction blended with the inter prediction K2 left
+ * in the block.  Not covered (the flattener must refuse them): ISP, palette, ACT, IBC CUs, intra / CIIP together with LMCS.
  * Blocks of one list are processed in list order; a block may read what earlier blocks of the list wrote. */
 enum { B200_INTRA_PLANAR = 0, B200_INTRA_DC = 1 /* 2..66 angular */, B200_INTRA_BDPCM_HOR = 67, B200_INTRA_BDPCM_VER = 68,
        B200_INTRA_MIP = 69 /* matrix intra prediction: b200_intra_tu::mip = mode index | transposed << 7 */,
@@ -279,7 +280,8 @@ typedef struct b200_intra_tu {
   uint8_t  numLeft;       /* m_neighborSize[2]: available units left + below-left                                    */
   uint8_t  mip;           /* B200_INTRA_MIP: cu.intraDir[luma] (MIP mode index) | cu.mipTransposedFlag() << 7                    */
   uint8_t  lmAbove, lmLeft;/* CCLM: template units (2 chroma samples) xGetLMParameters finds available above(+right) / left(+below) (:1762-1795) */
-  uint8_t  rsv;
+  uint8_t  ciip;          /* 0, or wIntra = 1..3 of a CIIP CU (predBlendIntraCiip :887): the block's samples hold the inter prediction (K2);
+                             K6 stores (wIntra * intra + (4 - wIntra) * inter + 2) >> 2 (then + residual).  mode is planar.          */
 } b200_intra_tu;          /* 16 bytes */
 /* Kernel-level K6: host planes in (reconstructed neighbourhood), prediction written into the blocks, host planes out. */
 B200_API int b200_intra_predict(const b200_geom* g, int16_t* const planes[3], const b200_intra_tu* tus, size_t numTus);

@@ -341,6 +341,8 @@ void orc_intra_tu(const b200_geom* g, int16_t* const planes[3], const b200_intra
   if ((t->flags & B200_INTRA_FILTER_REF) && !c && !mrl) { filter_ref(ref, flt, w, h); src = flt; }
   int16_t* dst = planes[c] + (ptrdiff_t)t->y * g->stride[c] + t->x;
   const ptrdiff_t ds = g->stride[c];
+  int16_t* inter = NULL;                                        /* CIIP: the block holds the inter prediction; keep it for the blend */
+  if (t->ciip) { inter = (int16_t*)malloc(sizeof(int16_t) * w * h); for (int y = 0; y < h; y++) memcpy(inter + y * w, dst + y * ds, sizeof(int16_t) * w); }
   const int doPDPC = w >= 4 && h >= 4 && mrl == 0;
   if (t->mode == B200_INTRA_PLANAR) pred_planar(src, stride, w, h, dst, ds);
   else if (t->mode == B200_INTRA_DC) {
@@ -364,6 +366,11 @@ void orc_intra_tu(const b200_geom* g, int16_t* const planes[3], const b200_intra
         dst[y * ds + x] = (int16_t)(v + ((wL * (left - v) + wT * (top - v) + 32) >> 6));
       }
     }
+  }
+  if (inter) {                                                  /* predBlendIntraCiip :925-938 */
+    const int wI = t->ciip, wM = 4 - wI;
+    for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) dst[y * ds + x] = (int16_t)((wM * inter[y * w + x] + wI * dst[y * ds + x] + 2) >> 2);
+    free(inter);
   }
   free(ref);
 }

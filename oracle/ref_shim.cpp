@@ -767,6 +767,29 @@ extern "C" int ref_picture_hash( int method, int bitDepth, int16_t* const planes
 static int intraPredictCu( IntraPrediction& ip, CodingStructure& cs, CodingUnit& cu, const b200_geom* g, const int16_t* const resi[3], bool addResi, b200_intra_tu* recs, int capRecs, int& n )
 {
   TransformUnit& tu = cu.firstTU;
+  if( cu.ciipFlag() )
+  {
+    // the planes hold the CU's inter prediction; predBlendIntraCiip (DecCu.cpp:450-453) blends the planar intra prediction into it
+    for( int c = 0; c < 3; c++ )
+    {
+      b200_intra_tu r;
+      if( b200glue::flattenCiipBlock( cu, ComponentID( c ), r ) != b200glue::FLATTEN_INTRA_OK ) continue;
+      if( addResi && resi && resi[c] ) r.flags |= B200_INTRA_ADD_RESI;
+      if( n < capRecs ) recs[n] = r;
+      n++;
+    }
+    PelUnitBuf predUnit = cs.getRecoBuf( cu );
+    ip.predBlendIntraCiip( predUnit, cu );
+    if( addResi && resi )
+      for( const CompArea& area : cu.blocks )
+      {
+        if( !area.valid() || ( !isLuma( area.compID() ) && cu.chromaSize().width <= 2 ) ) continue;
+        PelBuf p = cs.getRecoBuf( area ); const int pmax = ( 1 << g->bitDepth ) - 1, c = area.compID();
+        for( unsigned y = 0; y < area.height; y++ ) for( unsigned x = 0; x < area.width; x++ )
+          p.buf[y * p.stride + x] = (Pel) std::min( pmax, std::max( 0, p.buf[y * p.stride + x] + resi[c][( area.y + y ) * g->stride[c] + area.x + x] ) );
+      }
+    return 0;
+  }
   for( const CompArea& area : tu.blocks )
   {
     if( !area.valid() ) continue;
@@ -845,12 +868,13 @@ extern "C" int ref_intra_case( int simd, const b200_geom* g, int16_t* const plan
       const CodingUnit* above = cs.getCURestricted( pos.offset( 0, -1 ), pos, 0, 0, CH_L );
       CodingUnit& cu = cs.addCU( ua, CH_L, c.rsv[0] ? TREE_L : TREE_D, c.rsv[0] ? MODE_TYPE_INTRA : MODE_TYPE_ALL, left, above );
       cu.slice = sl; cu.pps = cur.pps.get(); cu.sps = cur.sps.get();
-      cu.setPredMode( MODE_INTRA );
+      cu.setPredMode( ( c.rsv[2] & 12 ) ? MODE_INTER : MODE_INTRA );                                    // bit 2: CIIP CU, bit 3: plain inter CU (a neighbour)
       cu.intraDir[0] = c.dirL; cu.intraDir[1] = c.dirC;
+      if( c.rsv[2] & 4 ) { cu.setCiipFlag( true ); cu.intraDir[0] = PLANAR_IDX; cu.intraDir[1] = DM_CHROMA_IDX; }
       cu.setMultiRefIdx( c.multiRefIdx ); cu.setBdpcmMode( c.bdpcm ); cu.setBdpcmModeChroma( c.bdpcmC );
       if( c.rsv[2] & 1 ) { cu.setMipFlag( true ); cu.setMipTransposedFlag( ( c.rsv[2] & 2 ) != 0 ); }      // dirL is the MIP mode index then
       cs.addTU( ua, CH_L, cu );
-      if( all || i == numCus - 1 )
+      if( ( all || i == numCus - 1 ) && !( c.rsv[2] & 8 ) )                                                // plain inter CUs: their samples are given
         if( int rc = intraPredictCu( ip, cs, cu, g, resi, c.rsv[1] != 0, recs, capRecs, n ) ) return rc;
     }
     cur.getPlanes( *g, planes );

@@ -125,7 +125,8 @@ size_t ref_write_component(const int16_t* src, ptrdiff_t stride, int w, int h, i
 /* one intra CU of a test layout (luma samples; single tree; one TU) */
 typedef struct ref_intra_cu { uint16_t x, y, w, h; uint8_t dirL, dirC, multiRefIdx, bdpcm, bdpcmC, rsv[3]; } ref_intra_cu;
 /* the real IntraPrediction on the last CU of the list, or (all != 0) on every CU in order with the reconstruction step for CUs with rsv[1] set
- * (see ref_shim.cpp); rsv[0]: luma-only CU; rsv[2]: bit 0 MIP CU (dirL = MIP mode index), bit 1 transposed.  Returns the number of records, < 0 on error */
+ * (see ref_shim.cpp); rsv[0]: luma-only CU; rsv[2]: bit 0 MIP CU (dirL = MIP mode index), bit 1 transposed, bit 2 CIIP CU (its samples = the inter
+ * prediction), bit 3 plain inter CU (samples given, not predicted).  Returns the number of records, < 0 on error */
 int ref_intra_case(int simd, const b200_geom* g, int16_t* const planes[3], const int16_t* const resi[3], const ref_intra_cu* cus, int numCus, int all,
                    b200_intra_tu* recs, int capRecs, int cclmCollocated /* sps_chroma_vertical_collocated_flag */);
 /* the real FilmGrain (updateFGC + SIMD line kernels) on the last of `frames` frames; tables / line seeds of that frame are returned (see ref_shim.cpp) */

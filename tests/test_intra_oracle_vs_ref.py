@@ -121,3 +121,32 @@ def test_intra_cclm(oracle, ref, w, h, colloc):
         for mode in (67, 68, 69):
             for rep in range(3):
                 run_case(oracle, ref, rng, W, H, 10 if rep else 8, ctu, rep & 1, layout, k, int(rng.integers(0, 67)), mode, 0, 0, colloc=colloc)
+
+
+@pytest.mark.parametrize("w,h", [(8, 8), (16, 16), (32, 32), (64, 64), (16, 8), (8, 16), (64, 16), (16, 64), (32, 8), (4, 16), (16, 4)])
+def test_ciip_blend(oracle, ref, w, h):
+    """CIIP: the block holds an inter prediction; planar intra prediction (filtered references for luma blocks > 32 samples, PDPC) blended with weights
+    that depend on whether the left / above neighbour CUs are intra.  All four neighbour combinations, C and SIMD kernels, 8 / 10 bit."""
+    rng = np.random.default_rng(w * 9 + h)
+    W, H, ctu = 256, 128, 128
+    for inter_mask in range(4):                                        # bit 0: left neighbour CU is inter, bit 1: above neighbour CU is inter
+        layout = [(0, 0, 64, 64), (64, 0, 64, 64), (0, 64, 64, 64), (64, 64, w, h)]
+        g = abi.make_geom(W, H, 10 if inter_mask & 1 else 8, ctu=ctu)
+        planes = synth.noise_planes(rng, W, H, g.bitDepth)
+        cus = np.zeros(4, synth.REF_INTRA_CU_DTYPE)
+        for i, c in enumerate(layout): cus[i]["x"], cus[i]["y"], cus[i]["w"], cus[i]["h"] = c
+        cus[2]["rsv"][2] = 8 if inter_mask & 1 else 0                  # (0, 64): the left neighbour
+        cus[1]["rsv"][2] = 8 if inter_mask & 2 else 0                  # (64, 0): the above neighbour
+        cus[3]["rsv"][2] = 4
+        chroma_ok = (w // 2) > 2
+        want = [p.copy() for p in planes]
+        recs = np.zeros(3, abi.INTRA_TU_DTYPE)
+        n = ref.ref_intra_case(inter_mask & 1, C.byref(g), abi.plane_ptrs(want), None, cus.ctypes.data, 4, 0, recs.ctypes.data, 3, 0)
+        assert n == (3 if chroma_ok else 1), n
+        recs = recs[:n]
+        assert (recs["ciip"] == 3 - (inter_mask & 1) - (inter_mask >> 1)).all() and (recs["mode"] == 0).all()
+        got = [p.copy() for p in planes]
+        oracle.orc_intra_predict(C.byref(g), abi.plane_ptrs(got), recs.ctypes.data, n)
+        for c in range(3):
+            assert np.array_equal(got[c], want[c]), (c, inter_mask)
+        assert not np.array_equal(want[0][64:64 + h, 64:64 + w], planes[0][64:64 + h, 64:64 + w])

@@ -166,6 +166,7 @@ def test_picture_with_intra_cus(b200, oracle, W, H, ctu, intra_frac, seed):
         for i in range(2):
             pic = synth.gen_picture(rng, W, H, bd, ctu=ctu, dst_slot=4 + i, intra_frac=intra_frac)
             assert len(pic["intraTus"]) > 0 and (pic["tus"]["flags"] & abi.TU_RESI).any() and (pic["intraTus"]["flags"] & abi.INTRA_ADD_RESI).any()
+            assert intra_frac == 1.0 or (pic["intraTus"]["ciip"] > 0).any()          # CIIP CUs among the inter CUs
             want, dm_want = oracle_decompress(oracle, g, dpb, pic)
             h = b200.b200_decompress_picture(ctx, C.byref(pic["struct"])); assert h >= 0, b200.b200_last_error()
             dm = np.zeros((pic["ndmvr"] + 1, 2), np.int32)

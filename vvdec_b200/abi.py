@@ -94,11 +94,11 @@ class LmcsVpdu(C.Structure):
 class IntraTu(C.Structure):
     """b200_intra_tu (see include/vvdec_b200.h)."""
     _fields_ = [("x", C.c_uint16), ("y", C.c_uint16), ("log2w", C.c_uint8), ("log2h", C.c_uint8), ("comp", C.c_uint8), ("mode", C.c_uint8),
-                ("multiRefIdx", C.c_uint8), ("flags", C.c_uint8), ("numAbove", C.c_uint8), ("numLeft", C.c_uint8), ("mip", C.c_uint8), ("lmAbove", C.c_uint8), ("lmLeft", C.c_uint8), ("rsv", C.c_uint8)]
+                ("multiRefIdx", C.c_uint8), ("flags", C.c_uint8), ("numAbove", C.c_uint8), ("numLeft", C.c_uint8), ("mip", C.c_uint8), ("lmAbove", C.c_uint8), ("lmLeft", C.c_uint8), ("ciip", C.c_uint8)]
 
 
 INTRA_TU_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("log2w", "u1"), ("log2h", "u1"), ("comp", "u1"), ("mode", "u1"), ("multiRefIdx", "u1"), ("flags", "u1"),
-                           ("numAbove", "u1"), ("numLeft", "u1"), ("mip", "u1"), ("lmAbove", "u1"), ("lmLeft", "u1"), ("rsv", "u1")])
+                           ("numAbove", "u1"), ("numLeft", "u1"), ("mip", "u1"), ("lmAbove", "u1"), ("lmLeft", "u1"), ("ciip", "u1")])
 INTRA_FILTER_REF, INTRA_AVAIL_TL, INTRA_ADD_RESI = 1, 2, 4
 INTRA_BDPCM_HOR, INTRA_BDPCM_VER, INTRA_MIP, INTRA_LM, INTRA_MDLM_L, INTRA_MDLM_T = 67, 68, 69, 70, 71, 72
 INTRA_LM_ABOVE, INTRA_LM_LEFT, INTRA_LM_COLLOCATED = 8, 16, 32

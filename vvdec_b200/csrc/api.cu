@@ -197,6 +197,7 @@ B200_API int b200_intra_reconstruct(const b200_geom* g, int16_t* const planes[3]
     B200_CHECK(t.comp < nPl && t.log2w >= 2 && t.log2w <= 6 && t.log2h >= 1 && t.log2h <= 6 && t.x + w <= pw && t.y + h <= ph && !(t.x % unit) && !(t.y % unit),
                "b200_intra_reconstruct: record %zu: bad geometry", i);
     B200_CHECK(t.mode <= B200_INTRA_MDLM_T && t.multiRefIdx <= 2 && (!t.multiRefIdx || !t.comp), "b200_intra_reconstruct: record %zu: bad mode / reference line", i);
+    B200_CHECK(!t.ciip || (t.ciip <= 3 && t.mode == B200_INTRA_PLANAR), "b200_intra_reconstruct: record %zu: bad CIIP block", i);
     B200_CHECK(t.mode < B200_INTRA_LM || (t.comp && t.log2w <= 5 && t.log2h <= 5 && t.lmAbove <= w && t.lmLeft <= h && (!(t.flags & B200_INTRA_LM_ABOVE) || t.y >= 2) && (!(t.flags & B200_INTRA_LM_LEFT) || t.x >= 2)
                                         && t.x + std::max(w, 2 * (int)t.lmAbove) <= pw && t.y + std::max(h, 2 * (int)t.lmLeft) <= ph), "b200_intra_reconstruct: record %zu: bad CCLM block", i);
     B200_CHECK(t.mode != B200_INTRA_MIP || (!t.comp && !t.multiRefIdx && (t.mip & 0x7f) < ((w == 4 && h == 4) ? 16 : (w == 4 || h == 4 || (w == 8 && h == 8)) ? 8 : 6)),

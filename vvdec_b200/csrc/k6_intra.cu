@@ -196,7 +196,9 @@ __global__ void __launch_bounds__(IT_THREADS, 12) intra_kernel(const IntraParams
     const bool doPDPC = w >= 4 && h >= 4 && mrl == 0;
     int16_t* dst = P.planes[c] + (size_t)y0 * ps + x0;
     const int16_t* rs = (P.resi[c] && (t.flags & B200_INTRA_ADD_RESI)) ? P.resi[c] + (size_t)y0 * ps + x0 : nullptr;
-#define IT_STORE(x, y, v) do { int v_ = (v); if (rs) v_ = clip3(0, pmax, v_ + rs[(size_t)(y) * ps + (x)]); dst[(size_t)(y) * ps + (x)] = (int16_t)v_; } while (0)
+    const int ciipW = t.ciip;                                  // CIIP: the block holds the inter prediction; blend (predBlendIntraCiip :925-938)
+#define IT_STORE(x, y, v) do { int v_ = (v); int16_t* d_ = dst + (size_t)(y) * ps + (x); if (ciipW) v_ = ((4 - ciipW) * (int)*d_ + ciipW * v_ + 2) >> 2; \
+                               if (rs) v_ = clip3(0, pmax, v_ + rs[(size_t)(y) * ps + (x)]); *d_ = (int16_t)v_; } while (0)
 
     if (mode == B200_INTRA_PLANAR || mode == B200_INTRA_DC) {
       int dc = 0;
@@ -417,6 +419,7 @@ __global__ void __launch_bounds__(256) intra_validate_kernel(const b200_intra_tu
   const int w = 1 << t.log2w, h = 1 << t.log2h, pw = t.comp ? W >> 1 : W, ph = t.comp ? H >> 1 : H, unit = t.comp ? 2 : 4, m = t.multiRefIdx;
   bool ok = t.comp < (chroma ? 3 : 1) && t.log2w >= 2 && t.log2w <= 6 && t.log2h >= 1 && t.log2h <= 6 && t.x + w <= pw && t.y + h <= ph && !(t.x % unit) && !(t.y % unit);
   ok = ok && t.mode <= B200_INTRA_MDLM_T && m <= 2 && (!m || !t.comp);
+  if (t.ciip) ok = ok && t.ciip <= 3 && t.mode == B200_INTRA_PLANAR;
   if (t.mode >= B200_INTRA_LM) ok = ok && t.comp && t.log2w <= 5 && t.log2h <= 5 && t.lmAbove <= w && t.lmLeft <= h && (!(t.flags & B200_INTRA_LM_ABOVE) || t.y >= 2) && (!(t.flags & B200_INTRA_LM_LEFT) || t.x >= 2)
                                   && t.x + max(w, 2 * t.lmAbove) <= pw && t.y + max(h, 2 * t.lmLeft) <= ph;
   if (t.mode == B200_INTRA_MIP) ok = ok && !t.comp && !m && (t.mip & 0x7f) < ((w == 4 && h == 4) ? 16 : (w == 4 || h == 4 || (w == 8 && h == 8)) ? 8 : 6);

@@ -467,7 +467,7 @@ def gen_lmcs(rng, bit_depth, cus, W, H, ctu, chroma_adj=True):
 
 
 def gen_picture(rng, W, H, bit_depth=10, ctu=128, dst_slot=0, cu_kw=None, pu_kw=None, tu_kw=None, sao_p=0.4, alf_kw=None,
-                deblock=True, sao=True, alf=True, lmcs=False, lmcs_chroma=True, wp=False, inter=True, given=None, cu_intra=None, intra_frac=0.0):
+                deblock=True, sao=True, alf=True, lmcs=False, lmcs_chroma=True, wp=False, inter=True, given=None, cu_intra=None, intra_frac=0.0, p_ciip=0.25):
     """One synthetic post-parse picture: partition -> inter PUs (all CUs inter: intra-coded samples would
     be 'given' pixels) -> TUs/levels -> deblocking grids -> SAO / ALF CTU parameters.
     Returns a dict of numpy arrays (kept alive by the caller) plus `struct`, the abi.Picture that points into them."""
@@ -485,9 +485,32 @@ def gen_picture(rng, W, H, bit_depth=10, ctu=128, dst_slot=0, cu_kw=None, pu_kw=
         tus1, coefs1 = gen_tus(rng, intra_cus, bit_depth, **(tkw | {"p_intra": 1.0, "p_cbf": 0.6, "p_lfnst": 0.15, "p_bdpcm": 0.05}))
         tus1["coefOff"] += len(coefs0); tus1["flags"] |= A.TU_RESI
         tus, coefs = np.concatenate([tus0, tus1]), np.concatenate([coefs0, coefs1])
-        irecs = gen_intra_records(rng, cus, W, H, only=is_intra, p_lm=0.2, colloc=int(rng.integers(0, 2)))
+        # CIIP: plain merge-like inter CUs (no BDOF / DMVR / affine / GEO / BCW, at least 64 samples) also get a planar intra block that is blended
+        # with their inter prediction; the weight counts the intra CUs left (at the bottom-left corner) and above (at the top-right corner)
+        cu_idx = np.full(((H + 3) // 4, (W + 3) // 4), -1, np.int64)
+        for i, (x, y, w, h) in enumerate(cus): cu_idx[y // 4:(y + h) // 4, x // 4:(x + w) // 4] = i
+        inter_index = [i for i, f in enumerate(is_intra) if not f]
+        ciip = {}
+        for j, pu in enumerate(pus):
+            i = inter_index[j]; x, y, w, h = cus[i]
+            if pu["flags"] == 0 and pu["bcwW1"] == 4 and w * h >= 64 and rng.random() < p_ciip:
+                nl = cu_idx[(y + h - 1) // 4, x // 4 - 1] if x > 0 else -1; na = cu_idx[y // 4 - 1, (x + w - 1) // 4] if y > 0 else -1
+                ciip[i] = 3 - (0 if nl >= 0 and is_intra[nl] else 1) - (0 if na >= 0 and is_intra[na] else 1)
+        ciip_cus = [cus[i] for i in sorted(ciip)]
+        tus2, coefs2 = gen_tus(rng, ciip_cus, bit_depth, **(tkw | {"p_cbf": 0.6}))
+        tus2["coefOff"] += len(coefs0) + len(coefs1)
+        for t in tus2:                                              # chroma narrower than 4 has no CIIP block (predBlendIntraCiip :891): plain inter reconstruction there
+            if not (t["comp"] and (1 << int(t["log2w"])) <= 2): t["flags"] |= A.TU_RESI
+        # the plain inter TUs generated above for CIIP CUs are dropped: their residual goes through K6
+        ciip_pos = {(x, y) for (x, y, w, h) in ciip_cus}
+        keep = np.array([((int(t["x"]) << (1 if t["comp"] else 0), int(t["y"]) << (1 if t["comp"] else 0)) not in ciip_pos) for t in tus0], bool) if len(tus0) else np.zeros(0, bool)
+        tus0 = tus0[keep]
+        tus, coefs = np.concatenate([tus0, tus1, tus2]), np.concatenate([coefs0, coefs1, coefs2])
+        mask = is_intra.copy()
+        for i in ciip: mask[i] = True
+        irecs = gen_intra_records(rng, cus, W, H, only=mask, p_lm=0.2, colloc=int(rng.integers(0, 2)), ciip=ciip)
         coded = set()
-        for t in tus1:
+        for t in np.concatenate([tus1, tus2[(tus2["flags"] & A.TU_RESI) != 0]]):
             coded.add((int(t["comp"]), int(t["x"]), int(t["y"]))); 
             if t["ict"]: coded.add((3 - int(t["comp"]), int(t["x"]), int(t["y"])))
         for r in irecs:
@@ -664,7 +687,7 @@ def intra_filter_ref(w, h, mode, mrl, bdpcm):
     return diff > _INTRA_THR[(int(np.log2(w)) + int(np.log2(h))) >> 1] and (ang & 31) == 0
 
 
-def gen_intra_records(rng, layout, W, H, modes=None, p_mrl=0.15, p_bdpcm=0.08, p_resi=0.0, upto=None, only=None, p_mip=0.15, colloc=0, p_lm=0.0):
+def gen_intra_records(rng, layout, W, H, modes=None, p_mrl=0.15, p_bdpcm=0.08, p_resi=0.0, upto=None, only=None, p_mip=0.15, colloc=0, p_lm=0.0, ciip=None):
     """b200_intra_tu records (Y, Cb, Cr per CU, decoding order) for a single-tree all-intra layout of gen_intra_layout: random modes, MRL on some luma
     blocks, BDPCM prediction on some, availability as xFillReferenceSamples derives it from the decoding order (pinned against the reference's own
     analysis through the glue flattener by tests/test_intra_oracle_vs_ref.py).  Luma blocks whose chroma would be narrower than 4 or smaller than 16
@@ -688,6 +711,8 @@ def gen_intra_records(rng, layout, W, H, modes=None, p_mrl=0.15, p_bdpcm=0.08, p
             dirC = chroma_modes[int(rng.integers(len(chroma_modes)))]
             if rng.random() < p_lm: dirC = int(rng.integers(67, 70))
         if dirC < 0 or dirC == 70: dirC = 0 if mip else dirL            # DM (a MIP luma CU counts as planar: PU::getCoLocatedIntraLumaMode)
+        wc = ciip.get(i, 0) if ciip else 0                              # CIIP CU (inter): planar blocks blended with the inter prediction, weight wc
+        if wc: dirL, dirC, mrl, bdpcm, mip = 0, 0, 0, 0, 0
         lm = dirC in (67, 68, 69)                                       # LM_CHROMA_IDX, MDLM_L_IDX, MDLM_T_IDX
         if only is not None and not only[i]: continue                   # an inter CU of a mixed picture: a neighbour, not a block of the list
         def avail(ux, uy): return 0 <= ux < owner.shape[1] and 0 <= uy < owner.shape[0] and owner[uy, ux] < i
@@ -697,8 +722,10 @@ def gen_intra_records(rng, layout, W, H, modes=None, p_mrl=0.15, p_bdpcm=0.08, p
         nl = 0
         while nl < 2 * h // 4 and avail(x // 4 - 1, y // 4 + nl): nl += 1
         luma_only = w < 8 or (w // 2) * (h // 2) < 16
+        if wc: luma_only = (w // 2) <= 2
         for c in range(1 if luma_only else 3):
             r = np.zeros((), A.INTRA_TU_DTYPE)
+            r["ciip"] = wc
             sh = 1 if c else 0
             r["x"], r["y"], r["log2w"], r["log2h"], r["comp"] = x >> sh, y >> sh, int(np.log2(w >> sh)), int(np.log2(h >> sh)), c
             if c == 0 and mip: r["mode"], r["mip"] = A.INTRA_MIP, dirL | ((mip >> 1) << 7)

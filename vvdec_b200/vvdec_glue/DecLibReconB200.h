@@ -7,7 +7,7 @@
 //
 // The CPU keeps: parsing (DecLibParser / DecSlice), motion derivation (DecCu::TaskDeriveCtuMotionInfo, DecCu.cpp:62), boundary strengths
 // (LoopFilter::calcFilterStrengthsCTU, LoopFilter.cpp:360), TaskFinishMotionInfo (DecCu.cpp:161).  Pictures that use a tool the device path
-// does not have (ISP intra blocks, IBC / CIIP CUs, RPR, wrap-around, sub-picture clipping, virtual-boundary ALF) throw UnsupportedFeatureException; a
+// does not have (ISP intra blocks, IBC CUs, RPR, wrap-around, sub-picture clipping, virtual-boundary ALF) throw UnsupportedFeatureException; a
 // deployment keeps a stock DecLibRecon next to this class and routes those pictures to it.
 #pragma once
 #include <vector>
@@ -142,14 +142,27 @@ public:
             }
           continue;
         }
-        if( !CU::isInter( cu ) || cu.ciipFlag() ) THROW_UNSUPPORTED( "DecLibReconB200: IBC / CIIP CU (SURVEY 8f-1)" );
+        if( !CU::isInter( cu ) ) THROW_UNSUPPORTED( "DecLibReconB200: IBC CU (SURVEY 8f-1)" );
+        bool ciipComp[3] = { false, false, false };
+        if( cu.ciipFlag() )
+        {
+          // CIIP: the inter prediction comes from K2 like any merge CU; K6 blends a planar intra block into it (predBlendIntraCiip) and adds the residual
+          if( sps.getUseReshaper() && cs.picHeader->getLmcsEnabledFlag() ) THROW_UNSUPPORTED( "DecLibReconB200: CIIP CUs with LMCS" );
+          for( int c = 0; c < (int) getNumberValidComponents( cu.chromaFormat ); c++ )
+          {
+            b200_intra_tu ir;
+            if( flattenCiipBlock( cu, ComponentID( c ), ir ) != FLATTEN_INTRA_OK ) continue;
+            if( TU::getCbf( cu.firstTU, ComponentID( c ) ) || ( c && cu.firstTU.jointCbCr ) ) ir.flags |= B200_INTRA_ADD_RESI;
+            m_intra.v.push_back( ir ); ciipComp[c] = true;
+          }
+        }
         FlattenPuResult rc;
         if( cu.mergeType() == MRG_TYPE_SUBPU_ATMVP ) rc = flattenSbTmvp( cu, sm, wpIdxOf, [&]( const b200_pu& r ) { m_pus.v.push_back( r ); } );
         else { b200_pu r; rc = flattenPU( cu, sm, wpIdxOf, r ); if( rc == FLATTEN_PU_OK ) m_pus.v.push_back( r ); }
         if( rc != FLATTEN_PU_OK ) THROW_UNSUPPORTED( "DecLibReconB200: inter tool outside the device path" );
         if( cu.rootCbf() )
           for( auto& tu : TUTraverser( &cu.firstTU, cu.lastTU->next ) )
-            for( int c = 0; c < (int) getNumberValidComponents( cu.chromaFormat ); c++ ) { b200_tu r; if( flattenTU( tu, ComponentID( c ), *m_trQuant, m_coefs.v, r ) ) m_tus.v.push_back( r ); }
+            for( int c = 0; c < (int) getNumberValidComponents( cu.chromaFormat ); c++ ) { b200_tu r; if( flattenTU( tu, ComponentID( c ), *m_trQuant, m_coefs.v, r ) ) { if( ciipComp[c] ) r.flags |= B200_TU_RESI; m_tus.v.push_back( r ); } }
       }
 
     // ---- in-loop filter parameters ----

@@ -108,4 +108,21 @@ inline FlattenIntraResult flattenIntraTU( const TransformUnit& tu, const Compone
   return FLATTEN_INTRA_OK;
 }
 
+// CIIP CU (inter CU with cu.ciipFlag()): predBlendIntraCiip (IntraPrediction.cpp:887) predicts each component's CU block planar (through
+// cu.firstTU, reference filter decided as for an intra CU) and blends it with the inter prediction; the weight follows from whether the left
+// (at the bottom-left corner) and above (at the top-right corner) neighbour CUs are intra (:917-925).  Chroma only if it is wider than 2.
+// Returns FLATTEN_INTRA_UNSUPPORTED for a component that carries no CIIP block.
+inline FlattenIntraResult flattenCiipBlock( const CodingUnit& cu, const ComponentID compID, b200_intra_tu& r )
+{
+  if( !isLuma( compID ) && !( isChromaEnabled( cu.chromaFormat ) && cu.chromaSize().width > 2 ) ) return FLATTEN_INTRA_UNSUPPORTED;
+  if( flattenIntraTU( cu.firstTU, compID, r ) != FLATTEN_INTRA_OK ) return FLATTEN_INTRA_UNSUPPORTED;
+  r.mode = B200_INTRA_PLANAR; r.multiRefIdx = 0; r.mip = 0;
+  r.flags &= ~B200_INTRA_FILTER_REF;
+  if( isLuma( compID ) && IntraPrediction::useFilteredIntraRefSamples( COMPONENT_Y, cu, cu ) ) r.flags |= B200_INTRA_FILTER_REF;
+  const CodingUnit* cuLeft  = cu.cs->getCURestricted( cu.Y().bottomLeft().offset( -1, 0 ), cu, CHANNEL_TYPE_LUMA, cu.left );
+  const CodingUnit* cuAbove = cu.cs->getCURestricted( cu.Y().topRight().offset( 0, -1 ), cu, CHANNEL_TYPE_LUMA, cu.above );
+  r.ciip = (uint8_t) ( 3 - !( cuLeft && CU::isIntra( *cuLeft ) ) - !( cuAbove && CU::isIntra( *cuAbove ) ) );
+  return FLATTEN_INTRA_OK;
+}
+
 }   // namespace b200glue
