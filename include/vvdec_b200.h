@@ -199,7 +199,8 @@ B200_API int b200_alf_picture(const b200_geom* g, const int16_t* const src[3], i
  *             table (InterpolationFilter.h:113-120; .cpp:424-962).
  *   stays CPU: merge/AMVP/affine/TMVP motion derivation (MIDER) and the mode decisions of motionCompensation :1411-1440
  *             (bioApplied, checkDMVRCondition UnitTools.cpp:1277, xCheckIdenticalMotion :404) — the flattener stores them as flags.
- *   not yet:   explicit weighted prediction, GEO blending, CIIP, IBC, RPR-scaled references, wrap-around, sub-pictures.
+ *   also here: explicit weighted prediction (b200_wp), GEO blending (B200_PU_GEO); CIIP CUs take their inter half from here and the intra half from K6.
+ *   not yet:   IBC, RPR-scaled references, wrap-around, sub-pictures.
  * One record per CU (ATMVP: per merged sub-PU run, InterPrediction.cpp:438). Reference pictures live in DPB slots.
  * ---------------------------------------------------------------------------------------------- */
 enum {
@@ -299,8 +300,10 @@ B200_API int b200_intra_reconstruct(const b200_geom* g, int16_t* const planes[3]
  *                 K3 deblock V,H (in place) -> K4 SAO (-> second work plane) -> K5 ALF/CC-ALF (-> DPB slot)
  *   with LMCS:    K2 stores forward-mapped luma -> K1 luma TUs -> per-VPDU chroma scale -> K1 chroma TUs (scaled residual) ->
  *                 inverse luma map -> K3 ...
- * Intra-predicted / IBC / CIIP samples are not produced on the GPU yet: the caller supplies them in
- * `given` (whole planes, uploaded before K2), inter PUs and residuals overwrite/add on top.
+ *   with intra:   ... K1 (TUs of intra / CIIP CUs leave their residual in residual planes) -> K6 (intra and CIIP blocks in decoding order,
+ *                 prediction [blend] + residual) -> K3 ...
+ * Samples of tools the device path does not have (ISP, IBC) can be supplied in `given` (whole planes, uploaded before K2); inter PUs,
+ * residuals and K6 blocks overwrite/add on top.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct b200_ctx b200_ctx;
 
