@@ -147,6 +147,7 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   B200_CUDA(cudaSetDevice(c->device));
   const int ai = c->nextArena; c->nextArena = (c->nextArena + 1) % c->numArenas;
   Arena& A = c->arenas[ai];
+  A.valid = false;                                                    // until every copy of this upload has been enqueued
   const b200_geom& g = c->g;
   const size_t n4 = (size_t)((g.width + 3) >> 2) * ((g.height + 3) >> 2);
   const size_t nCtu = (size_t)((g.width + g.ctuSize - 1) / g.ctuSize) * ((g.height + g.ctuSize - 1) / g.ctuSize);
