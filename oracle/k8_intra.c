@@ -112,15 +112,16 @@ static void pred_planar(const int16_t* src, int stride, int w, int h, int16_t* d
   }
 }
 
-static void pred_angular(const int16_t* src, int stride, int w0, int h0, int chroma, int dirMode, int mrl, int filtered, int doPDPC, int pmax, int16_t* dst, ptrdiff_t ds)
+/* topLen / leftLen: m_topRefLength / m_leftRefLength (2w / 2h for a regular block; CU size + partition size with ISP); waW x waH: the size the wide-angle
+ * mapping looks at (the CU with ISP); isp: always the cubic filter (:745) */
+static void pred_angular_ex(const int16_t* src, int stride, int w0, int h0, int chroma, int dirMode, int mrl, int doPDPC, int pmax, int16_t* dst, ptrdiff_t ds,
+                            int topLen, int leftLen, int waW, int waH, int isp)
 {
   int w = w0, h = h0;
-  const int predMode = wide_angle(w, h, dirMode), ver = predMode >= 34;
+  const int predMode = wide_angle(waW, waH, dirMode), ver = predMode >= 34;
   const int angMode = ver ? predMode - 50 : -(predMode - 18), absMode = abs(angMode);
   const int invAngle = kInvAng[absMode], absAng = kAng[absMode], angle = angMode < 0 ? -absAng : absAng;
-  const int topLen = 2 * w0, leftLen = 2 * h0;
   int16_t refAbove[2 * 128 + 3 + 33 * 3], refLeft[2 * 128 + 3 + 33 * 3], *refMain, *refSide;
-  (void)filtered;
   if (angle < 0) {
     for (int x = 0; x <= w + 1 + mrl; x++) refAbove[x + h] = AT(x, 0);
     for (int y = 0; y <= h + 1 + mrl; y++) refLeft[y + w] = AT(0, y);
@@ -157,7 +158,7 @@ static void pred_angular(const int16_t* src, int stride, int w0, int h0, int chr
       if (!chroma) {
         const int diff = imin(abs(predMode - 18), abs(predMode - 50)), log2Size = (ilog2(w) + ilog2(h)) >> 1;
         const int interpolationFlag = diff > kIntraFilterThr[0][log2Size];       /* filterFlag, and the angle is fractional here */
-        const int cubic = !interpolationFlag || mrl > 0;
+        const int cubic = isp || !interpolationFlag || mrl > 0;
         for (int y = 0; y < h; y++, deltaPos += angle) {
           const int dI = deltaPos >> 5, dF = deltaPos & 31;
           int f[4];
@@ -328,6 +329,74 @@ static void pred_cclm(const b200_geom* g, const int16_t* luma, ptrdiff_t ls, con
     } else { a = 0; b = minC; shift = 0; }
   } else { a = 0; b = 1 << (g->bitDepth - 1); shift = 0; }
   for (int j = 0; j < h; j++) for (int i = 0; i < w; i++) dst[j * ds + i] = (int16_t)iclip(0, pmax, ((a * d0[j * TS + i]) >> shift) + b);
+}
+
+static void pred_angular(const int16_t* src, int stride, int w0, int h0, int chroma, int dirMode, int mrl, int filtered, int doPDPC, int pmax, int16_t* dst, ptrdiff_t ds)
+{
+  (void)filtered;
+  pred_angular_ex(src, stride, w0, h0, chroma, dirMode, mrl, doPDPC, pmax, dst, ds, 2 * w0, 2 * h0, w0, h0, 0);
+}
+
+/* Intra sub-partitions (ISP), luma of one CU.  Follows IntraPrediction::initIntraPatternChTypeISP :966-1070 (the CU's reference samples are fetched
+ * once; every later partition takes a window of that buffer and refreshes the row above / column left of it from the partition reconstructed just
+ * before), predIntraAng / xPredIntraAng with useISP (:474, :592: wide-angle mapping by the CU size, cubic filter, PDPC only for partitions >= 4x4),
+ * the 4-wide prediction regions of vertical splits of 4xN / 8xN CUs (CU::isPredRegDiffFromTB, UnitTools.cpp:3404; DecCu.cpp:341-371), partition sizes
+ * CU::getISPSplitDim (UnitTools.cpp:360).  ispMode 1: horizontal split (rows), 2: vertical.  resiMask bit k: partition k adds resi (DecCu.cpp:390).
+ * Test infrastructure for the next K6 slice: no device path uses this yet. */
+void orc_intra_isp_cu(const b200_geom* g, int16_t* luma, const int16_t* resi, int x0, int y0, int w, int h, int ispMode, int dirMode,
+                      int availTL, int numAbove, int numLeft, int leftAvail, int aboveAvail, unsigned resiMask)
+{
+  const ptrdiff_t ps = g->stride[0];
+  const int pmax = (1 << g->bitDepth) - 1, S = 2 * w + 1, rows = 2 * h + 1;
+  int16_t* B = (int16_t*)calloc((size_t)S * rows + 64, sizeof(int16_t));
+  fill_ref(luma, ps, x0, y0, w, h, 0, 4, 4, availTL, numAbove, numLeft, g->bitDepth, B, S);
+  const int hor = ispMode == 1, split = hor ? h : w, nonSplit = hor ? w : h;
+  const int part = imax(split >> 2, nonSplit < 16 ? 16 / nonSplit : 1), nParts = split / part;
+  const int regDiff = !hor && (w == 4 || (w == 8 && h > 4));                       /* vertical split with partitions narrower than 4: predict 4 wide */
+  for (int k = 0; k < nParts; k++) {
+    const int ox = hor ? 0 : k * part, oy = hor ? k * part : 0, tw = hor ? w : part, th = hor ? part : h;
+    if (!regDiff || (ox % 4) == 0) {
+      const int rw = regDiff ? 4 : tw, rh = th;
+      int16_t* W = B + oy * S + ox;
+      const int topLen = w + rw, leftLen = h + rh;
+      const int16_t* rec = luma + (ptrdiff_t)(y0 + oy) * ps + x0 + ox;
+      if (ox || oy) {
+        if (hor) {
+          for (int i = 0; i < rw; i++) W[1 + i] = rec[-ps + i];
+          for (int i = rw; i < topLen; i++) W[1 + i] = rec[-ps + rw - 1];
+          if (!leftAvail) for (int j = 0; j <= leftLen; j++) W[j * S] = rec[-ps];
+        } else {
+          for (int j = 0; j < rh; j++) W[(1 + j) * S] = rec[j * ps - 1];
+          for (int j = rh; j < leftLen; j++) W[(1 + j) * S] = rec[(rh - 1) * ps - 1];
+          if (!aboveAvail) for (int i = 0; i <= topLen; i++) W[i] = rec[-1];
+        }
+      }
+      int16_t* dst = luma + (ptrdiff_t)(y0 + oy) * ps + x0 + ox;
+      const int16_t* src = W; const int stride = S;
+      const int doPDPC = rw >= 4 && rh >= 4;
+      if (dirMode == 0) pred_planar(src, stride, rw, rh, dst, ps);
+      else if (dirMode == 1) {
+        int sum = 0; const int denom = rw == rh ? rw << 1 : imax(rw, rh);
+        if (rw >= rh) for (int i = 0; i < rw; i++) sum += AT(1 + i, 0);
+        if (rw <= rh) for (int i = 0; i < rh; i++) sum += AT(0, 1 + i);
+        const int16_t dc = (int16_t)((sum + (denom >> 1)) >> ilog2(denom));
+        for (int y = 0; y < rh; y++) for (int x = 0; x < rw; x++) dst[y * ps + x] = dc;
+      } else pred_angular_ex(src, stride, rw, rh, 0, dirMode, 0, doPDPC, pmax, dst, ps, topLen, leftLen, w, h, 1);
+      if (doPDPC && dirMode <= 1) {
+        const int scale = (ilog2(rw) - 2 + ilog2(rh) - 2 + 2) >> 2;
+        for (int y = 0; y < rh; y++) {
+          const int wT = 32 >> imin(31, (y << 1) >> scale), left = AT(0, y + 1);
+          for (int x = 0; x < rw; x++) { const int wL = 32 >> imin(31, (x << 1) >> scale), top = AT(x + 1, 0), v = dst[y * ps + x]; dst[y * ps + x] = (int16_t)(v + ((wL * (left - v) + wT * (top - v) + 32) >> 6)); }
+        }
+      }
+    }
+    if (resi && (resiMask >> k) & 1)
+      for (int y = 0; y < th; y++) for (int x = 0; x < tw; x++) {
+        const ptrdiff_t o = (ptrdiff_t)(y0 + oy + y) * ps + x0 + ox + x;
+        luma[o] = (int16_t)iclip(0, pmax, luma[o] + resi[o]);
+      }
+  }
+  free(B);
 }
 
 void orc_intra_tu(const b200_geom* g, int16_t* const planes[3], const b200_intra_tu* t)

@@ -834,6 +834,49 @@ static int intraPredictCu( IntraPrediction& ip, CodingStructure& cs, CodingUnit&
   return 0;
 }
 
+// ISP luma of one CU, as DecCu::predAndReco walks it (DecCu.cpp:284-398): per sub-TU initIntraPatternChTypeISP (or once per 4-wide prediction
+// region), predIntraAng, pred + residual.  rec returns what the oracle needs: CU geometry, mode, the CU-level availability counts, and in
+// lmLeft / lmAbove whether the CU has a left / above neighbour.
+static int intraPredictIspCu( IntraPrediction& ip, CodingStructure& cs, CodingUnit& cu, const b200_geom* g, const int16_t* const resi[3], unsigned resiMask, b200_intra_tu& rec )
+{
+  memset( &rec, 0, sizeof( rec ) );
+  int k = 0;
+  for( TransformUnit& tu : TUTraverser( &cu.firstTU, cu.lastTU->next ) )
+  {
+    const CompArea& area = tu.blocks[COMPONENT_Y];
+    const bool predRegDiffFromTB = CU::isPredRegDiffFromTB( cu, COMPONENT_Y );
+    const bool firstTBInPredReg  = CU::isFirstTBInPredReg( cu, COMPONENT_Y, area );
+    CompArea areaPredReg( COMPONENT_Y, area );
+    PelBuf piReco = cs.getRecoBuf( area );
+    if( predRegDiffFromTB ) { if( firstTBInPredReg ) { CU::adjustPredArea( areaPredReg ); ip.initIntraPatternChTypeISP( cu, areaPredReg, piReco ); } }
+    else ip.initIntraPatternChTypeISP( cu, area, piReco );
+    if( k == 0 )
+    {
+      rec.x = (uint16_t) cu.lx(); rec.y = (uint16_t) cu.ly(); rec.log2w = (uint8_t) getLog2( cu.lwidth() ); rec.log2h = (uint8_t) getLog2( cu.lheight() );
+      rec.mode = (uint8_t) PU::getFinalIntraMode( cu, CH_L ); rec.flags = ip.m_neighborSize[0] ? B200_INTRA_AVAIL_TL : 0;
+      rec.numAbove = (uint8_t) ip.m_neighborSize[1]; rec.numLeft = (uint8_t) ip.m_neighborSize[2];
+      rec.lmLeft  = nullptr != cs.getCURestricted( cu.lumaPos().offset( -1, 0 ), cu, CH_L, cu.left );
+      rec.lmAbove = nullptr != cs.getCURestricted( cu.lumaPos().offset( 0, -1 ), cu, CH_L, cu.above );
+    }
+    if( !predRegDiffFromTB || firstTBInPredReg )
+    {
+      PelBuf piPred = cs.getRecoBuf( areaPredReg );
+      ip.predIntraAng( COMPONENT_Y, piPred, cu, false );
+    }
+    if( resi && resi[0] && ( ( resiMask >> k ) & 1 ) )
+    {
+      const int pmax = ( 1 << g->bitDepth ) - 1;
+      for( unsigned y = 0; y < area.height; y++ ) for( unsigned x = 0; x < area.width; x++ )
+      {
+        Pel& p = piReco.buf[y * piReco.stride + x];
+        p = (Pel) std::min( pmax, std::max( 0, p + resi[0][( area.y + y ) * g->stride[0] + area.x + x] ) );
+      }
+    }
+    k++;
+  }
+  return k;
+}
+
 // all != 0: every CU of the list is predicted (and, with rsv[1] set and resi given, reconstructed) in order — a whole intra picture
 extern "C" int ref_intra_case( int simd, const b200_geom* g, int16_t* const planes[3], const int16_t* const resi[3], const ref_intra_cu* cus, int numCus, int all,
                                b200_intra_tu* recs, int capRecs, int cclmCollocated )
@@ -873,6 +916,29 @@ extern "C" int ref_intra_case( int simd, const b200_geom* g, int16_t* const plan
       if( c.rsv[2] & 4 ) { cu.setCiipFlag( true ); cu.intraDir[0] = PLANAR_IDX; cu.intraDir[1] = DM_CHROMA_IDX; }
       cu.setMultiRefIdx( c.multiRefIdx ); cu.setBdpcmMode( c.bdpcm ); cu.setBdpcmModeChroma( c.bdpcmC );
       if( c.rsv[2] & 1 ) { cu.setMipFlag( true ); cu.setMipTransposedFlag( ( c.rsv[2] & 2 ) != 0 ); }      // dirL is the MIP mode index then
+      const int isp = ( c.rsv[2] >> 4 ) & 3;                                                                // 1 horizontal, 2 vertical split into sub-partitions
+      if( isp )
+      {
+        // sub-TUs like PartitionerImpl::getTUIntraSubPartitions (UnitPartitioner.cpp:628): luma strips, the chroma blocks ride in the last one
+        cu.setIspMode( isp );
+        const int part = (int) CU::getISPSplitDim( c.w, c.h, isp == 1 ? TU_1D_HORZ_SPLIT : TU_1D_VERT_SPLIT ), nParts = ( isp == 1 ? c.h : c.w ) / part;
+        for( int k = 0; k < nParts; k++ )
+        {
+          UnitArea sub = ua;
+          CompArea& y = sub.blocks[COMPONENT_Y];
+          if( isp == 1 ) { y.height = part; y.y = c.y + k * part; } else { y.width = part; y.x = c.x + k * part; }
+          if( k + 1 < nParts ) { sub.blocks[1] = CompArea(); sub.blocks[2] = CompArea(); }
+          cs.addTU( sub, CH_L, cu );
+        }
+        if( all || i == numCus - 1 )
+        {
+          b200_intra_tu r;
+          if( intraPredictIspCu( ip, cs, cu, g, resi, c.bdpcmC /* residual mask of the partitions */, r ) <= 0 ) return -4;
+          if( n < capRecs ) recs[n] = r;
+          n++;
+        }
+        continue;
+      }
       cs.addTU( ua, CH_L, cu );
       if( ( all || i == numCus - 1 ) && !( c.rsv[2] & 8 ) )                                                // plain inter CUs: their samples are given
         if( int rc = intraPredictCu( ip, cs, cu, g, resi, c.rsv[1] != 0, recs, capRecs, n ) ) return rc;

@@ -68,6 +68,9 @@ void orc_narrow8(const int16_t* src, ptrdiff_t stride, int w, int h, int bitDept
 /* K6 intra prediction of regular modes (k8_intra.c): blocks in list order, prediction written into the planes */
 void orc_intra_tu(const b200_geom* g, int16_t* const planes[3], const b200_intra_tu* t);
 void orc_intra_predict(const b200_geom* g, int16_t* const planes[3], const b200_intra_tu* tus, size_t numTus);
+/* intra sub-partitions of one luma CU (groundwork for the next K6 slice; see k8_intra.c) */
+void orc_intra_isp_cu(const b200_geom* g, int16_t* luma, const int16_t* resi, int x0, int y0, int w, int h, int ispMode, int dirMode,
+                      int availTL, int numAbove, int numLeft, int leftAvail, int aboveAvail, unsigned resiMask);
 void orc_intra_reconstruct(const b200_geom* g, int16_t* const planes[3], const int16_t* const resi[3], const b200_intra_tu* tus, size_t numTus);
 /* film grain synthesis, per-sample part (FilmGrainImpl::add_grain_block); tables as FilmGrainImpl holds them after FilmGrain::updateFGC:
  * pattern [2][8][64][64], sLUT / pLUT [3][256], lineSeeds [(h+15)/16] (FilmGrain::prepareBlockSeeds); 4:2:0, planes in place */

@@ -150,3 +150,38 @@ def test_ciip_blend(oracle, ref, w, h):
         for c in range(3):
             assert np.array_equal(got[c], want[c]), (c, inter_mask)
         assert not np.array_equal(want[0][64:64 + h, 64:64 + w], planes[0][64:64 + h, 64:64 + w])
+
+
+@pytest.mark.parametrize("w,h", [(4, 8), (8, 4), (8, 8), (4, 16), (16, 4), (8, 16), (16, 8), (16, 16), (32, 8), (8, 32), (32, 32), (64, 64), (64, 16), (16, 64), (4, 32), (32, 4)])
+def test_intra_isp_luma(oracle, ref, w, h):
+    """Intra sub-partitions (groundwork for the next K6 slice): the oracle's ISP restatement against the real initIntraPatternChTypeISP / predIntraAng
+    walk of DecCu — both split directions, partitions 1 / 2 samples thin (4-wide prediction regions), residual added on some partitions, interior /
+    edge / corner CUs, planar, DC and angular modes (wide angles by the CU shape)."""
+    rng = np.random.default_rng(w * 3 + h)
+    W, H, ctu = 256, 128, 128
+    layouts = [([(0, 0, 64, 64), (64, 0, 64, 64), (0, 64, 64, 64), (64, 64, w, h)], 3), ([(0, 0, w, h)], 0), ([(0, 0, 64, 64), (64, 0, w, h)], 1), ([(0, 0, 64, 64), (0, 64, w, h)], 1)]
+    modes = [0, 1, 2, 18, 34, 50, 66] + [int(m) for m in rng.integers(2, 67, size=8)]
+    for isp in (1, 2):
+        split, non = (h, w) if isp == 1 else (w, h)
+        part = max(split >> 2, 16 // non if non < 16 else 1)
+        if part < 1 or split // part < 2: continue
+        for layout, k in layouts:
+            for mode in modes:
+                bd = 10 if mode % 2 else 8
+                g = abi.make_geom(W, H, bd, ctu=ctu)
+                planes = synth.noise_planes(rng, W, H, bd)
+                resi = [rng.integers(-30, 31, size=p.shape).astype(np.int16) for p in planes]
+                cus = np.zeros(k + 1, synth.REF_INTRA_CU_DTYPE)
+                for i in range(k + 1): cus[i]["x"], cus[i]["y"], cus[i]["w"], cus[i]["h"] = layout[i]
+                mask = int(rng.integers(0, 16))
+                cus[k]["dirL"], cus[k]["rsv"][2], cus[k]["bdpcmC"], cus[k]["rsv"][0] = mode, isp << 4, mask, 1      # luma-only CU (chroma goes the regular way)
+                want = [p.copy() for p in planes]
+                rec = np.zeros(1, abi.INTRA_TU_DTYPE)
+                n = ref.ref_intra_case(mode & 1, C.byref(g), abi.plane_ptrs(want), abi.plane_ptrs(resi), cus.ctypes.data, k + 1, 0, rec.ctypes.data, 1, 0)
+                assert n == 1, n
+                r = rec[0]
+                got = planes[0].copy()
+                x, y = layout[k][0], layout[k][1]
+                oracle.orc_intra_isp_cu(C.byref(g), got, resi[0].ctypes.data, x, y, w, h, isp, mode, int(bool(r["flags"] & 2)), int(r["numAbove"]), int(r["numLeft"]),
+                                        int(r["lmLeft"]), int(r["lmAbove"]), mask)
+                assert np.array_equal(got, want[0]), (isp, layout[k], mode, mask)
