@@ -218,3 +218,26 @@ def test_tu_level_ts_bdpcm_jccr(oracle, ref):
         rec = _tu_case(oracle, ref, s, lv)
         if kind == 2: icts.add(rec.ict)
     assert icts == {-3, -2, -1, 1, 2, 3}
+
+
+def test_tu_level_isp_thin_partitions(oracle, ref):
+    """ISP groundwork: luma TUs of intra sub-partitions — 1 and 2 samples wide / high (the 1-D branches of TrQuant::xIT, :466-482) and the regular
+    widths — with the implicit transform selection of ISP (getTrTypes), DC-only blocks and dependent quantisation."""
+    rng = np.random.default_rng(17)
+    seen = set()
+    shapes = [(1, 16), (1, 32), (1, 64), (2, 8), (2, 16), (2, 32), (16, 1), (32, 1), (64, 1), (8, 2), (16, 2), (32, 2), (4, 4), (4, 16), (16, 4), (8, 8), (16, 16), (4, 32)]
+    for case in range(900):
+        s = RefTuSyntax()
+        s.comp = 0
+        s.w, s.h = shapes[case % len(shapes)]
+        s.ispMode = 2 if s.w < s.h else 1 if s.h < s.w else int(rng.integers(1, 3))
+        s.bitDepth = int(rng.choice([8, 10, 10, 12])); s.qp = int(rng.integers(-6 * (s.bitDepth - 8), 64))
+        s.predMode = 1; s.depQuant = int(rng.integers(0, 2))
+        s.spsMTS = int(rng.integers(0, 2)); s.spsIntraMTS = int(rng.integers(0, 2))
+        s.intraDirL = int(rng.integers(0, 67))
+        s.maxScanPosX = int(rng.integers(0, min(s.w, 32))); s.maxScanPosY = int(rng.integers(0, min(s.h, 32)))
+        if case % 5 == 0: s.maxScanPosX = s.maxScanPosY = 0
+        lv = _levels(rng, s.w, s.h, s.maxScanPosX, s.maxScanPosY, case % 11 == 0)
+        rec = _tu_case(oracle, ref, s, lv)
+        seen.add((rec.log2w, rec.log2h, rec.trType))
+    assert any(k[0] == 0 for k in seen) and any(k[1] == 0 for k in seen) and len({k[2] for k in seen}) >= 3
