@@ -375,6 +375,10 @@ B200_API int  b200_pic_run(b200_ctx* ctx, int arena);
 B200_API int  b200_wait_picture(b200_ctx* ctx, int arena, int32_t* dmvrMv, size_t numDmvr);
 /* Output: DPB slot -> host planes (vvdec_frame planes; xAddPicture vvdecimpl.cpp:957). Synchronous D2H. */
 B200_API int  b200_get_frame(b200_ctx* ctx, int slot, int16_t* const planes[3]);
+/* The same two transfers for host planes with margins (vvdec's PelStorage, Buffer.cpp:645: stride > width), strides in samples:
+ * reference pictures reconstructed by the CPU back end enter the device DPB, finished pictures land in Picture::m_bufs. */
+B200_API int  b200_ctx_load_slot_strided(b200_ctx* ctx, int slot, const int16_t* const planes[3], const ptrdiff_t strides[3]);
+B200_API int  b200_get_frame_strided(b200_ctx* ctx, int slot, int16_t* const planes[3], const ptrdiff_t strides[3]);
 /* Asynchronous output: the D2H copy runs on a second stream after the picture is final and overlaps the next pictures' kernels;
  * the context makes later pictures wait before they overwrite a buffer that is still being read.  Returns a ticket (>= 0);
  * b200_frame_wait(ticket) blocks until those planes are complete in host memory (pinned memory recommended). */

@@ -1526,3 +1526,6 @@ extern "C" double ref_decompress_picture_mt( const b200_geom* g, const int16_t* 
 {
   return ref_decompress_picture_out( g, refs, pic, threads, simd, nullptr );
 }
+
+// ================================================================================================ the DecLibRecon seam, executed
+#include "ref_seam.h"

@@ -143,6 +143,36 @@ void ref_lmcs_scale_block(int16_t* ptr, ptrdiff_t stride, int w, int h, int scal
 int  ref_lmcs_vpdu_scale(const b200_geom* g, int16_t* const planes[3], int x, int y);            /* calculateChromaAdjVpduNei on a picture with one CU per CTU */
 double ref_decompress_picture_out(const b200_geom* g, const int16_t* const* refs, const b200_picture* pic, int threads, int simd, int16_t* const out[3]);
 
+/* ---- the DecLibRecon seam, executed (oracle/ref_seam.h): a synthetic PARSED picture (real CodingStructure: CU / TU lists through the reference's
+ * allocators and Partitioner, levels in the reconstruction plane, CtuData, slice / APS state; motion left as merge / AMVP syntax) reconstructed by
+ * (i) the reference's own DecLibRecon with a ThreadPool of `threads` threads, or (ii) b200glue::DecLibReconB200 (the GPU back end, same calls). ---- */
+enum { SEAM_BDOF = 1, SEAM_DMVR = 2, SEAM_BCW = 4, SEAM_PROF = 8, SEAM_MMVD = 16, SEAM_GEO = 32, SEAM_CIIP = 64, SEAM_SMVD = 128, SEAM_AMVR = 256,
+       SEAM_MTS = 512, SEAM_LFNST = 1024, SEAM_SBT = 2048, SEAM_MRL = 4096, SEAM_MIP = 8192, SEAM_CCLM = 16384, SEAM_JCCR = 32768, SEAM_TS = 65536,
+       SEAM_BDPCM = 1 << 17, SEAM_SAO = 1 << 18, SEAM_ALF = 1 << 19, SEAM_LMCS = 1 << 20, SEAM_DEPQUANT = 1 << 21, SEAM_LOCAL_DUAL_TREE = 1 << 22 };
+typedef struct ref_seam_cfg {
+  uint32_t seed;
+  int32_t  sliceType;        /* 0 B, 1 P, 2 I                                                                  */
+  int32_t  tools;            /* SEAM_* : SPS / PH / slice tool flags                                            */
+  int32_t  qp;               /* slice QP; CU QPs walk around it                                                 */
+  int32_t  intraPct;         /* intra CUs in P / B slices, percent                                              */
+  int32_t  skipPct, mergePct, affinePct, biPct;
+  int32_t  rootCbfPct, cbfPct;
+  int32_t  splitPct;         /* probability of splitting a 64-sample-wide block further (scaled for other sizes) */
+  int32_t  ispPct;           /* > 0 switches sps ISP on                                                         */
+  int32_t  mvdSigmaQpel;     /* sigma of the MVDs in quarter samples                                            */
+  int32_t  lmcsMinBin, lmcsMaxBin, lmcsDeltaCW[16], lmcsChrOffset, lmcsChromaAdj;   /* LMCS APS syntax (SEAM_LMCS) */
+} ref_seam_cfg;
+/* refs[slot*3+comp]: 4 reference pictures as in ref_mc_predict (unused for I pictures); filt: deblocking offsets / SAO / ALF parameters of the picture
+ * (b200_picture::lfSlices, sao, alf, alfTabs and the DEBLOCK / SAO / ALF flags; the other members are ignored). */
+void*  ref_seam_create(const b200_geom* g, const ref_seam_cfg* cfg, const int16_t* const* refs, const b200_picture* filt);
+void   ref_seam_destroy(void* h);
+size_t ref_seam_col_motion_bytes(void* h);
+void   ref_seam_stats(void* h, int32_t st[16]);
+/* Each handle can be reconstructed ONCE (reconstruction overwrites the levels, MIDER overwrites the motion syntax).  Both return the seconds between
+ * decompressPicture() and the return of waitForPrevDecompressedPic(), < 0 on error (-4: the picture uses a tool the device path refuses). */
+double ref_seam_run_stock(void* h, int threads, int16_t* const out[3], uint8_t* colMotion, size_t colBytes);
+double ref_seam_run_b200(void* h, int threads, int dry, int16_t* const out[3], uint8_t* colMotion, size_t colBytes, b200_picture* flat);
+
 #ifdef __cplusplus
 }
 #endif

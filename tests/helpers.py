@@ -104,7 +104,140 @@ def load_ref():
     lib.ref_decompress_picture_out.restype = C.c_double
     lib.ref_decompress_picture_mt.argtypes = [C.POINTER(abi.Geom), C.POINTER(C.c_void_p), C.POINTER(abi.Picture), C.c_int, C.c_int]
     lib.ref_decompress_picture_mt.restype = C.c_double
+    declare_seam(lib)
     return lib
+
+
+# ---- the DecLibRecon seam (oracle/ref_seam.h) ----
+SEAM = dict(BDOF=1, DMVR=2, BCW=4, PROF=8, MMVD=16, GEO=32, CIIP=64, SMVD=128, AMVR=256, MTS=512, LFNST=1024, SBT=2048, MRL=4096, MIP=8192, CCLM=16384,
+            JCCR=32768, TS=65536, BDPCM=1 << 17, SAO=1 << 18, ALF=1 << 19, LMCS=1 << 20, DEPQUANT=1 << 21, LOCAL_DUAL_TREE=1 << 22)
+SEAM_INTER_TOOLS = sum(SEAM[k] for k in ("BDOF", "DMVR", "BCW", "PROF", "MMVD", "GEO", "SMVD", "AMVR"))
+SEAM_RESI_TOOLS = sum(SEAM[k] for k in ("MTS", "SBT", "JCCR", "TS", "DEPQUANT"))
+SEAM_INTRA_TOOLS = sum(SEAM[k] for k in ("LFNST", "MRL", "MIP", "CCLM", "BDPCM", "CIIP"))
+SEAM_FILTERS = SEAM["SAO"] | SEAM["ALF"]
+
+
+class SeamCfg(C.Structure):
+    _fields_ = [("seed", C.c_uint32)] + [(n, C.c_int32) for n in ("sliceType", "tools", "qp", "intraPct", "skipPct", "mergePct", "affinePct", "biPct", "rootCbfPct",
+                                                                    "cbfPct", "splitPct", "ispPct", "mvdSigmaQpel", "lmcsMinBin", "lmcsMaxBin")] + \
+               [("lmcsDeltaCW", C.c_int32 * 16), ("lmcsChrOffset", C.c_int32), ("lmcsChromaAdj", C.c_int32)]
+
+
+def seam_cfg(seed, slice_type=0, tools=None, qp=32, intra=15, skip=15, merge=50, affine=12, bi=60, root_cbf=45, cbf=35, split=75, isp=0, mvd_sigma=12, lmcs=None):
+    c = SeamCfg()
+    c.seed = seed; c.sliceType = slice_type
+    c.tools = (SEAM_INTER_TOOLS | SEAM_RESI_TOOLS | SEAM_INTRA_TOOLS | SEAM_FILTERS) if tools is None else tools
+    c.qp = qp; c.intraPct = intra; c.skipPct = skip; c.mergePct = merge; c.affinePct = affine; c.biPct = bi; c.rootCbfPct = root_cbf; c.cbfPct = cbf
+    c.splitPct = split; c.ispPct = isp; c.mvdSigmaQpel = mvd_sigma
+    if lmcs is not None:                                      # the dict synth.gen_lmcs returns
+        c.tools |= SEAM["LMCS"]; c.lmcsMinBin = lmcs["minBin"]; c.lmcsMaxBin = lmcs["maxBin"]; c.lmcsChrOffset = lmcs["chrOff"]; c.lmcsChromaAdj = int(lmcs["struct"].chromaAdj)
+        for i in range(16): c.lmcsDeltaCW[i] = lmcs["delta"][i]
+    return c
+
+
+def declare_seam(lib):
+    if not hasattr(lib, "ref_seam_create"):
+        return
+    PL = C.POINTER(C.POINTER(C.c_int16))
+    lib.ref_seam_create.argtypes = [C.POINTER(abi.Geom), C.POINTER(SeamCfg), C.POINTER(C.c_void_p), C.POINTER(abi.Picture)]; lib.ref_seam_create.restype = C.c_void_p
+    lib.ref_seam_destroy.argtypes = [C.c_void_p]; lib.ref_seam_destroy.restype = None
+    lib.ref_seam_col_motion_bytes.argtypes = [C.c_void_p]; lib.ref_seam_col_motion_bytes.restype = C.c_size_t
+    lib.ref_seam_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]; lib.ref_seam_stats.restype = None
+    lib.ref_seam_run_stock.argtypes = [C.c_void_p, C.c_int, PL, C.c_void_p, C.c_size_t]; lib.ref_seam_run_stock.restype = C.c_double
+    lib.ref_seam_run_b200.argtypes = [C.c_void_p, C.c_int, C.c_int, PL, C.c_void_p, C.c_size_t, C.POINTER(abi.Picture)]; lib.ref_seam_run_b200.restype = C.c_double
+
+
+class SeamCase:
+    """One synthetic parsed picture: geometry, reference pictures, filter parameters and generator configuration.  build() makes a fresh
+    reference-side Picture from them (every back end consumes the one it reconstructs)."""
+    def __init__(self, ref, rng, W, H, bd=10, ctu=128, lmcs=False, deblock=True, **cfg_kw):
+        self.ref, self.g, self.W, self.H, self.bd = ref, abi.make_geom(W, H, bd, ctu=ctu), W, H, bd
+        seed = int(rng.integers(1, 1 << 30))
+        self.refs = [synth.noise_planes(rng, W, H, bd) for _ in range(4)]
+        # filter-stage parameters only: deblocking offsets, SAO, ALF (+ an LMCS model); the CU-level content comes from the seam generator
+        self.filt = synth.gen_picture(rng, W, H, bd, ctu=ctu, dst_slot=4, inter=False, cu_kw=dict(min_dim=32, min_area=1024), tu_kw=dict(p_cbf=0.0), lmcs=lmcs, deblock=deblock)
+        if deblock: self.filt["lfSlices"]["beta"] = rng.integers(-3, 4, size=(1, 3)); self.filt["lfSlices"]["tc"] = rng.integers(-3, 4, size=(1, 3))
+        self.cfg = seam_cfg(seed, lmcs=self.filt.get("lmcs"), **cfg_kw)
+
+    def build(self):
+        h = self.ref.ref_seam_create(C.byref(self.g), C.byref(self.cfg), ref_ptrs(self.refs), C.byref(self.filt["struct"]))
+        assert h, "ref_seam_create failed"
+        return h
+
+    def stats(self):
+        h = self.build(); st = (C.c_int32 * 16)(); self.ref.ref_seam_stats(h, st); self.ref.ref_seam_destroy(h)
+        names = ["cus", "intra", "tus", "skip", "merge", "affine", "geo", "ciip", "mmvd", "resi", "sbt", "lfnst", "mts", "isp", "mip", "chromaTree"]
+        return dict(zip(names, list(st)))
+
+    def _out(self):
+        return [np.zeros((self.H, self.W), np.int16), np.zeros((self.H // 2, self.W // 2), np.int16), np.zeros((self.H // 2, self.W // 2), np.int16)]
+
+    def run_stock(self, threads=0):
+        h = self.build(); out = self._out(); col = np.zeros(self.ref.ref_seam_col_motion_bytes(h), np.uint8)
+        secs = self.ref.ref_seam_run_stock(h, threads, abi.plane_ptrs(out), col.ctypes.data, len(col))
+        self.ref.ref_seam_destroy(h)
+        assert secs >= 0, f"stock DecLibRecon failed ({secs})"
+        return out, col, secs
+
+    def run_b200(self, threads=0):
+        h = self.build(); out = self._out(); col = np.zeros(self.ref.ref_seam_col_motion_bytes(h), np.uint8)
+        secs = self.ref.ref_seam_run_b200(h, threads, 0, abi.plane_ptrs(out), col.ctypes.data, len(col), None)
+        self.ref.ref_seam_destroy(h)
+        return out, col, secs
+
+    def flatten(self, threads=0):
+        """Host stages of DecLibReconB200 only (no device): the work lists as a picture dict of copies, usable with helpers.oracle_decompress / the C ABI."""
+        h = self.build(); flat = abi.Picture()
+        secs = self.ref.ref_seam_run_b200(h, threads, 1, None, None, 0, C.byref(flat))
+        self.ref.ref_seam_destroy(h)
+        if secs < 0: return None, secs
+        return picture_from_struct(flat, self.g, self.filt), secs
+
+
+def _copy(ptr, n, dtype):
+    if not n: return np.zeros(0, dtype)
+    return np.frombuffer((C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr), dtype=dtype).copy()
+
+
+def picture_from_struct(st, g, filt):
+    """Deep copy of a b200_picture (pointers into the recon object) into the dict layout of synth.gen_picture."""
+    W4, H4 = (g.width + 3) // 4, (g.height + 3) // 4
+    nctu = ((g.width + g.ctuSize - 1) // g.ctuSize) * ((g.height + g.ctuSize - 1) // g.ctuSize)
+    d = dict(pus=_copy(st.pus, st.numPus, synth.PU_DTYPE), ndmvr=int(st.numDmvr) - 1, tus=_copy(st.tus, st.numTus, abi.TU_DTYPE), coefs=_copy(st.coefs, st.numCoefs, np.int16))
+    if len(d["coefs"]) == 0: d["coefs"] = np.zeros(1, np.int16)
+    p = abi.Picture(); p.dstSlot = st.dstSlot; p.flags = st.flags
+    p.pus = d["pus"].ctypes.data; p.numPus = len(d["pus"]); p.numDmvr = st.numDmvr
+    p.tus = d["tus"].ctypes.data; p.numTus = len(d["tus"]); p.coefs = d["coefs"].ctypes.data; p.numCoefs = st.numCoefs
+    if st.numIntraTus:
+        d["intraTus"] = _copy(st.intraTus, st.numIntraTus, abi.INTRA_TU_DTYPE); p.intraTus = d["intraTus"].ctypes.data; p.numIntraTus = st.numIntraTus
+    if st.flags & abi.PIC_DEBLOCK:
+        d["lfV"] = _copy(st.lfV, W4 * H4, synth.LF_DTYPE); d["lfH"] = _copy(st.lfH, W4 * H4, synth.LF_DTYPE); d["lfSlices"] = _copy(st.lfSlices, 1, synth.LFSLICE_DTYPE)
+        p.lfV = d["lfV"].ctypes.data; p.lfH = d["lfH"].ctypes.data; p.lfSlices = d["lfSlices"].ctypes.data; p.numLfSlices = 1
+    if st.flags & abi.PIC_SAO:
+        d["sao"] = _copy(st.sao, nctu, synth.SAO_DTYPE); p.sao = d["sao"].ctypes.data
+    if st.flags & abi.PIC_ALF:
+        d["alf"] = dict(ctus=_copy(st.alf, nctu, synth.ALFCTU_DTYPE)); p.alf = d["alf"]["ctus"].ctypes.data
+        T = C.cast(st.alfTabs, C.POINTER(abi.AlfTables)).contents
+        d["alfArrays"] = dict(lumaCoeff=_copy(T.lumaCoeff, T.numLumaSets * 1300, np.int16), lumaClip=_copy(T.lumaClip, T.numLumaSets * 1300, np.int16),
+                              chromaCoeff=_copy(T.chromaCoeff, max(1, T.numChromaAlts) * 7, np.int16), chromaClip=_copy(T.chromaClip, max(1, T.numChromaAlts) * 7, np.int16),
+                              cc0=_copy(T.ccCoeff[0], max(1, T.numCc[0]) * 7, np.int16), cc1=_copy(T.ccCoeff[1], max(1, T.numCc[1]) * 7, np.int16))
+        A = abi.AlfTables(); a = d["alfArrays"]
+        A.lumaCoeff = a["lumaCoeff"].ctypes.data; A.lumaClip = a["lumaClip"].ctypes.data; A.numLumaSets = T.numLumaSets
+        A.chromaCoeff = a["chromaCoeff"].ctypes.data; A.chromaClip = a["chromaClip"].ctypes.data; A.numChromaAlts = T.numChromaAlts
+        A.ccCoeff[0] = a["cc0"].ctypes.data; A.ccCoeff[1] = a["cc1"].ctypes.data; A.numCc[0] = T.numCc[0]; A.numCc[1] = T.numCc[1]
+        d["alfTabs"] = A; p.alfTabs = C.addressof(A)
+    if st.numWp:
+        d["wp"] = _copy(st.wp, st.numWp, synth.WP_DTYPE); p.wp = d["wp"].ctypes.data; p.numWp = st.numWp
+    if st.flags & abi.PIC_LMCS:
+        L = C.cast(st.lmcs, C.POINTER(abi.Lmcs)).contents
+        vs = 64 if g.ctuSize == 128 else g.ctuSize
+        nv = ((g.width + vs - 1) // vs) * ((g.height + vs - 1) // vs)
+        L2 = abi.Lmcs(); C.memmove(C.byref(L2), C.byref(L), C.sizeof(abi.Lmcs))
+        inv = _copy(L.invLUT, 1 << g.bitDepth, np.int16); vp = _copy(L.vpdus, nv, synth.LMCS_VPDU_DTYPE) if L.vpdus else np.zeros(nv, synth.LMCS_VPDU_DTYPE)
+        L2.invLUT = inv.ctypes.data; L2.vpdus = vp.ctypes.data
+        d["lmcs"] = dict(struct=L2, invLUT=inv, vpdus=vp); p.lmcs = C.addressof(L2)
+    d["struct"] = p
+    return d
 
 
 def aligned(shape, dtype, fill=0, align=64):

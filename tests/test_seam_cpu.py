@@ -1,0 +1,70 @@
+"""The DecLibRecon seam, executed on the CPU (SURVEY 8c level L1): a synthetic PARSED picture (oracle/ref_seam.h — real CodingStructure built through
+the reference's Partitioner / addCU / addTU, levels in the reconstruction plane, motion as merge / AMVP syntax) is reconstructed by
+  (i)  the reference's own DecLibRecon::decompressPicture / waitForPrevDecompressedPic (DecLibRecon.cpp:429,684) on a ThreadPool, and
+  (ii) the host stages of the drop-in class b200glue::DecLibReconB200 (MIDER, boundary strengths, CU / TU walk -> work lists) followed by the oracle chain
+       (K2 -> K1 -> K6 -> LMCS -> K3 -> K4 -> K5) on those lists — what the device executes (tests/test_seam_gpu.py runs the same pictures on the GPU).
+Bit-exact equality of the three planes is required.  This pins the flatten walk over a parsed picture and the oracle chain at picture level against the
+unmodified reference's picture-level entry point."""
+import numpy as np, pytest
+from tests import helpers
+
+ref = helpers.load_ref()
+pytestmark = pytest.mark.skipif(ref is None or not hasattr(ref, "ref_seam_create"), reason="oracle/_ref not built")
+
+T_INTER = helpers.SEAM_INTER_TOOLS | helpers.SEAM_RESI_TOOLS | helpers.SEAM_FILTERS
+CASES = {
+    "B_mixed_intra": dict(),                                                    # 15 % intra CUs, CIIP, GEO, affine, MMVD, SBT, MTS, LFNST, MIP, CCLM, full filter chain
+    "B_intra_heavy": dict(intra=45, skip=5),
+    "I_picture": dict(slice_type=2),
+    "P_picture": dict(slice_type=1),
+    "B_lmcs_inter": dict(lmcs=True, intra=0, tools=T_INTER),                    # LMCS with chroma scaling; inter CUs only (intra + LMCS: see test_seam_gpu / DESIGN)
+    "B_ctu64": dict(ctu=64),
+    "B_ctu32_8bit": dict(ctu=32, bd=8),
+    "B_no_filters": dict(deblock=False, tools=helpers.SEAM_INTER_TOOLS | helpers.SEAM_RESI_TOOLS | helpers.SEAM_INTRA_TOOLS),
+}
+
+
+def run_case(seed, W, H, threads, **kw):
+    oracle = helpers.load_oracle()
+    case = helpers.SeamCase(ref, np.random.default_rng(seed), W, H, **kw)
+    out, col, secs = case.run_stock(threads=threads)
+    pic, s2 = case.flatten(threads=threads)
+    assert pic is not None, f"DecLibReconB200 refused the picture ({s2})"
+    want, _ = helpers.oracle_decompress(oracle, case.g, case.refs + [[np.zeros_like(p) for p in case.refs[0]]], pic)
+    for c in range(3):
+        assert np.array_equal(want[c], out[c]), f"plane {c}: {np.count_nonzero(want[c] != out[c])} samples differ from the reference's DecLibRecon"
+    return case
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_stock_declibrecon_vs_flatten_oracle(name, seed):
+    run_case(seed, 416, 240, 0, **CASES[name])
+
+
+def test_tool_coverage_of_the_generator():
+    st = helpers.SeamCase(ref, np.random.default_rng(7), 832, 480).stats()
+    for k in ("intra", "skip", "merge", "affine", "geo", "ciip", "mmvd", "resi", "sbt", "lfnst", "mts", "mip"):
+        assert st[k] > 0, (k, st)
+    assert 0.05 < st["intra"] / st["cus"] < 0.3, st
+
+
+def test_thread_pool_runs_match_single_thread():
+    """Both back ends on a pool of 4 threads (wave-front MIDER rows, parallel flatten rows) give what the single-threaded runs give."""
+    run_case(11, 832, 480, 4)
+    run_case(12, 832, 480, 4, slice_type=2)
+
+
+def test_1080p_picture():
+    run_case(21, 1920, 1080, 4)
+
+
+def test_unsupported_tool_follows_the_error_contract():
+    """An ISP picture: the stock back end reconstructs it; DecLibReconB200 throws UnsupportedFeatureException inside a pool task, which must surface
+    as pic->error + reconDone exception (DecLibRecon.cpp:704-715) — rc -4 here — and leave the recon object usable for the next picture."""
+    case = helpers.SeamCase(ref, np.random.default_rng(5), 416, 240, isp=40)
+    assert case.stats()["isp"] > 0
+    case.run_stock(threads=0)
+    pic, rc = case.flatten(threads=0)
+    assert pic is None and rc == -4.0
+    run_case(6, 416, 240, 0)            # the same (static) recon object afterwards

@@ -1,0 +1,42 @@
+"""The DecLibRecon seam on the GPU (SURVEY 8c level L1): the reference's own DecLibRecon (CPU, ThreadPool) and the drop-in class
+b200glue::DecLibReconB200 (device, through the C ABI) reconstruct the SAME synthetic parsed Picture — same create / decompressPicture /
+waitForPrevDecompressedPic calls (oracle/ref_seam.h).  Required bit-exact: the three reconstruction planes as they land in Picture::m_bufs and the
+collocated motion field (CodingStructure::m_colMiMap: what TaskFinishMotionInfo leaves for later pictures' TMVP, DMVR refinements included)."""
+import numpy as np, pytest
+from tests import helpers
+
+ref = helpers.load_ref()
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(ref is None or not hasattr(ref, "ref_seam_create"), reason="oracle/_ref not built")]
+
+T_INTER = helpers.SEAM_INTER_TOOLS | helpers.SEAM_RESI_TOOLS | helpers.SEAM_FILTERS
+
+
+def both(seed, W, H, threads=4, **kw):
+    case = helpers.SeamCase(ref, np.random.default_rng(seed), W, H, **kw)
+    want, col_want, t_cpu = case.run_stock(threads=threads)
+    got, col_got, t_gpu = case.run_b200(threads=threads)
+    assert t_gpu >= 0, f"DecLibReconB200 failed ({t_gpu})"
+    for c in range(3):
+        assert np.array_equal(want[c], got[c]), f"plane {c}: {np.count_nonzero(want[c] != got[c])} samples differ"
+    assert np.array_equal(col_want, col_got), "collocated motion (colMotion / DMVR write-back) differs"
+    return t_cpu, t_gpu
+
+
+@pytest.mark.parametrize("name,kw", [("B_mixed_intra", dict()), ("I_picture", dict(slice_type=2)), ("P_picture", dict(slice_type=1)),
+                                     ("B_lmcs_inter", dict(lmcs=True, intra=0, tools=T_INTER)), ("B_ctu64", dict(ctu=64))])
+@pytest.mark.parametrize("seed", [1, 2])
+def test_seam_small(name, kw, seed):
+    both(seed, 416, 240, **kw)
+
+
+def test_seam_1080p_and_4k():
+    both(31, 1920, 1080, threads=8)
+    both(32, 3840, 2160, threads=16)
+    both(33, 3840, 2160, threads=16, lmcs=True, intra=0, tools=T_INTER)
+
+
+def test_seam_error_contract_on_the_device_path():
+    case = helpers.SeamCase(ref, np.random.default_rng(5), 416, 240, isp=40)
+    _, _, rc = case.run_b200(threads=2)
+    assert rc == -4.0
+    both(6, 416, 240)

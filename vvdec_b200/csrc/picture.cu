@@ -382,6 +382,33 @@ B200_API int b200_get_frame(b200_ctx* c, int slot, int16_t* const planes[3])
   return 0;
 }
 
+// Picture buffers of the host decoder carry margins (stride > width): 2-D copies between the margin-less device planes and strided host planes.
+B200_API int b200_ctx_load_slot_strided(b200_ctx* c, int slot, const int16_t* const planes[3], const ptrdiff_t strides[3])
+{
+  B200_CHECK(c && planes && strides && slot >= 0 && slot < c->numSlots, "b200_ctx_load_slot_strided: bad argument");
+  DevPlanes d = c->planes(c->slotBuf[slot]);
+  for (int k = 0; k < (c->g.chromaFormat ? 3 : 1); k++) {
+    const size_t w = k ? c->g.width >> 1 : c->g.width, h = k ? c->g.height >> 1 : c->g.height;
+    B200_CHECK(planes[k] && strides[k] >= (ptrdiff_t)w, "b200_ctx_load_slot_strided: plane %d", k);
+    B200_CUDA(cudaMemcpy2DAsync(d.p[k], (size_t)c->g.stride[k] * 2, planes[k], (size_t)strides[k] * 2, w * 2, h, cudaMemcpyHostToDevice, c->stream));
+  }
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+B200_API int b200_get_frame_strided(b200_ctx* c, int slot, int16_t* const planes[3], const ptrdiff_t strides[3])
+{
+  B200_CHECK(c && planes && strides && slot >= 0 && slot < c->numSlots, "b200_get_frame_strided: bad argument");
+  DevPlanes d = c->planes(c->slotBuf[slot]);
+  for (int k = 0; k < (c->g.chromaFormat ? 3 : 1); k++) {
+    const size_t w = k ? c->g.width >> 1 : c->g.width, h = k ? c->g.height >> 1 : c->g.height;
+    B200_CHECK(planes[k] && strides[k] >= (ptrdiff_t)w, "b200_get_frame_strided: plane %d", k);
+    B200_CUDA(cudaMemcpy2DAsync(planes[k], (size_t)strides[k] * 2, d.p[k], (size_t)c->g.stride[k] * 2, w * 2, h, cudaMemcpyDeviceToHost, c->stream));
+  }
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 B200_API int b200_get_frame_async(b200_ctx* c, int slot, int16_t* const planes[3])
 {
   B200_CHECK(c && planes && slot >= 0 && slot < c->numSlots, "b200_get_frame_async: bad argument");

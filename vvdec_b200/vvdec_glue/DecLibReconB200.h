@@ -1,17 +1,33 @@
-// DecLibReconB200.h — the drop-in for DecLibRecon (reference DecoderLib/DecLibRecon.h:143-200): same five methods, reconstruction on a B200
-// through the C ABI of include/vvdec_b200.h.  Header-only glue that lives INSIDE a VVdeC build; it is compiled against
-// the reference headers by oracle/Makefile.ref (it is included by oracle/ref_shim.cpp), its building blocks — flattenTU, flattenPU /
-// flattenSbTmvp, flattenSAO / flattenALF / buildAlfTables / flattenLfCtu — are pinned one by one against the reference
-// (tests/test_k1_oracle_vs_ref.py, test_flatten_pu_vs_ref.py, test_flatten_filters_vs_ref.py).  What cannot be exercised on the build box is
-// the walk over a *parsed* picture: there is no VVC bitstream or encoder here.
+// DecLibReconB200.h — the drop-in for DecLibRecon (reference DecoderLib/DecLibRecon.h:143-200): the same methods with the same signatures
+// and the same contract — create( ThreadPool*, unsigned, bool ), destroy(), decompressPicture( Picture* ), waitForPrevDecompressedPic(),
+// cleanupOnException(), getCurrPic() — reconstruction on a B200 through the C ABI of include/vvdec_b200.h.  Header-only glue that lives INSIDE a
+// VVdeC build.  It is compiled against the reference headers by oracle/Makefile.ref and EXECUTED by oracle/ref_seam.h: the stock
+// DecLibRecon and this class reconstruct the same parsed Picture, bit-exactly (tests/test_seam_*.py).  Its building blocks — flattenTU, flattenPU /
+// flattenSbTmvp, flattenIntraTU / flattenCiipBlock, flattenSAO / flattenALF / buildAlfTables / flattenLfCtu — are also pinned one by one.
 //
-// The CPU keeps: parsing (DecLibParser / DecSlice), motion derivation (DecCu::TaskDeriveCtuMotionInfo, DecCu.cpp:62), boundary strengths
-// (LoopFilter::calcFilterStrengthsCTU, LoopFilter.cpp:360), TaskFinishMotionInfo (DecCu.cpp:161).  Pictures that use a tool the device path
-// does not have (ISP intra blocks, IBC CUs, RPR, wrap-around, sub-picture clipping, virtual-boundary ALF) throw UnsupportedFeatureException; a
-// deployment keeps a stock DecLibRecon next to this class and routes those pictures to it.
+// decompressPicture() returns at once, like the reference's (DecLibRecon.cpp:429-681): the host stages run as tasks of the decoder's thread pool,
+//   MIDER   one task per CTU row, wave front over rows (DecCu::TaskDeriveCtuMotionInfo, the MIDER case of ctuTask :762-781), may start while
+//           the rows below are still being parsed (ctuParsedBarrier, RECO_WHILE_PARSE)
+//   FLATTEN one task per CTU row: boundary strengths (calcFilterStrengthsCTU, the LF_INIT case :808-829), the CU / TU walk of TaskTrafoCtu /
+//           TaskInterCtu / TaskCriticalIntraKernel (DecCu.cpp:106-159) into per-row work lists, SAO / ALF CTU records
+//   SUBMIT  one task: lists joined in CTU order (K6 needs decoding order), references that are not resident uploaded, b200_decompress_picture
+// and waitForPrevDecompressedPic() waits for the device, takes the DMVR deltas, runs TaskFinishMotionInfo (DecCu.cpp:161) and copies the
+// finished planes into Picture::m_bufs (output / CPU fallback of later pictures).
+// Errors follow DecLibRecon.cpp:684-722: an exception on any task parks in the task's counter / barrier, waitForPrevDecompressedPic() sets
+// pic->error and reconDone.setException() and clears the pool of this picture's tasks (cleanupOnException).  B200_ERR_UNSUPPORTED maps to
+// UnsupportedFeatureException, B200_ERR_PARAM to RecoverableException, every other failure to Exception (TypeDef.h:828-831).
+//
+// The CPU keeps: parsing, motion derivation, boundary strengths, TaskFinishMotionInfo.  Pictures that use a tool the device path does not
+// have throw UnsupportedFeatureException (see refuse() below for the list); a deployment keeps a stock DecLibRecon next to this class and
+// routes those pictures to it — their output is imported into the device DPB when a later picture references it (importReference).
+// DecLib owns two recon instances that alternate (DecLib.h:70): the device context and its DPB bookkeeping are shared by all instances
+// created with the same ThreadPool.
 #pragma once
 #include <vector>
 #include <map>
+#include <mutex>
+#include <memory>
+#include <atomic>
 #include "vvdec_b200.h"
 #include "flatten_tu.h"
 #include "flatten_pu.h"
@@ -21,124 +37,187 @@
 #include "CommonLib/LoopFilter.h"
 #include "CommonLib/Reshape.h"
 #include "CommonLib/WeightPrediction.h"
+#include "CommonLib/InterPrediction.h"
 #include "DecoderLib/DecCu.h"
+#include "Utilities/ThreadPool.h"
 
 namespace b200glue
 {
 using namespace vvdec;
 
-// grow-only pinned host array (cudaHostAlloc through the C ABI's registration call: memory stays owned by the vector)
+// grow-only pinned host array (cudaHostRegister through the C ABI: the memory stays owned by the vector)
 template<class T> struct PinnedVec
 {
   std::vector<T> v; const void* reg = nullptr; size_t regBytes = 0;
   void clear() { v.clear(); }
-  void pin() { if( v.capacity() * sizeof( T ) != regBytes || (const void*) v.data() != reg ) { if( reg ) b200_host_unregister( const_cast<void*>( reg ) ); reg = v.data(); regBytes = v.capacity() * sizeof( T ); if( regBytes ) b200_host_register( const_cast<void*>( reg ), regBytes ); } }
+  void pin() { if( v.capacity() * sizeof( T ) != regBytes || (const void*) v.data() != reg ) { if( reg ) b200_host_unregister( const_cast<void*>( reg ) ); reg = nullptr; regBytes = 0; if( v.capacity() && b200_host_register( v.data(), v.capacity() * sizeof( T ) ) == 0 ) { reg = v.data(); regBytes = v.capacity() * sizeof( T ); } } }
   ~PinnedVec() { if( reg ) b200_host_unregister( const_cast<void*>( reg ) ); }
 };
 
 class DecLibReconB200
 {
-  b200_ctx*  m_ctx = nullptr;
-  b200_geom  m_geom{};
-  int        m_numSlots = 0, m_arena = -1;
-  Picture*   m_currDecompPic = nullptr;
-  std::map<const Picture*, int> m_slotOf;          // DPB slot of every picture the device holds
-  std::vector<const Picture*>   m_slotOwner;
+  // ---- device context + DPB bookkeeping, shared by the recon instances of one decoder ----
+  struct Shared
+  {
+    std::mutex m; b200_ctx* ctx = nullptr; b200_geom geom{}; int numSlots = 0;
+    std::map<const Picture*, int> slotOf; std::vector<const Picture*> owner; std::vector<uint8_t> valid;   // valid: the slot holds the owner's final samples
+    ~Shared() { if( ctx ) b200_ctx_destroy( ctx ); }
+  };
+  static std::shared_ptr<Shared> sharedFor( const void* key )
+  {
+    static std::mutex m; static std::map<const void*, std::weak_ptr<Shared>> reg;
+    std::lock_guard<std::mutex> l( m );
+    std::shared_ptr<Shared> s = reg[key].lock();
+    if( !s ) { s = std::make_shared<Shared>(); reg[key] = s; }
+    return s;
+  }
+  std::shared_ptr<Shared> m_sh;
+
+  // ---- per-row work lists ----
+  struct Row
+  {
+    DecLibReconB200* self = nullptr; int line = 0, col = 0;
+    std::vector<b200_pu> pus; std::vector<b200_tu> tus; std::vector<int16_t> coefs; std::vector<b200_intra_tu> intra;
+  };
+
+  ThreadPool* m_pool = nullptr; int m_numThreads = 1; unsigned m_id = 0; int m_dpbSlots = 17;
+  Picture*    m_currDecompPic = nullptr;
+  int         m_arena = -1, m_dstSlot = -1;
+  std::vector<Row> m_rows; std::unique_ptr<std::atomic<int>[]> m_miderCols;
+  std::vector<MotionHist> m_hist;
+  WaitCounter m_miderCounter, m_flattenCounter, m_submitCounter;
   // per-picture work lists (pinned)
   PinnedVec<b200_pu> m_pus; PinnedVec<b200_tu> m_tus; PinnedVec<int16_t> m_coefs; PinnedVec<b200_intra_tu> m_intra;
   PinnedVec<b200_lf_param> m_lf[2]; PinnedVec<b200_sao_ctu> m_sao; PinnedVec<b200_alf_ctu> m_alf; PinnedVec<b200_lmcs_vpdu> m_vpdus;
   PinnedVec<int32_t> m_dmvr;
-  std::vector<b200_wp> m_wp; std::map<std::pair<int, int>, int> m_wpIdx;
+  std::vector<b200_wp> m_wp; int m_wpStride = 0; std::vector<int> m_wpIdx;
   AlfTableStore m_alfStore; b200_alf_tables m_alfTabs{}; b200_lmcs m_lmcs{}; b200_vb m_vb{}; b200_lf_slice m_lfSlice{}; b200_lf_seq m_lfSeq{};
+  b200_picture m_pic{};
+  SlotMap m_slotMap{};
+  bool m_doSao = false, m_doAlf = false, m_doLmcs = false, m_dryRun = false;
   // the CPU stages that stay
   std::vector<MotionInfo> m_motionInfo; std::vector<LoopFilterParam> m_loopFilterParam; std::vector<Mv> m_dmvrMvCache;
-  LoopFilter m_cLoopFilter; SampleAdaptiveOffset m_cSAO; AdaptiveLoopFilter m_cALF; Reshape m_cReshaper; DecCu m_cCuDecoder; TrQuant* m_trQuant = nullptr;
+  LoopFilter m_cLoopFilter; SampleAdaptiveOffset m_cSAO; AdaptiveLoopFilter m_cALF; Reshape m_cReshaper;
+  std::vector<std::unique_ptr<DecCu>> m_cuDecoders; InterPrediction m_interPred; std::unique_ptr<TrQuant> m_trQuant;
   PelStorage m_fltBuf;
 
   static void check( int rc ) { if( rc == B200_ERR_UNSUPPORTED ) THROW_UNSUPPORTED( b200_last_error() ); if( rc == B200_ERR_PARAM ) THROW_RECOVERABLE( b200_last_error() ); if( rc < 0 ) THROW_FATAL( b200_last_error() ); }
 
-  int slotFor( const Picture* pic )
+  // ---- DPB slots.  A picture the device did not reconstruct itself (CPU fallback, lost picture filled grey) is uploaded when it is first referenced.
+  int slotLocked( const Picture* pic )
   {
-    auto it = m_slotOf.find( pic ); if( it != m_slotOf.end() ) return it->second;
-    for( int s = 0; s < m_numSlots; s++ ) if( !m_slotOwner[s] || !m_slotOwner[s]->stillReferenced ) { if( m_slotOwner[s] ) m_slotOf.erase( m_slotOwner[s] ); m_slotOwner[s] = pic; m_slotOf[pic] = s; return s; }
+    Shared& S = *m_sh;
+    auto it = S.slotOf.find( pic ); if( it != S.slotOf.end() ) return it->second;
+    for( int s = 0; s < S.numSlots; s++ )
+      if( !S.owner[s] || ( !S.owner[s]->stillReferenced && S.owner[s]->progress >= Picture::reconstructed && S.owner[s] != m_currDecompPic ) )
+      { if( S.owner[s] ) S.slotOf.erase( S.owner[s] ); S.owner[s] = pic; S.valid[s] = 0; S.slotOf[pic] = s; return s; }
     THROW_FATAL( "DecLibReconB200: device DPB is full" );
   }
-
-public:
-  void create( TrQuant* trQuant, int dpbSlots ) { m_trQuant = trQuant; m_numSlots = dpbSlots; m_slotOwner.assign( dpbSlots, nullptr ); }
-  void destroy() { if( m_ctx ) b200_ctx_destroy( m_ctx ); m_ctx = nullptr; }
-  Picture* getCurrPic() const { return m_currDecompPic; }
-
-  // DecLibRecon::decompressPicture (DecLibRecon.cpp:429): flatten the parsed picture and hand it to the device; returns without waiting.
-  void decompressPicture( Picture* pic )
+  int importReference( const Picture* ref )
   {
-    m_currDecompPic = pic;
-    CodingStructure& cs = *pic->cs;
-    const SPS& sps = *cs.sps; const PPS& pps = *cs.pps; const PreCalcValues& pcv = *cs.pcv;
-    pic->progress = Picture::reconstructing;
-    if( !m_ctx )
-    {
-      m_geom.width = pcv.lumaWidth; m_geom.height = pcv.lumaHeight; m_geom.bitDepth = sps.getBitDepth(); m_geom.chromaFormat = sps.getChromaFormatIdc() == CHROMA_420 ? 1 : 0;
-      m_geom.ctuSize = pcv.maxCUWidth; m_geom.stride[0] = pcv.lumaWidth; m_geom.stride[1] = m_geom.stride[2] = pcv.lumaWidth >> 1;
-      if( sps.getChromaFormatIdc() != CHROMA_420 && sps.getChromaFormatIdc() != CHROMA_400 ) THROW_UNSUPPORTED( "DecLibReconB200: 4:2:0 and 4:0:0 only" );
-      check( b200_ctx_create( &m_ctx, &m_geom, m_numSlots, 4, -1 ) );
-    }
+    Shared& S = *m_sh;
+    const int s = slotLocked( ref );
+    if( S.valid[s] ) return s;
+    CHECK_FATAL( ref->progress < Picture::reconstructed, "DecLibReconB200: reference picture is neither on the device nor reconstructed on the host" );
+    const int16_t* planes[3] = { nullptr, nullptr, nullptr }; ptrdiff_t strides[3] = { 0, 0, 0 };
+    for( int c = 0; c < ( S.geom.chromaFormat ? 3 : 1 ); c++ ) { const CPelBuf b = ref->getRecoBuf( ComponentID( c ) ); planes[c] = b.buf; strides[c] = b.stride; }
+    if( !m_dryRun ) check( b200_ctx_load_slot_strided( S.ctx, s, planes, strides ) );
+    S.valid[s] = 1;
+    return s;
+  }
+
+  // ---- what the device path does not have: the picture goes to the stock DecLibRecon ----
+  void refuse( const Picture* pic ) const
+  {
+    const CodingStructure& cs = *pic->cs; const SPS& sps = *cs.sps; const PPS& pps = *cs.pps;
+    if( sps.getChromaFormatIdc() != CHROMA_420 && sps.getChromaFormatIdc() != CHROMA_400 ) THROW_UNSUPPORTED( "DecLibReconB200: 4:2:0 and 4:0:0 only" );
     if( sps.getUseWrapAround() || pic->subPictures.size() > 1 || cs.picHeader->getVirtualBoundariesPresentFlag() ) THROW_UNSUPPORTED( "DecLibReconB200: wrap-around / sub-pictures / virtual boundaries" );
-    pic->parseDone.wait();
-
-    // ---- CPU stages per CTU, in the order of ctuTask's MIDER / LF_INIT cases (DecLibRecon.cpp:762-829) ----
-    m_motionInfo.resize( (size_t) pcv.num4x4CtuBlks * pcv.sizeInCtus ); m_loopFilterParam.assign( (size_t) pcv.num4x4CtuBlks * pcv.sizeInCtus * 2, LoopFilterParam{} );
-    m_dmvrMvCache.assign( (size_t) pcv.num8x8CtuBlks * pcv.sizeInCtus, Mv() ); cs.m_dmvrMvCache = m_dmvrMvCache.data();
-    std::vector<MotionHist> hist( pcv.heightInCtus );
-    for( unsigned a = 0; a < pcv.sizeInCtus; a++ )
-    {
-      CtuData& cd = cs.getCtuData( a );
-      cd.motion = &m_motionInfo[(size_t) pcv.num4x4CtuBlks * a];
-      const UnitArea ctuArea = getCtuArea( cs, a % pcv.widthInCtus, a / pcv.widthInCtus, true );
-      if( !cd.slice->isIntra() ) m_cCuDecoder.TaskDeriveCtuMotionInfo( cs, a, ctuArea, hist[a / pcv.widthInCtus] );            // ctuTask MIDER (DecLibRecon.cpp:762-781)
-    }
-    for( unsigned a = 0; a < pcv.sizeInCtus; a++ )
-    {
-      CtuData& cd = cs.getCtuData( a );
-      cd.lfParam[0] = &m_loopFilterParam[(size_t) pcv.num4x4CtuBlks * ( 2 * a )]; cd.lfParam[1] = &m_loopFilterParam[(size_t) pcv.num4x4CtuBlks * ( 2 * a + 1 )];
-      m_cLoopFilter.calcFilterStrengthsCTU( cs, a );
-    }
-
-    // ---- reference pictures -> device DPB slots, explicit weights ----
-    const Slice& slice0 = *pic->slices[0];
-    SlotMap sm; memset( &sm, -1, sizeof( sm ) );
-    for( int l = 0; l < 2; l++ ) for( int i = 0; i < slice0.getNumRefIdx( RefPicList( l ) ); i++ ) sm.slot[l][i] = (int8_t) slotFor( slice0.getRefPic( RefPicList( l ), i ) );
     if( pic->slices.size() > 1 ) THROW_UNSUPPORTED( "DecLibReconB200: one slice per picture (reference lists and ALF / LMCS tables are per slice)" );
-    m_wp.clear(); m_wpIdx.clear();
-    auto wpIdxOf = [&]( int r0, int r1 ) -> int
-    {
-      auto it = m_wpIdx.find( { r0, r1 } ); if( it != m_wpIdx.end() ) return it->second;
-      WPScalingParam w0[3], w1[3]; WeightPrediction wpObj; wpObj.getWpScaling( &slice0, r0, r1, w0, w1 );
-      b200_wp e{}; const bool bi = r0 >= 0 && r1 >= 0; const WPScalingParam* u = r0 >= 0 ? w0 : w1;
-      for( int c = 0; c < 3; c++ ) { e.w0[c] = bi ? w0[c].w : u[c].w; e.w1[c] = bi ? w1[c].w : 0; e.offset[c] = bi ? w0[c].offset : u[c].offset; e.shift[c] = bi ? w0[c].shift : u[c].shift; }
-      m_wp.push_back( e ); return m_wpIdx[{ r0, r1 }] = (int) m_wp.size();
-    };
+    if( pps.getNumTiles() > 1 && !pps.getLoopFilterAcrossTilesEnabledFlag() ) THROW_UNSUPPORTED( "DecLibReconB200: tiles with in-loop filtering disabled across them (ALF clip path, AdaptiveLoopFilter.cpp:685)" );
+    if( !pps.getLoopFilterAcrossSlicesEnabledFlag() && pic->slices.size() > 1 ) THROW_UNSUPPORTED( "DecLibReconB200: in-loop filtering disabled across slices" );
+    if( pic->slices[0]->getExplicitScalingListUsed() ) THROW_UNSUPPORTED( "DecLibReconB200: explicit scaling lists (the per-picture table arena is not built by this class)" );
+    if( sps.getIBCFlag() ) THROW_UNSUPPORTED( "DecLibReconB200: IBC" );
+    if( sps.getUseColorTrans() ) THROW_UNSUPPORTED( "DecLibReconB200: adaptive colour transform" );
+  }
 
-    // ---- flatten CUs / TUs (TaskTrafoCtu + TaskInterCtu walks, DecCu.cpp:106-134) ----
-    m_pus.clear(); m_tus.clear(); m_coefs.clear(); m_intra.clear();
-    for( unsigned a = 0; a < pcv.sizeInCtus; a++ )
+  // ---- tasks ----
+  // A task never lets an exception escape into the pool (a task that throws while the single-threaded pool executes it directly is queued again,
+  // ThreadPool.h:451-458): the first exception of the picture is parked here, the remaining tasks of the picture finish as no-ops, and
+  // waitForPrevDecompressedPic() rethrows it on the API thread — where DecLibRecon's own exceptions surface too (DecLibRecon.cpp:704-715).
+  std::mutex m_failMutex; std::exception_ptr m_failure; std::atomic<bool> m_failed{ false };
+  void park( std::exception_ptr e ) { std::lock_guard<std::mutex> l( m_failMutex ); if( !m_failure ) m_failure = e; m_failed.store( true ); }
+  template<class F> bool guarded( F f ) { if( m_failed.load() ) return true; try { return f(); } catch( ... ) { park( std::current_exception() ); return true; } }
+
+  static bool miderTask( int tid, void* p )
+  {
+    Row& r = *static_cast<Row*>( p );
+    return r.self->guarded( [&] { return miderRow( tid, r ); } );
+  }
+  static bool miderRow( int tid, Row& r )
+  {
+    DecLibReconB200& d = *r.self;
+    CodingStructure& cs = *d.m_currDecompPic->cs; const PreCalcValues& pcv = *cs.pcv;
+    const int W = pcv.widthInCtus;
+    for( ; r.col < W; )
+    {
+      if( d.m_failed.load() ) return true;
+      // the merge / AMVP candidates of a CU reach into the CTU above-right (ctuTask MIDER preconditions, DecLibRecon.cpp:764-778)
+      if( r.line > 0 && d.m_miderCols[r.line - 1].load( std::memory_order_acquire ) < std::min( r.col + 2, W ) ) return false;
+      const int a = r.line * W + r.col;
+      CtuData& cd = cs.getCtuData( a );
+      cd.motion = &d.m_motionInfo[(size_t) pcv.num4x4CtuBlks * a];
+      if( !cd.slice->isIntra() || cs.sps->getIBCFlag() ) d.m_cuDecoders[tid]->TaskDeriveCtuMotionInfo( cs, a, getCtuArea( cs, r.col, r.line, true ), d.m_hist[r.line] );
+      else memset( NO_WARNING_class_memaccess( cd.motion ), MI_NOT_VALID, sizeof( MotionInfo ) * pcv.num4x4CtuBlks );
+      d.m_miderCols[r.line].store( ++r.col, std::memory_order_release );
+    }
+    return true;
+  }
+
+  static bool flattenTask( int, void* p )
+  {
+    Row& r = *static_cast<Row*>( p );
+    return r.self->guarded( [&] { r.self->flattenRow( r ); return true; } );
+  }
+
+  static bool submitTask( int, void* p ) { DecLibReconB200* d = static_cast<DecLibReconB200*>( p ); return d->guarded( [&] { d->submit(); return true; } ); }
+
+  int wpIdxOf( int r0, int r1 ) const { return m_wpIdx.empty() ? 0 : m_wpIdx[( r0 + 1 ) * m_wpStride + ( r1 + 1 )]; }
+
+  void flattenRow( Row& r )
+  {
+    Picture* pic = m_currDecompPic; CodingStructure& cs = *pic->cs; const SPS& sps = *cs.sps; const PreCalcValues& pcv = *cs.pcv;
+    const int W = pcv.widthInCtus, W4 = ( pcv.lumaWidth + 3 ) >> 2;
+    const bool lmcsOn = sps.getUseReshaper() && cs.picHeader->getLmcsEnabledFlag();
+    auto wp = [this]( int r0, int r1 ) { return wpIdxOf( r0, r1 ); };
+    r.pus.clear(); r.tus.clear(); r.coefs.clear(); r.intra.clear();
+    for( int col = 0; col < W; col++ )
+    {
+      const int a = r.line * W + col;
+      CtuData& cd = cs.getCtuData( a );
+      // LF_INIT (DecLibRecon.cpp:808-829)
+      cd.lfParam[0] = &m_loopFilterParam[(size_t) pcv.num4x4CtuBlks * ( 2 * a )]; cd.lfParam[1] = &m_loopFilterParam[(size_t) pcv.num4x4CtuBlks * ( 2 * a + 1 )];
+      memset( cd.lfParam[0], 0, sizeof( LoopFilterParam ) * 2 * pcv.num4x4CtuBlks );
+      m_cLoopFilter.calcFilterStrengthsCTU( cs, a );
+      for( int dir = 0; dir < 2; dir++ ) flattenLfCtu( cs, a, dir, m_lf[dir].v.data() );
+      (void) W4;
+      // the CU / TU walks of TaskTrafoCtu + TaskInterCtu + TaskCriticalIntraKernel (DecCu.cpp:106-159)
       for( auto& cu : cs.traverseCUs( a ) )
       {
         if( CU::isIntra( cu ) )
         {
-          // K6: regular intra modes on the device.  One b200_intra_tu per TU component in decoding order (the order DecCu::predAndReco walks them,
-          // DecCu.cpp:284-288); the residual of a coded component goes through K1 into the residual planes (B200_TU_RESI) and is added by K6.
-          if( sps.getUseReshaper() && cs.picHeader->getLmcsEnabledFlag() ) THROW_UNSUPPORTED( "DecLibReconB200: intra CUs with LMCS" );
+          // K6: one b200_intra_tu per TU component in decoding order (the order DecCu::predAndReco walks them, DecCu.cpp:284-288); the residual of
+          // a coded component goes through K1 into the residual planes (B200_TU_RESI) and is added by K6
+          if( lmcsOn ) THROW_UNSUPPORTED( "DecLibReconB200: intra CUs with LMCS" );
           for( auto& tu : TUTraverser( &cu.firstTU, cu.lastTU->next ) )
             for( const CompArea& area : tu.blocks )
             {
               if( !area.valid() ) continue;
               b200_intra_tu ir;
               if( flattenIntraTU( tu, area.compID(), ir ) != FLATTEN_INTRA_OK ) THROW_UNSUPPORTED( "DecLibReconB200: ISP / ACT intra block (SURVEY 8f-1)" );
-              b200_tu r;
-              if( flattenTU( tu, area.compID(), *m_trQuant, m_coefs.v, r ) ) { r.flags |= B200_TU_RESI; m_tus.v.push_back( r ); }
+              b200_tu t;
+              if( flattenTU( tu, area.compID(), *m_trQuant, r.coefs, t ) ) { t.flags |= B200_TU_RESI; r.tus.push_back( t ); }
               if( TU::getCbf( tu, area.compID() ) || ( isChroma( area.compID() ) && tu.jointCbCr ) ) ir.flags |= B200_INTRA_ADD_RESI;      // DecCu.cpp:390
-              m_intra.v.push_back( ir );
+              r.intra.push_back( ir );
             }
           continue;
         }
@@ -147,47 +226,104 @@ public:
         if( cu.ciipFlag() )
         {
           // CIIP: the inter prediction comes from K2 like any merge CU; K6 blends a planar intra block into it (predBlendIntraCiip) and adds the residual
-          if( sps.getUseReshaper() && cs.picHeader->getLmcsEnabledFlag() ) THROW_UNSUPPORTED( "DecLibReconB200: CIIP CUs with LMCS" );
+          if( lmcsOn ) THROW_UNSUPPORTED( "DecLibReconB200: CIIP CUs with LMCS" );
           for( int c = 0; c < (int) getNumberValidComponents( cu.chromaFormat ); c++ )
           {
             b200_intra_tu ir;
             if( flattenCiipBlock( cu, ComponentID( c ), ir ) != FLATTEN_INTRA_OK ) continue;
-            if( TU::getCbf( cu.firstTU, ComponentID( c ) ) || ( c && cu.firstTU.jointCbCr ) ) ir.flags |= B200_INTRA_ADD_RESI;
-            m_intra.v.push_back( ir ); ciipComp[c] = true;
+            if( cu.rootCbf() && ( TU::getCbf( cu.firstTU, ComponentID( c ) ) || ( c && cu.firstTU.jointCbCr ) ) ) ir.flags |= B200_INTRA_ADD_RESI;
+            r.intra.push_back( ir ); ciipComp[c] = true;
           }
         }
         FlattenPuResult rc;
-        if( cu.mergeType() == MRG_TYPE_SUBPU_ATMVP ) rc = flattenSbTmvp( cu, sm, wpIdxOf, [&]( const b200_pu& r ) { m_pus.v.push_back( r ); } );
-        else { b200_pu r; rc = flattenPU( cu, sm, wpIdxOf, r ); if( rc == FLATTEN_PU_OK ) m_pus.v.push_back( r ); }
-        if( rc != FLATTEN_PU_OK ) THROW_UNSUPPORTED( "DecLibReconB200: inter tool outside the device path" );
+        if( cu.mergeType() == MRG_TYPE_SUBPU_ATMVP ) rc = flattenSbTmvp( cu, m_slotMap, wp, [&]( const b200_pu& q ) { r.pus.push_back( q ); } );
+        else { b200_pu q; rc = flattenPU( cu, m_slotMap, wp, q ); if( rc == FLATTEN_PU_OK ) r.pus.push_back( q ); }
+        if( rc != FLATTEN_PU_OK ) THROW_UNSUPPORTED( "DecLibReconB200: inter tool outside the device path (RPR-scaled reference, wrap-around, sub-picture clipping)" );
         if( cu.rootCbf() )
           for( auto& tu : TUTraverser( &cu.firstTU, cu.lastTU->next ) )
-            for( int c = 0; c < (int) getNumberValidComponents( cu.chromaFormat ); c++ ) { b200_tu r; if( flattenTU( tu, ComponentID( c ), *m_trQuant, m_coefs.v, r ) ) { if( ciipComp[c] ) r.flags |= B200_TU_RESI; m_tus.v.push_back( r ); } }
+            for( int c = 0; c < (int) getNumberValidComponents( cu.chromaFormat ); c++ ) { b200_tu t; if( flattenTU( tu, ComponentID( c ), *m_trQuant, r.coefs, t ) ) { if( ciipComp[c] ) t.flags |= B200_TU_RESI; r.tus.push_back( t ); } }
       }
+      // in-loop filter parameters of the CTU
+      if( m_doSao )
+      {
+        bool av[8];
+        m_cSAO.deriveLoopFilterBoundaryAvailibility( cs, Position( col * pcv.maxCUWidth, r.line * pcv.maxCUHeight ), av[0], av[1], av[2], av[3], av[4], av[5], av[6], av[7] );
+        flattenSAO( cd.saoParam, av, getNumberValidComponents( pcv.chrFormat ), m_sao.v[a] );     // saoParam after reconstructBlkSAOParam (parser side)
+      }
+      if( m_doAlf ) flattenALF( cd.alfParam, m_alf.v[a] );
+    }
+  }
 
-    // ---- in-loop filter parameters ----
-    const int W4 = ( pcv.lumaWidth + 3 ) >> 2, H4 = ( pcv.lumaHeight + 3 ) >> 2;
-    for( int d = 0; d < 2; d++ ) { m_lf[d].v.assign( (size_t) W4 * H4, b200_lf_param{} ); for( unsigned a = 0; a < pcv.sizeInCtus; a++ ) flattenLfCtu( cs, a, d, m_lf[d].v.data() ); }
+  // picture-level tables (slice / APS / SPS level state), before the row tasks start
+  void preparePicture( Picture* pic )
+  {
+    CodingStructure& cs = *pic->cs; const SPS& sps = *cs.sps; const PPS& pps = *cs.pps; const PreCalcValues& pcv = *cs.pcv;
+    Shared& S = *m_sh;
+    {
+      std::lock_guard<std::mutex> l( S.m );
+      if( !S.ctx && !m_dryRun )
+      {
+        S.geom.width = pcv.lumaWidth; S.geom.height = pcv.lumaHeight; S.geom.bitDepth = sps.getBitDepth(); S.geom.chromaFormat = sps.getChromaFormatIdc() == CHROMA_420 ? 1 : 0;
+        S.geom.ctuSize = pcv.maxCUWidth; S.geom.stride[0] = pcv.lumaWidth; S.geom.stride[1] = S.geom.stride[2] = pcv.lumaWidth >> 1;
+        S.numSlots = m_dpbSlots; S.owner.assign( S.numSlots, nullptr ); S.valid.assign( S.numSlots, 0 );
+        check( b200_ctx_create( &S.ctx, &S.geom, S.numSlots, 4, -1 ) );
+      }
+      else if( S.owner.empty() )
+      {
+        S.geom.width = pcv.lumaWidth; S.geom.height = pcv.lumaHeight; S.geom.bitDepth = sps.getBitDepth(); S.geom.chromaFormat = sps.getChromaFormatIdc() == CHROMA_420 ? 1 : 0;
+        S.geom.ctuSize = pcv.maxCUWidth; S.geom.stride[0] = pcv.lumaWidth; S.geom.stride[1] = S.geom.stride[2] = pcv.lumaWidth >> 1;
+        S.numSlots = m_dpbSlots; S.owner.assign( S.numSlots, nullptr ); S.valid.assign( S.numSlots, 0 );
+      }
+      if( (int) pcv.lumaWidth != S.geom.width || (int) pcv.lumaHeight != S.geom.height || sps.getBitDepth() != S.geom.bitDepth ) THROW_UNSUPPORTED( "DecLibReconB200: picture size / bit depth change inside a context (RPR)" );
+      // reference pictures -> device DPB slots (uploaded if the device does not hold them)
+      memset( &m_slotMap, -1, sizeof( m_slotMap ) );
+      const Slice& slice0 = *pic->slices[0];
+      for( int l = 0; l < 2; l++ ) for( int i = 0; i < slice0.getNumRefIdx( RefPicList( l ) ); i++ ) m_slotMap.slot[l][i] = (int8_t) importReference( slice0.getRefPic( RefPicList( l ), i ) );
+      m_dstSlot = slotLocked( pic ); S.valid[m_dstSlot] = 0;
+    }
+    const Slice& slice0 = *pic->slices[0];
+    // explicit weighted prediction: one entry per (refIdx0, refIdx1) combination (getWpScaling, WeightPrediction.cpp:67)
+    m_wp.clear(); m_wpIdx.clear();
+    if( ( pps.getWPBiPred() && slice0.isInterB() ) || ( pps.getUseWP() && slice0.isInterP() ) )
+    {
+      const int n0 = slice0.getNumRefIdx( REF_PIC_LIST_0 ), n1 = slice0.isInterB() ? slice0.getNumRefIdx( REF_PIC_LIST_1 ) : 0;
+      m_wpStride = n1 + 1; m_wpIdx.assign( (size_t) ( n0 + 1 ) * ( n1 + 1 ), 0 );
+      for( int r0 = -1; r0 < n0; r0++ ) for( int r1 = -1; r1 < n1; r1++ )
+      {
+        if( r0 < 0 && r1 < 0 ) continue;
+        WPScalingParam w0[3], w1[3]; WeightPrediction wpObj; wpObj.getWpScaling( &slice0, r0, r1, w0, w1 );
+        b200_wp e{}; const bool bi = r0 >= 0 && r1 >= 0; const WPScalingParam* u = r0 >= 0 ? w0 : w1;
+        for( int c = 0; c < 3; c++ ) { e.w0[c] = bi ? w0[c].w : u[c].w; e.w1[c] = bi ? w1[c].w : 0; e.offset[c] = bi ? w0[c].offset : u[c].offset; e.shift[c] = bi ? w0[c].shift : u[c].shift; }
+        m_wp.push_back( e ); m_wpIdx[( r0 + 1 ) * m_wpStride + ( r1 + 1 )] = (int) m_wp.size();
+      }
+      if( m_wp.size() > 255 ) THROW_UNSUPPORTED( "DecLibReconB200: more than 255 weighted-prediction combinations" );
+    }
+    // deblocking: slice offsets and the SPS's luma-adaptive QP offsets (deriveLADFShift, LoopFilter.cpp:1363)
     m_lfSlice = b200_lf_slice{}; m_lfSlice.disable = slice0.getDeblockingFilterDisable();
     m_lfSlice.betaOffsetDiv2[0] = slice0.getDeblockingFilterBetaOffsetDiv2(); m_lfSlice.tcOffsetDiv2[0] = slice0.getDeblockingFilterTcOffsetDiv2();
     m_lfSlice.betaOffsetDiv2[1] = slice0.getDeblockingFilterCbBetaOffsetDiv2(); m_lfSlice.tcOffsetDiv2[1] = slice0.getDeblockingFilterCbTcOffsetDiv2();
     m_lfSlice.betaOffsetDiv2[2] = slice0.getDeblockingFilterCrBetaOffsetDiv2(); m_lfSlice.tcOffsetDiv2[2] = slice0.getDeblockingFilterCrTcOffsetDiv2();
-    const bool doSao = sps.getUseSAO(), doAlf = sps.getUseALF() && ( slice0.getAlfEnabledFlag( COMPONENT_Y ) || slice0.getAlfEnabledFlag( COMPONENT_Cb ) || slice0.getAlfEnabledFlag( COMPONENT_Cr ) );
-    m_sao.v.assign( pcv.sizeInCtus, b200_sao_ctu{} ); m_alf.v.assign( pcv.sizeInCtus, b200_alf_ctu{} );
-    for( unsigned a = 0; a < pcv.sizeInCtus && doSao; a++ )
+    m_lfSeq = b200_lf_seq{};
+    if( sps.getLadfEnabled() )
     {
-      bool av[8];
-      m_cSAO.deriveLoopFilterBoundaryAvailibility( cs, Position( ( a % pcv.widthInCtus ) * pcv.maxCUWidth, ( a / pcv.widthInCtus ) * pcv.maxCUHeight ), av[0], av[1], av[2], av[3], av[4], av[5], av[6], av[7] );
-      flattenSAO( cs.getCtuData( a ).saoParam, av, getNumberValidComponents( pcv.chrFormat ), m_sao.v[a] );     // saoParam after reconstructBlkSAOParam (parser side)
+      m_lfSeq.ladfEnabled = 1; m_lfSeq.ladfNumIntervals = sps.getLadfNumIntervals();
+      for( int k = 0; k < sps.getLadfNumIntervals() && k < 5; k++ ) { m_lfSeq.ladfQpOffset[k] = sps.getLadfQpOffset( k ); m_lfSeq.ladfIntervalLowerBound[k] = sps.getLadfIntervalLowerBound( k ); }
     }
-    if( doAlf )
+    m_doSao = sps.getUseSAO();
+    m_doAlf = sps.getUseALF() && !AdaptiveLoopFilter::getAlfSkipPic( cs );
+    const int W4 = ( pcv.lumaWidth + 3 ) >> 2, H4 = ( pcv.lumaHeight + 3 ) >> 2;
+    for( int d = 0; d < 2; d++ ) { m_lf[d].v.assign( (size_t) W4 * H4, b200_lf_param{} ); m_lf[d].pin(); }
+    m_sao.v.assign( pcv.sizeInCtus, b200_sao_ctu{} ); m_alf.v.assign( pcv.sizeInCtus, b200_alf_ctu{} ); m_sao.pin(); m_alf.pin();
+    for( auto& s : m_sao.v ) s.type[0] = s.type[1] = s.type[2] = B200_SAO_OFF;
+    if( m_doAlf )
     {
-      for( unsigned a = 0; a < pcv.sizeInCtus; a++ ) flattenALF( cs.getCtuData( a ).alfParam, m_alf.v[a] );
+      if( m_fltBuf.bufs.empty() ) m_fltBuf.create( pcv.chrFormat, Size( 16, 16 ), pcv.maxCUWidth, 0, MEMORY_ALIGN_DEF_SIZE );
+      m_cALF.create( cs.picHeader.get(), &sps, &pps, 1, m_fltBuf );              // fills m_clipDefault for the bit depth
       m_alfTabs = buildAlfTables( slice0, &m_cALF.m_fixedFilterSetCoeffDec[0][0], m_cALF.m_clipDefault, m_alfStore );
     }
-    // ---- LMCS ----
-    const bool doLmcs = sps.getUseReshaper() && cs.picHeader->getLmcsEnabledFlag() && slice0.getLmcsEnabledFlag();
-    if( doLmcs )
+    // LMCS tables (Reshape::initSlice as DecLibRecon.cpp:448-452)
+    m_doLmcs = sps.getUseReshaper() && cs.picHeader->getLmcsEnabledFlag() && slice0.getLmcsEnabledFlag();
+    if( m_doLmcs )
     {
       m_cReshaper.createDec( sps.getBitDepth() ); m_cReshaper.initSlice( slice0.getNalUnitLayerId(), *slice0.getPicHeader(), slice0.getVPS_nothrow() );
       m_lmcs = b200_lmcs{}; m_lmcs.chromaAdj = m_cReshaper.m_sliceReshapeInfo.enableChromaAdj;
@@ -195,6 +331,27 @@ public:
       for( int i = 0; i < 17; i++ ) { m_lmcs.reshapePivot[i] = m_cReshaper.m_reshapePivot[i]; m_lmcs.inputPivot[i] = m_cReshaper.m_inputPivot[i]; }
       for( int i = 0; i < 16; i++ ) { m_lmcs.fwdScaleCoef[i] = m_cReshaper.m_fwdScaleCoef[i]; m_lmcs.chromaAdjHelpLUT[i] = m_cReshaper.m_chromaAdjHelpLUT[i]; }
       m_lmcs.invLUT = m_cReshaper.m_invLUT;
+    }
+  }
+
+  // joins the row lists, derives the VPDU records and hands the picture to the device
+  void submit()
+  {
+    Picture* pic = m_currDecompPic; CodingStructure& cs = *pic->cs; const PreCalcValues& pcv = *cs.pcv; const Slice& slice0 = *pic->slices[0];
+    size_t nP = 0, nT = 0, nC = 0, nI = 0;
+    for( const Row& r : m_rows ) { nP += r.pus.size(); nT += r.tus.size(); nC += r.coefs.size(); nI += r.intra.size(); }
+    m_pus.v.resize( nP ); m_tus.v.resize( nT ); m_coefs.v.resize( nC ); m_intra.v.resize( nI );
+    nP = nT = nC = nI = 0;
+    for( Row& r : m_rows )
+    {
+      if( !r.pus.empty() ) memcpy( &m_pus.v[nP], r.pus.data(), r.pus.size() * sizeof( b200_pu ) );
+      for( size_t i = 0; i < r.tus.size(); i++ ) { m_tus.v[nT + i] = r.tus[i]; m_tus.v[nT + i].coefOff += (uint32_t) nC; }
+      if( !r.coefs.empty() ) memcpy( &m_coefs.v[nC], r.coefs.data(), r.coefs.size() * sizeof( int16_t ) );
+      if( !r.intra.empty() ) memcpy( &m_intra.v[nI], r.intra.data(), r.intra.size() * sizeof( b200_intra_tu ) );
+      nP += r.pus.size(); nT += r.tus.size(); nC += r.coefs.size(); nI += r.intra.size();
+    }
+    if( m_doLmcs )
+    {
       const int vs = pcv.maxCUWidth == 128 ? 64 : pcv.maxCUWidth, vW = ( pcv.lumaWidth + vs - 1 ) / vs, vH = ( pcv.lumaHeight + vs - 1 ) / vs;
       m_vpdus.v.assign( (size_t) vW * vH, b200_lmcs_vpdu{} );
       for( int j = 0; j < vH; j++ ) for( int i = 0; i < vW; i++ )
@@ -207,44 +364,142 @@ public:
       }
       m_lmcs.vpdus = m_vpdus.v.data();
     }
-
-    // ---- submit ----
-    for( PinnedVec<b200_lf_param>& l : m_lf ) l.pin();
-    m_pus.pin(); m_tus.pin(); m_coefs.pin(); m_sao.pin(); m_alf.pin(); m_intra.pin();
-    b200_picture p{};
-    p.dstSlot = slotFor( pic );
-    p.flags = ( slice0.getDeblockingFilterDisable() ? 0 : B200_PIC_DEBLOCK ) | ( doSao ? B200_PIC_SAO : 0 ) | ( doAlf ? B200_PIC_ALF : 0 ) | ( doLmcs ? B200_PIC_LMCS : 0 );
+    m_pus.pin(); m_tus.pin(); m_coefs.pin(); m_intra.pin();
+    b200_picture& p = m_pic; p = b200_picture{};
+    p.dstSlot = m_dstSlot;
+    p.flags = ( slice0.getDeblockingFilterDisable() ? 0 : B200_PIC_DEBLOCK ) | ( m_doSao ? B200_PIC_SAO : 0 ) | ( m_doAlf ? B200_PIC_ALF : 0 ) | ( m_doLmcs ? B200_PIC_LMCS : 0 );
     p.pus = m_pus.v.data(); p.numPus = m_pus.v.size(); p.numDmvr = m_dmvrMvCache.size();
     p.tus = m_tus.v.data(); p.numTus = m_tus.v.size(); p.coefs = m_coefs.v.data(); p.numCoefs = m_coefs.v.size();
     p.lfV = m_lf[0].v.data(); p.lfH = m_lf[1].v.data(); p.lfSlices = &m_lfSlice; p.numLfSlices = 1; p.lfSeq = &m_lfSeq;
     p.sao = m_sao.v.data(); p.vb = &m_vb; p.alf = m_alf.v.data(); p.alfTabs = &m_alfTabs;
-    p.wp = m_wp.data(); p.numWp = (int32_t) m_wp.size(); p.lmcs = doLmcs ? &m_lmcs : nullptr;
+    p.wp = m_wp.data(); p.numWp = (int32_t) m_wp.size(); p.lmcs = m_doLmcs ? &m_lmcs : nullptr;
     p.intraTus = m_intra.v.data(); p.numIntraTus = m_intra.v.size();
-    m_arena = b200_decompress_picture( m_ctx, &p );
+    if( m_dryRun ) return;
+    std::lock_guard<std::mutex> l( m_sh->m );               // two recon instances share the context: submissions are serialised (stream order = decoding order)
+    m_arena = b200_decompress_picture( m_sh->ctx, &p );
     check( m_arena );
   }
 
-  // DecLibRecon::waitForPrevDecompressedPic (DecLibRecon.cpp:684): device done -> DMVR deltas -> TaskFinishMotionInfo -> output planes.
+public:
+  DecLibReconB200() = default;
+  ~DecLibReconB200() = default;
+  CLASS_COPY_MOVE_DELETE( DecLibReconB200 )
+
+  // DecLibRecon::create (DecLibRecon.cpp:127)
+  void create( ThreadPool* threadPool, unsigned instanceId, bool upscaleOutputEnabled )
+  {
+    CHECK_FATAL( upscaleOutputEnabled, "DecLibReconB200: output upscaling is not part of the device path" );
+    m_pool = threadPool; m_id = instanceId; m_numThreads = std::max( 1, threadPool ? threadPool->numThreads() : 1 );
+    m_sh = sharedFor( threadPool );
+    m_trQuant.reset( new TrQuant( &m_interPred ) );
+    m_cuDecoders.clear();
+    for( int i = 0; i < m_numThreads; i++ ) { m_cuDecoders.emplace_back( new DecCu ); m_cuDecoders.back()->init( nullptr, &m_interPred, nullptr, m_trQuant.get() ); }
+  }
+  void destroy() { m_cuDecoders.clear(); m_trQuant.reset(); m_sh.reset(); m_pool = nullptr; }
+  Picture* getCurrPic() const { return m_currDecompPic; }
+  void setDpbSlots( int n ) { m_dpbSlots = n; }            // before the first picture; default 17 (MAX_NUM_REF_PICS + the current picture)
+  // test hook: run every host stage and keep the work lists (flattened()), without a device
+  void setDryRun( bool b ) { m_dryRun = b; }
+  const b200_picture& flattened() const { return m_pic; }
+  // forget every picture of the device DPB (their Picture objects are about to be destroyed: end of sequence, test harness)
+  void resetDpb() { if( !m_sh ) return; std::lock_guard<std::mutex> l( m_sh->m ); m_sh->slotOf.clear(); std::fill( m_sh->owner.begin(), m_sh->owner.end(), nullptr ); std::fill( m_sh->valid.begin(), m_sh->valid.end(), 0 ); }
+  const std::vector<Mv>& dmvrMvCache() const { return m_dmvrMvCache; }
+
+  // DecLibRecon::decompressPicture (DecLibRecon.cpp:429): schedules the host stages of the picture; returns without waiting.
+  void decompressPicture( Picture* pic )
+  {
+    m_currDecompPic = pic;
+    CodingStructure& cs = *pic->cs; const PreCalcValues& pcv = *cs.pcv;
+    pic->progress = Picture::reconstructing;
+    m_failure = nullptr; m_failed.store( false );
+    refuse( pic );
+    m_motionInfo.resize( (size_t) pcv.num4x4CtuBlks * pcv.sizeInCtus ); m_loopFilterParam.resize( (size_t) pcv.num4x4CtuBlks * pcv.sizeInCtus * 2 );
+    m_dmvrMvCache.assign( (size_t) pcv.num8x8CtuBlks * pcv.sizeInCtus, Mv() ); cs.m_dmvrMvCache = m_dmvrMvCache.data();
+    m_trQuant->init( pic );
+    pic->startProcessingTimer();
+    preparePicture( pic );
+
+    const int W = pcv.widthInCtus, H = pcv.heightInCtus;
+    m_rows.resize( H ); m_hist.assign( H, MotionHist() );
+    m_miderCols.reset( new std::atomic<int>[H] );
+    for( int y = 0; y < H; y++ ) { m_rows[y].self = this; m_rows[y].line = y; m_rows[y].col = 0; m_miderCols[y].store( 0 ); }
+    pic->reconDone.lock();
+    for( int y = 0; y < H; y++ )
+    {
+      CBarrierVec bars;
+#if RECO_WHILE_PARSE
+      if( pic->parseDone.isBlocked() ) bars.push_back( &pic->ctuParsedBarrier[( y + 1 ) * W - 1] );   // the last CTU of the row is parsed (DecLibRecon.cpp:619-625)
+#else
+      bars.push_back( &pic->parseDone );
+#endif
+      m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 mider " + std::to_string( y ) ) miderTask, &m_rows[y], &m_miderCounter, nullptr, std::move( bars ) );
+    }
+    for( int y = 0; y < H; y++ )
+      m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 flatten " + std::to_string( y ) ) flattenTask, &m_rows[y], &m_flattenCounter, nullptr, { m_miderCounter.donePtr(), &pic->parseDone } );
+    m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 submit" ) submitTask, this, &m_submitCounter, nullptr, { m_flattenCounter.donePtr() } );
+  }
+
+  // DecLibRecon::waitForPrevDecompressedPic (DecLibRecon.cpp:684): host stages done -> device done -> DMVR deltas -> TaskFinishMotionInfo -> planes.
   Picture* waitForPrevDecompressedPic()
   {
-    Picture* pic = m_currDecompPic; if( !pic ) return nullptr;
-    CodingStructure& cs = *pic->cs; const PreCalcValues& pcv = *cs.pcv;
-    m_dmvr.v.assign( m_dmvrMvCache.size() * 2, 0 ); m_dmvr.pin();
-    check( b200_wait_picture( m_ctx, m_arena, m_dmvr.v.data(), m_dmvrMvCache.size() ) );
-    for( size_t i = 0; i < m_dmvrMvCache.size(); i++ ) m_dmvrMvCache[i] = Mv( m_dmvr.v[2 * i], m_dmvr.v[2 * i + 1] );
-    for( unsigned a = 0; a < pcv.sizeInCtus; a++ )                                                                                         // colMotion for later TMVP (DecCu.cpp:161),
-      if( !cs.getCtuData( a ).slice->isIntra() && pic->stillReferenced ) m_cCuDecoder.TaskFinishMotionInfo( cs, a, a % pcv.widthInCtus, a / pcv.widthInCtus );   // under ctuTask's conditions (DecLibRecon.cpp:860-867)
-    if( pic->neededForOutput )
+    if( !m_currDecompPic ) return nullptr;
+    Picture* pic = m_currDecompPic;
+    try
     {
-      int16_t* planes[3] = { cs.getRecoBuf( COMPONENT_Y ).buf, nullptr, nullptr };
-      if( m_geom.chromaFormat ) { planes[1] = cs.getRecoBuf( COMPONENT_Cb ).buf; planes[2] = cs.getRecoBuf( COMPONENT_Cr ).buf; }
-      if( cs.getRecoBuf( COMPONENT_Y ).stride != (ptrdiff_t) m_geom.stride[0] ) THROW_UNSUPPORTED( "DecLibReconB200: output planes must be allocated without margins (vvdec_decoder_open_with_allocator)" );
-      check( b200_get_frame( m_ctx, m_slotOf[pic], planes ) );
+      if( m_pool->numThreads() == 0 ) m_pool->processTasksOnMainThread();
+      m_miderCounter.wait(); m_flattenCounter.wait(); m_submitCounter.wait();
+      if( m_failed.load() ) std::rethrow_exception( m_failure );
+      const Slice*   lastSlice           = pic->slices.back();
+      const unsigned lastSliceLastCtuIdx = lastSlice->getCtuAddrInSlice( lastSlice->getNumCtuInSlice() - 1 );
+      CHECK( lastSliceLastCtuIdx != pic->cs->pcv->sizeInCtus - 1, "Picture incomplete. A slice was probably lost." );
+      if( !m_dryRun ) finishOnHost( pic );
+      pic->cs->deallocTempInternals();
+      pic->stopProcessingTimer();
+      pic->progress = Picture::reconstructed;
+      pic->reconDone.unlock();
     }
-    pic->progress = Picture::reconstructed;
-    pic->reconDone.unlock();
-    m_currDecompPic = nullptr;
-    return pic;
+    catch( ... )
+    {
+      pic->error = true;
+      pic->reconDone.setException( std::current_exception() );
+    }
+    if( pic->error || pic->reconDone.hasException() ) cleanupOnException();
+    return std::exchange( m_currDecompPic, nullptr );
+  }
+
+  // DecLibRecon::cleanupOnException (DecLibRecon.cpp:724): no task of the broken picture may survive in the pool; its device slot is released
+  void cleanupOnException()
+  {
+    m_miderCounter.wait_nothrow(); m_flattenCounter.wait_nothrow(); m_submitCounter.wait_nothrow();
+    m_miderCounter.clearException(); m_flattenCounter.clearException(); m_submitCounter.clearException();
+    if( m_currDecompPic ) m_currDecompPic->waitForAllTasks();
+    if( m_sh && m_currDecompPic )
+    {
+      std::lock_guard<std::mutex> l( m_sh->m );
+      auto it = m_sh->slotOf.find( m_currDecompPic );
+      if( it != m_sh->slotOf.end() ) { m_sh->owner[it->second] = nullptr; m_sh->valid[it->second] = 0; m_sh->slotOf.erase( it ); }
+    }
+  }
+
+private:
+  void finishOnHost( Picture* pic )
+  {
+    CodingStructure& cs = *pic->cs; const PreCalcValues& pcv = *cs.pcv; Shared& S = *m_sh;
+    m_dmvr.v.assign( m_dmvrMvCache.size() * 2, 0 ); m_dmvr.pin();
+    {
+      std::lock_guard<std::mutex> l( S.m );
+      check( b200_wait_picture( S.ctx, m_arena, m_dmvr.v.data(), m_dmvrMvCache.size() ) );
+      S.valid[m_dstSlot] = 1;
+    }
+    for( size_t i = 0; i < m_dmvrMvCache.size(); i++ ) m_dmvrMvCache[i] = Mv( m_dmvr.v[2 * i], m_dmvr.v[2 * i + 1] );
+    if( pic->stillReferenced )                                                                                    // colMotion for later TMVP (DecCu.cpp:161),
+      for( unsigned a = 0; a < pcv.sizeInCtus; a++ )                                                              // under ctuTask's conditions (DecLibRecon.cpp:860-867)
+        if( !cs.getCtuData( a ).slice->isIntra() ) m_cuDecoders[0]->TaskFinishMotionInfo( cs, a, a % pcv.widthInCtus, a / pcv.widthInCtus );
+    // the finished planes go back into Picture::m_bufs: output frames alias them (vvdecimpl.cpp:1051) and a CPU fallback picture may reference them
+    int16_t* planes[3] = { nullptr, nullptr, nullptr }; ptrdiff_t strides[3] = { 0, 0, 0 };
+    for( int c = 0; c < ( S.geom.chromaFormat ? 3 : 1 ); c++ ) { PelBuf b = cs.getRecoBuf( ComponentID( c ) ); planes[c] = b.buf; strides[c] = b.stride; }
+    std::lock_guard<std::mutex> l( S.m );
+    check( b200_get_frame_strided( S.ctx, m_dstSlot, planes, strides ) );
   }
 };
 

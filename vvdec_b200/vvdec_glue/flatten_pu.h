@@ -41,7 +41,8 @@ inline FlattenPuResult flattenPU( const CodingUnit& cu, const SlotMap& sm, WpIdx
 {
   if( !CU::isInter( cu ) || CU::isIBC( cu ) ) return FLATTEN_PU_NOT_INTER;
   // tools the device path does not have: the caller sends such CUs (or the picture) down the CPU path
-  if( cu.ciipFlag() || cu.mergeType() == MRG_TYPE_SUBPU_ATMVP || cu.sps->getUseWrapAround() ) return FLATTEN_PU_UNSUPPORTED;   // SbTMVP: flattenSbTmvp
+  // (CIIP CUs: this record is their inter half, BDOF excluded below as in motionCompensation :1412; the intra half is flattenCiipBlock's)
+  if( cu.mergeType() == MRG_TYPE_SUBPU_ATMVP || cu.sps->getUseWrapAround() ) return FLATTEN_PU_UNSUPPORTED;   // SbTMVP: flattenSbTmvp
   const Slice& slice = *cu.slice;
   const PPS&   pps   = *cu.pps;
   if( cu.geoFlag() )
@@ -115,7 +116,7 @@ inline FlattenPuResult flattenPU( const CodingUnit& cu, const SlotMap& sm, WpIdx
   const bool wpB = pps.getWPBiPred() && slice.getSliceType() == B_SLICE && cu.BcwIdx() == BCW_DEFAULT;
   const bool wpP = pps.getUseWP() && slice.getSliceType() == P_SLICE;
   if( !bioApplied && !dmvrApplied && ( wpB || wpP ) ) r.wpIdx = (uint8_t) wpIdxOf( refIdx[0], refIdx[1] );
-  else if( bi && cu.BcwIdx() != BCW_DEFAULT ) r.bcwW1 = getBcwWeight( g_BcwInternBcw[cu.BcwIdx()], REF_PIC_LIST_1 );   // xWeightedAverage :1357
+  else if( bi && cu.BcwIdx() != BCW_DEFAULT && !cu.ciipFlag() ) r.bcwW1 = getBcwWeight( g_BcwInternBcw[cu.BcwIdx()], REF_PIC_LIST_1 );   // xWeightedAverage :1353: a CIIP CU keeps the merge candidate's BcwIdx but averages plainly
   return FLATTEN_PU_OK;
 }
 
