@@ -1,20 +1,33 @@
 #!/usr/bin/env python
-"""bench.py — decoded frames/s of the VVC pixel-reconstruction back end on synthetic post-parse pictures.
+"""bench.py — decoded frames/s of the VVC pixel-reconstruction back end behind VVdeC's DecLibRecon seam.
 
 Metric (BASELINE.json): decoded frames/sec, 4K 10-bit Main10 RA, bit-exact vs reference.
-Workload (config.workload): `--width x --height` 10-bit 4:2:0 pictures (default 3840x2160 = BASELINE.json configs[2]) drawn by
-vvdec_b200.synth.gen_picture (SURVEY §8d config 2/3 model: QT+BT partition, all CUs inter with uni / bi / BCW / BDOF / DMVR /
-affine+PROF, residual on ~35 % of CUs with MTS / TS / joint-CbCr, deblocking grids, SAO on 40 % of CTUs, ALF + CC-ALF).
-A *step* is one picture through the whole chain K2 -> K1 -> K3 -> K4 -> K5 into a device-resident DPB; pictures cycle through
-a GOP of `--gop` distinct work lists and 6 DPB slots (each picture references slots written by earlier steps).
+Workload (config.workload, identical in both arms): `--width x --height` 10-bit 4:2:0 synthetic PARSED pictures of a random-access GOP
+(SURVEY §8d config 3): one I picture per `--gop` steps, B pictures otherwise with 85 % inter / 15 % intra CUs — merge / MMVD / GEO / CIIP /
+affine (+PROF) / AMVP with AMVR, BCW, SMVD, BDOF and DMVR where the POC distances allow, residual with MTS / LFNST / SBT / TS / joint CbCr,
+intra CUs with angular / MRL / MIP / CCLM / BDPCM — followed by deblocking, SAO, ALF + CC-ALF.  The pictures are built by oracle/ref_seam.h as
+real VVdeC `Picture` objects (CodingStructure through the reference's Partitioner / addCU / addTU, levels in the reconstruction plane,
+motion left as merge / AMVP syntax): exactly what DecLibRecon::decompressPicture receives from the parser.
 
-  value  = frames/s with the work lists already resident in HBM (b200_pic_run only), CUDA events on the launching stream.
-  e2e    = frames/s through the reference-facing call b200_decompress_picture with pinned HOST work lists (H2D inside the timed
-           region) + b200_get_frame of every output picture into pinned host planes (D2H inside the timed region).
-  --impl reference: the reference's own CPU implementation (oracle/_ref = unmodified VVdeC kernels, SIMD on, all host threads)
-           on the same pictures (see oracle/ref_shim.cpp: ref_decompress_picture_mt).
-Multi-GPU (--gpus N under torchrun): closed GOPs are independent -> each rank decodes its own GOP, no data-path
-collective; value = total frames / max-over-ranks time ("weak" scaling).
+  --impl reference : the reference's own DecLibRecon (create / decompressPicture / waitForPrevDecompressedPic, DecLibRecon.cpp:127,429,684)
+                     with a ThreadPool of all host threads on those pictures — BASELINE.md level B1.  A step = one picture; the time of a
+                     step is the time between decompressPicture() and the return of waitForPrevDecompressedPic().
+  --impl b200 (default): the same pictures through the product:
+     value  = frames/s of the device chain (b200_pic_run: K2 -> K1 -> K6 -> K3 -> K4 -> K5) with the pictures' work lists resident in HBM —
+              the lists are what the drop-in class DecLibReconB200 flattens from each parsed Picture (untimed preparation, like the
+              reference arm's picture construction); CUDA events on the launching stream.
+     e2e    = frames/s through the C ABI with HOST buffers: every step uploads one picture's pinned host work lists (b200_pic_upload,
+              bucketing kernels included), runs it and copies the 16-bit output frame to pinned host memory, inside the timed region.
+     seam   = frames/s of DecLibReconB200::decompressPicture + waitForPrevDecompressedPic on live parsed Pictures (host MIDER + boundary
+              strengths + flatten on the decoder's thread pool, H2D, device chain, DMVR read-back, TaskFinishMotionInfo, D2H into
+              Picture::m_bufs) — the number a VVdeC built with this back end would see per recon instance, reported beside e2e.
+Multi-GPU (--gpus N under torchrun): closed GOPs are independent -> each rank decodes its own GOPs (vvdec_b200.gop_shard), no
+data-path collective while decoding; finished frames are gathered to rank 0 in display order over NCCL (--gather, on a side stream).
+value = total frames / max-over-ranks time ("weak" scaling).
+
+oracle/_ref (the compiled, unmodified reference) is used for three things only: building the parsed pictures (both arms), the reference arm /
+cpu_baseline leg, and hosting the product's glue class for the seam leg (the glue lives inside a VVdeC build by design).  Every timed GPU
+region runs libvvdec_b200.so alone.
 """
 import argparse, ctypes as C, json, os, subprocess, sys, threading, time
 
@@ -22,54 +35,60 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import numpy as np
 
+METRIC = "decoded frames/sec, 4K 10-bit Main10 RA, bit-exact YUV vs reference"
+
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
-    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
-    ap.add_argument("--gop", type=int, default=8)
+    ap.add_argument("--gop", type=int, default=32, help="one I picture every GOP steps")
+    ap.add_argument("--distinct", type=int, default=6, help="distinct B pictures cycled through")
+    ap.add_argument("--intra-pct", type=int, default=15)
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--cpu-sample", type=int, default=2, help="pictures timed for the cpu_baseline leg")
+    ap.add_argument("--cpu-sample", type=int, default=6, help="B pictures timed for the cpu_baseline leg (plus one I picture)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-seam", action="store_true")
+    ap.add_argument("--host-threads", type=int, default=0, help="threads of the reference's ThreadPool (0: all)")
     return ap.parse_args()
 
 
-# ------------------------------------------------------------------------------------------------ workload
-SLOT_ORDER = [4, 5, 0, 2, 1, 3]     # destination slot of step i (mod 6); refs are always slots 0..3 (synth.gen_pus)
-
-
-def make_gop(args, rank=0):
-    from vvdec_b200 import synth
-    rng = np.random.default_rng(args.seed + 1000 * rank)
-    pics = [synth.gen_picture(rng, args.width, args.height, 10, dst_slot=SLOT_ORDER[i % 6]) for i in range(args.gop)]
-    refs = [synth.noise_planes(rng, args.width, args.height, 10) for _ in range(4)]
-    return pics, refs
-
-
-def algorithmic_bytes(args, pic):
-    """SURVEY.md §8(d) algorithmic bytes per picture for each kernel family (see DESIGN.md §5)."""
+# ------------------------------------------------------------------------------------------------ workload (both arms)
+def workload_config(args, world):
     W, H = args.width, args.height
-    S = W * H * 3 // 2
-    pus, tus = pic["pus"], pic["tus"]
-    nref = (pus["refSlot"] >= 0).sum(axis=1)
-    w, h = pus["w"].astype(np.int64), pus["h"].astype(np.int64)
-    aff = (pus["flags"] & 8) != 0
-    # per PU: luma (w+7)(h+7) + 2 chroma (w/2+3)(h/2+3) read per list, w*h*1.5 written; affine: 6-tap per 4x4 -> (4+5)^2 per sub-block
-    rd = np.where(aff, (w // 4) * (h // 4) * 81 + 2 * (w // 8) * (h // 8) * 49, (w + 7) * (h + 7) + 2 * (w // 2 + 3) * (h // 2 + 3))
-    mc = 2 * (nref * rd).sum() + 2 * (w * h * 3 // 2).sum() + 64 * len(pus)
-    ncoef = ((tus["maxX"].astype(np.int64) + 1) * (tus["maxY"].astype(np.int64) + 1)).sum()
-    R = ((1 << tus["log2w"].astype(np.int64)) * (1 << tus["log2h"].astype(np.int64)) * np.where(tus["ict"] != 0, 2, 1)).sum()
-    k1 = 2 * ncoef + 4 * R + 32 * len(tus)            # levels + pred read & reco write of the covered samples + records
-    n4 = (W // 4) * (H // 4)
-    lf = 2 * S + 2 * S + 2 * 6 * n4                    # planes read+written once (V+H counted once, §8d) + both grids
-    nctu = ((W + 127) // 128) * ((H + 127) // 128)
-    sao = 4 * S + 24 * nctu
-    alf = 4 * S + 8 * nctu
-    return {"mc": int(mc), "k1": int(k1), "lf": int(lf), "sao": int(sao), "alf": int(alf)}
+    return {"workload": f"{W}x{H} 10-bit 4:2:0 synthetic PARSED RA pictures at the DecLibRecon seam (oracle/ref_seam.h, seed {args.seed}): 1 I picture per {args.gop} steps, "
+                        f"B pictures with {args.intra_pct} % intra CUs otherwise ({args.distinct} distinct, cycled); merge/MMVD/GEO/CIIP/affine+PROF/AMVP+AMVR/BCW/SMVD/BDOF/DMVR, "
+                        "residual MTS/LFNST/SBT/TS/JCCR, intra angular/MRL/MIP/CCLM/BDPCM, deblocking + SAO + ALF/CC-ALF",
+            "l2": "inputs larger than L2 (6 x 25 MB DPB buffers + work-list arenas cycled)", "parallelism": f"gop-per-gpu x{world}"}
+
+
+class Workload:
+    """The GOP's parsed pictures: one template (reference pictures, filter parameters) and per-picture generator seeds."""
+    def __init__(self, args, rank):
+        from tests import helpers
+        self.helpers, self.args = helpers, args
+        self.ref = helpers.load_ref()
+        if self.ref is None or not hasattr(self.ref, "ref_seam_create"):
+            raise RuntimeError("oracle/_ref/libvvdec_ref.so (the compiled reference + seam shim) is missing: run `python -c 'import __graft_entry__ as g; g.build()'` where /root/reference exists")
+        rng = np.random.default_rng(args.seed + 1000 * rank)
+        self.base = helpers.SeamCase(self.ref, rng, args.width, args.height, intra=args.intra_pct)
+        seeds = [int(s) for s in rng.integers(1, 1 << 30, size=args.distinct + 1)]
+        self.B = [self.base.variant(s) for s in seeds[:-1]]
+        self.I = self.base.variant(seeds[-1], slice_type=2)
+
+    def sched(self, i):
+        """Picture of step i: ('I', case) or ('B', case)."""
+        if i % self.args.gop == 0: return "I", self.I, -1
+        k = (i - 1 - i // self.args.gop) % len(self.B)
+        return "B", self.B[k], k
+
+
+def threads_all(args):
+    return args.host_threads or os.cpu_count()
 
 
 class ClockSampler(threading.Thread):
@@ -100,35 +119,12 @@ class ClockSampler(threading.Thread):
 
 
 def dist_env():
-    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
-    return rank, world, local
-
-
-def pin_pic(lib, pic):
-    """Pin every host array of a synthetic picture (cudaHostRegister) so the H2D copies are truly asynchronous."""
-    arrs = [pic["pus"], pic["tus"], pic["coefs"], pic.get("lfV"), pic.get("lfH"), pic.get("sao")]
-    if "alf" in pic: arrs += [pic["alf"]["ctus"], pic["alf"]["lumaCoeff"], pic["alf"]["lumaClip"]]
-    n = 0
-    for a in arrs:
-        if a is not None and a.nbytes:
-            lib.b200_host_register(a.ctypes.data, a.nbytes); n += a.nbytes
-    return n
-
-
-def h2d_bytes(pic):
-    n = pic["pus"].nbytes + pic["tus"].nbytes + pic["coefs"].nbytes
-    n += 4 * sum(((int(w) + 15) // 16) * ((int(h) + 15) // 16) for w, h in zip(pic["pus"]["w"], pic["pus"]["h"]))   # tile list
-    for k in ("lfV", "lfH", "sao"):
-        if k in pic: n += pic[k].nbytes
-    if "alf" in pic:
-        a = pic["alf"]; n += a["ctus"].nbytes + a["lumaCoeff"].nbytes + a["lumaClip"].nbytes + a["chromaCoeff"].nbytes + a["chromaClip"].nbytes + sum(c.nbytes for c in a["cc"])
-    return n
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 
 
 def bind_to_gpu_numa_node(local):
     """Run this process (and first-touch its pinned buffers) on the NUMA node the GPU hangs off: H2D/D2H then do not cross the socket link."""
     try:
-        import subprocess
         bdf = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)], capture_output=True, text=True, timeout=10).stdout.strip().lower()
         if bdf.startswith("00000000:"): bdf = bdf[4:]
         node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
@@ -140,6 +136,51 @@ def bind_to_gpu_numa_node(local):
         return {"node": node, "cpus": len(cpus)}
     except Exception as e:
         return {"node": None, "error": str(e)[:80]}
+
+
+def pic_arrays(pic):
+    arrs = [pic["pus"], pic["tus"], pic["coefs"], pic.get("lfV"), pic.get("lfH"), pic.get("sao"), pic.get("intraTus"), pic.get("wp")]
+    if "alf" in pic: arrs += [pic["alf"]["ctus"]] + list(pic["alfArrays"].values())
+    return [a for a in arrs if a is not None and a.nbytes]
+
+
+def h2d_bytes(pic):
+    n = sum(a.nbytes for a in pic_arrays(pic))
+    n += 4 * sum(((int(w) + 15) // 16) * ((int(h) + 15) // 16) for w, h in zip(pic["pus"]["w"], pic["pus"]["h"])) if False else 0
+    return n
+
+
+def algorithmic_bytes(args, pic):
+    """SURVEY.md §8(d) algorithmic bytes per picture for each kernel family (DESIGN.md §5)."""
+    W, H = args.width, args.height
+    S = W * H * 3 // 2
+    pus, tus = pic["pus"], pic["tus"]
+    out = {}
+    if len(pus):
+        nref = (pus["refSlot"] >= 0).sum(axis=1)
+        w, h = pus["w"].astype(np.int64), pus["h"].astype(np.int64)
+        aff = (pus["flags"] & 8) != 0
+        # per PU: luma (w+7)(h+7) + 2 chroma (w/2+3)(h/2+3) read per list, w*h*1.5 written; affine: 6-tap per 4x4 -> (4+5)^2 per sub-block
+        rd = np.where(aff, (w // 4) * (h // 4) * 81 + 2 * (w // 8) * (h // 8) * 49, (w + 7) * (h + 7) + 2 * (w // 2 + 3) * (h // 2 + 3))
+        out["mc"] = int(2 * (nref * rd).sum() + 2 * (w * h * 3 // 2).sum() + 64 * len(pus))
+    else: out["mc"] = 0
+    if len(tus):
+        ncoef = ((tus["maxX"].astype(np.int64) + 1) * (tus["maxY"].astype(np.int64) + 1)).sum()
+        R = ((1 << tus["log2w"].astype(np.int64)) * (1 << tus["log2h"].astype(np.int64)) * np.where(tus["ict"] != 0, 2, 1)).sum()
+        out["k1"] = int(2 * ncoef + 4 * R + 32 * len(tus))     # levels + pred read & reco write of the covered samples + records
+    else: out["k1"] = 0
+    it = pic.get("intraTus")
+    if it is not None and len(it):
+        bw, bh = (1 << it["log2w"].astype(np.int64)), (1 << it["log2h"].astype(np.int64))
+        resi = (it["flags"] & 4) != 0
+        out["intra"] = int((2 * (2 * bw + 2 * bh + 1) + 2 * bw * bh + np.where(resi, 2 * bw * bh, 0)).sum() + 16 * len(it))   # reference samples + block write (+ residual read) + record
+    else: out["intra"] = 0
+    n4 = (W // 4) * (H // 4)
+    out["lf"] = 2 * S + 2 * S + 2 * 6 * n4                    # planes read+written once (V+H counted once, §8d) + both grids
+    nctu = ((W + 127) // 128) * ((H + 127) // 128)
+    out["sao"] = 4 * S + 24 * nctu
+    out["alf"] = 4 * S + 8 * nctu
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -155,17 +196,32 @@ def run_b200(args):
     lib = vvdec_b200.lib()
     W, H = args.width, args.height
     g = abi.make_geom(W, H, 10)
-    pics, refs = make_gop(args, rank)
+    try: os.sched_setaffinity(0, range(os.cpu_count()))               # the (untimed) preparation uses every core
+    except Exception: pass
+    wl = Workload(args, rank)
+    T = threads_all(args)
+    # ---- preparation (untimed): every distinct parsed picture flattened by the drop-in class's host stages into pinned work lists ----
+    flat = {}
+    host_stage_s = []
+    for key, case in [("I", wl.I)] + [(k, c) for k, c in enumerate(wl.B)]:
+        pic, secs = case.flatten(threads=T)
+        assert pic is not None, f"DecLibReconB200 refused a workload picture ({secs})"
+        pic["struct"].dstSlot = 5 if key == "I" else 4
+        for a in pic_arrays(pic): lib.b200_host_register(a.ctypes.data, a.nbytes)
+        flat[key] = pic; host_stage_s.append(secs)
+    numa = bind_to_gpu_numa_node(local)
+
+    def pic_of(i):
+        kind, _, k = wl.sched(i)
+        return flat["I"] if kind == "I" else flat[k]
+
     ctx = C.c_void_p()
-    vvdec_b200.check(lib.b200_ctx_create(C.byref(ctx), C.byref(g), 6, args.gop, local))
-    for s in range(4): vvdec_b200.check(lib.b200_ctx_load_slot(ctx, s, abi.plane_ptrs(refs[s])))
-    for s in (4, 5): vvdec_b200.check(lib.b200_ctx_load_slot(ctx, s, abi.plane_ptrs(refs[0])))
-    for p in pics: pin_pic(lib, p)
+    vvdec_b200.check(lib.b200_ctx_create(C.byref(ctx), C.byref(g), 6, len(flat), local))
+    for s in range(4): vvdec_b200.check(lib.b200_ctx_load_slot(ctx, s, abi.plane_ptrs(wl.base.refs[s])))
+    for s in (4, 5): vvdec_b200.check(lib.b200_ctx_load_slot(ctx, s, abi.plane_ptrs(wl.base.refs[0])))
     outs = [[np.zeros((H, W), np.int16), np.zeros((H // 2, W // 2), np.int16), np.zeros((H // 2, W // 2), np.int16)] for _ in range(2)]
     for out in outs:
         for o in out: lib.b200_host_register(o.ctypes.data, o.nbytes)
-    out = outs[0]
-    structs = [p["struct"] for p in pics]
 
     def barrier():
         if world > 1: dist.barrier()
@@ -176,49 +232,64 @@ def run_b200(args):
         t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
 
     # ---- value: work lists resident in HBM ----
-    handles = []
-    for st in structs:
-        h = lib.b200_pic_upload(ctx, C.byref(st)); assert h >= 0, lib.b200_last_error(); handles.append(h)
+    handle = {}
+    for key, pic in flat.items():
+        h = lib.b200_pic_upload(ctx, C.byref(pic["struct"])); assert h >= 0, lib.b200_last_error(); handle[key] = h
     vvdec_b200.check(lib.b200_wait_picture(ctx, -1, None, 0))
-    for i in range(args.warmup): vvdec_b200.check(lib.b200_pic_run(ctx, handles[i % args.gop]))
+
+    def h_of(i):
+        kind, _, k = wl.sched(i)
+        return handle["I"] if kind == "I" else handle[k]
+
+    for i in range(args.warmup): vvdec_b200.check(lib.b200_pic_run(ctx, h_of(i + 1)))
+    vvdec_b200.check(lib.b200_pic_run(ctx, handle["I"]))                  # the I picture's path is warm too
     barrier()
     sampler = ClockSampler(local); sampler.start()
     l0 = lib.b200_ctx_kernel_launches(ctx)
     vvdec_b200.check(lib.b200_ctx_mark(ctx, 0))
-    for i in range(args.steps): vvdec_b200.check(lib.b200_pic_run(ctx, handles[i % args.gop]))
+    for i in range(args.steps): vvdec_b200.check(lib.b200_pic_run(ctx, h_of(i)))
     vvdec_b200.check(lib.b200_ctx_mark(ctx, 1))
     ms = C.c_float(); vvdec_b200.check(lib.b200_ctx_elapsed_ms(ctx, C.byref(ms)))
     barrier()
     launches = lib.b200_ctx_kernel_launches(ctx) - l0
     ms_dev = max_over_ranks(ms.value)
 
-    # ---- per-kernel device time (same workload, events around each family) ----
+    # ---- per-kernel-family device time (same schedule, events around each family) + the I / B split ----
+    NF = 10
     lib.b200_ctx_set_profiling(ctx, 1)
-    for i in range(args.steps): vvdec_b200.check(lib.b200_pic_run(ctx, handles[i % args.gop]))
-    kms = (C.c_float * 8)(); kcnt = (C.c_int * 8)()
-    vvdec_b200.check(lib.b200_ctx_get_kernel_ms(ctx, kms, kcnt))
+    for i in range(args.steps): vvdec_b200.check(lib.b200_pic_run(ctx, h_of(i)))
+    kms = (C.c_float * NF)(); kcnt = (C.c_int * NF)()
+    vvdec_b200.check(lib.b200_ctx_get_kernel_ms_n(ctx, kms, kcnt, NF))
     lib.b200_ctx_set_profiling(ctx, 0)
+    split = {}
+    for name, hh in (("I_picture_ms", handle["I"]), ("B_picture_ms", handle[0])):
+        for _ in range(2): vvdec_b200.check(lib.b200_pic_run(ctx, hh))
+        vvdec_b200.check(lib.b200_ctx_mark(ctx, 0))
+        for _ in range(8): vvdec_b200.check(lib.b200_pic_run(ctx, hh))
+        vvdec_b200.check(lib.b200_ctx_mark(ctx, 1))
+        t = C.c_float(); vvdec_b200.check(lib.b200_ctx_elapsed_ms(ctx, C.byref(t))); split[name] = round(t.value / 8, 4)
 
     # ---- e2e: host work lists in, host frames out, every step ----
     for i in range(max(3, args.warmup // 2)):
-        h = lib.b200_decompress_picture(ctx, C.byref(structs[i % args.gop])); assert h >= 0
-        vvdec_b200.check(lib.b200_get_frame(ctx, structs[i % args.gop].dstSlot, abi.plane_ptrs(out)))
+        p = pic_of(i)
+        h = lib.b200_decompress_picture(ctx, C.byref(p["struct"])); assert h >= 0, lib.b200_last_error()
+        vvdec_b200.check(lib.b200_get_frame(ctx, p["struct"].dstSlot, abi.plane_ptrs(outs[0])))
     barrier()
     t0 = time.perf_counter()
     vvdec_b200.check(lib.b200_ctx_mark(ctx, 0))
     tickets = [None, None]
-    nxt = lib.b200_pic_upload(ctx, C.byref(structs[0])); assert nxt >= 0, lib.b200_last_error()
+    nxt = lib.b200_pic_upload(ctx, C.byref(pic_of(0)["struct"])); assert nxt >= 0, lib.b200_last_error()
     for i in range(args.steps):
         # every step: H2D of one picture's host work lists (the NEXT picture's: the caller keeps one upload in flight, as a decoder whose
         # parser runs ahead of reconstruction does) + this picture's kernels + D2H of its output frame into one of two pinned host frames;
         # the D2H of step i overlaps the H2D/kernels of step i+1 (copy stream), a host frame is reused only after its copy completed
         cur = nxt
         if i + 1 < args.steps:
-            nxt = lib.b200_pic_upload(ctx, C.byref(structs[(i + 1) % args.gop])); assert nxt >= 0, lib.b200_last_error()
+            nxt = lib.b200_pic_upload(ctx, C.byref(pic_of(i + 1)["struct"])); assert nxt >= 0, lib.b200_last_error()
         vvdec_b200.check(lib.b200_pic_run(ctx, cur))
         k = i & 1
         if tickets[k] is not None: vvdec_b200.check(lib.b200_frame_wait(ctx, tickets[k]))
-        tickets[k] = lib.b200_get_frame_async(ctx, structs[i % args.gop].dstSlot, abi.plane_ptrs(outs[k])); assert tickets[k] >= 0
+        tickets[k] = lib.b200_get_frame_async(ctx, pic_of(i)["struct"].dstSlot, abi.plane_ptrs(outs[k])); assert tickets[k] >= 0
     for t in tickets:
         if t is not None: vvdec_b200.check(lib.b200_frame_wait(ctx, t))
     vvdec_b200.check(lib.b200_ctx_mark(ctx, 1))
@@ -226,152 +297,151 @@ def run_b200(args):
     barrier()
     wall_e2e = (time.perf_counter() - t0) * 1e3
     ms_e2e = max_over_ranks(max(ms2.value, wall_e2e))
-    # ---- the same end-to-end loop with the application's packed output format (pyuv, 4 samples in 5 bytes): the frame is
-    # converted on the device, so 15.6 MB instead of 24.9 MB cross PCIe per frame.  Reported beside the headline, which stays 16-bit planes.
-    pouts = [[np.zeros(lib.b200_frame_bytes(C.byref(g), 1, c), np.uint8) for c in range(3)] for _ in range(2)]
-    for po in pouts:
-        for o in po: lib.b200_host_register(o.ctypes.data, o.nbytes)
-    pptrs = [(C.c_void_p * 3)(*[o.ctypes.data for o in po]) for po in pouts]
-    n_p = min(args.steps, 200)
-    barrier()
-    t1 = time.perf_counter(); tickets = [None, None]
-    nxt = lib.b200_pic_upload(ctx, C.byref(structs[0])); assert nxt >= 0, lib.b200_last_error()
-    for i in range(n_p):
-        cur = nxt
-        if i + 1 < n_p:
-            nxt = lib.b200_pic_upload(ctx, C.byref(structs[(i + 1) % args.gop])); assert nxt >= 0, lib.b200_last_error()
-        vvdec_b200.check(lib.b200_pic_run(ctx, cur))
-        k = i & 1
-        if tickets[k] is not None: vvdec_b200.check(lib.b200_frame_wait(ctx, tickets[k]))
-        tickets[k] = lib.b200_get_frame_fmt_async(ctx, structs[i % args.gop].dstSlot, 1, pptrs[k]); assert tickets[k] >= 0, lib.b200_last_error()
-    for t in tickets:
-        if t is not None: vvdec_b200.check(lib.b200_frame_wait(ctx, t))
+
+    # ---- where the end-to-end time goes (untimed diagnostics): the link alone, in each direction and both at once (the PCIe ceiling) ----
+    n_diag = min(args.steps, 32)
     vvdec_b200.check(lib.b200_wait_picture(ctx, -1, None, 0))
-    barrier()
-    fps_pyuv = world * n_p / max_over_ranks(time.perf_counter() - t1)
-    # ---- where the end-to-end time goes (untimed diagnostics): host time inside the upload call, H2D alone, D2H alone ----
-    n_diag = min(args.steps, 64)
     t1 = time.perf_counter()
-    for i in range(n_diag): assert lib.b200_pic_upload(ctx, C.byref(structs[i % args.gop])) >= 0
+    for i in range(n_diag): assert lib.b200_pic_upload(ctx, C.byref(pic_of(i + 1)["struct"])) >= 0
     host_up = (time.perf_counter() - t1) * 1e3 / n_diag
     vvdec_b200.check(lib.b200_wait_picture(ctx, -1, None, 0))
     up_total = (time.perf_counter() - t1) * 1e3 / n_diag
     t1 = time.perf_counter()
     for i in range(n_diag): vvdec_b200.check(lib.b200_get_frame(ctx, 0, abi.plane_ptrs(outs[i & 1])))
     d2h_ms = (time.perf_counter() - t1) * 1e3 / n_diag
-    t1 = time.perf_counter(); tk = None
-    for i in range(n_diag):
-        assert lib.b200_pic_upload(ctx, C.byref(structs[i % args.gop])) >= 0
-        if tk is not None: vvdec_b200.check(lib.b200_frame_wait(ctx, tk))
-        tk = lib.b200_get_frame_async(ctx, 0, abi.plane_ptrs(outs[i & 1]))
-    vvdec_b200.check(lib.b200_frame_wait(ctx, tk)); vvdec_b200.check(lib.b200_wait_picture(ctx, -1, None, 0))
-    both_ms = (time.perf_counter() - t1) * 1e3 / n_diag
-    e2e_diag = {"host_ms_in_upload_call": round(host_up, 4), "upload_ms_incl_h2d": round(up_total, 4), "d2h_frame_ms": round(d2h_ms, 4),
-                "h2d_and_d2h_concurrent_ms": round(both_ms, 4),
-                "e2e_pyuv_output_fps": round(fps_pyuv, 2), "pyuv_d2h_bytes_per_step": int(sum(o.nbytes for o in pouts[0]))}
+    pcie = pcie_ceiling(torch)
+    h2d_step = float(np.mean([h2d_bytes(pic_of(i)) for i in range(args.steps)])); d2h_step = int(sum(o.nbytes for o in outs[0]))
+    e2e_diag = {"host_ms_in_upload_call": round(host_up, 4), "upload_ms_incl_h2d": round(up_total, 4), "d2h_frame_ms": round(d2h_ms, 4), "pcie": pcie,
+                "link_bound_fps": round(1e3 / max(1e-9, max(h2d_step / (pcie["h2d_gbs_duplex"] * 1e6), d2h_step / (pcie["d2h_gbs_duplex"] * 1e6))), 1) if pcie.get("h2d_gbs_duplex") else None}
     sampler.stop_flag = True; sampler.join(timeout=2)
+    lib.b200_ctx_destroy(ctx)
+
+    # ---- seam: DecLibReconB200 live on parsed Pictures (its own device context) ----
+    seam = None
+    if not args.no_seam and rank == 0:
+        try: os.sched_setaffinity(0, range(os.cpu_count()))
+        except Exception: pass
+        ts = []
+        for i in range(min(args.steps, 12) + 2):
+            _, case, _ = wl.sched(i)
+            _, _, secs = case.run_b200(threads=T)
+            assert secs >= 0, "DecLibReconB200 failed on a workload picture"
+            if i >= 2: ts.append(secs)
+        seam = {"value": round(len(ts) / sum(ts), 2), "unit": "frames/s", "host_threads": T, "pictures": len(ts),
+                "host_stage_ms_per_picture": round(1e3 * float(np.mean(host_stage_s)), 3),
+                "api": "b200glue::DecLibReconB200::decompressPicture + waitForPrevDecompressedPic on a live parsed Picture, one recon instance, no overlap between pictures"}
 
     if rank != 0:
         if world > 1: dist.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel ----
+    # ---- roofline of the dominant kernel family ----
     peaks = {"hbm_gbs": 6650.0, "src": "fallback"}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))); peaks["src"] = "measured"
     except Exception:
         pass
-    ab = [algorithmic_bytes(args, p) for p in pics]
-    fam = {"mc": [0, 1], "k1": [2], "lf": [3, 4], "sao": [5], "alf": [6, 7]}
+    ab = [algorithmic_bytes(args, pic_of(i)) for i in range(args.steps)]
+    fam = {"mc": [0, 1], "k1": [2], "lf": [3, 4], "sao": [5], "alf": [6, 7], "intra": [8]}
     per = {}
     for name, idx in fam.items():
-        t = sum(kms[i] for i in idx); n = max(1, max(kcnt[i] for i in idx))
-        per[name] = {"ms_per_picture": t / n, "bytes_per_picture": float(np.mean([a[name] for a in ab]))}
-    dom = max(per, key=lambda k: per[k]["ms_per_picture"])
-    ach = per[dom]["bytes_per_picture"] / (per[dom]["ms_per_picture"] * 1e-3) / 1e9
-    total_k = sum(v["ms_per_picture"] for v in per.values())
-    # DRAM bytes the family's launches of one picture moved, from the committed ncu pass of this same command (tools/ncu_traffic.py);
-    # only valid for the configuration it was captured on
+        per[name] = {"ms_per_step": sum(kms[i] for i in idx) / args.steps, "bytes_per_step": float(np.mean([a[name] for a in ab]))}
+    dom = max(per, key=lambda k: per[k]["ms_per_step"])
+    ach = per[dom]["bytes_per_step"] / (per[dom]["ms_per_step"] * 1e-3) / 1e9
+    total_k = sum(v["ms_per_step"] for v in per.values())
     traffic, traffic_src = None, None
     try:
-        if (args.width, args.height) == (3840, 2160):
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_v15.json")))
-            traffic = int(tj["per_family"][dom]["dram_read_bytes"] + tj["per_family"][dom]["dram_write_bytes"]); traffic_src = "profiles/r01_traffic_v15.json"
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        if (tj.get("width"), tj.get("height")) == (W, H):
+            traffic = int(tj["per_family"][dom]["dram_read_bytes"] + tj["per_family"][dom]["dram_write_bytes"]); traffic_src = "profiles/r02_traffic.json"
     except Exception:
         pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4),
-            "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": int(per[dom]["bytes_per_picture"]),
-            "note": "family of kernels launched together on forked streams (one launch list per tile class); issue-bound, not HBM-bound (DESIGN.md 5)", "peak_source": peaks["src"] + " (of measured)" if peaks["src"] == "measured" else "fallback",
-            "share_of_step": round(per[dom]["ms_per_picture"] / total_k, 3),
-            "per_kernel": {k: {"ms": round(v["ms_per_picture"], 4), "GBps": round(v["bytes_per_picture"] / (v["ms_per_picture"] * 1e-3) / 1e9, 1) if v["ms_per_picture"] > 0 else None} for k, v in per.items()}}
+            "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": int(per[dom]["bytes_per_step"]),
+            "note": "family time = CUDA events around the family's launches inside b200_pic_run, averaged over the steps of the schedule (I picture included)",
+            "peak_source": peaks["src"] + " (of measured)" if peaks["src"] == "measured" else "fallback",
+            "share_of_step": round(per[dom]["ms_per_step"] / total_k, 3),
+            "per_kernel": {k: {"ms": round(v["ms_per_step"], 4), "GBps": round(v["bytes_per_step"] / (v["ms_per_step"] * 1e-3) / 1e9, 1) if v["ms_per_step"] > 0 else None} for k, v in per.items()}}
     fps = world * args.steps / (ms_dev * 1e-3)
     fps_e2e = world * args.steps / (ms_e2e * 1e-3)
-    line = {"metric": "decoded frames/sec, 4K 10-bit Main10 RA, bit-exact YUV vs reference", "value": round(fps, 2), "unit": "frames/s", "n_gpus": world,
+    line = {"metric": METRIC, "value": round(fps, 2), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int16 samples / int32 accumulate", "data": "synthetic",
-            "config": {"workload": f"{W}x{H} 10-bit 4:2:0 synthetic RA back-end pictures (SURVEY 8d config 3), GOP of {args.gop} work lists, 6-slot DPB, "
-                                   "stages K2(MC uni/bi/BCW/BDOF/DMVR/affine+PROF)+K1(dequant/LFNST-off/DCT2/DST7/DCT8/TS/JCCR+reco)+K3 deblock+K4 SAO+K5 ALF/CC-ALF; "
-                                   "all CUs inter (intra samples would be given pixels)",
-                       "l2": "inputs larger than L2 (6x25 MB DPB + %d work-list arenas cycled)" % args.gop, "parallelism": f"gop-per-gpu x{world}"},
-            "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(np.mean([h2d_bytes(p) for p in pics])),
-                    "d2h_bytes_per_step": int(sum(o.nbytes for o in out)), "diag": e2e_diag, "api": "b200_pic_upload (one picture ahead) + b200_pic_run + b200_get_frame_async (D2H overlapped with the next picture), pinned host buffers; every step uploads one picture's work lists and downloads one frame"},
+            "config": workload_config(args, world),
+            "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": d2h_step, "diag": e2e_diag,
+                    "api": "b200_pic_upload (one picture ahead) + b200_pic_run + b200_get_frame_async (D2H overlapped with the next picture), pinned host buffers; every step uploads one picture's work lists and downloads one frame"},
+            "seam": seam, "picture_ms": split,
             "gpu_launches": int(launches), "numa": numa, "clocks": sampler.summary(), "roofline": roof}
     if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args, pics, refs)
+        line["cpu_baseline"] = cpu_baseline(args, wl)
     print(json.dumps(line), flush=True)
-    lib.b200_ctx_destroy(ctx)
     if world > 1: dist.destroy_process_group()
 
 
-# ------------------------------------------------------------------------------------------------ CPU legs (the only place bench.py touches oracle/)
-def cpu_baseline(args, pics, refs, threads=None):
-    """Reference kernels on the host cores for a bounded sample of the same pictures."""
-    from tests import helpers
-    from vvdec_b200 import abi
-    ref = helpers.load_ref()
-    g = abi.make_geom(args.width, args.height, 10)
-    n = min(args.cpu_sample, len(pics))
-    cores = threads or os.cpu_count()
-    if ref is not None and hasattr(ref, "ref_decompress_picture_mt"):
-        ref.ref_decompress_picture_mt.restype = C.c_double
-        try: os.sched_setaffinity(0, range(os.cpu_count()))          # the GPU arm binds itself to the GPU's NUMA node; the CPU baseline gets every core
-        except Exception: pass
-        ref.ref_decompress_picture_mt(C.byref(g), helpers.ref_ptrs(refs), C.byref(pics[0]["struct"]), cores, 1)   # untimed warm-up (page faults, thread start-up)
-        t = 0.0
-        for i in range(n):
-            t += ref.ref_decompress_picture_mt(C.byref(g), helpers.ref_ptrs(refs), C.byref(pics[i]["struct"]), cores, 1)
-        return {"value": round(n / t, 3), "unit": "frames/s", "cores": cores, "kind": "reference",
-                "sample": f"{n} of the {len(pics)} GOP pictures, VVdeC kernels ({ref.ref_simd_level().decode()}) via oracle/_ref, {cores} threads"}
-    oracle = helpers.load_oracle()
-    t0 = time.perf_counter()
-    for i in range(n): helpers.oracle_decompress(oracle, g, refs, pics[i])
-    t = time.perf_counter() - t0
-    return {"value": round(n / t, 3), "unit": "frames/s", "cores": 1, "kind": "port", "sample": f"{n} pictures, scalar C oracle, 1 thread"}
+def pcie_ceiling(torch, mb=256, reps=4):
+    """Measured host<->device link: one large pinned buffer each way, alone and both directions at once (GB/s)."""
+    try:
+        n = mb << 20
+        h1 = torch.empty(n, dtype=torch.uint8, pin_memory=True); h2 = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        d1 = torch.empty(n, dtype=torch.uint8, device="cuda"); d2 = torch.empty(n, dtype=torch.uint8, device="cuda")
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def timed(fn):
+            torch.cuda.synchronize(); t = time.perf_counter(); fn(); torch.cuda.synchronize(); return time.perf_counter() - t
+        def up():
+            with torch.cuda.stream(s1):
+                for _ in range(reps): d1.copy_(h1, non_blocking=True)
+        def down():
+            with torch.cuda.stream(s2):
+                for _ in range(reps): h2.copy_(d2, non_blocking=True)
+        up(); down()
+        tu, td = timed(up), timed(down)
+        tb = timed(lambda: (up(), down()))
+        gb = reps * n / 1e9
+        return {"h2d_gbs": round(gb / tu, 1), "d2h_gbs": round(gb / td, 1), "h2d_gbs_duplex": round(gb / tb, 1), "d2h_gbs_duplex": round(gb / tb, 1), "buffer_mb": mb}
+    except Exception as e:
+        return {"error": str(e)[:100]}
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs (the reference's own DecLibRecon)
+def cpu_baseline(args, wl):
+    """The reference's DecLibRecon + ThreadPool on a bounded sample of the same pictures; the GOP mix is weighted like the schedule."""
+    try: os.sched_setaffinity(0, range(os.cpu_count()))          # the GPU arm binds itself to the GPU's NUMA node; the CPU baseline gets every core
+    except Exception: pass
+    T = threads_all(args)
+    wl.B[0].run_stock(threads=T)                                 # untimed warm-up (pool start-up, page faults)
+    tB = [wl.B[i % len(wl.B)].run_stock(threads=T)[2] for i in range(args.cpu_sample)]
+    tI = wl.I.run_stock(threads=T)[2]
+    nB = args.gop - 1
+    fps = args.gop / (tI + nB * float(np.mean(tB)))
+    return {"value": round(fps, 3), "unit": "frames/s", "cores": T, "kind": "reference",
+            "sample": f"DecLibRecon::decompressPicture..waitForPrevDecompressedPic with ThreadPool({T}) ({wl.ref.ref_simd_level().decode()}) on {args.cpu_sample} B pictures "
+                      f"({1e3 * float(np.mean(tB)):.2f} ms each) + 1 I picture ({1e3 * tI:.2f} ms) of the workload, weighted 1 I : {nB} B"}
 
 
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0: return
-    pics, refs = make_gop(args, 0)
-    W, H = args.width, args.height
-    vals = []
-    a2 = argparse.Namespace(**vars(args)); a2.cpu_sample = 1
-    for i in range(args.warmup + args.steps):
-        r = cpu_baseline(a2, [pics[i % len(pics)]], refs)
-        if i >= args.warmup: vals.append(1.0 / r["value"])
-    fps = len(vals) / sum(vals)
-    r["value"] = round(fps, 3); r["sample"] = f"each step = 1 picture of the GOP; {r['sample']}"
-    line = {"impl": "reference", "metric": "decoded frames/sec, 4K 10-bit Main10 RA, bit-exact YUV vs reference", "value": round(fps, 3), "unit": "frames/s",
+    wl = Workload(args, 0)
+    T = threads_all(args)
+    ts = []
+    for i in range(-args.warmup, args.steps):
+        _, case, _ = wl.sched(i if i >= 0 else -i)           # warm-up: B pictures
+        secs = case.run_stock(threads=T)[2]
+        if i >= 0: ts.append(secs)
+    fps = len(ts) / sum(ts)
+    cb = {"value": round(fps, 3), "unit": "frames/s", "cores": T, "kind": "reference",
+          "sample": f"each step = one picture of the schedule through DecLibRecon::decompressPicture..waitForPrevDecompressedPic, ThreadPool({T}), {wl.ref.ref_simd_level().decode()}"}
+    line = {"impl": "reference", "metric": METRIC, "value": round(fps, 3), "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 / fps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int16 samples / int32 accumulate", "data": "synthetic",
-            "config": {"workload": f"{W}x{H} 10-bit 4:2:0 synthetic RA back-end pictures (same generator/seed as the b200 arm)"},
-            "cpu_baseline": r, "e2e": {"value": round(fps, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "config": workload_config(args, args.gpus),
+            "cpu_baseline": cb, "e2e": {"value": round(fps, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
-        if a.steps == 400 and a.warmup == 16: a.steps, a.warmup = 4, 1
         run_reference(a)
     else:
         run_b200(a)

@@ -424,9 +424,11 @@ B200_API long long b200_ctx_kernel_launches(b200_ctx* ctx);
 /* Per-kernel-family device time (CUDA events on the context stream around each family's launches of b200_pic_run).
  * Families: 0 K2 translational tiles, 1 K2 affine tiles, 2 K1, 3 K3 vertical, 4 K3 horizontal, 5 K4, 6 K5 luma, 7 K5 chroma.
  * set_profiling(1) enables event recording (adds a few us per picture); get_kernel_ms sums and resets the collected times. */
-enum { B200_KF_MC_TILE = 0, B200_KF_MC_AFFINE, B200_KF_K1, B200_KF_LF_V, B200_KF_LF_H, B200_KF_SAO, B200_KF_ALF_LUMA, B200_KF_ALF_CHROMA, B200_KF_COUNT };
+enum { B200_KF_MC_TILE = 0, B200_KF_MC_AFFINE, B200_KF_K1, B200_KF_LF_V, B200_KF_LF_H, B200_KF_SAO, B200_KF_ALF_LUMA, B200_KF_ALF_CHROMA,
+       B200_KF_INTRA /* K6 incl. its ordering pre-passes */, B200_KF_LMCS /* per-VPDU scale + inverse map */, B200_KF_COUNT };
 B200_API int  b200_ctx_set_profiling(b200_ctx* ctx, int on);
-B200_API int  b200_ctx_get_kernel_ms(b200_ctx* ctx, float ms[8], int counts[8]);
+B200_API int  b200_ctx_get_kernel_ms(b200_ctx* ctx, float ms[8], int counts[8]);          /* the first eight families */
+B200_API int  b200_ctx_get_kernel_ms_n(b200_ctx* ctx, float* ms, int* counts, int n);     /* n <= B200_KF_COUNT families */
 /* Pin / unpin caller-owned host memory (cudaHostRegister) so that the H2D / D2H copies of the picture-level calls are asynchronous. */
 B200_API int  b200_host_register(void* ptr, size_t bytes);
 B200_API int  b200_host_unregister(void* ptr);

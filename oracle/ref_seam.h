@@ -754,8 +754,10 @@ extern "C" double ref_seam_run_b200( void* h, int threads, int dry, int16_t* con
       pic->reconDone.clearException();
       return rc;
     }
+    if( getenv( "SEAM_TIMING" ) ) { const double* st = S.rec->stageTimes(); fprintf( stderr, "b200 host stages [ms]: tables %.2f | mider %.2f | flatten %.2f | submit %.2f | joined %.2f | finish %.2f\n", st[0] * 1e3, ( st[1] - st[0] ) * 1e3, ( st[2] - st[1] ) * 1e3, ( st[3] - st[2] ) * 1e3, ( st[4] - st[3] ) * 1e3, ( st[5] - st[4] ) * 1e3 ); }
     if( flat ) *flat = S.rec->flattened();
     if( !dry ) seam::readOut( P, out, colMotion, colBytes );
+    else if( colMotion ) seam::readOut( P, nullptr, colMotion, colBytes );      // dry run: the motion field with zero DMVR deltas
     return secs;
   }
   catch( std::exception& e ) { fprintf( stderr, "ref_seam_run_b200: %s\n", e.what() ); return -2.0; }

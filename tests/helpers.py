@@ -159,6 +159,15 @@ class SeamCase:
         if deblock: self.filt["lfSlices"]["beta"] = rng.integers(-3, 4, size=(1, 3)); self.filt["lfSlices"]["tc"] = rng.integers(-3, 4, size=(1, 3))
         self.cfg = seam_cfg(seed, lmcs=self.filt.get("lmcs"), **cfg_kw)
 
+    def variant(self, seed, slice_type=None):
+        """Another picture with the same reference pictures and filter parameters: a different generator seed (and slice type)."""
+        import copy
+        v = copy.copy(self)
+        v.cfg = SeamCfg.from_buffer_copy(self.cfg)
+        v.cfg.seed = seed
+        if slice_type is not None: v.cfg.sliceType = slice_type
+        return v
+
     def build(self):
         h = self.ref.ref_seam_create(C.byref(self.g), C.byref(self.cfg), ref_ptrs(self.refs), C.byref(self.filt["struct"]))
         assert h, "ref_seam_create failed"
@@ -187,11 +196,33 @@ class SeamCase:
 
     def flatten(self, threads=0):
         """Host stages of DecLibReconB200 only (no device): the work lists as a picture dict of copies, usable with helpers.oracle_decompress / the C ABI."""
-        h = self.build(); flat = abi.Picture()
-        secs = self.ref.ref_seam_run_b200(h, threads, 1, None, None, 0, C.byref(flat))
+        h = self.build(); flat = abi.Picture(); col = np.zeros(self.ref.ref_seam_col_motion_bytes(h), np.uint8)
+        secs = self.ref.ref_seam_run_b200(h, threads, 1, None, col.ctypes.data, len(col), C.byref(flat))
         self.ref.ref_seam_destroy(h)
         if secs < 0: return None, secs
-        return picture_from_struct(flat, self.g, self.filt), secs
+        pic = picture_from_struct(flat, self.g, self.filt); pic["colMotion"] = col            # colMotion: with zero DMVR deltas (no device in a dry run)
+        return pic, secs
+
+
+COL_MOTION_DTYPE = np.dtype([("mv", "<i4", (2, 2)), ("ref", "i1", (2,)), ("pad", "u1", (2,))])      # vvdec::ColocatedMotionInfo (MotionInfo.h:154), 20 bytes
+
+
+def col_motion_diff(a, b, g=None):
+    """Number of 8x8 entries whose collocated motion differs: reference indices, and MVs where the list is in use (the structs are copied with
+    their padding, and the MV of an unused list is whatever the motion buffer held).  g: geometry — entries of the CTU-major map
+    ([ctu][ctu/8][ctu/8]) that lie outside the picture are never written and are left out."""
+    A, B = a.view(COL_MOTION_DTYPE), b.view(COL_MOTION_DTYPE)
+    bad = (A["ref"] != B["ref"]).any(axis=1)
+    if g is not None:
+        n8 = g.ctuSize // 8; cw = (g.width + g.ctuSize - 1) // g.ctuSize
+        idx = np.arange(len(A)); ctu, r = idx // (n8 * n8), idx % (n8 * n8)
+        inside = ((ctu % cw) * g.ctuSize + (r % n8) * 8 < g.width) & ((ctu // cw) * g.ctuSize + (r // n8) * 8 < g.height)
+    else:
+        inside = np.ones(len(A), bool)
+    bad &= inside
+    for l in range(2):
+        bad |= inside & (A["ref"][:, l] >= 0) & (A["mv"][:, l] != B["mv"][:, l]).any(axis=1)
+    return int(bad.sum())
 
 
 def _copy(ptr, n, dtype):

@@ -20,6 +20,7 @@ CASES = {
     "B_lmcs_inter": dict(lmcs=True, intra=0, tools=T_INTER),                    # LMCS with chroma scaling; inter CUs only (intra + LMCS: see test_seam_gpu / DESIGN)
     "B_ctu64": dict(ctu=64),
     "B_ctu32_8bit": dict(ctu=32, bd=8),
+    "B_no_dmvr": dict(tools=(helpers.SEAM_INTER_TOOLS | helpers.SEAM_RESI_TOOLS | helpers.SEAM_INTRA_TOOLS | helpers.SEAM_FILTERS) & ~helpers.SEAM["DMVR"]),
     "B_no_filters": dict(deblock=False, tools=helpers.SEAM_INTER_TOOLS | helpers.SEAM_RESI_TOOLS | helpers.SEAM_INTRA_TOOLS),
 }
 
@@ -33,6 +34,9 @@ def run_case(seed, W, H, threads, **kw):
     want, _ = helpers.oracle_decompress(oracle, case.g, case.refs + [[np.zeros_like(p) for p in case.refs[0]]], pic)
     for c in range(3):
         assert np.array_equal(want[c], out[c]), f"plane {c}: {np.count_nonzero(want[c] != out[c])} samples differ from the reference's DecLibRecon"
+    if not (case.cfg.tools & helpers.SEAM["DMVR"]) or case.cfg.sliceType != 0:
+        # collocated motion (what TaskFinishMotionInfo leaves for later pictures' TMVP); a dry run has no DMVR deltas, so only pictures without DMVR compare here
+        assert helpers.col_motion_diff(col, pic["colMotion"], case.g) == 0
     return case
 
 

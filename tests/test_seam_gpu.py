@@ -18,7 +18,7 @@ def both(seed, W, H, threads=4, **kw):
     assert t_gpu >= 0, f"DecLibReconB200 failed ({t_gpu})"
     for c in range(3):
         assert np.array_equal(want[c], got[c]), f"plane {c}: {np.count_nonzero(want[c] != got[c])} samples differ"
-    assert np.array_equal(col_want, col_got), "collocated motion (colMotion / DMVR write-back) differs"
+    assert helpers.col_motion_diff(col_want, col_got, case.g) == 0, "collocated motion (colMotion / DMVR write-back) differs"
     return t_cpu, t_gpu
 
 

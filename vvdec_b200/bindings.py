@@ -57,11 +57,12 @@ def declare(lib):
     lib.b200_ctx_kernel_launches.argtypes = [CTX]; lib.b200_ctx_kernel_launches.restype = C.c_longlong
     lib.b200_ctx_set_profiling.argtypes = [CTX, C.c_int]
     lib.b200_ctx_get_kernel_ms.argtypes = [CTX, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    lib.b200_ctx_get_kernel_ms_n.argtypes = [CTX, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]
     lib.b200_host_register.argtypes = [C.c_void_p, C.c_size_t]
     lib.b200_host_unregister.argtypes = [C.c_void_p]
 
 
 EXPORTS = ["b200_ctx_create", "b200_ctx_destroy", "b200_ctx_load_slot", "b200_decompress_picture", "b200_pic_upload", "b200_pic_run",
-           "b200_wait_picture", "b200_get_frame", "b200_ctx_load_slot_strided", "b200_get_frame_strided", "b200_get_frame_async", "b200_frame_wait", "b200_frame_bytes", "b200_get_frame_fmt_async", "b200_frame_hash_async", "b200_intra_predict", "b200_intra_reconstruct", "b200_get_frame_grain_async", "b200_ctx_mark", "b200_ctx_elapsed_ms", "b200_ctx_kernel_launches", "b200_ctx_set_profiling", "b200_ctx_get_kernel_ms", "b200_host_register", "b200_host_unregister",
+           "b200_wait_picture", "b200_get_frame", "b200_ctx_load_slot_strided", "b200_get_frame_strided", "b200_get_frame_async", "b200_frame_wait", "b200_frame_bytes", "b200_get_frame_fmt_async", "b200_frame_hash_async", "b200_intra_predict", "b200_intra_reconstruct", "b200_get_frame_grain_async", "b200_ctx_mark", "b200_ctx_elapsed_ms", "b200_ctx_kernel_launches", "b200_ctx_set_profiling", "b200_ctx_get_kernel_ms", "b200_ctx_get_kernel_ms_n", "b200_host_register", "b200_host_unregister",
            "b200_mc_predict", "b200_mc_predict_wp", "b200_last_error", "b200_version", "b200_device_count", "b200_k1_residual", "b200_lf_deblock",
            "b200_sao_picture", "b200_alf_picture"]

@@ -410,6 +410,398 @@ __global__ void __launch_bounds__(IT_THREADS, 12) intra_kernel(const IntraParams
   }
 }
 
+
+// ================================================================================================ K6 v2: one CTA per CTU, the CTU resident in shared memory
+// The dependency chains of an intra picture run block to block; v1 pays a global-memory round trip per hop (ticket, owner lookup, done flag, reference
+// samples through L2: ~4 us).  v2 keeps the hops on chip: a CTA owns one CTU at a time (CTUs handed out in wave-front order, key x + 2 y), loads the
+// CTU's samples (inter prediction + residual reconstruction so far) and residual planes into shared memory, and its warps take the CTU's blocks in
+// decoding order — one warp per block, every sample of a block independent once the reference arrays are built.  A block waits on shared-memory done
+// flags for earlier blocks of its own CTU and on the global done words only for blocks of the neighbouring CTUs (left, above-left, above, above-right:
+// all earlier in the wave front, so the oldest unfinished block never waits on a block that has not been started — no deadlock at any residency).
+// Samples are written through: to the shared tile for the CTU's own later blocks, to the plane for the other CTUs and the in-loop filters.
+constexpr int V2_WARPS = 8, V2_THREADS = V2_WARPS * 32;
+constexpr int V2_LS = 130, V2_CS = 66;                       // tile row pitch in samples (odd word count: a column walk touches 32 different banks)
+constexpr int V2_TILE = 128 * V2_LS + 2 * 64 * V2_CS;        // samples of one tile set (Y, Cb, Cr)
+constexpr int V2_RECS = 1024;                                // records staged in shared memory (a CTU with more blocks reads the rest from global memory)
+constexpr int V2_FLAGS = 128 * 128 / 16 + 2 * (64 * 64 / 4); // most blocks a CTU can hold
+struct V2Scratch { int16_t T[2][IT_REF], L[2][IT_REF], M[IT_ARR], S[IT_ARR], Lm[32 * 32], LmTop[64], LmLeft[64]; int LmPar[4]; };
+constexpr size_t V2_SMEM = (size_t)2 * V2_TILE * sizeof(int16_t) + V2_WARPS * sizeof(V2Scratch) + V2_RECS * sizeof(b200_intra_tu) + V2_FLAGS + 64;
+
+struct V2Tile {
+  int16_t* rec[3]; int16_t* res[3]; int ox[3], oy[3], tw[3], th[3], ts[3];
+  const int16_t* plane[3]; int ps[3];
+  __device__ __forceinline__ bool inside(int c, int x, int y) const { return (unsigned)(x - ox[c]) < (unsigned)tw[c] && (unsigned)(y - oy[c]) < (unsigned)th[c]; }
+  __device__ __forceinline__ int pix(int c, int x, int y) const
+  {
+    if (inside(c, x, y)) return rec[c][(y - oy[c]) * ts[c] + (x - ox[c])];
+    return __ldcg(plane[c] + (size_t)y * ps[c] + x);
+  }
+};
+
+__global__ void intra_ctu_order_kernel(const IntraParams P, int* ctuOrder, int* counters)
+{
+  int n = 0;
+  for (int d = 0; d < P.ctusW + 2 * P.ctusH; d++)
+    for (int y = 0; y < P.ctusH; y++) { const int x = d - 2 * y; if (x >= 0 && x < P.ctusW && P.ctuCnt[y * P.ctusW + x] > 0) ctuOrder[n++] = y * P.ctusW + x; }
+  counters[0] = n; counters[1] = 0;
+}
+// contiguity of every CTU's blocks in the list (decoding order): entry i belongs to the run [ctuFirst, ctuFirst + ctuCnt) of its CTU
+__global__ void __launch_bounds__(256) intra_ctu_check_kernel(const IntraParams P)
+{
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= P.numTus) return;
+  const int c = intra_ctu_of(P, P.tus[i]);
+  if (i - P.ctuFirst[c] >= P.ctuCnt[c]) atomicOr(P.err, 2);
+}
+
+__device__ __forceinline__ void v2_wait(const IntraParams& P, const volatile uint8_t* sflag, int o, int me, int first)
+{
+  if (o < 0 || o >= me) return;
+  int spins = 0;
+  if (o >= first) { while (sflag[o - first] == 0) { if (++spins > (1 << 24)) { atomicOr(P.err, 1); break; } } }
+  else { const volatile int* d = P.done + o; const volatile int* e = P.err; while (*d == 0) { __nanosleep(32); if (*e || ++spins > (1 << 22)) { atomicOr(P.err, 1); break; } } }
+}
+
+__global__ void __launch_bounds__(V2_THREADS, 1) intra_ctu_kernel(const IntraParams P, const int* __restrict__ ctuOrder, int* counters)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  int16_t* tileRec = reinterpret_cast<int16_t*>(smem);
+  int16_t* tileRes = tileRec + V2_TILE;
+  V2Scratch* scratch = reinterpret_cast<V2Scratch*>(tileRes + V2_TILE);
+  b200_intra_tu* srec = reinterpret_cast<b200_intra_tu*>(scratch + V2_WARPS);
+  volatile uint8_t* sflag = reinterpret_cast<volatile uint8_t*>(srec + V2_RECS);
+  __shared__ int sCtu, sNext;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nComp = P.planes[1] ? 3 : 1;
+  const int ctuSize = 1 << P.ctuLog2;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) { sCtu = atomicAdd(&counters[1], 1); sNext = 0; }
+    __syncthreads();
+    if (sCtu >= counters[0]) return;
+    const int ctu = ctuOrder[sCtu], first = P.ctuFirst[ctu], cnt = P.ctuCnt[ctu];
+    V2Tile TL;
+    {
+      const int cx = (ctu % P.ctusW) << P.ctuLog2, cy = (ctu / P.ctusW) << P.ctuLog2;
+      int16_t* r = tileRec; int16_t* q = tileRes;
+      for (int c = 0; c < 3; c++) {
+        const int sh = c ? 1 : 0;
+        TL.ox[c] = cx >> sh; TL.oy[c] = cy >> sh; TL.tw[c] = min(ctuSize, P.W - cx) >> sh; TL.th[c] = min(ctuSize, P.H - cy) >> sh; TL.ts[c] = c ? V2_CS : V2_LS;
+        TL.rec[c] = r; TL.res[c] = q; TL.plane[c] = P.planes[c]; TL.ps[c] = P.stride[c];
+        r += (c ? 64 * V2_CS : 128 * V2_LS); q += (c ? 64 * V2_CS : 128 * V2_LS);
+        if (c >= nComp) { TL.tw[c] = TL.th[c] = 0; }
+      }
+    }
+    // ---- the CTU's samples and residuals -> shared memory (32-bit words: the pitch is not a multiple of 16 bytes), records, flags
+    for (int c = 0; c < nComp; c++) {
+      const int wWords = TL.tw[c] >> 1, n = wWords * TL.th[c];
+      const int16_t* src = P.planes[c] + (size_t)TL.oy[c] * P.stride[c] + TL.ox[c];
+      const int16_t* rsrc = P.resi[c] ? P.resi[c] + (size_t)TL.oy[c] * P.stride[c] + TL.ox[c] : nullptr;
+      for (int k = tid; k < n; k += V2_THREADS) {
+        const int y = k / wWords, x = (k - y * wWords) * 2;
+        *reinterpret_cast<uint32_t*>(TL.rec[c] + y * TL.ts[c] + x) = __ldcg(reinterpret_cast<const uint32_t*>(src + (size_t)y * P.stride[c] + x));
+        if (rsrc) *reinterpret_cast<uint32_t*>(TL.res[c] + y * TL.ts[c] + x) = __ldcg(reinterpret_cast<const uint32_t*>(rsrc + (size_t)y * P.stride[c] + x));
+      }
+    }
+    for (int k = tid; k < min(cnt, V2_RECS) * 4; k += V2_THREADS) reinterpret_cast<uint32_t*>(srec)[k] = reinterpret_cast<const uint32_t*>(P.tus + first)[k];
+    for (int k = tid; k < cnt; k += V2_THREADS) sflag[k] = 0;
+    __syncthreads();
+
+    // ---- the CTU's blocks, one warp each, in decoding order
+    V2Scratch& SC = scratch[warp];
+    for (;;) {
+      int k = 0;
+      if (lane == 0) k = atomicAdd(&sNext, 1);
+      k = __shfl_sync(0xffffffffu, k, 0);
+      if (k >= cnt) break;
+      const int me = first + k;
+      const b200_intra_tu t = k < V2_RECS ? srec[k] : P.tus[me];
+      const int c = t.comp, w = 1 << t.log2w, h = 1 << t.log2h, mrl = c ? 0 : t.multiRefIdx, unit = c ? 2 : 4;
+      const int x0 = t.x, y0 = t.y, ps = P.stride[c], pmax = (1 << P.bitDepth) - 1;
+      const int availTL = (t.flags & B200_INTRA_AVAIL_TL) ? 1 : 0, numAbove = t.numAbove, numLeft = t.numLeft;
+      // ---- wait for the earlier blocks this one reads from
+      for (int dep = lane; dep < 96; dep += 32) {                        // dependency slots: 0 corner, 1..32 above units, 64..95 left units
+        int ux = -1, uy = -1;
+        if (dep == 0) { if (availTL) { ux = x0 - 1; uy = y0 - 1; } }
+        else if (dep <= numAbove) { ux = x0 + (dep - 1) * unit; uy = y0 - 1; }
+        else if (dep - 64 >= 0 && dep - 64 < numLeft) { ux = x0 - 1; uy = y0 + (dep - 64) * unit; }
+        if (ux >= 0 && uy >= 0) v2_wait(P, sflag, P.owner[c][(uy / unit) * P.ownerStride[c] + ux / unit], me, first);
+      }
+      if (t.mode >= B200_INTRA_LM) {
+        const bool aCu = t.flags & B200_INTRA_LM_ABOVE, lCu = t.flags & B200_INTRA_LM_LEFT;
+        const int nA = max(w, aCu ? (t.mode == B200_INTRA_MDLM_T ? 2 * t.lmAbove : w) : 0), nL = max(h, lCu ? (t.mode == B200_INTRA_MDLM_L ? 2 * t.lmLeft : h) : 0);
+        const int ux0 = max(0, (2 * x0 - (lCu ? 4 : 0)) >> 2), ux1 = min(P.W - 1, 2 * x0 + 2 * nA - 1) >> 2;
+        const int uy0 = max(0, (2 * y0 - (aCu ? 4 : 0)) >> 2), uy1 = min(P.H - 1, 2 * y0 + 2 * nL - 1) >> 2;
+        const int uw = ux1 - ux0 + 1, nU = uw * (uy1 - uy0 + 1);
+        for (int u = lane; u < nU; u += 32) v2_wait(P, sflag, P.owner[0][(uy0 + u / uw) * P.ownerStride[0] + ux0 + u % uw], me, first);
+      }
+      __threadfence();
+      __syncwarp();
+
+      // ---- reference samples (xFillReferenceSamples): T[j] = row above incl. the corner, L[i] = left column, T[0] = L[0] = corner
+      const int predSize = 2 * w, predHSize = 2 * h;
+      const int totalUnits = (predSize + unit - 1) / unit + (predHSize + unit - 1) / unit + 1, n = availTL + numAbove + numLeft;
+      const int aboveLen = min(numAbove * unit, predSize), leftLen = min(numLeft * unit, predHSize);
+      int16_t *T = SC.T[0], *L = SC.L[0];
+      for (int j = lane; j <= predSize + mrl; j += 32) {
+        int v;
+        if (n == 0) v = 1 << (P.bitDepth - 1);
+        else if (n == totalUnits) v = TL.pix(c, x0 - 1 - mrl + j, y0 - 1 - mrl);
+        else if (j <= mrl) {
+          if (numLeft > 0) v = availTL ? TL.pix(c, x0 - 1 - mrl + j, y0 - 1 - mrl) : TL.pix(c, x0 - 1 - mrl, y0);
+          else v = TL.pix(c, x0, y0 - 1 - mrl);
+        } else {
+          const int kk = j - 1 - mrl;
+          if (numAbove) v = TL.pix(c, x0 + min(kk, aboveLen - 1), y0 - 1 - mrl);
+          else v = availTL ? TL.pix(c, x0 - 1, y0 - 1 - mrl) : TL.pix(c, x0 - 1 - mrl, y0);
+        }
+        T[j] = (int16_t)v;
+      }
+      for (int i = lane; i <= predHSize + mrl; i += 32) {
+        if (i == 0) continue;
+        int v;
+        if (n == 0) v = 1 << (P.bitDepth - 1);
+        else if (n == totalUnits) v = TL.pix(c, x0 - 1 - mrl, y0 - 1 - mrl + i);
+        else if (numLeft > 0) {
+          if (i <= mrl) v = availTL ? TL.pix(c, x0 - 1 - mrl, y0 - 1 - mrl + i) : TL.pix(c, x0 - 1 - mrl, y0);
+          else v = TL.pix(c, x0 - 1 - mrl, y0 + min(i - 1 - mrl, leftLen - 1));
+        } else v = TL.pix(c, x0, y0 - 1 - mrl);
+        L[i] = (int16_t)v;
+      }
+      __syncwarp();
+      if (lane == 0) L[0] = T[0];
+      __syncwarp();
+      if ((t.flags & B200_INTRA_FILTER_REF) && !c && !mrl) {     // xFilterReferenceSamples
+        int16_t *FT = SC.T[1], *FL = SC.L[1];
+        for (int j = lane; j <= predSize; j += 32)
+          FT[j] = j == 0 ? (int16_t)((L[1] + 2 * T[0] + T[1] + 2) >> 2) : j == predSize ? T[j] : (int16_t)((T[j + 1] + 2 * T[j] + T[j - 1] + 2) >> 2);
+        for (int i = lane + 1; i <= predHSize; i += 32)
+          FL[i] = i == predHSize ? L[i] : (int16_t)((L[i + 1] + 2 * L[i] + L[i - 1] + 2) >> 2);
+        __syncwarp();
+        if (lane == 0) FL[0] = FT[0];
+        T = FT; L = FL;
+        __syncwarp();
+      }
+
+      const int mode = t.mode;
+      const bool doPDPC = w >= 4 && h >= 4 && mrl == 0;
+      int16_t* dstG = P.planes[c] + (size_t)y0 * ps + x0;
+      int16_t* dstT = TL.rec[c] + (y0 - TL.oy[c]) * TL.ts[c] + (x0 - TL.ox[c]);
+      const int tsC = TL.ts[c];
+      const int16_t* rsT = (P.resi[c] && (t.flags & B200_INTRA_ADD_RESI)) ? TL.res[c] + (y0 - TL.oy[c]) * tsC + (x0 - TL.ox[c]) : nullptr;
+      const int ciipW = t.ciip;
+#define V2_STORE(x, y, v) do { int v_ = (v); int16_t* d_ = dstT + (y) * tsC + (x); if (ciipW) v_ = ((4 - ciipW) * (int)*d_ + ciipW * v_ + 2) >> 2; \
+                               if (rsT) v_ = clip3(0, pmax, v_ + rsT[(y) * tsC + (x)]); *d_ = (int16_t)v_; dstG[(size_t)(y) * ps + (x)] = (int16_t)v_; } while (0)
+
+      if (mode == B200_INTRA_PLANAR || mode == B200_INTRA_DC) {
+        int dc = 0;
+        if (mode == B200_INTRA_DC) {                             // xGetPredValDc
+          int part = 0;
+          for (int i = lane; i < w + h; i += 32) {
+            if (i < w) { if (w >= h) part += T[mrl + 1 + i]; }
+            else if (w <= h) part += L[mrl + 1 + i - w];
+          }
+          for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+          const int denom = w == h ? w << 1 : max(w, h);
+          dc = (part + (denom >> 1)) >> (31 - __clz(denom));
+        }
+        const int l2w = t.log2w, l2h = t.log2h, scale = (l2w - 2 + l2h - 2 + 2) >> 2;
+        const int bl = L[h + 1], tr = T[w + 1];
+        for (int kk = lane; kk < w * h; kk += 32) {
+          const int y = kk >> l2w, x = kk & (w - 1);
+          int v;
+          if (mode == B200_INTRA_PLANAR) {
+            const int hor = (L[y + 1] << l2w) + (x + 1) * (tr - L[y + 1]), vert = (T[x + 1] << l2h) + (y + 1) * (bl - T[x + 1]);
+            v = ((hor << l2h) + (vert << l2w) + (1 << (l2w + l2h))) >> (1 + l2w + l2h);
+          } else v = dc;
+          v = (int16_t)v;
+          if (doPDPC) {
+            const int wT = 32 >> min(31, (y << 1) >> scale), wL = 32 >> min(31, (x << 1) >> scale);
+            v = (int16_t)(v + ((wL * (L[y + 1] - v) + wT * (T[x + 1] - v) + 32) >> 6));
+          }
+          V2_STORE(x, y, v);
+        }
+      } else if (mode >= B200_INTRA_LM) {
+        // ---- cross-component linear model, 4:2:0: luma at (lx0 + dx, ly0 + dy) read through the tile
+        const bool aCu = t.flags & B200_INTRA_LM_ABOVE, lCu = t.flags & B200_INTRA_LM_LEFT, colloc = t.flags & B200_INTRA_LM_COLLOCATED;
+        const int lx0 = 2 * x0, ly0 = 2 * y0;
+        const bool firstRowOfCtu = ((2 * y0) & ((1 << P.ctuLog2) - 1)) == 0;
+        const int nTop = aCu ? (mode == B200_INTRA_MDLM_T ? 2 * t.lmAbove : w) : 0, nLeft = lCu ? (mode == B200_INTRA_MDLM_L ? 2 * t.lmLeft : h) : 0;
+#define LY(dx, dy) TL.pix(0, lx0 + (dx), ly0 + (dy))
+        for (int kk = lane; kk < nTop + nLeft + w * h; kk += 32) {
+          if (kk < nTop) {
+            const int i = kk, m = (i == 0 && !lCu) ? 0 : 1;
+            int v;
+            if (firstRowOfCtu) v = (LY(2 * i, -1) * 2 + LY(2 * i - m, -1) + LY(2 * i + 1, -1) + 2) >> 2;
+            else if (colloc) v = (LY(2 * i, -3) + LY(2 * i, -2) * 4 + LY(2 * i - m, -2) + LY(2 * i + 1, -2) + LY(2 * i, -1) + 4) >> 3;
+            else v = (LY(2 * i, -2) * 2 + LY(2 * i - m, -2) + LY(2 * i + 1, -2) + LY(2 * i, -1) * 2 + LY(2 * i - m, -1) + LY(2 * i + 1, -1) + 4) >> 3;
+            SC.LmTop[i] = (int16_t)v;
+          } else if (kk < nTop + nLeft) {
+            const int j = kk - nTop;
+            int v;
+            if (colloc) v = (LY(-2, 2 * j - ((j == 0 && !aCu) ? 0 : 1)) + LY(-2, 2 * j) * 4 + LY(-3, 2 * j) + LY(-1, 2 * j) + LY(-2, 2 * j + 1) + 4) >> 3;
+            else v = (LY(-2, 2 * j) * 2 + LY(-3, 2 * j) + LY(-1, 2 * j) + LY(-2, 2 * j + 1) * 2 + LY(-3, 2 * j + 1) + LY(-1, 2 * j + 1) + 4) >> 3;
+            SC.LmLeft[j] = (int16_t)v;
+          } else {
+            const int q = kk - nTop - nLeft, j = q >> t.log2w, i = q & (w - 1), m = (i == 0 && !lCu) ? 0 : 1;
+            int v;
+            if (colloc) { const int up = (j == 0 && !aCu) ? 0 : 1; v = (LY(2 * i, 2 * j - up) + LY(2 * i, 2 * j) * 4 + LY(2 * i - m, 2 * j) + LY(2 * i + 1, 2 * j) + LY(2 * i, 2 * j + 1) + 4) >> 3; }
+            else v = (LY(2 * i, 2 * j) * 2 + LY(2 * i + 1, 2 * j) + LY(2 * i - m, 2 * j) + LY(2 * i, 2 * j + 1) * 2 + LY(2 * i + 1, 2 * j + 1) + LY(2 * i - m, 2 * j + 1) + 4) >> 3;
+            SC.Lm[q] = (int16_t)v;
+          }
+        }
+#undef LY
+        __syncwarp();
+        if (lane == 0) {                                            // xGetLMParameters
+          const int tuWU = w >> 1, tuHU = h >> 1;
+          bool aboveAvail = false, leftAvail = false; int topNum = 0, leftNum = 0;
+          if (mode == B200_INTRA_MDLM_T) { aboveAvail = t.lmAbove >= tuWU; topNum = 2 * t.lmAbove; }
+          else if (mode == B200_INTRA_MDLM_L) { leftAvail = t.lmLeft >= tuHU; leftNum = 2 * t.lmLeft; }
+          else { aboveAvail = aCu; leftAvail = lCu; topNum = w; leftNum = h; }
+          const int aboveIs4 = leftAvail ? 0 : 1, leftIs4 = aboveAvail ? 0 : 1;
+          const int start0 = topNum >> (2 + aboveIs4), step0 = max(1, topNum >> (1 + aboveIs4)), start1 = leftNum >> (2 + leftIs4), step1 = max(1, leftNum >> (1 + leftIs4));
+          int sl[4] = {0, 0, 0, 0}, sc[4] = {0, 0, 0, 0}, cntT = 0, cntL = 0;
+          if (aboveAvail) { cntT = min(topNum, (1 + aboveIs4) << 1); for (int q = 0, pos = start0; q < cntT; q++, pos += step0) { sl[q] = SC.LmTop[pos]; sc[q] = T[1 + pos]; } }
+          if (leftAvail) { cntL = min(leftNum, (1 + leftIs4) << 1); for (int q = 0, pos = start1; q < cntL; q++, pos += step1) { sl[q + cntT] = SC.LmLeft[pos]; sc[q + cntT] = L[1 + pos]; } }
+          if (cntT + cntL == 2) { sl[3] = sl[0]; sc[3] = sc[0]; sl[2] = sl[1]; sc[2] = sc[1]; sl[0] = sl[1]; sc[0] = sc[1]; sl[1] = sl[3]; sc[1] = sc[3]; }
+          int mn0 = 0, mn1 = 2, mx0 = 1, mx1 = 3, tt;
+          if (sl[mn0] > sl[mn1]) { tt = mn0; mn0 = mn1; mn1 = tt; }
+          if (sl[mx0] > sl[mx1]) { tt = mx0; mx0 = mx1; mx1 = tt; }
+          if (sl[mn0] > sl[mx1]) { tt = mn0; mn0 = mx0; mx0 = tt; tt = mn1; mn1 = mx1; mx1 = tt; }
+          if (sl[mn1] > sl[mx0]) { tt = mn1; mn1 = mx0; mx0 = tt; }
+          const int minL = (sl[mn0] + sl[mn1] + 1) >> 1, minC = (sc[mn0] + sc[mn1] + 1) >> 1, maxL = (sl[mx0] + sl[mx1] + 1) >> 1, maxC = (sc[mx0] + sc[mx1] + 1) >> 1;
+          int a = 0, b = 1 << (P.bitDepth - 1), shift = 0;
+          if (leftAvail || aboveAvail) {
+            const int diff = maxL - minL;
+            if (diff > 0) {
+              const int diffC = maxC - minC;
+              int x = 31 - __clz(diff);
+              const int normDiff = (diff << 4 >> x) & 15;
+              const int v = (int)((0x0765544332211110ull >> (4 * (15 - normDiff))) & 15) | 8;
+              x += normDiff != 0;
+              const int y = diffC == 0 ? 0 : (31 - __clz(abs(diffC))) + 1, add = 1 << y >> 1;
+              a = (diffC * v + add) >> y; shift = 3 + x - y;
+              if (shift < 1) { shift = 1; a = a == 0 ? 0 : a < 0 ? -15 : 15; }
+              b = minC - ((a * minL) >> shift);
+            } else { a = 0; b = minC; shift = 0; }
+          }
+          SC.LmPar[0] = a; SC.LmPar[1] = b; SC.LmPar[2] = shift;
+        }
+        __syncwarp();
+        const int a = SC.LmPar[0], b = SC.LmPar[1], shift = SC.LmPar[2];
+        for (int kk = lane; kk < w * h; kk += 32) { const int y = kk >> t.log2w, x = kk & (w - 1); V2_STORE(x, y, clip3(0, pmax, ((a * SC.Lm[kk]) >> shift) + b)); }
+      } else if (mode == B200_INTRA_MIP) {
+        const int sizeId = (w == 4 && h == 4) ? 0 : (w == 4 || h == 4 || (w == 8 && h == 8)) ? 1 : 2;
+        const int bdry = sizeId == 0 ? 2 : 4, red = sizeId < 2 ? 4 : 8, upH = w / red, upV = h / red, inSize = 2 * bdry;
+        const int modeIdx = t.mip & 0x7f; const bool transpose = t.mip >> 7;
+        int16_t* in = SC.S; int16_t* sM = SC.M;
+        if (lane < inSize) {
+          const bool fromLeft = (lane >= bdry) != transpose; const int d = lane % bdry, len = fromLeft ? h : w;
+          const int16_t* full = (fromLeft ? L : T) + 1;
+          int v;
+          if (bdry < len) { const int f = len / bdry; int sum = 0; for (int j = 0; j < f; j++) sum += full[d * f + j]; v = (sum + (f >> 1)) >> (31 - __clz(f)); }
+          else v = full[d];
+          in[lane] = (int16_t)v;
+        }
+        __syncwarp();
+        const int inputOffset = in[0];
+        __syncwarp();
+        if (lane < inSize) in[lane] = (int16_t)(lane == 0 ? (sizeId < 2 ? (1 << (P.bitDepth - 1)) - inputOffset : 0) : in[lane] - inputOffset);
+        __syncwarp();
+        for (int o = lane; o < red * red; o += 32) {
+          const int redSize = sizeId == 2, stride = inSize - redSize;
+          const uint8_t* wgt = (sizeId == 0 ? kMip4x4 + modeIdx * 64 : sizeId == 1 ? kMip8x8 + modeIdx * 128 : kMip16x16 + modeIdx * 448) + o * stride;
+          int sum = 0, acc = 0;
+          for (int i = 0; i < inSize; i++) sum += in[i];
+          for (int i = redSize; i < inSize; i++) acc += in[i] * wgt[i - redSize];
+          const int v = clip3(0, pmax, ((acc + 32 - 32 * sum) >> 6) + inputOffset);
+          sM[transpose ? (o % red) * red + o / red : o] = (int16_t)v;
+        }
+        __syncwarp();
+        const int l2H = 31 - __clz(upH), l2V = 31 - __clz(upV);
+        for (int kk = lane; kk < w * h; kk += 32) {
+          const int y = kk >> t.log2w, x = kk & (w - 1), kr = y / upV, i = y % upV;
+          int hv[2];
+#pragma unroll
+          for (int q = 0; q < 2; q++) {
+            const int k2 = kr - 1 + q;
+            if (k2 < 0) hv[q] = T[x + 1];
+            else if (upH == 1) hv[q] = sM[k2 * red + x];
+            else {
+              const int j = x / upH, ii = x % upH, before = j == 0 ? L[(k2 + 1) * upV] : sM[k2 * red + j - 1], behind = sM[k2 * red + j];
+              hv[q] = (int16_t)(before * upH + (upH >> 1) + (ii + 1) * (behind - before)) >> l2H;
+            }
+          }
+          V2_STORE(x, y, upV == 1 ? hv[1] : (int16_t)(hv[0] * upV + (upV >> 1) + (i + 1) * (hv[1] - hv[0])) >> l2V);
+        }
+      } else if (mode >= B200_INTRA_BDPCM_HOR) {
+        for (int kk = lane; kk < w * h; kk += 32) { const int y = kk >> t.log2w, x = kk & (w - 1); V2_STORE(x, y, mode == B200_INTRA_BDPCM_HOR ? L[y + 1] : T[x + 1]); }
+      } else {
+        // ---- angular (xPredIntraAng)
+        const int predMode = wide_angle(w, h, mode);
+        const bool ver = predMode >= 34;
+        const int angMode = ver ? predMode - 50 : -(predMode - 18), absMode = abs(angMode);
+        const int invAngle = cInvAng[absMode], absAng = cAng[absMode], angle = angMode < 0 ? -absAng : absAng;
+        const int16_t *mainSrc = ver ? T : L, *sideSrc = ver ? L : T;
+        const int mw = ver ? w : h, mh = ver ? h : w;
+        int16_t *M = SC.M + IT_ORG, *S = SC.S + IT_ORG;
+        if (angle < 0) {
+          for (int kk = lane - mh; kk <= mw + 1 + mrl; kk += 32) M[kk] = kk >= 0 ? mainSrc[kk] : sideSrc[min((-kk * invAngle + 256) >> 9, mh)];
+          for (int kk = lane; kk <= mh + 1 + mrl; kk += 32) S[kk] = sideSrc[kk];
+        } else {
+          const int l2r = (31 - __clz(mw)) - (31 - __clz(mh)), sft = max(0, l2r), maxIndex = (mrl << sft) + 2, refLength = 2 * mw;
+          for (int kk = lane; kk <= refLength + mrl + maxIndex; kk += 32) M[kk] = mainSrc[min(kk, refLength + mrl)];
+          for (int kk = lane; kk <= 2 * mh + mrl; kk += 32) S[kk] = sideSrc[kk];
+        }
+        __syncwarp();
+        const int16_t *Mp = M + mrl, *Sp = S + mrl;
+        const int l2mw = 31 - __clz(mw), l2mh = 31 - __clz(mh);
+        const int topLeft = T[0];
+        const int scale0 = (l2mw - 2 + l2mh - 2 + 2) >> 2;
+        const int lev = min(3 << scale0, mw);
+        const bool frac = (absAng & 31) != 0;
+        const int diff = min(abs(predMode - 18), abs(predMode - 50));
+        const bool cubic = !(diff > cIntraFilterThr[(l2mw + l2mh) >> 1]) || mrl > 0;
+        int angularScale = -1;
+        if (angle > 0 && doPDPC) angularScale = min(2, l2mh - ((31 - __clz(3 * invAngle - 2)) - 8));
+        for (int kk = lane; kk < mw * mh; kk += 32) {
+          const int yy = kk >> l2mw, xx = kk & (mw - 1);
+          int v;
+          if (angle == 0) {
+            if (doPDPC && xx < lev) { const int wL = 32 >> min(31, (xx << 1) >> scale0); v = clip3(0, pmax, (wL * (Sp[yy + 1] - topLeft) + Mp[xx + 1] * 64 + 32) >> 6); }
+            else v = Mp[xx + 1];
+          } else {
+            const int deltaPos = angle * (1 + mrl + yy), dI = deltaPos >> 5, dF = deltaPos & 31;
+            if (!frac) v = Mp[dI + 1 + xx];
+            else if (c) v = (int16_t)(((32 - dF) * Mp[dI + 1 + xx] + dF * Mp[dI + 2 + xx] + 16) >> 5);
+            else {
+              const int16_t* p = Mp + dI + xx;
+              int f0, f1, f2, f3;
+              if (cubic) { f0 = kIfChroma[dF * 4]; f1 = kIfChroma[dF * 4 + 1]; f2 = kIfChroma[dF * 4 + 2]; f3 = kIfChroma[dF * 4 + 3]; }
+              else { f0 = 16 - (dF >> 1); f1 = 32 - (dF >> 1); f2 = 16 + (dF >> 1); f3 = dF >> 1; }
+              v = (int16_t)((f0 * p[0] + f1 * p[1] + f2 * p[2] + f3 * p[3] + 32) >> 6);
+              if (cubic) v = clip3(0, pmax, v);
+            }
+            if (angularScale >= 0 && xx < min(3 << angularScale, mw)) {
+              const int invAngleSum = 256 + (xx + 1) * invAngle, wL = 32 >> (2 * xx >> angularScale), left = Sp[yy + (invAngleSum >> 9) + 1];
+              v = (int16_t)(v + ((wL * (left - v) + 32) >> 6));
+            }
+          }
+          if (ver) V2_STORE(xx, yy, v); else V2_STORE(yy, xx, v);
+        }
+      }
+#undef V2_STORE
+      // ---- publish: the CTU's own later blocks see the tile, the other CTUs the plane
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) sflag[k] = 1;
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicExch(P.done + me, 1);
+    }
+  }
+}
+
 // record checks of the picture path (the kernel-level wrapper checks on the host): everything K6 uses as an address
 __global__ void __launch_bounds__(256) intra_validate_kernel(const b200_intra_tu* __restrict__ tus, int n, int W, int H, int chroma, int* meta)
 {
@@ -441,27 +833,44 @@ int launch_intra(const IntraLaunch& L, cudaStream_t s)
   if (!L.numTus) return 0;
   IntraParams P;
   for (int c = 0; c < 3; c++) { P.planes[c] = L.planes.p[c]; P.resi[c] = L.resi[c]; P.stride[c] = L.planes.stride[c]; P.owner[c] = L.owner[c]; P.ownerStride[c] = L.ownerStride[c]; }
+  if (!L.geom.chromaFormat) { P.planes[1] = P.planes[2] = nullptr; }
   P.W = L.geom.width; P.H = L.geom.height; P.bitDepth = L.geom.bitDepth; P.tus = L.tus; P.numTus = (int)L.numTus;
   P.done = L.sync; P.ticket = L.sync + L.numTus; P.err = L.sync + L.numTus + 1;
   B200_CUDA(cudaMemsetAsync(L.sync, 0, (L.numTus + 2) * sizeof(int), s));
   for (int c = 0; c < (L.geom.chromaFormat ? 3 : 1); c++) B200_CUDA(cudaMemsetAsync(L.owner[c], 0xff, L.ownerBytes[c], s));
   P.perm = nullptr; P.ctuCnt = P.ctuFirst = P.ctuBase = nullptr;
   P.ctuLog2 = L.geom.ctuSize == 128 ? 7 : L.geom.ctuSize == 64 ? 6 : 5; P.ctusW = (L.geom.width + L.geom.ctuSize - 1) / L.geom.ctuSize; P.ctusH = (L.geom.height + L.geom.ctuSize - 1) / L.geom.ctuSize;
+  static const char* variant = getenv("B200_INTRA_KERNEL");      // measurement switch: "v1" = one CTA per block through global memory (round 1)
+  const bool v1 = !L.order || (variant && !strcmp(variant, "v1")) || ((P.stride[0] | P.stride[1] | P.stride[2]) & 1);   // the tile loads move 32-bit words
+  const unsigned grid = (unsigned)((L.numTus + 255) / 256);
+  intra_owner_kernel<<<(unsigned)L.numTus, 64, 0, s>>>(P);
+  if (!v1) {
+    // v2: per-CTU runs of the list (decoding order keeps a CTU's blocks together), CTUs in wave-front order, one CTA per CTU at a time
+    const size_t nCtu = (size_t)P.ctusW * P.ctusH;
+    int* base = L.order; P.ctuCnt = base; P.ctuFirst = base + nCtu; int* ctuOrder = base + 2 * nCtu; int* counters = base + 3 * nCtu;
+    B200_CUDA(cudaMemsetAsync(P.ctuCnt, 0, nCtu * sizeof(int), s));
+    B200_CUDA(cudaMemsetAsync(P.ctuFirst, 0x7f, nCtu * sizeof(int), s));
+    intra_ctu_count_kernel<<<grid, 256, 0, s>>>(P);
+    intra_ctu_check_kernel<<<grid, 256, 0, s>>>(P);
+    intra_ctu_order_kernel<<<1, 1, 0, s>>>(P, ctuOrder, counters);
+    static bool attr = false;
+    if (!attr) { B200_CUDA(cudaFuncSetAttribute(intra_ctu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM)); attr = true; }
+    const int ctas = (int)std::min<size_t>(nCtu, (size_t)num_sms());
+    intra_ctu_kernel<<<ctas, V2_THREADS, V2_SMEM, s>>>(P, ctuOrder, counters);
+    B200_CUDA(cudaGetLastError());
+    return 0;
+  }
   static const bool listOrder = getenv("B200_INTRA_ORDER") && !strcmp(getenv("B200_INTRA_ORDER"), "decode");   // measurement switch: tickets in list order
-  // the wavefront order pays off when CTUs are dense with intra blocks (I pictures: 14 ms vs 65 ms at 4K); for the few intra CUs of a B picture the
-  // chains are short and the three extra launches cost more than they give (0.79 vs 0.70 ms), so those keep the list order
   if (L.order && !listOrder && L.numTus >= 100 * std::max<size_t>(1, (size_t)L.geom.width * L.geom.height >> 14)) {   // >= 100 blocks per 128x128 luma area
     const size_t nCtu = (size_t)P.ctusW * P.ctusH;
     int* perm = L.order; P.ctuCnt = perm + L.numTus; P.ctuFirst = P.ctuCnt + nCtu; P.ctuBase = P.ctuFirst + nCtu;
     B200_CUDA(cudaMemsetAsync(P.ctuCnt, 0, nCtu * sizeof(int), s));
     B200_CUDA(cudaMemsetAsync(P.ctuFirst, 0x7f, nCtu * sizeof(int), s));
-    const unsigned grid = (unsigned)((L.numTus + 255) / 256);
     intra_ctu_count_kernel<<<grid, 256, 0, s>>>(P);
     intra_ctu_base_kernel<<<1, 1, 0, s>>>(P);
     intra_perm_kernel<<<grid, 256, 0, s>>>(P, perm);
     P.perm = perm;
   }
-  intra_owner_kernel<<<(unsigned)L.numTus, 64, 0, s>>>(P);
   const int ctas = (int)std::min<size_t>(L.numTus, (size_t)num_sms() * 12);
   intra_kernel<<<ctas, IT_THREADS, 0, s>>>(P);
   B200_CUDA(cudaGetLastError());

@@ -300,7 +300,9 @@ B200_API int b200_pic_run(b200_ctx* c, int ai)
     if (A.lmcs && A.lmcsChromaAdj) {
       L.compSel = 1;
       if (int rc = launch_k1_residual(L, c->ss, c->profiling ? &c->prof : nullptr)) return rc;
+      if (c->profiling) c->prof.begin(B200_KF_LMCS, s);
       if (int rc = launch_lmcs_vpdu(LM, s)) return rc;
+      if (c->profiling) c->prof.end(B200_KF_LMCS, s);
       L.compSel = 2; L.vpduScale = A.lmcsScale;
       if (int rc = launch_k1_residual(L, c->ss, c->profiling ? &c->prof : nullptr)) return rc;
       c->launches += 2 * k1_launch_count(L) + 1;
@@ -316,11 +318,13 @@ B200_API int b200_pic_run(b200_ctx* c, int ai)
     uint8_t* rb = c->resiBuf.as<uint8_t>();
     L.resi[0] = reinterpret_cast<int16_t*>(rb); L.resi[1] = reinterpret_cast<int16_t*>(rb + c->planeBytes[0]); L.resi[2] = reinterpret_cast<int16_t*>(rb + c->planeBytes[0] + c->planeBytes[1]);
     for (int k = 0; k < 3; k++) { L.owner[k] = A.intraOwner[k]; L.ownerStride[k] = A.intraOwnerStride[k]; L.ownerBytes[k] = A.intraOwnerBytes[k]; }
+    if (c->profiling) c->prof.begin(B200_KF_INTRA, s);
     if (int rc = launch_intra(L, s)) return rc;
+    if (c->profiling) c->prof.end(B200_KF_INTRA, s);
     c->launches += 5;
     B200_CUDA(cudaMemcpyAsync(A.hMeta + 2 * LM_INTS, A.intraSync + A.numIntraTus + 1, sizeof(int), cudaMemcpyDeviceToHost, s));   // timeout bit, read by b200_wait_picture
   }
-  if (A.lmcs) { if (int rc = launch_lmcs_inv(LM, s)) return rc; c->launches += 1; }   // RSP stage (DecLibRecon.cpp:935)
+  if (A.lmcs) { if (c->profiling) c->prof.begin(B200_KF_LMCS, s); if (int rc = launch_lmcs_inv(LM, s)) return rc; if (c->profiling) c->prof.end(B200_KF_LMCS, s); c->launches += 1; }   // RSP stage (DecLibRecon.cpp:935)
   // 3. K3 deblocking
   if (A.flags & B200_PIC_DEBLOCK) {
     LfLaunch L; L.geom = g; L.planes = P; L.lfV = A.lfV; L.lfH = A.lfH; L.ctuSlice = A.ctuSlice; L.slices = A.lfSlices; L.seq = A.lfSeq; L.dirs = 3;
@@ -545,15 +549,16 @@ B200_API long long b200_ctx_kernel_launches(b200_ctx* c) { return c ? c->launche
 
 B200_API int b200_ctx_set_profiling(b200_ctx* c, int on) { B200_CHECK(c, "b200_ctx_set_profiling"); c->profiling = on != 0; return 0; }
 
-B200_API int b200_ctx_get_kernel_ms(b200_ctx* c, float ms[8], int counts[8])
+B200_API int b200_ctx_get_kernel_ms_n(b200_ctx* c, float* ms, int* counts, int n)
 {
-  B200_CHECK(c && ms && counts, "b200_ctx_get_kernel_ms");
+  B200_CHECK(c && ms && counts && n >= 1 && n <= B200_KF_COUNT, "b200_ctx_get_kernel_ms_n");
   B200_CUDA(cudaStreamSynchronize(c->stream));
-  for (int i = 0; i < 8; i++) { ms[i] = 0; counts[i] = 0; }
-  for (auto& r : c->prof.recs) { float t = 0; cudaEventElapsedTime(&t, r.a, r.b); ms[r.family] += t; counts[r.family]++; c->prof.pool.push_back(r.a); c->prof.pool.push_back(r.b); }
+  for (int i = 0; i < n; i++) { ms[i] = 0; counts[i] = 0; }
+  for (auto& r : c->prof.recs) { float t = 0; cudaEventElapsedTime(&t, r.a, r.b); if (r.family < n) { ms[r.family] += t; counts[r.family]++; } c->prof.pool.push_back(r.a); c->prof.pool.push_back(r.b); }
   c->prof.recs.clear();
   return 0;
 }
+B200_API int b200_ctx_get_kernel_ms(b200_ctx* c, float ms[8], int counts[8]) { return b200_ctx_get_kernel_ms_n(c, ms, counts, 8); }
 
 B200_API int b200_host_register(void* ptr, size_t bytes) { B200_CHECK(ptr && bytes, "b200_host_register"); if (int rc = ensure_device()) return rc; B200_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault)); return 0; }
 B200_API int b200_host_unregister(void* ptr) { B200_CHECK(ptr, "b200_host_unregister"); B200_CUDA(cudaHostUnregister(ptr)); return 0; }

@@ -28,6 +28,7 @@
 #include <mutex>
 #include <memory>
 #include <atomic>
+#include <chrono>
 #include "vvdec_b200.h"
 #include "flatten_tu.h"
 #include "flatten_pu.h"
@@ -73,7 +74,7 @@ class DecLibReconB200
   }
   std::shared_ptr<Shared> m_sh;
 
-  // ---- per-row work lists ----
+  // ---- per-CTU work lists (one pool task per CTU: MIDER, then boundary strengths + flatten of the same CTU) ----
   struct Row
   {
     DecLibReconB200* self = nullptr; int line = 0, col = 0;
@@ -83,9 +84,9 @@ class DecLibReconB200
   ThreadPool* m_pool = nullptr; int m_numThreads = 1; unsigned m_id = 0; int m_dpbSlots = 17;
   Picture*    m_currDecompPic = nullptr;
   int         m_arena = -1, m_dstSlot = -1;
-  std::vector<Row> m_rows; std::unique_ptr<std::atomic<int>[]> m_miderCols;
+  std::vector<Row> m_rows; std::unique_ptr<std::atomic<uint8_t>[]> m_ctuDone; int m_ctusW = 0;
   std::vector<MotionHist> m_hist;
-  WaitCounter m_miderCounter, m_flattenCounter, m_submitCounter;
+  WaitCounter m_flattenCounter, m_submitCounter, m_finishCounter;
   // per-picture work lists (pinned)
   PinnedVec<b200_pu> m_pus; PinnedVec<b200_tu> m_tus; PinnedVec<int16_t> m_coefs; PinnedVec<b200_intra_tu> m_intra;
   PinnedVec<b200_lf_param> m_lf[2]; PinnedVec<b200_sao_ctu> m_sao; PinnedVec<b200_alf_ctu> m_alf; PinnedVec<b200_lmcs_vpdu> m_vpdus;
@@ -95,6 +96,9 @@ class DecLibReconB200
   b200_picture m_pic{};
   SlotMap m_slotMap{};
   bool m_doSao = false, m_doAlf = false, m_doLmcs = false, m_dryRun = false;
+  // host-stage timing (seconds since decompressPicture): end of preparePicture, first flatten row start (= MIDER done), submit start, submit end, wait end
+  std::chrono::steady_clock::time_point m_t0; std::atomic<int64_t> m_tFlat0{ 0 }; double m_stage[6] = { 0, 0, 0, 0, 0, 0 };
+  double since() const { return std::chrono::duration<double>( std::chrono::steady_clock::now() - m_t0 ).count(); }
   // the CPU stages that stay
   std::vector<MotionInfo> m_motionInfo; std::vector<LoopFilterParam> m_loopFilterParam; std::vector<Mv> m_dmvrMvCache;
   LoopFilter m_cLoopFilter; SampleAdaptiveOffset m_cSAO; AdaptiveLoopFilter m_cALF; Reshape m_cReshaper;
@@ -148,50 +152,56 @@ class DecLibReconB200
   void park( std::exception_ptr e ) { std::lock_guard<std::mutex> l( m_failMutex ); if( !m_failure ) m_failure = e; m_failed.store( true ); }
   template<class F> bool guarded( F f ) { if( m_failed.load() ) return true; try { return f(); } catch( ... ) { park( std::current_exception() ); return true; } }
 
-  static bool miderTask( int tid, void* p )
+  // one task per CTU.  Ready when the CTU to the left and the CTU above-right (the last one of the row: above) have run: the merge / AMVP candidates of
+  // a CU reach into them (the MIDER preconditions of ctuTask, DecLibRecon.cpp:764-778); boundary strengths then read the CUs left and above.
+  static bool ctuReady( int, void* p )
   {
-    Row& r = *static_cast<Row*>( p );
-    return r.self->guarded( [&] { return miderRow( tid, r ); } );
-  }
-  static bool miderRow( int tid, Row& r )
-  {
-    DecLibReconB200& d = *r.self;
-    CodingStructure& cs = *d.m_currDecompPic->cs; const PreCalcValues& pcv = *cs.pcv;
-    const int W = pcv.widthInCtus;
-    for( ; r.col < W; )
-    {
-      if( d.m_failed.load() ) return true;
-      // the merge / AMVP candidates of a CU reach into the CTU above-right (ctuTask MIDER preconditions, DecLibRecon.cpp:764-778)
-      if( r.line > 0 && d.m_miderCols[r.line - 1].load( std::memory_order_acquire ) < std::min( r.col + 2, W ) ) return false;
-      const int a = r.line * W + r.col;
-      CtuData& cd = cs.getCtuData( a );
-      cd.motion = &d.m_motionInfo[(size_t) pcv.num4x4CtuBlks * a];
-      if( !cd.slice->isIntra() || cs.sps->getIBCFlag() ) d.m_cuDecoders[tid]->TaskDeriveCtuMotionInfo( cs, a, getCtuArea( cs, r.col, r.line, true ), d.m_hist[r.line] );
-      else memset( NO_WARNING_class_memaccess( cd.motion ), MI_NOT_VALID, sizeof( MotionInfo ) * pcv.num4x4CtuBlks );
-      d.m_miderCols[r.line].store( ++r.col, std::memory_order_release );
-    }
+    const Row& r = *static_cast<Row*>( p ); const DecLibReconB200& d = *r.self;
+    const int W = d.m_ctusW;
+    if( r.col > 0 && !d.m_ctuDone[r.line * W + r.col - 1].load( std::memory_order_acquire ) ) return false;
+    if( r.line > 0 && !d.m_ctuDone[( r.line - 1 ) * W + std::min( r.col + 1, W - 1 )].load( std::memory_order_acquire ) ) return false;
     return true;
   }
-
-  static bool flattenTask( int, void* p )
+  static bool ctuTask( int tid, void* p )
   {
-    Row& r = *static_cast<Row*>( p );
-    return r.self->guarded( [&] { r.self->flattenRow( r ); return true; } );
+    Row& r = *static_cast<Row*>( p ); DecLibReconB200& d = *r.self;
+    if( !d.m_failed.load() && !ctuReady( tid, p ) ) return false;
+    { int64_t z = 0; d.m_tFlat0.compare_exchange_strong( z, (int64_t) ( d.since() * 1e9 ) + 1 ); }
+    const bool done = d.guarded( [&] { d.miderCtu( tid, r ); d.flattenCtu( r ); return true; } );
+    d.m_ctuDone[r.line * d.m_ctusW + r.col].store( 1, std::memory_order_release );
+    return done;
+  }
+  void miderCtu( int tid, Row& r )
+  {
+    CodingStructure& cs = *m_currDecompPic->cs; const PreCalcValues& pcv = *cs.pcv;
+    const int a = r.line * m_ctusW + r.col;
+    CtuData& cd = cs.getCtuData( a );
+    cd.motion = &m_motionInfo[(size_t) pcv.num4x4CtuBlks * a];
+    if( !cd.slice->isIntra() || cs.sps->getIBCFlag() ) m_cuDecoders[tid]->TaskDeriveCtuMotionInfo( cs, a, getCtuArea( cs, r.col, r.line, true ), m_hist[r.line] );
+    else memset( NO_WARNING_class_memaccess( cd.motion ), MI_NOT_VALID, sizeof( MotionInfo ) * pcv.num4x4CtuBlks );
   }
 
-  static bool submitTask( int, void* p ) { DecLibReconB200* d = static_cast<DecLibReconB200*>( p ); return d->guarded( [&] { d->submit(); return true; } ); }
+  static bool finishMotionTask( int tid, void* p )
+  {
+    Row& r = *static_cast<Row*>( p ); DecLibReconB200& d = *r.self;
+    return d.guarded( [&] {
+      CodingStructure& cs = *d.m_currDecompPic->cs;
+      for( int x = 0; x < d.m_ctusW; x++ ) { const int a = r.line * d.m_ctusW + x; if( !cs.getCtuData( a ).slice->isIntra() ) d.m_cuDecoders[tid]->TaskFinishMotionInfo( cs, a, x, r.line ); }
+      return true; } );
+  }
+  static bool submitTask( int, void* p ) { DecLibReconB200* d = static_cast<DecLibReconB200*>( p ); d->m_stage[2] = d->since(); const bool r = d->guarded( [&] { d->submit(); return true; } ); d->m_stage[3] = d->since(); return r; }
 
   int wpIdxOf( int r0, int r1 ) const { return m_wpIdx.empty() ? 0 : m_wpIdx[( r0 + 1 ) * m_wpStride + ( r1 + 1 )]; }
 
-  void flattenRow( Row& r )
+  void flattenCtu( Row& r )
   {
     Picture* pic = m_currDecompPic; CodingStructure& cs = *pic->cs; const SPS& sps = *cs.sps; const PreCalcValues& pcv = *cs.pcv;
     const int W = pcv.widthInCtus, W4 = ( pcv.lumaWidth + 3 ) >> 2;
     const bool lmcsOn = sps.getUseReshaper() && cs.picHeader->getLmcsEnabledFlag();
     auto wp = [this]( int r0, int r1 ) { return wpIdxOf( r0, r1 ); };
     r.pus.clear(); r.tus.clear(); r.coefs.clear(); r.intra.clear();
-    for( int col = 0; col < W; col++ )
     {
+      const int col = r.col;
       const int a = r.line * W + col;
       CtuData& cd = cs.getCtuData( a );
       // LF_INIT (DecLibRecon.cpp:808-829)
@@ -243,14 +253,6 @@ class DecLibReconB200
           for( auto& tu : TUTraverser( &cu.firstTU, cu.lastTU->next ) )
             for( int c = 0; c < (int) getNumberValidComponents( cu.chromaFormat ); c++ ) { b200_tu t; if( flattenTU( tu, ComponentID( c ), *m_trQuant, r.coefs, t ) ) { if( ciipComp[c] ) t.flags |= B200_TU_RESI; r.tus.push_back( t ); } }
       }
-      // in-loop filter parameters of the CTU
-      if( m_doSao )
-      {
-        bool av[8];
-        m_cSAO.deriveLoopFilterBoundaryAvailibility( cs, Position( col * pcv.maxCUWidth, r.line * pcv.maxCUHeight ), av[0], av[1], av[2], av[3], av[4], av[5], av[6], av[7] );
-        flattenSAO( cd.saoParam, av, getNumberValidComponents( pcv.chrFormat ), m_sao.v[a] );     // saoParam after reconstructBlkSAOParam (parser side)
-      }
-      if( m_doAlf ) flattenALF( cd.alfParam, m_alf.v[a] );
     }
   }
 
@@ -312,7 +314,7 @@ class DecLibReconB200
     m_doSao = sps.getUseSAO();
     m_doAlf = sps.getUseALF() && !AdaptiveLoopFilter::getAlfSkipPic( cs );
     const int W4 = ( pcv.lumaWidth + 3 ) >> 2, H4 = ( pcv.lumaHeight + 3 ) >> 2;
-    for( int d = 0; d < 2; d++ ) { m_lf[d].v.assign( (size_t) W4 * H4, b200_lf_param{} ); m_lf[d].pin(); }
+    for( int d = 0; d < 2; d++ ) { m_lf[d].v.resize( (size_t) W4 * H4 ); m_lf[d].pin(); }          // every entry is rewritten by flattenLfCtu
     m_sao.v.assign( pcv.sizeInCtus, b200_sao_ctu{} ); m_alf.v.assign( pcv.sizeInCtus, b200_alf_ctu{} ); m_sao.pin(); m_alf.pin();
     for( auto& s : m_sao.v ) s.type[0] = s.type[1] = s.type[2] = B200_SAO_OFF;
     if( m_doAlf )
@@ -349,6 +351,18 @@ class DecLibReconB200
       if( !r.coefs.empty() ) memcpy( &m_coefs.v[nC], r.coefs.data(), r.coefs.size() * sizeof( int16_t ) );
       if( !r.intra.empty() ) memcpy( &m_intra.v[nI], r.intra.data(), r.intra.size() * sizeof( b200_intra_tu ) );
       nP += r.pus.size(); nT += r.tus.size(); nC += r.coefs.size(); nI += r.intra.size();
+    }
+    // in-loop filter parameters of every CTU (the SAO availability looks at the CTUs below: the whole picture is parsed by now)
+    for( unsigned a = 0; a < pcv.sizeInCtus; a++ )
+    {
+      CtuData& cd = cs.getCtuData( a );
+      if( m_doSao )
+      {
+        bool av[8];
+        m_cSAO.deriveLoopFilterBoundaryAvailibility( cs, Position( ( a % pcv.widthInCtus ) * pcv.maxCUWidth, ( a / pcv.widthInCtus ) * pcv.maxCUHeight ), av[0], av[1], av[2], av[3], av[4], av[5], av[6], av[7] );
+        flattenSAO( cd.saoParam, av, getNumberValidComponents( pcv.chrFormat ), m_sao.v[a] );     // saoParam after reconstructBlkSAOParam (parser side)
+      }
+      if( m_doAlf ) flattenALF( cd.alfParam, m_alf.v[a] );
     }
     if( m_doLmcs )
     {
@@ -404,6 +418,8 @@ public:
   // forget every picture of the device DPB (their Picture objects are about to be destroyed: end of sequence, test harness)
   void resetDpb() { if( !m_sh ) return; std::lock_guard<std::mutex> l( m_sh->m ); m_sh->slotOf.clear(); std::fill( m_sh->owner.begin(), m_sh->owner.end(), nullptr ); std::fill( m_sh->valid.begin(), m_sh->valid.end(), 0 ); }
   const std::vector<Mv>& dmvrMvCache() const { return m_dmvrMvCache; }
+  // seconds since decompressPicture(): [0] tables ready, [1] MIDER done (first flatten row starts), [2] flatten done (submit starts), [3] submitted, [4] host tasks joined, [5] device + finish done
+  const double* stageTimes() const { return m_stage; }
 
   // DecLibRecon::decompressPicture (DecLibRecon.cpp:429): schedules the host stages of the picture; returns without waiting.
   void decompressPicture( Picture* pic )
@@ -415,28 +431,29 @@ public:
     refuse( pic );
     m_motionInfo.resize( (size_t) pcv.num4x4CtuBlks * pcv.sizeInCtus ); m_loopFilterParam.resize( (size_t) pcv.num4x4CtuBlks * pcv.sizeInCtus * 2 );
     m_dmvrMvCache.assign( (size_t) pcv.num8x8CtuBlks * pcv.sizeInCtus, Mv() ); cs.m_dmvrMvCache = m_dmvrMvCache.data();
+    m_t0 = std::chrono::steady_clock::now(); m_tFlat0.store( 0 );
     m_trQuant->init( pic );
     pic->startProcessingTimer();
     preparePicture( pic );
+    m_stage[0] = since();
 
     const int W = pcv.widthInCtus, H = pcv.heightInCtus;
-    m_rows.resize( H ); m_hist.assign( H, MotionHist() );
-    m_miderCols.reset( new std::atomic<int>[H] );
-    for( int y = 0; y < H; y++ ) { m_rows[y].self = this; m_rows[y].line = y; m_rows[y].col = 0; m_miderCols[y].store( 0 ); }
+    m_ctusW = W;
+    m_rows.resize( (size_t) W * H ); m_hist.assign( H, MotionHist() );
+    m_ctuDone.reset( new std::atomic<uint8_t>[(size_t) W * H] );
+    for( int a = 0; a < W * H; a++ ) { m_rows[a].self = this; m_rows[a].line = a / W; m_rows[a].col = a % W; m_ctuDone[a].store( 0 ); }
     pic->reconDone.lock();
-    for( int y = 0; y < H; y++ )
+    for( int a = 0; a < W * H; a++ )
     {
       CBarrierVec bars;
 #if RECO_WHILE_PARSE
-      if( pic->parseDone.isBlocked() ) bars.push_back( &pic->ctuParsedBarrier[( y + 1 ) * W - 1] );   // the last CTU of the row is parsed (DecLibRecon.cpp:619-625)
+      if( pic->parseDone.isBlocked() ) bars.push_back( &pic->ctuParsedBarrier[( a / W + 1 ) * W - 1] );   // the last CTU of the row is parsed (DecLibRecon.cpp:619-625)
 #else
       bars.push_back( &pic->parseDone );
 #endif
-      m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 mider " + std::to_string( y ) ) miderTask, &m_rows[y], &m_miderCounter, nullptr, std::move( bars ) );
+      m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 ctu " + std::to_string( a ) ) ctuTask, &m_rows[a], &m_flattenCounter, nullptr, std::move( bars ), ctuReady );
     }
-    for( int y = 0; y < H; y++ )
-      m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 flatten " + std::to_string( y ) ) flattenTask, &m_rows[y], &m_flattenCounter, nullptr, { m_miderCounter.donePtr(), &pic->parseDone } );
-    m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 submit" ) submitTask, this, &m_submitCounter, nullptr, { m_flattenCounter.donePtr() } );
+    m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 submit" ) submitTask, this, &m_submitCounter, nullptr, { m_flattenCounter.donePtr(), &pic->parseDone } );
   }
 
   // DecLibRecon::waitForPrevDecompressedPic (DecLibRecon.cpp:684): host stages done -> device done -> DMVR deltas -> TaskFinishMotionInfo -> planes.
@@ -447,12 +464,15 @@ public:
     try
     {
       if( m_pool->numThreads() == 0 ) m_pool->processTasksOnMainThread();
-      m_miderCounter.wait(); m_flattenCounter.wait(); m_submitCounter.wait();
+      m_flattenCounter.wait(); m_submitCounter.wait();
       if( m_failed.load() ) std::rethrow_exception( m_failure );
       const Slice*   lastSlice           = pic->slices.back();
       const unsigned lastSliceLastCtuIdx = lastSlice->getCtuAddrInSlice( lastSlice->getNumCtuInSlice() - 1 );
       CHECK( lastSliceLastCtuIdx != pic->cs->pcv->sizeInCtus - 1, "Picture incomplete. A slice was probably lost." );
-      if( !m_dryRun ) finishOnHost( pic );
+      m_stage[1] = m_tFlat0.load() * 1e-9; m_stage[4] = since();
+      finishOnHost( pic );
+      m_stage[5] = since();
+      if( m_failed.load() ) std::rethrow_exception( m_failure );
       pic->cs->deallocTempInternals();
       pic->stopProcessingTimer();
       pic->progress = Picture::reconstructed;
@@ -470,8 +490,8 @@ public:
   // DecLibRecon::cleanupOnException (DecLibRecon.cpp:724): no task of the broken picture may survive in the pool; its device slot is released
   void cleanupOnException()
   {
-    m_miderCounter.wait_nothrow(); m_flattenCounter.wait_nothrow(); m_submitCounter.wait_nothrow();
-    m_miderCounter.clearException(); m_flattenCounter.clearException(); m_submitCounter.clearException();
+    m_flattenCounter.wait_nothrow(); m_submitCounter.wait_nothrow(); m_finishCounter.wait_nothrow();
+    m_flattenCounter.clearException(); m_submitCounter.clearException(); m_finishCounter.clearException();
     if( m_currDecompPic ) m_currDecompPic->waitForAllTasks();
     if( m_sh && m_currDecompPic )
     {
@@ -486,20 +506,28 @@ private:
   {
     CodingStructure& cs = *pic->cs; const PreCalcValues& pcv = *cs.pcv; Shared& S = *m_sh;
     m_dmvr.v.assign( m_dmvrMvCache.size() * 2, 0 ); m_dmvr.pin();
+    if( !m_dryRun )
     {
       std::lock_guard<std::mutex> l( S.m );
       check( b200_wait_picture( S.ctx, m_arena, m_dmvr.v.data(), m_dmvrMvCache.size() ) );
       S.valid[m_dstSlot] = 1;
     }
     for( size_t i = 0; i < m_dmvrMvCache.size(); i++ ) m_dmvrMvCache[i] = Mv( m_dmvr.v[2 * i], m_dmvr.v[2 * i + 1] );
-    if( pic->stillReferenced )                                                                                    // colMotion for later TMVP (DecCu.cpp:161),
-      for( unsigned a = 0; a < pcv.sizeInCtus; a++ )                                                              // under ctuTask's conditions (DecLibRecon.cpp:860-867)
-        if( !cs.getCtuData( a ).slice->isIntra() ) m_cuDecoders[0]->TaskFinishMotionInfo( cs, a, a % pcv.widthInCtus, a / pcv.widthInCtus );
+    if( pic->stillReferenced )                                                                                    // colMotion for later TMVP (DecCu.cpp:161), under ctuTask's
+    {                                                                                                             // conditions (DecLibRecon.cpp:860-867); one pool task per CTU row
+      for( unsigned y = 0; y < pcv.heightInCtus; y++ )
+        m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 finishMotion " + std::to_string( y ) ) finishMotionTask, &m_rows[(size_t) y * pcv.widthInCtus], &m_finishCounter );
+      if( m_pool->numThreads() == 0 ) m_pool->processTasksOnMainThread();
+    }
+    if( m_dryRun ) { m_finishCounter.wait(); return; }
     // the finished planes go back into Picture::m_bufs: output frames alias them (vvdecimpl.cpp:1051) and a CPU fallback picture may reference them
     int16_t* planes[3] = { nullptr, nullptr, nullptr }; ptrdiff_t strides[3] = { 0, 0, 0 };
     for( int c = 0; c < ( S.geom.chromaFormat ? 3 : 1 ); c++ ) { PelBuf b = cs.getRecoBuf( ComponentID( c ) ); planes[c] = b.buf; strides[c] = b.stride; }
-    std::lock_guard<std::mutex> l( S.m );
-    check( b200_get_frame_strided( S.ctx, m_dstSlot, planes, strides ) );
+    {
+      std::lock_guard<std::mutex> l( S.m );
+      check( b200_get_frame_strided( S.ctx, m_dstSlot, planes, strides ) );       // the copy runs while the pool finishes the motion field
+    }
+    m_finishCounter.wait();
   }
 };
 
