@@ -471,10 +471,34 @@ struct Gen
 };
 
 // ---------------------------------------------------------------------------------------------------------------- picture state
+// the four reference pictures, shared by every handle built from the same planes (a decoder's references stay in the DPB — and on the device —
+// from picture to picture; rebuilding them per handle would charge four 25 MB uploads to every picture of the GPU arm)
+struct RefSet { b200_geom g; const int16_t* key[12]; uint64_t sum; std::unique_ptr<FakePicture> ref[4]; };
+static std::shared_ptr<RefSet> refSetFor( const b200_geom& g, const int16_t* const* refs )
+{
+  static std::mutex m; static std::shared_ptr<RefSet> last;
+  std::lock_guard<std::mutex> l( m );
+  uint64_t sum = 0; for( int i = 0; i < 64; i++ ) sum = sum * 1315423911u + (uint16_t) refs[0][(size_t) i * 97 % ( (size_t) g.width * 8 )];
+  if( last && !memcmp( &last->g, &g, sizeof( g ) ) && !memcmp( last->key, refs, sizeof( last->key ) ) && last->sum == sum ) return last;
+  std::shared_ptr<RefSet> R( new RefSet ); R->g = g; memcpy( R->key, refs, sizeof( R->key ) ); R->sum = sum;
+  const int pocs[4] = { 4, 0, 12, 16 };
+  for( int s = 0; s < 4; s++ )
+  {
+    R->ref[s].reset( new FakePicture( g, 1 ) );
+    int16_t* p3[3] = { (int16_t*) refs[s * 3], (int16_t*) refs[s * 3 + 1], (int16_t*) refs[s * 3 + 2] };
+    R->ref[s]->setPlanes( g, p3 );
+    Picture& rp = R->ref[s]->pic;
+    rp.poc = pocs[s]; rp.progress = Picture::reconstructed; rp.reconDone.unlock(); rp.parseDone.unlock(); rp.stillReferenced = true;
+    rp.extendPicBorder(); rp.borderExtStarted = true;
+  }
+  last = R;
+  return R;
+}
+
 struct Pic
 {
   b200_geom g;
-  std::unique_ptr<FakePicture> cur, ref[4];
+  std::unique_ptr<FakePicture> cur; std::shared_ptr<RefSet> refs; FakePicture* ref[4] = { nullptr, nullptr, nullptr, nullptr };
   std::shared_ptr<APS> lmcsAps;
   std::shared_ptr<APS> alfAps[ALF_CTB_MAX_NUM_APS];
   ref_seam_cfg cfg;
@@ -534,15 +558,10 @@ static Pic* build( const b200_geom* g, const ref_seam_cfg* c, const int16_t* con
   const bool intraPic = c->sliceType == 2;
   const int pocs[4] = { 4, 0, 12, 16 };
   if( !intraPic )
-    for( int s = 0; s < 4; s++ )
-    {
-      P->ref[s].reset( new FakePicture( *g, 1 ) );
-      int16_t* p3[3] = { (int16_t*) refs[s * 3], (int16_t*) refs[s * 3 + 1], (int16_t*) refs[s * 3 + 2] };
-      P->ref[s]->setPlanes( *g, p3 );
-      Picture& rp = P->ref[s]->pic;
-      rp.poc = pocs[s]; rp.progress = Picture::reconstructed; rp.reconDone.unlock(); rp.parseDone.unlock(); rp.stillReferenced = true;
-      if( s ) { rp.extendPicBorder(); rp.borderExtStarted = true; }                // every reference is extended once in its life: one of the four inside the run
-    }
+  {
+    P->refs = refSetFor( *g, refs );
+    for( int s = 0; s < 4; s++ ) P->ref[s] = P->refs->ref[s].get();
+  }
   SEAM_TR( "build: refs done\n" );
   CodingStructure& cs = *cur.pic.cs;
   const PreCalcValues& pcv = *cs.pcv;
@@ -714,6 +733,7 @@ extern "C" double ref_seam_run_stock( void* h, int threads, int16_t* const out[3
   {
     seam::StockCtx& S = seam::stockCtx( threads );
     Picture* pic = &P.cur->pic;
+    if( P.ref[0] ) P.ref[0]->pic.borderExtStarted = false;      // every reference is extended once in its life: one of the four inside each run (the extension is idempotent)
     const auto t0 = std::chrono::steady_clock::now();
     S.rec->decompressPicture( pic );
     Picture* done = S.rec->waitForPrevDecompressedPic();
@@ -738,13 +758,14 @@ extern "C" double ref_seam_run_b200( void* h, int threads, int dry, int16_t* con
   try
   {
     seam::B200Ctx& S = seam::b200Ctx( threads, dry != 0, P.g );
+    { static const void* lastRefs = nullptr; if( lastRefs != (const void*) P.refs.get() ) { S.rec->resetDpb(); lastRefs = P.refs.get(); } }   // another reference set: its predecessor's Pictures are gone
     Picture* pic = &P.cur->pic;
     const auto t0 = std::chrono::steady_clock::now();
     try { S.rec->decompressPicture( pic ); }
     catch( ... ) { pic->reconDone.setException( std::current_exception() ); pic->error = true; }          // DecLib::reconPicture (DecLib.cpp:618-626)
     Picture* done = S.rec->waitForPrevDecompressedPic();
     const double secs = std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
-    S.rec->resetDpb();                                                   // the pictures of this handle die with it
+    S.rec->releasePicture( pic );                                        // the picture dies with its handle; the shared references stay resident on the device
     if( done != pic || pic->error || pic->reconDone.hasException() )
     {
       int rc = -1;

@@ -425,7 +425,14 @@ constexpr int V2_TILE = 128 * V2_LS + 2 * 64 * V2_CS;        // samples of one t
 constexpr int V2_RECS = 1024;                                // records staged in shared memory (a CTU with more blocks reads the rest from global memory)
 constexpr int V2_FLAGS = 128 * 128 / 16 + 2 * (64 * 64 / 4); // most blocks a CTU can hold
 struct V2Scratch { int16_t T[2][IT_REF], L[2][IT_REF], M[IT_ARR], S[IT_ARR], Lm[32 * 32], LmTop[64], LmLeft[64]; int LmPar[4]; };
-constexpr size_t V2_SMEM = (size_t)2 * V2_TILE * sizeof(int16_t) + V2_WARPS * sizeof(V2Scratch) + V2_RECS * sizeof(b200_intra_tu) + V2_FLAGS + 64;
+constexpr int V2_OWN = 3 * 32 * 32;                         // owner words of the CTU's units: luma 32 x 32 (4x4 units), Cb / Cr 32 x 32 each (2x2 units)
+constexpr size_t V2_SMEM = (size_t)2 * V2_TILE * sizeof(int16_t) + V2_WARPS * sizeof(V2Scratch) + V2_RECS * sizeof(b200_intra_tu) + V2_OWN * sizeof(int) + V2_FLAGS + 64;
+__device__ __forceinline__ void v2_cp4(void* smemDst, const void* gmemSrc)      // asynchronous 4-byte global -> shared copy (LDGSTS): the whole CTU in flight before one wait
+{
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(d), "l"(gmemSrc));
+}
+__device__ __forceinline__ void v2_cp_wait() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 struct V2Tile {
   int16_t* rec[3]; int16_t* res[3]; int ox[3], oy[3], tw[3], th[3], ts[3];
@@ -469,7 +476,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) intra_ctu_kernel(const IntraPar
   int16_t* tileRes = tileRec + V2_TILE;
   V2Scratch* scratch = reinterpret_cast<V2Scratch*>(tileRes + V2_TILE);
   b200_intra_tu* srec = reinterpret_cast<b200_intra_tu*>(scratch + V2_WARPS);
-  volatile uint8_t* sflag = reinterpret_cast<volatile uint8_t*>(srec + V2_RECS);
+  int* sown = reinterpret_cast<int*>(srec + V2_RECS);
+  volatile uint8_t* sflag = reinterpret_cast<volatile uint8_t*>(sown + V2_OWN);
   __shared__ int sCtu, sNext;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nComp = P.planes[1] ? 3 : 1;
@@ -492,19 +500,23 @@ __global__ void __launch_bounds__(V2_THREADS, 1) intra_ctu_kernel(const IntraPar
         if (c >= nComp) { TL.tw[c] = TL.th[c] = 0; }
       }
     }
-    // ---- the CTU's samples and residuals -> shared memory (32-bit words: the pitch is not a multiple of 16 bytes), records, flags
+    // ---- the CTU's samples, residuals and owner words -> shared memory (asynchronous 32-bit copies: the pitch is not a multiple of 16 bytes), records, flags
     for (int c = 0; c < nComp; c++) {
       const int wWords = TL.tw[c] >> 1, n = wWords * TL.th[c];
       const int16_t* src = P.planes[c] + (size_t)TL.oy[c] * P.stride[c] + TL.ox[c];
       const int16_t* rsrc = P.resi[c] ? P.resi[c] + (size_t)TL.oy[c] * P.stride[c] + TL.ox[c] : nullptr;
       for (int k = tid; k < n; k += V2_THREADS) {
         const int y = k / wWords, x = (k - y * wWords) * 2;
-        *reinterpret_cast<uint32_t*>(TL.rec[c] + y * TL.ts[c] + x) = __ldcg(reinterpret_cast<const uint32_t*>(src + (size_t)y * P.stride[c] + x));
-        if (rsrc) *reinterpret_cast<uint32_t*>(TL.res[c] + y * TL.ts[c] + x) = __ldcg(reinterpret_cast<const uint32_t*>(rsrc + (size_t)y * P.stride[c] + x));
+        v2_cp4(TL.rec[c] + y * TL.ts[c] + x, src + (size_t)y * P.stride[c] + x);
+        if (rsrc) v2_cp4(TL.res[c] + y * TL.ts[c] + x, rsrc + (size_t)y * P.stride[c] + x);
       }
+      const int unit = c ? 2 : 4, uw = TL.tw[c] / unit, uh = TL.th[c] / unit;
+      const int* osrc = P.owner[c] + (size_t)(TL.oy[c] / unit) * P.ownerStride[c] + TL.ox[c] / unit;
+      for (int k = tid; k < uw * uh; k += V2_THREADS) { const int y = k / uw, x = k - y * uw; v2_cp4(sown + c * 1024 + y * 32 + x, osrc + (size_t)y * P.ownerStride[c] + x); }
     }
-    for (int k = tid; k < min(cnt, V2_RECS) * 4; k += V2_THREADS) reinterpret_cast<uint32_t*>(srec)[k] = reinterpret_cast<const uint32_t*>(P.tus + first)[k];
+    for (int k = tid; k < min(cnt, V2_RECS) * 4; k += V2_THREADS) v2_cp4(reinterpret_cast<uint32_t*>(srec) + k, reinterpret_cast<const uint32_t*>(P.tus + first) + k);
     for (int k = tid; k < cnt; k += V2_THREADS) sflag[k] = 0;
+    v2_cp_wait();
     __syncthreads();
 
     // ---- the CTU's blocks, one warp each, in decoding order
@@ -525,7 +537,11 @@ __global__ void __launch_bounds__(V2_THREADS, 1) intra_ctu_kernel(const IntraPar
         if (dep == 0) { if (availTL) { ux = x0 - 1; uy = y0 - 1; } }
         else if (dep <= numAbove) { ux = x0 + (dep - 1) * unit; uy = y0 - 1; }
         else if (dep - 64 >= 0 && dep - 64 < numLeft) { ux = x0 - 1; uy = y0 + (dep - 64) * unit; }
-        if (ux >= 0 && uy >= 0) v2_wait(P, sflag, P.owner[c][(uy / unit) * P.ownerStride[c] + ux / unit], me, first);
+        if (ux >= 0 && uy >= 0) {
+          const int ox = ux / unit - TL.ox[c] / unit, oy = uy / unit - TL.oy[c] / unit;          // inside the CTU: the staged owner word
+          const int o = ((unsigned)ox < 32u && (unsigned)oy < 32u && ux < TL.ox[c] + TL.tw[c] && uy < TL.oy[c] + TL.th[c]) ? sown[c * 1024 + oy * 32 + ox] : __ldcg(P.owner[c] + (size_t)(uy / unit) * P.ownerStride[c] + ux / unit);
+          v2_wait(P, sflag, o, me, first);
+        }
       }
       if (t.mode >= B200_INTRA_LM) {
         const bool aCu = t.flags & B200_INTRA_LM_ABOVE, lCu = t.flags & B200_INTRA_LM_LEFT;
@@ -533,7 +549,11 @@ __global__ void __launch_bounds__(V2_THREADS, 1) intra_ctu_kernel(const IntraPar
         const int ux0 = max(0, (2 * x0 - (lCu ? 4 : 0)) >> 2), ux1 = min(P.W - 1, 2 * x0 + 2 * nA - 1) >> 2;
         const int uy0 = max(0, (2 * y0 - (aCu ? 4 : 0)) >> 2), uy1 = min(P.H - 1, 2 * y0 + 2 * nL - 1) >> 2;
         const int uw = ux1 - ux0 + 1, nU = uw * (uy1 - uy0 + 1);
-        for (int u = lane; u < nU; u += 32) v2_wait(P, sflag, P.owner[0][(uy0 + u / uw) * P.ownerStride[0] + ux0 + u % uw], me, first);
+        for (int u = lane; u < nU; u += 32) {
+          const int gx = ux0 + u % uw, gy = uy0 + u / uw, ox = gx - TL.ox[0] / 4, oy = gy - TL.oy[0] / 4;
+          const int o = ((unsigned)ox < 32u && (unsigned)oy < 32u && gx * 4 < TL.ox[0] + TL.tw[0] && gy * 4 < TL.oy[0] + TL.th[0]) ? sown[oy * 32 + ox] : __ldcg(P.owner[0] + (size_t)gy * P.ownerStride[0] + gx);
+          v2_wait(P, sflag, o, me, first);
+        }
       }
       __threadfence();
       __syncwarp();

@@ -152,24 +152,33 @@ class DecLibReconB200
   void park( std::exception_ptr e ) { std::lock_guard<std::mutex> l( m_failMutex ); if( !m_failure ) m_failure = e; m_failed.store( true ); }
   template<class F> bool guarded( F f ) { if( m_failed.load() ) return true; try { return f(); } catch( ... ) { park( std::current_exception() ); return true; } }
 
-  // one task per CTU.  Ready when the CTU to the left and the CTU above-right (the last one of the row: above) have run: the merge / AMVP candidates of
-  // a CU reach into them (the MIDER preconditions of ctuTask, DecLibRecon.cpp:764-778); boundary strengths then read the CUs left and above.
-  static bool ctuReady( int, void* p )
+  // Two tasks per CTU.  MIDER: ready when the CTU to the left and the CTU above-right (the last one of the row: above) have run — the merge / AMVP
+  // candidates of a CU reach into them (the MIDER preconditions of ctuTask, DecLibRecon.cpp:764-778): a wave front.  FLATTEN (boundary strengths,
+  // CU / TU walk): ready when the CTU's own MIDER ran (the CTUs left and above ran before it), so only MIDER is on the wave front's critical path.
+  static bool miderReady( int, void* p )
   {
     const Row& r = *static_cast<Row*>( p ); const DecLibReconB200& d = *r.self;
     const int W = d.m_ctusW;
+    if( d.m_failed.load() ) return true;
     if( r.col > 0 && !d.m_ctuDone[r.line * W + r.col - 1].load( std::memory_order_acquire ) ) return false;
     if( r.line > 0 && !d.m_ctuDone[( r.line - 1 ) * W + std::min( r.col + 1, W - 1 )].load( std::memory_order_acquire ) ) return false;
     return true;
   }
-  static bool ctuTask( int tid, void* p )
+  static bool miderTask( int tid, void* p )
   {
     Row& r = *static_cast<Row*>( p ); DecLibReconB200& d = *r.self;
-    if( !d.m_failed.load() && !ctuReady( tid, p ) ) return false;
-    { int64_t z = 0; d.m_tFlat0.compare_exchange_strong( z, (int64_t) ( d.since() * 1e9 ) + 1 ); }
-    const bool done = d.guarded( [&] { d.miderCtu( tid, r ); d.flattenCtu( r ); return true; } );
+    if( !miderReady( tid, p ) ) return false;
+    const bool done = d.guarded( [&] { d.miderCtu( tid, r ); return true; } );
     d.m_ctuDone[r.line * d.m_ctusW + r.col].store( 1, std::memory_order_release );
     return done;
+  }
+  static bool flattenReady( int, void* p ) { const Row& r = *static_cast<Row*>( p ); return r.self->m_failed.load() || r.self->m_ctuDone[r.line * r.self->m_ctusW + r.col].load( std::memory_order_acquire ) != 0; }
+  static bool flattenTask( int tid, void* p )
+  {
+    Row& r = *static_cast<Row*>( p ); DecLibReconB200& d = *r.self;
+    if( !flattenReady( tid, p ) ) return false;
+    { int64_t z = 0; d.m_tFlat0.compare_exchange_strong( z, (int64_t) ( d.since() * 1e9 ) + 1 ); }
+    return d.guarded( [&] { d.flattenCtu( r ); return true; } );
   }
   void miderCtu( int tid, Row& r )
   {
@@ -247,7 +256,11 @@ class DecLibReconB200
         }
         FlattenPuResult rc;
         if( cu.mergeType() == MRG_TYPE_SUBPU_ATMVP ) rc = flattenSbTmvp( cu, m_slotMap, wp, [&]( const b200_pu& q ) { r.pus.push_back( q ); } );
-        else { b200_pu q; rc = flattenPU( cu, m_slotMap, wp, q ); if( rc == FLATTEN_PU_OK ) r.pus.push_back( q ); }
+        else
+        {
+          b200_pu q; rc = flattenPU( cu, m_slotMap, wp, q );
+          if( rc == FLATTEN_PU_OK ) { r.pus.push_back( q ); if( q.flags & B200_PU_DMVR ) cu.setDmvrCondition( true ); }   // motionCompensation :1436 sets it on the CPU path; TaskFinishMotionInfo reads it
+        }
         if( rc != FLATTEN_PU_OK ) THROW_UNSUPPORTED( "DecLibReconB200: inter tool outside the device path (RPR-scaled reference, wrap-around, sub-picture clipping)" );
         if( cu.rootCbf() )
           for( auto& tu : TUTraverser( &cu.firstTU, cu.lastTU->next ) )
@@ -415,6 +428,8 @@ public:
   // test hook: run every host stage and keep the work lists (flattened()), without a device
   void setDryRun( bool b ) { m_dryRun = b; }
   const b200_picture& flattened() const { return m_pic; }
+  // forget one picture (its Picture object is about to be destroyed or reused: PicListManager would call this where it recycles a picture)
+  void releasePicture( const Picture* pic ) { if( !m_sh ) return; std::lock_guard<std::mutex> l( m_sh->m ); auto it = m_sh->slotOf.find( pic ); if( it != m_sh->slotOf.end() ) { m_sh->owner[it->second] = nullptr; m_sh->valid[it->second] = 0; m_sh->slotOf.erase( it ); } }
   // forget every picture of the device DPB (their Picture objects are about to be destroyed: end of sequence, test harness)
   void resetDpb() { if( !m_sh ) return; std::lock_guard<std::mutex> l( m_sh->m ); m_sh->slotOf.clear(); std::fill( m_sh->owner.begin(), m_sh->owner.end(), nullptr ); std::fill( m_sh->valid.begin(), m_sh->valid.end(), 0 ); }
   const std::vector<Mv>& dmvrMvCache() const { return m_dmvrMvCache; }
@@ -451,7 +466,9 @@ public:
 #else
       bars.push_back( &pic->parseDone );
 #endif
-      m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 ctu " + std::to_string( a ) ) ctuTask, &m_rows[a], &m_flattenCounter, nullptr, std::move( bars ), ctuReady );
+      CBarrierVec bars2 = bars;
+      m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 mider " + std::to_string( a ) ) miderTask, &m_rows[a], &m_flattenCounter, nullptr, std::move( bars ), miderReady );
+      m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 flatten " + std::to_string( a ) ) flattenTask, &m_rows[a], &m_flattenCounter, nullptr, std::move( bars2 ), flattenReady );
     }
     m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 submit" ) submitTask, this, &m_submitCounter, nullptr, { m_flattenCounter.donePtr(), &pic->parseDone } );
   }
