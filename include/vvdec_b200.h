@@ -262,7 +262,7 @@ B200_API int b200_mc_predict_wp(const b200_geom* g, int16_t* const dst[3], const
  *             as DecCu::predAndReco calls them for an intra TU (DecCu.cpp:316-371).
  * The availability analysis (cs.getCURestricted walks, IntraPrediction.cpp:1098-1130, :1762-1795) stays host code in the flattener and
  * arrives as counts.  CIIP CUs (predBlendIntraCiip :887) are blocks of this list too: planar prediction blended with the inter prediction K2 left
- * in the block.  Not covered (the flattener must refuse them): ISP, palette, ACT, IBC CUs, intra / CIIP together with LMCS.
+ * in the block.  Not covered (the flattener must refuse them): ISP, palette, ACT, IBC CUs.
  * Blocks of one list are processed in list order; a block may read what earlier blocks of the list wrote. */
 enum { B200_INTRA_PLANAR = 0, B200_INTRA_DC = 1 /* 2..66 angular */, B200_INTRA_BDPCM_HOR = 67, B200_INTRA_BDPCM_VER = 68,
        B200_INTRA_MIP = 69 /* matrix intra prediction: b200_intra_tu::mip = mode index | transposed << 7 */,
@@ -298,8 +298,8 @@ B200_API int b200_intra_reconstruct(const b200_geom* g, int16_t* const planes[3]
  * slot written by an earlier submission — the stream order replaces the reference's reconDone barriers).
  *   per picture:  H2D work lists -> K2 (prediction into the work plane) -> K1 (residual + reco, in place) ->
  *                 K3 deblock V,H (in place) -> K4 SAO (-> second work plane) -> K5 ALF/CC-ALF (-> DPB slot)
- *   with LMCS:    K2 stores forward-mapped luma -> K1 luma TUs -> per-VPDU chroma scale -> K1 chroma TUs (scaled residual) ->
- *                 inverse luma map -> K3 ...
+ *   with LMCS:    K2 stores forward-mapped luma -> K1 luma TUs -> K6 luma blocks -> per-VPDU chroma scale (from the reconstructed, mapped luma) ->
+ *                 K1 chroma TUs (scaled residual) -> K6 chroma blocks -> inverse luma map -> K3 ...
  *   with intra:   ... K1 (TUs of intra / CIIP CUs leave their residual in residual planes) -> K6 (intra and CIIP blocks in decoding order,
  *                 prediction [blend] + residual) -> K3 ...
  * Samples of tools the device path does not have (ISP, IBC) can be supplied in `given` (whole planes, uploaded before K2); inter PUs,
@@ -344,10 +344,11 @@ typedef struct b200_picture {
   const b200_alf_ctu* alf;               /* K5 (B200_PIC_ALF) */
   const b200_alf_tables* alfTabs;
   const b200_wp* wp; int32_t numWp;      /* explicit weighted prediction entries referenced by b200_pu::wpIdx, or NULL / 0 */
-  const b200_lmcs* lmcs;                 /* B200_PIC_LMCS: every slice of the picture has LMCS on and all CUs are inter
-                                            (samples in `given` must already be in the mapped domain)                  */
-  const b200_intra_tu* intraTus;         /* K6: intra blocks of the picture in decoding order (regular modes), or NULL.  Runs after K2 and K1:  */
-  size_t numIntraTus;                    /* blocks read the reconstruction of inter and earlier intra neighbours.  Not together with LMCS.       */
+  const b200_lmcs* lmcs;                 /* B200_PIC_LMCS: every slice of the picture has LMCS on (samples in `given` must already be in the
+                                            mapped domain); intra / CIIP blocks are predicted in the mapped domain                               */
+  const b200_intra_tu* intraTus;         /* K6: intra blocks of the picture in decoding order, or NULL.  Runs after K2 and K1: blocks read the     */
+  size_t numIntraTus;                    /* reconstruction of inter and earlier intra neighbours.  With LMCS chroma scaling: luma blocks, then the
+                                            per-VPDU scales, then the chroma blocks (see "with LMCS" above)                                     */
 } b200_picture;
 enum { B200_PIC_DEBLOCK = 1, B200_PIC_SAO = 2, B200_PIC_ALF = 4, B200_PIC_LMCS = 8 };
 

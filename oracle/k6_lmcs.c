@@ -106,3 +106,48 @@ void orc_lmcs_inv_plane(const b200_geom* g, int16_t* luma, const b200_lmcs* L)
 {
   for (int y = 0; y < g->height; y++) for (int x = 0; x < g->width; x++) { int16_t* p = &luma[(size_t)y * g->stride[0] + x]; *p = L->invLUT[*p]; }
 }
+
+/* ---- LMCS together with intra / CIIP CUs (DecCu.cpp:316-403 intra branch with doChrScale :619-633, :483 finishLMCSAndReco; the chroma scale of a VPDU
+ * comes from its reconstructed luma neighbourhood, intra blocks included, so the chain is: luma TUs -> luma intra blocks -> scales -> chroma TUs ->
+ * chroma intra blocks).  orc_lmcs_vpdu_scales: the scale of every VPDU from the luma plane as it stands. */
+void orc_lmcs_vpdu_scales(const b200_geom* g, const int16_t* luma, const b200_lmcs* L, int32_t* scale)
+{
+  const int vs = g->ctuSize == 128 ? 64 : g->ctuSize, vW = (g->width + vs - 1) / vs, vH = (g->height + vs - 1) / vs;
+  for (int i = 0; i < vW * vH; i++) scale[i] = orc_lmcs_vpdu_scale(g, luma, L, &L->vpdus[i]);
+}
+
+/* K1 over the TUs of one channel (compSel 1 luma, 2 chroma, 0 all): TUs flagged B200_TU_RESI leave their residual in the resi planes (K6 adds it),
+ * the others are reconstructed into the planes; chroma residuals of blocks with more than 4 samples are scaled by their VPDU's scale (scale != NULL). */
+void orc_k1_residual_sel(const b200_geom* g, int16_t* const planes[3], int16_t* const resi[3], const b200_tu* tus, size_t numTus,
+                         const int16_t* coefs, const int32_t* scaling, int compSel, const int32_t* scale)
+{
+  const int pmax = (1 << g->bitDepth) - 1;
+  const int vs = g->ctuSize == 128 ? 64 : g->ctuSize, vl = ilog2(vs), vW = (g->width + vs - 1) / vs;
+  int16_t r0[64 * 64], r1[64 * 64];
+  for (size_t t = 0; t < numTus; t++) {
+    const b200_tu* tu = &tus[t];
+    if ((compSel == 1 && tu->comp != 0) || (compSel == 2 && tu->comp == 0)) continue;
+    const int w = 1 << tu->log2w, h = 1 << tu->log2h;
+    orc_tu_residual(tu, g->bitDepth, coefs, scaling, r0, w);
+    int nOut = 1, comp1 = 0;
+    if (tu->ict) {
+      const int m = tu->ict;
+      comp1 = tu->comp == 1 ? 2 : 1; nOut = 2;
+      for (int i = 0; i < w * h; i++) { const int c = r0[i]; r1[i] = (int16_t)((m == 2) ? c : (m == -2) ? -c : (m == 1 || m == 3) ? (c >> 1) : ((-c) >> 1)); }
+    }
+    const int doScale = scale && tu->comp != 0 && w * h > 4;
+    const int sc = doScale ? scale[((tu->y * 2) >> vl) * vW + ((tu->x * 2) >> vl)] : 0;
+    const int toResi = (tu->flags & B200_TU_RESI) && resi;
+    for (int o = 0; o < nOut; o++) {
+      const int comp = o ? comp1 : tu->comp;
+      const int16_t* r = o ? r1 : r0;
+      int16_t* p = (toResi ? resi[comp] : planes[comp]) + (size_t)tu->y * g->stride[comp] + tu->x;
+      for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+        int16_t* d = &p[(size_t)y * g->stride[comp] + x];
+        const int rr = doScale ? orc_lmcs_scale_resi(r[y * w + x], sc, g->bitDepth) : r[y * w + x];
+        if (toResi) *d = (int16_t)rr;
+        else { const int v = *d + rr; *d = (int16_t)(v < 0 ? 0 : v > pmax ? pmax : v); }
+      }
+    }
+  }
+}

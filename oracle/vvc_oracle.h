@@ -122,4 +122,8 @@ void orc_mc_predict_wp(const b200_geom* g, int16_t* const dst[3], const int16_t*
 #ifdef __cplusplus
 }
 #endif
+/* LMCS together with intra / CIIP blocks (k6_lmcs.c) */
+void orc_lmcs_vpdu_scales(const b200_geom* g, const int16_t* luma, const b200_lmcs* L, int32_t* scale);
+void orc_k1_residual_sel(const b200_geom* g, int16_t* const planes[3], int16_t* const resi[3], const b200_tu* tus, size_t numTus,
+                         const int16_t* coefs, const int32_t* scaling, int compSel, const int32_t* scale);
 #endif

@@ -44,6 +44,8 @@ def load_oracle():
     lib.orc_lmcs_scale_resi.argtypes = [C.c_int] * 3
     lib.orc_k1_residual_lmcs.argtypes = [C.POINTER(abi.Geom), PL, V, C.c_size_t, i16p, V, LP]
     lib.orc_lmcs_inv_plane.argtypes = [C.POINTER(abi.Geom), i16p, LP]
+    lib.orc_lmcs_vpdu_scales.argtypes = [C.POINTER(abi.Geom), i16p, LP, C.c_void_p]
+    lib.orc_k1_residual_sel.argtypes = [C.POINTER(abi.Geom), PL, PL, C.c_void_p, C.c_size_t, i16p, C.c_void_p, C.c_int, C.c_void_p]
     u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
     lib.orc_pack_pyuv.argtypes = [i16p, C.c_ssize_t, C.c_int, C.c_int, u8p]
     lib.orc_narrow8.argtypes = [i16p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, u8p]
@@ -308,7 +310,23 @@ def oracle_decompress(oracle, g, dpb, pic):
         cur = [p.copy() for p in pic["given"]]
     oracle.orc_mc_predict_wp(C.byref(g), abi.plane_ptrs(cur), ref_ptrs(dpb), pic["pus"].ctypes.data, len(pic["pus"]), dm.ctypes.data,
                              pic["wp"].ctypes.data if "wp" in pic else None)
-    if st.flags & abi.PIC_LMCS:
+    if st.flags & abi.PIC_LMCS and "intraTus" in pic:
+        # LMCS with intra / CIIP blocks: everything before the inverse map lives in the mapped domain.  The chroma residual scale of a VPDU comes from its
+        # reconstructed luma neighbourhood (intra blocks included), so: luma TUs -> luma intra blocks -> scales -> chroma TUs (scaled) -> chroma intra blocks
+        L = C.byref(pic["lmcs"]["struct"]); chroma_adj = bool(pic["lmcs"]["struct"].chromaAdj)
+        oracle.orc_lmcs_fwd_pus(C.byref(g), cur[0], pic["pus"].ctypes.data, len(pic["pus"]), L)
+        resi = [np.zeros_like(p) for p in cur]
+        it = pic["intraTus"]; it_y, it_c = np.ascontiguousarray(it[it["comp"] == 0]), np.ascontiguousarray(it[it["comp"] != 0])
+        tus = pic["tus"]; n = len(tus)
+        oracle.orc_k1_residual_sel(C.byref(g), abi.plane_ptrs(cur), abi.plane_ptrs(resi), tus.ctypes.data, n, pic["coefs"], None, 1, None)
+        oracle.orc_intra_reconstruct(C.byref(g), abi.plane_ptrs(cur), abi.plane_ptrs(resi), it_y.ctypes.data, len(it_y))
+        vs = 64 if g.ctuSize == 128 else g.ctuSize
+        scale = np.zeros(((W + vs - 1) // vs) * ((H + vs - 1) // vs), np.int32)
+        if chroma_adj: oracle.orc_lmcs_vpdu_scales(C.byref(g), cur[0], L, scale.ctypes.data)
+        oracle.orc_k1_residual_sel(C.byref(g), abi.plane_ptrs(cur), abi.plane_ptrs(resi), tus.ctypes.data, n, pic["coefs"], None, 2, scale.ctypes.data if chroma_adj else None)
+        oracle.orc_intra_reconstruct(C.byref(g), abi.plane_ptrs(cur), abi.plane_ptrs(resi), it_c.ctypes.data, len(it_c))
+        oracle.orc_lmcs_inv_plane(C.byref(g), cur[0], L)
+    elif st.flags & abi.PIC_LMCS:
         # DecCu.cpp:458-476 forward map of every inter CU's luma prediction; :483 finishLMCSAndReco; DecLibRecon.cpp:935 inverse map
         L = C.byref(pic["lmcs"]["struct"])
         oracle.orc_lmcs_fwd_pus(C.byref(g), cur[0], pic["pus"].ctypes.data, len(pic["pus"]), L)

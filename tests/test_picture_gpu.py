@@ -77,6 +77,20 @@ def test_invalid_records_are_reported(b200):
             pic[arr][field][idx] = bad
             assert b200.b200_decompress_picture(ctx, C.byref(pic["struct"])) == -2 and what in b200.b200_last_error(), (arr, field)
             pic[arr][field][idx] = keep
+        # fields the kernels index tables / working sets with: LFNST byte, joint-CbCr mode on a luma TU, transform-skip / BDPCM blocks wider than 32
+        tus = pic["tus"]
+        i_luma = int(np.flatnonzero((tus["comp"] == 0) & (tus["log2w"] >= 2) & (tus["log2h"] >= 2) & ((tus["flags"] & 7) == 0))[0])
+        for field, bad in (("lfnst", 0x10), ("lfnst", 3), ("lfnst", 0x41), ("ict", 2)):
+            keep = tus[field][i_luma].copy(); tus[field][i_luma] = bad
+            assert b200.b200_decompress_picture(ctx, C.byref(pic["struct"])) == -2 and b"TU list" in b200.b200_last_error(), (field, bad)
+            tus[field][i_luma] = keep
+        keep = tus[i_luma].copy()
+        tus["flags"][i_luma] |= 1; tus["log2w"][i_luma] = 6; tus["x"][i_luma] = 0                      # a 64-wide transform-skip block
+        assert b200.b200_decompress_picture(ctx, C.byref(pic["struct"])) == -2 and b"TU list" in b200.b200_last_error()
+        tus[i_luma] = keep
+        tus["flags"][i_luma] |= 2                                                                      # BDPCM without transform skip / with a partial corner
+        assert b200.b200_decompress_picture(ctx, C.byref(pic["struct"])) == -2 and b"TU list" in b200.b200_last_error()
+        tus[i_luma] = keep
         fpic = synth.gen_picture(rng, W, H, bd, dst_slot=4)               # with filters: CTU records are range-checked too
         for arr, field, bad in (("alf", "lumaSet", 250), ("sao", "type", 7), ("alf", "ccIdx", 200)):
             recs = fpic["alf"]["ctus"] if arr == "alf" else fpic["sao"]

@@ -17,7 +17,9 @@ CASES = {
     "B_intra_heavy": dict(intra=45, skip=5),
     "I_picture": dict(slice_type=2),
     "P_picture": dict(slice_type=1),
-    "B_lmcs_inter": dict(lmcs=True, intra=0, tools=T_INTER),                    # LMCS with chroma scaling; inter CUs only (intra + LMCS: see test_seam_gpu / DESIGN)
+    "B_lmcs_inter": dict(lmcs=True, intra=0, tools=T_INTER),                    # LMCS with chroma scaling; inter CUs only
+    "B_lmcs_intra_ciip": dict(lmcs=True),                                       # ... with intra and CIIP CUs (mapped-domain intra, luma-first ordering of the chroma scales)
+    "I_lmcs": dict(lmcs=True, slice_type=2),
     "B_ctu64": dict(ctu=64),
     "B_ctu32_8bit": dict(ctu=32, bd=8),
     "B_no_dmvr": dict(tools=(helpers.SEAM_INTER_TOOLS | helpers.SEAM_RESI_TOOLS | helpers.SEAM_INTRA_TOOLS | helpers.SEAM_FILTERS) & ~helpers.SEAM["DMVR"]),

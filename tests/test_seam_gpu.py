@@ -23,7 +23,8 @@ def both(seed, W, H, threads=4, **kw):
 
 
 @pytest.mark.parametrize("name,kw", [("B_mixed_intra", dict()), ("I_picture", dict(slice_type=2)), ("P_picture", dict(slice_type=1)),
-                                     ("B_lmcs_inter", dict(lmcs=True, intra=0, tools=T_INTER)), ("B_ctu64", dict(ctu=64))])
+                                     ("B_lmcs_inter", dict(lmcs=True, intra=0, tools=T_INTER)), ("B_lmcs_intra_ciip", dict(lmcs=True)), ("I_lmcs", dict(lmcs=True, slice_type=2)),
+                                     ("B_ctu64", dict(ctu=64))])
 @pytest.mark.parametrize("seed", [1, 2])
 def test_seam_small(name, kw, seed):
     both(seed, 416, 240, **kw)
@@ -32,7 +33,8 @@ def test_seam_small(name, kw, seed):
 def test_seam_1080p_and_4k():
     both(31, 1920, 1080, threads=8)
     both(32, 3840, 2160, threads=16)
-    both(33, 3840, 2160, threads=16, lmcs=True, intra=0, tools=T_INTER)
+    both(33, 3840, 2160, threads=16, lmcs=True)
+    both(34, 3840, 2160, threads=16, lmcs=True, slice_type=2)
 
 
 def test_seam_error_contract_on_the_device_path():

@@ -104,6 +104,15 @@ __device__ __forceinline__ int tu_class(const b200_tu* tus, int i, bool& ok, con
     if ((unsigned long long)t.coefOff + (unsigned)((t.maxX + 1) * (t.maxY + 1)) > lim.numCoefs) ok = false;
     if ((t.flags & B200_TU_SCALING) && (unsigned long long)t.slOff + (unsigned)(w * h) > lim.numScaling) ok = false;
     if (t.inBits < 1 || t.inBits > 32 || t.rightShift < -31 || t.rightShift > 31) ok = false;
+    // transform skip / BDPCM blocks are at most 32 wide (sps log2MaxTransformSkipBlockSize <= 5): K1 keeps them in the 32x32 working set of their class;
+    // BDPCM accumulates over the whole block, so its level corner is the block
+    const bool bdpcm = t.flags & (B200_TU_BDPCM_H | B200_TU_BDPCM_V);
+    if ((ts || bdpcm) && (w > 32 || h > 32)) ok = false;
+    if (bdpcm && (!ts || t.maxX != w - 1 || t.maxY != h - 1 || (t.flags & (B200_TU_BDPCM_H | B200_TU_BDPCM_V)) == (B200_TU_BDPCM_H | B200_TU_BDPCM_V))) ok = false;
+    // LFNST: index 1 or 2, no stray bits, at least 4x4, never with transform skip (the kernel indexes kLfnst* with it)
+    if (t.lfnst && ((t.lfnst & 3) < 1 || (t.lfnst & 3) > 2 || (t.lfnst & 0xe0) || ts || w < 4 || h < 4)) ok = false;
+    // joint CbCr writes the partner chroma plane at the same position
+    if (t.ict && (t.comp == 0 || !lim.chroma || t.ict < -3 || t.ict > 3)) ok = false;
   }
   return m <= 3 ? 0 : m == 4 ? 1 : m == 5 ? 2 : 3;
 }

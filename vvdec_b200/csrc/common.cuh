@@ -160,7 +160,10 @@ int launch_pack(const DevPlanes& src, const b200_geom& g, int fmt, uint8_t* cons
 
 // K6 (k6_intra.cu): blocks in decoding order; sync = numTus + 2 ints (done flags, ticket, error bit); owner[c] = one int per 4x4 luma / 2x2 chroma unit
 struct IntraLaunch { b200_geom geom; DevPlanes planes; const int16_t* resi[3]; const b200_intra_tu* tus; size_t numTus; int* owner[3]; int ownerStride[3]; size_t ownerBytes[3]; int* sync;
-                     int* order = nullptr; };   // order: numTus + 3 * numCtus ints of scratch for the wavefront processing order, or null: list order
+                     int* order = nullptr;      // order: numTus + 8 + 3 * numCtus ints of scratch for the wavefront processing order, or null: list order
+                     int compSel = 0;           // 0: every block; 1: luma blocks only; 2: chroma blocks only, continuing a compSel == 1 launch on the same list (LMCS:
+                                                // the chroma residual scale of a VPDU is derived from the finished luma, so luma goes first)
+                   };
 inline size_t intra_order_ints(const b200_geom& g, size_t numTus) { return numTus + 8 + 3 * (size_t)((g.width + g.ctuSize - 1) / g.ctuSize) * ((g.height + g.ctuSize - 1) / g.ctuSize); }
 int launch_intra(const IntraLaunch& L, cudaStream_t s);
 int launch_intra_validate(const b200_intra_tu* tus, size_t numTus, const b200_geom& g, int* meta, cudaStream_t s);   // error bit 8 of the PU meta block (after launch_mc_bucket)

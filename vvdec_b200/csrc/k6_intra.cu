@@ -36,6 +36,7 @@ struct IntraParams {
   int* done; int* ticket; int* err;
   const int* perm;                          // processing order (wavefront over CTUs), or null: list order
   int* ctuCnt; int* ctuFirst; int* ctuBase; int ctuLog2, ctusW, ctusH;
+  int compSel;                              // 0 all blocks, 1 luma only, 2 chroma only (second launch on the same list: the luma blocks' done words are set)
 };
 
 __device__ __forceinline__ int wide_angle(int w, int h, int mode)
@@ -103,8 +104,10 @@ __global__ void __launch_bounds__(IT_THREADS, 12) intra_kernel(const IntraParams
     if (tid == 0) { sTicket = atomicAdd(P.ticket, 1); sSum = 0; }
     __syncthreads();
     if (sTicket >= P.numTus) return;
+    if (P.perm && (*(volatile int*)P.err & 2)) return;          // the list is not in decoding order (CTU runs not contiguous): perm holds holes, nothing is run
     const int me = P.perm ? P.perm[sTicket] : sTicket;
     const b200_intra_tu t = P.tus[me];
+    if ((P.compSel == 1 && t.comp != 0) || (P.compSel == 2 && t.comp == 0)) continue;      // the other channel's pass
     const int c = t.comp, w = 1 << t.log2w, h = 1 << t.log2h, mrl = c ? 0 : t.multiRefIdx, unit = c ? 2 : 4;
     const int x0 = t.x, y0 = t.y, ps = P.stride[c], pmax = (1 << P.bitDepth) - 1;
     const int16_t* plane = P.planes[c];
@@ -511,7 +514,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) intra_ctu_kernel(const IntraPar
     __syncthreads();
     if (tid == 0) { sCtu = atomicAdd(&counters[1], 1); sNext = 0; }
     __syncthreads();
-    if (sCtu >= counters[0]) return;
+    if (sCtu >= counters[0] || (*(volatile int*)P.err & 2)) return;          // bit 2: a CTU's blocks are not contiguous in the list (intra_ctu_check_kernel)
     const int ctu = ctuOrder[sCtu], first = P.ctuFirst[ctu], cnt = P.ctuCnt[ctu];
     long long tp = clock64(); (void)tp;
     V2Tile TL;
@@ -550,7 +553,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) intra_ctu_kernel(const IntraPar
       for (int k = tid; k < uw * uh; k += V2_THREADS) { const int y = k / uw, x = k - y * uw; v2_cp4(sown + c * 1024 + y * 32 + x, osrc + (size_t)y * P.ownerStride[c] + x); }
     }
     for (int k = tid; k < min(cnt, V2_RECS) * 4; k += V2_THREADS) v2_cp4(reinterpret_cast<uint32_t*>(srec) + k, reinterpret_cast<const uint32_t*>(P.tus + first) + k);
-    for (int k = tid; k < cnt; k += V2_THREADS) sflag[k] = 0;
+    for (int k = tid; k < cnt; k += V2_THREADS) sflag[k] = P.compSel == 2 ? (uint8_t)(__ldcg(P.done + first + k) != 0) : 0;      // chroma pass: the luma blocks are finished
     v2_cp_wait();
     __syncthreads();
     K6P(0, tp); K6C(8);       // [0] CTU set-up cycles, [8] CTU count (per group)
@@ -567,6 +570,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) intra_ctu_kernel(const IntraPar
       tp = clock64();
       const int me = first + k;
       const b200_intra_tu t = k < V2_RECS ? srec[k] : P.tus[me];
+      if ((P.compSel == 1 && t.comp != 0) || (P.compSel == 2 && t.comp == 0)) continue;      // the other channel's pass
       const int c = t.comp, w = 1 << t.log2w, h = 1 << t.log2h, mrl = c ? 0 : t.multiRefIdx, unit = c ? 2 : 4;
       const int x0 = t.x, y0 = t.y, ps = P.stride[c], pmax = (1 << P.bitDepth) - 1;
       const int availTL = (t.flags & B200_INTRA_AVAIL_TL) ? 1 : 0, numAbove = t.numAbove, numLeft = t.numLeft;
@@ -921,9 +925,13 @@ int launch_intra(const IntraLaunch& L, cudaStream_t s)
   for (int c = 0; c < 3; c++) { P.planes[c] = L.planes.p[c]; P.resi[c] = L.resi[c]; P.stride[c] = L.planes.stride[c]; P.owner[c] = L.owner[c]; P.ownerStride[c] = L.ownerStride[c]; }
   if (!L.geom.chromaFormat) { P.planes[1] = P.planes[2] = nullptr; }
   P.W = L.geom.width; P.H = L.geom.height; P.bitDepth = L.geom.bitDepth; P.tus = L.tus; P.numTus = (int)L.numTus;
-  P.done = L.sync; P.ticket = L.sync + L.numTus; P.err = L.sync + L.numTus + 1;
-  B200_CUDA(cudaMemsetAsync(L.sync, 0, (L.numTus + 2) * sizeof(int), s));
-  for (int c = 0; c < (L.geom.chromaFormat ? 3 : 1); c++) B200_CUDA(cudaMemsetAsync(L.owner[c], 0xff, L.ownerBytes[c], s));
+  P.done = L.sync; P.ticket = L.sync + L.numTus; P.err = L.sync + L.numTus + 1; P.compSel = L.compSel;
+  const bool cont = L.compSel == 2;                            // second launch on the list: done words, owner maps and the processing order are kept
+  if (cont) B200_CUDA(cudaMemsetAsync(P.ticket, 0, sizeof(int), s));
+  else {
+    B200_CUDA(cudaMemsetAsync(L.sync, 0, (L.numTus + 2) * sizeof(int), s));
+    for (int c = 0; c < (L.geom.chromaFormat ? 3 : 1); c++) B200_CUDA(cudaMemsetAsync(L.owner[c], 0xff, L.ownerBytes[c], s));
+  }
   P.perm = nullptr; P.ctuCnt = P.ctuFirst = P.ctuBase = nullptr;
   P.ctuLog2 = L.geom.ctuSize == 128 ? 7 : L.geom.ctuSize == 64 ? 6 : 5; P.ctusW = (L.geom.width + L.geom.ctuSize - 1) / L.geom.ctuSize; P.ctusH = (L.geom.height + L.geom.ctuSize - 1) / L.geom.ctuSize;
   static const char* variant = getenv("B200_INTRA_KERNEL");      // measurement switch: "v1" = one CTA per block through global memory (round 1)
@@ -932,16 +940,19 @@ int launch_intra(const IntraLaunch& L, cudaStream_t s)
   const bool dense = L.numTus >= 48 * std::max<size_t>(1, (size_t)L.geom.width * L.geom.height >> 14);                   // >= 48 blocks per 128x128 luma area
   const bool v1 = !L.order || (variant ? !strcmp(variant, "v1") : !dense) || ((P.stride[0] | P.stride[1] | P.stride[2]) & 1);   // the tile loads move 32-bit words
   const unsigned grid = (unsigned)((L.numTus + 255) / 256);
-  intra_owner_kernel<<<(unsigned)L.numTus, 64, 0, s>>>(P);
+  if (!cont) intra_owner_kernel<<<(unsigned)L.numTus, 64, 0, s>>>(P);
   if (!v1) {
     // v2: per-CTU runs of the list (decoding order keeps a CTU's blocks together), CTUs in wave-front order, one CTA per CTU at a time
     const size_t nCtu = (size_t)P.ctusW * P.ctusH;
     int* base = L.order; P.ctuCnt = base; P.ctuFirst = base + nCtu; int* ctuOrder = base + 2 * nCtu; int* counters = base + 3 * nCtu;
-    B200_CUDA(cudaMemsetAsync(P.ctuCnt, 0, nCtu * sizeof(int), s));
-    B200_CUDA(cudaMemsetAsync(P.ctuFirst, 0x7f, nCtu * sizeof(int), s));
-    intra_ctu_count_kernel<<<grid, 256, 0, s>>>(P);
-    intra_ctu_check_kernel<<<grid, 256, 0, s>>>(P);
-    intra_ctu_order_kernel<<<1, 1024, nCtu * sizeof(int), s>>>(P, ctuOrder, counters);
+    if (cont) B200_CUDA(cudaMemsetAsync(counters + 1, 0, sizeof(int), s));
+    else {
+      B200_CUDA(cudaMemsetAsync(P.ctuCnt, 0, nCtu * sizeof(int), s));
+      B200_CUDA(cudaMemsetAsync(P.ctuFirst, 0x7f, nCtu * sizeof(int), s));
+      intra_ctu_count_kernel<<<grid, 256, 0, s>>>(P);
+      intra_ctu_check_kernel<<<grid, 256, 0, s>>>(P);
+      intra_ctu_order_kernel<<<1, 1024, nCtu * sizeof(int), s>>>(P, ctuOrder, counters);
+    }
     static bool attr = false;
     if (!attr) { B200_CUDA(cudaFuncSetAttribute(intra_ctu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM)); attr = true; }
     const int ctas = (int)std::min<size_t>(nCtu, (size_t)num_sms());
@@ -953,11 +964,13 @@ int launch_intra(const IntraLaunch& L, cudaStream_t s)
   if (L.order && !listOrder && L.numTus >= 100 * std::max<size_t>(1, (size_t)L.geom.width * L.geom.height >> 14)) {   // >= 100 blocks per 128x128 luma area
     const size_t nCtu = (size_t)P.ctusW * P.ctusH;
     int* perm = L.order; P.ctuCnt = perm + L.numTus; P.ctuFirst = P.ctuCnt + nCtu; P.ctuBase = P.ctuFirst + nCtu;
-    B200_CUDA(cudaMemsetAsync(P.ctuCnt, 0, nCtu * sizeof(int), s));
-    B200_CUDA(cudaMemsetAsync(P.ctuFirst, 0x7f, nCtu * sizeof(int), s));
-    intra_ctu_count_kernel<<<grid, 256, 0, s>>>(P);
-    intra_ctu_base_kernel<<<1, 1, 0, s>>>(P);
-    intra_perm_kernel<<<grid, 256, 0, s>>>(P, perm);
+    if (!cont) {
+      B200_CUDA(cudaMemsetAsync(P.ctuCnt, 0, nCtu * sizeof(int), s));
+      B200_CUDA(cudaMemsetAsync(P.ctuFirst, 0x7f, nCtu * sizeof(int), s));
+      intra_ctu_count_kernel<<<grid, 256, 0, s>>>(P);
+      intra_ctu_base_kernel<<<1, 1, 0, s>>>(P);
+      intra_perm_kernel<<<grid, 256, 0, s>>>(P, perm);
+    }
     P.perm = perm;
   }
   const int ctas = (int)std::min<size_t>(L.numTus, (size_t)num_sms() * 12);

@@ -143,7 +143,6 @@ B200_API int b200_pic_upload(b200_ctx* c, const b200_picture* p)
   B200_CHECK(p->numWp >= 0 && p->numWp <= 255 && (p->wp || !p->numWp), "b200_pic_upload: weighted-prediction table (at most 255 entries)");
   B200_CHECK(!(p->flags & B200_PIC_LMCS) || (p->lmcs && p->lmcs->invLUT && (!p->lmcs->chromaAdj || p->lmcs->vpdus) && p->lmcs->orgCW == (1 << c->g.bitDepth) / 16), "b200_pic_upload: LMCS data missing or inconsistent");
   B200_CHECK(!p->numIntraTus || (p->intraTus && p->numIntraTus < (1u << 30)), "b200_pic_upload: intra list missing");
-  if (p->numIntraTus && (p->flags & B200_PIC_LMCS)) { set_error("b200_pic_upload: intra blocks together with LMCS are not supported on the device"); return B200_ERR_UNSUPPORTED; }
   B200_CUDA(cudaSetDevice(c->device));
   const int ai = c->nextArena; c->nextArena = (c->nextArena + 1) % c->numArenas;
   Arena& A = c->arenas[ai];
@@ -291,39 +290,48 @@ B200_API int b200_pic_run(b200_ctx* c, int ai)
     if (int rc = launch_mc(L, c->ss, c->profiling ? &c->prof : nullptr)) return rc;
     c->launches += mc_launch_count(L);
   }
-  // 2. K1 residual + reco.  With LMCS chroma scaling: luma TUs, the per-VPDU scale from the reconstructed luma, then the chroma TUs.
+  // 2. K1 residual + reco, 2b. K6 intra blocks in decoding order (prediction from the reconstruction so far — inter CUs, earlier intra blocks — + their
+  // residual).  With LMCS chroma scaling the chroma residual scale of a VPDU is derived from its reconstructed (mapped-domain) luma neighbourhood
+  // (Reshape.cpp:192), intra blocks included: luma TUs -> luma intra blocks -> per-VPDU scale -> chroma TUs (scaled) -> chroma intra blocks.
   LmcsLaunch LM; LM.geom = g; LM.planes = P; LM.lmcs = A.lmcs; LM.vpdus = A.lmcsVpdus; LM.invLut = A.lmcsInv; LM.scale = A.lmcsScale;
-  if (A.numTus) {
-    K1Launch L; L.geom = g; L.planes = P; L.tus = A.tus; L.numTus = A.numTus; L.idx = A.tuIdx; L.meta = A.tuMeta; L.coefs = A.coefs; L.scaling = A.scaling; L.mode = 0;
-    if (A.numIntraTus) { uint8_t* rb = c->resiBuf.as<uint8_t>(); L.resi[0] = reinterpret_cast<int16_t*>(rb); L.resi[1] = reinterpret_cast<int16_t*>(rb + c->planeBytes[0]); L.resi[2] = reinterpret_cast<int16_t*>(rb + c->planeBytes[0] + c->planeBytes[1]); }
-    for (int l = 0; l < K1_LISTS; l++) L.cnt[l] = A.hMeta[LM_INTS + LM_CNT + l];
-    if (A.lmcs && A.lmcsChromaAdj) {
-      L.compSel = 1;
-      if (int rc = launch_k1_residual(L, c->ss, c->profiling ? &c->prof : nullptr)) return rc;
-      if (c->profiling) c->prof.begin(B200_KF_LMCS, s);
-      if (int rc = launch_lmcs_vpdu(LM, s)) return rc;
-      if (c->profiling) c->prof.end(B200_KF_LMCS, s);
-      L.compSel = 2; L.vpduScale = A.lmcsScale;
-      if (int rc = launch_k1_residual(L, c->ss, c->profiling ? &c->prof : nullptr)) return rc;
-      c->launches += 2 * k1_launch_count(L) + 1;
-    } else {
-      if (int rc = launch_k1_residual(L, c->ss, c->profiling ? &c->prof : nullptr)) return rc;
-      c->launches += k1_launch_count(L);
-    }
-  }
-  // 2b. K6 intra blocks in decoding order: prediction from the reconstruction so far (inter CUs, earlier intra blocks) + their residual
+  const bool twoPass = A.lmcs && A.lmcsChromaAdj;
   A.hMeta[2 * LM_INTS] = 0;
-  if (A.numIntraTus) {
-    IntraLaunch L; L.geom = g; L.planes = P; L.tus = A.intraTus; L.numTus = A.numIntraTus; L.sync = A.intraSync; L.order = A.intraOrder;
-    uint8_t* rb = c->resiBuf.as<uint8_t>();
-    L.resi[0] = reinterpret_cast<int16_t*>(rb); L.resi[1] = reinterpret_cast<int16_t*>(rb + c->planeBytes[0]); L.resi[2] = reinterpret_cast<int16_t*>(rb + c->planeBytes[0] + c->planeBytes[1]);
-    for (int k = 0; k < 3; k++) { L.owner[k] = A.intraOwner[k]; L.ownerStride[k] = A.intraOwnerStride[k]; L.ownerBytes[k] = A.intraOwnerBytes[k]; }
+  int16_t* resiPl[3] = {nullptr, nullptr, nullptr};
+  if (A.numIntraTus) { uint8_t* rb = c->resiBuf.as<uint8_t>(); resiPl[0] = reinterpret_cast<int16_t*>(rb); resiPl[1] = reinterpret_cast<int16_t*>(rb + c->planeBytes[0]); resiPl[2] = reinterpret_cast<int16_t*>(rb + c->planeBytes[0] + c->planeBytes[1]); }
+  auto runK1 = [&](int compSel, const int* vpduScale) -> int {
+    if (!A.numTus) return 0;
+    K1Launch L; L.geom = g; L.planes = P; L.tus = A.tus; L.numTus = A.numTus; L.idx = A.tuIdx; L.meta = A.tuMeta; L.coefs = A.coefs; L.scaling = A.scaling; L.mode = 0;
+    for (int k = 0; k < 3; k++) L.resi[k] = resiPl[k];
+    for (int l = 0; l < K1_LISTS; l++) L.cnt[l] = A.hMeta[LM_INTS + LM_CNT + l];
+    L.compSel = compSel; L.vpduScale = vpduScale;
+    if (int rc = launch_k1_residual(L, c->ss, c->profiling ? &c->prof : nullptr)) return rc;
+    c->launches += k1_launch_count(L);
+    return 0;
+  };
+  auto runK6 = [&](int compSel) -> int {
+    if (!A.numIntraTus) return 0;
+    IntraLaunch L; L.geom = g; L.planes = P; L.tus = A.intraTus; L.numTus = A.numIntraTus; L.sync = A.intraSync; L.order = A.intraOrder; L.compSel = compSel;
+    for (int k = 0; k < 3; k++) { L.resi[k] = resiPl[k]; L.owner[k] = A.intraOwner[k]; L.ownerStride[k] = A.intraOwnerStride[k]; L.ownerBytes[k] = A.intraOwnerBytes[k]; }
     if (c->profiling) c->prof.begin(B200_KF_INTRA, s);
     if (int rc = launch_intra(L, s)) return rc;
     if (c->profiling) c->prof.end(B200_KF_INTRA, s);
-    c->launches += 5;
-    B200_CUDA(cudaMemcpyAsync(A.hMeta + 2 * LM_INTS, A.intraSync + A.numIntraTus + 1, sizeof(int), cudaMemcpyDeviceToHost, s));   // timeout bit, read by b200_wait_picture
+    c->launches += compSel == 2 ? 1 : 5;
+    return 0;
+  };
+  if (twoPass) {
+    if (int rc = runK1(1, nullptr)) return rc;
+    if (int rc = runK6(1)) return rc;
+    if (c->profiling) c->prof.begin(B200_KF_LMCS, s);
+    if (int rc = launch_lmcs_vpdu(LM, s)) return rc;
+    if (c->profiling) c->prof.end(B200_KF_LMCS, s);
+    c->launches += 1;
+    if (int rc = runK1(2, A.lmcsScale)) return rc;
+    if (int rc = runK6(2)) return rc;
+  } else {
+    if (int rc = runK1(0, nullptr)) return rc;
+    if (int rc = runK6(0)) return rc;
   }
+  if (A.numIntraTus) B200_CUDA(cudaMemcpyAsync(A.hMeta + 2 * LM_INTS, A.intraSync + A.numIntraTus + 1, sizeof(int), cudaMemcpyDeviceToHost, s));   // timeout bit, read by b200_wait_picture
   if (A.lmcs) { if (c->profiling) c->prof.begin(B200_KF_LMCS, s); if (int rc = launch_lmcs_inv(LM, s)) return rc; if (c->profiling) c->prof.end(B200_KF_LMCS, s); c->launches += 1; }   // RSP stage (DecLibRecon.cpp:935)
   // 3. K3 deblocking
   if (A.flags & B200_PIC_DEBLOCK) {

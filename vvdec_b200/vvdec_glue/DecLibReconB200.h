@@ -206,7 +206,6 @@ class DecLibReconB200
   {
     Picture* pic = m_currDecompPic; CodingStructure& cs = *pic->cs; const SPS& sps = *cs.sps; const PreCalcValues& pcv = *cs.pcv;
     const int W = pcv.widthInCtus, W4 = ( pcv.lumaWidth + 3 ) >> 2;
-    const bool lmcsOn = sps.getUseReshaper() && cs.picHeader->getLmcsEnabledFlag();
     auto wp = [this]( int r0, int r1 ) { return wpIdxOf( r0, r1 ); };
     r.pus.clear(); r.tus.clear(); r.coefs.clear(); r.intra.clear();
     {
@@ -226,7 +225,6 @@ class DecLibReconB200
         {
           // K6: one b200_intra_tu per TU component in decoding order (the order DecCu::predAndReco walks them, DecCu.cpp:284-288); the residual of
           // a coded component goes through K1 into the residual planes (B200_TU_RESI) and is added by K6
-          if( lmcsOn ) THROW_UNSUPPORTED( "DecLibReconB200: intra CUs with LMCS" );
           for( auto& tu : TUTraverser( &cu.firstTU, cu.lastTU->next ) )
             for( const CompArea& area : tu.blocks )
             {
@@ -245,7 +243,6 @@ class DecLibReconB200
         if( cu.ciipFlag() )
         {
           // CIIP: the inter prediction comes from K2 like any merge CU; K6 blends a planar intra block into it (predBlendIntraCiip) and adds the residual
-          if( lmcsOn ) THROW_UNSUPPORTED( "DecLibReconB200: CIIP CUs with LMCS" );
           for( int c = 0; c < (int) getNumberValidComponents( cu.chromaFormat ); c++ )
           {
             b200_intra_tu ir;
