@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=6, help="B pictures timed for the cpu_baseline leg (plus one I picture)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-seam", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="multi-GPU: leave the frames on their GPUs")
     ap.add_argument("--host-threads", type=int, default=0, help="threads of the reference's ThreadPool (0: all)")
     return ap.parse_args()
 
@@ -243,16 +244,44 @@ def run_b200(args):
 
     for i in range(args.warmup): vvdec_b200.check(lib.b200_pic_run(ctx, h_of(i + 1)))
     vvdec_b200.check(lib.b200_pic_run(ctx, handle["I"]))                  # the I picture's path is warm too
+    # multi-GPU: every rank decodes its own GOPs; finished frames stay on the device and go to rank 0 in display order over NCCL, on a side stream
+    # that overlaps the following pictures (vvdec_b200/gather.py).  GOP k of the sequence belongs to rank k mod N (gop_shard.assign).
+    G = None; gather_info = None
+    if world > 1 and not args.no_gather:
+        from vvdec_b200 import gather, gop_shard
+        n_local = -(-args.steps // args.gop)
+        lengths = []
+        for k in range(n_local * world): lengths.append(min(args.gop, args.steps - (k // world) * args.gop))
+        numel = W * H * 3 // 2
+        G = gather.FrameGather(rank, world, lengths, numel, torch.device("cuda", local))
+        side = torch.cuda.Stream()
+        poff = [0, W * H, W * H + (W // 2) * (H // 2)]
     barrier()
     sampler = ClockSampler(local); sampler.start()
     l0 = lib.b200_ctx_kernel_launches(ctx)
+    t_wall = time.perf_counter()
     vvdec_b200.check(lib.b200_ctx_mark(ctx, 0))
-    for i in range(args.steps): vvdec_b200.check(lib.b200_pic_run(ctx, h_of(i)))
+    for i in range(args.steps):
+        vvdec_b200.check(lib.b200_pic_run(ctx, h_of(i)))
+        if G is not None:
+            dst = G.slot(i); base = dst.data_ptr()
+            pl = (C.c_void_p * 3)(base + 2 * poff[0], base + 2 * poff[1], base + 2 * poff[2])
+            vvdec_b200.check(lib.b200_get_frame_device_async(ctx, pic_of(i)["struct"].dstSlot, pl, C.c_void_p(side.cuda_stream)))
+            with torch.cuda.stream(side): G.push(i)
     vvdec_b200.check(lib.b200_ctx_mark(ctx, 1))
     ms = C.c_float(); vvdec_b200.check(lib.b200_ctx_elapsed_ms(ctx, C.byref(ms)))
+    if G is not None:
+        with torch.cuda.stream(side): G.finish()
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t_wall) * 1e3
+        ms.value = max(ms.value, wall_ms)                                  # the timed region ends when the last frame has arrived on rank 0
     barrier()
     launches = lib.b200_ctx_kernel_launches(ctx) - l0
     ms_dev = max_over_ranks(ms.value)
+    if G is not None and rank == 0:
+        nb = G.bytes_received()
+        gather_info = {"frames_received": int(nb // (numel * 2)), "bytes": int(nb), "GBps_over_timed_region": round(nb / (ms_dev * 1e-3) / 1e9, 2),
+                       "note": "display-order gather to rank 0 (NCCL send/recv per peer on a side stream), inside the timed region; NVLink 5: 900 GB/s per direction per GPU"}
 
     # ---- per-kernel-family device time (same schedule, events around each family) + the I / B split ----
     NF = 10
@@ -369,7 +398,7 @@ def run_b200(args):
             "config": workload_config(args, world),
             "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": d2h_step, "diag": e2e_diag,
                     "api": "b200_pic_upload (one picture ahead) + b200_pic_run + b200_get_frame_async (D2H overlapped with the next picture), pinned host buffers; every step uploads one picture's work lists and downloads one frame"},
-            "seam": seam, "picture_ms": split,
+            "seam": seam, "picture_ms": split, "gather": gather_info,
             "gpu_launches": int(launches), "numa": numa, "clocks": sampler.summary(), "roofline": roof}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, wl)

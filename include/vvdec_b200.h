@@ -385,6 +385,9 @@ B200_API int  b200_get_frame_strided(b200_ctx* ctx, int slot, int16_t* const pla
  * b200_frame_wait(ticket) blocks until those planes are complete in host memory (pinned memory recommended). */
 B200_API int  b200_get_frame_async(b200_ctx* ctx, int slot, int16_t* const planes[3]);
 B200_API int  b200_frame_wait(b200_ctx* ctx, int ticket);
+/* Device-resident output for the multi-GPU gather: the frame is copied device to device into planesDev[] (geometry strides) on the CUDA
+ * stream the caller passes (cudaStream_t as void*; e.g. the stream NCCL sends from): that stream first waits for every picture submitted so far. */
+B200_API int  b200_get_frame_device_async(b200_ctx* ctx, int slot, int16_t* const planesDev[3], void* cudaStream);
 /* Output formats of the application layer, converted on the device before the D2H copy:
  *   B200_OUT_16    int16 planes, stride = geometry stride (what vvdecFrame carries for bit depths > 8)
  *   B200_OUT_PYUV  4 samples in 5 bytes, rows back to back, W*5/4 bytes per row — the `.pyuv` / --pyuv writer of vvdecapp

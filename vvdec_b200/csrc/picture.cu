@@ -436,6 +436,24 @@ B200_API int b200_get_frame_async(b200_ctx* c, int slot, int16_t* const planes[3
   return t;
 }
 
+// Device-to-device output on a stream of the caller's (multi-GPU gather: the frame goes to a send buffer, NCCL takes it from there): the caller's stream
+// waits for everything submitted so far, the copies run on it, and later pictures wait for them before they overwrite the DPB buffer.
+B200_API int b200_get_frame_device_async(b200_ctx* c, int slot, int16_t* const planesDev[3], void* cudaStream)
+{
+  B200_CHECK(c && planesDev && slot >= 0 && slot < c->numSlots, "b200_get_frame_device_async: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(cudaStream);
+  const int buf = c->slotBuf[slot];
+  DevPlanes d = c->planes(buf);
+  B200_CUDA(cudaEventRecord(c->finalEv, c->stream));
+  B200_CUDA(cudaStreamWaitEvent(st, c->finalEv, 0));
+  for (int k = 0; k < (c->g.chromaFormat ? 3 : 1); k++) {
+    B200_CHECK(planesDev[k], "b200_get_frame_device_async: plane %d", k);
+    B200_CUDA(cudaMemcpyAsync(planesDev[k], d.p[k], (size_t)c->g.stride[k] * (k ? c->g.height >> 1 : c->g.height) * 2, cudaMemcpyDeviceToDevice, st));
+  }
+  B200_CUDA(cudaEventRecord(c->readDone[buf], st)); c->readPending[buf] = 1;
+  return 0;
+}
+
 B200_API size_t b200_frame_bytes(const b200_geom* g, int fmt, int comp)
 {
   if (!g || comp < 0 || comp > 2 || (comp && !g->chromaFormat)) return 0;
