@@ -252,7 +252,7 @@ def run_b200(args):
         n_local = -(-args.steps // args.gop)
         lengths = []
         for k in range(n_local * world): lengths.append(min(args.gop, args.steps - (k // world) * args.gop))
-        numel = W * H * 3 // 2
+        numel = W * H * 3                                                    # bytes of a 16-bit 4:2:0 frame
         G = gather.FrameGather(rank, world, lengths, numel, torch.device("cuda", local))
         side = torch.cuda.Stream()
         poff = [0, W * H, W * H + (W // 2) * (H // 2)]
@@ -280,7 +280,7 @@ def run_b200(args):
     ms_dev = max_over_ranks(ms.value)
     if G is not None and rank == 0:
         nb = G.bytes_received()
-        gather_info = {"frames_received": int(nb // (numel * 2)), "bytes": int(nb), "GBps_over_timed_region": round(nb / (ms_dev * 1e-3) / 1e9, 2),
+        gather_info = {"frames_received": int(nb // numel), "bytes": int(nb), "GBps_over_timed_region": round(nb / (ms_dev * 1e-3) / 1e9, 2),
                        "note": "display-order gather to rank 0 (NCCL send/recv per peer on a side stream), inside the timed region; NVLink 5: 900 GB/s per direction per GPU"}
 
     # ---- per-kernel-family device time (same schedule, events around each family) + the I / B split ----

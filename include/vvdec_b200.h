@@ -269,7 +269,15 @@ enum { B200_INTRA_PLANAR = 0, B200_INTRA_DC = 1 /* 2..66 angular */, B200_INTRA_
        B200_INTRA_LM = 70, B200_INTRA_MDLM_L = 71, B200_INTRA_MDLM_T = 72 /* cross-component linear model (LM_CHROMA_IDX, MDLM_L_IDX, MDLM_T_IDX), chroma only */ };
 enum { B200_INTRA_FILTER_REF = 1, B200_INTRA_AVAIL_TL = 2, B200_INTRA_ADD_RESI = 4 /* reconstruct: clip(pred + residual), see b200_intra_reconstruct */,
        B200_INTRA_LM_ABOVE = 8, B200_INTRA_LM_LEFT = 16 /* CCLM: the CU has an above / left neighbour (xGetLumaRecPixels :1461,:1464) */,
-       B200_INTRA_LM_COLLOCATED = 32 /* CCLM: sps_chroma_vertical_collocated_flag (SPS::getCclmCollocatedChromaFlag) */ };
+       B200_INTRA_LM_COLLOCATED = 32 /* CCLM: sps_chroma_vertical_collocated_flag (SPS::getCclmCollocatedChromaFlag) */,
+       B200_INTRA_ISP = 64 /* luma prediction region of an intra-sub-partition CU, see below */ };
+/* Intra sub-partitions (ISP: initIntraPatternChTypeISP IntraPrediction.cpp:966, DecCu.cpp:341-371, CU::getISPSplitDim UnitTools.cpp:360).  One luma record per
+ * PREDICTION REGION of the CU, in decoding order: a sub-partition, or — vertical splits of 4xN / 8xN CUs, whose sub-partitions are 1 / 2 samples wide — the 4-wide
+ * region that holds four / two of them (CU::isPredRegDiffFromTB).  x, y, log2w, log2h: the region; mode: the CU's final luma mode (planar, DC, angular);
+ * mip: split (1 horizontal: regions stacked top to bottom, 2 vertical) | region index << 2 | log2(regions of the CU) << 4 — the CU is rebuilt from them;
+ * numAbove / numLeft / B200_INTRA_AVAIL_TL: the CU-level neighbourhood (the CU's reference samples are fetched once, for 2W and 2H); lmLeft / lmAbove: the CU
+ * has a left / above neighbour CU; ciip: bit i = the i-th transform unit inside the region carries a residual (B200_INTRA_ADD_RESI: any).  A region reads the
+ * reconstruction of the region before it, so the records of a CU must follow each other. */
 typedef struct b200_intra_tu {
   uint16_t x, y;          /* top-left in the component's plane, samples                                              */
   uint8_t  log2w, log2h;  /* 2..6 (chroma: height may be 2 = log2h 1)                                                */

@@ -399,8 +399,68 @@ void orc_intra_isp_cu(const b200_geom* g, int16_t* luma, const int16_t* resi, in
   free(B);
 }
 
+/* One ISP prediction region from its record (B200_INTRA_ISP, include/vvdec_b200.h): the body of orc_intra_isp_cu for region k, the CU rebuilt from the record. */
+static int isp_cu_of(const b200_intra_tu* t, int* x0, int* y0, int* W, int* H)
+{
+  const int isp = t->mip & 3, k = (t->mip >> 2) & 3, nReg = 1 << ((t->mip >> 4) & 3), rw = 1 << t->log2w, rh = 1 << t->log2h;
+  if (isp == 1) { *W = rw; *H = rh * nReg; *x0 = t->x; *y0 = t->y - k * rh; } else { *W = rw * nReg; *H = rh; *x0 = t->x - k * rw; *y0 = t->y; }
+  return isp;
+}
+static void intra_isp_region(const b200_geom* g, int16_t* luma, const b200_intra_tu* t)
+{
+  int x0, y0, w, h;
+  const int hor = isp_cu_of(t, &x0, &y0, &w, &h) == 1, rw = 1 << t->log2w, rh = 1 << t->log2h, ox = t->x - x0, oy = t->y - y0;
+  const ptrdiff_t ps = g->stride[0];
+  const int pmax = (1 << g->bitDepth) - 1, S = 2 * w + 1, rows = 2 * h + 1, dirMode = t->mode;
+  const int leftAvail = t->lmLeft, aboveAvail = t->lmAbove;
+  int16_t* B = (int16_t*)calloc((size_t)S * rows + 64, sizeof(int16_t));
+  fill_ref(luma, ps, x0, y0, w, h, 0, 4, 4, (t->flags & B200_INTRA_AVAIL_TL) ? 1 : 0, t->numAbove, t->numLeft, g->bitDepth, B, S);
+  int16_t* W = B + oy * S + ox;
+  const int topLen = w + rw, leftLen = h + rh;
+  const int16_t* rec = luma + (ptrdiff_t)(y0 + oy) * ps + x0 + ox;
+  if (ox || oy) {
+    if (hor) {
+      for (int i = 0; i < rw; i++) W[1 + i] = rec[-ps + i];
+      for (int i = rw; i < topLen; i++) W[1 + i] = rec[-ps + rw - 1];
+      if (!leftAvail) for (int j = 0; j <= leftLen; j++) W[j * S] = rec[-ps];
+    } else {
+      for (int j = 0; j < rh; j++) W[(1 + j) * S] = rec[j * ps - 1];
+      for (int j = rh; j < leftLen; j++) W[(1 + j) * S] = rec[(rh - 1) * ps - 1];
+      if (!aboveAvail) for (int i = 0; i <= topLen; i++) W[i] = rec[-1];
+    }
+  }
+  int16_t* dst = luma + (ptrdiff_t)(y0 + oy) * ps + x0 + ox;
+  const int16_t* src = W; const int stride = S;
+  const int doPDPC = rw >= 4 && rh >= 4;
+  if (dirMode == 0) pred_planar(src, stride, rw, rh, dst, ps);
+  else if (dirMode == 1) {
+    int sum = 0; const int denom = rw == rh ? rw << 1 : imax(rw, rh);
+    if (rw >= rh) for (int i = 0; i < rw; i++) sum += AT(1 + i, 0);
+    if (rw <= rh) for (int i = 0; i < rh; i++) sum += AT(0, 1 + i);
+    const int16_t dc = (int16_t)((sum + (denom >> 1)) >> ilog2(denom));
+    for (int y = 0; y < rh; y++) for (int x = 0; x < rw; x++) dst[y * ps + x] = dc;
+  } else pred_angular_ex(src, stride, rw, rh, 0, dirMode, 0, doPDPC, pmax, dst, ps, topLen, leftLen, w, h, 1);
+  if (doPDPC && dirMode <= 1) {
+    const int scale = (ilog2(rw) - 2 + ilog2(rh) - 2 + 2) >> 2;
+    for (int y = 0; y < rh; y++) {
+      const int wT = 32 >> imin(31, (y << 1) >> scale), left = AT(0, y + 1);
+      for (int x = 0; x < rw; x++) { const int wL = 32 >> imin(31, (x << 1) >> scale), top = AT(x + 1, 0), v = dst[y * ps + x]; dst[y * ps + x] = (int16_t)(v + ((wL * (left - v) + wT * (top - v) + 32) >> 6)); }
+    }
+  }
+  free(B);
+}
+/* width of the transform units inside an ISP region (several only where the region is wider than the sub-partitions) */
+int orc_isp_tu_width(const b200_intra_tu* t)
+{
+  int x0, y0, w, h;
+  const int isp = isp_cu_of(t, &x0, &y0, &w, &h);
+  if (isp == 2 && (w == 4 || (w == 8 && h > 4))) return imax(w >> 2, h < 16 ? 16 / h : 1);
+  return 1 << t->log2w;
+}
+
 void orc_intra_tu(const b200_geom* g, int16_t* const planes[3], const b200_intra_tu* t)
 {
+  if (t->flags & B200_INTRA_ISP) { intra_isp_region(g, planes[0], t); return; }
   const int c = t->comp, w = 1 << t->log2w, h = 1 << t->log2h, mrl = c ? 0 : t->multiRefIdx, pmax = (1 << g->bitDepth) - 1;
   const int unit = c ? 2 : 4, stride = 2 * w + 1 + mrl, rows = 2 * h + 1 + mrl;
   int16_t* ref = (int16_t*)calloc((size_t)stride * rows * 2 + 64, sizeof(int16_t));
@@ -456,11 +516,14 @@ void orc_intra_reconstruct(const b200_geom* g, int16_t* const planes[3], const i
   for (size_t i = 0; i < numTus; i++) {
     const b200_intra_tu* t = &tus[i];
     orc_intra_tu(g, planes, t);
-    if (resi && resi[t->comp] && (t->flags & B200_INTRA_ADD_RESI))
+    if (resi && resi[t->comp] && (t->flags & B200_INTRA_ADD_RESI)) {
+      const int isp = t->flags & B200_INTRA_ISP, tw = isp ? orc_isp_tu_width(t) : 1 << t->log2w;
       for (int y = 0; y < (1 << t->log2h); y++)
         for (int x = 0; x < (1 << t->log2w); x++) {
+          if (isp && !((t->ciip >> (x / tw)) & 1)) continue;                 /* transform units of the region without a residual */
           const ptrdiff_t o = (ptrdiff_t)(t->y + y) * g->stride[t->comp] + t->x + x;
           planes[t->comp][o] = (int16_t)iclip(0, pmax, planes[t->comp][o] + resi[t->comp][o]);
         }
+    }
   }
 }

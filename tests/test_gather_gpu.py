@@ -26,7 +26,7 @@ def test_two_rank_nccl_gather_display_order(tmp_path):
         g = abi.make_geom(W, H, 10)
         ctx = C.c_void_p(); vvdec_b200.check(lib.b200_ctx_create(C.byref(ctx), C.byref(g), 4, 2, local))
         lengths = [3, 2, 4, 1]                                   # GOPs 0, 2 on rank 0; 1, 3 on rank 1
-        numel = W * H * 3 // 2
+        numel = W * H * 3                                         # bytes of a 16-bit 4:2:0 frame
         G = gather.FrameGather(r, w, lengths, numel, torch.device("cuda", local))
         side = torch.cuda.Stream()
         def frame(k, i):                                          # the content of frame i of GOP k
@@ -48,7 +48,7 @@ def test_two_rank_nccl_gather_display_order(tmp_path):
             got = store.cpu().numpy(); d = 0
             for k in range(len(lengths)):
                 for i in range(lengths[k]):
-                    want = np.concatenate([p.ravel() for p in frame(k, i)])
+                    want = np.concatenate([p.ravel() for p in frame(k, i)]).view(np.uint8)
                     assert np.array_equal(got[d], want), (k, i)
                     d += 1
             print("GATHER_OK", d)

@@ -101,7 +101,7 @@ INTRA_TU_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("log2w", "u1"), ("log2h"
                            ("numAbove", "u1"), ("numLeft", "u1"), ("mip", "u1"), ("lmAbove", "u1"), ("lmLeft", "u1"), ("ciip", "u1")])
 INTRA_FILTER_REF, INTRA_AVAIL_TL, INTRA_ADD_RESI = 1, 2, 4
 INTRA_BDPCM_HOR, INTRA_BDPCM_VER, INTRA_MIP, INTRA_LM, INTRA_MDLM_L, INTRA_MDLM_T = 67, 68, 69, 70, 71, 72
-INTRA_LM_ABOVE, INTRA_LM_LEFT, INTRA_LM_COLLOCATED = 8, 16, 32
+INTRA_LM_ABOVE, INTRA_LM_LEFT, INTRA_LM_COLLOCATED, INTRA_ISP = 8, 16, 32, 64
 
 
 class FilmGrain(C.Structure):

@@ -11,7 +11,8 @@ from . import gop_shard
 
 
 class FrameGather:
-    def __init__(self, rank: int, world: int, gop_lengths: Sequence[int], frame_numel: int, device, dtype=torch.int16):
+    def __init__(self, rank: int, world: int, gop_lengths: Sequence[int], frame_numel: int, device, dtype=torch.uint8):
+        # frames travel as bytes: torch's NCCL process group has no 16-bit integer type
         self.rank, self.world, self.numel = rank, world, frame_numel
         self.assignment = gop_shard.assign(len(gop_lengths), world)
         self.order = gop_shard.output_order(self.assignment, gop_lengths)              # display index -> (rank, local frame index)
@@ -46,5 +47,5 @@ class FrameGather:
         self.reqs = []
         return self.store
 
-    def bytes_received(self, itemsize=2) -> int:
+    def bytes_received(self, itemsize=1) -> int:
         return sum(1 for r, _ in self.order if r != 0) * self.numel * itemsize if self.rank == 0 else 0

@@ -225,12 +225,20 @@ class DecLibReconB200
         {
           // K6: one b200_intra_tu per TU component in decoding order (the order DecCu::predAndReco walks them, DecCu.cpp:284-288); the residual of
           // a coded component goes through K1 into the residual planes (B200_TU_RESI) and is added by K6
+          if( cu.ispMode() && isLuma( cu.chType() ) )
+          {
+            // intra sub-partitions: K6 takes the luma as one record per prediction region (the regions read each other's reconstruction, in order), K1 the
+            // residual of every sub-partition with a coded block flag — 1- and 2-sample-wide transform units included (TrQuant.cpp:466-482)
+            if( flattenIspCu( cu, [&]( const b200_intra_tu& q ) { r.intra.push_back( q ); } ) != FLATTEN_INTRA_OK ) THROW_UNSUPPORTED( "DecLibReconB200: ISP CU outside the device path" );
+            for( auto& tu : TUTraverser( &cu.firstTU, cu.lastTU->next ) ) { b200_tu t; if( flattenTU( tu, COMPONENT_Y, *m_trQuant, r.coefs, t ) ) { t.flags |= B200_TU_RESI; r.tus.push_back( t ); } }
+          }
           for( auto& tu : TUTraverser( &cu.firstTU, cu.lastTU->next ) )
             for( const CompArea& area : tu.blocks )
             {
               if( !area.valid() ) continue;
+              if( cu.ispMode() && isLuma( area.compID() ) ) continue;              // done above
               b200_intra_tu ir;
-              if( flattenIntraTU( tu, area.compID(), ir ) != FLATTEN_INTRA_OK ) THROW_UNSUPPORTED( "DecLibReconB200: ISP / ACT intra block (SURVEY 8f-1)" );
+              if( flattenIntraTU( tu, area.compID(), ir ) != FLATTEN_INTRA_OK ) THROW_UNSUPPORTED( "DecLibReconB200: ACT intra block (SURVEY 8f-1)" );
               b200_tu t;
               if( flattenTU( tu, area.compID(), *m_trQuant, r.coefs, t ) ) { t.flags |= B200_TU_RESI; r.tus.push_back( t ); }
               if( TU::getCbf( tu, area.compID() ) || ( isChroma( area.compID() ) && tu.jointCbCr ) ) ir.flags |= B200_INTRA_ADD_RESI;      // DecCu.cpp:390

@@ -74,10 +74,14 @@ inline FlattenIntraResult flattenIntraTU( const TransformUnit& tu, const Compone
 
   // neighbourhood (xFillReferenceSamples :1086-1130).  The reference analyses it once per TU, for the first component of the CU's channel
   // type, and reuses the three counts for the other components (m_lastCUidx, :1101): in a single tree the chroma blocks take the luma block's.
+  // ISP CUs: the luma of the first sub-partition analysed the whole CU (initIntraPatternChTypeISP :997, with cu.firstTU), and that is what the chroma blocks in the
+  // last transform unit inherit.
+  const bool        isp     = cu.ispMode() != 0;
+  const TransformUnit& tuA  = isp ? cu.firstTU : tu;
   const ComponentID anaComp = getFirstComponentOfChannel( cu.chType() );
   const ChannelType anaCh   = toChannelType( anaComp );
-  const CompArea&   ana     = tu.blocks[anaComp].valid() ? tu.blocks[anaComp] : area;
-  const ChannelType ch      = tu.blocks[anaComp].valid() ? anaCh : chType;
+  const CompArea&   ana     = isp ? cu.blocks[anaComp] : tu.blocks[anaComp].valid() ? tu.blocks[anaComp] : area;
+  const ChannelType ch      = ( isp || tu.blocks[anaComp].valid() ) ? anaCh : chType;
   const int csx = getChannelTypeScaleX( ch, pcv.chrFormat ), csy = getChannelTypeScaleY( ch, pcv.chrFormat );
   const int unitW = pcv.minCUWidth >> csx, unitH = pcv.minCUHeight >> csy;
   const int totalAbove = ( 2 * (int) ana.width + unitW - 1 ) / unitW, totalLeft = ( 2 * (int) ana.height + unitH - 1 ) / unitH;
@@ -86,9 +90,9 @@ inline FlattenIntraResult flattenIntraTU( const TransformUnit& tu, const Compone
   const bool sameCTU = ( posLT.x & ( pcv.maxCUWidthMask >> csx ) ) && ( posLT.y & ( pcv.maxCUHeightMask >> csy ) );
   if( sameCTU || cs.getCURestricted( posLT.offset( -1, -1 ), cu, ch, cu.left ? cu.left : cu.above ) ) r.flags |= B200_INTRA_AVAIL_TL;
   if( cu.above || ana.y > cu.blocks[ch].y )
-    r.numAbove = (uint8_t) ( numAbove + intraUnitsAvailable( tu, ch, Position( posLT.x + (PosType) ana.width, posLT.y ), totalAbove - numAbove, unitW, true ) );
+    r.numAbove = (uint8_t) ( numAbove + intraUnitsAvailable( tuA, ch, Position( posLT.x + (PosType) ana.width, posLT.y ), totalAbove - numAbove, unitW, true ) );
   if( cu.left || ana.x > cu.blocks[ch].x )
-    r.numLeft = (uint8_t) ( numLeft + intraUnitsAvailable( tu, ch, Position( posLT.x, posLT.y + (PosType) ana.height ), totalLeft - numLeft, unitH, false ) );
+    r.numLeft = (uint8_t) ( numLeft + intraUnitsAvailable( tuA, ch, Position( posLT.x, posLT.y + (PosType) ana.height ), totalLeft - numLeft, unitH, false ) );
   if( lm )
   {
     // CCLM: what xGetLumaRecPixels (:1461-1465) and xGetLMParameters (:1762-1795) derive from the CU map, in the chroma channel
@@ -104,6 +108,50 @@ inline FlattenIntraResult flattenIntraTU( const TransformUnit& tu, const Compone
       r.lmAbove = (uint8_t) ( aboveUnits + intraUnitsAvailable( tu, CHANNEL_TYPE_CHROMA, Position( area.x + (PosType) area.width, area.y ), std::min( totalAbove - aboveUnits, (int) area.height / unit ), unit, true ) );
     if( finalMode == MDLM_L_IDX && left )
       r.lmLeft = (uint8_t) ( leftUnits + intraUnitsAvailable( tu, CHANNEL_TYPE_CHROMA, Position( area.x, area.y + (PosType) area.height ), std::min( totalLeft - leftUnits, (int) area.width / unit ), unit, false ) );
+  }
+  return FLATTEN_INTRA_OK;
+}
+
+// ISP CU: one B200_INTRA_ISP record per luma prediction region (include/vvdec_b200.h), in decoding order.  The CU-level neighbourhood is what
+// initIntraPatternChTypeISP (IntraPrediction.cpp:966) derives with its first call; the per-region availability of the CU's left / above neighbour (:971-972)
+// is the CU's.  emit( const b200_intra_tu& ) is called per region.
+template<class Emit>
+inline FlattenIntraResult flattenIspCu( const CodingUnit& cu, Emit emit )
+{
+  if( !cu.ispMode() || !isLuma( cu.chType() ) || cu.colorTransform() || cu.mipFlag() || cu.multiRefIdx() || cu.bdpcmMode() ) return FLATTEN_INTRA_UNSUPPORTED;
+  const CodingStructure& cs = *cu.cs; const PreCalcValues& pcv = *cs.pcv;
+  const CompArea& Y = cu.Y();
+  const int W = Y.width, H = Y.height;
+  const bool hor = cu.ispMode() == HOR_INTRA_SUBPARTITIONS;
+  const int part = (int) CU::getISPSplitDim( W, H, hor ? TU_1D_HORZ_SPLIT : TU_1D_VERT_SPLIT );
+  const bool regDiff = CU::isPredRegDiffFromTB( cu, COMPONENT_Y );                  // vertical split with sub-partitions narrower than 4
+  const int rw = hor ? W : ( regDiff ? 4 : part ), rh = hor ? part : H, nReg = hor ? H / part : W / rw;
+  b200_intra_tu base; memset( &base, 0, sizeof( base ) );
+  base.comp = 0; base.mode = (uint8_t) PU::getFinalIntraMode( cu, CH_L ); base.flags = B200_INTRA_ISP;
+  base.log2w = (uint8_t) getLog2( rw ); base.log2h = (uint8_t) getLog2( rh );
+  // CU-level neighbourhood (xFillReferenceSamples :1098-1130 on cu.Y() with cu.firstTU)
+  const int unit = pcv.minCUWidth, totalAbove = ( 2 * W + unit - 1 ) / unit, totalLeft = ( 2 * H + unit - 1 ) / unit, numAbove = W / unit, numLeft = H / unit;
+  const Position posLT = Y.pos();
+  const bool sameCTU = ( posLT.x & pcv.maxCUWidthMask ) && ( posLT.y & pcv.maxCUHeightMask );
+  if( sameCTU || cs.getCURestricted( posLT.offset( -1, -1 ), cu, CH_L, cu.left ? cu.left : cu.above ) ) base.flags |= B200_INTRA_AVAIL_TL;
+  if( cu.above ) base.numAbove = (uint8_t) ( numAbove + intraUnitsAvailable( cu.firstTU, CH_L, Position( posLT.x + W, posLT.y ), totalAbove - numAbove, unit, true ) );
+  if( cu.left )  base.numLeft  = (uint8_t) ( numLeft  + intraUnitsAvailable( cu.firstTU, CH_L, Position( posLT.x, posLT.y + H ), totalLeft - numLeft, unit, false ) );
+  base.lmLeft  = nullptr != cs.getCURestricted( posLT.offset( -1, 0 ), cu, CH_L, cu.left );
+  base.lmAbove = nullptr != cs.getCURestricted( posLT.offset( 0, -1 ), cu, CH_L, cu.above );
+  // residual flags of the transform units, region by region
+  const TransformUnit* tu = &cu.firstTU;
+  const int tusPerReg = regDiff ? rw / part : 1;
+  for( int k = 0; k < nReg; k++ )
+  {
+    b200_intra_tu r = base;
+    r.x = (uint16_t) ( Y.x + ( hor ? 0 : k * rw ) ); r.y = (uint16_t) ( Y.y + ( hor ? k * rh : 0 ) );
+    r.mip = (uint8_t) ( cu.ispMode() | ( k << 2 ) | ( getLog2( nReg ) << 4 ) );
+    for( int i = 0; i < tusPerReg; i++, tu = tu->next )
+    {
+      if( !tu ) return FLATTEN_INTRA_UNSUPPORTED;
+      if( TU::getCbf( *tu, COMPONENT_Y ) ) { r.ciip |= (uint8_t) ( 1 << i ); r.flags |= B200_INTRA_ADD_RESI; }
+    }
+    emit( r );
   }
   return FLATTEN_INTRA_OK;
 }
