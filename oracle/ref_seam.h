@@ -543,6 +543,7 @@ static void setupSps( FakePicture& fp, const ref_seam_cfg& c, const b200_geom& g
   ph.setMaxNumAffineMergeCand( c.affinePct > 0 ? 5 : 0 ); ph.setEnableTMVPFlag( false ); ph.setMvdL1ZeroFlag( false );
   ph.setDisBdofFlag( false ); ph.setDisDmvrFlag( false ); ph.setDisProfFlag( false ); ph.setJointCbCrSignFlag( ( c.seed >> 1 ) & 1 );
   ph.setSplitConsOverrideFlag( false ); ph.setDisFracMMVD( false );
+  ph.setVirtualBoundariesPresentFlag( c.tools & SEAM_VIRTUAL_BOUNDARIES ); ph.setNumVerVirtualBoundaries( 0 ); ph.setNumHorVirtualBoundaries( 0 );
   (void) g;
 }
 

@@ -60,6 +60,38 @@ def test_k1_every_size_dense_extreme(b200, oracle):
     assert np.array_equal(a[0], b[0])
 
 
+def test_k1_isp_thin_partitions(b200, oracle):
+    """One-sample-wide / -high luma transform units (sub-partitions of 4xN / Nx4 ISP CUs, TrQuant.cpp:466-482): a single 1-D stage with the combined shift;
+    DCT-2 and the implicit DST-7 (length 16), sparse and full corners, DC-only, extreme levels.  A thin chroma block or a thin block with LFNST is refused."""
+    rng = np.random.default_rng(21)
+    recs, coefs, n = [], [], 0
+    W, H = 512, 256
+    x = y = 0
+    for rep in range(6):
+        for l2 in (4, 5, 6):
+            for vert in (0, 1):
+                for tr in ((0, 2) if l2 == 4 else (0,)):
+                    w, h = (1, 1 << l2) if vert else (1 << l2, 1)
+                    lim = min(1 << l2, 32)
+                    m = [lim, 1, int(rng.integers(1, lim + 1))][rep % 3]
+                    if x + w > W: x = 0; y += 64
+                    lv = rng.choice(np.array([-32768, 32767, -1, 1, 0, 1234, -77], np.int16), size=m) if rep < 3 else rng.integers(-300, 300, size=m).astype(np.int16)
+                    lv[-1] = 911
+                    trType = (tr << 2) if vert else tr
+                    recs.append((x, y, 0 if vert else l2, l2 if vert else 0, 0, 0, 0 if vert else m - 1, m - 1 if vert else 0, trType, 0, 0, int(rng.integers(-1, 5)), 16, [64, 90][l2 & 1], n, 0, (0, 0)))
+                    coefs.append(lv); n += len(lv); x += max(w, 4)
+    tus = np.array(recs, dtype=abi.TU_DTYPE); arena = np.concatenate(coefs)
+    for bd, mode in ((10, 1), (8, 0), (12, 0)):
+        planes = synth.noise_planes(rng, W, H, bd)
+        a, b = _run_both(b200, oracle, W, H, bd, tus, arena, planes, mode)
+        assert np.array_equal(a[0], b[0]), (bd, mode, np.argwhere(a[0] != b[0])[:5])
+    g = abi.make_geom(W, H, 10)
+    planes = synth.noise_planes(rng, W, H, 10)
+    for field, val in (("comp", 1), ("lfnst", 1)):
+        bad = tus[:1].copy(); bad[field] = val
+        assert b200.b200_k1_residual(C.byref(g), abi.plane_ptrs(planes), bad.ctypes.data, 1, arena.ctypes.data, len(arena), None, 0, 0) != 0
+
+
 def test_k1_empty_and_errors(b200):
     g = abi.make_geom(64, 64, 10)
     planes = [np.zeros((64, 64), np.int16), np.zeros((32, 32), np.int16), np.zeros((32, 32), np.int16)]

@@ -31,6 +31,30 @@ def test_intra_picture_vs_oracle(b200, oracle, W, H, bd, ctu, min_size, p_resi, 
     assert all((recs["mode"] == m).any() for m in (abi.INTRA_LM, abi.INTRA_MDLM_L, abi.INTRA_MDLM_T))
 
 
+@pytest.mark.parametrize("W,H,bd,ctu,min_size,seed", [(256, 128, 10, 128, 4, 11), (416, 240, 8, 64, 4, 12), (832, 480, 10, 128, 8, 13), (1920, 1080, 10, 128, 4, 14)])
+def test_intra_sub_partitions_vs_oracle(b200, oracle, W, H, bd, ctu, min_size, seed):
+    """ISP CUs among regular ones (one record per prediction region, thin regions, per-TU residual masks): the small pictures run the one-CTA-per-block
+    kernel, the dense 1080p list the CTU-resident one."""
+    rng = np.random.default_rng(seed)
+    g = abi.make_geom(W, H, bd, ctu=ctu)
+    layout = synth.gen_intra_layout(rng, W, H, ctu, min_size=min_size)
+    recs = synth.gen_intra_records(rng, layout, W, H, p_resi=0.5, p_lm=0.2, p_isp=0.4)
+    isp = recs[(recs["flags"] & abi.INTRA_ISP) != 0]
+    assert len(isp) > 20 and (isp["log2h"] == 0).any() and ((isp["mip"] & 3) == 2).any() and (isp["ciip"] > 1).any()
+    planes = synth.noise_planes(rng, W, H, bd)
+    resi = [rng.integers(-40, 41, size=p.shape).astype(np.int16) for p in planes]
+    want = [p.copy() for p in planes]; got = [p.copy() for p in planes]
+    oracle.orc_intra_reconstruct(C.byref(g), abi.plane_ptrs(want), abi.plane_ptrs(resi), recs.ctypes.data, len(recs))
+    vvdec_b200.check(b200.b200_intra_reconstruct(C.byref(g), abi.plane_ptrs(got), abi.plane_ptrs(resi), recs.ctypes.data, len(recs)))
+    for c in range(3):
+        bad = np.argwhere(got[c] != want[c])
+        assert len(bad) == 0, (c, len(bad), bad[:4].tolist())
+    # a region whose predecessor is missing is refused
+    k = int(np.flatnonzero(((recs["flags"] & abi.INTRA_ISP) != 0) & (((recs["mip"] >> 2) & 3) == 1))[0])
+    broken = np.delete(recs, k - 1)
+    assert b200.b200_intra_reconstruct(C.byref(g), abi.plane_ptrs(got), abi.plane_ptrs(resi), broken.ctypes.data, len(broken)) == -2 and b"ISP" in b200.b200_last_error()
+
+
 def test_intra_predict_only_and_golden(b200, oracle):
     z = np.load(GOLD)
     W, H, bd, ctu = [int(v) for v in z["geom"]]

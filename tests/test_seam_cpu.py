@@ -20,6 +20,8 @@ CASES = {
     "B_lmcs_inter": dict(lmcs=True, intra=0, tools=T_INTER),                    # LMCS with chroma scaling; inter CUs only
     "B_lmcs_intra_ciip": dict(lmcs=True),                                       # ... with intra and CIIP CUs (mapped-domain intra, luma-first ordering of the chroma scales)
     "I_lmcs": dict(lmcs=True, slice_type=2),
+    "B_isp": dict(isp=40),                                                      # intra sub-partitions among the intra CUs
+    "I_isp_lmcs": dict(isp=60, slice_type=2, lmcs=True),
     "B_ctu64": dict(ctu=64),
     "B_ctu32_8bit": dict(ctu=32, bd=8),
     "B_no_dmvr": dict(tools=(helpers.SEAM_INTER_TOOLS | helpers.SEAM_RESI_TOOLS | helpers.SEAM_INTRA_TOOLS | helpers.SEAM_FILTERS) & ~helpers.SEAM["DMVR"]),
@@ -66,10 +68,9 @@ def test_1080p_picture():
 
 
 def test_unsupported_tool_follows_the_error_contract():
-    """An ISP picture: the stock back end reconstructs it; DecLibReconB200 throws UnsupportedFeatureException inside a pool task, which must surface
-    as pic->error + reconDone exception (DecLibRecon.cpp:704-715) — rc -4 here — and leave the recon object usable for the next picture."""
-    case = helpers.SeamCase(ref, np.random.default_rng(5), 416, 240, isp=40)
-    assert case.stats()["isp"] > 0
+    """A picture whose header announces virtual boundaries: the stock back end reconstructs it; DecLibReconB200 throws UnsupportedFeatureException,
+    which must surface as pic->error + reconDone exception (DecLibRecon.cpp:704-715) — rc -4 here — and leave the recon object usable for the next picture."""
+    case = helpers.SeamCase(ref, np.random.default_rng(5), 416, 240, virtual_boundaries=True)
     case.run_stock(threads=0)
     pic, rc = case.flatten(threads=0)
     assert pic is None and rc == -4.0

@@ -24,7 +24,8 @@ def both(seed, W, H, threads=4, **kw):
 
 @pytest.mark.parametrize("name,kw", [("B_mixed_intra", dict()), ("I_picture", dict(slice_type=2)), ("P_picture", dict(slice_type=1)),
                                      ("B_lmcs_inter", dict(lmcs=True, intra=0, tools=T_INTER)), ("B_lmcs_intra_ciip", dict(lmcs=True)), ("I_lmcs", dict(lmcs=True, slice_type=2)),
-                                     ("B_ctu64", dict(ctu=64))])
+                                     ("B_ctu64", dict(ctu=64)),
+                                     ("B_isp", dict(isp=40)), ("I_isp", dict(isp=60, slice_type=2)), ("I_isp_lmcs", dict(isp=60, slice_type=2, lmcs=True)), ("I_isp_ctu32", dict(isp=70, slice_type=2, ctu=32))])
 @pytest.mark.parametrize("seed", [1, 2])
 def test_seam_small(name, kw, seed):
     both(seed, 416, 240, **kw)
@@ -35,10 +36,12 @@ def test_seam_1080p_and_4k():
     both(32, 3840, 2160, threads=16)
     both(33, 3840, 2160, threads=16, lmcs=True)
     both(34, 3840, 2160, threads=16, lmcs=True, slice_type=2)
+    both(35, 3840, 2160, threads=16, isp=50, slice_type=2)                   # dense list: the CTU-resident K6
+    both(36, 3840, 2160, threads=16, isp=50)                                 # sparse list: one CTA per block
 
 
 def test_seam_error_contract_on_the_device_path():
-    case = helpers.SeamCase(ref, np.random.default_rng(5), 416, 240, isp=40)
+    case = helpers.SeamCase(ref, np.random.default_rng(5), 416, 240, virtual_boundaries=True)
     _, _, rc = case.run_b200(threads=2)
     assert rc == -4.0
     both(6, 416, 240)

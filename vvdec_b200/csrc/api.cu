@@ -194,6 +194,7 @@ B200_API int b200_intra_reconstruct(const b200_geom* g, int16_t* const planes[3]
   for (size_t i = 0; i < numTus; i++) {                      // kernel-level wrapper: records are checked here (the picture path checks on the device)
     const b200_intra_tu& t = tus[i];
     const int w = 1 << t.log2w, h = 1 << t.log2h, pw = t.comp ? g->width >> 1 : g->width, ph = t.comp ? g->height >> 1 : g->height, unit = t.comp ? 2 : 4;
+    if (t.flags & B200_INTRA_ISP) { B200_CHECK(intra_isp_record_ok(t, i ? &tus[i - 1] : nullptr, g->width, g->height), "b200_intra_reconstruct: record %zu: bad ISP region", i); continue; }
     B200_CHECK(t.comp < nPl && t.log2w >= 2 && t.log2w <= 6 && t.log2h >= 1 && t.log2h <= 6 && t.x + w <= pw && t.y + h <= ph && !(t.x % unit) && !(t.y % unit),
                "b200_intra_reconstruct: record %zu: bad geometry", i);
     B200_CHECK(t.mode <= B200_INTRA_MDLM_T && t.multiRefIdx <= 2 && (!t.multiRefIdx || !t.comp), "b200_intra_reconstruct: record %zu: bad mode / reference line", i);

@@ -95,7 +95,9 @@ __device__ __forceinline__ int tu_class(const b200_tu* tus, int i, bool& ok, con
 {
   const b200_tu& t = tus[i];
   const int l2w = t.log2w, l2h = t.log2h, m = max(l2w, l2h);
-  ok = l2w >= 1 && l2h >= 1 && m <= 6 && t.comp < 3;
+  ok = m <= 6 && t.comp < 3;
+  // one-sample-wide / -high blocks exist only as luma sub-partitions of an ISP CU (4xN, N >= 16 and the transpose): regular transform, no LFNST
+  if ((l2w == 0 || l2h == 0) && (t.comp != 0 || m < 4 || l2w == l2h || t.lfnst || t.ict || (t.flags & (B200_TU_TS | B200_TU_BDPCM_H | B200_TU_BDPCM_V)))) ok = false;
   if (ok) {
     // inside its plane (the joint-CbCr partner plane has the same geometry), level corner and scaling table inside their arrays
     const int w = 1 << l2w, h = 1 << l2h, pw = t.comp ? lim.W >> 1 : lim.W, ph = t.comp ? lim.H >> 1 : lim.H;

@@ -165,6 +165,21 @@ struct IntraLaunch { b200_geom geom; DevPlanes planes; const int16_t* resi[3]; c
                                                 // the chroma residual scale of a VPDU is derived from the finished luma, so luma goes first)
                    };
 inline size_t intra_order_ints(const b200_geom& g, size_t numTus) { return numTus + 8 + 3 * (size_t)((g.width + g.ctuSize - 1) / g.ctuSize) * ((g.height + g.ctuSize - 1) / g.ctuSize); }
+// ISP region record (B200_INTRA_ISP, include/vvdec_b200.h): everything K6 derives addresses from.  prev = the record before it in the list (null for the first).
+__host__ __device__ inline bool intra_isp_record_ok(const b200_intra_tu& t, const b200_intra_tu* prev, int W, int H)
+{
+  const int sp = t.mip & 3, k = (t.mip >> 2) & 3, l2n = (t.mip >> 4) & 3, nReg = 1 << l2n, rw = 1 << t.log2w, rh = 1 << t.log2h;
+  if (t.comp || t.mode > 66 || t.multiRefIdx || (sp != 1 && sp != 2) || l2n < 1 || l2n > 2 || k >= nReg || (t.mip >> 6) || t.log2w < 2 || t.log2w > 6 || t.log2h > 6) return false;
+  const int cw = sp == 2 ? rw * nReg : rw, ch = sp == 1 ? rh * nReg : rh, cx = t.x - (sp == 2 ? k * rw : 0), cy = t.y - (sp == 1 ? k * rh : 0);
+  if (cw > 64 || ch > 64 || ch < 4 || cw * ch < 32 || cx < 0 || cy < 0 || (cx & 3) || (cy & 3) || cx + cw > W || cy + ch > H) return false;
+  if (t.numAbove > 2 * cw / 4 || t.numLeft > 2 * ch / 4 || (t.numAbove && !cy) || (t.numLeft && !cx) || ((t.flags & B200_INTRA_AVAIL_TL) && (!cx || !cy))
+      || cx + (int)t.numAbove * 4 > W || cy + (int)t.numLeft * 4 > H || (t.lmLeft && !cx) || (t.lmAbove && !cy)) return false;
+  if (k) {                                                     // the region before it is the record before it
+    if (!prev || !(prev->flags & B200_INTRA_ISP) || prev->mip != (uint8_t)(t.mip - 4) || prev->log2w != t.log2w || prev->log2h != t.log2h || prev->mode != t.mode
+        || prev->x != t.x - (sp == 2 ? rw : 0) || prev->y != t.y - (sp == 1 ? rh : 0)) return false;
+  }
+  return true;
+}
 int launch_intra(const IntraLaunch& L, cudaStream_t s);
 int launch_intra_validate(const b200_intra_tu* tus, size_t numTus, const b200_geom& g, int* meta, cudaStream_t s);   // error bit 8 of the PU meta block (after launch_mc_bucket)
 int launch_film_grain(const DevPlanes& src, const DevPlanes& dst, const b200_geom& g, const int8_t* pattern, const uint8_t* sLUT, const uint8_t* pLUT,

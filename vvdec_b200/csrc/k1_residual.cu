@@ -195,8 +195,9 @@ __device__ __forceinline__ void k1_tu(const b200_tu* __restrict__ tus, int t, co
 
   // ---- 4. DC-only shortcut (TrQuant.cpp:429-448) ----
   if (maxX == 0 && maxY == 0 && trH == B200_TR_DCT2 && trV == B200_TR_DCT2) {
-    int dc = ((int)cb[0] * 64 + (1 << (shift1 - 1))) >> shift1;
-    dc = (dc * 64 + (1 << (shift2 - 1))) >> shift2;
+    int dc;
+    if (w > 1 && h > 1) { dc = ((int)cb[0] * 64 + (1 << (shift1 - 1))) >> shift1; dc = (dc * 64 + (1 << (shift2 - 1))) >> shift2; }
+    else                { dc = ((int)cb[0] * 64 + (1 << shift2)) >> (shift2 + 1); }       // one-sample-wide ISP partition: a single stage (:436)
     for (int i = lane; i < w * h; i += G) emit(i & (w - 1), i >> log2w, dc);
     return;
   }
@@ -206,6 +207,22 @@ __device__ __forceinline__ void k1_tu(const b200_tu* __restrict__ tus, int t, co
   const int zoH = (trV != B200_TR_DCT2 && h == 32) ? 16 : min(h, 32);
   const int nCols = min(maxX + 1, zoW);   // = w - skipWidth
   const int nRows = min(maxY + 1, zoH);   // = h - skipHeight
+
+  // ---- 5b. one-sample-wide / -high luma partitions of an ISP CU: one 1-D stage with the combined shift, no intermediate clip (TrQuant.cpp:466-482) ----
+  if (w == 1 || h == 1) {
+    const bool vert = w == 1;
+    const int n = vert ? h : w, nIn = vert ? nRows : nCols, cstep = vert ? 1 : 2, sh = shift2 + 1;
+    const int16_t* mp = tr_pair(vert ? trV : trH, vert ? log2h : log2w);
+    for (int j = lane; j < n; j += G) {
+      int acc = 0;
+      for (int k = 0; k < nIn; k++) {
+        const int mm = __ldg(mp + (k >> 1) * n + j);
+        acc += (int)cb[k * cstep] * ((k & 1) ? (int)(int8_t)(mm >> 8) : (int)(int8_t)(mm & 0xff));
+      }
+      emit(vert ? 0 : j, vert ? j : 0, clip16((acc + (1 << (sh - 1))) >> sh));
+    }
+    return;
+  }
 
   // ---- 6. stage 1: vertical, round >>7, clip to 16 bit (TrQuant_EMT.cpp:103-121, clip branch) ----
   // item = (column, group of 4 output rows); output columns are stored in pairs for stage 2; an odd last column gets a zero partner

@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(256) intra_owner_kernel(const IntraParams P)
   const int i = blockIdx.x;
   const b200_intra_tu t = P.tus[i];
   const int c = t.comp, unit = c ? 2 : 4, uw = max(1, (1 << t.log2w) / unit), uh = max(1, (1 << t.log2h) / unit);
-  for (int k = threadIdx.x; k < uw * uh; k += blockDim.x) P.owner[c][(t.y / unit + k / uw) * P.ownerStride[c] + t.x / unit + k % uw] = i;
+  // ISP regions can be 1 or 2 rows high: several share a unit, the last of them completes it
+  for (int k = threadIdx.x; k < uw * uh; k += blockDim.x) atomicMax(&P.owner[c][(t.y / unit + k / uw) * P.ownerStride[c] + t.x / unit + k % uw], i);
 }
 
 // Processing order.  The list is in decoding order (CTU raster); handing tickets out in that order keeps only the next few CTUs of a CTU row
@@ -91,6 +92,52 @@ __global__ void __launch_bounds__(256) intra_perm_kernel(const IntraParams P, in
 
 __device__ __forceinline__ int pix(const int16_t* __restrict__ plane, int stride, int x, int y) { return __ldcg(plane + (size_t)y * stride + x); }
 
+// ISP regions (B200_INTRA_ISP): the neighbourhood in the record is the CU's (bx, by, bw, bh rebuilt from the region and its index); region k > 0 takes the row
+// above (horizontal split) / the column left (vertical split) from the region before it, padded with its last sample, and the other side from the CU's
+// reference arrays at the region's offset — or, where the CU has no neighbour on that side, the sample next to the region's corner
+// (initIntraPatternChTypeISP, IntraPrediction.cpp:966-1070).  topLen / sideLen: m_topRefLength / m_leftRefLength.
+#define ISP_GEOMETRY \
+    const bool isp = t.flags & B200_INTRA_ISP; \
+    int bx = x0, by = y0, bw = w, bh = h, ispK = 0, ispSplit = 0, resiMask = 0xff, l2tu = 16; \
+    if (isp) { \
+      ispSplit = t.mip & 3; ispK = (t.mip >> 2) & 3; const int nReg_ = 1 << ((t.mip >> 4) & 3); \
+      if (ispSplit == 1) { bh = h * nReg_; by = y0 - ispK * h; } else { bw = w * nReg_; bx = x0 - ispK * w; } \
+      int tuW_ = w; if (ispSplit == 2 && (bw == 4 || (bw == 8 && bh > 4))) tuW_ = max(bw >> 2, bh < 16 ? 16 / bh : 1);      /* transform units narrower than the region */ \
+      l2tu = 31 - __clz(tuW_); resiMask = t.ciip; \
+    } \
+    const int topLen = isp ? bw + w : 2 * w, sideLen = isp ? bh + h : 2 * h;
+
+#define ISP_REFERENCE_LAMBDAS \
+    auto refT = [&](int j) -> int {                              /* row above (bx, by) incl. the corner: xFillReferenceSamples :1072 */ \
+      if (n == 0) return 1 << (P.bitDepth - 1); \
+      if (n == totalUnits) return PIXR(bx - 1 - mrl + j, by - 1 - mrl); \
+      if (j <= mrl) {                                            /* corner part of the row */ \
+        if (numLeft > 0) return availTL ? PIXR(bx - 1 - mrl + j, by - 1 - mrl) : PIXR(bx - 1 - mrl, by); \
+        return PIXR(bx, by - 1 - mrl); \
+      } \
+      if (numAbove) return PIXR(bx + min(j - 1 - mrl, aboveLen - 1), by - 1 - mrl); \
+      return availTL ? PIXR(bx - 1, by - 1 - mrl) : PIXR(bx - 1 - mrl, by);      /* = T[mrl]; numLeft > 0 here */ \
+    }; \
+    auto refL = [&](int i) -> int {                              /* left column, i >= 1 */ \
+      if (n == 0) return 1 << (P.bitDepth - 1); \
+      if (n == totalUnits) return PIXR(bx - 1 - mrl, by - 1 - mrl + i); \
+      if (numLeft > 0) { \
+        if (i <= mrl) return availTL ? PIXR(bx - 1 - mrl, by - 1 - mrl + i) : PIXR(bx - 1 - mrl, by); \
+        return PIXR(bx - 1 - mrl, by + min(i - 1 - mrl, leftLen - 1)); \
+      } \
+      return PIXR(bx, by - 1 - mrl); \
+    }; \
+    auto regT = [&](int j) -> int { \
+      if (!ispK) return refT(j); \
+      if (ispSplit == 1) return j == 0 ? (t.lmLeft ? refL(y0 - by) : PIXR(x0, y0 - 1)) : PIXR(x0 + min(j - 1, w - 1), y0 - 1); \
+      return t.lmAbove ? refT(x0 - bx + j) : PIXR(x0 - 1, y0); \
+    }; \
+    auto regL = [&](int i) -> int { \
+      if (!ispK) return refL(i); \
+      if (ispSplit == 1) return t.lmLeft ? refL(y0 - by + i) : PIXR(x0, y0 - 1); \
+      return PIXR(x0 - 1, y0 + min(i - 1, h - 1)); \
+    };
+
 __global__ void __launch_bounds__(IT_THREADS, 12) intra_kernel(const IntraParams P)
 {
   __shared__ int16_t sT[2][IT_REF], sL[2][IT_REF];          // [0] unfiltered, [1] filtered
@@ -112,14 +159,19 @@ __global__ void __launch_bounds__(IT_THREADS, 12) intra_kernel(const IntraParams
     const int x0 = t.x, y0 = t.y, ps = P.stride[c], pmax = (1 << P.bitDepth) - 1;
     const int16_t* plane = P.planes[c];
     const int availTL = (t.flags & B200_INTRA_AVAIL_TL) ? 1 : 0, numAbove = t.numAbove, numLeft = t.numLeft;
+    ISP_GEOMETRY
 
     // ---- wait for the earlier blocks this one reads from
     {
+      if (ispK && tid == 0) {                                          // ISP: the region before this one is the record before it
+        const volatile int* d = P.done + me - 1; const volatile int* e = P.err; int spins = 0;
+        while (*d == 0) { __nanosleep(64); if (*e || ++spins > (1 << 22)) { atomicOr(P.err, 1); break; } }
+      }
       for (int dep = tid; dep < 96; dep += IT_THREADS) {               // dependency slots: 0 corner, 1..32 above units, 64..95 left units
       int ux = -1, uy = -1;
-      if (dep == 0) { if (availTL) { ux = x0 - 1; uy = y0 - 1; } }
-      else if (dep <= numAbove) { ux = x0 + (dep - 1) * unit; uy = y0 - 1; }
-      else if (dep - 64 >= 0 && dep - 64 < numLeft) { ux = x0 - 1; uy = y0 + (dep - 64) * unit; }
+      if (dep == 0) { if (availTL) { ux = bx - 1; uy = by - 1; } }
+      else if (dep <= numAbove) { ux = bx + (dep - 1) * unit; uy = by - 1; }
+      else if (dep - 64 >= 0 && dep - 64 < numLeft) { ux = bx - 1; uy = by + (dep - 64) * unit; }
       if (ux >= 0 && uy >= 0) {
         const int o = P.owner[c][(uy / unit) * P.ownerStride[c] + ux / unit];
         if (o >= 0 && o < me) {
@@ -151,35 +203,16 @@ __global__ void __launch_bounds__(IT_THREADS, 12) intra_kernel(const IntraParams
     __syncthreads();
 
     // ---- reference samples (xFillReferenceSamples): T[j] = row above incl. the corner, L[i] = left column, T[0] = L[0] = corner
-    const int predSize = 2 * w, predHSize = 2 * h;
+    // (bx, by, bw, bh): the block the neighbourhood was analysed for — the block itself, or the CU of an ISP region
+    const int predSize = 2 * bw, predHSize = 2 * bh;
     const int totalUnits = (predSize + unit - 1) / unit + (predHSize + unit - 1) / unit + 1, n = availTL + numAbove + numLeft;
     const int aboveLen = min(numAbove * unit, predSize), leftLen = min(numLeft * unit, predHSize);
     int16_t *T = sT[0], *L = sL[0];
-    for (int j = tid; j <= predSize + mrl; j += IT_THREADS) {
-      int v;
-      if (n == 0) v = 1 << (P.bitDepth - 1);
-      else if (n == totalUnits) v = pix(plane, ps, x0 - 1 - mrl + j, y0 - 1 - mrl);
-      else if (j <= mrl) {                                     // corner part of the row
-        if (numLeft > 0) v = availTL ? pix(plane, ps, x0 - 1 - mrl + j, y0 - 1 - mrl) : pix(plane, ps, x0 - 1 - mrl, y0);
-        else v = pix(plane, ps, x0, y0 - 1 - mrl);
-      } else {
-        const int k = j - 1 - mrl;
-        if (numAbove) v = pix(plane, ps, x0 + min(k, aboveLen - 1), y0 - 1 - mrl);
-        else v = availTL ? pix(plane, ps, x0 - 1, y0 - 1 - mrl) : pix(plane, ps, x0 - 1 - mrl, y0);    // = T[mrl]; numLeft > 0 here
-      }
-      T[j] = (int16_t)v;
-    }
-    for (int i = tid; i <= predHSize + mrl; i += IT_THREADS) {
-      if (i == 0) continue;                                    // L[0] is T[0], set below
-      int v;
-      if (n == 0) v = 1 << (P.bitDepth - 1);
-      else if (n == totalUnits) v = pix(plane, ps, x0 - 1 - mrl, y0 - 1 - mrl + i);
-      else if (numLeft > 0) {
-        if (i <= mrl) v = availTL ? pix(plane, ps, x0 - 1 - mrl, y0 - 1 - mrl + i) : pix(plane, ps, x0 - 1 - mrl, y0);
-        else v = pix(plane, ps, x0 - 1 - mrl, y0 + min(i - 1 - mrl, leftLen - 1));
-      } else v = pix(plane, ps, x0, y0 - 1 - mrl);
-      L[i] = (int16_t)v;
-    }
+#define PIXR(x, y) pix(plane, ps, (x), (y))
+    ISP_REFERENCE_LAMBDAS
+    for (int j = tid; j <= topLen + mrl; j += IT_THREADS) T[j] = (int16_t)regT(j);
+    for (int i = tid + 1; i <= sideLen + mrl; i += IT_THREADS) L[i] = (int16_t)regL(i);       // L[0] is T[0], set below
+#undef PIXR
     __syncthreads();
     if (tid == 0) L[0] = T[0];
     __syncthreads();
@@ -199,9 +232,9 @@ __global__ void __launch_bounds__(IT_THREADS, 12) intra_kernel(const IntraParams
     const bool doPDPC = w >= 4 && h >= 4 && mrl == 0;
     int16_t* dst = P.planes[c] + (size_t)y0 * ps + x0;
     const int16_t* rs = (P.resi[c] && (t.flags & B200_INTRA_ADD_RESI)) ? P.resi[c] + (size_t)y0 * ps + x0 : nullptr;
-    const int ciipW = t.ciip;                                  // CIIP: the block holds the inter prediction; blend (predBlendIntraCiip :925-938)
+    const int ciipW = isp ? 0 : t.ciip;                        // CIIP: the block holds the inter prediction; blend (predBlendIntraCiip :925-938)
 #define IT_STORE(x, y, v) do { int v_ = (v); int16_t* d_ = dst + (size_t)(y) * ps + (x); if (ciipW) v_ = ((4 - ciipW) * (int)*d_ + ciipW * v_ + 2) >> 2; \
-                               if (rs) v_ = clip3(0, pmax, v_ + rs[(size_t)(y) * ps + (x)]); *d_ = (int16_t)v_; } while (0)
+                               if (rs && ((resiMask >> ((x) >> l2tu)) & 1)) v_ = clip3(0, pmax, v_ + rs[(size_t)(y) * ps + (x)]); *d_ = (int16_t)v_; } while (0)
 
     if (mode == B200_INTRA_PLANAR || mode == B200_INTRA_DC) {
       int dc = 0;
@@ -353,7 +386,7 @@ __global__ void __launch_bounds__(IT_THREADS, 12) intra_kernel(const IntraParams
       for (int k = tid; k < w * h; k += IT_THREADS) { const int y = k >> t.log2w, x = k & (w - 1); IT_STORE(x, y, mode == B200_INTRA_BDPCM_HOR ? L[y + 1] : T[x + 1]); }
     } else {
       // ---- angular (xPredIntraAng): main / side reference arrays, then every sample on its own
-      const int predMode = wide_angle(w, h, mode);
+      const int predMode = wide_angle(bw, bh, mode);                 // ISP: the CU decides (:610)
       const bool ver = predMode >= 34;
       const int angMode = ver ? predMode - 50 : -(predMode - 18), absMode = abs(angMode);
       const int invAngle = cInvAng[absMode], absAng = cAng[absMode], angle = angMode < 0 ? -absAng : absAng;
@@ -364,9 +397,9 @@ __global__ void __launch_bounds__(IT_THREADS, 12) intra_kernel(const IntraParams
         for (int k = tid - mh; k <= mw + 1 + mrl; k += IT_THREADS) M[k] = k >= 0 ? mainSrc[k] : sideSrc[min((-k * invAngle + 256) >> 9, mh)];
         for (int k = tid; k <= mh + 1 + mrl; k += IT_THREADS) S[k] = sideSrc[k];
       } else {
-        const int l2r = (31 - __clz(mw)) - (31 - __clz(mh)), s = max(0, l2r), maxIndex = (mrl << s) + 2, refLength = 2 * mw;
+        const int l2r = (31 - __clz(mw)) - (31 - __clz(mh)), s = max(0, l2r), maxIndex = (mrl << s) + 2, refLength = ver ? topLen : sideLen;
         for (int k = tid; k <= refLength + mrl + maxIndex; k += IT_THREADS) M[k] = mainSrc[min(k, refLength + mrl)];
-        for (int k = tid; k <= 2 * mh + mrl; k += IT_THREADS) S[k] = sideSrc[k];
+        for (int k = tid; k <= (ver ? sideLen : topLen) + mrl; k += IT_THREADS) S[k] = sideSrc[k];
       }
       __syncthreads();
       const int16_t *Mp = M + mrl, *Sp = S + mrl;
@@ -376,7 +409,7 @@ __global__ void __launch_bounds__(IT_THREADS, 12) intra_kernel(const IntraParams
       const int lev = min(3 << scale0, mw);                    // lev[scale] = min(3, 6, 12, 24; width)
       const bool frac = (absAng & 31) != 0;
       const int diff = min(abs(predMode - 18), abs(predMode - 50));
-      const bool cubic = !(diff > cIntraFilterThr[(l2mw + l2mh) >> 1]) || mrl > 0;
+      const bool cubic = isp || !(diff > cIntraFilterThr[(l2mw + l2mh) >> 1]) || mrl > 0;
       int angularScale = -1;
       if (angle > 0 && doPDPC) angularScale = min(2, l2mh - ((31 - __clz(3 * invAngle - 2)) - 8));
       for (int k = tid; k < mw * mh; k += IT_THREADS) {
@@ -574,6 +607,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) intra_ctu_kernel(const IntraPar
       const int c = t.comp, w = 1 << t.log2w, h = 1 << t.log2h, mrl = c ? 0 : t.multiRefIdx, unit = c ? 2 : 4;
       const int x0 = t.x, y0 = t.y, ps = P.stride[c], pmax = (1 << P.bitDepth) - 1;
       const int availTL = (t.flags & B200_INTRA_AVAIL_TL) ? 1 : 0, numAbove = t.numAbove, numLeft = t.numLeft;
+      ISP_GEOMETRY
       // the tile of the block's component, in registers (indexing the per-component arrays with a run-time index would go through local memory)
       const int tox = TL.ox[c], toy = TL.oy[c], ttw = TL.tw[c], tth = TL.th[c], tts = TL.ts[c];
       const int16_t* trec = TL.rec[c]; const int16_t* tplane = TL.plane[c];
@@ -582,11 +616,12 @@ __global__ void __launch_bounds__(V2_THREADS, 1) intra_ctu_kernel(const IntraPar
       };
       // ---- wait for the earlier blocks this one reads from
       bool far = false;
+      if (ispK && lane == 0) far |= v2_wait(P, sflag, me - 1, me, first);     // ISP: the region before this one is the record before it
       for (int dep = lane; dep < 96; dep += V2_GROUP) {                        // dependency slots: 0 corner, 1..32 above units, 64..95 left units
         int ux = -1, uy = -1;
-        if (dep == 0) { if (availTL) { ux = x0 - 1; uy = y0 - 1; } }
-        else if (dep <= numAbove) { ux = x0 + (dep - 1) * unit; uy = y0 - 1; }
-        else if (dep - 64 >= 0 && dep - 64 < numLeft) { ux = x0 - 1; uy = y0 + (dep - 64) * unit; }
+        if (dep == 0) { if (availTL) { ux = bx - 1; uy = by - 1; } }
+        else if (dep <= numAbove) { ux = bx + (dep - 1) * unit; uy = by - 1; }
+        else if (dep - 64 >= 0 && dep - 64 < numLeft) { ux = bx - 1; uy = by + (dep - 64) * unit; }
         if (ux >= 0 && uy >= 0) {
           const int ush = c ? 1 : 2, ox = (ux >> ush) - (tox >> ush), oy = (uy >> ush) - (toy >> ush);          // inside the CTU: the staged owner word
           const int o = ((unsigned)ox < 32u && (unsigned)oy < 32u && ux < tox + ttw && uy < toy + tth) ? sown[c * 1024 + oy * 32 + ox] : __ldcg(P.owner[c] + (size_t)(uy >> ush) * P.ownerStride[c] + (ux >> ush));
@@ -610,35 +645,15 @@ __global__ void __launch_bounds__(V2_THREADS, 1) intra_ctu_kernel(const IntraPar
       K6P(1, tp); tp = clock64();                               // [1] dependency wait
 
       // ---- reference samples (xFillReferenceSamples): T[j] = row above incl. the corner, L[i] = left column, T[0] = L[0] = corner
-      const int predSize = 2 * w, predHSize = 2 * h;
+      const int predSize = 2 * bw, predHSize = 2 * bh;
       const int totalUnits = (predSize + unit - 1) / unit + (predHSize + unit - 1) / unit + 1, n = availTL + numAbove + numLeft;
       const int aboveLen = min(numAbove * unit, predSize), leftLen = min(numLeft * unit, predHSize);
       int16_t *T = SC.T[0], *L = SC.L[0];
-      for (int j = lane; j <= predSize + mrl; j += V2_GROUP) {
-        int v;
-        if (n == 0) v = 1 << (P.bitDepth - 1);
-        else if (n == totalUnits) v = pixC(x0 - 1 - mrl + j, y0 - 1 - mrl);
-        else if (j <= mrl) {
-          if (numLeft > 0) v = availTL ? pixC(x0 - 1 - mrl + j, y0 - 1 - mrl) : pixC(x0 - 1 - mrl, y0);
-          else v = pixC(x0, y0 - 1 - mrl);
-        } else {
-          const int kk = j - 1 - mrl;
-          if (numAbove) v = pixC(x0 + min(kk, aboveLen - 1), y0 - 1 - mrl);
-          else v = availTL ? pixC(x0 - 1, y0 - 1 - mrl) : pixC(x0 - 1 - mrl, y0);
-        }
-        T[j] = (int16_t)v;
-      }
-      for (int i = lane; i <= predHSize + mrl; i += V2_GROUP) {
-        if (i == 0) continue;
-        int v;
-        if (n == 0) v = 1 << (P.bitDepth - 1);
-        else if (n == totalUnits) v = pixC(x0 - 1 - mrl, y0 - 1 - mrl + i);
-        else if (numLeft > 0) {
-          if (i <= mrl) v = availTL ? pixC(x0 - 1 - mrl, y0 - 1 - mrl + i) : pixC(x0 - 1 - mrl, y0);
-          else v = pixC(x0 - 1 - mrl, y0 + min(i - 1 - mrl, leftLen - 1));
-        } else v = pixC(x0, y0 - 1 - mrl);
-        L[i] = (int16_t)v;
-      }
+#define PIXR(x, y) pixC((x), (y))
+      ISP_REFERENCE_LAMBDAS
+      for (int j = lane; j <= topLen + mrl; j += V2_GROUP) T[j] = (int16_t)regT(j);
+      for (int i = lane + 1; i <= sideLen + mrl; i += V2_GROUP) L[i] = (int16_t)regL(i);
+#undef PIXR
       V2_SYNC();
       if (lane == 0) L[0] = T[0];
       V2_SYNC();
@@ -661,9 +676,9 @@ __global__ void __launch_bounds__(V2_THREADS, 1) intra_ctu_kernel(const IntraPar
       int16_t* dstT = const_cast<int16_t*>(trec) + (y0 - toy) * tts + (x0 - tox);
       const int tsC = tts;
       const int16_t* rsT = (P.resi[c] && (t.flags & B200_INTRA_ADD_RESI)) ? TL.res[c] + (y0 - toy) * tsC + (x0 - tox) : nullptr;
-      const int ciipW = t.ciip;
+      const int ciipW = isp ? 0 : t.ciip;
 #define V2_STORE(x, y, v) do { int v_ = (v); int16_t* d_ = dstT + (y) * tsC + (x); if (ciipW) v_ = ((4 - ciipW) * (int)*d_ + ciipW * v_ + 2) >> 2; \
-                               if (rsT) v_ = clip3(0, pmax, v_ + rsT[(y) * tsC + (x)]); *d_ = (int16_t)v_; dstG[(size_t)(y) * ps + (x)] = (int16_t)v_; } while (0)
+                               if (rsT && ((resiMask >> ((x) >> l2tu)) & 1)) v_ = clip3(0, pmax, v_ + rsT[(y) * tsC + (x)]); *d_ = (int16_t)v_; dstG[(size_t)(y) * ps + (x)] = (int16_t)v_; } while (0)
 
       if (mode == B200_INTRA_PLANAR || mode == B200_INTRA_DC) {
         int dc = 0;
@@ -816,7 +831,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) intra_ctu_kernel(const IntraPar
         for (int kk = lane; kk < w * h; kk += V2_GROUP) { const int y = kk >> t.log2w, x = kk & (w - 1); V2_STORE(x, y, mode == B200_INTRA_BDPCM_HOR ? L[y + 1] : T[x + 1]); }
       } else {
         // ---- angular (xPredIntraAng)
-        const int predMode = wide_angle(w, h, mode);
+        const int predMode = wide_angle(bw, bh, mode);                 // ISP: the CU decides (:610)
         const bool ver = predMode >= 34;
         const int angMode = ver ? predMode - 50 : -(predMode - 18), absMode = abs(angMode);
         const int invAngle = cInvAng[absMode], absAng = cAng[absMode], angle = angMode < 0 ? -absAng : absAng;
@@ -827,9 +842,9 @@ __global__ void __launch_bounds__(V2_THREADS, 1) intra_ctu_kernel(const IntraPar
           for (int kk = lane - mh; kk <= mw + 1 + mrl; kk += V2_GROUP) M[kk] = kk >= 0 ? mainSrc[kk] : sideSrc[min((-kk * invAngle + 256) >> 9, mh)];
           for (int kk = lane; kk <= mh + 1 + mrl; kk += V2_GROUP) S[kk] = sideSrc[kk];
         } else {
-          const int l2r = (31 - __clz(mw)) - (31 - __clz(mh)), sft = max(0, l2r), maxIndex = (mrl << sft) + 2, refLength = 2 * mw;
+          const int l2r = (31 - __clz(mw)) - (31 - __clz(mh)), sft = max(0, l2r), maxIndex = (mrl << sft) + 2, refLength = ver ? topLen : sideLen;
           for (int kk = lane; kk <= refLength + mrl + maxIndex; kk += V2_GROUP) M[kk] = mainSrc[min(kk, refLength + mrl)];
-          for (int kk = lane; kk <= 2 * mh + mrl; kk += V2_GROUP) S[kk] = sideSrc[kk];
+          for (int kk = lane; kk <= (ver ? sideLen : topLen) + mrl; kk += V2_GROUP) S[kk] = sideSrc[kk];
         }
         V2_SYNC();
         const int16_t *Mp = M + mrl, *Sp = S + mrl;
@@ -839,7 +854,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) intra_ctu_kernel(const IntraPar
         const int lev = min(3 << scale0, mw);
         const bool frac = (absAng & 31) != 0;
         const int diff = min(abs(predMode - 18), abs(predMode - 50));
-        const bool cubic = !(diff > cIntraFilterThr[(l2mw + l2mh) >> 1]) || mrl > 0;
+        const bool cubic = isp || !(diff > cIntraFilterThr[(l2mw + l2mh) >> 1]) || mrl > 0;
         int angularScale = -1;
         if (angle > 0 && doPDPC) angularScale = min(2, l2mh - ((31 - __clz(3 * invAngle - 2)) - 8));
         for (int kk = lane; kk < mw * mh; kk += V2_GROUP) {
@@ -889,6 +904,7 @@ __global__ void __launch_bounds__(256) intra_validate_kernel(const b200_intra_tu
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   const b200_intra_tu t = tus[i];
+  if (t.flags & B200_INTRA_ISP) { b200_intra_tu prev; if (i) prev = tus[i - 1]; if (!intra_isp_record_ok(t, i ? &prev : nullptr, W, H)) atomicOr(&meta[LM_ERR], 8); return; }
   const int w = 1 << t.log2w, h = 1 << t.log2h, pw = t.comp ? W >> 1 : W, ph = t.comp ? H >> 1 : H, unit = t.comp ? 2 : 4, m = t.multiRefIdx;
   bool ok = t.comp < (chroma ? 3 : 1) && t.log2w >= 2 && t.log2w <= 6 && t.log2h >= 1 && t.log2h <= 6 && t.x + w <= pw && t.y + h <= ph && !(t.x % unit) && !(t.y % unit);
   ok = ok && t.mode <= B200_INTRA_MDLM_T && m <= 2 && (!m || !t.comp);

@@ -687,7 +687,17 @@ def intra_filter_ref(w, h, mode, mrl, bdpcm):
     return diff > _INTRA_THR[(int(np.log2(w)) + int(np.log2(h))) >> 1] and (ang & 31) == 0
 
 
-def gen_intra_records(rng, layout, W, H, modes=None, p_mrl=0.15, p_bdpcm=0.08, p_resi=0.0, upto=None, only=None, p_mip=0.15, colloc=0, p_lm=0.0, ciip=None):
+def isp_regions(w, h, split):
+    """Prediction regions (dx, dy, rw, rh) of an ISP CU and the width of its transform units (CU::getISPSplitDim UnitTools.cpp:360, isPredRegDiffFromTB):
+    split 1 = horizontal (regions stacked), 2 = vertical; vertical sub-partitions narrower than 4 share a 4-wide region."""
+    sd, nd = (h, w) if split == 1 else (w, h)
+    part = max(sd >> 2, 16 // nd if nd < 16 else 1)
+    if split == 1: return [(0, k * part, w, part) for k in range(h // part)], w
+    rw = max(part, 4)
+    return [(k * rw, 0, rw, h) for k in range(w // rw)], part
+
+
+def gen_intra_records(rng, layout, W, H, modes=None, p_mrl=0.15, p_bdpcm=0.08, p_resi=0.0, upto=None, only=None, p_mip=0.15, colloc=0, p_lm=0.0, ciip=None, p_isp=0.0):
     """b200_intra_tu records (Y, Cb, Cr per CU, decoding order) for a single-tree all-intra layout of gen_intra_layout: random modes, MRL on some luma
     blocks, BDPCM prediction on some, availability as xFillReferenceSamples derives it from the decoding order (pinned against the reference's own
     analysis through the glue flattener by tests/test_intra_oracle_vs_ref.py).  Luma blocks whose chroma would be narrower than 4 or smaller than 16
@@ -723,7 +733,22 @@ def gen_intra_records(rng, layout, W, H, modes=None, p_mrl=0.15, p_bdpcm=0.08, p
         while nl < 2 * h // 4 and avail(x // 4 - 1, y // 4 + nl): nl += 1
         luma_only = w < 8 or (w // 2) * (h // 2) < 16
         if wc: luma_only = (w // 2) <= 2
+        isp = 0
+        if p_isp and not (mip or mrl or bdpcm or wc) and w * h > 16 and rng.random() < p_isp: isp = int(rng.integers(1, 3))
+        if isp:
+            # intra sub-partitions: one record per prediction region, the CU-level neighbourhood in each (include/vvdec_b200.h, B200_INTRA_ISP)
+            regions, tuw = isp_regions(w, h, isp)
+            for k, (dx, dy, rw, rh) in enumerate(regions):
+                r = np.zeros((), A.INTRA_TU_DTYPE)
+                r["x"], r["y"], r["log2w"], r["log2h"], r["mode"] = x + dx, y + dy, int(np.log2(rw)), int(np.log2(rh)), dirL
+                r["mip"] = isp | (k << 2) | (int(np.log2(len(regions))) << 4)
+                mask = int(rng.integers(0, 1 << (rw // tuw))) if rng.random() < max(p_resi, 0.0) * 1.5 else 0
+                r["ciip"] = mask
+                r["flags"] = A.INTRA_ISP | (A.INTRA_AVAIL_TL if tl else 0) | (4 if mask else 0)
+                r["numAbove"], r["numLeft"], r["lmLeft"], r["lmAbove"] = na, nl, int(avail(x // 4 - 1, y // 4)), int(avail(x // 4, y // 4 - 1))
+                recs.append(r)
         for c in range(1 if luma_only else 3):
+            if isp and c == 0: continue
             r = np.zeros((), A.INTRA_TU_DTYPE)
             r["ciip"] = wc
             sh = 1 if c else 0

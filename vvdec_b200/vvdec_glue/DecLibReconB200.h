@@ -448,7 +448,13 @@ public:
     CodingStructure& cs = *pic->cs; const PreCalcValues& pcv = *cs.pcv;
     pic->progress = Picture::reconstructing;
     m_failure = nullptr; m_failed.store( false );
-    refuse( pic );
+    // a picture refused here throws on the caller's thread (DecLib::reconPicture records it in pic->reconDone, DecLib.cpp:618-626); the parked copy makes
+    // waitForPrevDecompressedPic() skip the picture instead of finishing work that was never scheduled
+    try { refuse( pic ); prepareAndSchedule( pic ); } catch( ... ) { park( std::current_exception() ); throw; }
+  }
+  void prepareAndSchedule( Picture* pic )
+  {
+    CodingStructure& cs = *pic->cs; const PreCalcValues& pcv = *cs.pcv;
     m_motionInfo.resize( (size_t) pcv.num4x4CtuBlks * pcv.sizeInCtus ); m_loopFilterParam.resize( (size_t) pcv.num4x4CtuBlks * pcv.sizeInCtus * 2 );
     m_dmvrMvCache.assign( (size_t) pcv.num8x8CtuBlks * pcv.sizeInCtus, Mv() ); cs.m_dmvrMvCache = m_dmvrMvCache.data();
     m_t0 = std::chrono::steady_clock::now(); m_tFlat0.store( 0 );
