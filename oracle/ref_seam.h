@@ -784,3 +784,48 @@ extern "C" double ref_seam_run_b200( void* h, int threads, int dry, int16_t* con
   }
   catch( std::exception& e ) { fprintf( stderr, "ref_seam_run_b200: %s\n", e.what() ); return -2.0; }
 }
+
+// (iii) Either back end the way DecLib drives it (DecLib.h:70, DecLib.cpp:560-640): `depth` recon instances on one thread pool take the pictures in turn;
+// an instance is handed its next picture as soon as its previous one has been waited for, so up to `depth` pictures are in flight.  Returns the seconds
+// for all n pictures (no output read-back), < 0 on error.  backend 0: the reference's DecLibRecon, 1: DecLibReconB200, 2: DecLibReconB200 in dry-run mode (host stages only).
+// ref_seam_read_out() fetches a picture's planes / motion field afterwards.
+extern "C" double ref_seam_run_pipelined( void* const* hs, int n, int threads, int backend, int depth )
+{
+  if( n <= 0 || depth < 1 || depth > 4 ) return -3.0;
+  try
+  {
+    seam::Pic& P0 = *static_cast<seam::Pic*>( hs[0] );
+    static std::unique_ptr<ThreadPool> pool; static int poolThreads = -1;
+    static std::vector<std::unique_ptr<DecLibRecon>> stock; static std::vector<std::unique_ptr<b200glue::DecLibReconB200>> dev; static b200_geom devGeom{};
+    if( poolThreads != threads || ( backend >= 1 && memcmp( &devGeom, &P0.g, sizeof( devGeom ) ) ) )
+    {
+      for( auto& r : stock ) r->destroy(); for( auto& r : dev ) r->destroy();
+      stock.clear(); dev.clear(); pool.reset( new ThreadPool( threads, "seamPipe" ) ); poolThreads = threads; devGeom = P0.g;
+    }
+    while( backend == 0 && (int) stock.size() < depth ) { stock.emplace_back( new DecLibRecon ); stock.back()->create( pool.get(), (unsigned) stock.size() - 1, false ); }
+    while( backend >= 1 && (int) dev.size() < depth )   { dev.emplace_back( new b200glue::DecLibReconB200 ); dev.back()->create( pool.get(), (unsigned) dev.size() - 1, false ); }
+    if( backend >= 1 ) { for( auto& r : dev ) r->setDryRun( backend == 2 ); dev[0]->resetDpb(); }
+    bool bad = false;
+    auto waitOne = [&]( int k )
+    {
+      Picture* done = backend ? dev[k]->waitForPrevDecompressedPic() : stock[k]->waitForPrevDecompressedPic();
+      if( !done ) return;
+      if( done->error || done->reconDone.hasException() ) { bad = true; done->reconDone.clearException(); }
+      if( backend ) dev[k]->releasePicture( done );
+    };
+    const auto t0 = std::chrono::steady_clock::now();
+    for( int i = 0; i < n; i++ )
+    {
+      const int k = i % depth;
+      waitOne( k );
+      Picture* pic = &static_cast<seam::Pic*>( hs[i] )->cur->pic;
+      try { if( backend ) dev[k]->decompressPicture( pic ); else stock[k]->decompressPicture( pic ); }
+      catch( ... ) { pic->reconDone.setException( std::current_exception() ); pic->error = true; }
+    }
+    for( int j = 0; j < depth; j++ ) waitOne( ( n + j ) % depth );
+    const double secs = std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
+    return bad ? -1.0 : secs;
+  }
+  catch( std::exception& e ) { fprintf( stderr, "ref_seam_run_pipelined: %s\n", e.what() ); return -2.0; }
+}
+extern "C" void ref_seam_read_out( void* h, int16_t* const out[3], uint8_t* colMotion, size_t colBytes ) { seam::readOut( *static_cast<seam::Pic*>( h ), out, colMotion, colBytes ); }

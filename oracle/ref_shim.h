@@ -173,6 +173,8 @@ void   ref_seam_stats(void* h, int32_t st[16]);
  * decompressPicture() and the return of waitForPrevDecompressedPic(), < 0 on error (-4: the picture uses a tool the device path refuses). */
 double ref_seam_run_stock(void* h, int threads, int16_t* const out[3], uint8_t* colMotion, size_t colBytes);
 double ref_seam_run_b200(void* h, int threads, int dry, int16_t* const out[3], uint8_t* colMotion, size_t colBytes, b200_picture* flat);
+double ref_seam_run_pipelined(void* const* hs, int n, int threads, int backend, int depth);   /* DecLib's alternating recon instances, see ref_seam.h */
+void ref_seam_read_out(void* h, int16_t* const out[3], uint8_t* colMotion, size_t colBytes);
 
 #ifdef __cplusplus
 }

@@ -147,7 +147,24 @@ def declare_seam(lib):
     lib.ref_seam_col_motion_bytes.argtypes = [C.c_void_p]; lib.ref_seam_col_motion_bytes.restype = C.c_size_t
     lib.ref_seam_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]; lib.ref_seam_stats.restype = None
     lib.ref_seam_run_stock.argtypes = [C.c_void_p, C.c_int, PL, C.c_void_p, C.c_size_t]; lib.ref_seam_run_stock.restype = C.c_double
+    lib.ref_seam_read_out.argtypes = [C.c_void_p, PL, C.c_void_p, C.c_size_t]; lib.ref_seam_read_out.restype = None
+    lib.ref_seam_run_pipelined.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int]; lib.ref_seam_run_pipelined.restype = C.c_double
     lib.ref_seam_run_b200.argtypes = [C.c_void_p, C.c_int, C.c_int, PL, C.c_void_p, C.c_size_t, C.POINTER(abi.Picture)]; lib.ref_seam_run_b200.restype = C.c_double
+
+
+def seam_pipelined(ref, cases, threads, backend, depth, read=True):
+    """Runs the pictures of `cases` (SeamCase objects, one fresh Picture each) through `depth` alternating recon instances (ref_seam_run_pipelined).
+    Returns (seconds, [(planes, colMotion) per picture])"""
+    hs = [c.build() for c in cases]
+    arr = (C.c_void_p * len(hs))(*hs)
+    secs = ref.ref_seam_run_pipelined(arr, len(hs), threads, backend, depth)
+    outs = []
+    if read and secs >= 0 and backend != 2:
+        for c, h in zip(cases, hs):
+            out = c._out(); col = np.zeros(ref.ref_seam_col_motion_bytes(h), np.uint8)
+            ref.ref_seam_read_out(h, abi.plane_ptrs(out), col.ctypes.data, len(col)); outs.append((out, col))
+    for h in hs: ref.ref_seam_destroy(h)
+    return secs, outs
 
 
 class SeamCase:

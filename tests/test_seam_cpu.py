@@ -75,3 +75,20 @@ def test_unsupported_tool_follows_the_error_contract():
     pic, rc = case.flatten(threads=0)
     assert pic is None and rc == -4.0
     run_case(6, 416, 240, 0)            # the same (static) recon object afterwards
+
+
+def test_two_alternating_recon_instances():
+    """DecLib keeps two recon instances on one thread pool and hands them pictures in turn (DecLib.h:70): the stock back end run that way gives what the
+    one-picture-at-a-time runs give, and two DecLibReconB200 instances (dry run: host stages, shared DPB bookkeeping) get through the same pictures."""
+    rng = np.random.default_rng(77)
+    base = helpers.SeamCase(ref, rng, 416, 240)
+    cases = [base.variant(seed=100 + i, slice_type=2 if i == 2 else 0) for i in range(5)]
+    secs, outs = helpers.seam_pipelined(ref, cases, 4, 0, 2)
+    assert secs >= 0 and len(outs) == 5
+    for c, (out, col) in zip(cases, outs):
+        want, col_want, _ = c.run_stock(threads=4)
+        for k in range(3): assert np.array_equal(want[k], out[k])
+        assert helpers.col_motion_diff(col_want, col, c.g) == 0
+    secs, _ = helpers.seam_pipelined(ref, cases, 4, 2, 2)
+    assert secs >= 0
+

@@ -45,3 +45,18 @@ def test_seam_error_contract_on_the_device_path():
     _, _, rc = case.run_b200(threads=2)
     assert rc == -4.0
     both(6, 416, 240)
+
+
+def test_two_alternating_recon_instances_on_the_device():
+    """Two DecLibReconB200 instances on one pool and one device context take pictures in turn, as DecLib runs its recon instances (DecLib.h:70):
+    every picture comes out as the stock back end reconstructs it."""
+    rng = np.random.default_rng(78)
+    base = helpers.SeamCase(ref, rng, 832, 480, isp=20)
+    cases = [base.variant(seed=200 + i, slice_type=2 if i == 3 else 0) for i in range(7)]
+    secs, outs = helpers.seam_pipelined(ref, cases, 4, 1, 2)
+    assert secs >= 0 and len(outs) == 7
+    for c, (out, col) in zip(cases, outs):
+        want, col_want, _ = c.run_stock(threads=4)
+        for k in range(3): assert np.array_equal(want[k], out[k]), f"plane {k}"
+        assert helpers.col_motion_diff(col_want, col, c.g) == 0
+

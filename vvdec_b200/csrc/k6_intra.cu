@@ -455,14 +455,15 @@ __global__ void __launch_bounds__(IT_THREADS, 12) intra_kernel(const IntraParams
 // flags for earlier blocks of its own CTU and on the global done words only for blocks of the neighbouring CTUs (left, above-left, above, above-right:
 // all earlier in the wave front, so the oldest unfinished block never waits on a block that has not been started — no deadlock at any residency).
 // Samples are written through: to the shared tile for the CTU's own later blocks, to the plane for the other CTUs and the in-loop filters.
-constexpr int V2_GROUP = 128, V2_GROUPS = 4, V2_THREADS = V2_GROUP * V2_GROUPS;   // a block is worked on by a group of 4 warps; four blocks of the CTU at a time
+// a block is worked on by a group of V2_GROUP threads, V2_GROUPS blocks of the CTU at a time (template parameters of the kernel: the chains of an intra CTU
+// are Y -> Y -> Y, Cb -> Cb, Cr -> Cr, so about three blocks can run at once and the latency of one block is what counts)
 constexpr int V2_LS = 136, V2_CS = 72;                       // tile row pitch in samples: a multiple of 16 bytes (16-byte asynchronous copies), rows 4 banks apart
 constexpr int V2_TILE = 128 * V2_LS + 2 * 64 * V2_CS;        // samples of one tile set (Y, Cb, Cr)
 constexpr int V2_RECS = 1024;                                // records staged in shared memory (a CTU with more blocks reads the rest from global memory)
 constexpr int V2_FLAGS = 128 * 128 / 16 + 2 * (64 * 64 / 4); // most blocks a CTU can hold
 struct V2Scratch { int16_t T[2][IT_REF], L[2][IT_REF], M[IT_ARR], S[IT_ARR], Lm[32 * 32], LmTop[64], LmLeft[64]; int LmPar[4]; int ticket, sum; };
 constexpr int V2_OWN = 3 * 32 * 32;                         // owner words of the CTU's units: luma 32 x 32 (4x4 units), Cb / Cr 32 x 32 each (2x2 units)
-constexpr size_t V2_SMEM = (size_t)2 * V2_TILE * sizeof(int16_t) + V2_GROUPS * sizeof(V2Scratch) + V2_RECS * sizeof(b200_intra_tu) + V2_OWN * sizeof(int) + V2_FLAGS + 64;
+constexpr size_t v2_smem(int groups) { return (size_t)2 * V2_TILE * sizeof(int16_t) + groups * sizeof(V2Scratch) + V2_RECS * sizeof(b200_intra_tu) + V2_OWN * sizeof(int) + V2_FLAGS + 64; }
 __device__ __forceinline__ void v2_cp4(void* smemDst, const void* gmemSrc)      // asynchronous 4-byte global -> shared copy (LDGSTS): the whole CTU in flight before one wait
 {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
@@ -516,7 +517,7 @@ __device__ __forceinline__ bool v2_wait(const IntraParams& P, const volatile uin
 {
   if (o < 0 || o >= me) return false;
   int spins = 0;
-  if (o >= first) { while (sflag[o - first] == 0) { __nanosleep(20); if (++spins > (1 << 24)) { atomicOr(P.err, 1); break; } } return false; }
+  if (o >= first) { while (sflag[o - first] == 0) { if (++spins > 64) __nanosleep(20); if (spins > (1 << 24)) { atomicOr(P.err, 1); break; } } return false; }
   const volatile int* d = P.done + o; const volatile int* e = P.err;
   while (*d == 0) { __nanosleep(32); if (*e || ++spins > (1 << 22)) { atomicOr(P.err, 1); break; } }
   return true;
@@ -530,8 +531,10 @@ __device__ unsigned long long gK6Prof[16];
 #define K6P(i, t0) do {} while (0)
 #define K6C(i) do {} while (0)
 #endif
-__global__ void __launch_bounds__(V2_THREADS, 1) intra_ctu_kernel(const IntraParams P, const int* __restrict__ ctuOrder, int* counters)
+template <int V2_GROUP, int V2_GROUPS>
+__global__ void __launch_bounds__(V2_GROUP * V2_GROUPS, 1) intra_ctu_kernel(const IntraParams P, const int* __restrict__ ctuOrder, int* counters)
 {
+  constexpr int V2_THREADS = V2_GROUP * V2_GROUPS;
   extern __shared__ __align__(16) unsigned char smem[];
   int16_t* tileRec = reinterpret_cast<int16_t*>(smem);
   int16_t* tileRes = tileRec + V2_TILE;
@@ -586,14 +589,14 @@ __global__ void __launch_bounds__(V2_THREADS, 1) intra_ctu_kernel(const IntraPar
       for (int k = tid; k < uw * uh; k += V2_THREADS) { const int y = k / uw, x = k - y * uw; v2_cp4(sown + c * 1024 + y * 32 + x, osrc + (size_t)y * P.ownerStride[c] + x); }
     }
     for (int k = tid; k < min(cnt, V2_RECS) * 4; k += V2_THREADS) v2_cp4(reinterpret_cast<uint32_t*>(srec) + k, reinterpret_cast<const uint32_t*>(P.tus + first) + k);
-    for (int k = tid; k < cnt; k += V2_THREADS) sflag[k] = P.compSel == 2 ? (uint8_t)(__ldcg(P.done + first + k) != 0) : 0;      // chroma pass: the luma blocks are finished
+    for (int k = tid; k < cnt; k += V2_THREADS) sflag[k] = P.compSel == 2 ? (uint8_t)(P.tus[first + k].comp == 0) : 0;      // chroma pass: the luma blocks are finished (the pass before)
     v2_cp_wait();
     __syncthreads();
     K6P(0, tp); K6C(8);       // [0] CTU set-up cycles, [8] CTU count (per group)
 
     // ---- the CTU's blocks, one group each, in decoding order
     V2Scratch& SC = scratch[grp];
-#define V2_SYNC() asm volatile("bar.sync %0, %1;" :: "r"(grp + 1), "r"(V2_GROUP) : "memory")
+#define V2_SYNC() do { if (V2_GROUP == 32) __syncwarp(); else asm volatile("bar.sync %0, %1;" :: "r"(grp + 1), "r"(V2_GROUP) : "memory"); } while (0)
     for (;;) {
       V2_SYNC();
       if (lane == 0) { SC.ticket = atomicAdd(&sNext, 1); SC.sum = 0; }
@@ -884,14 +887,17 @@ __global__ void __launch_bounds__(V2_THREADS, 1) intra_ctu_kernel(const IntraPar
         }
       }
 #undef V2_STORE
-      // ---- publish: the CTU's own later blocks see the tile, the other CTUs the plane
+      // ---- publish: the CTU's own later blocks see the tile; other CTUs read the plane, and only the samples of the CTU's last column and last row
+      // (left, above and above-right references of the CTUs right of / below it): blocks that touch neither skip the device-scope fence and the done word
       __threadfence_block();
       V2_SYNC();
       K6P(3, tp); tp = clock64();                               // [3] prediction + stores
       if (lane == 0) sflag[k] = 1;
-      __threadfence();
-      V2_SYNC();
-      if (lane == 0) atomicExch(P.done + me, 1);
+      if (x0 + w == tox + ttw || y0 + h == toy + tth) {
+        __threadfence();
+        V2_SYNC();
+        if (lane == 0) atomicExch(P.done + me, 1);
+      }
       K6P(4, tp); K6C(9);                        // [4] device fence + done word, [9] blocks
     }
 #undef V2_SYNC
@@ -969,10 +975,12 @@ int launch_intra(const IntraLaunch& L, cudaStream_t s)
       intra_ctu_check_kernel<<<grid, 256, 0, s>>>(P);
       intra_ctu_order_kernel<<<1, 1024, nCtu * sizeof(int), s>>>(P, ctuOrder, counters);
     }
-    static bool attr = false;
-    if (!attr) { B200_CUDA(cudaFuncSetAttribute(intra_ctu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM)); attr = true; }
     const int ctas = (int)std::min<size_t>(nCtu, (size_t)num_sms());
-    intra_ctu_kernel<<<ctas, V2_THREADS, V2_SMEM, s>>>(P, ctuOrder, counters);
+    static const int shape = getenv("B200_INTRA_GROUP") ? atoi(getenv("B200_INTRA_GROUP")) : 0;      // measurement switch: threads per block group
+#define V2_GO(G, N) do { static bool attr = false; if (!attr) { B200_CUDA(cudaFuncSetAttribute(intra_ctu_kernel<G, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2_smem(N))); attr = true; } \
+                         intra_ctu_kernel<G, N><<<ctas, G * N, v2_smem(N), s>>>(P, ctuOrder, counters); } while (0)
+    if (shape == 64) V2_GO(64, 6); else if (shape == 32) V2_GO(32, 8); else if (shape == 2566) V2_GO(256, 3); else V2_GO(128, 4);
+#undef V2_GO
     B200_CUDA(cudaGetLastError());
     return 0;
   }

@@ -61,7 +61,9 @@ class DecLibReconB200
   struct Shared
   {
     std::mutex m; b200_ctx* ctx = nullptr; b200_geom geom{}; int numSlots = 0;
-    std::map<const Picture*, int> slotOf; std::vector<const Picture*> owner; std::vector<uint8_t> valid;   // valid: the slot holds the owner's final samples
+    // valid[slot]: 0 nothing usable; 1 the owner's final samples are resident; 2 the owner is being reconstructed by a recon instance and its work is not yet
+    // in the stream; 3 ... and has been submitted (whatever is submitted later reads the finished samples: one stream, in order)
+    std::map<const Picture*, int> slotOf; std::vector<const Picture*> owner; std::vector<uint8_t> valid;
     ~Shared() { if( ctx ) b200_ctx_destroy( ctx ); }
   };
   static std::shared_ptr<Shared> sharedFor( const void* key )
@@ -82,6 +84,7 @@ class DecLibReconB200
   };
 
   ThreadPool* m_pool = nullptr; int m_numThreads = 1; unsigned m_id = 0; int m_dpbSlots = 17;
+  std::vector<int> m_waitSlots;            // slots of reference pictures that were in flight on another instance when this picture was set up
   Picture*    m_currDecompPic = nullptr;
   int         m_arena = -1, m_dstSlot = -1;
   std::vector<Row> m_rows; std::unique_ptr<std::atomic<uint8_t>[]> m_ctuDone; int m_ctusW = 0;
@@ -121,7 +124,8 @@ class DecLibReconB200
   {
     Shared& S = *m_sh;
     const int s = slotLocked( ref );
-    if( S.valid[s] ) return s;
+    if( S.valid[s] == 1 || S.valid[s] == 3 ) return s;
+    if( S.valid[s] == 2 ) { m_waitSlots.push_back( s ); return s; }        // the other recon instance has it in flight: this picture is submitted behind it (submitReady)
     CHECK_FATAL( ref->progress < Picture::reconstructed, "DecLibReconB200: reference picture is neither on the device nor reconstructed on the host" );
     const int16_t* planes[3] = { nullptr, nullptr, nullptr }; ptrdiff_t strides[3] = { 0, 0, 0 };
     for( int c = 0; c < ( S.geom.chromaFormat ? 3 : 1 ); c++ ) { const CPelBuf b = ref->getRecoBuf( ComponentID( c ) ); planes[c] = b.buf; strides[c] = b.stride; }
@@ -197,6 +201,16 @@ class DecLibReconB200
       CodingStructure& cs = *d.m_currDecompPic->cs;
       for( int x = 0; x < d.m_ctusW; x++ ) { const int a = r.line * d.m_ctusW + x; if( !cs.getCtuData( a ).slice->isIntra() ) d.m_cuDecoders[tid]->TaskFinishMotionInfo( cs, a, x, r.line ); }
       return true; } );
+  }
+  // SUBMIT: ready when the pictures this one references that another recon instance is still flattening have gone into the stream
+  static bool submitReady( int, void* p )
+  {
+    DecLibReconB200* d = static_cast<DecLibReconB200*>( p );
+    if( d->m_failed.load() || d->m_waitSlots.empty() ) return true;
+    std::unique_lock<std::mutex> l( d->m_sh->m, std::try_to_lock );
+    if( !l.owns_lock() ) return false;
+    for( int s : d->m_waitSlots ) if( d->m_sh->valid[s] == 2 ) return false;
+    return true;
   }
   static bool submitTask( int, void* p ) { DecLibReconB200* d = static_cast<DecLibReconB200*>( p ); d->m_stage[2] = d->since(); const bool r = d->guarded( [&] { d->submit(); return true; } ); d->m_stage[3] = d->since(); return r; }
 
@@ -296,10 +310,10 @@ class DecLibReconB200
       }
       if( (int) pcv.lumaWidth != S.geom.width || (int) pcv.lumaHeight != S.geom.height || sps.getBitDepth() != S.geom.bitDepth ) THROW_UNSUPPORTED( "DecLibReconB200: picture size / bit depth change inside a context (RPR)" );
       // reference pictures -> device DPB slots (uploaded if the device does not hold them)
-      memset( &m_slotMap, -1, sizeof( m_slotMap ) );
+      memset( &m_slotMap, -1, sizeof( m_slotMap ) ); m_waitSlots.clear();
       const Slice& slice0 = *pic->slices[0];
       for( int l = 0; l < 2; l++ ) for( int i = 0; i < slice0.getNumRefIdx( RefPicList( l ) ); i++ ) m_slotMap.slot[l][i] = (int8_t) importReference( slice0.getRefPic( RefPicList( l ), i ) );
-      m_dstSlot = slotLocked( pic ); S.valid[m_dstSlot] = 0;
+      m_dstSlot = slotLocked( pic ); S.valid[m_dstSlot] = 2;
     }
     const Slice& slice0 = *pic->slices[0];
     // explicit weighted prediction: one entry per (refIdx0, refIdx1) combination (getWpScaling, WeightPrediction.cpp:67)
@@ -406,10 +420,12 @@ class DecLibReconB200
     p.sao = m_sao.v.data(); p.vb = &m_vb; p.alf = m_alf.v.data(); p.alfTabs = &m_alfTabs;
     p.wp = m_wp.data(); p.numWp = (int32_t) m_wp.size(); p.lmcs = m_doLmcs ? &m_lmcs : nullptr;
     p.intraTus = m_intra.v.data(); p.numIntraTus = m_intra.v.size();
-    if( m_dryRun ) return;
+    if( m_dryRun ) { std::lock_guard<std::mutex> l( m_sh->m ); m_sh->valid[m_dstSlot] = 3; return; }
     std::lock_guard<std::mutex> l( m_sh->m );               // two recon instances share the context: submissions are serialised (stream order = decoding order)
+    for( int s : m_waitSlots ) if( m_sh->valid[s] != 1 && m_sh->valid[s] != 3 ) THROW_RECOVERABLE( "DecLibReconB200: a reference picture was not reconstructed" );
     m_arena = b200_decompress_picture( m_sh->ctx, &p );
     check( m_arena );
+    m_sh->valid[m_dstSlot] = 3;
   }
 
 public:
@@ -481,7 +497,7 @@ public:
       m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 mider " + std::to_string( a ) ) miderTask, &m_rows[a], &m_flattenCounter, nullptr, std::move( bars ), miderReady );
       m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 flatten " + std::to_string( a ) ) flattenTask, &m_rows[a], &m_flattenCounter, nullptr, std::move( bars2 ), flattenReady );
     }
-    m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 submit" ) submitTask, this, &m_submitCounter, nullptr, { m_flattenCounter.donePtr(), &pic->parseDone } );
+    m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 submit" ) submitTask, this, &m_submitCounter, nullptr, { m_flattenCounter.donePtr(), &pic->parseDone }, submitReady );
   }
 
   // DecLibRecon::waitForPrevDecompressedPic (DecLibRecon.cpp:684): host stages done -> device done -> DMVR deltas -> TaskFinishMotionInfo -> planes.
