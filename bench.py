@@ -447,20 +447,20 @@ def cpu_baseline(args, wl):
     T = threads_all(args)
     wl.B[0].run_stock(threads=T)                                 # untimed warm-up (pool start-up, page faults)
     D = max(1, args.recon_depth)
+    tB1 = float(np.mean([wl.B[i % len(wl.B)].run_stock(threads=T)[2] for i in range(args.cpu_sample)]))
+    tB, used = tB1, 1
     if D > 1:
         wl.helpers.seam_pipelined(wl.ref, [wl.B[i % len(wl.B)] for i in range(D)], T, 0, D, read=False)
         nb = max(args.cpu_sample, 2 * D)
         secs, _ = wl.helpers.seam_pipelined(wl.ref, [wl.B[i % len(wl.B)] for i in range(nb)], T, 0, D, read=False)
-        assert secs > 0, "stock DecLibRecon failed"
-        tB = [secs / nb]
-    else:
-        tB = [wl.B[i % len(wl.B)].run_stock(threads=T)[2] for i in range(args.cpu_sample)]
+        if secs > 0 and secs / nb < tB: tB, used = secs / nb, D
     tI = wl.I.run_stock(threads=T)[2]
     nB = args.gop - 1
-    fps = args.gop / (tI + nB * float(np.mean(tB)))
-    return {"value": round(fps, 3), "unit": "frames/s", "cores": T, "kind": "reference", "recon_instances": D,
-            "sample": f"{D} DecLibRecon instance(s) taking pictures in turn (DecLib.h:70), decompressPicture..waitForPrevDecompressedPic, ThreadPool({T}) ({wl.ref.ref_simd_level().decode()}): "
-                      f"{max(args.cpu_sample, 2 * D) if D > 1 else args.cpu_sample} B pictures ({1e3 * float(np.mean(tB)):.2f} ms each) + 1 I picture alone ({1e3 * tI:.2f} ms) of the workload, weighted 1 I : {nB} B"}
+    fps = args.gop / (tI + nB * tB)
+    return {"value": round(fps, 3), "unit": "frames/s", "cores": T, "kind": "reference", "recon_instances": used,
+            "sample": f"the reference's DecLibRecon (decompressPicture..waitForPrevDecompressedPic), ThreadPool({T}) ({wl.ref.ref_simd_level().decode()}): B pictures {1e3 * tB1:.2f} ms each one at a time"
+                      + (f", {1e3 * tB:.2f} ms each with {D} instances taking pictures in turn (DecLib.h:70)" if used > 1 else (f" ({D} alternating instances were not faster)" if D > 1 else ""))
+                      + f"; 1 I picture alone {1e3 * tI:.2f} ms; weighted 1 I : {nB} B with the faster B figure"}
 
 
 def run_reference(args):
@@ -469,21 +469,25 @@ def run_reference(args):
     wl = Workload(args, 0)
     T = threads_all(args)
     D = max(1, args.recon_depth)
+    # (a) one recon instance, picture after picture
+    ts = []
+    for i in range(-args.warmup, args.steps):
+        _, case, _ = wl.sched(i if i >= 0 else -i)           # warm-up: B pictures
+        secs = case.run_stock(threads=T)[2]
+        if i >= 0: ts.append(secs)
+    fps1 = len(ts) / sum(ts); fps, used = fps1, 1
+    fpsD = None
     if D > 1:
-        # the schedule's pictures through D alternating DecLibRecon instances on one pool, the way DecLib runs them
-        if args.warmup: wl.helpers.seam_pipelined(wl.ref, [wl.sched(i + 1)[1] for i in range(args.warmup)], T, 0, D, read=False)
+        # (b) the schedule's pictures through D alternating DecLibRecon instances on one pool, the way DecLib runs them; the better of the two is the arm's value
+        if args.warmup: wl.helpers.seam_pipelined(wl.ref, [wl.sched(i + 1)[1] for i in range(min(args.warmup, 4))], T, 0, D, read=False)
         secs, _ = wl.helpers.seam_pipelined(wl.ref, [wl.sched(i)[1] for i in range(args.steps)], T, 0, D, read=False)
-        assert secs > 0, "stock DecLibRecon failed"
-        fps = args.steps / secs
-    else:
-        ts = []
-        for i in range(-args.warmup, args.steps):
-            _, case, _ = wl.sched(i if i >= 0 else -i)           # warm-up: B pictures
-            secs = case.run_stock(threads=T)[2]
-            if i >= 0: ts.append(secs)
-        fps = len(ts) / sum(ts)
-    cb = {"value": round(fps, 3), "unit": "frames/s", "cores": T, "kind": "reference", "recon_instances": D,
-          "sample": f"the {args.steps} pictures of the schedule through {D} DecLibRecon instance(s) taking them in turn (decompressPicture..waitForPrevDecompressedPic), ThreadPool({T}), {wl.ref.ref_simd_level().decode()}"}
+        if secs > 0:
+            fpsD = args.steps / secs
+            if fpsD > fps: fps, used = fpsD, D
+    cb = {"value": round(fps, 3), "unit": "frames/s", "cores": T, "kind": "reference", "recon_instances": used,
+          "one_instance_fps": round(fps1, 3), "alternating_instances_fps": round(fpsD, 3) if fpsD else None,
+          "sample": f"the {args.steps} pictures of the schedule through the reference's DecLibRecon (decompressPicture..waitForPrevDecompressedPic), ThreadPool({T}), {wl.ref.ref_simd_level().decode()}: "
+                    f"one instance picture after picture, and {D} instances taking pictures in turn as DecLib runs them (DecLib.h:70); value = the faster ({used} instance(s))"}
     line = {"impl": "reference", "metric": METRIC, "value": round(fps, 3), "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 / fps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int16 samples / int32 accumulate", "data": "synthetic",

@@ -40,7 +40,8 @@ def test_intra_sub_partitions_vs_oracle(b200, oracle, W, H, bd, ctu, min_size, s
     layout = synth.gen_intra_layout(rng, W, H, ctu, min_size=min_size)
     recs = synth.gen_intra_records(rng, layout, W, H, p_resi=0.5, p_lm=0.2, p_isp=0.4)
     isp = recs[(recs["flags"] & abi.INTRA_ISP) != 0]
-    assert len(isp) > 20 and (isp["log2h"] == 0).any() and ((isp["mip"] & 3) == 2).any() and (isp["ciip"] > 1).any()
+    assert len(isp) > 20 and ((isp["mip"] & 3) == 2).any()
+    if min_size == 4: assert (isp["log2h"] == 0).any() and (isp["ciip"] > 1).any() and (((isp["mip"] >> 4) & 3) == 0).any()      # 1-high regions, several TUs in a region, 4-wide CUs
     planes = synth.noise_planes(rng, W, H, bd)
     resi = [rng.integers(-40, 41, size=p.shape).astype(np.int16) for p in planes]
     want = [p.copy() for p in planes]; got = [p.copy() for p in planes]

@@ -6,7 +6,7 @@ is missing, calls raise."""
 import os, ctypes as C
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libvvdec_b200.so")
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(_HERE, "csrc", "libvvdec_b200.so")      # B200_LIB: an instrumented build of the same library (tools/)
 _lib = None
 
 

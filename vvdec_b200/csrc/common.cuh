@@ -175,7 +175,7 @@ inline size_t intra_order_ints(const b200_geom& g, size_t numTus) { return numTu
 __host__ __device__ inline bool intra_isp_record_ok(const b200_intra_tu& t, const b200_intra_tu* prev, int W, int H)
 {
   const int sp = t.mip & 3, k = (t.mip >> 2) & 3, l2n = (t.mip >> 4) & 3, nReg = 1 << l2n, rw = 1 << t.log2w, rh = 1 << t.log2h;
-  if (t.comp || t.mode > 66 || t.multiRefIdx || (sp != 1 && sp != 2) || l2n < 1 || l2n > 2 || k >= nReg || (t.mip >> 6) || t.log2w < 2 || t.log2w > 6 || t.log2h > 6) return false;
+  if (t.comp || t.mode > 66 || t.multiRefIdx || (sp != 1 && sp != 2) || l2n > 2 || (l2n == 0 && (sp != 2 || rw != 4)) /* one region: a 4-wide CU split into 1- or 2-sample columns */ || k >= nReg || (t.mip >> 6) || t.log2w < 2 || t.log2w > 6 || t.log2h > 6) return false;
   const int cw = sp == 2 ? rw * nReg : rw, ch = sp == 1 ? rh * nReg : rh, cx = t.x - (sp == 2 ? k * rw : 0), cy = t.y - (sp == 1 ? k * rh : 0);
   if (cw > 64 || ch > 64 || ch < 4 || cw * ch < 32 || cx < 0 || cy < 0 || (cx & 3) || (cy & 3) || cx + cw > W || cy + ch > H) return false;
   if (t.numAbove > 2 * cw / 4 || t.numLeft > 2 * ch / 4 || (t.numAbove && !cy) || (t.numLeft && !cx) || ((t.flags & B200_INTRA_AVAIL_TL) && (!cx || !cy))

@@ -524,7 +524,7 @@ __device__ __forceinline__ bool v2_wait(const IntraParams& P, const volatile uin
 }
 
 #ifdef B200_K6_PROF
-__device__ unsigned long long gK6Prof[16];
+__device__ unsigned long long gK6Prof[48];
 #define K6P(i, t0) do { if (lane == 0) atomicAdd(&gK6Prof[i], (unsigned long long)(clock64() - (t0))); } while (0)
 #define K6C(i) do { if (lane == 0) atomicAdd(&gK6Prof[i], 1ull); } while (0)
 #else
@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(V2_GROUP * V2_GROUPS, 1) intra_ctu_kernel(cons
       V2_SYNC();
       const int k = SC.ticket;
       if (k >= cnt) break;
-      tp = clock64();
+      tp = clock64(); const long long tb0 = tp; (void)tb0;
       const int me = first + k;
       const b200_intra_tu t = k < V2_RECS ? srec[k] : P.tus[me];
       if ((P.compSel == 1 && t.comp != 0) || (P.compSel == 2 && t.comp == 0)) continue;      // the other channel's pass
@@ -645,7 +645,8 @@ __global__ void __launch_bounds__(V2_GROUP * V2_GROUPS, 1) intra_ctu_kernel(cons
       }
       if (far) __threadfence(); else __threadfence_block();      // a thread that saw another CTU's done word orders the plane reads of its group behind it
       V2_SYNC();
-      K6P(1, tp); tp = clock64();                               // [1] dependency wait
+      const int pb = c ? 16 : 0; (void)pb;
+      K6P(pb + 1, tp); tp = clock64();                          // [1] dependency wait
 
       // ---- reference samples (xFillReferenceSamples): T[j] = row above incl. the corner, L[i] = left column, T[0] = L[0] = corner
       const int predSize = 2 * bw, predHSize = 2 * bh;
@@ -672,7 +673,7 @@ __global__ void __launch_bounds__(V2_GROUP * V2_GROUPS, 1) intra_ctu_kernel(cons
         V2_SYNC();
       }
 
-      K6P(2, tp); tp = clock64();                               // [2] reference samples (+ filter)
+      K6P(pb + 2, tp); tp = clock64();                          // [2] reference samples (+ filter)
       const int mode = t.mode;
       const bool doPDPC = w >= 4 && h >= 4 && mrl == 0;
       int16_t* dstG = P.planes[c] + (size_t)y0 * ps + x0;
@@ -891,14 +892,14 @@ __global__ void __launch_bounds__(V2_GROUP * V2_GROUPS, 1) intra_ctu_kernel(cons
       // (left, above and above-right references of the CTUs right of / below it): blocks that touch neither skip the device-scope fence and the done word
       __threadfence_block();
       V2_SYNC();
-      K6P(3, tp); tp = clock64();                               // [3] prediction + stores
+      K6P(pb + 3, tp); tp = clock64();                          // [3] prediction + stores
       if (lane == 0) sflag[k] = 1;
       if (x0 + w == tox + ttw || y0 + h == toy + tth) {
         __threadfence();
         V2_SYNC();
         if (lane == 0) atomicExch(P.done + me, 1);
       }
-      K6P(4, tp); K6C(9);                        // [4] device fence + done word, [9] blocks
+      K6P(pb + 4, tp); K6C(pb + 9); K6P(pb + 10 + min(4, max(0, ((int)t.log2w + (int)t.log2h - 4) >> 1)), tb0);   // [4] device fence + done word, [9] blocks, [10..14] whole block by size class
     }
 #undef V2_SYNC
   }
@@ -926,9 +927,14 @@ __global__ void __launch_bounds__(256) intra_validate_kernel(const b200_intra_tu
 #ifdef B200_K6_PROF
 extern "C" __attribute__((visibility("default"))) void b200_k6_prof_dump(int reset)
 {
-  unsigned long long h[16]; cudaDeviceSynchronize(); cudaMemcpyFromSymbol(h, gK6Prof, sizeof(h));
-  const double nb = (double)(h[9] ? h[9] : 1), nc = (double)(h[8] ? h[8] : 1);
-  fprintf(stderr, "K6 prof: %.0f blocks, %.0f group-CTUs | per CTU set-up %.0f cyc | per block: wait %.0f, refs %.0f, predict %.0f, publish %.0f cyc\n", nb, nc, h[0] / nc, h[1] / nb, h[2] / nb, h[3] / nb, h[4] / nb);
+  unsigned long long h[48]; cudaDeviceSynchronize(); cudaMemcpyFromSymbol(h, gK6Prof, sizeof(h));
+  const double nc = (double)(h[8] ? h[8] : 1);
+  fprintf(stderr, "K6 prof: %.0f group-CTUs, set-up %.0f cyc each\n", nc, h[0] / nc);
+  for (int c = 0; c < 2; c++) {
+    const int b = c * 16; const double nb = (double)(h[b + 9] ? h[b + 9] : 1);
+    fprintf(stderr, "  %s: %.0f blocks | wait %.0f, refs %.0f, predict %.0f, publish %.0f cyc | whole block by size class (<=32, <=128, <=512, <=2048, more samples): %.0f %.0f %.0f %.0f %.0f cyc-sums/blocks\n", c ? "chroma" : "luma", nb,
+            h[b + 1] / nb, h[b + 2] / nb, h[b + 3] / nb, h[b + 4] / nb, h[b + 10] / nb, h[b + 11] / nb, h[b + 12] / nb, h[b + 13] / nb, h[b + 14] / nb);
+  }
   if (reset) { memset(h, 0, sizeof(h)); cudaMemcpyToSymbol(gK6Prof, h, sizeof(h)); }
 }
 #endif
@@ -979,7 +985,8 @@ int launch_intra(const IntraLaunch& L, cudaStream_t s)
     static const int shape = getenv("B200_INTRA_GROUP") ? atoi(getenv("B200_INTRA_GROUP")) : 0;      // measurement switch: threads per block group
 #define V2_GO(G, N) do { static bool attr = false; if (!attr) { B200_CUDA(cudaFuncSetAttribute(intra_ctu_kernel<G, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2_smem(N))); attr = true; } \
                          intra_ctu_kernel<G, N><<<ctas, G * N, v2_smem(N), s>>>(P, ctuOrder, counters); } while (0)
-    if (shape == 64) V2_GO(64, 6); else if (shape == 32) V2_GO(32, 8); else if (shape == 2566) V2_GO(256, 3); else V2_GO(128, 4);
+    // measured on a 4K I picture (66810 blocks): 128x4 7.45 ms, 128x6 6.97 ms, 128x8 7.70 ms, 64x6 7.62 ms, 64x12 7.61 ms, 256x3 9.22 ms, 32x8 17.9 ms
+    if (shape == 1284) V2_GO(128, 4); else if (shape == 32) V2_GO(32, 8); else V2_GO(128, 6);
 #undef V2_GO
     B200_CUDA(cudaGetLastError());
     return 0;
