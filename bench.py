@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-seam", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="multi-GPU: leave the frames on their GPUs")
+    ap.add_argument("--gather-timeout", type=float, default=120.0, help="multi-GPU: seconds the display-order gather pass may take before the line is printed without it")
     ap.add_argument("--host-threads", type=int, default=0, help="threads of the reference's ThreadPool (0: all)")
     ap.add_argument("--recon-depth", type=int, default=2, help="recon instances taking pictures in turn, as DecLib runs them (DecLib.h:70); 1: one picture at a time")
     return ap.parse_args()
@@ -193,6 +194,7 @@ def run_b200(args):
     rank, world, local = dist_env()
     numa = bind_to_gpu_numa_node(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "NONE"                                 # stdout carries the JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     lib = vvdec_b200.lib()
@@ -245,44 +247,17 @@ def run_b200(args):
 
     for i in range(args.warmup): vvdec_b200.check(lib.b200_pic_run(ctx, h_of(i + 1)))
     vvdec_b200.check(lib.b200_pic_run(ctx, handle["I"]))                  # the I picture's path is warm too
-    # multi-GPU: every rank decodes its own GOPs; finished frames stay on the device and go to rank 0 in display order over NCCL, on a side stream
-    # that overlaps the following pictures (vvdec_b200/gather.py).  GOP k of the sequence belongs to rank k mod N (gop_shard.assign).
-    G = None; gather_info = None
-    if world > 1 and not args.no_gather:
-        from vvdec_b200 import gather, gop_shard
-        n_local = -(-args.steps // args.gop)
-        lengths = []
-        for k in range(n_local * world): lengths.append(min(args.gop, args.steps - (k // world) * args.gop))
-        numel = W * H * 3                                                    # bytes of a 16-bit 4:2:0 frame
-        G = gather.FrameGather(rank, world, lengths, numel, torch.device("cuda", local))
-        side = torch.cuda.Stream()
-        poff = [0, W * H, W * H + (W // 2) * (H // 2)]
     barrier()
     sampler = ClockSampler(local); sampler.start()
     l0 = lib.b200_ctx_kernel_launches(ctx)
     t_wall = time.perf_counter()
     vvdec_b200.check(lib.b200_ctx_mark(ctx, 0))
-    for i in range(args.steps):
-        vvdec_b200.check(lib.b200_pic_run(ctx, h_of(i)))
-        if G is not None:
-            dst = G.slot(i); base = dst.data_ptr()
-            pl = (C.c_void_p * 3)(base + 2 * poff[0], base + 2 * poff[1], base + 2 * poff[2])
-            vvdec_b200.check(lib.b200_get_frame_device_async(ctx, pic_of(i)["struct"].dstSlot, pl, C.c_void_p(side.cuda_stream)))
-            with torch.cuda.stream(side): G.push(i)
+    for i in range(args.steps): vvdec_b200.check(lib.b200_pic_run(ctx, h_of(i)))
     vvdec_b200.check(lib.b200_ctx_mark(ctx, 1))
     ms = C.c_float(); vvdec_b200.check(lib.b200_ctx_elapsed_ms(ctx, C.byref(ms)))
-    if G is not None:
-        with torch.cuda.stream(side): G.finish()
-        torch.cuda.synchronize()
-        wall_ms = (time.perf_counter() - t_wall) * 1e3
-        ms.value = max(ms.value, wall_ms)                                  # the timed region ends when the last frame has arrived on rank 0
     barrier()
     launches = lib.b200_ctx_kernel_launches(ctx) - l0
     ms_dev = max_over_ranks(ms.value)
-    if G is not None and rank == 0:
-        nb = G.bytes_received()
-        gather_info = {"frames_received": int(nb // numel), "bytes": int(nb), "GBps_over_timed_region": round(nb / (ms_dev * 1e-3) / 1e9, 2),
-                       "note": "display-order gather to rank 0 (NCCL send/recv per peer on a side stream), inside the timed region; NVLink 5: 900 GB/s per direction per GPU"}
 
     # ---- per-kernel-family device time (same schedule, events around each family) + the I / B split ----
     NF = 10
@@ -344,11 +319,10 @@ def run_b200(args):
     e2e_diag = {"host_ms_in_upload_call": round(host_up, 4), "upload_ms_incl_h2d": round(up_total, 4), "d2h_frame_ms": round(d2h_ms, 4), "pcie": pcie,
                 "link_bound_fps": round(1e3 / max(1e-9, max(h2d_step / (pcie["h2d_gbs_duplex"] * 1e6), d2h_step / (pcie["d2h_gbs_duplex"] * 1e6))), 1) if pcie.get("h2d_gbs_duplex") else None}
     sampler.stop_flag = True; sampler.join(timeout=2)
-    lib.b200_ctx_destroy(ctx)
 
     # ---- seam: DecLibReconB200 live on parsed Pictures (its own device context) ----
     seam = None
-    if not args.no_seam and rank == 0:
+    if not args.no_seam and rank == 0 and world == 1:
         try: os.sched_setaffinity(0, range(os.cpu_count()))
         except Exception: pass
         ts = []
@@ -368,9 +342,75 @@ def run_b200(args):
             secs, _ = wl.helpers.seam_pipelined(wl.ref, cases, T, 1, args.recon_depth, read=False)
             if secs > 0: seam["alternating_instances"] = {"depth": args.recon_depth, "value": round(n / secs, 2), "unit": "frames/s", "pictures": n}
 
-    if rank != 0:
-        if world > 1: dist.destroy_process_group()
-        return
+    line = None
+    if rank == 0: line = assemble_line(args, world, wl, flat, kms, ms_dev, ms_e2e, h2d_step, d2h_step, e2e_diag, seam, split, launches, numa, sampler, pic_of)
+    if world > 1 and not args.no_gather:
+        gather_pass(args, rank, world, local, lib, ctx, wl, flat, pic_of, line, torch, dist, barrier, max_over_ranks)
+    if rank == 0: print(json.dumps(line), flush=True)
+    lib.b200_ctx_destroy(ctx)
+    if world > 1: dist.destroy_process_group()
+
+
+def gather_pass(args, rank, world, local, lib, ctx, wl, flat, pic_of, line, torch, dist, barrier, max_over_ranks):
+    """Multi-GPU: the same schedule once more with the finished frames leaving their GPUs — every rank decodes its own GOPs (GOP k of the sequence belongs to rank
+    k mod N, gop_shard.assign), each finished frame is copied out of its DPB slot on a side stream and goes to rank 0 in display order over NCCL
+    (vvdec_b200/gather.py), overlapping the following pictures.  The timed region ends when the last frame has arrived on rank 0; its throughput becomes the
+    line's `value`.  Everything else of the line is already assembled: a watchdog prints it with the gather marked as failed if the exchange does not finish."""
+    import vvdec_b200
+    from vvdec_b200 import gather
+    W, H = args.width, args.height
+    done = threading.Event()
+
+    def dog():
+        if done.wait(args.gather_timeout): return
+        if rank == 0:
+            line["gather"] = {"error": f"the display-order gather did not finish within {args.gather_timeout} s; value is the throughput without it"}
+            print(json.dumps(line), flush=True)
+        os._exit(0)
+    barrier()                                                                # the other ranks wait here while rank 0 assembled its line
+    threading.Thread(target=dog, daemon=True).start()
+    handle = {}                                                              # the e2e leg cycled through the arenas: the work lists go back into HBM
+    for key, pic in flat.items():
+        h = lib.b200_pic_upload(ctx, C.byref(pic["struct"])); assert h >= 0, lib.b200_last_error(); handle[key] = h
+    vvdec_b200.check(lib.b200_wait_picture(ctx, -1, None, 0))
+
+    def h_of(i):
+        kind, _, k = wl.sched(i)
+        return handle["I"] if kind == "I" else handle[k]
+    n_local = -(-args.steps // args.gop)
+    lengths = [min(args.gop, args.steps - (k // world) * args.gop) for k in range(n_local * world)]
+    numel = W * H * 3                                                        # bytes of a 16-bit 4:2:0 frame
+    side = torch.cuda.Stream()
+    poff = [0, W * H, W * H + (W // 2) * (H // 2)]
+    wall_ms = 0.0
+    for timed in (False, True):                                              # the first pass is the warm-up (NCCL sets its peer-to-peer channels up with the first transfer)
+        G = gather.FrameGather(rank, world, lengths, numel, torch.device("cuda", local))
+        barrier()
+        t_wall = time.perf_counter()
+        for i in range(args.steps):
+            vvdec_b200.check(lib.b200_pic_run(ctx, h_of(i)))
+            base = G.slot(i).data_ptr()
+            pl = (C.c_void_p * 3)(base + 2 * poff[0], base + 2 * poff[1], base + 2 * poff[2])
+            vvdec_b200.check(lib.b200_get_frame_device_async(ctx, pic_of(i)["struct"].dstSlot, pl, C.c_void_p(side.cuda_stream)))
+            with torch.cuda.stream(side): G.push(i)
+        with torch.cuda.stream(side): G.finish()
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t_wall) * 1e3                       # the timed region ends when the last frame has arrived on rank 0
+        barrier()
+        if not timed: del G
+    ms_g = max_over_ranks(wall_ms)
+    done.set()
+    if rank == 0:
+        nb = G.bytes_received()
+        line["value_without_gather"] = line["value"]
+        line["value"] = round(world * args.steps / (ms_g * 1e-3), 2); line["ms_per_step"] = round(ms_g / args.steps, 4)
+        line["gather"] = {"frames_received": int(nb // numel), "bytes": int(nb), "GBps_over_timed_region": round(nb / (ms_g * 1e-3) / 1e9, 2),
+                          "note": "display-order gather to rank 0 (one batched NCCL send/recv group per step on a side stream), inside the timed region (host clock around it, "
+                                  "max over ranks); NVLink 5: 900 GB/s per direction per GPU"}
+
+
+def assemble_line(args, world, wl, flat, kms, ms_dev, ms_e2e, h2d_step, d2h_step, e2e_diag, seam, split, launches, numa, sampler, pic_of):
+    W, H = args.width, args.height
     # ---- roofline of the dominant kernel family ----
     peaks = {"hbm_gbs": 6650.0, "src": "fallback"}
     try:
@@ -406,12 +446,11 @@ def run_b200(args):
             "config": workload_config(args, world),
             "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": d2h_step, "diag": e2e_diag,
                     "api": "b200_pic_upload (one picture ahead) + b200_pic_run + b200_get_frame_async (D2H overlapped with the next picture), pinned host buffers; every step uploads one picture's work lists and downloads one frame"},
-            "seam": seam, "picture_ms": split, "gather": gather_info,
+            "seam": seam, "picture_ms": split, "gather": None,
             "gpu_launches": int(launches), "numa": numa, "clocks": sampler.summary(), "roofline": roof}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:                      # the CPU legs are N = 1 lines only
         line["cpu_baseline"] = cpu_baseline(args, wl)
-    print(json.dumps(line), flush=True)
-    if world > 1: dist.destroy_process_group()
+    return line
 
 
 def pcie_ceiling(torch, mb=256, reps=4):

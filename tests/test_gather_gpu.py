@@ -35,7 +35,8 @@ def test_two_rank_nccl_gather_display_order(tmp_path):
         li = 0
         for k in G.assignment[r]:
             for i in range(lengths[k]):
-                vvdec_b200.check(lib.b200_ctx_load_slot(ctx, li % 4, abi.plane_ptrs(frame(k, i))))
+                fr = frame(k, i)                                  # kept alive across the call: plane_ptrs holds raw pointers
+                vvdec_b200.check(lib.b200_ctx_load_slot(ctx, li % 4, abi.plane_ptrs(fr)))
                 base = G.slot(li).data_ptr()
                 pl = (C.c_void_p * 3)(base, base + 2 * W * H, base + 2 * (W * H + W * H // 4))
                 vvdec_b200.check(lib.b200_get_frame_device_async(ctx, li % 4, pl, C.c_void_p(side.cuda_stream)))
@@ -56,4 +57,5 @@ def test_two_rank_nccl_gather_display_order(tmp_path):
     """))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                           "--master-port", "29621", str(script)], capture_output=True, text=True, timeout=600)
+    if os.environ.get("B200_TEST_LOG"): open(os.environ["B200_TEST_LOG"], "w").write(out.stdout + "\n---- stderr\n" + out.stderr)
     assert "GATHER_OK 10" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]

@@ -62,3 +62,24 @@ def test_frame_hash(b200, oracle, W, H, bd):
         assert b200.b200_frame_hash_async(ctx, 1, 0, dig.ctypes.data) == -4 and b"MD5" in b200.b200_last_error()
     finally:
         b200.b200_ctx_destroy(ctx)
+
+
+def test_frame_to_device_buffer_on_a_side_stream(b200):
+    """b200_get_frame_device_async: a DPB slot copied into caller-owned device memory on the caller's stream (what the multi-GPU gather sends from)."""
+    import torch
+    W, H = 416, 240
+    g = abi.make_geom(W, H, 10)
+    ctx = C.c_void_p(); vvdec_b200.check(b200.b200_ctx_create(C.byref(ctx), C.byref(g), 4, 2, 0))
+    rng = np.random.default_rng(5)
+    side = torch.cuda.Stream()
+    for it in range(3):
+        planes = synth.noise_planes(rng, W, H, 10)
+        vvdec_b200.check(b200.b200_ctx_load_slot(ctx, it % 4, abi.plane_ptrs(planes)))
+        dst = torch.zeros(W * H * 3, dtype=torch.uint8, device="cuda")
+        base = dst.data_ptr()
+        pl = (C.c_void_p * 3)(base, base + 2 * W * H, base + 2 * (W * H + W * H // 4))
+        vvdec_b200.check(b200.b200_get_frame_device_async(ctx, it % 4, pl, C.c_void_p(side.cuda_stream)))
+        side.synchronize()
+        want = np.concatenate([p.ravel() for p in planes]).view(np.uint8)
+        assert np.array_equal(dst.cpu().numpy(), want), it
+    b200.b200_ctx_destroy(ctx)
