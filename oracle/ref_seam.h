@@ -551,7 +551,8 @@ static Pic* build( const b200_geom* g, const ref_seam_cfg* c, const int16_t* con
 {
   std::unique_ptr<Pic> P( new Pic );
   P->g = *g; P->cfg = *c;
-  P->cur.reset( new FakePicture( *g, 1 ) );
+  const int nSl = std::max( 1, std::min( (int) c->numSlices, 16 ) );
+  P->cur.reset( new FakePicture( *g, nSl ) );
   FakePicture& cur = *P->cur;
   SEAM_TR( "build: picture created\n" );
   setupSps( cur, *c, *g );
@@ -566,32 +567,39 @@ static Pic* build( const b200_geom* g, const ref_seam_cfg* c, const int16_t* con
   SEAM_TR( "build: refs done\n" );
   CodingStructure& cs = *cur.pic.cs;
   const PreCalcValues& pcv = *cs.pcv;
-  Slice* sl = cur.pic.slices[0];
+  auto sliceOfCtu = [&]( unsigned a ) { return (int) ( (uint64_t) a * nSl / pcv.sizeInCtus ); };
+  const bool doLf = filt && ( filt->flags & B200_PIC_DEBLOCK ), doSao = filt && ( filt->flags & B200_PIC_SAO ) && ( c->tools & SEAM_SAO ), doAlf = filt && ( filt->flags & B200_PIC_ALF ) && ( c->tools & SEAM_ALF );
+  const APS* apss[ALF_CTB_MAX_NUM_APS] = { nullptr };
+  if( doAlf ) for( int i = 0; i < ALF_CTB_MAX_NUM_APS; i++ ) { P->alfAps[i] = std::make_shared<APS>(); P->alfAps[i]->setAPSId( i ); apss[i] = P->alfAps[i].get(); }
+  for( int s = 0; s < nSl; s++ )
+  {
+  Slice* sl = cur.pic.slices[s];
+  const bool odd = s & 1;
   sl->setSliceType( intraPic ? I_SLICE : c->sliceType == 1 ? P_SLICE : B_SLICE ); sl->setPOC( 8 ); cur.pic.poc = 8;
   sl->setSliceQp( c->qp ); sl->setDepQuantEnabledFlag( c->tools & SEAM_DEPQUANT ); sl->setSignDataHidingEnabledFlag( false ); sl->setTSResidualCodingDisabledFlag( false );
-  sl->setExplicitScalingListUsed( false ); sl->setIndependentSliceIdx( 0 ); sl->setCheckLDC( false );
+  sl->setExplicitScalingListUsed( false ); sl->setIndependentSliceIdx( s ); sl->setCheckLDC( false );
   if( !intraPic )
   {
     const int nL1 = sl->isInterB() ? 2 : 0;
     for( int l = 0; l < 2; l++ ) for( int i = 0; i < 2; i++ )
-    { sl->m_apcRefPicList[l][i] = &P->ref[l * 2 + i]->pic; sl->m_aiRefPOCList[l][i] = pocs[l * 2 + i]; sl->m_bIsUsedAsLongTerm[l][i] = false; }
+    { const int k = l * 2 + ( odd ? 1 - i : i ); sl->m_apcRefPicList[l][i] = &P->ref[k]->pic; sl->m_aiRefPOCList[l][i] = pocs[k]; sl->m_bIsUsedAsLongTerm[l][i] = false; }
     sl->setNumRefIdx( REF_PIC_LIST_0, 2 ); sl->setNumRefIdx( REF_PIC_LIST_1, nL1 );
     sl->resetWpScaling();
-    if( sl->isInterB() ) sl->setBiDirPred( true, 0, 0 );                            // POC 4 and 12: the closest pair around POC 8 (Slice::setSMVDParam)
+    if( sl->isInterB() ) sl->setBiDirPred( true, odd ? 1 : 0, odd ? 1 : 0 );        // POC 4 and 12: the closest pair around POC 8 (Slice::setSMVDParam)
   }
-  { SliceMap sm; sm.addCtusToSlice( 0, pcv.widthInCtus, 0, pcv.heightInCtus, pcv.widthInCtus ); sl->setSliceMap( sm ); }
+  { SliceMap sm; for( unsigned a = 0; a < pcv.sizeInCtus; a++ ) if( sliceOfCtu( a ) == s ) sm.addCtusToSlice( a % pcv.widthInCtus, a % pcv.widthInCtus + 1, a / pcv.widthInCtus, a / pcv.widthInCtus + 1, pcv.widthInCtus ); sl->setSliceMap( sm ); }
   cur.pic.stillReferenced = true; cur.pic.neededForOutput = true;
   SEAM_TR( "build: slice done\n" );
   // deblocking / SAO / ALF / LMCS state from the flat description (the same content the other tests use)
-  const bool doLf = filt && ( filt->flags & B200_PIC_DEBLOCK ), doSao = filt && ( filt->flags & B200_PIC_SAO ) && ( c->tools & SEAM_SAO ), doAlf = filt && ( filt->flags & B200_PIC_ALF ) && ( c->tools & SEAM_ALF );
   sl->setDeblockingFilterDisable( !doLf );
   if( doLf )
   {
-    sl->setDeblockingFilterBetaOffsetDiv2( filt->lfSlices[0].betaOffsetDiv2[0] ); sl->setDeblockingFilterTcOffsetDiv2( filt->lfSlices[0].tcOffsetDiv2[0] );
-    sl->setDeblockingFilterCbBetaOffsetDiv2( filt->lfSlices[0].betaOffsetDiv2[1] ); sl->setDeblockingFilterCbTcOffsetDiv2( filt->lfSlices[0].tcOffsetDiv2[1] );
-    sl->setDeblockingFilterCrBetaOffsetDiv2( filt->lfSlices[0].betaOffsetDiv2[2] ); sl->setDeblockingFilterCrTcOffsetDiv2( filt->lfSlices[0].tcOffsetDiv2[2] );
+    auto off = [&]( int v, int k ) { return std::max( -12, std::min( 12, v + ( s ? ( s * 3 + k ) % 5 - 2 : 0 ) ) ); };      // other slices: other offsets
+    sl->setDeblockingFilterBetaOffsetDiv2( off( filt->lfSlices[0].betaOffsetDiv2[0], 0 ) ); sl->setDeblockingFilterTcOffsetDiv2( off( filt->lfSlices[0].tcOffsetDiv2[0], 1 ) );
+    sl->setDeblockingFilterCbBetaOffsetDiv2( off( filt->lfSlices[0].betaOffsetDiv2[1], 2 ) ); sl->setDeblockingFilterCbTcOffsetDiv2( off( filt->lfSlices[0].tcOffsetDiv2[1], 3 ) );
+    sl->setDeblockingFilterCrBetaOffsetDiv2( off( filt->lfSlices[0].betaOffsetDiv2[2], 4 ) ); sl->setDeblockingFilterCrTcOffsetDiv2( off( filt->lfSlices[0].tcOffsetDiv2[2], 5 ) );
   }
-  for( unsigned a = 0; a < pcv.sizeInCtus; a++ )
+  if( s == 0 ) for( unsigned a = 0; a < pcv.sizeInCtus; a++ )
   {
     SAOBlkParam& bp = cs.getCtuData( a ).saoParam; bp.reset();
     if( !doSao ) continue;
@@ -607,41 +615,49 @@ static Pic* build( const b200_geom* g, const ref_seam_cfg* c, const int16_t* con
   if( doAlf )
   {
     const b200_alf_tables* T = filt->alfTabs;
-    const APS* apss[ALF_CTB_MAX_NUM_APS] = { nullptr };
-    for( int i = 0; i < ALF_CTB_MAX_NUM_APS; i++ ) { P->alfAps[i] = std::make_shared<APS>(); P->alfAps[i]->setAPSId( i ); apss[i] = P->alfAps[i].get(); }
+    const int nAps = T->numLumaSets - 16;
+    const bool noCc = s % 3 == 2;                                    // every third slice: CC-ALF and the Cr filter off
     AlfApsIdVec ids;
-    for( int i = 0; i < T->numLumaSets - 16; i++ )
+    for( int i = 0; i < nAps; i++ )
     {
-      AlfSliceParam& p = P->alfAps[i]->getAlfAPSParam();
-      memcpy( p.lumaCoeffFinal, T->lumaCoeff + (size_t) ( 16 + i ) * 1300, 2600 ); memcpy( p.lumaClippFinal, T->lumaClip + (size_t) ( 16 + i ) * 1300, 2600 );
-      p.lumaFinalDone = true; ids.push_back( i );
+      if( s == 0 )
+      {
+        AlfSliceParam& p = P->alfAps[i]->getAlfAPSParam();
+        memcpy( p.lumaCoeffFinal, T->lumaCoeff + (size_t) ( 16 + i ) * 1300, 2600 ); memcpy( p.lumaClippFinal, T->lumaClip + (size_t) ( 16 + i ) * 1300, 2600 );
+        p.lumaFinalDone = true;
+      }
+      ids.push_back( odd ? nAps - 1 - i : i );                       // odd slices list the luma APSs backwards: the same CTU index means another filter set
     }
-    sl->setNumAlfAps( T->numLumaSets - 16 ); sl->setAlfApsIdsLuma( ids );
-    AlfSliceParam& pc = P->alfAps[7]->getAlfAPSParam();
-    pc.numAlternativesChroma = T->numChromaAlts;
-    memcpy( pc.chromaCoeff, T->chromaCoeff, T->numChromaAlts * 14 ); memcpy( pc.chrmClippFinal, T->chromaClip, T->numChromaAlts * 14 ); pc.chrmFinalDone = true;
+    sl->setNumAlfAps( nAps ); sl->setAlfApsIdsLuma( ids );
+    if( s == 0 )
+    {
+      AlfSliceParam& pc = P->alfAps[7]->getAlfAPSParam();
+      pc.numAlternativesChroma = T->numChromaAlts;
+      memcpy( pc.chromaCoeff, T->chromaCoeff, T->numChromaAlts * 14 ); memcpy( pc.chrmClippFinal, T->chromaClip, T->numChromaAlts * 14 ); pc.chrmFinalDone = true;
+      for( int k = 0; k < 2; k++ )
+      {
+        CcAlfFilterParam& cp = P->alfAps[6 - k]->getCcAlfAPSParam();
+        for( int f = 0; f < T->numCc[k]; f++ ) memcpy( cp.ccAlfCoeff[k][f], T->ccCoeff[k] + f * 7, 14 );
+        cp.ccAlfFilterCount[k] = (uint8_t) T->numCc[k];
+      }
+    }
     sl->setAlfApsIdChroma( 7 );
-    for( int k = 0; k < 2; k++ )
-    {
-      CcAlfFilterParam& cp = P->alfAps[6 - k]->getCcAlfAPSParam();
-      for( int f = 0; f < T->numCc[k]; f++ ) memcpy( cp.ccAlfCoeff[k][f], T->ccCoeff[k] + f * 7, 14 );
-      cp.ccAlfFilterCount[k] = (uint8_t) T->numCc[k];
-    }
-    sl->setCcAlfCbEnabledFlag( T->numCc[0] > 0 ); sl->setCcAlfCrEnabledFlag( T->numCc[1] > 0 ); sl->setCcAlfCbApsId( 6 ); sl->setCcAlfCrApsId( 5 );
+    sl->setCcAlfCbEnabledFlag( T->numCc[0] > 0 && !noCc ); sl->setCcAlfCrEnabledFlag( T->numCc[1] > 0 && !noCc ); sl->setCcAlfCbApsId( 6 ); sl->setCcAlfCrApsId( 5 );
     sl->setAlfApss( apss );
-    for( int k = 0; k < 3; k++ ) sl->setAlfEnabledFlag( ComponentID( k ), true );
+    for( int k = 0; k < 3; k++ ) sl->setAlfEnabledFlag( ComponentID( k ), !( noCc && k == 2 ) );
     for( unsigned a = 0; a < pcv.sizeInCtus; a++ )
     {
+      if( sliceOfCtu( a ) != s ) continue;
       CtuAlfData& d = cs.getCtuData( a ).alfParam;
-      for( int k = 0; k < 3; k++ ) d.alfCtuEnableFlag[k] = filt->alf[a].enable[k] & 1;
+      for( int k = 0; k < 3; k++ ) d.alfCtuEnableFlag[k] = ( filt->alf[a].enable[k] & 1 ) && !( noCc && k == 2 );     // what the parser leaves when the slice flag is off
       d.alfCtbFilterIndex = filt->alf[a].lumaSet;
-      for( int k = 0; k < 2; k++ ) { d.alfCtuAlternative[k] = filt->alf[a].chromaAlt[k]; d.ccAlfFilterControl[k] = filt->alf[a].ccIdx[k]; }
+      for( int k = 0; k < 2; k++ ) { d.alfCtuAlternative[k] = filt->alf[a].chromaAlt[k]; d.ccAlfFilterControl[k] = noCc ? 0 : filt->alf[a].ccIdx[k]; }
     }
   }
   else for( int k = 0; k < 3; k++ ) sl->setAlfEnabledFlag( ComponentID( k ), false );
   if( c->tools & SEAM_LMCS )
   {
-    P->lmcsAps = std::make_shared<APS>(); P->lmcsAps->setAPSId( 0 ); P->lmcsAps->setAPSType( LMCS_APS );
+    if( s == 0 ) { P->lmcsAps = std::make_shared<APS>(); P->lmcsAps->setAPSId( 0 ); P->lmcsAps->setAPSType( LMCS_APS ); }
     SliceReshapeInfo& si = P->lmcsAps->getReshaperAPSInfo();
     si.sliceReshaperEnableFlag = true; si.sliceReshaperModelPresentFlag = true; si.enableChromaAdj = c->lmcsChromaAdj;
     si.reshaperModelMinBinIdx = c->lmcsMinBin; si.reshaperModelMaxBinIdx = c->lmcsMaxBin; si.chrResScalingOffset = c->lmcsChrOffset;
@@ -649,10 +665,11 @@ static Pic* build( const b200_geom* g, const ref_seam_cfg* c, const int16_t* con
     cur.ph->setLmcsEnabledFlag( true ); cur.ph->setLmcsChromaResidualScaleFlag( c->lmcsChromaAdj != 0 ); cur.ph->setLmcsAPS( P->lmcsAps );
     sl->setLmcsEnabledFlag( true );
   }
+  }   // slices
   // the coding tree of every CTU
   SEAM_TR( "build: state ready, generating %u CTUs\n", pcv.sizeInCtus );
-  Gen gen( cur, sl, *c );
-  for( unsigned a = 0; a < pcv.sizeInCtus; a++ ) { SEAM_TR( "ctu %u\n", a ); gen.ctu( a ); }
+  Gen gen( cur, cur.pic.slices[0], *c );
+  for( unsigned a = 0; a < pcv.sizeInCtus; a++ ) { SEAM_TR( "ctu %u\n", a ); gen.sl = cur.pic.slices[sliceOfCtu( a )]; gen.ctu( a ); }
   cur.pic.progress = Picture::parsed;
   cur.pic.parseDone.unlock();
   return P.release();

@@ -162,6 +162,8 @@ typedef struct ref_seam_cfg {
   int32_t  ispPct;           /* > 0 switches sps ISP on                                                         */
   int32_t  mvdSigmaQpel;     /* sigma of the MVDs in quarter samples                                            */
   int32_t  lmcsMinBin, lmcsMaxBin, lmcsDeltaCW[16], lmcsChrOffset, lmcsChromaAdj;   /* LMCS APS syntax (SEAM_LMCS) */
+  int32_t  numSlices;        /* raster-scan slices of about equal size (0 / 1: one); odd slices list their reference pictures in the opposite order, use other
+                              deblocking offsets and list their ALF luma APSs backwards; every third slice has CC-ALF and Cr ALF switched off        */
 } ref_seam_cfg;
 /* refs[slot*3+comp]: 4 reference pictures as in ref_mc_predict (unused for I pictures); filt: deblocking offsets / SAO / ALF parameters of the picture
  * (b200_picture::lfSlices, sao, alf, alfTabs and the DEBLOCK / SAO / ALF flags; the other members are ignored). */

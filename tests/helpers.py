@@ -122,16 +122,17 @@ SEAM_FILTERS = SEAM["SAO"] | SEAM["ALF"]
 class SeamCfg(C.Structure):
     _fields_ = [("seed", C.c_uint32)] + [(n, C.c_int32) for n in ("sliceType", "tools", "qp", "intraPct", "skipPct", "mergePct", "affinePct", "biPct", "rootCbfPct",
                                                                     "cbfPct", "splitPct", "ispPct", "mvdSigmaQpel", "lmcsMinBin", "lmcsMaxBin")] + \
-               [("lmcsDeltaCW", C.c_int32 * 16), ("lmcsChrOffset", C.c_int32), ("lmcsChromaAdj", C.c_int32)]
+               [("lmcsDeltaCW", C.c_int32 * 16), ("lmcsChrOffset", C.c_int32), ("lmcsChromaAdj", C.c_int32), ("numSlices", C.c_int32)]
 
 
-def seam_cfg(seed, slice_type=0, tools=None, qp=32, intra=15, skip=15, merge=50, affine=12, bi=60, root_cbf=45, cbf=35, split=75, isp=0, mvd_sigma=12, lmcs=None, virtual_boundaries=False):
+def seam_cfg(seed, slice_type=0, tools=None, qp=32, intra=15, skip=15, merge=50, affine=12, bi=60, root_cbf=45, cbf=35, split=75, isp=0, mvd_sigma=12, lmcs=None, virtual_boundaries=False, slices=1):
     c = SeamCfg()
     c.seed = seed; c.sliceType = slice_type
     c.tools = (SEAM_INTER_TOOLS | SEAM_RESI_TOOLS | SEAM_INTRA_TOOLS | SEAM_FILTERS) if tools is None else tools
     c.qp = qp; c.intraPct = intra; c.skipPct = skip; c.mergePct = merge; c.affinePct = affine; c.biPct = bi; c.rootCbfPct = root_cbf; c.cbfPct = cbf
     c.splitPct = split; c.ispPct = isp; c.mvdSigmaQpel = mvd_sigma
     if virtual_boundaries: c.tools |= SEAM["VIRTUAL_BOUNDARIES"]
+    c.numSlices = slices
     if lmcs is not None:                                      # the dict synth.gen_lmcs returns
         c.tools |= SEAM["LMCS"]; c.lmcsMinBin = lmcs["minBin"]; c.lmcsMaxBin = lmcs["maxBin"]; c.lmcsChrOffset = lmcs["chrOff"]; c.lmcsChromaAdj = int(lmcs["struct"].chromaAdj)
         for i in range(16): c.lmcsDeltaCW[i] = lmcs["delta"][i]
@@ -262,8 +263,9 @@ def picture_from_struct(st, g, filt):
     if st.numIntraTus:
         d["intraTus"] = _copy(st.intraTus, st.numIntraTus, abi.INTRA_TU_DTYPE); p.intraTus = d["intraTus"].ctypes.data; p.numIntraTus = st.numIntraTus
     if st.flags & abi.PIC_DEBLOCK:
-        d["lfV"] = _copy(st.lfV, W4 * H4, synth.LF_DTYPE); d["lfH"] = _copy(st.lfH, W4 * H4, synth.LF_DTYPE); d["lfSlices"] = _copy(st.lfSlices, 1, synth.LFSLICE_DTYPE)
-        p.lfV = d["lfV"].ctypes.data; p.lfH = d["lfH"].ctypes.data; p.lfSlices = d["lfSlices"].ctypes.data; p.numLfSlices = 1
+        d["lfV"] = _copy(st.lfV, W4 * H4, synth.LF_DTYPE); d["lfH"] = _copy(st.lfH, W4 * H4, synth.LF_DTYPE); d["lfSlices"] = _copy(st.lfSlices, st.numLfSlices, synth.LFSLICE_DTYPE)
+        p.lfV = d["lfV"].ctypes.data; p.lfH = d["lfH"].ctypes.data; p.lfSlices = d["lfSlices"].ctypes.data; p.numLfSlices = st.numLfSlices
+        if st.ctuSlice: d["ctuSlice"] = _copy(st.ctuSlice, nctu, np.uint8); p.ctuSlice = d["ctuSlice"].ctypes.data
     if st.flags & abi.PIC_SAO:
         d["sao"] = _copy(st.sao, nctu, synth.SAO_DTYPE); p.sao = d["sao"].ctypes.data
     if st.flags & abi.PIC_ALF:
@@ -361,7 +363,7 @@ def oracle_decompress(oracle, g, dpb, pic):
     else:
         oracle.orc_k1_residual(C.byref(g), abi.plane_ptrs(cur), pic["tus"].ctypes.data, len(pic["tus"]), pic["coefs"], None, 0)
     if st.flags & abi.PIC_DEBLOCK:
-        oracle.orc_lf_deblock(C.byref(g), abi.plane_ptrs(cur), pic["lfV"].ctypes.data, pic["lfH"].ctypes.data, None,
+        oracle.orc_lf_deblock(C.byref(g), abi.plane_ptrs(cur), pic["lfV"].ctypes.data, pic["lfH"].ctypes.data, pic["ctuSlice"].ctypes.data if "ctuSlice" in pic else None,
                               pic["lfSlices"].ctypes.data, None, 3)
     if st.flags & abi.PIC_SAO:
         nxt = [np.zeros_like(p) for p in cur]

@@ -22,6 +22,9 @@ CASES = {
     "I_lmcs": dict(lmcs=True, slice_type=2),
     "B_isp": dict(isp=40),                                                      # intra sub-partitions among the intra CUs
     "I_isp_lmcs": dict(isp=60, slice_type=2, lmcs=True),
+    "B_3slices": dict(slices=3),                                                # per-slice reference lists, deblocking offsets, ALF APS lists / switches
+    "B_4slices_lmcs_isp": dict(slices=4, lmcs=True, isp=30),
+    "P_5slices": dict(slices=5, slice_type=1),
     "B_ctu64": dict(ctu=64),
     "B_ctu32_8bit": dict(ctu=32, bd=8),
     "B_no_dmvr": dict(tools=(helpers.SEAM_INTER_TOOLS | helpers.SEAM_RESI_TOOLS | helpers.SEAM_INTRA_TOOLS | helpers.SEAM_FILTERS) & ~helpers.SEAM["DMVR"]),

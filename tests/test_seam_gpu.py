@@ -25,6 +25,7 @@ def both(seed, W, H, threads=4, **kw):
 @pytest.mark.parametrize("name,kw", [("B_mixed_intra", dict()), ("I_picture", dict(slice_type=2)), ("P_picture", dict(slice_type=1)),
                                      ("B_lmcs_inter", dict(lmcs=True, intra=0, tools=T_INTER)), ("B_lmcs_intra_ciip", dict(lmcs=True)), ("I_lmcs", dict(lmcs=True, slice_type=2)),
                                      ("B_ctu64", dict(ctu=64)),
+                                     ("B_3slices", dict(slices=3)), ("B_4slices_lmcs_isp", dict(slices=4, lmcs=True, isp=30)), ("I_2slices", dict(slices=2, slice_type=2)),
                                      ("B_isp", dict(isp=40)), ("I_isp", dict(isp=60, slice_type=2)), ("I_isp_lmcs", dict(isp=60, slice_type=2, lmcs=True)), ("I_isp_ctu32", dict(isp=70, slice_type=2, ctu=32))])
 @pytest.mark.parametrize("seed", [1, 2])
 def test_seam_small(name, kw, seed):
@@ -38,6 +39,7 @@ def test_seam_1080p_and_4k():
     both(34, 3840, 2160, threads=16, lmcs=True, slice_type=2)
     both(35, 3840, 2160, threads=16, isp=50, slice_type=2)                   # dense list: the CTU-resident K6
     both(36, 3840, 2160, threads=16, isp=50)                                 # sparse list: one CTA per block
+    both(37, 1920, 1080, threads=8, slices=6, isp=20)
 
 
 def test_seam_error_contract_on_the_device_path():

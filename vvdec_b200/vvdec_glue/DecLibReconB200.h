@@ -98,6 +98,10 @@ class DecLibReconB200
   AlfTableStore m_alfStore; b200_alf_tables m_alfTabs{}; b200_lmcs m_lmcs{}; b200_vb m_vb{}; b200_lf_slice m_lfSlice{}; b200_lf_seq m_lfSeq{};
   b200_picture m_pic{};
   SlotMap m_slotMap{};
+  // per slice of the picture (pic->slices order): reference slots, weighted-prediction index table, bases of its ALF sets in the picture-level tables
+  struct SliceTabs { const Slice* slice = nullptr; SlotMap slotMap{}; std::vector<int> wpIdx; int wpStride = 0; AlfSliceBase alf; };
+  std::vector<SliceTabs> m_sl; std::vector<b200_lf_slice> m_lfSlices; PinnedVec<uint8_t> m_ctuSlice;
+  int sliceIdx( const Slice* s ) const { for( size_t i = 0; i < m_sl.size(); i++ ) if( m_sl[i].slice == s ) return (int) i; THROW_FATAL( "DecLibReconB200: a CU of a slice the picture does not list" ); }
   bool m_doSao = false, m_doAlf = false, m_doLmcs = false, m_dryRun = false;
   // host-stage timing (seconds since decompressPicture): end of preparePicture, first flatten row start (= MIDER done), submit start, submit end, wait end
   std::chrono::steady_clock::time_point m_t0; std::atomic<int64_t> m_tFlat0{ 0 }; double m_stage[6] = { 0, 0, 0, 0, 0, 0 };
@@ -140,7 +144,12 @@ class DecLibReconB200
     const CodingStructure& cs = *pic->cs; const SPS& sps = *cs.sps; const PPS& pps = *cs.pps;
     if( sps.getChromaFormatIdc() != CHROMA_420 && sps.getChromaFormatIdc() != CHROMA_400 ) THROW_UNSUPPORTED( "DecLibReconB200: 4:2:0 and 4:0:0 only" );
     if( sps.getUseWrapAround() || pic->subPictures.size() > 1 || cs.picHeader->getVirtualBoundariesPresentFlag() ) THROW_UNSUPPORTED( "DecLibReconB200: wrap-around / sub-pictures / virtual boundaries" );
-    if( pic->slices.size() > 1 ) THROW_UNSUPPORTED( "DecLibReconB200: one slice per picture (reference lists and ALF / LMCS tables are per slice)" );
+    if( pic->slices.size() > 64 ) THROW_UNSUPPORTED( "DecLibReconB200: more than 64 slices in a picture" );
+    for( const Slice* sl : pic->slices )
+    {
+      if( sl->getLmcsEnabledFlag() != pic->slices[0]->getLmcsEnabledFlag() ) THROW_UNSUPPORTED( "DecLibReconB200: LMCS switched per slice" );
+      if( sl->getExplicitScalingListUsed() ) THROW_UNSUPPORTED( "DecLibReconB200: explicit scaling lists (the per-picture table arena is not built by this class)" );
+    }
     if( pps.getNumTiles() > 1 && !pps.getLoopFilterAcrossTilesEnabledFlag() ) THROW_UNSUPPORTED( "DecLibReconB200: tiles with in-loop filtering disabled across them (ALF clip path, AdaptiveLoopFilter.cpp:685)" );
     if( !pps.getLoopFilterAcrossSlicesEnabledFlag() && pic->slices.size() > 1 ) THROW_UNSUPPORTED( "DecLibReconB200: in-loop filtering disabled across slices" );
     if( pic->slices[0]->getExplicitScalingListUsed() ) THROW_UNSUPPORTED( "DecLibReconB200: explicit scaling lists (the per-picture table arena is not built by this class)" );
@@ -214,13 +223,13 @@ class DecLibReconB200
   }
   static bool submitTask( int, void* p ) { DecLibReconB200* d = static_cast<DecLibReconB200*>( p ); d->m_stage[2] = d->since(); const bool r = d->guarded( [&] { d->submit(); return true; } ); d->m_stage[3] = d->since(); return r; }
 
-  int wpIdxOf( int r0, int r1 ) const { return m_wpIdx.empty() ? 0 : m_wpIdx[( r0 + 1 ) * m_wpStride + ( r1 + 1 )]; }
 
   void flattenCtu( Row& r )
   {
     Picture* pic = m_currDecompPic; CodingStructure& cs = *pic->cs; const SPS& sps = *cs.sps; const PreCalcValues& pcv = *cs.pcv;
     const int W = pcv.widthInCtus, W4 = ( pcv.lumaWidth + 3 ) >> 2;
-    auto wp = [this]( int r0, int r1 ) { return wpIdxOf( r0, r1 ); };
+    const SliceTabs* st = nullptr;                            // the tables of the slice the current CU belongs to
+    auto wp = [&st]( int r0, int r1 ) { return st->wpIdx.empty() ? 0 : st->wpIdx[( r0 + 1 ) * st->wpStride + ( r1 + 1 )]; };
     r.pus.clear(); r.tus.clear(); r.coefs.clear(); r.intra.clear();
     {
       const int col = r.col;
@@ -235,6 +244,7 @@ class DecLibReconB200
       // the CU / TU walks of TaskTrafoCtu + TaskInterCtu + TaskCriticalIntraKernel (DecCu.cpp:106-159)
       for( auto& cu : cs.traverseCUs( a ) )
       {
+        if( !st || st->slice != cu.slice ) st = &m_sl[sliceIdx( cu.slice )];
         if( CU::isIntra( cu ) )
         {
           // K6: one b200_intra_tu per TU component in decoding order (the order DecCu::predAndReco walks them, DecCu.cpp:284-288); the residual of
@@ -274,10 +284,10 @@ class DecLibReconB200
           }
         }
         FlattenPuResult rc;
-        if( cu.mergeType() == MRG_TYPE_SUBPU_ATMVP ) rc = flattenSbTmvp( cu, m_slotMap, wp, [&]( const b200_pu& q ) { r.pus.push_back( q ); } );
+        if( cu.mergeType() == MRG_TYPE_SUBPU_ATMVP ) rc = flattenSbTmvp( cu, st->slotMap, wp, [&]( const b200_pu& q ) { r.pus.push_back( q ); } );
         else
         {
-          b200_pu q; rc = flattenPU( cu, m_slotMap, wp, q );
+          b200_pu q; rc = flattenPU( cu, st->slotMap, wp, q );
           if( rc == FLATTEN_PU_OK ) { r.pus.push_back( q ); if( q.flags & B200_PU_DMVR ) cu.setDmvrCondition( true ); }   // motionCompensation :1436 sets it on the CPU path; TaskFinishMotionInfo reads it
         }
         if( rc != FLATTEN_PU_OK ) THROW_UNSUPPORTED( "DecLibReconB200: inter tool outside the device path (RPR-scaled reference, wrap-around, sub-picture clipping)" );
@@ -310,33 +320,46 @@ class DecLibReconB200
       }
       if( (int) pcv.lumaWidth != S.geom.width || (int) pcv.lumaHeight != S.geom.height || sps.getBitDepth() != S.geom.bitDepth ) THROW_UNSUPPORTED( "DecLibReconB200: picture size / bit depth change inside a context (RPR)" );
       // reference pictures -> device DPB slots (uploaded if the device does not hold them)
-      memset( &m_slotMap, -1, sizeof( m_slotMap ) ); m_waitSlots.clear();
-      const Slice& slice0 = *pic->slices[0];
-      for( int l = 0; l < 2; l++ ) for( int i = 0; i < slice0.getNumRefIdx( RefPicList( l ) ); i++ ) m_slotMap.slot[l][i] = (int8_t) importReference( slice0.getRefPic( RefPicList( l ), i ) );
+      m_waitSlots.clear();
+      m_sl.assign( pic->slices.size(), SliceTabs() );
+      for( size_t si = 0; si < pic->slices.size(); si++ )
+      {
+        const Slice& sl = *pic->slices[si]; SliceTabs& st = m_sl[si]; st.slice = &sl;
+        memset( &st.slotMap, -1, sizeof( st.slotMap ) );
+        for( int l = 0; l < 2; l++ ) for( int i = 0; i < sl.getNumRefIdx( RefPicList( l ) ); i++ ) st.slotMap.slot[l][i] = (int8_t) importReference( sl.getRefPic( RefPicList( l ), i ) );
+      }
+      m_slotMap = m_sl[0].slotMap;
       m_dstSlot = slotLocked( pic ); S.valid[m_dstSlot] = 2;
     }
     const Slice& slice0 = *pic->slices[0];
-    // explicit weighted prediction: one entry per (refIdx0, refIdx1) combination (getWpScaling, WeightPrediction.cpp:67)
-    m_wp.clear(); m_wpIdx.clear();
-    if( ( pps.getWPBiPred() && slice0.isInterB() ) || ( pps.getUseWP() && slice0.isInterP() ) )
+    // explicit weighted prediction: one entry per (refIdx0, refIdx1) combination of every slice (getWpScaling, WeightPrediction.cpp:67)
+    m_wp.clear();
+    for( SliceTabs& st : m_sl )
     {
-      const int n0 = slice0.getNumRefIdx( REF_PIC_LIST_0 ), n1 = slice0.isInterB() ? slice0.getNumRefIdx( REF_PIC_LIST_1 ) : 0;
-      m_wpStride = n1 + 1; m_wpIdx.assign( (size_t) ( n0 + 1 ) * ( n1 + 1 ), 0 );
+      const Slice& sl = *st.slice;
+      if( !( ( pps.getWPBiPred() && sl.isInterB() ) || ( pps.getUseWP() && sl.isInterP() ) ) ) continue;
+      const int n0 = sl.getNumRefIdx( REF_PIC_LIST_0 ), n1 = sl.isInterB() ? sl.getNumRefIdx( REF_PIC_LIST_1 ) : 0;
+      st.wpStride = n1 + 1; st.wpIdx.assign( (size_t) ( n0 + 1 ) * ( n1 + 1 ), 0 );
       for( int r0 = -1; r0 < n0; r0++ ) for( int r1 = -1; r1 < n1; r1++ )
       {
         if( r0 < 0 && r1 < 0 ) continue;
-        WPScalingParam w0[3], w1[3]; WeightPrediction wpObj; wpObj.getWpScaling( &slice0, r0, r1, w0, w1 );
+        WPScalingParam w0[3], w1[3]; WeightPrediction wpObj; wpObj.getWpScaling( &sl, r0, r1, w0, w1 );
         b200_wp e{}; const bool bi = r0 >= 0 && r1 >= 0; const WPScalingParam* u = r0 >= 0 ? w0 : w1;
         for( int c = 0; c < 3; c++ ) { e.w0[c] = bi ? w0[c].w : u[c].w; e.w1[c] = bi ? w1[c].w : 0; e.offset[c] = bi ? w0[c].offset : u[c].offset; e.shift[c] = bi ? w0[c].shift : u[c].shift; }
-        m_wp.push_back( e ); m_wpIdx[( r0 + 1 ) * m_wpStride + ( r1 + 1 )] = (int) m_wp.size();
+        m_wp.push_back( e ); st.wpIdx[( r0 + 1 ) * st.wpStride + ( r1 + 1 )] = (int) m_wp.size();
       }
-      if( m_wp.size() > 255 ) THROW_UNSUPPORTED( "DecLibReconB200: more than 255 weighted-prediction combinations" );
     }
+    if( m_wp.size() > 255 ) THROW_UNSUPPORTED( "DecLibReconB200: more than 255 weighted-prediction combinations" );
     // deblocking: slice offsets and the SPS's luma-adaptive QP offsets (deriveLADFShift, LoopFilter.cpp:1363)
-    m_lfSlice = b200_lf_slice{}; m_lfSlice.disable = slice0.getDeblockingFilterDisable();
-    m_lfSlice.betaOffsetDiv2[0] = slice0.getDeblockingFilterBetaOffsetDiv2(); m_lfSlice.tcOffsetDiv2[0] = slice0.getDeblockingFilterTcOffsetDiv2();
-    m_lfSlice.betaOffsetDiv2[1] = slice0.getDeblockingFilterCbBetaOffsetDiv2(); m_lfSlice.tcOffsetDiv2[1] = slice0.getDeblockingFilterCbTcOffsetDiv2();
-    m_lfSlice.betaOffsetDiv2[2] = slice0.getDeblockingFilterCrBetaOffsetDiv2(); m_lfSlice.tcOffsetDiv2[2] = slice0.getDeblockingFilterCrTcOffsetDiv2();
+    m_lfSlices.assign( m_sl.size(), b200_lf_slice{} );
+    for( size_t si = 0; si < m_sl.size(); si++ )
+    {
+      const Slice& sl = *m_sl[si].slice; b200_lf_slice& f = m_lfSlices[si];
+      f.disable = sl.getDeblockingFilterDisable();
+      f.betaOffsetDiv2[0] = sl.getDeblockingFilterBetaOffsetDiv2();   f.tcOffsetDiv2[0] = sl.getDeblockingFilterTcOffsetDiv2();
+      f.betaOffsetDiv2[1] = sl.getDeblockingFilterCbBetaOffsetDiv2(); f.tcOffsetDiv2[1] = sl.getDeblockingFilterCbTcOffsetDiv2();
+      f.betaOffsetDiv2[2] = sl.getDeblockingFilterCrBetaOffsetDiv2(); f.tcOffsetDiv2[2] = sl.getDeblockingFilterCrTcOffsetDiv2();
+    }
     m_lfSeq = b200_lf_seq{};
     if( sps.getLadfEnabled() )
     {
@@ -353,7 +376,11 @@ class DecLibReconB200
     {
       if( m_fltBuf.bufs.empty() ) m_fltBuf.create( pcv.chrFormat, Size( 16, 16 ), pcv.maxCUWidth, 0, MEMORY_ALIGN_DEF_SIZE );
       m_cALF.create( cs.picHeader.get(), &sps, &pps, 1, m_fltBuf );              // fills m_clipDefault for the bit depth
-      m_alfTabs = buildAlfTables( slice0, &m_cALF.m_fixedFilterSetCoeffDec[0][0], m_cALF.m_clipDefault, m_alfStore );
+      std::vector<const Slice*> sls; for( const SliceTabs& st : m_sl ) sls.push_back( st.slice );
+      std::vector<AlfSliceBase> bases;
+      m_alfTabs = buildAlfTablesOfSlices( sls, &m_cALF.m_fixedFilterSetCoeffDec[0][0], m_cALF.m_clipDefault, m_alfStore, bases );
+      for( size_t si = 0; si < m_sl.size(); si++ ) m_sl[si].alf = bases[si];
+      if( m_alfTabs.numLumaSets > 255 || m_alfTabs.numChromaAlts > 255 || m_alfTabs.numCc[0] > 254 || m_alfTabs.numCc[1] > 254 ) THROW_UNSUPPORTED( "DecLibReconB200: more ALF sets in a picture than a CTU record can address" );
     }
     // LMCS tables (Reshape::initSlice as DecLibRecon.cpp:448-452)
     m_doLmcs = sps.getUseReshaper() && cs.picHeader->getLmcsEnabledFlag() && slice0.getLmcsEnabledFlag();
@@ -385,6 +412,7 @@ class DecLibReconB200
       nP += r.pus.size(); nT += r.tus.size(); nC += r.coefs.size(); nI += r.intra.size();
     }
     // in-loop filter parameters of every CTU (the SAO availability looks at the CTUs below: the whole picture is parsed by now)
+    m_ctuSlice.v.assign( pcv.sizeInCtus, 0 ); m_ctuSlice.pin();
     for( unsigned a = 0; a < pcv.sizeInCtus; a++ )
     {
       CtuData& cd = cs.getCtuData( a );
@@ -394,7 +422,23 @@ class DecLibReconB200
         m_cSAO.deriveLoopFilterBoundaryAvailibility( cs, Position( ( a % pcv.widthInCtus ) * pcv.maxCUWidth, ( a / pcv.widthInCtus ) * pcv.maxCUHeight ), av[0], av[1], av[2], av[3], av[4], av[5], av[6], av[7] );
         flattenSAO( cd.saoParam, av, getNumberValidComponents( pcv.chrFormat ), m_sao.v[a] );     // saoParam after reconstructBlkSAOParam (parser side)
       }
-      if( m_doAlf ) flattenALF( cd.alfParam, m_alf.v[a] );
+      const int si = sliceIdx( cd.slice ); m_ctuSlice.v[a] = (uint8_t) si;
+      if( m_doAlf )
+      {
+        // CTU-level indices are relative to the slice's own APS lists: moved behind the sets of the slices before it (buildAlfTablesOfSlices)
+        b200_alf_ctu& q = m_alf.v[a]; flattenALF( cd.alfParam, q );
+        const Slice& sl = *cd.slice; const AlfSliceBase& ab = m_sl[si].alf;
+        if( !sl.getAlfEnabledFlag( COMPONENT_Y ) ) q.enable[0] = 0;
+        if( !sl.getAlfEnabledFlag( COMPONENT_Cb ) ) q.enable[1] = 0;
+        if( !sl.getAlfEnabledFlag( COMPONENT_Cr ) ) q.enable[2] = 0;
+        if( q.lumaSet >= NUM_FIXED_FILTER_SETS ) q.lumaSet = (uint8_t) ( q.lumaSet + ab.luma );
+        for( int k = 0; k < 2; k++ )
+        {
+          q.chromaAlt[k] = (uint8_t) ( q.chromaAlt[k] + ab.chroma );
+          if( !( k == 0 ? sl.getCcAlfCbEnabledFlag() : sl.getCcAlfCrEnabledFlag() ) ) q.ccIdx[k] = 0;
+          else if( q.ccIdx[k] ) q.ccIdx[k] = (uint8_t) ( q.ccIdx[k] + ab.cc[k] );
+        }
+      }
     }
     if( m_doLmcs )
     {
@@ -413,10 +457,11 @@ class DecLibReconB200
     m_pus.pin(); m_tus.pin(); m_coefs.pin(); m_intra.pin();
     b200_picture& p = m_pic; p = b200_picture{};
     p.dstSlot = m_dstSlot;
-    p.flags = ( slice0.getDeblockingFilterDisable() ? 0 : B200_PIC_DEBLOCK ) | ( m_doSao ? B200_PIC_SAO : 0 ) | ( m_doAlf ? B200_PIC_ALF : 0 ) | ( m_doLmcs ? B200_PIC_LMCS : 0 );
+    bool anyLf = false; for( const b200_lf_slice& f : m_lfSlices ) anyLf = anyLf || !f.disable;
+    p.flags = ( anyLf ? B200_PIC_DEBLOCK : 0 ) | ( m_doSao ? B200_PIC_SAO : 0 ) | ( m_doAlf ? B200_PIC_ALF : 0 ) | ( m_doLmcs ? B200_PIC_LMCS : 0 );
     p.pus = m_pus.v.data(); p.numPus = m_pus.v.size(); p.numDmvr = m_dmvrMvCache.size();
     p.tus = m_tus.v.data(); p.numTus = m_tus.v.size(); p.coefs = m_coefs.v.data(); p.numCoefs = m_coefs.v.size();
-    p.lfV = m_lf[0].v.data(); p.lfH = m_lf[1].v.data(); p.lfSlices = &m_lfSlice; p.numLfSlices = 1; p.lfSeq = &m_lfSeq;
+    p.lfV = m_lf[0].v.data(); p.lfH = m_lf[1].v.data(); p.lfSlices = m_lfSlices.data(); p.numLfSlices = (int32_t) m_lfSlices.size(); p.ctuSlice = m_lfSlices.size() > 1 ? m_ctuSlice.v.data() : nullptr; p.lfSeq = &m_lfSeq;
     p.sao = m_sao.v.data(); p.vb = &m_vb; p.alf = m_alf.v.data(); p.alfTabs = &m_alfTabs;
     p.wp = m_wp.data(); p.numWp = (int32_t) m_wp.size(); p.lmcs = m_doLmcs ? &m_lmcs : nullptr;
     p.intraTus = m_intra.v.data(); p.numIntraTus = m_intra.v.size();

@@ -50,6 +50,49 @@ inline void flattenALF( const CtuAlfData& a, b200_alf_ctu& r )
 // slice's luma APSs in list order (lumaCoeffFinal / lumaClippFinal, reconstructCoeffAPSs :335), the chroma APS's alternatives and the
 // CC-ALF filters.  `store` owns the memory the returned struct points into (pin it once: the tables change per slice at most).
 struct AlfTableStore { std::vector<int16_t> lumaCoeff, lumaClip, chromaCoeff, chromaClip, cc[2]; };
+// Several slices: every slice's sets go behind the ones before it; `bases` receives, per slice, what has to be added to the CTU-level indices of its CTUs
+// (luma sets >= 16, chroma alternatives, CC-ALF filter numbers 1..n) so that they address the picture-level tables.
+struct AlfSliceBase { int luma = 0, chroma = 0, cc[2] = { 0, 0 }; };
+inline b200_alf_tables buildAlfTablesOfSlices( const std::vector<const Slice*>& slices, const short* fixedSetCoeffDec, const short* clipDefault, AlfTableStore& store, std::vector<AlfSliceBase>& bases )
+{
+  constexpr int SET = MAX_NUM_ALF_TRANSPOSE_ID * MAX_NUM_ALF_CLASSES * MAX_NUM_ALF_LUMA_COEFF;
+  store.lumaCoeff.assign( (size_t) NUM_FIXED_FILTER_SETS * SET, 0 ); store.lumaClip.assign( store.lumaCoeff.size(), 0 );
+  memcpy( store.lumaCoeff.data(), fixedSetCoeffDec, sizeof( int16_t ) * NUM_FIXED_FILTER_SETS * SET );
+  for( int i = 0; i < NUM_FIXED_FILTER_SETS * SET; i++ ) store.lumaClip[i] = clipDefault[i % MAX_NUM_ALF_LUMA_COEFF];
+  store.chromaCoeff.clear(); store.chromaClip.clear(); store.cc[0].clear(); store.cc[1].clear();
+  bases.assign( slices.size(), AlfSliceBase() );
+  b200_alf_tables t; memset( &t, 0, sizeof( t ) );
+  int nLuma = 0;
+  for( size_t s = 0; s < slices.size(); s++ )
+  {
+    const Slice& slice = *slices[s]; const APS* const* apss = slice.getAlfAPSs();
+    bases[s].luma = nLuma; bases[s].chroma = t.numChromaAlts; bases[s].cc[0] = t.numCc[0]; bases[s].cc[1] = t.numCc[1];
+    if( slice.getAlfEnabledFlag( COMPONENT_Y ) )
+      for( int i = 0; i < slice.getNumAlfAps(); i++, nLuma++ )
+      {
+        const AlfSliceParam& p = apss[slice.getAlfApsIdsLuma()[i]]->getAlfAPSParam();
+        store.lumaCoeff.insert( store.lumaCoeff.end(), p.lumaCoeffFinal, p.lumaCoeffFinal + SET ); store.lumaClip.insert( store.lumaClip.end(), p.lumaClippFinal, p.lumaClippFinal + SET );
+      }
+    if( slice.getAlfEnabledFlag( COMPONENT_Cb ) || slice.getAlfEnabledFlag( COMPONENT_Cr ) )
+    {
+      const AlfSliceParam& p = apss[slice.getAlfApsIdChroma()]->getAlfAPSParam();
+      for( int a = 0; a < p.numAlternativesChroma; a++ )
+        for( int k = 0; k < MAX_NUM_ALF_CHROMA_COEFF; k++ ) { store.chromaCoeff.push_back( p.chromaCoeff[a * MAX_NUM_ALF_CHROMA_COEFF + k] ); store.chromaClip.push_back( p.chrmClippFinal[a * MAX_NUM_ALF_CHROMA_COEFF + k] ); }
+      t.numChromaAlts += p.numAlternativesChroma;
+    }
+    for( int c = 0; c < 2; c++ )
+      if( c == 0 ? slice.getCcAlfCbEnabledFlag() : slice.getCcAlfCrEnabledFlag() )
+      {
+        const CcAlfFilterParam& cp = apss[c == 0 ? slice.getCcAlfCbApsId() : slice.getCcAlfCrApsId()]->getCcAlfAPSParam();
+        for( int f = 0; f < cp.ccAlfFilterCount[c]; f++ ) for( int k = 0; k < 7; k++ ) store.cc[c].push_back( cp.ccAlfCoeff[c][f][k] );
+        t.numCc[c] += cp.ccAlfFilterCount[c];
+      }
+  }
+  t.lumaCoeff = store.lumaCoeff.data(); t.lumaClip = store.lumaClip.data(); t.numLumaSets = NUM_FIXED_FILTER_SETS + nLuma;
+  t.chromaCoeff = store.chromaCoeff.data(); t.chromaClip = store.chromaClip.data(); t.ccCoeff[0] = store.cc[0].data(); t.ccCoeff[1] = store.cc[1].data();
+  return t;
+}
+
 inline b200_alf_tables buildAlfTables( const Slice& slice, const short* fixedSetCoeffDec /* [16][1300] */, const short* clipDefault /* [13] */, AlfTableStore& store )
 {
   constexpr int SET = MAX_NUM_ALF_TRANSPOSE_ID * MAX_NUM_ALF_CLASSES * MAX_NUM_ALF_LUMA_COEFF;   // 4 * 25 * 13
