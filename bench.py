@@ -360,6 +360,7 @@ def run_b200(args):
     if rank == 0: print(json.dumps(line), flush=True)
     lib.b200_ctx_destroy(ctx)
     if world > 1: dist.destroy_process_group()
+    leave()
 
 
 def gather_pass(args, rank, world, local, lib, ctx, wl, flat, pic_of, line, torch, dist, barrier, max_over_ranks):
@@ -490,6 +491,12 @@ def pcie_ceiling(torch, mb=256, reps=4):
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs (the reference's own DecLibRecon)
+def leave():
+    """The line is out: skip interpreter tear-down (the reference library's static thread pools and recon objects are destroyed in an order of the loader's choosing)."""
+    sys.stdout.flush(); sys.stderr.flush()
+    os._exit(0)
+
+
 def thread_candidates(args):
     T = threads_all(args)
     if args.host_threads: return [T]
@@ -515,6 +522,10 @@ def stock_sweep(args, wl, n=6):
                 table[f"{T}x{D}"] = round(n / secs, 1)
                 if n / secs > best[0]: best = (n / secs, T, D)
     return best[1], best[2], table
+
+
+def parse_cfg(key):
+    t, d = key.split("x"); return int(t), int(d)
 
 
 def stock_fps(wl, cases, T, D):
@@ -548,10 +559,16 @@ def run_reference(args):
     wl = Workload(args, 0)
     T = threads_all(args)
     Tb, D, table = stock_sweep(args, wl)
-    if args.warmup: stock_fps(wl, [wl.sched(i + 1)[1] for i in range(min(args.warmup, 4))], Tb, D)
-    fps = stock_fps(wl, [wl.sched(i)[1] for i in range(args.steps)], Tb, D)
+    # the schedule in the two fastest configurations of the sweep (two instances on many threads are bistable: the same pair can run 3x slower in the next
+    # call); the better run is the arm's value
+    runs = {}
+    for key in sorted(table, key=lambda k: -table[k])[:2]:
+        t, d = parse_cfg(key)
+        if args.warmup: stock_fps(wl, [wl.sched(i + 1)[1] for i in range(min(args.warmup, 4))], t, d)
+        runs[key] = stock_fps(wl, [wl.sched(i)[1] for i in range(args.steps)], t, d)
+    bestkey = max(runs, key=lambda k: runs[k]); fps = runs[bestkey]; Tb, D = parse_cfg(bestkey)
     T = Tb
-    cb = {"value": round(fps, 3), "unit": "frames/s", "cores": T, "kind": "reference", "recon_instances": D, "sweep_fps": table,
+    cb = {"value": round(fps, 3), "unit": "frames/s", "cores": T, "kind": "reference", "recon_instances": D, "sweep_fps": table, "schedule_fps": {k: round(v, 1) for k, v in runs.items()},
           "sample": f"the {args.steps} pictures of the schedule through the reference's DecLibRecon (decompressPicture..waitForPrevDecompressedPic, {wl.ref.ref_simd_level().decode()}) in the fastest "
                     f"configuration of a sweep over host threads x recon instances taking pictures in turn (DecLib.h:70) on 6 B pictures: ThreadPool({T}) x {D}"}
     line = {"impl": "reference", "metric": METRIC, "value": round(fps, 3), "unit": "frames/s",
@@ -560,6 +577,7 @@ def run_reference(args):
             "config": workload_config(args, args.gpus),
             "cpu_baseline": cb, "e2e": {"value": round(fps, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+    leave()
 
 
 if __name__ == "__main__":

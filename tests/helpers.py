@@ -65,10 +65,14 @@ class RefTuSyntax(C.Structure):
                  "spsMTS", "spsIntraMTS", "spsInterMTS", "spsLFNST", "sepTree"]]
 
 
+_ref_lib = None                                               # set once the compiled reference has been loaded (tests/conftest.py leaves without its static destructors)
+
+
 def load_ref():
+    global _ref_lib
     if not os.path.exists(REF_SO):
         return None
-    lib = C.CDLL(REF_SO)
+    lib = C.CDLL(REF_SO); _ref_lib = lib
     lib.ref_simd_level.restype = C.c_char_p
     lib.ref_dequant.argtypes = [C.c_int] * 5 + [i16p, C.c_size_t, i32p, C.c_int, C.c_int, C.c_int32]
     lib.ref_dequant_scaling.argtypes = [C.c_int] * 5 + [i32p, i16p, C.c_size_t, i32p, C.c_int, C.c_int, C.c_int32]

@@ -13,3 +13,5 @@ for f in ("gpurun_out/r02_ref_g.json", "gpurun_out/r02_bench_g.json"):
         if "roofline" in d: print({k: v for k, v in d["roofline"].items() if k != "per_kernel"}); print(d["roofline"]["per_kernel"])
     except Exception as e: print(f, "failed", e)
 PY
+python tools/k6_probe.py 2>&1 | grep "picture ms"
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2

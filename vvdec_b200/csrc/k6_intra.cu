@@ -655,11 +655,15 @@ __global__ void __launch_bounds__(V2_GROUP * V2_GROUPS, 1) intra_ctu_kernel(cons
       int16_t *T = SC.T[0], *L = SC.L[0];
 #define PIXR(x, y) pixC((x), (y))
       ISP_REFERENCE_LAMBDAS
-      for (int j = lane; j <= topLen + mrl; j += V2_GROUP) T[j] = (int16_t)regT(j);
-      for (int i = lane + 1; i <= sideLen + mrl; i += V2_GROUP) L[i] = (int16_t)regL(i);
+      // one pass over both arrays: a thread takes entry j of the row and entry j of the column (two independent fetches in flight); entry 0 of the column is the corner
+      for (int j = lane; j <= max(topLen, sideLen) + mrl; j += V2_GROUP) {
+        const bool doT = j <= topLen + mrl, doL = j >= 1 && j <= sideLen + mrl;
+        const int vt = doT ? regT(j) : 0, vl = doL ? regL(j) : 0;
+        if (doT) T[j] = (int16_t)vt;
+        if (doL) L[j] = (int16_t)vl;
+        if (j == 0) L[0] = (int16_t)vt;
+      }
 #undef PIXR
-      V2_SYNC();
-      if (lane == 0) L[0] = T[0];
       V2_SYNC();
       if ((t.flags & B200_INTRA_FILTER_REF) && !c && !mrl) {     // xFilterReferenceSamples
         int16_t *FT = SC.T[1], *FL = SC.L[1];
@@ -700,6 +704,7 @@ __global__ void __launch_bounds__(V2_GROUP * V2_GROUPS, 1) intra_ctu_kernel(cons
         }
         const int l2w = t.log2w, l2h = t.log2h, scale = (l2w - 2 + l2h - 2 + 2) >> 2;
         const int bl = L[h + 1], tr = T[w + 1];
+#pragma unroll 2
         for (int kk = lane; kk < w * h; kk += V2_GROUP) {
           const int y = kk >> l2w, x = kk & (w - 1);
           int v;
@@ -861,6 +866,7 @@ __global__ void __launch_bounds__(V2_GROUP * V2_GROUPS, 1) intra_ctu_kernel(cons
         const bool cubic = isp || !(diff > cIntraFilterThr[(l2mw + l2mh) >> 1]) || mrl > 0;
         int angularScale = -1;
         if (angle > 0 && doPDPC) angularScale = min(2, l2mh - ((31 - __clz(3 * invAngle - 2)) - 8));
+#pragma unroll 2
         for (int kk = lane; kk < mw * mh; kk += V2_GROUP) {
           const int yy = kk >> l2mw, xx = kk & (mw - 1);
           int v;
