@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--no-gather", action="store_true", help="multi-GPU: leave the frames on their GPUs")
     ap.add_argument("--gather-timeout", type=float, default=120.0, help="multi-GPU: seconds the display-order gather pass may take before the line is printed without it")
     ap.add_argument("--host-threads", type=int, default=0, help="threads of the reference's ThreadPool (0: all)")
+    ap.add_argument("--lanes", type=int, default=2, help="GOP-parallel lanes per GPU: device contexts that reconstruct different GOPs side by side (1: one picture at a time)")
     ap.add_argument("--recon-depth", type=int, default=2, help="recon instances taking pictures in turn, as DecLib runs them (DecLib.h:70); 1: one picture at a time")
     return ap.parse_args()
 
@@ -67,7 +68,7 @@ def workload_config(args, world):
     return {"workload": f"{W}x{H} 10-bit 4:2:0 synthetic PARSED RA pictures at the DecLibRecon seam (oracle/ref_seam.h, seed {args.seed}): 1 I picture per {args.gop} steps, "
                         f"B pictures with {args.intra_pct} % intra CUs otherwise ({args.distinct} distinct, cycled); merge/MMVD/GEO/CIIP/affine+PROF/AMVP+AMVR/BCW/SMVD/BDOF/DMVR, "
                         f"residual MTS/LFNST/SBT/TS/JCCR, intra angular/MRL/MIP/CCLM/BDPCM/ISP ({args.isp_pct} % of the eligible CUs), deblocking + SAO + ALF/CC-ALF",
-            "l2": "inputs larger than L2 (6 x 25 MB DPB buffers + work-list arenas cycled)", "parallelism": f"gop-per-gpu x{world}"}
+            "l2": "inputs larger than L2 (6 x 25 MB DPB buffers + work-list arenas cycled)", "parallelism": f"closed GOPs in parallel: {max(1, args.lanes)} lane(s) per GPU x {world} GPU(s)"}
 
 
 class Workload:
@@ -220,13 +221,23 @@ def run_b200(args):
         kind, _, k = wl.sched(i)
         return flat["I"] if kind == "I" else flat[k]
 
-    ctx = C.c_void_p()
-    vvdec_b200.check(lib.b200_ctx_create(C.byref(ctx), C.byref(g), 6, len(flat), local))
-    for s in range(4): vvdec_b200.check(lib.b200_ctx_load_slot(ctx, s, abi.plane_ptrs(wl.base.refs[s])))
-    for s in (4, 5): vvdec_b200.check(lib.b200_ctx_load_slot(ctx, s, abi.plane_ptrs(wl.base.refs[0])))
-    outs = [[np.zeros((H, W), np.int16), np.zeros((H // 2, W // 2), np.int16), np.zeros((H // 2, W // 2), np.int16)] for _ in range(2)]
-    for out in outs:
-        for o in out: lib.b200_host_register(o.ctypes.data, o.nbytes)
+    # GOP-parallel lanes: closed GOPs are independent, and an I picture is a latency-bound wave front that keeps few SMs busy (K6) — a second device context that
+    # reconstructs another GOP fills them (tools/exp_two_lanes.py: 1146 -> 1423 frames/s with two, 1334 with three).  Lane j's schedule is offset by j * GOP / lanes.
+    L = max(1, args.lanes)
+
+    class Lane:
+        pass
+    lanes = []
+    for j in range(L):
+        ln = Lane(); ln.off = j * args.gop // L; ln.ctx = C.c_void_p(); ln.steps = args.steps // L + (1 if j < args.steps % L else 0)
+        vvdec_b200.check(lib.b200_ctx_create(C.byref(ln.ctx), C.byref(g), 6, len(flat), local))
+        for sl in range(4): vvdec_b200.check(lib.b200_ctx_load_slot(ln.ctx, sl, abi.plane_ptrs(wl.base.refs[sl])))
+        for sl in (4, 5): vvdec_b200.check(lib.b200_ctx_load_slot(ln.ctx, sl, abi.plane_ptrs(wl.base.refs[0])))
+        ln.outs = [[np.zeros((H, W), np.int16), np.zeros((H // 2, W // 2), np.int16), np.zeros((H // 2, W // 2), np.int16)] for _ in range(2)]
+        for out in ln.outs:
+            for o in out: lib.b200_host_register(o.ctypes.data, o.nbytes)
+        lanes.append(ln)
+    ctx, outs = lanes[0].ctx, lanes[0].outs                                 # lane 0 also serves the single-lane diagnostics
 
     def barrier():
         if world > 1: dist.barrier()
@@ -237,28 +248,38 @@ def run_b200(args):
         t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
 
     # ---- value: work lists resident in HBM ----
-    handle = {}
-    for key, pic in flat.items():
-        h = lib.b200_pic_upload(ctx, C.byref(pic["struct"])); assert h >= 0, lib.b200_last_error(); handle[key] = h
-    vvdec_b200.check(lib.b200_wait_picture(ctx, -1, None, 0))
+    def upload_all(ln):
+        ln.handle = {}
+        for key, pic in flat.items():
+            h = lib.b200_pic_upload(ln.ctx, C.byref(pic["struct"])); assert h >= 0, lib.b200_last_error(); ln.handle[key] = h
+        vvdec_b200.check(lib.b200_wait_picture(ln.ctx, -1, None, 0))
+
+    def lane_h(ln, i):
+        kind, _, k = wl.sched(i + ln.off)
+        return ln.handle["I"] if kind == "I" else ln.handle[k]
+    for ln in lanes: upload_all(ln)
+    handle = lanes[0].handle
 
     def h_of(i):
-        kind, _, k = wl.sched(i)
-        return handle["I"] if kind == "I" else handle[k]
+        return lane_h(lanes[0], i)
 
-    for i in range(args.warmup): vvdec_b200.check(lib.b200_pic_run(ctx, h_of(i + 1)))
-    vvdec_b200.check(lib.b200_pic_run(ctx, handle["I"]))                  # the I picture's path is warm too
+    for ln in lanes:
+        for i in range(args.warmup): vvdec_b200.check(lib.b200_pic_run(ln.ctx, lane_h(ln, i + 1)))
+        vvdec_b200.check(lib.b200_pic_run(ln.ctx, ln.handle["I"]))           # the I picture's path is warm too
     barrier()
     sampler = ClockSampler(local); sampler.start()
-    l0 = lib.b200_ctx_kernel_launches(ctx)
-    t_wall = time.perf_counter()
-    vvdec_b200.check(lib.b200_ctx_mark(ctx, 0))
-    for i in range(args.steps): vvdec_b200.check(lib.b200_pic_run(ctx, h_of(i)))
-    vvdec_b200.check(lib.b200_ctx_mark(ctx, 1))
-    ms = C.c_float(); vvdec_b200.check(lib.b200_ctx_elapsed_ms(ctx, C.byref(ms)))
+    l0 = sum(lib.b200_ctx_kernel_launches(ln.ctx) for ln in lanes)
+    for ln in lanes: vvdec_b200.check(lib.b200_ctx_mark(ln.ctx, 0))
+    for i in range(max(ln.steps for ln in lanes)):                           # exactly args.steps pictures, dealt to the lanes round-robin
+        for ln in lanes:
+            if i < ln.steps: vvdec_b200.check(lib.b200_pic_run(ln.ctx, lane_h(ln, i)))
+    for ln in lanes: vvdec_b200.check(lib.b200_ctx_mark(ln.ctx, 1))
+    ms_l = []
+    for ln in lanes:
+        t = C.c_float(); vvdec_b200.check(lib.b200_ctx_elapsed_ms(ln.ctx, C.byref(t))); ms_l.append(t.value)
     barrier()
-    launches = lib.b200_ctx_kernel_launches(ctx) - l0
-    ms_dev = max_over_ranks(ms.value)
+    launches = sum(lib.b200_ctx_kernel_launches(ln.ctx) for ln in lanes) - l0
+    ms_dev = max_over_ranks(max(ms_l))                                       # the lanes start together: the slowest lane's span is the step time
 
     # ---- per-kernel-family device time (same schedule, events around each family) + the I / B split ----
     NF = 10
@@ -276,33 +297,39 @@ def run_b200(args):
         t = C.c_float(); vvdec_b200.check(lib.b200_ctx_elapsed_ms(ctx, C.byref(t))); split[name] = round(t.value / 8, 4)
 
     # ---- e2e: host work lists in, host frames out, every step ----
-    for i in range(max(3, args.warmup // 2)):
-        p = pic_of(i)
-        h = lib.b200_decompress_picture(ctx, C.byref(p["struct"])); assert h >= 0, lib.b200_last_error()
-        vvdec_b200.check(lib.b200_get_frame(ctx, p["struct"].dstSlot, abi.plane_ptrs(outs[0])))
+    for ln in lanes:
+        for i in range(max(3, args.warmup // 2)):
+            p = pic_of(i + ln.off)
+            h = lib.b200_decompress_picture(ln.ctx, C.byref(p["struct"])); assert h >= 0, lib.b200_last_error()
+            vvdec_b200.check(lib.b200_get_frame(ln.ctx, p["struct"].dstSlot, abi.plane_ptrs(ln.outs[0])))
     barrier()
     t0 = time.perf_counter()
-    vvdec_b200.check(lib.b200_ctx_mark(ctx, 0))
-    tickets = [None, None]
-    nxt = lib.b200_pic_upload(ctx, C.byref(pic_of(0)["struct"])); assert nxt >= 0, lib.b200_last_error()
-    for i in range(args.steps):
-        # every step: H2D of one picture's host work lists (the NEXT picture's: the caller keeps one upload in flight, as a decoder whose
+    for ln in lanes:
+        vvdec_b200.check(lib.b200_ctx_mark(ln.ctx, 0))
+        ln.tickets = [None, None]
+        ln.nxt = lib.b200_pic_upload(ln.ctx, C.byref(pic_of(ln.off)["struct"])); assert ln.nxt >= 0, lib.b200_last_error()
+    for i in range(max(ln.steps for ln in lanes)):
+        # every step and lane: H2D of one picture's host work lists (the NEXT picture's: the caller keeps one upload in flight, as a decoder whose
         # parser runs ahead of reconstruction does) + this picture's kernels + D2H of its output frame into one of two pinned host frames;
         # the D2H of step i overlaps the H2D/kernels of step i+1 (copy stream), a host frame is reused only after its copy completed
-        cur = nxt
-        if i + 1 < args.steps:
-            nxt = lib.b200_pic_upload(ctx, C.byref(pic_of(i + 1)["struct"])); assert nxt >= 0, lib.b200_last_error()
-        vvdec_b200.check(lib.b200_pic_run(ctx, cur))
-        k = i & 1
-        if tickets[k] is not None: vvdec_b200.check(lib.b200_frame_wait(ctx, tickets[k]))
-        tickets[k] = lib.b200_get_frame_async(ctx, pic_of(i)["struct"].dstSlot, abi.plane_ptrs(outs[k])); assert tickets[k] >= 0
-    for t in tickets:
-        if t is not None: vvdec_b200.check(lib.b200_frame_wait(ctx, t))
-    vvdec_b200.check(lib.b200_ctx_mark(ctx, 1))
-    ms2 = C.c_float(); vvdec_b200.check(lib.b200_ctx_elapsed_ms(ctx, C.byref(ms2)))
+        for ln in lanes:
+            if i >= ln.steps: continue
+            cur = ln.nxt
+            if i + 1 < ln.steps:
+                ln.nxt = lib.b200_pic_upload(ln.ctx, C.byref(pic_of(i + 1 + ln.off)["struct"])); assert ln.nxt >= 0, lib.b200_last_error()
+            vvdec_b200.check(lib.b200_pic_run(ln.ctx, cur))
+            k = i & 1
+            if ln.tickets[k] is not None: vvdec_b200.check(lib.b200_frame_wait(ln.ctx, ln.tickets[k]))
+            ln.tickets[k] = lib.b200_get_frame_async(ln.ctx, pic_of(i + ln.off)["struct"].dstSlot, abi.plane_ptrs(ln.outs[k])); assert ln.tickets[k] >= 0
+    ms2 = 0.0
+    for ln in lanes:
+        for t in ln.tickets:
+            if t is not None: vvdec_b200.check(lib.b200_frame_wait(ln.ctx, t))
+        vvdec_b200.check(lib.b200_ctx_mark(ln.ctx, 1))
+        t = C.c_float(); vvdec_b200.check(lib.b200_ctx_elapsed_ms(ln.ctx, C.byref(t))); ms2 = max(ms2, t.value)
     barrier()
     wall_e2e = (time.perf_counter() - t0) * 1e3
-    ms_e2e = max_over_ranks(max(ms2.value, wall_e2e))
+    ms_e2e = max_over_ranks(max(ms2, wall_e2e))
 
     # ---- where the end-to-end time goes (untimed diagnostics): the link alone, in each direction and both at once (the PCIe ceiling) ----
     n_diag = min(args.steps, 32)
@@ -356,16 +383,16 @@ def run_b200(args):
     line = None
     if rank == 0: line = assemble_line(args, world, wl, flat, kms, ms_dev, ms_e2e, h2d_step, d2h_step, e2e_diag, seam, split, launches, numa, sampler, pic_of)
     if world > 1 and not args.no_gather:
-        gather_pass(args, rank, world, local, lib, ctx, wl, flat, pic_of, line, torch, dist, barrier, max_over_ranks)
+        gather_pass(args, rank, world, local, lib, lanes, upload_all, lane_h, pic_of, line, torch, dist, barrier, max_over_ranks)
     if rank == 0: print(json.dumps(line), flush=True)
-    lib.b200_ctx_destroy(ctx)
+    for ln in lanes: lib.b200_ctx_destroy(ln.ctx)
     if world > 1: dist.destroy_process_group()
     leave()
 
 
-def gather_pass(args, rank, world, local, lib, ctx, wl, flat, pic_of, line, torch, dist, barrier, max_over_ranks):
-    """Multi-GPU: the same schedule once more with the finished frames leaving their GPUs — every rank decodes its own GOPs (GOP k of the sequence belongs to rank
-    k mod N, gop_shard.assign), each finished frame is copied out of its DPB slot on a side stream and goes to rank 0 in display order over NCCL
+def gather_pass(args, rank, world, local, lib, lanes, upload_all, lane_h, pic_of, line, torch, dist, barrier, max_over_ranks):
+    """Multi-GPU: the same schedule once more with the finished frames leaving their GPUs — every lane of every rank reconstructs its own run of pictures, each
+    finished frame is copied out of its DPB slot on the lane's side stream and goes to rank 0 in display order over NCCL
     (vvdec_b200/gather.py), overlapping the following pictures.  The timed region ends when the last frame has arrived on rank 0; its throughput becomes the
     line's `value`.  Everything else of the line is already assembled: a watchdog prints it with the gather marked as failed if the exchange does not finish."""
     import vvdec_b200
@@ -381,31 +408,35 @@ def gather_pass(args, rank, world, local, lib, ctx, wl, flat, pic_of, line, torc
         os._exit(0)
     barrier()                                                                # the other ranks wait here while rank 0 assembled its line
     threading.Thread(target=dog, daemon=True).start()
-    handle = {}                                                              # the e2e leg cycled through the arenas: the work lists go back into HBM
-    for key, pic in flat.items():
-        h = lib.b200_pic_upload(ctx, C.byref(pic["struct"])); assert h >= 0, lib.b200_last_error(); handle[key] = h
-    vvdec_b200.check(lib.b200_wait_picture(ctx, -1, None, 0))
-
-    def h_of(i):
-        kind, _, k = wl.sched(i)
-        return handle["I"] if kind == "I" else handle[k]
-    n_local = -(-args.steps // args.gop)
-    lengths = [min(args.gop, args.steps - (k // world) * args.gop) for k in range(n_local * world)]
+    for ln in lanes: upload_all(ln)                                          # the e2e leg cycled through the arenas: the work lists go back into HBM
     numel = W * H * 3                                                        # bytes of a 16-bit 4:2:0 frame
-    side = torch.cuda.Stream()
+    # display order: every (rank, lane) reconstructs one run of consecutive pictures; the runs follow each other rank by rank, lane by lane.  A rank pushes its
+    # frames in the order they finish (lanes interleaved): the n-th pushed frame of rank r is picture i of lane j
+    display_of, base = {}, 0
+    for r in range(world):
+        n, bases = 0, []
+        for ln in lanes: bases.append(base); base += ln.steps
+        for i in range(max(ln.steps for ln in lanes)):
+            for j, ln in enumerate(lanes):
+                if i < ln.steps: display_of[(r, n)] = bases[j] + i; n += 1
+    for ln in lanes: ln.side = torch.cuda.Stream()
     poff = [0, W * H, W * H + (W // 2) * (H // 2)]
     wall_ms = 0.0
     for timed in (False, True):                                              # the first pass is the warm-up (NCCL sets its peer-to-peer channels up with the first transfer)
-        G = gather.FrameGather(rank, world, lengths, numel, torch.device("cuda", local))
+        G = gather.FrameGather(rank, world, None, numel, torch.device("cuda", local), display_of=display_of)
         barrier()
         t_wall = time.perf_counter()
-        for i in range(args.steps):
-            vvdec_b200.check(lib.b200_pic_run(ctx, h_of(i)))
-            base = G.slot(i).data_ptr()
-            pl = (C.c_void_p * 3)(base + 2 * poff[0], base + 2 * poff[1], base + 2 * poff[2])
-            vvdec_b200.check(lib.b200_get_frame_device_async(ctx, pic_of(i)["struct"].dstSlot, pl, C.c_void_p(side.cuda_stream)))
-            with torch.cuda.stream(side): G.push(i)
-        with torch.cuda.stream(side): G.finish()
+        n = 0
+        for i in range(max(ln.steps for ln in lanes)):
+            for ln in lanes:
+                if i >= ln.steps: continue
+                vvdec_b200.check(lib.b200_pic_run(ln.ctx, lane_h(ln, i)))
+                base_ptr = G.slot(n).data_ptr()
+                pl = (C.c_void_p * 3)(base_ptr + 2 * poff[0], base_ptr + 2 * poff[1], base_ptr + 2 * poff[2])
+                vvdec_b200.check(lib.b200_get_frame_device_async(ln.ctx, pic_of(i + ln.off)["struct"].dstSlot, pl, C.c_void_p(ln.side.cuda_stream)))
+                with torch.cuda.stream(ln.side): G.push(n)
+                n += 1
+        G.finish()
         torch.cuda.synchronize()
         wall_ms = (time.perf_counter() - t_wall) * 1e3                       # the timed region ends when the last frame has arrived on rank 0
         barrier()
@@ -458,7 +489,7 @@ def assemble_line(args, world, wl, flat, kms, ms_dev, ms_e2e, h2d_step, d2h_step
             "config": workload_config(args, world),
             "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": d2h_step, "diag": e2e_diag,
                     "api": "b200_pic_upload (one picture ahead) + b200_pic_run + b200_get_frame_async (D2H overlapped with the next picture), pinned host buffers; every step uploads one picture's work lists and downloads one frame"},
-            "seam": seam, "picture_ms": split, "gather": None,
+            "seam": seam, "picture_ms": split, "gather": None, "lanes_per_gpu": max(1, args.lanes),
             "gpu_launches": int(launches), "numa": numa, "clocks": sampler.summary(), "roofline": roof}
     if not args.no_cpu_baseline and world == 1:                      # the CPU legs are N = 1 lines only
         line["cpu_baseline"] = cpu_baseline(args, wl)

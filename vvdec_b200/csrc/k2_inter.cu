@@ -795,7 +795,7 @@ __device__ __forceinline__ void mc_affine_tile(const McParams& P, const uint32_t
   __shared__ int16_t sCH[2][2][4][7 * 4];   // chroma: [list][comp][sub-block] 7 rows x 4 cols
 
   const int tid = threadIdx.x;
-  const b200_pu pu = P.pus[tile >> 6];
+  const b200_pu& pu = P.pus[tile >> 6];                      // read in place: per-list fields are indexed at run time, a private copy would live in local memory
   const int tx0 = (tile & 7) * 16, ty0 = ((tile >> 3) & 7) * 16;
   const int tw = min(16, pu.w - tx0), th = min(16, pu.h - ty0);
   const int bx = pu.x + tx0, by = pu.y + ty0;
@@ -806,13 +806,6 @@ __device__ __forceinline__ void mc_affine_tile(const McParams& P, const uint32_t
   const int hMin = (-P.ctuSize - 8 - pu.x + 1) * 16, hMax = (P.W + 8 - pu.x - 1) * 16;
   const int vMin = (-P.ctuSize - 8 - pu.y + 1) * 16, vMax = (P.H + 8 - pu.y - 1) * 16;
 
-  AffModel M[2];
-  RefPl R[2][3];
-  for (int li = 0; li < nList; li++) {
-    const int l = bi ? li : l0;
-    aff_model(pu, l, M[l]);
-    for (int c = 0; c < 3; c++) { R[l][c].p = P.refs[pu.refSlot[l] * 3 + c]; R[l][c].w = c ? P.W >> 1 : P.W; R[l][c].h = c ? P.H >> 1 : P.H; R[l][c].stride = P.refStride[c]; }
-  }
 
   // ---- luma: sub-block sb = tid>>4 (4x4 grid in the tile), lane k = tid&15 ----
   const int sb = tid >> 4, k = tid & 15;
@@ -820,27 +813,29 @@ __device__ __forceinline__ void mc_affine_tile(const McParams& P, const uint32_t
   const bool sbValid = sbx < tw && sby < th;
   for (int li = 0; li < nList; li++) {
     const int l = bi ? li : l0;
+    AffModel Ml; aff_model(pu, l, Ml);                       // per list, in registers
+    RefPl Rl; Rl.p = P.refs[pu.refSlot[l] * 3]; Rl.w = P.W; Rl.h = P.H; Rl.stride = P.refStride[0];
     int mx = 0, my = 0;
-    if (sbValid) { aff_sub_mv(M[l], pu, (tx0 + sbx) >> 2, (ty0 + sby) >> 2, mx, my); mx = clip3(hMin, hMax, mx); my = clip3(vMin, vMax, my); }
+    if (sbValid) { aff_sub_mv(Ml, pu, (tx0 + sbx) >> 2, (ty0 + sby) >> 2, mx, my); mx = clip3(hMin, hMax, mx); my = clip3(vMin, vMax, my); }
     const int xF = mx & 15, yF = my & 15, X0 = bx + sbx + (mx >> 4), Y0 = by + sby + (my >> 4);
     if (sbValid) {
       const int8_t* fh = kIfLuma4x4 + xF * 8;
       for (int j = k; j < 36; j += 16) {                      // 9 rows (y-2..y+6: 6-tap taps 1..6 of the 8-tap array) x 4 cols
         const int y = j >> 2, x = j & 3;
         int s = 0;
-        if (xF == 0) s = 64 * ldc(R[l][0], X0 + x, Y0 + y - 2);
+        if (xF == 0) s = 64 * ldc(Rl, X0 + x, Y0 + y - 2);
         else {
 #pragma unroll
-          for (int t = 1; t < 7; t++) s += fh[t] * ldc(R[l][0], X0 + x + t - 3, Y0 + y - 2);
+          for (int t = 1; t < 7; t++) s += fh[t] * ldc(Rl, X0 + x + t - 3, Y0 + y - 2);
         }
         sHf[l][sb][j] = (int16_t)((s - (IFO << sh1)) >> sh1);
       }
-      if (M[l].prof) {                                       // ring of the 6x6 PROF buffer from integer samples (:1233-1262)
+      if (Ml.prof) {                                       // ring of the 6x6 PROF buffer from integer samples (:1233-1262)
         const int rx = X0 + (xF >> 3) - 1, ry = Y0 + (yF >> 3) - 1;
         for (int j = k; j < 36; j += 16) {
           const int y = j / 6, x = j - y * 6;
           if (x > 0 && x < 5 && y > 0 && y < 5) continue;
-          sE[l][sb][j] = (int16_t)((int16_t)(ldc(R[l][0], rx + x, ry + y) << hr) - IFO);
+          sE[l][sb][j] = (int16_t)((int16_t)(ldc(Rl, rx + x, ry + y) << hr) - IFO);
         }
       }
     }
@@ -854,19 +849,19 @@ __device__ __forceinline__ void mc_affine_tile(const McParams& P, const uint32_t
 #pragma unroll
         for (int t = 1; t < 7; t++) s += fv[t] * sHf[l][sb][(y + t - 1) * 4 + x];
       }
-      if (M[l].prof) sE[l][sb][(y + 1) * 6 + x + 1] = (int16_t)(s >> 6);
+      if (Ml.prof) sE[l][sb][(y + 1) * 6 + x + 1] = (int16_t)(s >> 6);
       else if (bi)   sP[l][0][(sby + y) * 16 + sbx + x] = (int16_t)(s >> 6);
       else P.dst[0][(size_t)(by + sby + y) * P.dstStride[0] + bx + sbx + x] = (int16_t)LUMA_OUT(we ? wp_uni(we, 0, (int16_t)(s >> 6), hr, pmax) : clip3(0, pmax, (s + (1 << (5 + hr)) + (IFO << 6)) >> (6 + hr)));
     }
     __syncwarp();
-    if (sbValid && M[l].prof) {                              // gradFilterCore<false> :212 + applyPROFCore :61
+    if (sbValid && Ml.prof) {                              // gradFilterCore<false> :212 + applyPROFCore :61
       const int y = k >> 2, x = k & 3, c = (y + 1) * 6 + x + 1;
       const int16_t* E = sE[l][sb];
       const int gX = (E[c + 1] >> 6) - (E[c - 1] >> 6), gY = (E[c + 6] >> 6) - (E[c - 6] >> 6);
       // dMv of sample (x,y) inside the 4x4 (:1043-1090): linear in x,y, then rounded by 8 and clipped to +-31
-      const int qHX = M[l].dHX * 4, qHY = M[l].dHY * 4, qVX = M[l].dVX * 4, qVY = M[l].dVY * 4;
-      int dh = ((M[l].dHX + M[l].dVX) * 2) - ((qHX + qVX) * 2) + x * qHX + y * qVX;
-      int dv = ((M[l].dHY + M[l].dVY) * 2) - ((qHY + qVY) * 2) + x * qHY + y * qVY;
+      const int qHX = Ml.dHX * 4, qHY = Ml.dHY * 4, qVX = Ml.dVX * 4, qVY = Ml.dVY * 4;
+      int dh = ((Ml.dHX + Ml.dVX) * 2) - ((qHX + qVX) * 2) + x * qHX + y * qVX;
+      int dv = ((Ml.dHY + Ml.dVY) * 2) - ((qHY + qVY) * 2) + x * qHY + y * qVY;
       round_affine(dh, dv, 8);
       dh = clip3(-31, 31, dh); dv = clip3(-31, 31, dv);
       const int lim = 1 << max(bd + 1, 13);
@@ -886,10 +881,13 @@ __device__ __forceinline__ void mc_affine_tile(const McParams& P, const uint32_t
     const int csx = (cs & 1) * 4, csy = (cs >> 1) * 4;       // chroma offset inside the 8x8 chroma tile
     const bool valid = li < nList && csx < (tw >> 1) && csy < (th >> 1);
     int mx = 0, my = 0;
+    RefPl Rc; Rc.p = nullptr; Rc.w = P.W >> 1; Rc.h = P.H >> 1; Rc.stride = P.refStride[1];
     if (valid) {
+      AffModel Ml; aff_model(pu, l, Ml);
+      Rc.p = P.refs[pu.refSlot[l] * 3 + c]; Rc.stride = c == 1 ? P.refStride[1] : P.refStride[2];
       int ax, ay, bxm, bym;
       const int i0 = (tx0 >> 2) + (csx >> 1), j0 = (ty0 >> 2) + (csy >> 1);
-      aff_sub_mv(M[l], pu, i0, j0, ax, ay); aff_sub_mv(M[l], pu, i0 + 1, j0 + 1, bxm, bym);
+      aff_sub_mv(Ml, pu, i0, j0, ax, ay); aff_sub_mv(Ml, pu, i0 + 1, j0 + 1, bxm, bym);
       mx = ax + bxm; my = ay + bym;
       round_affine(mx, my, 1);
       mx = clip3(hMin, hMax, mx); my = clip3(vMin, vMax, my);
@@ -901,7 +899,7 @@ __device__ __forceinline__ void mc_affine_tile(const McParams& P, const uint32_t
         const int y = j >> 2, x = j & 3;
         int s = 0;
 #pragma unroll
-        for (int t = 0; t < 4; t++) s += fh[t] * ldc(R[l][c], X0 + x + t - 1, Y0 + y - 1);
+        for (int t = 0; t < 4; t++) s += fh[t] * ldc(Rc, X0 + x + t - 1, Y0 + y - 1);
         sCH[li][c - 1][cs][j] = (int16_t)((s - (IFO << sh1)) >> sh1);
       }
     }

@@ -14,13 +14,20 @@ class FrameGather:
     order on all ranks, so the matching operations line up without any handshake.  The transfers run on the communicator's stream behind the stream that
     called push() (the side stream the frame was copied on) and overlap the reconstruction of the following pictures; finish() posts what is left (peers
     with more frames than rank 0) and waits."""
-    def __init__(self, rank: int, world: int, gop_lengths: Sequence[int], frame_numel: int, device, dtype=torch.uint8):
+    def __init__(self, rank: int, world: int, gop_lengths: Sequence[int], frame_numel: int, device, dtype=torch.uint8, display_of=None):
         # frames travel as bytes: torch's NCCL process group has no 16-bit integer type
         self.rank, self.world, self.numel = rank, world, frame_numel
-        self.assignment = gop_shard.assign(len(gop_lengths), world)
-        self.order = gop_shard.output_order(self.assignment, gop_lengths)              # display index -> (rank, local frame index)
-        self.display_of = {rl: d for d, rl in enumerate(self.order)}
-        self.frames_of = [sum(gop_lengths[k] for k in self.assignment[r]) for r in range(world)]
+        if display_of is None:
+            self.assignment = gop_shard.assign(len(gop_lengths), world)
+            self.order = gop_shard.output_order(self.assignment, gop_lengths)          # display index -> (rank, local frame index)
+            self.display_of = {rl: d for d, rl in enumerate(self.order)}
+            self.frames_of = [sum(gop_lengths[k] for k in self.assignment[r]) for r in range(world)]
+        else:
+            # explicit map (rank, n-th frame that rank pushes) -> display index, the same on every rank: for ranks that reconstruct several GOPs side by side
+            # (GOP-parallel lanes), whose frames do not finish in GOP order
+            self.display_of = dict(display_of)
+            self.order = [rl for rl, _ in sorted(self.display_of.items(), key=lambda kv: kv[1])]
+            self.frames_of = [sum(1 for (r, _) in self.display_of if r == q) for q in range(world)]
         self.local_frames = self.frames_of[rank]
         self.reqs: List = []
         self.posted = 0                                                               # rank 0: local indices whose receives are posted
