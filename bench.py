@@ -351,39 +351,48 @@ def run_b200(args):
     # ---- seam: DecLibReconB200 live on parsed Pictures (its own device context) ----
     seam = None
     if not args.no_seam and rank == 0 and world == 1:
-        try: os.sched_setaffinity(0, range(os.cpu_count()))
-        except Exception: pass
-        # host threads x recon instances: the fastest pair on 6 B pictures (the pool's task scan contends on many threads, like the reference's own back end)
-        sample = [wl.B[i % len(wl.B)] for i in range(6)]
-        table, best = {}, (0.0, T, 1)
-        for Ts in thread_candidates(args):
-            sample[0].run_b200(threads=Ts)
-            ts = [c.run_b200(threads=Ts)[2] for c in sample]
-            assert min(ts) >= 0, "DecLibReconB200 failed on a workload picture"
-            f1 = len(ts) / sum(ts); table[f"{Ts}x1"] = round(f1, 1)
-            if f1 > best[0]: best = (f1, Ts, 1)
-            if args.recon_depth > 1:
-                wl.helpers.seam_pipelined(wl.ref, sample[:2], Ts, 1, args.recon_depth, read=False)
-                secs, _ = wl.helpers.seam_pipelined(wl.ref, sample, Ts, 1, args.recon_depth, read=False)
-                if secs > 0:
-                    table[f"{Ts}x{args.recon_depth}"] = round(len(sample) / secs, 1)
-                    if len(sample) / secs > best[0]: best = (len(sample) / secs, Ts, args.recon_depth)
-        _, Ts, Ds = best
-        n = min(args.steps, 16)
-        cases = [wl.sched(i)[1] for i in range(n)]
-        if Ds == 1:
-            ts = [c.run_b200(threads=Ts)[2] for c in cases]; fps_seam = len(ts) / sum(ts)
-        else:
-            secs, _ = wl.helpers.seam_pipelined(wl.ref, cases, Ts, 1, Ds, read=False); assert secs > 0; fps_seam = n / secs
-        seam = {"value": round(fps_seam, 2), "unit": "frames/s", "host_threads": Ts, "recon_instances": Ds, "pictures": n, "sweep_fps": table,
-                "host_stage_ms_per_picture": round(1e3 * float(np.mean(host_stage_s)), 3),
-                "api": "b200glue::DecLibReconB200::decompressPicture + waitForPrevDecompressedPic on live parsed Pictures of the schedule (I picture included), in the fastest "
-                       "configuration of a sweep over host threads x recon instances taking pictures in turn (DecLib.h:70), as the reference arm is measured"}
+        try:
+            try: os.sched_setaffinity(0, range(os.cpu_count()))
+            except Exception: pass
+            # host threads x recon instances: the fastest pair on 6 B pictures (the pool's task scan contends on many threads, like the reference's own back end)
+            sample = [wl.B[i % len(wl.B)] for i in range(6)]
+            table, best = {}, (0.0, T, 1)
+            for Ts in thread_candidates(args):
+                sample[0].run_b200(threads=Ts)
+                ts = [c.run_b200(threads=Ts)[2] for c in sample]
+                assert min(ts) >= 0, "DecLibReconB200 failed on a workload picture"
+                f1 = len(ts) / sum(ts); table[f"{Ts}x1"] = round(f1, 1)
+                if f1 > best[0]: best = (f1, Ts, 1)
+                if args.recon_depth > 1:
+                    wl.helpers.seam_pipelined(wl.ref, sample[:2], Ts, 1, args.recon_depth, read=False)
+                    secs, _ = wl.helpers.seam_pipelined(wl.ref, sample, Ts, 1, args.recon_depth, read=False)
+                    if secs > 0:
+                        table[f"{Ts}x{args.recon_depth}"] = round(len(sample) / secs, 1)
+                        if len(sample) / secs > best[0]: best = (len(sample) / secs, Ts, args.recon_depth)
+            _, Ts, Ds = best
+            n = min(args.steps, 16)
+            cases = [wl.sched(i)[1] for i in range(n)]
+            if Ds == 1:
+                ts = [c.run_b200(threads=Ts)[2] for c in cases]; fps_seam = len(ts) / sum(ts)
+            else:
+                secs, _ = wl.helpers.seam_pipelined(wl.ref, cases, Ts, 1, Ds, read=False); assert secs > 0; fps_seam = n / secs
+            seam = {"value": round(fps_seam, 2), "unit": "frames/s", "host_threads": Ts, "recon_instances": Ds, "pictures": n, "sweep_fps": table,
+                    "host_stage_ms_per_picture": round(1e3 * float(np.mean(host_stage_s)), 3),
+                    "api": "b200glue::DecLibReconB200::decompressPicture + waitForPrevDecompressedPic on live parsed Pictures of the schedule (I picture included), in the fastest "
+                           "configuration of a sweep over host threads x recon instances taking pictures in turn (DecLib.h:70), as the reference arm is measured"}
+        except Exception as e:
+            seam = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
 
     line = None
     if rank == 0: line = assemble_line(args, world, wl, flat, kms, ms_dev, ms_e2e, h2d_step, d2h_step, e2e_diag, seam, split, launches, numa, sampler, pic_of)
     if world > 1 and not args.no_gather:
-        gather_pass(args, rank, world, local, lib, lanes, upload_all, lane_h, pic_of, line, torch, dist, barrier, max_over_ranks)
+        try:
+            gather_pass(args, rank, world, local, lib, lanes, upload_all, lane_h, pic_of, line, torch, dist, barrier, max_over_ranks)
+        except Exception as e:                                               # the line (throughput without the gather) must not be lost to a failed exchange
+            if rank == 0:
+                line["gather"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+                print(json.dumps(line), flush=True)
+            leave()
     if rank == 0: print(json.dumps(line), flush=True)
     for ln in lanes: lib.b200_ctx_destroy(ln.ctx)
     if world > 1: dist.destroy_process_group()
@@ -492,7 +501,8 @@ def assemble_line(args, world, wl, flat, kms, ms_dev, ms_e2e, h2d_step, d2h_step
             "seam": seam, "picture_ms": split, "gather": None, "lanes_per_gpu": max(1, args.lanes),
             "gpu_launches": int(launches), "numa": numa, "clocks": sampler.summary(), "roofline": roof}
     if not args.no_cpu_baseline and world == 1:                      # the CPU legs are N = 1 lines only
-        line["cpu_baseline"] = cpu_baseline(args, wl)
+        try: line["cpu_baseline"] = cpu_baseline(args, wl)
+        except Exception as e: line["cpu_baseline"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     return line
 
 
