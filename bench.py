@@ -354,32 +354,12 @@ def run_b200(args):
         try:
             try: os.sched_setaffinity(0, range(os.cpu_count()))
             except Exception: pass
-            # host threads x recon instances: the fastest pair on 6 B pictures (the pool's task scan contends on many threads, like the reference's own back end)
-            sample = [wl.B[i % len(wl.B)] for i in range(6)]
-            table, best = {}, (0.0, T, 1)
-            for Ts in thread_candidates(args):
-                sample[0].run_b200(threads=Ts)
-                ts = [c.run_b200(threads=Ts)[2] for c in sample]
-                assert min(ts) >= 0, "DecLibReconB200 failed on a workload picture"
-                f1 = len(ts) / sum(ts); table[f"{Ts}x1"] = round(f1, 1)
-                if f1 > best[0]: best = (f1, Ts, 1)
-                if args.recon_depth > 1:
-                    wl.helpers.seam_pipelined(wl.ref, sample[:2], Ts, 1, args.recon_depth, read=False)
-                    secs, _ = wl.helpers.seam_pipelined(wl.ref, sample, Ts, 1, args.recon_depth, read=False)
-                    if secs > 0:
-                        table[f"{Ts}x{args.recon_depth}"] = round(len(sample) / secs, 1)
-                        if len(sample) / secs > best[0]: best = (len(sample) / secs, Ts, args.recon_depth)
-            _, Ts, Ds = best
-            n = min(args.steps, 16)
-            cases = [wl.sched(i)[1] for i in range(n)]
-            if Ds == 1:
-                ts = [c.run_b200(threads=Ts)[2] for c in cases]; fps_seam = len(ts) / sum(ts)
-            else:
-                secs, _ = wl.helpers.seam_pipelined(wl.ref, cases, Ts, 1, Ds, read=False); assert secs > 0; fps_seam = n / secs
-            seam = {"value": round(fps_seam, 2), "unit": "frames/s", "host_threads": Ts, "recon_instances": Ds, "pictures": n, "sweep_fps": table,
+            table = backend_sweep(args, wl, 1)
+            fps_seam, Ts, Ds, runs = backend_schedule(args, wl, 1, table)
+            seam = {"value": round(fps_seam, 2), "unit": "frames/s", "host_threads": Ts, "recon_instances": Ds, "pictures": args.steps, "sweep_estimate_fps": table, "schedule_fps": runs,
                     "host_stage_ms_per_picture": round(1e3 * float(np.mean(host_stage_s)), 3),
-                    "api": "b200glue::DecLibReconB200::decompressPicture + waitForPrevDecompressedPic on live parsed Pictures of the schedule (I picture included), in the fastest "
-                           "configuration of a sweep over host threads x recon instances taking pictures in turn (DecLib.h:70), as the reference arm is measured"}
+                    "api": "b200glue::DecLibReconB200::decompressPicture + waitForPrevDecompressedPic on the live parsed pictures of the schedule, measured like the reference arm: the faster of "
+                           "the two best configurations of a sweep over host threads x recon instances taking pictures in turn (DecLib.h:70)"}
         except Exception as e:
             seam = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
 
@@ -544,54 +524,63 @@ def thread_candidates(args):
     return sorted({t for t in (16, 32, 64, T) if t <= T} | {T})
 
 
-def stock_sweep(args, wl, n=6):
-    """The reference's DecLibRecon is not fastest on every host thread: its pool's task scan contends (profiles/r02_seam_threads.json: 4K B pictures, 128-thread box:
-    32 threads x 2 alternating instances 172 frames/s, 128 threads x 1 instance 89, 128 x 2 34).  Times n B pictures for every (threads, recon instances) pair and
-    returns the fastest pair with the table."""
+def run_one(case, backend, T):
+    secs = case.run_stock(threads=T)[2] if backend == 0 else case.run_b200(threads=T)[2]
+    assert secs >= 0, "the back end failed on a workload picture"
+    return secs
+
+
+def backend_fps(wl, cases, backend, T, D):
+    """Pictures per second of `cases` through one back end behind the seam (0: the reference's DecLibRecon, 1: DecLibReconB200) on ThreadPool(T) with D recon instances
+    taking pictures in turn."""
+    if D == 1: return len(cases) / sum(run_one(c, backend, T) for c in cases)
+    secs, _ = wl.helpers.seam_pipelined(wl.ref, cases, T, backend, D, read=False)
+    assert secs > 0, "the back end failed on a workload picture"
+    return len(cases) / secs
+
+
+def backend_sweep(args, wl, backend, n=6):
+    """Neither back end is fastest on every host thread: the pool's task scan contends (profiles/r02_seam_threads.json: stock DecLibRecon, 4K B pictures, 128-thread box:
+    32 threads x 2 alternating instances 172 frames/s, 128 x 1 89, 128 x 2 34), and an I picture wants more threads than a B picture.  For every (threads, recon
+    instances) pair: n B pictures and one I picture, combined in the schedule's proportion.  Returns {"TxD": estimated frames/s of the schedule}."""
+    nI = sum(1 for i in range(args.steps) if wl.sched(i)[0] == "I"); nB = args.steps - nI
     cases = [wl.B[i % len(wl.B)] for i in range(n)]
-    table, best = {}, (0.0, threads_all(args), 1)
+    table = {}
     for T in thread_candidates(args):
-        cases[0].run_stock(threads=T)                            # pool start-up
-        f1 = n / sum(c.run_stock(threads=T)[2] for c in cases)
-        table[f"{T}x1"] = round(f1, 1)
-        if f1 > best[0]: best = (f1, T, 1)
-        if args.recon_depth > 1:
-            D = args.recon_depth
-            wl.helpers.seam_pipelined(wl.ref, cases[:D], T, 0, D, read=False)
-            secs, _ = wl.helpers.seam_pipelined(wl.ref, cases, T, 0, D, read=False)
-            if secs > 0:
-                table[f"{T}x{D}"] = round(n / secs, 1)
-                if n / secs > best[0]: best = (n / secs, T, D)
-    return best[1], best[2], table
+        run_one(cases[0], backend, T)                            # pool start-up
+        tI = run_one(wl.I, backend, T) if nI else 0.0
+        for D in sorted({1, max(1, args.recon_depth)}):
+            if D > 1: wl.helpers.seam_pipelined(wl.ref, cases[:D], T, backend, D, read=False)
+            fB = backend_fps(wl, cases, backend, T, D)
+            table[f"{T}x{D}"] = round(args.steps / (nI * tI + nB / fB), 1)
+    return table
+
+
+def backend_schedule(args, wl, backend, table):
+    """The schedule's pictures in the two configurations the sweep rates fastest (two instances on many threads are bistable: the same pair can run 3x slower in the
+    next call); returns (frames/s, threads, instances, {config: frames/s})."""
+    runs = {}
+    for key in sorted(table, key=lambda k: -table[k])[:2]:
+        T, D = parse_cfg(key)
+        if args.warmup: backend_fps(wl, [wl.sched(i + 1)[1] for i in range(min(args.warmup, 4))], backend, T, D)
+        runs[key] = backend_fps(wl, [wl.sched(i)[1] for i in range(args.steps)], backend, T, D)
+    best = max(runs, key=lambda k: runs[k]); T, D = parse_cfg(best)
+    return runs[best], T, D, {k: round(v, 1) for k, v in runs.items()}
 
 
 def parse_cfg(key):
     t, d = key.split("x"); return int(t), int(d)
 
 
-def stock_fps(wl, cases, T, D):
-    if D == 1:
-        ts = [c.run_stock(threads=T)[2] for c in cases]
-        return len(ts) / sum(ts)
-    secs, _ = wl.helpers.seam_pipelined(wl.ref, cases, T, 0, D, read=False)
-    assert secs > 0, "stock DecLibRecon failed"
-    return len(cases) / secs
-
-
 def cpu_baseline(args, wl):
-    """The reference's DecLibRecon + ThreadPool on a bounded sample of the same pictures, in its fastest (threads, recon instances) configuration; the GOP mix is
-    weighted like the schedule."""
+    """The reference's DecLibRecon + ThreadPool on the schedule's pictures, in its fastest (threads, recon instances) configuration."""
     try: os.sched_setaffinity(0, range(os.cpu_count()))          # the GPU arm binds itself to the GPU's NUMA node; the CPU baseline gets every core
     except Exception: pass
-    T, D, table = stock_sweep(args, wl)
-    nb = max(args.cpu_sample, 2 * D)
-    tB = 1.0 / stock_fps(wl, [wl.B[i % len(wl.B)] for i in range(nb)], T, D)
-    tI = min(wl.I.run_stock(threads=T)[2] for _ in range(2))
-    nB = args.gop - 1
-    fps = args.gop / (tI + nB * tB)
-    return {"value": round(fps, 3), "unit": "frames/s", "cores": T, "kind": "reference", "recon_instances": D, "sweep_fps": table,
-            "sample": f"the reference's DecLibRecon (decompressPicture..waitForPrevDecompressedPic, {wl.ref.ref_simd_level().decode()}) in its fastest configuration of the sweep "
-                      f"(threads x recon instances taking pictures in turn, DecLib.h:70): ThreadPool({T}) x {D}; {nb} B pictures {1e3 * tB:.2f} ms each, 1 I picture alone {1e3 * tI:.2f} ms, weighted 1 I : {nB} B"}
+    table = backend_sweep(args, wl, 0)
+    fps, T, D, runs = backend_schedule(args, wl, 0, table)
+    return {"value": round(fps, 3), "unit": "frames/s", "cores": T, "kind": "reference", "recon_instances": D, "sweep_estimate_fps": table, "schedule_fps": runs,
+            "sample": f"the {args.steps} pictures of the schedule through the reference's DecLibRecon (decompressPicture..waitForPrevDecompressedPic, {wl.ref.ref_simd_level().decode()}) in the faster of "
+                      f"the two best configurations of a sweep over host threads x recon instances taking pictures in turn (DecLib.h:70; 6 B pictures + the I picture each): ThreadPool({T}) x {D}"}
 
 
 def run_reference(args):
@@ -599,19 +588,11 @@ def run_reference(args):
     if rank != 0: return
     wl = Workload(args, 0)
     T = threads_all(args)
-    Tb, D, table = stock_sweep(args, wl)
-    # the schedule in the two fastest configurations of the sweep (two instances on many threads are bistable: the same pair can run 3x slower in the next
-    # call); the better run is the arm's value
-    runs = {}
-    for key in sorted(table, key=lambda k: -table[k])[:2]:
-        t, d = parse_cfg(key)
-        if args.warmup: stock_fps(wl, [wl.sched(i + 1)[1] for i in range(min(args.warmup, 4))], t, d)
-        runs[key] = stock_fps(wl, [wl.sched(i)[1] for i in range(args.steps)], t, d)
-    bestkey = max(runs, key=lambda k: runs[k]); fps = runs[bestkey]; Tb, D = parse_cfg(bestkey)
-    T = Tb
-    cb = {"value": round(fps, 3), "unit": "frames/s", "cores": T, "kind": "reference", "recon_instances": D, "sweep_fps": table, "schedule_fps": {k: round(v, 1) for k, v in runs.items()},
-          "sample": f"the {args.steps} pictures of the schedule through the reference's DecLibRecon (decompressPicture..waitForPrevDecompressedPic, {wl.ref.ref_simd_level().decode()}) in the fastest "
-                    f"configuration of a sweep over host threads x recon instances taking pictures in turn (DecLib.h:70) on 6 B pictures: ThreadPool({T}) x {D}"}
+    table = backend_sweep(args, wl, 0)
+    fps, T, D, runs = backend_schedule(args, wl, 0, table)
+    cb = {"value": round(fps, 3), "unit": "frames/s", "cores": T, "kind": "reference", "recon_instances": D, "sweep_estimate_fps": table, "schedule_fps": runs,
+          "sample": f"the {args.steps} pictures of the schedule through the reference's DecLibRecon (decompressPicture..waitForPrevDecompressedPic, {wl.ref.ref_simd_level().decode()}) in the faster of "
+                    f"the two best configurations of a sweep over host threads x recon instances taking pictures in turn (DecLib.h:70; 6 B pictures + the I picture each): ThreadPool({T}) x {D}"}
     line = {"impl": "reference", "metric": METRIC, "value": round(fps, 3), "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 / fps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int16 samples / int32 accumulate", "data": "synthetic",
