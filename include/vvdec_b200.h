@@ -168,8 +168,15 @@ B200_API int b200_sao_picture(const b200_geom* g, const int16_t* const src[3], i
  *   not yet:   slices/tiles/subpictures with loop filtering disabled across them and explicit virtual
  *             boundaries (the isCrssByVBs path, :745-852) -> B200_ERR_UNSUPPORTED at the flattener.
  * ---------------------------------------------------------------------------------------------- */
+/* CTUs whose neighbours ALF may not read (in-loop filtering disabled across slices / tiles: AdaptiveLoopFilter::isClipOrCrossedByVirtualBoundaries :118 and the
+ * isCrssByVBs path of filterCTU :763-848): bits of b200_alf_ctu::enable[0].  CLIP_x: samples beyond that side of the CTU are replicas of its edge samples.
+ * PAD_TL / PAD_BR (raster-scan slices: the CTU above-left / below-right belongs to another slice while both sides are readable): the corner region takes, row by
+ * row, the sample of the CTU's first / last column (padBorderPel, Buffer.h:608).  enable[1], enable[2] bit 1 (B200_ALF_PAD_WIDE): the component is padded by 4 instead
+ * of 2 chroma samples — what the reference does for a chroma component whose slice has CC-ALF off (AreaBuf::padBorderPel called with the luma margin, :794-803):
+ * the region reaches 2 samples into the CTU and takes the sample 2 columns inside. */
+enum { B200_ALF_CLIP_TOP = 2, B200_ALF_CLIP_BOTTOM = 4, B200_ALF_CLIP_LEFT = 8, B200_ALF_CLIP_RIGHT = 16, B200_ALF_PAD_TL = 32, B200_ALF_PAD_BR = 64, B200_ALF_PAD_WIDE = 2 };
 typedef struct b200_alf_ctu {
-  uint8_t enable[3];      /* alfCtuEnableFlag per component (bit 0)                                            */
+  uint8_t enable[3];      /* alfCtuEnableFlag per component (bit 0); enable[0] bits 1..6: B200_ALF_CLIP_* / PAD_*, enable[1..2] bit 1: B200_ALF_PAD_WIDE */
   uint8_t lumaSet;        /* index into lumaCoeff/lumaClip: 0..15 fixed sets, 16.. the slice's APS sets        */
   uint8_t chromaAlt[2];   /* index into chromaCoeff/chromaClip (APS alternative, resolved per slice)           */
   uint8_t ccIdx[2];       /* 0: CC-ALF off for Cb/Cr, else 1 + index into ccCoeff[comp]                         */

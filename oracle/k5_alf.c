@@ -147,18 +147,42 @@ void orc_alf_picture(const b200_geom* g, const int16_t* const src[3], int16_t* c
   const int ctu = g->ctuSize, ctusW = (g->width + ctu - 1) / ctu, ctusH = (g->height + ctu - 1) / ctu;
   const int vbH = ctu, vbPos = ctu - 4, vbHc = ctu >> 1, vbPosC = (ctu >> 1) - 2;
   uint16_t cls[64];
+  int16_t* tmp[3] = { NULL, NULL, NULL };                      /* CTU + 8-sample frame, for CTUs with clipped sides / padded corners */
+  const ptrdiff_t tstr = 128 + 16;
   for (int cy = 0; cy < ctusH; cy++) for (int cx = 0; cx < ctusW; cx++) {
     const b200_alf_ctu* p = &ctus[cy * ctusW + cx];
     const int x0 = cx * ctu, y0 = cy * ctu;
     const int w = x0 + ctu > g->width ? g->width - x0 : ctu, h = y0 + ctu > g->height ? g->height - y0 : ctu;
+    const int16_t* srcC[3] = { org[0], org[1], org[2] }; ptrdiff_t strC[3] = { ps[0], ps[1], ps[2] };
+    if (p->enable[0] & ~1) {
+      /* filterCTU :763-848 with no virtual boundary inside the CTU: the CTU is copied with 4 (chroma 2) extra samples on the sides that may be read, the raster-slice
+       * corners are padded, then the copy is extended by replication (extendBorderPel) — classification and filters run on the copy */
+      const int f = p->enable[0];
+      for (int c = 0; c < nComp; c++) {
+        const int sh = c ? 1 : 0, bx = x0 >> sh, by = y0 >> sh, bw = w >> sh, bh = h >> sh, m = 4 >> sh;
+        const int pl = (f & B200_ALF_CLIP_LEFT) || bx == 0 ? 0 : m, pr = (f & B200_ALF_CLIP_RIGHT) || bx + bw == (g->width >> sh) ? 0 : m;
+        const int pt = (f & B200_ALF_CLIP_TOP) || by == 0 ? 0 : m, pb = (f & B200_ALF_CLIP_BOTTOM) || by + bh == (g->height >> sh) ? 0 : m;
+        if (!tmp[c]) tmp[c] = (int16_t*)malloc(sizeof(int16_t) * (size_t)tstr * (128 + 16));
+        int16_t* B = tmp[c] + 8 * tstr + 8;                      /* B[0] = sample (bx, by) */
+        const int cw2 = bw + pl + pr, ch2 = bh + pt + pb;        /* the copied area starts at (-pl, -pt) */
+        for (int y = -pt; y < bh + pb; y++) for (int x = -pl; x < bw + pr; x++) B[y * tstr + x] = org[c][(ptrdiff_t)(by + y) * ps[c] + bx + x];
+        const int mg = (c && (p->enable[c] & B200_ALF_PAD_WIDE)) ? 4 : m;      /* padBorderPel margin: :794-803 pass the luma margin for a chroma plane on its own */
+        int16_t* P0 = B - pt * tstr - pl;                        /* origin of the copied area */
+        if (f & B200_ALF_PAD_TL) for (int y = 0; y < mg; y++) for (int x = 0; x < mg; x++) P0[y * tstr + x] = P0[y * tstr + mg];
+        if (f & B200_ALF_PAD_BR) { int16_t* q = P0 + (ptrdiff_t)(ch2 - mg) * tstr + cw2 - mg; for (int y = 0; y < mg; y++) for (int x = 0; x < mg; x++) q[y * tstr + x] = q[y * tstr - 1]; }
+        for (int y = 0; y < ch2; y++) for (int k = 1; k <= 4; k++) { P0[y * tstr - k] = P0[y * tstr]; P0[y * tstr + cw2 - 1 + k] = P0[y * tstr + cw2 - 1]; }     /* extendBorderPel(4) */
+        for (int k = 1; k <= 4; k++) { memcpy(P0 - k * tstr - 4, P0 - 4, sizeof(int16_t) * (cw2 + 8)); memcpy(P0 + (ptrdiff_t)(ch2 - 1 + k) * tstr - 4, P0 + (ptrdiff_t)(ch2 - 1) * tstr - 4, sizeof(int16_t) * (cw2 + 8)); }
+        srcC[c] = B - (ptrdiff_t)by * tstr - bx; strC[c] = tstr;  /* so that srcC[c][y * stride + x] is sample (x, y) of the picture */
+      }
+    }
     /* luma */
     if (p->enable[0] & 1) {
       const int16_t* coeff = T->lumaCoeff + (size_t)p->lumaSet * 4 * 25 * 13;
       const int16_t* clip  = T->lumaClip  + (size_t)p->lumaSet * 4 * 25 * 13;
       for (int by = 0; by < h; by += 32) for (int bx = 0; bx < w; bx += 32) {
         const int bw = bx + 32 > w ? w - bx : 32, bh = by + 32 > h ? h - by : 32;
-        orc_alf_classify(cls, org[0], ps[0], x0 + bx, y0 + by, bw, bh, g->bitDepth + 4, vbH, vbPos);
-        orc_alf_filter_blk(1, cls, dst[0], g->stride[0], org[0], ps[0], x0 + bx, y0 + by, bw, bh, coeff, clip, g->bitDepth, vbH, vbPos);
+        orc_alf_classify(cls, srcC[0], strC[0], x0 + bx, y0 + by, bw, bh, g->bitDepth + 4, vbH, vbPos);
+        orc_alf_filter_blk(1, cls, dst[0], g->stride[0], srcC[0], strC[0], x0 + bx, y0 + by, bw, bh, coeff, clip, g->bitDepth, vbH, vbPos);
       }
     } else {
       for (int y = y0; y < y0 + h; y++) memcpy(dst[0] + (size_t)y * g->stride[0] + x0, src[0] + (size_t)y * g->stride[0] + x0, w * sizeof(int16_t));
@@ -167,13 +191,13 @@ void orc_alf_picture(const b200_geom* g, const int16_t* const src[3], int16_t* c
     for (int c = 1; c < nComp; c++) {
       const int cx0 = x0 >> 1, cy0 = y0 >> 1, cw = w >> 1, chh = h >> 1;
       if (p->enable[c] & 1)
-        orc_alf_filter_blk(0, NULL, dst[c], g->stride[c], org[c], ps[c], cx0, cy0, cw, chh, T->chromaCoeff + p->chromaAlt[c - 1] * 7,
+        orc_alf_filter_blk(0, NULL, dst[c], g->stride[c], srcC[c], strC[c], cx0, cy0, cw, chh, T->chromaCoeff + p->chromaAlt[c - 1] * 7,
                            T->chromaClip + p->chromaAlt[c - 1] * 7, g->bitDepth, vbHc, vbPosC);
       else
         for (int y = cy0; y < cy0 + chh; y++) memcpy(dst[c] + (size_t)y * g->stride[c] + cx0, src[c] + (size_t)y * g->stride[c] + cx0, cw * sizeof(int16_t));
       if (p->ccIdx[c - 1])
-        orc_alf_ccalf_blk(dst[c], g->stride[c], org[0], ps[0], cx0, cy0, cw, chh, T->ccCoeff[c - 1] + (p->ccIdx[c - 1] - 1) * 7, g->bitDepth, vbH, vbPos);
+        orc_alf_ccalf_blk(dst[c], g->stride[c], srcC[0], strC[0], cx0, cy0, cw, chh, T->ccCoeff[c - 1] + (p->ccIdx[c - 1] - 1) * 7, g->bitDepth, vbH, vbPos);
     }
   }
-  for (int c = 0; c < nComp; c++) free(pad[c]);
+  for (int c = 0; c < nComp; c++) { free(pad[c]); free(tmp[c]); }
 }

@@ -538,7 +538,7 @@ static void setupSps( FakePicture& fp, const ref_seam_cfg& c, const b200_geom& g
   pps.setNumExpTileColumns( 1 ); pps.setNumExpTileRows( 1 ); pps.addTileColumnWidth( pps.getPicWidthInCtu() ); pps.addTileRowHeight( pps.getPicHeightInCtu() );
   pps.initTiles();
   SEAM_TR( "sps: tiles\n" );
-  pps.setLoopFilterAcrossSlicesEnabledFlag( true ); pps.setLoopFilterAcrossTilesEnabledFlag( true );
+  pps.setLoopFilterAcrossSlicesEnabledFlag( !( c.tools & SEAM_NO_LF_ACROSS_SLICES ) ); pps.setLoopFilterAcrossTilesEnabledFlag( true );
   pps.setQpOffset( COMPONENT_Cb, 1 ); pps.setQpOffset( COMPONENT_Cr, -1 ); pps.setQpOffset( JOINT_CbCr, 0 );
   ph.setMaxNumAffineMergeCand( c.affinePct > 0 ? 5 : 0 ); ph.setEnableTMVPFlag( false ); ph.setMvdL1ZeroFlag( false );
   ph.setDisBdofFlag( false ); ph.setDisDmvrFlag( false ); ph.setDisProfFlag( false ); ph.setJointCbCrSignFlag( ( c.seed >> 1 ) & 1 );

@@ -25,6 +25,8 @@ CASES = {
     "B_3slices": dict(slices=3),                                                # per-slice reference lists, deblocking offsets, ALF APS lists / switches
     "B_4slices_lmcs_isp": dict(slices=4, lmcs=True, isp=30),
     "P_5slices": dict(slices=5, slice_type=1),
+    "B_5slices_no_lf_across": dict(slices=5, ctu=64, lf_across_slices=False),    # ALF clipped sides / padded raster-slice corners, SAO / deblocking stop at slices
+    "I_6slices_no_lf_across": dict(slices=6, ctu=64, lf_across_slices=False, slice_type=2),
     "B_ctu64": dict(ctu=64),
     "B_ctu32_8bit": dict(ctu=32, bd=8),
     "B_no_dmvr": dict(tools=(helpers.SEAM_INTER_TOOLS | helpers.SEAM_RESI_TOOLS | helpers.SEAM_INTRA_TOOLS | helpers.SEAM_FILTERS) & ~helpers.SEAM["DMVR"]),

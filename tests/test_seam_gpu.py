@@ -26,6 +26,7 @@ def both(seed, W, H, threads=4, **kw):
                                      ("B_lmcs_inter", dict(lmcs=True, intra=0, tools=T_INTER)), ("B_lmcs_intra_ciip", dict(lmcs=True)), ("I_lmcs", dict(lmcs=True, slice_type=2)),
                                      ("B_ctu64", dict(ctu=64)),
                                      ("B_3slices", dict(slices=3)), ("B_4slices_lmcs_isp", dict(slices=4, lmcs=True, isp=30)), ("I_2slices", dict(slices=2, slice_type=2)),
+                                     ("B_5slices_no_lf_across", dict(slices=5, ctu=64, lf_across_slices=False)), ("B_7slices_no_lf_across_ctu32", dict(slices=7, ctu=32, lf_across_slices=False)),
                                      ("B_isp", dict(isp=40)), ("I_isp", dict(isp=60, slice_type=2)), ("I_isp_lmcs", dict(isp=60, slice_type=2, lmcs=True)), ("I_isp_ctu32", dict(isp=70, slice_type=2, ctu=32))])
 @pytest.mark.parametrize("seed", [1, 2])
 def test_seam_small(name, kw, seed):

@@ -102,6 +102,7 @@ INTRA_TU_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("log2w", "u1"), ("log2h"
 INTRA_FILTER_REF, INTRA_AVAIL_TL, INTRA_ADD_RESI = 1, 2, 4
 INTRA_BDPCM_HOR, INTRA_BDPCM_VER, INTRA_MIP, INTRA_LM, INTRA_MDLM_L, INTRA_MDLM_T = 67, 68, 69, 70, 71, 72
 INTRA_LM_ABOVE, INTRA_LM_LEFT, INTRA_LM_COLLOCATED, INTRA_ISP = 8, 16, 32, 64
+ALF_CLIP_TOP, ALF_CLIP_BOTTOM, ALF_CLIP_LEFT, ALF_CLIP_RIGHT, ALF_PAD_TL, ALF_PAD_BR, ALF_PAD_WIDE = 2, 4, 8, 16, 32, 64, 2
 
 
 class FilmGrain(C.Structure):

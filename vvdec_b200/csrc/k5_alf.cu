@@ -32,6 +32,17 @@ __device__ __forceinline__ void cp_async8(void* smemDst, const void* gmemSrc)   
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(d), "l"(gmemSrc));
 }
 
+// CTUs whose neighbours may not be read (b200_alf_ctu::enable[0] bits, include/vvdec_b200.h): where a sample comes from.  (x0, y0)-(x1, y1): the CTU in the
+// component's samples; pm: 0, or 2 for a chroma plane padded with the luma margin (B200_ALF_PAD_WIDE).
+struct AlfExt { int x0, y0, x1, y1, W, H, f, pm; };
+__device__ __forceinline__ void alf_map(const AlfExt& E, int& x, int& y)
+{
+  if ((E.f & B200_ALF_PAD_TL) && x < E.x0 + E.pm && y < E.y0 + E.pm) x = E.x0 + E.pm;             // raster-slice corners: the row's sample of the CTU's first / last column
+  else if ((E.f & B200_ALF_PAD_BR) && x > E.x1 - E.pm && y > E.y1 - E.pm) x = E.x1 - E.pm;
+  x = min(max(x, (E.f & B200_ALF_CLIP_LEFT) ? E.x0 : 0), (E.f & B200_ALF_CLIP_RIGHT) ? E.x1 : E.W - 1);
+  y = min(max(y, (E.f & B200_ALF_CLIP_TOP) ? E.y0 : 0), (E.f & B200_ALF_CLIP_BOTTOM) ? E.y1 : E.H - 1);
+}
+
 __device__ __forceinline__ int clipd(int c, int ref, int a, int b) { return clip3(-c, c, a - ref) + clip3(-c, c, b - ref); }
 
 __global__ void __launch_bounds__(256) alf_luma_kernel(const AlfParams P)
@@ -53,7 +64,17 @@ __global__ void __launch_bounds__(256) alf_luma_kernel(const AlfParams P)
   }
 
   // ---- stage tile + halo, clamped ----
-  if (P.vecOk && bx0 >= HALO && bx0 + TB + HALO <= P.W && by0 >= HALO && by0 + TB + HALO <= P.H) {
+  const int clipF = cp.enable[0] & ~1;
+  if (clipF) {                                              // a side of the CTU may not be read, or a corner is padded (filterCTU :763-848)
+    AlfExt E; E.x0 = (bx0 >> P.ctuLog2) << P.ctuLog2; E.y0 = (by0 >> P.ctuLog2) << P.ctuLog2; E.x1 = min(E.x0 + P.ctuSize, P.W) - 1; E.y1 = min(E.y0 + P.ctuSize, P.H) - 1;
+    E.W = P.W; E.H = P.H; E.f = clipF; E.pm = 0;
+    for (int i = tid; i < TS * TS; i += 256) {
+      const int ty = i / TS, tx = i - ty * TS;
+      int gx = bx0 + tx - HALO, gy = by0 + ty - HALO;
+      alf_map(E, gx, gy);
+      t[ty][tx] = P.src[0][(size_t)gy * stride + gx];
+    }
+  } else if (P.vecOk && bx0 >= HALO && bx0 + TB + HALO <= P.W && by0 >= HALO && by0 + TB + HALO <= P.H) {
     const int16_t* s0 = P.src[0] + (size_t)(by0 - HALO) * stride + bx0 - HALO;      // interior tile: 40 rows x 10 8-byte words
     for (int i = tid; i < TS * (TS / 4); i += 256) {
       const int ty = i / (TS / 4), c = i - ty * (TS / 4);
@@ -259,10 +280,13 @@ __global__ void __launch_bounds__(256) alf_chroma_kernel(const AlfParams P)
   const int stride = P.stride[c];
   const int16_t* s = P.src[c];
   const int pmax = (1 << P.bitDepth) - 1;
-  const bool inner = P.vecOkC && x >= 4 && x + 8 <= pw;
+  const int clipF = cp.enable[0] & ~1;
+  const bool inner = P.vecOkC && x >= 4 && x + 8 <= pw && !clipF;
   int out[4];
+  AlfExt E; E.x0 = (x >> l2cs) << l2cs; E.y0 = (y >> l2cs) << l2cs; E.x1 = min(E.x0 + cs, pw) - 1; E.y1 = min(E.y0 + cs, ph) - 1; E.W = pw; E.H = ph; E.f = clipF;
+  E.pm = (cp.enable[c] & B200_ALF_PAD_WIDE) ? 2 : 0;
   auto rowp = [&](int yy) { return s + (size_t)min(max(yy, 0), ph - 1) * stride; };
-  auto at = [&](int xx, int yy) { return (int)rowp(yy)[min(max(xx, 0), pw - 1)]; };
+  auto at = [&](int xx, int yy) { if (clipF) { alf_map(E, xx, yy); return (int)s[(size_t)yy * stride + xx]; } return (int)rowp(yy)[min(max(xx, 0), pw - 1)]; };
   if (cp.enable[c] & 1) {
     const int16_t* f = P.chromaCoeff + cp.chromaAlt[c - 1] * 7; const int16_t* cl = P.chromaClip + cp.chromaAlt[c - 1] * 7;
     int fc[6], cc[6];
@@ -321,8 +345,9 @@ __global__ void __launch_bounds__(256) alf_chroma_kernel(const AlfParams P)
     int o1 = 1, o2 = -1, o3 = 2;
     if (pos == vbPos - 2 || pos == vbPos + 1) o3 = 1;
     else if (pos == vbPos - 1 || pos == vbPos) o1 = o2 = o3 = 0;
+    AlfExt EL; EL.x0 = E.x0 << 1; EL.y0 = E.y0 << 1; EL.x1 = min(EL.x0 + P.ctuSize, P.W) - 1; EL.y1 = min(EL.y0 + P.ctuSize, P.H) - 1; EL.W = P.W; EL.H = P.H; EL.f = clipF; EL.pm = 0;
     auto lrow = [&](int yy) { return L + (size_t)min(max(yy, 0), P.H - 1) * ls; };
-    auto lat = [&](int xx, int yy) { return (int)lrow(yy)[min(max(xx, 0), P.W - 1)]; };
+    auto lat = [&](int xx, int yy) { if (clipF) { alf_map(EL, xx, yy); return (int)L[(size_t)yy * ls + xx]; } return (int)lrow(yy)[min(max(xx, 0), P.W - 1)]; };
     const int half = (1 << P.bitDepth) >> 1;
     // luma windows: a[k], b[k] = luma sample 2x-1+k of rows ly, ly+o1 (9); up[i], dn[i] = luma sample 2(x+i) of rows ly+o2, ly+o3
     int a[9], bb[9], up[4], dn[4];

@@ -108,7 +108,8 @@ class DecLibReconB200
   double since() const { return std::chrono::duration<double>( std::chrono::steady_clock::now() - m_t0 ).count(); }
   // the CPU stages that stay
   std::vector<MotionInfo> m_motionInfo; std::vector<LoopFilterParam> m_loopFilterParam; std::vector<Mv> m_dmvrMvCache;
-  LoopFilter m_cLoopFilter; SampleAdaptiveOffset m_cSAO; AdaptiveLoopFilter m_cALF; Reshape m_cReshaper;
+  struct AlfAccess : AdaptiveLoopFilter { using AdaptiveLoopFilter::isClipOrCrossedByVirtualBoundaries; };     // protected in the reference: the glue asks it per CTU
+  LoopFilter m_cLoopFilter; SampleAdaptiveOffset m_cSAO; AlfAccess m_cALF; Reshape m_cReshaper;
   std::vector<std::unique_ptr<DecCu>> m_cuDecoders; InterPrediction m_interPred; std::unique_ptr<TrQuant> m_trQuant;
   PelStorage m_fltBuf;
 
@@ -150,8 +151,6 @@ class DecLibReconB200
       if( sl->getLmcsEnabledFlag() != pic->slices[0]->getLmcsEnabledFlag() ) THROW_UNSUPPORTED( "DecLibReconB200: LMCS switched per slice" );
       if( sl->getExplicitScalingListUsed() ) THROW_UNSUPPORTED( "DecLibReconB200: explicit scaling lists (the per-picture table arena is not built by this class)" );
     }
-    if( pps.getNumTiles() > 1 && !pps.getLoopFilterAcrossTilesEnabledFlag() ) THROW_UNSUPPORTED( "DecLibReconB200: tiles with in-loop filtering disabled across them (ALF clip path, AdaptiveLoopFilter.cpp:685)" );
-    if( !pps.getLoopFilterAcrossSlicesEnabledFlag() && pic->slices.size() > 1 ) THROW_UNSUPPORTED( "DecLibReconB200: in-loop filtering disabled across slices" );
     if( pic->slices[0]->getExplicitScalingListUsed() ) THROW_UNSUPPORTED( "DecLibReconB200: explicit scaling lists (the per-picture table arena is not built by this class)" );
     if( sps.getIBCFlag() ) THROW_UNSUPPORTED( "DecLibReconB200: IBC" );
     if( sps.getUseColorTrans() ) THROW_UNSUPPORTED( "DecLibReconB200: adaptive colour transform" );
@@ -428,9 +427,23 @@ class DecLibReconB200
         // CTU-level indices are relative to the slice's own APS lists: moved behind the sets of the slices before it (buildAlfTablesOfSlices)
         b200_alf_ctu& q = m_alf.v[a]; flattenALF( cd.alfParam, q );
         const Slice& sl = *cd.slice; const AlfSliceBase& ab = m_sl[si].alf;
-        if( !sl.getAlfEnabledFlag( COMPONENT_Y ) ) q.enable[0] = 0;
-        if( !sl.getAlfEnabledFlag( COMPONENT_Cb ) ) q.enable[1] = 0;
-        if( !sl.getAlfEnabledFlag( COMPONENT_Cr ) ) q.enable[2] = 0;
+        {
+          // CTUs whose neighbours ALF may not read (in-loop filtering disabled across slices / tiles): the reference's own derivation (AdaptiveLoopFilter.cpp:118)
+          bool cT, cB, cL, cR; int nH = 0, nV = 0, hp[3], vp[3], rasterPad = 0;
+          const Position ctuPos( ( a % pcv.widthInCtus ) * pcv.maxCUWidth, ( a / pcv.widthInCtus ) * pcv.maxCUHeight );
+          const Size ctuSize( std::min<int>( pcv.maxCUWidth, pcv.lumaWidth - ctuPos.x ), std::min<int>( pcv.maxCUHeight, pcv.lumaHeight - ctuPos.y ) );
+          if( m_cALF.isClipOrCrossedByVirtualBoundaries( cs, Area( ctuPos, ctuSize ), cT, cB, cL, cR, nH, nV, hp, vp, rasterPad ) )
+          {
+            if( nH || nV ) THROW_UNSUPPORTED( "DecLibReconB200: a virtual boundary inside a CTU" );
+            q.enable[0] |= ( cT ? B200_ALF_CLIP_TOP : 0 ) | ( cB ? B200_ALF_CLIP_BOTTOM : 0 ) | ( cL ? B200_ALF_CLIP_LEFT : 0 ) | ( cR ? B200_ALF_CLIP_RIGHT : 0 )
+                         | ( ( rasterPad & 1 ) ? B200_ALF_PAD_TL : 0 ) | ( ( rasterPad & 2 ) ? B200_ALF_PAD_BR : 0 );
+            if( !sl.getCcAlfCbEnabledFlag() ) q.enable[1] |= B200_ALF_PAD_WIDE;      // a chroma plane padded on its own gets the luma margin (filterCTU :794-803)
+            if( !sl.getCcAlfCrEnabledFlag() ) q.enable[2] |= B200_ALF_PAD_WIDE;
+          }
+        }
+        if( !sl.getAlfEnabledFlag( COMPONENT_Y ) ) q.enable[0] &= ~1;
+        if( !sl.getAlfEnabledFlag( COMPONENT_Cb ) ) q.enable[1] &= ~1;
+        if( !sl.getAlfEnabledFlag( COMPONENT_Cr ) ) q.enable[2] &= ~1;
         if( q.lumaSet >= NUM_FIXED_FILTER_SETS ) q.lumaSet = (uint8_t) ( q.lumaSet + ab.luma );
         for( int k = 0; k < 2; k++ )
         {
