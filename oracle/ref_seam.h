@@ -539,6 +539,7 @@ static void setupSps( FakePicture& fp, const ref_seam_cfg& c, const b200_geom& g
   pps.initTiles();
   SEAM_TR( "sps: tiles\n" );
   pps.setLoopFilterAcrossSlicesEnabledFlag( !( c.tools & SEAM_NO_LF_ACROSS_SLICES ) ); pps.setLoopFilterAcrossTilesEnabledFlag( true );
+  pps.setUseWP( c.tools & SEAM_WP ); pps.setWPBiPred( c.tools & SEAM_WP );
   pps.setQpOffset( COMPONENT_Cb, 1 ); pps.setQpOffset( COMPONENT_Cr, -1 ); pps.setQpOffset( JOINT_CbCr, 0 );
   ph.setMaxNumAffineMergeCand( c.affinePct > 0 ? 5 : 0 ); ph.setEnableTMVPFlag( false ); ph.setMvdL1ZeroFlag( false );
   ph.setDisBdofFlag( false ); ph.setDisDmvrFlag( false ); ph.setDisProfFlag( false ); ph.setJointCbCrSignFlag( ( c.seed >> 1 ) & 1 );
@@ -585,6 +586,22 @@ static Pic* build( const b200_geom* g, const ref_seam_cfg* c, const int16_t* con
     { const int k = l * 2 + ( odd ? 1 - i : i ); sl->m_apcRefPicList[l][i] = &P->ref[k]->pic; sl->m_aiRefPOCList[l][i] = pocs[k]; sl->m_bIsUsedAsLongTerm[l][i] = false; }
     sl->setNumRefIdx( REF_PIC_LIST_0, 2 ); sl->setNumRefIdx( REF_PIC_LIST_1, nL1 );
     sl->resetWpScaling();
+    if( c->tools & SEAM_WP )
+    {
+      // pred_weight_table (HLSyntaxReader.cpp: parsePredWeightTable): one luma and one chroma denominator per slice, weights / offsets per reference and component
+      std::mt19937 wr( c->seed * 977u + 31u * s + 5u );
+      const unsigned dL = wr() % 8, dC = wr() % 8;
+      static thread_local WPScalingParam tab[NUM_REF_PIC_LIST_01][MAX_NUM_REF][MAX_NUM_COMPONENT];
+      for( auto& a : tab ) for( auto& b : a ) for( auto& w : b ) w = WPScalingParam();
+      for( int l = 0; l < 2; l++ ) for( int i = 0; i < 2; i++ ) for( int k = 0; k < 3; k++ )
+      {
+        WPScalingParam& w = tab[l][i][k];
+        w.uiLog2WeightDenom = k ? dC : dL;
+        w.bPresentFlag = wr() % 100 < 65;
+        if( w.bPresentFlag ) { w.iWeight = ( 1 << w.uiLog2WeightDenom ) + (int) ( wr() % 65 ) - 32; w.iOffset = (int) ( wr() % ( k ? 21 : 41 ) ) - ( k ? 10 : 20 ); }
+      }
+      sl->setWpScaling( tab ); sl->initWpScaling( cur.sps.get() );
+    }
     if( sl->isInterB() ) sl->setBiDirPred( true, odd ? 1 : 0, odd ? 1 : 0 );        // POC 4 and 12: the closest pair around POC 8 (Slice::setSMVDParam)
   }
   { SliceMap sm; for( unsigned a = 0; a < pcv.sizeInCtus; a++ ) if( sliceOfCtu( a ) == s ) sm.addCtusToSlice( a % pcv.widthInCtus, a % pcv.widthInCtus + 1, a / pcv.widthInCtus, a / pcv.widthInCtus + 1, pcv.widthInCtus ); sl->setSliceMap( sm ); }

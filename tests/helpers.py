@@ -116,7 +116,7 @@ def load_ref():
 
 # ---- the DecLibRecon seam (oracle/ref_seam.h) ----
 SEAM = dict(BDOF=1, DMVR=2, BCW=4, PROF=8, MMVD=16, GEO=32, CIIP=64, SMVD=128, AMVR=256, MTS=512, LFNST=1024, SBT=2048, MRL=4096, MIP=8192, CCLM=16384,
-            JCCR=32768, TS=65536, BDPCM=1 << 17, SAO=1 << 18, ALF=1 << 19, LMCS=1 << 20, DEPQUANT=1 << 21, LOCAL_DUAL_TREE=1 << 22, VIRTUAL_BOUNDARIES=1 << 23, NO_LF_ACROSS_SLICES=1 << 24)
+            JCCR=32768, TS=65536, BDPCM=1 << 17, SAO=1 << 18, ALF=1 << 19, LMCS=1 << 20, DEPQUANT=1 << 21, LOCAL_DUAL_TREE=1 << 22, VIRTUAL_BOUNDARIES=1 << 23, NO_LF_ACROSS_SLICES=1 << 24, WP=1 << 25)
 SEAM_INTER_TOOLS = sum(SEAM[k] for k in ("BDOF", "DMVR", "BCW", "PROF", "MMVD", "GEO", "SMVD", "AMVR"))
 SEAM_RESI_TOOLS = sum(SEAM[k] for k in ("MTS", "SBT", "JCCR", "TS", "DEPQUANT"))
 SEAM_INTRA_TOOLS = sum(SEAM[k] for k in ("LFNST", "MRL", "MIP", "CCLM", "BDPCM", "CIIP"))
@@ -129,7 +129,7 @@ class SeamCfg(C.Structure):
                [("lmcsDeltaCW", C.c_int32 * 16), ("lmcsChrOffset", C.c_int32), ("lmcsChromaAdj", C.c_int32), ("numSlices", C.c_int32)]
 
 
-def seam_cfg(seed, slice_type=0, tools=None, qp=32, intra=15, skip=15, merge=50, affine=12, bi=60, root_cbf=45, cbf=35, split=75, isp=0, mvd_sigma=12, lmcs=None, virtual_boundaries=False, slices=1, lf_across_slices=True):
+def seam_cfg(seed, slice_type=0, tools=None, qp=32, intra=15, skip=15, merge=50, affine=12, bi=60, root_cbf=45, cbf=35, split=75, isp=0, mvd_sigma=12, lmcs=None, virtual_boundaries=False, slices=1, lf_across_slices=True, wp=False):
     c = SeamCfg()
     c.seed = seed; c.sliceType = slice_type
     c.tools = (SEAM_INTER_TOOLS | SEAM_RESI_TOOLS | SEAM_INTRA_TOOLS | SEAM_FILTERS) if tools is None else tools
@@ -138,6 +138,7 @@ def seam_cfg(seed, slice_type=0, tools=None, qp=32, intra=15, skip=15, merge=50,
     if virtual_boundaries: c.tools |= SEAM["VIRTUAL_BOUNDARIES"]
     c.numSlices = slices
     if not lf_across_slices: c.tools |= SEAM["NO_LF_ACROSS_SLICES"]
+    if wp: c.tools |= SEAM["WP"]
     if lmcs is not None:                                      # the dict synth.gen_lmcs returns
         c.tools |= SEAM["LMCS"]; c.lmcsMinBin = lmcs["minBin"]; c.lmcsMaxBin = lmcs["maxBin"]; c.lmcsChrOffset = lmcs["chrOff"]; c.lmcsChromaAdj = int(lmcs["struct"].chromaAdj)
         for i in range(16): c.lmcsDeltaCW[i] = lmcs["delta"][i]

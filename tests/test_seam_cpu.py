@@ -12,6 +12,7 @@ ref = helpers.load_ref()
 pytestmark = pytest.mark.skipif(ref is None or not hasattr(ref, "ref_seam_create"), reason="oracle/_ref not built")
 
 T_INTER = helpers.SEAM_INTER_TOOLS | helpers.SEAM_RESI_TOOLS | helpers.SEAM_FILTERS
+ALL_TOOLS = helpers.SEAM_INTER_TOOLS | helpers.SEAM_RESI_TOOLS | helpers.SEAM_INTRA_TOOLS | helpers.SEAM_FILTERS
 CASES = {
     "B_mixed_intra": dict(),                                                    # 15 % intra CUs, CIIP, GEO, affine, MMVD, SBT, MTS, LFNST, MIP, CCLM, full filter chain
     "B_intra_heavy": dict(intra=45, skip=5),
@@ -27,6 +28,10 @@ CASES = {
     "P_5slices": dict(slices=5, slice_type=1),
     "B_5slices_no_lf_across": dict(slices=5, ctu=64, lf_across_slices=False),    # ALF clipped sides / padded raster-slice corners, SAO / deblocking stop at slices
     "I_6slices_no_lf_across": dict(slices=6, ctu=64, lf_across_slices=False, slice_type=2),
+    "B_weighted_prediction": dict(wp=True),                                     # explicit weights per slice: the glue's getWpScaling tables
+    "P_wp_3slices": dict(wp=True, slice_type=1, slices=3),
+    "B_local_dual_tree_isp": dict(tools=ALL_TOOLS | helpers.SEAM["LOCAL_DUAL_TREE"], isp=40),   # chroma-tree CUs, 4xN luma CUs (single-region ISP)
+    "I_local_dual_tree_isp_lmcs": dict(tools=ALL_TOOLS | helpers.SEAM["LOCAL_DUAL_TREE"], isp=40, slice_type=2, lmcs=True),
     "B_ctu64": dict(ctu=64),
     "B_ctu32_8bit": dict(ctu=32, bd=8),
     "B_no_dmvr": dict(tools=(helpers.SEAM_INTER_TOOLS | helpers.SEAM_RESI_TOOLS | helpers.SEAM_INTRA_TOOLS | helpers.SEAM_FILTERS) & ~helpers.SEAM["DMVR"]),

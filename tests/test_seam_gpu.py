@@ -27,6 +27,9 @@ def both(seed, W, H, threads=4, **kw):
                                      ("B_ctu64", dict(ctu=64)),
                                      ("B_3slices", dict(slices=3)), ("B_4slices_lmcs_isp", dict(slices=4, lmcs=True, isp=30)), ("I_2slices", dict(slices=2, slice_type=2)),
                                      ("B_5slices_no_lf_across", dict(slices=5, ctu=64, lf_across_slices=False)), ("B_7slices_no_lf_across_ctu32", dict(slices=7, ctu=32, lf_across_slices=False)),
+                                     ("B_weighted_prediction", dict(wp=True)), ("P_wp_3slices", dict(wp=True, slice_type=1, slices=3)),
+                                     ("B_local_dual_tree_isp", dict(tools=T_INTER | helpers.SEAM_INTRA_TOOLS | helpers.SEAM["LOCAL_DUAL_TREE"], isp=40)),
+                                     ("I_local_dual_tree_isp", dict(tools=T_INTER | helpers.SEAM_INTRA_TOOLS | helpers.SEAM["LOCAL_DUAL_TREE"], isp=40, slice_type=2)),
                                      ("B_isp", dict(isp=40)), ("I_isp", dict(isp=60, slice_type=2)), ("I_isp_lmcs", dict(isp=60, slice_type=2, lmcs=True)), ("I_isp_ctu32", dict(isp=70, slice_type=2, ctu=32))])
 @pytest.mark.parametrize("seed", [1, 2])
 def test_seam_small(name, kw, seed):
