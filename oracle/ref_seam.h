@@ -499,7 +499,7 @@ struct Pic
 {
   b200_geom g;
   std::unique_ptr<FakePicture> cur; std::shared_ptr<RefSet> refs; FakePicture* ref[4] = { nullptr, nullptr, nullptr, nullptr };
-  std::shared_ptr<APS> lmcsAps;
+  std::shared_ptr<APS> lmcsAps, slAps;
   std::shared_ptr<APS> alfAps[ALF_CTB_MAX_NUM_APS];
   ref_seam_cfg cfg;
   std::vector<MotionInfo> colMotionScratch;
@@ -524,6 +524,7 @@ static void setupSps( FakePicture& fp, const ref_seam_cfg& c, const b200_geom& g
   sps.setUseReshaper( c.tools & SEAM_LMCS );
   sps.setUseDualITree( false ); sps.setIBCFlag( false ); sps.setUseColorTrans( false ); sps.setUseWrapAround( false );
   sps.setDepQuantEnabledFlag( true );
+  sps.setScalingListFlag( c.tools & SEAM_SCALING_LIST ); sps.setDisableScalingMatrixForLfnstBlks( ( c.seed >> 2 ) & 1 );
   // partitioning limits (Partitioner::initCtu reads them, UnitPartitioner.cpp:158-188): index 0 intra slices, 1 inter slices, 2 chroma of a dual tree
   sps.setMinQTSizes( PartitionConstraints{ 8, 8, 4 } ); sps.setMaxMTTHierarchyDepths( PartitionConstraints{ 3, 3, 3 } );
   sps.setMaxBTSizes( PartitionConstraints{ 64, 128, 64 } ); sps.setMaxTTSizes( PartitionConstraints{ 64, 64, 32 } );
@@ -578,7 +579,20 @@ static Pic* build( const b200_geom* g, const ref_seam_cfg* c, const int16_t* con
   const bool odd = s & 1;
   sl->setSliceType( intraPic ? I_SLICE : c->sliceType == 1 ? P_SLICE : B_SLICE ); sl->setPOC( 8 ); cur.pic.poc = 8;
   sl->setSliceQp( c->qp ); sl->setDepQuantEnabledFlag( c->tools & SEAM_DEPQUANT ); sl->setSignDataHidingEnabledFlag( false ); sl->setTSResidualCodingDisabledFlag( false );
-  sl->setExplicitScalingListUsed( false ); sl->setIndependentSliceIdx( s ); sl->setCheckLDC( false );
+  sl->setExplicitScalingListUsed( ( c->tools & SEAM_SCALING_LIST ) != 0 ); sl->setIndependentSliceIdx( s ); sl->setCheckLDC( false );
+  if( ( c->tools & SEAM_SCALING_LIST ) && s == 0 )
+  {
+    // scaling_list_data: 28 matrices (2x2, 4x4, 8x8 coded sizes) + DC values for the lists of 16x16 and larger (Quant::setScalingListDec up-samples them)
+    P->slAps = std::make_shared<APS>(); P->slAps->setAPSId( 1 ); P->slAps->setAPSType( SCALING_LIST_APS );
+    std::mt19937 qr( c->seed * 131u + 7u );
+    ScalingList& L = P->slAps->getScalingList();
+    for( int id = 0; id < 28; id++ )
+    {
+      for( int& v : L.getScalingListVec( id ) ) v = 1 + (int) ( qr() % 255 );
+      L.setScalingListDC( id, 1 + qr() % 255 );
+    }
+    cur.ph->setExplicitScalingListEnabledFlag( true ); cur.ph->setScalingListAPS( P->slAps );
+  }
   if( !intraPic )
   {
     const int nL1 = sl->isInterB() ? 2 : 0;

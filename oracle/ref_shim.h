@@ -151,7 +151,8 @@ enum { SEAM_BDOF = 1, SEAM_DMVR = 2, SEAM_BCW = 4, SEAM_PROF = 8, SEAM_MMVD = 16
        SEAM_BDPCM = 1 << 17, SEAM_SAO = 1 << 18, SEAM_ALF = 1 << 19, SEAM_LMCS = 1 << 20, SEAM_DEPQUANT = 1 << 21, SEAM_LOCAL_DUAL_TREE = 1 << 22,
        SEAM_VIRTUAL_BOUNDARIES = 1 << 23 /* picture header announces virtual boundaries (none are listed): a picture DecLibReconB200 refuses */,
        SEAM_NO_LF_ACROSS_SLICES = 1 << 24 /* pps_loop_filter_across_slices_enabled_flag = 0 (with numSlices > 1) */,
-       SEAM_WP = 1 << 25 /* explicit weighted prediction (pps_weighted_pred / bipred), a random pred_weight_table per slice */ };
+       SEAM_WP = 1 << 25 /* explicit weighted prediction (pps_weighted_pred / bipred), a random pred_weight_table per slice */,
+       SEAM_SCALING_LIST = 1 << 26 /* explicit scaling lists: a scaling-list APS with random matrices */ };
 typedef struct ref_seam_cfg {
   uint32_t seed;
   int32_t  sliceType;        /* 0 B, 1 P, 2 I                                                                  */

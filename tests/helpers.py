@@ -116,7 +116,7 @@ def load_ref():
 
 # ---- the DecLibRecon seam (oracle/ref_seam.h) ----
 SEAM = dict(BDOF=1, DMVR=2, BCW=4, PROF=8, MMVD=16, GEO=32, CIIP=64, SMVD=128, AMVR=256, MTS=512, LFNST=1024, SBT=2048, MRL=4096, MIP=8192, CCLM=16384,
-            JCCR=32768, TS=65536, BDPCM=1 << 17, SAO=1 << 18, ALF=1 << 19, LMCS=1 << 20, DEPQUANT=1 << 21, LOCAL_DUAL_TREE=1 << 22, VIRTUAL_BOUNDARIES=1 << 23, NO_LF_ACROSS_SLICES=1 << 24, WP=1 << 25)
+            JCCR=32768, TS=65536, BDPCM=1 << 17, SAO=1 << 18, ALF=1 << 19, LMCS=1 << 20, DEPQUANT=1 << 21, LOCAL_DUAL_TREE=1 << 22, VIRTUAL_BOUNDARIES=1 << 23, NO_LF_ACROSS_SLICES=1 << 24, WP=1 << 25, SCALING_LIST=1 << 26)
 SEAM_INTER_TOOLS = sum(SEAM[k] for k in ("BDOF", "DMVR", "BCW", "PROF", "MMVD", "GEO", "SMVD", "AMVR"))
 SEAM_RESI_TOOLS = sum(SEAM[k] for k in ("MTS", "SBT", "JCCR", "TS", "DEPQUANT"))
 SEAM_INTRA_TOOLS = sum(SEAM[k] for k in ("LFNST", "MRL", "MIP", "CCLM", "BDPCM", "CIIP"))
@@ -129,7 +129,7 @@ class SeamCfg(C.Structure):
                [("lmcsDeltaCW", C.c_int32 * 16), ("lmcsChrOffset", C.c_int32), ("lmcsChromaAdj", C.c_int32), ("numSlices", C.c_int32)]
 
 
-def seam_cfg(seed, slice_type=0, tools=None, qp=32, intra=15, skip=15, merge=50, affine=12, bi=60, root_cbf=45, cbf=35, split=75, isp=0, mvd_sigma=12, lmcs=None, virtual_boundaries=False, slices=1, lf_across_slices=True, wp=False):
+def seam_cfg(seed, slice_type=0, tools=None, qp=32, intra=15, skip=15, merge=50, affine=12, bi=60, root_cbf=45, cbf=35, split=75, isp=0, mvd_sigma=12, lmcs=None, virtual_boundaries=False, slices=1, lf_across_slices=True, wp=False, scaling_lists=False):
     c = SeamCfg()
     c.seed = seed; c.sliceType = slice_type
     c.tools = (SEAM_INTER_TOOLS | SEAM_RESI_TOOLS | SEAM_INTRA_TOOLS | SEAM_FILTERS) if tools is None else tools
@@ -139,6 +139,7 @@ def seam_cfg(seed, slice_type=0, tools=None, qp=32, intra=15, skip=15, merge=50,
     c.numSlices = slices
     if not lf_across_slices: c.tools |= SEAM["NO_LF_ACROSS_SLICES"]
     if wp: c.tools |= SEAM["WP"]
+    if scaling_lists: c.tools |= SEAM["SCALING_LIST"]
     if lmcs is not None:                                      # the dict synth.gen_lmcs returns
         c.tools |= SEAM["LMCS"]; c.lmcsMinBin = lmcs["minBin"]; c.lmcsMaxBin = lmcs["maxBin"]; c.lmcsChrOffset = lmcs["chrOff"]; c.lmcsChromaAdj = int(lmcs["struct"].chromaAdj)
         for i in range(16): c.lmcsDeltaCW[i] = lmcs["delta"][i]
@@ -263,9 +264,11 @@ def picture_from_struct(st, g, filt):
     nctu = ((g.width + g.ctuSize - 1) // g.ctuSize) * ((g.height + g.ctuSize - 1) // g.ctuSize)
     d = dict(pus=_copy(st.pus, st.numPus, synth.PU_DTYPE), ndmvr=int(st.numDmvr) - 1, tus=_copy(st.tus, st.numTus, abi.TU_DTYPE), coefs=_copy(st.coefs, st.numCoefs, np.int16))
     if len(d["coefs"]) == 0: d["coefs"] = np.zeros(1, np.int16)
+    if st.numScaling: d["scaling"] = _copy(st.scaling, st.numScaling, np.int32)
     p = abi.Picture(); p.dstSlot = st.dstSlot; p.flags = st.flags
     p.pus = d["pus"].ctypes.data; p.numPus = len(d["pus"]); p.numDmvr = st.numDmvr
     p.tus = d["tus"].ctypes.data; p.numTus = len(d["tus"]); p.coefs = d["coefs"].ctypes.data; p.numCoefs = st.numCoefs
+    if st.numScaling: p.scaling = d["scaling"].ctypes.data; p.numScaling = st.numScaling
     if st.numIntraTus:
         d["intraTus"] = _copy(st.intraTus, st.numIntraTus, abi.INTRA_TU_DTYPE); p.intraTus = d["intraTus"].ctypes.data; p.numIntraTus = st.numIntraTus
     if st.flags & abi.PIC_DEBLOCK:
@@ -326,6 +329,7 @@ def ref_ptrs(ref_pics):
 
 
 def oracle_decompress(oracle, g, dpb, pic):
+    SC = pic["scaling"].ctypes.data if "scaling" in pic else None      # explicit scaling lists: the picture's dequantisation tables
     """CPU chain of the whole back end on one synthetic picture: K2 -> K1 -> K3 -> K4 -> K5 with the pinned oracle.
     dpb: list of [Y,Cb,Cr] per slot (refs are read from it); returns the new picture planes and the DMVR deltas."""
     W, H = g.width, g.height
@@ -344,30 +348,30 @@ def oracle_decompress(oracle, g, dpb, pic):
         resi = [np.zeros_like(p) for p in cur]
         it = pic["intraTus"]; it_y, it_c = np.ascontiguousarray(it[it["comp"] == 0]), np.ascontiguousarray(it[it["comp"] != 0])
         tus = pic["tus"]; n = len(tus)
-        oracle.orc_k1_residual_sel(C.byref(g), abi.plane_ptrs(cur), abi.plane_ptrs(resi), tus.ctypes.data, n, pic["coefs"], None, 1, None)
+        oracle.orc_k1_residual_sel(C.byref(g), abi.plane_ptrs(cur), abi.plane_ptrs(resi), tus.ctypes.data, n, pic["coefs"], SC, 1, None)
         oracle.orc_intra_reconstruct(C.byref(g), abi.plane_ptrs(cur), abi.plane_ptrs(resi), it_y.ctypes.data, len(it_y))
         vs = 64 if g.ctuSize == 128 else g.ctuSize
         scale = np.zeros(((W + vs - 1) // vs) * ((H + vs - 1) // vs), np.int32)
         if chroma_adj: oracle.orc_lmcs_vpdu_scales(C.byref(g), cur[0], L, scale.ctypes.data)
-        oracle.orc_k1_residual_sel(C.byref(g), abi.plane_ptrs(cur), abi.plane_ptrs(resi), tus.ctypes.data, n, pic["coefs"], None, 2, scale.ctypes.data if chroma_adj else None)
+        oracle.orc_k1_residual_sel(C.byref(g), abi.plane_ptrs(cur), abi.plane_ptrs(resi), tus.ctypes.data, n, pic["coefs"], SC, 2, scale.ctypes.data if chroma_adj else None)
         oracle.orc_intra_reconstruct(C.byref(g), abi.plane_ptrs(cur), abi.plane_ptrs(resi), it_c.ctypes.data, len(it_c))
         oracle.orc_lmcs_inv_plane(C.byref(g), cur[0], L)
     elif st.flags & abi.PIC_LMCS:
         # DecCu.cpp:458-476 forward map of every inter CU's luma prediction; :483 finishLMCSAndReco; DecLibRecon.cpp:935 inverse map
         L = C.byref(pic["lmcs"]["struct"])
         oracle.orc_lmcs_fwd_pus(C.byref(g), cur[0], pic["pus"].ctypes.data, len(pic["pus"]), L)
-        oracle.orc_k1_residual_lmcs(C.byref(g), abi.plane_ptrs(cur), pic["tus"].ctypes.data, len(pic["tus"]), pic["coefs"], None, L)
+        oracle.orc_k1_residual_lmcs(C.byref(g), abi.plane_ptrs(cur), pic["tus"].ctypes.data, len(pic["tus"]), pic["coefs"], SC, L)
         oracle.orc_lmcs_inv_plane(C.byref(g), cur[0], L)
     elif "intraTus" in pic:
         # intra CUs on the device: their TUs (TU_RESI) leave the residual in separate planes, K6 predicts + reconstructs them in decoding order
         tus = pic["tus"]; rs = (tus["flags"] & abi.TU_RESI) != 0
         t0, t1 = np.ascontiguousarray(tus[~rs]), np.ascontiguousarray(tus[rs])
         resi = [np.zeros_like(p) for p in cur]
-        oracle.orc_k1_residual(C.byref(g), abi.plane_ptrs(cur), t0.ctypes.data, len(t0), pic["coefs"], None, 0)
-        oracle.orc_k1_residual(C.byref(g), abi.plane_ptrs(resi), t1.ctypes.data, len(t1), pic["coefs"], None, 1)
+        oracle.orc_k1_residual(C.byref(g), abi.plane_ptrs(cur), t0.ctypes.data, len(t0), pic["coefs"], SC, 0)
+        oracle.orc_k1_residual(C.byref(g), abi.plane_ptrs(resi), t1.ctypes.data, len(t1), pic["coefs"], SC, 1)
         oracle.orc_intra_reconstruct(C.byref(g), abi.plane_ptrs(cur), abi.plane_ptrs(resi), pic["intraTus"].ctypes.data, len(pic["intraTus"]))
     else:
-        oracle.orc_k1_residual(C.byref(g), abi.plane_ptrs(cur), pic["tus"].ctypes.data, len(pic["tus"]), pic["coefs"], None, 0)
+        oracle.orc_k1_residual(C.byref(g), abi.plane_ptrs(cur), pic["tus"].ctypes.data, len(pic["tus"]), pic["coefs"], SC, 0)
     if st.flags & abi.PIC_DEBLOCK:
         oracle.orc_lf_deblock(C.byref(g), abi.plane_ptrs(cur), pic["lfV"].ctypes.data, pic["lfH"].ctypes.data, pic["ctuSlice"].ctypes.data if "ctuSlice" in pic else None,
                               pic["lfSlices"].ctypes.data, None, 3)

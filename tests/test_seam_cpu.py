@@ -32,6 +32,8 @@ CASES = {
     "P_wp_3slices": dict(wp=True, slice_type=1, slices=3),
     "B_local_dual_tree_isp": dict(tools=ALL_TOOLS | helpers.SEAM["LOCAL_DUAL_TREE"], isp=40),   # chroma-tree CUs, 4xN luma CUs (single-region ISP)
     "I_local_dual_tree_isp_lmcs": dict(tools=ALL_TOOLS | helpers.SEAM["LOCAL_DUAL_TREE"], isp=40, slice_type=2, lmcs=True),
+    "B_scaling_lists": dict(scaling_lists=True),                                # explicit scaling lists: the reference's table set as the picture's scaling arena
+    "I_scaling_lists_isp_lmcs": dict(scaling_lists=True, slice_type=2, isp=30, lmcs=True),
     "B_ctu64": dict(ctu=64),
     "B_ctu32_8bit": dict(ctu=32, bd=8),
     "B_no_dmvr": dict(tools=(helpers.SEAM_INTER_TOOLS | helpers.SEAM_RESI_TOOLS | helpers.SEAM_INTRA_TOOLS | helpers.SEAM_FILTERS) & ~helpers.SEAM["DMVR"]),

@@ -30,6 +30,7 @@ def both(seed, W, H, threads=4, **kw):
                                      ("B_weighted_prediction", dict(wp=True)), ("P_wp_3slices", dict(wp=True, slice_type=1, slices=3)),
                                      ("B_local_dual_tree_isp", dict(tools=T_INTER | helpers.SEAM_INTRA_TOOLS | helpers.SEAM["LOCAL_DUAL_TREE"], isp=40)),
                                      ("I_local_dual_tree_isp", dict(tools=T_INTER | helpers.SEAM_INTRA_TOOLS | helpers.SEAM["LOCAL_DUAL_TREE"], isp=40, slice_type=2)),
+                                     ("B_scaling_lists", dict(scaling_lists=True)), ("I_scaling_lists_isp", dict(scaling_lists=True, slice_type=2, isp=30)),
                                      ("B_isp", dict(isp=40)), ("I_isp", dict(isp=60, slice_type=2)), ("I_isp_lmcs", dict(isp=60, slice_type=2, lmcs=True)), ("I_isp_ctu32", dict(isp=70, slice_type=2, ctu=32))])
 @pytest.mark.parametrize("seed", [1, 2])
 def test_seam_small(name, kw, seed):

@@ -37,6 +37,7 @@
 #include "CommonLib/Picture.h"
 #include "CommonLib/LoopFilter.h"
 #include "CommonLib/Reshape.h"
+#include "CommonLib/Quant.h"
 #include "CommonLib/WeightPrediction.h"
 #include "CommonLib/InterPrediction.h"
 #include "DecoderLib/DecCu.h"
@@ -108,6 +109,15 @@ class DecLibReconB200
   double since() const { return std::chrono::duration<double>( std::chrono::steady_clock::now() - m_t0 ).count(); }
   // the CPU stages that stay
   std::vector<MotionInfo> m_motionInfo; std::vector<LoopFilterParam> m_loopFilterParam; std::vector<Mv> m_dmvrMvCache;
+  // explicit scaling lists: the reference's own table set (Quant::init -> setScalingListDec, Quant.cpp:386) in one contiguous buffer; a TU's table is addressed by its
+  // offset in it (b200_tu::slOff).  TrQuant derives privately from Quant, so the glue keeps a Quant of its own for the tables
+  std::unique_ptr<Quant> m_quant; bool m_useSL = false; const int* m_slBase = nullptr; size_t m_slCount = 0; const void* m_slReg = nullptr;
+  void setSlOff( const CodingUnit& cu, b200_tu& t ) const
+  {
+    if( !( t.flags & B200_TU_SCALING ) ) return;
+    const int list = ( CU::isIntra( cu ) ? 0 : MAX_NUM_COMPONENT ) + t.comp;                  // getScalingListType, Quant.cpp:289
+    t.slOff = (uint32_t) ( m_quant->getDequantCoeff( list, t.log2w, t.log2h ) - m_slBase );
+  }
   struct AlfAccess : AdaptiveLoopFilter { using AdaptiveLoopFilter::isClipOrCrossedByVirtualBoundaries; };     // protected in the reference: the glue asks it per CTU
   LoopFilter m_cLoopFilter; SampleAdaptiveOffset m_cSAO; AlfAccess m_cALF; Reshape m_cReshaper;
   std::vector<std::unique_ptr<DecCu>> m_cuDecoders; InterPrediction m_interPred; std::unique_ptr<TrQuant> m_trQuant;
@@ -149,9 +159,7 @@ class DecLibReconB200
     for( const Slice* sl : pic->slices )
     {
       if( sl->getLmcsEnabledFlag() != pic->slices[0]->getLmcsEnabledFlag() ) THROW_UNSUPPORTED( "DecLibReconB200: LMCS switched per slice" );
-      if( sl->getExplicitScalingListUsed() ) THROW_UNSUPPORTED( "DecLibReconB200: explicit scaling lists (the per-picture table arena is not built by this class)" );
     }
-    if( pic->slices[0]->getExplicitScalingListUsed() ) THROW_UNSUPPORTED( "DecLibReconB200: explicit scaling lists (the per-picture table arena is not built by this class)" );
     if( sps.getIBCFlag() ) THROW_UNSUPPORTED( "DecLibReconB200: IBC" );
     if( sps.getUseColorTrans() ) THROW_UNSUPPORTED( "DecLibReconB200: adaptive colour transform" );
   }
@@ -253,7 +261,7 @@ class DecLibReconB200
             // intra sub-partitions: K6 takes the luma as one record per prediction region (the regions read each other's reconstruction, in order), K1 the
             // residual of every sub-partition with a coded block flag — 1- and 2-sample-wide transform units included (TrQuant.cpp:466-482)
             if( flattenIspCu( cu, [&]( const b200_intra_tu& q ) { r.intra.push_back( q ); } ) != FLATTEN_INTRA_OK ) THROW_UNSUPPORTED( "DecLibReconB200: ISP CU outside the device path" );
-            for( auto& tu : TUTraverser( &cu.firstTU, cu.lastTU->next ) ) { b200_tu t; if( flattenTU( tu, COMPONENT_Y, *m_trQuant, r.coefs, t ) ) { t.flags |= B200_TU_RESI; r.tus.push_back( t ); } }
+            for( auto& tu : TUTraverser( &cu.firstTU, cu.lastTU->next ) ) { b200_tu t; if( flattenTU( tu, COMPONENT_Y, *m_trQuant, r.coefs, t ) ) { t.flags |= B200_TU_RESI; setSlOff( cu, t ); r.tus.push_back( t ); } }
           }
           for( auto& tu : TUTraverser( &cu.firstTU, cu.lastTU->next ) )
             for( const CompArea& area : tu.blocks )
@@ -263,7 +271,7 @@ class DecLibReconB200
               b200_intra_tu ir;
               if( flattenIntraTU( tu, area.compID(), ir ) != FLATTEN_INTRA_OK ) THROW_UNSUPPORTED( "DecLibReconB200: ACT intra block (SURVEY 8f-1)" );
               b200_tu t;
-              if( flattenTU( tu, area.compID(), *m_trQuant, r.coefs, t ) ) { t.flags |= B200_TU_RESI; r.tus.push_back( t ); }
+              if( flattenTU( tu, area.compID(), *m_trQuant, r.coefs, t ) ) { t.flags |= B200_TU_RESI; setSlOff( cu, t ); r.tus.push_back( t ); }
               if( TU::getCbf( tu, area.compID() ) || ( isChroma( area.compID() ) && tu.jointCbCr ) ) ir.flags |= B200_INTRA_ADD_RESI;      // DecCu.cpp:390
               r.intra.push_back( ir );
             }
@@ -292,7 +300,7 @@ class DecLibReconB200
         if( rc != FLATTEN_PU_OK ) THROW_UNSUPPORTED( "DecLibReconB200: inter tool outside the device path (RPR-scaled reference, wrap-around, sub-picture clipping)" );
         if( cu.rootCbf() )
           for( auto& tu : TUTraverser( &cu.firstTU, cu.lastTU->next ) )
-            for( int c = 0; c < (int) getNumberValidComponents( cu.chromaFormat ); c++ ) { b200_tu t; if( flattenTU( tu, ComponentID( c ), *m_trQuant, r.coefs, t ) ) { if( ciipComp[c] ) t.flags |= B200_TU_RESI; r.tus.push_back( t ); } }
+            for( int c = 0; c < (int) getNumberValidComponents( cu.chromaFormat ); c++ ) { b200_tu t; if( flattenTU( tu, ComponentID( c ), *m_trQuant, r.coefs, t ) ) { if( ciipComp[c] ) t.flags |= B200_TU_RESI; setSlOff( cu, t ); r.tus.push_back( t ); } }
       }
     }
   }
@@ -364,6 +372,16 @@ class DecLibReconB200
     {
       m_lfSeq.ladfEnabled = 1; m_lfSeq.ladfNumIntervals = sps.getLadfNumIntervals();
       for( int k = 0; k < sps.getLadfNumIntervals() && k < 5; k++ ) { m_lfSeq.ladfQpOffset[k] = sps.getLadfQpOffset( k ); m_lfSeq.ladfIntervalLowerBound[k] = sps.getLadfIntervalLowerBound( k ); }
+    }
+    // explicit scaling lists (Quant::init: the first slice that uses them names the APS, Quant.cpp:623-672)
+    m_useSL = false; for( const Slice* sl : pic->slices ) m_useSL = m_useSL || sl->getExplicitScalingListUsed();
+    if( m_useSL )
+    {
+      if( !m_quant ) m_quant.reset( new Quant( nullptr ) );
+      m_quant->init( pic );
+      m_slBase = m_quant->getDequantCoeff( 0, 0, 0 );
+      m_slCount = (size_t) ( m_quant->getDequantCoeff( SCALING_LIST_NUM - 1, SCALING_LIST_SIZE_NUM - 1, SCALING_LIST_SIZE_NUM - 1 ) - m_slBase ) + 64 * 64;
+      if( m_slReg != m_slBase && !m_dryRun ) { if( b200_host_register( const_cast<int*>( m_slBase ), m_slCount * sizeof( int ) ) == 0 ) m_slReg = m_slBase; }
     }
     m_doSao = sps.getUseSAO();
     m_doAlf = sps.getUseALF() && !AdaptiveLoopFilter::getAlfSkipPic( cs );
@@ -474,6 +492,7 @@ class DecLibReconB200
     p.flags = ( anyLf ? B200_PIC_DEBLOCK : 0 ) | ( m_doSao ? B200_PIC_SAO : 0 ) | ( m_doAlf ? B200_PIC_ALF : 0 ) | ( m_doLmcs ? B200_PIC_LMCS : 0 );
     p.pus = m_pus.v.data(); p.numPus = m_pus.v.size(); p.numDmvr = m_dmvrMvCache.size();
     p.tus = m_tus.v.data(); p.numTus = m_tus.v.size(); p.coefs = m_coefs.v.data(); p.numCoefs = m_coefs.v.size();
+    if( m_useSL ) { p.scaling = m_slBase; p.numScaling = m_slCount; }
     p.lfV = m_lf[0].v.data(); p.lfH = m_lf[1].v.data(); p.lfSlices = m_lfSlices.data(); p.numLfSlices = (int32_t) m_lfSlices.size(); p.ctuSlice = m_lfSlices.size() > 1 ? m_ctuSlice.v.data() : nullptr; p.lfSeq = &m_lfSeq;
     p.sao = m_sao.v.data(); p.vb = &m_vb; p.alf = m_alf.v.data(); p.alfTabs = &m_alfTabs;
     p.wp = m_wp.data(); p.numWp = (int32_t) m_wp.size(); p.lmcs = m_doLmcs ? &m_lmcs : nullptr;
