@@ -824,6 +824,7 @@ extern "C" double ref_seam_run_b200( void* h, int threads, int dry, int16_t* con
       pic->reconDone.clearException();
       return rc;
     }
+    if( getenv( "SEAM_TIMING" ) ) { double cm[3]; S.rec->cpuStageMs( cm ); fprintf( stderr, "b200 host CPU ms summed over threads: MIDER %.2f | Bs + grid %.2f | CU / TU walk %.2f\n", cm[0], cm[1], cm[2] ); }
     if( getenv( "SEAM_TIMING" ) ) { const double* st = S.rec->stageTimes(); fprintf( stderr, "b200 host stages [ms]: tables %.2f | mider %.2f | flatten %.2f | submit %.2f | joined %.2f | finish %.2f\n", st[0] * 1e3, ( st[1] - st[0] ) * 1e3, ( st[2] - st[1] ) * 1e3, ( st[3] - st[2] ) * 1e3, ( st[4] - st[3] ) * 1e3, ( st[5] - st[4] ) * 1e3 ); }
     if( flat ) *flat = S.rec->flattened();
     if( !dry ) seam::readOut( P, out, colMotion, colBytes );

@@ -6,15 +6,17 @@
 // flattenSbTmvp, flattenIntraTU / flattenCiipBlock, flattenSAO / flattenALF / buildAlfTables / flattenLfCtu — are also pinned one by one.
 //
 // decompressPicture() returns at once, like the reference's (DecLibRecon.cpp:429-681): the host stages run as tasks of the decoder's thread pool,
-//   MIDER   one task per CTU row, wave front over rows (DecCu::TaskDeriveCtuMotionInfo, the MIDER case of ctuTask :762-781), may start while
-//           the rows below are still being parsed (ctuParsedBarrier, RECO_WHILE_PARSE)
-//   FLATTEN one task per CTU row: boundary strengths (calcFilterStrengthsCTU, the LF_INIT case :808-829), the CU / TU walk of TaskTrafoCtu /
-//           TaskInterCtu / TaskCriticalIntraKernel (DecCu.cpp:106-159) into per-row work lists, SAO / ALF CTU records
-//   SUBMIT  one task: lists joined in CTU order (K6 needs decoding order), references that are not resident uploaded, b200_decompress_picture
+//   MIDER   one task per CTU row, wave front over rows (DecCu::TaskDeriveCtuMotionInfo, the MIDER case of ctuTask :762-781): the task walks its CTUs as far
+//           as the row above allows and hands itself back to the pool when it has to wait; may start while the rows below are still being parsed
+//           (ctuParsedBarrier, RECO_WHILE_PARSE)
+//   FLATTEN one task per run of three CTUs, ready when their motion is derived: boundary strengths (calcFilterStrengthsCTU, the LF_INIT case :808-829),
+//           the CU / TU walk of TaskTrafoCtu / TaskInterCtu / TaskCriticalIntraKernel (DecCu.cpp:106-159) into per-CTU work lists
+//   SUBMIT  one task: lists joined in CTU order (K6 needs decoding order), SAO / ALF CTU records, per-slice tables, b200_decompress_picture (stream-ordered
+//           behind the pictures it references, also those another recon instance is still flattening)
 // and waitForPrevDecompressedPic() waits for the device, takes the DMVR deltas, runs TaskFinishMotionInfo (DecCu.cpp:161) and copies the
 // finished planes into Picture::m_bufs (output / CPU fallback of later pictures).
-// Errors follow DecLibRecon.cpp:684-722: an exception on any task parks in the task's counter / barrier, waitForPrevDecompressedPic() sets
-// pic->error and reconDone.setException() and clears the pool of this picture's tasks (cleanupOnException).  B200_ERR_UNSUPPORTED maps to
+// Errors follow DecLibRecon.cpp:684-722: the first exception of a picture is parked (no task lets one escape into the pool), waitForPrevDecompressedPic()
+// rethrows it, sets pic->error and reconDone.setException() and clears the pool of this picture's tasks (cleanupOnException).  B200_ERR_UNSUPPORTED maps to
 // UnsupportedFeatureException, B200_ERR_PARAM to RecoverableException, every other failure to Exception (TypeDef.h:828-831).
 //
 // The CPU keeps: parsing, motion derivation, boundary strengths, TaskFinishMotionInfo.  Pictures that use a tool the device path does not
@@ -85,10 +87,12 @@ class DecLibReconB200
   };
 
   ThreadPool* m_pool = nullptr; int m_numThreads = 1; unsigned m_id = 0; int m_dpbSlots = 17;
+  std::atomic<long long> m_cpuNs[5] = {};   // CPU time of the host stages summed over the pool's threads: MIDER, Bs + grid copy, CU / TU walk, submit, finish
+  struct CpuTimer { std::atomic<long long>& acc; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(); ~CpuTimer() { acc += std::chrono::duration_cast<std::chrono::nanoseconds>( std::chrono::steady_clock::now() - t0 ).count(); } };
   std::vector<int> m_waitSlots;            // slots of reference pictures that were in flight on another instance when this picture was set up
   Picture*    m_currDecompPic = nullptr;
   int         m_arena = -1, m_dstSlot = -1;
-  std::vector<Row> m_rows; std::unique_ptr<std::atomic<uint8_t>[]> m_ctuDone; int m_ctusW = 0;
+  std::vector<Row> m_rows; int m_ctusW = 0;
   std::vector<MotionHist> m_hist;
   WaitCounter m_flattenCounter, m_submitCounter, m_finishCounter;
   // per-picture work lists (pinned)
@@ -172,36 +176,46 @@ class DecLibReconB200
   void park( std::exception_ptr e ) { std::lock_guard<std::mutex> l( m_failMutex ); if( !m_failure ) m_failure = e; m_failed.store( true ); }
   template<class F> bool guarded( F f ) { if( m_failed.load() ) return true; try { return f(); } catch( ... ) { park( std::current_exception() ); return true; } }
 
-  // Two tasks per CTU.  MIDER: ready when the CTU to the left and the CTU above-right (the last one of the row: above) have run — the merge / AMVP
-  // candidates of a CU reach into them (the MIDER preconditions of ctuTask, DecLibRecon.cpp:764-778): a wave front.  FLATTEN (boundary strengths,
-  // CU / TU walk): ready when the CTU's own MIDER ran (the CTUs left and above ran before it), so only MIDER is on the wave front's critical path.
-  static bool miderReady( int, void* p )
+  // Host tasks of a picture.  MIDER: one task per CTU row that walks its CTUs as far as the row above allows — a CTU needs the CTU to its left and the CTU
+  // above-right (the last one of the row: above) done, the merge / AMVP candidates of a CU reach into them (the MIDER preconditions of ctuTask,
+  // DecLibRecon.cpp:764-778) — and hands itself back to the pool when it has to wait (the pool runs it again: ThreadPool.h task contract), so the wave front costs
+  // one task per row, not per CTU.  FLATTEN (boundary strengths, CU / TU walk): one task per run of FLATTEN_RUN CTUs, ready when their MIDER has run; only MIDER is
+  // on the wave front's critical path.  (One task per CTU — 1020 at 4K — spent more time in the pool's task scan than in the work.)
+  static constexpr int FLATTEN_RUN = 3;
+  struct RowTask { DecLibReconB200* self = nullptr; int line = 0; };
+  struct RunTask { DecLibReconB200* self = nullptr; int line = 0, col0 = 0, col1 = 0; };
+  std::vector<RowTask> m_rowTasks; std::vector<RunTask> m_runTasks; std::unique_ptr<std::atomic<int>[]> m_miderDone;      // per row: CTUs whose motion is derived
+  static bool miderRowReady( int, void* p )
   {
-    const Row& r = *static_cast<Row*>( p ); const DecLibReconB200& d = *r.self;
+    const RowTask& t = *static_cast<RowTask*>( p ); const DecLibReconB200& d = *t.self;
+    if( d.m_failed.load() || t.line == 0 ) return true;
+    const int W = d.m_ctusW, col = d.m_miderDone[t.line].load( std::memory_order_relaxed );
+    return d.m_miderDone[t.line - 1].load( std::memory_order_acquire ) >= std::min( col + 2, W );
+  }
+  static bool miderRowTask( int tid, void* p )
+  {
+    RowTask& t = *static_cast<RowTask*>( p ); DecLibReconB200& d = *t.self;
     const int W = d.m_ctusW;
-    if( d.m_failed.load() ) return true;
-    if( r.col > 0 && !d.m_ctuDone[r.line * W + r.col - 1].load( std::memory_order_acquire ) ) return false;
-    if( r.line > 0 && !d.m_ctuDone[( r.line - 1 ) * W + std::min( r.col + 1, W - 1 )].load( std::memory_order_acquire ) ) return false;
+    int col = d.m_miderDone[t.line].load( std::memory_order_relaxed );                       // only this task advances it
+    while( col < W )
+    {
+      if( !d.m_failed.load() && t.line > 0 && d.m_miderDone[t.line - 1].load( std::memory_order_acquire ) < std::min( col + 2, W ) ) return false;
+      d.guarded( [&] { d.miderCtu( tid, d.m_rows[(size_t) t.line * W + col] ); return true; } );
+      d.m_miderDone[t.line].store( ++col, std::memory_order_release );
+    }
     return true;
   }
-  static bool miderTask( int tid, void* p )
+  static bool flattenRunReady( int, void* p ) { const RunTask& t = *static_cast<RunTask*>( p ); return t.self->m_failed.load() || t.self->m_miderDone[t.line].load( std::memory_order_acquire ) >= t.col1; }
+  static bool flattenRunTask( int tid, void* p )
   {
-    Row& r = *static_cast<Row*>( p ); DecLibReconB200& d = *r.self;
-    if( !miderReady( tid, p ) ) return false;
-    const bool done = d.guarded( [&] { d.miderCtu( tid, r ); return true; } );
-    d.m_ctuDone[r.line * d.m_ctusW + r.col].store( 1, std::memory_order_release );
-    return done;
-  }
-  static bool flattenReady( int, void* p ) { const Row& r = *static_cast<Row*>( p ); return r.self->m_failed.load() || r.self->m_ctuDone[r.line * r.self->m_ctusW + r.col].load( std::memory_order_acquire ) != 0; }
-  static bool flattenTask( int tid, void* p )
-  {
-    Row& r = *static_cast<Row*>( p ); DecLibReconB200& d = *r.self;
-    if( !flattenReady( tid, p ) ) return false;
+    RunTask& t = *static_cast<RunTask*>( p ); DecLibReconB200& d = *t.self;
+    if( !flattenRunReady( tid, p ) ) return false;
     { int64_t z = 0; d.m_tFlat0.compare_exchange_strong( z, (int64_t) ( d.since() * 1e9 ) + 1 ); }
-    return d.guarded( [&] { d.flattenCtu( r ); return true; } );
+    return d.guarded( [&] { for( int col = t.col0; col < t.col1; col++ ) d.flattenCtu( d.m_rows[(size_t) t.line * d.m_ctusW + col] ); return true; } );
   }
   void miderCtu( int tid, Row& r )
   {
+    CpuTimer tm{ m_cpuNs[0] };
     CodingStructure& cs = *m_currDecompPic->cs; const PreCalcValues& pcv = *cs.pcv;
     const int a = r.line * m_ctusW + r.col;
     CtuData& cd = cs.getCtuData( a );
@@ -245,9 +259,13 @@ class DecLibReconB200
       // LF_INIT (DecLibRecon.cpp:808-829)
       cd.lfParam[0] = &m_loopFilterParam[(size_t) pcv.num4x4CtuBlks * ( 2 * a )]; cd.lfParam[1] = &m_loopFilterParam[(size_t) pcv.num4x4CtuBlks * ( 2 * a + 1 )];
       memset( cd.lfParam[0], 0, sizeof( LoopFilterParam ) * 2 * pcv.num4x4CtuBlks );
-      m_cLoopFilter.calcFilterStrengthsCTU( cs, a );
-      for( int dir = 0; dir < 2; dir++ ) flattenLfCtu( cs, a, dir, m_lf[dir].v.data() );
+      {
+        CpuTimer tm{ m_cpuNs[1] };
+        m_cLoopFilter.calcFilterStrengthsCTU( cs, a );
+        for( int dir = 0; dir < 2; dir++ ) flattenLfCtu( cs, a, dir, m_lf[dir].v.data() );
+      }
       (void) W4;
+      CpuTimer tm2{ m_cpuNs[2] };
       // the CU / TU walks of TaskTrafoCtu + TaskInterCtu + TaskCriticalIntraKernel (DecCu.cpp:106-159)
       for( auto& cu : cs.traverseCUs( a ) )
       {
@@ -533,6 +551,8 @@ public:
   const std::vector<Mv>& dmvrMvCache() const { return m_dmvrMvCache; }
   // seconds since decompressPicture(): [0] tables ready, [1] MIDER done (first flatten row starts), [2] flatten done (submit starts), [3] submitted, [4] host tasks joined, [5] device + finish done
   const double* stageTimes() const { return m_stage; }
+  // CPU milliseconds of the host stages of the last picture, summed over the pool's threads: MIDER, boundary strengths + grid copy, CU / TU walk
+  void cpuStageMs( double out[3] ) const { for( int i = 0; i < 3; i++ ) out[i] = m_cpuNs[i].load() * 1e-6; }
 
   // DecLibRecon::decompressPicture (DecLibRecon.cpp:429): schedules the host stages of the picture; returns without waiting.
   void decompressPicture( Picture* pic )
@@ -550,7 +570,7 @@ public:
     CodingStructure& cs = *pic->cs; const PreCalcValues& pcv = *cs.pcv;
     m_motionInfo.resize( (size_t) pcv.num4x4CtuBlks * pcv.sizeInCtus ); m_loopFilterParam.resize( (size_t) pcv.num4x4CtuBlks * pcv.sizeInCtus * 2 );
     m_dmvrMvCache.assign( (size_t) pcv.num8x8CtuBlks * pcv.sizeInCtus, Mv() ); cs.m_dmvrMvCache = m_dmvrMvCache.data();
-    m_t0 = std::chrono::steady_clock::now(); m_tFlat0.store( 0 );
+    m_t0 = std::chrono::steady_clock::now(); m_tFlat0.store( 0 ); for( auto& c : m_cpuNs ) c.store( 0 );
     m_trQuant->init( pic );
     pic->startProcessingTimer();
     preparePicture( pic );
@@ -559,20 +579,28 @@ public:
     const int W = pcv.widthInCtus, H = pcv.heightInCtus;
     m_ctusW = W;
     m_rows.resize( (size_t) W * H ); m_hist.assign( H, MotionHist() );
-    m_ctuDone.reset( new std::atomic<uint8_t>[(size_t) W * H] );
-    for( int a = 0; a < W * H; a++ ) { m_rows[a].self = this; m_rows[a].line = a / W; m_rows[a].col = a % W; m_ctuDone[a].store( 0 ); }
+    for( int a = 0; a < W * H; a++ ) { m_rows[a].self = this; m_rows[a].line = a / W; m_rows[a].col = a % W; }
+    m_miderDone.reset( new std::atomic<int>[(size_t) H] ); for( int y = 0; y < H; y++ ) m_miderDone[y].store( 0 );
+    const int runsPerRow = ( W + FLATTEN_RUN - 1 ) / FLATTEN_RUN;
+    m_rowTasks.assign( H, RowTask() ); m_runTasks.assign( (size_t) H * runsPerRow, RunTask() );
     pic->reconDone.lock();
-    for( int a = 0; a < W * H; a++ )
+    for( int y = 0; y < H; y++ )
     {
-      CBarrierVec bars;
+      auto bars = [&] {
+        CBarrierVec b;
 #if RECO_WHILE_PARSE
-      if( pic->parseDone.isBlocked() ) bars.push_back( &pic->ctuParsedBarrier[( a / W + 1 ) * W - 1] );   // the last CTU of the row is parsed (DecLibRecon.cpp:619-625)
+        if( pic->parseDone.isBlocked() ) b.push_back( &pic->ctuParsedBarrier[( y + 1 ) * W - 1] );   // the last CTU of the row is parsed (DecLibRecon.cpp:619-625)
 #else
-      bars.push_back( &pic->parseDone );
+        b.push_back( &pic->parseDone );
 #endif
-      CBarrierVec bars2 = bars;
-      m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 mider " + std::to_string( a ) ) miderTask, &m_rows[a], &m_flattenCounter, nullptr, std::move( bars ), miderReady );
-      m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 flatten " + std::to_string( a ) ) flattenTask, &m_rows[a], &m_flattenCounter, nullptr, std::move( bars2 ), flattenReady );
+        return b; };
+      m_rowTasks[y].self = this; m_rowTasks[y].line = y;
+      m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 mider row " + std::to_string( y ) ) miderRowTask, &m_rowTasks[y], &m_flattenCounter, nullptr, bars(), miderRowReady );
+      for( int k = 0; k < runsPerRow; k++ )
+      {
+        RunTask& t = m_runTasks[(size_t) y * runsPerRow + k]; t.self = this; t.line = y; t.col0 = k * FLATTEN_RUN; t.col1 = std::min( W, t.col0 + FLATTEN_RUN );
+        m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 flatten " + std::to_string( y ) + ":" + std::to_string( k ) ) flattenRunTask, &t, &m_flattenCounter, nullptr, bars(), flattenRunReady );
+      }
     }
     m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 submit" ) submitTask, this, &m_submitCounter, nullptr, { m_flattenCounter.donePtr(), &pic->parseDone }, submitReady );
   }
