@@ -549,22 +549,27 @@ static void setupSps( FakePicture& fp, const ref_seam_cfg& c, const b200_geom& g
   (void) g;
 }
 
-static Pic* build( const b200_geom* g, const ref_seam_cfg* c, const int16_t* const* refs, const b200_picture* filt )
+// prev: the picture (POC 8) the new one (then POC 10) predicts from as its first list-0 reference, in place of the shared reference picture of POC 4 — a chain of
+// pictures as a decoder sees them: the reference may still be in reconstruction when this picture is handed to a recon instance
+static Pic* build( const b200_geom* g, const ref_seam_cfg* c, const int16_t* const* refs, const b200_picture* filt, Pic* prev = nullptr )
 {
   std::unique_ptr<Pic> P( new Pic );
   P->g = *g; P->cfg = *c;
-  const int nSl = std::max( 1, std::min( (int) c->numSlices, 16 ) );
+  const int nCtus = ( ( g->width + g->ctuSize - 1 ) / g->ctuSize ) * ( ( g->height + g->ctuSize - 1 ) / g->ctuSize );
+  const int nSl = std::max( 1, std::min( std::min( (int) c->numSlices, 16 ), nCtus ) );      // every slice holds at least one CTU
   P->cur.reset( new FakePicture( *g, nSl ) );
   FakePicture& cur = *P->cur;
   SEAM_TR( "build: picture created\n" );
   setupSps( cur, *c, *g );
   SEAM_TR( "build: sps done\n" );
   const bool intraPic = c->sliceType == 2;
-  const int pocs[4] = { 4, 0, 12, 16 };
+  const int curPoc = prev ? 10 : 8;
+  const int pocs[4] = { prev ? 8 : 4, 0, 12, 16 };
   if( !intraPic )
   {
     P->refs = refSetFor( *g, refs );
     for( int s = 0; s < 4; s++ ) P->ref[s] = P->refs->ref[s].get();
+    if( prev ) P->ref[0] = prev->cur.get();
   }
   SEAM_TR( "build: refs done\n" );
   CodingStructure& cs = *cur.pic.cs;
@@ -577,7 +582,7 @@ static Pic* build( const b200_geom* g, const ref_seam_cfg* c, const int16_t* con
   {
   Slice* sl = cur.pic.slices[s];
   const bool odd = s & 1;
-  sl->setSliceType( intraPic ? I_SLICE : c->sliceType == 1 ? P_SLICE : B_SLICE ); sl->setPOC( 8 ); cur.pic.poc = 8;
+  sl->setSliceType( intraPic ? I_SLICE : c->sliceType == 1 ? P_SLICE : B_SLICE ); sl->setPOC( curPoc ); cur.pic.poc = curPoc;
   sl->setSliceQp( c->qp ); sl->setDepQuantEnabledFlag( c->tools & SEAM_DEPQUANT ); sl->setSignDataHidingEnabledFlag( false ); sl->setTSResidualCodingDisabledFlag( false );
   sl->setExplicitScalingListUsed( ( c->tools & SEAM_SCALING_LIST ) != 0 ); sl->setIndependentSliceIdx( s ); sl->setCheckLDC( false );
   if( ( c->tools & SEAM_SCALING_LIST ) && s == 0 )
@@ -751,6 +756,11 @@ extern "C" void* ref_seam_create( const b200_geom* g, const ref_seam_cfg* cfg, c
   try { return seam::build( g, cfg, refs, filt ); }
   catch( std::exception& e ) { fprintf( stderr, "ref_seam_create: %s\n", e.what() ); return nullptr; }
 }
+extern "C" void* ref_seam_create_chained( const b200_geom* g, const ref_seam_cfg* cfg, const int16_t* const* refs, const b200_picture* filt, void* prev )
+{
+  try { return seam::build( g, cfg, refs, filt, static_cast<seam::Pic*>( prev ) ); }
+  catch( std::exception& e ) { fprintf( stderr, "ref_seam_create_chained: %s\n", e.what() ); return nullptr; }
+}
 extern "C" void ref_seam_destroy( void* h ) { delete static_cast<seam::Pic*>( h ); }
 
 extern "C" size_t ref_seam_col_motion_bytes( void* h )
@@ -834,6 +844,15 @@ extern "C" double ref_seam_run_b200( void* h, int threads, int dry, int16_t* con
   catch( std::exception& e ) { fprintf( stderr, "ref_seam_run_b200: %s\n", e.what() ); return -2.0; }
 }
 
+namespace seam { static std::vector<std::unique_ptr<b200glue::DecLibReconB200>>& pipeDev() { static std::vector<std::unique_ptr<b200glue::DecLibReconB200>> v; return v; } }
+// the work lists instance k of the last ref_seam_run_pipelined( backend 1 / 2 ) call flattened last (pointers into the recon object)
+extern "C" int ref_seam_pipelined_flat( int k, b200_picture* flat )
+{
+  auto& dev = seam::pipeDev();
+  if( k < 0 || k >= (int) dev.size() || !flat ) return -1;
+  *flat = dev[k]->flattened(); return 0;
+}
+
 // (iii) Either back end the way DecLib drives it (DecLib.h:70, DecLib.cpp:560-640): `depth` recon instances on one thread pool take the pictures in turn;
 // an instance is handed its next picture as soon as its previous one has been waited for, so up to `depth` pictures are in flight.  Returns the seconds
 // for all n pictures (no output read-back), < 0 on error.  backend 0: the reference's DecLibRecon, 1: DecLibReconB200, 2: DecLibReconB200 in dry-run mode (host stages only).
@@ -845,7 +864,7 @@ extern "C" double ref_seam_run_pipelined( void* const* hs, int n, int threads, i
   {
     seam::Pic& P0 = *static_cast<seam::Pic*>( hs[0] );
     static std::unique_ptr<ThreadPool> pool; static int poolThreads = -1;
-    static std::vector<std::unique_ptr<DecLibRecon>> stock; static std::vector<std::unique_ptr<b200glue::DecLibReconB200>> dev; static b200_geom devGeom{};
+    static std::vector<std::unique_ptr<DecLibRecon>> stock; auto& dev = seam::pipeDev(); static b200_geom devGeom{};
     if( poolThreads != threads || ( backend >= 1 && memcmp( &devGeom, &P0.g, sizeof( devGeom ) ) ) )
     {
       for( auto& r : stock ) r->destroy(); for( auto& r : dev ) r->destroy();

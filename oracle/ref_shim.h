@@ -180,6 +180,8 @@ double ref_seam_run_stock(void* h, int threads, int16_t* const out[3], uint8_t* 
 double ref_seam_run_b200(void* h, int threads, int dry, int16_t* const out[3], uint8_t* colMotion, size_t colBytes, b200_picture* flat);
 double ref_seam_run_pipelined(void* const* hs, int n, int threads, int backend, int depth);   /* DecLib's alternating recon instances, see ref_seam.h */
 void ref_seam_read_out(void* h, int16_t* const out[3], uint8_t* colMotion, size_t colBytes);
+void* ref_seam_create_chained(const b200_geom* g, const ref_seam_cfg* cfg, const int16_t* const* refs, const b200_picture* filt, void* prev);   /* prev (POC 8) = first list-0 reference of the new picture (POC 10) */
+int ref_seam_pipelined_flat(int k, b200_picture* flat);
 
 #ifdef __cplusplus
 }

@@ -155,15 +155,19 @@ def declare_seam(lib):
     lib.ref_seam_col_motion_bytes.argtypes = [C.c_void_p]; lib.ref_seam_col_motion_bytes.restype = C.c_size_t
     lib.ref_seam_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]; lib.ref_seam_stats.restype = None
     lib.ref_seam_run_stock.argtypes = [C.c_void_p, C.c_int, PL, C.c_void_p, C.c_size_t]; lib.ref_seam_run_stock.restype = C.c_double
+    lib.ref_seam_create_chained.argtypes = [C.POINTER(abi.Geom), C.POINTER(SeamCfg), C.POINTER(C.c_void_p), C.POINTER(abi.Picture), C.c_void_p]; lib.ref_seam_create_chained.restype = C.c_void_p
+    lib.ref_seam_pipelined_flat.argtypes = [C.c_int, C.POINTER(abi.Picture)]; lib.ref_seam_pipelined_flat.restype = C.c_int
     lib.ref_seam_read_out.argtypes = [C.c_void_p, PL, C.c_void_p, C.c_size_t]; lib.ref_seam_read_out.restype = None
     lib.ref_seam_run_pipelined.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int]; lib.ref_seam_run_pipelined.restype = C.c_double
     lib.ref_seam_run_b200.argtypes = [C.c_void_p, C.c_int, C.c_int, PL, C.c_void_p, C.c_size_t, C.POINTER(abi.Picture)]; lib.ref_seam_run_b200.restype = C.c_double
 
 
-def seam_pipelined(ref, cases, threads, backend, depth, read=True):
+def seam_pipelined(ref, cases, threads, backend, depth, read=True, chain=False, flat=False):
     """Runs the pictures of `cases` (SeamCase objects, one fresh Picture each) through `depth` alternating recon instances (ref_seam_run_pipelined).
-    Returns (seconds, [(planes, colMotion) per picture])"""
-    hs = [c.build() for c in cases]
+    chain: every picture takes the one before it as its first list-0 reference (ref_seam_create_chained).  flat (dry-run back end, as many pictures as instances):
+    also returns the work lists the instances flattened.  Returns (seconds, [(planes, colMotion) per picture][, lists])"""
+    hs = []
+    for c in cases: hs.append(c.build(prev=hs[-1] if chain and hs else None))
     arr = (C.c_void_p * len(hs))(*hs)
     secs = ref.ref_seam_run_pipelined(arr, len(hs), threads, backend, depth)
     outs = []
@@ -171,8 +175,13 @@ def seam_pipelined(ref, cases, threads, backend, depth, read=True):
         for c, h in zip(cases, hs):
             out = c._out(); col = np.zeros(ref.ref_seam_col_motion_bytes(h), np.uint8)
             ref.ref_seam_read_out(h, abi.plane_ptrs(out), col.ctypes.data, len(col)); outs.append((out, col))
-    for h in hs: ref.ref_seam_destroy(h)
-    return secs, outs
+    lists = []
+    if flat and secs >= 0:
+        for k, c in enumerate(cases):
+            st = abi.Picture(); assert ref.ref_seam_pipelined_flat(k, C.byref(st)) == 0
+            lists.append(picture_from_struct(st, c.g, c.filt))
+    for h in reversed(hs): ref.ref_seam_destroy(h)
+    return (secs, outs, lists) if flat else (secs, outs)
 
 
 class SeamCase:
@@ -196,8 +205,9 @@ class SeamCase:
         if slice_type is not None: v.cfg.sliceType = slice_type
         return v
 
-    def build(self):
-        h = self.ref.ref_seam_create(C.byref(self.g), C.byref(self.cfg), ref_ptrs(self.refs), C.byref(self.filt["struct"]))
+    def build(self, prev=None):
+        if prev is not None: h = self.ref.ref_seam_create_chained(C.byref(self.g), C.byref(self.cfg), ref_ptrs(self.refs), C.byref(self.filt["struct"]), prev)
+        else: h = self.ref.ref_seam_create(C.byref(self.g), C.byref(self.cfg), ref_ptrs(self.refs), C.byref(self.filt["struct"]))
         assert h, "ref_seam_create failed"
         return h
 
@@ -329,9 +339,9 @@ def ref_ptrs(ref_pics):
 
 
 def oracle_decompress(oracle, g, dpb, pic):
-    SC = pic["scaling"].ctypes.data if "scaling" in pic else None      # explicit scaling lists: the picture's dequantisation tables
     """CPU chain of the whole back end on one synthetic picture: K2 -> K1 -> K3 -> K4 -> K5 with the pinned oracle.
     dpb: list of [Y,Cb,Cr] per slot (refs are read from it); returns the new picture planes and the DMVR deltas."""
+    SC = pic["scaling"].ctypes.data if "scaling" in pic else None      # explicit scaling lists: the picture's dequantisation tables
     W, H = g.width, g.height
     cur = [np.zeros((H, W), np.int16), np.zeros((H // 2, W // 2), np.int16), np.zeros((H // 2, W // 2), np.int16)]
     dm = np.zeros((pic["ndmvr"] + 1, 2), np.int32)

@@ -104,3 +104,27 @@ def test_two_alternating_recon_instances():
     secs, _ = helpers.seam_pipelined(ref, cases, 4, 2, 2)
     assert secs >= 0
 
+
+def test_reference_still_in_flight_on_the_other_instance():
+    """Picture B predicts from picture A while A is still with the other recon instance (what DecLib's two alternating instances produce all the time).  Stock: the two
+    instances give B the same samples as one instance after the other.  DecLibReconB200 (dry run): B's submission waits until A is in the stream, B's lists name A's
+    DPB slot, and the oracle chain A -> B over those lists reproduces the stock pictures."""
+    oracle = helpers.load_oracle()
+    rng = np.random.default_rng(91)
+    base = helpers.SeamCase(ref, rng, 416, 240, intra=10)
+    A, B = base.variant(seed=301), base.variant(seed=302)
+    secs, outs = helpers.seam_pipelined(ref, [A, B], 4, 0, 2, chain=True)
+    assert secs >= 0
+    secs, _, lists = helpers.seam_pipelined(ref, [A, B], 4, 2, 2, read=False, chain=True, flat=True)
+    assert secs >= 0
+    fa, fb = lists
+    slotA, slotB = fa["struct"].dstSlot, fb["struct"].dstSlot
+    assert slotA != slotB and (fb["pus"]["refSlot"] == slotA).any(), "B's lists do not reference A's slot"
+    zeros = [np.zeros_like(p) for p in base.refs[0]]
+    dpb = [base.refs[0], base.refs[1], base.refs[2], base.refs[3]] + [zeros] * 4
+    wantA, _ = helpers.oracle_decompress(oracle, base.g, dpb, fa)
+    for c in range(3): assert np.array_equal(wantA[c], outs[0][0][c]), f"A plane {c}"
+    dpb[slotA] = wantA
+    wantB, _ = helpers.oracle_decompress(oracle, base.g, dpb, fb)
+    for c in range(3): assert np.array_equal(wantB[c], outs[1][0][c]), f"B plane {c}: {np.count_nonzero(wantB[c] != outs[1][0][c])} samples differ"
+
