@@ -3,6 +3,7 @@
 // (vvdec_b200/vvdec_glue) against the reference's own functions, and provides the "reference"
 // CPU baseline for bench.py.  Same construction trick as tests/vvdec_unit_test/vvdec_unit_test.cpp.
 #include "ref_shim.h"
+#include "ref_stream.h"
 #include <mutex>
 #include <random>
 #include <memory>

@@ -1,0 +1,362 @@
+"""TEST INFRASTRUCTURE (not shipped, not on the product path): a minimal VVC bitstream WRITER, so that the DecLibRecon seam can be tested from a real
+bitstream.
+
+Three steps (see oracle/gen_bindecoder.cpp for why this yields valid streams with every CU-level tool the parameter sets switch on):
+  1. the high-level syntax — SPS, PPS, APSs, picture / slice headers — is written here, field by field in the order the reference READS it
+     (HLSyntaxReader.cpp: parseSPS :1421, parsePPS :205, parseAPS :855, parsePictureHeader :2694, parseSliceHeader :3438, parseRefPicList :112);
+  2. the slice data is DRAWN: oracle/_ref/libvvdec_gen.so (the reference with its BinDecoder replaced by a recording generator) decodes the headers
+     followed by a one-byte dummy payload; its CABACReader decides every context / binarisation, the generator decides every bin;
+  3. the recorded (context, bin) sequences are arithmetic-encoded (ref_cabac_encode: the reference's probability models, our encoder) and spliced
+     behind the slice headers; emulation prevention and start codes make it an Annex-B stream.
+The stock reference (oracle/_ref/libvvdec_ref.so: ref_decode_stream) must then decode the stream to exactly the pictures step 2 reconstructed."""
+import ctypes as C, os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "_ref", "libvvdec_ref.so")
+GEN_SO = os.path.join(HERE, "_ref", "libvvdec_gen.so")
+SWAP_SO = os.path.join(HERE, "_ref", "libvvdec_swapped.so")
+
+NAL_TRAIL, NAL_STSA, NAL_RADL, NAL_RASL, NAL_IDR_W_RADL, NAL_IDR_N_LP, NAL_CRA, NAL_GDR = 0, 1, 2, 3, 7, 8, 9, 10
+NAL_VPS, NAL_SPS, NAL_PPS, NAL_PREFIX_APS, NAL_SUFFIX_APS, NAL_PH, NAL_AUD = 14, 15, 16, 17, 18, 19, 20
+SLICE_B, SLICE_P, SLICE_I = 0, 1, 2
+
+
+class Bits:
+    """RBSP bit writer: u(n), ue(v), se(v), flags."""
+    def __init__(self): self.b = []
+    def u(self, n, v):
+        assert 0 <= v < (1 << n) or n == 0, (n, v)
+        for i in range(n - 1, -1, -1): self.b.append((v >> i) & 1)
+        return self
+    def f(self, v): self.b.append(1 if v else 0); return self
+    def ue(self, v):
+        assert v >= 0
+        n = (v + 1).bit_length() - 1
+        return self.u(n, 0).u(n + 1, v + 1)
+    def se(self, v): return self.ue(2 * v - 1 if v > 0 else -2 * v)
+    def aligned(self): return len(self.b) % 8 == 0
+    def align_zero(self):
+        while not self.aligned(): self.b.append(0)
+        return self
+    def trailing(self):                                          # rbsp_trailing_bits() / byte_alignment(): a one, then zeros
+        self.b.append(1)
+        return self.align_zero()
+    def bytes(self):
+        assert self.aligned()
+        return bytes(int("".join(map(str, self.b[i:i + 8])), 2) for i in range(0, len(self.b), 8))
+
+
+def escape(rbsp):
+    """emulation prevention (7.4.2): 00 00 0x -> 00 00 03 0x"""
+    out = bytearray(); zeros = 0
+    for byte in rbsp:
+        if zeros >= 2 and byte <= 3: out.append(3); zeros = 0
+        out.append(byte); zeros = zeros + 1 if byte == 0 else 0
+    if out and out[-1] == 0: out.append(3)
+    return bytes(out)
+
+
+def nal_unit(nal_type, rbsp, tid=0, layer=0):
+    hdr = Bits().f(0).f(0).u(6, layer).u(5, nal_type).u(3, tid + 1).bytes()
+    return b"\x00\x00\x00\x01" + hdr + escape(rbsp)
+
+
+def log2(v):
+    assert v > 0 and v & (v - 1) == 0, v
+    return v.bit_length() - 1
+
+
+DEFAULTS = dict(
+    width=256, height=128, ctu=64, bit_depth=10, chroma_format=1, min_cb=4, poc_bits=8, level_idc=102, dpb_size=6,
+    # partitioning (luma samples): smallest quad-tree leaf, multi-type-tree depth, largest binary / ternary split, per slice class
+    min_qt_intra=8, mtt_depth_intra=2, max_bt_intra=32, max_tt_intra=32, dual_tree=False,
+    min_qt_intra_c=8, mtt_depth_intra_c=2, max_bt_intra_c=32, max_tt_intra_c=32,            # chroma tree of dual-tree I slices (in luma samples)
+    min_qt_inter=8, mtt_depth_inter=2, max_bt_inter=64, max_tt_inter=64,
+    max_tb64=True, transform_skip=False, bdpcm=False, mts=False, mts_intra=False, mts_inter=False, lfnst=False, jccr=False,
+    sao=False, alf=False, ccalf=False, lmcs=False, weighted_pred=False, weighted_bipred=False,
+    temporal_mvp=False, sbtmvp=False, amvr=False, bdof=False, smvd=False, dmvr=False, mmvd=False, max_merge=6, sbt=False, affine=False, affine_6param=False,
+    affine_amvr=False, prof=False, max_sub_merge=5, bcw=False, ciip=False, gpm=False, max_gpm=6, isp=False, mrl=False, mip=False, cclm=False,
+    chroma_collocated=(True, False), dep_quant=False, sign_hiding=False, scaling_lists=False,
+    init_qp=32, cu_qp_delta=False, cabac_init_present=False, deblocking_disabled=False, beta_offset_div2=0, tc_offset_div2=0,
+)
+
+
+class Config(dict):
+    def __init__(self, **kw):
+        bad = set(kw) - set(DEFAULTS); assert not bad, bad
+        super().__init__(DEFAULTS); self.update(kw)
+    __getattr__ = dict.__getitem__
+
+
+def write_sps(c):
+    """HLSyntaxReader::parseSPS (HLSyntaxReader.cpp:1421-2316), single layer, no sub-pictures, no VUI / HRD."""
+    w = Bits()
+    ctb_log2, min_cb_log2 = log2(c.ctu), log2(c.min_cb)
+    w.u(4, 0).u(4, 0).u(3, 0).u(2, c.chroma_format).u(2, ctb_log2 - 5)
+    w.f(1)                                                       # sps_ptl_dpb_hrd_params_present_flag
+    w.u(7, 1).f(0).u(8, c.level_idc).f(1).f(0)                   # profile_tier_level(): Main 10, main tier, level, frame only, single layer
+    w.f(0).align_zero()                                          #   general_constraints_info(): gci_present_flag = 0, alignment
+    w.align_zero().u(8, 0)                                       #   ptl alignment; ptl_num_sub_profiles
+    w.f(0).f(0)                                                  # gdr, ref_pic_resampling
+    w.ue(c.width).ue(c.height).f(0).f(0)                         # size, no conformance window, no sub-pictures
+    w.ue(c.bit_depth - 8).f(0).f(0)                              # bit depth, no wavefronts, no entry points
+    w.u(4, c.poc_bits - 4).f(0).u(2, 0).u(2, 0)                  # POC lsb bits, no msb cycle, no extra PH / SH bits
+    w.ue(c.dpb_size - 1).ue(min(c.dpb_size - 1, 4)).ue(0)        # dpb_parameters(): max_dec_pic_buffering_minus1, max_num_reorder_pics, max_latency_increase_plus1
+    w.ue(min_cb_log2 - 2).f(0)                                   # min CB, no partition-constraint override
+    min_qt_i = log2(c.min_qt_intra)
+    w.ue(min_qt_i - min_cb_log2).ue(c.mtt_depth_intra)
+    if c.mtt_depth_intra: w.ue(log2(c.max_bt_intra) - min_qt_i).ue(log2(c.max_tt_intra) - min_qt_i)
+    if c.chroma_format: w.f(c.dual_tree)
+    if c.dual_tree:
+        min_qt_c = log2(c.min_qt_intra_c)
+        w.ue(min_qt_c - min_cb_log2).ue(c.mtt_depth_intra_c)
+        if c.mtt_depth_intra_c: w.ue(log2(c.max_bt_intra_c) - min_qt_c).ue(log2(c.max_tt_intra_c) - min_qt_c)
+    min_qt_p = log2(c.min_qt_inter)
+    w.ue(min_qt_p - min_cb_log2).ue(c.mtt_depth_inter)
+    if c.mtt_depth_inter: w.ue(log2(c.max_bt_inter) - min_qt_p).ue(log2(c.max_tt_inter) - min_qt_p)
+    if c.ctu > 32: w.f(c.max_tb64)
+    w.f(c.transform_skip)
+    if c.transform_skip: w.ue(3).f(c.bdpcm)                      # transform skip up to 32x32
+    w.f(c.mts)
+    if c.mts: w.f(c.mts_intra).f(c.mts_inter)
+    w.f(c.lfnst)
+    if c.chroma_format:
+        w.f(c.jccr).f(1)                                         # one chroma QP table for Cb / Cr / joint
+        w.se(0).ue(0).ue(0).ue(0)                                #   start at 26, one pivot: in 26 -> out 26, in 27 -> out 26, slope 1 above
+    w.f(c.sao).f(c.alf)
+    if c.alf and c.chroma_format: w.f(c.ccalf)
+    w.f(c.lmcs).f(c.weighted_pred).f(c.weighted_bipred).f(0)     # ..., no long-term references
+    w.f(0).f(1).ue(0)                                            # sps_idr_rpl_present_flag, rpl1_same_as_rpl0, no RPL candidates (lists come in the slice headers)
+    w.f(0)                                                       # wrap-around
+    w.f(c.temporal_mvp)
+    if c.temporal_mvp: w.f(c.sbtmvp)
+    w.f(c.amvr).f(c.bdof)
+    if c.bdof: w.f(0)
+    w.f(c.smvd).f(c.dmvr)
+    if c.dmvr: w.f(0)
+    w.f(c.mmvd)
+    if c.mmvd: w.f(0)
+    w.ue(6 - c.max_merge).f(c.sbt).f(c.affine)
+    if c.affine:
+        w.ue(5 - c.max_sub_merge).f(c.affine_6param)
+        if c.amvr: w.f(c.affine_amvr)
+        w.f(c.prof)
+        if c.prof: w.f(0)
+    w.f(c.bcw).f(c.ciip)
+    if c.max_merge >= 2:
+        w.f(c.gpm)
+        if c.gpm and c.max_merge >= 3: w.ue(c.max_merge - c.max_gpm)
+    w.ue(0)                                                      # parallel merge level 4
+    w.f(c.isp).f(c.mrl).f(c.mip)
+    if c.chroma_format: w.f(c.cclm)
+    if c.chroma_format == 1: w.f(c.chroma_collocated[0]).f(c.chroma_collocated[1])
+    w.f(0)                                                       # palette
+    if c.chroma_format == 3 and not c.max_tb64: w.f(0)           # ACT
+    if c.transform_skip: w.ue(0)                                 # min_qp_prime_ts
+    w.f(0).f(0)                                                  # IBC, LADF
+    w.f(c.scaling_lists)
+    if c.lfnst and c.scaling_lists: w.f(0)
+    w.f(c.dep_quant).f(c.sign_hiding).f(0)                       # ..., no virtual boundaries
+    w.f(0)                                                       # sps_timing_hrd_params_present_flag
+    w.f(0).f(0).f(0)                                             # field_seq, VUI, extension
+    return nal_unit(NAL_SPS, w.trailing().bytes())
+
+
+def write_pps(c):
+    """HLSyntaxReader::parsePPS (HLSyntaxReader.cpp:205-850): one tile, one slice (pps_no_pic_partition_flag)."""
+    w = Bits()
+    w.u(6, 0).u(4, 0).f(0).ue(c.width).ue(c.height).f(0).f(0).f(0)      # ids, mixed NAL types, size, conformance / scaling window, output flag
+    w.f(1).f(0)                                                        # no_pic_partition, no sub-picture id mapping
+    w.f(c.cabac_init_present).ue(0).ue(0).f(0)                         # one active reference per list by default, no rpl1 index
+    w.f(c.weighted_pred).f(c.weighted_bipred).f(0)                     # ..., wrap-around
+    w.se(c.init_qp - 26).f(c.cu_qp_delta)
+    w.f(0)                                                             # pps_chroma_tool_offsets_present_flag
+    w.f(1).f(0).f(c.deblocking_disabled)                               # deblocking control present, no override, disabled flag
+    if not c.deblocking_disabled: w.se(c.beta_offset_div2).se(c.tc_offset_div2)
+    w.f(0).f(0).f(0)                                                   # PH / SH extension, PPS extension
+    return nal_unit(NAL_PPS, w.trailing().bytes())
+
+
+class Pic(dict):
+    """One picture of the stream: poc, slice_type, refs = ([POCs list 0], [POCs list 1]), qp, tid and per-picture tool switches."""
+    def __init__(self, poc, slice_type=SLICE_I, refs=((), ()), qp=None, idr=None, referenced=True, **kw):
+        super().__init__(poc=poc, slice_type=slice_type, refs=refs, qp=qp, idr=(poc == 0 if idr is None else idr), referenced=referenced,
+                         sao=(True, True), dep_quant=True, sign_hiding=True, temporal_mvp=True, col_from_l0=True, mvd_l1_zero=False, cabac_init=False)
+        bad = set(kw) - set(self); assert not bad, bad
+        self.update(kw)
+    __getattr__ = dict.__getitem__
+
+
+def write_ref_pic_list(w, c, poc, ref_pocs):
+    """parseRefPicList (HLSyntaxReader.cpp:112-200) for a list signalled in the header (rplsIdx = -1): short-term entries only."""
+    w.ue(len(ref_pocs))
+    prev = 0
+    for i, r in enumerate(ref_pocs):
+        delta = (poc - r) - prev                                   # DeltaPocValSt accumulates: entry i refers to POC poc - sum( delta[0..i] )
+        prev += delta
+        a = abs(delta)
+        if (not c.weighted_pred and not c.weighted_bipred) or i == 0:
+            assert a >= 1, "equal POCs need abs_delta_poc_st = 0, which only later entries of weighted-prediction streams can signal"
+            w.ue(a - 1)
+        else:
+            w.ue(a)
+        if a > 0: w.f(delta < 0)
+
+
+def write_slice(c, p):
+    """Slice NAL header + picture header in the slice header: parseSliceHeader (HLSyntaxReader.cpp:3438-4065) with parsePictureHeader (:2694-3360)."""
+    inter = p.slice_type != SLICE_I
+    irap = p.idr
+    w = Bits()
+    w.f(1)                                                       # sh_picture_header_in_slice_header_flag
+    # ---- picture_header_structure()
+    w.f(irap).f(not p.referenced)
+    if irap: w.f(0)                                              # ph_gdr_pic_flag
+    w.f(inter)
+    if inter: w.f(0)                                             # ph_intra_slice_allowed_flag: one slice per picture, so inter pictures carry no intra slice
+    w.ue(0).u(c.poc_bits, p.poc & ((1 << c.poc_bits) - 1))
+    if c.lmcs: w.f(0)                                            # ph_lmcs_enabled_flag (LMCS needs its APS: see write_lmcs_aps users)
+    if c.scaling_lists: w.f(0)
+    if not inter:
+        if c.cu_qp_delta: w.ue(0)                                # ph_cu_qp_delta_subdiv_intra_slice
+    else:
+        if c.cu_qp_delta: w.ue(0)
+        if c.temporal_mvp: w.f(p.temporal_mvp)
+        if c.mmvd and False: w.f(0)                              # ph_fpel_mmvd_enabled_flag only with sps_mmvd_fullpel_only_flag
+        w.f(p.mvd_l1_zero)                                       # RPLs are in the slice header: ph_mvd_l1_zero_flag is always present
+    if c.jccr: w.f(0)                                            # ph_joint_cbcr_sign_flag
+    # ---- slice header proper
+    if inter: w.ue(p.slice_type)
+    if irap: w.f(0)                                              # sh_no_output_of_prior_pics_flag
+    if c.alf: w.f(0)                                             # sh_alf_enabled_flag
+    if not irap:                                                 # IDR without sps_idr_rpl_present_flag carries no lists
+        for l in (0, 1):
+            write_ref_pic_list(w, c, p.poc, p.refs[l])
+    n_active = [0, 0]
+    if inter:
+        n0, n1 = len(p.refs[0]), len(p.refs[1])
+        assert n0 >= 1 and (p.slice_type != SLICE_B or n1 >= 1)
+        if n0 > 1 or (p.slice_type == SLICE_B and n1 > 1):
+            w.f(1)                                               # sh_num_ref_idx_active_override_flag: all entries active
+            if n0 > 1: w.ue(n0 - 1)
+            if p.slice_type == SLICE_B and n1 > 1: w.ue(n1 - 1)
+        n_active = [n0, n1 if p.slice_type == SLICE_B else 0]
+        if c.cabac_init_present: w.f(p.cabac_init)
+        if c.temporal_mvp and p.temporal_mvp:
+            if p.slice_type == SLICE_B: w.f(p.col_from_l0)
+            col_l0 = p.col_from_l0 or p.slice_type != SLICE_B
+            if (col_l0 and n_active[0] > 1) or (not col_l0 and n_active[1] > 1): w.ue(0)
+        assert not (c.weighted_pred and p.slice_type == SLICE_P) and not (c.weighted_bipred and p.slice_type == SLICE_B), "pred_weight_table not written"
+    qp = c.init_qp if p.qp is None else p.qp
+    w.se(qp - c.init_qp)
+    if c.sao:
+        w.f(p.sao[0])
+        if c.chroma_format: w.f(p.sao[1])
+    dq = c.dep_quant and p.dep_quant
+    if c.dep_quant: w.f(dq)
+    sdh = c.sign_hiding and not dq and p.sign_hiding
+    if c.sign_hiding and not dq: w.f(sdh)
+    if c.transform_skip and not dq and not sdh: w.f(0)           # sh_ts_residual_coding_disabled_flag
+    w.trailing()                                                 # byte_alignment()
+    nal_type = (NAL_IDR_N_LP if irap else NAL_TRAIL)
+    return nal_type, w.bytes()
+
+
+# ---- libraries -----------------------------------------------------------------------------------------------------------------------------------------
+_libs = {}
+
+
+def _lib(path):
+    if path not in _libs:
+        lib = C.CDLL(path)
+        u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+        lib.ref_decode_stream.argtypes = [u8p, np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS"), C.c_int, C.c_int,
+                                          np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS"), C.c_long, C.POINTER(C.c_int), C.c_char_p, C.c_int]
+        lib.ref_cabac_encode.argtypes = [C.c_int, C.c_int, np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS"), u8p, C.c_long, u8p, C.c_long]
+        lib.ref_cabac_encode.restype = C.c_long
+        lib.ref_ctx_offset.argtypes = [C.c_char_p]
+        lib.ref_ctx_names.restype = C.c_char_p
+        if hasattr(lib, "gen_segment"):
+            lib.gen_segment.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_long]; lib.gen_segment.restype = C.c_long
+            lib.gen_reset.argtypes = [C.c_uint32]; lib.gen_set_bias.argtypes = [C.c_int] * 3
+        _libs[path] = lib
+    return _libs[path]
+
+
+def available():
+    return os.path.exists(REF_SO) and os.path.exists(GEN_SO)
+
+
+class DecodeError(RuntimeError):
+    pass
+
+
+def decode(lib_path, aus, threads=1, max_frames=None, frame_samples=None):
+    """The stream (list of access-unit byte strings) through vvdec_decode / vvdec_flush of the given build.  Returns [(Y, Cb, Cr)] in output order."""
+    lib = _lib(lib_path)
+    stream = np.frombuffer(b"".join(aus), np.uint8).copy()
+    offs = np.zeros(len(aus) + 1, np.int64); offs[1:] = np.cumsum([len(a) for a in aus])
+    cap = (frame_samples or 1 << 22) * (max_frames or len(aus))
+    out = np.zeros(cap, np.int16); dims = (C.c_int * 6)(); err = C.create_string_buffer(1024)
+    n = lib.ref_decode_stream(stream, offs, len(aus), threads, out, cap, dims, err, len(err))
+    if n < 0: raise DecodeError(f"vvdec error {n}: {err.value.decode(errors='replace')}")
+    w, h, cw, ch = dims[0], dims[1], dims[2], dims[3]
+    frames, pos = [], 0
+    for _ in range(n):
+        y = out[pos:pos + w * h].reshape(h, w).copy(); pos += w * h
+        cb = out[pos:pos + cw * ch].reshape(ch, cw).copy(); pos += cw * ch
+        cr = out[pos:pos + cw * ch].reshape(ch, cw).copy(); pos += cw * ch
+        frames.append((y, cb, cr))
+    return frames
+
+
+def ctx_sets():
+    """{name: (offset, size)} of the reference's context sets (Contexts.h ContextSetCfg); arrays of sets as name0, name1, ..."""
+    lib = _lib(REF_SO)
+    names = []
+    for ln in lib.ref_ctx_names().decode().split():
+        if ":" in ln:
+            n, k = ln.split(":"); names += [f"{n}{i}" for i in range(int(k))]
+        else: names.append(ln)
+    offs = {n: lib.ref_ctx_offset(n.encode()) for n in names}
+    total = lib.ref_ctx_offset(b"total")
+    order = sorted(set(offs.values())) + [total]
+    return {n: (o, order[order.index(o) + 1] - o) for n, o in offs.items()}
+
+
+# bin statistics that keep drawn pictures varied but bounded: P( bin = 1 ) * 256 per context set (every other context: 128)
+DEFAULT_BIAS = {"SplitFlag": 150, "SplitQtFlag": 140, "QtCbf0": 150, "QtCbf1": 90, "QtCbf2": 90, "SkipFlag": 60, "MergeFlag": 120,
+                "SigCoeffGroup0": 90, "SigCoeffGroup1": 90, "DeltaQP": 60, "LastX0": 110, "LastY0": 110, "LastX1": 100, "LastY1": 100,
+                "GtxFlag0": 90, "GtxFlag1": 90, "GtxFlag2": 90, "GtxFlag3": 90, "Mvd": 150}
+for _k in range(6): DEFAULT_BIAS[f"SigFlag{_k}"] = 90
+
+
+def build_stream(cfg, pics, seed=1, bias=None, bypass_p=128, max_bypass_run=12):
+    """Writes the stream for `pics` (decoding order).  Returns (access units, frames the generating library reconstructed, bins per slice)."""
+    gen, ref = _lib(GEN_SO), _lib(REF_SO)
+    params = write_sps(cfg) + write_pps(cfg)
+    heads = [write_slice(cfg, p) for p in pics]
+    # step 2: draw the slice data
+    gen.gen_reset(seed)
+    sets = ctx_sets()
+    gen.gen_set_bias(0, 1023, 128)
+    for name, p in {**DEFAULT_BIAS, **(bias or {})}.items():
+        o, n = sets[name]; gen.gen_set_bias(o, n, p)
+    gen.gen_set_bias(-1, 0, bypass_p); gen.gen_set_max_bypass_run(max_bypass_run)
+    aus = [(params if i == 0 else b"") + nal_unit(t, h + b"\x80") for i, (t, h) in enumerate(heads)]
+    drawn = decode(GEN_SO, aus, frame_samples=cfg.width * cfg.height * 3 // 2 + 64)
+    nseg = gen.gen_num_segments()
+    assert nseg == len(pics), (nseg, len(pics))
+    # step 3: encode and splice
+    out, nbins = [], []
+    for i, (t, h) in enumerate(heads):
+        info = (C.c_int * 3)(); n = gen.gen_segment(i, info, None, None, 0)
+        ctx = np.zeros(n, np.int16); bins = np.zeros(n, np.uint8)
+        gen.gen_segment(i, info, ctx.ctypes.data, bins.ctypes.data, n)
+        buf = np.zeros(n // 4 + 64, np.uint8)
+        m = ref.ref_cabac_encode(info[0], info[1], ctx, bins, n, buf, len(buf))
+        assert m > 0
+        out.append((params if i == 0 else b"") + nal_unit(t, h + bytes(buf[:m])))
+        nbins.append(n)
+    return out, drawn, nbins

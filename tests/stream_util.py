@@ -1,0 +1,62 @@
+"""Bitstream-level test plumbing: a stream written by oracle/vvc_stream.py decoded by (a) the stock reference and (b) the reference with the drop-in class behind
+the DecLibRecon seam (oracle/_ref/libvvdec_swapped.so).  On a machine without a GPU (b) runs its host stages for real and the oracle chain in place of the device
+(DecLibReconB200::TestHooks); on the GPU box it is the product path."""
+import ctypes as C, numpy as np
+from tests import helpers
+from vvdec_b200 import abi
+from oracle import vvc_stream as vs
+
+NUM_SLOTS = 17                                                   # DecLibReconB200::m_dpbSlots
+
+_HOOK = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(abi.Picture), C.POINTER(abi.Geom), C.POINTER(C.c_int32), C.c_size_t,
+                    C.POINTER(C.POINTER(C.c_int16)), C.POINTER(C.c_ssize_t), C.c_int)
+
+
+def swapped_lib():
+    lib = vs._lib(vs.SWAP_SO)
+    lib.swapped_set_hooks.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    return lib
+
+
+class OracleDevice:
+    """Stands where the device would: reconstructs every flattened picture with the oracle chain and keeps the decoded-picture buffer by slot."""
+    def __init__(self, oracle):
+        self.oracle, self.dpb, self.log, self.error = oracle, None, [], None
+        self.cb = _HOOK(self._picture)
+
+    def _picture(self, user, lists, geom, dmvr, ndmvr, planes, strides, poc):
+        try:
+            g = geom.contents; st = lists.contents
+            if self.dpb is None:
+                self.dpb = [[np.zeros((g.height, g.width), np.int16), np.zeros((g.height // 2, g.width // 2), np.int16), np.zeros((g.height // 2, g.width // 2), np.int16)]
+                            for _ in range(NUM_SLOTS)]
+            pic = helpers.picture_from_struct(st, g, None)
+            out, dm = helpers.oracle_decompress(self.oracle, g, self.dpb, pic)
+            self.dpb[st.dstSlot] = out
+            n = min(int(ndmvr), len(dm))
+            for i in range(n): dmvr[2 * i], dmvr[2 * i + 1] = int(dm[i][0]), int(dm[i][1])
+            for c in range(3 if g.chromaFormat else 1):
+                h, w = out[c].shape
+                dst = np.ctypeslib.as_array(planes[c], shape=((h - 1) * strides[c] + w,))
+                np.lib.stride_tricks.as_strided(dst, shape=(h, w), strides=(strides[c] * 2, 2))[...] = out[c]
+            self.log.append(dict(poc=poc, slot=int(st.dstSlot), pus=int(st.numPus), tus=int(st.numTus), intra=int(st.numIntraTus), flags=int(st.flags)))
+        except BaseException as e:                                # never unwind through the C++ frames
+            import traceback; self.error = traceback.format_exc()
+
+
+def decode_swapped_cpu(aus, oracle, threads=1, **kw):
+    """The stream through the swapped build without a device: glue host stages + oracle chain.  Returns (frames, per-picture log)."""
+    lib = swapped_lib(); dev = OracleDevice(oracle)
+    lib.swapped_set_hooks(1, C.cast(dev.cb, C.c_void_p), None)
+    try:
+        frames = vs.decode(vs.SWAP_SO, aus, threads=threads, **kw)
+    finally:
+        lib.swapped_set_hooks(1, None, None)
+    assert dev.error is None, dev.error
+    return frames, dev.log
+
+
+def decode_swapped_device(aus, threads=8, **kw):
+    """The stream through the swapped build on the product path (GPU)."""
+    lib = swapped_lib(); lib.swapped_set_hooks(0, None, None)
+    return vs.decode(vs.SWAP_SO, aus, threads=threads, **kw)

@@ -534,6 +534,9 @@ public:
     CHECK_FATAL( upscaleOutputEnabled, "DecLibReconB200: output upscaling is not part of the device path" );
     m_pool = threadPool; m_id = instanceId; m_numThreads = std::max( 1, threadPool ? threadPool->numThreads() : 1 );
     m_sh = sharedFor( threadPool );
+#ifdef B200_GLUE_TEST_HOOKS
+    m_dryRun = testHooks().dryRun;
+#endif
     m_trQuant.reset( new TrQuant( &m_interPred ) );
     m_cuDecoders.clear();
     for( int i = 0; i < m_numThreads; i++ ) { m_cuDecoders.emplace_back( new DecCu ); m_cuDecoders.back()->init( nullptr, &m_interPred, nullptr, m_trQuant.get() ); }
@@ -543,6 +546,16 @@ public:
   void setDpbSlots( int n ) { m_dpbSlots = n; }            // before the first picture; default 17 (MAX_NUM_REF_PICS + the current picture)
   // test hook: run every host stage and keep the work lists (flattened()), without a device
   void setDryRun( bool b ) { m_dryRun = b; }
+#ifdef B200_GLUE_TEST_HOOKS
+  // Test builds only (oracle/swapped_api.cpp: the reference's DecLib compiled with this class in place of DecLibRecon, on a machine without a GPU): instances
+  // start in dry-run mode and, where the device result would be fetched, hand the work lists to a callback that may fill the DMVR deltas and the picture's planes.
+  struct TestHooks
+  {
+    bool dryRun = false; void* user = nullptr;
+    void ( *picture )( void* user, const b200_picture* lists, const b200_geom* geom, int32_t* dmvrDeltas, size_t numDmvr, int16_t* const planes[3], const ptrdiff_t strides[3], int poc ) = nullptr;
+  };
+  static TestHooks& testHooks() { static TestHooks h; return h; }
+#endif
   const b200_picture& flattened() const { return m_pic; }
   // forget one picture (its Picture object is about to be destroyed or reused: PicListManager would call this where it recycles a picture)
   void releasePicture( const Picture* pic ) { if( !m_sh ) return; std::lock_guard<std::mutex> l( m_sh->m ); auto it = m_sh->slotOf.find( pic ); if( it != m_sh->slotOf.end() ) { m_sh->owner[it->second] = nullptr; m_sh->valid[it->second] = 0; m_sh->slotOf.erase( it ); } }
@@ -661,6 +674,14 @@ private:
       check( b200_wait_picture( S.ctx, m_arena, m_dmvr.v.data(), m_dmvrMvCache.size() ) );
       S.valid[m_dstSlot] = 1;
     }
+#ifdef B200_GLUE_TEST_HOOKS
+    else if( testHooks().picture )
+    {
+      int16_t* planes[3] = { nullptr, nullptr, nullptr }; ptrdiff_t strides[3] = { 0, 0, 0 };
+      for( int c = 0; c < ( S.geom.chromaFormat ? 3 : 1 ); c++ ) { PelBuf b = cs.getRecoBuf( ComponentID( c ) ); planes[c] = b.buf; strides[c] = b.stride; }
+      testHooks().picture( testHooks().user, &m_pic, &S.geom, m_dmvr.v.data(), m_dmvrMvCache.size(), planes, strides, pic->poc );
+    }
+#endif
     for( size_t i = 0; i < m_dmvrMvCache.size(); i++ ) m_dmvrMvCache[i] = Mv( m_dmvr.v[2 * i], m_dmvr.v[2 * i + 1] );
     if( pic->stillReferenced )                                                                                    // colMotion for later TMVP (DecCu.cpp:161), under ctuTask's
     {                                                                                                             // conditions (DecLibRecon.cpp:860-867); one pool task per CTU row
