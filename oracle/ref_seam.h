@@ -706,6 +706,22 @@ static Pic* build( const b200_geom* g, const ref_seam_cfg* c, const int16_t* con
   SEAM_TR( "build: state ready, generating %u CTUs\n", pcv.sizeInCtus );
   Gen gen( cur, cur.pic.slices[0], *c );
   for( unsigned a = 0; a < pcv.sizeInCtus; a++ ) { SEAM_TR( "ctu %u\n", a ); gen.sl = cur.pic.slices[sliceOfCtu( a )]; gen.ctu( a ); }
+  // SAO merge syntax the way the parser leaves it (CABACReader.cpp:249-390: every component SAO_MODE_MERGE, typeIdc = SAO_MERGE_LEFT / _ABOVE), for about a
+  // third of the CTUs whose neighbour is a merge candidate (same slice and tile: the first CU's left / above pointer, SampleAdaptiveOffset.cpp:573-620)
+  if( doSao )
+  {
+    std::mt19937 mrng( c->seed * 7919u + 13u );
+    for( unsigned a = 0; a < pcv.sizeInCtus; a++ )
+    {
+      const CodingUnit* cu = cs.getCtuData( a ).cuPtr[CH_L][0];
+      if( !cu || mrng() % 3 ) continue;
+      const bool left = a % pcv.widthInCtus && cu->left, above = a >= pcv.widthInCtus && cu->above;
+      if( !left && !above ) continue;
+      const int type = left && ( !above || ( mrng() & 1 ) ) ? SAO_MERGE_LEFT : SAO_MERGE_ABOVE;
+      SAOBlkParam& bp = cs.getCtuData( a ).saoParam; bp.reset();
+      for( int k = 0; k < 3; k++ ) { bp[k].modeIdc = SAO_MODE_MERGE; bp[k].typeIdc = type; }
+    }
+  }
   cur.pic.progress = Picture::parsed;
   cur.pic.parseDone.unlock();
   return P.release();

@@ -448,6 +448,19 @@ class DecLibReconB200
     }
     // in-loop filter parameters of every CTU (the SAO availability looks at the CTUs below: the whole picture is parsed by now)
     m_ctuSlice.v.assign( pcv.sizeInCtus, 0 ); m_ctuSlice.pin();
+    if( m_doSao )
+    {
+      // the parser leaves SAO_MODE_MERGE entries and coded offsets: resolved the way SAOPrepareCTULine does (SampleAdaptiveOffset.cpp:400-424), in raster order,
+      // with the reference's own merge candidates (left / above CTU of the same slice and tile) and offset scaling
+      PelUnitBuf none;
+      m_cSAO.create( pcv.lumaWidth, pcv.lumaHeight, pcv.chrFormat, pcv.maxCUWidth, pcv.maxCUHeight, 0, (uint32_t) std::max( 0, cs.sps->getBitDepth() - MAX_SAO_TRUNCATED_BITDEPTH ), none );
+      for( unsigned a = 0; a < pcv.sizeInCtus; a++ )
+      {
+        SAOBlkParam* mergeList[NUM_SAO_MERGE_TYPES] = { nullptr, nullptr };
+        m_cSAO.getMergeList( cs, (int) a, mergeList );
+        m_cSAO.reconstructBlkSAOParam( cs.getCtuData( a ).saoParam, mergeList );
+      }
+    }
     for( unsigned a = 0; a < pcv.sizeInCtus; a++ )
     {
       CtuData& cd = cs.getCtuData( a );
@@ -455,7 +468,7 @@ class DecLibReconB200
       {
         bool av[8];
         m_cSAO.deriveLoopFilterBoundaryAvailibility( cs, Position( ( a % pcv.widthInCtus ) * pcv.maxCUWidth, ( a / pcv.widthInCtus ) * pcv.maxCUHeight ), av[0], av[1], av[2], av[3], av[4], av[5], av[6], av[7] );
-        flattenSAO( cd.saoParam, av, getNumberValidComponents( pcv.chrFormat ), m_sao.v[a] );     // saoParam after reconstructBlkSAOParam (parser side)
+        flattenSAO( cd.saoParam, av, getNumberValidComponents( pcv.chrFormat ), m_sao.v[a] );
       }
       const int si = sliceIdx( cd.slice ); m_ctuSlice.v[a] = (uint8_t) si;
       if( m_doAlf )
