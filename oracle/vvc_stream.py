@@ -193,7 +193,7 @@ def write_ref_pic_list(w, c, poc, ref_pocs):
     w.ue(len(ref_pocs))
     prev = 0
     for i, r in enumerate(ref_pocs):
-        delta = (poc - r) - prev                                   # DeltaPocValSt accumulates: entry i refers to POC poc - sum( delta[0..i] )
+        delta = (r - poc) - prev                                   # the deltas accumulate: entry i refers to POC poc + sum( delta[0..i] ) (Slice.cpp:484)
         prev += delta
         a = abs(delta)
         if (not c.weighted_pred and not c.weighted_bipred) or i == 0:
