@@ -1,0 +1,122 @@
+"""The DecLibRecon seam from a real BITSTREAM, on the CPU (SURVEY 8c level L2, row f-4).
+
+oracle/vvc_stream.py writes a VVC stream: headers field by field, slice data drawn by the reference's own CABACReader over a recording bin source and
+arithmetic-encoded with the reference's probability models.  Every stream is decoded
+  (i)   by the build that drew it (its reconstruction is what the stream means),
+  (ii)  by the stock reference through its public API (vvdec_decode / vvdec_flush) — (i) == (ii) pins the writer / arithmetic encoder, and
+  (iii) by the reference with b200glue::DecLibReconB200 compiled in behind the seam (oracle/_ref/libvvdec_swapped.so): parser, DecLib scheduling, picture
+        recycling and output are the reference's, the drop-in class runs its host stages, and the oracle chain stands where the device would be
+        (tests/test_stream_gpu.py runs the same streams on the GPU).
+Bit-exact equality of all output frames is required."""
+import os, numpy as np, pytest
+from tests import helpers
+from oracle import vvc_stream as vs
+
+pytestmark = pytest.mark.skipif(not (vs.available() and os.path.exists(vs.SWAP_SO)), reason="oracle/_ref not built")
+
+INTRA = dict(isp=True, mrl=True, mip=True, cclm=True, lfnst=True, mts=True, mts_intra=True, mts_inter=True, jccr=True, dep_quant=True, sign_hiding=True, sao=True)
+INTER = dict(temporal_mvp=True, sbtmvp=True, amvr=True, bdof=True, smvd=True, dmvr=True, mmvd=True, sbt=True, affine=True, affine_6param=True, affine_amvr=True,
+             prof=True, bcw=True, ciip=True, gpm=True)
+ALL = {**INTRA, **INTER}
+
+
+def gop4(base=0, idr=True):
+    """random-access GOP of 4 in decoding order: I/P anchor, B at the middle, two non-reference Bs"""
+    b = base
+    first = vs.Pic(b, idr=True) if idr else vs.Pic(b, vs.SLICE_P, ((b - 4,), ()))
+    return [first, vs.Pic(b + 4, vs.SLICE_P, ((b,), ())), vs.Pic(b + 2, vs.SLICE_B, ((b,), (b + 4,))),
+            vs.Pic(b + 1, vs.SLICE_B, ((b, b + 2), (b + 2, b + 4)), referenced=False), vs.Pic(b + 3, vs.SLICE_B, ((b + 2, b), (b + 4,)), referenced=False)]
+
+
+def low_delay(n):
+    """I P P P ... each picture predicting from the two before it; the last list-1 entry repeats list 0 (low-delay B)"""
+    pics = [vs.Pic(0)]
+    for p in range(1, n):
+        refs = tuple(r for r in (p - 1, p - 2) if r >= 0)
+        pics.append(vs.Pic(p, vs.SLICE_B if p % 3 else vs.SLICE_P, (refs, refs if p % 3 else ())))
+    return pics
+
+
+CASES = {
+    "I_all_intra_tools": (dict(INTRA), lambda: [vs.Pic(0)]),
+    "I_dual_tree_ctu128": (dict(INTRA, ctu=128, dual_tree=True), lambda: [vs.Pic(0), vs.Pic(1, idr=True)]),
+    "I_transform_skip_bdpcm": (dict(INTRA, transform_skip=True, bdpcm=True), lambda: [vs.Pic(0, dep_quant=False, sign_hiding=False)]),
+    "I_sign_hiding": (dict(INTRA), lambda: [vs.Pic(0, dep_quant=False)]),
+    "gop_no_inter_tools": (dict(INTRA), gop4),
+    "gop_all_tools": (dict(ALL), gop4),
+    "gop_all_tools_ctu128": (dict(ALL, ctu=128), gop4),
+    "gop_ctu32_8bit": (dict(ALL, ctu=32, max_bt_inter=32, max_tt_inter=32, bit_depth=8), gop4),
+    "gop_picture_not_ctu_aligned": (dict(ALL, width=200, height=104), gop4),
+    "gop_cu_qp_delta": (dict(ALL, cu_qp_delta=True), gop4),
+    "gop_min_cb8_qp20": (dict(ALL, min_cb=8, min_qt_intra=16, min_qt_inter=16, min_qt_intra_c=16, init_qp=20), gop4),
+    "gop_no_deblocking": (dict(ALL, deblocking_disabled=True), gop4),
+    "low_delay_8": (dict(ALL), lambda: low_delay(8)),
+}
+
+
+def _diff(a, b):
+    assert len(a) == len(b), (len(a), len(b))
+    return [sum(int((x != y).sum()) for x, y in zip(fa, fb)) for fa, fb in zip(a, b)]
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return helpers.load_oracle()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("seed", [1, 2])
+def test_stream_stock_vs_swapped_decoder(name, seed, oracle):
+    from tests import stream_util as su
+    kw, pics = CASES[name]
+    cfg = vs.Config(**kw)
+    aus, drawn, nbins = vs.build_stream(cfg, pics(), seed=seed * 7 + len(name))
+    assert min(nbins) > 0
+    stock = vs.decode(vs.REF_SO, aus)
+    assert len(stock) == len(aus) and _diff(drawn, stock) == [0] * len(aus), "the stock reference does not decode the stream to the pictures it was drawn as"
+    swapped, log = su.decode_swapped_cpu(aus, oracle)
+    assert len(log) == len(aus)                                         # every picture went through the drop-in class
+    assert _diff(swapped, stock) == [0] * len(aus)
+    assert any(f[0].std() > 1 for f in stock)                           # not a flat picture
+
+
+def test_long_stream_recycles_pictures_and_slots(oracle):
+    """28 pictures (seven GOPs, open on P anchors): the reference's PicListManager recycles Picture objects and the class's DPB slots turn over
+    (17 slots, DecLibReconB200::slotLocked evicts what is no longer referenced)."""
+    from tests import stream_util as su
+    cfg = vs.Config(**dict(ALL, width=128, height=64))
+    pics = []
+    for k in range(7): pics += gop4(4 * k, idr=(k == 0))[(0 if k == 0 else 1):]
+    aus, drawn, nbins = vs.build_stream(cfg, pics, seed=5)
+    stock = vs.decode(vs.REF_SO, aus)
+    assert _diff(drawn, stock) == [0] * len(aus)
+    swapped, log = su.decode_swapped_cpu(aus, oracle)
+    assert _diff(swapped, stock) == [0] * len(aus)
+    assert len({l["slot"] for l in log}) < len(log)                     # slots were reused
+
+
+def test_swapped_decoder_with_a_thread_pool(oracle):
+    """the same through DecLib's thread pool (parse and reconstruction tasks on 4 threads, two recon instances in flight)"""
+    from tests import stream_util as su
+    cfg = vs.Config(**ALL)
+    aus, drawn, _ = vs.build_stream(cfg, gop4() + gop4(4, idr=False)[1:], seed=11)
+    stock = vs.decode(vs.REF_SO, aus, threads=4)
+    assert _diff(drawn, stock) == [0] * len(aus)
+    swapped, log = su.decode_swapped_cpu(aus, oracle, threads=4)
+    assert _diff(swapped, stock) == [0] * len(aus)
+
+
+def test_arithmetic_encoder_round_trip():
+    """ref_cabac_encode against the reference's BinDecoder: random context / bypass / terminate sequences come back bin for bin (the generating build
+    reads them with drawn bins, the stock build decodes the bytes — compared through a whole slice in the tests above; here: the stop-bit / carry paths
+    on many short segments, via streams of one tiny picture)."""
+    cfg = vs.Config(width=64, height=64, **INTRA)
+    for seed in range(1, 25):
+        aus, drawn, nbins = vs.build_stream(cfg, [vs.Pic(0)], seed=seed)
+        assert _diff(drawn, vs.decode(vs.REF_SO, aus)) == [0]
+
+
+def test_emulation_prevention_and_exp_golomb():
+    assert vs.escape(bytes([0, 0, 1, 0, 0, 0, 0, 3, 0, 0])) == bytes([0, 0, 3, 1, 0, 0, 3, 0, 0, 3, 3, 0, 0, 3])
+    w = vs.Bits().ue(0).ue(1).ue(2).ue(7).se(1).se(-1).se(0)
+    assert "".join(map(str, w.b)) == "1" "010" "011" "0001000" "010" "011" "1"

@@ -67,6 +67,7 @@ class DecLibReconB200
     // valid[slot]: 0 nothing usable; 1 the owner's final samples are resident; 2 the owner is being reconstructed by a recon instance and its work is not yet
     // in the stream; 3 ... and has been submitted (whatever is submitted later reads the finished samples: one stream, in order)
     std::map<const Picture*, int> slotOf; std::vector<const Picture*> owner; std::vector<uint8_t> valid;
+    std::vector<DecLibReconB200*> instances;                                   // the recon instances on this pool (DecLib keeps two, DecLib.h:70)
     ~Shared() { if( ctx ) b200_ctx_destroy( ctx ); }
   };
   static std::shared_ptr<Shared> sharedFor( const void* key )
@@ -108,6 +109,7 @@ class DecLibReconB200
   std::vector<SliceTabs> m_sl; std::vector<b200_lf_slice> m_lfSlices; PinnedVec<uint8_t> m_ctuSlice;
   int sliceIdx( const Slice* s ) const { for( size_t i = 0; i < m_sl.size(); i++ ) if( m_sl[i].slice == s ) return (int) i; THROW_FATAL( "DecLibReconB200: a CU of a slice the picture does not list" ); }
   bool m_doSao = false, m_doAlf = false, m_doLmcs = false, m_dryRun = false;
+  bool m_finished = false;                 // the current picture has been finished ahead of waitForPrevDecompressedPic() (finishCollocatedPictures)
   // host-stage timing (seconds since decompressPicture): end of preparePicture, first flatten row start (= MIDER done), submit start, submit end, wait end
   std::chrono::steady_clock::time_point m_t0; std::atomic<int64_t> m_tFlat0{ 0 }; double m_stage[6] = { 0, 0, 0, 0, 0, 0 };
   double since() const { return std::chrono::duration<double>( std::chrono::steady_clock::now() - m_t0 ).count(); }
@@ -547,6 +549,7 @@ public:
     CHECK_FATAL( upscaleOutputEnabled, "DecLibReconB200: output upscaling is not part of the device path" );
     m_pool = threadPool; m_id = instanceId; m_numThreads = std::max( 1, threadPool ? threadPool->numThreads() : 1 );
     m_sh = sharedFor( threadPool );
+    { std::lock_guard<std::mutex> l( m_sh->m ); m_sh->instances.push_back( this ); }
 #ifdef B200_GLUE_TEST_HOOKS
     m_dryRun = testHooks().dryRun;
 #endif
@@ -554,7 +557,11 @@ public:
     m_cuDecoders.clear();
     for( int i = 0; i < m_numThreads; i++ ) { m_cuDecoders.emplace_back( new DecCu ); m_cuDecoders.back()->init( nullptr, &m_interPred, nullptr, m_trQuant.get() ); }
   }
-  void destroy() { m_cuDecoders.clear(); m_trQuant.reset(); m_sh.reset(); m_pool = nullptr; }
+  void destroy()
+  {
+    if( m_sh ) { std::lock_guard<std::mutex> l( m_sh->m ); auto& v = m_sh->instances; v.erase( std::remove( v.begin(), v.end(), this ), v.end() ); }
+    m_cuDecoders.clear(); m_trQuant.reset(); m_sh.reset(); m_pool = nullptr;
+  }
   Picture* getCurrPic() const { return m_currDecompPic; }
   void setDpbSlots( int n ) { m_dpbSlots = n; }            // before the first picture; default 17 (MAX_NUM_REF_PICS + the current picture)
   // test hook: run every host stage and keep the work lists (flattened()), without a device
@@ -586,10 +593,26 @@ public:
     m_currDecompPic = pic;
     CodingStructure& cs = *pic->cs; const PreCalcValues& pcv = *cs.pcv;
     pic->progress = Picture::reconstructing;
-    m_failure = nullptr; m_failed.store( false );
+    m_failure = nullptr; m_failed.store( false ); m_finished = false;
     // a picture refused here throws on the caller's thread (DecLib::reconPicture records it in pic->reconDone, DecLib.cpp:618-626); the parked copy makes
     // waitForPrevDecompressedPic() skip the picture instead of finishing work that was never scheduled
-    try { refuse( pic ); prepareAndSchedule( pic ); } catch( ... ) { park( std::current_exception() ); throw; }
+    try { refuse( pic ); finishCollocatedPictures( pic ); prepareAndSchedule( pic ); } catch( ... ) { park( std::current_exception() ); throw; }
+  }
+  // TMVP: MIDER reads the collocated picture's motion field (PU::getColocatedMVP -> CodingStructure::getColInfo), which TaskFinishMotionInfo writes once the
+  // picture's DMVR deltas are known — for this class, when its device work has been fetched.  A collocated picture that is still with another recon instance
+  // (low-delay structures: the picture decoded just before) is therefore finished here, before this picture's MIDER tasks are scheduled; DecLib's later
+  // waitForPrevDecompressedPic() on that instance finds it done.
+  void finishCollocatedPictures( const Picture* pic )
+  {
+    for( const Slice* sl : pic->slices )
+    {
+      if( sl->isIntra() || !sl->getPicHeader()->getEnableTMVPFlag() ) continue;
+      const Picture* col = sl->getRefPic( RefPicList( sl->isInterB() ? 1 - sl->getColFromL0Flag() : 0 ), sl->getColRefIdx() );
+      if( !col ) continue;
+      std::vector<DecLibReconB200*> others;
+      { std::lock_guard<std::mutex> l( m_sh->m ); others = m_sh->instances; }
+      for( DecLibReconB200* o : others ) if( o != this && o->m_currDecompPic == col && !o->m_finished ) o->finishCurrent();
+    }
   }
   void prepareAndSchedule( Picture* pic )
   {
@@ -636,6 +659,15 @@ public:
   {
     if( !m_currDecompPic ) return nullptr;
     Picture* pic = m_currDecompPic;
+    if( !m_finished ) finishCurrent();
+    m_finished = false;
+    if( pic->error || pic->reconDone.hasException() ) cleanupOnException();
+    return std::exchange( m_currDecompPic, nullptr );
+  }
+  void finishCurrent()
+  {
+    Picture* pic = m_currDecompPic;
+    m_finished = true;
     try
     {
       if( m_pool->numThreads() == 0 ) m_pool->processTasksOnMainThread();
@@ -658,8 +690,6 @@ public:
       pic->error = true;
       pic->reconDone.setException( std::current_exception() );
     }
-    if( pic->error || pic->reconDone.hasException() ) cleanupOnException();
-    return std::exchange( m_currDecompPic, nullptr );
   }
 
   // DecLibRecon::cleanupOnException (DecLibRecon.cpp:724): no task of the broken picture may survive in the pool; its device slot is released
