@@ -1,0 +1,43 @@
+"""The DecLibRecon seam from a real BITSTREAM, on the GPU (SURVEY 8c level L2, row f-4; VERDICT r1 item 1 "execute the seam").
+
+A VVC stream written by oracle/vvc_stream.py (see tests/test_stream_cpu.py) is decoded twice through the reference's public API (vvdec_decode / vvdec_flush):
+by the stock library, and by the same library with b200glue::DecLibReconB200 compiled in behind the DecLibRecon seam (oracle/_ref/libvvdec_swapped.so,
+swap_recon.h) — parser, DecLib scheduling, picture list and output of the reference; reconstruction on the device through the C ABI.  All output frames must
+be bit-exact.  (Runs last among the GPU tests: the file name sorts behind test_seam_gpu.py.)"""
+import os, numpy as np, pytest
+from oracle import vvc_stream as vs
+from tests.test_stream_cpu import ALL, INTRA, gop4, low_delay, _diff
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not (vs.available() and os.path.exists(vs.SWAP_SO)), reason="oracle/_ref not built")]
+
+CASES = {
+    "I_all_intra_tools": (dict(INTRA, width=416, height=240), lambda: [vs.Pic(0), vs.Pic(1, idr=True)]),
+    "I_dual_tree_ctu128": (dict(INTRA, width=416, height=240, ctu=128, dual_tree=True), lambda: [vs.Pic(0)]),
+    "gop_all_tools": (dict(ALL, width=416, height=240), gop4),
+    "gop_all_tools_ctu128": (dict(ALL, width=416, height=240, ctu=128), gop4),
+    "gop_ctu32": (dict(ALL, width=256, height=128, ctu=32, max_bt_inter=32, max_tt_inter=32), gop4),
+    "gop_cu_qp_delta": (dict(ALL, width=256, height=128, cu_qp_delta=True), gop4),
+    "low_delay_8": (dict(ALL, width=416, height=240), lambda: low_delay(8)),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_stream_stock_vs_device_decoder(name):
+    from tests import stream_util as su
+    kw, pics = CASES[name]
+    aus, drawn, _ = vs.build_stream(vs.Config(**kw), pics(), seed=3 + len(name))
+    stock = vs.decode(vs.REF_SO, aus, threads=4)
+    assert _diff(drawn, stock) == [0] * len(aus)
+    got = su.decode_swapped_device(aus, threads=4)
+    assert _diff(got, stock) == [0] * len(aus)
+
+
+def test_long_stream_on_the_device():
+    """five GOPs: picture recycling in the reference's PicListManager, slot turnover in the device DPB, two recon instances alternating"""
+    from tests import stream_util as su
+    pics = []
+    for k in range(5): pics += gop4(4 * k, idr=(k == 0))[(0 if k == 0 else 1):]
+    aus, drawn, _ = vs.build_stream(vs.Config(**dict(ALL, width=256, height=128)), pics, seed=9)
+    stock = vs.decode(vs.REF_SO, aus, threads=4)
+    got = su.decode_swapped_device(aus, threads=4)
+    assert _diff(got, stock) == [0] * len(aus)
