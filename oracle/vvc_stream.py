@@ -178,11 +178,98 @@ def write_pps(c):
     return nal_unit(NAL_PPS, w.trailing().bytes())
 
 
+ALF_APS, LMCS_APS, SCALING_LIST_APS = 0, 1, 2
+
+
+def write_aps(aps_type, aps_id, body, chroma_present=True):
+    """HLSyntaxReader::parseAPS (HLSyntaxReader.cpp:855-903): type, id, chroma flag, payload, no extension."""
+    w = Bits().u(3, aps_type).u(5, aps_id).f(chroma_present)
+    body(w)
+    return nal_unit(NAL_PREFIX_APS, w.f(0).trailing().bytes())
+
+
+def random_alf_aps(rng, luma=True, chroma=True, cc=(True, True)):
+    """ALF APS content: luma classes -> up to 25 filters of 12 coded taps (+ clipping indices), up to 8 chroma alternatives of 6 taps, up to 4 cross-component
+    filters of 7 power-of-two taps per chroma component.  Tap magnitudes stay small enough for the sum constraints of the filters' centre taps."""
+    a = dict(luma=None, chroma=None, cc=[None, None])
+    if luma:
+        n = int(rng.integers(1, 26))
+        a["luma"] = dict(clip=bool(rng.integers(0, 2)), n=n, delta_idx=[int(rng.integers(0, n)) for _ in range(25)] if n > 1 else [0] * 25,
+                         coeff=rng.integers(-12, 13, size=(n, 12)).tolist(), clip_idx=rng.integers(0, 4, size=(n, 12)).tolist())
+    if chroma:
+        n = int(rng.integers(1, 9))
+        a["chroma"] = dict(clip=bool(rng.integers(0, 2)), n=n, coeff=rng.integers(-20, 21, size=(n, 6)).tolist(), clip_idx=rng.integers(0, 4, size=(n, 6)).tolist())
+    for k in range(2):
+        if cc[k]:
+            n = int(rng.integers(1, 5))
+            a["cc"][k] = dict(n=n, mapped=rng.integers(0, 5, size=(n, 7)).tolist(), sign=rng.integers(0, 2, size=(n, 7)).tolist())
+    return a
+
+
+def write_alf_aps(aps_id, a):
+    """parseAlfAps / alfFilterCoeffs (HLSyntaxReader.cpp:905-1012, 4659-4710)"""
+    def coeffs(w, n, taps, f):
+        for i in range(n):
+            for j in range(taps):
+                v = f["coeff"][i][j]; w.ue(abs(v))
+                if v: w.f(v < 0)
+        if f["clip"]:
+            for i in range(n):
+                for j in range(taps): w.u(2, f["clip_idx"][i][j])
+    def body(w):
+        w.f(a["luma"] is not None).f(a["chroma"] is not None).f(a["cc"][0] is not None).f(a["cc"][1] is not None)
+        if a["luma"]:
+            f = a["luma"]; w.f(f["clip"]).ue(f["n"] - 1)
+            if f["n"] > 1:
+                bits = (f["n"] - 1).bit_length()
+                for k in range(25): w.u(bits, f["delta_idx"][k])
+            coeffs(w, f["n"], 12, f)
+        if a["chroma"]:
+            f = a["chroma"]; w.f(f["clip"]).ue(f["n"] - 1)
+            for alt in range(f["n"]): coeffs(w, 1, 6, dict(coeff=[f["coeff"][alt]], clip=f["clip"], clip_idx=[f["clip_idx"][alt]]))
+        for k in range(2):
+            f = a["cc"][k]
+            if f:
+                w.ue(f["n"] - 1)
+                for i in range(f["n"]):
+                    for j in range(7):
+                        w.u(3, f["mapped"][i][j])
+                        if f["mapped"][i][j]: w.f(f["sign"][i][j])
+    return write_aps(ALF_APS, aps_id, body)
+
+
+def random_lmcs_aps(rng, bit_depth=10):
+    """LMCS model: bins [min, max] with codeword deltas around OrgCW = 2^bitDepth / 16, the sum of the codewords below 2^bitDepth"""
+    org = (1 << bit_depth) // 16
+    lo, hi = int(rng.integers(0, 3)), int(rng.integers(12, 16))
+    while True:
+        d = rng.integers(-org // 2, org // 2 + 1, size=hi - lo + 1)
+        if (org * len(d) + d.sum()) <= (1 << bit_depth) - 1: break
+    crs_min = max(-7, (org >> 3) - int(org + d.min()))           # lmcsCW[i] + lmcsDeltaCrs stays within [OrgCW >> 3, (OrgCW << 3) - 1] (Reshape.cpp:335)
+    return dict(min_bin=lo, max_bin=hi, delta=d.tolist(), crs=int(rng.integers(crs_min, 8)))
+
+
+def write_lmcs_aps(aps_id, m):
+    """parseLmcsAps (HLSyntaxReader.cpp:1014-1054)"""
+    def body(w):
+        prec = max(1, max(abs(v) for v in m["delta"]).bit_length())
+        w.ue(m["min_bin"]).ue(15 - m["max_bin"]).ue(prec - 1)
+        for v in m["delta"]:
+            w.u(prec, abs(v))
+            if v: w.f(v < 0)
+        w.u(3, abs(m["crs"]))
+        if m["crs"]: w.f(m["crs"] < 0)
+    return write_aps(LMCS_APS, aps_id, body)
+
+
 class Pic(dict):
     """One picture of the stream: poc, slice_type, refs = ([POCs list 0], [POCs list 1]), qp, tid and per-picture tool switches."""
     def __init__(self, poc, slice_type=SLICE_I, refs=((), ()), qp=None, idr=None, referenced=True, **kw):
         super().__init__(poc=poc, slice_type=slice_type, refs=refs, qp=qp, idr=(poc == 0 if idr is None else idr), referenced=referenced,
-                         sao=(True, True), dep_quant=True, sign_hiding=True, temporal_mvp=True, col_from_l0=True, mvd_l1_zero=False, cabac_init=False)
+                         sao=(True, True), dep_quant=True, sign_hiding=True, temporal_mvp=True, col_from_l0=True, mvd_l1_zero=False, cabac_init=False,
+                         aps=[],            # parameter-set NAL units (write_alf_aps / write_lmcs_aps) sent ahead of this picture
+                         alf=None,          # dict(luma=[APS ids], cb=bool, cr=bool, chroma_aps=id, cc_cb=id or None, cc_cr=id or None)
+                         lmcs=None)         # dict(aps=id, chroma_scale=bool)
         bad = set(kw) - set(self); assert not bad, bad
         self.update(kw)
     __getattr__ = dict.__getitem__
@@ -216,7 +303,11 @@ def write_slice(c, p):
     w.f(inter)
     if inter: w.f(0)                                             # ph_intra_slice_allowed_flag: one slice per picture, so inter pictures carry no intra slice
     w.ue(0).u(c.poc_bits, p.poc & ((1 << c.poc_bits) - 1))
-    if c.lmcs: w.f(0)                                            # ph_lmcs_enabled_flag (LMCS needs its APS: see write_lmcs_aps users)
+    if c.lmcs:
+        w.f(p.lmcs is not None)                                  # ph_lmcs_enabled_flag (the slice inherits it: the picture header sits in the slice header)
+        if p.lmcs is not None:
+            w.u(2, p.lmcs["aps"])
+            if c.chroma_format: w.f(p.lmcs.get("chroma_scale", True))
     if c.scaling_lists: w.f(0)
     if not inter:
         if c.cu_qp_delta: w.ue(0)                                # ph_cu_qp_delta_subdiv_intra_slice
@@ -229,7 +320,19 @@ def write_slice(c, p):
     # ---- slice header proper
     if inter: w.ue(p.slice_type)
     if irap: w.f(0)                                              # sh_no_output_of_prior_pics_flag
-    if c.alf: w.f(0)                                             # sh_alf_enabled_flag
+    if c.alf:
+        w.f(p.alf is not None)                                   # sh_alf_enabled_flag
+        if p.alf is not None:
+            a = p.alf
+            w.u(3, len(a["luma"]))
+            for i in a["luma"]: w.u(3, i)
+            if c.chroma_format:
+                w.f(a.get("cb", False)).f(a.get("cr", False))
+                if a.get("cb") or a.get("cr"): w.u(3, a["chroma_aps"])
+            if c.ccalf:
+                for k in ("cc_cb", "cc_cr"):
+                    w.f(a.get(k) is not None)
+                    if a.get(k) is not None: w.u(3, a[k])
     if not irap:                                                 # IDR without sps_idr_rpl_present_flag carries no lists
         for l in (0, 1):
             write_ref_pic_list(w, c, p.poc, p.refs[l])
@@ -261,6 +364,24 @@ def write_slice(c, p):
     w.trailing()                                                 # byte_alignment()
     nal_type = (NAL_IDR_N_LP if irap else NAL_TRAIL)
     return nal_type, w.bytes()
+
+
+def with_alf(pics, rng, cc=True):
+    """every picture sends a new ALF APS (ids cycle through 0..7) and filters with it and the one before it; CC-ALF filters from both"""
+    for i, p in enumerate(pics):
+        p["aps"] = p["aps"] + [write_alf_aps(i % 8, random_alf_aps(rng, cc=(cc, cc)))]
+        p["alf"] = dict(luma=[i % 8] + ([(i - 1) % 8] if i else []), cb=True, cr=bool(i & 1) or i == 0, chroma_aps=i % 8,
+                        cc_cb=(i % 8 if cc else None), cc_cr=((i - 1) % 8 if cc and i else None))
+    return pics
+
+
+def with_lmcs(pics, rng, bit_depth=10, every=1):
+    """pictures send a new LMCS APS (ids cycle through 0..3) and use it, with or without chroma residual scaling"""
+    for i, p in enumerate(pics):
+        if i % every: continue
+        p["aps"] = p["aps"] + [write_lmcs_aps(i % 4, random_lmcs_aps(rng, bit_depth))]
+        p["lmcs"] = dict(aps=i % 4, chroma_scale=bool(i & 1) or i == 0)
+    return pics
 
 
 # ---- libraries -----------------------------------------------------------------------------------------------------------------------------------------
@@ -344,7 +465,8 @@ def build_stream(cfg, pics, seed=1, bias=None, bypass_p=128, max_bypass_run=12):
     for name, p in {**DEFAULT_BIAS, **(bias or {})}.items():
         o, n = sets[name]; gen.gen_set_bias(o, n, p)
     gen.gen_set_bias(-1, 0, bypass_p); gen.gen_set_max_bypass_run(max_bypass_run)
-    aus = [(params if i == 0 else b"") + nal_unit(t, h + b"\x80") for i, (t, h) in enumerate(heads)]
+    pre = [(params if i == 0 else b"") + b"".join(p.aps) for i, p in enumerate(pics)]
+    aus = [pre[i] + nal_unit(t, h + b"\x80") for i, (t, h) in enumerate(heads)]
     drawn = decode(GEN_SO, aus, frame_samples=cfg.width * cfg.height * 3 // 2 + 64)
     nseg = gen.gen_num_segments()
     assert nseg == len(pics), (nseg, len(pics))
@@ -357,6 +479,6 @@ def build_stream(cfg, pics, seed=1, bias=None, bypass_p=128, max_bypass_run=12):
         buf = np.zeros(n // 4 + 64, np.uint8)
         m = ref.ref_cabac_encode(info[0], info[1], ctx, bins, n, buf, len(buf))
         assert m > 0
-        out.append((params if i == 0 else b"") + nal_unit(t, h + bytes(buf[:m])))
+        out.append(pre[i] + nal_unit(t, h + bytes(buf[:m])))
         nbins.append(n)
     return out, drawn, nbins

@@ -265,6 +265,7 @@ def col_motion_diff(a, b, g=None):
 
 def _copy(ptr, n, dtype):
     if not n: return np.zeros(0, dtype)
+    if not ptr: return np.zeros(n, dtype)                        # a table the picture does not use (e.g. no CC-ALF filters)
     return np.frombuffer((C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr), dtype=dtype).copy()
 
 

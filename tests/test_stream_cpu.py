@@ -51,6 +51,12 @@ CASES = {
     "gop_min_cb8_qp20": (dict(ALL, min_cb=8, min_qt_intra=16, min_qt_inter=16, min_qt_intra_c=16, init_qp=20), gop4),
     "gop_no_deblocking": (dict(ALL, deblocking_disabled=True), gop4),
     "low_delay_8": (dict(ALL), lambda: low_delay(8)),
+    "gop_alf": (dict(ALL, alf=True), lambda: vs.with_alf(gop4(), np.random.default_rng(3), cc=False)),
+    "gop_alf_ccalf": (dict(ALL, alf=True, ccalf=True), lambda: vs.with_alf(gop4(), np.random.default_rng(4))),
+    "gop_lmcs": (dict(ALL, lmcs=True), lambda: vs.with_lmcs(gop4(), np.random.default_rng(5))),
+    "I_lmcs_dual_tree": (dict(INTRA, lmcs=True, dual_tree=True), lambda: vs.with_lmcs([vs.Pic(0)], np.random.default_rng(6))),
+    "low_delay_alf_lmcs": (dict(ALL, alf=True, ccalf=True, lmcs=True), lambda: vs.with_lmcs(vs.with_alf(low_delay(6), np.random.default_rng(7)), np.random.default_rng(8), every=2)),
+    "gop_alf_lmcs_8bit": (dict(ALL, alf=True, ccalf=True, lmcs=True, bit_depth=8), lambda: vs.with_lmcs(vs.with_alf(gop4(), np.random.default_rng(9)), np.random.default_rng(10), bit_depth=8)),
 }
 
 

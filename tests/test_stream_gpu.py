@@ -18,6 +18,8 @@ CASES = {
     "gop_ctu32": (dict(ALL, width=256, height=128, ctu=32, max_bt_inter=32, max_tt_inter=32), gop4),
     "gop_cu_qp_delta": (dict(ALL, width=256, height=128, cu_qp_delta=True), gop4),
     "low_delay_8": (dict(ALL, width=416, height=240), lambda: low_delay(8)),
+    "gop_alf_ccalf_lmcs": (dict(ALL, width=416, height=240, alf=True, ccalf=True, lmcs=True), lambda: vs.with_lmcs(vs.with_alf(gop4(), np.random.default_rng(4)), np.random.default_rng(5))),
+    "low_delay_alf_lmcs": (dict(ALL, width=416, height=240, alf=True, ccalf=True, lmcs=True), lambda: vs.with_lmcs(vs.with_alf(low_delay(6), np.random.default_rng(7)), np.random.default_rng(8), every=2)),
 }
 
 

@@ -414,6 +414,9 @@ class DecLibReconB200
       if( m_fltBuf.bufs.empty() ) m_fltBuf.create( pcv.chrFormat, Size( 16, 16 ), pcv.maxCUWidth, 0, MEMORY_ALIGN_DEF_SIZE );
       m_cALF.create( cs.picHeader.get(), &sps, &pps, 1, m_fltBuf );              // fills m_clipDefault for the bit depth
       std::vector<const Slice*> sls; for( const SliceTabs& st : m_sl ) sls.push_back( st.slice );
+      // the per-class tables (lumaCoeffFinal / lumaClippFinal / chrmClippFinal) are derived from the coded APS by the slice PARSE task (DecSlice.cpp:87), which
+      // need not have run yet when DecLib hands the picture over (RECO_WHILE_PARSE): derived here if not done (idempotent, under the APS's own mutex)
+      for( const Slice* sl : sls ) AdaptiveLoopFilter::reconstructCoeffAPSs( *const_cast<Slice*>( sl ) );
       std::vector<AlfSliceBase> bases;
       m_alfTabs = buildAlfTablesOfSlices( sls, &m_cALF.m_fixedFilterSetCoeffDec[0][0], m_cALF.m_clipDefault, m_alfStore, bases );
       for( size_t si = 0; si < m_sl.size(); si++ ) m_sl[si].alf = bases[si];
