@@ -79,6 +79,10 @@ DEFAULTS = dict(
     affine_amvr=False, prof=False, max_sub_merge=5, bcw=False, ciip=False, gpm=False, max_gpm=6, isp=False, mrl=False, mip=False, cclm=False,
     chroma_collocated=(True, False), dep_quant=False, sign_hiding=False, scaling_lists=False,
     init_qp=32, cu_qp_delta=False, cabac_init_present=False, deblocking_disabled=False, beta_offset_div2=0, tc_offset_div2=0,
+    slice_rows=None,               # several rectangular slices in the one tile: CTU rows per slice, e.g. (1, 2, 1); None: one slice, picture header in the slice header
+    lf_across_slices=True, deblocking_override=False,                # in-loop filters across slice borders; per-slice deblocking offsets
+    chroma_qp_offsets=None,        # (cb, cr, joint) PPS offsets; slices add their own (sh_cb_qp_offset ...) and CUs pick from a list (cu_chroma_qp_offset) if set
+    slice_chroma_qp_offsets=False, cu_chroma_qp_offset_list=(),       # list entries: (cb, cr, joint)
 )
 
 
@@ -164,16 +168,42 @@ def write_sps(c):
 
 
 def write_pps(c):
-    """HLSyntaxReader::parsePPS (HLSyntaxReader.cpp:205-850): one tile, one slice (pps_no_pic_partition_flag)."""
+    """HLSyntaxReader::parsePPS (HLSyntaxReader.cpp:205-850): one tile; one slice (pps_no_pic_partition_flag) or rectangular slices of whole CTU rows."""
     w = Bits()
     w.u(6, 0).u(4, 0).f(0).ue(c.width).ue(c.height).f(0).f(0).f(0)      # ids, mixed NAL types, size, conformance / scaling window, output flag
-    w.f(1).f(0)                                                        # no_pic_partition, no sub-picture id mapping
+    multi = c.slice_rows is not None
+    w.f(not multi).f(0)                                                # no_pic_partition, no sub-picture id mapping
+    if multi:
+        wc, hc = -(-c.width // c.ctu), -(-c.height // c.ctu)
+        rows = list(c.slice_rows); n = len(rows)
+        assert n >= 2 and sum(rows) == hc and min(rows) >= 1 and rows[-1] <= rows[-2], "slice_rows: whole CTU rows, the last slice not taller than the one before"
+        w.u(2, log2(c.ctu) - 5).ue(0).ue(0).ue(wc - 1).ue(hc - 1)        # one explicit tile column / row spanning the picture
+        w.f(0)                                                         # (one tile: rectangular slices inferred) pps_single_slice_per_subpic_flag
+        w.ue(n - 1)
+        if n - 1 > 1: w.f(0)                                           # pps_tile_idx_delta_present_flag
+        w.ue(n - 1)                                                    # pps_num_exp_slices_in_tile: all but the last height explicit, the rest of the tile is the last slice
+        for r in rows[:-1]: w.ue(r - 1)
+        w.f(c.lf_across_slices)
     w.f(c.cabac_init_present).ue(0).ue(0).f(0)                         # one active reference per list by default, no rpl1 index
     w.f(c.weighted_pred).f(c.weighted_bipred).f(0)                     # ..., wrap-around
     w.se(c.init_qp - 26).f(c.cu_qp_delta)
-    w.f(0)                                                             # pps_chroma_tool_offsets_present_flag
-    w.f(1).f(0).f(c.deblocking_disabled)                               # deblocking control present, no override, disabled flag
-    if not c.deblocking_disabled: w.se(c.beta_offset_div2).se(c.tc_offset_div2)
+    w.f(c.chroma_qp_offsets is not None)                               # pps_chroma_tool_offsets_present_flag
+    if c.chroma_qp_offsets is not None:
+        cb, cr, joint = c.chroma_qp_offsets
+        w.se(cb).se(cr).f(c.jccr)
+        if c.jccr: w.se(joint)
+        w.f(c.slice_chroma_qp_offsets).f(len(c.cu_chroma_qp_offset_list) > 0)
+        if c.cu_chroma_qp_offset_list:
+            w.ue(len(c.cu_chroma_qp_offset_list) - 1)
+            for e in c.cu_chroma_qp_offset_list:
+                w.se(e[0]).se(e[1])
+                if c.jccr: w.se(e[2])
+    w.f(1).f(c.deblocking_override).f(c.deblocking_disabled)           # deblocking control present, override enabled, disabled flag
+    if multi and c.deblocking_override: w.f(0)                         # pps_dbf_info_in_ph_flag
+    if not c.deblocking_disabled:
+        w.se(c.beta_offset_div2).se(c.tc_offset_div2)
+        if c.chroma_qp_offsets is not None: w.se(c.beta_offset_div2).se(c.tc_offset_div2).se(c.beta_offset_div2).se(c.tc_offset_div2)
+    if multi: w.f(0).f(0).f(0).f(0)                                    # RPL / SAO / ALF / QP delta stay in the slice headers (no weighted-prediction tables in the PH either)
     w.f(0).f(0).f(0)                                                   # PH / SH extension, PPS extension
     return nal_unit(NAL_PPS, w.trailing().bytes())
 
@@ -269,7 +299,9 @@ class Pic(dict):
                          sao=(True, True), dep_quant=True, sign_hiding=True, temporal_mvp=True, col_from_l0=True, mvd_l1_zero=False, cabac_init=False,
                          aps=[],            # parameter-set NAL units (write_alf_aps / write_lmcs_aps) sent ahead of this picture
                          alf=None,          # dict(luma=[APS ids], cb=bool, cr=bool, chroma_aps=id, cc_cb=id or None, cc_cr=id or None)
-                         lmcs=None)         # dict(aps=id, chroma_scale=bool)
+                         lmcs=None,         # dict(aps=id, chroma_scale=bool)
+                         slice_types=None,  # several slices: a type per slice (default: the picture's); I slices may sit in P / B pictures
+                         wp=None)           # seed of the explicit prediction weights (streams with weighted_pred / weighted_bipred)
         bad = set(kw) - set(self); assert not bad, bad
         self.update(kw)
     __getattr__ = dict.__getitem__
@@ -291,79 +323,128 @@ def write_ref_pic_list(w, c, poc, ref_pocs):
         if a > 0: w.f(delta < 0)
 
 
-def write_slice(c, p):
-    """Slice NAL header + picture header in the slice header: parseSliceHeader (HLSyntaxReader.cpp:3438-4065) with parsePictureHeader (:2694-3360)."""
-    inter = p.slice_type != SLICE_I
-    irap = p.idr
-    w = Bits()
-    w.f(1)                                                       # sh_picture_header_in_slice_header_flag
-    # ---- picture_header_structure()
-    w.f(irap).f(not p.referenced)
-    if irap: w.f(0)                                              # ph_gdr_pic_flag
+def write_pred_weight_table(w, c, rng, n_active, slice_type):
+    """parsePredWeightTable (HLSyntaxReader.cpp:4359-4508), tables in the slice header: per list luma flags, chroma flags, then weights / offsets"""
+    denom = int(rng.integers(4, 8)); w.ue(denom)
+    if c.chroma_format: w.se(int(rng.integers(-1, 2)) if denom < 7 else -1)
+    for l in (0, 1):
+        n = n_active[l] if (l == 0 or (slice_type == SLICE_B and c.weighted_bipred)) else 0
+        luma = [bool(rng.integers(0, 2)) for _ in range(n)]; chroma = [bool(rng.integers(0, 2)) for _ in range(n)]
+        for f in luma: w.f(f)
+        if c.chroma_format:
+            for f in chroma: w.f(f)
+        for i in range(n):
+            if luma[i]: w.se(int(rng.integers(-10, 11))).se(int(rng.integers(-20, 21)))
+            if c.chroma_format and chroma[i]:
+                for _ in range(2): w.se(int(rng.integers(-10, 11))).se(int(rng.integers(-30, 31)))
+
+
+def write_picture_header(w, c, p):
+    """picture_header_structure(): parsePictureHeader (HLSyntaxReader.cpp:2694-3360)"""
+    types = slice_types_of(c, p)
+    inter, intra = any(t != SLICE_I for t in types), any(t == SLICE_I for t in types)
+    w.f(p.idr).f(not p.referenced)
+    if p.idr: w.f(0)                                             # ph_gdr_pic_flag
     w.f(inter)
-    if inter: w.f(0)                                             # ph_intra_slice_allowed_flag: one slice per picture, so inter pictures carry no intra slice
+    if inter: w.f(intra)                                         # ph_intra_slice_allowed_flag
     w.ue(0).u(c.poc_bits, p.poc & ((1 << c.poc_bits) - 1))
     if c.lmcs:
-        w.f(p.lmcs is not None)                                  # ph_lmcs_enabled_flag (the slice inherits it: the picture header sits in the slice header)
+        w.f(p.lmcs is not None)                                  # ph_lmcs_enabled_flag
         if p.lmcs is not None:
             w.u(2, p.lmcs["aps"])
             if c.chroma_format: w.f(p.lmcs.get("chroma_scale", True))
     if c.scaling_lists: w.f(0)
-    if not inter:
+    if intra or not inter:
         if c.cu_qp_delta: w.ue(0)                                # ph_cu_qp_delta_subdiv_intra_slice
-    else:
-        if c.cu_qp_delta: w.ue(0)
-        if c.temporal_mvp: w.f(p.temporal_mvp)
-        if c.mmvd and False: w.f(0)                              # ph_fpel_mmvd_enabled_flag only with sps_mmvd_fullpel_only_flag
-        w.f(p.mvd_l1_zero)                                       # RPLs are in the slice header: ph_mvd_l1_zero_flag is always present
-    if c.jccr: w.f(0)                                            # ph_joint_cbcr_sign_flag
-    # ---- slice header proper
-    if inter: w.ue(p.slice_type)
-    if irap: w.f(0)                                              # sh_no_output_of_prior_pics_flag
-    if c.alf:
-        w.f(p.alf is not None)                                   # sh_alf_enabled_flag
-        if p.alf is not None:
-            a = p.alf
-            w.u(3, len(a["luma"]))
-            for i in a["luma"]: w.u(3, i)
-            if c.chroma_format:
-                w.f(a.get("cb", False)).f(a.get("cr", False))
-                if a.get("cb") or a.get("cr"): w.u(3, a["chroma_aps"])
-            if c.ccalf:
-                for k in ("cc_cb", "cc_cr"):
-                    w.f(a.get(k) is not None)
-                    if a.get(k) is not None: w.u(3, a[k])
-    if not irap:                                                 # IDR without sps_idr_rpl_present_flag carries no lists
-        for l in (0, 1):
-            write_ref_pic_list(w, c, p.poc, p.refs[l])
-    n_active = [0, 0]
+        if c.cu_chroma_qp_offset_list: w.ue(0)
     if inter:
-        n0, n1 = len(p.refs[0]), len(p.refs[1])
-        assert n0 >= 1 and (p.slice_type != SLICE_B or n1 >= 1)
-        if n0 > 1 or (p.slice_type == SLICE_B and n1 > 1):
-            w.f(1)                                               # sh_num_ref_idx_active_override_flag: all entries active
-            if n0 > 1: w.ue(n0 - 1)
-            if p.slice_type == SLICE_B and n1 > 1: w.ue(n1 - 1)
-        n_active = [n0, n1 if p.slice_type == SLICE_B else 0]
-        if c.cabac_init_present: w.f(p.cabac_init)
-        if c.temporal_mvp and p.temporal_mvp:
-            if p.slice_type == SLICE_B: w.f(p.col_from_l0)
-            col_l0 = p.col_from_l0 or p.slice_type != SLICE_B
-            if (col_l0 and n_active[0] > 1) or (not col_l0 and n_active[1] > 1): w.ue(0)
-        assert not (c.weighted_pred and p.slice_type == SLICE_P) and not (c.weighted_bipred and p.slice_type == SLICE_B), "pred_weight_table not written"
-    qp = c.init_qp if p.qp is None else p.qp
-    w.se(qp - c.init_qp)
-    if c.sao:
-        w.f(p.sao[0])
-        if c.chroma_format: w.f(p.sao[1])
-    dq = c.dep_quant and p.dep_quant
-    if c.dep_quant: w.f(dq)
-    sdh = c.sign_hiding and not dq and p.sign_hiding
-    if c.sign_hiding and not dq: w.f(sdh)
-    if c.transform_skip and not dq and not sdh: w.f(0)           # sh_ts_residual_coding_disabled_flag
-    w.trailing()                                                 # byte_alignment()
-    nal_type = (NAL_IDR_N_LP if irap else NAL_TRAIL)
-    return nal_type, w.bytes()
+        if c.cu_qp_delta: w.ue(0)
+        if c.cu_chroma_qp_offset_list: w.ue(0)
+        if c.temporal_mvp: w.f(p.temporal_mvp)
+        w.f(p.mvd_l1_zero)                                       # RPLs are in the slice headers: ph_mvd_l1_zero_flag is always present
+    if c.jccr: w.f(0)                                            # ph_joint_cbcr_sign_flag
+
+
+def slice_types_of(c, p):
+    n = len(c.slice_rows) if c.slice_rows is not None else 1
+    return list(p.slice_types) if p.slice_types is not None else [p.slice_type] * n
+
+
+def write_slices(c, p):
+    """The VCL side of one picture: [(nal type, rbsp bytes up to and including byte_alignment())] — a PH NAL first when the picture has several slices.
+    parseSliceHeader (HLSyntaxReader.cpp:3438-4065)."""
+    import numpy as _np
+    types = slice_types_of(c, p)
+    multi = c.slice_rows is not None
+    irap = p.idr
+    nals = []
+    if multi:
+        w = Bits(); write_picture_header(w, c, p); nals.append((NAL_PH, w.trailing().bytes(), False))
+    inter_allowed = any(t != SLICE_I for t in types)
+    for k, st in enumerate(types):
+        inter = st != SLICE_I
+        w = Bits()
+        w.f(not multi)                                           # sh_picture_header_in_slice_header_flag
+        if not multi: write_picture_header(w, c, p)
+        if multi and len(types) > 1: w.u((len(types) - 1).bit_length(), k)     # sh_slice_address: index of the slice in the (only) sub-picture
+        if inter_allowed: w.ue(st)
+        if irap: w.f(0)                                          # sh_no_output_of_prior_pics_flag
+        if c.alf:
+            a = p.alf[k % len(p.alf)] if isinstance(p.alf, (list, tuple)) else p.alf
+            w.f(a is not None)                                   # sh_alf_enabled_flag
+            if a is not None:
+                w.u(3, len(a["luma"]))
+                for i in a["luma"]: w.u(3, i)
+                if c.chroma_format:
+                    w.f(a.get("cb", False)).f(a.get("cr", False))
+                    if a.get("cb") or a.get("cr"): w.u(3, a["chroma_aps"])
+                if c.ccalf:
+                    for key in ("cc_cb", "cc_cr"):
+                        w.f(a.get(key) is not None)
+                        if a.get(key) is not None: w.u(3, a[key])
+        if multi and c.lmcs and p.lmcs is not None: w.f(1)       # sh_lmcs_used_flag
+        refs = [list(p.refs[0]), list(p.refs[1])]
+        if k & 1: refs = [r[::-1] for r in refs]                 # odd slices list the same pictures in the opposite order
+        if not irap:                                             # IDR without sps_idr_rpl_present_flag carries no lists
+            for l in (0, 1): write_ref_pic_list(w, c, p.poc, refs[l])
+        if inter:
+            n0, n1 = len(refs[0]), len(refs[1])
+            assert n0 >= 1 and (st != SLICE_B or n1 >= 1)
+            if n0 > 1 or (st == SLICE_B and n1 > 1):
+                w.f(1)                                           # sh_num_ref_idx_active_override_flag: all entries active
+                if n0 > 1: w.ue(n0 - 1)
+                if st == SLICE_B and n1 > 1: w.ue(n1 - 1)
+            n_active = [n0, n1 if st == SLICE_B else 0]
+            if c.cabac_init_present: w.f(p.cabac_init)
+            if c.temporal_mvp and p.temporal_mvp:
+                if st == SLICE_B: w.f(p.col_from_l0)
+                col_l0 = p.col_from_l0 or st != SLICE_B
+                if (col_l0 and n_active[0] > 1) or (not col_l0 and n_active[1] > 1): w.ue(0)
+            if (c.weighted_pred and st == SLICE_P) or (c.weighted_bipred and st == SLICE_B):
+                write_pred_weight_table(w, c, _np.random.default_rng((p.wp or 0) * 131 + k), n_active, st)
+        qp = (c.init_qp if p.qp is None else p.qp) + (k % 3 - (1 if k else 0)) * 2 * (1 if multi else 0)
+        w.se(qp - c.init_qp)
+        if c.chroma_qp_offsets is not None and c.slice_chroma_qp_offsets:
+            w.se((k % 3) - 1).se(1 - (k % 3))
+            if c.jccr: w.se(k % 2)
+        if c.cu_chroma_qp_offset_list: w.f(1)                    # sh_cu_chroma_qp_offset_enabled_flag
+        if c.sao:
+            sao = p.sao if not multi else (p.sao[0] and k % 3 != 2, p.sao[1] and k % 4 != 3)
+            w.f(sao[0])
+            if c.chroma_format: w.f(sao[1])
+        if c.deblocking_override:
+            w.f(1)                                               # sh_deblocking_params_present_flag
+            if not c.deblocking_disabled: w.f(0)                 # sh_deblocking_filter_disabled_flag
+            w.se((k * 5 + p.poc) % 7 - 3).se((k * 3 + p.poc) % 5 - 2)
+            if c.chroma_qp_offsets is not None: w.se(k % 3 - 1).se(1 - k % 3).se((k + 1) % 3 - 1).se(k % 2)
+        dq = c.dep_quant and p.dep_quant and not (multi and k % 2)
+        if c.dep_quant: w.f(dq)
+        sdh = c.sign_hiding and not dq and p.sign_hiding
+        if c.sign_hiding and not dq: w.f(sdh)
+        if c.transform_skip and not dq and not sdh: w.f(0)       # sh_ts_residual_coding_disabled_flag
+        w.trailing()                                             # byte_alignment()
+        nals.append((NAL_IDR_N_LP if irap else NAL_TRAIL, w.bytes(), True))
+    return nals
 
 
 def with_alf(pics, rng, cc=True):
@@ -457,7 +538,7 @@ def build_stream(cfg, pics, seed=1, bias=None, bypass_p=128, max_bypass_run=12):
     """Writes the stream for `pics` (decoding order).  Returns (access units, frames the generating library reconstructed, bins per slice)."""
     gen, ref = _lib(GEN_SO), _lib(REF_SO)
     params = write_sps(cfg) + write_pps(cfg)
-    heads = [write_slice(cfg, p) for p in pics]
+    heads = [write_slices(cfg, p) for p in pics]                  # per picture: [(nal type, header bytes, is a slice)]
     # step 2: draw the slice data
     gen.gen_reset(seed)
     sets = ctx_sets()
@@ -466,19 +547,22 @@ def build_stream(cfg, pics, seed=1, bias=None, bypass_p=128, max_bypass_run=12):
         o, n = sets[name]; gen.gen_set_bias(o, n, p)
     gen.gen_set_bias(-1, 0, bypass_p); gen.gen_set_max_bypass_run(max_bypass_run)
     pre = [(params if i == 0 else b"") + b"".join(p.aps) for i, p in enumerate(pics)]
-    aus = [pre[i] + nal_unit(t, h + b"\x80") for i, (t, h) in enumerate(heads)]
+    aus = [pre[i] + b"".join(nal_unit(t, h + (b"\x80" if vcl else b"")) for t, h, vcl in nals) for i, nals in enumerate(heads)]
     drawn = decode(GEN_SO, aus, frame_samples=cfg.width * cfg.height * 3 // 2 + 64)
     nseg = gen.gen_num_segments()
-    assert nseg == len(pics), (nseg, len(pics))
+    assert nseg == sum(vcl for nals in heads for _, _, vcl in nals), (nseg, len(pics))
     # step 3: encode and splice
-    out, nbins = [], []
-    for i, (t, h) in enumerate(heads):
-        info = (C.c_int * 3)(); n = gen.gen_segment(i, info, None, None, 0)
-        ctx = np.zeros(n, np.int16); bins = np.zeros(n, np.uint8)
-        gen.gen_segment(i, info, ctx.ctypes.data, bins.ctypes.data, n)
-        buf = np.zeros(n // 4 + 64, np.uint8)
-        m = ref.ref_cabac_encode(info[0], info[1], ctx, bins, n, buf, len(buf))
-        assert m > 0
-        out.append(pre[i] + nal_unit(t, h + bytes(buf[:m])))
-        nbins.append(n)
+    out, nbins, seg = [], [], 0
+    for i, nals in enumerate(heads):
+        au = pre[i]
+        for t, h, vcl in nals:
+            if not vcl: au += nal_unit(t, h); continue
+            info = (C.c_int * 3)(); n = gen.gen_segment(seg, info, None, None, 0)
+            ctx = np.zeros(n, np.int16); bins = np.zeros(n, np.uint8)
+            gen.gen_segment(seg, info, ctx.ctypes.data, bins.ctypes.data, n)
+            buf = np.zeros(n // 4 + 64, np.uint8)
+            m = ref.ref_cabac_encode(info[0], info[1], ctx, bins, n, buf, len(buf))
+            assert m > 0
+            au += nal_unit(t, h + bytes(buf[:m])); nbins.append(n); seg += 1
+        out.append(au)
     return out, drawn, nbins

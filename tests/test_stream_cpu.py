@@ -37,6 +37,18 @@ def low_delay(n):
     return pics
 
 
+def _mixed_slice_types():
+    pics = gop4()
+    for q in pics[1:]: q["slice_types"] = [q.slice_type, vs.SLICE_I, q.slice_type]        # an intra slice between two inter slices
+    return pics
+
+
+def _weighted(pics):
+    for i, q in enumerate(pics): q["wp"] = 40 + i
+    return pics
+
+
+SL3 = dict(width=256, height=256, slice_rows=(2, 1, 1))
 CASES = {
     "I_all_intra_tools": (dict(INTRA), lambda: [vs.Pic(0)]),
     "I_dual_tree_ctu128": (dict(INTRA, ctu=128, dual_tree=True), lambda: [vs.Pic(0), vs.Pic(1, idr=True)]),
@@ -51,6 +63,15 @@ CASES = {
     "gop_min_cb8_qp20": (dict(ALL, min_cb=8, min_qt_intra=16, min_qt_inter=16, min_qt_intra_c=16, init_qp=20), gop4),
     "gop_no_deblocking": (dict(ALL, deblocking_disabled=True), gop4),
     "low_delay_8": (dict(ALL), lambda: low_delay(8)),
+    "gop_3slices": (dict(ALL, **SL3), gop4),                                                                       # per-slice QP, SAO switches, reference order, dep. quant
+    "gop_4slices_no_lf_across_deblock_override": (dict(ALL, width=256, height=256, slice_rows=(1, 1, 1, 1), lf_across_slices=False, deblocking_override=True), gop4),
+    "gop_intra_slice_in_inter_pictures": (dict(ALL, **SL3), _mixed_slice_types),
+    "gop_3slices_alf_lmcs": (dict(ALL, **SL3, alf=True, ccalf=True, lmcs=True, lf_across_slices=False),
+                             lambda: vs.with_lmcs(vs.with_alf(gop4(), np.random.default_rng(11)), np.random.default_rng(12))),
+    "gop_weighted_prediction": (dict(ALL, weighted_pred=True, weighted_bipred=True), lambda: _weighted(gop4())),
+    "low_delay_weighted_3slices": (dict(ALL, weighted_pred=True, weighted_bipred=True, **SL3), lambda: _weighted(low_delay(5))),
+    "gop_chroma_qp_offsets": (dict(ALL, chroma_qp_offsets=(2, -3, 1), slice_chroma_qp_offsets=True), gop4),
+    "gop_cu_chroma_qp_offsets": (dict(ALL, chroma_qp_offsets=(1, -1, 0), cu_chroma_qp_offset_list=((2, -2, 1), (-3, 3, -1), (5, 4, 3)), cu_qp_delta=True), gop4),
     "gop_alf": (dict(ALL, alf=True), lambda: vs.with_alf(gop4(), np.random.default_rng(3), cc=False)),
     "gop_alf_ccalf": (dict(ALL, alf=True, ccalf=True), lambda: vs.with_alf(gop4(), np.random.default_rng(4))),
     "gop_lmcs": (dict(ALL, lmcs=True), lambda: vs.with_lmcs(gop4(), np.random.default_rng(5))),

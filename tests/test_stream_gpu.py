@@ -6,7 +6,7 @@ swap_recon.h) — parser, DecLib scheduling, picture list and output of the refe
 be bit-exact.  (Runs last among the GPU tests: the file name sorts behind test_seam_gpu.py.)"""
 import os, numpy as np, pytest
 from oracle import vvc_stream as vs
-from tests.test_stream_cpu import ALL, INTRA, gop4, low_delay, _diff
+from tests.test_stream_cpu import ALL, INTRA, SL3, gop4, low_delay, _diff, _mixed_slice_types, _weighted
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not (vs.available() and os.path.exists(vs.SWAP_SO)), reason="oracle/_ref not built")]
 
@@ -19,6 +19,10 @@ CASES = {
     "gop_cu_qp_delta": (dict(ALL, width=256, height=128, cu_qp_delta=True), gop4),
     "low_delay_8": (dict(ALL, width=416, height=240), lambda: low_delay(8)),
     "gop_alf_ccalf_lmcs": (dict(ALL, width=416, height=240, alf=True, ccalf=True, lmcs=True), lambda: vs.with_lmcs(vs.with_alf(gop4(), np.random.default_rng(4)), np.random.default_rng(5))),
+    "gop_intra_slice_in_inter_pictures": (dict(ALL, **SL3), _mixed_slice_types),
+    "gop_3slices_alf_lmcs_no_lf_across": (dict(ALL, **SL3, alf=True, ccalf=True, lmcs=True, lf_across_slices=False),
+                                          lambda: vs.with_lmcs(vs.with_alf(gop4(), np.random.default_rng(11)), np.random.default_rng(12))),
+    "gop_weighted_prediction": (dict(ALL, width=416, height=240, weighted_pred=True, weighted_bipred=True), lambda: _weighted(gop4())),
     "low_delay_alf_lmcs": (dict(ALL, width=416, height=240, alf=True, ccalf=True, lmcs=True), lambda: vs.with_lmcs(vs.with_alf(low_delay(6), np.random.default_rng(7)), np.random.default_rng(8), every=2)),
 }
 
