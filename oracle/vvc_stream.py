@@ -236,7 +236,7 @@ def random_alf_aps(rng, luma=True, chroma=True, cc=(True, True)):
     return a
 
 
-def write_alf_aps(aps_id, a):
+def write_alf_aps(aps_id, a, chroma_present=True):
     """parseAlfAps / alfFilterCoeffs (HLSyntaxReader.cpp:905-1012, 4659-4710)"""
     def coeffs(w, n, taps, f):
         for i in range(n):
@@ -247,7 +247,9 @@ def write_alf_aps(aps_id, a):
             for i in range(n):
                 for j in range(taps): w.u(2, f["clip_idx"][i][j])
     def body(w):
-        w.f(a["luma"] is not None).f(a["chroma"] is not None).f(a["cc"][0] is not None).f(a["cc"][1] is not None)
+        w.f(a["luma"] is not None)
+        if chroma_present: w.f(a["chroma"] is not None).f(a["cc"][0] is not None).f(a["cc"][1] is not None)
+        else: assert a["chroma"] is None and a["cc"] == [None, None]
         if a["luma"]:
             f = a["luma"]; w.f(f["clip"]).ue(f["n"] - 1)
             if f["n"] > 1:
@@ -265,7 +267,7 @@ def write_alf_aps(aps_id, a):
                     for j in range(7):
                         w.u(3, f["mapped"][i][j])
                         if f["mapped"][i][j]: w.f(f["sign"][i][j])
-    return write_aps(ALF_APS, aps_id, body)
+    return write_aps(ALF_APS, aps_id, body, chroma_present)
 
 
 def random_lmcs_aps(rng, bit_depth=10):
@@ -279,7 +281,7 @@ def random_lmcs_aps(rng, bit_depth=10):
     return dict(min_bin=lo, max_bin=hi, delta=d.tolist(), crs=int(rng.integers(crs_min, 8)))
 
 
-def write_lmcs_aps(aps_id, m):
+def write_lmcs_aps(aps_id, m, chroma_present=True):
     """parseLmcsAps (HLSyntaxReader.cpp:1014-1054)"""
     def body(w):
         prec = max(1, max(abs(v) for v in m["delta"]).bit_length())
@@ -287,9 +289,57 @@ def write_lmcs_aps(aps_id, m):
         for v in m["delta"]:
             w.u(prec, abs(v))
             if v: w.f(v < 0)
-        w.u(3, abs(m["crs"]))
-        if m["crs"]: w.f(m["crs"] < 0)
-    return write_aps(LMCS_APS, aps_id, body)
+        if chroma_present:
+            w.u(3, abs(m["crs"]))
+            if m["crs"]: w.f(m["crs"] < 0)
+    return write_aps(LMCS_APS, aps_id, body, chroma_present)
+
+
+def _diag_scan8():
+    """the 8x8 up-right diagonal scan as (x, y) pairs (g_scanOrder[SCAN_UNGROUPED]: anti-diagonals from the bottom-left end)"""
+    out = []
+    for d in range(15):
+        for y in range(min(d, 7), -1, -1):
+            x = d - y
+            if x < 8: out.append((x, y))
+    return out
+
+
+def random_scaling_list_aps(rng):
+    """28 lists (2 of 2x2, 6 of 4x4, 20 of 8x8 with a DC value from the 16x16 lists on): each either copied (from the flat 16 default or an earlier list) or
+    coded explicitly as DPCM of values around 16"""
+    lists = []
+    for i in range(28):
+        n = 2 if i < 2 else 4 if i < 8 else 8
+        max_delta = i if i < 2 else (i - 2 if i < 8 else i - 8)
+        if rng.random() < 0.35:
+            lists.append(dict(copy=True, pred_delta=int(rng.integers(0, max_delta + 1)) if i not in (0, 2, 8) else 0))
+        else:
+            walk = np.clip(16 + np.cumsum(rng.integers(-3, 4, size=n * n + 1)), 4, 120)
+            lists.append(dict(copy=False, dc=int(walk[0]), values=[int(v) for v in walk[1:]]))
+    return lists
+
+
+def write_scaling_list_aps(aps_id, lists, chroma_present=True):
+    """parseScalingList / decodeScalingList (HLSyntaxReader.cpp:4509-4628): copy mode or explicit DPCM (no prediction from another list + deltas)"""
+    scan = _diag_scan8()
+    def body(w):
+        for i, l in enumerate(lists):
+            if not chroma_present and i % 3 != 2 and i != 27: continue      # (luma lists only: ScalingList::isLumaScalingList)
+            w.f(l["copy"])
+            if l["copy"]:
+                if i not in (0, 2, 8): w.ue(l["pred_delta"])
+                continue
+            w.f(0)                                                          # scaling_list_pred_mode_flag
+            n = 2 if i < 2 else 4 if i < 8 else 8
+            nxt = 0
+            if i > 13:
+                w.se(l["dc"] - 8); nxt = l["dc"] - 8
+            for k in range(n * n):
+                if i > 25 and scan[k][0] >= 4 and scan[k][1] >= 4: continue
+                d = (l["values"][k] - 8) - nxt
+                w.se(d); nxt += d
+    return write_aps(SCALING_LIST_APS, aps_id, body, chroma_present)
 
 
 class Pic(dict):
@@ -301,7 +351,8 @@ class Pic(dict):
                          alf=None,          # dict(luma=[APS ids], cb=bool, cr=bool, chroma_aps=id, cc_cb=id or None, cc_cr=id or None)
                          lmcs=None,         # dict(aps=id, chroma_scale=bool)
                          slice_types=None,  # several slices: a type per slice (default: the picture's); I slices may sit in P / B pictures
-                         wp=None)           # seed of the explicit prediction weights (streams with weighted_pred / weighted_bipred)
+                         wp=None,           # seed of the explicit prediction weights (streams with weighted_pred / weighted_bipred)
+                         scaling_list=None) # id of the scaling-list APS the picture quantises with
         bad = set(kw) - set(self); assert not bad, bad
         self.update(kw)
     __getattr__ = dict.__getitem__
@@ -353,7 +404,9 @@ def write_picture_header(w, c, p):
         if p.lmcs is not None:
             w.u(2, p.lmcs["aps"])
             if c.chroma_format: w.f(p.lmcs.get("chroma_scale", True))
-    if c.scaling_lists: w.f(0)
+    if c.scaling_lists:
+        w.f(p.scaling_list is not None)                          # ph_explicit_scaling_list_enabled_flag
+        if p.scaling_list is not None: w.u(3, p.scaling_list)
     if intra or not inter:
         if c.cu_qp_delta: w.ue(0)                                # ph_cu_qp_delta_subdiv_intra_slice
         if c.cu_chroma_qp_offset_list: w.ue(0)
@@ -403,6 +456,7 @@ def write_slices(c, p):
                         w.f(a.get(key) is not None)
                         if a.get(key) is not None: w.u(3, a[key])
         if multi and c.lmcs and p.lmcs is not None: w.f(1)       # sh_lmcs_used_flag
+        if multi and c.scaling_lists and p.scaling_list is not None: w.f(1)     # sh_explicit_scaling_list_used_flag
         refs = [list(p.refs[0]), list(p.refs[1])]
         if k & 1: refs = [r[::-1] for r in refs]                 # odd slices list the same pictures in the opposite order
         if not irap:                                             # IDR without sps_idr_rpl_present_flag carries no lists
@@ -447,20 +501,33 @@ def write_slices(c, p):
     return nals
 
 
-def with_alf(pics, rng, cc=True):
+def with_alf(pics, rng, cc=True, chroma=True):
     """every picture sends a new ALF APS (ids cycle through 0..7) and filters with it and the one before it; CC-ALF filters from both"""
     for i, p in enumerate(pics):
-        p["aps"] = p["aps"] + [write_alf_aps(i % 8, random_alf_aps(rng, cc=(cc, cc)))]
+        p["aps"] = p["aps"] + [write_alf_aps(i % 8, random_alf_aps(rng, chroma=chroma, cc=(cc and chroma, cc and chroma)), chroma)]
+        if not chroma:
+            p["alf"] = dict(luma=[i % 8] + ([(i - 1) % 8] if i else [])); continue
         p["alf"] = dict(luma=[i % 8] + ([(i - 1) % 8] if i else []), cb=True, cr=bool(i & 1) or i == 0, chroma_aps=i % 8,
                         cc_cb=(i % 8 if cc else None), cc_cr=((i - 1) % 8 if cc and i else None))
     return pics
 
 
-def with_lmcs(pics, rng, bit_depth=10, every=1):
+def with_scaling_lists(pics, rng, chroma_present=True):
+    """every other picture sends a new scaling-list APS (ids cycle through 0..7); all pictures quantise with the latest"""
+    last = None
+    for i, p in enumerate(pics):
+        if i % 2 == 0:
+            last = (i // 2) % 8
+            p["aps"] = p["aps"] + [write_scaling_list_aps(last, random_scaling_list_aps(rng), chroma_present)]
+        p["scaling_list"] = last
+    return pics
+
+
+def with_lmcs(pics, rng, bit_depth=10, every=1, chroma=True):
     """pictures send a new LMCS APS (ids cycle through 0..3) and use it, with or without chroma residual scaling"""
     for i, p in enumerate(pics):
         if i % every: continue
-        p["aps"] = p["aps"] + [write_lmcs_aps(i % 4, random_lmcs_aps(rng, bit_depth))]
+        p["aps"] = p["aps"] + [write_lmcs_aps(i % 4, random_lmcs_aps(rng, bit_depth), chroma)]
         p["lmcs"] = dict(aps=i % 4, chroma_scale=bool(i & 1) or i == 0)
     return pics
 

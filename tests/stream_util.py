@@ -39,7 +39,7 @@ class OracleDevice:
                 h, w = out[c].shape
                 dst = np.ctypeslib.as_array(planes[c], shape=((h - 1) * strides[c] + w,))
                 np.lib.stride_tricks.as_strided(dst, shape=(h, w), strides=(strides[c] * 2, 2))[...] = out[c]
-            self.log.append(dict(poc=poc, slot=int(st.dstSlot), pus=int(st.numPus), tus=int(st.numTus), intra=int(st.numIntraTus), flags=int(st.flags)))
+            self.log.append(dict(poc=poc, slot=int(st.dstSlot), pus=int(st.numPus), tus=int(st.numTus), intra=int(st.numIntraTus), flags=int(st.flags), scaling=int(st.numScaling), wp=int(st.numWp), lfSlices=int(st.numLfSlices)))
         except BaseException as e:                                # never unwind through the C++ frames
             import traceback; self.error = traceback.format_exc()
 

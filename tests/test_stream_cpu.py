@@ -72,6 +72,12 @@ CASES = {
     "low_delay_weighted_3slices": (dict(ALL, weighted_pred=True, weighted_bipred=True, **SL3), lambda: _weighted(low_delay(5))),
     "gop_chroma_qp_offsets": (dict(ALL, chroma_qp_offsets=(2, -3, 1), slice_chroma_qp_offsets=True), gop4),
     "gop_cu_chroma_qp_offsets": (dict(ALL, chroma_qp_offsets=(1, -1, 0), cu_chroma_qp_offset_list=((2, -2, 1), (-3, 3, -1), (5, 4, 3)), cu_qp_delta=True), gop4),
+    "gop_scaling_lists": (dict(ALL, scaling_lists=True), lambda: vs.with_scaling_lists(gop4(), np.random.default_rng(13))),
+    "gop_scaling_lists_3slices_lmcs": (dict(ALL, scaling_lists=True, lmcs=True, **SL3),
+                                       lambda: vs.with_lmcs(vs.with_scaling_lists(gop4(), np.random.default_rng(14)), np.random.default_rng(15))),
+    "gop_monochrome": (dict(ALL, chroma_format=0, cclm=False, jccr=False), gop4),
+    "gop_monochrome_lmcs_alf": (dict(ALL, chroma_format=0, cclm=False, jccr=False, lmcs=True, alf=True),
+                                lambda: vs.with_alf(vs.with_lmcs(gop4(), np.random.default_rng(16), chroma=False), np.random.default_rng(17), chroma=False)),
     "gop_alf": (dict(ALL, alf=True), lambda: vs.with_alf(gop4(), np.random.default_rng(3), cc=False)),
     "gop_alf_ccalf": (dict(ALL, alf=True, ccalf=True), lambda: vs.with_alf(gop4(), np.random.default_rng(4))),
     "gop_lmcs": (dict(ALL, lmcs=True), lambda: vs.with_lmcs(gop4(), np.random.default_rng(5))),
@@ -105,6 +111,9 @@ def test_stream_stock_vs_swapped_decoder(name, seed, oracle):
     assert len(log) == len(aus)                                         # every picture went through the drop-in class
     assert _diff(swapped, stock) == [0] * len(aus)
     assert any(f[0].std() > 1 for f in stock)                           # not a flat picture
+    if "scaling_lists" in name: assert all(l["scaling"] > 0 for l in log)            # the tools the case is about reached the work lists
+    if "weighted" in name: assert any(l["wp"] > 0 for l in log)
+    if "slices" in name: assert all(l["lfSlices"] == len(cfg.slice_rows) for l in log)
 
 
 def test_long_stream_recycles_pictures_and_slots(oracle):
