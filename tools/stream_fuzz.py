@@ -1,0 +1,87 @@
+"""Randomised bitstream fuzz of the DecLibRecon seam on the CPU (test infrastructure): random parameter sets / GOP structures / tool switches through
+oracle/vvc_stream.py, decoded by the stock reference and by the swapped build with the oracle chain as the device (tests/stream_util.py).
+    python tools/stream_fuzz.py FIRST_SEED COUNT
+Prints one line per stream; exit code 1 if any stream differed."""
+import sys, os, numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import vvc_stream as vs
+from tests import helpers, stream_util as su
+from tests.test_stream_cpu import INTRA, INTER, gop4, low_delay, _diff
+
+
+def random_case(seed):
+    r = np.random.default_rng(seed)
+    pick = lambda *a: a[int(r.integers(len(a)))]
+    kw = {k: bool(r.integers(0, 4)) for k in list(INTRA) + list(INTER)}          # each tool on with probability 3/4
+    kw["mts_intra"] &= kw["mts"]; kw["mts_inter"] &= kw["mts"]; kw["sbtmvp"] &= kw["temporal_mvp"]
+    kw["affine_6param"] &= kw["affine"]; kw["prof"] &= kw["affine"]; kw["affine_amvr"] &= kw["affine"] and kw["amvr"]
+    ctu = pick(32, 64, 128)
+    kw.update(ctu=ctu, bit_depth=pick(8, 10, 10), init_qp=int(r.integers(18, 40)), cu_qp_delta=bool(r.integers(0, 2)), max_merge=int(r.integers(1, 7)),
+              dual_tree=bool(r.integers(0, 2)), transform_skip=bool(r.integers(0, 2)), deblocking_disabled=r.random() < 0.15,
+              beta_offset_div2=int(r.integers(-3, 4)), tc_offset_div2=int(r.integers(-3, 4)), cabac_init_present=bool(r.integers(0, 2)),
+              chroma_collocated=(bool(r.integers(0, 2)), bool(r.integers(0, 2))), max_tb64=bool(r.integers(0, 4)))
+    kw["bdpcm"] = kw["transform_skip"] and bool(r.integers(0, 2))
+    kw["max_gpm"] = int(r.integers(2, kw["max_merge"] + 1)) if kw["max_merge"] >= 2 else 2
+    if kw["max_merge"] < 2: kw["gpm"] = False
+    kw["max_sub_merge"] = int(r.integers(1 if kw["sbtmvp"] else 0, 6)) if kw["affine"] else 5
+    if ctu == 32: kw.update(max_bt_inter=32, max_tt_inter=32)
+    if r.random() < 0.3: kw.update(min_cb=8, min_qt_intra=16, min_qt_inter=16, min_qt_intra_c=16)
+    mono = r.random() < 0.1
+    if mono: kw.update(chroma_format=0, cclm=False, jccr=False, dual_tree=False)
+    wc = int(r.integers(2, 5)); hc = int(r.integers(2, 5))
+    W = wc * ctu - pick(0, 0, 8, 24 if ctu > 32 else 8); H = hc * ctu - pick(0, 0, 8, 16)
+    if ctu == 128: W, H = min(W, 384), min(H, 256)
+    kw.update(width=W, height=H)
+    rows = -(-H // ctu)
+    if rows >= 2 and r.random() < 0.4:
+        n = int(r.integers(2, rows + 1)); cut = sorted(r.choice(np.arange(1, rows), size=n - 1, replace=False).tolist())
+        sl = [b - a for a, b in zip([0] + cut, cut + [rows])]
+        if sl[-1] > sl[-2]: sl[-1], sl[-2] = sl[-2], sl[-1]
+        kw.update(slice_rows=tuple(sl), lf_across_slices=bool(r.integers(0, 2)), deblocking_override=bool(r.integers(0, 2)))
+    if not mono and r.random() < 0.4:
+        kw.update(chroma_qp_offsets=(int(r.integers(-4, 5)), int(r.integers(-4, 5)), int(r.integers(-4, 5))), slice_chroma_qp_offsets=bool(r.integers(0, 2)))
+        if r.random() < 0.5: kw["cu_chroma_qp_offset_list"] = tuple((int(r.integers(-5, 6)), int(r.integers(-5, 6)), int(r.integers(-5, 6))) for _ in range(int(r.integers(1, 5))))
+    structure = pick("gop", "gop", "low_delay", "intra")
+    pics = gop4() + (gop4(4, idr=False)[1:] if r.random() < 0.3 else []) if structure == "gop" else low_delay(int(r.integers(3, 7))) if structure == "low_delay" else [vs.Pic(0), vs.Pic(1, idr=True)]
+    if r.random() < 0.3 and structure != "intra":
+        kw.update(weighted_pred=True, weighted_bipred=bool(r.integers(0, 2)))
+        for i, q in enumerate(pics): q["wp"] = seed * 7 + i
+    if r.random() < 0.5:
+        kw.update(alf=True, ccalf=(not mono) and bool(r.integers(0, 2))); vs.with_alf(pics, r, cc=kw["ccalf"], chroma=not mono)
+    if r.random() < 0.4:
+        kw["lmcs"] = True; vs.with_lmcs(pics, r, bit_depth=kw["bit_depth"], every=pick(1, 2), chroma=not mono)
+        for q in pics:                                                  # (a picture without its own model keeps LMCS off)
+            pass
+    if r.random() < 0.3:
+        kw["scaling_lists"] = True; vs.with_scaling_lists(pics, r, chroma_present=not mono)
+    if kw.get("slice_rows") and structure != "intra" and r.random() < 0.5:
+        n = len(kw["slice_rows"])
+        for q in pics[1:]: q["slice_types"] = [vs.SLICE_I if (k + q.poc) % 3 == 1 else q.slice_type for k in range(n)]
+        if kw.get("weighted_pred"): pass
+    for q in pics:
+        q["qp"] = kw["init_qp"] + int(r.integers(-4, 5)); q["dep_quant"] = bool(r.integers(0, 2)); q["sign_hiding"] = bool(r.integers(0, 2))
+        q["sao"] = (bool(r.integers(0, 4)), bool(r.integers(0, 4))); q["mvd_l1_zero"] = r.random() < 0.2; q["col_from_l0"] = bool(r.integers(0, 2)); q["cabac_init"] = bool(r.integers(0, 2))
+    return kw, pics, structure
+
+
+if __name__ == "__main__":
+    first, count = int(sys.argv[1]), int(sys.argv[2])
+    oracle = helpers.load_oracle(); bad = 0
+    for seed in range(first, first + count):
+        kw, pics, structure = random_case(seed)
+        tag = f"{seed} {structure} {kw['width']}x{kw['height']} ctu{kw['ctu']} {kw['bit_depth']}b slices={kw.get('slice_rows')} " + "".join(k[0] for k in ("alf", "lmcs", "scaling_lists", "weighted_pred") if kw.get(k))
+        try:
+            aus, drawn, nb = vs.build_stream(vs.Config(**kw), pics, seed=seed)
+        except (vs.DecodeError, AssertionError) as e:
+            print(tag, "not drawn:", str(e)[-220:].replace("\n", " "), flush=True); continue
+        stock = vs.decode(vs.REF_SO, aus)
+        d0 = _diff(drawn, stock)
+        try:
+            sw, log = su.decode_swapped_cpu(aus, oracle, threads=int(seed % 3 == 0) * 3 + 1)
+            d1 = _diff(sw, stock)
+        except Exception as e:
+            d1 = "FAILED " + str(e)[-300:].replace("\n", " ")
+        ok = d0 == [0] * len(aus) and d1 == [0] * len(aus)
+        bad += not ok
+        print(tag, "bins", sum(nb), "OK" if ok else f"DIFF writer {d0} seam {d1}", flush=True)
+    sys.exit(1 if bad else 0)
