@@ -22,6 +22,7 @@ class OracleDevice:
     """Stands where the device would: reconstructs every flattened picture with the oracle chain and keeps the decoded-picture buffer by slot."""
     def __init__(self, oracle):
         self.oracle, self.dpb, self.log, self.error = oracle, None, [], None
+        self.keep, self.pics = False, {}                            # keep: the flattened lists of every picture by POC (diagnosis)
         self.cb = _HOOK(self._picture)
 
     def _picture(self, user, lists, geom, dmvr, ndmvr, planes, strides, poc):
@@ -33,6 +34,7 @@ class OracleDevice:
             pic = helpers.picture_from_struct(st, g, None)
             out, dm = helpers.oracle_decompress(self.oracle, g, self.dpb, pic)
             self.dpb[st.dstSlot] = out
+            if self.keep: self.pics[poc] = pic
             n = min(int(ndmvr), len(dm))
             for i in range(n): dmvr[2 * i], dmvr[2 * i + 1] = int(dm[i][0]), int(dm[i][1])
             for c in range(3 if g.chromaFormat else 1):
@@ -44,9 +46,11 @@ class OracleDevice:
             import traceback; self.error = traceback.format_exc()
 
 
-def decode_swapped_cpu(aus, oracle, threads=1, **kw):
-    """The stream through the swapped build without a device: glue host stages + oracle chain.  Returns (frames, per-picture log)."""
+def decode_swapped_cpu(aus, oracle, threads=1, keep=None, **kw):
+    """The stream through the swapped build without a device: glue host stages + oracle chain.  Returns (frames, per-picture log).
+    keep: a dict that receives the flattened work lists of every picture by POC."""
     lib = swapped_lib(); dev = OracleDevice(oracle)
+    if keep is not None: dev.keep, dev.pics = True, keep
     lib.swapped_set_hooks(1, C.cast(dev.cb, C.c_void_p), None)
     try:
         frames = vs.decode(vs.SWAP_SO, aus, threads=threads, **kw)

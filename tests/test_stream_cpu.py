@@ -63,6 +63,7 @@ CASES = {
     "gop_min_cb8_qp20": (dict(ALL, min_cb=8, min_qt_intra=16, min_qt_inter=16, min_qt_intra_c=16, init_qp=20), gop4),
     "gop_no_deblocking": (dict(ALL, deblocking_disabled=True), gop4),
     "low_delay_8": (dict(ALL), lambda: low_delay(8)),
+    "gop_max_transform_32": (dict(ALL, max_tb64=False), gop4),                                                      # 64x64 CUs carry four TUs; CIIP still predicts the CU block
     "gop_3slices": (dict(ALL, **SL3), gop4),                                                                       # per-slice QP, SAO switches, reference order, dep. quant
     "gop_4slices_no_lf_across_deblock_override": (dict(ALL, width=256, height=256, slice_rows=(1, 1, 1, 1), lf_across_slices=False, deblocking_override=True), gop4),
     "gop_intra_slice_in_inter_pictures": (dict(ALL, **SL3), _mixed_slice_types),

@@ -19,6 +19,7 @@ CASES = {
     "gop_cu_qp_delta": (dict(ALL, width=256, height=128, cu_qp_delta=True), gop4),
     "low_delay_8": (dict(ALL, width=416, height=240), lambda: low_delay(8)),
     "gop_alf_ccalf_lmcs": (dict(ALL, width=416, height=240, alf=True, ccalf=True, lmcs=True), lambda: vs.with_lmcs(vs.with_alf(gop4(), np.random.default_rng(4)), np.random.default_rng(5))),
+    "gop_max_transform_32": (dict(ALL, width=416, height=240, max_tb64=False), gop4),
     "gop_intra_slice_in_inter_pictures": (dict(ALL, **SL3), _mixed_slice_types),
     "gop_3slices_alf_lmcs_no_lf_across": (dict(ALL, **SL3, alf=True, ccalf=True, lmcs=True, lf_across_slices=False),
                                           lambda: vs.with_lmcs(vs.with_alf(gop4(), np.random.default_rng(11)), np.random.default_rng(12))),

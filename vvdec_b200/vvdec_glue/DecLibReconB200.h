@@ -306,7 +306,8 @@ class DecLibReconB200
           {
             b200_intra_tu ir;
             if( flattenCiipBlock( cu, ComponentID( c ), ir ) != FLATTEN_INTRA_OK ) continue;
-            if( cu.rootCbf() && ( TU::getCbf( cu.firstTU, ComponentID( c ) ) || ( c && cu.firstTU.jointCbCr ) ) ) ir.flags |= B200_INTRA_ADD_RESI;
+            if( cu.rootCbf() )                                           // (a CU larger than the maximum transform size carries several TUs under the one CIIP block)
+              for( auto& tu : TUTraverser( &cu.firstTU, cu.lastTU->next ) ) if( TU::getCbf( tu, ComponentID( c ) ) || ( c && tu.jointCbCr ) ) ir.flags |= B200_INTRA_ADD_RESI;
             r.intra.push_back( ir ); ciipComp[c] = true;
           }
         }

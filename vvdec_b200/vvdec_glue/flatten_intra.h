@@ -50,13 +50,15 @@ inline int intraUnitsAvailable( const TransformUnit& tu, const ChannelType chTyp
   return std::min( d / unitSize, numUnits );
 }
 
-inline FlattenIntraResult flattenIntraTU( const TransformUnit& tu, const ComponentID compID, b200_intra_tu& r )
+// wholeCu: the block is the CU's (cu.blocks[compID]) although the CU carries several transform units — CIIP predicts the CU block in one piece also where the
+// CU is larger than the maximum transform size (predBlendIntraCiip: initIntraPatternChType( cu.firstTU, cu.blocks[compID] ), IntraPrediction.cpp:909).
+inline FlattenIntraResult flattenIntraTU( const TransformUnit& tu, const ComponentID compID, b200_intra_tu& r, const bool wholeCu = false )
 {
   const CodingUnit&      cu     = *tu.cu;
   const CodingStructure& cs     = *cu.cs;
   const PreCalcValues&   pcv    = *cs.pcv;
   const ChannelType      chType = toChannelType( compID );
-  const CompArea&        area   = tu.blocks[compID];
+  const CompArea&        area   = wholeCu ? cu.blocks[compID] : tu.blocks[compID];
   memset( &r, 0, sizeof( r ) );
   if( cu.colorTransform() || ( isLuma( compID ) && cu.ispMode() ) ) return FLATTEN_INTRA_UNSUPPORTED;
   const bool mip = CU::isMIP( cu, chType );
@@ -76,7 +78,7 @@ inline FlattenIntraResult flattenIntraTU( const TransformUnit& tu, const Compone
   // type, and reuses the three counts for the other components (m_lastCUidx, :1101): in a single tree the chroma blocks take the luma block's.
   // ISP CUs: the luma of the first sub-partition analysed the whole CU (initIntraPatternChTypeISP :997, with cu.firstTU), and that is what the chroma blocks in the
   // last transform unit inherit.
-  const bool        isp     = cu.ispMode() != 0;
+  const bool        isp     = cu.ispMode() != 0 || wholeCu;                                  // (the neighbourhood of the CU block, analysed through cu.firstTU)
   const TransformUnit& tuA  = isp ? cu.firstTU : tu;
   const ComponentID anaComp = getFirstComponentOfChannel( cu.chType() );
   const ChannelType anaCh   = toChannelType( anaComp );
@@ -163,7 +165,7 @@ inline FlattenIntraResult flattenIspCu( const CodingUnit& cu, Emit emit )
 inline FlattenIntraResult flattenCiipBlock( const CodingUnit& cu, const ComponentID compID, b200_intra_tu& r )
 {
   if( !isLuma( compID ) && !( isChromaEnabled( cu.chromaFormat ) && cu.chromaSize().width > 2 ) ) return FLATTEN_INTRA_UNSUPPORTED;
-  if( flattenIntraTU( cu.firstTU, compID, r ) != FLATTEN_INTRA_OK ) return FLATTEN_INTRA_UNSUPPORTED;
+  if( flattenIntraTU( cu.firstTU, compID, r, true ) != FLATTEN_INTRA_OK ) return FLATTEN_INTRA_UNSUPPORTED;
   r.mode = B200_INTRA_PLANAR; r.multiRefIdx = 0; r.mip = 0;
   r.flags &= ~B200_INTRA_FILTER_REF;
   if( isLuma( compID ) && IntraPrediction::useFilteredIntraRefSamples( COMPONENT_Y, cu, cu ) ) r.flags |= B200_INTRA_FILTER_REF;
