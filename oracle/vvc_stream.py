@@ -79,6 +79,8 @@ DEFAULTS = dict(
     affine_amvr=False, prof=False, max_sub_merge=5, bcw=False, ciip=False, gpm=False, max_gpm=6, isp=False, mrl=False, mip=False, cclm=False,
     chroma_collocated=(True, False), dep_quant=False, sign_hiding=False, scaling_lists=False,
     init_qp=32, cu_qp_delta=False, cabac_init_present=False, deblocking_disabled=False, beta_offset_div2=0, tc_offset_div2=0,
+    tiles=None,                    # ((column widths), (row heights)) in CTUs; with slice_per_tile every tile is a slice, else one slice holds all tiles
+    slice_per_tile=False, lf_across_tiles=True,
     slice_rows=None,               # several rectangular slices in the one tile: CTU rows per slice, e.g. (1, 2, 1); None: one slice, picture header in the slice header
     lf_across_slices=True, deblocking_override=False,                # in-loop filters across slice borders; per-slice deblocking offsets
     chroma_qp_offsets=None,        # (cb, cr, joint) PPS offsets; slices add their own (sh_cb_qp_offset ...) and CUs pick from a list (cu_chroma_qp_offset) if set
@@ -172,9 +174,10 @@ def write_pps(c):
     w = Bits()
     w.u(6, 0).u(4, 0).f(0).ue(c.width).ue(c.height).f(0).f(0).f(0)      # ids, mixed NAL types, size, conformance / scaling window, output flag
     multi = c.slice_rows is not None
-    w.f(not multi).f(0)                                                # no_pic_partition, no sub-picture id mapping
+    assert not (multi and c.tiles), "slice_rows (slices inside the one tile) and tiles are alternatives"
+    w.f(not (multi or c.tiles)).f(0)                                   # no_pic_partition, no sub-picture id mapping
+    wc, hc = -(-c.width // c.ctu), -(-c.height // c.ctu)
     if multi:
-        wc, hc = -(-c.width // c.ctu), -(-c.height // c.ctu)
         rows = list(c.slice_rows); n = len(rows)
         assert n >= 2 and sum(rows) == hc and min(rows) >= 1 and rows[-1] <= rows[-2], "slice_rows: whole CTU rows, the last slice not taller than the one before"
         w.u(2, log2(c.ctu) - 5).ue(0).ue(0).ue(wc - 1).ue(hc - 1)        # one explicit tile column / row spanning the picture
@@ -183,6 +186,22 @@ def write_pps(c):
         if n - 1 > 1: w.f(0)                                           # pps_tile_idx_delta_present_flag
         w.ue(n - 1)                                                    # pps_num_exp_slices_in_tile: all but the last height explicit, the rest of the tile is the last slice
         for r in rows[:-1]: w.ue(r - 1)
+        w.f(c.lf_across_slices)
+    elif c.tiles:
+        cols, rows = c.tiles; nt = len(cols) * len(rows)
+        assert sum(cols) == wc and sum(rows) == hc and nt > 1
+        w.u(2, log2(c.ctu) - 5).ue(len(cols) - 1).ue(len(rows) - 1)
+        for v in cols: w.ue(v - 1)
+        for v in rows: w.ue(v - 1)
+        w.f(c.lf_across_tiles).f(1)                                    # ..., pps_rect_slice_flag
+        w.f(not c.slice_per_tile)                                      # pps_single_slice_per_subpic_flag: the picture is the one sub-picture
+        if c.slice_per_tile:
+            w.ue(nt - 1)
+            if nt - 1 > 1: w.f(0)                                      # pps_tile_idx_delta_present_flag
+            for t in range(nt - 1):                                    # slice i = tile i: one tile wide and high
+                if t % len(cols) != len(cols) - 1: w.ue(0)
+                if t // len(cols) != len(rows) - 1 and t % len(cols) == 0: w.ue(0)
+                if rows[t // len(cols)] > 1: w.ue(0)                   # pps_num_exp_slices_in_tile: the tile is one slice
         w.f(c.lf_across_slices)
     w.f(c.cabac_init_present).ue(0).ue(0).f(0)                         # one active reference per list by default, no rpl1 index
     w.f(c.weighted_pred).f(c.weighted_bipred).f(0)                     # ..., wrap-around
@@ -199,11 +218,11 @@ def write_pps(c):
                 w.se(e[0]).se(e[1])
                 if c.jccr: w.se(e[2])
     w.f(1).f(c.deblocking_override).f(c.deblocking_disabled)           # deblocking control present, override enabled, disabled flag
-    if multi and c.deblocking_override: w.f(0)                         # pps_dbf_info_in_ph_flag
+    if (multi or c.tiles) and c.deblocking_override: w.f(0)            # pps_dbf_info_in_ph_flag
     if not c.deblocking_disabled:
         w.se(c.beta_offset_div2).se(c.tc_offset_div2)
         if c.chroma_qp_offsets is not None: w.se(c.beta_offset_div2).se(c.tc_offset_div2).se(c.beta_offset_div2).se(c.tc_offset_div2)
-    if multi: w.f(0).f(0).f(0).f(0)                                    # RPL / SAO / ALF / QP delta stay in the slice headers (no weighted-prediction tables in the PH either)
+    if multi or c.tiles: w.f(0).f(0).f(0).f(0)                         # RPL / SAO / ALF / QP delta stay in the slice headers (no weighted-prediction tables in the PH either)
     w.f(0).f(0).f(0)                                                   # PH / SH extension, PPS extension
     return nal_unit(NAL_PPS, w.trailing().bytes())
 
@@ -419,7 +438,7 @@ def write_picture_header(w, c, p):
 
 
 def slice_types_of(c, p):
-    n = len(c.slice_rows) if c.slice_rows is not None else 1
+    n = len(c.slice_rows) if c.slice_rows is not None else len(c.tiles[0]) * len(c.tiles[1]) if (c.tiles and c.slice_per_tile) else 1
     return list(p.slice_types) if p.slice_types is not None else [p.slice_type] * n
 
 
@@ -428,11 +447,12 @@ def write_slices(c, p):
     parseSliceHeader (HLSyntaxReader.cpp:3438-4065)."""
     import numpy as _np
     types = slice_types_of(c, p)
-    multi = c.slice_rows is not None
+    multi = len(types) > 1
     irap = p.idr
     nals = []
+    segments = 1 if (not c.tiles or c.slice_per_tile) else len(c.tiles[0]) * len(c.tiles[1])      # CABAC segments per slice: one per tile it holds
     if multi:
-        w = Bits(); write_picture_header(w, c, p); nals.append((NAL_PH, w.trailing().bytes(), False))
+        w = Bits(); write_picture_header(w, c, p); nals.append((NAL_PH, w.trailing().bytes(), 0))
     inter_allowed = any(t != SLICE_I for t in types)
     for k, st in enumerate(types):
         inter = st != SLICE_I
@@ -497,7 +517,7 @@ def write_slices(c, p):
         if c.sign_hiding and not dq: w.f(sdh)
         if c.transform_skip and not dq and not sdh: w.f(0)       # sh_ts_residual_coding_disabled_flag
         w.trailing()                                             # byte_alignment()
-        nals.append((NAL_IDR_N_LP if irap else NAL_TRAIL, w.bytes(), True))
+        nals.append((NAL_IDR_N_LP if irap else NAL_TRAIL, w.bytes(), segments))
     return nals
 
 
@@ -617,19 +637,22 @@ def build_stream(cfg, pics, seed=1, bias=None, bypass_p=128, max_bypass_run=12):
     aus = [pre[i] + b"".join(nal_unit(t, h + (b"\x80" if vcl else b"")) for t, h, vcl in nals) for i, nals in enumerate(heads)]
     drawn = decode(GEN_SO, aus, frame_samples=cfg.width * cfg.height * 3 // 2 + 64)
     nseg = gen.gen_num_segments()
-    assert nseg == sum(vcl for nals in heads for _, _, vcl in nals), (nseg, len(pics))
+    assert nseg == sum(vcl for nals in heads for _, _, vcl in nals), (nseg, len(pics))      # (vcl: CABAC segments of the NAL, 0 for a PH)
     # step 3: encode and splice
     out, nbins, seg = [], [], 0
     for i, nals in enumerate(heads):
         au = pre[i]
         for t, h, vcl in nals:
             if not vcl: au += nal_unit(t, h); continue
-            info = (C.c_int * 3)(); n = gen.gen_segment(seg, info, None, None, 0)
-            ctx = np.zeros(n, np.int16); bins = np.zeros(n, np.uint8)
-            gen.gen_segment(seg, info, ctx.ctypes.data, bins.ctypes.data, n)
-            buf = np.zeros(n // 4 + 64, np.uint8)
-            m = ref.ref_cabac_encode(info[0], info[1], ctx, bins, n, buf, len(buf))
-            assert m > 0
-            au += nal_unit(t, h + bytes(buf[:m])); nbins.append(n); seg += 1
+            data = b""
+            for _ in range(vcl):                                  # a tile ends with its own terminating bin, stop bit and alignment; the next starts on fresh contexts
+                info = (C.c_int * 3)(); n = gen.gen_segment(seg, info, None, None, 0)
+                ctx = np.zeros(n, np.int16); bins = np.zeros(n, np.uint8)
+                gen.gen_segment(seg, info, ctx.ctypes.data, bins.ctypes.data, n)
+                buf = np.zeros(n // 4 + 64, np.uint8)
+                m = ref.ref_cabac_encode(info[0], info[1], ctx, bins, n, buf, len(buf))
+                assert m > 0
+                data += bytes(buf[:m]); nbins.append(n); seg += 1
+            au += nal_unit(t, h + data)
         out.append(au)
     return out, drawn, nbins

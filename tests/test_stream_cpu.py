@@ -64,6 +64,10 @@ CASES = {
     "gop_no_deblocking": (dict(ALL, deblocking_disabled=True), gop4),
     "low_delay_8": (dict(ALL), lambda: low_delay(8)),
     "gop_max_transform_32": (dict(ALL, max_tb64=False), gop4),                                                      # 64x64 CUs carry four TUs; CIIP still predicts the CU block
+    "gop_4tiles_one_slice": (dict(ALL, width=256, height=192, tiles=((2, 2), (1, 2))), gop4),                       # CABAC restarts per tile inside the slice data
+    "gop_4tiles_4slices": (dict(ALL, width=256, height=192, tiles=((1, 3), (2, 1)), slice_per_tile=True), gop4),
+    "gop_4tiles_no_lf_across_alf": (dict(ALL, width=256, height=192, tiles=((2, 2), (1, 2)), lf_across_tiles=False, alf=True, ccalf=True),
+                                    lambda: vs.with_alf(gop4(), np.random.default_rng(21))),
     "gop_3slices": (dict(ALL, **SL3), gop4),                                                                       # per-slice QP, SAO switches, reference order, dep. quant
     "gop_4slices_no_lf_across_deblock_override": (dict(ALL, width=256, height=256, slice_rows=(1, 1, 1, 1), lf_across_slices=False, deblocking_override=True), gop4),
     "gop_intra_slice_in_inter_pictures": (dict(ALL, **SL3), _mixed_slice_types),
@@ -114,7 +118,7 @@ def test_stream_stock_vs_swapped_decoder(name, seed, oracle):
     assert any(f[0].std() > 1 for f in stock)                           # not a flat picture
     if "scaling_lists" in name: assert all(l["scaling"] > 0 for l in log)            # the tools the case is about reached the work lists
     if "weighted" in name: assert any(l["wp"] > 0 for l in log)
-    if "slices" in name: assert all(l["lfSlices"] == len(cfg.slice_rows) for l in log)
+    if "3slices" in name or "_slices_" in name: assert all(l["lfSlices"] == len(cfg.slice_rows) for l in log)
 
 
 def test_long_stream_recycles_pictures_and_slots(oracle):

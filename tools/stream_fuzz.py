@@ -38,6 +38,13 @@ def random_case(seed):
         sl = [b - a for a, b in zip([0] + cut, cut + [rows])]
         if sl[-1] > sl[-2]: sl[-1], sl[-2] = sl[-2], sl[-1]
         kw.update(slice_rows=tuple(sl), lf_across_slices=bool(r.integers(0, 2)), deblocking_override=bool(r.integers(0, 2)))
+    elif r.random() < 0.25 and (wc >= 2 or rows >= 2):
+        def cut(n):
+            k = int(r.integers(1, min(n, 3) + 1)); c = sorted(r.choice(np.arange(1, n), size=k - 1, replace=False).tolist()) if k > 1 else []
+            return tuple(b - a for a, b in zip([0] + c, c + [n]))
+        cols, trs = cut(-(-W // ctu)), cut(rows)
+        if len(cols) * len(trs) > 1:
+            kw.update(tiles=(cols, trs), slice_per_tile=bool(r.integers(0, 2)), lf_across_tiles=bool(r.integers(0, 2)), lf_across_slices=bool(r.integers(0, 2)))
     if not mono and r.random() < 0.4:
         kw.update(chroma_qp_offsets=(int(r.integers(-4, 5)), int(r.integers(-4, 5)), int(r.integers(-4, 5))), slice_chroma_qp_offsets=bool(r.integers(0, 2)))
         if r.random() < 0.5: kw["cu_chroma_qp_offset_list"] = tuple((int(r.integers(-5, 6)), int(r.integers(-5, 6)), int(r.integers(-5, 6))) for _ in range(int(r.integers(1, 5))))
@@ -54,8 +61,9 @@ def random_case(seed):
             pass
     if r.random() < 0.3:
         kw["scaling_lists"] = True; vs.with_scaling_lists(pics, r, chroma_present=not mono)
-    if kw.get("slice_rows") and structure != "intra" and r.random() < 0.5:
-        n = len(kw["slice_rows"])
+    n_slices = len(kw["slice_rows"]) if kw.get("slice_rows") else len(kw["tiles"][0]) * len(kw["tiles"][1]) if kw.get("tiles") and kw.get("slice_per_tile") else 1
+    if n_slices > 1 and structure != "intra" and r.random() < 0.5:
+        n = n_slices
         for q in pics[1:]: q["slice_types"] = [vs.SLICE_I if (k + q.poc) % 3 == 1 else q.slice_type for k in range(n)]
         if kw.get("weighted_pred"): pass
     for q in pics:
@@ -69,7 +77,7 @@ if __name__ == "__main__":
     oracle = helpers.load_oracle(); bad = 0
     for seed in range(first, first + count):
         kw, pics, structure = random_case(seed)
-        tag = f"{seed} {structure} {kw['width']}x{kw['height']} ctu{kw['ctu']} {kw['bit_depth']}b slices={kw.get('slice_rows')} " + "".join(k[0] for k in ("alf", "lmcs", "scaling_lists", "weighted_pred") if kw.get(k))
+        tag = f"{seed} {structure} {kw['width']}x{kw['height']} ctu{kw['ctu']} {kw['bit_depth']}b slices={kw.get('slice_rows')} tiles={kw.get('tiles')}{'S' if kw.get('slice_per_tile') else ''} " + "".join(k[0] for k in ("alf", "lmcs", "scaling_lists", "weighted_pred") if kw.get(k))
         try:
             aus, drawn, nb = vs.build_stream(vs.Config(**kw), pics, seed=seed)
         except (vs.DecodeError, AssertionError) as e:
