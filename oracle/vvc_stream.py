@@ -79,6 +79,10 @@ DEFAULTS = dict(
     affine_amvr=False, prof=False, max_sub_merge=5, bcw=False, ciip=False, gpm=False, max_gpm=6, isp=False, mrl=False, mip=False, cclm=False,
     chroma_collocated=(True, False), dep_quant=False, sign_hiding=False, scaling_lists=False,
     init_qp=32, cu_qp_delta=False, cabac_init_present=False, deblocking_disabled=False, beta_offset_div2=0, tc_offset_div2=0,
+    chroma_qp_tables=None,         # None: one table, identity from 27 up; else 1 (shared), 2 or 3 (with jccr) tables of (start_minus26, [(delta_in_minus1, delta_out), ...])
+    ladf=None,                     # luma-adaptive deblocking: (lowest interval QP offset, [(QP offset, delta_threshold_minus1), ...]) with 1..4 further intervals
+    ph_tool_control=False,         # sps_bdof / dmvr / prof _control_present_in_ph_flag: pictures switch the tools (Pic.bdof / dmvr / prof)
+    lfnst_scaling_disabled=False, min_qp_prime_ts=0, parallel_merge_level=2, ts_max_size=5, cb_cr_deblock_offsets=None,       # (cb beta, cb tc, cr beta, cr tc) with chroma_qp_offsets
     tiles=None,                    # ((column widths), (row heights)) in CTUs; with slice_per_tile every tile is a slice, else one slice holds all tiles
     slice_per_tile=False, lf_across_tiles=True,
     slice_rows=None,               # several rectangular slices in the one tile: CTU rows per slice, e.g. (1, 2, 1); None: one slice, picture header in the slice header
@@ -123,13 +127,20 @@ def write_sps(c):
     if c.mtt_depth_inter: w.ue(log2(c.max_bt_inter) - min_qt_p).ue(log2(c.max_tt_inter) - min_qt_p)
     if c.ctu > 32: w.f(c.max_tb64)
     w.f(c.transform_skip)
-    if c.transform_skip: w.ue(3).f(c.bdpcm)                      # transform skip up to 32x32
+    if c.transform_skip: w.ue(c.ts_max_size - 2).f(c.bdpcm)      # largest transform-skip block (log2)
     w.f(c.mts)
     if c.mts: w.f(c.mts_intra).f(c.mts_inter)
     w.f(c.lfnst)
     if c.chroma_format:
-        w.f(c.jccr).f(1)                                         # one chroma QP table for Cb / Cr / joint
-        w.se(0).ue(0).ue(0).ue(0)                                #   start at 26, one pivot: in 26 -> out 26, in 27 -> out 26, slope 1 above
+        w.f(c.jccr)
+        if c.chroma_qp_tables is None:
+            w.f(1).se(0).ue(0).ue(0).ue(0)                       # one chroma QP table for Cb / Cr / joint: start at 26, one pivot (27 -> 26), slope 1 above
+        else:
+            t = c.chroma_qp_tables; assert len(t) in ((1, 3) if c.jccr else (1, 2))
+            w.f(len(t) == 1)                                     # sps_same_qp_table_for_chroma_flag
+            for start, pts in t:
+                w.se(start).ue(len(pts) - 1)
+                for din, dout in pts: w.ue(din).ue(dout ^ din)   # sps_delta_qp_diff_val = delta out XOR delta_in_minus1
     w.f(c.sao).f(c.alf)
     if c.alf and c.chroma_format: w.f(c.ccalf)
     w.f(c.lmcs).f(c.weighted_pred).f(c.weighted_bipred).f(0)     # ..., no long-term references
@@ -138,9 +149,9 @@ def write_sps(c):
     w.f(c.temporal_mvp)
     if c.temporal_mvp: w.f(c.sbtmvp)
     w.f(c.amvr).f(c.bdof)
-    if c.bdof: w.f(0)
+    if c.bdof: w.f(c.ph_tool_control)
     w.f(c.smvd).f(c.dmvr)
-    if c.dmvr: w.f(0)
+    if c.dmvr: w.f(c.ph_tool_control)
     w.f(c.mmvd)
     if c.mmvd: w.f(0)
     w.ue(6 - c.max_merge).f(c.sbt).f(c.affine)
@@ -148,21 +159,25 @@ def write_sps(c):
         w.ue(5 - c.max_sub_merge).f(c.affine_6param)
         if c.amvr: w.f(c.affine_amvr)
         w.f(c.prof)
-        if c.prof: w.f(0)
+        if c.prof: w.f(c.ph_tool_control)
     w.f(c.bcw).f(c.ciip)
     if c.max_merge >= 2:
         w.f(c.gpm)
         if c.gpm and c.max_merge >= 3: w.ue(c.max_merge - c.max_gpm)
-    w.ue(0)                                                      # parallel merge level 4
+    w.ue(c.parallel_merge_level - 2)                             # log2 of the parallel merge level
     w.f(c.isp).f(c.mrl).f(c.mip)
     if c.chroma_format: w.f(c.cclm)
     if c.chroma_format == 1: w.f(c.chroma_collocated[0]).f(c.chroma_collocated[1])
     w.f(0)                                                       # palette
     if c.chroma_format == 3 and not c.max_tb64: w.f(0)           # ACT
-    if c.transform_skip: w.ue(0)                                 # min_qp_prime_ts
-    w.f(0).f(0)                                                  # IBC, LADF
+    if c.transform_skip: w.ue(c.min_qp_prime_ts)                 # (sps_internal_bit_depth_minus_input_bit_depth: MinQpPrimeTs = 4 + 6 * value)
+    w.f(0).f(c.ladf is not None)                                 # IBC, LADF
+    if c.ladf is not None:
+        low, steps = c.ladf; assert 1 <= len(steps) <= 4
+        w.u(2, len(steps) - 1).se(low)
+        for off, thr in steps: w.se(off).ue(thr)
     w.f(c.scaling_lists)
-    if c.lfnst and c.scaling_lists: w.f(0)
+    if c.lfnst and c.scaling_lists: w.f(c.lfnst_scaling_disabled)
     w.f(c.dep_quant).f(c.sign_hiding).f(0)                       # ..., no virtual boundaries
     w.f(0)                                                       # sps_timing_hrd_params_present_flag
     w.f(0).f(0).f(0)                                             # field_seq, VUI, extension
@@ -221,7 +236,8 @@ def write_pps(c):
     if (multi or c.tiles) and c.deblocking_override: w.f(0)            # pps_dbf_info_in_ph_flag
     if not c.deblocking_disabled:
         w.se(c.beta_offset_div2).se(c.tc_offset_div2)
-        if c.chroma_qp_offsets is not None: w.se(c.beta_offset_div2).se(c.tc_offset_div2).se(c.beta_offset_div2).se(c.tc_offset_div2)
+        if c.chroma_qp_offsets is not None:
+            for v in (c.cb_cr_deblock_offsets or (c.beta_offset_div2, c.tc_offset_div2) * 2): w.se(v)
     if multi or c.tiles: w.f(0).f(0).f(0).f(0)                         # RPL / SAO / ALF / QP delta stay in the slice headers (no weighted-prediction tables in the PH either)
     w.f(0).f(0).f(0)                                                   # PH / SH extension, PPS extension
     return nal_unit(NAL_PPS, w.trailing().bytes())
@@ -371,7 +387,8 @@ class Pic(dict):
                          lmcs=None,         # dict(aps=id, chroma_scale=bool)
                          slice_types=None,  # several slices: a type per slice (default: the picture's); I slices may sit in P / B pictures
                          wp=None,           # seed of the explicit prediction weights (streams with weighted_pred / weighted_bipred)
-                         scaling_list=None) # id of the scaling-list APS the picture quantises with
+                         scaling_list=None, # id of the scaling-list APS the picture quantises with
+                         bdof=True, dmvr=True, prof=True, jccr_sign=False)    # picture-level tool switches (ph_tool_control), sign of the joint Cb-Cr residual
         bad = set(kw) - set(self); assert not bad, bad
         self.update(kw)
     __getattr__ = dict.__getitem__
@@ -434,7 +451,10 @@ def write_picture_header(w, c, p):
         if c.cu_chroma_qp_offset_list: w.ue(0)
         if c.temporal_mvp: w.f(p.temporal_mvp)
         w.f(p.mvd_l1_zero)                                       # RPLs are in the slice headers: ph_mvd_l1_zero_flag is always present
-    if c.jccr: w.f(0)                                            # ph_joint_cbcr_sign_flag
+        if c.bdof and c.ph_tool_control: w.f(not p.bdof)         # ph_bdof_disabled_flag
+        if c.dmvr and c.ph_tool_control: w.f(not p.dmvr)
+        if c.affine and c.prof and c.ph_tool_control: w.f(not p.prof)
+    if c.jccr: w.f(p.jccr_sign)                                  # ph_joint_cbcr_sign_flag
 
 
 def slice_types_of(c, p):

@@ -286,6 +286,8 @@ def picture_from_struct(st, g, filt):
         d["lfV"] = _copy(st.lfV, W4 * H4, synth.LF_DTYPE); d["lfH"] = _copy(st.lfH, W4 * H4, synth.LF_DTYPE); d["lfSlices"] = _copy(st.lfSlices, st.numLfSlices, synth.LFSLICE_DTYPE)
         p.lfV = d["lfV"].ctypes.data; p.lfH = d["lfH"].ctypes.data; p.lfSlices = d["lfSlices"].ctypes.data; p.numLfSlices = st.numLfSlices
         if st.ctuSlice: d["ctuSlice"] = _copy(st.ctuSlice, nctu, np.uint8); p.ctuSlice = d["ctuSlice"].ctypes.data
+        if st.lfSeq:                                             # luma-adaptive deblocking offsets of the SPS
+            d["lfSeq"] = abi.LfSeq.from_buffer_copy(C.string_at(st.lfSeq, C.sizeof(abi.LfSeq))); p.lfSeq = C.addressof(d["lfSeq"])
     if st.flags & abi.PIC_SAO:
         d["sao"] = _copy(st.sao, nctu, synth.SAO_DTYPE); p.sao = d["sao"].ctypes.data
     if st.flags & abi.PIC_ALF:
@@ -385,7 +387,7 @@ def oracle_decompress(oracle, g, dpb, pic):
         oracle.orc_k1_residual(C.byref(g), abi.plane_ptrs(cur), pic["tus"].ctypes.data, len(pic["tus"]), pic["coefs"], SC, 0)
     if st.flags & abi.PIC_DEBLOCK:
         oracle.orc_lf_deblock(C.byref(g), abi.plane_ptrs(cur), pic["lfV"].ctypes.data, pic["lfH"].ctypes.data, pic["ctuSlice"].ctypes.data if "ctuSlice" in pic else None,
-                              pic["lfSlices"].ctypes.data, None, 3)
+                              pic["lfSlices"].ctypes.data, C.byref(pic["lfSeq"]) if "lfSeq" in pic else None, 3)
     if st.flags & abi.PIC_SAO:
         nxt = [np.zeros_like(p) for p in cur]
         oracle.orc_sao_picture(C.byref(g), abi.plane_ptrs(cur), abi.plane_ptrs(nxt), pic["sao"].ctypes.data, None)

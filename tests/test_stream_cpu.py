@@ -48,6 +48,12 @@ def _weighted(pics):
     return pics
 
 
+def _picture_switches():
+    pics = gop4()
+    for i, q in enumerate(pics): q["bdof"], q["dmvr"], q["prof"], q["jccr_sign"] = bool(i & 1), bool(i & 2), bool((i + 1) & 2), bool(i & 1)
+    return pics
+
+
 SL3 = dict(width=256, height=256, slice_rows=(2, 1, 1))
 CASES = {
     "I_all_intra_tools": (dict(INTRA), lambda: [vs.Pic(0)]),
@@ -68,6 +74,11 @@ CASES = {
     "gop_4tiles_4slices": (dict(ALL, width=256, height=192, tiles=((1, 3), (2, 1)), slice_per_tile=True), gop4),
     "gop_4tiles_no_lf_across_alf": (dict(ALL, width=256, height=192, tiles=((2, 2), (1, 2)), lf_across_tiles=False, alf=True, ccalf=True),
                                     lambda: vs.with_alf(gop4(), np.random.default_rng(21))),
+    "gop_picture_level_tool_switches": (dict(ALL, ph_tool_control=True), _picture_switches),                        # ph_bdof / dmvr / prof _disabled_flag, ph_joint_cbcr_sign_flag
+    "gop_chroma_qp_tables": (dict(ALL, chroma_qp_tables=((-4, [(1, 1), (3, 2), (0, 0)]), (2, [(2, 3)]), (-10, [(5, 2), (1, 2)])), chroma_qp_offsets=(1, -2, 3), slice_chroma_qp_offsets=True), gop4),
+    "gop_ladf_chroma_deblock_offsets": (dict(ALL, ladf=(-3, [(2, 100), (-4, 200), (5, 150)]), chroma_qp_offsets=(0, 0, 0), cb_cr_deblock_offsets=(3, -2, -4, 5), beta_offset_div2=-2, tc_offset_div2=4), gop4),
+    "gop_ts_min_qp_lfnst_without_scaling": (dict(ALL, transform_skip=True, bdpcm=True, min_qp_prime_ts=3, ts_max_size=4, scaling_lists=True, lfnst_scaling_disabled=True, parallel_merge_level=5),
+                                            lambda: vs.with_scaling_lists(gop4(), np.random.default_rng(22))),
     "gop_3slices": (dict(ALL, **SL3), gop4),                                                                       # per-slice QP, SAO switches, reference order, dep. quant
     "gop_4slices_no_lf_across_deblock_override": (dict(ALL, width=256, height=256, slice_rows=(1, 1, 1, 1), lf_across_slices=False, deblocking_override=True), gop4),
     "gop_intra_slice_in_inter_pictures": (dict(ALL, **SL3), _mixed_slice_types),

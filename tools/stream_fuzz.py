@@ -48,6 +48,15 @@ def random_case(seed):
     if not mono and r.random() < 0.4:
         kw.update(chroma_qp_offsets=(int(r.integers(-4, 5)), int(r.integers(-4, 5)), int(r.integers(-4, 5))), slice_chroma_qp_offsets=bool(r.integers(0, 2)))
         if r.random() < 0.5: kw["cu_chroma_qp_offset_list"] = tuple((int(r.integers(-5, 6)), int(r.integers(-5, 6)), int(r.integers(-5, 6))) for _ in range(int(r.integers(1, 5))))
+    if r.random() < 0.3: kw["ladf"] = (int(r.integers(-5, 6)), [(int(r.integers(-6, 7)), int(r.integers(20, (1 << kw["bit_depth"]) // 5))) for _ in range(int(r.integers(1, 5)))])
+    if not mono and r.random() < 0.4:
+        def table():
+            start = int(r.integers(-8, 5)); pts = [(int(r.integers(0, 4)), 0) for _ in range(int(r.integers(1, 5)))]
+            return (start, [(a, int(r.integers(0, a + 2))) for a, _ in pts])
+        kw["chroma_qp_tables"] = tuple(table() for _ in range(pick(1, 3 if kw["jccr"] else 2)))
+    kw.update(ph_tool_control=bool(r.integers(0, 2)), parallel_merge_level=int(r.integers(2, 6)), lfnst_scaling_disabled=bool(r.integers(0, 2)))
+    if kw["transform_skip"]: kw.update(min_qp_prime_ts=int(r.integers(0, 4)), ts_max_size=int(r.integers(2, 6)))
+    if kw.get("chroma_qp_offsets") is not None and r.random() < 0.5: kw["cb_cr_deblock_offsets"] = tuple(int(v) for v in r.integers(-4, 5, size=4))
     structure = pick("gop", "gop", "low_delay", "intra")
     pics = gop4() + (gop4(4, idr=False)[1:] if r.random() < 0.3 else []) if structure == "gop" else low_delay(int(r.integers(3, 7))) if structure == "low_delay" else [vs.Pic(0), vs.Pic(1, idr=True)]
     if r.random() < 0.3 and structure != "intra":
@@ -68,6 +77,7 @@ def random_case(seed):
         if kw.get("weighted_pred"): pass
     for q in pics:
         q["qp"] = kw["init_qp"] + int(r.integers(-4, 5)); q["dep_quant"] = bool(r.integers(0, 2)); q["sign_hiding"] = bool(r.integers(0, 2))
+        q["bdof"], q["dmvr"], q["prof"], q["jccr_sign"] = (bool(r.integers(0, 2)) for _ in range(4))
         q["sao"] = (bool(r.integers(0, 4)), bool(r.integers(0, 4))); q["mvd_l1_zero"] = r.random() < 0.2; q["col_from_l0"] = bool(r.integers(0, 2)); q["cabac_init"] = bool(r.integers(0, 2))
     return kw, pics, structure
 
