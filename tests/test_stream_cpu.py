@@ -158,6 +158,19 @@ def test_swapped_decoder_with_a_thread_pool(oracle):
     assert _diff(swapped, stock) == [0] * len(aus)
 
 
+def test_refused_picture_surfaces_as_unsupported(oracle):
+    """What the device path leaves to the stock back end is refused on the API thread in decompressPicture (DecLib::reconPicture records it) and comes out of
+    vvdec_decode as VVDEC_ERR_NOT_SUPPORTED.  Case: CIIP under LMCS with a 32x32 maximum transform size — the reference maps residual-free CIIP blocks of CUs
+    larger than a transform unit through the LMCS forward curve twice (DecCu.cpp:466-476 after CABACReader.cpp:1449-1456 cleared rootCbf); the stock decoder
+    still decodes the stream to what it was drawn as."""
+    from tests import stream_util as su
+    cfg = vs.Config(**dict(ALL, lmcs=True, max_tb64=False))
+    aus, drawn, _ = vs.build_stream(cfg, vs.with_lmcs(gop4(), np.random.default_rng(3)), seed=3)
+    assert _diff(drawn, vs.decode(vs.REF_SO, aus)) == [0] * len(aus)
+    with pytest.raises(vs.DecodeError, match="unsupported feature.*CIIP under LMCS"):
+        su.decode_swapped_cpu(aus, oracle)
+
+
 def test_arithmetic_encoder_round_trip():
     """ref_cabac_encode against the reference's BinDecoder: random context / bypass / terminate sequences come back bin for bin (the generating build
     reads them with drawn bins, the stock build decodes the bytes — compared through a whole slice in the tests above; here: the stop-bit / carry paths
