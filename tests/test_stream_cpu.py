@@ -167,7 +167,7 @@ def test_refused_picture_surfaces_as_unsupported(oracle):
     cfg = vs.Config(**dict(ALL, lmcs=True, max_tb64=False))
     aus, drawn, _ = vs.build_stream(cfg, vs.with_lmcs(gop4(), np.random.default_rng(3)), seed=3)
     assert _diff(drawn, vs.decode(vs.REF_SO, aus)) == [0] * len(aus)
-    with pytest.raises(vs.DecodeError, match="unsupported feature.*CIIP under LMCS"):
+    with pytest.raises(vs.DecodeError, match="(?s)unsupported feature.*CIIP under LMCS"):
         su.decode_swapped_cpu(aus, oracle)
 
 
