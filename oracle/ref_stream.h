@@ -155,8 +155,9 @@ extern "C" const char* ref_ctx_names()
 
 // The whole stream through the reference's public API.  `stream`: Annex-B access units, auOffsets[0..nAu] their byte ranges (each vvdec_decode call takes
 // one).  Frames come out in output order as 16-bit planes, appended to `out` (Y, Cb, Cr per frame, tightly packed); dims[0..5] = luma w, h, chroma w, h,
-// bit depth, frames.  Returns the number of frames, or a negative vvdec error code (message in errBuf).
-extern "C" int ref_decode_stream( const uint8_t* stream, const long* auOffsets, int nAu, int threads, int16_t* out, long outCap, int* dims, char* errBuf, int errCap )
+// bit depth, frames.  frameDims (may be null, 4 ints per frame, room for maxFrames): the plane sizes of every frame (streams that change resolution).
+// Returns the number of frames, or a negative vvdec error code (message in errBuf).
+extern "C" int ref_decode_stream2( const uint8_t* stream, const long* auOffsets, int nAu, int threads, int16_t* out, long outCap, int* dims, char* errBuf, int errCap, int* frameDims, int maxFrames )
 {
   vvdecParams params; vvdec_params_default( &params );
   params.threads = threads; params.logLevel = VVDEC_SILENT; params.errHandlingFlags = VVDEC_ERR_HANDLING_OFF;
@@ -171,7 +172,7 @@ extern "C" int ref_decode_stream( const uint8_t* stream, const long* auOffsets, 
     for( unsigned c = 0; c < f->numPlanes; c++ )
     {
       const vvdecPlane& p = f->planes[c];
-      if( c < 2 ) { dims[2 * c] = p.width; dims[2 * c + 1] = p.height; }
+      if( c < 2 ) { dims[2 * c] = p.width; dims[2 * c + 1] = p.height; if( frameDims && frames < maxFrames ) { frameDims[4 * frames + 2 * c] = p.width; frameDims[4 * frames + 2 * c + 1] = p.height; } }
       if( used + (long) p.width * p.height > outCap ) { rc = -998; break; }
       for( unsigned y = 0; y < p.height; y++ )
       {
@@ -181,6 +182,7 @@ extern "C" int ref_decode_stream( const uint8_t* stream, const long* auOffsets, 
       }
       used += (long) p.width * p.height;
     }
+    if( f->numPlanes == 1 && frameDims && frames < maxFrames ) frameDims[4 * frames + 2] = frameDims[4 * frames + 3] = 0;
     dims[4] = f->bitDepth; frames++;
     vvdec_frame_unref( dec, f );
   };
@@ -209,4 +211,8 @@ extern "C" int ref_decode_stream( const uint8_t* stream, const long* auOffsets, 
   vvdec_decoder_close( dec );
   dims[5] = frames;
   return rc ? rc : frames;
+}
+extern "C" int ref_decode_stream( const uint8_t* stream, const long* auOffsets, int nAu, int threads, int16_t* out, long outCap, int* dims, char* errBuf, int errCap )
+{
+  return ref_decode_stream2( stream, auOffsets, nAu, threads, out, outCap, dims, errBuf, errCap, nullptr, 0 );
 }

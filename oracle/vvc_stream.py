@@ -582,6 +582,7 @@ def _lib(path):
         u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
         lib.ref_decode_stream.argtypes = [u8p, np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS"), C.c_int, C.c_int,
                                           np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS"), C.c_long, C.POINTER(C.c_int), C.c_char_p, C.c_int]
+        lib.ref_decode_stream2.argtypes = lib.ref_decode_stream.argtypes + [np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS"), C.c_int]
         lib.ref_cabac_encode.argtypes = [C.c_int, C.c_int, np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS"), u8p, C.c_long, u8p, C.c_long]
         lib.ref_cabac_encode.restype = C.c_long
         lib.ref_ctx_offset.argtypes = [C.c_char_p]
@@ -608,11 +609,12 @@ def decode(lib_path, aus, threads=1, max_frames=None, frame_samples=None):
     offs = np.zeros(len(aus) + 1, np.int64); offs[1:] = np.cumsum([len(a) for a in aus])
     cap = (frame_samples or 1 << 22) * (max_frames or len(aus))
     out = np.zeros(cap, np.int16); dims = (C.c_int * 6)(); err = C.create_string_buffer(1024)
-    n = lib.ref_decode_stream(stream, offs, len(aus), threads, out, cap, dims, err, len(err))
+    nmax = (max_frames or len(aus)) + 2; fd = np.zeros(4 * nmax, np.int32)
+    n = lib.ref_decode_stream2(stream, offs, len(aus), threads, out, cap, dims, err, len(err), fd, nmax)
     if n < 0: raise DecodeError(f"vvdec error {n}: {err.value.decode(errors='replace')}")
-    w, h, cw, ch = dims[0], dims[1], dims[2], dims[3]
     frames, pos = [], 0
-    for _ in range(n):
+    for i in range(n):
+        w, h, cw, ch = (int(v) for v in fd[4 * i:4 * i + 4])
         y = out[pos:pos + w * h].reshape(h, w).copy(); pos += w * h
         cb = out[pos:pos + cw * ch].reshape(ch, cw).copy(); pos += cw * ch
         cr = out[pos:pos + cw * ch].reshape(ch, cw).copy(); pos += cw * ch

@@ -158,6 +158,25 @@ def test_swapped_decoder_with_a_thread_pool(oracle):
     assert _diff(swapped, stock) == [0] * len(aus)
 
 
+def sequence_change_stream():
+    """three coded video sequences in one stream: 256x128 CTU 64 10 bit, 192x192 CTU 32 10 bit, 256x128 CTU 64 8 bit (each starts with its own SPS / PPS and an IDR)"""
+    a1, d1, _ = vs.build_stream(vs.Config(**dict(ALL, width=256, height=128)), gop4(), seed=1)
+    a2, d2, _ = vs.build_stream(vs.Config(**dict(ALL, width=192, height=192, ctu=32, max_bt_inter=32, max_tt_inter=32)), gop4(), seed=2)
+    a3, d3, _ = vs.build_stream(vs.Config(**dict(ALL, width=256, height=128, bit_depth=8)), gop4(), seed=3)
+    return a1 + a2 + a3, d1 + d2 + d3
+
+
+def test_new_sequence_with_another_picture_size_ctu_size_and_bit_depth(oracle):
+    """the class finishes what the other instance still holds and rebuilds its device context when an IRAP picture starts a sequence with another geometry"""
+    from tests import stream_util as su
+    aus, drawn = sequence_change_stream()
+    stock = vs.decode(vs.REF_SO, aus, threads=4, frame_samples=256 * 192 * 2)
+    assert [f[0].shape for f in stock] == [(128, 256)] * 5 + [(192, 192)] * 5 + [(128, 256)] * 5
+    assert _diff(drawn, stock) == [0] * 15
+    swapped, log = su.decode_swapped_cpu(aus, oracle, threads=4, frame_samples=256 * 192 * 2)
+    assert _diff(swapped, stock) == [0] * 15
+
+
 def test_refused_picture_surfaces_as_unsupported(oracle):
     """What the device path leaves to the stock back end is refused on the API thread in decompressPicture (DecLib::reconPicture records it) and comes out of
     vvdec_decode as VVDEC_ERR_NOT_SUPPORTED.  Case: CIIP under LMCS with a 32x32 maximum transform size — the reference maps residual-free CIIP blocks of CUs

@@ -48,3 +48,13 @@ def test_long_stream_on_the_device():
     stock = vs.decode(vs.REF_SO, aus, threads=4)
     got = su.decode_swapped_device(aus, threads=4)
     assert _diff(got, stock) == [0] * len(aus)
+
+
+def test_new_sequence_with_another_geometry_on_the_device():
+    """an IDR with new parameter sets (picture size, CTU size, bit depth): the class rebuilds its device context (DecLibReconB200::preparePicture)"""
+    from tests import stream_util as su
+    from tests.test_stream_cpu import sequence_change_stream
+    aus, drawn = sequence_change_stream()
+    stock = vs.decode(vs.REF_SO, aus, threads=4, frame_samples=256 * 192 * 2)
+    got = su.decode_swapped_device(aus, threads=4, frame_samples=256 * 192 * 2)
+    assert _diff(got, stock) == [0] * len(aus)

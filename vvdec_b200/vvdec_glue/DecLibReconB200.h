@@ -127,7 +127,7 @@ class DecLibReconB200
   struct AlfAccess : AdaptiveLoopFilter { using AdaptiveLoopFilter::isClipOrCrossedByVirtualBoundaries; };     // protected in the reference: the glue asks it per CTU
   LoopFilter m_cLoopFilter; SampleAdaptiveOffset m_cSAO; AlfAccess m_cALF; Reshape m_cReshaper;
   std::vector<std::unique_ptr<DecCu>> m_cuDecoders; InterPrediction m_interPred; std::unique_ptr<TrQuant> m_trQuant;
-  PelStorage m_fltBuf;
+  PelStorage m_fltBuf; ChromaFormat m_fltFmt = CHROMA_420; int m_fltCtu = 0;
 
   static void check( int rc ) { if( rc == B200_ERR_UNSUPPORTED ) THROW_UNSUPPORTED( b200_last_error() ); if( rc == B200_ERR_PARAM ) THROW_RECOVERABLE( b200_last_error() ); if( rc < 0 ) THROW_FATAL( b200_last_error() ); }
 
@@ -338,6 +338,30 @@ class DecLibReconB200
     CodingStructure& cs = *pic->cs; const SPS& sps = *cs.sps; const PPS& pps = *cs.pps; const PreCalcValues& pcv = *cs.pcv;
     Shared& S = *m_sh;
     {
+      // A new coded video sequence with another picture size / bit depth / CTU size / chroma format (an IRAP picture after new parameter sets): nothing of the old
+      // sequence can be referenced any more.  The pictures the other recon instances still hold are finished (their planes go back to the host, output reads those),
+      // then the device context is rebuilt for the new geometry.  Anything else that changes the size is reference picture resampling: refused.
+      bool changed;
+      {
+        std::lock_guard<std::mutex> l( S.m );
+        changed = !S.owner.empty() && ( (int) pcv.lumaWidth != S.geom.width || (int) pcv.lumaHeight != S.geom.height || sps.getBitDepth() != S.geom.bitDepth
+                                        || (int) pcv.maxCUWidth != S.geom.ctuSize || ( sps.getChromaFormatIdc() == CHROMA_420 ? 1 : 0 ) != S.geom.chromaFormat );
+      }
+      if( changed )
+      {
+        if( !std::all_of( pic->slices.begin(), pic->slices.end(), []( const Slice* sl ) { return sl->isIRAP() && sl->isIntra(); } ) )
+          THROW_UNSUPPORTED( "DecLibReconB200: picture size / bit depth change inside a coded video sequence (RPR)" );
+        std::vector<DecLibReconB200*> others;
+        { std::lock_guard<std::mutex> l( S.m ); others = S.instances; }
+        for( DecLibReconB200* o : others ) if( o != this && o->m_currDecompPic && !o->m_finished ) o->finishCurrent();
+        std::lock_guard<std::mutex> l( S.m );
+        if( S.ctx ) { b200_ctx_destroy( S.ctx ); S.ctx = nullptr; }
+        S.slotOf.clear(); S.owner.clear(); S.valid.clear();
+      }
+    }
+    if( !m_fltBuf.bufs.empty() && ( m_fltFmt != pcv.chrFormat || m_fltCtu != (int) pcv.maxCUWidth ) ) m_fltBuf.destroy();
+    m_fltFmt = pcv.chrFormat; m_fltCtu = (int) pcv.maxCUWidth;
+    {
       std::lock_guard<std::mutex> l( S.m );
       if( !S.ctx && !m_dryRun )
       {
@@ -352,7 +376,6 @@ class DecLibReconB200
         S.geom.ctuSize = pcv.maxCUWidth; S.geom.stride[0] = pcv.lumaWidth; S.geom.stride[1] = S.geom.stride[2] = pcv.lumaWidth >> 1;
         S.numSlots = m_dpbSlots; S.owner.assign( S.numSlots, nullptr ); S.valid.assign( S.numSlots, 0 );
       }
-      if( (int) pcv.lumaWidth != S.geom.width || (int) pcv.lumaHeight != S.geom.height || sps.getBitDepth() != S.geom.bitDepth ) THROW_UNSUPPORTED( "DecLibReconB200: picture size / bit depth change inside a context (RPR)" );
       // reference pictures -> device DPB slots (uploaded if the device does not hold them)
       m_waitSlots.clear();
       m_sl.assign( pic->slices.size(), SliceTabs() );
