@@ -10,8 +10,10 @@
 
 typedef void ( *swapped_picture_fn )( void* user, const b200_picture* lists, const b200_geom* geom, int32_t* dmvrDeltas, size_t numDmvr, int16_t* const planes[3], const ptrdiff_t strides[3], int poc );
 
-extern "C" void swapped_set_hooks( int dryRun, swapped_picture_fn fn, void* user )
+typedef void ( *swapped_load_fn )( void* user, int slot, const int16_t* const planes[3], const ptrdiff_t strides[3], const b200_geom* geom );
+
+extern "C" void swapped_set_hooks( int dryRun, swapped_picture_fn fn, swapped_load_fn load, void* user )
 {
   auto& h = b200glue::DecLibReconB200::testHooks();
-  h.dryRun = dryRun != 0; h.picture = fn; h.user = user;
+  h.dryRun = dryRun != 0; h.picture = fn; h.loadSlot = load; h.user = user;
 }

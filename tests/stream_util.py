@@ -12,9 +12,12 @@ _HOOK = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(abi.Picture), C.POINTER(abi.Geom
                     C.POINTER(C.POINTER(C.c_int16)), C.POINTER(C.c_ssize_t), C.c_int)
 
 
+_LOAD = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.POINTER(C.c_int16)), C.POINTER(C.c_ssize_t), C.POINTER(abi.Geom))
+
+
 def swapped_lib():
     lib = vs._lib(vs.SWAP_SO)
-    lib.swapped_set_hooks.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    lib.swapped_set_hooks.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     return lib
 
 
@@ -23,14 +26,28 @@ class OracleDevice:
     def __init__(self, oracle):
         self.oracle, self.dpb, self.log, self.error = oracle, None, [], None
         self.keep, self.pics = False, {}                            # keep: the flattened lists of every picture by POC (diagnosis)
-        self.cb = _HOOK(self._picture)
+        self.cb = _HOOK(self._picture); self.load_cb = _LOAD(self._load)
+
+    def _slots(self, g):
+        if self.dpb is None or self.dpb[0][0].shape != (g.height, g.width):          # (first picture, or the context was rebuilt for another geometry)
+            self.dpb = [[np.zeros((g.height, g.width), np.int16), np.zeros((g.height // 2, g.width // 2), np.int16), np.zeros((g.height // 2, g.width // 2), np.int16)]
+                        for _ in range(NUM_SLOTS)]
+
+    def _load(self, user, slot, planes, strides, geom):
+        """b200_ctx_load_slot_strided: a reference the device does not hold is taken from its host planes"""
+        try:
+            g = geom.contents; self._slots(g)
+            for c in range(3 if g.chromaFormat else 1):
+                h, w = self.dpb[slot][c].shape
+                src = np.ctypeslib.as_array(planes[c], shape=((h - 1) * strides[c] + w,))
+                self.dpb[slot][c] = np.lib.stride_tricks.as_strided(src, shape=(h, w), strides=(strides[c] * 2, 2)).copy()
+        except BaseException:
+            import traceback; self.error = traceback.format_exc()
 
     def _picture(self, user, lists, geom, dmvr, ndmvr, planes, strides, poc):
         try:
             g = geom.contents; st = lists.contents
-            if self.dpb is None:
-                self.dpb = [[np.zeros((g.height, g.width), np.int16), np.zeros((g.height // 2, g.width // 2), np.int16), np.zeros((g.height // 2, g.width // 2), np.int16)]
-                            for _ in range(NUM_SLOTS)]
+            self._slots(g)
             pic = helpers.picture_from_struct(st, g, None)
             out, dm = helpers.oracle_decompress(self.oracle, g, self.dpb, pic)
             self.dpb[st.dstSlot] = out
@@ -51,16 +68,16 @@ def decode_swapped_cpu(aus, oracle, threads=1, keep=None, **kw):
     keep: a dict that receives the flattened work lists of every picture by POC."""
     lib = swapped_lib(); dev = OracleDevice(oracle)
     if keep is not None: dev.keep, dev.pics = True, keep
-    lib.swapped_set_hooks(1, C.cast(dev.cb, C.c_void_p), None)
+    lib.swapped_set_hooks(1, C.cast(dev.cb, C.c_void_p), C.cast(dev.load_cb, C.c_void_p), None)
     try:
         frames = vs.decode(vs.SWAP_SO, aus, threads=threads, **kw)
     finally:
-        lib.swapped_set_hooks(1, None, None)
+        lib.swapped_set_hooks(1, None, None, None)
     assert dev.error is None, dev.error
     return frames, dev.log
 
 
 def decode_swapped_device(aus, threads=8, **kw):
     """The stream through the swapped build on the product path (GPU)."""
-    lib = swapped_lib(); lib.swapped_set_hooks(0, None, None)
+    lib = swapped_lib(); lib.swapped_set_hooks(0, None, None, None)
     return vs.decode(vs.SWAP_SO, aus, threads=threads, **kw)

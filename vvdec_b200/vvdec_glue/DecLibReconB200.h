@@ -150,7 +150,11 @@ class DecLibReconB200
     CHECK_FATAL( ref->progress < Picture::reconstructed, "DecLibReconB200: reference picture is neither on the device nor reconstructed on the host" );
     const int16_t* planes[3] = { nullptr, nullptr, nullptr }; ptrdiff_t strides[3] = { 0, 0, 0 };
     for( int c = 0; c < ( S.geom.chromaFormat ? 3 : 1 ); c++ ) { const CPelBuf b = ref->getRecoBuf( ComponentID( c ) ); planes[c] = b.buf; strides[c] = b.stride; }
+    if( (int) ref->getRecoBuf( COMPONENT_Y ).width != S.geom.width || (int) ref->getRecoBuf( COMPONENT_Y ).height != S.geom.height ) THROW_UNSUPPORTED( "DecLibReconB200: reference picture of another size (RPR)" );
     if( !m_dryRun ) check( b200_ctx_load_slot_strided( S.ctx, s, planes, strides ) );
+#ifdef B200_GLUE_TEST_HOOKS
+    else if( testHooks().loadSlot ) testHooks().loadSlot( testHooks().user, s, planes, strides, &S.geom );
+#endif
     S.valid[s] = 1;
     return s;
   }
@@ -338,9 +342,11 @@ class DecLibReconB200
     CodingStructure& cs = *pic->cs; const SPS& sps = *cs.sps; const PPS& pps = *cs.pps; const PreCalcValues& pcv = *cs.pcv;
     Shared& S = *m_sh;
     {
-      // A new coded video sequence with another picture size / bit depth / CTU size / chroma format (an IRAP picture after new parameter sets): nothing of the old
-      // sequence can be referenced any more.  The pictures the other recon instances still hold are finished (their planes go back to the host, output reads those),
-      // then the device context is rebuilt for the new geometry.  Anything else that changes the size is reference picture resampling: refused.
+      // A picture with another picture size / bit depth / CTU size / chroma format than the device context was built for: a new coded video sequence (new
+      // parameter sets at an IRAP picture).  The pictures the other recon instances still hold are finished (their planes go back to the host, output reads those),
+      // then the device context is rebuilt for this geometry.  With several threads DecLib may still hand over a picture of the OLD sequence afterwards
+      // (DecLibParser::getNextDecodablePicture): the context then switches back and the references are uploaded from their host planes (importReference).
+      // A REFERENCE of another size than the picture itself is reference picture resampling: refused there.
       bool changed;
       {
         std::lock_guard<std::mutex> l( S.m );
@@ -349,8 +355,6 @@ class DecLibReconB200
       }
       if( changed )
       {
-        if( !std::all_of( pic->slices.begin(), pic->slices.end(), []( const Slice* sl ) { return sl->isIRAP() && sl->isIntra(); } ) )
-          THROW_UNSUPPORTED( "DecLibReconB200: picture size / bit depth change inside a coded video sequence (RPR)" );
         std::vector<DecLibReconB200*> others;
         { std::lock_guard<std::mutex> l( S.m ); others = S.instances; }
         for( DecLibReconB200* o : others ) if( o != this && o->m_currDecompPic && !o->m_finished ) o->finishCurrent();
@@ -606,6 +610,7 @@ public:
   {
     bool dryRun = false; void* user = nullptr;
     void ( *picture )( void* user, const b200_picture* lists, const b200_geom* geom, int32_t* dmvrDeltas, size_t numDmvr, int16_t* const planes[3], const ptrdiff_t strides[3], int poc ) = nullptr;
+    void ( *loadSlot )( void* user, int slot, const int16_t* const planes[3], const ptrdiff_t strides[3], const b200_geom* geom ) = nullptr;    // b200_ctx_load_slot_strided
   };
   static TestHooks& testHooks() { static TestHooks h; return h; }
 #endif
