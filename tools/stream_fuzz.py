@@ -68,7 +68,7 @@ def random_case(seed):
         kw["lmcs"] = True; vs.with_lmcs(pics, r, bit_depth=kw["bit_depth"], every=pick(1, 2), chroma=not mono)
         for q in pics:                                                  # (a picture without its own model keeps LMCS off)
             pass
-    if kw.get("lmcs") and not kw["max_tb64"]: kw["ciip"] = False    # (refused by the class: the reference maps residual-free CIIP blocks forward twice there, DecLibReconB200::refuse)
+    if kw.get("lmcs") and not kw["max_tb64"] and ctu > 32: kw["ciip"] = False    # (refused by the class: the reference maps residual-free CIIP blocks forward twice there, DecLibReconB200::refuse)
     if r.random() < 0.3:
         kw["scaling_lists"] = True; vs.with_scaling_lists(pics, r, chroma_present=not mono)
     n_slices = len(kw["slice_rows"]) if kw.get("slice_rows") else len(kw["tiles"][0]) * len(kw["tiles"][1]) if kw.get("tiles") and kw.get("slice_per_tile") else 1

@@ -174,7 +174,7 @@ class DecLibReconB200
     // (CABACReader.cpp:1449-1456) and the reference maps the blended block through the LMCS forward curve a SECOND time (DecCu.cpp:466-476, the `else` branch runs in
     // the inter pass and again in the CIIP pass).  Only possible with sps_max_luma_transform_size_64_flag == 0; the device path (one forward map, as the standard
     // has it) would differ from the reference there, so those pictures are left to the stock back end.
-    if( sps.getLog2MaxTbSize() < 6 && sps.getUseCiip() && pic->slices[0]->getLmcsEnabledFlag() && std::any_of( pic->slices.begin(), pic->slices.end(), []( const Slice* sl ) { return !sl->isIntra(); } ) )
+    if( sps.getLog2MaxTbSize() < 6 && sps.getCTUSize() > ( 1u << sps.getLog2MaxTbSize() ) && sps.getUseCiip() && pic->slices[0]->getLmcsEnabledFlag() && std::any_of( pic->slices.begin(), pic->slices.end(), []( const Slice* sl ) { return !sl->isIntra(); } ) )
       THROW_UNSUPPORTED( "DecLibReconB200: CIIP under LMCS with 32x32 maximum transform size (the reference's double forward mapping of residual-free CIIP blocks)" );
     if( sps.getIBCFlag() ) THROW_UNSUPPORTED( "DecLibReconB200: IBC" );
     if( sps.getUseColorTrans() ) THROW_UNSUPPORTED( "DecLibReconB200: adaptive colour transform" );
