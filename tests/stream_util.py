@@ -81,3 +81,27 @@ def decode_swapped_device(aus, threads=8, **kw):
     """The stream through the swapped build on the product path (GPU)."""
     lib = swapped_lib(); lib.swapped_set_hooks(0, None, None, None)
     return vs.decode(vs.SWAP_SO, aus, threads=threads, **kw)
+
+
+def corruption_run(seed, n, threads):
+    """n streams with 1-3 flipped bits in a later access unit through the swapped build (oracle device); prints `ok` per stream that came back — with an error code
+    or with frames — and exits.  Run in a child process (tests/test_stream_cpu.py): a crash or a hang of the class's error paths must not take the test run down."""
+    import os
+    from tests.test_stream_cpu import ALL, gop4, low_delay
+    oracle = helpers.load_oracle(); rng = np.random.default_rng(seed)
+    for it in range(n):
+        aus, _, _ = vs.build_stream(vs.Config(**dict(ALL, sao=True)), low_delay(5) if it % 2 else gop4(), seed=int(rng.integers(1, 1 << 20)))
+        k = int(rng.integers(1, len(aus))); au = bytearray(aus[k])
+        for _ in range(int(rng.integers(1, 4))):
+            au[int(rng.integers(12, len(au)))] ^= 1 << int(rng.integers(0, 8))
+        bad = list(aus); bad[k] = bytes(au)
+        try:
+            frames, _ = decode_swapped_cpu(bad, oracle, threads=threads); print("ok frames", len(frames), flush=True)
+        except vs.DecodeError as e:
+            print("ok error", str(e).split("|")[0].strip(), flush=True)
+    os._exit(0)
+
+
+if __name__ == "__main__":
+    import sys
+    corruption_run(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]))

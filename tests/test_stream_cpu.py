@@ -190,6 +190,18 @@ def test_refused_picture_surfaces_as_unsupported(oracle):
         su.decode_swapped_cpu(aus, oracle)
 
 
+@pytest.mark.parametrize("threads", [1, 4])
+def test_corrupted_streams_come_back_with_an_error(threads):
+    """Bit flips in the slice data: the parser throws while the class's tasks for the picture are scheduled or waiting on the parse barriers.  The error contract of
+    DecLibRecon (DecLibRecon.cpp:684-722: first exception parked, tasks drained, picture marked) must bring every stream back — an error code or frames, no crash, no hang."""
+    import subprocess, sys
+    p = subprocess.run([sys.executable, "-m", "tests.stream_util", "7", "6", str(threads)], capture_output=True, text=True, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    lines = [l for l in p.stdout.splitlines() if l.startswith("ok")]
+    assert p.returncode == 0 and len(lines) == 6, (p.returncode, p.stdout[-400:], p.stderr[-400:])
+    assert any(l.startswith("ok error") for l in lines)
+
+
 def test_arithmetic_encoder_round_trip():
     """ref_cabac_encode against the reference's BinDecoder: random context / bypass / terminate sequences come back bin for bin (the generating build
     reads them with drawn bins, the stock build decodes the bytes — compared through a whole slice in the tests above; here: the stop-bit / carry paths
