@@ -873,6 +873,9 @@ extern "C" int ref_seam_pipelined_flat( int k, b200_picture* flat )
 // an instance is handed its next picture as soon as its previous one has been waited for, so up to `depth` pictures are in flight.  Returns the seconds
 // for all n pictures (no output read-back), < 0 on error.  backend 0: the reference's DecLibRecon, 1: DecLibReconB200, 2: DecLibReconB200 in dry-run mode (host stages only).
 // ref_seam_read_out() fetches a picture's planes / motion field afterwards.
+// the DecLibReconB200 instances of ref_seam_run_pipelined() complete their pictures in a pool task of their own (setAsyncFinish) from the next run on
+extern "C" void ref_seam_set_async_finish( int on ) { b200glue::DecLibReconB200::asyncFinishDefault() = on != 0; }
+
 extern "C" double ref_seam_run_pipelined( void* const* hs, int n, int threads, int backend, int depth )
 {
   if( n <= 0 || depth < 1 || depth > 4 ) return -3.0;
@@ -888,14 +891,17 @@ extern "C" double ref_seam_run_pipelined( void* const* hs, int n, int threads, i
     }
     while( backend == 0 && (int) stock.size() < depth ) { stock.emplace_back( new DecLibRecon ); stock.back()->create( pool.get(), (unsigned) stock.size() - 1, false ); }
     while( backend >= 1 && (int) dev.size() < depth )   { dev.emplace_back( new b200glue::DecLibReconB200 ); dev.back()->create( pool.get(), (unsigned) dev.size() - 1, false ); }
-    if( backend >= 1 ) { for( auto& r : dev ) r->setDryRun( backend == 2 ); dev[0]->resetDpb(); }
-    bool bad = false;
+    if( backend >= 1 ) { for( auto& r : dev ) { r->setDryRun( backend == 2 ); r->setAsyncFinish( b200glue::DecLibReconB200::asyncFinishDefault() ); } dev[0]->resetDpb(); }
+    bool bad = false; std::vector<Picture*> pendingRelease;
     auto waitOne = [&]( int k )
     {
       Picture* done = backend ? dev[k]->waitForPrevDecompressedPic() : stock[k]->waitForPrevDecompressedPic();
       if( !done ) return;
       if( done->error || done->reconDone.hasException() ) { bad = true; done->reconDone.clearException(); }
-      if( backend ) dev[k]->releasePicture( done );
+      // the slot of a finished picture is given back once no picture in flight can still wait on it: a picture handed over earlier may reference it and not have been
+      // submitted yet (its submission polls the slot's state, and a NEW picture taking the slot over would look like a reference in flight).  DecLib's picture list
+      // keeps such a picture referenced (stillReferenced); here: released `depth` pictures later.
+      if( backend ) { pendingRelease.push_back( done ); while( (int) pendingRelease.size() > depth ) { dev[0]->releasePicture( pendingRelease.front() ); pendingRelease.erase( pendingRelease.begin() ); } }
     };
     const auto t0 = std::chrono::steady_clock::now();
     for( int i = 0; i < n; i++ )
@@ -907,6 +913,7 @@ extern "C" double ref_seam_run_pipelined( void* const* hs, int n, int threads, i
       catch( ... ) { pic->reconDone.setException( std::current_exception() ); pic->error = true; }
     }
     for( int j = 0; j < depth; j++ ) waitOne( ( n + j ) % depth );
+    if( backend ) for( Picture* p : pendingRelease ) dev[0]->releasePicture( p );
     const double secs = std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
     return bad ? -1.0 : secs;
   }

@@ -96,7 +96,11 @@ struct BinEncoder
     while( nbits ) put( 0, 1 );
   }
 };
+inline int& lastHashErrors() { static int n = 0; return n; }
 }   // namespace refstream
+
+// pictures of the last ref_decode_stream() call whose decoded-picture-hash SEI did not match what the decoder reconstructed (vvdec_get_hash_error_count)
+extern "C" int ref_last_hash_errors() { return refstream::lastHashErrors(); }
 
 // One CABAC segment (what lies between two context initialisations: a slice without tiles / wavefronts).  ctx[i] >= 0: context-coded bin with that
 // context index; -1: bypass bin; -2: terminating bin (the last entry of a segment, value 1).  Returns the bytes written (the slice_data() bytes,
@@ -161,6 +165,7 @@ extern "C" int ref_decode_stream2( const uint8_t* stream, const long* auOffsets,
 {
   vvdecParams params; vvdec_params_default( &params );
   params.threads = threads; params.logLevel = VVDEC_SILENT; params.errHandlingFlags = VVDEC_ERR_HANDLING_OFF;
+  params.verifyPictureHash = true;                                           // decoded-picture-hash SEIs are checked by the decoder itself (ref_last_hash_errors)
   if( threads <= 1 ) params.parseDelay = 0;
   vvdecDecoder* dec = vvdec_decoder_open( &params );
   if( !dec ) { if( errBuf ) snprintf( errBuf, errCap, "vvdec_decoder_open failed" ); return -1000; }
@@ -208,6 +213,7 @@ extern "C" int ref_decode_stream2( const uint8_t* stream, const long* auOffsets,
     if( r == VVDEC_EOF || !f ) break;
   }
   vvdec_accessUnit_free( au );
+  refstream::lastHashErrors() = vvdec_get_hash_error_count( dec );
   vvdec_decoder_close( dec );
   dims[5] = frames;
   return rc ? rc : frames;

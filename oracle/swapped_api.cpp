@@ -17,3 +17,6 @@ extern "C" void swapped_set_hooks( int dryRun, swapped_picture_fn fn, swapped_lo
   auto& h = b200glue::DecLibReconB200::testHooks();
   h.dryRun = dryRun != 0; h.picture = fn; h.loadSlot = load; h.user = user;
 }
+
+// instances created from now on complete their pictures in a pool task (DecLibReconB200::setAsyncFinish) instead of in waitForPrevDecompressedPic()
+extern "C" void swapped_set_async_finish( int on ) { b200glue::DecLibReconB200::asyncFinishDefault() = on != 0; }

@@ -19,6 +19,7 @@ SWAP_SO = os.path.join(HERE, "_ref", "libvvdec_swapped.so")
 
 NAL_TRAIL, NAL_STSA, NAL_RADL, NAL_RASL, NAL_IDR_W_RADL, NAL_IDR_N_LP, NAL_CRA, NAL_GDR = 0, 1, 2, 3, 7, 8, 9, 10
 NAL_VPS, NAL_SPS, NAL_PPS, NAL_PREFIX_APS, NAL_SUFFIX_APS, NAL_PH, NAL_AUD = 14, 15, 16, 17, 18, 19, 20
+NAL_PREFIX_SEI, NAL_SUFFIX_SEI = 23, 24
 SLICE_B, SLICE_P, SLICE_I = 0, 1, 2
 
 
@@ -572,6 +573,35 @@ def with_lmcs(pics, rng, bit_depth=10, every=1, chroma=True):
     return pics
 
 
+def write_hash_sei(method, planes, bit_depth):
+    """Suffix SEI with the decoded picture hash of `planes` (SEIread.cpp:443 xParseSEIDecodedPictureHash; PicYuvMD5.cpp: MD5 of the little-endian samples per
+    component, or the 16-bit CRC / 32-bit checksum restated in oracle/k7_output.c)."""
+    import hashlib
+    kind = {"md5": 0, "crc": 1, "checksum": 2}[method]
+    digest = b""
+    for pl in planes:
+        if pl.size == 0: continue
+        if kind == 0: digest += hashlib.md5((pl.astype("<u2") if bit_depth > 8 else pl.astype("u1")).tobytes()).digest()
+        else:
+            orc = C.CDLL(os.path.join(HERE, "liboracle.so")); out = np.zeros(16, np.uint8); a = np.ascontiguousarray(pl)
+            orc.orc_plane_hash.argtypes = [C.c_int, C.c_int, np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS"), C.c_ssize_t, C.c_int, C.c_int, np.ctypeslib.ndpointer(np.uint8)]
+            n = orc.orc_plane_hash(kind, bit_depth, a, a.shape[1], a.shape[1], a.shape[0], out); digest += bytes(out[:n])
+    single = len([pl for pl in planes if pl.size]) == 1
+    payload = bytes([kind, 0x80 if single else 0]) + digest
+    return nal_unit(NAL_SUFFIX_SEI, bytes([132, len(payload)]) + payload + b"\x80")
+
+
+def output_order(pics):
+    """index of every picture (decoding order) among the output frames: IDR periods in turn, POC order inside"""
+    groups, cur = [], []
+    for i, p in enumerate(pics):
+        if p.idr and cur: groups.append(cur); cur = []
+        cur.append(i)
+    groups.append(cur)
+    order = [i for g in groups for i in sorted(g, key=lambda k: pics[k].poc)]
+    return {i: n for n, i in enumerate(order)}
+
+
 # ---- libraries -----------------------------------------------------------------------------------------------------------------------------------------
 _libs = {}
 
@@ -586,6 +616,7 @@ def _lib(path):
         lib.ref_cabac_encode.argtypes = [C.c_int, C.c_int, np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS"), u8p, C.c_long, u8p, C.c_long]
         lib.ref_cabac_encode.restype = C.c_long
         lib.ref_ctx_offset.argtypes = [C.c_char_p]
+        lib.ref_last_hash_errors.restype = C.c_int
         lib.ref_ctx_names.restype = C.c_char_p
         if hasattr(lib, "gen_segment"):
             lib.gen_segment.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_long]; lib.gen_segment.restype = C.c_long
@@ -619,6 +650,7 @@ def decode(lib_path, aus, threads=1, max_frames=None, frame_samples=None):
         cb = out[pos:pos + cw * ch].reshape(ch, cw).copy(); pos += cw * ch
         cr = out[pos:pos + cw * ch].reshape(ch, cw).copy(); pos += cw * ch
         frames.append((y, cb, cr))
+    decode.hash_errors = lib.ref_last_hash_errors()              # pictures whose decoded-picture-hash SEI did not match (0 if the stream carries none)
     return frames
 
 
@@ -643,8 +675,9 @@ DEFAULT_BIAS = {"SplitFlag": 150, "SplitQtFlag": 140, "QtCbf0": 150, "QtCbf1": 9
 for _k in range(6): DEFAULT_BIAS[f"SigFlag{_k}"] = 90
 
 
-def build_stream(cfg, pics, seed=1, bias=None, bypass_p=128, max_bypass_run=12):
-    """Writes the stream for `pics` (decoding order).  Returns (access units, frames the generating library reconstructed, bins per slice)."""
+def build_stream(cfg, pics, seed=1, bias=None, bypass_p=128, max_bypass_run=12, hash_sei=None):
+    """Writes the stream for `pics` (decoding order).  Returns (access units, frames the generating library reconstructed, bins per slice).
+    hash_sei: "md5" / "crc" / "checksum" — every picture carries a decoded-picture-hash SEI of what it was drawn as (a decoder with verifyPictureHash checks itself)."""
     gen, ref = _lib(GEN_SO), _lib(REF_SO)
     params = write_sps(cfg) + write_pps(cfg)
     heads = [write_slices(cfg, p) for p in pics]                  # per picture: [(nal type, header bytes, is a slice)]
@@ -676,5 +709,6 @@ def build_stream(cfg, pics, seed=1, bias=None, bypass_p=128, max_bypass_run=12):
                 assert m > 0
                 data += bytes(buf[:m]); nbins.append(n); seg += 1
             au += nal_unit(t, h + data)
+        if hash_sei: au += write_hash_sei(hash_sei, drawn[output_order(pics)[i]], cfg.bit_depth)
         out.append(au)
     return out, drawn, nbins

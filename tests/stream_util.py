@@ -18,6 +18,7 @@ _LOAD = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.POINTER(C.c_int16)), 
 def swapped_lib():
     lib = vs._lib(vs.SWAP_SO)
     lib.swapped_set_hooks.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.swapped_set_async_finish.argtypes = [C.c_int]
     return lib
 
 
@@ -63,24 +64,26 @@ class OracleDevice:
             import traceback; self.error = traceback.format_exc()
 
 
-def decode_swapped_cpu(aus, oracle, threads=1, keep=None, **kw):
+def decode_swapped_cpu(aus, oracle, threads=1, keep=None, async_finish=False, **kw):
     """The stream through the swapped build without a device: glue host stages + oracle chain.  Returns (frames, per-picture log).
     keep: a dict that receives the flattened work lists of every picture by POC."""
     lib = swapped_lib(); dev = OracleDevice(oracle)
     if keep is not None: dev.keep, dev.pics = True, keep
     lib.swapped_set_hooks(1, C.cast(dev.cb, C.c_void_p), C.cast(dev.load_cb, C.c_void_p), None)
+    lib.swapped_set_async_finish(int(async_finish))            # pictures complete in a pool task (DecLibReconB200::setAsyncFinish) instead of in waitForPrevDecompressedPic()
     try:
         frames = vs.decode(vs.SWAP_SO, aus, threads=threads, **kw)
     finally:
-        lib.swapped_set_hooks(1, None, None, None)
+        lib.swapped_set_hooks(1, None, None, None); lib.swapped_set_async_finish(0)
     assert dev.error is None, dev.error
     return frames, dev.log
 
 
-def decode_swapped_device(aus, threads=8, **kw):
+def decode_swapped_device(aus, threads=8, async_finish=False, **kw):
     """The stream through the swapped build on the product path (GPU)."""
-    lib = swapped_lib(); lib.swapped_set_hooks(0, None, None, None)
-    return vs.decode(vs.SWAP_SO, aus, threads=threads, **kw)
+    lib = swapped_lib(); lib.swapped_set_hooks(0, None, None, None); lib.swapped_set_async_finish(int(async_finish))
+    try: return vs.decode(vs.SWAP_SO, aus, threads=threads, **kw)
+    finally: lib.swapped_set_async_finish(0)
 
 
 def corruption_run(seed, n, threads):

@@ -105,6 +105,21 @@ def test_two_alternating_recon_instances():
     assert secs >= 0
 
 
+@pytest.mark.parametrize("threads", [0, 1, 4])
+def test_pictures_completed_by_a_pool_task(threads):
+    """setAsyncFinish: the class releases pic->reconDone from a task of its own, as the reference's finishReconTask does, instead of inside
+    waitForPrevDecompressedPic() — two alternating instances, chained pictures (dry run), with no, one and four pool threads."""
+    rng = np.random.default_rng(78)
+    base = helpers.SeamCase(ref, rng, 416, 240)
+    cases = [base.variant(seed=200 + i, slice_type=2 if i == 0 else 0) for i in range(6)]
+    ref.ref_seam_set_async_finish(1)
+    try:
+        secs, _ = helpers.seam_pipelined(ref, cases, threads, 2, 2, read=False, chain=True)
+    finally:
+        ref.ref_seam_set_async_finish(0)
+    assert secs >= 0
+
+
 def test_reference_still_in_flight_on_the_other_instance():
     """Picture B predicts from picture A while A is still with the other recon instance (what DecLib's two alternating instances produce all the time).  Stock: the two
     instances give B the same samples as one instance after the other.  DecLibReconB200 (dry run): B's submission waits until A is in the stream, B's lists name A's

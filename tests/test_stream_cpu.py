@@ -177,6 +177,33 @@ def test_new_sequence_with_another_picture_size_ctu_size_and_bit_depth(oracle):
     assert _diff(swapped, stock) == [0] * 15
 
 
+@pytest.mark.parametrize("method,bit_depth,threads,structure", [("md5", 10, 1, "gop"), ("crc", 10, 4, "low_delay"), ("checksum", 8, 0, "gop"), ("md5", 8, 2, "low_delay")])
+def test_decoded_picture_hash_sei_with_pictures_completed_by_a_pool_task(oracle, method, bit_depth, threads, structure):
+    """Every picture carries a decoded-picture-hash SEI (MD5 / CRC / checksum of what it was drawn as); the decoders verify themselves (verifyPictureHash,
+    vvdec_get_hash_error_count).  With parseFrameDelay == 0 the parser meets the SEI and waits for pic->reconDone ON THE API THREAD (DecLibParser.cpp:249-261): the
+    class has to complete the picture without waitForPrevDecompressedPic() being called — setAsyncFinish — or the decoder never returns."""
+    from tests import stream_util as su
+    pics = gop4() if structure == "gop" else low_delay(6)
+    aus, drawn, _ = vs.build_stream(vs.Config(**dict(ALL, bit_depth=bit_depth)), pics, seed=4, hash_sei=method)
+    stock = vs.decode(vs.REF_SO, aus, threads=threads)
+    assert vs.decode.hash_errors == 0 and _diff(drawn, stock) == [0] * len(aus)
+    damaged = list(aus); b = bytearray(damaged[2]); b[-3] ^= 0x55; damaged[2] = bytes(b)          # (a wrong digest is noticed)
+    vs.decode(vs.REF_SO, damaged, threads=threads); assert vs.decode.hash_errors == 1
+    swapped, _ = su.decode_swapped_cpu(aus, oracle, threads=threads, async_finish=True)
+    assert vs.decode.hash_errors == 0 and _diff(swapped, stock) == [0] * len(aus)
+
+
+@pytest.mark.parametrize("name", ["gop_all_tools", "low_delay_alf_lmcs", "gop_4tiles_4slices", "gop_3slices_alf_lmcs"])
+def test_stream_cases_with_pictures_completed_by_a_pool_task(oracle, name):
+    from tests import stream_util as su
+    kw, pics = CASES[name]
+    aus, drawn, _ = vs.build_stream(vs.Config(**kw), pics(), seed=31)
+    stock = vs.decode(vs.REF_SO, aus, threads=4)
+    for threads in (1, 4):
+        swapped, _ = su.decode_swapped_cpu(aus, oracle, threads=threads, async_finish=True)
+        assert _diff(swapped, stock) == [0] * len(aus)
+
+
 def test_refused_picture_surfaces_as_unsupported(oracle):
     """What the device path leaves to the stock back end is refused on the API thread in decompressPicture (DecLib::reconPicture records it) and comes out of
     vvdec_decode as VVDEC_ERR_NOT_SUPPORTED.  Case: CIIP under LMCS with a 32x32 maximum transform size — the reference maps residual-free CIIP blocks of CUs

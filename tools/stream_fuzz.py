@@ -90,13 +90,13 @@ if __name__ == "__main__":
         kw, pics, structure = random_case(seed)
         tag = f"{seed} {structure} {kw['width']}x{kw['height']} ctu{kw['ctu']} {kw['bit_depth']}b slices={kw.get('slice_rows')} tiles={kw.get('tiles')}{'S' if kw.get('slice_per_tile') else ''} " + "".join(k[0] for k in ("alf", "lmcs", "scaling_lists", "weighted_pred") if kw.get(k))
         try:
-            aus, drawn, nb = vs.build_stream(vs.Config(**kw), pics, seed=seed)
+            aus, drawn, nb = vs.build_stream(vs.Config(**kw), pics, seed=seed, hash_sei=("md5", "crc", "checksum")[seed % 3] if seed & 1 else None)
         except (vs.DecodeError, AssertionError) as e:
             print(tag, "not drawn:", str(e)[-220:].replace("\n", " "), flush=True); continue
         stock = vs.decode(vs.REF_SO, aus)
         d0 = _diff(drawn, stock)
         try:
-            sw, log = su.decode_swapped_cpu(aus, oracle, threads=int(seed % 3 == 0) * 3 + 1)
+            sw, log = su.decode_swapped_cpu(aus, oracle, threads=int(seed % 3 == 0) * 3 + 1, async_finish=bool(seed & 1))
             d1 = _diff(sw, stock)
         except Exception as e:
             d1 = "FAILED " + str(e)[-300:].replace("\n", " ")

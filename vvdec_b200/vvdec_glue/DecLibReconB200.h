@@ -95,7 +95,8 @@ class DecLibReconB200
   int         m_arena = -1, m_dstSlot = -1;
   std::vector<Row> m_rows; int m_ctusW = 0;
   std::vector<MotionHist> m_hist;
-  WaitCounter m_flattenCounter, m_submitCounter, m_finishCounter;
+  WaitCounter m_flattenCounter, m_submitCounter, m_finishCounter, m_doneCounter;
+  std::recursive_mutex m_finishMutex; bool m_asyncFinish = false; std::vector<int> m_refSlots;
   // per-picture work lists (pinned)
   PinnedVec<b200_pu> m_pus; PinnedVec<b200_tu> m_tus; PinnedVec<int16_t> m_coefs; PinnedVec<b200_intra_tu> m_intra;
   PinnedVec<b200_lf_param> m_lf[2]; PinnedVec<b200_sao_ctu> m_sao; PinnedVec<b200_alf_ctu> m_alf; PinnedVec<b200_lmcs_vpdu> m_vpdus;
@@ -357,7 +358,7 @@ class DecLibReconB200
       {
         std::vector<DecLibReconB200*> others;
         { std::lock_guard<std::mutex> l( S.m ); others = S.instances; }
-        for( DecLibReconB200* o : others ) if( o != this && o->m_currDecompPic && !o->m_finished ) o->finishCurrent();
+        for( DecLibReconB200* o : others ) if( o != this && o->m_currDecompPic ) o->finishCurrent();
         std::lock_guard<std::mutex> l( S.m );
         if( S.ctx ) { b200_ctx_destroy( S.ctx ); S.ctx = nullptr; }
         S.slotOf.clear(); S.owner.clear(); S.valid.clear();
@@ -381,13 +382,13 @@ class DecLibReconB200
         S.numSlots = m_dpbSlots; S.owner.assign( S.numSlots, nullptr ); S.valid.assign( S.numSlots, 0 );
       }
       // reference pictures -> device DPB slots (uploaded if the device does not hold them)
-      m_waitSlots.clear();
+      m_waitSlots.clear(); m_refSlots.clear();
       m_sl.assign( pic->slices.size(), SliceTabs() );
       for( size_t si = 0; si < pic->slices.size(); si++ )
       {
         const Slice& sl = *pic->slices[si]; SliceTabs& st = m_sl[si]; st.slice = &sl;
         memset( &st.slotMap, -1, sizeof( st.slotMap ) );
-        for( int l = 0; l < 2; l++ ) for( int i = 0; i < sl.getNumRefIdx( RefPicList( l ) ); i++ ) st.slotMap.slot[l][i] = (int8_t) importReference( sl.getRefPic( RefPicList( l ), i ) );
+        for( int l = 0; l < 2; l++ ) for( int i = 0; i < sl.getNumRefIdx( RefPicList( l ) ); i++ ) { st.slotMap.slot[l][i] = (int8_t) importReference( sl.getRefPic( RefPicList( l ), i ) ); m_refSlots.push_back( st.slotMap.slot[l][i] ); }
       }
       m_slotMap = m_sl[0].slotMap;
       m_dstSlot = slotLocked( pic ); S.valid[m_dstSlot] = 2;
@@ -587,6 +588,7 @@ public:
     m_pool = threadPool; m_id = instanceId; m_numThreads = std::max( 1, threadPool ? threadPool->numThreads() : 1 );
     m_sh = sharedFor( threadPool );
     { std::lock_guard<std::mutex> l( m_sh->m ); m_sh->instances.push_back( this ); }
+    m_asyncFinish = asyncFinishDefault();
 #ifdef B200_GLUE_TEST_HOOKS
     m_dryRun = testHooks().dryRun;
 #endif
@@ -649,7 +651,7 @@ public:
       if( !col ) continue;
       std::vector<DecLibReconB200*> others;
       { std::lock_guard<std::mutex> l( m_sh->m ); others = m_sh->instances; }
-      for( DecLibReconB200* o : others ) if( o != this && o->m_currDecompPic == col && !o->m_finished ) o->finishCurrent();
+      for( DecLibReconB200* o : others ) if( o != this && o->m_currDecompPic == col ) o->finishCurrent();
     }
   }
   void prepareAndSchedule( Picture* pic )
@@ -690,32 +692,58 @@ public:
       }
     }
     m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 submit" ) submitTask, this, &m_submitCounter, nullptr, { m_flattenCounter.donePtr(), &pic->parseDone }, submitReady );
+    // FINISH as a task of its own (setAsyncFinish): the picture completes — pic->reconDone is released — without the API thread having to call
+    // waitForPrevDecompressedPic() first, as the reference's finishReconTask does (DecLibRecon.cpp:663-671).  The parser relies on that when it meets a
+    // decoded-picture-hash SEI with parseFrameDelay == 0 (DecLibParser.cpp:249-261: reconDone.wait() on the API thread).  The task blocks its pool thread while the device works.
+    if( m_asyncFinish )
+      m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 finish" ) finishTask, this, &m_doneCounter, nullptr, { m_submitCounter.donePtr() } );
   }
+  // On the device the stream orders a picture behind the pictures it references.  The test hook that stands in for the device (dry run) computes a picture when it is
+  // finished: there the FINISH task only completes a picture whose references are finished and otherwise leaves it to waitForPrevDecompressedPic() (no polling: a pool
+  // whose threads all found nothing ready sleeps until a task is added, ThreadPool.cpp:540-551).
+  bool referencesFinished()
+  {
+    std::lock_guard<std::mutex> l( m_sh->m );
+    for( int s : m_refSlots ) if( s >= 0 && ( m_sh->valid[s] == 2 || m_sh->valid[s] == 3 ) ) return false;
+    return true;
+  }
+  static bool finishTask( int tid, void* p ) { static_cast<DecLibReconB200*>( p )->finishCurrent( tid ); return true; }
 
   // DecLibRecon::waitForPrevDecompressedPic (DecLibRecon.cpp:684): host stages done -> device done -> DMVR deltas -> TaskFinishMotionInfo -> planes.
   Picture* waitForPrevDecompressedPic()
   {
     if( !m_currDecompPic ) return nullptr;
     Picture* pic = m_currDecompPic;
-    if( !m_finished ) finishCurrent();
+    finishCurrent();
+    if( m_asyncFinish ) { if( m_pool->numThreads() == 0 ) m_pool->processTasksOnMainThread(); m_doneCounter.wait_nothrow(); m_doneCounter.clearException(); }      // (the task itself, if it was not the one that finished the picture)
     m_finished = false;
     if( pic->error || pic->reconDone.hasException() ) cleanupOnException();
     return std::exchange( m_currDecompPic, nullptr );
   }
-  void finishCurrent()
+  // Completes the current picture once: from waitForPrevDecompressedPic(), from another instance that needs this picture finished (finishCollocatedPictures, change of
+  // geometry), or from the FINISH task (taskTid >= 0: on a pool thread, so nothing here may wait for other pool tasks — the motion field is finished inline).
+  void finishCurrent( const int taskTid = -1 )
   {
+    // (the task never blocks on the mutex: whoever holds it is finishing the picture and may be waiting for pool tasks)
+    std::unique_lock<std::recursive_mutex> lock( m_finishMutex, std::defer_lock );
+    if( taskTid >= 0 ) { if( !lock.try_lock() ) return; } else lock.lock();
+    if( m_finished ) return;
+    if( taskTid >= 0 && m_dryRun && !referencesFinished() ) return;
     Picture* pic = m_currDecompPic;
     m_finished = true;
     try
     {
-      if( m_pool->numThreads() == 0 ) m_pool->processTasksOnMainThread();
-      m_flattenCounter.wait(); m_submitCounter.wait();
+      if( taskTid < 0 )
+      {
+        if( m_pool->numThreads() == 0 ) m_pool->processTasksOnMainThread();
+        m_flattenCounter.wait(); m_submitCounter.wait();
+      }
       if( m_failed.load() ) std::rethrow_exception( m_failure );
       const Slice*   lastSlice           = pic->slices.back();
       const unsigned lastSliceLastCtuIdx = lastSlice->getCtuAddrInSlice( lastSlice->getNumCtuInSlice() - 1 );
       CHECK( lastSliceLastCtuIdx != pic->cs->pcv->sizeInCtus - 1, "Picture incomplete. A slice was probably lost." );
       m_stage[1] = m_tFlat0.load() * 1e-9; m_stage[4] = since();
-      finishOnHost( pic );
+      finishOnHost( pic, taskTid );
       m_stage[5] = since();
       if( m_failed.load() ) std::rethrow_exception( m_failure );
       pic->cs->deallocTempInternals();
@@ -729,12 +757,15 @@ public:
       pic->reconDone.setException( std::current_exception() );
     }
   }
+  // Completion without the API thread (see prepareAndSchedule); before the first picture.
+  void setAsyncFinish( bool b ) { m_asyncFinish = b; }
+  static bool& asyncFinishDefault() { static bool b = false; return b; }
 
   // DecLibRecon::cleanupOnException (DecLibRecon.cpp:724): no task of the broken picture may survive in the pool; its device slot is released
   void cleanupOnException()
   {
-    m_flattenCounter.wait_nothrow(); m_submitCounter.wait_nothrow(); m_finishCounter.wait_nothrow();
-    m_flattenCounter.clearException(); m_submitCounter.clearException(); m_finishCounter.clearException();
+    m_flattenCounter.wait_nothrow(); m_submitCounter.wait_nothrow(); m_finishCounter.wait_nothrow(); m_doneCounter.wait_nothrow();
+    m_flattenCounter.clearException(); m_submitCounter.clearException(); m_finishCounter.clearException(); m_doneCounter.clearException();
     if( m_currDecompPic ) m_currDecompPic->waitForAllTasks();
     if( m_sh && m_currDecompPic )
     {
@@ -745,7 +776,7 @@ public:
   }
 
 private:
-  void finishOnHost( Picture* pic )
+  void finishOnHost( Picture* pic, const int taskTid = -1 )
   {
     CodingStructure& cs = *pic->cs; const PreCalcValues& pcv = *cs.pcv; Shared& S = *m_sh;
     m_dmvr.v.assign( m_dmvrMvCache.size() * 2, 0 ); m_dmvr.pin();
@@ -763,8 +794,13 @@ private:
       testHooks().picture( testHooks().user, &m_pic, &S.geom, m_dmvr.v.data(), m_dmvrMvCache.size(), planes, strides, pic->poc );
     }
 #endif
+    if( m_dryRun ) { std::lock_guard<std::mutex> l( S.m ); S.valid[m_dstSlot] = 1; }
     for( size_t i = 0; i < m_dmvrMvCache.size(); i++ ) m_dmvrMvCache[i] = Mv( m_dmvr.v[2 * i], m_dmvr.v[2 * i + 1] );
-    if( pic->stillReferenced )                                                                                    // colMotion for later TMVP (DecCu.cpp:161), under ctuTask's
+    if( pic->stillReferenced && taskTid >= 0 )                                                                    // (inside the FINISH task: inline, a task must not wait for tasks)
+    {
+      for( unsigned a = 0; a < pcv.sizeInCtus; a++ ) if( !cs.getCtuData( a ).slice->isIntra() ) m_cuDecoders[taskTid]->TaskFinishMotionInfo( cs, a, a % pcv.widthInCtus, a / pcv.widthInCtus );
+    }
+    else if( pic->stillReferenced )                                                                               // colMotion for later TMVP (DecCu.cpp:161), under ctuTask's
     {                                                                                                             // conditions (DecLibRecon.cpp:860-867); one pool task per CTU row
       for( unsigned y = 0; y < pcv.heightInCtus; y++ )
         m_pool->addBarrierTask( TP_TASK_NAME_ARG( "POC:" + std::to_string( pic->poc ) + " b200 finishMotion " + std::to_string( y ) ) finishMotionTask, &m_rows[(size_t) y * pcv.widthInCtus], &m_finishCounter );
