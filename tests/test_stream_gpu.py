@@ -58,3 +58,14 @@ def test_new_sequence_with_another_geometry_on_the_device():
     stock = vs.decode(vs.REF_SO, aus, threads=4, frame_samples=256 * 192 * 2)
     got = su.decode_swapped_device(aus, threads=4, frame_samples=256 * 192 * 2)
     assert _diff(got, stock) == [0] * len(aus)
+
+
+def test_hash_sei_with_parse_delay_0_on_the_device():
+    """decoded-picture-hash SEIs with one thread (parseFrameDelay 0): the parser waits for pic->reconDone on the API thread, the class completes the picture from a pool
+    task (setAsyncFinish); the decoder verifies the hashes of what came back from the device itself"""
+    from tests import stream_util as su
+    aus, drawn, _ = vs.build_stream(vs.Config(**dict(ALL, width=416, height=240)), gop4(), seed=4, hash_sei="md5")
+    stock = vs.decode(vs.REF_SO, aus, threads=1)
+    assert vs.decode.hash_errors == 0
+    got = su.decode_swapped_device(aus, threads=1, async_finish=True)
+    assert vs.decode.hash_errors == 0 and _diff(got, stock) == [0] * len(aus)
