@@ -105,6 +105,33 @@ def corruption_run(seed, n, threads):
     os._exit(0)
 
 
+def device_child(in_path, out_path, threads, async_finish):
+    """child process of decode_swapped_device_guarded(): decodes on the device path and stores the frames"""
+    import os, pickle
+    aus, kw = pickle.load(open(in_path, "rb"))
+    try:
+        frames = decode_swapped_device(aus, threads=threads, async_finish=async_finish, **kw)
+        pickle.dump(dict(frames=frames, hash_errors=vs.decode.hash_errors), open(out_path, "wb"))
+    except vs.DecodeError as e:
+        pickle.dump(dict(error=str(e)), open(out_path, "wb"))
+    os._exit(0)
+
+
+def decode_swapped_device_guarded(aus, threads=4, async_finish=False, timeout=600, **kw):
+    """decode_swapped_device() in a child process with a time limit: a crash or a hang on the device path fails the one test instead of taking the test run down.
+    Returns (frames, hash errors)."""
+    import os, pickle, subprocess, sys, tempfile
+    with tempfile.TemporaryDirectory() as d:
+        pickle.dump((aus, kw), open(os.path.join(d, "in.pkl"), "wb"))
+        p = subprocess.run([sys.executable, "-m", "tests.stream_util", "device", os.path.join(d, "in.pkl"), os.path.join(d, "out.pkl"), str(threads), str(int(async_finish))],
+                           capture_output=True, text=True, timeout=timeout, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert p.returncode == 0 and os.path.exists(os.path.join(d, "out.pkl")), f"device decode died (rc {p.returncode}): {p.stderr[-600:]}"
+        r = pickle.load(open(os.path.join(d, "out.pkl"), "rb"))
+    assert "error" not in r, r.get("error")
+    return r["frames"], r["hash_errors"]
+
+
 if __name__ == "__main__":
     import sys
+    if sys.argv[1] == "device": device_child(sys.argv[2], sys.argv[3], int(sys.argv[4]), bool(int(sys.argv[5])))
     corruption_run(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]))
