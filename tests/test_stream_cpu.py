@@ -204,6 +204,21 @@ def test_stream_cases_with_pictures_completed_by_a_pool_task(oracle, name):
         assert _diff(swapped, stock) == [0] * len(aus)
 
 
+@pytest.mark.parametrize("seed", [2003, 2017, 2130, 3179, 5001, 5014])
+def test_random_streams(oracle, seed):
+    """a few draws of tools/stream_fuzz.py (random parameter sets / structures / tools; odd seeds: hash SEIs and completion by a pool task) as a regression"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import stream_fuzz as sf
+    from tests import stream_util as su
+    kw, pics, _ = sf.random_case(seed)
+    aus, drawn, _ = vs.build_stream(vs.Config(**kw), pics, seed=seed, hash_sei="md5" if seed & 1 else None)
+    stock = vs.decode(vs.REF_SO, aus)
+    assert _diff(drawn, stock) == [0] * len(aus)
+    swapped, _ = su.decode_swapped_cpu(aus, oracle, threads=1 + 3 * (seed % 3 == 0), async_finish=bool(seed & 1))
+    assert _diff(swapped, stock) == [0] * len(aus) and vs.decode.hash_errors == 0
+
+
 def test_refused_picture_surfaces_as_unsupported(oracle):
     """What the device path leaves to the stock back end is refused on the API thread in decompressPicture (DecLib::reconPicture records it) and comes out of
     vvdec_decode as VVDEC_ERR_NOT_SUPPORTED.  Case: CIIP under LMCS with a 32x32 maximum transform size — the reference maps residual-free CIIP blocks of CUs
