@@ -28,6 +28,24 @@ def gop4(base=0, idr=True):
             vs.Pic(b + 1, vs.SLICE_B, ((b, b + 2), (b + 2, b + 4)), referenced=False), vs.Pic(b + 3, vs.SLICE_B, ((b + 2, b), (b + 4,)), referenced=False)]
 
 
+def gop8(base=0, idr=True, n_gops=1):
+    """hierarchical-B random-access GOPs of 8 (decoding order 8 4 2 1 3 6 5 7 after the anchor), up to three references per list, non-reference pictures at the top level"""
+    pics = []
+    for g in range(n_gops):
+        b = base + 8 * g
+        if g == 0: pics.append(vs.Pic(b, idr=True) if idr else vs.Pic(b, vs.SLICE_P, ((b - 8,), ())))
+        B = vs.SLICE_B
+        pics += [vs.Pic(b + 8, vs.SLICE_P if g % 2 == 0 else B, ((b,), ()) if g % 2 == 0 else ((b,), (b,))),
+                 vs.Pic(b + 4, B, ((b, b + 8), (b + 8, b))),
+                 vs.Pic(b + 2, B, ((b, b + 4), (b + 4, b + 8))),
+                 vs.Pic(b + 1, B, ((b, b + 2), (b + 2, b + 4, b + 8)), referenced=False),
+                 vs.Pic(b + 3, B, ((b + 2, b), (b + 4, b + 8)), referenced=False),
+                 vs.Pic(b + 6, B, ((b + 4, b + 2, b), (b + 8,))),
+                 vs.Pic(b + 5, B, ((b + 4, b), (b + 6, b + 8)), referenced=False),
+                 vs.Pic(b + 7, B, ((b + 6, b + 4), (b + 8,)), referenced=False)]
+    return pics
+
+
 def low_delay(n):
     """I P P P ... each picture predicting from the two before it; the last list-1 entry repeats list 0 (low-delay B)"""
     pics = [vs.Pic(0)]
@@ -69,6 +87,8 @@ CASES = {
     "gop_min_cb8_qp20": (dict(ALL, min_cb=8, min_qt_intra=16, min_qt_inter=16, min_qt_intra_c=16, init_qp=20), gop4),
     "gop_no_deblocking": (dict(ALL, deblocking_disabled=True), gop4),
     "low_delay_8": (dict(ALL), lambda: low_delay(8)),
+    "gop8_x2": (dict(ALL, dpb_size=8), lambda: gop8(n_gops=2)),
+    "gop8_alf_lmcs_3slices": (dict(ALL, dpb_size=8, alf=True, ccalf=True, lmcs=True, **SL3), lambda: vs.with_lmcs(vs.with_alf(gop8(), np.random.default_rng(41)), np.random.default_rng(42), every=3)),
     "gop_max_transform_32": (dict(ALL, max_tb64=False), gop4),                                                      # 64x64 CUs carry four TUs; CIIP still predicts the CU block
     "gop_4tiles_one_slice": (dict(ALL, width=256, height=192, tiles=((2, 2), (1, 2))), gop4),                       # CABAC restarts per tile inside the slice data
     "gop_4tiles_4slices": (dict(ALL, width=256, height=192, tiles=((1, 3), (2, 1)), slice_per_tile=True), gop4),

@@ -6,7 +6,7 @@ import sys, os, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import vvc_stream as vs
 from tests import helpers, stream_util as su
-from tests.test_stream_cpu import INTRA, INTER, gop4, low_delay, _diff
+from tests.test_stream_cpu import INTRA, INTER, gop4, gop8, low_delay, _diff
 
 
 def random_case(seed):
@@ -57,8 +57,9 @@ def random_case(seed):
     kw.update(ph_tool_control=bool(r.integers(0, 2)), parallel_merge_level=int(r.integers(2, 6)), lfnst_scaling_disabled=bool(r.integers(0, 2)))
     if kw["transform_skip"]: kw.update(min_qp_prime_ts=int(r.integers(0, 4)), ts_max_size=int(r.integers(2, 6)))
     if kw.get("chroma_qp_offsets") is not None and r.random() < 0.5: kw["cb_cr_deblock_offsets"] = tuple(int(v) for v in r.integers(-4, 5, size=4))
-    structure = pick("gop", "gop", "low_delay", "intra")
-    pics = gop4() + (gop4(4, idr=False)[1:] if r.random() < 0.3 else []) if structure == "gop" else low_delay(int(r.integers(3, 7))) if structure == "low_delay" else [vs.Pic(0), vs.Pic(1, idr=True)]
+    structure = pick("gop", "gop", "low_delay", "intra", "gop8")
+    if structure == "gop8": kw["dpb_size"] = 8
+    pics = gop8(n_gops=pick(1, 2)) if structure == "gop8" else gop4() + (gop4(4, idr=False)[1:] if r.random() < 0.3 else []) if structure == "gop" else low_delay(int(r.integers(3, 7))) if structure == "low_delay" else [vs.Pic(0), vs.Pic(1, idr=True)]
     if r.random() < 0.3 and structure != "intra":
         kw.update(weighted_pred=True, weighted_bipred=bool(r.integers(0, 2)))
         for i, q in enumerate(pics): q["wp"] = seed * 7 + i
