@@ -7,7 +7,7 @@ be bit-exact.  (Runs last among the GPU tests: the file name sorts behind test_s
 this file was written after the round's GPU budget was spent and has only run on the CPU path — same streams, oracle chain in place of the device.)"""
 import os, numpy as np, pytest
 from oracle import vvc_stream as vs
-from tests.test_stream_cpu import ALL, INTRA, SL3, gop4, low_delay, _diff, _mixed_slice_types, _weighted
+from tests.test_stream_cpu import ALL, INTRA, SL3, gop4, gop8, low_delay, _diff, _mixed_slice_types, _weighted
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not (vs.available() and os.path.exists(vs.SWAP_SO)), reason="oracle/_ref not built")]
 
@@ -19,6 +19,7 @@ CASES = {
     "gop_ctu32": (dict(ALL, width=256, height=128, ctu=32, max_bt_inter=32, max_tt_inter=32), gop4),
     "gop_cu_qp_delta": (dict(ALL, width=256, height=128, cu_qp_delta=True), gop4),
     "low_delay_8": (dict(ALL, width=416, height=240), lambda: low_delay(8)),
+    "gop8_x2": (dict(ALL, width=416, height=240, dpb_size=8), lambda: gop8(n_gops=2)),
     "gop_alf_ccalf_lmcs": (dict(ALL, width=416, height=240, alf=True, ccalf=True, lmcs=True), lambda: vs.with_lmcs(vs.with_alf(gop4(), np.random.default_rng(4)), np.random.default_rng(5))),
     "gop_max_transform_32": (dict(ALL, width=416, height=240, max_tb64=False), gop4),
     "gop_intra_slice_in_inter_pictures": (dict(ALL, **SL3), _mixed_slice_types),
