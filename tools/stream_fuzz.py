@@ -1,6 +1,6 @@
 """Randomised bitstream fuzz of the DecLibRecon seam on the CPU (test infrastructure): random parameter sets / GOP structures / tool switches through
 oracle/vvc_stream.py, decoded by the stock reference and by the swapped build with the oracle chain as the device (tests/stream_util.py).
-    python tools/stream_fuzz.py FIRST_SEED COUNT
+    python tools/stream_fuzz.py FIRST_SEED COUNT [big]
 Prints one line per stream; exit code 1 if any stream differed."""
 import sys, os, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,7 +9,8 @@ from tests import helpers, stream_util as su
 from tests.test_stream_cpu import INTRA, INTER, gop4, gop8, low_delay, _diff
 
 
-def random_case(seed):
+def random_case(seed, big=False):
+    """big: pictures of 4..9 CTUs a side (up to 1152x1152) instead of 2..4"""
     r = np.random.default_rng(seed)
     pick = lambda *a: a[int(r.integers(len(a)))]
     kw = {k: bool(r.integers(0, 4)) for k in list(INTRA) + list(INTER)}          # each tool on with probability 3/4
@@ -28,9 +29,9 @@ def random_case(seed):
     if r.random() < 0.3: kw.update(min_cb=8, min_qt_intra=16, min_qt_inter=16, min_qt_intra_c=16)
     mono = r.random() < 0.1
     if mono: kw.update(chroma_format=0, cclm=False, jccr=False, dual_tree=False)
-    wc = int(r.integers(2, 5)); hc = int(r.integers(2, 5))
+    wc = int(r.integers(4, 10) if big else r.integers(2, 5)); hc = int(r.integers(4, 10) if big else r.integers(2, 5))
     W = wc * ctu - pick(0, 0, 8, 24 if ctu > 32 else 8); H = hc * ctu - pick(0, 0, 8, 16)
-    if ctu == 128: W, H = min(W, 384), min(H, 256)
+    if ctu == 128 and not big: W, H = min(W, 384), min(H, 256)
     kw.update(width=W, height=H)
     rows = -(-H // ctu)
     if rows >= 2 and r.random() < 0.4:
@@ -88,16 +89,16 @@ if __name__ == "__main__":
     first, count = int(sys.argv[1]), int(sys.argv[2])
     oracle = helpers.load_oracle(); bad = 0
     for seed in range(first, first + count):
-        kw, pics, structure = random_case(seed)
+        kw, pics, structure = random_case(seed, big=len(sys.argv) > 3 and sys.argv[3] == "big")
         tag = f"{seed} {structure} {kw['width']}x{kw['height']} ctu{kw['ctu']} {kw['bit_depth']}b slices={kw.get('slice_rows')} tiles={kw.get('tiles')}{'S' if kw.get('slice_per_tile') else ''} " + "".join(k[0] for k in ("alf", "lmcs", "scaling_lists", "weighted_pred") if kw.get(k))
         try:
             aus, drawn, nb = vs.build_stream(vs.Config(**kw), pics, seed=seed, hash_sei=("md5", "crc", "checksum")[seed % 3] if seed & 1 else None)
         except (vs.DecodeError, AssertionError) as e:
             print(tag, "not drawn:", str(e)[-220:].replace("\n", " "), flush=True); continue
-        stock = vs.decode(vs.REF_SO, aus)
+        stock = vs.decode(vs.REF_SO, aus, frame_samples=kw['width'] * kw['height'] * 2)
         d0 = _diff(drawn, stock)
         try:
-            sw, log = su.decode_swapped_cpu(aus, oracle, threads=int(seed % 3 == 0) * 3 + 1, async_finish=bool(seed & 1))
+            sw, log = su.decode_swapped_cpu(aus, oracle, threads=int(seed % 3 == 0) * 3 + 1, async_finish=bool(seed & 1), frame_samples=kw['width'] * kw['height'] * 2)
             d1 = _diff(sw, stock)
         except Exception as e:
             d1 = "FAILED " + str(e)[-300:].replace("\n", " ")
