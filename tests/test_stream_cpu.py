@@ -73,6 +73,12 @@ def _picture_switches():
 
 
 SL3 = dict(width=256, height=256, slice_rows=(2, 1, 1))
+def _intra_pictures_inside():
+    P, B, I = vs.SLICE_P, vs.SLICE_B, vs.SLICE_I                      # non-IDR intra pictures (their reference lists are written, one of them empty)
+    return [vs.Pic(0), vs.Pic(1, P, ((0,), ())), vs.Pic(2, B, ((1, 0), (1,))), vs.Pic(3, I, ((2, 1), (2,)), idr=False), vs.Pic(4, P, ((3, 2), ())),
+            vs.Pic(5, I, ((), ()), idr=False), vs.Pic(6, B, ((5,), (5,)))]
+
+
 CASES = {
     "I_all_intra_tools": (dict(INTRA), lambda: [vs.Pic(0)]),
     "I_dual_tree_ctu128": (dict(INTRA, ctu=128, dual_tree=True), lambda: [vs.Pic(0), vs.Pic(1, idr=True)]),
@@ -87,6 +93,7 @@ CASES = {
     "gop_min_cb8_qp20": (dict(ALL, min_cb=8, min_qt_intra=16, min_qt_inter=16, min_qt_intra_c=16, init_qp=20), gop4),
     "gop_no_deblocking": (dict(ALL, deblocking_disabled=True), gop4),
     "low_delay_8": (dict(ALL), lambda: low_delay(8)),
+    "low_delay_with_intra_pictures": (dict(ALL), _intra_pictures_inside),
     "gop8_x2": (dict(ALL, dpb_size=8), lambda: gop8(n_gops=2)),
     "gop8_alf_lmcs_3slices": (dict(ALL, dpb_size=8, alf=True, ccalf=True, lmcs=True, **SL3), lambda: vs.with_lmcs(vs.with_alf(gop8(), np.random.default_rng(41)), np.random.default_rng(42), every=3)),
     "gop_max_transform_32": (dict(ALL, max_tb64=False), gop4),                                                      # 64x64 CUs carry four TUs; CIIP still predicts the CU block
