@@ -117,7 +117,7 @@ def device_child(in_path, out_path, threads, async_finish):
     os._exit(0)
 
 
-def decode_swapped_device_guarded(aus, threads=4, async_finish=False, timeout=600, **kw):
+def decode_swapped_device_guarded(aus, threads=4, async_finish=False, timeout=240, **kw):
     """decode_swapped_device() in a child process with a time limit: a crash or a hang on the device path fails the one test instead of taking the test run down.
     Returns (frames, hash errors)."""
     import os, pickle, subprocess, sys, tempfile

@@ -69,5 +69,5 @@ def test_hash_sei_with_parse_delay_0_on_the_device():
     aus, drawn, _ = vs.build_stream(vs.Config(**dict(ALL, width=416, height=240)), gop4(), seed=4, hash_sei="md5")
     stock = vs.decode(vs.REF_SO, aus, threads=1)
     assert vs.decode.hash_errors == 0
-    got, hash_errors = su.decode_swapped_device_guarded(aus, threads=1, async_finish=True, timeout=300)
+    got, hash_errors = su.decode_swapped_device_guarded(aus, threads=1, async_finish=True, timeout=180)
     assert hash_errors == 0 and _diff(got, stock) == [0] * len(aus)
